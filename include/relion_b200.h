@@ -1,0 +1,295 @@
+/*
+ * relion_b200 — C-ABI of the B200-native (sm_100a) expectation-step library.
+ *
+ * This is the drop-in boundary for RELION's accelerator path (library target `relion_gpu_util`,
+ * /root/reference/src/apps/CMakeLists.txt:246-248): the functions below are what a replacement for
+ * MlDeviceBundle / MlOptimiserCuda / AccProjector / AccBackprojector
+ * (src/acc/cuda/cuda_ml_optimiser.h:18-144, src/acc/acc_projector.h:17-104,
+ * src/acc/acc_backprojector.h:24-99) binds to.  INTEGRATION.md shows the C++ adapter.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes.  HOST pointers unless a name says `_dev`.
+ *   - every function returns 0 (RB_OK) or a negative rb_status; rb_last_error() gives the text
+ *     (thread-local).  The adapter turns a non-zero status into RelionError, matching
+ *     HANDLE_ERROR -> CRITICAL -> REPORT_ERROR (src/acc/cuda/cuda_settings.h:48-68).
+ *   - the library owns all device memory; the caller owns host buffers.
+ *   - one rb_ctx per device.  A ctx is thread-compatible (calls on one ctx must be serialised);
+ *     the batched rb_estep_pool() replaces the reference's "one particle per OpenMP thread" fan-out
+ *     (src/ml_optimiser.cpp:4280), so no concurrent entry is needed.
+ *   - there is NO CPU fallback: without a CUDA device rb_ctx_create() fails with RB_ERR_CUDA.
+ *   - scope: 3D reference / 2D images, nr_bodies == 1, no helical/tomo, no CC first iteration,
+ *     no SGD/VDAM back-projection (DESIGN.md "out of scope").
+ *
+ * Index conventions follow the reference:
+ *   coarse hidden index  ihidden      = ((iclass*n_dir + idir)*n_psi + ipsi)*n_trans + itrans
+ *   fine hidden index    ihidden_over = (ihidden*n_over_rot + iover_rot)*n_over_trans + iover_trans
+ *   where (idir, ipsi) index the particle's own (prior-selected) lists when local searches are on.
+ *   Fourier half-image: pixel = iy*(n/2+1) + x, y = iy <= n/2 ? iy : iy-n  (FFTW layout, x fastest).
+ *   Volume: voxel = (z-zinit)*Y*X + (y-yinit)*X + x, x in [0, X).
+ */
+#ifndef RELION_B200_H_
+#define RELION_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RB_VERSION 100
+
+typedef enum {
+	RB_OK = 0,
+	RB_ERR_CUDA = -1,          /* CUDA runtime error (message has file:line)                      */
+	RB_ERR_ARG = -2,           /* invalid argument / unsupported configuration                    */
+	RB_ERR_STATE = -3,         /* call order (e.g. estep before set_reference)                    */
+	RB_ERR_CAPACITY = -4,      /* fine-pass workspace too small for this pool: split the pool     */
+	RB_ERR_TRANSLIM = -5,      /* more translations than supported (ERR_TRANSLIM analogue,
+	                              acc_helper_functions_impl.h:1247-1253)                          */
+	RB_ERR_NO_SIGNIFICANT = -6,/* ERRFILTEREDZERO / ERRNOSIGNIFS (acc_ml_optimiser_impl.h:2242-2299) */
+	RB_ERR_SUMWEIGHT_ZERO = -7,/* ERRSUMWEIGHTZERO (acc_ml_optimiser_impl.h:2505-2520)            */
+	RB_ERR_PMAX = -8           /* Pmax > 1 (acc_ml_optimiser_impl.h:2924-2929)                    */
+} rb_status;
+
+typedef struct rb_ctx rb_ctx;
+
+/* ------------------------------------------------------------------------------------------------
+ * Context  (MlDeviceBundle ctor/setDevice/dtor — cuda_ml_optimiser.h:18-76, cuda_ml_optimiser.cu:85)
+ * ---------------------------------------------------------------------------------------------- */
+int rb_ctx_create(int device, rb_ctx **out);
+void rb_ctx_destroy(rb_ctx *ctx);
+const char *rb_last_error(void);
+int rb_version(void);
+/* device synchronise (MlDeviceBundle::syncAllBackprojects, cuda_ml_optimiser.h:60-64) */
+int rb_sync(rb_ctx *ctx);
+/* number of kernel launches issued by this ctx since creation (bench.py "gpu_launches") */
+long long rb_launch_count(rb_ctx *ctx);
+/* device time (ms) spent in the named stage during the last rb_estep_pool call; stages:
+ * "coarse", "weights_coarse", "fine_setup", "fine", "weights_fine", "store", "total".
+ * Valid after rb_sync().  Returns <0 if unknown. */
+double rb_stage_ms(rb_ctx *ctx, const char *stage);
+
+/* ------------------------------------------------------------------------------------------------
+ * Reference volumes (AccProjector::setMdlDim + initMdl, acc_projector_impl.h:5-312; fed from
+ * MlModel::PPref[k].data, cuda_ml_optimiser.cu:116-127).
+ * vol: complex (re,im) pairs, [mdlZ][mdlY][mdlX], x >= 0 half, mdlInitY = mdlInitZ = -(mdlY-1)/2.
+ * ---------------------------------------------------------------------------------------------- */
+int rb_set_reference(rb_ctx *ctx, int iclass, const double *vol_complex,
+                     int mdlX, int mdlY, int mdlZ, int mdlInitY, int mdlInitZ,
+                     int mdlMaxR, double padding_factor);
+int rb_set_reference_f32(rb_ctx *ctx, int iclass, const float *vol_complex,
+                         int mdlX, int mdlY, int mdlZ, int mdlInitY, int mdlInitZ,
+                         int mdlMaxR, double padding_factor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Back-projection accumulators (AccBackprojector::setMdlDim/initMdl/clear/getMdlData,
+ * acc_backprojector_impl.h:13-186).  Device layout is one interleaved float4 (re, im, weight, 0)
+ * per voxel so that each trilinear corner is one 16-byte vector reduction.
+ * ---------------------------------------------------------------------------------------------- */
+int rb_bp_init(rb_ctx *ctx, int iclass, int mdlX, int mdlY, int mdlZ,
+               int mdlInitY, int mdlInitZ, int maxR, double padding_factor);
+int rb_bp_clear(rb_ctx *ctx, int iclass);
+/* getMdlData: three SoA arrays of mdlX*mdlY*mdlZ floats (src/ml_optimiser.cpp:3813-3838) */
+int rb_bp_get(rb_ctx *ctx, int iclass, float *real, float *imag, float *weight);
+/* device pointer + float count of the interleaved accumulator, for the per-iteration sum over GPUs
+ * (ncclAllReduce(ncclFloat, ncclSum) replaces MlOptimiserMpi::combineAllWeightedSums,
+ * src/ml_optimiser_mpi.cpp:2028-2185).  The pointer stays valid until rb_bp_init/rb_ctx_destroy. */
+int rb_bp_device_buffer(rb_ctx *ctx, int iclass, void **dptr, size_t *n_floats);
+
+/* ------------------------------------------------------------------------------------------------
+ * Sampling tables for this iteration (outputs of HealpixSampling, src/healpix_sampling.cpp:
+ * getDirection/getPsiAngle :1662-1700, getOrientations :1832, getTranslationsInPixel :1724).
+ * Host-side list generation stays RELION's; the library turns angles into matrices itself:
+ * coarse in fp32 on the device (cuda_kernel_make_eulers_3D, helper.cuh:713-840), fine in fp64
+ * then cast (generateEulerMatrices, acc_helper_functions_impl.h:198-262).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+	int n_dir, n_psi;            /* full coarse grid                                         */
+	const double *rot, *tilt;    /* [n_dir] degrees                                          */
+	const double *psi;           /* [n_psi] degrees                                          */
+	int n_over_rot;              /* oversamplingFactorOrientations: 1 or 8                   */
+	/* oversampled triplets [(idir*n_psi+ipsi)*n_over_rot + iover] degrees; may be NULL when
+	 * n_over_rot == 1 (then the coarse angles are used)                                     */
+	const double *over_rot, *over_tilt, *over_psi;
+	int n_trans;                 /* coarse translations                                      */
+	const double *trans_x, *trans_y;           /* [n_trans] pixels (oversampling 0)          */
+	int n_over_trans;            /* oversamplingFactorTranslations: 1 or 4                   */
+	const double *over_trans_x, *over_trans_y; /* [n_trans*n_over_trans] pixels              */
+} rb_sampling;
+int rb_set_sampling(rb_ctx *ctx, const rb_sampling *s);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model / optimiser state read by the E-step (data contract of SURVEY.md §8b):
+ * MlModel (src/ml_model.h) + MlOptimiser flags (src/ml_optimiser.h).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+	int nr_classes;
+	int ori_size;                /* mymodel.ori_size == image_full_size (single optics-group size) */
+	int coarse_size;             /* image_coarse_size  (src/ml_optimiser.cpp:5743-5777)      */
+	int current_size;            /* image_current_size                                       */
+	double pixel_size;           /* Angstrom / pixel                                         */
+	int nr_optics_groups;
+	const double *sigma2_noise;  /* [nr_optics_groups][ori_size/2+1]                         */
+	int nr_groups;
+	const double *scale_correction;   /* [nr_groups]                                         */
+	const double *pdf_class;          /* [nr_classes]                                        */
+	const double *pdf_direction;      /* [nr_classes][n_dir] (used when no orientational prior) */
+	const double *data_vs_prior_class;/* [nr_classes][ori_size/2+1] (scale-correction shells) */
+	double sigma2_offset;        /* Angstrom^2 (mymodel.sigma2_offset)                       */
+	double offset_range;         /* >0: sigma2 = range^2/9 (acc_ml_optimiser_impl.h:1916-1921) */
+	double sigma2_fudge;
+	double adaptive_fraction;    /* --adaptive_fraction, default 0.999                       */
+	int maximum_significants;    /* --maxsig, <=0: off                                       */
+	int do_ctf_correction, refs_are_ctf_corrected, do_scale_correction, do_map;
+	int ctf_premultiplied;
+	int bp_circle_bound;         /* 1: drop x >= floor(sqrt((n/2)^2-y^2)) like ALTCPU BP.h:565 (default);
+	                                0: CUDA BP.cuh behaviour (no extra bound)                */
+} rb_model;
+int rb_set_model(rb_ctx *ctx, const rb_model *m);
+/* Call order: rb_set_model, rb_set_sampling, then (without orientational priors) rb_set_pdf_direction:
+ * [nr_classes][n_dir] needs both the model (values) and the sampling (n_dir).  rb_set_model picks
+ * m->pdf_direction up itself when the sampling is already known. */
+int rb_set_pdf_direction(rb_ctx *ctx, const double *pdf_direction);
+
+/* ------------------------------------------------------------------------------------------------
+ * One pool of particles (what getFourierTransformsAndCtfs leaves in OptimisationParamters,
+ * acc_ml_optimiser_impl.h:11-1010: Fimg, Fimg_nomask, Fctf at image_current_size, highres_Xi2,
+ * old_offset, prior; plus the per-particle prior-selected orientation lists of local searches,
+ * HealpixSampling::selectOrientationsWithNonZeroPriorProbability, healpix_sampling.cpp:695).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+	int n_particles;
+	/* [P][current_size][current_size/2+1] complex (re,im) fp32: masked image FT, unmasked image FT */
+	const float *Fimg, *Fimg_nomask;
+	/* [P][current_size][current_size/2+1] fp32 CTF (ignored if !do_ctf_correction) */
+	const float *Fctf;
+	const int *group_id;         /* [P] */
+	const int *optics_group;     /* [P] */
+	const double *highres_Xi2;   /* [P]  power beyond current_size (op.highres_Xi2_img)          */
+	const double *old_offset;    /* [P][2] pixels (already applied to the image)                  */
+	const double *prior_offset;  /* [P][2] pixels (op.prior)                                      */
+	/* local angular searches: per-particle lists; all NULL => every (dir,psi) with
+	 * pdf_direction > 0 is searched (NOPRIOR, global search)                                     */
+	const int *dir_off;          /* [P+1] offsets into dir_idx/dir_prior                          */
+	const int *dir_idx;          /* pointer_dir_nonzeroprior: indices into the full n_dir grid    */
+	const double *dir_prior;     /* directions_prior                                              */
+	const int *psi_off;          /* [P+1]                                                         */
+	const int *psi_idx;          /* pointer_psi_nonzeroprior                                      */
+	const double *psi_prior;     /* psi_prior                                                     */
+} rb_particles;
+
+/* Per-particle results (what storeWeightedSums writes to exp_metadata and folds into wsum_model,
+ * acc_ml_optimiser_impl.h:2858-2931, 3466-3656).  The host adapter finishes the bookkeeping in
+ * double exactly where the reference does (norm correction, dLL - logsigma2, scale XA/AA / scale). */
+typedef struct {
+	int64_t best_ihidden_over;   /* op.max_index.fineIdx                                          */
+	int best_class, best_idir, best_ipsi, best_iover_rot, best_itrans, best_iover_trans;
+	int nr_significant_coarse;   /* METADATA_NR_SIGN                                              */
+	int n_fine_orient, n_fine_samples; /* sizes of the fine pass (diagnostics / roofline)         */
+	float min_diff2_coarse;
+	float sum_weight_coarse;
+	float significant_weight_coarse;
+	float min_diff2;             /* op.min_diff2 after the fine pass (+50 - max shift applied)    */
+	float max_weight;            /* op.max_weight                                                 */
+	float sum_weight;            /* op.sum_weight (fine pass)                                     */
+	float significant_weight;    /* op.significant_weight (fine pass)                             */
+	float pmax;                  /* METADATA_PMAX = max_weight / sum_weight                       */
+	double dLL_nolog;            /* log(sum_weight) - min_diff2  (host subtracts logsigma2)       */
+	double wsum_norm_correction; /* sum over shells ires>-1 of wdiff2                              */
+	double wsum_XA, wsum_AA;     /* exp_wsum_scale_correction_XA/AA before the /scale division     */
+	double sumw;                 /* thr_sumw_group                                                */
+	double wsum_sigma2_offset;   /* thr_wsum_sigma2_offset (Angstrom^2)                           */
+} rb_particle_out;
+
+typedef struct {
+	rb_particle_out *particles;  /* [P]                                                           */
+	float *wsum_sigma2_noise;    /* [P][ori_size/2+1] per-particle thr_wsum_sigma2_noise (may be NULL) */
+	double *wsum_pdf_direction;  /* [nr_classes][n_dir]  += over the pool (may be NULL)           */
+	double *wsum_pdf_class;      /* [nr_classes]         += over the pool (may be NULL)           */
+} rb_pool_out;
+
+/* Batched E-step over a pool: coarse diff2 -> weights/significance -> fine diff2 -> weights ->
+ * weighted sums + back-projection (accDoExpectationOneParticle for every particle of the pool,
+ * acc_ml_optimiser_impl.h:3672-3962).  Back-projection lands in the ctx's accumulators.
+ * flags: bit0 = skip back-projection/wavg (do_skip_maximization). */
+int rb_estep_pool(rb_ctx *ctx, const rb_particles *pool, rb_pool_out *out, unsigned flags);
+
+/* Same, split in two so a caller can overlap the H2D upload of pool i+1 with the compute of pool i:
+ * rb_pool_upload stages the pool into one of two device slots asynchronously (pinned host memory
+ * recommended); rb_estep_slot runs the E-step on a staged slot. */
+int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool);
+int rb_estep_slot(rb_ctx *ctx, int slot, rb_pool_out *out, unsigned flags);
+/* Device-resident timing helper for roofline measurement: re-runs the compute of an already
+ * uploaded slot without any host<->device copy of particle data or results. */
+int rb_estep_slot_nocopy(rb_ctx *ctx, int slot, unsigned flags);
+/* fetch results of the last rb_estep_slot_nocopy */
+int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out);
+
+/* ------------------------------------------------------------------------------------------------
+ * Stage-level entry points (kernel-granularity twins of AccUtilities::* / run*Kernel,
+ * src/acc/utilities.h:946-1620, acc_helper_functions_impl.h).  Used by the parity tests and usable
+ * by an adapter that keeps the reference's per-particle driver.
+ * ---------------------------------------------------------------------------------------------- */
+/* AccProjectorKernel::project3Dmodel over a half image, fine-pass y-wrap; eulers [n][9] fp32,
+ * out [n][imgY][imgX] complex interleaved */
+int rb_project(rb_ctx *ctx, int iclass, int img_size, const float *eulers, int n, float *out_complex);
+
+/* runDiff2KernelCoarse (acc_helper_functions_impl.h:1139): diff2s[o*T+t] = sum 0.5*corr*|A_o - S_t X|^2 */
+int rb_diff2_coarse(rb_ctx *ctx, int iclass, int img_size,
+                    const float *eulers, int n_orient,
+                    const float *trans_x, const float *trans_y, int n_trans,
+                    const float *img_re, const float *img_im, const float *corr,
+                    float *diff2s);
+
+/* runDiff2KernelFine (acc_helper_functions_impl.h:1813) with the reference's job lists */
+int rb_diff2_fine(rb_ctx *ctx, int iclass, int img_size,
+                  const float *eulers, int n_orient,
+                  const float *trans_x, const float *trans_y, int n_trans,
+                  const float *img_re, const float *img_im, const float *corr, float sum_init,
+                  const uint64_t *rot_idx, const uint64_t *trans_idx,
+                  const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
+                  float *diff2s, int n_weights);
+
+/* convertAllSquaredDifferencesToWeights, dense form (acc_ml_optimiser_impl.h:2188-2345):
+ * in: diff2 [n_orient*n_trans] (Mweight), priors; out: weights in place, significance flags.
+ * filter_zero=1 is the coarse pass (weights>0 only enter the sort), 0 the fine pass. */
+typedef struct {
+	float min_diff2;
+	float max_weight; int64_t max_index;
+	float sum_weight; float significant_weight;
+	int nr_significant; int n_nonzero;
+} rb_weights_out;
+int rb_convert_weights(rb_ctx *ctx, float *weights, int64_t n_orient, int n_trans,
+                       const float *pdf_orientation, const unsigned char *pdf_orientation_zeros,
+                       const float *pdf_offset, const unsigned char *pdf_offset_zeros,
+                       double adaptive_fraction, int maximum_significants, int filter_zero,
+                       unsigned char *significant, rb_weights_out *out);
+
+/* runWavgKernel (acc_helper_functions_impl.h:316): per-pixel sums over orientations/translations */
+int rb_wavg(rb_ctx *ctx, int iclass, int img_size,
+            const float *eulers, int n_orient,
+            const float *trans_x, const float *trans_y, int n_trans,
+            const float *img_re, const float *img_im, const float *weights, const float *ctfs,
+            float weight_norm, float significant_weight,
+            float *wdiff2s_parts, float *wdiff2s_AA, float *wdiff2s_XA);
+
+/* runBackProjectKernel (acc_helper_functions_impl.h:505) into class iclass' accumulator */
+int rb_backproject(rb_ctx *ctx, int iclass, int img_size,
+                   const float *eulers, int n_orient,
+                   const float *trans_x, const float *trans_y, int n_trans,
+                   const float *img_re, const float *img_im,
+                   const float *weights, const float *Minvsigma2s, const float *ctfs,
+                   float weight_norm, float significant_weight);
+
+/* relion_reconstruct-style posed back-projection (BASELINE config #2; Reconstructor::backprojectOneParticle,
+ * src/reconstructor.cpp:328-744 -> BackProjector::backproject2Dto3D, src/backprojector.cpp:55-357):
+ * n images [n][img_size][img_size/2+1] complex already multiplied by CTF, weights Fctf=ctf^2,
+ * one inverted 3x3 matrix per image. */
+int rb_backproject_posed(rb_ctx *ctx, int iclass, int img_size, int n,
+                         const float *F2D_complex, const float *Fctf, const float *eulers);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RELION_B200_H_ */

@@ -1,0 +1,183 @@
+/*
+ * TEST INFRASTRUCTURE ONLY — builds oracle/_ref/librefkernels.so (git-ignored).
+ *
+ * This translation unit contains NO algorithm of its own: it #includes the reference's own ALTCPU
+ * kernel headers from where they lie under /root/reference (never copied into this repo) and wraps
+ * them behind the C table declared in oracle/oracle_kernels.h, so that
+ *   (a) oracle/port_kernels.cpp (our restatement) can be pinned against the real reference code, and
+ *   (b) bench.py --impl reference can time the reference's own CPU implementation of the path.
+ *
+ * Build recipe: oracle/Makefile (target _ref), flags as verified in SURVEY.md §8(c)/Appendix D:
+ *   g++ -O3 -march=native -std=c++17 -fopenmp -DALTCPU=1 -DACC_CUDA=2 -DACC_CPU=1 -DPROJECTOR_NO_TEXTURES
+ *       -Ioracle/shim -I/root/reference
+ * Header closure: acc_ptr.h, complex.h, error.h, macros.h, parallel.h, pipeline_control.h,
+ * jaz/single_particle/t_complex.h, cpu_settings.h, settings.h — no FFTW/MPI/TIFF/TBB needed
+ * (tbb::spin_mutex comes from oracle/shim/tbb/spin_mutex.h).
+ *
+ * The two helpers that live in src/acc/cpu/cpu_kernels/helper.cpp (exponentiate_weights_fine,
+ * cpu_kernel_make_eulers_3D) cannot be taken from that file: it includes src/acc/utilities.h and
+ * acc_helper_functions.h, which pull in MlOptimiser (FFTW, MPI, TIFF).  For those two entries the
+ * table points at the restatement in port_kernels.cpp (flagged in `kind_notes`).
+ */
+#include "src/acc/cpu/device_stubs.h"
+#include "src/acc/acc_ptr.h"
+#include "src/acc/acc_projector.h"
+#include "src/acc/acc_backprojector.h"
+#include "src/acc/cpu/cpu_kernels/cpu_utils.h"
+#include "src/acc/acc_projectorkernel_impl.h"
+#include "src/acc/cpu/cpu_kernels/helper.h"
+#include "src/acc/cpu/cpu_kernels/diff2.h"
+#include "src/acc/cpu/cpu_kernels/wavg.h"
+#include "src/acc/cpu/cpu_kernels/BP.h"
+
+#include <vector>
+#include <complex>
+#include <cstring>
+
+#include "oracle_kernels.h"
+
+// restated helpers (see header comment) — defined in port_kernels.cpp, compiled into this .so too
+extern "C" void portk_make_eulers_3d(const float *, const float *, const float *, float *, unsigned long);
+extern "C" void portk_exponentiate_weights_fine(const float *, const unsigned char *, const float *,
+		const unsigned char *, float *, float, unsigned long, unsigned long, const unsigned long *,
+		const unsigned long *, const unsigned long *, const unsigned long *, long);
+
+namespace {
+
+AccProjectorKernel make_kernel(const ok_projector *p, int imgX, int imgY)
+{
+	// AccProjectorKernel::makeKernel (acc_projectorkernel_impl.h:301-319) with imgMaxR = imgX-1
+	// as every caller passes (acc_ml_optimiser_impl.h:1322-1327)
+	int imgMaxR = imgX - 1;
+	int maxR = p->mdlMaxR >= imgMaxR ? imgMaxR : p->mdlMaxR;
+	return AccProjectorKernel(p->mdlX, p->mdlY, p->mdlZ, imgX, imgY, 1,
+	                          p->mdlInitY, p->mdlInitZ, p->padding_factor, maxR,
+	                          (std::complex<XFLOAT> *) p->mdl);
+}
+
+void refk_project(const ok_projector *p, int imgX, int imgY, const float *e, float *out_re, float *out_im)
+{
+	AccProjectorKernel k = make_kernel(p, imgX, imgY);
+	for (int iy = 0; iy < imgY; iy++)
+	{
+		// fine-pass row handling of diff2_fine_2D / wavg_ref3D (diff2.h:344-355, wavg.h:71-82)
+		int xstart = 0, xend = imgX, y = iy;
+		if (iy > k.maxR)
+		{
+			if (iy >= imgY - k.maxR) y = iy - imgY;
+			else { xstart = k.maxR; xend = xstart + 1; }
+		}
+		for (int x = 0; x < imgX; x++) { out_re[iy * imgX + x] = 0.f; out_im[iy * imgX + x] = 0.f; }
+		for (int x = xstart; x < xend; x++)
+			k.project3Dmodel(x, y, e[0], e[1], e[3], e[4], e[6], e[7], out_re[iy * imgX + x], out_im[iy * imgX + x]);
+	}
+}
+
+void refk_diff2_coarse(const ok_projector *p, int imgX, int imgY,
+		const float *eulers, unsigned long O,
+		const float *trans_x, const float *trans_y, unsigned long T,
+		const float *img_re, const float *img_im, const float *corr, float *diff2s)
+{
+	AccProjectorKernel k = make_kernel(p, imgX, imgY);
+	unsigned long image_size = (unsigned long) imgX * imgY;
+	std::vector<float> tz(T, 0.f);
+	// dispatch as runDiff2KernelCoarse does (acc_helper_functions_impl.h:1247-1300):
+	unsigned long rest = O % D2C_BLOCK_SIZE_REF3D;
+	unsigned long even = O - rest;
+	if (even)
+		CpuKernels::diff2_coarse<true, false, D2C_BLOCK_SIZE_REF3D, D2C_EULERS_PER_BLOCK_REF3D, PREFETCH_FRACTION_3D>(
+			even / D2C_EULERS_PER_BLOCK_REF3D, (XFLOAT *) eulers, (XFLOAT *) trans_x, (XFLOAT *) trans_y, tz.data(),
+			(XFLOAT *) img_re, (XFLOAT *) img_im, k, (XFLOAT *) corr, diff2s, T, image_size);
+	if (rest)
+		CpuKernels::diff2_coarse<true, false, D2C_BLOCK_SIZE_REF3D, 1, PREFETCH_FRACTION_3D>(
+			rest, (XFLOAT *) &eulers[9 * even], (XFLOAT *) trans_x, (XFLOAT *) trans_y, tz.data(),
+			(XFLOAT *) img_re, (XFLOAT *) img_im, k, (XFLOAT *) corr, &diff2s[T * even], T, image_size);
+}
+
+void refk_diff2_fine(const ok_projector *p, int imgX, int imgY, const float *eulers,
+		const float *trans_x, const float *trans_y,
+		const float *img_re, const float *img_im, const float *corr, float sum_init,
+		unsigned long orientation_num, unsigned long translation_num, unsigned long num_jobs,
+		const unsigned long *rot_idx, const unsigned long *trans_idx,
+		const unsigned long *job_idx, const unsigned long *job_num, float *diff2s)
+{
+	AccProjectorKernel k = make_kernel(p, imgX, imgY);
+	CpuKernels::diff2_fine_2D<true>(num_jobs, (XFLOAT *) eulers, (XFLOAT *) img_re, (XFLOAT *) img_im,
+		(XFLOAT *) trans_x, (XFLOAT *) trans_y, (XFLOAT *) trans_x /*unused z*/, k, (XFLOAT *) corr, diff2s,
+		(unsigned long) imgX * imgY, sum_init, orientation_num, translation_num, num_jobs,
+		(unsigned long *) rot_idx, (unsigned long *) trans_idx, (unsigned long *) job_idx, (unsigned long *) job_num);
+}
+
+void refk_weights_exponent_coarse(const float *pdf_o, const unsigned char *pdf_oz,
+		const float *pdf_t, const unsigned char *pdf_tz, float *w, float min_diff2,
+		unsigned long no, unsigned long nt, size_t max_idx)
+{
+	static_assert(sizeof(bool) == 1, "bool must be 1 byte");
+	CpuKernels::weights_exponent_coarse<XFLOAT>((XFLOAT *) pdf_o, (bool *) pdf_oz, (XFLOAT *) pdf_t, (bool *) pdf_tz,
+		w, min_diff2, no, nt, max_idx);
+}
+
+void refk_exponentiate(float *a, float add, size_t n) { CpuKernels::exponentiate<XFLOAT>(a, add, n); }
+
+void refk_collect2jobs(int grid_size, const float *ox, const float *oy, const float *o2,
+		const float *w, float sig, float sum, unsigned long ct, unsigned long ot, unsigned long oo,
+		unsigned long ov, float *o_w, float *px, float *py, float *s2,
+		const unsigned long *rot_idx, const unsigned long *trans_idx,
+		const unsigned long *job_idx, const unsigned long *job_num)
+{
+	CpuKernels::collect2jobs<false>(grid_size, SUMW_BLOCK_SIZE, (XFLOAT *) ox, (XFLOAT *) oy, (XFLOAT *) ox,
+		(XFLOAT *) o2, (XFLOAT *) w, sig, sum, ct, ot, oo, ov, false, o_w, px, py, px /*z unused*/, s2,
+		(unsigned long *) rot_idx, (unsigned long *) trans_idx, (unsigned long *) job_idx, (unsigned long *) job_num);
+}
+
+void refk_wavg(const ok_projector *p, int imgX, int imgY, const float *eulers, unsigned long orientation_num,
+		const float *img_re, const float *img_im, const float *trans_x, const float *trans_y,
+		const float *weights, const float *ctfs, float *parts, float *AA, float *XA,
+		unsigned long trans_num, float weight_norm, float significant_weight, float part_scale)
+{
+	AccProjectorKernel k = make_kernel(p, imgX, imgY);
+	// refs_are_ctf_corrected branch of runWavgKernel (acc_helper_functions_impl.h:343-370)
+	CpuKernels::wavg_ref3D<true, true>((XFLOAT *) eulers, k, (unsigned long) imgX * imgY, orientation_num,
+		(XFLOAT *) img_re, (XFLOAT *) img_im, (XFLOAT *) trans_x, (XFLOAT *) trans_y, (XFLOAT *) trans_x,
+		(XFLOAT *) weights, (XFLOAT *) ctfs, parts, AA, XA, trans_num, weight_norm, significant_weight, part_scale);
+}
+
+void refk_backproject(const ok_backprojector *bp, int imgX, int imgY,
+		const float *img_re, const float *img_im, const float *trans_x, const float *trans_y,
+		const float *weights, const float *Minvsigma2s, const float *ctfs,
+		unsigned long trans_num, float significant_weight, float weight_norm,
+		const float *eulers, unsigned long image_count)
+{
+	std::vector<tbb::spin_mutex> local;
+	tbb::spin_mutex *mutexes = (tbb::spin_mutex *) bp->sync;
+	if (!mutexes) { local = std::vector<tbb::spin_mutex>((size_t) bp->mdlZ * bp->mdlY); mutexes = local.data(); }
+	CpuKernels::backprojectRef3D<false>(image_count, (XFLOAT *) img_re, (XFLOAT *) img_im,
+		(XFLOAT *) trans_x, (XFLOAT *) trans_y, (XFLOAT *) weights, (XFLOAT *) Minvsigma2s, (XFLOAT *) ctfs,
+		trans_num, significant_weight, weight_norm, (XFLOAT *) eulers,
+		bp->real, bp->imag, bp->weight, bp->maxR, bp->maxR * bp->maxR, bp->padding_factor,
+		(unsigned) imgX, (unsigned) imgY, 1u, (size_t) imgX * imgY,
+		(unsigned) bp->mdlX, (unsigned) bp->mdlY, bp->mdlInitY, bp->mdlInitZ, mutexes);
+}
+
+void *refk_bp_sync_alloc(int mdlY, int mdlZ) { return new tbb::spin_mutex[(size_t) mdlY * mdlZ]; }
+void refk_bp_sync_free(void *s) { delete[] (tbb::spin_mutex *) s; }
+
+const ok_kernel_table table = {
+	"reference",
+	portk_make_eulers_3d,            // restated: helper.cpp is not buildable standalone
+	refk_project,
+	refk_diff2_coarse,
+	refk_diff2_fine,
+	refk_weights_exponent_coarse,
+	refk_exponentiate,
+	portk_exponentiate_weights_fine, // restated: helper.cpp is not buildable standalone
+	refk_collect2jobs,
+	refk_wavg,
+	refk_backproject,
+	refk_bp_sync_alloc,
+	refk_bp_sync_free,
+};
+
+} // namespace
+
+extern "C" const ok_kernel_table *refk_kernel_table(void) { return &table; }

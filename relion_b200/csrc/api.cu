@@ -1,0 +1,847 @@
+// relion_b200 — C-ABI glue (include/relion_b200.h): context, model/sampling upload, pool pipeline.
+// Product code: no reference to oracle/; fails loudly without a CUDA device (no CPU fallback).
+#include "common.cuh"
+#include <cstdarg>
+#include <cstdlib>
+#include <cmath>
+#include <algorithm>
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+
+void rb_set_error(const char *fmt, ...)
+{
+	va_list ap;
+	va_start(ap, fmt);
+	vsnprintf(g_err, sizeof(g_err), fmt, ap);
+	va_end(ap);
+}
+
+extern "C" const char *rb_last_error(void) { return g_err; }
+extern "C" int rb_version(void) { return RB_VERSION; }
+
+int DevBuf::ensure(size_t n)
+{
+	if (n <= bytes && p) return RB_OK;
+	if (n == 0) n = 16;
+	if (p) { RB_CUDA(cudaFree(p)); p = nullptr; bytes = 0; }
+	RB_CUDA(cudaMalloc(&p, n));
+	bytes = n;
+	return RB_OK;
+}
+void DevBuf::release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+
+static int upload(rb_ctx *ctx, DevBuf &b, const void *src, size_t bytes)
+{
+	RB_CHECK(b.ensure(bytes));
+	if (bytes) RB_CUDA(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+extern "C" int rb_ctx_create(int device, rb_ctx **out)
+{
+	RB_ARG(out != nullptr, "rb_ctx_create: out is NULL");
+	int ndev = 0;
+	cudaError_t e = cudaGetDeviceCount(&ndev);
+	if (e != cudaSuccess || ndev == 0)
+	{
+		rb_set_error("rb_ctx_create: no CUDA device available (%s); this library has no CPU fallback",
+		             e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+		return RB_ERR_CUDA;
+	}
+	RB_ARG(device >= 0 && device < ndev, "rb_ctx_create: device %d out of range (have %d)", device, ndev);
+	RB_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop;
+	RB_CUDA(cudaGetDeviceProperties(&prop, device));
+	if (prop.major < 10)
+	{
+		rb_set_error("rb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
+		return RB_ERR_CUDA;
+	}
+	rb_ctx *ctx = new rb_ctx();
+	ctx->device = device;
+	ctx->num_sms = prop.multiProcessorCount;
+	RB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+	RB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < RB_NUM_SLOTS; i++) RB_CUDA(cudaEventCreateWithFlags(&ctx->slot[i].uploaded, cudaEventDisableTiming));
+	memset(ctx->proj, 0, sizeof(ctx->proj));
+	memset(ctx->bp, 0, sizeof(ctx->bp));
+	*out = ctx;
+	return RB_OK;
+}
+
+static void release_slot(PoolSlot &s)
+{
+	DevBuf *bufs[] = {&s.Fimg, &s.Fnomask, &s.Fctf, &s.meta, &s.state, &s.dir_idx, &s.dir_prior, &s.psi_idx, &s.psi_prior,
+	                  &s.Mweight, &s.pdf_orient, &s.pdf_orient_zero, &s.pdf_offset, &s.pdf_offset_zero,
+	                  &s.so_list, &s.pair_list, &s.fo, &s.fs_w, &s.fs_ihid, &s.counters, &s.shells, &s.out_pdf_dir, &s.out_pdf_class};
+	for (DevBuf *b : bufs) b->release();
+	if (s.uploaded) cudaEventDestroy(s.uploaded);
+}
+
+extern "C" void rb_ctx_destroy(rb_ctx *ctx)
+{
+	if (!ctx) return;
+	cudaSetDevice(ctx->device);
+	cudaDeviceSynchronize();
+	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->bp_buf[i].release(); }
+	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
+	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
+	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp};
+	for (DevBuf *b : bufs) b->release();
+	for (auto &b : ctx->scratch) b.release();
+	for (int i = 0; i < RB_NUM_SLOTS; i++) release_slot(ctx->slot[i]);
+	for (auto &kv : ctx->stage_ev) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
+	cudaStreamDestroy(ctx->stream);
+	cudaStreamDestroy(ctx->copy_stream);
+	delete ctx;
+}
+
+extern "C" int rb_sync(rb_ctx *ctx)
+{
+	RB_ARG(ctx, "rb_sync: ctx is NULL");
+	RB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" long long rb_launch_count(rb_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+int rb_stage_begin(rb_ctx *ctx, const char *name)
+{
+	auto it = ctx->stage_ev.find(name);
+	if (it == ctx->stage_ev.end())
+	{
+		cudaEvent_t a, b;
+		RB_CUDA(cudaEventCreate(&a)); RB_CUDA(cudaEventCreate(&b));
+		it = ctx->stage_ev.emplace(name, std::make_pair(a, b)).first;
+	}
+	RB_CUDA(cudaEventRecord(it->second.first, ctx->stream));
+	return RB_OK;
+}
+int rb_stage_end(rb_ctx *ctx, const char *name)
+{
+	auto it = ctx->stage_ev.find(name);
+	if (it == ctx->stage_ev.end()) return RB_OK;
+	RB_CUDA(cudaEventRecord(it->second.second, ctx->stream));
+	return RB_OK;
+}
+extern "C" double rb_stage_ms(rb_ctx *ctx, const char *stage)
+{
+	if (!ctx || !stage) return -1.;
+	auto it = ctx->stage_ev.find(stage);
+	if (it == ctx->stage_ev.end()) return -1.;
+	float ms = 0.f;
+	if (cudaEventElapsedTime(&ms, it->second.first, it->second.second) != cudaSuccess) { cudaGetLastError(); return -1.; }
+	return (double) ms;
+}
+
+int rb_sync_tables(rb_ctx *ctx)
+{
+	RB_CHECK(upload(ctx, ctx->d_proj, ctx->proj, sizeof(ctx->proj)));
+	RB_CHECK(upload(ctx, ctx->d_bp, ctx->bp, sizeof(ctx->bp)));
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// reference volumes / accumulators
+// ---------------------------------------------------------------------------------------------
+static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int initY, int initZ, int maxR, double pf)
+{
+	RB_ARG(ctx, "ctx is NULL");
+	RB_ARG(k >= 0 && k < RB_MAX_CLASSES, "class index %d out of range", k);
+	RB_ARG(mdlX > 1 && mdlY > 1 && mdlZ > 1, "rb_set_reference: only 3D references are supported (got %dx%dx%d)", mdlX, mdlY, mdlZ);
+	RB_CUDA(cudaSetDevice(ctx->device));
+	size_t n = (size_t) mdlX * mdlY * mdlZ;
+	RB_CHECK(ctx->proj_buf[k].ensure(n * sizeof(float2)));
+	RbProjector &p = ctx->proj[k];
+	p.mdl = ctx->proj_buf[k].as<float2>();
+	p.mdlX = mdlX; p.mdlY = mdlY; p.mdlZ = mdlZ; p.mdlXY = mdlX * mdlY;
+	p.mdlInitY = initY; p.mdlInitZ = initZ; p.mdlMaxR = maxR; p.padding_factor = (float) pf;
+	ctx->has_proj[k] = true;
+	return RB_OK;
+}
+
+extern "C" int rb_set_reference(rb_ctx *ctx, int k, const double *vol, int mdlX, int mdlY, int mdlZ,
+                                int initY, int initZ, int maxR, double pf)
+{
+	RB_CHECK(set_reference_common(ctx, k, mdlX, mdlY, mdlZ, initY, initZ, maxR, pf));
+	size_t n = (size_t) mdlX * mdlY * mdlZ;
+	RB_CHECK(ctx->scratch[2].ensure(n * 2 * sizeof(double)));
+	RB_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, vol, n * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CHECK(rbk_convert_volume(ctx, ctx->scratch[2].as<double>(), ctx->proj_buf[k].as<float2>(), n));
+	RB_CHECK(rb_sync_tables(ctx));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->scratch[2].release();
+	return RB_OK;
+}
+
+extern "C" int rb_set_reference_f32(rb_ctx *ctx, int k, const float *vol, int mdlX, int mdlY, int mdlZ,
+                                    int initY, int initZ, int maxR, double pf)
+{
+	RB_CHECK(set_reference_common(ctx, k, mdlX, mdlY, mdlZ, initY, initZ, maxR, pf));
+	size_t n = (size_t) mdlX * mdlY * mdlZ;
+	RB_CUDA(cudaMemcpyAsync(ctx->proj_buf[k].p, vol, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CHECK(rb_sync_tables(ctx));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_bp_init(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int initY, int initZ, int maxR, double pf)
+{
+	RB_ARG(ctx, "ctx is NULL");
+	RB_ARG(k >= 0 && k < RB_MAX_CLASSES, "class index %d out of range", k);
+	RB_ARG(mdlX > 1 && mdlY > 1 && mdlZ > 1, "rb_bp_init: only 3D accumulators are supported");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	size_t n = (size_t) mdlX * mdlY * mdlZ;
+	RB_CHECK(ctx->bp_buf[k].ensure(n * sizeof(float4)));
+	RbBackprojector &b = ctx->bp[k];
+	b.vol = ctx->bp_buf[k].as<float4>();
+	b.mdlX = mdlX; b.mdlY = mdlY; b.mdlZ = mdlZ; b.mdlInitY = initY; b.mdlInitZ = initZ; b.maxR = maxR; b.padding_factor = (float) pf;
+	ctx->has_bp[k] = true;
+	RB_CUDA(cudaMemsetAsync(b.vol, 0, n * sizeof(float4), ctx->stream));
+	RB_CHECK(rb_sync_tables(ctx));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_bp_clear(rb_ctx *ctx, int k)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_clear: accumulator %d not initialised", k);
+	const RbBackprojector &b = ctx->bp[k];
+	RB_CUDA(cudaMemsetAsync(b.vol, 0, (size_t) b.mdlX * b.mdlY * b.mdlZ * sizeof(float4), ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_bp_get(rb_ctx *ctx, int k, float *real, float *imag, float *weight)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_get: accumulator %d not initialised", k);
+	const RbBackprojector &b = ctx->bp[k];
+	size_t n = (size_t) b.mdlX * b.mdlY * b.mdlZ;
+	RB_CHECK(ctx->scratch[2].ensure(3 * n * sizeof(float)));
+	float *t = ctx->scratch[2].as<float>();
+	RB_CHECK(rbk_bp_deinterleave(ctx, b.vol, t, t + n, t + 2 * n, n));
+	RB_CUDA(cudaMemcpyAsync(real, t, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(imag, t + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(weight, t + 2 * n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->scratch[2].release();
+	return RB_OK;
+}
+
+extern "C" int rb_bp_device_buffer(rb_ctx *ctx, int k, void **dptr, size_t *n_floats)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_device_buffer: accumulator %d not initialised", k);
+	const RbBackprojector &b = ctx->bp[k];
+	if (dptr) *dptr = b.vol;
+	if (n_floats) *n_floats = (size_t) b.mdlX * b.mdlY * b.mdlZ * 4;
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling
+// ---------------------------------------------------------------------------------------------
+extern "C" int rb_set_sampling(rb_ctx *ctx, const rb_sampling *s)
+{
+	RB_ARG(ctx && s, "rb_set_sampling: NULL argument");
+	RB_ARG(s->n_dir > 0 && s->n_psi > 0 && s->n_trans > 0, "rb_set_sampling: empty sampling");
+	RB_ARG(s->rot && s->tilt && s->psi && s->trans_x && s->trans_y, "rb_set_sampling: NULL table");
+	RB_ARG(s->n_over_rot >= 1 && s->n_over_trans >= 1, "rb_set_sampling: oversampling factors must be >= 1");
+	RB_ARG(s->n_over_rot == 1 || (s->over_rot && s->over_tilt && s->over_psi), "rb_set_sampling: oversampled orientations missing");
+	RB_ARG(s->n_over_trans == 1 || (s->over_trans_x && s->over_trans_y), "rb_set_sampling: oversampled translations missing");
+	RB_ARG(ctx->has_model, "rb_set_sampling: call rb_set_model first (translations are scaled by ori_size)");
+	if ((long long) s->n_trans * s->n_over_trans > 2048)
+	{
+		rb_set_error("rb_set_sampling: %d translations x %d oversampling exceeds the supported 2048 (ERR_TRANSLIM)", s->n_trans, s->n_over_trans);
+		return RB_ERR_TRANSLIM;
+	}
+	RB_CUDA(cudaSetDevice(ctx->device));
+	ctx->h_samp = *s;
+	const size_t no = (size_t) s->n_dir * s->n_psi;
+	const int T = s->n_trans, Tf = T * s->n_over_trans;
+	// angles (fp64 for the fine pass, fp32 for the coarse kernel like AccProjectorPlan's XFLOAT alphas/betas/gammas)
+	RB_CHECK(upload(ctx, ctx->s_rot, s->rot, s->n_dir * sizeof(double)));
+	RB_CHECK(upload(ctx, ctx->s_tilt, s->tilt, s->n_dir * sizeof(double)));
+	RB_CHECK(upload(ctx, ctx->s_psi, s->psi, s->n_psi * sizeof(double)));
+	std::vector<float> fr(s->n_dir), ft(s->n_dir), fp(s->n_psi);
+	for (int i = 0; i < s->n_dir; i++) { fr[i] = (float) s->rot[i]; ft[i] = (float) s->tilt[i]; }
+	for (int i = 0; i < s->n_psi; i++) fp[i] = (float) s->psi[i];
+	RB_CHECK(upload(ctx, ctx->scratch[3], fr.data(), fr.size() * 4));
+	RB_CHECK(upload(ctx, ctx->scratch[4], ft.data(), ft.size() * 4));
+	RB_CHECK(upload(ctx, ctx->scratch[5], fp.data(), fp.size() * 4));
+	RB_CHECK(ctx->s_coarse_eulers.ensure(no * 9 * sizeof(float)));
+	RB_CHECK(rbk_make_coarse_eulers(ctx, ctx->scratch[3].as<float>(), ctx->scratch[4].as<float>(), ctx->scratch[5].as<float>(),
+	                                s->n_dir, s->n_psi, ctx->s_coarse_eulers.as<float>()));
+	if (s->n_over_rot > 1 || s->over_rot)
+	{
+		RB_CHECK(upload(ctx, ctx->s_over_rot, s->over_rot, no * s->n_over_rot * sizeof(double)));
+		RB_CHECK(upload(ctx, ctx->s_over_tilt, s->over_tilt, no * s->n_over_rot * sizeof(double)));
+		RB_CHECK(upload(ctx, ctx->s_over_psi, s->over_psi, no * s->n_over_rot * sizeof(double)));
+	}
+	// translations: pixels (for priors) and -2*pi*shift/ori_size (acc_ml_optimiser_impl.h:1239-1241, 1549-1551)
+	const double os = (double) ctx->h_model.ori_size;
+	std::vector<float> ctxv(T), ctyv(T), ftxv(Tf), ftyv(Tf);
+	std::vector<double> otx(Tf), oty(Tf);
+	for (int t = 0; t < T; t++)
+	{
+		ctxv[t] = (float) (-2 * M_PI * s->trans_x[t] / os);
+		ctyv[t] = (float) (-2 * M_PI * s->trans_y[t] / os);
+	}
+	for (int t = 0; t < Tf; t++)
+	{
+		otx[t] = s->over_trans_x ? s->over_trans_x[t] : s->trans_x[t];
+		oty[t] = s->over_trans_y ? s->over_trans_y[t] : s->trans_y[t];
+		ftxv[t] = (float) (-2 * M_PI * otx[t] / os);
+		ftyv[t] = (float) (-2 * M_PI * oty[t] / os);
+	}
+	RB_CHECK(upload(ctx, ctx->s_ctx, ctxv.data(), T * 4)); RB_CHECK(upload(ctx, ctx->s_cty, ctyv.data(), T * 4));
+	RB_CHECK(upload(ctx, ctx->s_ftx, ftxv.data(), Tf * 4)); RB_CHECK(upload(ctx, ctx->s_fty, ftyv.data(), Tf * 4));
+	RB_CHECK(upload(ctx, ctx->s_tx, s->trans_x, T * 8)); RB_CHECK(upload(ctx, ctx->s_ty, s->trans_y, T * 8));
+	RB_CHECK(upload(ctx, ctx->s_otx, otx.data(), Tf * 8)); RB_CHECK(upload(ctx, ctx->s_oty, oty.data(), Tf * 8));
+
+	RbSamplingDev &d = ctx->d_samp;
+	d.n_dir = s->n_dir; d.n_psi = s->n_psi; d.n_over_rot = s->n_over_rot; d.n_trans = T; d.n_over_trans = s->n_over_trans;
+	d.coarse_eulers = ctx->s_coarse_eulers.as<float>();
+	const bool have_over = (s->over_rot != nullptr);
+	d.over_rot = have_over ? ctx->s_over_rot.as<double>() : nullptr;
+	d.over_tilt = have_over ? ctx->s_over_tilt.as<double>() : nullptr;
+	d.over_psi = have_over ? ctx->s_over_psi.as<double>() : nullptr;
+	d.rot = ctx->s_rot.as<double>(); d.tilt = ctx->s_tilt.as<double>(); d.psi = ctx->s_psi.as<double>();
+	d.ctx = ctx->s_ctx.as<float>(); d.cty = ctx->s_cty.as<float>(); d.ftx = ctx->s_ftx.as<float>(); d.fty = ctx->s_fty.as<float>();
+	d.trans_x = ctx->s_tx.as<double>(); d.trans_y = ctx->s_ty.as<double>();
+	d.over_trans_x = ctx->s_otx.as<double>(); d.over_trans_y = ctx->s_oty.as<double>();
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));   // host vectors above are temporaries
+	ctx->h_samp.rot = ctx->h_samp.tilt = ctx->h_samp.psi = nullptr;
+	ctx->has_sampling = true;
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// model
+// ---------------------------------------------------------------------------------------------
+static inline int iround(double x) { return (int) (x > 0 ? floor(x + 0.5) : -floor(-x + 0.5)); }
+
+// pixels with Mresol >= 0 for window n (src/ml_optimiser.cpp:5784-5811), in FFTW order
+static void make_pixlist(int n, std::vector<uint32_t> &out)
+{
+	const int xs = n / 2 + 1;
+	out.clear();
+	for (int iy = 0; iy < n; iy++)
+	{
+		const int ip = iy < xs ? iy : iy - n;
+		for (int jp = 0; jp < xs; jp++)
+		{
+			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
+			if (ires < xs && !(jp == 0 && ip < 0)) out.push_back(rb_pack_pix(jp, ip, ires));
+		}
+	}
+}
+
+extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
+{
+	RB_ARG(ctx && m, "rb_set_model: NULL argument");
+	RB_ARG(m->nr_classes >= 1 && m->nr_classes <= RB_MAX_CLASSES, "rb_set_model: nr_classes %d unsupported", m->nr_classes);
+	RB_ARG(m->ori_size > 0 && m->ori_size % 2 == 0 && m->ori_size <= 1000, "rb_set_model: ori_size %d unsupported (even, <= 1000)", m->ori_size);
+	RB_ARG(m->current_size > 0 && m->current_size % 2 == 0 && m->current_size <= m->ori_size, "rb_set_model: bad current_size %d", m->current_size);
+	RB_ARG(m->coarse_size > 0 && m->coarse_size % 2 == 0 && m->coarse_size <= m->current_size, "rb_set_model: bad coarse_size %d", m->coarse_size);
+	RB_ARG(m->sigma2_noise && m->pdf_class && m->nr_optics_groups >= 1 && m->nr_groups >= 1, "rb_set_model: NULL table");
+	RB_ARG(!m->do_scale_correction || m->scale_correction, "rb_set_model: scale_correction missing");
+	RB_ARG(m->sigma2_fudge > 0., "rb_set_model: sigma2_fudge must be > 0");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	ctx->h_model = *m;
+	const int nshell = m->ori_size / 2 + 1, K = m->nr_classes;
+	std::vector<uint32_t> pc, pf;
+	make_pixlist(m->coarse_size, pc); make_pixlist(m->current_size, pf);
+	RB_CHECK(upload(ctx, ctx->m_pix_c, pc.data(), pc.size() * 4));
+	RB_CHECK(upload(ctx, ctx->m_pix_f, pf.data(), pf.size() * 4));
+	// Minvsigma2 per shell (src/ml_optimiser.cpp:6868-6879); entry 0 holds the DC value restored for the
+	// store stage (acc_ml_optimiser_impl.h:2586), the diff2 kernels ignore it
+	std::vector<float> mv((size_t) m->nr_optics_groups * nshell);
+	for (int g = 0; g < m->nr_optics_groups; g++)
+		for (int i = 0; i < nshell; i++)
+			mv[(size_t) g * nshell + i] = (float) (1. / (m->sigma2_fudge * m->sigma2_noise[(size_t) g * nshell + i]));
+	RB_CHECK(upload(ctx, ctx->m_minvs2, mv.data(), mv.size() * 4));
+	RB_CHECK(upload(ctx, ctx->m_pdf_class, m->pdf_class, K * sizeof(double)));
+	std::vector<unsigned char> dvp((size_t) K * nshell, 0);
+	if (m->data_vs_prior_class)
+		for (size_t i = 0; i < dvp.size(); i++) dvp[i] = m->data_vs_prior_class[i] > 3.;
+	RB_CHECK(upload(ctx, ctx->m_dvp, dvp.data(), dvp.size()));
+	ctx->h_scale_correction.assign(m->nr_groups, 1.);
+	if (m->scale_correction) ctx->h_scale_correction.assign(m->scale_correction, m->scale_correction + m->nr_groups);
+
+	RbModelDev &d = ctx->d_model;
+	d.nr_classes = K; d.ori_size = m->ori_size; d.coarse_size = m->coarse_size; d.current_size = m->current_size; d.nshell = nshell;
+	d.Npc = m->coarse_size * (m->coarse_size / 2 + 1); d.Npf = m->current_size * (m->current_size / 2 + 1);
+	d.nvc = (int) pc.size(); d.nvf = (int) pf.size();
+	d.pix_c = ctx->m_pix_c.as<uint32_t>(); d.pix_f = ctx->m_pix_f.as<uint32_t>();
+	d.minvs2 = ctx->m_minvs2.as<float>();
+	d.pdf_class = ctx->m_pdf_class.as<double>();
+	d.pdf_direction = nullptr;
+	d.dvp_gt3 = ctx->m_dvp.as<unsigned char>();
+	d.pixel_size = m->pixel_size;
+	d.s2off = (m->offset_range > 0.) ? (m->offset_range * m->offset_range) / 9. : m->sigma2_offset;   // :1916-1926
+	d.adaptive_fraction = m->adaptive_fraction; d.maximum_significants = m->maximum_significants;
+	d.do_ctf_correction = m->do_ctf_correction; d.refs_are_ctf_corrected = m->refs_are_ctf_corrected;
+	d.do_scale_correction = m->do_scale_correction; d.do_map = m->do_map; d.ctf_premultiplied = m->ctf_premultiplied;
+	d.bp_circle_bound = m->bp_circle_bound;
+	// pdf_direction needs n_dir, which belongs to the sampling: keep a host copy until both are known
+	ctx->m_pdf_dir.release();
+	if (m->pdf_direction && ctx->has_sampling)
+	{
+		RB_CHECK(upload(ctx, ctx->m_pdf_dir, m->pdf_direction, (size_t) K * ctx->d_samp.n_dir * sizeof(double)));
+		d.pdf_direction = ctx->m_pdf_dir.as<double>();
+	}
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->h_model.sigma2_noise = nullptr; ctx->h_model.scale_correction = nullptr; ctx->h_model.pdf_class = nullptr;
+	ctx->h_model.data_vs_prior_class = nullptr;
+	ctx->has_model = true;
+	return RB_OK;
+}
+
+// pdf_direction depends on both model (values) and sampling (n_dir): dedicated setter so call order is free
+extern "C" int rb_set_pdf_direction(rb_ctx *ctx, const double *pdf_direction)
+{
+	RB_ARG(ctx && pdf_direction && ctx->has_model && ctx->has_sampling, "rb_set_pdf_direction: needs model and sampling");
+	RB_CHECK(upload(ctx, ctx->m_pdf_dir, pdf_direction, (size_t) ctx->d_model.nr_classes * ctx->d_samp.n_dir * sizeof(double)));
+	ctx->d_model.pdf_direction = ctx->m_pdf_dir.as<double>();
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool upload
+// ---------------------------------------------------------------------------------------------
+static size_t env_size(const char *name, size_t dflt)
+{
+	const char *v = getenv(name);
+	if (!v || !*v) return dflt;
+	return (size_t) strtoull(v, nullptr, 10);
+}
+
+extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool)
+{
+	RB_ARG(ctx && pool, "rb_pool_upload: NULL argument");
+	RB_ARG(slot >= 0 && slot < RB_NUM_SLOTS, "rb_pool_upload: slot %d out of range", slot);
+	if (!ctx->has_model || !ctx->has_sampling) { rb_set_error("rb_pool_upload: set model and sampling first"); return RB_ERR_STATE; }
+	const int P = pool->n_particles;
+	RB_ARG(P > 0, "rb_pool_upload: empty pool");
+	RB_ARG(pool->Fimg && pool->Fimg_nomask && pool->group_id && pool->optics_group && pool->highres_Xi2 && pool->old_offset && pool->prior_offset,
+	       "rb_pool_upload: NULL particle array");
+	RB_ARG(!ctx->h_model.do_ctf_correction || pool->Fctf, "rb_pool_upload: Fctf missing with do_ctf_correction");
+	const bool priors = pool->dir_idx != nullptr;
+	RB_ARG(!priors || (pool->dir_off && pool->dir_prior && pool->psi_off && pool->psi_idx && pool->psi_prior), "rb_pool_upload: incomplete prior lists");
+	RB_ARG(priors || ctx->d_model.pdf_direction, "rb_pool_upload: pdf_direction needed without orientational priors");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	PoolSlot &s = ctx->slot[slot];
+	const RbModelDev &M = ctx->d_model;
+	const RbSamplingDev &S = ctx->d_samp;
+	const int K = M.nr_classes, T = S.n_trans;
+
+	s.P = P; s.has_priors = priors;
+	s.h_meta.resize(P);
+	long long coff = 0, poff = 0; int max_no = 0;
+	for (int p = 0; p < P; p++)
+	{
+		RbPartMeta &m = s.h_meta[p];
+		if (priors)
+		{
+			m.nd = pool->dir_off[p + 1] - pool->dir_off[p]; m.np = pool->psi_off[p + 1] - pool->psi_off[p];
+			m.dir_off = pool->dir_off[p]; m.psi_off = pool->psi_off[p];
+			RB_ARG(m.nd > 0 && m.np > 0, "rb_pool_upload: particle %d has an empty orientation list", p);
+		}
+		else { m.nd = S.n_dir; m.np = S.n_psi; m.dir_off = -1; m.psi_off = -1; }
+		m.group = pool->group_id[p]; m.og = pool->optics_group[p];
+		RB_ARG(m.group >= 0 && m.group < ctx->h_model.nr_groups && m.og >= 0 && m.og < ctx->h_model.nr_optics_groups,
+		       "rb_pool_upload: particle %d group/optics group out of range", p);
+		double sc = ctx->h_model.do_scale_correction ? ctx->h_scale_correction[m.group] : 1.;
+		m.scale = (float) sc;
+		float ps = 1.f;
+		if (ctx->h_model.do_scale_correction)
+		{
+			ps = (float) sc;
+			if (ps > 10000.f) { rb_set_error("rlnMicrographScaleCorrection %g of group %d is too high (ERRHIGHSCALE)", sc, m.group + 1); return RB_ERR_ARG; }
+			if (ps < 0.001f) ps = 0.001f;                                              // :3069-3078
+		}
+		m.part_scale = ps;
+		m.xi2_half = (float) (pool->highres_Xi2[p] / 2.);
+		m.oldx = pool->old_offset[2 * p]; m.oldy = pool->old_offset[2 * p + 1];
+		m.prx = pool->prior_offset[2 * p]; m.pry = pool->prior_offset[2 * p + 1];
+		m.coarse_off = coff; m.prior_off = poff;
+		const long long no = (long long) m.nd * m.np;
+		coff += (long long) K * no * T; poff += (long long) K * no;
+		max_no = std::max<long long>(max_no, no);
+	}
+	s.total_coarse = coff; s.total_prior = poff; s.max_no = max_no;
+
+	cudaStream_t cs = ctx->copy_stream;
+	const size_t img_bytes = (size_t) P * M.Npf * sizeof(float2);
+	RB_CHECK(s.Fimg.ensure(img_bytes)); RB_CHECK(s.Fnomask.ensure(img_bytes));
+	RB_CUDA(cudaMemcpyAsync(s.Fimg.p, pool->Fimg, img_bytes, cudaMemcpyHostToDevice, cs));
+	RB_CUDA(cudaMemcpyAsync(s.Fnomask.p, pool->Fimg_nomask, img_bytes, cudaMemcpyHostToDevice, cs));
+	if (ctx->h_model.do_ctf_correction)
+	{
+		RB_CHECK(s.Fctf.ensure(img_bytes / 2));
+		RB_CUDA(cudaMemcpyAsync(s.Fctf.p, pool->Fctf, img_bytes / 2, cudaMemcpyHostToDevice, cs));
+	}
+	RB_CHECK(s.meta.ensure(P * sizeof(RbPartMeta)));
+	RB_CUDA(cudaMemcpyAsync(s.meta.p, s.h_meta.data(), P * sizeof(RbPartMeta), cudaMemcpyHostToDevice, cs));
+	if (priors)
+	{
+		const size_t nd = pool->dir_off[P], np = pool->psi_off[P];
+		RB_CHECK(s.dir_idx.ensure(nd * 4)); RB_CHECK(s.dir_prior.ensure(nd * 8));
+		RB_CHECK(s.psi_idx.ensure(np * 4)); RB_CHECK(s.psi_prior.ensure(np * 8));
+		RB_CUDA(cudaMemcpyAsync(s.dir_idx.p, pool->dir_idx, nd * 4, cudaMemcpyHostToDevice, cs));
+		RB_CUDA(cudaMemcpyAsync(s.dir_prior.p, pool->dir_prior, nd * 8, cudaMemcpyHostToDevice, cs));
+		RB_CUDA(cudaMemcpyAsync(s.psi_idx.p, pool->psi_idx, np * 4, cudaMemcpyHostToDevice, cs));
+		RB_CUDA(cudaMemcpyAsync(s.psi_prior.p, pool->psi_prior, np * 8, cudaMemcpyHostToDevice, cs));
+	}
+	RB_CUDA(cudaEventRecord(s.uploaded, cs));
+
+	// work buffers
+	RB_CHECK(s.state.ensure(P * sizeof(RbPartState)));
+	RB_CHECK(s.Mweight.ensure((size_t) s.total_coarse * 4));
+	RB_CHECK(s.pdf_orient.ensure((size_t) s.total_prior * 4)); RB_CHECK(s.pdf_orient_zero.ensure((size_t) s.total_prior));
+	RB_CHECK(s.pdf_offset.ensure((size_t) P * T * 4)); RB_CHECK(s.pdf_offset_zero.ensure((size_t) P * T));
+	RB_CHECK(s.counters.ensure(64));
+	RB_CHECK(s.shells.ensure((size_t) P * M.nshell * 4));
+	RB_CHECK(s.out_pdf_dir.ensure((size_t) K * S.n_dir * 8)); RB_CHECK(s.out_pdf_class.ensure((size_t) K * 8));
+	// fine-pass capacity: all coarse samples significant is the worst case; bound it by a budget
+	const long long ov = (long long) S.n_over_rot * S.n_over_trans;
+	size_t cap_fs = (size_t) std::min<long long>(s.total_coarse * ov, (long long) env_size("RB_FINE_SAMPLE_CAP", (size_t) 1 << 26));
+	size_t cap_fo = (size_t) std::min<long long>(s.total_prior * S.n_over_rot, (long long) env_size("RB_FINE_ORIENT_CAP", (size_t) 1 << 22));
+	ctx->fine_sample_capacity = cap_fs; ctx->fine_orient_capacity = cap_fo;
+	RB_CHECK(s.fs_w.ensure(cap_fs * 4)); RB_CHECK(s.fs_ihid.ensure(cap_fs * 8));
+	RB_CHECK(s.fo.ensure(cap_fo * sizeof(RbFineOrient)));
+	RB_CHECK(s.pair_list.ensure((cap_fs / ov + 1) * 4));
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool E-step
+// ---------------------------------------------------------------------------------------------
+static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
+{
+	const RbModelDev &M = ctx->d_model;
+	const RbSamplingDev &S = ctx->d_samp;
+	for (int k = 0; k < M.nr_classes; k++)
+	{
+		if (!ctx->has_proj[k]) { rb_set_error("rb_estep: reference %d not set", k); return RB_ERR_STATE; }
+		if (!(flags & 1u) && !ctx->has_bp[k]) { rb_set_error("rb_estep: accumulator %d not initialised", k); return RB_ERR_STATE; }
+	}
+	RB_CUDA(cudaSetDevice(ctx->device));
+	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+	RB_CHECK(rb_stage_begin(ctx, "total"));
+	RB_CUDA(cudaMemsetAsync(s.counters.p, 0, 64, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(s.shells.p, 0, (size_t) s.P * M.nshell * 4, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(s.out_pdf_dir.p, 0, (size_t) M.nr_classes * S.n_dir * 8, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(s.out_pdf_class.p, 0, (size_t) M.nr_classes * 8, ctx->stream));
+
+	RB_CHECK(rb_stage_begin(ctx, "coarse"));
+	RB_CHECK(rbk_prep_priors(ctx, s));
+	RB_CHECK(rbk_diff2_coarse_pool(ctx, s));
+	RB_CHECK(rb_stage_end(ctx, "coarse"));
+
+	RB_CHECK(rb_stage_begin(ctx, "weights_coarse"));
+	RB_CHECK(rbk_weights_coarse_pool(ctx, s));
+	RB_CHECK(rb_stage_end(ctx, "weights_coarse"));
+
+	RB_CHECK(rb_stage_begin(ctx, "fine_setup"));
+	RB_CHECK(rbk_fine_setup_pool(ctx, s));
+	RB_CHECK(rb_stage_end(ctx, "fine_setup"));
+
+	RB_CHECK(rb_stage_begin(ctx, "fine"));
+	RB_CHECK(rbk_diff2_fine_pool(ctx, s));
+	RB_CHECK(rb_stage_end(ctx, "fine"));
+
+	RB_CHECK(rb_stage_begin(ctx, "weights_fine"));
+	RB_CHECK(rbk_weights_fine_pool(ctx, s));
+	RB_CHECK(rbk_collect_pool(ctx, s));
+	RB_CHECK(rb_stage_end(ctx, "weights_fine"));
+
+	RB_CHECK(rb_stage_begin(ctx, "store"));
+	if (!(flags & 1u)) RB_CHECK(rbk_store_pool(ctx, s));
+	RB_CHECK(rb_stage_end(ctx, "store"));
+	RB_CHECK(rb_stage_end(ctx, "total"));
+	return RB_OK;
+}
+
+static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
+{
+	const RbModelDev &M = ctx->d_model;
+	const RbSamplingDev &S = ctx->d_samp;
+	const int P = s.P, K = M.nr_classes, T = S.n_trans, NOR = S.n_over_rot, NOT = S.n_over_trans;
+	std::vector<RbPartState> st(P);
+	std::vector<float> shells((size_t) P * M.nshell);
+	std::vector<double> pd((size_t) K * S.n_dir), pcl(K);
+	int counters[16];
+	RB_CUDA(cudaMemcpyAsync(st.data(), s.state.p, P * sizeof(RbPartState), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(shells.data(), s.shells.p, shells.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(pd.data(), s.out_pdf_dir.p, pd.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(pcl.data(), s.out_pdf_class.p, K * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(counters, s.counters.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (counters[2])
+	{
+		rb_set_error("fine-pass workspace too small: %lld orientations / %lld samples needed, capacity %zu / %zu; split the pool or raise "
+		             "RB_FINE_ORIENT_CAP / RB_FINE_SAMPLE_CAP", ((long long *) counters)[2], ((long long *) counters)[3],
+		             ctx->fine_orient_capacity, ctx->fine_sample_capacity);
+		return RB_ERR_CAPACITY;
+	}
+	int status = RB_OK;
+	if (out && out->particles)
+	{
+		for (int p = 0; p < P; p++)
+		{
+			const RbPartState &q = st[p];
+			const RbPartMeta &m = s.h_meta[p];
+			rb_particle_out &o = out->particles[p];
+			memset(&o, 0, sizeof(o));
+			o.nr_significant_coarse = q.nr_sig_coarse;
+			o.n_fine_orient = q.n_so * NOR; o.n_fine_samples = q.n_pairs * NOR * NOT;
+			o.min_diff2_coarse = q.min_diff2; o.sum_weight_coarse = q.csum_weight; o.significant_weight_coarse = q.csig_weight;
+			if (q.status != 0)
+			{
+				if (status == RB_OK)
+				{
+					status = q.status;
+					rb_set_error("particle %d of the pool: %s", p,
+					             q.status == RB_ERR_NO_SIGNIFICANT ? "no significant coarse samples (ERRFILTEREDZERO/ERRNOSIGNIFS)" :
+					             q.status == RB_ERR_SUMWEIGHT_ZERO ? "sum of fine weights is zero (ERRSUMWEIGHTZERO)" : "failed");
+				}
+				continue;
+			}
+			o.best_ihidden_over = q.best_ihid;
+			{   // Indices::fineIndexToFineIndices (src/acc/acc_ml_optimiser.h:78-95)
+				long long t = q.best_ihid, ov = (long long) NOR * NOT, no = (long long) m.nd * m.np;
+				o.best_class = (int) (t / (no * T * ov)); t -= (long long) o.best_class * no * T * ov;
+				o.best_idir = (int) (t / ((long long) m.np * T * ov)); t -= (long long) o.best_idir * m.np * T * ov;
+				o.best_ipsi = (int) (t / ((long long) T * ov)); t -= (long long) o.best_ipsi * T * ov;
+				o.best_itrans = (int) (t / ov); t -= (long long) o.best_itrans * ov;
+				o.best_iover_rot = (int) (t / NOT); t -= (long long) o.best_iover_rot * NOT;
+				o.best_iover_trans = (int) t;
+			}
+			o.min_diff2 = (float) q.min_diff2_final; o.max_weight = q.fmax_weight; o.sum_weight = q.fsum_weight;
+			o.significant_weight = q.fsig_weight;
+			o.pmax = q.fmax_weight / q.fsum_weight;                                          // :2924
+			if (o.pmax > 1.f && status == RB_OK) { status = RB_ERR_PMAX; rb_set_error("particle %d: normalised probability > 1", p); }
+			o.dLL_nolog = log((double) q.fsum_weight) - q.min_diff2_final;                   // :3574
+			double nc = 0.;
+			for (int i = 0; i < M.nshell; i++) nc += (double) shells[(size_t) p * M.nshell + i];
+			o.wsum_norm_correction = nc;
+			o.wsum_XA = q.wsum_XA; o.wsum_AA = q.wsum_AA; o.sumw = q.sumw; o.wsum_sigma2_offset = q.wsum_s2off;
+		}
+	}
+	if (out && out->wsum_sigma2_noise) memcpy(out->wsum_sigma2_noise, shells.data(), shells.size() * 4);
+	if (out && out->wsum_pdf_direction) for (size_t i = 0; i < pd.size(); i++) out->wsum_pdf_direction[i] += pd[i];
+	if (out && out->wsum_pdf_class) for (int k = 0; k < K; k++) out->wsum_pdf_class[k] += pcl[k];
+	return status;
+}
+
+extern "C" int rb_estep_slot_nocopy(rb_ctx *ctx, int slot, unsigned flags)
+{
+	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_estep_slot_nocopy: slot %d not uploaded", slot);
+	return run_slot(ctx, ctx->slot[slot], flags);
+}
+
+extern "C" int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out)
+{
+	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_estep_fetch: slot %d not uploaded", slot);
+	return fetch_slot(ctx, ctx->slot[slot], out);
+}
+
+extern "C" int rb_estep_slot(rb_ctx *ctx, int slot, rb_pool_out *out, unsigned flags)
+{
+	RB_CHECK(rb_estep_slot_nocopy(ctx, slot, flags));
+	return fetch_slot(ctx, ctx->slot[slot], out);
+}
+
+extern "C" int rb_estep_pool(rb_ctx *ctx, const rb_particles *pool, rb_pool_out *out, unsigned flags)
+{
+	RB_CHECK(rb_pool_upload(ctx, 0, pool));
+	return rb_estep_slot(ctx, 0, out, flags);
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage-level entry points (host pointers in/out)
+// ---------------------------------------------------------------------------------------------
+struct StageBufs {
+	rb_ctx *ctx; int next = 0; std::vector<DevBuf> owned;
+	explicit StageBufs(rb_ctx *c) : ctx(c) {}
+	~StageBufs() { for (auto &b : owned) b.release(); }
+	template <typename T> int up(const T *src, size_t n, T **dst)
+	{
+		owned.emplace_back();
+		DevBuf &b = owned.back();
+		RB_CHECK(b.ensure(std::max<size_t>(n, 1) * sizeof(T)));
+		if (src && n) RB_CUDA(cudaMemcpyAsync(b.p, src, n * sizeof(T), cudaMemcpyHostToDevice, ctx->stream));
+		else RB_CUDA(cudaMemsetAsync(b.p, 0, std::max<size_t>(n, 1) * sizeof(T), ctx->stream));
+		*dst = b.as<T>();
+		return RB_OK;
+	}
+};
+
+static int check_proj(rb_ctx *ctx, int k, int img_size)
+{
+	RB_ARG(ctx, "ctx is NULL");
+	RB_ARG(k >= 0 && k < RB_MAX_CLASSES && ctx->has_proj[k], "reference %d not set", k);
+	RB_ARG(img_size > 0 && img_size % 2 == 0 && img_size <= 1000, "image size %d unsupported", img_size);
+	RB_CUDA(cudaSetDevice(ctx->device));
+	return RB_OK;
+}
+
+extern "C" int rb_project(rb_ctx *ctx, int k, int n, const float *eulers, int count, float *out_complex)
+{
+	RB_CHECK(check_proj(ctx, k, n));
+	StageBufs sb(ctx);
+	float *d_e; float2 *d_o;
+	const size_t np = (size_t) n * (n / 2 + 1);
+	RB_CHECK(sb.up(eulers, (size_t) count * 9, &d_e));
+	RB_CHECK(sb.up((const float2 *) nullptr, np * count, &d_o));
+	RB_CHECK(rbk_project(ctx, ctx->proj[k], n, d_e, count, d_o));
+	RB_CUDA(cudaMemcpyAsync(out_complex, d_o, np * count * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_diff2_coarse(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                               const float *tx, const float *ty, int T,
+                               const float *re, const float *im, const float *corr, float *diff2s)
+{
+	RB_CHECK(check_proj(ctx, k, n));
+	StageBufs sb(ctx);
+	const size_t np = (size_t) n * (n / 2 + 1);
+	float *d_e, *d_tx, *d_ty, *d_re, *d_im, *d_c, *d_o;
+	RB_CHECK(sb.up(eulers, (size_t) O * 9, &d_e)); RB_CHECK(sb.up(tx, T, &d_tx)); RB_CHECK(sb.up(ty, T, &d_ty));
+	RB_CHECK(sb.up(re, np, &d_re)); RB_CHECK(sb.up(im, np, &d_im)); RB_CHECK(sb.up(corr, np, &d_c));
+	RB_CHECK(sb.up(diff2s, (size_t) O * T, &d_o));
+	RB_CHECK(rbk_diff2_coarse_stage(ctx, ctx->proj[k], n, d_e, O, d_tx, d_ty, T, d_re, d_im, d_c, d_o));
+	RB_CUDA(cudaMemcpyAsync(diff2s, d_o, (size_t) O * T * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_diff2_fine(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                             const float *tx, const float *ty, int T,
+                             const float *re, const float *im, const float *corr, float sum_init,
+                             const uint64_t *rot_idx, const uint64_t *trans_idx,
+                             const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
+                             float *diff2s, int n_weights)
+{
+	RB_CHECK(check_proj(ctx, k, n));
+	for (int j = 0; j < n_jobs; j++) RB_ARG(job_num[j] <= 8, "rb_diff2_fine: job %d has %llu translations (max 8)", j, (unsigned long long) job_num[j]);
+	StageBufs sb(ctx);
+	const size_t np = (size_t) n * (n / 2 + 1);
+	float *d_e, *d_tx, *d_ty, *d_re, *d_im, *d_c, *d_o;
+	unsigned long long *d_ri, *d_ti, *d_ji, *d_jn;
+	RB_CHECK(sb.up(eulers, (size_t) O * 9, &d_e)); RB_CHECK(sb.up(tx, T, &d_tx)); RB_CHECK(sb.up(ty, T, &d_ty));
+	RB_CHECK(sb.up(re, np, &d_re)); RB_CHECK(sb.up(im, np, &d_im)); RB_CHECK(sb.up(corr, np, &d_c));
+	RB_CHECK(sb.up(diff2s, (size_t) n_weights, &d_o));
+	RB_CHECK(sb.up((const unsigned long long *) rot_idx, (size_t) n_weights, &d_ri));
+	RB_CHECK(sb.up((const unsigned long long *) trans_idx, (size_t) n_weights, &d_ti));
+	RB_CHECK(sb.up((const unsigned long long *) job_idx, (size_t) n_jobs, &d_ji));
+	RB_CHECK(sb.up((const unsigned long long *) job_num, (size_t) n_jobs, &d_jn));
+	RB_CHECK(rbk_diff2_fine_stage(ctx, ctx->proj[k], n, d_e, d_tx, d_ty, d_re, d_im, d_c, sum_init, d_ri, d_ti, d_ji, d_jn, n_jobs, d_o));
+	RB_CUDA(cudaMemcpyAsync(diff2s, d_o, (size_t) n_weights * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_convert_weights(rb_ctx *ctx, float *weights, int64_t n_orient, int n_trans,
+                                  const float *pdf_o, const unsigned char *pdf_oz,
+                                  const float *pdf_t, const unsigned char *pdf_tz,
+                                  double adaptive_fraction, int maxsig, int filter_zero,
+                                  unsigned char *significant, rb_weights_out *out)
+{
+	RB_ARG(ctx && weights && pdf_o && pdf_oz && pdf_t && pdf_tz && out, "rb_convert_weights: NULL argument");
+	RB_ARG(n_orient > 0 && n_trans > 0, "rb_convert_weights: empty input");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	StageBufs sb(ctx);
+	const size_t n = (size_t) n_orient * n_trans;
+	float *d_w, *d_po, *d_pt; unsigned char *d_oz, *d_tz, *d_sig; rb_weights_out *d_out;
+	RB_CHECK(sb.up(weights, n, &d_w)); RB_CHECK(sb.up(pdf_o, (size_t) n_orient, &d_po)); RB_CHECK(sb.up(pdf_t, (size_t) n_trans, &d_pt));
+	RB_CHECK(sb.up(pdf_oz, (size_t) n_orient, &d_oz)); RB_CHECK(sb.up(pdf_tz, (size_t) n_trans, &d_tz));
+	RB_CHECK(sb.up((const unsigned char *) nullptr, n, &d_sig)); RB_CHECK(sb.up((const rb_weights_out *) nullptr, 1, &d_out));
+	RB_CHECK(rbk_convert_weights_stage(ctx, d_w, n_orient, n_trans, d_po, d_oz, d_pt, d_tz, adaptive_fraction, maxsig, filter_zero, d_sig, d_out));
+	RB_CUDA(cudaMemcpyAsync(weights, d_w, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	if (significant) RB_CUDA(cudaMemcpyAsync(significant, d_sig, n, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(out, d_out, sizeof(rb_weights_out), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_wavg(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                       const float *tx, const float *ty, int T,
+                       const float *re, const float *im, const float *weights, const float *ctfs,
+                       float weight_norm, float sig_w, float *parts, float *AA, float *XA)
+{
+	RB_CHECK(check_proj(ctx, k, n));
+	StageBufs sb(ctx);
+	const size_t np = (size_t) n * (n / 2 + 1);
+	float *d_e, *d_tx, *d_ty, *d_re, *d_im, *d_w, *d_c, *d_p, *d_a, *d_x;
+	RB_CHECK(sb.up(eulers, (size_t) O * 9, &d_e)); RB_CHECK(sb.up(tx, T, &d_tx)); RB_CHECK(sb.up(ty, T, &d_ty));
+	RB_CHECK(sb.up(re, np, &d_re)); RB_CHECK(sb.up(im, np, &d_im)); RB_CHECK(sb.up(weights, (size_t) O * T, &d_w));
+	RB_CHECK(sb.up(ctfs, np, &d_c)); RB_CHECK(sb.up(parts, np, &d_p)); RB_CHECK(sb.up(AA, np, &d_a)); RB_CHECK(sb.up(XA, np, &d_x));
+	RB_CHECK(rbk_wavg_stage(ctx, ctx->proj[k], n, d_e, O, d_tx, d_ty, T, d_re, d_im, d_w, d_c, weight_norm, sig_w, d_p, d_a, d_x));
+	RB_CUDA(cudaMemcpyAsync(parts, d_p, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(AA, d_a, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(XA, d_x, np * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_backproject(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                              const float *tx, const float *ty, int T,
+                              const float *re, const float *im,
+                              const float *weights, const float *Minvsigma2s, const float *ctfs,
+                              float weight_norm, float sig_w)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_backproject: accumulator %d not initialised", k);
+	RB_ARG(n > 0 && n % 2 == 0 && n <= 1000, "image size %d unsupported", n);
+	RB_CUDA(cudaSetDevice(ctx->device));
+	StageBufs sb(ctx);
+	const size_t np = (size_t) n * (n / 2 + 1);
+	float *d_e, *d_tx, *d_ty, *d_re, *d_im, *d_w, *d_m, *d_c;
+	RB_CHECK(sb.up(eulers, (size_t) O * 9, &d_e)); RB_CHECK(sb.up(tx, T, &d_tx)); RB_CHECK(sb.up(ty, T, &d_ty));
+	RB_CHECK(sb.up(re, np, &d_re)); RB_CHECK(sb.up(im, np, &d_im)); RB_CHECK(sb.up(weights, (size_t) O * T, &d_w));
+	RB_CHECK(sb.up(Minvsigma2s, np, &d_m)); RB_CHECK(sb.up(ctfs, np, &d_c));
+	const int circle = ctx->has_model ? ctx->h_model.bp_circle_bound : 1;
+	const int premult = ctx->has_model ? ctx->h_model.ctf_premultiplied : 0;
+	RB_CHECK(rbk_backproject_stage(ctx, ctx->bp[k], n, d_e, O, d_tx, d_ty, T, d_re, d_im, d_w, d_m, d_c, weight_norm, sig_w, circle, premult));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+// relion_reconstruct-style posed back-projection: one orientation and unit weight per image, F2D already
+// CTF-multiplied, Fctf = ctf^2 (src/reconstructor.cpp:632-737).  Expressed through the same scatter kernel:
+// img = F2D, ctf = 1, Minvsigma2 = Fctf  =>  F = F2D, Fweight = Fctf.  r_max and the skipped x=0,y<0 half
+// column follow BackProjector::backproject2Dto3D (src/backprojector.cpp:90-91, 150-160).
+extern "C" int rb_backproject_posed(rb_ctx *ctx, int k, int n, int count,
+                                    const float *F2D_complex, const float *Fctf, const float *eulers)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_backproject_posed: accumulator %d not initialised", k);
+	RB_ARG(n > 0 && n % 2 == 0 && n <= 1000 && count > 0, "rb_backproject_posed: bad sizes");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	const size_t np = (size_t) n * (n / 2 + 1);
+	const int xs = n / 2 + 1;
+	std::vector<float> re(np), im(np), mw(np), ones(np, 1.f);
+	float one = 1.f, zero = 0.f;
+	for (int i = 0; i < count; i++)
+	{
+		const float *F = F2D_complex + (size_t) i * np * 2, *W = Fctf + (size_t) i * np;
+		for (size_t j = 0; j < np; j++) { re[j] = F[2 * j]; im[j] = F[2 * j + 1]; mw[j] = W[j]; }
+		for (int iy = xs; iy < n; iy++) mw[(size_t) iy * xs] = 0.f;   // first_allowed_x = 1 for negative y rows
+		StageBufs sb(ctx);
+		float *d_e, *d_tx, *d_ty, *d_re, *d_im, *d_w, *d_m, *d_c;
+		RB_CHECK(sb.up(eulers + (size_t) i * 9, 9, &d_e)); RB_CHECK(sb.up(&zero, 1, &d_tx)); RB_CHECK(sb.up(&zero, 1, &d_ty));
+		RB_CHECK(sb.up(re.data(), np, &d_re)); RB_CHECK(sb.up(im.data(), np, &d_im)); RB_CHECK(sb.up(&one, 1, &d_w));
+		RB_CHECK(sb.up(mw.data(), np, &d_m)); RB_CHECK(sb.up(ones.data(), np, &d_c));
+		RB_CHECK(rbk_backproject_stage(ctx, ctx->bp[k], n, d_e, 1, d_tx, d_ty, 1, d_re, d_im, d_w, d_m, d_c, 1.f, 0.5f, 0, 0));
+		RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	return RB_OK;
+}

@@ -1,0 +1,248 @@
+// relion_b200 — shared declarations for the sm_100a E-step kernels and the C-ABI glue.
+// Product code: must not reference anything under oracle/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <cfloat>
+#include <string>
+#include <vector>
+#include <map>
+
+#include "relion_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// error handling (HANDLE_ERROR analogue, /root/reference/src/acc/cuda/cuda_settings.h:48-68)
+// ---------------------------------------------------------------------------------------------
+void rb_set_error(const char *fmt, ...);
+
+#define RB_CUDA(call)                                                                          \
+	do {                                                                                       \
+		cudaError_t e__ = (call);                                                              \
+		if (e__ != cudaSuccess) {                                                              \
+			rb_set_error("CUDA error %s (%d) at %s:%d: %s", cudaGetErrorName(e__), (int) e__,  \
+			             __FILE__, __LINE__, cudaGetErrorString(e__));                         \
+			return RB_ERR_CUDA;                                                                \
+		}                                                                                      \
+	} while (0)
+
+#define RB_CHECK(st)                                                                           \
+	do { int s__ = (st); if (s__ != RB_OK) return s__; } while (0)
+
+#define RB_ARG(cond, ...)                                                                      \
+	do { if (!(cond)) { rb_set_error(__VA_ARGS__); return RB_ERR_ARG; } } while (0)
+
+static const int RB_MAX_CLASSES = 64;
+static const int RB_NUM_SLOTS = 2;
+#define RB_LOWEST (-FLT_MAX)
+
+// ---------------------------------------------------------------------------------------------
+// device-side descriptors
+// ---------------------------------------------------------------------------------------------
+
+// AccProjectorKernel state (acc_projectorkernel_impl.h:19-69); volume is interleaved (re,im)
+struct RbProjector {
+	const float2 *mdl;
+	int mdlX, mdlY, mdlZ;
+	int mdlXY;
+	int mdlInitY, mdlInitZ;
+	int mdlMaxR;
+	float padding_factor;
+};
+
+// AccBackprojector state (acc_backprojector.h:24-60); accumulator is float4 (re, im, weight, 0)
+struct RbBackprojector {
+	float4 *vol;
+	int mdlX, mdlY, mdlZ;
+	int mdlInitY, mdlInitZ;
+	int maxR;
+	float padding_factor;
+};
+
+// Pixel list entry for one window size: packed (x:10 | (y+512):11 | (ires+1):11).
+// The list holds only pixels with Mresol >= 0 (ires >= 0), i.e. inside the Nyquist circle and not
+// on the redundant x=0,y<0 half column (src/ml_optimiser.cpp:5784-5811).  Every other pixel has
+// Minvsigma2 == 0 (src/ml_optimiser.cpp:6868-6879) and therefore contributes exactly 0 to diff2,
+// wavg shell sums and back-projection weights.
+__host__ __device__ inline uint32_t rb_pack_pix(int x, int y, int ires) { return (uint32_t) x | ((uint32_t) (y + 512) << 10) | ((uint32_t) (ires + 1) << 21); }
+__host__ __device__ inline int rb_pix_x(uint32_t v) { return (int) (v & 1023u); }
+__host__ __device__ inline int rb_pix_y(uint32_t v) { return (int) ((v >> 10) & 2047u) - 512; }
+__host__ __device__ inline int rb_pix_ires(uint32_t v) { return (int) (v >> 21) - 1; }
+
+// per-particle metadata resident on the device for one pool slot
+struct RbPartMeta {
+	int nd, np;              // sp.nr_dir, sp.nr_psi of this particle
+	int dir_off, psi_off;    // offsets into the pool's dir/psi lists (-1: identity lists)
+	int group, og;
+	float scale;             // scale_correction[group] (1 if !do_scale_correction)
+	float part_scale;        // clamped scale used by wavg/BP (acc_ml_optimiser_impl.h:3059-3079)
+	float xi2_half;          // (XFLOAT)(highres_Xi2 / 2)
+	double oldx, oldy, prx, pry;
+	long long coarse_off;    // offset of this particle's dense Mweight block
+	long long prior_off;     // offset of its pdf_orientation block (K*nd*np)
+};
+
+// per-particle running results on the device
+struct RbPartState {
+	int min_diff2_bits;      // float bits, atomicMin (diff2 >= 0)
+	float min_diff2;         // coarse
+	float cmax_weight; long long cmax_index;
+	float csum_weight, csig_weight;
+	int nr_sig_coarse, n_nonzero;
+	int n_so, n_pairs;       // significant coarse orientations / significant coarse (o,t) pairs
+	long long so_base, pair_base, fo_base, fs_base;  // bases into pool-level lists
+	int fmin_bits;           // fine min diff2 bits
+	float fmin_diff2;
+	float fmax_weight; long long fmax_sample;
+	float fsum_weight, fsig_weight;
+	double min_diff2_final;
+	long long best_ihid;     // ihidden_over of the maximum-weight fine sample
+	int status;
+	// store-stage accumulators
+	double wsum_norm, wsum_XA, wsum_AA, sumw, wsum_s2off;
+};
+
+// one fine (oversampled) orientation of one particle
+struct RbFineOrient {
+	int particle;
+	int iclass;
+	int iorient;             // dense orientation index within the class (idl*np + ipl)
+	int iover_rot;
+	int pair_off;            // offset (pool-level) of the list of significant coarse translations
+	int n_t;                 // number of significant coarse translations
+	long long sample_off;    // pool-level offset of its n_t*NOT fine samples
+	float e[9];
+};
+
+struct RbSamplingDev {
+	int n_dir, n_psi, n_over_rot, n_trans, n_over_trans;
+	const float *coarse_eulers;       // [n_dir*n_psi][9]
+	const double *over_rot, *over_tilt, *over_psi; // [n_dir*n_psi*n_over_rot] (or coarse angles when n_over_rot==1)
+	const double *rot, *tilt, *psi;
+	const float *ctx, *cty;           // coarse trans, radians/pixel
+	const float *ftx, *fty;           // fine trans
+	const double *trans_x, *trans_y;  // coarse, pixels
+	const double *over_trans_x, *over_trans_y;
+};
+
+struct RbModelDev {
+	int nr_classes, ori_size, coarse_size, current_size, nshell;
+	int Npc, Npf;            // full half-image sizes n*(n/2+1)
+	int nvc, nvf;            // valid-pixel list lengths
+	const uint32_t *pix_c, *pix_f;
+	const float *minvs2;     // [nr_optics_groups][nshell] 1/(fudge*sigma2), entry 0 kept (DC restored for store)
+	const double *pdf_direction; // [K][n_dir]
+	const double *pdf_class;
+	const unsigned char *dvp_gt3; // [K][nshell] data_vs_prior_class > 3
+	double pixel_size, s2off, adaptive_fraction;
+	int maximum_significants;
+	int do_ctf_correction, refs_are_ctf_corrected, do_scale_correction, do_map, ctf_premultiplied, bp_circle_bound;
+};
+
+// ---------------------------------------------------------------------------------------------
+// host-side context
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+	void *p = nullptr; size_t bytes = 0;
+	int ensure(size_t n);   // grows (never shrinks); returns status
+	void release();
+	template <typename T> T *as() const { return (T *) p; }
+};
+
+struct PoolSlot {
+	int P = 0;
+	bool has_priors = false;
+	int max_no = 0;                 // max over particles of nd*np
+	long long total_coarse = 0;     // sum over particles of K*nd*np*T
+	long long total_prior = 0;
+	DevBuf Fimg, Fnomask, Fctf, meta, state, dir_idx, dir_prior, psi_idx, psi_prior;
+	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;
+	DevBuf so_list, pair_list, fo, fs_w, fs_ihid, counters, shells, out_pdf_dir, out_pdf_class;
+	std::vector<RbPartMeta> h_meta;
+	cudaEvent_t uploaded = nullptr;
+};
+
+struct rb_ctx {
+	int device = 0;
+	int num_sms = 0;
+	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	long long launches = 0;
+
+	RbProjector proj[RB_MAX_CLASSES];
+	DevBuf proj_buf[RB_MAX_CLASSES];
+	RbBackprojector bp[RB_MAX_CLASSES];
+	DevBuf bp_buf[RB_MAX_CLASSES];
+	bool has_proj[RB_MAX_CLASSES] = {false}, has_bp[RB_MAX_CLASSES] = {false};
+
+	bool has_sampling = false, has_model = false;
+	rb_sampling h_samp{};            // scalar fields only (pointers are not kept)
+	rb_model h_model{};
+	RbSamplingDev d_samp{};
+	RbModelDev d_model{};
+	DevBuf s_coarse_eulers, s_over_rot, s_over_tilt, s_over_psi, s_rot, s_tilt, s_psi, s_ctx, s_cty, s_ftx, s_fty,
+	       s_tx, s_ty, s_otx, s_oty;
+	DevBuf m_pix_c, m_pix_f, m_minvs2, m_pdf_dir, m_pdf_class, m_dvp;
+	DevBuf d_proj, d_bp;             // device copies of the projector / backprojector tables
+	std::vector<double> h_scale_correction;
+
+	PoolSlot slot[RB_NUM_SLOTS];
+	size_t fine_orient_capacity = 0, fine_sample_capacity = 0;
+
+	// stage timing
+	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
+	DevBuf scratch[8];
+};
+
+int rb_stage_begin(rb_ctx *ctx, const char *name);
+int rb_stage_end(rb_ctx *ctx, const char *name);
+int rb_sync_tables(rb_ctx *ctx);   // refresh d_proj / d_bp device tables
+
+// ---------------------------------------------------------------------------------------------
+// kernel launchers (one per .cu)
+// ---------------------------------------------------------------------------------------------
+// kernels_misc.cu
+int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt, const float *d_psi, int n_dir, int n_psi, float *d_eulers);
+int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
+int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
+int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out);
+
+// kernels_diff2.cu
+int rbk_prep_priors(rb_ctx *ctx, PoolSlot &s);
+int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int O,
+                           const float *d_tx, const float *d_ty, int T, const float *d_re, const float *d_im,
+                           const float *d_corr, float *d_out);
+int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers,
+                         const float *d_tx, const float *d_ty, const float *d_re, const float *d_im,
+                         const float *d_corr, float sum_init,
+                         const unsigned long long *d_rot_idx, const unsigned long long *d_trans_idx,
+                         const unsigned long long *d_job_idx, const unsigned long long *d_job_num, int n_jobs,
+                         float *d_out);
+
+// kernels_weights.cu
+int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_fine_setup_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_weights_fine_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_convert_weights_stage(rb_ctx *ctx, float *d_w, long long n_orient, int n_trans,
+                              const float *d_pdf_o, const unsigned char *d_pdf_oz,
+                              const float *d_pdf_t, const unsigned char *d_pdf_tz,
+                              double adaptive_fraction, int maxsig, int filter_zero,
+                              unsigned char *d_sig, rb_weights_out *d_out);
+
+// kernels_store.cu
+int rbk_collect_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_store_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_wavg_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int O,
+                   const float *d_tx, const float *d_ty, int T, const float *d_re, const float *d_im,
+                   const float *d_w, const float *d_ctf, float weight_norm, float sig_w,
+                   float *d_parts, float *d_AA, float *d_XA);
+int rbk_backproject_stage(rb_ctx *ctx, const RbBackprojector &bp, int n, const float *d_eulers, int O,
+                          const float *d_tx, const float *d_ty, int T, const float *d_re, const float *d_im,
+                          const float *d_w, const float *d_minvs2, const float *d_ctf,
+                          float weight_norm, float sig_w, int circle_bound, int ctf_premultiplied);
+
+#define RB_LAUNCH_CHECK(ctx)                                                                   \
+	do { (ctx)->launches++; RB_CUDA(cudaGetLastError()); } while (0)

@@ -1,0 +1,92 @@
+// relion_b200 — small kernels: Euler matrices, volume upload conversion, accumulator read-back,
+// stand-alone projection, posed back-projection.
+#include "device_utils.cuh"
+
+// cuda_kernel_make_eulers_3D<invert=true,doL=false,doR=false> (helper.cuh:713-840): fp32 degrees ->
+// radians -> sincosf -> ZYZ matrix, written transposed (inverse of a rotation).
+__global__ void k_make_coarse_eulers(const float *rot, const float *tilt, const float *psi, int n_dir, int n_psi, float *eulers)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n_dir * n_psi) return;
+	const int d = i / n_psi, q = i - d * n_psi;
+	const float a = rot[d] * (float) 3.14159265358979323846 / 180.0f;
+	const float b = tilt[d] * (float) 3.14159265358979323846 / 180.0f;
+	const float g = psi[q] * (float) 3.14159265358979323846 / 180.0f;
+	float sa, ca, sb, cb, sg, cg;
+	sincosf(a, &sa, &ca); sincosf(b, &sb, &cb); sincosf(g, &sg, &cg);
+	const float cc = cb * ca, cs = cb * sa, sc = sb * ca, ss = sb * sa;
+	float *e = eulers + (size_t) i * 9;
+	e[0] = cg * cc - sg * sa;  e[3] = cg * cs + sg * ca;  e[6] = -cg * sb;
+	e[1] = -sg * cc - cg * sa; e[4] = -sg * cs + cg * ca; e[7] = sg * sb;
+	e[2] = sc;                 e[5] = ss;                 e[8] = cb;
+}
+
+int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt, const float *d_psi, int n_dir, int n_psi, float *d_eulers)
+{
+	const int n = n_dir * n_psi;
+	k_make_coarse_eulers<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_rot, d_tilt, d_psi, n_dir, n_psi, d_eulers);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// fp64 -> fp32 cast of the reference volume (AccProjector::initMdl, acc_projector_impl.h:196-312)
+__global__ void k_convert_volume(const double *in, float2 *out, size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+		out[i] = make_float2((float) in[2 * i], (float) in[2 * i + 1]);
+}
+
+int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n)
+{
+	k_convert_volume<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_in, d_out, n);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// AccBackprojector::getMdlData (acc_backprojector_impl.h:109-138): interleaved float4 -> three SoA arrays
+__global__ void k_bp_deinterleave(const float4 *vol, float *re, float *im, float *w, size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const float4 v = vol[i];
+		re[i] = v.x; im[i] = v.y; w[i] = v.z;
+	}
+}
+
+int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n)
+{
+	k_bp_deinterleave<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(vol, re, im, w, n);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// Fourier-slice projection of `count` orientations (fine-pass row rule, see rbk_diff2_fine_stage)
+__global__ void k_project(RbProjector pj, int n, const float *eulers, float2 *out)
+{
+	const int imgX = n / 2 + 1;
+	const RbProjK pk = rb_make_projk(pj, imgX);
+	const float *e = eulers + (size_t) blockIdx.y * 9;
+	float2 *o = out + (size_t) blockIdx.y * n * imgX;
+	for (int pix = blockIdx.x * blockDim.x + threadIdx.x; pix < n * imgX; pix += gridDim.x * blockDim.x)
+	{
+		int x = pix % imgX, iy = pix / imgX, y = iy;
+		float2 v = make_float2(0.f, 0.f);
+		bool skip = false;
+		if (iy > pk.maxR)
+		{
+			if (iy >= n - pk.maxR) y = iy - n;
+			else skip = (x != pk.maxR);
+		}
+		if (!skip) v = rb_project3d(pk, x, y, e[0], e[1], e[3], e[4], e[6], e[7]);
+		o[pix] = v;
+	}
+}
+
+int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out)
+{
+	if (count < 1) return RB_OK;
+	dim3 grid((n * (n / 2 + 1) + 255) / 256, count);
+	k_project<<<grid, 256, 0, ctx->stream>>>(pj, n, d_eulers, d_out);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}

@@ -1,0 +1,405 @@
+// relion_b200 — weighted sums and back-projection (storeWeightedSums), sm_100a.
+//
+// Replaces cuda_kernel_collect2jobs (helper.cuh:69-165), cuda_kernel_wavg (wavg.cuh:13-152) and
+// cuda_kernel_backproject3D (BP.cuh:174-403) of /root/reference/src/acc/cuda/cuda_kernels and their
+// ALTCPU twins (cpu_kernels/helper.h:65-153, wavg.h:22-199, BP.h:497-753); orchestration being
+// replaced: storeWeightedSums (acc_ml_optimiser_impl.h:2553-3667).
+//
+// B200-first choices:
+//  * wavg and back-projection are ONE kernel per pool: both walk (fine orientation, pixel,
+//    significant translation); the reference slice, the phase factors and the weights are computed
+//    once and feed both the sigma2/XA/AA sums and the scatter.
+//  * shell sums are reduced in shared memory per orientation (the reference writes per-pixel arrays
+//    with atomics and sums the shells on the host, acc_ml_optimiser_impl.h:3466-3494).
+//  * the accumulator volume is float4 (re, im, weight, 0): each trilinear corner is one 16-byte vector
+//    reduction (red.global.add.v4.f32) instead of three scalar atomics into three arrays; the two x
+//    neighbours of a corner pair share a 32-byte sector.
+#include "device_utils.cuh"
+
+static const int ST_THREADS = 256;
+static const int ST_TC = 8;       // significant translations per table chunk
+static const int ST_MAXSAMP = 2048;
+
+__device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c)
+{
+	// 16-byte vector reduction, sm_90+ (PTX ISA 8.1: red.global.add.v4.f32)
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
+}
+
+// 8-corner trilinear scatter with Hermitian fold (BP.cuh:301-401 / BP.h:632-748)
+__device__ __forceinline__ void bp_scatter(const RbBackprojector &bp, int max_r2_vol, int x, int y,
+                                           float e0, float e1, float e3, float e4, float e6, float e7,
+                                           float real, float imag, float Fweight)
+{
+	float xp = (e0 * x + e1 * y) * bp.padding_factor;
+	float yp = (e3 * x + e4 * y) * bp.padding_factor;
+	float zp = (e6 * x + e7 * y) * bp.padding_factor;
+	if (xp * xp + yp * yp + zp * zp > (float) max_r2_vol) return;
+	if (xp < 0.f) { xp = -xp; yp = -yp; zp = -zp; imag = -imag; }
+	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+	const float fx = xp - fx0, fy = yp - fy0, fz = zp - fz0;
+	const int x0 = (int) fx0, y0 = (int) fy0 - bp.mdlInitY, z0 = (int) fz0 - bp.mdlInitZ;
+	const float mfx = 1.f - fx, mfy = 1.f - fy, mfz = 1.f - fz;
+	float4 *b = bp.vol + ((size_t) z0 * bp.mdlY + y0) * (size_t) bp.mdlX + x0;
+	const size_t sy = bp.mdlX, sz = (size_t) bp.mdlX * bp.mdlY;
+	float d;
+	d = mfz * mfy * mfx; red_add_v4(b, d * real, d * imag, d * Fweight);
+	d = mfz * mfy * fx;  red_add_v4(b + 1, d * real, d * imag, d * Fweight);
+	d = mfz * fy * mfx;  red_add_v4(b + sy, d * real, d * imag, d * Fweight);
+	d = mfz * fy * fx;   red_add_v4(b + sy + 1, d * real, d * imag, d * Fweight);
+	d = fz * mfy * mfx;  red_add_v4(b + sz, d * real, d * imag, d * Fweight);
+	d = fz * mfy * fx;   red_add_v4(b + sz + 1, d * real, d * imag, d * Fweight);
+	d = fz * fy * mfx;   red_add_v4(b + sz + sy, d * real, d * imag, d * Fweight);
+	d = fz * fy * fx;    red_add_v4(b + sz + sy + 1, d * real, d * imag, d * Fweight);
+}
+
+__device__ __forceinline__ void build_tables_st(float2 *tab_x, float2 *tab_y, int imgX, int ny, int yoff,
+                                                const float *tx, const float *ty, int ntr)
+{
+	for (int i = threadIdx.x; i < ntr * imgX; i += blockDim.x)
+	{
+		int t = i / imgX, x = i - t * imgX;
+		float s, c; sincosf(x * tx[t], &s, &c);
+		tab_x[i] = make_float2(c, s);
+	}
+	for (int i = threadIdx.x; i < ntr * ny; i += blockDim.x)
+	{
+		int t = i / ny, yy = i - t * ny, y = yy - yoff;
+		float s, c; sincosf((y < 0 ? -y : y) * ty[t], &s, &c);
+		tab_y[i] = make_float2(c, y < 0 ? -s : s);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// collect (collect2jobs + host loop acc_ml_optimiser_impl.h:2821-2854): one thread per fine orientation
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_collect(const RbPartMeta *metas, RbPartState *states, const RbFineOrient *fo, const int *pair_list,
+          const float *fs_w, const long long *fs_ihid, const int *dir_idx, RbModelDev M, RbSamplingDev S,
+          double *out_pdf_dir, double *out_pdf_class, const int *counters)
+{
+	__shared__ double dred[32];
+	if (counters[2]) return;
+	const int p = blockIdx.x;
+	const RbPartMeta m = metas[p];
+	RbPartState *st = states + p;
+	if (st->status != 0) return;
+	const int NOR = S.n_over_rot, NOT = S.n_over_trans;
+	const int nfo = st->n_so * NOR;
+	const float sig = st->fsig_weight, sumw = st->fsum_weight;
+	double a_w = 0., a_s2 = 0.;
+	for (int i = threadIdx.x; i < nfo; i += blockDim.x)
+	{
+		const RbFineOrient F = fo[st->fo_base + i];
+		float sw = 0.f, ss2 = 0.f;
+		for (int j = 0; j < F.n_t * NOT; j++)
+		{
+			float w = fs_w[F.sample_off + j];
+			w = (w >= sig) ? w / sumw : 0.f;                                          // helper.cuh:118-127
+			const int it = pair_list[F.pair_off + j / NOT] * NOT + (j % NOT);
+			const double xs = m.oldx + S.over_trans_x[it], ys = m.oldy + S.over_trans_y[it];
+			const double dx = m.prx - xs, dy = m.pry - ys;
+			const float o2 = (float) (dx * dx + dy * dy);                             // :2728-2736
+			sw += w; ss2 += w * o2;
+		}
+		const int idl = F.iorient / m.np;
+		const int mydir = m.dir_off < 0 ? idl : dir_idx[m.dir_off + idl];             // :2833-2837
+		if (sw != 0.f)
+		{
+			atomicAdd(out_pdf_dir + (size_t) F.iclass * S.n_dir + mydir, (double) sw);
+			atomicAdd(out_pdf_class + F.iclass, (double) sw);
+		}
+		a_w += (double) sw;
+		a_s2 += M.pixel_size * M.pixel_size * (double) ss2;                           // :2845
+	}
+	a_w = block_sum(a_w, dred);
+	a_s2 = block_sum(a_s2, dred);
+	if (threadIdx.x == 0)
+	{
+		st->sumw = a_w; st->wsum_s2off = a_s2;
+		st->best_ihid = fs_ihid[st->fs_base + st->fmax_sample];
+	}
+}
+
+int rbk_collect_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	k_collect<<<s.P, 256, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(), s.fo.as<RbFineOrient>(),
+		s.pair_list.as<int>(), s.fs_w.as<float>(), s.fs_ihid.as<long long>(), s.dir_idx.as<int>(),
+		ctx->d_model, ctx->d_samp, s.out_pdf_dir.as<double>(), s.out_pdf_class.as<double>(), s.counters.as<int>());
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused wavg + back-projection over the pool
+// ---------------------------------------------------------------------------------------------
+struct StoreArgs {
+	const RbPartMeta *metas; RbPartState *states;
+	const float2 *Fimg, *Fnomask; const float *Fctf;
+	const RbFineOrient *fo; const int *pair_list; const int *counters;
+	const float *fs_w;
+	float *shells;                 // [P][nshell]
+	const RbProjector *projs; const RbBackprojector *bps;
+	const uint32_t *pix; int npix; int n;
+	const float *tx, *ty; int NOT;
+};
+
+__global__ void __launch_bounds__(ST_THREADS)
+k_store(StoreArgs A, RbModelDev M)
+{
+	extern __shared__ float2 smem2[];
+	__shared__ float s_tx[ST_TC], s_ty[ST_TC], s_wn[ST_TC], s_wr[ST_TC];
+	__shared__ float s_e[6];
+	__shared__ int s_nsig;
+	__shared__ int s_sigidx[ST_MAXSAMP];
+	__shared__ double dred[32];
+	__shared__ float s_shell[1024];
+
+	const int imgX = A.n / 2 + 1;
+	const int ny = A.n + 1, yoff = A.n / 2;
+	float2 *tab_x = smem2;
+	float2 *tab_y = smem2 + ST_TC * imgX;
+	const int nwork = A.counters[0];
+	const int half = A.n / 2;
+
+	for (int w = blockIdx.x; w < nwork; w += gridDim.x)
+	{
+		const RbFineOrient F = A.fo[w];
+		const int p = F.particle;
+		const RbPartState *st = A.states + p;
+		if (st->status != 0) continue;
+		const float sig = st->fsig_weight, sumw = st->fsum_weight;
+		const int nsamp = F.n_t * A.NOT;
+		// ordered list of significant samples (warp 0)
+		__syncthreads();
+		if (threadIdx.x < 32)
+		{
+			int cnt = 0;
+			for (int j0 = 0; j0 < nsamp; j0 += 32)
+			{
+				const int j = j0 + threadIdx.x;
+				const bool s = j < nsamp && A.fs_w[F.sample_off + j] >= sig;          // wavg.cuh:106 / BP.cuh:278
+				const unsigned b = __ballot_sync(RB_FULL_MASK, s);
+				if (s) { int pos = cnt + __popc(b & ((1u << threadIdx.x) - 1)); if (pos < ST_MAXSAMP) s_sigidx[pos] = j; }
+				cnt += __popc(b);
+			}
+			if (threadIdx.x == 0) s_nsig = min(cnt, ST_MAXSAMP);
+		}
+		if (threadIdx.x < 6) { const int map[6] = {0, 1, 3, 4, 6, 7}; s_e[threadIdx.x] = A.fo[w].e[map[threadIdx.x]]; }
+		for (int i = threadIdx.x; i < M.nshell; i += ST_THREADS) s_shell[i] = 0.f;
+		__syncthreads();
+		const int nsig = s_nsig;
+		if (nsig == 0) continue;
+
+		const RbPartMeta m = A.metas[p];
+		const float2 *X = A.Fimg + (size_t) p * M.Npf, *X0 = A.Fnomask + (size_t) p * M.Npf;
+		const float *C = A.Fctf ? A.Fctf + (size_t) p * M.Npf : nullptr;
+		const float *mtab = M.minvs2 + (size_t) m.og * M.nshell;
+		const unsigned char *dvp = M.dvp_gt3 + (size_t) F.iclass * M.nshell;
+		const RbProjK pk = rb_make_projk(A.projs[F.iclass], imgX);
+		const RbBackprojector bp = A.bps[F.iclass];
+		const int max_r2_vol = (int) (bp.maxR * bp.maxR * bp.padding_factor * bp.padding_factor);   // BP.cuh:209
+		const float wni = 1.0f / sumw;
+		double aXA = 0., aAA = 0.;
+
+		for (int c0 = 0; c0 < nsig; c0 += ST_TC)
+		{
+			const int ntr = min(ST_TC, nsig - c0);
+			__syncthreads();
+			if (threadIdx.x < ntr)
+			{
+				const int j = s_sigidx[c0 + threadIdx.x];
+				const int it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
+				s_tx[threadIdx.x] = A.tx[it]; s_ty[threadIdx.x] = A.ty[it];
+				const float wt = A.fs_w[F.sample_off + j];
+				s_wr[threadIdx.x] = wt;              // raw weight (BP)
+				s_wn[threadIdx.x] = wt * wni;        // weight * weight_norm_inverse (wavg.h:138)
+			}
+			__syncthreads();
+			build_tables_st(tab_x, tab_y, imgX, ny, yoff, s_tx, s_ty, ntr);
+			__syncthreads();
+			const float e0 = s_e[0], e1 = s_e[1], e3 = s_e[2], e4 = s_e[3], e6 = s_e[4], e7 = s_e[5];
+
+			for (int ip = threadIdx.x; ip < A.npix; ip += ST_THREADS)
+			{
+				const uint32_t pkx = __ldg(A.pix + ip);
+				const int x = rb_pix_x(pkx), y = rb_pix_y(pkx), ires = rb_pix_ires(pkx);
+				const int idx = rb_src_index(x, y, A.n);
+				const float2 img = __ldg(X + idx), img0 = __ldg(X0 + idx);
+				const float ctf = C ? __ldg(C + idx) * m.part_scale : m.part_scale;               // :3087-3096
+				float minvs2 = M.do_map ? __ldg(mtab + ires) : 1.f;                               // :2586, :3110-3115
+				float2 ref = rb_project3d(pk, x, y, e0, e1, e3, e4, e6, e7);
+				if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                     // wavg.cuh:96-104
+				else { ref.x *= m.part_scale; ref.y *= m.part_scale; }
+				float wd = 0.f, xa = 0.f, aa = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
+				const float2 *txp = tab_x + x, *typ = tab_y + (y + yoff);
+				const float refn = ref.x * ref.x + ref.y * ref.y;
+#pragma unroll
+				for (int t = 0; t < ST_TC; t++)
+				{
+					if (t < ntr)
+					{
+						const float2 a = txp[t * imgX], b = typ[t * ny];
+						const float ss = a.y * b.x + a.x * b.y;
+						const float cc = a.x * b.x - a.y * b.y;
+						const float tr = cc * img.x - ss * img.y, ti = cc * img.y + ss * img.x;
+						const float dr = ref.x - tr, di = ref.y - ti;
+						const float wn = s_wn[t];
+						wd += wn * (dr * dr + di * di);                                           // wavg.cuh:124-135
+						xa += wn * (ref.x * tr + ref.y * ti);
+						aa += wn * refn;
+						float myw;
+						if (M.ctf_premultiplied) myw = s_wr[t] * (wni * minvs2);                  // BP.cuh:280-289
+						else myw = s_wr[t] * (wni * ctf * minvs2);
+						Fw += myw * ctf;
+						Fr += (cc * img0.x - ss * img0.y) * myw;
+						Fi += (cc * img0.y + ss * img0.x) * myw;
+					}
+				}
+				atomicAdd(&s_shell[ires], wd);
+				if (dvp[ires] && M.do_scale_correction) { aXA += (double) xa; aAA += (double) aa; }   // :3473-3479
+				bool do_bp = Fw > 0.f;
+				if (M.bp_circle_bound)
+				{
+					const int xmax = (int) sqrtf((float) (half * half - y * y));                 // BP.h:565
+					do_bp = do_bp && (x < xmax);
+				}
+				if (do_bp) bp_scatter(bp, max_r2_vol, x, y, e0, e1, e3, e4, e6, e7, Fr, Fi, Fw);
+			}
+		}
+		__syncthreads();
+		for (int i = threadIdx.x; i < M.nshell; i += ST_THREADS)
+		{
+			const float v = s_shell[i];
+			if (v != 0.f) atomicAdd(A.shells + (size_t) p * M.nshell + i, v);
+		}
+		aXA = block_sum(aXA, dred);
+		aAA = block_sum(aAA, dred);
+		if (threadIdx.x == 0 && (aXA != 0. || aAA != 0.))
+		{
+			atomicAdd(&A.states[p].wsum_XA, aXA);
+			atomicAdd(&A.states[p].wsum_AA, aAA);
+		}
+	}
+}
+
+static size_t store_smem(int n) { return (size_t) ST_TC * ((n / 2 + 1) + (n + 1)) * sizeof(float2); }
+
+int rbk_store_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	StoreArgs A;
+	memset(&A, 0, sizeof(A));
+	A.metas = s.meta.as<RbPartMeta>(); A.states = s.state.as<RbPartState>();
+	A.Fimg = s.Fimg.as<float2>(); A.Fnomask = s.Fnomask.as<float2>();
+	A.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
+	A.fo = s.fo.as<RbFineOrient>(); A.pair_list = s.pair_list.as<int>(); A.counters = s.counters.as<int>();
+	A.fs_w = s.fs_w.as<float>(); A.shells = s.shells.as<float>();
+	A.projs = ctx->d_proj.as<RbProjector>(); A.bps = ctx->d_bp.as<RbBackprojector>();
+	A.pix = ctx->d_model.pix_f; A.npix = ctx->d_model.nvf; A.n = ctx->d_model.current_size;
+	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
+	size_t sm = store_smem(A.n);
+	static size_t configured = 0;
+	if (sm > configured)
+	{
+		RB_CUDA(cudaFuncSetAttribute(k_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+		configured = sm;
+	}
+	k_store<<<ctx->num_sms * 4, ST_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// stage entry points: reference-style dense inputs (one CTA per orientation, all translations)
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_wavg_stage(RbProjector pj, int n, const float *eulers, const float *tx, const float *ty, int T,
+             const float *re, const float *im, const float *weights, const float *ctfs,
+             float weight_norm, float sig_w, float *parts, float *AA, float *XA)
+{
+	const int imgX = n / 2 + 1;
+	const RbProjK pk = rb_make_projk(pj, imgX);
+	const int o = blockIdx.x;
+	const float *e = eulers + (size_t) o * 9;
+	const float wni = 1.0f / weight_norm;
+	for (int pix = threadIdx.x; pix < n * imgX; pix += blockDim.x)
+	{
+		int x = pix % imgX, iy = pix / imgX, y = iy;
+		if (iy > pk.maxR)                                                                    // wavg.cuh:81-87
+		{
+			if (iy >= n - pk.maxR) y = iy - n;
+			else if (x != pk.maxR) continue;   // ALTCPU visits only x = maxR in the dead band (wavg.h:74-82)
+		}
+		float2 ref = rb_project3d(pk, x, y, e[0], e[1], e[3], e[4], e[6], e[7]);
+		const float ctf = ctfs[pix];
+		ref.x *= ctf; ref.y *= ctf;
+		const float ir = re[pix], ii = im[pix];
+		float wd = 0.f, xa = 0.f, aa = 0.f;
+		for (int t = 0; t < T; t++)
+		{
+			float w = weights[(size_t) o * T + t];
+			if (w < sig_w) continue;
+			w *= wni;
+			float s, c; sincosf(x * tx[t] + y * ty[t], &s, &c);                              // translatePixel
+			const float tr = c * ir - s * ii, ti = c * ii + s * ir;
+			const float dr = ref.x - tr, di = ref.y - ti;
+			wd += w * (dr * dr + di * di);
+			xa += w * (ref.x * tr + ref.y * ti);
+			aa += w * (ref.x * ref.x + ref.y * ref.y);
+		}
+		atomicAdd(parts + pix, wd); atomicAdd(XA + pix, xa); atomicAdd(AA + pix, aa);
+	}
+}
+
+int rbk_wavg_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int O,
+                   const float *d_tx, const float *d_ty, int T, const float *d_re, const float *d_im,
+                   const float *d_w, const float *d_ctf, float weight_norm, float sig_w,
+                   float *d_parts, float *d_AA, float *d_XA)
+{
+	if (O < 1) return RB_OK;
+	k_wavg_stage<<<O, 256, 0, ctx->stream>>>(pj, n, d_eulers, d_tx, d_ty, T, d_re, d_im, d_w, d_ctf, weight_norm, sig_w, d_parts, d_AA, d_XA);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+__global__ void __launch_bounds__(128)
+k_backproject_stage(RbBackprojector bp, int n, const float *eulers, const float *tx, const float *ty, int T,
+                    const float *re, const float *im, const float *weights, const float *minvs2s, const float *ctfs,
+                    float weight_norm, float sig_w, int circle_bound, int ctf_premultiplied)
+{
+	const int imgX = n / 2 + 1, half = n / 2;
+	const int o = blockIdx.x;
+	const float *e = eulers + (size_t) o * 9;
+	const int max_r2_vol = (int) (bp.maxR * bp.maxR * bp.padding_factor * bp.padding_factor);
+	const float wni = 1.0f / weight_norm;
+	for (int pix = threadIdx.x; pix < n * imgX; pix += blockDim.x)
+	{
+		int x = pix % imgX, iy = pix / imgX, y = iy > half ? iy - n : iy;                    // BP.cuh:258-261
+		if (circle_bound) { int xmax = (int) sqrtf((float) (half * half - y * y)); if (x >= xmax) continue; }
+		const float minvs2 = minvs2s[pix], ctf = ctfs[pix], ir = re[pix], ii = im[pix];
+		float Fr = 0.f, Fi = 0.f, Fw = 0.f;
+		for (int t = 0; t < T; t++)
+		{
+			const float w = weights[(size_t) o * T + t];
+			if (w < sig_w) continue;
+			float myw = ctf_premultiplied ? w * (wni * minvs2) : w * (wni * ctf * minvs2);
+			Fw += myw * ctf;
+			float s, c; sincosf(x * tx[t] + y * ty[t], &s, &c);
+			Fr += (c * ir - s * ii) * myw;
+			Fi += (c * ii + s * ir) * myw;
+		}
+		if (Fw > 0.f) bp_scatter(bp, max_r2_vol, x, y, e[0], e[1], e[3], e[4], e[6], e[7], Fr, Fi, Fw);
+	}
+}
+
+int rbk_backproject_stage(rb_ctx *ctx, const RbBackprojector &bp, int n, const float *d_eulers, int O,
+                          const float *d_tx, const float *d_ty, int T, const float *d_re, const float *d_im,
+                          const float *d_w, const float *d_minvs2, const float *d_ctf,
+                          float weight_norm, float sig_w, int circle_bound, int ctf_premultiplied)
+{
+	if (O < 1) return RB_OK;
+	k_backproject_stage<<<O, 128, 0, ctx->stream>>>(bp, n, d_eulers, d_tx, d_ty, T, d_re, d_im, d_w, d_minvs2, d_ctf,
+		weight_norm, sig_w, circle_bound, ctf_premultiplied);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}

@@ -1,0 +1,523 @@
+// relion_b200 — diff2 -> posterior weights, sort-free significance threshold, fine-pass job construction.
+//
+// Replaces, per pool and without host round trips:
+//   cuda_kernel_weights_exponent_coarse / cuda_kernel_exponentiate (helper.cuh:16-67),
+//   cuda_kernel_exponentiate_weights_fine (helper.cu:36-77),
+//   CUB filter>0 + radix sort + inclusive scan + cuda_kernel_find_threshold_idx_in_cumulative +
+//   cuda_kernel_array_over_threshold (cuda_utils_cub.cuh:30-359, cuda_device_utils.cuh:191-220),
+//   generateProjectionSetupFine / makeJobsForDiff2Fine host loops (acc_helper_functions_impl.h:26-102, 265-314)
+// of /root/reference/src/acc.  Orchestration being replaced: convertAllSquaredDifferencesToWeights
+// (acc_ml_optimiser_impl.h:1895-2548).
+//
+// Significance rule (acc_ml_optimiser_impl.h:2240-2345): with the non-zero weights sorted ascending and
+// cum their running sum, thresholdIdx = first i with cum[i] > (1-adaptive_fraction)*sum; significant_weight =
+// sorted[thresholdIdx].  We find the same element without sorting: an 8-pass, 4-bit radix descent on the
+// fp32 bit pattern (weights >= 0, so bit order == value order) that carries the exact (fp64) mass and count of
+// everything below the current prefix.  Sums are fixed-tree fp64 reductions, hence deterministic.
+#include "device_utils.cuh"
+
+static const int WT_THREADS = 512;   // 16 fp64 bins + 16 counters per thread: keep 128 registers available
+
+struct SelResult {
+	double total;        // fp64 sum of all weights
+	float sum_f;         // (float) total  == op.sum_weight
+	float sig_w;         // sorted[thresholdIdx]
+	long long n_nonzero; // filteredSize
+	long long thr_idx;   // thresholdIdx among the non-zero weights
+};
+
+struct SelSmem {
+	double ws[32][16];
+	int wc[32][16];
+	double bs[16];
+	long long bc[16];
+	double dred[32];
+	long long lred[32];
+	unsigned prefix; double base; long long cbelow; long long cequal; int found;
+};
+
+// reduce per-thread 16-bin (sum,count) histograms over the CTA into sm.bs / sm.bc
+__device__ __forceinline__ void reduce_bins(double (&s)[16], int (&c)[16], SelSmem &sm)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+	for (int b = 0; b < 16; b++)
+	{
+		double vs = warp_sum(s[b]);
+		int vc = warp_sum(c[b]);
+		if (lane == 0) { sm.ws[wid][b] = vs; sm.wc[wid][b] = vc; }
+	}
+	__syncthreads();
+	if (threadIdx.x < 16)
+	{
+		double a = 0.; long long n = 0;
+		for (int w = 0; w < nw; w++) { a += sm.ws[w][threadIdx.x]; n += sm.wc[w][threadIdx.x]; }
+		sm.bs[threadIdx.x] = a; sm.bc[threadIdx.x] = n;
+	}
+	__syncthreads();
+}
+
+// Radix descent.  by_rank == false: smallest value v with (mass of weights <= v) > thr.
+//                 by_rank == true : value of ascending rank `rank` among the non-zero weights.
+__device__ void radix_descend(const float *w, long long n, bool by_rank, double thr, long long rank, SelSmem &sm)
+{
+	if (threadIdx.x == 0) { sm.prefix = 0u; sm.base = 0.; sm.cbelow = 0; sm.cequal = 0; }
+	__syncthreads();
+	for (int pass = 0; pass < 8; pass++)
+	{
+		const int shift = 28 - 4 * pass;
+		const unsigned prefix = sm.prefix;
+		double s[16]; int c[16];
+#pragma unroll
+		for (int b = 0; b < 16; b++) { s[b] = 0.; c[b] = 0; }
+		for (long long i = threadIdx.x; i < n; i += blockDim.x)
+		{
+			const float v = w[i];
+			const unsigned bits = __float_as_uint(v);
+			if (v > 0.f && (pass == 0 || (bits >> (shift + 4)) == (prefix >> (shift + 4))))
+			{
+				const int bin = (bits >> shift) & 15;
+#pragma unroll
+				for (int b = 0; b < 16; b++) { const bool h = (bin == b); s[b] += h ? (double) v : 0.; c[b] += h ? 1 : 0; }
+			}
+		}
+		reduce_bins(s, c, sm);
+		if (threadIdx.x == 0)
+		{
+			double cum = sm.base; long long cc = sm.cbelow; int sel = -1;
+			for (int b = 0; b < 16; b++)
+			{
+				if (sm.bc[b] > 0)
+				{
+					bool hit = by_rank ? (cc + sm.bc[b] > rank) : (cum + sm.bs[b] > thr);
+					if (hit) { sel = b; break; }
+				}
+				cum += sm.bs[b]; cc += sm.bc[b];
+			}
+			if (sel < 0)
+			{
+				// nothing crosses the threshold (thr >= total): the reference's search leaves idx = 0
+				sm.found = 0;
+			}
+			else
+			{
+				sm.found = 1;
+				sm.prefix = prefix | ((unsigned) sel << shift);
+				sm.base = cum; sm.cbelow = cc; sm.cequal = sm.bc[sel];
+			}
+		}
+		__syncthreads();
+		if (!sm.found) return;
+	}
+}
+
+// Whole significance computation for one array; all threads of the CTA must call.
+__device__ SelResult block_significance(const float *w, long long n, double adaptive_fraction, int maxsig, SelSmem &sm)
+{
+	SelResult r;
+	// total mass and number of non-zero weights
+	double t = 0.; long long cnt = 0;
+	for (long long i = threadIdx.x; i < n; i += blockDim.x) { float v = w[i]; if (v > 0.f) { t += (double) v; cnt++; } }
+	r.total = block_sum(t, sm.dred);
+	r.n_nonzero = block_sum(cnt, sm.lred);
+	r.sum_f = (float) r.total;
+	r.sig_w = 0.f; r.thr_idx = 0;
+	if (r.n_nonzero == 0) return r;
+	const double thr = (double) (float) ((1. - adaptive_fraction) * (double) r.sum_f);   // (XFLOAT) threshold, :2277-2278
+	radix_descend(w, n, false, thr, 0, sm);
+	__syncthreads();
+	if (!sm.found)
+	{
+		r.thr_idx = 0;
+		radix_descend(w, n, true, 0., 0, sm);   // sorted[0]
+		__syncthreads();
+		r.sig_w = __uint_as_float(sm.prefix);
+	}
+	else
+	{
+		const float v = __uint_as_float(sm.prefix);
+		// k-th copy of v is the first whose running sum exceeds thr
+		double kk = floor((thr - sm.base) / (double) v) + 1.;
+		long long k = kk < 1. ? 1 : (kk > (double) sm.cequal ? sm.cequal : (long long) kk);
+		r.thr_idx = sm.cbelow + k - 1;
+		r.sig_w = v;
+	}
+	__syncthreads();
+	if (maxsig > 0 && r.n_nonzero - r.thr_idx > maxsig)                                   // :2301-2306
+	{
+		r.thr_idx = r.n_nonzero - maxsig;
+		radix_descend(w, n, true, 0., r.thr_idx, sm);
+		__syncthreads();
+		r.sig_w = __uint_as_float(sm.prefix);
+		__syncthreads();
+	}
+	return r;
+}
+
+struct ArgMaxSmem { float v[32]; long long i[32]; };
+
+// first index holding the maximum value
+__device__ void block_argmax(float v, long long idx, ArgMaxSmem &sm, float &out_v, long long &out_i)
+{
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		float ov = __shfl_xor_sync(RB_FULL_MASK, v, o);
+		long long oi = __shfl_xor_sync(RB_FULL_MASK, idx, o);
+		if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+	}
+	__syncthreads();
+	if (lane == 0) { sm.v[wid] = v; sm.i[wid] = idx; }
+	__syncthreads();
+	v = lane < nw ? sm.v[lane] : RB_LOWEST; idx = lane < nw ? sm.i[lane] : 0x7fffffffffffffffLL;
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1)
+	{
+		float ov = __shfl_xor_sync(RB_FULL_MASK, v, o);
+		long long oi = __shfl_xor_sync(RB_FULL_MASK, idx, o);
+		if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+	}
+	out_v = v; out_i = idx;
+}
+
+struct DenseOut { float min_diff2, wmax, max_weight; long long max_index; SelResult sel; };
+
+// dense [n_orient][T] conversion in place (weights_exponent_coarse + exponentiate + significance + argmax)
+__device__ DenseOut dense_convert(float *w, long long n, int T, const float *po, const unsigned char *pz,
+                                  const float *pt, const unsigned char *tz, float min_diff2,
+                                  double adaptive_fraction, int maxsig, SelSmem &sm, ArgMaxSmem &am, float *fred)
+{
+	DenseOut o;
+	o.min_diff2 = min_diff2;
+	float mx = RB_LOWEST;
+	for (long long i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const long long io = i / T; const int it = (int) (i - io * T);
+		const float d = w[i];
+		float l;
+		if (d < min_diff2 || pz[io] || tz[it]) l = RB_LOWEST;                      // helper.cuh:39-42
+		else l = po[io] + pt[it] + min_diff2 - d;
+		w[i] = l;
+		mx = fmaxf(mx, l);
+	}
+	o.wmax = block_max(mx, fred);
+	const float add = 50.f - o.wmax;                                               // acc_ml_optimiser_impl.h:2201-2207
+	float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
+	__syncthreads();
+	for (long long i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const float a = w[i] + add;
+		const float e = (a < -88.f) ? 0.f : expf(a);                               // helper.cuh:57-66
+		w[i] = e;
+		if (e > bv) { bv = e; bi = i; }
+	}
+	__syncthreads();
+	block_argmax(bv, bi, am, o.max_weight, o.max_index);
+	o.sel = block_significance(w, n, adaptive_fraction, maxsig, sm);
+	return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(WT_THREADS)
+k_weights_coarse(const RbPartMeta *metas, RbPartState *states, float *Mweight,
+                 const float *pdf_orient, const unsigned char *pdf_orient_zero,
+                 const float *pdf_offset, const unsigned char *pdf_offset_zero, RbModelDev M, int T)
+{
+	__shared__ SelSmem sm;
+	__shared__ ArgMaxSmem am;
+	__shared__ float fred[32];
+	const int p = blockIdx.x;
+	const RbPartMeta m = metas[p];
+	RbPartState *st = states + p;
+	const long long n = (long long) M.nr_classes * m.nd * m.np * T;
+	float *w = Mweight + m.coarse_off;
+	const float min_diff2 = __int_as_float(st->min_diff2_bits);
+	DenseOut o = dense_convert(w, n, T, pdf_orient + m.prior_off, pdf_orient_zero + m.prior_off,
+	                           pdf_offset + (size_t) p * T, pdf_offset_zero + (size_t) p * T, min_diff2,
+	                           M.adaptive_fraction, M.maximum_significants, sm, am, fred);
+	if (threadIdx.x == 0)
+	{
+		st->min_diff2 = min_diff2;
+		st->cmax_weight = o.max_weight; st->cmax_index = o.max_index;
+		st->csum_weight = o.sel.sum_f; st->n_nonzero = (int) o.sel.n_nonzero;
+		if (n == 1) { st->csig_weight = 0.f; st->nr_sig_coarse = 1; }                  // :2347-2350
+		else
+		{
+			st->csig_weight = o.sel.sig_w;
+			st->nr_sig_coarse = (int) (o.sel.n_nonzero - o.sel.thr_idx);
+			if (o.sel.n_nonzero == 0 || st->nr_sig_coarse == 0) st->status = RB_ERR_NO_SIGNIFICANT;   // :2242, :2282
+		}
+	}
+}
+
+int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	k_weights_coarse<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
+		s.Mweight.as<float>(), s.pdf_orient.as<float>(), s.pdf_orient_zero.as<unsigned char>(),
+		s.pdf_offset.as<float>(), s.pdf_offset_zero.as<unsigned char>(), ctx->d_model, ctx->d_samp.n_trans);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// ---- fine-pass setup -------------------------------------------------------------------------
+static const int FS_THREADS = 256;
+
+__global__ void __launch_bounds__(FS_THREADS)
+k_fine_count(const RbPartMeta *metas, RbPartState *states, const float *Mweight, RbModelDev M, int T)
+{
+	__shared__ int red[32];
+	const int p = blockIdx.x;
+	const RbPartMeta m = metas[p];
+	RbPartState *st = states + p;
+	const int ndense = M.nr_classes * m.nd * m.np;
+	const float *w = Mweight + m.coarse_off;
+	const float sig = st->csig_weight;
+	int nso = 0, npair = 0;
+	for (int o = threadIdx.x; o < ndense; o += FS_THREADS)
+	{
+		int cnt = 0;
+		for (int t = 0; t < T; t++) cnt += (w[(long long) o * T + t] >= sig) ? 1 : 0;   // arrayOverThreshold
+		nso += cnt > 0; npair += cnt;
+	}
+	nso = block_sum(nso, red);
+	npair = block_sum(npair, red);
+	if (threadIdx.x == 0) { st->n_so = nso; st->n_pairs = npair; }
+}
+
+// exclusive scan over the particles of the pool (single CTA)
+__global__ void __launch_bounds__(1024)
+k_fine_scan(RbPartState *states, int P, int NOR, int NOT, long long cap_fo, long long cap_fs, int *counters)
+{
+	__shared__ long long s_a[1024], s_b[1024];
+	const int per = (P + 1023) / 1024;
+	const int i0 = threadIdx.x * per, i1 = min(P, i0 + per);
+	long long a = 0, b = 0;
+	for (int i = i0; i < i1; i++) { a += states[i].n_so; b += states[i].n_pairs; }
+	s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+	__syncthreads();
+	for (int off = 1; off < 1024; off <<= 1)
+	{
+		long long ta = 0, tb = 0;
+		if (threadIdx.x >= off) { ta = s_a[threadIdx.x - off]; tb = s_b[threadIdx.x - off]; }
+		__syncthreads();
+		s_a[threadIdx.x] += ta; s_b[threadIdx.x] += tb;
+		__syncthreads();
+	}
+	long long ea = s_a[threadIdx.x] - a, eb = s_b[threadIdx.x] - b;   // exclusive prefix of this thread's chunk
+	for (int i = i0; i < i1; i++)
+	{
+		states[i].so_base = ea; states[i].pair_base = eb;
+		states[i].fo_base = ea * NOR; states[i].fs_base = eb * NOR * NOT;
+		ea += states[i].n_so; eb += states[i].n_pairs;
+	}
+	if (threadIdx.x == 1023)
+	{
+		long long tfo = s_a[1023] * NOR, tfs = s_b[1023] * NOR * NOT;
+		int overflow = (tfo > cap_fo) || (tfs > cap_fs) || tfo > 0x7fffffffLL;
+		counters[0] = overflow ? 0 : (int) tfo;
+		counters[2] = overflow;
+		((long long *) counters)[2] = tfo;   // counters[4..5]
+		((long long *) counters)[3] = tfs;   // counters[6..7]
+	}
+}
+
+__global__ void __launch_bounds__(FS_THREADS)
+k_fine_fill(const RbPartMeta *metas, const RbPartState *states, const float *Mweight,
+            const int *dir_idx, const int *psi_idx, RbModelDev M, RbSamplingDev S,
+            int *pair_list, RbFineOrient *fo, long long *fs_ihid, const int *counters)
+{
+	__shared__ int s_scan_f[FS_THREADS], s_scan_c[FS_THREADS];
+	__shared__ int s_run_f, s_run_c;
+	if (counters[2]) return;   // capacity overflow: host reports RB_ERR_CAPACITY
+	const int p = blockIdx.x;
+	const RbPartMeta m = metas[p];
+	const RbPartState st = states[p];
+	const int T = S.n_trans, NOR = S.n_over_rot, NOT = S.n_over_trans;
+	const int no = m.nd * m.np, ndense = M.nr_classes * no;
+	const float *w = Mweight + m.coarse_off;
+	const float sig = st.csig_weight;
+	if (threadIdx.x == 0) { s_run_f = 0; s_run_c = 0; }
+	__syncthreads();
+	for (int c0 = 0; c0 < ndense; c0 += FS_THREADS)
+	{
+		const int o = c0 + threadIdx.x;
+		int cnt = 0;
+		if (o < ndense) for (int t = 0; t < T; t++) cnt += (w[(long long) o * T + t] >= sig) ? 1 : 0;
+		const int flag = cnt > 0;
+		s_scan_f[threadIdx.x] = flag; s_scan_c[threadIdx.x] = cnt;
+		__syncthreads();
+		for (int off = 1; off < FS_THREADS; off <<= 1)
+		{
+			int tf = 0, tc = 0;
+			if (threadIdx.x >= off) { tf = s_scan_f[threadIdx.x - off]; tc = s_scan_c[threadIdx.x - off]; }
+			__syncthreads();
+			s_scan_f[threadIdx.x] += tf; s_scan_c[threadIdx.x] += tc;
+			__syncthreads();
+		}
+		const int sidx = s_run_f + s_scan_f[threadIdx.x] - flag;     // index among significant orientations
+		const int poff = s_run_c + s_scan_c[threadIdx.x] - cnt;      // pairs before this orientation
+		if (flag)
+		{
+			const int k = o / no, oi = o - k * no, idl = oi / m.np, ipl = oi - idl * m.np;
+			const int gd = m.dir_off < 0 ? idl : dir_idx[m.dir_off + idl];
+			const int gp = m.psi_off < 0 ? ipl : psi_idx[m.psi_off + ipl];
+			const long long pair_off = st.pair_base + poff;
+			int j = 0;
+			for (int t = 0; t < T; t++) if (w[(long long) o * T + t] >= sig) pair_list[pair_off + j++] = t;
+			for (int io = 0; io < NOR; io++)
+			{
+				RbFineOrient F;
+				F.particle = p; F.iclass = k; F.iorient = oi; F.iover_rot = io;
+				F.pair_off = (int) pair_off; F.n_t = cnt;
+				F.sample_off = st.fs_base + ((long long) poff * NOR + (long long) io * cnt) * NOT;
+				double rot, tilt, psi;
+				if (S.over_rot)
+				{
+					const size_t g = ((size_t) gd * S.n_psi + gp) * NOR + io;
+					rot = S.over_rot[g]; tilt = S.over_tilt[g]; psi = S.over_psi[g];
+				}
+				else { rot = S.rot[gd]; tilt = S.tilt[gd]; psi = S.psi[gp]; }
+				rb_euler_fine(rot, tilt, psi, F.e);
+				fo[st.fo_base + (long long) sidx * NOR + io] = F;
+				// ihidden_over (acc_helper_functions_impl.h:63)
+				j = 0;
+				for (int t = 0; t < T; t++)
+					if (w[(long long) o * T + t] >= sig)
+					{
+						const long long ihidden = (long long) o * T + t;
+						for (int iot = 0; iot < NOT; iot++)
+							fs_ihid[F.sample_off + (long long) j * NOT + iot] = (ihidden * NOR + io) * NOT + iot;
+						j++;
+					}
+			}
+		}
+		__syncthreads();
+		if (threadIdx.x == FS_THREADS - 1) { s_run_f += s_scan_f[threadIdx.x]; s_run_c += s_scan_c[threadIdx.x]; }
+		__syncthreads();
+	}
+}
+
+int rbk_fine_setup_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	const int T = ctx->d_samp.n_trans;
+	k_fine_count<<<s.P, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
+		s.Mweight.as<float>(), ctx->d_model, T);
+	RB_LAUNCH_CHECK(ctx);
+	k_fine_scan<<<1, 1024, 0, ctx->stream>>>(s.state.as<RbPartState>(), s.P, ctx->d_samp.n_over_rot, ctx->d_samp.n_over_trans,
+		(long long) ctx->fine_orient_capacity, (long long) ctx->fine_sample_capacity, s.counters.as<int>());
+	RB_LAUNCH_CHECK(ctx);
+	k_fine_fill<<<s.P, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
+		s.Mweight.as<float>(), s.dir_idx.as<int>(), s.psi_idx.as<int>(), ctx->d_model, ctx->d_samp,
+		s.pair_list.as<int>(), s.fo.as<RbFineOrient>(), s.fs_ihid.as<long long>(), s.counters.as<int>());
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// ---- fine-pass weights -----------------------------------------------------------------------
+__global__ void __launch_bounds__(WT_THREADS)
+k_weights_fine(const RbPartMeta *metas, RbPartState *states, float *fs_w, const long long *fs_ihid,
+               const float *pdf_orient, const unsigned char *pdf_orient_zero,
+               const float *pdf_offset, const unsigned char *pdf_offset_zero,
+               RbModelDev M, int T, int NOR, int NOT, const int *counters)
+{
+	__shared__ SelSmem sm;
+	__shared__ ArgMaxSmem am;
+	__shared__ float fred[32];
+	if (counters[2]) return;
+	const int p = blockIdx.x;
+	const RbPartMeta m = metas[p];
+	RbPartState *st = states + p;
+	const long long n = (long long) st->n_pairs * NOR * NOT;
+	if (n == 0) { if (threadIdx.x == 0 && st->status == 0) st->status = RB_ERR_NO_SIGNIFICANT; return; }
+	float *w = fs_w + st->fs_base;
+	const long long *ih = fs_ihid + st->fs_base;
+	const float *po = pdf_orient + m.prior_off; const unsigned char *pz = pdf_orient_zero + m.prior_off;
+	const float *pt = pdf_offset + (size_t) p * T; const unsigned char *tz = pdf_offset_zero + (size_t) p * T;
+	const float min_diff2 = __int_as_float(st->fmin_bits);                                  // :1881
+	const long long ov = (long long) NOR * NOT;
+	float mx = RB_LOWEST;
+	for (long long i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const long long ihidden = ih[i] / ov;
+		const int it = (int) (ihidden % T); const long long io = ihidden / T;
+		const float d = w[i];
+		float l;
+		if (d < min_diff2 || pz[io] || tz[it]) l = RB_LOWEST;                               // helper.cu:66-74
+		else l = po[io] + pt[it] + min_diff2 - d;
+		w[i] = l;
+		mx = fmaxf(mx, l);
+	}
+	const float wmax = block_max(mx, fred);
+	const float add = 50.f - wmax;                                                          // :2440
+	float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
+	__syncthreads();
+	for (long long i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const float a = w[i] + add;
+		const float e = (a < -88.f) ? 0.f : expf(a);
+		w[i] = e;
+		if (e > bv) { bv = e; bi = i; }
+	}
+	__syncthreads();
+	float maxw; long long maxi;
+	block_argmax(bv, bi, am, maxw, maxi);
+	SelResult sel = block_significance(w, n, M.adaptive_fraction, 0, sm);
+	if (threadIdx.x == 0)
+	{
+		st->fmin_diff2 = min_diff2;
+		st->min_diff2_final = (double) min_diff2 + (double) add;                            // :2444
+		st->fmax_weight = maxw; st->fmax_sample = maxi;
+		st->fsum_weight = sel.sum_f; st->fsig_weight = sel.sig_w;
+		if (sel.sum_f == 0.f && st->status == 0) st->status = RB_ERR_SUMWEIGHT_ZERO;        // :2505
+	}
+}
+
+int rbk_weights_fine_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	k_weights_fine<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
+		s.fs_w.as<float>(), s.fs_ihid.as<long long>(), s.pdf_orient.as<float>(), s.pdf_orient_zero.as<unsigned char>(),
+		s.pdf_offset.as<float>(), s.pdf_offset_zero.as<unsigned char>(), ctx->d_model,
+		ctx->d_samp.n_trans, ctx->d_samp.n_over_rot, ctx->d_samp.n_over_trans, s.counters.as<int>());
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// ---- stage entry: dense conversion of one array ----------------------------------------------
+__global__ void __launch_bounds__(WT_THREADS)
+k_convert_stage(float *w, long long n, int T, const float *po, const unsigned char *pz,
+                const float *pt, const unsigned char *tz, double adaptive_fraction, int maxsig,
+                unsigned char *sig, rb_weights_out *out)
+{
+	__shared__ SelSmem sm;
+	__shared__ ArgMaxSmem am;
+	__shared__ float fred[32];
+	float mn = FLT_MAX;
+	for (long long i = threadIdx.x; i < n; i += blockDim.x) { float d = w[i]; if (d > RB_LOWEST) mn = fminf(mn, d); }
+	mn = -block_max(-mn, fred);
+	__syncthreads();
+	DenseOut o = dense_convert(w, n, T, po, pz, pt, tz, mn, adaptive_fraction, maxsig, sm, am, fred);
+	__syncthreads();
+	const float sigw = (n == 1) ? 0.f : o.sel.sig_w;
+	if (sig) for (long long i = threadIdx.x; i < n; i += blockDim.x) sig[i] = w[i] >= sigw;
+	if (threadIdx.x == 0)
+	{
+		out->min_diff2 = mn; out->max_weight = o.max_weight; out->max_index = o.max_index;
+		out->sum_weight = o.sel.sum_f; out->significant_weight = o.sel.sig_w;
+		out->nr_significant = (int) (o.sel.n_nonzero - o.sel.thr_idx); out->n_nonzero = (int) o.sel.n_nonzero;
+	}
+}
+
+int rbk_convert_weights_stage(rb_ctx *ctx, float *d_w, long long n_orient, int n_trans,
+                              const float *d_pdf_o, const unsigned char *d_pdf_oz,
+                              const float *d_pdf_t, const unsigned char *d_pdf_tz,
+                              double adaptive_fraction, int maxsig, int /*filter_zero*/,
+                              unsigned char *d_sig, rb_weights_out *d_out)
+{
+	k_convert_stage<<<1, WT_THREADS, 0, ctx->stream>>>(d_w, n_orient * n_trans, n_trans, d_pdf_o, d_pdf_oz, d_pdf_t, d_pdf_tz,
+		adaptive_fraction, maxsig, d_sig, d_out);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}

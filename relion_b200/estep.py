@@ -1,0 +1,413 @@
+"""Host-side mirror of RELION's accelerator boundary for the expectation step.
+
+`MlDeviceBundle` plays the role of the reference's MlDeviceBundle + MlOptimiserCuda
+(/root/reference/src/acc/cuda/cuda_ml_optimiser.h:18-144): per-device projectors
+(`set_reference` = AccProjector::setMdlDim/initMdl), back-projectors (`bp_init`/`bp_get` =
+AccBackprojector::setMdlDim/initMdl/getMdlData) and the E-step over a pool of particles
+(`expectation_some_particles` = doThreadExpectationSomeParticles for the whole pool at once).
+Everything numerical happens in the C-ABI library (relion_b200/capi.py); this file only marshals
+numpy / torch host buffers and keeps them alive across the asynchronous calls.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional
+
+import numpy as np
+
+from . import capi
+from .sampling import Sampling
+
+
+def _ptr(a, ctype):
+    """ctypes pointer to a contiguous numpy array or (pinned) CPU torch tensor, or NULL."""
+    if a is None:
+        return C.cast(None, C.POINTER(ctype))
+    if hasattr(a, "data_ptr"):  # torch tensor
+        assert a.is_contiguous() and a.device.type == "cpu"
+        return C.cast(a.data_ptr(), C.POINTER(ctype))
+    assert a.flags["C_CONTIGUOUS"], "array must be C-contiguous"
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+@dataclasses.dataclass
+class ModelParams:
+    """What the E-step reads from MlModel / MlOptimiser (SURVEY.md §8b data contract)."""
+    nr_classes: int
+    ori_size: int
+    coarse_size: int
+    current_size: int
+    pixel_size: float
+    sigma2_noise: np.ndarray                 # [nr_optics_groups, ori_size/2+1]
+    scale_correction: np.ndarray             # [nr_groups]
+    pdf_class: np.ndarray                    # [K]
+    pdf_direction: Optional[np.ndarray]      # [K, n_dir]
+    data_vs_prior_class: Optional[np.ndarray] = None  # [K, ori_size/2+1]
+    sigma2_offset: float = 9.0
+    offset_range: float = 0.0
+    sigma2_fudge: float = 1.0
+    adaptive_fraction: float = 0.999
+    maximum_significants: int = 0
+    do_ctf_correction: bool = True
+    refs_are_ctf_corrected: bool = True
+    do_scale_correction: bool = True
+    do_map: bool = True
+    ctf_premultiplied: bool = False
+    bp_circle_bound: bool = True
+
+
+@dataclasses.dataclass
+class ParticlePool:
+    """One pool of particles after image preparation (getFourierTransformsAndCtfs outputs)."""
+    Fimg: np.ndarray                # [P, n, n/2+1] complex64 (masked), n = current_size
+    Fimg_nomask: np.ndarray         # [P, n, n/2+1] complex64
+    Fctf: Optional[np.ndarray]      # [P, n, n/2+1] float32
+    group_id: np.ndarray            # [P] int32
+    optics_group: np.ndarray        # [P] int32
+    highres_Xi2: np.ndarray         # [P] float64
+    old_offset: np.ndarray          # [P, 2] float64 (pixels)
+    prior_offset: np.ndarray        # [P, 2] float64
+    dir_off: Optional[np.ndarray] = None
+    dir_idx: Optional[np.ndarray] = None
+    dir_prior: Optional[np.ndarray] = None
+    psi_off: Optional[np.ndarray] = None
+    psi_idx: Optional[np.ndarray] = None
+    psi_prior: Optional[np.ndarray] = None
+
+    @property
+    def n_particles(self):
+        return int(self.Fimg.shape[0])
+
+
+_OUT_DTYPE = np.dtype([
+    ("best_ihidden_over", np.int64),
+    ("best_class", np.int32), ("best_idir", np.int32), ("best_ipsi", np.int32),
+    ("best_iover_rot", np.int32), ("best_itrans", np.int32), ("best_iover_trans", np.int32),
+    ("nr_significant_coarse", np.int32), ("n_fine_orient", np.int32), ("n_fine_samples", np.int32),
+    ("min_diff2_coarse", np.float32), ("sum_weight_coarse", np.float32), ("significant_weight_coarse", np.float32),
+    ("min_diff2", np.float32), ("max_weight", np.float32), ("sum_weight", np.float32),
+    ("significant_weight", np.float32), ("pmax", np.float32),
+    ("dLL_nolog", np.float64), ("wsum_norm_correction", np.float64),
+    ("wsum_XA", np.float64), ("wsum_AA", np.float64), ("sumw", np.float64), ("wsum_sigma2_offset", np.float64),
+], align=True)
+assert _OUT_DTYPE.itemsize == C.sizeof(capi.rb_particle_out), (_OUT_DTYPE.itemsize, C.sizeof(capi.rb_particle_out))
+
+
+@dataclasses.dataclass
+class PoolResult:
+    particles: np.ndarray           # structured array, one row per particle (rb_particle_out)
+    wsum_sigma2_noise: np.ndarray   # [P, ori_size/2+1] float32
+    wsum_pdf_direction: np.ndarray  # [K, n_dir] float64
+    wsum_pdf_class: np.ndarray      # [K] float64
+
+
+class _Marshalled:
+    """ctypes structs plus the host arrays they point into (kept alive together)."""
+
+    def __init__(self):
+        self.keep = []
+
+    def hold(self, a):
+        self.keep.append(a)
+        return a
+
+
+def marshal_sampling(s: Sampling):
+    m = _Marshalled()
+    st = capi.rb_sampling()
+    st.n_dir, st.n_psi = s.n_dir, s.n_psi
+    st.rot = _ptr(m.hold(_f64(s.rot)), C.c_double)
+    st.tilt = _ptr(m.hold(_f64(s.tilt)), C.c_double)
+    st.psi = _ptr(m.hold(_f64(s.psi)), C.c_double)
+    st.n_over_rot = s.n_over_rot
+    st.over_rot = _ptr(m.hold(_f64(s.over_rot)), C.c_double)
+    st.over_tilt = _ptr(m.hold(_f64(s.over_tilt)), C.c_double)
+    st.over_psi = _ptr(m.hold(_f64(s.over_psi)), C.c_double)
+    st.n_trans = s.n_trans
+    st.trans_x = _ptr(m.hold(_f64(s.trans_x)), C.c_double)
+    st.trans_y = _ptr(m.hold(_f64(s.trans_y)), C.c_double)
+    st.n_over_trans = s.n_over_trans
+    st.over_trans_x = _ptr(m.hold(_f64(s.over_trans_x)), C.c_double)
+    st.over_trans_y = _ptr(m.hold(_f64(s.over_trans_y)), C.c_double)
+    m.struct = st
+    return m
+
+
+def marshal_model(p: ModelParams):
+    m = _Marshalled()
+    st = capi.rb_model()
+    st.nr_classes, st.ori_size, st.coarse_size, st.current_size = p.nr_classes, p.ori_size, p.coarse_size, p.current_size
+    st.pixel_size = p.pixel_size
+    s2 = m.hold(_f64(np.atleast_2d(p.sigma2_noise)))
+    st.nr_optics_groups = s2.shape[0]
+    st.sigma2_noise = _ptr(s2, C.c_double)
+    sc = m.hold(_f64(np.atleast_1d(p.scale_correction)))
+    st.nr_groups = sc.shape[0]
+    st.scale_correction = _ptr(sc, C.c_double)
+    st.pdf_class = _ptr(m.hold(_f64(p.pdf_class)), C.c_double)
+    st.pdf_direction = _ptr(m.hold(_f64(p.pdf_direction)), C.c_double)
+    st.data_vs_prior_class = _ptr(m.hold(_f64(p.data_vs_prior_class)), C.c_double)
+    st.sigma2_offset, st.offset_range, st.sigma2_fudge = p.sigma2_offset, p.offset_range, p.sigma2_fudge
+    st.adaptive_fraction, st.maximum_significants = p.adaptive_fraction, p.maximum_significants
+    st.do_ctf_correction = int(p.do_ctf_correction)
+    st.refs_are_ctf_corrected = int(p.refs_are_ctf_corrected)
+    st.do_scale_correction = int(p.do_scale_correction)
+    st.do_map = int(p.do_map)
+    st.ctf_premultiplied = int(p.ctf_premultiplied)
+    st.bp_circle_bound = int(p.bp_circle_bound)
+    m.struct = st
+    return m
+
+
+def marshal_pool(pool: ParticlePool):
+    m = _Marshalled()
+    st = capi.rb_particles()
+    st.n_particles = pool.n_particles
+
+    def img(a, dtype):
+        if a is None:
+            return None
+        if hasattr(a, "data_ptr"):
+            return m.hold(a)
+        return m.hold(np.ascontiguousarray(a, dtype=dtype))
+
+    st.Fimg = _ptr(img(pool.Fimg, np.complex64), C.c_float)
+    st.Fimg_nomask = _ptr(img(pool.Fimg_nomask, np.complex64), C.c_float)
+    st.Fctf = _ptr(img(pool.Fctf, np.float32), C.c_float)
+    st.group_id = _ptr(m.hold(_i32(pool.group_id)), C.c_int)
+    st.optics_group = _ptr(m.hold(_i32(pool.optics_group)), C.c_int)
+    st.highres_Xi2 = _ptr(m.hold(_f64(pool.highres_Xi2)), C.c_double)
+    st.old_offset = _ptr(m.hold(_f64(pool.old_offset)), C.c_double)
+    st.prior_offset = _ptr(m.hold(_f64(pool.prior_offset)), C.c_double)
+    st.dir_off = _ptr(m.hold(_i32(pool.dir_off)), C.c_int)
+    st.dir_idx = _ptr(m.hold(_i32(pool.dir_idx)), C.c_int)
+    st.dir_prior = _ptr(m.hold(_f64(pool.dir_prior)), C.c_double)
+    st.psi_off = _ptr(m.hold(_i32(pool.psi_off)), C.c_int)
+    st.psi_idx = _ptr(m.hold(_i32(pool.psi_idx)), C.c_int)
+    st.psi_prior = _ptr(m.hold(_f64(pool.psi_prior)), C.c_double)
+    m.struct = st
+    return m
+
+
+def make_pool_out(n_particles: int, nshell: int, nr_classes: int, n_dir: int):
+    m = _Marshalled()
+    parts = m.hold(np.zeros(n_particles, dtype=_OUT_DTYPE))
+    shells = m.hold(np.zeros((n_particles, nshell), dtype=np.float32))
+    pdir = m.hold(np.zeros((nr_classes, n_dir), dtype=np.float64))
+    pcls = m.hold(np.zeros(nr_classes, dtype=np.float64))
+    st = capi.rb_pool_out()
+    st.particles = C.cast(parts.ctypes.data, C.POINTER(capi.rb_particle_out))
+    st.wsum_sigma2_noise = _ptr(shells, C.c_float)
+    st.wsum_pdf_direction = _ptr(pdir, C.c_double)
+    st.wsum_pdf_class = _ptr(pcls, C.c_double)
+    m.struct = st
+    m.result = PoolResult(parts, shells, pdir, pcls)
+    return m
+
+
+class MlDeviceBundle:
+    """One per GPU (cuda_ml_optimiser.h:18-76)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load_library()
+        h = C.c_void_p()
+        capi.check(self.lib, self.lib.rb_ctx_create(device, C.byref(h)))
+        self.ctx = h
+        self.device_id = device
+        self.model: Optional[ModelParams] = None
+        self.sampling: Optional[Sampling] = None
+        self._keep = {}
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.rb_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- projectors / back-projectors ---------------------------------------------------------
+    def set_reference(self, iclass: int, vol: np.ndarray, r_max: int, padding_factor: float = 2.0):
+        """vol: complex [Z, Y, X] padded Fourier volume (MlModel::PPref[k].data layout)."""
+        z, y, x = vol.shape
+        init = -((y - 1) // 2)
+        if vol.dtype == np.complex128:
+            v = np.ascontiguousarray(vol)
+            st = self.lib.rb_set_reference(self.ctx, iclass, _ptr(v.view(np.float64), C.c_double), x, y, z, init, init, r_max, padding_factor)
+        else:
+            v = np.ascontiguousarray(vol, dtype=np.complex64)
+            st = self.lib.rb_set_reference_f32(self.ctx, iclass, _ptr(v.view(np.float32), C.c_float), x, y, z, init, init, r_max, padding_factor)
+        capi.check(self.lib, st)
+
+    def bp_init(self, iclass: int, shape_zyx, r_max: int, padding_factor: float = 2.0):
+        z, y, x = shape_zyx
+        init = -((y - 1) // 2)
+        capi.check(self.lib, self.lib.rb_bp_init(self.ctx, iclass, x, y, z, init, init, r_max, padding_factor))
+        self._keep[("bp_shape", iclass)] = (z, y, x)
+
+    def bp_clear(self, iclass: int):
+        capi.check(self.lib, self.lib.rb_bp_clear(self.ctx, iclass))
+
+    def bp_get(self, iclass: int):
+        z, y, x = self._keep[("bp_shape", iclass)]
+        re = np.empty((z, y, x), np.float32)
+        im = np.empty_like(re)
+        w = np.empty_like(re)
+        capi.check(self.lib, self.lib.rb_bp_get(self.ctx, iclass, _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(w, C.c_float)))
+        return re, im, w
+
+    def bp_device_tensor(self, iclass: int):
+        """The interleaved (re, im, weight, 0) accumulator as a torch CUDA tensor sharing the library's memory
+        (for torch.distributed.all_reduce over NCCL — replaces MlOptimiserMpi::combineAllWeightedSums)."""
+        import torch
+        p = C.c_void_p()
+        n = C.c_size_t()
+        capi.check(self.lib, self.lib.rb_bp_device_buffer(self.ctx, iclass, C.byref(p), C.byref(n)))
+
+        class _Wrap:
+            pass
+
+        wrap = _Wrap()
+        wrap.__cuda_array_interface__ = {"shape": (n.value,), "typestr": "<f4", "data": (p.value, False), "version": 2}
+        return torch.as_tensor(wrap, device=f"cuda:{self.device_id}")
+
+    def sync_all_backprojects(self):
+        capi.check(self.lib, self.lib.rb_sync(self.ctx))
+
+    # ---- per-iteration state --------------------------------------------------------------------
+    def set_model(self, p: ModelParams):
+        m = marshal_model(p)
+        capi.check(self.lib, self.lib.rb_set_model(self.ctx, C.byref(m.struct)))
+        self.model = p
+        if self.sampling is not None and p.pdf_direction is not None:
+            pd = _f64(p.pdf_direction)
+            capi.check(self.lib, self.lib.rb_set_pdf_direction(self.ctx, _ptr(pd, C.c_double)))
+
+    def set_sampling(self, s: Sampling):
+        assert self.model is not None, "set_model first (translations are scaled by ori_size)"
+        m = marshal_sampling(s)
+        capi.check(self.lib, self.lib.rb_set_sampling(self.ctx, C.byref(m.struct)))
+        self.sampling = s
+        if self.model.pdf_direction is not None:
+            pd = _f64(self.model.pdf_direction)
+            assert pd.shape == (self.model.nr_classes, s.n_dir), pd.shape
+            capi.check(self.lib, self.lib.rb_set_pdf_direction(self.ctx, _ptr(pd, C.c_double)))
+
+    # ---- the E-step -----------------------------------------------------------------------------
+    def _new_out(self, n_particles):
+        return make_pool_out(n_particles, self.model.ori_size // 2 + 1, self.model.nr_classes, self.sampling.n_dir)
+
+    def expectation_some_particles(self, pool: ParticlePool, skip_maximization: bool = False) -> PoolResult:
+        """H2D of the pool, all E-step stages, D2H of the per-particle results (rb_estep_pool)."""
+        mp = marshal_pool(pool)
+        out = self._new_out(pool.n_particles)
+        st = self.lib.rb_estep_pool(self.ctx, C.byref(mp.struct), C.byref(out.struct), 1 if skip_maximization else 0)
+        capi.check(self.lib, st)
+        return out.result
+
+    def pool_upload(self, slot: int, pool: ParticlePool):
+        mp = marshal_pool(pool)
+        self._keep[("pool", slot)] = mp   # host buffers must outlive the asynchronous copy
+        capi.check(self.lib, self.lib.rb_pool_upload(self.ctx, slot, C.byref(mp.struct)))
+        self._keep[("pool_n", slot)] = pool.n_particles
+
+    def estep_slot(self, slot: int, skip_maximization: bool = False) -> PoolResult:
+        out = self._new_out(self._keep[("pool_n", slot)])
+        capi.check(self.lib, self.lib.rb_estep_slot(self.ctx, slot, C.byref(out.struct), 1 if skip_maximization else 0))
+        return out.result
+
+    def estep_slot_nocopy(self, slot: int, skip_maximization: bool = False):
+        capi.check(self.lib, self.lib.rb_estep_slot_nocopy(self.ctx, slot, 1 if skip_maximization else 0))
+
+    def estep_fetch(self, slot: int) -> PoolResult:
+        out = self._new_out(self._keep[("pool_n", slot)])
+        capi.check(self.lib, self.lib.rb_estep_fetch(self.ctx, slot, C.byref(out.struct)))
+        return out.result
+
+    def stage_ms(self, name: str) -> float:
+        return float(self.lib.rb_stage_ms(self.ctx, name.encode()))
+
+    def launch_count(self) -> int:
+        return int(self.lib.rb_launch_count(self.ctx))
+
+    # ---- stage-level entry points (parity tests) --------------------------------------------------
+    def project(self, iclass, img_size, eulers):
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        out = np.empty((e.shape[0], img_size, img_size // 2 + 1), np.complex64)
+        capi.check(self.lib, self.lib.rb_project(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0], _ptr(out.view(np.float32), C.c_float)))
+        return out
+
+    def diff2_coarse(self, iclass, img_size, eulers, tx, ty, re, im, corr, init=None):
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32); corr = np.ascontiguousarray(corr, np.float32)
+        out = np.zeros((e.shape[0], len(tx)), np.float32) if init is None else np.ascontiguousarray(init, np.float32).copy()
+        capi.check(self.lib, self.lib.rb_diff2_coarse(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0],
+                                                      _ptr(tx, C.c_float), _ptr(ty, C.c_float), len(tx),
+                                                      _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(corr, C.c_float), _ptr(out, C.c_float)))
+        return out
+
+    def diff2_fine(self, iclass, img_size, eulers, tx, ty, re, im, corr, sum_init, rot_idx, trans_idx, job_idx, job_num):
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32); corr = np.ascontiguousarray(corr, np.float32)
+        ri = np.ascontiguousarray(rot_idx, np.uint64); ti = np.ascontiguousarray(trans_idx, np.uint64)
+        ji = np.ascontiguousarray(job_idx, np.uint64); jn = np.ascontiguousarray(job_num, np.uint64)
+        out = np.zeros(len(ri), np.float32)
+        capi.check(self.lib, self.lib.rb_diff2_fine(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0],
+                                                    _ptr(tx, C.c_float), _ptr(ty, C.c_float), len(tx),
+                                                    _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(corr, C.c_float), float(sum_init),
+                                                    _ptr(ri, C.c_uint64), _ptr(ti, C.c_uint64), _ptr(ji, C.c_uint64), _ptr(jn, C.c_uint64),
+                                                    len(ji), _ptr(out, C.c_float), len(ri)))
+        return out
+
+    def convert_weights(self, diff2, pdf_o, pdf_oz, pdf_t, pdf_tz, adaptive_fraction=0.999, maxsig=0, filter_zero=True):
+        w = np.ascontiguousarray(diff2, np.float32).copy()
+        no, nt = w.shape
+        po = np.ascontiguousarray(pdf_o, np.float32); pt = np.ascontiguousarray(pdf_t, np.float32)
+        oz = np.ascontiguousarray(pdf_oz, np.uint8); tz = np.ascontiguousarray(pdf_tz, np.uint8)
+        sig = np.zeros(w.shape, np.uint8)
+        out = capi.rb_weights_out()
+        capi.check(self.lib, self.lib.rb_convert_weights(self.ctx, _ptr(w, C.c_float), no, nt, _ptr(po, C.c_float), _ptr(oz, C.c_ubyte),
+                                                         _ptr(pt, C.c_float), _ptr(tz, C.c_ubyte), adaptive_fraction, maxsig,
+                                                         int(filter_zero), _ptr(sig, C.c_ubyte), C.byref(out)))
+        return w, sig, out
+
+    def wavg(self, iclass, img_size, eulers, tx, ty, re, im, weights, ctfs, weight_norm, sig_w):
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32)
+        w = np.ascontiguousarray(weights, np.float32); c = np.ascontiguousarray(ctfs, np.float32)
+        np_ = img_size * (img_size // 2 + 1)
+        parts = np.zeros(np_, np.float32); AA = np.zeros(np_, np.float32); XA = np.zeros(np_, np.float32)
+        capi.check(self.lib, self.lib.rb_wavg(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0], _ptr(tx, C.c_float), _ptr(ty, C.c_float), len(tx),
+                                              _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(w, C.c_float), _ptr(c, C.c_float),
+                                              float(weight_norm), float(sig_w), _ptr(parts, C.c_float), _ptr(AA, C.c_float), _ptr(XA, C.c_float)))
+        return parts, AA, XA
+
+    def backproject(self, iclass, img_size, eulers, tx, ty, re, im, weights, minvsigma2, ctfs, weight_norm, sig_w):
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32)
+        w = np.ascontiguousarray(weights, np.float32); c = np.ascontiguousarray(ctfs, np.float32); mi = np.ascontiguousarray(minvsigma2, np.float32)
+        capi.check(self.lib, self.lib.rb_backproject(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0], _ptr(tx, C.c_float), _ptr(ty, C.c_float), len(tx),
+                                                     _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(w, C.c_float), _ptr(mi, C.c_float), _ptr(c, C.c_float),
+                                                     float(weight_norm), float(sig_w)))
+
+    def backproject_posed(self, iclass, img_size, F2D, Fctf, eulers):
+        F = np.ascontiguousarray(F2D, np.complex64); W = np.ascontiguousarray(Fctf, np.float32)
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        capi.check(self.lib, self.lib.rb_backproject_posed(self.ctx, iclass, img_size, F.shape[0], _ptr(F.view(np.float32), C.c_float),
+                                                           _ptr(W, C.c_float), _ptr(e, C.c_float)))

@@ -1,0 +1,128 @@
+"""Seeded E-step workloads (references + sampling + model state + particle pool).
+
+Used by tests/, __graft_entry__.smoke() and bench.py so that the CUDA path, the CPU oracle and the
+reference arm all see byte-identical inputs.  Pure host code (numpy).
+"""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Callable, Optional
+
+import numpy as np
+
+from . import sampling as smp
+from . import synth
+from .estep import ModelParams, ParticlePool
+
+
+@dataclasses.dataclass
+class Workload:
+    name: str
+    model: ModelParams
+    sampling: smp.Sampling
+    refs: list                 # list of complex64 [Z, Y, X] padded Fourier volumes, one per class
+    r_max: int
+    padding_factor: float
+    pool: ParticlePool
+    truth: dict                # true class / angles / shifts of every particle
+    bp_shape: tuple
+
+
+def coarse_size_for(ori_size: int, pixel_size: float, angular_step: float, particle_diameter: float, current_size: int) -> int:
+    """image_coarse_size for adaptive_oversampling > 0 (src/ml_optimiser.cpp:5757-5767), 3D reference."""
+    rotated_distance = (angular_step / 360.0) * math.pi * particle_diameter
+    coarse_resolution = rotated_distance / 1.2
+    c = 2 * int(math.ceil(pixel_size * ori_size / coarse_resolution))
+    return max(2, min(current_size, c))
+
+
+def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optional[int] = None,
+                  healpix_order: int = 1, offset_range: float = 3.0, offset_step: float = 2.0,
+                  n_particles: int = 8, nr_classes: int = 1, snr: float = 0.5, seed: int = 1993,
+                  local_search: bool = False, sigma_ang: Optional[float] = None,
+                  pixel_size: float = 2.0, particle_diameter: Optional[float] = None,
+                  nr_groups: int = 2, adaptive_fraction: float = 0.999, coarse_size: Optional[int] = None,
+                  projector: Optional[Callable] = None, n_blobs: int = 40, phantom_size: Optional[int] = None) -> Workload:
+    """Build a complete, seeded E-step problem.
+
+    projector(vol_complex64, r_max, pf, eulers[n,9] float32, n) -> [n_img, n, n//2+1] complex: how noise-free
+    slices are made (default: the float64 numpy projector; bench.py passes the CUDA projector for 256 px).
+    """
+    rng = np.random.default_rng(seed)
+    current_size = current_size or ori_size
+    pf = 2.0
+    # ---- references -------------------------------------------------------------------------
+    refs = []
+    r_max = None
+    for k in range(nr_classes):
+        vol = synth.make_phantom(ori_size, n_blobs=n_blobs, seed=seed + 17 * k)
+        data, r_max = synth.reference_ft(vol, current_size=current_size, padding_factor=pf)
+        refs.append(data.astype(np.complex64))
+    # ---- sampling ---------------------------------------------------------------------------
+    s = smp.make_sampling(healpix_order, offset_range, offset_step, oversampling=1)
+    ang_step = smp.angular_sampling(healpix_order)
+    diameter = particle_diameter or 0.7 * ori_size * pixel_size
+    if coarse_size is None:
+        coarse_size = coarse_size_for(ori_size, pixel_size, ang_step, diameter, current_size)
+    # ---- true poses ---------------------------------------------------------------------------
+    P = n_particles
+    cls = rng.integers(0, nr_classes, P)
+    # true orientations: a random fine-grid orientation (so that the maximum is well defined)
+    idir = rng.integers(0, s.n_dir, P)
+    ipsi = rng.integers(0, s.n_psi, P)
+    io = rng.integers(0, s.n_over_rot, P)
+    g = (idir * s.n_psi + ipsi) * s.n_over_rot + io
+    rot, tilt, psi = s.over_rot[g], s.over_tilt[g], s.over_psi[g]
+    it = rng.integers(0, s.n_trans * s.n_over_trans, P)
+    shifts = np.stack([s.over_trans_x[it], s.over_trans_y[it]], axis=1)
+    eul = synth.inverse_euler_f32(rot, tilt, psi)
+    # ---- noise-free slices ----------------------------------------------------------------------
+    n = current_size
+    if projector is None:
+        slices = np.empty((P, n, n // 2 + 1), np.complex128)
+        for p in range(P):
+            A_inv = eul[p].reshape(3, 3).astype(np.float64)
+            slices[p] = synth.project_numpy(refs[cls[p]].astype(np.complex128), r_max, pf, A_inv, n)
+    else:
+        slices = np.empty((P, n, n // 2 + 1), np.complex64)
+        for k in range(nr_classes):
+            sel = np.nonzero(cls == k)[0]
+            if len(sel):
+                slices[sel] = projector(k, eul[sel], n)
+    parts = synth.make_particles(slices, ori_size, pixel_size, snr, seed + 1, rot, tilt, psi, shifts)
+    # ---- model state -----------------------------------------------------------------------------
+    nshell = ori_size // 2 + 1
+    sigma2 = np.tile(parts.sigma2_noise[None, :], (1, 1))
+    scale = 1.0 + 0.05 * rng.standard_normal(nr_groups)
+    pdf_class = np.full(nr_classes, 1.0 / nr_classes)
+    pdf_direction = np.full((nr_classes, s.n_dir), 1.0 / s.n_dir)
+    dvp = np.zeros((nr_classes, nshell))
+    dvp[:, : max(2, nshell // 2)] = 10.0
+    model = ModelParams(nr_classes=nr_classes, ori_size=ori_size, coarse_size=coarse_size, current_size=current_size,
+                        pixel_size=pixel_size, sigma2_noise=sigma2, scale_correction=scale, pdf_class=pdf_class,
+                        pdf_direction=None if local_search else pdf_direction, data_vs_prior_class=dvp,
+                        sigma2_offset=(offset_range * pixel_size / 1.5) ** 2, adaptive_fraction=adaptive_fraction)
+    # ---- pool ------------------------------------------------------------------------------------
+    group = rng.integers(0, nr_groups, P).astype(np.int32)
+    pool = ParticlePool(Fimg=parts.Fimg, Fimg_nomask=parts.Fimg_nomask, Fctf=parts.Fctf, group_id=group,
+                        optics_group=np.zeros(P, np.int32), highres_Xi2=parts.highres_Xi2,
+                        old_offset=np.zeros((P, 2)), prior_offset=np.zeros((P, 2)))
+    if local_search:
+        sig = sigma_ang if sigma_ang is not None else 2.0 * ang_step / 2.0   # 2 x oversampled step (src/ml_optimiser.cpp:2316-2326)
+        doff, poff = [0], [0]
+        di, dp, pi_, pp = [], [], [], []
+        for p in range(P):
+            # prior centre: the true orientation perturbed by ~half a coarse step
+            pr = rot[p] + rng.normal(0, 0.3 * ang_step)
+            pt = float(np.clip(tilt[p] + rng.normal(0, 0.3 * ang_step), 0.0, 180.0))
+            pq = (psi[p] + rng.normal(0, 0.3 * ang_step)) % 360.0
+            a, b, c, d = smp.select_nonzero_prior(s, pr, pt, pq, sig, sig, sig)
+            di.append(a); dp.append(b); pi_.append(c); pp.append(d)
+            doff.append(doff[-1] + len(a)); poff.append(poff[-1] + len(c))
+        pool.dir_off = np.array(doff, np.int32); pool.psi_off = np.array(poff, np.int32)
+        pool.dir_idx = np.concatenate(di).astype(np.int32); pool.dir_prior = np.concatenate(dp)
+        pool.psi_idx = np.concatenate(pi_).astype(np.int32); pool.psi_prior = np.concatenate(pp)
+    pad = refs[0].shape[0]
+    truth = dict(cls=cls, rot=rot, tilt=tilt, psi=psi, shifts=shifts, idir=idir, ipsi=ipsi, iover_rot=io, itrans_over=it)
+    return Workload(name, model, s, refs, r_max, pf, pool, truth, (pad, pad, pad // 2 + 1))

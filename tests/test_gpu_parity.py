@@ -1,0 +1,258 @@
+"""Parity of the CUDA path (through the C-ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerances (fp32 kernels, sums of O(1e3) terms, different association order and FMA contraction):
+  projection values               1e-5 of the slice maximum
+  diff2 / wavg sums               2e-5 relative
+  weights after expf              2e-4 relative (CUDA expf vs glibc expf, <= 2 ulp, amplified by exp(50-max))
+  back-projected volumes          1e-4 of the volume maximum (fp32 atomics, order dependent)
+  significance selection          bit-exact against the oracle's exact-arithmetic rule on the same weights
+  log-likelihood                  1e-4 relative (north_star)
+  max-posterior pose              >= 99.5 % of particles (north_star)
+"""
+import numpy as np
+import pytest
+
+from relion_b200 import synth
+from relion_b200.workload import make_workload
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle.bindings import Oracle
+    return Oracle("port")
+
+
+def _setup(device, wl):
+    device.set_model(wl.model)
+    device.set_sampling(wl.sampling)
+    for k, v in enumerate(wl.refs):
+        device.set_reference(k, v, wl.r_max, wl.padding_factor)
+        device.bp_init(k, wl.bp_shape, wl.r_max, wl.padding_factor)
+
+
+def _stage_inputs(wl, n, seed, n_orient, n_trans):
+    rng = np.random.default_rng(seed)
+    xs = n // 2 + 1
+    eul = synth.inverse_euler_f32(rng.uniform(-180, 180, n_orient), rng.uniform(0, 180, n_orient), rng.uniform(0, 360, n_orient))
+    tx = (-2 * np.pi * rng.uniform(-4, 4, n_trans) / wl.model.ori_size).astype(np.float32)
+    ty = (-2 * np.pi * rng.uniform(-4, 4, n_trans) / wl.model.ori_size).astype(np.float32)
+    re = rng.standard_normal((n, xs)).astype(np.float32)
+    im = rng.standard_normal((n, xs)).astype(np.float32)
+    corr = rng.uniform(0.5, 2.0, (n, xs)).astype(np.float32)
+    corr[0, 0] = 0
+    return eul, tx, ty, re, im, corr
+
+
+@pytest.mark.parametrize("n,r_max_cut", [(32, False), (20, False), (32, True)])
+def test_project(device, oracle, n, r_max_cut):
+    from oracle.bindings import Projector
+    wl = make_workload(ori_size=32, n_particles=2, seed=11)
+    r_max = 10 if r_max_cut else wl.r_max
+    device.set_reference(0, wl.refs[0], r_max, wl.padding_factor)
+    ref = Projector(wl.refs[0], r_max, wl.padding_factor)
+    eul = _stage_inputs(wl, n, 1, 9, 1)[0]
+    got = device.project(0, n, eul)
+    for i in range(len(eul)):
+        want = oracle.project(ref, n, eul[i])
+        assert np.abs(got[i] - want).max() <= 1e-5 * np.abs(want).max()
+
+
+@pytest.mark.parametrize("n,O,T,r_max_cut", [(14, 37, 9, False), (32, 5, 21, False), (32, 256 + 3, 30, False), (24, 8, 5, True), (16, 1, 1, False)])
+def test_diff2_coarse_stage(device, oracle, n, O, T, r_max_cut):
+    from oracle.bindings import Projector
+    wl = make_workload(ori_size=32, n_particles=2, seed=12)
+    r_max = 7 if r_max_cut else wl.r_max
+    device.set_reference(0, wl.refs[0], r_max, wl.padding_factor)
+    ref = Projector(wl.refs[0], r_max, wl.padding_factor)
+    eul, tx, ty, re, im, corr = _stage_inputs(wl, n, 2, O, T)
+    init = np.full((O, T), 3.25, np.float32)
+    got = device.diff2_coarse(0, n, eul, tx, ty, re, im, corr, init=init)
+    want = oracle.diff2_coarse(ref, n, eul, tx, ty, re, im, corr, init=init)
+    np.testing.assert_allclose(got, want, rtol=2e-5)
+
+
+@pytest.mark.parametrize("n,r_max_cut", [(32, False), (18, False), (32, True)])
+def test_diff2_fine_stage(device, oracle, n, r_max_cut):
+    from oracle.bindings import Projector
+    wl = make_workload(ori_size=32, n_particles=2, seed=13)
+    r_max = 9 if r_max_cut else wl.r_max
+    device.set_reference(0, wl.refs[0], r_max, wl.padding_factor)
+    ref = Projector(wl.refs[0], r_max, wl.padding_factor)
+    O, T = 11, 36
+    eul, tx, ty, re, im, corr = _stage_inputs(wl, n, 3, O, T)
+    rng = np.random.default_rng(5)
+    # jobs: runs of <= 4 consecutive translations of one orientation (makeJobsForDiff2Fine)
+    rot_idx, trans_idx, job_idx, job_num = [], [], [], []
+    for o in range(O):
+        t = 0
+        while t < T:
+            if rng.random() < 0.5:
+                t += 1
+                continue
+            ln = int(min(rng.integers(1, 5), T - t))
+            job_idx.append(len(rot_idx)); job_num.append(ln)
+            for j in range(ln):
+                rot_idx.append(o); trans_idx.append(t + j)
+            t += ln + 1
+    got = device.diff2_fine(0, n, eul, tx, ty, re, im, corr, 1.5, rot_idx, trans_idx, job_idx, job_num)
+    want = oracle.diff2_fine(ref, n, eul, tx, ty, re, im, corr, 1.5, rot_idx, trans_idx, job_idx, job_num)
+    np.testing.assert_allclose(got, want, rtol=2e-5)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_convert_weights(device, oracle, seed):
+    rng = np.random.default_rng(100 + seed)
+    no, nt = int(rng.integers(1, 400)), int(rng.integers(1, 30))
+    spread = [0.5, 3.0, 30.0, 300.0][seed % 4]
+    d2 = (1000.0 + spread * rng.random((no, nt))).astype(np.float32)
+    if seed % 3 == 0:
+        d2[rng.random((no, nt)) < 0.2] = np.finfo(np.float32).min        # orientations never computed
+        d2[0, 0] = 1000.0
+    pdf = rng.random(no)
+    pdf[rng.random(no) < 0.1] = 0.0
+    pdf[0] = 0.5
+    po = np.where(pdf > 0, np.log(np.where(pdf > 0, pdf, 1.0)), 0.0).astype(np.float32)
+    oz = (pdf == 0).astype(np.uint8)
+    pt = (-rng.random(nt)).astype(np.float32)
+    tz = np.zeros(nt, np.uint8)
+    maxsig = 5 if seed % 5 == 4 else 0
+    w, sig, out = device.convert_weights(d2, po, oz, pt, tz, 0.999, maxsig)
+    ref = oracle.convert_weights_coarse(d2, po, oz, pt, tz, 0.999, maxsig, exact=True)
+    np.testing.assert_allclose(w, ref["weights"], rtol=2e-4, atol=0)
+    assert out.min_diff2 == np.float32(ref["min_diff2"])
+    # the selector itself, on the GPU's own weights: bit-exact
+    own = oracle.significance(w, 0.999, maxsig, True, exact=True)
+    assert out.n_nonzero == own["n_filtered"]
+    assert out.nr_significant == own["n_filtered"] - own["threshold_idx"]
+    assert np.float32(out.significant_weight) == np.float32(own["significant_weight"])
+    assert np.float32(out.sum_weight) == np.float32(own["sum_weight"])
+    assert np.array_equal(sig.astype(bool), w >= np.float32(own["significant_weight"]))
+    assert int(out.max_index) == int(np.argmax(w))
+
+
+def test_convert_weights_ties_and_edges(device, oracle):
+    # many identical weights: the threshold falls inside a run of ties
+    d2 = np.full((50, 4), 1000.0, np.float32)
+    po = np.zeros(50, np.float32); oz = np.zeros(50, np.uint8); pt = np.zeros(4, np.float32); tz = np.zeros(4, np.uint8)
+    for frac in (0.999, 0.5, 0.9, 1.0, 0.0):
+        w, sig, out = device.convert_weights(d2, po, oz, pt, tz, frac, 0)
+        own = oracle.significance(w, frac, 0, True, exact=True)
+        assert out.nr_significant == own["n_filtered"] - own["threshold_idx"], frac
+        assert np.float32(out.significant_weight) == np.float32(own["significant_weight"])
+    # a single sample
+    w, sig, out = device.convert_weights(np.array([[7.0]], np.float32), po[:1], oz[:1], pt[:1], tz[:1], 0.999, 0)
+    assert sig[0, 0] == 1
+
+
+def test_wavg_and_backproject_stage(device, oracle):
+    from oracle.bindings import Projector, Backprojector
+    wl = make_workload(ori_size=32, n_particles=2, seed=14)
+    n, O, T = 32, 6, 8
+    device.set_model(wl.model)
+    device.set_reference(0, wl.refs[0], wl.r_max, wl.padding_factor)
+    device.bp_init(0, wl.bp_shape, wl.r_max, wl.padding_factor)
+    ref = Projector(wl.refs[0], wl.r_max, wl.padding_factor)
+    bp = Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor)
+    eul, tx, ty, re, im, corr = _stage_inputs(wl, n, 4, O, T)
+    rng = np.random.default_rng(6)
+    weights = rng.random((O, T)).astype(np.float32)
+    weights[rng.random((O, T)) < 0.5] = np.finfo(np.float32).min
+    ctfs = rng.uniform(-1, 1, (n, n // 2 + 1)).astype(np.float32)
+    minvs2 = corr
+    got = device.wavg(0, n, eul, tx, ty, re, im, weights, ctfs, 3.7, 0.2)
+    want = oracle.wavg(ref, n, eul, tx, ty, re, im, weights, ctfs, 3.7, 0.2)
+    for g, w in zip(got, want):
+        np.testing.assert_allclose(g, w, rtol=2e-5, atol=1e-6 * np.abs(w).max())
+    device.backproject(0, n, eul, tx, ty, re, im, weights, minvs2, ctfs, 3.7, 0.2)
+    oracle.backproject(bp, n, eul, tx, ty, re, im, weights, minvs2, ctfs, 3.7, 0.2)
+    gre, gim, gw = device.bp_get(0)
+    for g, w in ((gre, bp.real), (gim, bp.imag), (gw, bp.weight)):
+        assert np.abs(w).max() > 0
+        assert np.abs(g - w).max() <= 1e-4 * np.abs(w).max()
+
+
+def _compare_pool(device, oracle, wl, pose_frac=0.995):
+    from oracle.bindings import Projector, Backprojector
+    _setup(device, wl)
+    res = device.expectation_some_particles(wl.pool)
+    refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
+    bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
+    st, ores, _ = oracle.estep_pool(wl.model, wl.sampling, refs, bps, wl.pool, num_threads=0, exact_threshold=True)
+    assert st == 0
+    g, o = res.particles, ores.particles
+    agree = np.mean(g["best_ihidden_over"] == o["best_ihidden_over"])
+    assert agree >= pose_frac, agree
+    np.testing.assert_allclose(g["min_diff2_coarse"], o["min_diff2_coarse"], rtol=2e-5)
+    # counts: identical unless the oracle's own decision sits on a rounding edge (different diff2 rounding)
+    same = g["nr_significant_coarse"] == o["nr_significant_coarse"]
+    assert same.mean() >= 0.9, (g["nr_significant_coarse"], o["nr_significant_coarse"])
+    ok = same & (g["n_fine_samples"] == o["n_fine_samples"]) & (g["best_ihidden_over"] == o["best_ihidden_over"])
+    np.testing.assert_allclose(g["dLL_nolog"], o["dLL_nolog"], rtol=1e-4)
+    np.testing.assert_allclose(g["pmax"][ok], o["pmax"][ok], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(g["sum_weight"][ok], o["sum_weight"][ok], rtol=2e-3)
+    np.testing.assert_allclose(g["sumw"][ok], o["sumw"][ok], rtol=1e-4)
+    np.testing.assert_allclose(g["wsum_sigma2_offset"][ok], o["wsum_sigma2_offset"][ok], rtol=2e-3, atol=1e-6)
+    np.testing.assert_allclose(g["wsum_norm_correction"][ok], o["wsum_norm_correction"][ok], rtol=2e-3)
+    np.testing.assert_allclose(g["wsum_XA"][ok], o["wsum_XA"][ok], rtol=5e-3, atol=1e-3 * np.abs(o["wsum_XA"]).max())
+    np.testing.assert_allclose(g["wsum_AA"][ok], o["wsum_AA"][ok], rtol=5e-3)
+    sh = np.abs(ores.wsum_sigma2_noise).max()
+    assert np.abs(res.wsum_sigma2_noise[ok] - ores.wsum_sigma2_noise[ok]).max() <= 5e-3 * sh
+    if ok.all():
+        np.testing.assert_allclose(res.wsum_pdf_class, ores.wsum_pdf_class, rtol=1e-4)
+        assert np.abs(res.wsum_pdf_direction - ores.wsum_pdf_direction).max() <= 2e-3
+        for k in range(wl.model.nr_classes):
+            gre, gim, gw = device.bp_get(k)
+            for a, b in ((gre, bps[k].real), (gim, bps[k].imag), (gw, bps[k].weight)):
+                assert np.abs(a - b).max() <= 5e-3 * max(np.abs(b).max(), 1e-12)
+    return res, ores
+
+
+def test_pool_global_search(device, oracle):
+    wl = make_workload(ori_size=32, healpix_order=1, n_particles=12, nr_classes=2, seed=21, snr=0.3)
+    _compare_pool(device, oracle, wl)
+
+
+def test_pool_local_search(device, oracle):
+    wl = make_workload(ori_size=32, healpix_order=2, n_particles=10, nr_classes=1, seed=22, snr=0.2, local_search=True)
+    _compare_pool(device, oracle, wl)
+
+
+def test_pool_reduced_current_size(device, oracle):
+    wl = make_workload(ori_size=40, current_size=28, healpix_order=1, n_particles=6, seed=23, snr=0.3)
+    _compare_pool(device, oracle, wl)
+
+
+def test_pool_low_snr_many_significant(device, oracle):
+    wl = make_workload(ori_size=24, healpix_order=1, n_particles=6, seed=24, snr=0.01, adaptive_fraction=0.999)
+    res, _ = _compare_pool(device, oracle, wl, pose_frac=0.8)
+    assert res.particles["nr_significant_coarse"].max() > 5
+
+
+def test_pool_single_particle_and_skip_maximization(device, oracle):
+    wl = make_workload(ori_size=24, healpix_order=1, n_particles=1, seed=25)
+    _setup(device, wl)
+    r1 = device.expectation_some_particles(wl.pool, skip_maximization=True)
+    assert r1.particles["wsum_norm_correction"][0] == 0.0
+    assert np.all(device.bp_get(0)[2] == 0)
+    r2 = device.expectation_some_particles(wl.pool)
+    assert r2.particles["best_ihidden_over"][0] == r1.particles["best_ihidden_over"][0]
+    assert r2.particles["wsum_norm_correction"][0] > 0
+
+
+def test_pool_capacity_error(device, oracle, monkeypatch):
+    from relion_b200.capi import RelionB200Error, RB_ERR_CAPACITY
+    wl = make_workload(ori_size=24, healpix_order=1, n_particles=4, seed=26, snr=0.01)
+    _setup(device, wl)
+    monkeypatch.setenv("RB_FINE_SAMPLE_CAP", "8")
+    with pytest.raises(RelionB200Error) as e:
+        device.expectation_some_particles(wl.pool)
+    assert e.value.status == RB_ERR_CAPACITY
+    monkeypatch.delenv("RB_FINE_SAMPLE_CAP")
+    device.expectation_some_particles(wl.pool)
+
+
+def test_smoke_entry():
+    import __graft_entry__ as g
+    g.smoke()

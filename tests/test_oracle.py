@@ -1,0 +1,196 @@
+"""CPU-only tests: the oracle against the reference's golden vectors, host logic, and the C-ABI surface.
+
+* tests/golden/estep_reference_*.npz were produced by the reference's own ALTCPU kernels compiled from
+  /root/reference (tests/golden/make_golden.py).  The restated kernels must reproduce them.
+* tests/ctf.cpp:5-10 of the reference is the only known-answer test in its tree (CTF value 0.59154).
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from relion_b200 import sampling as smp
+from relion_b200 import synth
+from relion_b200.workload import make_workload
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(GOLD, "make_golden.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _check_against(d, g, rtol=5e-5):
+    for f in g["particles"].dtype.names:
+        a, b = d["particles"][f], g["particles"][f]
+        if a.dtype.kind in "iu":
+            assert np.array_equal(a, b), f
+        else:
+            np.testing.assert_allclose(a, b, rtol=1e-3 if "weight" in f or f in ("pmax", "wsum_XA", "wsum_AA") else rtol, err_msg=f)
+    assert np.array_equal(d["coarse_significant"], g["coarse_significant"])
+    assert np.array_equal(d["fine_ihidden_over"], g["fine_ihidden_over"])
+    m = g["coarse_diff2"] > -1e30
+    assert np.array_equal(m, d["coarse_diff2"] > -1e30)
+    np.testing.assert_allclose(d["coarse_diff2"][m], g["coarse_diff2"][m], rtol=rtol)
+    np.testing.assert_allclose(d["fine_diff2"], g["fine_diff2"], rtol=rtol)
+    np.testing.assert_allclose(d["coarse_weights"], g["coarse_weights"], rtol=2e-3, atol=1e-30)
+    np.testing.assert_allclose(d["fine_weights"], g["fine_weights"], rtol=2e-3, atol=1e-30)
+    for k in ("wdiff2s_parts", "wdiff2s_AA", "wdiff2s_XA", "shells", "pdf_direction", "pdf_class"):
+        np.testing.assert_allclose(d[k], g[k], rtol=1e-3, atol=1e-5 * max(np.abs(g[k]).max(), 1e-30), err_msg=k)
+    for k in g.files:
+        if k.startswith("bp") and k.endswith("_sample"):
+            assert np.abs(d[k] - g[k]).max() <= 1e-4 * max(np.abs(g[k]).max(), 1e-30), k
+        if k.startswith("bp") and k.endswith("_abs"):
+            np.testing.assert_allclose(d[k], g[k], rtol=1e-4, err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["global_k2", "local_k1", "window_k1"])
+def test_port_matches_reference_golden(name):
+    mod = _cases()
+    g = np.load(os.path.join(GOLD, f"estep_reference_{name}.npz"))
+    d = mod.run_case("port", mod.CASES[name])
+    _check_against(d, g)
+
+
+@pytest.mark.parametrize("name", ["global_k2"])
+def test_compiled_reference_matches_golden(name):
+    from oracle.bindings import have_reference
+    if not have_reference():
+        pytest.skip("oracle/_ref/librefkernels.so not built (needs /root/reference)")
+    mod = _cases()
+    g = np.load(os.path.join(GOLD, f"estep_reference_{name}.npz"))
+    d = mod.run_case("reference", mod.CASES[name])
+    _check_against(d, g, rtol=1e-6)
+
+
+def test_ctf_known_answer():
+    # tests/ctf.cpp:5-10: setValues(10000, 12000, 90, 300, 2.7, 0.1, 0, 1, 0); getCTF(10, 10) == Approx(0.59154)
+    c = synth.CTF(10000.0, 12000.0, 90.0, 300.0, 2.7, 0.1, 0.0, 1.0, 0.0)
+    assert float(c.get_ctf(10.0, 10.0)) == pytest.approx(0.59154, rel=1e-4)
+
+
+def test_sampling_tables():
+    # HEALPix: 12*4^order pixels, unit vectors cover the sphere evenly (SURVEY.md §8 sizes)
+    for order, ndir, npsi in ((1, 48, 12), (2, 192, 24), (3, 768, 48)):
+        s = smp.make_sampling(order, 5.0, 2.0, oversampling=1, build_oversampled=(order < 3))
+        assert s.n_dir == ndir and s.n_psi == npsi
+        v = np.stack([np.sin(np.radians(s.tilt)) * np.cos(np.radians(s.rot)),
+                      np.sin(np.radians(s.tilt)) * np.sin(np.radians(s.rot)), np.cos(np.radians(s.tilt))], 1)
+        assert np.abs(v.mean(0)).max() < 1e-9
+        assert s.n_trans == 21 and s.n_over_trans == 4 and s.n_over_rot == 8
+    assert smp.make_sampling(1, 3.0, 2.0).n_trans == 9
+    assert smp.make_sampling(1, 5.0, 1.0).n_trans == 81
+    s = smp.make_sampling(1, 3.0, 2.0)
+    # children of a coarse pixel lie closer to it than to any other coarse pixel
+    d = smp._direction(s.rot, s.tilt)
+    g = (5 * s.n_psi + 3) * 8
+    child = smp._direction(s.over_rot[g:g + 8], s.over_tilt[g:g + 8])
+    assert np.all(np.argmax(child @ d.T, axis=1) == 5)
+    # oversampled translations average back to the coarse one
+    np.testing.assert_allclose(s.over_trans_x.reshape(-1, 4).mean(1), s.trans_x, atol=1e-12)
+    # nested <-> xyf round trip
+    ip = np.arange(12 * 16)
+    x, y, f = smp.nest2xyf(2, ip)
+    assert np.array_equal(smp.xyf2nest(2, x, y, f), ip)
+
+
+def test_local_search_lists():
+    s = smp.make_sampling(2, 3.0, 1.0)
+    di, dp, pi_, pp = smp.select_nonzero_prior(s, 30.0, 60.0, 100.0, 7.5, 7.5, 7.5)
+    assert 0 < len(di) < s.n_dir and 0 < len(pi_) < s.n_psi
+    assert dp.sum() == pytest.approx(1.0) and pp.sum() == pytest.approx(1.0)
+    # far-away prior with a tiny sigma still selects the nearest direction
+    di, dp, _, _ = smp.select_nonzero_prior(s, 30.0, 60.0, 100.0, 0.01, 0.01, 0.01)
+    assert len(di) == 1 and dp[0] == 1.0
+
+
+def test_reference_ft_central_slice_matches_projection_fft():
+    # a central slice of PPref equals the normalised 2D FFT of the real-space projection
+    n = 24
+    vol = synth.make_phantom(n, n_blobs=10, seed=3)
+    data, r_max = synth.reference_ft(vol, padding_factor=2.0, do_gridding=False)
+    sl = synth.project_numpy(data, r_max, 2.0, np.eye(3), n)
+    proj = vol.sum(axis=0)                       # project along z (identity orientation)
+    F = np.fft.rfft2(np.fft.ifftshift(proj)) / (n * n)
+    M = synth.mresol(n)
+    m = (M >= 0) & (M < n // 2 - 1)
+    assert np.abs(sl[m] - F[m]).max() <= 2e-3 * np.abs(F[m]).max()
+
+
+def test_significance_exact_vs_sequential():
+    from oracle.bindings import Oracle
+    o = Oracle("port")
+    rng = np.random.default_rng(0)
+    differ = 0
+    for i in range(200):
+        n = int(rng.integers(2, 3000))
+        w = np.exp(rng.normal(0, 4, n)).astype(np.float32)
+        w[rng.random(n) < 0.1] = 0
+        a = o.significance(w, 0.999, 0, True, exact=False)
+        b = o.significance(w, 0.999, 0, True, exact=True)
+        assert a["n_filtered"] == b["n_filtered"]
+        assert abs(a["threshold_idx"] - b["threshold_idx"]) <= 1      # only rounding-edge cases may move by one
+        differ += a["threshold_idx"] != b["threshold_idx"]
+        np.testing.assert_allclose(a["sum_weight"], b["sum_weight"], rtol=1e-5)
+    assert differ <= 10
+    # maxsig caps the count
+    w = np.arange(1, 101, dtype=np.float32)
+    a = o.significance(w, 0.5, 7, True, exact=False)
+    assert a["n_filtered"] - a["threshold_idx"] == 7 and a["significant_weight"] == 94.0
+
+
+def test_library_exports_every_declared_symbol():
+    from relion_b200 import capi
+    hdr = open(os.path.join(ROOT, "include", "relion_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(rb_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"rb_ctx"}
+    assert declared == set(capi.PROTOTYPES), declared ^ set(capi.PROTOTYPES)
+    lib = capi.load_library()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rb_version() == 100
+    # struct layouts agree with the C header (compile a probe with the host compiler)
+    src = '#include "relion_b200.h"\n#include <stdio.h>\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n", sizeof(rb_sampling), sizeof(rb_model), sizeof(rb_particles), sizeof(rb_particle_out), sizeof(rb_pool_out), sizeof(rb_weights_out));return 0;}'
+    exe = os.path.join(ROOT, "tests", "_probe_sizes")
+    subprocess.run(["/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc", "-x", "c", "-", "-I", os.path.join(ROOT, "include"), "-o", exe],
+                   input=src.encode(), check=True)
+    sizes = list(map(int, subprocess.run([exe], capture_output=True, check=True).stdout.split()))
+    os.remove(exe)
+    assert sizes == [ctypes.sizeof(t) for t in (capi.rb_sampling, capi.rb_model, capi.rb_particles, capi.rb_particle_out,
+                                                 capi.rb_pool_out, capi.rb_weights_out)]
+
+
+def test_no_gpu_means_loud_failure():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from relion_b200 import capi
+    from relion_b200.estep import MlDeviceBundle
+    with pytest.raises(capi.RelionB200Error) as e:
+        MlDeviceBundle(0)
+    assert e.value.status == capi.RB_ERR_CUDA
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_never_touches_the_oracle():
+    bad = []
+    for d, _, files in os.walk(os.path.join(ROOT, "relion_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp", "Makefile")):
+                t = open(os.path.join(d, f), errors="replace").read()
+                if re.search(r"(from|import)\s+oracle|oracle/|liboracle|librefkernels|oracle_kernels\.h|estep_driver", t):
+                    if "must not reference anything under oracle/" in t or "no reference to oracle/" in t:
+                        t2 = re.sub(r".*(must not reference anything under|no reference to) oracle/.*", "", t)
+                        if not re.search(r"(from|import)\s+oracle|oracle/|liboracle|librefkernels|oracle_kernels\.h|estep_driver", t2):
+                            continue
+                    bad.append(os.path.join(d, f))
+    assert not bad, bad

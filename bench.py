@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py — particles/s of the E-step hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME] [--pool P]
+
+A "step" is one pass of the whole hot path (coarse diff2 -> weights/significance -> fine diff2 -> weights ->
+weighted sums + back-projection) over one pool of P synthetic particles.  Headline workload:
+`refine3d_256_local` = late 3D auto-refine iteration at 256 px (C1, K=1, HEALPix order 4 coarse -> order 5
+oversampled, local angular searches with sigma = 2 x oversampled step, offset range 3 / step 1 px, full-size
+256-px window, 515^3 padded reference and accumulator), the regime BASELINE.json's metric is quoted on.
+
+  value  device-resident throughput: the pool is already in HBM; K steps timed with CUDA events on the stream
+         the kernels run on; max over ranks.  One NCCL all-reduce of the back-projection accumulator closes
+         the timed region when N > 1 (the per-iteration reduction that replaces MPI).
+  e2e    same metric through the public C-ABI call (rb_estep_pool) with pinned HOST buffers: H2D of the
+         pool and D2H of the results are inside the timed region, every step.
+  roofline      dominant kernel's algorithmic bytes / its CUDA-event time vs MEASURED_PEAKS.json.
+  cpu_baseline  the CPU oracle on a bounded sample of the same pool, all host cores (rank 0, N == 1).
+
+`--impl reference` times the reference's own CPU implementation of the path (oracle/_ref: RELION's ALTCPU
+kernels compiled from /root/reference; else the restated port) on all host threads, bounded sample per step.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particles/sec per E-step (3D refine, 256 px)"
+UNIT = "particles/s"
+
+WORKLOADS = {
+    # name: (make_workload kwargs, default pool size)
+    "refine3d_256_local": (dict(ori_size=256, healpix_order=4, offset_range=3.0, offset_step=1.0, nr_classes=1, snr=0.05,
+                                local_search=True, pixel_size=1.0, n_blobs=200, nr_groups=8), 512),
+    "refine3d_128_local": (dict(ori_size=128, healpix_order=3, offset_range=3.0, offset_step=1.0, nr_classes=1, snr=0.05,
+                                local_search=True, pixel_size=2.0, n_blobs=100, nr_groups=8), 512),
+    "refine3d_128_global": (dict(ori_size=128, current_size=64, healpix_order=2, offset_range=5.0, offset_step=2.0, nr_classes=1,
+                                 snr=0.05, pixel_size=2.0, n_blobs=100, nr_groups=8), 256),
+    "tiny": (dict(ori_size=32, healpix_order=1, nr_classes=1, snr=0.3, n_blobs=20), 16),
+}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(name, pool, seed, projector=None):
+    from relion_b200.workload import make_workload
+    kw, dflt = WORKLOADS[name]
+    P = pool or dflt
+    return make_workload(name, n_particles=P, seed=seed, projector=projector, **kw), P
+
+
+def valid_pixels(n):
+    from relion_b200.synth import mresol
+    return int((mresol(n) >= 0).sum())
+
+
+def stage_bytes(wl, res):
+    """Algorithmic bytes per step of the three gather/scatter kernels."""
+    p = res.particles
+    s = wl.sampling
+    T = s.n_trans
+    npf, npc = valid_pixels(wl.model.current_size), valid_pixels(wl.model.coarse_size)
+    K = wl.model.nr_classes
+    if wl.pool.dir_off is not None:
+        n_or = (np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off)).astype(np.float64) * K
+    else:
+        n_or = np.full(len(p), K * s.n_dir * s.n_psi, np.float64)
+    ofs = p["n_fine_orient"].astype(np.float64)
+    sf = p["n_fine_samples"].astype(np.float64)
+    coarse = (64.0 * n_or * npc + 12.0 * npc + 4.0 * n_or * T).sum()
+    fine = (64.0 * ofs * npf + 12.0 * npf + 4.0 * sf).sum()
+    # fused wavg + back-projection: 64 B gather + 28 B images/ctf + 8 corners x 16 B x 2 (read-modify-write) per pixel
+    store = ((64.0 + 28.0 + 256.0) * ofs * npf).sum()
+    return {"coarse": coarse, "fine": fine, "store": store}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from relion_b200.estep import MlDeviceBundle
+    from relion_b200 import parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    dev = MlDeviceBundle(local)
+
+    # data generation (not timed): slices of the 256-px pool come from the device projector
+    ref_holder = {}
+
+    def projector(k, eul, n):
+        return dev.project(k, n, eul)
+
+    from relion_b200.workload import make_workload
+    kw, dflt = WORKLOADS[args.workload]
+    P = args.pool or dflt
+    t0 = time.time()
+    # references first (the projector callback needs them on the device)
+    from relion_b200 import synth
+    refs = []
+    for k in range(kw.get("nr_classes", 1)):
+        vol = synth.make_phantom(kw["ori_size"], n_blobs=kw.get("n_blobs", 40), seed=1993 + 17 * k)
+        data, r_max = synth.reference_ft(vol, current_size=kw.get("current_size") or kw["ori_size"], padding_factor=2.0)
+        refs.append(data.astype(np.complex64))
+        dev.set_reference(k, refs[-1], r_max, 2.0)
+    # every rank searches its own shard of the data set: same references, different particles (weak scaling)
+    wl = make_workload(args.workload, n_particles=P, seed=1993 + 1000 * rank, projector=projector,
+                       refs_override=(refs, r_max), **kw)
+    gen_s = time.time() - t0
+    dev.set_model(wl.model)
+    dev.set_sampling(wl.sampling)
+    for k in range(wl.model.nr_classes):
+        dev.bp_init(k, wl.bp_shape, wl.r_max, wl.padding_factor)
+
+    # pinned host copies of the pool (what the RELION adapter would stage per pool)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    hF, hF0, hC = pin(wl.pool.Fimg.view(np.float32)), pin(wl.pool.Fimg_nomask.view(np.float32)), pin(wl.pool.Fctf)
+    pool = wl.pool
+    pool.Fimg, pool.Fimg_nomask, pool.Fctf = hF, hF0, hC
+    h2d = hF.numel() * 4 + hF0.numel() * 4 + hC.numel() * 4 + P * 80
+    out_probe = dev._new_out(P)
+    d2h = sum(a.nbytes for a in (out_probe.result.particles, out_probe.result.wsum_sigma2_noise,
+                                 out_probe.result.wsum_pdf_direction, out_probe.result.wsum_pdf_class)) + P * 200
+
+    def barrier():
+        dev.sync_all_backprojects()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    dev.pool_upload(0, pool)
+    dev.sync_all_backprojects()
+    for _ in range(args.warmup):
+        dev.estep_slot_nocopy(0)
+    res0 = dev.estep_fetch(0)
+    for k in range(wl.model.nr_classes):
+        dev.bp_clear(k)
+    launches0 = dev.launch_count()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    stage_names = ["coarse", "weights_coarse", "fine_setup", "fine", "weights_fine", "store", "total"]
+    stage_ms = {s: 0.0 for s in stage_names}
+    dev.timer_start()
+    for _ in range(args.steps):
+        dev.estep_slot_nocopy(0)
+    if world > 1:
+        parallel.all_reduce_backprojectors(dev, wl.model.nr_classes)
+        torch.cuda.synchronize()
+    ms = dev.timer_stop()
+    for s in stage_names:   # stage events of the last timed step (all steps do identical work)
+        stage_ms[s] = dev.stage_ms(s)
+    barrier()
+    clocks = sampler.stop()
+    launches = dev.launch_count() - launches0
+    t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = P * world * args.steps / (ms_max / 1e3)
+
+    # ---- end-to-end through rb_estep_pool with host buffers ---------------------------------------
+    for _ in range(min(args.warmup, 2)):
+        dev.expectation_some_particles(pool)
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        res = dev.expectation_some_particles(pool)   # H2D + all stages + D2H of per-particle results
+    dev.sync_all_backprojects()
+    e2e_s = time.perf_counter() - t1
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = P * world * args.steps / float(t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # ---- roofline of the dominant kernel ----------------------------------------------------------
+    peak, peak_src = peaks()
+    by = stage_bytes(wl, res0)
+    dom = max(("coarse", "fine", "store"), key=lambda s: stage_ms[s])
+    stages = {s: {"ms": round(stage_ms[s], 4)} for s in stage_names}
+    for s in ("coarse", "fine", "store"):
+        if stage_ms[s] > 0:
+            stages[s]["algorithmic_GBps"] = round(by[s] / (stage_ms[s] * 1e-3) / 1e9, 1)
+            stages[s]["frac_of_hbm_peak"] = round(by[s] / (stage_ms[s] * 1e-3) / 1e9 / peak, 4)
+    ach = by[dom] / (stage_ms[dom] * 1e-3) / 1e9
+    roofline = {"kernel": {"coarse": "k_diff2_coarse", "fine": "k_diff2_fine", "store": "k_store"}[dom],
+                "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+                "traffic": None, "peak_source": peak_src, "share_of_step": round(stage_ms[dom] / max(stage_ms["total"], 1e-9), 3),
+                "algorithmic_bytes_per_launch": by[dom]}
+
+    # ---- CPU baseline on a bounded sample (all host cores) ------------------------------------------
+    cpu = cpu_baseline(wl, sample=args.cpu_sample)
+
+    pr = res0.particles
+    out = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "box": wl.model.ori_size, "current_size": wl.model.current_size,
+                   "coarse_size": wl.model.coarse_size, "classes": wl.model.nr_classes, "pool_particles_per_gpu": P,
+                   "healpix_order": wl.sampling.healpix_order, "coarse_translations": wl.sampling.n_trans,
+                   "oversampling": 1, "search": "local" if wl.pool.dir_off is not None else "global",
+                   "mean_coarse_orientations": float(np.mean(np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off))) if wl.pool.dir_off is not None else wl.sampling.n_dir * wl.sampling.n_psi,
+                   "mean_fine_orientations": float(pr["n_fine_orient"].mean()), "mean_fine_samples": float(pr["n_fine_samples"].mean()),
+                   "l2_policy": "inputs larger than L2 (pool images + 515^3 reference/accumulator >> 126 MB), no flush",
+                   "parallelism": f"particles sharded over {world} GPU(s), references replicated"},
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
+        "datagen_s": round(gen_s, 1),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(wl, sample, kind=None, steps=1, warmup=0):
+    """The CPU oracle on the first `sample` particles of the pool, one particle per OpenMP thread."""
+    from oracle.bindings import Oracle, Projector, Backprojector, have_reference
+    from relion_b200.estep import ParticlePool
+    kind = kind or ("reference" if have_reference() else "port")
+    o = Oracle(kind)
+    n = min(sample, wl.pool.n_particles)
+    p = wl.pool
+    as_np = lambda a, dt: np.asarray(a.numpy() if hasattr(a, "numpy") else a).view(dt) if a is not None else None
+    F = as_np(p.Fimg, np.complex64) if not np.iscomplexobj(p.Fimg) else p.Fimg
+    F0 = as_np(p.Fimg_nomask, np.complex64) if not np.iscomplexobj(p.Fimg_nomask) else p.Fimg_nomask
+    Cc = as_np(p.Fctf, np.float32)
+    xs = wl.model.current_size // 2 + 1
+    F = np.asarray(F).reshape(p.group_id.shape[0], wl.model.current_size, xs)
+    F0 = np.asarray(F0).reshape(F.shape)
+    sub = ParticlePool(Fimg=F[:n], Fimg_nomask=F0[:n], Fctf=np.asarray(Cc).reshape(F.shape)[:n], group_id=p.group_id[:n],
+                       optics_group=p.optics_group[:n], highres_Xi2=p.highres_Xi2[:n], old_offset=p.old_offset[:n],
+                       prior_offset=p.prior_offset[:n])
+    if p.dir_off is not None:
+        sub.dir_off = p.dir_off[:n + 1]; sub.psi_off = p.psi_off[:n + 1]
+        sub.dir_idx = p.dir_idx[:p.dir_off[n]]; sub.dir_prior = p.dir_prior[:p.dir_off[n]]
+        sub.psi_idx = p.psi_idx[:p.psi_off[n]]; sub.psi_prior = p.psi_prior[:p.psi_off[n]]
+    refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
+    bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
+    cores = os.cpu_count() or 1
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        st, _, _ = o.estep_pool(wl.model, wl.sampling, refs, bps, sub, num_threads=cores)
+        dt = time.perf_counter() - t0
+        assert st == 0, st
+        if i >= warmup:
+            times.append(dt)
+    tot = sum(times)
+    return {"value": round(n * len(times) / tot, 3), "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{n} particles of the same pool per step, {len(times)} step(s), one particle per OpenMP thread", "seconds": round(tot, 2)}
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path on all host cores; rank 0 only."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    kw, dflt = WORKLOADS[args.workload]
+    from relion_b200.workload import make_workload
+    n = args.cpu_sample
+    wl = make_workload(args.workload, n_particles=n, seed=1993, **kw)   # numpy projector: none of our kernels on this path
+    cpu = cpu_baseline(wl, sample=n, steps=args.steps, warmup=min(args.warmup, 1))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": round(1e3 * n / cpu["value"], 3), "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "box": wl.model.ori_size, "current_size": wl.model.current_size,
+                      "coarse_size": wl.model.coarse_size, "classes": wl.model.nr_classes, "sample_particles_per_step": n,
+                      "healpix_order": wl.sampling.healpix_order, "coarse_translations": wl.sampling.n_trans, "world_size": world},
+           "cpu_baseline": cpu,
+           "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="refine3d_256_local", choices=sorted(WORKLOADS))
+    ap.add_argument("--pool", type=int, default=0, help="particles per pool per GPU (default: workload specific)")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="particles in the bounded CPU sample")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -69,6 +69,11 @@ long long rb_launch_count(rb_ctx *ctx);
  * "coarse", "weights_coarse", "fine_setup", "fine", "weights_fine", "store", "total".
  * Valid after rb_sync().  Returns <0 if unknown. */
 double rb_stage_ms(rb_ctx *ctx, const char *stage);
+/* CUDA-event stopwatch on the stream the kernels are launched on (bench.py's timed region):
+ * rb_timer_start records an event; rb_timer_stop records another, waits for it and returns the
+ * elapsed device time in milliseconds through *ms. */
+int rb_timer_start(rb_ctx *ctx);
+int rb_timer_stop(rb_ctx *ctx, double *ms);
 
 /* ------------------------------------------------------------------------------------------------
  * Reference volumes (AccProjector::setMdlDim + initMdl, acc_projector_impl.h:5-312; fed from

@@ -107,6 +107,8 @@ PROTOTYPES = {
     "rb_sync": (C.c_int, [C.c_void_p]),
     "rb_launch_count": (C.c_longlong, [C.c_void_p]),
     "rb_stage_ms": (C.c_double, [C.c_void_p, C.c_char_p]),
+    "rb_timer_start": (C.c_int, [C.c_void_p]),
+    "rb_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
     "rb_set_reference": (C.c_int, [C.c_void_p, C.c_int, c_double_p] + [C.c_int] * 6 + [C.c_double]),
     "rb_set_reference_f32": (C.c_int, [C.c_void_p, C.c_int, c_float_p] + [C.c_int] * 6 + [C.c_double]),
     "rb_bp_init": (C.c_int, [C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_double]),

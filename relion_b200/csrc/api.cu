@@ -141,6 +141,21 @@ extern "C" double rb_stage_ms(rb_ctx *ctx, const char *stage)
 	return (double) ms;
 }
 
+extern "C" int rb_timer_start(rb_ctx *ctx)
+{
+	RB_ARG(ctx, "rb_timer_start: ctx is NULL");
+	return rb_stage_begin(ctx, "__timer");
+}
+
+extern "C" int rb_timer_stop(rb_ctx *ctx, double *ms)
+{
+	RB_ARG(ctx && ms, "rb_timer_stop: NULL argument");
+	RB_CHECK(rb_stage_end(ctx, "__timer"));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	*ms = rb_stage_ms(ctx, "__timer");
+	return RB_OK;
+}
+
 int rb_sync_tables(rb_ctx *ctx)
 {
 	RB_CHECK(upload(ctx, ctx->d_proj, ctx->proj, sizeof(ctx->proj)));

@@ -339,6 +339,14 @@ class MlDeviceBundle:
     def stage_ms(self, name: str) -> float:
         return float(self.lib.rb_stage_ms(self.ctx, name.encode()))
 
+    def timer_start(self):
+        capi.check(self.lib, self.lib.rb_timer_start(self.ctx))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double()
+        capi.check(self.lib, self.lib.rb_timer_stop(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
     def launch_count(self) -> int:
         return int(self.lib.rb_launch_count(self.ctx))
 

@@ -30,10 +30,9 @@ from .sampling import euler_matrix
 def make_phantom(n: int, n_blobs: int = 60, seed: int = 1993, radius_frac: float = 0.32) -> np.ndarray:
     """Asymmetric sum of Gaussian blobs inside a sphere of radius radius_frac*n; [n, n, n] float64, origin at n//2."""
     rng = np.random.default_rng(seed)
-    c = np.arange(n) - n // 2
-    z, y, x = np.meshgrid(c, c, c, indexing="ij")
     vol = np.zeros((n, n, n), np.float64)
     R = radius_frac * n
+    o = n // 2
     for _ in range(n_blobs):
         while True:
             p = rng.uniform(-R, R, 3)
@@ -41,7 +40,15 @@ def make_phantom(n: int, n_blobs: int = 60, seed: int = 1993, radius_frac: float
                 break
         s = rng.uniform(0.02, 0.06) * n
         a = rng.uniform(0.5, 1.5)
-        vol += a * np.exp(-((x - p[0]) ** 2 + (y - p[1]) ** 2 + (z - p[2]) ** 2) / (2 * s * s))
+        # evaluate each blob inside its +-5 sigma box only (exp(-12.5) ~ 4e-6 outside)
+        h = int(math.ceil(5 * s))
+        lo = [max(0, int(round(p[i])) + o - h) for i in range(3)]      # x, y, z
+        hi = [min(n, int(round(p[i])) + o + h + 1) for i in range(3)]
+        gx = np.arange(lo[0], hi[0]) - o - p[0]
+        gy = np.arange(lo[1], hi[1]) - o - p[1]
+        gz = np.arange(lo[2], hi[2]) - o - p[2]
+        ex, ey, ez = (np.exp(-g * g / (2 * s * s)) for g in (gx, gy, gz))
+        vol[lo[2]:hi[2], lo[1]:hi[1], lo[0]:hi[0]] += a * ez[:, None, None] * ey[None, :, None] * ex[None, None, :]
     return vol
 
 
@@ -75,7 +82,19 @@ def reference_ft(vol: np.ndarray, current_size: int | None = None, padding_facto
     Mpad = np.zeros((padori,) * 3, np.float64)
     o = padori // 2 - ori // 2
     Mpad[o:o + ori, o:o + ori, o:o + ori] = v
-    F = np.fft.rfftn(np.fft.ifftshift(Mpad)) / float(padori) ** 3          # normalised forward FFT (src/fftw.cpp:333-360)
+    F = None
+    if padori >= 256:
+        # data generation only: use the GPU's FFT for the 512^3 transform when one is there
+        try:
+            import torch
+            if torch.cuda.is_available():
+                t = torch.from_numpy(np.fft.ifftshift(Mpad)).cuda()
+                F = (torch.fft.rfftn(t) / float(padori) ** 3).cpu().numpy()
+                del t
+        except Exception:
+            F = None
+    if F is None:
+        F = np.fft.rfftn(np.fft.ifftshift(Mpad)) / float(padori) ** 3      # normalised forward FFT (src/fftw.cpp:333-360)
     normfft = pf * pf * pf * ori                                            # 3D reference, 2D data (:147-163)
     pad = pad_size_for(r_max, pf)
     h = (pad - 1) // 2
@@ -232,27 +251,34 @@ def make_particles(slices: np.ndarray, ori_size: int, angpix: float, snr: float,
     rng = np.random.default_rng(seed)
     P, n, xs = slices.shape
     Fctf = np.empty((P, n, xs), np.float32)
-    sig = np.empty((P, n, xs), np.complex128)
+    Fn = np.empty((P, n, xs), np.complex64)
+    Fn0 = np.empty((P, n, xs), np.complex64)
     for p in range(P):
         d = rng.uniform(*defocus_range)
         ctf = CTF(d, d + rng.uniform(-500.0, 500.0), rng.uniform(0.0, 180.0))
         c = ctf.fftw_image(n, ori_size, angpix)
         Fctf[p] = c
-        sig[p] = slices[p] * c * np.conj(phase_shift_image(n, ori_size, shifts[p, 0], shifts[p, 1]))
+        Fn[p] = slices[p] * c * np.conj(phase_shift_image(n, ori_size, shifts[p, 0], shifts[p, 1]))
     M = mresol(n)
     valid = M > 0
-    signal_power = float(np.mean(np.abs(sig[:, valid]) ** 2))
+    nsamp = min(P, 64)
+    signal_power = float(np.mean(np.abs(Fn[:nsamp][:, valid].astype(np.complex128)) ** 2))
     s2 = signal_power / (2.0 * snr) if snr > 0 else 1.0        # variance of re and of im
-    noise = (rng.standard_normal((P, n, xs)) + 1j * rng.standard_normal((P, n, xs))) * math.sqrt(s2)
-    Fn = sig + noise
-    extra = (rng.standard_normal((P, n, xs)) + 1j * rng.standard_normal((P, n, xs))) * math.sqrt(s2) * nomask_extra
+    sd = math.sqrt(s2)
+    for p0 in range(0, P, 64):                                  # chunked: keeps the 256-px pools within a few GB
+        p1 = min(P, p0 + 64)
+        shp = (p1 - p0, n, xs)
+        noise = (rng.standard_normal(shp, dtype=np.float32) + 1j * rng.standard_normal(shp, dtype=np.float32)) * np.float32(sd)
+        extra = (rng.standard_normal(shp, dtype=np.float32) + 1j * rng.standard_normal(shp, dtype=np.float32)) * np.float32(sd * nomask_extra)
+        Fn[p0:p1] += noise
+        Fn0[p0:p1] = Fn[p0:p1] + extra
     sigma2 = np.full(ori_size // 2 + 1, s2, np.float64)
     xi2 = np.zeros(P, np.float64)
     if n < ori_size:
         # power between the current window and Nyquist that the windowed images no longer carry
         npix_hi = math.pi / 2 * ((ori_size / 2) ** 2 - (n / 2) ** 2)
         xi2 = rng.uniform(0.9, 1.1, P) * 2.0 * s2 * npix_hi
-    return SyntheticParticles(Fn.astype(np.complex64), (Fn + extra).astype(np.complex64), Fctf,
+    return SyntheticParticles(Fn, Fn0, Fctf,
                               np.asarray(rot, np.float64), np.asarray(tilt, np.float64), np.asarray(psi, np.float64),
                               np.asarray(shifts, np.float64), sigma2, xi2)
 

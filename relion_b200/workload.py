@@ -43,7 +43,8 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
                   local_search: bool = False, sigma_ang: Optional[float] = None,
                   pixel_size: float = 2.0, particle_diameter: Optional[float] = None,
                   nr_groups: int = 2, adaptive_fraction: float = 0.999, coarse_size: Optional[int] = None,
-                  projector: Optional[Callable] = None, n_blobs: int = 40, phantom_size: Optional[int] = None) -> Workload:
+                  projector: Optional[Callable] = None, n_blobs: int = 40, refs_override=None,
+                  ref_seed: int = 1993) -> Workload:
     """Build a complete, seeded E-step problem.
 
     projector(vol_complex64, r_max, pf, eulers[n,9] float32, n) -> [n_img, n, n//2+1] complex: how noise-free
@@ -53,12 +54,15 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
     current_size = current_size or ori_size
     pf = 2.0
     # ---- references -------------------------------------------------------------------------
-    refs = []
-    r_max = None
-    for k in range(nr_classes):
-        vol = synth.make_phantom(ori_size, n_blobs=n_blobs, seed=seed + 17 * k)
-        data, r_max = synth.reference_ft(vol, current_size=current_size, padding_factor=pf)
-        refs.append(data.astype(np.complex64))
+    if refs_override is not None:
+        refs, r_max = refs_override
+    else:
+        refs = []
+        r_max = None
+        for k in range(nr_classes):
+            vol = synth.make_phantom(ori_size, n_blobs=n_blobs, seed=ref_seed + 17 * k)
+            data, r_max = synth.reference_ft(vol, current_size=current_size, padding_factor=pf)
+            refs.append(data.astype(np.complex64))
     # ---- sampling ---------------------------------------------------------------------------
     s = smp.make_sampling(healpix_order, offset_range, offset_step, oversampling=1)
     ang_step = smp.angular_sampling(healpix_order)
@@ -83,7 +87,7 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
         slices = np.empty((P, n, n // 2 + 1), np.complex128)
         for p in range(P):
             A_inv = eul[p].reshape(3, 3).astype(np.float64)
-            slices[p] = synth.project_numpy(refs[cls[p]].astype(np.complex128), r_max, pf, A_inv, n)
+            slices[p] = synth.project_numpy(refs[cls[p]], r_max, pf, A_inv, n)
     else:
         slices = np.empty((P, n, n // 2 + 1), np.complex64)
         for k in range(nr_classes):

@@ -133,8 +133,9 @@ def stage_bytes(wl, res):
     sf = p["n_fine_samples"].astype(np.float64)
     coarse = (64.0 * n_or * npc + 12.0 * npc + 4.0 * n_or * T).sum()
     fine = (64.0 * ofs * npf + 12.0 * npf + 4.0 * sf).sum()
-    # fused wavg + back-projection: 64 B gather + 28 B images/ctf + 8 corners x 16 B x 2 (read-modify-write) per pixel
-    store = ((64.0 + 28.0 + 256.0) * ofs * npf).sum()
+    # fused wavg + back-projection, SURVEY.md §8d figures: wavg gather 64 B + back-projection 204 B
+    # (8 corners x 3 arrays x 4 B, x2 read-modify-write, + 12 B inputs) per pixel of every fine orientation
+    store = ((64.0 + 204.0) * ofs * npf).sum()
     return {"coarse": coarse, "fine": fine, "store": store}
 
 

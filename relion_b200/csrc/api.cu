@@ -89,7 +89,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->bp_buf[i].release(); }
+	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->bp_buf[i].release(); }
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp};
@@ -174,8 +174,10 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ
 	RB_CUDA(cudaSetDevice(ctx->device));
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
 	RB_CHECK(ctx->proj_buf[k].ensure(n * sizeof(float2)));
+	RB_CHECK(ctx->proj8_buf[k].ensure(n * 4 * sizeof(float4)));
 	RbProjector &p = ctx->proj[k];
 	p.mdl = ctx->proj_buf[k].as<float2>();
+	p.mdl8 = ctx->proj8_buf[k].as<float4>();
 	p.mdlX = mdlX; p.mdlY = mdlY; p.mdlZ = mdlZ; p.mdlXY = mdlX * mdlY;
 	p.mdlInitY = initY; p.mdlInitZ = initZ; p.mdlMaxR = maxR; p.padding_factor = (float) pf;
 	ctx->has_proj[k] = true;
@@ -190,6 +192,7 @@ extern "C" int rb_set_reference(rb_ctx *ctx, int k, const double *vol, int mdlX,
 	RB_CHECK(ctx->scratch[2].ensure(n * 2 * sizeof(double)));
 	RB_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, vol, n * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	RB_CHECK(rbk_convert_volume(ctx, ctx->scratch[2].as<double>(), ctx->proj_buf[k].as<float2>(), n));
+	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>()));
 	RB_CHECK(rb_sync_tables(ctx));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->scratch[2].release();
@@ -202,6 +205,7 @@ extern "C" int rb_set_reference_f32(rb_ctx *ctx, int k, const float *vol, int md
 	RB_CHECK(set_reference_common(ctx, k, mdlX, mdlY, mdlZ, initY, initZ, maxR, pf));
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
 	RB_CUDA(cudaMemcpyAsync(ctx->proj_buf[k].p, vol, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>()));
 	RB_CHECK(rb_sync_tables(ctx));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return RB_OK;
@@ -748,7 +752,7 @@ extern "C" int rb_diff2_fine(rb_ctx *ctx, int k, int n, const float *eulers, int
                              float *diff2s, int n_weights)
 {
 	RB_CHECK(check_proj(ctx, k, n));
-	for (int j = 0; j < n_jobs; j++) RB_ARG(job_num[j] <= 8, "rb_diff2_fine: job %d has %llu translations (max 8)", j, (unsigned long long) job_num[j]);
+	for (int j = 0; j < n_jobs; j++) RB_ARG(job_num[j] <= 16, "rb_diff2_fine: job %d has %llu translations (max 16)", j, (unsigned long long) job_num[j]);
 	StageBufs sb(ctx);
 	const size_t np = (size_t) n * (n / 2 + 1);
 	float *d_e, *d_tx, *d_ty, *d_re, *d_im, *d_c, *d_o;

@@ -45,6 +45,9 @@ static const int RB_NUM_SLOTS = 2;
 // AccProjectorKernel state (acc_projectorkernel_impl.h:19-69); volume is interleaved (re,im)
 struct RbProjector {
 	const float2 *mdl;
+	// neighbourhood-expanded copy: per voxel its 2x2x2 trilinear cell (8 x (re,im) = 64 B, 64-B aligned), so a
+	// sample at an arbitrary position costs exactly two 32-B sectors instead of the 4-8 a compact layout touches
+	const float4 *mdl8;
 	int mdlX, mdlY, mdlZ;
 	int mdlXY;
 	int mdlInitY, mdlInitZ;
@@ -172,6 +175,7 @@ struct rb_ctx {
 
 	RbProjector proj[RB_MAX_CLASSES];
 	DevBuf proj_buf[RB_MAX_CLASSES];
+	DevBuf proj8_buf[RB_MAX_CLASSES];
 	RbBackprojector bp[RB_MAX_CLASSES];
 	DevBuf bp_buf[RB_MAX_CLASSES];
 	bool has_proj[RB_MAX_CLASSES] = {false}, has_bp[RB_MAX_CLASSES] = {false};
@@ -205,6 +209,7 @@ int rb_sync_tables(rb_ctx *ctx);   // refresh d_proj / d_bp device tables
 // kernels_misc.cu
 int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt, const float *d_psi, int n_dir, int n_psi, float *d_eulers);
 int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
+int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
 int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out);
 

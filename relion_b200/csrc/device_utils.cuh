@@ -116,6 +116,113 @@ __device__ __forceinline__ float2 rb_project3d(const RbProjK &k, int x, int y,
 	return r;
 }
 
+// Same sample from the neighbourhood-expanded volume (RbProjector::mdl8): four aligned 16-byte loads that cover
+// exactly two 32-byte sectors.  Arithmetic identical to rb_project3d.
+struct RbProjK8 {
+	const float4 *mdl8;
+	int mdlX, mdlXY, mdlInitY, mdlInitZ, maxR, maxR2_padded;
+	float pf;
+};
+__host__ __device__ inline RbProjK8 rb_make_projk8(const RbProjector &p, int imgX)
+{
+	RbProjK8 k;
+	int imgMaxR = imgX - 1;
+	k.maxR = p.mdlMaxR >= imgMaxR ? imgMaxR : p.mdlMaxR;
+	k.mdl8 = p.mdl8; k.mdlX = p.mdlX; k.mdlXY = p.mdlXY; k.mdlInitY = p.mdlInitY; k.mdlInitZ = p.mdlInitZ;
+	k.pf = p.padding_factor;
+	k.maxR2_padded = (int) (k.maxR * k.maxR * k.pf * k.pf);
+	return k;
+}
+__device__ __forceinline__ float2 rb_project3d_x8(const RbProjK8 &k, int x, int y,
+                                                  float e0, float e1, float e3, float e4, float e6, float e7)
+{
+	float xp = (e0 * x + e1 * y) * k.pf;
+	float yp = (e3 * x + e4 * y) * k.pf;
+	float zp = (e6 * x + e7 * y) * k.pf;
+	int r2 = (int) (xp * xp + yp * yp + zp * zp);
+	if (r2 > k.maxR2_padded) return make_float2(0.f, 0.f);
+	const bool inv = xp < 0.f;
+	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+	const float fx = xp - fx0, fy = yp - fy0, fz = zp - fz0;
+	const int x0 = (int) fx0, y0 = (int) fy0, z0 = (int) fz0;
+	const float4 *b = k.mdl8 + 4 * ((size_t) (z0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) (y0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) x0);
+	const float4 q0 = __ldg(b), q1 = __ldg(b + 1), q2 = __ldg(b + 2), q3 = __ldg(b + 3);
+	float2 r;
+	{
+		float dx00 = q0.x + (q0.z - q0.x) * fx, dx10 = q1.x + (q1.z - q1.x) * fx;
+		float dx01 = q2.x + (q2.z - q2.x) * fx, dx11 = q3.x + (q3.z - q3.x) * fx;
+		float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy;
+		r.x = dxy0 + (dxy1 - dxy0) * fz;
+	}
+	{
+		float dx00 = q0.y + (q0.w - q0.y) * fx, dx10 = q1.y + (q1.w - q1.y) * fx;
+		float dx01 = q2.y + (q2.w - q2.y) * fx, dx11 = q3.y + (q3.w - q3.y) * fx;
+		float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy;
+		r.y = dxy0 + (dxy1 - dxy0) * fz;
+	}
+	if (inv) r.y = -r.y;
+	return r;
+}
+
+// Split form of rb_project3d_x8 for software pipelining: rb_proj_issue computes the sample position and
+// issues the four 16-byte loads; rb_proj_finish does the lerps once the data is needed.
+struct RbProjFetch {
+	float4 q0, q1, q2, q3;
+	float fx, fy, fz;
+	int flags;   // bit0: inside r_max (else the sample is zero), bit1: Hermitian mate (conjugate)
+};
+__device__ __forceinline__ void rb_proj_issue(const RbProjK8 &k, int x, int y,
+                                              float e0, float e1, float e3, float e4, float e6, float e7, RbProjFetch &f)
+{
+	float xp = (e0 * x + e1 * y) * k.pf;
+	float yp = (e3 * x + e4 * y) * k.pf;
+	float zp = (e6 * x + e7 * y) * k.pf;
+	const int r2 = (int) (xp * xp + yp * yp + zp * zp);
+	const bool inside = r2 <= k.maxR2_padded;
+	const bool inv = xp < 0.f;
+	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+	f.fx = xp - fx0; f.fy = yp - fy0; f.fz = zp - fz0;
+	f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
+	if (inside)
+	{
+		const float4 *b = k.mdl8 + 4 * ((size_t) ((int) fz0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) ((int) fy0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) (int) fx0);
+		f.q0 = __ldg(b); f.q1 = __ldg(b + 1); f.q2 = __ldg(b + 2); f.q3 = __ldg(b + 3);
+	}
+	else f.q0 = f.q1 = f.q2 = f.q3 = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+__device__ __forceinline__ float2 rb_proj_finish(const RbProjFetch &f)
+{
+	float2 r;
+	{
+		float dx00 = f.q0.x + (f.q0.z - f.q0.x) * f.fx, dx10 = f.q1.x + (f.q1.z - f.q1.x) * f.fx;
+		float dx01 = f.q2.x + (f.q2.z - f.q2.x) * f.fx, dx11 = f.q3.x + (f.q3.z - f.q3.x) * f.fx;
+		float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		r.x = dxy0 + (dxy1 - dxy0) * f.fz;
+	}
+	{
+		float dx00 = f.q0.y + (f.q0.w - f.q0.y) * f.fx, dx10 = f.q1.y + (f.q1.w - f.q1.y) * f.fx;
+		float dx01 = f.q2.y + (f.q2.w - f.q2.y) * f.fx, dx11 = f.q3.y + (f.q3.w - f.q3.y) * f.fx;
+		float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		r.y = dxy0 + (dxy1 - dxy0) * f.fz;
+	}
+	if (f.flags & 2) r.y = -r.y;
+	return r;
+}
+
+// Phase factor (cos, sin)(x*tx + y*ty) of a translation given in TURNS per pixel (ux = tx / 2pi): the turn count is
+// reduced exactly to [-0.5, 0.5] before the fast hardware sincos, so the absolute error stays ~5e-7 for any shift
+// (translatePixel, cuda_device_utils.cuh:110-160, uses sincosf of the same argument).
+__device__ __forceinline__ float2 rb_phase(int x, int y, float ux, float uy)
+{
+	float u = fmaf((float) x, ux, (float) y * uy);
+	u -= rintf(u);
+	float s, c;
+	__sincosf(6.283185307179586f * u, &s, &c);
+	return make_float2(c, s);
+}
+
 // index of pixel (x, y) of an n-window inside an array stored at window nfull (windowFourierTransform,
 // src/fftw.h:850-856): same (x, y), row = y<0 ? y+nfull : y
 __device__ __forceinline__ int rb_src_index(int x, int y, int nfull)

@@ -156,8 +156,9 @@ int rbk_prep_priors(rb_ctx *ctx, PoolSlot &s)
 // coarse pass
 // ---------------------------------------------------------------------------------------------
 static const int CO_THREADS = 128;
-static const int CO_EO = 4;    // orientations per CTA
-static const int CO_TT = 24;   // translations per register chunk (EO*TT = 96 accumulators)
+// CO_EO orientations per CTA x CO_TT translations per register chunk = 96 accumulators per thread; the launcher
+// picks (EO, TT) from {(8,12), (4,24), (3,32)} so that all translations fit one chunk whenever T <= 32 and every
+// projected sample is gathered once.
 
 struct CoarseArgs {
 	// pool mode
@@ -176,6 +177,7 @@ struct CoarseArgs {
 	int tiles_per_class;           // CTAs per class (tiles never straddle classes)
 };
 
+template <int CO_EO, int CO_TT>
 __global__ void __launch_bounds__(CO_THREADS)
 k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 {
@@ -317,22 +319,28 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 	}
 }
 
-static size_t coarse_smem(int n, int ny) { return (size_t) CO_TT * ((n / 2 + 1) + ny) * sizeof(float2); }
-
-static int launch_coarse(rb_ctx *ctx, CoarseArgs &A, int no_max, int n_classes, int P)
+template <int EO, int TT>
+static int launch_coarse_cfg(rb_ctx *ctx, CoarseArgs &A, int no_max, int n_classes, int P)
 {
-	size_t sm = coarse_smem(A.n, A.ny);
+	size_t sm = (size_t) TT * ((A.n / 2 + 1) + A.ny) * sizeof(float2);
 	static size_t configured = 0;
 	if (sm > configured)
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_diff2_coarse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+		RB_CUDA(cudaFuncSetAttribute(k_diff2_coarse<EO, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
 		configured = sm;
 	}
-	A.tiles_per_class = (no_max + CO_EO - 1) / CO_EO;
+	A.tiles_per_class = (no_max + EO - 1) / EO;
 	dim3 grid(A.tiles_per_class * n_classes, P);
-	k_diff2_coarse<<<grid, CO_THREADS, sm, ctx->stream>>>(A, ctx->d_model, ctx->d_samp);
+	k_diff2_coarse<EO, TT><<<grid, CO_THREADS, sm, ctx->stream>>>(A, ctx->d_model, ctx->d_samp);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
+}
+
+static int launch_coarse(rb_ctx *ctx, CoarseArgs &A, int no_max, int n_classes, int P)
+{
+	if (A.T <= 12) return launch_coarse_cfg<8, 12>(ctx, A, no_max, n_classes, P);
+	if (A.T <= 24) return launch_coarse_cfg<4, 24>(ctx, A, no_max, n_classes, P);
+	return launch_coarse_cfg<3, 32>(ctx, A, no_max, n_classes, P);
 }
 
 __global__ void k_fill(float *p, float v, size_t n)
@@ -393,7 +401,7 @@ int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const floa
 // for all of that orientation's significant translations
 // ---------------------------------------------------------------------------------------------
 static const int FI_THREADS = 256;
-static const int FI_TF = 8;    // fine translations per register chunk
+static const int FI_TF = 32;   // fine translations accumulated per pass (8 significant coarse translations x 4)
 
 struct FineArgs {
 	// pool mode
@@ -411,18 +419,35 @@ struct FineArgs {
 	const float *tx, *ty; int NOT;
 };
 
-__global__ void __launch_bounds__(FI_THREADS)
+struct FinePix {
+	RbProjFetch pf;
+	float2 X;
+	float hc;
+	int x, y;
+};
+
+__device__ __forceinline__ void fine_issue(const FineArgs &A, const ImgSrc &src, const RbProjK8 &pk, int ip,
+                                           float e0, float e1, float e3, float e4, float e6, float e7, FinePix &f)
+{
+	const uint32_t pkx = __ldg(A.pix + ip);
+	f.x = rb_pix_x(pkx); f.y = rb_pix_y(pkx);
+	rb_proj_issue(pk, f.x, f.y, e0, e1, e3, e4, e6, e7, f.pf);
+	float corr;
+	img_load(src, pkx, f.X, corr);
+	f.hc = corr * 0.5f;
+}
+
+// diff2[t] = sum_pix hc*|ref - S_t X|^2 evaluated as  sum hc*(|ref|^2 + |X|^2)  -  2 * sum Re(hc*conj(ref)*X * e^{i phi_t}):
+// the cross term is the only part that depends on the translation (the contraction the north star names), so each
+// (pixel, translation) costs one phase factor and two FMAs; accumulation stays fp32.
+__global__ void __launch_bounds__(FI_THREADS, 2)
 k_diff2_fine(FineArgs A, RbModelDev M)
 {
-	extern __shared__ float2 smem2[];
-	__shared__ float s_tx[FI_TF], s_ty[FI_TF];
-	__shared__ float s_red[FI_THREADS / 32][FI_TF];
+	__shared__ float s_ux[FI_TF], s_uy[FI_TF];
+	__shared__ float s_red[FI_THREADS / 32][FI_TF + 1];
 	__shared__ float s_e[6];
 
 	const int imgX = A.n / 2 + 1;
-	const int ny = 2 * A.n, yoff = A.n;   // stage lists may carry un-wrapped rows (dead band), so cover [-n, n)
-	float2 *tab_x = smem2;
-	float2 *tab_y = smem2 + FI_TF * imgX;
 	const bool stage = (A.fo == nullptr);
 	const int nwork = stage ? A.st_njobs : A.counters[0];
 
@@ -446,7 +471,7 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 			eu = A.fo[w].e;
 		}
 		__syncthreads();
-		if (threadIdx.x < 6) { const int map[6] = {0, 1, 3, 4, 6, 7}; s_e[threadIdx.x] = eu[map[threadIdx.x]]; }
+		if (threadIdx.x < 6) s_e[threadIdx.x] = eu[threadIdx.x + threadIdx.x / 2];   // elements 0,1,3,4,6,7
 		ImgSrc src;
 		float xi2_half;
 		if (stage) { src.re = A.st_re; src.im = A.st_im; src.corr = A.st_corr; src.n_array = A.n; xi2_half = A.st_sum_init; }
@@ -462,61 +487,74 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 			src.n_array = M.current_size;
 			xi2_half = m.xi2_half;
 		}
-		const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
+		const RbProjK8 pk = rb_make_projk8(A.projs[cls], imgX);
 		float bmin = FLT_MAX;
 
 		for (int c0 = 0; c0 < nsamp; c0 += FI_TF)
 		{
 			const int ntr = min(FI_TF, nsamp - c0);
 			__syncthreads();
-			if (threadIdx.x < ntr)
+			if (threadIdx.x < FI_TF)
 			{
-				int j = c0 + threadIdx.x, it;
-				if (stage) it = (int) A.st_trans_idx[A.st_job_idx[w]] + j;                   // consecutive translations in a job
-				else it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
-				s_tx[threadIdx.x] = A.tx[it]; s_ty[threadIdx.x] = A.ty[it];
+				float ux = 0.f, uy = 0.f;
+				if (threadIdx.x < ntr)
+				{
+					int j = c0 + threadIdx.x, it;
+					if (stage) it = (int) A.st_trans_idx[A.st_job_idx[w]] + j;                   // consecutive translations in a job
+					else it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
+					ux = A.tx[it] * 0.15915494309189535f; uy = A.ty[it] * 0.15915494309189535f;  // radians -> turns per pixel
+				}
+				s_ux[threadIdx.x] = ux; s_uy[threadIdx.x] = uy;
 			}
-			__syncthreads();
-			build_tables(tab_x, tab_y, imgX, ny, yoff, s_tx, s_ty, ntr);
 			__syncthreads();
 			const float e0 = s_e[0], e1 = s_e[1], e3 = s_e[2], e4 = s_e[3], e6 = s_e[4], e7 = s_e[5];
 
 			float acc[FI_TF];
 #pragma unroll
 			for (int i = 0; i < FI_TF; i++) acc[i] = 0.f;
-			for (int ip = threadIdx.x; ip < A.npix; ip += FI_THREADS)
+			float base = 0.f;
+
+			// software-pipelined pixel loop: the next pixel's gathers are in flight while this one is accumulated
+			int ip = threadIdx.x;
+			bool have = ip < A.npix;
+			FinePix cur;
+			if (have) fine_issue(A, src, pk, ip, e0, e1, e3, e4, e6, e7, cur);
+			while (have)
 			{
-				const uint32_t pkx = __ldg(A.pix + ip);
-				const int x = rb_pix_x(pkx), y = rb_pix_y(pkx);
-				float2 X; float corr;
-				img_load(src, pkx, X, corr);
-				const float hc = corr * 0.5f;
-				const float2 ref = rb_project3d(pk, x, y, e0, e1, e3, e4, e6, e7);
-				const float2 *txp = tab_x + x, *typ = tab_y + (y + yoff);
+				const int ipn = ip + FI_THREADS;
+				const bool haven = ipn < A.npix;
+				FinePix nxt;
+				if (haven) fine_issue(A, src, pk, ipn, e0, e1, e3, e4, e6, e7, nxt);
+
+				const float2 ref = (cur.pf.flags & 1) ? rb_proj_finish(cur.pf) : make_float2(0.f, 0.f);
+				const float zr = cur.hc * (ref.x * cur.X.x + ref.y * cur.X.y);
+				const float zi = cur.hc * (ref.x * cur.X.y - ref.y * cur.X.x);
+				base += cur.hc * ((ref.x * ref.x + ref.y * ref.y) + (cur.X.x * cur.X.x + cur.X.y * cur.X.y));
 #pragma unroll
 				for (int t = 0; t < FI_TF; t++)
 				{
 					if (t < ntr)
 					{
-						const float2 a = txp[t * imgX], b = typ[t * ny];
-						const float ss = a.y * b.x + a.x * b.y;
-						const float cc = a.x * b.x - a.y * b.y;
-						const float dr = ref.x - (cc * X.x - ss * X.y);
-						const float di = ref.y - (cc * X.y + ss * X.x);
-						acc[t] += (dr * dr + di * di) * hc;
+						const float2 ph = rb_phase(cur.x, cur.y, s_ux[t], s_uy[t]);
+						acc[t] += zr * ph.x - zi * ph.y;
 					}
 				}
+				if (haven) cur = nxt;
+				ip = ipn; have = haven;
 			}
+			warp_transpose_reduce<FI_TF>(acc);
+			base = warp_sum(base);
 			const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-#pragma unroll
-			for (int t = 0; t < FI_TF; t++) { float v = warp_sum(acc[t]); if (lane == 0) s_red[wid][t] = v; }
+			s_red[wid][lane] = acc[0];
+			if (lane == 0) s_red[wid][FI_TF] = base;
 			__syncthreads();
 			if (threadIdx.x < ntr)
 			{
-				float v = 0.f;
+				float c = 0.f, b = 0.f;
 #pragma unroll
-				for (int ww = 0; ww < FI_THREADS / 32; ww++) v += s_red[ww][threadIdx.x];
-				v += xi2_half;
+				for (int ww = 0; ww < FI_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][FI_TF]; }
+				float v = (b - 2.f * c) + xi2_half;
+				v = fmaxf(v, 0.f);
 				if (stage) A.st_out[out_off + c0 + threadIdx.x] += v;                         // diff2.h:424-428
 				else { A.fs_w[out_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v); }
 			}
@@ -525,18 +563,9 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 	}
 }
 
-static size_t fine_smem(int n) { return (size_t) FI_TF * ((n / 2 + 1) + 2 * n) * sizeof(float2); }
-
 static int launch_fine(rb_ctx *ctx, FineArgs &A, int grid)
 {
-	size_t sm = fine_smem(A.n);
-	static size_t configured = 0;
-	if (sm > configured)
-	{
-		RB_CUDA(cudaFuncSetAttribute(k_diff2_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-		configured = sm;
-	}
-	k_diff2_fine<<<grid, FI_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
+	k_diff2_fine<<<grid, FI_THREADS, 0, ctx->stream>>>(A, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
@@ -552,7 +581,7 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	A.projs = ctx->d_proj.as<RbProjector>();
 	A.pix = ctx->d_model.pix_f; A.npix = ctx->d_model.nvf; A.n = ctx->d_model.current_size;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
-	return launch_fine(ctx, A, ctx->num_sms * 4);
+	return launch_fine(ctx, A, ctx->num_sms * 2);
 }
 
 int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers,
@@ -591,7 +620,7 @@ int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float 
 	A.projs = ctx->scratch[1].as<RbProjector>();
 	A.pix = ctx->scratch[0].as<uint32_t>(); A.npix = (int) pix.size(); A.n = n;
 	A.tx = d_tx; A.ty = d_ty; A.NOT = 1;
-	int grid = n_jobs < ctx->num_sms * 4 ? n_jobs : ctx->num_sms * 4;
+	int grid = n_jobs < ctx->num_sms * 2 ? n_jobs : ctx->num_sms * 2;
 	if (grid < 1) return RB_OK;
 	return launch_fine(ctx, A, grid);
 }

@@ -43,6 +43,39 @@ int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n)
 	return RB_OK;
 }
 
+// Neighbourhood-expanded reference: out[4*v + {0,1,2,3}] = {(v000,v001), (v010,v011), (v100,v101), (v110,v111)} of voxel v,
+// zeros beyond the array edge.  8x the memory (4.4 GB per class at 256 px, 16.6 GB at 400 px — sized for 180 GB HBM3e),
+// in exchange every trilinear sample of the fine pass / store stage is one aligned 64-byte read.
+__global__ void k_expand_volume(RbProjector pj, float4 *out)
+{
+	const size_t n = (size_t) pj.mdlXY * pj.mdlZ;
+	for (size_t v = blockIdx.x * (size_t) blockDim.x + threadIdx.x; v < n; v += (size_t) gridDim.x * blockDim.x)
+	{
+		const int x = (int) (v % pj.mdlX);
+		const int y = (int) ((v / pj.mdlX) % pj.mdlY);
+		const int z = (int) (v / pj.mdlXY);
+		const bool hx = x + 1 < pj.mdlX, hy = y + 1 < pj.mdlY, hz = z + 1 < pj.mdlZ;
+		const float2 zero = make_float2(0.f, 0.f);
+		const float2 *b = pj.mdl + v;
+		const float2 d000 = b[0], d001 = hx ? b[1] : zero;
+		const float2 d010 = hy ? b[pj.mdlX] : zero, d011 = (hy && hx) ? b[pj.mdlX + 1] : zero;
+		const float2 d100 = hz ? b[pj.mdlXY] : zero, d101 = (hz && hx) ? b[pj.mdlXY + 1] : zero;
+		const float2 d110 = (hz && hy) ? b[pj.mdlXY + pj.mdlX] : zero, d111 = (hz && hy && hx) ? b[pj.mdlXY + pj.mdlX + 1] : zero;
+		float4 *o = out + 4 * v;
+		o[0] = make_float4(d000.x, d000.y, d001.x, d001.y);
+		o[1] = make_float4(d010.x, d010.y, d011.x, d011.y);
+		o[2] = make_float4(d100.x, d100.y, d101.x, d101.y);
+		o[3] = make_float4(d110.x, d110.y, d111.x, d111.y);
+	}
+}
+
+int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out)
+{
+	k_expand_volume<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(pj, d_out);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
 // AccBackprojector::getMdlData (acc_backprojector_impl.h:109-138): interleaved float4 -> three SoA arrays
 __global__ void k_bp_deinterleave(const float4 *vol, float *re, float *im, float *w, size_t n)
 {

@@ -17,7 +17,6 @@
 #include "device_utils.cuh"
 
 static const int ST_THREADS = 256;
-static const int ST_TC = 8;       // significant translations per table chunk
 static const int ST_MAXSAMP = 2048;
 
 __device__ __forceinline__ void red_add_v4(float4 *addr, float a, float b, float c)
@@ -144,21 +143,46 @@ struct StoreArgs {
 	const float *tx, *ty; int NOT;
 };
 
-__global__ void __launch_bounds__(ST_THREADS)
+static const int ST_CHUNK = 256;   // significant samples held in shared memory at a time
+
+struct StorePix {
+	RbProjFetch pf;
+	float2 X, X0;
+	float ctf;
+	int x, y, ires;
+};
+
+__device__ __forceinline__ void store_issue(const StoreArgs &A, const RbProjK8 &pk, const float2 *X, const float2 *X0,
+                                            const float *C, float part_scale, int ip,
+                                            float e0, float e1, float e3, float e4, float e6, float e7, StorePix &f)
+{
+	const uint32_t pkx = __ldg(A.pix + ip);
+	f.x = rb_pix_x(pkx); f.y = rb_pix_y(pkx); f.ires = rb_pix_ires(pkx);
+	rb_proj_issue(pk, f.x, f.y, e0, e1, e3, e4, e6, e7, f.pf);
+	const int idx = rb_src_index(f.x, f.y, A.n);
+	f.X = __ldg(X + idx); f.X0 = __ldg(X0 + idx);
+	f.ctf = C ? __ldg(C + idx) * part_scale : part_scale;                                     // :3087-3096
+}
+
+// Per pixel everything the store stage needs from the translations is  Phi = sum_t wn_t * e^{i phi_t}  and
+// W = sum_t wn_t  (wn_t = weight_t / sum_weight over the significant samples of this orientation):
+//   XA    = Re(conj(ref) * X * Phi)                      (wavg.cuh:131-133 summed over t)
+//   AA    = W * |ref|^2
+//   wdiff = W * (|ref|^2 + |X|^2) - 2 * XA               (= sum_t wn_t |ref - S_t X|^2)
+//   F     = g * X0 * Phi,  Fweight = W * g * ctf,  g = ctf * Minvsigma2   (BP.cuh:276-299)
+// so the per-sample work is one phase factor and two FMAs, and no sample count limit applies.
+__global__ void __launch_bounds__(ST_THREADS, 2)
 k_store(StoreArgs A, RbModelDev M)
 {
-	extern __shared__ float2 smem2[];
-	__shared__ float s_tx[ST_TC], s_ty[ST_TC], s_wn[ST_TC], s_wr[ST_TC];
+	__shared__ float s_ux[ST_CHUNK], s_uy[ST_CHUNK], s_wn[ST_CHUNK];
 	__shared__ float s_e[6];
 	__shared__ int s_nsig;
+	__shared__ float s_W;
 	__shared__ int s_sigidx[ST_MAXSAMP];
 	__shared__ double dred[32];
 	__shared__ float s_shell[1024];
 
 	const int imgX = A.n / 2 + 1;
-	const int ny = A.n + 1, yoff = A.n / 2;
-	float2 *tab_x = smem2;
-	float2 *tab_y = smem2 + ST_TC * imgX;
 	const int nwork = A.counters[0];
 	const int half = A.n / 2;
 
@@ -185,7 +209,7 @@ k_store(StoreArgs A, RbModelDev M)
 			}
 			if (threadIdx.x == 0) s_nsig = min(cnt, ST_MAXSAMP);
 		}
-		if (threadIdx.x < 6) { const int map[6] = {0, 1, 3, 4, 6, 7}; s_e[threadIdx.x] = A.fo[w].e[map[threadIdx.x]]; }
+		if (threadIdx.x < 6) s_e[threadIdx.x] = A.fo[w].e[threadIdx.x + threadIdx.x / 2];   // elements 0,1,3,4,6,7
 		for (int i = threadIdx.x; i < M.nshell; i += ST_THREADS) s_shell[i] = 0.f;
 		__syncthreads();
 		const int nsig = s_nsig;
@@ -196,75 +220,77 @@ k_store(StoreArgs A, RbModelDev M)
 		const float *C = A.Fctf ? A.Fctf + (size_t) p * M.Npf : nullptr;
 		const float *mtab = M.minvs2 + (size_t) m.og * M.nshell;
 		const unsigned char *dvp = M.dvp_gt3 + (size_t) F.iclass * M.nshell;
-		const RbProjK pk = rb_make_projk(A.projs[F.iclass], imgX);
+		const RbProjK8 pk = rb_make_projk8(A.projs[F.iclass], imgX);
 		const RbBackprojector bp = A.bps[F.iclass];
 		const int max_r2_vol = (int) (bp.maxR * bp.maxR * bp.padding_factor * bp.padding_factor);   // BP.cuh:209
 		const float wni = 1.0f / sumw;
 		double aXA = 0., aAA = 0.;
 
-		for (int c0 = 0; c0 < nsig; c0 += ST_TC)
+		for (int c0 = 0; c0 < nsig; c0 += ST_CHUNK)
 		{
-			const int ntr = min(ST_TC, nsig - c0);
+			const int ntr = min(ST_CHUNK, nsig - c0);
 			__syncthreads();
-			if (threadIdx.x < ntr)
+			for (int i = threadIdx.x; i < ntr; i += ST_THREADS)
 			{
-				const int j = s_sigidx[c0 + threadIdx.x];
+				const int j = s_sigidx[c0 + i];
 				const int it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
-				s_tx[threadIdx.x] = A.tx[it]; s_ty[threadIdx.x] = A.ty[it];
-				const float wt = A.fs_w[F.sample_off + j];
-				s_wr[threadIdx.x] = wt;              // raw weight (BP)
-				s_wn[threadIdx.x] = wt * wni;        // weight * weight_norm_inverse (wavg.h:138)
+				s_ux[i] = A.tx[it] * 0.15915494309189535f; s_uy[i] = A.ty[it] * 0.15915494309189535f;
+				s_wn[i] = A.fs_w[F.sample_off + j] * wni;                              // weight * weight_norm_inverse (wavg.h:138)
 			}
 			__syncthreads();
-			build_tables_st(tab_x, tab_y, imgX, ny, yoff, s_tx, s_ty, ntr);
+			if (threadIdx.x == 0) { float Wt = 0.f; for (int i = 0; i < ntr; i++) Wt += s_wn[i]; s_W = Wt; }
 			__syncthreads();
+			const float W = s_W;
 			const float e0 = s_e[0], e1 = s_e[1], e3 = s_e[2], e4 = s_e[3], e6 = s_e[4], e7 = s_e[5];
 
-			for (int ip = threadIdx.x; ip < A.npix; ip += ST_THREADS)
+			int ip = threadIdx.x;
+			bool have = ip < A.npix;
+			StorePix cur;
+			if (have) store_issue(A, pk, X, X0, C, m.part_scale, ip, e0, e1, e3, e4, e6, e7, cur);
+			while (have)
 			{
-				const uint32_t pkx = __ldg(A.pix + ip);
-				const int x = rb_pix_x(pkx), y = rb_pix_y(pkx), ires = rb_pix_ires(pkx);
-				const int idx = rb_src_index(x, y, A.n);
-				const float2 img = __ldg(X + idx), img0 = __ldg(X0 + idx);
-				const float ctf = C ? __ldg(C + idx) * m.part_scale : m.part_scale;               // :3087-3096
-				float minvs2 = M.do_map ? __ldg(mtab + ires) : 1.f;                               // :2586, :3110-3115
-				float2 ref = rb_project3d(pk, x, y, e0, e1, e3, e4, e6, e7);
+				const int ipn = ip + ST_THREADS;
+				const bool haven = ipn < A.npix;
+				StorePix nxt;
+				if (haven) store_issue(A, pk, X, X0, C, m.part_scale, ipn, e0, e1, e3, e4, e6, e7, nxt);
+
+				const int x = cur.x, y = cur.y, ires = cur.ires;
+				float2 ref = (cur.pf.flags & 1) ? rb_proj_finish(cur.pf) : make_float2(0.f, 0.f);
+				const float ctf = cur.ctf;
 				if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                     // wavg.cuh:96-104
 				else { ref.x *= m.part_scale; ref.y *= m.part_scale; }
-				float wd = 0.f, xa = 0.f, aa = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
-				const float2 *txp = tab_x + x, *typ = tab_y + (y + yoff);
-				const float refn = ref.x * ref.x + ref.y * ref.y;
-#pragma unroll
-				for (int t = 0; t < ST_TC; t++)
+				float phr = 0.f, phi = 0.f;
+				for (int t = 0; t < ntr; t++)
 				{
-					if (t < ntr)
-					{
-						const float2 a = txp[t * imgX], b = typ[t * ny];
-						const float ss = a.y * b.x + a.x * b.y;
-						const float cc = a.x * b.x - a.y * b.y;
-						const float tr = cc * img.x - ss * img.y, ti = cc * img.y + ss * img.x;
-						const float dr = ref.x - tr, di = ref.y - ti;
-						const float wn = s_wn[t];
-						wd += wn * (dr * dr + di * di);                                           // wavg.cuh:124-135
-						xa += wn * (ref.x * tr + ref.y * ti);
-						aa += wn * refn;
-						float myw;
-						if (M.ctf_premultiplied) myw = s_wr[t] * (wni * minvs2);                  // BP.cuh:280-289
-						else myw = s_wr[t] * (wni * ctf * minvs2);
-						Fw += myw * ctf;
-						Fr += (cc * img0.x - ss * img0.y) * myw;
-						Fi += (cc * img0.y + ss * img0.x) * myw;
-					}
+					const float2 ph = rb_phase(x, y, s_ux[t], s_uy[t]);
+					const float wn = s_wn[t];
+					phr = fmaf(wn, ph.x, phr); phi = fmaf(wn, ph.y, phi);
 				}
+				const float refn = ref.x * ref.x + ref.y * ref.y;
+				const float Xn = cur.X.x * cur.X.x + cur.X.y * cur.X.y;
+				const float xa = (ref.x * cur.X.x + ref.y * cur.X.y) * phr - (ref.x * cur.X.y - ref.y * cur.X.x) * phi;
+				const float aa = W * refn;
+				const float wd = fmaxf(W * (refn + Xn) - 2.f * xa, 0.f);
 				atomicAdd(&s_shell[ires], wd);
 				if (dvp[ires] && M.do_scale_correction) { aXA += (double) xa; aAA += (double) aa; }   // :3473-3479
+				// back-projection
+				const float minvs2 = M.do_map ? __ldg(mtab + ires) : 1.f;                          // :2586, :3110-3115
+				const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                       // BP.cuh:280-289
+				const float Fw = W * g * ctf;
 				bool do_bp = Fw > 0.f;
 				if (M.bp_circle_bound)
 				{
-					const int xmax = (int) sqrtf((float) (half * half - y * y));                 // BP.h:565
+					const int xmax = (int) sqrtf((float) (half * half - y * y));                  // BP.h:565
 					do_bp = do_bp && (x < xmax);
 				}
-				if (do_bp) bp_scatter(bp, max_r2_vol, x, y, e0, e1, e3, e4, e6, e7, Fr, Fi, Fw);
+				if (do_bp)
+				{
+					const float Fr = (cur.X0.x * phr - cur.X0.y * phi) * g;
+					const float Fi = (cur.X0.x * phi + cur.X0.y * phr) * g;
+					bp_scatter(bp, max_r2_vol, x, y, e0, e1, e3, e4, e6, e7, Fr, Fi, Fw);
+				}
+				if (haven) cur = nxt;
+				ip = ipn; have = haven;
 			}
 		}
 		__syncthreads();
@@ -283,8 +309,6 @@ k_store(StoreArgs A, RbModelDev M)
 	}
 }
 
-static size_t store_smem(int n) { return (size_t) ST_TC * ((n / 2 + 1) + (n + 1)) * sizeof(float2); }
-
 int rbk_store_pool(rb_ctx *ctx, PoolSlot &s)
 {
 	StoreArgs A;
@@ -297,14 +321,7 @@ int rbk_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.projs = ctx->d_proj.as<RbProjector>(); A.bps = ctx->d_bp.as<RbBackprojector>();
 	A.pix = ctx->d_model.pix_f; A.npix = ctx->d_model.nvf; A.n = ctx->d_model.current_size;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
-	size_t sm = store_smem(A.n);
-	static size_t configured = 0;
-	if (sm > configured)
-	{
-		RB_CUDA(cudaFuncSetAttribute(k_store, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-		configured = sm;
-	}
-	k_store<<<ctx->num_sms * 4, ST_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
+	k_store<<<ctx->num_sms * 2, ST_THREADS, 0, ctx->stream>>>(A, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

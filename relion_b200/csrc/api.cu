@@ -79,7 +79,8 @@ static void release_slot(PoolSlot &s)
 {
 	DevBuf *bufs[] = {&s.Fimg, &s.Fnomask, &s.Fctf, &s.meta, &s.state, &s.dir_idx, &s.dir_prior, &s.psi_idx, &s.psi_prior,
 	                  &s.Mweight, &s.pdf_orient, &s.pdf_orient_zero, &s.pdf_offset, &s.pdf_offset_zero,
-	                  &s.so_list, &s.pair_list, &s.fo, &s.fs_w, &s.fs_ihid, &s.counters, &s.shells, &s.out_pdf_dir, &s.out_pdf_class};
+	                  &s.so_list, &s.pair_list, &s.fo, &s.fs_w, &s.fs_ihid, &s.counters, &s.shells, &s.out_pdf_dir, &s.out_pdf_class,
+	                  &s.fimg4, &s.cimg4};
 	for (DevBuf *b : bufs) b->release();
 	if (s.uploaded) cudaEventDestroy(s.uploaded);
 }
@@ -92,6 +93,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->bp_buf[i].release(); }
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
+	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp};
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
@@ -361,6 +363,30 @@ static void make_pixlist(int n, std::vector<uint32_t> &out)
 	}
 }
 
+// the same pixel set as row runs + a dense shell map
+static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_map)
+{
+	const int xs = n / 2 + 1;
+	rows.clear();
+	ires_map.assign((size_t) n * xs, -1);
+	for (int iy = 0; iy < n; iy++)
+	{
+		const int ip = iy < xs ? iy : iy - n;
+		int lo = -1, hi = -1;
+		for (int jp = 0; jp < xs; jp++)
+		{
+			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
+			if (ires < xs && !(jp == 0 && ip < 0))
+			{
+				ires_map[(size_t) iy * xs + jp] = (short) ires;
+				if (lo < 0) lo = jp;
+				hi = jp;
+			}
+		}
+		if (lo >= 0) rows.push_back(RbRow{(short) iy, (short) ip, (short) lo, (short) hi});
+	}
+}
+
 extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 {
 	RB_ARG(ctx && m, "rb_set_model: NULL argument");
@@ -378,6 +404,13 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	make_pixlist(m->coarse_size, pc); make_pixlist(m->current_size, pf);
 	RB_CHECK(upload(ctx, ctx->m_pix_c, pc.data(), pc.size() * 4));
 	RB_CHECK(upload(ctx, ctx->m_pix_f, pf.data(), pf.size() * 4));
+	std::vector<RbRow> rc, rf;
+	std::vector<short> ic, iff;
+	make_rows(m->coarse_size, rc, ic); make_rows(m->current_size, rf, iff);
+	RB_CHECK(upload(ctx, ctx->m_rows_c, rc.data(), rc.size() * sizeof(RbRow)));
+	RB_CHECK(upload(ctx, ctx->m_rows_f, rf.data(), rf.size() * sizeof(RbRow)));
+	RB_CHECK(upload(ctx, ctx->m_ires_c, ic.data(), ic.size() * sizeof(short)));
+	RB_CHECK(upload(ctx, ctx->m_ires_f, iff.data(), iff.size() * sizeof(short)));
 	// Minvsigma2 per shell (src/ml_optimiser.cpp:6868-6879); entry 0 holds the DC value restored for the
 	// store stage (acc_ml_optimiser_impl.h:2586), the diff2 kernels ignore it
 	std::vector<float> mv((size_t) m->nr_optics_groups * nshell);
@@ -398,6 +431,9 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	d.Npc = m->coarse_size * (m->coarse_size / 2 + 1); d.Npf = m->current_size * (m->current_size / 2 + 1);
 	d.nvc = (int) pc.size(); d.nvf = (int) pf.size();
 	d.pix_c = ctx->m_pix_c.as<uint32_t>(); d.pix_f = ctx->m_pix_f.as<uint32_t>();
+	d.nrows_c = (int) rc.size(); d.nrows_f = (int) rf.size();
+	d.rows_c = ctx->m_rows_c.as<RbRow>(); d.rows_f = ctx->m_rows_f.as<RbRow>();
+	d.ires_c = ctx->m_ires_c.as<short>(); d.ires_f = ctx->m_ires_f.as<short>();
 	d.minvs2 = ctx->m_minvs2.as<float>();
 	d.pdf_class = ctx->m_pdf_class.as<double>();
 	d.pdf_direction = nullptr;

@@ -74,6 +74,11 @@ __host__ __device__ inline int rb_pix_x(uint32_t v) { return (int) (v & 1023u); 
 __host__ __device__ inline int rb_pix_y(uint32_t v) { return (int) ((v >> 10) & 2047u) - 512; }
 __host__ __device__ inline int rb_pix_ires(uint32_t v) { return (int) (v >> 21) - 1; }
 
+// One image row of a window: pixels x_lo..x_hi (inclusive) of FFTW row iy, whose signed frequency is y.
+// The translation phase e^{i(x tx + y ty)} factorises into a per-column and a per-row factor, so kernels that walk
+// a row keep sum_x Z(x,y) e^{i x tx} in registers and apply e^{i y ty} once per row (see kernels_diff2.cu).
+struct RbRow { short iy, y, x_lo, x_hi; };
+
 // per-particle metadata resident on the device for one pool slot
 struct RbPartMeta {
 	int nd, np;              // sp.nr_dir, sp.nr_psi of this particle
@@ -135,6 +140,10 @@ struct RbModelDev {
 	int Npc, Npf;            // full half-image sizes n*(n/2+1)
 	int nvc, nvf;            // valid-pixel list lengths
 	const uint32_t *pix_c, *pix_f;
+	// the same pixel sets as row runs (one entry per image row holding valid pixels) and dense shell maps
+	int nrows_c, nrows_f;
+	const RbRow *rows_c, *rows_f;
+	const short *ires_c, *ires_f;   // [n][n/2+1], -1 = excluded
 	const float *minvs2;     // [nr_optics_groups][nshell] 1/(fudge*sigma2), entry 0 kept (DC restored for store)
 	const double *pdf_direction; // [K][n_dir]
 	const double *pdf_class;
@@ -163,6 +172,7 @@ struct PoolSlot {
 	DevBuf Fimg, Fnomask, Fctf, meta, state, dir_idx, dir_prior, psi_idx, psi_prior;
 	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;
 	DevBuf so_list, pair_list, fo, fs_w, fs_ihid, counters, shells, out_pdf_dir, out_pdf_class;
+	DevBuf fimg4, cimg4;            // prepared (corrected) images of the pool at the fine / coarse window
 	std::vector<RbPartMeta> h_meta;
 	cudaEvent_t uploaded = nullptr;
 };
@@ -188,6 +198,7 @@ struct rb_ctx {
 	DevBuf s_coarse_eulers, s_over_rot, s_over_tilt, s_over_psi, s_rot, s_tilt, s_psi, s_ctx, s_cty, s_ftx, s_fty,
 	       s_tx, s_ty, s_otx, s_oty;
 	DevBuf m_pix_c, m_pix_f, m_minvs2, m_pdf_dir, m_pdf_class, m_dvp;
+	DevBuf m_rows_c, m_rows_f, m_ires_c, m_ires_f;
 	DevBuf d_proj, d_bp;             // device copies of the projector / backprojector tables
 	std::vector<double> h_scale_correction;
 

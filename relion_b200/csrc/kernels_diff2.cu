@@ -5,49 +5,7 @@
 // (src/acc/cpu/cpu_kernels/diff2.h:32-430) with kernels batched over a whole pool of particles:
 // no per-particle launch, no host sync, image corrections (pixel_correction, corr_img —
 // acc_ml_optimiser_impl.h:1251-1268, acc_helper_functions_impl.h:164-196) applied on the fly.
-#include "device_utils.cuh"
-
-// ---------------------------------------------------------------------------------------------
-// image source: either reference-style pre-corrected SoA arrays (stage API) or the pool's raw
-// Fimg / Fctf with the corrections computed in registers
-// ---------------------------------------------------------------------------------------------
-struct ImgSrc {
-	const float *re, *im, *corr;   // stage mode when re != nullptr
-	const float2 *F;               // pool mode
-	const float *ctf;
-	const float *minvs2;           // [nshell] of the particle's optics group
-	float inv_scale, scale2;
-	int do_ctf_refs;               // do_ctf_correction && refs_are_ctf_corrected
-	int do_scale;
-	int n_array;                   // window size the arrays are stored at
-};
-
-__device__ __forceinline__ void img_load(const ImgSrc &s, uint32_t pk, float2 &X, float &corr)
-{
-	const int x = rb_pix_x(pk), y = rb_pix_y(pk);
-	const int idx = rb_src_index(x, y, s.n_array);
-	if (s.re)
-	{
-		X = make_float2(__ldg(s.re + idx), __ldg(s.im + idx));
-		corr = __ldg(s.corr + idx);
-	}
-	else
-	{
-		const int ires = rb_pix_ires(pk);
-		float2 F = __ldg(s.F + idx);
-		float pc = s.inv_scale;
-		float c = ires > 0 ? __ldg(s.minvs2 + ires) : 0.f;       // DC excluded (src/ml_optimiser.cpp:6874-6879)
-		if (s.do_ctf_refs)
-		{
-			float ctf = __ldg(s.ctf + idx);
-			if (fabsf(ctf) > 1e-8f) pc = pc / ctf;               // acc_ml_optimiser_impl.h:1254-1264
-			c *= ctf * ctf;                                      // buildCorrImage
-		}
-		if (s.do_scale) c *= s.scale2;
-		X = make_float2(F.x * pc, F.y * pc);
-		corr = c;
-	}
-}
+#include "img_src.cuh"
 
 // phase tables for a chunk of translations: tab_x[t][x] = (cos, sin)(x*tx), tab_y[t][y+yoff] = (cos, sin)(y*ty)
 // (computeSincosLookupTable2D, cpu_kernels/helper.h:622-660; negative y uses cos(-a)=cos a, sin(-a)=-sin a)
@@ -394,233 +352,4 @@ int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const floa
 	A.tx = d_tx; A.ty = d_ty; A.T = T;
 	A.ny = 2 * n + 1; A.yoff = n;   // un-wrapped rows can reach -n when the projector's r_max < n/2
 	return launch_coarse(ctx, A, O, 1, 1);
-}
-
-// ---------------------------------------------------------------------------------------------
-// fine pass: one CTA per oversampled orientation (persistent grid), each projected pixel is reused
-// for all of that orientation's significant translations
-// ---------------------------------------------------------------------------------------------
-static const int FI_THREADS = 256;
-static const int FI_TF = 32;   // fine translations accumulated per pass (8 significant coarse translations x 4)
-
-struct FineArgs {
-	// pool mode
-	const RbPartMeta *metas; RbPartState *states;
-	const float2 *Fimg; const float *Fctf;
-	const RbFineOrient *fo; const int *pair_list; const int *counters; // counters[0] = number of fine orientations
-	float *fs_w;
-	// stage mode (fo == nullptr): the reference's job lists
-	const float *st_eulers, *st_re, *st_im, *st_corr; float st_sum_init;
-	const unsigned long long *st_rot_idx, *st_trans_idx, *st_job_idx, *st_job_num; int st_njobs;
-	float *st_out;
-	// common
-	const RbProjector *projs;
-	const uint32_t *pix; int npix; int n;
-	const float *tx, *ty; int NOT;
-};
-
-struct FinePix {
-	RbProjFetch pf;
-	float2 X;
-	float hc;
-	int x, y;
-};
-
-__device__ __forceinline__ void fine_issue(const FineArgs &A, const ImgSrc &src, const RbProjK8 &pk, int ip,
-                                           float e0, float e1, float e3, float e4, float e6, float e7, FinePix &f)
-{
-	const uint32_t pkx = __ldg(A.pix + ip);
-	f.x = rb_pix_x(pkx); f.y = rb_pix_y(pkx);
-	rb_proj_issue(pk, f.x, f.y, e0, e1, e3, e4, e6, e7, f.pf);
-	float corr;
-	img_load(src, pkx, f.X, corr);
-	f.hc = corr * 0.5f;
-}
-
-// diff2[t] = sum_pix hc*|ref - S_t X|^2 evaluated as  sum hc*(|ref|^2 + |X|^2)  -  2 * sum Re(hc*conj(ref)*X * e^{i phi_t}):
-// the cross term is the only part that depends on the translation (the contraction the north star names), so each
-// (pixel, translation) costs one phase factor and two FMAs; accumulation stays fp32.
-__global__ void __launch_bounds__(FI_THREADS, 2)
-k_diff2_fine(FineArgs A, RbModelDev M)
-{
-	__shared__ float s_ux[FI_TF], s_uy[FI_TF];
-	__shared__ float s_red[FI_THREADS / 32][FI_TF + 1];
-	__shared__ float s_e[6];
-
-	const int imgX = A.n / 2 + 1;
-	const bool stage = (A.fo == nullptr);
-	const int nwork = stage ? A.st_njobs : A.counters[0];
-
-	for (int w = blockIdx.x; w < nwork; w += gridDim.x)
-	{
-		int nsamp, cls = 0, p = 0;
-		long long out_off;
-		const float *eu;
-		RbFineOrient F;
-		if (stage)
-		{
-			unsigned long long j0 = A.st_job_idx[w];
-			nsamp = (int) A.st_job_num[w];
-			eu = A.st_eulers + A.st_rot_idx[j0] * 9;
-			out_off = (long long) j0;
-		}
-		else
-		{
-			F = A.fo[w];
-			nsamp = F.n_t * A.NOT; cls = F.iclass; p = F.particle; out_off = F.sample_off;
-			eu = A.fo[w].e;
-		}
-		__syncthreads();
-		if (threadIdx.x < 6) s_e[threadIdx.x] = eu[threadIdx.x + threadIdx.x / 2];   // elements 0,1,3,4,6,7
-		ImgSrc src;
-		float xi2_half;
-		if (stage) { src.re = A.st_re; src.im = A.st_im; src.corr = A.st_corr; src.n_array = A.n; xi2_half = A.st_sum_init; }
-		else
-		{
-			const RbPartMeta m = A.metas[p];
-			src.re = nullptr;
-			src.F = A.Fimg + (size_t) p * M.Npf; src.ctf = A.Fctf ? A.Fctf + (size_t) p * M.Npf : nullptr;
-			src.minvs2 = M.minvs2 + (size_t) m.og * M.nshell;
-			src.inv_scale = 1.0f / m.scale; src.scale2 = m.scale * m.scale;
-			src.do_ctf_refs = M.do_ctf_correction && M.refs_are_ctf_corrected && src.ctf;
-			src.do_scale = M.do_scale_correction;
-			src.n_array = M.current_size;
-			xi2_half = m.xi2_half;
-		}
-		const RbProjK8 pk = rb_make_projk8(A.projs[cls], imgX);
-		float bmin = FLT_MAX;
-
-		for (int c0 = 0; c0 < nsamp; c0 += FI_TF)
-		{
-			const int ntr = min(FI_TF, nsamp - c0);
-			__syncthreads();
-			if (threadIdx.x < FI_TF)
-			{
-				float ux = 0.f, uy = 0.f;
-				if (threadIdx.x < ntr)
-				{
-					int j = c0 + threadIdx.x, it;
-					if (stage) it = (int) A.st_trans_idx[A.st_job_idx[w]] + j;                   // consecutive translations in a job
-					else it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
-					ux = A.tx[it] * 0.15915494309189535f; uy = A.ty[it] * 0.15915494309189535f;  // radians -> turns per pixel
-				}
-				s_ux[threadIdx.x] = ux; s_uy[threadIdx.x] = uy;
-			}
-			__syncthreads();
-			const float e0 = s_e[0], e1 = s_e[1], e3 = s_e[2], e4 = s_e[3], e6 = s_e[4], e7 = s_e[5];
-
-			float acc[FI_TF];
-#pragma unroll
-			for (int i = 0; i < FI_TF; i++) acc[i] = 0.f;
-			float base = 0.f;
-
-			// software-pipelined pixel loop: the next pixel's gathers are in flight while this one is accumulated
-			int ip = threadIdx.x;
-			bool have = ip < A.npix;
-			FinePix cur;
-			if (have) fine_issue(A, src, pk, ip, e0, e1, e3, e4, e6, e7, cur);
-			while (have)
-			{
-				const int ipn = ip + FI_THREADS;
-				const bool haven = ipn < A.npix;
-				FinePix nxt;
-				if (haven) fine_issue(A, src, pk, ipn, e0, e1, e3, e4, e6, e7, nxt);
-
-				const float2 ref = (cur.pf.flags & 1) ? rb_proj_finish(cur.pf) : make_float2(0.f, 0.f);
-				const float zr = cur.hc * (ref.x * cur.X.x + ref.y * cur.X.y);
-				const float zi = cur.hc * (ref.x * cur.X.y - ref.y * cur.X.x);
-				base += cur.hc * ((ref.x * ref.x + ref.y * ref.y) + (cur.X.x * cur.X.x + cur.X.y * cur.X.y));
-#pragma unroll
-				for (int t = 0; t < FI_TF; t++)
-				{
-					if (t < ntr)
-					{
-						const float2 ph = rb_phase(cur.x, cur.y, s_ux[t], s_uy[t]);
-						acc[t] += zr * ph.x - zi * ph.y;
-					}
-				}
-				if (haven) cur = nxt;
-				ip = ipn; have = haven;
-			}
-			warp_transpose_reduce<FI_TF>(acc);
-			base = warp_sum(base);
-			const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-			s_red[wid][lane] = acc[0];
-			if (lane == 0) s_red[wid][FI_TF] = base;
-			__syncthreads();
-			if (threadIdx.x < ntr)
-			{
-				float c = 0.f, b = 0.f;
-#pragma unroll
-				for (int ww = 0; ww < FI_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][FI_TF]; }
-				float v = (b - 2.f * c) + xi2_half;
-				v = fmaxf(v, 0.f);
-				if (stage) A.st_out[out_off + c0 + threadIdx.x] += v;                         // diff2.h:424-428
-				else { A.fs_w[out_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v); }
-			}
-		}
-		if (!stage && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
-	}
-}
-
-static int launch_fine(rb_ctx *ctx, FineArgs &A, int grid)
-{
-	k_diff2_fine<<<grid, FI_THREADS, 0, ctx->stream>>>(A, ctx->d_model);
-	RB_LAUNCH_CHECK(ctx);
-	return RB_OK;
-}
-
-int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
-{
-	FineArgs A;
-	memset(&A, 0, sizeof(A));
-	A.metas = s.meta.as<RbPartMeta>(); A.states = s.state.as<RbPartState>();
-	A.Fimg = s.Fimg.as<float2>(); A.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
-	A.fo = s.fo.as<RbFineOrient>(); A.pair_list = s.pair_list.as<int>(); A.counters = s.counters.as<int>();
-	A.fs_w = s.fs_w.as<float>();
-	A.projs = ctx->d_proj.as<RbProjector>();
-	A.pix = ctx->d_model.pix_f; A.npix = ctx->d_model.nvf; A.n = ctx->d_model.current_size;
-	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
-	return launch_fine(ctx, A, ctx->num_sms * 2);
-}
-
-int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers,
-                         const float *d_tx, const float *d_ty, const float *d_re, const float *d_im,
-                         const float *d_corr, float sum_init,
-                         const unsigned long long *d_rot_idx, const unsigned long long *d_trans_idx,
-                         const unsigned long long *d_job_idx, const unsigned long long *d_job_num, int n_jobs,
-                         float *d_out)
-{
-	// pixel list with the fine kernels' row rule (diff2.cuh:268-274, diff2.h:344-355): rows in the dead
-	// band maxR < iy < imgY-maxR contribute only the pixel x = maxR (which projects to zero)
-	const int imgX = n / 2 + 1;
-	RbProjK pk = rb_make_projk(pj, imgX);
-	std::vector<uint32_t> pix;
-	pix.reserve((size_t) n * imgX);
-	for (int iy = 0; iy < n; iy++)
-	{
-		int xs = 0, xe = imgX, y = iy;
-		if (iy > pk.maxR)
-		{
-			if (iy >= n - pk.maxR) y = iy - n;
-			else { xs = pk.maxR; xe = xs + 1; }
-		}
-		for (int x = xs; x < xe; x++) pix.push_back(rb_pack_pix(x, y, 0));
-	}
-	RB_CHECK(ctx->scratch[0].ensure(pix.size() * 4));
-	RB_CHECK(ctx->scratch[1].ensure(sizeof(RbProjector)));
-	RB_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, pix.data(), pix.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-	RB_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, &pj, sizeof(RbProjector), cudaMemcpyHostToDevice, ctx->stream));
-	RB_CUDA(cudaStreamSynchronize(ctx->stream));
-	FineArgs A;
-	memset(&A, 0, sizeof(A));
-	A.st_eulers = d_eulers; A.st_re = d_re; A.st_im = d_im; A.st_corr = d_corr; A.st_sum_init = sum_init;
-	A.st_rot_idx = d_rot_idx; A.st_trans_idx = d_trans_idx; A.st_job_idx = d_job_idx; A.st_job_num = d_job_num;
-	A.st_njobs = n_jobs; A.st_out = d_out;
-	A.projs = ctx->scratch[1].as<RbProjector>();
-	A.pix = ctx->scratch[0].as<uint32_t>(); A.npix = (int) pix.size(); A.n = n;
-	A.tx = d_tx; A.ty = d_ty; A.NOT = 1;
-	int grid = n_jobs < ctx->num_sms * 2 ? n_jobs : ctx->num_sms * 2;
-	if (grid < 1) return RB_OK;
-	return launch_fine(ctx, A, grid);
 }

@@ -80,7 +80,7 @@ static void release_slot(PoolSlot &s)
 	DevBuf *bufs[] = {&s.Fimg, &s.Fnomask, &s.Fctf, &s.meta, &s.state, &s.dir_idx, &s.dir_prior, &s.psi_idx, &s.psi_prior,
 	                  &s.Mweight, &s.pdf_orient, &s.pdf_orient_zero, &s.pdf_offset, &s.pdf_offset_zero,
 	                  &s.so_list, &s.pair_list, &s.fo, &s.fs_w, &s.fs_ihid, &s.counters, &s.shells, &s.out_pdf_dir, &s.out_pdf_class,
-	                  &s.fimg4, &s.cimg4};
+	                  &s.fimg4, &s.cimg4, &s.slices};
 	for (DevBuf *b : bufs) b->release();
 	if (s.uploaded) cudaEventDestroy(s.uploaded);
 }
@@ -572,6 +572,14 @@ extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool)
 	ctx->fine_sample_capacity = cap_fs; ctx->fine_orient_capacity = cap_fo;
 	RB_CHECK(s.fs_w.ensure(cap_fs * 4)); RB_CHECK(s.fs_ihid.ensure(cap_fs * 8));
 	RB_CHECK(s.fo.ensure(cap_fo * sizeof(RbFineOrient)));
+	// slice cache: the fine pass leaves every projected slice here so the store stage streams it instead of
+	// gathering from the reference a second time; orientations beyond the budget fall back to the gather
+	{
+		const size_t slice_bytes = (size_t) M.Npf * sizeof(float2);
+		const size_t budget = env_size("RB_SLICE_CACHE_BYTES", (size_t) 4 << 30);
+		s.slice_capacity = (long long) std::min<size_t>(cap_fo, budget / slice_bytes);
+		RB_CHECK(s.slices.ensure((size_t) s.slice_capacity * slice_bytes));
+	}
 	RB_CHECK(s.pair_list.ensure((cap_fs / ov + 1) * 4));
 	return RB_OK;
 }

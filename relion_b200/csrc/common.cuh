@@ -173,6 +173,8 @@ struct PoolSlot {
 	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;
 	DevBuf so_list, pair_list, fo, fs_w, fs_ihid, counters, shells, out_pdf_dir, out_pdf_class;
 	DevBuf fimg4, cimg4;            // prepared (corrected) images of the pool at the fine / coarse window
+	DevBuf slices;                  // reference slices written by the fine pass, re-read by the store stage
+	long long slice_capacity = 0;   // number of fine orientations whose slice fits the cache
 	std::vector<RbPartMeta> h_meta;
 	cudaEvent_t uploaded = nullptr;
 };

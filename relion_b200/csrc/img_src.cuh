@@ -58,3 +58,39 @@ __device__ __forceinline__ void img_src_pool(ImgSrc &src, const RbModelDev &M, c
 	src.do_scale = M.do_scale_correction;
 	src.n_array = M.current_size;
 }
+
+// prepared image: corrections applied once per particle instead of once per (orientation, pixel)
+struct PrepArgs {
+	ImgSrc src;                    // stage mode: src.re != nullptr
+	const RbPartMeta *metas; const float2 *Fimg; const float *Fctf;   // pool mode
+	const short *ires;             // pool: dense shell map (-1 = excluded); stage: nullptr
+	const RbRow *rows; int nrows;  // valid runs
+	int n;
+	float4 *out;
+};
+
+static __global__ void k_prep_img4(PrepArgs A, RbModelDev M)
+{
+	const int xs = A.n / 2 + 1;
+	const int p = blockIdx.y;
+	ImgSrc src = A.src;
+	if (!src.re) img_src_pool(src, M, A.metas[p], A.Fimg, A.Fctf, p);
+	float4 *out = A.out + (size_t) p * A.n * xs;
+	// rows without any valid pixel keep zero weight: clear first, then fill the runs
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nrows * xs; i += gridDim.x * blockDim.x)
+	{
+		const int r = i / xs, x = i - r * xs;
+		const RbRow rd = A.rows[r];
+		const int idx = rd.iy * xs + x;                       // position in the n-window
+		float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+		const int ires = A.ires ? (int) A.ires[idx] : 0;
+		if (x >= rd.x_lo && x <= rd.x_hi && ires >= 0)
+		{
+			float2 X; float corr;
+			img_load_idx(src, rb_src_index(x, rd.y, src.n_array), ires, X, corr);   // windowFourierTransform (src/fftw.h:850-856)
+			v = make_float4(X.x, X.y, corr * 0.5f, 0.f);
+		}
+		out[idx] = v;
+	}
+}
+

@@ -1,10 +1,15 @@
-// relion_b200 — squared-difference kernels (coarse and fine pass), sm_100a.
+// relion_b200 — coarse-pass squared differences (sm_100a).
 //
-// Replaces cuda_kernel_diff2_coarse / cuda_kernel_diff2_fine
-// (/root/reference/src/acc/cuda/cuda_kernels/diff2.cuh:24-189, 193-332) and their ALTCPU twins
-// (src/acc/cpu/cpu_kernels/diff2.h:32-430) with kernels batched over a whole pool of particles:
-// no per-particle launch, no host sync, image corrections (pixel_correction, corr_img —
-// acc_ml_optimiser_impl.h:1251-1268, acc_helper_functions_impl.h:164-196) applied on the fly.
+// Replaces cuda_kernel_diff2_coarse (/root/reference/src/acc/cuda/cuda_kernels/diff2.cuh:24-189; ALTCPU twin
+// src/acc/cpu/cpu_kernels/diff2.h:32-282) and mapAllWeightsToMweights (helper.cu:782-796) for a whole pool:
+// one launch, no host sync, images corrected once per particle (k_prep_img4).
+//
+// diff2[o][t] = sum c (|A_o|^2 + |X|^2) - 2 Re sum Z_o e^{i phi_t},  Z_o = c conj(A_o) X,  c = corr/2:
+// per (pixel, translation) one phase factor (two table lookups + a complex product) is shared by the CO_EO
+// orientations of the CTA, each of which then costs two FMAs.  Lanes walk consecutive x of a row, so the gathers of
+// neighbouring lanes fall into the same 128-byte lines of the (L2-resident, ~20 MB) low-resolution core of the
+// compact reference.  A quad-per-row variant with separable phases (as in the fine pass) was measured slower here
+// (16.2 ms vs 10.6 ms for the headline pool): with only ~30 translations the 4x redundant coordinate math dominates.
 #include "img_src.cuh"
 
 // phase tables for a chunk of translations: tab_x[t][x] = (cos, sin)(x*tx), tab_y[t][y+yoff] = (cos, sin)(y*ty)
@@ -52,65 +57,6 @@ __device__ __forceinline__ void warp_transpose_reduce(float (&v)[N])
 }
 
 // ---------------------------------------------------------------------------------------------
-// priors: pdf_orientation = log(pdf), zero flags (initOrientations, utilities_impl.h:656-668);
-// pdf_offset (acc_ml_optimiser_impl.h:2094-2171)
-// ---------------------------------------------------------------------------------------------
-__global__ void k_prep_priors(const RbPartMeta *metas, RbModelDev M, RbSamplingDev S,
-                              const int *dir_idx, const double *dir_prior, const int *psi_idx, const double *psi_prior,
-                              float *pdf_orient, unsigned char *pdf_orient_zero,
-                              float *pdf_offset, unsigned char *pdf_offset_zero, RbPartState *states)
-{
-	const int p = blockIdx.y;
-	const RbPartMeta m = metas[p];
-	const int no = m.nd * m.np;
-	const int ndense = M.nr_classes * no;
-	for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < ndense; o += gridDim.x * blockDim.x)
-	{
-		int k = o / no, oi = o - k * no, idl = oi / m.np, ipl = oi - idl * m.np;
-		double pdf;
-		if (m.dir_off < 0) pdf = M.pdf_direction[(size_t) k * S.n_dir + idl];
-		else pdf = dir_prior[m.dir_off + idl] * psi_prior[m.psi_off + ipl];
-		if (!(M.pdf_class[k] > 0.)) pdf = 0.;   // classes with zero pdf_class are never evaluated (:1069)
-		pdf_orient_zero[m.prior_off + o] = (pdf == 0.);
-		pdf_orient[m.prior_off + o] = (pdf == 0.) ? 0.f : (float) log(pdf);
-	}
-	if (blockIdx.x == 0)
-	{
-		for (int t = threadIdx.x; t < S.n_trans; t += blockDim.x)
-		{
-			double offx = m.oldx + S.trans_x[t], offy = m.oldy + S.trans_y[t];
-			double tdiff2 = (offx - m.prx) * (offx - m.prx) / (-2. * M.s2off) + (offy - m.pry) * (offy - m.pry) / (-2. * M.s2off);
-			tdiff2 *= M.pixel_size * M.pixel_size;
-			double pdf; bool z;
-			if (M.s2off < 0.0001) { z = tdiff2 > 0.; pdf = z ? 0. : 1.; }
-			else { z = false; pdf = tdiff2; }
-			pdf_offset_zero[(size_t) p * S.n_trans + t] = z;
-			pdf_offset[(size_t) p * S.n_trans + t] = (float) pdf;
-		}
-		if (threadIdx.x == 0)
-		{
-			RbPartState st;
-			memset(&st, 0, sizeof(st));
-			st.min_diff2_bits = 0x7f7fffff; st.fmin_bits = 0x7f7fffff;
-			states[p] = st;
-		}
-	}
-}
-
-int rbk_prep_priors(rb_ctx *ctx, PoolSlot &s)
-{
-	dim3 grid((s.max_no * ctx->d_model.nr_classes + 255) / 256, s.P);
-	if (grid.x > 64) grid.x = 64;
-	if (grid.x < 1) grid.x = 1;
-	k_prep_priors<<<grid, 256, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), ctx->d_model, ctx->d_samp,
-		s.dir_idx.as<int>(), s.dir_prior.as<double>(), s.psi_idx.as<int>(), s.psi_prior.as<double>(),
-		s.pdf_orient.as<float>(), s.pdf_orient_zero.as<unsigned char>(),
-		s.pdf_offset.as<float>(), s.pdf_offset_zero.as<unsigned char>(), s.state.as<RbPartState>());
-	RB_LAUNCH_CHECK(ctx);
-	return RB_OK;
-}
-
-// ---------------------------------------------------------------------------------------------
 // coarse pass
 // ---------------------------------------------------------------------------------------------
 static const int CO_THREADS = 128;
@@ -121,12 +67,12 @@ static const int CO_THREADS = 128;
 struct CoarseArgs {
 	// pool mode
 	const RbPartMeta *metas; RbPartState *states;
-	const float2 *Fimg; const float *Fctf;
 	const int *dir_idx, *psi_idx;
 	const unsigned char *pdf_orient_zero;
 	float *Mweight;
 	// stage mode (metas == nullptr)
-	const float *st_eulers; const float *st_re, *st_im, *st_corr; float *st_out; int st_O; int st_class;
+	const float *st_eulers; float *st_out; int st_O; int st_class;
+	const float4 *img4;            // prepared images at the coarse window [P][n][n/2+1]: (X'.re, X'.im, corr/2, 0)
 	// common
 	const RbProjector *projs;
 	const uint32_t *pix; int npix; int n; // window
@@ -144,6 +90,7 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 	__shared__ int s_valid[CO_EO];
 	__shared__ float s_red[CO_THREADS / 32][CO_EO * CO_TT];
 	__shared__ float s_min[32];
+	__shared__ float s_base[CO_THREADS / 32][CO_EO];
 
 	const int imgX = A.n / 2 + 1;
 	const int ny = A.ny, yoff = A.yoff;
@@ -187,18 +134,7 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 	for (int e = 0; e < CO_EO; e++) any |= (s_valid[e] != 0);
 	if (!any) return;   // Mweight stays lowest() (acc_ml_optimiser_impl.h:3849)
 
-	ImgSrc src;
-	if (stage) { src.re = A.st_re; src.im = A.st_im; src.corr = A.st_corr; src.n_array = A.n; }
-	else
-	{
-		src.re = nullptr;
-		src.F = A.Fimg + (size_t) p * M.Npf; src.ctf = A.Fctf ? A.Fctf + (size_t) p * M.Npf : nullptr;
-		src.minvs2 = M.minvs2 + (size_t) m.og * M.nshell;
-		src.inv_scale = 1.0f / m.scale; src.scale2 = m.scale * m.scale;
-		src.do_ctf_refs = M.do_ctf_correction && M.refs_are_ctf_corrected && src.ctf;
-		src.do_scale = M.do_scale_correction;
-		src.n_array = M.current_size;
-	}
+	const float4 *img = A.img4 + (size_t) p * A.n * imgX;
 	const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
 
 	float bmin = FLT_MAX;
@@ -212,19 +148,26 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 		float acc[CO_EO * CO_TT];
 #pragma unroll
 		for (int i = 0; i < CO_EO * CO_TT; i++) acc[i] = 0.f;
+		float base[CO_EO];
+#pragma unroll
+		for (int e = 0; e < CO_EO; e++) base[e] = 0.f;
 
 		for (int ip = threadIdx.x; ip < A.npix; ip += CO_THREADS)
 		{
 			const uint32_t pkx = __ldg(A.pix + ip);
 			const int x = rb_pix_x(pkx), y = rb_pix_y(pkx);
-			float2 X; float corr;
-			img_load(src, pkx, X, corr);
-			const float hc = corr * 0.5f;                       // s_corr = corr/2 (diff2.h:114)
-			float2 ref[CO_EO];
+			const float4 im = __ldg(img + rb_src_index(x, y, A.n));
+			const float hc = im.z;                              // s_corr = corr/2 (diff2.h:114)
+			float zr[CO_EO], zi[CO_EO];
 #pragma unroll
 			for (int e = 0; e < CO_EO; e++)
-				ref[e] = s_valid[e] ? rb_project3d(pk, x, y, s_e[e][0], s_e[e][1], s_e[e][2], s_e[e][3], s_e[e][4], s_e[e][5])
-				                    : make_float2(0.f, 0.f);
+			{
+				const float2 ref = s_valid[e] ? rb_project3d(pk, x, y, s_e[e][0], s_e[e][1], s_e[e][2], s_e[e][3], s_e[e][4], s_e[e][5])
+				                              : make_float2(0.f, 0.f);
+				zr[e] = hc * (ref.x * im.x + ref.y * im.y);
+				zi[e] = hc * (ref.x * im.y - ref.y * im.x);
+				base[e] += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
+			}
 			const float2 *txp = tab_x + x, *typ = tab_y + (y + yoff);
 #pragma unroll
 			for (int t = 0; t < CO_TT; t++)
@@ -234,14 +177,9 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 					const float2 a = txp[t * imgX], b = typ[t * ny];
 					const float ss = a.y * b.x + a.x * b.y;     // sin(x tx + y ty)
 					const float cc = a.x * b.x - a.y * b.y;     // cos
-					const float sr = cc * X.x - ss * X.y;
-					const float si = cc * X.y + ss * X.x;
 #pragma unroll
 					for (int e = 0; e < CO_EO; e++)
-					{
-						const float dr = ref[e].x - sr, di = ref[e].y - si;
-						acc[e * CO_TT + t] += (dr * dr + di * di) * hc;
-					}
+						acc[e * CO_TT + t] = fmaf(zr[e], cc, fmaf(-zi[e], ss, acc[e * CO_TT + t]));
 				}
 			}
 		}
@@ -250,15 +188,18 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 		const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
 		for (int g = 0; g < CO_EO * CO_TT / 32; g++) s_red[wid][g * 32 + lane] = acc[g * 32];
+#pragma unroll
+		for (int e = 0; e < CO_EO; e++) { const float bsum = warp_sum(base[e]); if (lane == 0) s_base[wid][e] = bsum; }
 		__syncthreads();
 		if (threadIdx.x < CO_EO * CO_TT)
 		{
 			const int e = threadIdx.x / CO_TT, t = threadIdx.x - e * CO_TT;
 			if (t < ntr && s_valid[e])
 			{
-				float v = 0.f;
+				float cr = 0.f, bs = 0.f;
 #pragma unroll
-				for (int w = 0; w < CO_THREADS / 32; w++) v += s_red[w][threadIdx.x];
+				for (int w = 0; w < CO_THREADS / 32; w++) { cr += s_red[w][threadIdx.x]; bs += s_base[w][e]; }
+				float v = fmaxf(bs - 2.f * cr, 0.f);
 				const int o = o0 + e;
 				if (stage) A.st_out[(size_t) o * A.T + t0 + t] += v;          // += like the reference kernel
 				else
@@ -311,10 +252,24 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 	// Mweight <- lowest() (acc_ml_optimiser_impl.h:3849)
 	k_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(s.Mweight.as<float>(), RB_LOWEST, (size_t) s.total_coarse);
 	RB_LAUNCH_CHECK(ctx);
+	// images at the coarse window with all corrections applied, once per particle
+	const RbModelDev &M = ctx->d_model;
+	const int nc = M.coarse_size, xsc = nc / 2 + 1;
+	RB_CHECK(s.cimg4.ensure((size_t) s.P * nc * xsc * sizeof(float4)));
+	RB_CUDA(cudaMemsetAsync(s.cimg4.p, 0, (size_t) s.P * nc * xsc * sizeof(float4), ctx->stream));
+	PrepArgs PA;
+	memset(&PA, 0, sizeof(PA));
+	PA.metas = s.meta.as<RbPartMeta>(); PA.Fimg = s.Fimg.as<float2>();
+	PA.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
+	PA.ires = M.ires_c; PA.rows = M.rows_c; PA.nrows = M.nrows_c; PA.n = nc; PA.out = s.cimg4.as<float4>();
+	dim3 pg((M.nrows_c * xsc + 255) / 256, s.P);
+	k_prep_img4<<<pg, 256, 0, ctx->stream>>>(PA, M);
+	RB_LAUNCH_CHECK(ctx);
+
 	CoarseArgs A;
 	memset(&A, 0, sizeof(A));
 	A.metas = s.meta.as<RbPartMeta>(); A.states = s.state.as<RbPartState>();
-	A.Fimg = s.Fimg.as<float2>(); A.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
+	A.img4 = s.cimg4.as<float4>();
 	A.dir_idx = s.dir_idx.as<int>(); A.psi_idx = s.psi_idx.as<int>();
 	A.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>();
 	A.Mweight = s.Mweight.as<float>();
@@ -343,10 +298,23 @@ int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const floa
 	RB_CHECK(ctx->scratch[1].ensure(sizeof(RbProjector)));
 	RB_CUDA(cudaMemcpyAsync(ctx->scratch[0].p, pix.data(), pix.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
 	RB_CUDA(cudaMemcpyAsync(ctx->scratch[1].p, &pj, sizeof(RbProjector), cudaMemcpyHostToDevice, ctx->stream));
-	RB_CUDA(cudaStreamSynchronize(ctx->stream));   // `pix` is a pageable temporary
+	std::vector<RbRow> rows;
+	for (int iy = 0; iy < n; iy++)
+		rows.push_back(RbRow{(short) iy, (short) (iy > pk.maxR ? iy - n : iy), (short) 0, (short) (imgX - 1)});
+	RB_CHECK(ctx->scratch[7].ensure(rows.size() * sizeof(RbRow)));
+	RB_CHECK(ctx->scratch[6].ensure((size_t) n * imgX * sizeof(float4)));
+	RB_CUDA(cudaMemcpyAsync(ctx->scratch[7].p, rows.data(), rows.size() * sizeof(RbRow), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));   // `pix` and `rows` are pageable temporaries
+	PrepArgs PA;
+	memset(&PA, 0, sizeof(PA));
+	PA.src.re = d_re; PA.src.im = d_im; PA.src.corr = d_corr; PA.src.n_array = n;
+	PA.rows = ctx->scratch[7].as<RbRow>(); PA.nrows = (int) rows.size(); PA.n = n; PA.out = ctx->scratch[6].as<float4>();
+	k_prep_img4<<<dim3((n * imgX + 255) / 256, 1), 256, 0, ctx->stream>>>(PA, ctx->d_model);
+	RB_LAUNCH_CHECK(ctx);
 	CoarseArgs A;
 	memset(&A, 0, sizeof(A));
-	A.st_eulers = d_eulers; A.st_re = d_re; A.st_im = d_im; A.st_corr = d_corr; A.st_out = d_out; A.st_O = O; A.st_class = 0;
+	A.st_eulers = d_eulers; A.st_out = d_out; A.st_O = O; A.st_class = 0;
+	A.img4 = ctx->scratch[6].as<float4>();
 	A.projs = ctx->scratch[1].as<RbProjector>();
 	A.pix = ctx->scratch[0].as<uint32_t>(); A.npix = (int) pix.size(); A.n = n;
 	A.tx = d_tx; A.ty = d_ty; A.T = T;

@@ -32,45 +32,11 @@ struct FineArgs {
 	float *st_out;
 	// common
 	const float4 *img4;            // [P][n][n/2+1] (X'.re, X'.im, corr/2, 0); zero weight outside the valid runs
+	float2 *slices; long long slice_capacity;   // pool mode: cache of the projected slices for the store stage
 	const RbProjector *projs;
 	const RbRow *rows; int nrows; int n;
 	const float *tx, *ty; int NOT;
 };
-
-// prepared image: corrections applied once per particle instead of once per (orientation, pixel)
-struct PrepArgs {
-	ImgSrc src;                    // stage mode: src.re != nullptr
-	const RbPartMeta *metas; const float2 *Fimg; const float *Fctf;   // pool mode
-	const short *ires;             // pool: dense shell map (-1 = excluded); stage: nullptr
-	const RbRow *rows; int nrows;  // valid runs
-	int n;
-	float4 *out;
-};
-
-__global__ void k_prep_img4(PrepArgs A, RbModelDev M)
-{
-	const int xs = A.n / 2 + 1;
-	const int p = blockIdx.y;
-	ImgSrc src = A.src;
-	if (!src.re) img_src_pool(src, M, A.metas[p], A.Fimg, A.Fctf, p);
-	float4 *out = A.out + (size_t) p * A.n * xs;
-	// rows without any valid pixel keep zero weight: clear first, then fill the runs
-	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nrows * xs; i += gridDim.x * blockDim.x)
-	{
-		const int r = i / xs, x = i - r * xs;
-		const RbRow rd = A.rows[r];
-		const int idx = rd.iy * xs + x;
-		float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-		const int ires = A.ires ? (int) A.ires[idx] : 0;
-		if (x >= rd.x_lo && x <= rd.x_hi && ires >= 0)
-		{
-			float2 X; float corr;
-			img_load_idx(src, idx, ires, X, corr);
-			v = make_float4(X.x, X.y, corr * 0.5f, 0.f);
-		}
-		out[idx] = v;
-	}
-}
 
 struct FineFetch {
 	float4 q;      // this lane's quarter of the 2x2x2 cell
@@ -165,6 +131,7 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 		__syncthreads();
 		if (threadIdx.x < 6) s_e[threadIdx.x] = eu[threadIdx.x + threadIdx.x / 2];   // elements 0,1,3,4,6,7
 		const float4 *img = A.img4 + (size_t) p * A.n * xs;
+		float2 *slice = (!stage && A.slices && w < A.slice_capacity) ? A.slices + (size_t) w * A.n * xs : nullptr;
 		const RbProjK8 pk = rb_make_projk8(A.projs[cls], xs);
 		float bmin = FLT_MAX;
 
@@ -207,6 +174,7 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 			{
 				const RbRow rd = A.rows[r];
 				const float4 *img_row = img + (size_t) rd.iy * xs;
+				float2 *slice_row = (slice && c0 == 0) ? slice + (size_t) rd.iy * xs : nullptr;
 				float accr[8], acci[8];
 #pragma unroll
 				for (int i = 0; i < 8; i++) { accr[i] = 0.f; acci[i] = 0.f; }
@@ -220,6 +188,7 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 					if (haven) fine_issue(pk, img_row, k, x + 1, rd.y, e0, e1, e3, e4, e6, e7, nxt);
 
 					const float2 ref = fine_finish(cur, k, qmask);
+					if (slice_row && k == 0) slice_row[x] = ref;   // the store stage streams this instead of gathering again
 					const float hc = cur.img.z;
 					const float zr = hc * (ref.x * cur.img.x + ref.y * cur.img.y);
 					const float zi = hc * (ref.x * cur.img.y - ref.y * cur.img.x);
@@ -318,6 +287,7 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	A.fo = s.fo.as<RbFineOrient>(); A.pair_list = s.pair_list.as<int>(); A.counters = s.counters.as<int>();
 	A.fs_w = s.fs_w.as<float>();
 	A.img4 = s.fimg4.as<float4>();
+	A.slices = s.slices.as<float2>(); A.slice_capacity = s.slice_capacity;
 	A.projs = ctx->d_proj.as<RbProjector>();
 	A.rows = M.rows_f; A.nrows = M.nrows_f; A.n = n;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;

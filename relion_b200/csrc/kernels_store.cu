@@ -141,6 +141,7 @@ struct StoreArgs {
 	const RbProjector *projs; const RbBackprojector *bps;
 	const uint32_t *pix; int npix; int n;
 	const float *tx, *ty; int NOT;
+	const float2 *slices; long long slice_capacity;   // slices cached by the fine pass ([fine orientation][n][n/2+1])
 };
 
 static const int ST_CHUNK = 256;   // significant samples held in shared memory at a time
@@ -153,13 +154,20 @@ struct StorePix {
 };
 
 __device__ __forceinline__ void store_issue(const StoreArgs &A, const RbProjK8 &pk, const float2 *X, const float2 *X0,
-                                            const float *C, float part_scale, int ip,
+                                            const float *C, const float2 *slice, float part_scale, int ip,
                                             float e0, float e1, float e3, float e4, float e6, float e7, StorePix &f)
 {
 	const uint32_t pkx = __ldg(A.pix + ip);
 	f.x = rb_pix_x(pkx); f.y = rb_pix_y(pkx); f.ires = rb_pix_ires(pkx);
-	rb_proj_issue(pk, f.x, f.y, e0, e1, e3, e4, e6, e7, f.pf);
 	const int idx = rb_src_index(f.x, f.y, A.n);
+	if (slice)
+	{
+		// slice cached by the fine pass: one streaming 8-byte read instead of a 64-byte gather
+		const float2 r = __ldg(slice + idx);
+		f.pf.q0 = make_float4(r.x, r.y, 0.f, 0.f);
+		f.pf.flags = 4;
+	}
+	else rb_proj_issue(pk, f.x, f.y, e0, e1, e3, e4, e6, e7, f.pf);
 	f.X = __ldg(X + idx); f.X0 = __ldg(X0 + idx);
 	f.ctf = C ? __ldg(C + idx) * part_scale : part_scale;                                     // :3087-3096
 }
@@ -218,6 +226,7 @@ k_store(StoreArgs A, RbModelDev M)
 		const RbPartMeta m = A.metas[p];
 		const float2 *X = A.Fimg + (size_t) p * M.Npf, *X0 = A.Fnomask + (size_t) p * M.Npf;
 		const float *C = A.Fctf ? A.Fctf + (size_t) p * M.Npf : nullptr;
+		const float2 *slice = (A.slices && w < A.slice_capacity) ? A.slices + (size_t) w * M.Npf : nullptr;
 		const float *mtab = M.minvs2 + (size_t) m.og * M.nshell;
 		const unsigned char *dvp = M.dvp_gt3 + (size_t) F.iclass * M.nshell;
 		const RbProjK8 pk = rb_make_projk8(A.projs[F.iclass], imgX);
@@ -246,16 +255,17 @@ k_store(StoreArgs A, RbModelDev M)
 			int ip = threadIdx.x;
 			bool have = ip < A.npix;
 			StorePix cur;
-			if (have) store_issue(A, pk, X, X0, C, m.part_scale, ip, e0, e1, e3, e4, e6, e7, cur);
+			if (have) store_issue(A, pk, X, X0, C, slice, m.part_scale, ip, e0, e1, e3, e4, e6, e7, cur);
 			while (have)
 			{
 				const int ipn = ip + ST_THREADS;
 				const bool haven = ipn < A.npix;
 				StorePix nxt;
-				if (haven) store_issue(A, pk, X, X0, C, m.part_scale, ipn, e0, e1, e3, e4, e6, e7, nxt);
+				if (haven) store_issue(A, pk, X, X0, C, slice, m.part_scale, ipn, e0, e1, e3, e4, e6, e7, nxt);
 
 				const int x = cur.x, y = cur.y, ires = cur.ires;
-				float2 ref = (cur.pf.flags & 1) ? rb_proj_finish(cur.pf) : make_float2(0.f, 0.f);
+				float2 ref = (cur.pf.flags & 4) ? make_float2(cur.pf.q0.x, cur.pf.q0.y)
+				                                : ((cur.pf.flags & 1) ? rb_proj_finish(cur.pf) : make_float2(0.f, 0.f));
 				const float ctf = cur.ctf;
 				if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                     // wavg.cuh:96-104
 				else { ref.x *= m.part_scale; ref.y *= m.part_scale; }
@@ -321,6 +331,7 @@ int rbk_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.projs = ctx->d_proj.as<RbProjector>(); A.bps = ctx->d_bp.as<RbBackprojector>();
 	A.pix = ctx->d_model.pix_f; A.npix = ctx->d_model.nvf; A.n = ctx->d_model.current_size;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
+	A.slices = s.slices.as<float2>(); A.slice_capacity = s.slice_capacity;
 	k_store<<<ctx->num_sms * 2, ST_THREADS, 0, ctx->stream>>>(A, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;

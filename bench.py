@@ -229,12 +229,19 @@ def run_ours(args):
     value = P * world * args.steps / (ms_max / 1e3)
 
     # ---- end-to-end through rb_estep_pool with host buffers ---------------------------------------
-    for _ in range(min(args.warmup, 2)):
-        dev.expectation_some_particles(pool)
+    # Every step: H2D of one pool from pinned host memory (rb_pool_upload), the whole E-step, D2H of the per-particle
+    # results (rb_estep_slot).  Two device slots: the upload of pool i+1 overlaps the compute of pool i, as a RELION
+    # adapter would do while its threads prepare the next pool.
+    for wslot in range(2):   # warm both slots (first use allocates their buffers)
+        dev.pool_upload(wslot, pool)
+        dev.estep_slot(wslot)
     barrier()
     t1 = time.perf_counter()
-    for _ in range(args.steps):
-        res = dev.expectation_some_particles(pool)   # H2D + all stages + D2H of per-particle results
+    dev.pool_upload(0, pool)
+    for i in range(args.steps):
+        if i + 1 < args.steps:
+            dev.pool_upload((i + 1) % 2, pool)
+        res = dev.estep_slot(i % 2)
     dev.sync_all_backprojects()
     e2e_s = time.perf_counter() - t1
     t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")

@@ -252,17 +252,23 @@ k_store(StoreArgs A, RbModelDev M)
 			const float W = s_W;
 			const float e0 = s_e[0], e1 = s_e[1], e3 = s_e[2], e4 = s_e[3], e6 = s_e[4], e7 = s_e[5];
 
+			// the trip count is uniform per warp (lanes past the end idle) because the scatter below is cooperative
 			int ip = threadIdx.x;
+			const int ip_end = ((A.npix + 31) & ~31);
 			bool have = ip < A.npix;
 			StorePix cur;
 			if (have) store_issue(A, pk, X, X0, C, slice, m.part_scale, ip, e0, e1, e3, e4, e6, e7, cur);
-			while (have)
+			for (; (ip & ~31) < ip_end; )
 			{
 				const int ipn = ip + ST_THREADS;
 				const bool haven = ipn < A.npix;
 				StorePix nxt;
 				if (haven) store_issue(A, pk, X, X0, C, slice, m.part_scale, ipn, e0, e1, e3, e4, e6, e7, nxt);
 
+				int cell = -1;           // accumulator voxel of corner (0,0,0), -1: nothing to scatter
+				float sfx = 0.f, sfy = 0.f, sfz = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
+				if (have)
+				{
 				const int x = cur.x, y = cur.y, ires = cur.ires;
 				float2 ref = (cur.pf.flags & 4) ? make_float2(cur.pf.q0.x, cur.pf.q0.y)
 				                                : ((cur.pf.flags & 1) ? rb_proj_finish(cur.pf) : make_float2(0.f, 0.f));
@@ -286,7 +292,7 @@ k_store(StoreArgs A, RbModelDev M)
 				// back-projection
 				const float minvs2 = M.do_map ? __ldg(mtab + ires) : 1.f;                          // :2586, :3110-3115
 				const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                       // BP.cuh:280-289
-				const float Fw = W * g * ctf;
+				Fw = W * g * ctf;
 				bool do_bp = Fw > 0.f;
 				if (M.bp_circle_bound)
 				{
@@ -295,9 +301,43 @@ k_store(StoreArgs A, RbModelDev M)
 				}
 				if (do_bp)
 				{
-					const float Fr = (cur.X0.x * phr - cur.X0.y * phi) * g;
-					const float Fi = (cur.X0.x * phi + cur.X0.y * phr) * g;
-					bp_scatter(bp, max_r2_vol, x, y, e0, e1, e3, e4, e6, e7, Fr, Fi, Fw);
+					Fr = (cur.X0.x * phr - cur.X0.y * phi) * g;
+					Fi = (cur.X0.x * phi + cur.X0.y * phr) * g;
+					// position in the accumulator (BP.cuh:301-347)
+					float xp = (e0 * x + e1 * y) * bp.padding_factor;
+					float yp = (e3 * x + e4 * y) * bp.padding_factor;
+					float zp = (e6 * x + e7 * y) * bp.padding_factor;
+					if (xp * xp + yp * yp + zp * zp <= (float) max_r2_vol)
+					{
+						if (xp < 0.f) { xp = -xp; yp = -yp; zp = -zp; Fi = -Fi; }
+						const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+						sfx = xp - fx0; sfy = yp - fy0; sfz = zp - fz0;
+						cell = (((int) fz0 - bp.mdlInitZ) * bp.mdlY + ((int) fy0 - bp.mdlInitY)) * bp.mdlX + (int) fx0;
+					}
+				}
+				}
+				// Cooperative scatter: two lanes per pixel, one per x-neighbour, so that the two 16-byte reductions of a
+				// corner pair sit in the same instruction and share one 32-byte sector / L1 wavefront.
+#pragma unroll
+				for (int h = 0; h < 2; h++)
+				{
+					const int src = 16 * h + ((threadIdx.x & 31) >> 1);
+					const int c = __shfl_sync(RB_FULL_MASK, cell, src);
+					const float fx = __shfl_sync(RB_FULL_MASK, sfx, src), fy = __shfl_sync(RB_FULL_MASK, sfy, src), fz = __shfl_sync(RB_FULL_MASK, sfz, src);
+					const float vr = __shfl_sync(RB_FULL_MASK, Fr, src), vi = __shfl_sync(RB_FULL_MASK, Fi, src), vw = __shfl_sync(RB_FULL_MASK, Fw, src);
+					if (c >= 0)
+					{
+						const int px = threadIdx.x & 1;
+						const float wx = px ? fx : 1.f - fx;
+						const float mfy = 1.f - fy, mfz = 1.f - fz;
+						float4 *b = bp.vol + (size_t) c + px;
+						const size_t sy = bp.mdlX, sz = (size_t) bp.mdlX * bp.mdlY;
+						float d;
+						d = mfz * mfy * wx; red_add_v4(b, d * vr, d * vi, d * vw);
+						d = mfz * fy * wx;  red_add_v4(b + sy, d * vr, d * vi, d * vw);
+						d = fz * mfy * wx;  red_add_v4(b + sz, d * vr, d * vi, d * vw);
+						d = fz * fy * wx;   red_add_v4(b + sz + sy, d * vr, d * vi, d * vw);
+					}
 				}
 				if (haven) cur = nxt;
 				ip = ipn; have = haven;

@@ -1,0 +1,131 @@
+"""CPU restatement (numpy, float64) of the reconstruction that turns back-projection accumulators into a map.
+
+TEST INFRASTRUCTURE ONLY (the checker): nothing under relion_b200/ imports this.  It exists so that the parity
+tests can apply north_star's criterion "the reconstructed half-maps have FSC >= 0.995 against the reference's maps
+at every shell to Nyquist" to the accumulators the CUDA path and the CPU oracle produce from the same particles.
+
+Follows, in /root/reference:
+  BackProjector::reconstruct, default `skip_gridding` branch        src/backprojector.cpp:1379-1575
+      (skip_gridding is the default: src/ml_optimiser.cpp:586 `--dont_skip_gridding` turns it off)
+  Projector::decenter                                                src/projector.h:249-260
+  MAP regularisation term (1/tau2 added to the weights)              src/backprojector.cpp:1463-1507
+  BackProjector::windowToOridimRealSpace                             src/backprojector.cpp:2530-2665
+  windowFourierTransform (shrinking branch)                          src/fftw.h:850-856
+  CenterFFTbySign                                                    src/fftw.h:390-403
+  softMaskOutsideMap (radius = xsize/2, cosine_width = 3)            src/mask.cpp:43-96
+  Projector::griddingCorrect (TRILINEAR: divide by sinc^2)           src/projector.cpp:595-628
+  getFSC                                                             src/fftw.cpp:481-513
+Parity: unpinned by reference tests (the reference has none for reconstruct); both maps of an FSC comparison go
+through this same code, so the comparison measures the accumulators, not this restatement.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def _fftw_freq(n: int) -> np.ndarray:
+    """FOR_ALL_ELEMENTS_IN_FFTW_TRANSFORM: kp = k < n/2+1 ? k : k - n."""
+    k = np.arange(n)
+    return np.where(k < n // 2 + 1, k, k - n)
+
+
+def decenter(centered: np.ndarray, max_r2: int) -> np.ndarray:
+    """Projector-centred [pad, pad, pad//2+1] (y,z origin at (pad-1)//2) -> FFTW order, zero beyond max_r2."""
+    pad = centered.shape[0]
+    h = (pad - 1) // 2
+    f = _fftw_freq(pad)
+    kz, ky, kx = np.meshgrid(f, f, np.arange(pad // 2 + 1), indexing="ij")
+    out = centered[kz + h, ky + h, kx]
+    return np.where(kz * kz + ky * ky + kx * kx <= max_r2, out, 0)
+
+
+def soft_mask_outside_map(vol: np.ndarray, cosine_width: float = 3.0) -> np.ndarray:
+    n = vol.shape[0]
+    c = np.arange(n) - n // 2
+    z, y, x = np.meshgrid(c, c, c, indexing="ij")
+    r = np.sqrt((x * x + y * y + z * z).astype(np.float64))
+    radius = n / 2.0
+    radius_p = radius + cosine_width
+    rc = np.where(r > radius_p, 1.0, np.where(r < radius, 0.0, 0.5 + 0.5 * np.cos(np.pi * (radius_p - r) / cosine_width)))
+    bg = float((rc * vol).sum() / rc.sum())
+    return (1.0 - rc) * vol + rc * bg
+
+
+def gridding_correct(vol: np.ndarray, ori_size: int, padding_factor: float) -> np.ndarray:
+    n = vol.shape[0]
+    c = np.arange(n) - n // 2
+    z, y, x = np.meshgrid(c, c, c, indexing="ij")
+    rval = np.sqrt((x * x + y * y + z * z).astype(np.float64)) / (ori_size * padding_factor)
+    sinc = np.ones_like(rval)
+    nz = rval > 0
+    sinc[nz] = np.sin(np.pi * rval[nz]) / (np.pi * rval[nz])
+    return vol / (sinc * sinc)
+
+
+def reconstruct(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, ori_size: int, r_max: int,
+                padding_factor: float = 2.0, tau2: np.ndarray | None = None, tau2_fudge: float = 1.0,
+                minres_map: int = 0) -> np.ndarray:
+    """BackProjector::reconstruct(skip_gridding) for a 3D reference built from 2D images: [ori, ori, ori] float64."""
+    data = real.astype(np.float64) + 1j * imag.astype(np.float64)
+    pad = data.shape[0]
+    rr = int(math.floor(r_max * padding_factor + 0.5))
+    max_r2 = rr * rr
+    f = _fftw_freq(pad)
+    kz, ky, kx = np.meshgrid(f, f, np.arange(pad // 2 + 1), indexing="ij")
+    r2 = kz * kz + ky * ky + kx * kx
+    Fweight = decenter(weight.astype(np.float64), max_r2)
+    if tau2 is not None:                                                           # :1463-1507
+        oversampling_correction = padding_factor ** 3
+        ires = np.floor(np.sqrt(r2.astype(np.float64)) / padding_factor + 0.5).astype(np.int64)
+        ires_c = np.minimum(ires, len(tau2) - 1)
+        t = np.asarray(tau2, np.float64)[ires_c]
+        invtau2 = np.where(t > 0, 1.0 / (oversampling_correction * tau2_fudge * np.where(t > 0, t, 1.0)),
+                           np.where(Fweight > 1e-20, 1.0 / (0.001 * np.where(Fweight > 1e-20, Fweight, 1.0)), 0.0))
+        Fweight = np.where((r2 < max_r2) & (ires >= minres_map), Fweight + invtau2, Fweight)
+    Fconv = decenter(data, max_r2)
+    # radial average of the weights / 1000 as the floor of the divisor (:1513-1573)
+    round_max_r2 = int(math.floor(r_max * padding_factor * r_max * padding_factor + 0.5))
+    iresf = np.floor(np.sqrt(r2.astype(np.float64)) / padding_factor).astype(np.int64)
+    inside = r2 < round_max_r2
+    radavg = np.bincount(iresf[inside], weights=Fweight[inside], minlength=r_max)[:r_max]
+    counter = np.bincount(iresf[inside], minlength=r_max)[:r_max].astype(np.float64)
+    radavg = radavg / (1000.0 * np.maximum(counter, 1.0))
+    w = np.maximum(Fweight, radavg[np.minimum(iresf, r_max - 1)])
+    Fconv = np.where(w != 0, Fconv / np.where(w != 0, w, 1.0), Fconv)
+
+    # windowToOridimRealSpace
+    padoridim = int(math.floor(padding_factor * ori_size + 0.5))
+    padoridim += padoridim % 2
+    fo = _fftw_freq(padoridim)
+    xo = padoridim // 2 + 1
+    xin = pad // 2 + 1
+    if xo > xin:                                               # enlarging branch: zero-pad
+        Fin = np.zeros((padoridim, padoridim, xo), np.complex128)
+        Fin[np.ix_(f % padoridim, f % padoridim, np.arange(xin))] = Fconv
+    else:
+        Fin = Fconv[np.ix_(fo % pad, fo % pad, np.arange(xo))]
+    k = np.arange(padoridim)
+    sign = 1 - 2 * ((k[:, None, None] ^ k[None, :, None] ^ np.arange(xo)[None, None, :]) & 1)
+    Fin = Fin * sign                                           # CenterFFTbySign
+    M = np.fft.irfftn(Fin, s=(padoridim,) * 3, axes=(0, 1, 2)) * float(padoridim) ** 3   # RELION's inverse transform is unnormalised
+    o = padoridim // 2 - ori_size // 2
+    M = M[o:o + ori_size, o:o + ori_size, o:o + ori_size]
+    M = M / (padding_factor ** 3 * ori_size)                   # normfft, ref_dim 3 / data_dim 2
+    M = soft_mask_outside_map(M)
+    return gridding_correct(M, ori_size, padding_factor)
+
+
+def fsc(map1: np.ndarray, map2: np.ndarray) -> np.ndarray:
+    """getFSC: shells 0..n/2 (fsc[i] = sum conj(z1) z2 / sqrt(sum|z1|^2 sum|z2|^2) over round(|k|) == i)."""
+    n = map1.shape[0]
+    F1, F2 = np.fft.rfftn(map1), np.fft.rfftn(map2)
+    f = _fftw_freq(n)
+    kz, ky, kx = np.meshgrid(f, f, np.arange(n // 2 + 1), indexing="ij")
+    idx = np.floor(np.sqrt((kz * kz + ky * ky + kx * kx).astype(np.float64)) + 0.5).astype(np.int64)
+    ok = idx < n // 2 + 1
+    num = np.bincount(idx[ok], weights=(np.conj(F1) * F2).real[ok], minlength=n // 2 + 1)
+    d1 = np.bincount(idx[ok], weights=(np.abs(F1) ** 2)[ok], minlength=n // 2 + 1)
+    d2 = np.bincount(idx[ok], weights=(np.abs(F2) ** 2)[ok], minlength=n // 2 + 1)
+    return num / np.sqrt(np.maximum(d1 * d2, 1e-300))

@@ -256,3 +256,30 @@ def test_pool_capacity_error(device, oracle, monkeypatch):
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+@pytest.mark.parametrize("kind", ["port", "reference"])
+def test_halfmap_fsc_against_reference(device, kind):
+    """north_star: the reconstructed half-maps have FSC >= 0.995 against the reference's maps at every shell to
+    Nyquist.  Two random half-sets go through the CUDA E-step and through the CPU oracle (RELION's own ALTCPU kernels
+    when oracle/_ref is there); each accumulator pair is reconstructed by the same restated BackProjector::reconstruct
+    (oracle/reconstruct.py) and compared shell by shell."""
+    from oracle.bindings import Oracle, Projector, Backprojector, have_reference
+    from oracle import reconstruct as rc
+    if kind == "reference" and not have_reference():
+        pytest.skip("oracle/_ref/librefkernels.so not built")
+    orc = Oracle(kind)
+    for half in range(2):
+        wl = make_workload(ori_size=32, healpix_order=1, n_particles=150, nr_classes=1, seed=40 + half, snr=0.5)
+        _setup(device, wl)
+        device.expectation_some_particles(wl.pool)
+        gre, gim, gw = device.bp_get(0)
+        refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
+        bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
+        st, _, _ = orc.estep_pool(wl.model, wl.sampling, refs, bps, wl.pool, num_threads=0, exact_threshold=(kind == "port"))
+        assert st == 0
+        ours = rc.reconstruct(gre, gim, gw, wl.model.ori_size, wl.r_max, wl.padding_factor)
+        want = rc.reconstruct(bps[0].real, bps[0].imag, bps[0].weight, wl.model.ori_size, wl.r_max, wl.padding_factor)
+        f = rc.fsc(ours, want)
+        assert f.shape[0] == wl.model.ori_size // 2 + 1
+        assert f.min() >= 0.995, (half, f)

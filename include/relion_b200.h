@@ -247,6 +247,13 @@ int rb_diff2_coarse(rb_ctx *ctx, int iclass, int img_size,
                     const float *img_re, const float *img_im, const float *corr,
                     float *diff2s);
 
+/* The coarse-pass contraction of GLOBAL searches, exposed for parity tests: C[M][N] = A[M][K] . B[N][K]^T on the
+ * tcgen05 tensor cores with 3xTF32 operand splitting (FP32-equivalent accuracy; north_star "tensor cores are used
+ * only for the coarse-pass cross term Re<X_t, CTF*A_r>").  Inside rb_estep_pool the same kernel computes
+ * cuda_kernel_diff2_coarse (diff2.cuh:24-189) for every particle of a pool at once when the pool has no
+ * per-particle orientation lists.  Environment RB_COARSE_GEMM=0 forces the SIMT kernel, 2 forces the tensor path. */
+int rb_gemm_tf32x3(rb_ctx *ctx, const float *A, const float *B, int M, int N, int K, float *C);
+
 /* runDiff2KernelFine (acc_helper_functions_impl.h:1813) with the reference's job lists */
 int rb_diff2_fine(rb_ctx *ctx, int iclass, int img_size,
                   const float *eulers, int n_orient,

@@ -126,6 +126,7 @@ PROTOTYPES = {
     "rb_project": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p]),
     "rb_diff2_coarse": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                   c_float_p, c_float_p, c_float_p, c_float_p]),
+    "rb_gemm_tf32x3": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p]),
     "rb_diff2_fine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                 c_float_p, c_float_p, c_float_p, C.c_float,
                                 c_u64_p, c_u64_p, c_u64_p, c_u64_p, C.c_int, c_float_p, C.c_int]),

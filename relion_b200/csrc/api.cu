@@ -90,13 +90,14 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->bp_buf[i].release(); }
+	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->proj2_buf[i].release(); ctx->bp_buf[i].release(); }
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp};
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
+	for (auto &b : ctx->gemm_buf) b.release();
 	for (int i = 0; i < RB_NUM_SLOTS; i++) release_slot(ctx->slot[i]);
 	for (auto &kv : ctx->stage_ev) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	cudaStreamDestroy(ctx->stream);
@@ -177,9 +178,11 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
 	RB_CHECK(ctx->proj_buf[k].ensure(n * sizeof(float2)));
 	RB_CHECK(ctx->proj8_buf[k].ensure(n * 4 * sizeof(float4)));
+	RB_CHECK(ctx->proj2_buf[k].ensure(n * sizeof(float4)));
 	RbProjector &p = ctx->proj[k];
 	p.mdl = ctx->proj_buf[k].as<float2>();
 	p.mdl8 = ctx->proj8_buf[k].as<float4>();
+	p.mdl2 = ctx->proj2_buf[k].as<float4>();
 	p.mdlX = mdlX; p.mdlY = mdlY; p.mdlZ = mdlZ; p.mdlXY = mdlX * mdlY;
 	p.mdlInitY = initY; p.mdlInitZ = initZ; p.mdlMaxR = maxR; p.padding_factor = (float) pf;
 	ctx->has_proj[k] = true;
@@ -194,7 +197,7 @@ extern "C" int rb_set_reference(rb_ctx *ctx, int k, const double *vol, int mdlX,
 	RB_CHECK(ctx->scratch[2].ensure(n * 2 * sizeof(double)));
 	RB_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, vol, n * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
 	RB_CHECK(rbk_convert_volume(ctx, ctx->scratch[2].as<double>(), ctx->proj_buf[k].as<float2>(), n));
-	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>()));
+	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>(), ctx->proj2_buf[k].as<float4>()));
 	RB_CHECK(rb_sync_tables(ctx));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->scratch[2].release();
@@ -207,7 +210,7 @@ extern "C" int rb_set_reference_f32(rb_ctx *ctx, int k, const float *vol, int md
 	RB_CHECK(set_reference_common(ctx, k, mdlX, mdlY, mdlZ, initY, initZ, maxR, pf));
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
 	RB_CUDA(cudaMemcpyAsync(ctx->proj_buf[k].p, vol, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
-	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>()));
+	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>(), ctx->proj2_buf[k].as<float4>()));
 	RB_CHECK(rb_sync_tables(ctx));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return RB_OK;
@@ -767,6 +770,21 @@ extern "C" int rb_project(rb_ctx *ctx, int k, int n, const float *eulers, int co
 	RB_CHECK(sb.up((const float2 *) nullptr, np * count, &d_o));
 	RB_CHECK(rbk_project(ctx, ctx->proj[k], n, d_e, count, d_o));
 	RB_CUDA(cudaMemcpyAsync(out_complex, d_o, np * count * sizeof(float2), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
+extern "C" int rb_gemm_tf32x3(rb_ctx *ctx, const float *A, const float *B, int M, int N, int K, float *Cout)
+{
+	RB_ARG(ctx && A && B && Cout, "rb_gemm_tf32x3: NULL argument");
+	RB_ARG(M > 0 && N > 0 && K > 0, "rb_gemm_tf32x3: empty problem %d x %d x %d", M, N, K);
+	RB_CUDA(cudaSetDevice(ctx->device));
+	StageBufs sb(ctx);
+	float *d_a, *d_b, *d_c;
+	RB_CHECK(sb.up(A, (size_t) M * K, &d_a)); RB_CHECK(sb.up(B, (size_t) N * K, &d_b));
+	RB_CHECK(sb.up((const float *) nullptr, (size_t) M * N, &d_c));
+	RB_CHECK(rbk_gemm_tf32x3_stage(ctx, d_a, d_b, M, N, K, d_c));
+	RB_CUDA(cudaMemcpyAsync(Cout, d_c, (size_t) M * N * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return RB_OK;
 }

@@ -48,6 +48,9 @@ struct RbProjector {
 	// neighbourhood-expanded copy: per voxel its 2x2x2 trilinear cell (8 x (re,im) = 64 B, 64-B aligned), so a
 	// sample at an arbitrary position costs exactly two 32-B sectors instead of the 4-8 a compact layout touches
 	const float4 *mdl8;
+	// x-pair copy: per voxel (v[x], v[x+1]) as one aligned 16-byte word (2x the memory): the coarse pass, whose working
+	// set has to stay in L2, gathers a trilinear sample with four 16-byte loads instead of eight 8-byte ones
+	const float4 *mdl2;
 	int mdlX, mdlY, mdlZ;
 	int mdlXY;
 	int mdlInitY, mdlInitZ;
@@ -188,6 +191,7 @@ struct rb_ctx {
 	RbProjector proj[RB_MAX_CLASSES];
 	DevBuf proj_buf[RB_MAX_CLASSES];
 	DevBuf proj8_buf[RB_MAX_CLASSES];
+	DevBuf proj2_buf[RB_MAX_CLASSES];
 	RbBackprojector bp[RB_MAX_CLASSES];
 	DevBuf bp_buf[RB_MAX_CLASSES];
 	bool has_proj[RB_MAX_CLASSES] = {false}, has_bp[RB_MAX_CLASSES] = {false};
@@ -210,6 +214,7 @@ struct rb_ctx {
 	// stage timing
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
 	DevBuf scratch[8];
+	DevBuf gemm_buf[10];             // operands of the tensor-core coarse pass (kernels_gemm.cu)
 };
 
 int rb_stage_begin(rb_ctx *ctx, const char *name);
@@ -222,7 +227,7 @@ int rb_sync_tables(rb_ctx *ctx);   // refresh d_proj / d_bp device tables
 // kernels_misc.cu
 int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt, const float *d_psi, int n_dir, int n_psi, float *d_eulers);
 int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
-int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out);
+int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
 int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out);
 
@@ -239,6 +244,11 @@ int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float 
                          const unsigned long long *d_rot_idx, const unsigned long long *d_trans_idx,
                          const unsigned long long *d_job_idx, const unsigned long long *d_job_num, int n_jobs,
                          float *d_out);
+
+// kernels_gemm.cu: global-search coarse pass as a 3xTF32 tcgen05 contraction
+bool rbk_coarse_gemm_applicable(rb_ctx *ctx, const PoolSlot &s);
+int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4);
+int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int M, int N, int K, float *dC);
 
 // kernels_weights.cu
 int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s);

@@ -116,6 +116,40 @@ __device__ __forceinline__ float2 rb_project3d(const RbProjK &k, int x, int y,
 	return r;
 }
 
+// Same sample from the x-pair copy (RbProjector::mdl2): four aligned 16-byte loads, one per (z, y) corner row.
+// Arithmetic identical to rb_project3d.
+__device__ __forceinline__ float2 rb_project3d_xp(const RbProjK &k, const float4 *mdl2, int x, int y,
+                                                  float e0, float e1, float e3, float e4, float e6, float e7)
+{
+	float xp = (e0 * x + e1 * y) * k.pf;
+	float yp = (e3 * x + e4 * y) * k.pf;
+	float zp = (e6 * x + e7 * y) * k.pf;
+	int r2 = (int) (xp * xp + yp * yp + zp * zp);
+	if (r2 > k.maxR2_padded) return make_float2(0.f, 0.f);
+	const bool inv = xp < 0.f;
+	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+	const float fx = xp - fx0, fy = yp - fy0, fz = zp - fz0;
+	const int x0 = (int) fx0, y0 = (int) fy0, z0 = (int) fz0;
+	const float4 *b = mdl2 + ((size_t) (z0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) (y0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) x0);
+	const float4 q0 = __ldg(b), q1 = __ldg(b + k.mdlX), q2 = __ldg(b + k.mdlXY), q3 = __ldg(b + k.mdlXY + k.mdlX);
+	float2 r;
+	{
+		float dx00 = q0.x + (q0.z - q0.x) * fx, dx10 = q1.x + (q1.z - q1.x) * fx;
+		float dx01 = q2.x + (q2.z - q2.x) * fx, dx11 = q3.x + (q3.z - q3.x) * fx;
+		float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy;
+		r.x = dxy0 + (dxy1 - dxy0) * fz;
+	}
+	{
+		float dx00 = q0.y + (q0.w - q0.y) * fx, dx10 = q1.y + (q1.w - q1.y) * fx;
+		float dx01 = q2.y + (q2.w - q2.y) * fx, dx11 = q3.y + (q3.w - q3.y) * fx;
+		float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy;
+		r.y = dxy0 + (dxy1 - dxy0) * fz;
+	}
+	if (inv) r.y = -r.y;
+	return r;
+}
+
 // Same sample from the neighbourhood-expanded volume (RbProjector::mdl8): four aligned 16-byte loads that cover
 // exactly two 32-byte sectors.  Arithmetic identical to rb_project3d.
 struct RbProjK8 {

@@ -11,6 +11,7 @@
 // compact reference.  A quad-per-row variant with separable phases (as in the fine pass) was measured slower here
 // (16.2 ms vs 10.6 ms for the headline pool): with only ~30 translations the 4x redundant coordinate math dominates.
 #include "img_src.cuh"
+#include <cstdlib>
 
 // phase tables for a chunk of translations: tab_x[t][x] = (cos, sin)(x*tx), tab_y[t][y+yoff] = (cos, sin)(y*ty)
 // (computeSincosLookupTable2D, cpu_kernels/helper.h:622-660; negative y uses cos(-a)=cos a, sin(-a)=-sin a)
@@ -81,7 +82,7 @@ struct CoarseArgs {
 	int tiles_per_class;           // CTAs per class (tiles never straddle classes)
 };
 
-template <int CO_EO, int CO_TT>
+template <int CO_EO, int CO_TT, bool XP>
 __global__ void __launch_bounds__(CO_THREADS)
 k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 {
@@ -136,6 +137,7 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 
 	const float4 *img = A.img4 + (size_t) p * A.n * imgX;
 	const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
+	const float4 *mdl2 = A.projs[cls].mdl2;   // nullptr in stage mode with a caller-supplied projector copy
 
 	float bmin = FLT_MAX;
 	for (int t0 = 0; t0 < A.T; t0 += CO_TT)
@@ -162,8 +164,10 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 #pragma unroll
 			for (int e = 0; e < CO_EO; e++)
 			{
-				const float2 ref = s_valid[e] ? rb_project3d(pk, x, y, s_e[e][0], s_e[e][1], s_e[e][2], s_e[e][3], s_e[e][4], s_e[e][5])
-				                              : make_float2(0.f, 0.f);
+				float2 ref = make_float2(0.f, 0.f);
+				if (s_valid[e])
+					ref = XP ? rb_project3d_xp(pk, mdl2, x, y, s_e[e][0], s_e[e][1], s_e[e][2], s_e[e][3], s_e[e][4], s_e[e][5])
+					         : rb_project3d(pk, x, y, s_e[e][0], s_e[e][1], s_e[e][2], s_e[e][3], s_e[e][4], s_e[e][5]);
 				zr[e] = hc * (ref.x * im.x + ref.y * im.y);
 				zi[e] = hc * (ref.x * im.y - ref.y * im.x);
 				base[e] += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
@@ -218,28 +222,36 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 	}
 }
 
-template <int EO, int TT>
+template <int EO, int TT, bool XP>
 static int launch_coarse_cfg(rb_ctx *ctx, CoarseArgs &A, int no_max, int n_classes, int P)
 {
 	size_t sm = (size_t) TT * ((A.n / 2 + 1) + A.ny) * sizeof(float2);
 	static size_t configured = 0;
 	if (sm > configured)
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_diff2_coarse<EO, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+		RB_CUDA(cudaFuncSetAttribute(k_diff2_coarse<EO, TT, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
 		configured = sm;
 	}
 	A.tiles_per_class = (no_max + EO - 1) / EO;
 	dim3 grid(A.tiles_per_class * n_classes, P);
-	k_diff2_coarse<EO, TT><<<grid, CO_THREADS, sm, ctx->stream>>>(A, ctx->d_model, ctx->d_samp);
+	k_diff2_coarse<EO, TT, XP><<<grid, CO_THREADS, sm, ctx->stream>>>(A, ctx->d_model, ctx->d_samp);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
 
 static int launch_coarse(rb_ctx *ctx, CoarseArgs &A, int no_max, int n_classes, int P)
 {
-	if (A.T <= 12) return launch_coarse_cfg<8, 12>(ctx, A, no_max, n_classes, P);
-	if (A.T <= 24) return launch_coarse_cfg<4, 24>(ctx, A, no_max, n_classes, P);
-	return launch_coarse_cfg<3, 32>(ctx, A, no_max, n_classes, P);
+	static int xp = -1;
+	if (xp < 0) { const char *e = getenv("RB_COARSE_XP"); xp = e ? atoi(e) : 1; }
+	if (xp)
+	{
+		if (A.T <= 12) return launch_coarse_cfg<8, 12, true>(ctx, A, no_max, n_classes, P);
+		if (A.T <= 24) return launch_coarse_cfg<4, 24, true>(ctx, A, no_max, n_classes, P);
+		return launch_coarse_cfg<3, 32, true>(ctx, A, no_max, n_classes, P);
+	}
+	if (A.T <= 12) return launch_coarse_cfg<8, 12, false>(ctx, A, no_max, n_classes, P);
+	if (A.T <= 24) return launch_coarse_cfg<4, 24, false>(ctx, A, no_max, n_classes, P);
+	return launch_coarse_cfg<3, 32, false>(ctx, A, no_max, n_classes, P);
 }
 
 __global__ void k_fill(float *p, float v, size_t n)
@@ -265,6 +277,9 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 	dim3 pg((M.nrows_c * xsc + 255) / 256, s.P);
 	k_prep_img4<<<pg, 256, 0, ctx->stream>>>(PA, M);
 	RB_LAUNCH_CHECK(ctx);
+
+	// global searches: the cross term is a dense contraction shared by the whole pool -> tensor cores
+	if (rbk_coarse_gemm_applicable(ctx, s)) return rbk_diff2_coarse_gemm_pool(ctx, s, s.cimg4.as<float4>());
 
 	CoarseArgs A;
 	memset(&A, 0, sizeof(A));

@@ -1,0 +1,538 @@
+// relion_b200 — coarse-pass cross term on the 5th-generation tensor cores (sm_100a: tcgen05 + TMEM + TMA).
+//
+// In GLOBAL searches every particle of a pool is compared with the same orientation grid, so the cross term of the
+// coarse squared difference (cuda_kernel_diff2_coarse, /root/reference/src/acc/cuda/cuda_kernels/diff2.cuh:24-189)
+//
+//     diff2[p][o][t] = sum_pix c_p (|A_o|^2 + |X'_p|^2)  -  2 Re sum_pix conj(A_o) . (c_p X'_p e^{i phi_t})
+//
+// is a dense real contraction  D[o][(p,t)] = sum_k A[o][k] B[(p,t)][k]  with
+//     A[o][2i], A[o][2i+1]   = Re, Im of the projected reference at valid pixel i            (M = orientations)
+//     B[n][2i], B[n][2i+1]   = Re, Im of c_p X'_p e^{i phi_t} at valid pixel i, n = p*T + t   (N = particles x translations)
+// and the norm term is a second, T times smaller contraction  base[o][p] = sum_i |A_o(i)|^2 c_p(i).
+// (CTF, scale and sigma2 weights are real per pixel, so they fold into the particle operand.)
+//
+// FP32-equivalent accuracy on tensor cores: every operand is split into a TF32 "hi" part and a TF32 "lo" remainder
+// (v = hi + lo to ~22 bits) and three MMAs accumulate hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator
+// ("3xTF32"); the dropped lo*lo term is ~2^-22 relative.  tests/test_gpu_parity.py::test_gemm_tf32x3 holds the kernel
+// to 2e-6 of sum|a||b| against float64.
+//
+// Kernel: one CTA per 128 x 256 output tile.  Warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, mbarrier
+// complete_tx), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M128 N256 K8, accumulator in
+// 256 TMEM columns), warps 2-5 = epilogue (tcgen05.ld 32x32b.x32 -> registers -> diff2 -> Mweight).  Two smem stages of
+// 96 KB (A_hi, A_lo 16 KB each; B_hi, B_lo 32 KB each) per K-block of 32.
+#include "img_src.cuh"
+#include <cuda.h>
+#include <cstdlib>
+
+static const int GM_BM = 128, GM_BN = 256, GM_BK = 32, GM_STAGES = 2;
+static const int GM_THREADS = 192;
+static const uint32_t GM_A_BYTES = GM_BM * GM_BK * 4, GM_B_BYTES = GM_BN * GM_BK * 4;
+static const uint32_t GM_STAGE_BYTES = 2 * GM_A_BYTES + 2 * GM_B_BYTES;
+static const size_t GM_SMEM = (size_t) GM_STAGES * GM_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+	asm volatile(
+		"{\n\t.reg .pred P1;\n\t"
+		"WAIT_LOOP:\n\t"
+		"mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+		"@P1 bra DONE;\n\t"
+		"bra WAIT_LOOP;\n\t"
+		"DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+	             ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit(uint32_t bar)
+{
+	asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+		::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+	             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+	               "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+	               "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+	               "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+	             : "r"(taddr));
+	asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile in shared memory, 128-byte swizzle (what TMA writes with CU_TENSOR_MAP_SWIZZLE_128B): rows of
+// 128 bytes, 8-row groups 1024 bytes apart.  Descriptor fields (PTX ISA "tcgen05 shared memory descriptor"):
+// start address >> 4 [0,14), leading byte offset >> 4 [16,30) (unused for swizzled K-major, 1), stride byte offset >> 4
+// [32,46) = 1024 >> 4, version 1 at [46,48), layout type SWIZZLE_128B = 2 at [61,64).
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
+{
+	uint64_t d = 0;
+	d |= (uint64_t) ((smem_addr & 0x3FFFF) >> 4);
+	d |= (uint64_t) 1 << 16;
+	d |= (uint64_t) (1024 >> 4) << 32;
+	d |= (uint64_t) 1 << 46;
+	d |= (uint64_t) 2 << 61;
+	return d;
+}
+
+// instruction descriptor, kind::tf32: D fp32 (1 @ [4,6)), A/B TF32 (2 @ [7,10), [10,13)), both K-major, N >> 3 @ [17,23),
+// M >> 4 @ [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
+{
+	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+
+__device__ __forceinline__ float tf32_round(float v)
+{
+	uint32_t r;
+	asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+	return __uint_as_float(r);
+}
+__device__ __forceinline__ void tf32_split(float v, float &hi, float &lo)
+{
+	hi = tf32_round(v);
+	lo = tf32_round(v - hi);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the GEMM
+// ---------------------------------------------------------------------------------------------
+struct GemmEpilogue {
+	int mode;                 // 0: C[m*ldc + n] = D;  1: coarse diff2 into Mweight
+	// mode 0
+	float *C; int ldc;
+	// mode 1
+	const RbPartMeta *metas; RbPartState *states;
+	const unsigned char *pdf_orient_zero;
+	float *Mweight;
+	const float *base; int ldbase;   // [o][p] norm term
+	const float *x2;                 // [p] sum c |X'|^2
+	int T, P, O, cls, o_first;       // o_first: first orientation of this M chunk
+	// common
+	int M, N;                        // valid extent of this launch (rows of the chunk, columns)
+};
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+              const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+              int num_kblocks, GemmEpilogue E)
+{
+	extern __shared__ uint8_t gm_smem_raw[];
+	const uint32_t raw = smem_u32(gm_smem_raw);
+	const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-byte aligned (128-byte swizzle atom)
+	const uint32_t bars = tiles + GM_STAGES * GM_STAGE_BYTES;            // full[stages], empty[stages], tmem_full, tmem slot
+	uint8_t *bars_generic = gm_smem_raw + (bars - raw);
+	const uint32_t full0 = bars, empty0 = bars + 8 * GM_STAGES, tmem_full = bars + 16 * GM_STAGES, tmem_slot = tmem_full + 8;
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+
+	if (warp == 0 && lane == 0)
+	{
+		for (int s = 0; s < GM_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+		mbar_init(tmem_full, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1)
+	{
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem_base = *(volatile uint32_t *) (bars_generic + 16 * GM_STAGES + 8);
+
+	if (warp == 0)
+	{
+		if (lane == 0)
+		{
+			for (int kb = 0; kb < num_kblocks; kb++)
+			{
+				const int s = kb % GM_STAGES;
+				const uint32_t ph = (kb / GM_STAGES) & 1;
+				mbar_wait(empty0 + 8 * s, ph ^ 1);                       // slot free (first round passes immediately)
+				const uint32_t st = tiles + s * GM_STAGE_BYTES;
+				mbar_expect_tx(full0 + 8 * s, GM_STAGE_BYTES);
+				tma_load_2d(st, &tmAhi, full0 + 8 * s, kb * GM_BK, m_tile * GM_BM);
+				tma_load_2d(st + GM_A_BYTES, &tmAlo, full0 + 8 * s, kb * GM_BK, m_tile * GM_BM);
+				tma_load_2d(st + 2 * GM_A_BYTES, &tmBhi, full0 + 8 * s, kb * GM_BK, n_tile * GM_BN);
+				tma_load_2d(st + 2 * GM_A_BYTES + GM_B_BYTES, &tmBlo, full0 + 8 * s, kb * GM_BK, n_tile * GM_BN);
+			}
+		}
+	}
+	else if (warp == 1)
+	{
+		if (lane == 0)
+		{
+			const uint32_t idesc = umma_idesc_tf32(GM_BM, GM_BN);
+			for (int kb = 0; kb < num_kblocks; kb++)
+			{
+				const int s = kb % GM_STAGES;
+				const uint32_t ph = (kb / GM_STAGES) & 1;
+				mbar_wait(full0 + 8 * s, ph);                            // TMA bytes have landed
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				const uint32_t st = tiles + s * GM_STAGE_BYTES;
+				const uint64_t ahi = umma_desc_k_sw128(st), alo = umma_desc_k_sw128(st + GM_A_BYTES);
+				const uint64_t bhi = umma_desc_k_sw128(st + 2 * GM_A_BYTES), blo = umma_desc_k_sw128(st + 2 * GM_A_BYTES + GM_B_BYTES);
+#pragma unroll
+				for (int ks = 0; ks < GM_BK / 8; ks++)
+				{
+					const uint64_t adv = (uint64_t) ((ks * 8 * 4) >> 4);  // 32 bytes per K step inside the swizzle atom
+					tcgen05_mma_tf32(tmem_base, alo + adv, bhi + adv, idesc, (kb | ks) != 0);
+					tcgen05_mma_tf32(tmem_base, ahi + adv, blo + adv, idesc, 1);
+					tcgen05_mma_tf32(tmem_base, ahi + adv, bhi + adv, idesc, 1);
+				}
+				tcgen05_commit(empty0 + 8 * s);                          // frees the smem slot when these MMAs retire
+			}
+			tcgen05_commit(tmem_full);                                   // accumulator complete
+		}
+	}
+	else
+	{
+		// epilogue warps 2..5: TMEM lanes 32*(warp%4) .. +31 <-> rows of the tile
+		const int q = warp & 3;
+		const int row = m_tile * GM_BM + q * 32 + lane;
+		mbar_wait(tmem_full, 0);
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+		const uint32_t trow = tmem_base + ((uint32_t) (q * 32) << 16);
+		const int n0 = n_tile * GM_BN;
+		if (E.mode == 0)
+		{
+			for (int c = 0; c < GM_BN / 32; c++)
+			{
+				uint32_t v[32];
+				tmem_ld32(trow + c * 32, v);
+				if (row < E.M)
+				{
+#pragma unroll
+					for (int j = 0; j < 32; j++)
+					{
+						const int n = n0 + c * 32 + j;
+						if (n < E.N) E.C[(size_t) row * E.ldc + n] = __uint_as_float(v[j]);
+					}
+				}
+			}
+		}
+		else
+		{
+			// column n = p*T + t.  All lanes of a warp walk the same columns, so particle boundaries are warp-uniform:
+			// one warp-reduced atomicMin per (warp, particle).
+			const int o = E.o_first + row;                               // orientation within the class
+			const bool row_ok = row < E.M;
+			int p = n0 / E.T, t = n0 - p * E.T;
+			float bmin = FLT_MAX;
+			bool pvalid = false; float bsum = 0.f, xi2 = 0.f; long long woff = 0;
+			auto load_particle = [&](int pp)
+			{
+				pvalid = false;
+				if (pp < E.P && row_ok)
+				{
+					const RbPartMeta m = E.metas[pp];
+					const long long oc = (long long) E.cls * E.O + o;
+					pvalid = !E.pdf_orient_zero[m.prior_off + oc];
+					bsum = E.base[(size_t) row * E.ldbase + pp] + E.x2[pp];
+					xi2 = m.xi2_half;
+					woff = m.coarse_off + oc * E.T;
+				}
+			};
+			auto flush_min = [&](int pp)
+			{
+				const float wm = -warp_max(-bmin);
+				if (lane == 0 && pp < E.P && wm < FLT_MAX) rb_atomic_min_pos(&E.states[pp].min_diff2_bits, wm);
+				bmin = FLT_MAX;
+			};
+			load_particle(p);
+			for (int c = 0; c < GM_BN / 32; c++)
+			{
+				uint32_t v[32];
+				tmem_ld32(trow + c * 32, v);
+#pragma unroll
+				for (int j = 0; j < 32; j++)
+				{
+					if (pvalid)
+					{
+						const float d = fmaxf(bsum - 2.f * __uint_as_float(v[j]), 0.f) + xi2;     // diff2.cuh:170-186, :1290-1296
+						E.Mweight[woff + t] = d;
+						bmin = fminf(bmin, d);
+					}
+					if (++t == E.T) { flush_min(p); t = 0; p++; load_particle(p); }
+				}
+			}
+			flush_min(p);
+		}
+		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	}
+	__syncthreads();
+	if (warp == 1)
+	{
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static int make_tmap(CUtensorMap *map, const float *base, size_t rows, size_t kpad, int box_rows)
+{
+	static PFN_encodeTiled fn = nullptr;
+	if (!fn)
+	{
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult qr;
+		RB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr));
+		if (!p || qr != cudaDriverEntryPointSuccess) { rb_set_error("cuTensorMapEncodeTiled not available from the driver"); return RB_ERR_CUDA; }
+		fn = (PFN_encodeTiled) p;
+	}
+	const cuuint64_t dims[2] = {(cuuint64_t) kpad, (cuuint64_t) rows};
+	const cuuint64_t strides[1] = {(cuuint64_t) kpad * sizeof(float)};
+	const cuuint32_t box[2] = {(cuuint32_t) GM_BK, (cuuint32_t) box_rows};
+	const cuuint32_t estr[2] = {1, 1};
+	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) { rb_set_error("cuTensorMapEncodeTiled failed (%d) rows=%zu kpad=%zu", (int) r, rows, kpad); return RB_ERR_CUDA; }
+	return RB_OK;
+}
+
+static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// A_hi/A_lo: [Mpad][Kpad], B_hi/B_lo: [Npad][Kpad] (Mpad % 128 == 0, Npad % 256 == 0, Kpad % 32 == 0, zero padded)
+static int launch_gemm(rb_ctx *ctx, const float *Ahi, const float *Alo, size_t Mpad, const float *Bhi, const float *Blo, size_t Npad,
+                       size_t Kpad, const GemmEpilogue &E)
+{
+	CUtensorMap ta, tal, tb, tbl;
+	RB_CHECK(make_tmap(&ta, Ahi, Mpad, Kpad, GM_BM)); RB_CHECK(make_tmap(&tal, Alo, Mpad, Kpad, GM_BM));
+	RB_CHECK(make_tmap(&tb, Bhi, Npad, Kpad, GM_BN)); RB_CHECK(make_tmap(&tbl, Blo, Npad, Kpad, GM_BN));
+	static bool configured = false;
+	if (!configured)
+	{
+		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GM_SMEM));
+		configured = true;
+	}
+	dim3 grid((unsigned) (Npad / GM_BN), (unsigned) (Mpad / GM_BM));
+	k_gemm_tf32x3<<<grid, GM_THREADS, GM_SMEM, ctx->stream>>>(ta, tal, tb, tbl, (int) (Kpad / GM_BK), E);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// operand builders
+// ---------------------------------------------------------------------------------------------
+// generic split of a row-major [rows][cols] fp32 matrix into zero-padded hi/lo [rows_pad][kpad]
+__global__ void k_split_pad(const float *src, int rows, int cols, float *hi, float *lo, size_t rows_pad, size_t kpad)
+{
+	const size_t n = rows_pad * kpad;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const size_t r = i / kpad, c = i - r * kpad;
+		float h = 0.f, l = 0.f;
+		if (r < (size_t) rows && c < (size_t) cols) tf32_split(src[r * cols + c], h, l);
+		hi[i] = h; lo[i] = l;
+	}
+}
+
+// A operands of one class for orientations [o_first, o_first + rows): projections at the coarse window
+// (AccProjectorKernel::project3Dmodel, acc_projectorkernel_impl.h:161-231), interleaved (re, im) per valid pixel, and
+// their squared moduli for the norm term.
+__global__ void __launch_bounds__(256)
+k_gemm_build_A(RbProjector pj, const float *coarse_eulers, const uint32_t *pix, int npix, int n, int o_first, int rows, int rows_pad,
+               float *Ahi, float *Alo, size_t kpad, float *A2hi, float *A2lo, size_t k2pad)
+{
+	const int r = blockIdx.y;
+	const int imgX = n / 2 + 1;
+	const RbProjK pk = rb_make_projk(pj, imgX);
+	const bool live = r < rows;
+	float e0 = 0, e1 = 0, e3 = 0, e4 = 0, e6 = 0, e7 = 0;
+	if (live)
+	{
+		const float *eu = coarse_eulers + (size_t) (o_first + r) * 9;
+		e0 = eu[0]; e1 = eu[1]; e3 = eu[3]; e4 = eu[4]; e6 = eu[6]; e7 = eu[7];
+	}
+	const int half = (int) (kpad / 2);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < half; i += gridDim.x * blockDim.x)
+	{
+		float2 ref = make_float2(0.f, 0.f);
+		if (live && i < npix)
+		{
+			const uint32_t pkx = __ldg(pix + i);
+			ref = rb_project3d_xp(pk, pj.mdl2, rb_pix_x(pkx), rb_pix_y(pkx), e0, e1, e3, e4, e6, e7);
+		}
+		float2 h, l;
+		tf32_split(ref.x, h.x, l.x); tf32_split(ref.y, h.y, l.y);
+		*(float2 *) (Ahi + (size_t) r * kpad + 2 * i) = h;
+		*(float2 *) (Alo + (size_t) r * kpad + 2 * i) = l;
+		if ((size_t) i < k2pad)
+		{
+			float h2, l2;
+			tf32_split(ref.x * ref.x + ref.y * ref.y, h2, l2);
+			A2hi[(size_t) r * k2pad + i] = h2; A2lo[(size_t) r * k2pad + i] = l2;
+		}
+	}
+}
+
+// B operands of the pool: column n = p*T + t holds c_p X'_p e^{i phi_t} over the valid pixels (translatePixel with the
+// table factorisation of computeSincosLookupTable2D, cpu_kernels/helper.h:622-660); B2 row p holds c_p; x2[p] = sum c |X'|^2.
+__global__ void __launch_bounds__(256)
+k_gemm_build_B(const float4 *img4, const uint32_t *pix, int npix, int n, const float *tx, const float *ty, int T, int P,
+               float *Bhi, float *Blo, size_t kpad, float *B2hi, float *B2lo, size_t k2pad, float *x2)
+{
+	__shared__ float red[32];
+	const int col = blockIdx.x;                  // 0 .. Npad-1
+	const int p = col / T, t = col - p * T;
+	const bool live = p < P;
+	const int imgX = n / 2 + 1;
+	const float4 *img = img4 + (size_t) (live ? p : 0) * n * imgX;
+	const float ttx = live ? tx[t] : 0.f, tty = live ? ty[t] : 0.f;
+	const int half = (int) (kpad / 2);
+	float acc = 0.f;
+	for (int i = threadIdx.x; i < half; i += blockDim.x)
+	{
+		float2 y = make_float2(0.f, 0.f);
+		float hc = 0.f;
+		if (live && i < npix)
+		{
+			const uint32_t pkx = __ldg(pix + i);
+			const int x = rb_pix_x(pkx), yy = rb_pix_y(pkx);
+			const float4 im = __ldg(img + rb_src_index(x, yy, n));
+			hc = im.z;
+			float sx, cx, sy, cy;
+			sincosf(x * ttx, &sx, &cx);
+			sincosf((yy < 0 ? -yy : yy) * tty, &sy, &cy);
+			if (yy < 0) sy = -sy;
+			const float ss = sx * cy + cx * sy, cc = cx * cy - sx * sy;
+			y.x = hc * (im.x * cc - im.y * ss);
+			y.y = hc * (im.y * cc + im.x * ss);
+			if (t == 0) acc += hc * (im.x * im.x + im.y * im.y);
+		}
+		float2 h, l;
+		tf32_split(y.x, h.x, l.x); tf32_split(y.y, h.y, l.y);
+		*(float2 *) (Bhi + (size_t) col * kpad + 2 * i) = h;
+		*(float2 *) (Blo + (size_t) col * kpad + 2 * i) = l;
+		if (t == 0 && live && (size_t) i < k2pad)
+		{
+			float h2, l2;
+			tf32_split(hc, h2, l2);
+			B2hi[(size_t) p * k2pad + i] = h2; B2lo[(size_t) p * k2pad + i] = l2;
+		}
+	}
+	if (t == 0 && live)
+	{
+		acc = block_sum(acc, red);
+		if (threadIdx.x == 0) x2[p] = acc;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// pool driver: global-search coarse pass on the tensor cores
+// ---------------------------------------------------------------------------------------------
+bool rbk_coarse_gemm_applicable(rb_ctx *ctx, const PoolSlot &s)
+{
+	if (s.has_priors) return false;                       // local searches: per-particle orientation lists, no shared A
+	const char *e = getenv("RB_COARSE_GEMM");
+	const int mode = e ? atoi(e) : 1;                     // 0: never, 1: when the orientation grid is large enough, 2: always
+	if (mode == 0) return false;
+	const long long O = (long long) ctx->d_samp.n_dir * ctx->d_samp.n_psi;
+	return mode == 2 || O >= 256;
+}
+
+int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
+{
+	const RbModelDev &M = ctx->d_model;
+	const RbSamplingDev &S = ctx->d_samp;
+	const int P = s.P, T = S.n_trans, K = M.nr_classes;
+	const int O = S.n_dir * S.n_psi;
+	const int npix = M.nvc, n = M.coarse_size;
+	const size_t kpad = round_up((size_t) 2 * npix, GM_BK), k2pad = round_up((size_t) npix, GM_BK);
+	const size_t Npad = round_up((size_t) P * T, GM_BN), N2pad = round_up((size_t) P, GM_BN);
+	// orientation chunk: bounded operand memory (A and A2, hi + lo)
+	const size_t budget = (size_t) 6 << 30;
+	size_t mchunk = budget / ((kpad + k2pad) * 2 * sizeof(float));
+	mchunk = std::max<size_t>(GM_BM, mchunk / GM_BM * GM_BM);
+	mchunk = std::min<size_t>(mchunk, round_up((size_t) O, GM_BM));
+
+	DevBuf &bAhi = ctx->gemm_buf[0], &bAlo = ctx->gemm_buf[1], &bA2hi = ctx->gemm_buf[2], &bA2lo = ctx->gemm_buf[3];
+	DevBuf &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5], &bB2hi = ctx->gemm_buf[6], &bB2lo = ctx->gemm_buf[7];
+	DevBuf &bBase = ctx->gemm_buf[8], &bX2 = ctx->gemm_buf[9];
+	RB_CHECK(bAhi.ensure(mchunk * kpad * 4)); RB_CHECK(bAlo.ensure(mchunk * kpad * 4));
+	RB_CHECK(bA2hi.ensure(mchunk * k2pad * 4)); RB_CHECK(bA2lo.ensure(mchunk * k2pad * 4));
+	RB_CHECK(bBhi.ensure(Npad * kpad * 4)); RB_CHECK(bBlo.ensure(Npad * kpad * 4));
+	RB_CHECK(bB2hi.ensure(N2pad * k2pad * 4)); RB_CHECK(bB2lo.ensure(N2pad * k2pad * 4));
+	RB_CHECK(bBase.ensure(mchunk * N2pad * 4)); RB_CHECK(bX2.ensure(N2pad * 4));
+
+	// particle operands (independent of the class)
+	RB_CUDA(cudaMemsetAsync(bB2hi.p, 0, N2pad * k2pad * 4, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(bB2lo.p, 0, N2pad * k2pad * 4, ctx->stream));
+	k_gemm_build_B<<<(unsigned) Npad, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, P,
+		bBhi.as<float>(), bBlo.as<float>(), kpad, bB2hi.as<float>(), bB2lo.as<float>(), k2pad, bX2.as<float>());
+	RB_LAUNCH_CHECK(ctx);
+
+	for (int cls = 0; cls < K; cls++)
+		for (int o0 = 0; o0 < O; o0 += (int) mchunk)
+		{
+			const int rows = std::min<int>((int) mchunk, O - o0);
+			const int rows_pad = (int) round_up((size_t) rows, GM_BM);
+			dim3 ga((unsigned) std::min<size_t>((kpad / 2 + 255) / 256, 64), (unsigned) rows_pad);
+			k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[cls], S.coarse_eulers, M.pix_c, npix, n, o0, rows, rows_pad,
+				bAhi.as<float>(), bAlo.as<float>(), kpad, bA2hi.as<float>(), bA2lo.as<float>(), k2pad);
+			RB_LAUNCH_CHECK(ctx);
+			// norm term base[o][p]
+			GemmEpilogue E0;
+			memset(&E0, 0, sizeof(E0));
+			E0.mode = 0; E0.C = bBase.as<float>(); E0.ldc = (int) N2pad; E0.M = rows; E0.N = P;
+			RB_CHECK(launch_gemm(ctx, bA2hi.as<float>(), bA2lo.as<float>(), rows_pad, bB2hi.as<float>(), bB2lo.as<float>(), N2pad, k2pad, E0));
+			// cross term + diff2 epilogue
+			GemmEpilogue E1;
+			memset(&E1, 0, sizeof(E1));
+			E1.mode = 1; E1.metas = s.meta.as<RbPartMeta>(); E1.states = s.state.as<RbPartState>();
+			E1.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>(); E1.Mweight = s.Mweight.as<float>();
+			E1.base = bBase.as<float>(); E1.ldbase = (int) N2pad; E1.x2 = bX2.as<float>();
+			E1.T = T; E1.P = P; E1.O = O; E1.cls = cls; E1.o_first = o0; E1.M = rows; E1.N = P * T;
+			RB_CHECK(launch_gemm(ctx, bAhi.as<float>(), bAlo.as<float>(), rows_pad, bBhi.as<float>(), bBlo.as<float>(), Npad, kpad, E1));
+		}
+	return RB_OK;
+}
+
+// stage entry: C[M][N] = A[M][K] . B[N][K]^T in 3xTF32 (device pointers, row-major)
+int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int Mr, int Nr, int Kr, float *dC)
+{
+	const size_t Mpad = round_up((size_t) Mr, GM_BM), Npad = round_up((size_t) Nr, GM_BN), Kpad = round_up((size_t) Kr, GM_BK);
+	DevBuf &bAhi = ctx->gemm_buf[0], &bAlo = ctx->gemm_buf[1], &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5];
+	RB_CHECK(bAhi.ensure(Mpad * Kpad * 4)); RB_CHECK(bAlo.ensure(Mpad * Kpad * 4));
+	RB_CHECK(bBhi.ensure(Npad * Kpad * 4)); RB_CHECK(bBlo.ensure(Npad * Kpad * 4));
+	k_split_pad<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(dA, Mr, Kr, bAhi.as<float>(), bAlo.as<float>(), Mpad, Kpad);
+	RB_LAUNCH_CHECK(ctx);
+	k_split_pad<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(dB, Nr, Kr, bBhi.as<float>(), bBlo.as<float>(), Npad, Kpad);
+	RB_LAUNCH_CHECK(ctx);
+	GemmEpilogue E;
+	memset(&E, 0, sizeof(E));
+	E.mode = 0; E.C = dC; E.ldc = Nr; E.M = Mr; E.N = Nr;
+	return launch_gemm(ctx, bAhi.as<float>(), bAlo.as<float>(), Mpad, bBhi.as<float>(), bBlo.as<float>(), Npad, Kpad, E);
+}

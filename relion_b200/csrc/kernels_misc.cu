@@ -46,7 +46,7 @@ int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n)
 // Neighbourhood-expanded reference: out[4*v + {0,1,2,3}] = {(v000,v001), (v010,v011), (v100,v101), (v110,v111)} of voxel v,
 // zeros beyond the array edge.  8x the memory (4.4 GB per class at 256 px, 16.6 GB at 400 px — sized for 180 GB HBM3e),
 // in exchange every trilinear sample of the fine pass / store stage is one aligned 64-byte read.
-__global__ void k_expand_volume(RbProjector pj, float4 *out)
+__global__ void k_expand_volume(RbProjector pj, float4 *out, float4 *out2)
 {
 	const size_t n = (size_t) pj.mdlXY * pj.mdlZ;
 	for (size_t v = blockIdx.x * (size_t) blockDim.x + threadIdx.x; v < n; v += (size_t) gridDim.x * blockDim.x)
@@ -66,12 +66,13 @@ __global__ void k_expand_volume(RbProjector pj, float4 *out)
 		o[1] = make_float4(d010.x, d010.y, d011.x, d011.y);
 		o[2] = make_float4(d100.x, d100.y, d101.x, d101.y);
 		o[3] = make_float4(d110.x, d110.y, d111.x, d111.y);
+		out2[v] = make_float4(d000.x, d000.y, d001.x, d001.y);
 	}
 }
 
-int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out)
+int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2)
 {
-	k_expand_volume<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(pj, d_out);
+	k_expand_volume<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(pj, d_out, d_out2);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

@@ -15,6 +15,7 @@
 //    reduction (red.global.add.v4.f32) instead of three scalar atomics into three arrays; the two x
 //    neighbours of a corner pair share a 32-byte sector.
 #include "device_utils.cuh"
+#include <cstdlib>
 
 static const int ST_THREADS = 256;
 static const int ST_MAXSAMP = 2048;
@@ -146,28 +147,30 @@ struct StoreArgs {
 
 static const int ST_CHUNK = 256;   // significant samples held in shared memory at a time
 
+// What one lane keeps in flight per pixel.  SLICED: the reference sample comes from the slice the fine pass cached
+// (one streaming 8-byte read); otherwise it is gathered from the expanded reference again (64 bytes + lerp state).
+template <bool SLICED> struct StoreRef;
+template <> struct StoreRef<true> { float2 r; };
+template <> struct StoreRef<false> { RbProjFetch pf; };
+
+template <bool SLICED>
 struct StorePix {
-	RbProjFetch pf;
+	StoreRef<SLICED> ref;
 	float2 X, X0;
 	float ctf;
-	int x, y, ires;
+	uint32_t pkx;
 };
 
+template <bool SLICED>
 __device__ __forceinline__ void store_issue(const StoreArgs &A, const RbProjK8 &pk, const float2 *X, const float2 *X0,
                                             const float *C, const float2 *slice, float part_scale, int ip,
-                                            float e0, float e1, float e3, float e4, float e6, float e7, StorePix &f)
+                                            float e0, float e1, float e3, float e4, float e6, float e7, StorePix<SLICED> &f)
 {
-	const uint32_t pkx = __ldg(A.pix + ip);
-	f.x = rb_pix_x(pkx); f.y = rb_pix_y(pkx); f.ires = rb_pix_ires(pkx);
-	const int idx = rb_src_index(f.x, f.y, A.n);
-	if (slice)
-	{
-		// slice cached by the fine pass: one streaming 8-byte read instead of a 64-byte gather
-		const float2 r = __ldg(slice + idx);
-		f.pf.q0 = make_float4(r.x, r.y, 0.f, 0.f);
-		f.pf.flags = 4;
-	}
-	else rb_proj_issue(pk, f.x, f.y, e0, e1, e3, e4, e6, e7, f.pf);
+	f.pkx = __ldg(A.pix + ip);
+	const int x = rb_pix_x(f.pkx), y = rb_pix_y(f.pkx);
+	const int idx = rb_src_index(x, y, A.n);
+	if constexpr (SLICED) f.ref.r = __ldg(slice + idx);
+	else rb_proj_issue(pk, x, y, e0, e1, e3, e4, e6, e7, f.ref.pf);
 	f.X = __ldg(X + idx); f.X0 = __ldg(X0 + idx);
 	f.ctf = C ? __ldg(C + idx) * part_scale : part_scale;                                     // :3087-3096
 }
@@ -179,7 +182,11 @@ __device__ __forceinline__ void store_issue(const StoreArgs &A, const RbProjK8 &
 //   wdiff = W * (|ref|^2 + |X|^2) - 2 * XA               (= sum_t wn_t |ref - S_t X|^2)
 //   F     = g * X0 * Phi,  Fweight = W * g * ctf,  g = ctf * Minvsigma2   (BP.cuh:276-299)
 // so the per-sample work is one phase factor and two FMAs, and no sample count limit applies.
-__global__ void __launch_bounds__(ST_THREADS, 2)
+//
+// SLICED launches cover the fine orientations whose slice sits in the cache (w < slice_capacity), the gather variant
+// the rest; DEPTH pixels are kept in flight per lane (the stage is latency-bound: 8 scattered reductions per pixel).
+template <bool SLICED, int DEPTH, int MINB>
+__global__ void __launch_bounds__(ST_THREADS, MINB)
 k_store(StoreArgs A, RbModelDev M)
 {
 	__shared__ float s_ux[ST_CHUNK], s_uy[ST_CHUNK], s_wn[ST_CHUNK];
@@ -191,10 +198,13 @@ k_store(StoreArgs A, RbModelDev M)
 	__shared__ float s_shell[1024];
 
 	const int imgX = A.n / 2 + 1;
-	const int nwork = A.counters[0];
+	const int nfo = A.counters[0];
+	const long long cap = A.slices ? A.slice_capacity : 0;
+	const int w_begin = SLICED ? 0 : (int) (cap < nfo ? cap : nfo);
+	const int w_end = SLICED ? (int) (cap < nfo ? cap : nfo) : nfo;
 	const int half = A.n / 2;
 
-	for (int w = blockIdx.x; w < nwork; w += gridDim.x)
+	for (int w = w_begin + blockIdx.x; w < w_end; w += gridDim.x)
 	{
 		const RbFineOrient F = A.fo[w];
 		const int p = F.particle;
@@ -226,7 +236,7 @@ k_store(StoreArgs A, RbModelDev M)
 		const RbPartMeta m = A.metas[p];
 		const float2 *X = A.Fimg + (size_t) p * M.Npf, *X0 = A.Fnomask + (size_t) p * M.Npf;
 		const float *C = A.Fctf ? A.Fctf + (size_t) p * M.Npf : nullptr;
-		const float2 *slice = (A.slices && w < A.slice_capacity) ? A.slices + (size_t) w * M.Npf : nullptr;
+		const float2 *slice = SLICED ? A.slices + (size_t) w * M.Npf : nullptr;
 		const float *mtab = M.minvs2 + (size_t) m.og * M.nshell;
 		const unsigned char *dvp = M.dvp_gt3 + (size_t) F.iclass * M.nshell;
 		const RbProjK8 pk = rb_make_projk8(A.projs[F.iclass], imgX);
@@ -253,94 +263,107 @@ k_store(StoreArgs A, RbModelDev M)
 			const float e0 = s_e[0], e1 = s_e[1], e3 = s_e[2], e4 = s_e[3], e6 = s_e[4], e7 = s_e[5];
 
 			// the trip count is uniform per warp (lanes past the end idle) because the scatter below is cooperative
-			int ip = threadIdx.x;
-			const int ip_end = ((A.npix + 31) & ~31);
-			bool have = ip < A.npix;
-			StorePix cur;
-			if (have) store_issue(A, pk, X, X0, C, slice, m.part_scale, ip, e0, e1, e3, e4, e6, e7, cur);
-			for (; (ip & ~31) < ip_end; )
-			{
-				const int ipn = ip + ST_THREADS;
-				const bool haven = ipn < A.npix;
-				StorePix nxt;
-				if (haven) store_issue(A, pk, X, X0, C, slice, m.part_scale, ipn, e0, e1, e3, e4, e6, e7, nxt);
-
-				int cell = -1;           // accumulator voxel of corner (0,0,0), -1: nothing to scatter
-				float sfx = 0.f, sfy = 0.f, sfz = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
-				if (have)
-				{
-				const int x = cur.x, y = cur.y, ires = cur.ires;
-				float2 ref = (cur.pf.flags & 4) ? make_float2(cur.pf.q0.x, cur.pf.q0.y)
-				                                : ((cur.pf.flags & 1) ? rb_proj_finish(cur.pf) : make_float2(0.f, 0.f));
-				const float ctf = cur.ctf;
-				if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                     // wavg.cuh:96-104
-				else { ref.x *= m.part_scale; ref.y *= m.part_scale; }
-				float phr = 0.f, phi = 0.f;
-				for (int t = 0; t < ntr; t++)
-				{
-					const float2 ph = rb_phase(x, y, s_ux[t], s_uy[t]);
-					const float wn = s_wn[t];
-					phr = fmaf(wn, ph.x, phr); phi = fmaf(wn, ph.y, phi);
-				}
-				const float refn = ref.x * ref.x + ref.y * ref.y;
-				const float Xn = cur.X.x * cur.X.x + cur.X.y * cur.X.y;
-				const float xa = (ref.x * cur.X.x + ref.y * cur.X.y) * phr - (ref.x * cur.X.y - ref.y * cur.X.x) * phi;
-				const float aa = W * refn;
-				const float wd = fmaxf(W * (refn + Xn) - 2.f * xa, 0.f);
-				atomicAdd(&s_shell[ires], wd);
-				if (dvp[ires] && M.do_scale_correction) { aXA += (double) xa; aAA += (double) aa; }   // :3473-3479
-				// back-projection
-				const float minvs2 = M.do_map ? __ldg(mtab + ires) : 1.f;                          // :2586, :3110-3115
-				const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                       // BP.cuh:280-289
-				Fw = W * g * ctf;
-				bool do_bp = Fw > 0.f;
-				if (M.bp_circle_bound)
-				{
-					const int xmax = (int) sqrtf((float) (half * half - y * y));                  // BP.h:565
-					do_bp = do_bp && (x < xmax);
-				}
-				if (do_bp)
-				{
-					Fr = (cur.X0.x * phr - cur.X0.y * phi) * g;
-					Fi = (cur.X0.x * phi + cur.X0.y * phr) * g;
-					// position in the accumulator (BP.cuh:301-347)
-					float xp = (e0 * x + e1 * y) * bp.padding_factor;
-					float yp = (e3 * x + e4 * y) * bp.padding_factor;
-					float zp = (e6 * x + e7 * y) * bp.padding_factor;
-					if (xp * xp + yp * yp + zp * zp <= (float) max_r2_vol)
-					{
-						if (xp < 0.f) { xp = -xp; yp = -yp; zp = -zp; Fi = -Fi; }
-						const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
-						sfx = xp - fx0; sfy = yp - fy0; sfz = zp - fz0;
-						cell = (((int) fz0 - bp.mdlInitZ) * bp.mdlY + ((int) fy0 - bp.mdlInitY)) * bp.mdlX + (int) fx0;
-					}
-				}
-				}
-				// Cooperative scatter: two lanes per pixel, one per x-neighbour, so that the two 16-byte reductions of a
-				// corner pair sit in the same instruction and share one 32-byte sector / L1 wavefront.
+			const int wbase = threadIdx.x & ~31;
+			const int nit = wbase < A.npix ? (A.npix - wbase + ST_THREADS - 1) / ST_THREADS : 0;
+			StorePix<SLICED> f[DEPTH];
 #pragma unroll
-				for (int h = 0; h < 2; h++)
+			for (int d = 0; d < DEPTH; d++)
+			{
+				const int ip = threadIdx.x + d * ST_THREADS;
+				if (d < nit && ip < A.npix) store_issue<SLICED>(A, pk, X, X0, C, slice, m.part_scale, ip, e0, e1, e3, e4, e6, e7, f[d]);
+			}
+			for (int it0 = 0; it0 < nit; it0 += DEPTH)
+			{
+#pragma unroll
+				for (int d = 0; d < DEPTH; d++)
 				{
-					const int src = 16 * h + ((threadIdx.x & 31) >> 1);
-					const int c = __shfl_sync(RB_FULL_MASK, cell, src);
-					const float fx = __shfl_sync(RB_FULL_MASK, sfx, src), fy = __shfl_sync(RB_FULL_MASK, sfy, src), fz = __shfl_sync(RB_FULL_MASK, sfz, src);
-					const float vr = __shfl_sync(RB_FULL_MASK, Fr, src), vi = __shfl_sync(RB_FULL_MASK, Fi, src), vw = __shfl_sync(RB_FULL_MASK, Fw, src);
-					if (c >= 0)
+					const int it = it0 + d;
+					if (it >= nit) break;
+					const int ip = threadIdx.x + it * ST_THREADS;
+					const bool have = ip < A.npix;
+					const StorePix<SLICED> cur = f[d];
 					{
-						const int px = threadIdx.x & 1;
-						const float wx = px ? fx : 1.f - fx;
-						const float mfy = 1.f - fy, mfz = 1.f - fz;
-						float4 *b = bp.vol + (size_t) c + px;
-						const size_t sy = bp.mdlX, sz = (size_t) bp.mdlX * bp.mdlY;
-						float d;
-						d = mfz * mfy * wx; red_add_v4(b, d * vr, d * vi, d * vw);
-						d = mfz * fy * wx;  red_add_v4(b + sy, d * vr, d * vi, d * vw);
-						d = fz * mfy * wx;  red_add_v4(b + sz, d * vr, d * vi, d * vw);
-						d = fz * fy * wx;   red_add_v4(b + sz + sy, d * vr, d * vi, d * vw);
+						const int ipn = ip + DEPTH * ST_THREADS;
+						if (it + DEPTH < nit && ipn < A.npix)
+							store_issue<SLICED>(A, pk, X, X0, C, slice, m.part_scale, ipn, e0, e1, e3, e4, e6, e7, f[d]);
+					}
+
+					int cell = -1;           // accumulator voxel of corner (0,0,0), -1: nothing to scatter
+					float sfx = 0.f, sfy = 0.f, sfz = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
+					if (have)
+					{
+						const int x = rb_pix_x(cur.pkx), y = rb_pix_y(cur.pkx), ires = rb_pix_ires(cur.pkx);
+						float2 ref;
+						if constexpr (SLICED) ref = cur.ref.r;
+						else ref = (cur.ref.pf.flags & 1) ? rb_proj_finish(cur.ref.pf) : make_float2(0.f, 0.f);
+						const float ctf = cur.ctf;
+						if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                     // wavg.cuh:96-104
+						else { ref.x *= m.part_scale; ref.y *= m.part_scale; }
+						float phr = 0.f, phi = 0.f;
+						for (int t = 0; t < ntr; t++)
+						{
+							const float2 ph = rb_phase(x, y, s_ux[t], s_uy[t]);
+							const float wn = s_wn[t];
+							phr = fmaf(wn, ph.x, phr); phi = fmaf(wn, ph.y, phi);
+						}
+						const float refn = ref.x * ref.x + ref.y * ref.y;
+						const float Xn = cur.X.x * cur.X.x + cur.X.y * cur.X.y;
+						const float xa = (ref.x * cur.X.x + ref.y * cur.X.y) * phr - (ref.x * cur.X.y - ref.y * cur.X.x) * phi;
+						const float aa = W * refn;
+						const float wd = fmaxf(W * (refn + Xn) - 2.f * xa, 0.f);
+						atomicAdd(&s_shell[ires], wd);
+						if (dvp[ires] && M.do_scale_correction) { aXA += (double) xa; aAA += (double) aa; }   // :3473-3479
+						// back-projection
+						const float minvs2 = M.do_map ? __ldg(mtab + ires) : 1.f;                          // :2586, :3110-3115
+						const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                       // BP.cuh:280-289
+						Fw = W * g * ctf;
+						bool do_bp = Fw > 0.f;
+						if (M.bp_circle_bound)
+						{
+							const int xmax = (int) sqrtf((float) (half * half - y * y));                  // BP.h:565
+							do_bp = do_bp && (x < xmax);
+						}
+						if (do_bp)
+						{
+							Fr = (cur.X0.x * phr - cur.X0.y * phi) * g;
+							Fi = (cur.X0.x * phi + cur.X0.y * phr) * g;
+							// position in the accumulator (BP.cuh:301-347)
+							float xp = (e0 * x + e1 * y) * bp.padding_factor;
+							float yp = (e3 * x + e4 * y) * bp.padding_factor;
+							float zp = (e6 * x + e7 * y) * bp.padding_factor;
+							if (xp * xp + yp * yp + zp * zp <= (float) max_r2_vol)
+							{
+								if (xp < 0.f) { xp = -xp; yp = -yp; zp = -zp; Fi = -Fi; }
+								const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+								sfx = xp - fx0; sfy = yp - fy0; sfz = zp - fz0;
+								cell = (((int) fz0 - bp.mdlInitZ) * bp.mdlY + ((int) fy0 - bp.mdlInitY)) * bp.mdlX + (int) fx0;
+							}
+						}
+					}
+					// Cooperative scatter: two lanes per pixel, one per x-neighbour, so that the two 16-byte reductions of a
+					// corner pair sit in the same instruction and share one 32-byte sector / L1 wavefront.
+#pragma unroll
+					for (int h = 0; h < 2; h++)
+					{
+						const int src = 16 * h + ((threadIdx.x & 31) >> 1);
+						const int c = __shfl_sync(RB_FULL_MASK, cell, src);
+						const float fx = __shfl_sync(RB_FULL_MASK, sfx, src), fy = __shfl_sync(RB_FULL_MASK, sfy, src), fz = __shfl_sync(RB_FULL_MASK, sfz, src);
+						const float vr = __shfl_sync(RB_FULL_MASK, Fr, src), vi = __shfl_sync(RB_FULL_MASK, Fi, src), vw = __shfl_sync(RB_FULL_MASK, Fw, src);
+						if (c >= 0)
+						{
+							const int px = threadIdx.x & 1;
+							const float wx = px ? fx : 1.f - fx;
+							const float mfy = 1.f - fy, mfz = 1.f - fz;
+							float4 *b = bp.vol + (size_t) c + px;
+							const size_t sy = bp.mdlX, sz = (size_t) bp.mdlX * bp.mdlY;
+							float d2;
+							d2 = mfz * mfy * wx; red_add_v4(b, d2 * vr, d2 * vi, d2 * vw);
+							d2 = mfz * fy * wx;  red_add_v4(b + sy, d2 * vr, d2 * vi, d2 * vw);
+							d2 = fz * mfy * wx;  red_add_v4(b + sz, d2 * vr, d2 * vi, d2 * vw);
+							d2 = fz * fy * wx;   red_add_v4(b + sz + sy, d2 * vr, d2 * vi, d2 * vw);
+						}
 					}
 				}
-				if (haven) cur = nxt;
-				ip = ipn; have = haven;
 			}
 		}
 		__syncthreads();
@@ -372,7 +395,15 @@ int rbk_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.pix = ctx->d_model.pix_f; A.npix = ctx->d_model.nvf; A.n = ctx->d_model.current_size;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
 	A.slices = s.slices.as<float2>(); A.slice_capacity = s.slice_capacity;
-	k_store<<<ctx->num_sms * 2, ST_THREADS, 0, ctx->stream>>>(A, ctx->d_model);
+	// measured on the headline pool (tools/sweep_variants.sh): depth 2 / 2 CTAs per SM 5.66 ms, depth 3 / 3 CTAs 5.93 ms,
+	// depth 4 / 3 CTAs 6.10 ms: the stage is bound by the reductions' L2 round trips, not by load latency
+	if (A.slices && A.slice_capacity > 0)
+	{
+		k_store<true, 2, 2><<<ctx->num_sms * 2, ST_THREADS, 0, ctx->stream>>>(A, ctx->d_model);
+		RB_LAUNCH_CHECK(ctx);
+	}
+	// fine orientations beyond the slice cache (none at the default budget unless the pool is very large)
+	k_store<false, 2, 2><<<ctx->num_sms * 2, ST_THREADS, 0, ctx->stream>>>(A, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

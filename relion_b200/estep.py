@@ -367,6 +367,15 @@ class MlDeviceBundle:
                                                       _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(corr, C.c_float), _ptr(out, C.c_float)))
         return out
 
+    def gemm_tf32x3(self, A, B):
+        """C = A @ B.T on the tcgen05 tensor cores with 3xTF32 splitting (rb_gemm_tf32x3); A [M, K], B [N, K] float32."""
+        A = np.ascontiguousarray(A, np.float32); B = np.ascontiguousarray(B, np.float32)
+        assert A.ndim == 2 and B.ndim == 2 and A.shape[1] == B.shape[1]
+        out = np.empty((A.shape[0], B.shape[0]), np.float32)
+        capi.check(self.lib, self.lib.rb_gemm_tf32x3(self.ctx, _ptr(A, C.c_float), _ptr(B, C.c_float), A.shape[0], B.shape[0], A.shape[1],
+                                                     _ptr(out, C.c_float)))
+        return out
+
     def diff2_fine(self, iclass, img_size, eulers, tx, ty, re, im, corr, sum_init, rot_idx, trans_idx, job_idx, job_num):
         e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
         tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)

@@ -253,6 +253,40 @@ def test_pool_capacity_error(device, oracle, monkeypatch):
     device.expectation_some_particles(wl.pool)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 256, 32), (128, 256, 96), (200, 300, 840), (1, 1, 1), (640, 1000, 3030), (129, 257, 33)])
+def test_gemm_tf32x3(device, M, N, K):
+    """The tcgen05 contraction behind the global-search coarse pass, held to FP32-equivalent accuracy: 3xTF32 splitting
+    must land within 2e-6 of sum|a||b| of the float64 product, or within 4x the error of a sequential fp32 dot product
+    for long K (plain TF32 would be ~1e-3)."""
+    rng = np.random.default_rng(M * 7 + N * 3 + K)
+    A = rng.standard_normal((M, K)).astype(np.float32) * rng.uniform(0.1, 10.0, (M, 1)).astype(np.float32)
+    B = rng.standard_normal((N, K)).astype(np.float32)
+    got = device.gemm_tf32x3(A, B)
+    want = A.astype(np.float64) @ B.astype(np.float64).T
+    bound = np.abs(A).astype(np.float64) @ np.abs(B).astype(np.float64).T
+    err = np.abs(got - want) / bound
+    # yardstick: a sequential fp32 dot product of the same data (the reference's kernels sum in fp32, in pixel order)
+    seq = np.zeros((min(M, 64), min(N, 64)), np.float32)
+    for k in range(K):
+        seq += A[:64, k:k + 1] * B[None, :64, k]
+    err_seq = np.abs(seq - want[:64, :64]) / bound[:64, :64]
+    assert err.max() <= max(2e-6, 4 * err_seq.max()), (err.max(), err_seq.max())
+    assert err.mean() <= max(3e-7, 2 * err_seq.mean()), (err.mean(), err_seq.mean())
+
+
+def test_pool_global_search_simt_and_tensor_paths_agree(device, oracle, monkeypatch):
+    """Global search: the SIMT coarse kernel (RB_COARSE_GEMM=0) and the tensor-core contraction (RB_COARSE_GEMM=2) must
+    both match the oracle, and select the same significant coarse samples as each other."""
+    wl = make_workload(ori_size=32, healpix_order=1, n_particles=12, nr_classes=2, seed=27, snr=0.3)
+    monkeypatch.setenv("RB_COARSE_GEMM", "0")
+    r0, _ = _compare_pool(device, oracle, wl)
+    monkeypatch.setenv("RB_COARSE_GEMM", "2")
+    r1, _ = _compare_pool(device, oracle, wl)
+    np.testing.assert_allclose(r0.particles["min_diff2_coarse"], r1.particles["min_diff2_coarse"], rtol=2e-5)
+    assert np.mean(r0.particles["nr_significant_coarse"] == r1.particles["nr_significant_coarse"]) >= 0.9
+    assert np.array_equal(r0.particles["best_ihidden_over"], r1.particles["best_ihidden_over"])
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -46,6 +46,10 @@ WORKLOADS = {
                                 local_search=True, pixel_size=2.0, n_blobs=100, nr_groups=8), 512),
     "refine3d_128_global": (dict(ori_size=128, current_size=64, healpix_order=2, offset_range=5.0, offset_step=2.0, nr_classes=1,
                                  snr=0.05, pixel_size=2.0, n_blobs=100, nr_groups=8), 256),
+    # BASELINE config #4 regime: 3D classification, global search at HEALPix order 3 (36 864 orientations), 21 translations,
+    # coarse window 54 px: the coarse cross term is the dense contraction that runs on the tensor cores
+    "class3d_256_global": (dict(ori_size=256, current_size=128, healpix_order=3, offset_range=5.0, offset_step=2.0, nr_classes=4,
+                                snr=0.05, pixel_size=1.0, n_blobs=200, nr_groups=8), 256),
     "tiny": (dict(ori_size=32, healpix_order=1, nr_classes=1, snr=0.3, n_blobs=20), 16),
 }
 
@@ -136,7 +140,9 @@ def stage_bytes(wl, res):
     # fused wavg + back-projection, SURVEY.md §8d figures: wavg gather 64 B + back-projection 204 B
     # (8 corners x 3 arrays x 4 B, x2 read-modify-write, + 12 B inputs) per pixel of every fine orientation
     store = ((64.0 + 204.0) * ofs * npf).sum()
-    return {"coarse": coarse, "fine": fine, "store": store}
+    # global searches: the coarse pass is the contraction [O x 2Np] . [2Np x P T] per class (+ the norm term [O x Np] . [Np x P])
+    coarse_flops = (2.0 * (2 * npc) * n_or * T + 2.0 * npc * n_or).sum() if wl.pool.dir_off is None else 0.0
+    return {"coarse": coarse, "fine": fine, "store": store, "coarse_flops": coarse_flops}
 
 
 def run_ours(args):
@@ -268,11 +274,25 @@ def run_ours(args):
         if stage_ms[s] > 0:
             stages[s]["algorithmic_GBps"] = round(by[s] / (stage_ms[s] * 1e-3) / 1e9, 1)
             stages[s]["frac_of_hbm_peak"] = round(by[s] / (stage_ms[s] * 1e-3) / 1e9 / peak, 4)
+    tensor_coarse = by["coarse_flops"] > 0 and os.environ.get("RB_COARSE_GEMM", "1") != "0"
+    if tensor_coarse:
+        # useful FLOPs (one fp32-equivalent product per operand pair); the kernel executes 3 TF32 MMAs per product
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        tf32_peak = float(d.get("bf16_tflops_sustained", 1400.0)) / 2.0     # TF32 dense = half the bf16 rate
+        tfs = by["coarse_flops"] / (stage_ms["coarse"] * 1e-3) / 1e12
+        stages["coarse"].update({"tensor_TFLOPs_useful": round(tfs, 1), "tensor_TFLOPs_executed": round(3 * tfs, 1),
+                                 "tf32_peak_TFLOPs": round(tf32_peak, 1), "frac_of_tf32_peak_executed": round(3 * tfs / tf32_peak, 4)})
     ach = by[dom] / (stage_ms[dom] * 1e-3) / 1e9
     roofline = {"kernel": {"coarse": "k_diff2_coarse", "fine": "k_diff2_fine", "store": "k_store"}[dom],
                 "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
                 "traffic": None, "peak_source": peak_src, "share_of_step": round(stage_ms[dom] / max(stage_ms["total"], 1e-9), 3),
                 "algorithmic_bytes_per_launch": by[dom]}
+    if dom == "coarse" and tensor_coarse:
+        roofline = {"kernel": "k_gemm_tf32x3", "bound": "tensor", "achieved": stages["coarse"]["tensor_TFLOPs_executed"],
+                    "peak": stages["coarse"]["tf32_peak_TFLOPs"], "unit": "TFLOP/s", "frac": stages["coarse"]["frac_of_tf32_peak_executed"],
+                    "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained / 2 (TF32 dense runs at half the bf16 rate)",
+                    "share_of_step": round(stage_ms[dom] / max(stage_ms["total"], 1e-9), 3),
+                    "note": "executed = 3 TF32 MMAs per fp32-equivalent product (3xTF32); useful = executed / 3"}
 
     # ---- CPU baseline on a bounded sample (all host cores) ------------------------------------------
     cpu = cpu_baseline(wl, sample=args.cpu_sample)

@@ -98,6 +98,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
+	for (auto &b : ctx->wc_buf) b.release();
 	for (int i = 0; i < RB_NUM_SLOTS; i++) release_slot(ctx->slot[i]);
 	for (auto &kv : ctx->stage_ev) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	cudaStreamDestroy(ctx->stream);

@@ -214,6 +214,7 @@ struct rb_ctx {
 	// stage timing
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
 	DevBuf scratch[8];
+	DevBuf wc_buf[10];               // partials / compact list of the multi-CTA coarse weight conversion
 	DevBuf gemm_buf[10];             // operands of the tensor-core coarse pass (kernels_gemm.cu)
 };
 

@@ -12,14 +12,15 @@
 // (CTF, scale and sigma2 weights are real per pixel, so they fold into the particle operand.)
 //
 // FP32-equivalent accuracy on tensor cores: every operand is split into a TF32 "hi" part and a TF32 "lo" remainder
-// (v = hi + lo to ~22 bits) and three MMAs accumulate hi*hi + hi*lo + lo*hi into the same fp32 TMEM accumulator
+// (v = hi + lo to ~22 bits) and three MMAs accumulate hi*hi + hi*lo + lo*hi into fp32 TMEM accumulators
 // ("3xTF32"); the dropped lo*lo term is ~2^-22 relative.  tests/test_gpu_parity.py::test_gemm_tf32x3 holds the kernel
 // to 2e-6 of sum|a||b| against float64.
 //
 // Kernel: one CTA per 128 x 256 output tile.  Warp 0 = TMA producer (cp.async.bulk.tensor, 128-byte swizzle, mbarrier
-// complete_tx), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M128 N256 K8, accumulator in
-// 256 TMEM columns), warps 2-5 = epilogue (tcgen05.ld 32x32b.x32 -> registers -> diff2 -> Mweight).  Two smem stages of
-// 96 KB (A_hi, A_lo 16 KB each; B_hi, B_lo 32 KB each) per K-block of 32.
+// complete_tx), warp 1 = TMEM allocator + single-thread tcgen05.mma issuer (kind::tf32, M128 N256 K8, accumulators in
+// 2 x 256 TMEM columns: main product and the two 3xTF32 correction products), warps 2-5 = epilogue (tcgen05.ld
+// 32x32b.x32 -> registers -> diff2 -> Mweight).  Two smem stages of 96 KB (A_hi, A_lo 16 KB each; B_hi, B_lo 32 KB each)
+// per K-block of 32.
 #include "img_src.cuh"
 #include <cuda.h>
 #include <cstdlib>
@@ -158,7 +159,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 	}
 	if (warp == 1)
 	{
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(256) : "memory");
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
 		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -202,9 +203,12 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 				for (int ks = 0; ks < GM_BK / 8; ks++)
 				{
 					const uint64_t adv = (uint64_t) ((ks * 8 * 4) >> 4);  // 32 bytes per K step inside the swizzle atom
-					tcgen05_mma_tf32(tmem_base, alo + adv, bhi + adv, idesc, (kb | ks) != 0);
-					tcgen05_mma_tf32(tmem_base, ahi + adv, blo + adv, idesc, 1);
-					tcgen05_mma_tf32(tmem_base, ahi + adv, bhi + adv, idesc, 1);
+					// the two correction products (2^-11 of the main one) go to their own accumulator: the tensor core truncates
+					// every accumulate to fp32, and three times fewer accumulations into the large sum means three times
+					// less truncation drift; the epilogue adds the two accumulators
+					tcgen05_mma_tf32(tmem_base + GM_BN, alo + adv, bhi + adv, idesc, (kb | ks) != 0);
+					tcgen05_mma_tf32(tmem_base + GM_BN, ahi + adv, blo + adv, idesc, 1);
+					tcgen05_mma_tf32(tmem_base, ahi + adv, bhi + adv, idesc, (kb | ks) != 0);
 				}
 				tcgen05_commit(empty0 + 8 * s);                          // frees the smem slot when these MMAs retire
 			}
@@ -224,8 +228,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 		{
 			for (int c = 0; c < GM_BN / 32; c++)
 			{
-				uint32_t v[32];
+				uint32_t v[32], v2[32];
 				tmem_ld32(trow + c * 32, v);
+				tmem_ld32(trow + GM_BN + c * 32, v2);
+#pragma unroll
+				for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
 				if (row < E.M)
 				{
 #pragma unroll
@@ -268,8 +275,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 			load_particle(p);
 			for (int c = 0; c < GM_BN / 32; c++)
 			{
-				uint32_t v[32];
+				uint32_t v[32], v2[32];
 				tmem_ld32(trow + c * 32, v);
+				tmem_ld32(trow + GM_BN + c * 32, v2);
+#pragma unroll
+				for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
 #pragma unroll
 				for (int j = 0; j < 32; j++)
 				{
@@ -290,7 +300,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 	if (warp == 1)
 	{
 		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256) : "memory");
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 	}
 }
 

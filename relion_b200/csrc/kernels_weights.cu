@@ -15,6 +15,7 @@
 // fp32 bit pattern (weights >= 0, so bit order == value order) that carries the exact (fp64) mass and count of
 // everything below the current prefix.  Sums are fixed-tree fp64 reductions, hence deterministic.
 #include "device_utils.cuh"
+#include <cstdlib>
 
 static const int WT_THREADS = 512;   // 16 fp64 bins + 16 counters per thread: keep 128 registers available
 
@@ -253,8 +254,381 @@ k_weights_coarse(const RbPartMeta *metas, RbPartState *states, float *Mweight,
 	}
 }
 
+// ---- the same conversion for LARGE dense arrays (global searches: K * n_dir * n_psi * T ~ 10^6..10^7 per particle) ----
+// One CTA per particle would stream ~13 passes over megabytes with 512 threads (65 ms for a 256-particle pool at
+// HEALPix order 3, where at low SNR most weights are non-zero).  Here every phase is spread over (chunk, particle) CTAs:
+//   k_wc_max     max of the log-weights                                         (read)
+//   k_wc_exp     weights in place + per-particle histogram over the top 13 bits of the fp32 pattern: (fp64 mass, count)
+//                per bin.  A bin holds values of ONE binary exponent, so its fp64 mass is exact (multiples of 2^(e-23),
+//                < 2^29 of them) whatever the order of the atomics: the result is deterministic.        (read + write)
+//   k_wc_pick    one CTA per particle: total mass, threshold, the bin in which the cumulative mass crosses it
+//   k_wc_gather  compaction of the elements of that bin (a tiny fraction)                                (read)
+//   k_wc_finish  the radix descent of block_significance on the compact list, seeded with the mass / count below the bin
+static const int WC_THREADS = 256;
+static const int WC_CHUNK = 1 << 15;            // elements per CTA
+static const int WC_BINS = 4096;                // top 13 bits of a positive float: 8 exponent + 4 mantissa bits
+static const int WC_SHIFT = 19;
+
+struct WcPick {
+	int mode;                 // 0: by mass in bin `bin`; 1: by rank (`rank`) in bin `bin`; -1: no non-zero weight
+	int bin; double base; long long cbelow;
+	int bin_r; long long cbelow_r, rank_r;   // maxsig candidate (rank mode), bin_r < 0: none
+	double total; long long n_nonzero; double thr;
+	long long off_a, off_r;   // compact list bases are fixed (particle block); counts:
+	int cnt_a, cnt_r;
+};
+
+struct WcArgs {
+	const RbPartMeta *metas; RbPartState *states; float *Mweight;
+	const float *pdf_orient; const unsigned char *pdf_orient_zero;
+	const float *pdf_offset; const unsigned char *pdf_offset_zero;
+	int T, nchunk, P; long long n;               // n: dense elements per particle (identical for all particles)
+	float *pmax; float *pav; long long *pai;
+	double *hsum; int *hcnt;                     // [P][WC_BINS]
+	WcPick *pick;                                // [P]
+	long long *gtot;                             // [P][2] number of gathered elements (picked bin, maxsig bin)
+	float *compact_a, *compact_r;                // [P][cap]
+	long long cap;
+};
+
+// log-weight of dense element (io, it) (cuda_kernel_weights_exponent_coarse, helper.cuh:16-46)
+__device__ __forceinline__ float wc_logw(const WcArgs &A, const RbPartMeta &m, int p, int io, int it, float d, float min_diff2)
+{
+	if (d < min_diff2 || A.pdf_orient_zero[m.prior_off + io] || A.pdf_offset_zero[(size_t) p * A.T + it]) return RB_LOWEST;   // helper.cuh:39-42
+	return A.pdf_orient[m.prior_off + io] + A.pdf_offset[(size_t) p * A.T + it] + min_diff2 - d;
+}
+
+// walks i = i0 + tid, += WC_THREADS while keeping (io, it) = (i / T, i % T) without a division per element
+struct WcIndex {
+	int io, it, dio, dit, T;
+	__device__ WcIndex(long long i, int T_) : T(T_) { io = (int) (i / T_); it = (int) (i - (long long) io * T_); dio = WC_THREADS / T_; dit = WC_THREADS - dio * T_; }
+	__device__ void next() { io += dio; it += dit; if (it >= T) { it -= T; io++; } }
+};
+
+__global__ void __launch_bounds__(WC_THREADS)
+k_wc_max(WcArgs A)
+{
+	__shared__ float fred[32];
+	const int c = blockIdx.x, p = blockIdx.y;
+	const RbPartMeta m = A.metas[p];
+	const float min_diff2 = __int_as_float(A.states[p].min_diff2_bits);
+	const float *w = A.Mweight + m.coarse_off;
+	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
+	float mx = RB_LOWEST;
+	WcIndex ix(i0 + threadIdx.x, A.T);
+	for (long long i = i0 + threadIdx.x; i < i1; i += WC_THREADS, ix.next()) mx = fmaxf(mx, wc_logw(A, m, p, ix.io, ix.it, w[i], min_diff2));
+	mx = block_max(mx, fred);
+	if (threadIdx.x == 0) A.pmax[(size_t) p * A.nchunk + c] = mx;
+}
+
+__global__ void __launch_bounds__(WC_THREADS)
+k_wc_exp(WcArgs A)
+{
+	extern __shared__ unsigned char wc_smem[];
+	double *h_s = (double *) wc_smem;                 // [WC_BINS]
+	int *h_c = (int *) (h_s + WC_BINS);               // [WC_BINS]
+	__shared__ ArgMaxSmem am;
+	__shared__ float s_wmax;
+	const int c = blockIdx.x, p = blockIdx.y;
+	const RbPartMeta m = A.metas[p];
+	const float min_diff2 = __int_as_float(A.states[p].min_diff2_bits);
+	float *w = A.Mweight + m.coarse_off;
+	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { h_s[i] = 0.; h_c[i] = 0; }
+	if (threadIdx.x < 32)
+	{
+		float mx = RB_LOWEST;
+		for (int k = threadIdx.x; k < A.nchunk; k += 32) mx = fmaxf(mx, A.pmax[(size_t) p * A.nchunk + k]);
+		mx = warp_max(mx);
+		if (threadIdx.x == 0) s_wmax = mx;
+	}
+	__syncthreads();
+	const float add = 50.f - s_wmax;                                               // acc_ml_optimiser_impl.h:2201-2207
+	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
+	float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
+	WcIndex ix(i0 + threadIdx.x, A.T);
+	for (long long i = i0 + threadIdx.x; i < i1; i += WC_THREADS, ix.next())
+	{
+		const float a = wc_logw(A, m, p, ix.io, ix.it, w[i], min_diff2) + add;
+		const float e = (a < -88.f) ? 0.f : expf(a);                               // helper.cuh:57-66
+		w[i] = e;
+		if (e > 0.f)
+		{
+			const int bin = (int) (__float_as_uint(e) >> WC_SHIFT);
+			atomicAdd(h_s + bin, (double) e); atomicAdd(h_c + bin, 1);
+		}
+		if (e > bv) { bv = e; bi = i; }
+	}
+	float ov; long long oi;
+	block_argmax(bv, bi, am, ov, oi);
+	if (threadIdx.x == 0) { A.pav[(size_t) p * A.nchunk + c] = ov; A.pai[(size_t) p * A.nchunk + c] = oi; }
+	__syncthreads();
+	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS)
+		if (h_c[i]) { atomicAdd(A.hsum + (size_t) p * WC_BINS + i, h_s[i]); atomicAdd(A.hcnt + (size_t) p * WC_BINS + i, h_c[i]); }
+}
+
+// one CTA per particle: argmax over chunks, total mass, threshold, bin selection
+__global__ void __launch_bounds__(WC_THREADS)
+k_wc_pick(WcArgs A, RbModelDev M)
+{
+	__shared__ double dred[32];
+	__shared__ long long lred[32];
+	const int p = blockIdx.x;
+	const double *hs = A.hsum + (size_t) p * WC_BINS;
+	const int *hc = A.hcnt + (size_t) p * WC_BINS;
+	double t = 0.; long long cnt = 0;
+	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { t += hs[i]; cnt += hc[i]; }
+	t = block_sum(t, dred);
+	cnt = block_sum(cnt, lred);
+	if (threadIdx.x != 0) return;
+	RbPartState *st = A.states + p;
+	{
+		float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
+		for (int c = 0; c < A.nchunk; c++)
+		{
+			const size_t k = (size_t) p * A.nchunk + c;
+			if (A.pav[k] > bv) { bv = A.pav[k]; bi = A.pai[k]; }                   // chunks in order: first index of the maximum
+		}
+		st->cmax_weight = bv; st->cmax_index = bi;
+	}
+	WcPick pk;
+	memset(&pk, 0, sizeof(pk));
+	pk.total = t; pk.n_nonzero = cnt; pk.bin_r = -1; pk.mode = -1;
+	if (cnt > 0)
+	{
+		const float sum_f = (float) t;
+		pk.thr = (double) (float) ((1. - M.adaptive_fraction) * (double) sum_f);   // (XFLOAT) threshold, :2277-2278
+		double cum = 0.; long long cc = 0; int sel = -1;
+		for (int b = 0; b < WC_BINS; b++)
+		{
+			if (hc[b] > 0 && cum + hs[b] > pk.thr) { sel = b; break; }
+			cum += hs[b]; cc += hc[b];
+		}
+		if (sel >= 0) { pk.mode = 0; pk.bin = sel; pk.base = cum; pk.cbelow = cc; }
+		else
+		{
+			// nothing crosses the threshold: the reference's search leaves idx = 0 -> sorted[0], the smallest weight
+			int b = 0; while (hc[b] == 0) b++;
+			pk.mode = 1; pk.bin = b; pk.base = 0.; pk.cbelow = 0;
+		}
+		if (M.maximum_significants > 0 && cnt > M.maximum_significants)            // :2301-2306 candidate
+		{
+			const long long r = cnt - M.maximum_significants;
+			long long c2 = 0; int b = 0;
+			for (; b < WC_BINS; b++) { if (c2 + hc[b] > r) break; c2 += hc[b]; }
+			pk.bin_r = b; pk.cbelow_r = c2; pk.rank_r = r;
+		}
+	}
+	A.pick[p] = pk;
+}
+
+// compaction of the elements falling in the picked bin(s).  Space is reserved per tile with one atomic, so the order of the
+// compact list varies from run to run, but its elements share one binary exponent: every fp64 partial sum over them is exact and
+// the selection that follows does not depend on the order.
+__global__ void __launch_bounds__(WC_THREADS)
+k_wc_gather(WcArgs A)
+{
+	__shared__ int s_scan[2][WC_THREADS];
+	__shared__ long long s_base[2];
+	const int c = blockIdx.x, p = blockIdx.y;
+	const WcPick pk = A.pick[p];
+	if (pk.mode < 0) return;
+	const RbPartMeta m = A.metas[p];
+	const float *w = A.Mweight + m.coarse_off;
+	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
+	const unsigned ba = (unsigned) pk.bin, br = pk.bin_r >= 0 ? (unsigned) pk.bin_r : 0xffffffffu;
+	const int RUN = 8;
+	for (long long t0 = i0; t0 < i1; t0 += (long long) WC_THREADS * RUN)
+	{
+		float v[RUN]; int ka = 0, kr = 0;
+		const long long b = t0 + (long long) threadIdx.x * RUN;
+#pragma unroll
+		for (int j = 0; j < RUN; j++)
+		{
+			v[j] = (b + j < i1) ? w[b + j] : 0.f;
+			const unsigned bin = __float_as_uint(v[j]) >> WC_SHIFT;
+			ka += (v[j] > 0.f && bin == ba); kr += (v[j] > 0.f && bin == br);
+		}
+		if (!__syncthreads_or(ka | kr)) continue;
+		s_scan[0][threadIdx.x] = ka; s_scan[1][threadIdx.x] = kr;
+		__syncthreads();
+		for (int off = 1; off < WC_THREADS; off <<= 1)
+		{
+			const int ta = threadIdx.x >= off ? s_scan[0][threadIdx.x - off] : 0, tr = threadIdx.x >= off ? s_scan[1][threadIdx.x - off] : 0;
+			__syncthreads();
+			s_scan[0][threadIdx.x] += ta; s_scan[1][threadIdx.x] += tr;
+			__syncthreads();
+		}
+		if (threadIdx.x == WC_THREADS - 1)
+		{
+			s_base[0] = s_scan[0][threadIdx.x] ? (long long) atomicAdd((unsigned long long *) (A.gtot + 2 * p), (unsigned long long) s_scan[0][threadIdx.x]) : 0;
+			s_base[1] = s_scan[1][threadIdx.x] ? (long long) atomicAdd((unsigned long long *) (A.gtot + 2 * p + 1), (unsigned long long) s_scan[1][threadIdx.x]) : 0;
+		}
+		__syncthreads();
+		long long pa = s_base[0] + s_scan[0][threadIdx.x] - ka, pr = s_base[1] + s_scan[1][threadIdx.x] - kr;
+#pragma unroll
+		for (int j = 0; j < RUN; j++)
+		{
+			const unsigned bin = __float_as_uint(v[j]) >> WC_SHIFT;
+			if (v[j] > 0.f && bin == ba) { if (pa < A.cap) A.compact_a[(size_t) p * A.cap + pa] = v[j]; pa++; }
+			if (v[j] > 0.f && bin == br) { if (pr < A.cap) A.compact_r[(size_t) p * A.cap + pr] = v[j]; pr++; }
+		}
+		__syncthreads();
+	}
+}
+
+// Radix descent over a compact list whose elements all share the top 13 bits `bin`; seeded with the mass / count below.
+__device__ void radix_descend_seeded(const float *w, long long n, bool by_rank, double thr, long long rank,
+                                     double base0, long long cbelow0, SelSmem &sm)
+{
+	if (threadIdx.x == 0) { sm.prefix = 0u; sm.base = base0; sm.cbelow = cbelow0; sm.cequal = 0; }
+	__syncthreads();
+	for (int pass = 0; pass < 8; pass++)
+	{
+		const int shift = 28 - 4 * pass;
+		const unsigned prefix = sm.prefix;
+		double s[16]; int c[16];
+#pragma unroll
+		for (int b = 0; b < 16; b++) { s[b] = 0.; c[b] = 0; }
+		for (long long i = threadIdx.x; i < n; i += blockDim.x)
+		{
+			const float v = w[i];
+			const unsigned bits = __float_as_uint(v);
+			if (v > 0.f && (pass == 0 || (bits >> (shift + 4)) == (prefix >> (shift + 4))))
+			{
+				const int bin = (bits >> shift) & 15;
+#pragma unroll
+				for (int b = 0; b < 16; b++) { const bool h = (bin == b); s[b] += h ? (double) v : 0.; c[b] += h ? 1 : 0; }
+			}
+		}
+		reduce_bins(s, c, sm);
+		if (threadIdx.x == 0)
+		{
+			double cum = sm.base; long long cc = sm.cbelow; int sel = -1;
+			for (int b = 0; b < 16; b++)
+			{
+				if (sm.bc[b] > 0)
+				{
+					bool hit = by_rank ? (cc + sm.bc[b] > rank) : (cum + sm.bs[b] > thr);
+					if (hit) { sel = b; break; }
+				}
+				cum += sm.bs[b]; cc += sm.bc[b];
+			}
+			if (sel < 0) sm.found = 0;
+			else
+			{
+				sm.found = 1;
+				sm.prefix = prefix | ((unsigned) sel << shift);
+				sm.base = cum; sm.cbelow = cc; sm.cequal = sm.bc[sel];
+			}
+		}
+		__syncthreads();
+		if (!sm.found) return;
+	}
+}
+
+__global__ void __launch_bounds__(WT_THREADS)
+k_wc_finish(WcArgs A, RbModelDev M)
+{
+	__shared__ SelSmem sm;
+	__shared__ int s_over;
+	const int p = blockIdx.x;
+	RbPartState *st = A.states + p;
+	const WcPick pk = A.pick[p];
+	if (pk.mode < 0)
+	{
+		if (threadIdx.x == 0)
+		{
+			st->min_diff2 = __int_as_float(st->min_diff2_bits);
+			st->csum_weight = 0.f; st->n_nonzero = 0; st->csig_weight = 0.f; st->nr_sig_coarse = 0; st->status = RB_ERR_NO_SIGNIFICANT;
+		}
+		return;
+	}
+	const long long na = A.gtot[2 * p], nr = A.gtot[2 * p + 1];
+	if (threadIdx.x == 0) s_over = (na > A.cap || nr > A.cap);
+	__syncthreads();
+	if (s_over)
+	{
+		if (threadIdx.x == 0) st->status = RB_ERR_CAPACITY;    // a single 1/16-octave bin larger than the compact buffer
+		return;
+	}
+	float sig_w; long long thr_idx;
+	radix_descend_seeded(A.compact_a + (size_t) p * A.cap, na, pk.mode == 1, pk.thr, 0, pk.base, pk.cbelow, sm);
+	__syncthreads();
+	if (pk.mode == 1) { thr_idx = 0; sig_w = __uint_as_float(sm.prefix); }
+	else
+	{
+		const float v = __uint_as_float(sm.prefix);
+		double kk = floor((pk.thr - sm.base) / (double) v) + 1.;                   // k-th copy of v crosses the threshold
+		long long k = kk < 1. ? 1 : (kk > (double) sm.cequal ? sm.cequal : (long long) kk);
+		thr_idx = sm.cbelow + k - 1;
+		sig_w = v;
+	}
+	__syncthreads();
+	if (pk.bin_r >= 0 && pk.n_nonzero - thr_idx > M.maximum_significants)          // :2301-2306
+	{
+		thr_idx = pk.rank_r;
+		radix_descend_seeded(A.compact_r + (size_t) p * A.cap, nr, true, 0., pk.rank_r, 0., pk.cbelow_r, sm);
+		__syncthreads();
+		sig_w = __uint_as_float(sm.prefix);
+	}
+	if (threadIdx.x == 0)
+	{
+		st->min_diff2 = __int_as_float(st->min_diff2_bits);
+		st->csum_weight = (float) pk.total; st->n_nonzero = (int) pk.n_nonzero;
+		st->csig_weight = sig_w;
+		st->nr_sig_coarse = (int) (pk.n_nonzero - thr_idx);
+		if (pk.n_nonzero == 0 || st->nr_sig_coarse == 0) st->status = RB_ERR_NO_SIGNIFICANT;   // :2242, :2282
+	}
+}
+
+static int weights_coarse_large(rb_ctx *ctx, PoolSlot &s, long long n)
+{
+	WcArgs A;
+	memset(&A, 0, sizeof(A));
+	const int P = s.P;
+	A.metas = s.meta.as<RbPartMeta>(); A.states = s.state.as<RbPartState>(); A.Mweight = s.Mweight.as<float>();
+	A.pdf_orient = s.pdf_orient.as<float>(); A.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>();
+	A.pdf_offset = s.pdf_offset.as<float>(); A.pdf_offset_zero = s.pdf_offset_zero.as<unsigned char>();
+	A.T = ctx->d_samp.n_trans; A.n = n; A.nchunk = (int) ((n + WC_CHUNK - 1) / WC_CHUNK); A.P = P;
+	const size_t np = (size_t) P * A.nchunk;
+	// one 1/16-octave bin of one particle; n / 8 is generous (the weights span ~200 octaves), overflow -> RB_ERR_CAPACITY
+	A.cap = std::max<long long>(1024, n / 8);
+	const bool maxsig = ctx->d_model.maximum_significants > 0;
+	RB_CHECK(ctx->wc_buf[0].ensure(np * 4)); RB_CHECK(ctx->wc_buf[1].ensure(np * 4)); RB_CHECK(ctx->wc_buf[2].ensure(np * 8));
+	RB_CHECK(ctx->wc_buf[3].ensure((size_t) P * WC_BINS * 8)); RB_CHECK(ctx->wc_buf[4].ensure((size_t) P * WC_BINS * 4));
+	RB_CHECK(ctx->wc_buf[5].ensure((size_t) P * sizeof(WcPick)));
+	RB_CHECK(ctx->wc_buf[6].ensure((size_t) P * 16));
+	RB_CHECK(ctx->wc_buf[8].ensure((size_t) P * A.cap * 4));
+	RB_CHECK(ctx->wc_buf[9].ensure(maxsig ? (size_t) P * A.cap * 4 : 16));
+	A.pmax = ctx->wc_buf[0].as<float>(); A.pav = ctx->wc_buf[1].as<float>(); A.pai = ctx->wc_buf[2].as<long long>();
+	A.hsum = ctx->wc_buf[3].as<double>(); A.hcnt = ctx->wc_buf[4].as<int>(); A.pick = ctx->wc_buf[5].as<WcPick>();
+	A.gtot = ctx->wc_buf[6].as<long long>();
+	A.compact_a = ctx->wc_buf[8].as<float>(); A.compact_r = ctx->wc_buf[9].as<float>();
+	RB_CUDA(cudaMemsetAsync(A.hsum, 0, (size_t) P * WC_BINS * 8, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(A.hcnt, 0, (size_t) P * WC_BINS * 4, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(A.gtot, 0, (size_t) P * 16, ctx->stream));
+	dim3 grid(A.nchunk, P);
+	const size_t hsm = (size_t) WC_BINS * 12;
+	static bool configured = false;
+	if (!configured) { RB_CUDA(cudaFuncSetAttribute(k_wc_exp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hsm)); configured = true; }
+	k_wc_max<<<grid, WC_THREADS, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
+	k_wc_exp<<<grid, WC_THREADS, hsm, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
+	k_wc_pick<<<P, WC_THREADS, 0, ctx->stream>>>(A, ctx->d_model); RB_LAUNCH_CHECK(ctx);
+	k_wc_gather<<<grid, WC_THREADS, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
+	k_wc_finish<<<P, WT_THREADS, 0, ctx->stream>>>(A, ctx->d_model); RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
 int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 {
+	if (!s.has_priors)
+	{
+		// global search: every particle has the same dense size
+		const long long n = (long long) ctx->d_model.nr_classes * ctx->d_samp.n_dir * ctx->d_samp.n_psi * ctx->d_samp.n_trans;
+		const char *e = getenv("RB_WEIGHTS_LARGE");
+		const long long min_n = e ? atoll(e) : (1 << 17);
+		if (n >= min_n && n > 1) return weights_coarse_large(ctx, s, n);
+	}
 	k_weights_coarse<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
 		s.Mweight.as<float>(), s.pdf_orient.as<float>(), s.pdf_orient_zero.as<unsigned char>(),
 		s.pdf_offset.as<float>(), s.pdf_offset_zero.as<unsigned char>(), ctx->d_model, ctx->d_samp.n_trans);

@@ -285,6 +285,30 @@ def test_pool_global_search_simt_and_tensor_paths_agree(device, oracle, monkeypa
     np.testing.assert_allclose(r0.particles["min_diff2_coarse"], r1.particles["min_diff2_coarse"], rtol=2e-5)
     assert np.mean(r0.particles["nr_significant_coarse"] == r1.particles["nr_significant_coarse"]) >= 0.9
     assert np.array_equal(r0.particles["best_ihidden_over"], r1.particles["best_ihidden_over"])
+    # the multi-CTA weight conversion used for large orientation grids must reproduce the one-CTA-per-particle kernel
+    monkeypatch.setenv("RB_WEIGHTS_LARGE", "1")
+    r2, _ = _compare_pool(device, oracle, wl)
+    for key in ("nr_significant_coarse", "best_ihidden_over", "n_fine_samples", "min_diff2_coarse", "significant_weight_coarse", "sum_weight_coarse"):
+        assert np.array_equal(r1.particles[key], r2.particles[key]), key
+
+
+@pytest.mark.parametrize("maxsig,fraction,snr", [(0, 0.999, 0.3), (7, 0.999, 0.01), (0, 0.0, 0.3), (0, 1.0, 0.05), (3, 0.5, 0.01)])
+def test_large_weight_conversion_matches_single_cta(device, monkeypatch, maxsig, fraction, snr):
+    """The multi-CTA coarse weight conversion (histogram over the top 13 bits + seeded radix descent) against the
+    one-CTA-per-particle kernel on the same pool: identical thresholds, counts, sums and fine-pass lists, including the
+    --maxsig branch and the 'nothing crosses the threshold' branch (adaptive_fraction 0)."""
+    wl = make_workload(ori_size=24, healpix_order=1, n_particles=9, nr_classes=2, seed=60 + maxsig, snr=snr, adaptive_fraction=fraction)
+    wl.model.maximum_significants = maxsig
+    res = []
+    for large in ("100000000", "1"):
+        monkeypatch.setenv("RB_WEIGHTS_LARGE", large)
+        _setup(device, wl)
+        res.append(device.expectation_some_particles(wl.pool).particles)
+    for key in ("nr_significant_coarse", "significant_weight_coarse", "sum_weight_coarse", "min_diff2_coarse", "n_fine_orient",
+                "n_fine_samples", "best_ihidden_over", "sum_weight", "pmax"):
+        assert np.array_equal(res[0][key], res[1][key]), (key, res[0][key], res[1][key])
+    if maxsig:
+        assert res[1]["nr_significant_coarse"].max() <= maxsig
 
 
 def test_smoke_entry():

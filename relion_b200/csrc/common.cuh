@@ -249,6 +249,8 @@ int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float 
 // kernels_gemm.cu: global-search coarse pass as a 3xTF32 tcgen05 contraction
 bool rbk_coarse_gemm_applicable(rb_ctx *ctx, const PoolSlot &s);
 int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4);
+bool rbk_coarse_fused_applicable(rb_ctx *ctx, const PoolSlot &s);
+int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4);
 int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int M, int N, int K, float *dC);
 
 // kernels_weights.cu

@@ -280,6 +280,8 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 
 	// global searches: the cross term is a dense contraction shared by the whole pool -> tensor cores
 	if (rbk_coarse_gemm_applicable(ctx, s)) return rbk_diff2_coarse_gemm_pool(ctx, s, s.cimg4.as<float4>());
+	// local searches: projection fused with the contraction, per (particle, 128-orientation tile)
+	if (rbk_coarse_fused_applicable(ctx, s)) return rbk_diff2_coarse_fused_pool(ctx, s, s.cimg4.as<float4>());
 
 	CoarseArgs A;
 	memset(&A, 0, sizeof(A));

@@ -410,14 +410,16 @@ k_gemm_build_A(RbProjector pj, const float *coarse_eulers, const uint32_t *pix, 
 
 // B operands of the pool: column n = p*T + t holds c_p X'_p e^{i phi_t} over the valid pixels (translatePixel with the
 // table factorisation of computeSincosLookupTable2D, cpu_kernels/helper.h:622-660); B2 row p holds c_p; x2[p] = sum c |X'|^2.
+// tstride: rows per particle (T for the pool-wide contraction, 32 for the per-particle tiles of the fused local kernel);
+// B2 / x2 outputs are optional (nullptr).
 __global__ void __launch_bounds__(256)
-k_gemm_build_B(const float4 *img4, const uint32_t *pix, int npix, int n, const float *tx, const float *ty, int T, int P,
+k_gemm_build_B(const float4 *img4, const uint32_t *pix, int npix, int n, const float *tx, const float *ty, int T, int tstride, int P,
                float *Bhi, float *Blo, size_t kpad, float *B2hi, float *B2lo, size_t k2pad, float *x2)
 {
 	__shared__ float red[32];
 	const int col = blockIdx.x;                  // 0 .. Npad-1
-	const int p = col / T, t = col - p * T;
-	const bool live = p < P;
+	const int p = col / tstride, t = col - p * tstride;
+	const bool live = p < P && t < T;
 	const int imgX = n / 2 + 1;
 	const float4 *img = img4 + (size_t) (live ? p : 0) * n * imgX;
 	const float ttx = live ? tx[t] : 0.f, tty = live ? ty[t] : 0.f;
@@ -446,7 +448,7 @@ k_gemm_build_B(const float4 *img4, const uint32_t *pix, int npix, int n, const f
 		tf32_split(y.x, h.x, l.x); tf32_split(y.y, h.y, l.y);
 		*(float2 *) (Bhi + (size_t) col * kpad + 2 * i) = h;
 		*(float2 *) (Blo + (size_t) col * kpad + 2 * i) = l;
-		if (t == 0 && live && (size_t) i < k2pad)
+		if (B2hi && t == 0 && live && (size_t) i < k2pad)
 		{
 			float h2, l2;
 			tf32_split(hc, h2, l2);
@@ -500,7 +502,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	// particle operands (independent of the class)
 	RB_CUDA(cudaMemsetAsync(bB2hi.p, 0, N2pad * k2pad * 4, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(bB2lo.p, 0, N2pad * k2pad * 4, ctx->stream));
-	k_gemm_build_B<<<(unsigned) Npad, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, P,
+	k_gemm_build_B<<<(unsigned) Npad, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, T, P,
 		bBhi.as<float>(), bBlo.as<float>(), kpad, bB2hi.as<float>(), bB2lo.as<float>(), k2pad, bX2.as<float>());
 	RB_LAUNCH_CHECK(ctx);
 
@@ -527,6 +529,290 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 			E1.T = T; E1.P = P; E1.O = O; E1.cls = cls; E1.o_first = o0; E1.M = rows; E1.N = P * T;
 			RB_CHECK(launch_gemm(ctx, bAhi.as<float>(), bAlo.as<float>(), rows_pad, bBhi.as<float>(), bBlo.as<float>(), Npad, kpad, E1));
 		}
+	return RB_OK;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// LOCAL searches: fused projection + contraction.  Every particle has its own (prior-selected) orientation list, so there
+// is no pool-wide A operand; instead the CTA of (particle, 128-orientation tile) lets 8 producer warps project its
+// orientations 16 pixels at a time straight into the swizzled shared-memory operand tiles (TF32 hi / lo), while one thread
+// feeds the tensor core:  D[128 o][32 t] += A[128 o][32 k] . B_p[32 t][32 k]  (B_p = the particle's phase-shifted,
+// weighted image for every translation, built once per pool and fetched by TMA).  The translation loop of the SIMT kernel
+// (2 shared-memory loads + 10 FP32 instructions per pixel, translation and 3 orientations) disappears from the SM's
+// issue slots; what is left is the gather.
+// ---------------------------------------------------------------------------------------------
+static const int FU_BM = 128, FU_BN = 32, FU_PIX = 16, FU_STAGES = 2;
+static const int FU_PRODUCERS = 256, FU_THREADS = 64 + FU_PRODUCERS;
+static const uint32_t FU_A_BYTES = FU_BM * 128, FU_B_BYTES = FU_BN * 128;
+static const uint32_t FU_STAGE_BYTES = 2 * FU_A_BYTES + 2 * FU_B_BYTES;            // 40 KB
+static const size_t FU_SMEM = (size_t) FU_STAGES * FU_STAGE_BYTES + 1024 + 128;
+
+struct FusedArgs {
+	const RbPartMeta *metas; RbPartState *states;
+	const int *dir_idx, *psi_idx;
+	const unsigned char *pdf_orient_zero;
+	float *Mweight;
+	const float4 *img4;            // prepared images at the coarse window (for c = corr/2)
+	const float *x2;               // [P] sum c |X'|^2
+	const RbProjector *projs;
+	const uint32_t *pix; int npix; int n;
+	int T; int tiles_per_class; int num_kblocks;
+};
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+__global__ void __launch_bounds__(FU_THREADS, 2)
+k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, FusedArgs A, RbSamplingDev S)
+{
+	extern __shared__ uint8_t fu_smem_raw[];
+	__shared__ float s_e[FU_BM][6];
+	__shared__ unsigned char s_valid[FU_BM];
+	__shared__ float s_base[FU_BM];
+	__shared__ float s_min[4];
+	const uint32_t raw = smem_u32(fu_smem_raw);
+	const uint32_t tiles = (raw + 1023u) & ~1023u;
+	const uint32_t bars = tiles + FU_STAGES * FU_STAGE_BYTES;
+	uint8_t *tiles_generic = fu_smem_raw + (tiles - raw);
+	uint8_t *bars_generic = fu_smem_raw + (bars - raw);
+	const uint32_t full0 = bars, empty0 = bars + 8 * FU_STAGES, tmem_full = bars + 16 * FU_STAGES, tmem_slot = tmem_full + 8;
+
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int p = blockIdx.y;
+	const int cls = blockIdx.x / A.tiles_per_class;
+	const int oi0 = (blockIdx.x - cls * A.tiles_per_class) * FU_BM;
+	const RbPartMeta m = A.metas[p];
+	const int no = m.nd * m.np;
+	if (oi0 >= no) return;
+	const int o0 = cls * no + oi0;
+
+	// orientation table of the tile
+	for (int r = threadIdx.x; r < FU_BM; r += FU_THREADS)
+	{
+		const int oi = oi0 + r;
+		bool valid = oi < no;
+		if (valid)
+		{
+			valid = !A.pdf_orient_zero[m.prior_off + o0 + r];
+			const int idl = oi / m.np, ipl = oi - idl * m.np;
+			const int gd = m.dir_off < 0 ? idl : A.dir_idx[m.dir_off + idl];
+			const int gp = m.psi_off < 0 ? ipl : A.psi_idx[m.psi_off + ipl];
+			const float *eu = S.coarse_eulers + ((size_t) gd * S.n_psi + gp) * 9;
+			s_e[r][0] = eu[0]; s_e[r][1] = eu[1]; s_e[r][2] = eu[3]; s_e[r][3] = eu[4]; s_e[r][4] = eu[6]; s_e[r][5] = eu[7];
+		}
+		s_valid[r] = valid;
+	}
+	if (warp == 0 && lane == 0)
+	{
+		for (int s = 0; s < FU_STAGES; s++) { mbar_init(full0 + 8 * s, FU_PRODUCERS + 1); mbar_init(empty0 + 8 * s, 1); }
+		mbar_init(tmem_full, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	}
+	if (warp == 1)
+	{
+		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(64) : "memory");
+		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+	}
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncthreads();
+	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+	const uint32_t tmem_base = *(volatile uint32_t *) (bars_generic + 16 * FU_STAGES + 8);
+	const int nkb = A.num_kblocks;
+
+	if (warp == 0)
+	{
+		if (lane == 0)
+		{
+			for (int kb = 0; kb < nkb; kb++)
+			{
+				const int s = kb % FU_STAGES;
+				const uint32_t ph = (kb / FU_STAGES) & 1;
+				mbar_wait(empty0 + 8 * s, ph ^ 1);
+				const uint32_t st = tiles + s * FU_STAGE_BYTES;
+				mbar_expect_tx(full0 + 8 * s, 2 * FU_B_BYTES);
+				tma_load_2d(st + 2 * FU_A_BYTES, &tmBhi, full0 + 8 * s, kb * 32, p * FU_BN);
+				tma_load_2d(st + 2 * FU_A_BYTES + FU_B_BYTES, &tmBlo, full0 + 8 * s, kb * 32, p * FU_BN);
+			}
+		}
+	}
+	else if (warp == 1)
+	{
+		if (lane == 0)
+		{
+			const uint32_t idesc = umma_idesc_tf32(FU_BM, FU_BN);
+			for (int kb = 0; kb < nkb; kb++)
+			{
+				const int s = kb % FU_STAGES;
+				const uint32_t ph = (kb / FU_STAGES) & 1;
+				mbar_wait(full0 + 8 * s, ph);
+				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+				const uint32_t st = tiles + s * FU_STAGE_BYTES;
+				const uint64_t ahi = umma_desc_k_sw128(st), alo = umma_desc_k_sw128(st + FU_A_BYTES);
+				const uint64_t bhi = umma_desc_k_sw128(st + 2 * FU_A_BYTES), blo = umma_desc_k_sw128(st + 2 * FU_A_BYTES + FU_B_BYTES);
+#pragma unroll
+				for (int ks = 0; ks < 4; ks++)
+				{
+					const uint64_t adv = (uint64_t) ((ks * 32) >> 4);
+					tcgen05_mma_tf32(tmem_base + FU_BN, alo + adv, bhi + adv, idesc, (kb | ks) != 0);
+					tcgen05_mma_tf32(tmem_base + FU_BN, ahi + adv, blo + adv, idesc, 1);
+					tcgen05_mma_tf32(tmem_base, ahi + adv, bhi + adv, idesc, (kb | ks) != 0);
+				}
+				tcgen05_commit(empty0 + 8 * s);
+			}
+			tcgen05_commit(tmem_full);
+		}
+	}
+	else
+	{
+		// ---- producers: 256 threads, thread -> pixel (lane & 15) of the K-block and 8 rows pw*16 + 2*j + (lane >> 4) ----
+		const int pt = threadIdx.x - 64;
+		const int pw = pt >> 5;
+		const int i = lane & 15, rsub = lane >> 4;
+		const int imgX = A.n / 2 + 1;
+		const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
+		const float4 *mdl2 = A.projs[cls].mdl2;
+		const float4 *img = A.img4 + (size_t) p * A.n * imgX;
+		float bacc[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) bacc[j] = 0.f;
+		for (int kb = 0; kb < nkb; kb++)
+		{
+			const int s = kb % FU_STAGES;
+			const uint32_t ph = (kb / FU_STAGES) & 1;
+			const int ip = kb * FU_PIX + i;
+			int x = 0, y = 0; float hc = 0.f;
+			const bool pix_ok = ip < A.npix;
+			if (pix_ok)
+			{
+				const uint32_t pkx = __ldg(A.pix + ip);
+				x = rb_pix_x(pkx); y = rb_pix_y(pkx);
+				hc = __ldg(img + rb_src_index(x, y, A.n)).z;
+			}
+			float2 ref[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				const int r = pw * 16 + 2 * j + rsub;
+				ref[j] = make_float2(0.f, 0.f);
+				if (pix_ok && s_valid[r])
+					ref[j] = rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
+				bacc[j] = fmaf(hc, ref[j].x * ref[j].x + ref[j].y * ref[j].y, bacc[j]);
+			}
+			mbar_wait(empty0 + 8 * s, ph ^ 1);                       // the MMAs that read this slot have retired
+			uint8_t *st = tiles_generic + (size_t) s * FU_STAGE_BYTES;
+#pragma unroll
+			for (int j = 0; j < 8; j++)
+			{
+				const int r = pw * 16 + 2 * j + rsub;
+				float2 h, l;
+				tf32_split(ref[j].x, h.x, l.x); tf32_split(ref[j].y, h.y, l.y);
+				const uint32_t off = (uint32_t) r * 128u + ((uint32_t) ((i >> 1) ^ (r & 7)) << 4) + (uint32_t) (i & 1) * 8u;
+				*(float2 *) (st + off) = h;
+				*(float2 *) (st + FU_A_BYTES + off) = l;
+			}
+			asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the tensor core
+			mbar_arrive(full0 + 8 * s);
+		}
+		// norm term per row: sum over the 16 lanes that share a row
+#pragma unroll
+		for (int j = 0; j < 8; j++)
+		{
+			float v = bacc[j];
+			v += __shfl_xor_sync(RB_FULL_MASK, v, 8); v += __shfl_xor_sync(RB_FULL_MASK, v, 4);
+			v += __shfl_xor_sync(RB_FULL_MASK, v, 2); v += __shfl_xor_sync(RB_FULL_MASK, v, 1);
+			if (i == 0) s_base[pw * 16 + 2 * j + rsub] = v;
+		}
+		asm volatile("bar.sync 1, %0;" ::"n"(FU_PRODUCERS) : "memory");     // producers only
+		if (pw < 4)
+		{
+			// ---- epilogue: warps 2..5 <-> TMEM lane quarters (warp % 4) ----
+			const int q = warp & 3;
+			const int r = q * 32 + lane;
+			mbar_wait(tmem_full, 0);
+			asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+			uint32_t v[32], v2[32];
+			tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16), v);
+			tmem_ld32(tmem_base + ((uint32_t) (q * 32) << 16) + FU_BN, v2);
+			float bmin = FLT_MAX;
+			if (s_valid[r])
+			{
+				const float bs = s_base[r] + A.x2[p];
+				float *out = A.Mweight + m.coarse_off + (long long) (o0 + r) * A.T;
+#pragma unroll
+				for (int t = 0; t < 32; t++)
+				{
+					if (t < A.T)
+					{
+						const float cr = __uint_as_float(v[t]) + __uint_as_float(v2[t]);
+						const float d = fmaxf(bs - 2.f * cr, 0.f) + m.xi2_half;           // diff2.cuh:170-186, :1290-1296
+						out[t] = d;
+						bmin = fminf(bmin, d);
+					}
+				}
+			}
+			bmin = -warp_max(-bmin);
+			if (lane == 0) s_min[q] = bmin;
+			asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		const float b = fminf(fminf(s_min[0], s_min[1]), fminf(s_min[2], s_min[3]));
+		if (b < FLT_MAX) rb_atomic_min_pos(&A.states[p].min_diff2_bits, b);
+	}
+	if (warp == 1)
+	{
+		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64) : "memory");
+	}
+}
+
+
+bool rbk_coarse_fused_applicable(rb_ctx *ctx, const PoolSlot &s)
+{
+	const char *e = getenv("RB_COARSE_FUSED");
+	const int mode = e ? atoi(e) : 1;
+	if (mode == 0 || ctx->d_samp.n_trans > FU_BN) return false;
+	return mode == 2 || s.has_priors;                      // default: the local-search path
+}
+
+int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
+{
+	const RbModelDev &M = ctx->d_model;
+	const RbSamplingDev &S = ctx->d_samp;
+	const int P = s.P, T = S.n_trans, K = M.nr_classes;
+	const int npix = M.nvc, n = M.coarse_size;
+	const int nkb = (npix + FU_PIX - 1) / FU_PIX;
+	const size_t kpad = (size_t) nkb * 32;
+	const size_t rows = (size_t) P * FU_BN;
+	DevBuf &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5], &bX2 = ctx->gemm_buf[9];
+	RB_CHECK(bBhi.ensure(rows * kpad * 4)); RB_CHECK(bBlo.ensure(rows * kpad * 4)); RB_CHECK(bX2.ensure((size_t) P * 4));
+	k_gemm_build_B<<<(unsigned) rows, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, FU_BN, P,
+		bBhi.as<float>(), bBlo.as<float>(), kpad, nullptr, nullptr, 0, bX2.as<float>());
+	RB_LAUNCH_CHECK(ctx);
+	CUtensorMap tb, tbl;
+	RB_CHECK(make_tmap(&tb, bBhi.as<float>(), rows, kpad, FU_BN)); RB_CHECK(make_tmap(&tbl, bBlo.as<float>(), rows, kpad, FU_BN));
+	FusedArgs A;
+	memset(&A, 0, sizeof(A));
+	A.metas = s.meta.as<RbPartMeta>(); A.states = s.state.as<RbPartState>();
+	A.dir_idx = s.dir_idx.as<int>(); A.psi_idx = s.psi_idx.as<int>();
+	A.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>(); A.Mweight = s.Mweight.as<float>();
+	A.img4 = cimg4; A.x2 = bX2.as<float>(); A.projs = ctx->d_proj.as<RbProjector>();
+	A.pix = M.pix_c; A.npix = npix; A.n = n; A.T = T; A.num_kblocks = nkb;
+	A.tiles_per_class = (s.max_no + FU_BM - 1) / FU_BM;
+	static bool configured = false;
+	if (!configured)
+	{
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		configured = true;
+	}
+	dim3 grid((unsigned) (A.tiles_per_class * K), (unsigned) P);
+	k_coarse_fused<<<grid, FU_THREADS, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
 

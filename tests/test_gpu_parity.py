@@ -214,8 +214,28 @@ def test_pool_global_search(device, oracle):
     _compare_pool(device, oracle, wl)
 
 
-def test_pool_local_search(device, oracle):
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_pool_local_search(device, oracle, monkeypatch, fused):
+    """Local searches; fused=1: projection + tcgen05 contraction per (particle, orientation tile) (k_coarse_fused),
+    fused=0: the SIMT coarse kernel."""
+    monkeypatch.setenv("RB_COARSE_FUSED", fused)
     wl = make_workload(ori_size=32, healpix_order=2, n_particles=10, nr_classes=1, seed=22, snr=0.2, local_search=True)
+    _compare_pool(device, oracle, wl)
+
+
+def test_pool_local_search_fused_two_classes_many_orientations(device, oracle, monkeypatch):
+    """More than one 128-orientation tile per particle and two classes through the fused kernel; wide prior."""
+    monkeypatch.setenv("RB_COARSE_FUSED", "1")
+    wl = make_workload(ori_size=32, healpix_order=2, n_particles=6, nr_classes=2, seed=28, snr=0.2, local_search=True, sigma_ang=25.0)
+    assert (np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off)).max() > 128
+    _compare_pool(device, oracle, wl)
+
+
+def test_pool_global_search_through_fused_kernel(device, oracle, monkeypatch):
+    """The fused kernel also handles identity orientation lists (global search) when forced."""
+    monkeypatch.setenv("RB_COARSE_GEMM", "0")
+    monkeypatch.setenv("RB_COARSE_FUSED", "2")
+    wl = make_workload(ori_size=32, healpix_order=1, n_particles=5, nr_classes=2, seed=29, snr=0.3)
     _compare_pool(device, oracle, wl)
 
 

@@ -361,6 +361,8 @@ def run_reference(args):
     """The reference's CPU implementation of the path on all host cores; rank 0 only."""
     if int(os.environ.get("RANK", "0")) != 0:
         return
+    if args.workload == "reconstruct_256":
+        return run_reference_reconstruct(args)
     kw, dflt = WORKLOADS[args.workload]
     from relion_b200.workload import make_workload
     n = args.cpu_sample
@@ -378,19 +380,175 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+def run_reconstruct(args):
+    """BASELINE config #2: posed back-projection only (relion_reconstruct's per-particle path), 256-px particles, pad 2."""
+    import torch
+    import torch.distributed as dist
+    from relion_b200.estep import MlDeviceBundle
+    from relion_b200 import parallel, synth
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    n, r_max, pf = 256, 128, 2.0
+    xs = n // 2 + 1
+    P = args.pool or 2048
+    rng = np.random.default_rng(1 + 1000 * rank)
+    # synthetic posed particles: noise spectra times a CTF (values do not change the work), weights ctf^2, uniform SO(3) poses
+    ctfs = np.stack([synth.CTF(d, d + 300.0, 30.0).fftw_image(n, n, 1.0) for d in rng.uniform(10000, 30000, 16)]).astype(np.float32)
+    ci = rng.integers(0, 16, P)
+    F = torch.empty((P, n, xs, 2), dtype=torch.float32).pin_memory()
+    W = torch.empty((P, n, xs), dtype=torch.float32).pin_memory()
+    Fn, Wn = F.numpy(), W.numpy()
+    for p0 in range(0, P, 256):
+        p1 = min(P, p0 + 256)
+        c = ctfs[ci[p0:p1]]
+        Fn[p0:p1] = rng.standard_normal((p1 - p0, n, xs, 2), dtype=np.float32) * c[..., None]
+        Wn[p0:p1] = c * c
+    Fn[:, 0, 0, :] = 0.0                                     # DC zeroed (src/reconstructor.cpp:716)
+    u = rng.standard_normal((P, 4)); u /= np.linalg.norm(u, axis=1, keepdims=True)     # uniform rotations from unit quaternions
+    a, b, c_, d = u.T
+    R = np.stack([a * a + b * b - c_ * c_ - d * d, 2 * (b * c_ - a * d), 2 * (b * d + a * c_),
+                  2 * (b * c_ + a * d), a * a - b * b + c_ * c_ - d * d, 2 * (c_ * d - a * b),
+                  2 * (b * d - a * c_), 2 * (c_ * d + a * b), a * a - b * b - c_ * c_ + d * d], axis=1).astype(np.float32)
+    pad = synth.pad_size_for(r_max, pf)
+    shape = (pad, pad, pad // 2 + 1)
+    dev = MlDeviceBundle(local)
+    dev.bp_init(0, shape, r_max, pf)
+
+    def barrier():
+        dev.sync_all_backprojects(); torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    dev.bp_posed_stage(n, F, W, R)
+    sampler = ClockSampler(local); sampler.start()
+    t_w = time.perf_counter(); n_w = 0
+    while n_w < args.warmup or time.perf_counter() - t_w < 1.0:
+        dev.bp_posed_run(0); dev.sync_all_backprojects(); n_w += 1
+    dev.bp_clear(0)
+    launches0 = dev.launch_count()
+    barrier()
+    dev.timer_start()
+    for _ in range(args.steps):
+        dev.bp_posed_run(0)
+    kernel_ms = dev.timer_stop()                             # the scatter kernels alone (roofline)
+    ms = kernel_ms
+    if world > 1:
+        dev.timer_start()
+        parallel.all_reduce_backprojectors(dev, 1)
+        torch.cuda.synchronize()
+        ms += dev.timer_stop()
+    barrier()
+    clocks = sampler.stop()
+    launches = dev.launch_count() - launches0
+    t = torch.tensor([ms, kernel_ms], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max, kernel_ms = float(t[0].item()), float(t[1].item())
+    value = P * world * args.steps / (ms_max / 1e3)
+    # end to end: host buffers through rb_backproject_posed (chunked H2D overlapped with the scatter)
+    dev.backproject_posed(0, n, F, W, R)
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        dev.backproject_posed(0, n, F, W, R)
+    dev.sync_all_backprojects()
+    e2e_s = time.perf_counter() - t1
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = P * world * args.steps / float(t.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    # pixels scattered per image: |(x, y)| <= r_max on the half image, minus the x = 0, y < 0 column, weight > 0
+    iy = np.arange(n); yy = np.where(iy < xs, iy, iy - n)[:, None]; xx = np.arange(xs)[None, :]
+    inside = (xx * xx + yy * yy <= r_max * r_max) & ~((xx == 0) & (yy < 0))
+    npr = float((inside[None] & (Wn[:64] > 0)).sum(axis=(1, 2)).mean())
+    peak, peak_src = peaks()
+    bytes_per_launch = 204.0 * npr * P                       # (2 x 96 + 12) B per scattered pixel
+    ach = bytes_per_launch * args.steps / (kernel_ms * 1e-3) / 1e9
+    # CPU baseline: the compiled restatement of BackProjector::backproject2Dto3D, one thread as relion_reconstruct runs it
+    from oracle.bindings import backproject_posed as cpu_bp
+    ns = min(P, max(8, args.cpu_sample * 16))
+    acc = tuple(np.zeros(shape, np.float64) for _ in range(3))
+    for a_ in acc:
+        a_.fill(0.0)                                         # map the pages before timing
+    Fs = np.ascontiguousarray(Fn[:ns].view(np.complex64)[..., 0])
+    t0 = time.perf_counter()
+    cpu_bp(shape, Fs, Wn[:ns], R[:ns], r_max, pf, out=acc)
+    cpu_s = time.perf_counter() - t0
+    cpu = {"value": round(ns / cpu_s, 2), "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{ns} images, double accumulators, one thread (Reconstructor::backprojectOneParticle loop)", "seconds": round(cpu_s, 2)}
+    out = {"metric": "particles/sec, posed back-projection only (relion_reconstruct path, 256 px, pad 2)", "value": round(value, 1), "unit": UNIT,
+           "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "reconstruct_256", "box": n, "padding": pf, "accumulator": list(shape), "particles_per_step_per_gpu": P,
+                      "poses": "uniform SO(3)", "scattered_pixels_per_image": npr,
+                      "l2_policy": "accumulator (1.1 GB) and image batch (0.8 GB) both larger than L2, no flush",
+                      "parallelism": f"particles sharded over {world} GPU(s), one accumulator per GPU"},
+           "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(P * n * xs * 12 + P * 36), "d2h_bytes_per_step": 0},
+           "gpu_launches": int(launches), "clocks": clocks,
+           "roofline": {"kernel": "k_backproject_posed", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                        "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_launch": bytes_per_launch},
+           "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference_reconstruct(args):
+    """Reference arm of the reconstruct workload: the compiled restatement of BackProjector::backproject2Dto3D on one thread
+    (relion_reconstruct back-projects one particle after the other), bounded sample per step."""
+    from relion_b200 import synth
+    from oracle.bindings import backproject_posed as cpu_bp
+    n, r_max, pf = 256, 128, 2.0
+    xs = n // 2 + 1
+    ns = max(8, args.cpu_sample * 16)
+    rng = np.random.default_rng(1)
+    c = synth.CTF(20000.0, 20300.0, 30.0).fftw_image(n, n, 1.0).astype(np.float32)
+    F = (rng.standard_normal((ns, n, xs)) + 1j * rng.standard_normal((ns, n, xs))).astype(np.complex64) * c
+    W = np.broadcast_to(c * c, (ns, n, xs)).copy()
+    R = synth.inverse_euler_f32(rng.uniform(-180, 180, ns), np.degrees(np.arccos(rng.uniform(-1, 1, ns))), rng.uniform(0, 360, ns))
+    pad = synth.pad_size_for(r_max, pf)
+    shape = (pad, pad, pad // 2 + 1)
+    times = []
+    acc = tuple(np.zeros(shape, np.float64) for _ in range(3))
+    for a_ in acc:
+        a_.fill(0.0)                                         # map the pages before timing
+    for i in range(min(args.warmup, 1) + args.steps):
+        t0 = time.perf_counter()
+        cpu_bp(shape, F, W, R, r_max, pf, out=acc)
+        if i >= min(args.warmup, 1):
+            times.append(time.perf_counter() - t0)
+    v = round(ns * len(times) / sum(times), 2)
+    cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{ns} images per step, {len(times)} step(s), one thread, double accumulators"}
+    print(json.dumps({"impl": "reference", "metric": "particles/sec, posed back-projection only (relion_reconstruct path, 256 px, pad 2)",
+                      "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                      "ms_per_step": round(1e3 * ns / v, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                      "data": "synthetic", "config": {"workload": "reconstruct_256", "box": n, "padding": pf, "sample_images_per_step": ns},
+                      "cpu_baseline": cpu, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="refine3d_256_local", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="refine3d_256_local", choices=sorted(WORKLOADS) + ["reconstruct_256"])
     ap.add_argument("--pool", type=int, default=0, help="particles per pool per GPU (default: workload specific)")
     ap.add_argument("--cpu-sample", type=int, default=32, help="particles in the bounded CPU sample")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
-    if args.impl == "reference":
+    if args.workload == "reconstruct_256" and args.impl == "ours":
+        run_reconstruct(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

@@ -295,11 +295,15 @@ int rb_backproject(rb_ctx *ctx, int iclass, int img_size,
                    float weight_norm, float significant_weight);
 
 /* relion_reconstruct-style posed back-projection (BASELINE config #2; Reconstructor::backprojectOneParticle,
- * src/reconstructor.cpp:328-744 -> BackProjector::backproject2Dto3D, src/backprojector.cpp:55-357):
- * n images [n][img_size][img_size/2+1] complex already multiplied by CTF, weights Fctf=ctf^2,
- * one inverted 3x3 matrix per image. */
+ * src/reconstructor.cpp:328-744 -> BackProjector::backproject2Dto3D, src/backprojector.cpp:55-357, TRILINEAR, no Ewald
+ * sphere): n images [n][img_size][img_size/2+1] complex already multiplied by their CTF, weights Fctf = ctf^2 (pixels
+ * with weight <= 0 are skipped), one INVERTED 3x3 matrix per image ([n][9] fp32, row-major).  Host buffers (pinned
+ * recommended); uploads are chunked and overlapped with the scatter. */
 int rb_backproject_posed(rb_ctx *ctx, int iclass, int img_size, int n,
                          const float *F2D_complex, const float *Fctf, const float *eulers);
+/* The same scatter on a batch that is staged on the device once (roofline measurement without the PCIe copy). */
+int rb_bp_posed_stage(rb_ctx *ctx, int img_size, int n, const float *F2D_complex, const float *Fctf, const float *eulers);
+int rb_bp_posed_run(rb_ctx *ctx, int iclass);
 
 #ifdef __cplusplus
 }

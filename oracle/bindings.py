@@ -102,6 +102,9 @@ def _load(kind: str):
                                        C.c_uint, C.c_int, C.c_int, C.POINTER(ok_debug)]
     port.oracle_significance.restype = C.c_int64
     port.oracle_significance.argtypes = [f32p, C.c_int64, C.c_double, C.c_int, C.c_int, C.c_int, f32p, f32p, C.POINTER(C.c_int64)]
+    f64p = C.POINTER(C.c_double)
+    port.oracle_backproject_posed.restype = C.c_int
+    port.oracle_backproject_posed.argtypes = [f64p, f64p, f64p, C.c_int, C.c_int, C.c_int, f32p, f32p, f32p, C.c_int, C.c_int, C.c_int, C.c_double]
     if kind == "port":
         table = port.portk_kernel_table()
     elif kind == "reference":
@@ -271,3 +274,21 @@ class Oracle:
         w = np.ascontiguousarray(weights, np.float32); c = np.ascontiguousarray(ctfs, np.float32); mi = np.ascontiguousarray(minvsigma2, np.float32)
         self.K.backproject(C.byref(bp.struct), n // 2 + 1, n, _fp(re), _fp(im), _fp(tx), _fp(ty), _fp(w), _fp(mi), _fp(c),
                            len(tx), float(sig_w), float(weight_norm), _fp(e), e.shape[0])
+
+
+def backproject_posed(shape_zyx, F2D, Fctf, eulers, r_max, padding_factor=2.0, out=None):
+    """Compiled restatement of BackProjector::backproject2Dto3D (oracle/estep_driver.cpp:oracle_backproject_posed), one
+    thread, double accumulators like relion_reconstruct: returns (real, imag, weight) float64 [Z, Y, X]."""
+    port, _ = _load("port")
+    z, y, x = shape_zyx
+    if out is None:
+        re = np.zeros((z, y, x), np.float64); im = np.zeros_like(re); w = np.zeros_like(re)
+    else:
+        re, im, w = out                                      # accumulate into caller-owned volumes (timing without the allocation)
+    F = np.ascontiguousarray(F2D, np.complex64); W = np.ascontiguousarray(Fctf, np.float32)
+    e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+    f64p = C.POINTER(C.c_double)
+    st = port.oracle_backproject_posed(re.ctypes.data_as(f64p), im.ctypes.data_as(f64p), w.ctypes.data_as(f64p), x, y, z,
+                                       F.view(np.float32).ctypes.data_as(f32p), _fp(W), _fp(e), F.shape[1], F.shape[0], r_max, padding_factor)
+    assert st == 0
+    return re, im, w

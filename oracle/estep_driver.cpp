@@ -569,6 +569,63 @@ int64_t oracle_significance(const float *weights, int64_t n, double adaptive_fra
 	return r.thresholdIdx;
 }
 
+// BackProjector::backproject2Dto3D (/root/reference/src/backprojector.cpp:55-357), TRILINEAR branch, no Ewald sphere and no
+// magnification matrix, in double like the reference (RFLOAT = double), one image after the other on one thread as
+// relion_reconstruct runs it (Reconstructor::backprojectOneParticle, src/reconstructor.cpp:328-744).
+// f2d: [count][s][s/2+1] complex fp32 (already CTF-multiplied), mweight: [count][s][s/2+1] fp32, ainv: [count][9] fp32
+// INVERTED matrices; data_re/data_im/weight: double [Z][Y][X] centred volumes (STARTINGY = -(Y-1)/2).
+int oracle_backproject_posed(double *data_re, double *data_im, double *weight, int xdim, int ydim, int zdim,
+                             const float *f2d, const float *mweight, const float *ainv, int s, int count,
+                             int r_max, double padding_factor)
+{
+	const int sh = s / 2 + 1;
+	const long rr = (long) floor(r_max * padding_factor + 0.5);
+	const double max_r2 = (double) (rr * rr);
+	const int starty = -((ydim - 1) / 2), startz = -((zdim - 1) / 2);
+	for (int img = 0; img < count; img++)
+	{
+		const float *e = ainv + (size_t) img * 9;
+		const double a00 = e[0] * padding_factor, a01 = e[1] * padding_factor, a10 = e[3] * padding_factor, a11 = e[4] * padding_factor,
+		             a20 = e[6] * padding_factor, a21 = e[7] * padding_factor;
+		const double AtA_xx = a00 * a00 + a10 * a10 + a20 * a20, AtA_xy = a00 * a01 + a10 * a11 + a20 * a21,
+		             AtA_yy = a01 * a01 + a11 * a11 + a21 * a21;
+		const float *F = f2d + (size_t) img * s * sh * 2, *W = mweight + (size_t) img * s * sh;
+		for (int i = 0; i < s; i++)
+		{
+			int y, first_allowed_x;
+			if (i < sh) { y = i; first_allowed_x = 0; } else { y = i - s; first_allowed_x = 1; }
+			const double discr = AtA_xy * AtA_xy * y * y - AtA_xx * (AtA_yy * y * y - max_r2);        // :118-128
+			if (discr < 0.0) continue;
+			const double d = sqrt(discr) / AtA_xx, q = -AtA_xy * y / AtA_xx;
+			int first_x = (int) ceil(q - d), last_x = (int) floor(q + d);
+			if (first_x < first_allowed_x) first_x = first_allowed_x;
+			if (last_x > sh - 1) last_x = sh - 1;
+			for (int x = first_x; x <= last_x; x++)
+			{
+				double vr = F[2 * ((size_t) i * sh + x)], vi = F[2 * ((size_t) i * sh + x) + 1];
+				const double w = W[(size_t) i * sh + x];
+				if (w <= 0.) continue;
+				double xp = a00 * x + a01 * y, yp = a10 * x + a11 * y, zp = a20 * x + a21 * y;
+				if (xp * xp + yp * yp + zp * zp > max_r2) continue;
+				if (xp < 0) { xp = -xp; yp = -yp; zp = -zp; vi = -vi; }
+				int x0 = (int) floor(xp); const double fx = xp - x0;
+				int y0 = (int) floor(yp); const double fy = yp - y0; y0 -= starty;
+				int z0 = (int) floor(zp); const double fz = zp - z0; z0 -= startz;
+				if (x0 < 0 || x0 + 1 >= xdim || y0 < 0 || y0 + 1 >= ydim || z0 < 0 || z0 + 1 >= zdim) continue;   // :213-218
+				const double mfx = 1. - fx, mfy = 1. - fy, mfz = 1. - fz;
+				const double dd[8] = {mfz * mfy * mfx, mfz * mfy * fx, mfz * fy * mfx, mfz * fy * fx,
+				                      fz * mfy * mfx, fz * mfy * fx, fz * fy * mfx, fz * fy * fx};
+				for (int c = 0; c < 8; c++)
+				{
+					const size_t idx = ((size_t) (z0 + (c >> 2)) * ydim + (y0 + ((c >> 1) & 1))) * xdim + x0 + (c & 1);
+					data_re[idx] += dd[c] * vr; data_im[idx] += dd[c] * vi; weight[idx] += dd[c] * w;
+				}
+			}
+		}
+	}
+	return 0;
+}
+
 int oracle_estep_pool(const ok_kernel_table *K, const rb_model *m, const rb_sampling *s,
                       const ok_projector *refs, ok_backprojector *bps,
                       const rb_particles *pool, rb_pool_out *out,

@@ -138,6 +138,8 @@ PROTOTYPES = {
     "rb_backproject": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                  c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_float, C.c_float]),
     "rb_backproject_posed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),
+    "rb_bp_posed_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),
+    "rb_bp_posed_run": (C.c_int, [C.c_void_p, C.c_int]),
 }
 
 _lib = None

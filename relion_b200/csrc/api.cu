@@ -99,6 +99,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
 	for (auto &b : ctx->wc_buf) b.release();
+	for (int i = 0; i < 2; i++) { for (auto &b : ctx->posed_buf[i]) b.release(); if (ctx->posed_ev[i]) cudaEventDestroy(ctx->posed_ev[i]); }
 	for (int i = 0; i < RB_NUM_SLOTS; i++) release_slot(ctx->slot[i]);
 	for (auto &kv : ctx->stage_ev) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	cudaStreamDestroy(ctx->stream);
@@ -902,28 +903,66 @@ extern "C" int rb_backproject(rb_ctx *ctx, int k, int n, const float *eulers, in
 // CTF-multiplied, Fctf = ctf^2 (src/reconstructor.cpp:632-737).  Expressed through the same scatter kernel:
 // img = F2D, ctf = 1, Minvsigma2 = Fctf  =>  F = F2D, Fweight = Fctf.  r_max and the skipped x=0,y<0 half
 // column follow BackProjector::backproject2Dto3D (src/backprojector.cpp:90-91, 150-160).
+// Host images in chunks through two device buffers: the H2D copy of chunk i+1 (copy stream) overlaps the scatter of chunk i.
 extern "C" int rb_backproject_posed(rb_ctx *ctx, int k, int n, int count,
                                     const float *F2D_complex, const float *Fctf, const float *eulers)
 {
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_backproject_posed: accumulator %d not initialised", k);
 	RB_ARG(n > 0 && n % 2 == 0 && n <= 1000 && count > 0, "rb_backproject_posed: bad sizes");
+	RB_ARG(F2D_complex && Fctf && eulers, "rb_backproject_posed: NULL argument");
 	RB_CUDA(cudaSetDevice(ctx->device));
 	const size_t np = (size_t) n * (n / 2 + 1);
-	const int xs = n / 2 + 1;
-	std::vector<float> re(np), im(np), mw(np), ones(np, 1.f);
-	float one = 1.f, zero = 0.f;
-	for (int i = 0; i < count; i++)
+	const int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) count, ((size_t) 512 << 20) / (np * 12)));
+	for (int b = 0; b < 2; b++)
 	{
-		const float *F = F2D_complex + (size_t) i * np * 2, *W = Fctf + (size_t) i * np;
-		for (size_t j = 0; j < np; j++) { re[j] = F[2 * j]; im[j] = F[2 * j + 1]; mw[j] = W[j]; }
-		for (int iy = xs; iy < n; iy++) mw[(size_t) iy * xs] = 0.f;   // first_allowed_x = 1 for negative y rows
-		StageBufs sb(ctx);
-		float *d_e, *d_tx, *d_ty, *d_re, *d_im, *d_w, *d_m, *d_c;
-		RB_CHECK(sb.up(eulers + (size_t) i * 9, 9, &d_e)); RB_CHECK(sb.up(&zero, 1, &d_tx)); RB_CHECK(sb.up(&zero, 1, &d_ty));
-		RB_CHECK(sb.up(re.data(), np, &d_re)); RB_CHECK(sb.up(im.data(), np, &d_im)); RB_CHECK(sb.up(&one, 1, &d_w));
-		RB_CHECK(sb.up(mw.data(), np, &d_m)); RB_CHECK(sb.up(ones.data(), np, &d_c));
-		RB_CHECK(rbk_backproject_stage(ctx, ctx->bp[k], n, d_e, 1, d_tx, d_ty, 1, d_re, d_im, d_w, d_m, d_c, 1.f, 0.5f, 0, 0));
-		RB_CUDA(cudaStreamSynchronize(ctx->stream));
+		RB_CHECK(ctx->posed_buf[b][0].ensure((size_t) chunk * np * 8)); RB_CHECK(ctx->posed_buf[b][1].ensure((size_t) chunk * np * 4));
+		RB_CHECK(ctx->posed_buf[b][2].ensure((size_t) chunk * 36));
+		if (!ctx->posed_ev[b]) RB_CUDA(cudaEventCreateWithFlags(&ctx->posed_ev[b], cudaEventDisableTiming));
 	}
+	ctx->posed_count = 0;   // the staging buffers are being reused
+	cudaEvent_t uploaded;
+	RB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+	int ib = 0;
+	for (int i0 = 0; i0 < count; i0 += chunk, ib ^= 1)
+	{
+		const int c = std::min(chunk, count - i0);
+		// the kernel that last read this buffer must have finished before it is overwritten
+		RB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->posed_ev[ib], 0));
+		RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[ib][0].p, F2D_complex + (size_t) i0 * np * 2, (size_t) c * np * 8, cudaMemcpyHostToDevice, ctx->copy_stream));
+		RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[ib][1].p, Fctf + (size_t) i0 * np, (size_t) c * np * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+		RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[ib][2].p, eulers + (size_t) i0 * 9, (size_t) c * 36, cudaMemcpyHostToDevice, ctx->copy_stream));
+		RB_CUDA(cudaEventRecord(uploaded, ctx->copy_stream));
+		RB_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded, 0));
+		RB_CHECK(rbk_backproject_posed(ctx, ctx->bp[k], n, c, ctx->posed_buf[ib][0].as<float2>(), ctx->posed_buf[ib][1].as<float>(), ctx->posed_buf[ib][2].as<float>()));
+		RB_CUDA(cudaEventRecord(ctx->posed_ev[ib], ctx->stream));
+	}
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	RB_CUDA(cudaEventDestroy(uploaded));
 	return RB_OK;
+}
+
+// Device-resident variant for roofline measurement: stage a batch once, then scatter it any number of times.
+extern "C" int rb_bp_posed_stage(rb_ctx *ctx, int n, int count, const float *F2D_complex, const float *Fctf, const float *eulers)
+{
+	RB_ARG(ctx && F2D_complex && Fctf && eulers, "rb_bp_posed_stage: NULL argument");
+	RB_ARG(n > 0 && n % 2 == 0 && n <= 1000 && count > 0, "rb_bp_posed_stage: bad sizes");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	const size_t np = (size_t) n * (n / 2 + 1);
+	RB_CHECK(ctx->posed_buf[0][0].ensure((size_t) count * np * 8)); RB_CHECK(ctx->posed_buf[0][1].ensure((size_t) count * np * 4));
+	RB_CHECK(ctx->posed_buf[0][2].ensure((size_t) count * 36));
+	RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[0][0].p, F2D_complex, (size_t) count * np * 8, cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[0][1].p, Fctf, (size_t) count * np * 4, cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[0][2].p, eulers, (size_t) count * 36, cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->posed_n = n; ctx->posed_count = count;
+	return RB_OK;
+}
+
+extern "C" int rb_bp_posed_run(rb_ctx *ctx, int k)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_posed_run: accumulator %d not initialised", k);
+	if (ctx->posed_count < 1) { rb_set_error("rb_bp_posed_run: nothing staged (rb_bp_posed_stage)"); return RB_ERR_STATE; }
+	RB_CUDA(cudaSetDevice(ctx->device));
+	return rbk_backproject_posed(ctx, ctx->bp[k], ctx->posed_n, ctx->posed_count, ctx->posed_buf[0][0].as<float2>(),
+	                             ctx->posed_buf[0][1].as<float>(), ctx->posed_buf[0][2].as<float>());
 }

@@ -214,7 +214,10 @@ struct rb_ctx {
 	// stage timing
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
 	DevBuf scratch[8];
-	DevBuf wc_buf[10];               // partials / compact list of the multi-CTA coarse weight conversion
+	DevBuf wc_buf[10];
+	DevBuf posed_buf[2][3];          // staged posed images (F2D, Fctf, matrices), two buffers for upload / compute overlap
+	int posed_n = 0, posed_count = 0;   // what rb_bp_posed_stage left in posed_buf[0]
+	cudaEvent_t posed_ev[2] = {nullptr, nullptr};               // partials / compact list of the multi-CTA coarse weight conversion
 	DevBuf gemm_buf[10];             // operands of the tensor-core coarse pass (kernels_gemm.cu)
 };
 
@@ -230,6 +233,7 @@ int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt,
 int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
 int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
+int rbk_backproject_posed(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers);
 int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out);
 
 // kernels_diff2.cu

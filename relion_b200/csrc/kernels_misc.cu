@@ -124,3 +124,104 @@ int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// relion_reconstruct-style posed back-projection (BASELINE config #2): BackProjector::backproject2Dto3D
+// (/root/reference/src/backprojector.cpp:55-357, TRILINEAR, no Ewald sphere / magnification), one orientation and unit
+// weight per image, images already multiplied by their CTF, weights Fctf = ctf^2 (src/reconstructor.cpp:632-716).
+// Positions are computed in fp64 like the reference (RFLOAT = double there), so the set of pixels inside r_max and their
+// cells are the reference's; the interpolation weights and the accumulation are fp32 (float4 (re, im, w, 0) voxels,
+// one 16-byte vector reduction per corner, two lanes per pixel so that the x-neighbours of a corner pair share a sector).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void red_add_v4_misc(float4 *addr, float a, float b, float c)
+{
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+k_backproject_posed(RbBackprojector bp, int n, int count, const float2 *F2D, const float *Fctf, const float *eulers)
+{
+	const int xs = n / 2 + 1;
+	const double pf = (double) bp.padding_factor;
+	const long long rr = (long long) floor((double) bp.maxR * pf + 0.5);
+	const double max_r2 = (double) (rr * rr);
+	const int npix = n * xs;
+	const int nit = (npix + 255) / 256;
+	const size_t sy = bp.mdlX, sz = (size_t) bp.mdlX * bp.mdlY;
+	for (int img = blockIdx.x; img < count; img += gridDim.x)
+	{
+		const float *e = eulers + (size_t) img * 9;
+		const double a00 = (double) e[0] * pf, a01 = (double) e[1] * pf, a10 = (double) e[3] * pf, a11 = (double) e[4] * pf,
+		             a20 = (double) e[6] * pf, a21 = (double) e[7] * pf;
+		const double AtA_xx = a00 * a00 + a10 * a10 + a20 * a20, AtA_xy = a00 * a01 + a10 * a11 + a20 * a21,
+		             AtA_yy = a01 * a01 + a11 * a11 + a21 * a21;
+		const float2 *F = F2D + (size_t) img * npix;
+		const float *W = Fctf + (size_t) img * npix;
+		for (int it = 0; it < nit; it++)                      // uniform trip count: the scatter below is warp-cooperative
+		{
+			const int pix = it * 256 + threadIdx.x;
+			long long cell = -1;
+			float sfx = 0.f, sfy = 0.f, sfz = 0.f, vr = 0.f, vi = 0.f, vw = 0.f;
+			if (pix < npix)
+			{
+				const int i = pix / xs, x = pix - i * xs;
+				const int y = i < xs ? i : i - n;
+				const int first_allowed_x = i < xs ? 0 : 1;
+				const double discr = AtA_xy * AtA_xy * y * y - AtA_xx * (AtA_yy * y * y - max_r2);   // :118-128
+				if (discr >= 0.)
+				{
+					const double d = sqrt(discr) / AtA_xx, q = -AtA_xy * y / AtA_xx;
+					int first_x = (int) ceil(q - d), last_x = (int) floor(q + d);
+					if (first_x < first_allowed_x) first_x = first_allowed_x;
+					if (last_x > xs - 1) last_x = xs - 1;
+					const float w = __ldg(W + pix);
+					if (x >= first_x && x <= last_x && w > 0.f)
+					{
+						double xp = a00 * x + a01 * y, yp = a10 * x + a11 * y, zp = a20 * x + a21 * y;
+						if (xp * xp + yp * yp + zp * zp <= max_r2)
+						{
+							float2 v = __ldg(F + pix);
+							if (xp < 0.) { xp = -xp; yp = -yp; zp = -zp; v.y = -v.y; }
+							const double fx0 = floor(xp), fy0 = floor(yp), fz0 = floor(zp);
+							const int x0 = (int) fx0, y0 = (int) fy0 - bp.mdlInitY, z0 = (int) fz0 - bp.mdlInitZ;
+							if (x0 >= 0 && x0 + 1 < bp.mdlX && y0 >= 0 && y0 + 1 < bp.mdlY && z0 >= 0 && z0 + 1 < bp.mdlZ)   // :213-218
+							{
+								sfx = (float) (xp - fx0); sfy = (float) (yp - fy0); sfz = (float) (zp - fz0);
+								vr = v.x; vi = v.y; vw = w;
+								cell = ((long long) z0 * bp.mdlY + y0) * bp.mdlX + x0;
+							}
+						}
+					}
+				}
+			}
+#pragma unroll
+			for (int h = 0; h < 2; h++)
+			{
+				const int src = 16 * h + ((threadIdx.x & 31) >> 1);
+				const long long c = __shfl_sync(0xffffffffu, cell, src);
+				const float fx = __shfl_sync(0xffffffffu, sfx, src), fy = __shfl_sync(0xffffffffu, sfy, src), fz = __shfl_sync(0xffffffffu, sfz, src);
+				const float r = __shfl_sync(0xffffffffu, vr, src), im = __shfl_sync(0xffffffffu, vi, src), w = __shfl_sync(0xffffffffu, vw, src);
+				if (c >= 0)
+				{
+					const int px = threadIdx.x & 1;
+					const float wx = px ? fx : 1.f - fx, mfy = 1.f - fy, mfz = 1.f - fz;
+					float4 *b = bp.vol + (size_t) c + px;
+					float dd;
+					dd = mfz * mfy * wx; red_add_v4_misc(b, dd * r, dd * im, dd * w);
+					dd = mfz * fy * wx;  red_add_v4_misc(b + sy, dd * r, dd * im, dd * w);
+					dd = fz * mfy * wx;  red_add_v4_misc(b + sz, dd * r, dd * im, dd * w);
+					dd = fz * fy * wx;   red_add_v4_misc(b + sz + sy, dd * r, dd * im, dd * w);
+				}
+			}
+		}
+	}
+}
+
+int rbk_backproject_posed(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers)
+{
+	if (count < 1) return RB_OK;
+	const int grid = count < ctx->num_sms * 8 ? count : ctx->num_sms * 8;
+	k_backproject_posed<<<grid, 256, 0, ctx->stream>>>(bp, n, count, d_F, d_W, d_eulers);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}

@@ -31,6 +31,15 @@ def _ptr(a, ctype):
     return a.ctypes.data_as(C.POINTER(ctype))
 
 
+def _fptr(a):
+    """float* to a float32 / complex64 numpy array or a CPU torch tensor (pinned host staging buffers)."""
+    if hasattr(a, "data_ptr"):
+        return _ptr(a, C.c_float)
+    a = np.ascontiguousarray(a)
+    assert a.dtype in (np.float32, np.complex64), a.dtype
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
 def _f64(a):
     return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
 
@@ -424,7 +433,14 @@ class MlDeviceBundle:
                                                      float(weight_norm), float(sig_w)))
 
     def backproject_posed(self, iclass, img_size, F2D, Fctf, eulers):
-        F = np.ascontiguousarray(F2D, np.complex64); W = np.ascontiguousarray(Fctf, np.float32)
+        """Reconstructor::backprojectOneParticle for a batch (rb_backproject_posed): F2D [n, s, s/2+1] complex64 (numpy or a
+        pinned torch tensor viewed as float32), Fctf [n, s, s/2+1] float32, eulers [n, 9] inverted matrices."""
         e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
-        capi.check(self.lib, self.lib.rb_backproject_posed(self.ctx, iclass, img_size, F.shape[0], _ptr(F.view(np.float32), C.c_float),
-                                                           _ptr(W, C.c_float), _ptr(e, C.c_float)))
+        capi.check(self.lib, self.lib.rb_backproject_posed(self.ctx, iclass, img_size, e.shape[0], _fptr(F2D), _fptr(Fctf), _ptr(e, C.c_float)))
+
+    def bp_posed_stage(self, img_size, F2D, Fctf, eulers):
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        capi.check(self.lib, self.lib.rb_bp_posed_stage(self.ctx, img_size, e.shape[0], _fptr(F2D), _fptr(Fctf), _ptr(e, C.c_float)))
+
+    def bp_posed_run(self, iclass):
+        capi.check(self.lib, self.lib.rb_bp_posed_run(self.ctx, iclass))

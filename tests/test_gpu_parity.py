@@ -331,6 +331,36 @@ def test_large_weight_conversion_matches_single_cta(device, monkeypatch, maxsig,
         assert res[1]["nr_significant_coarse"].max() <= maxsig
 
 
+@pytest.mark.parametrize("n,count,r_max", [(32, 24, 16), (24, 7, 9), (16, 300, 8)])
+def test_backproject_posed_against_reference_algorithm(device, n, count, r_max):
+    """BASELINE config #2: rb_backproject_posed against the restated BackProjector::backproject2Dto3D (float64) on random
+    poses; images already CTF-multiplied, weights ctf^2 with some non-positive entries (skipped pixels)."""
+    from oracle.backproject_posed import backproject2Dto3D
+    rng = np.random.default_rng(n * 100 + count)
+    xs = n // 2 + 1
+    pad = synth.pad_size_for(r_max, 2.0)
+    shape = (pad, pad, pad // 2 + 1)
+    device.bp_init(0, shape, r_max, 2.0)
+    F = (rng.standard_normal((count, n, xs)) + 1j * rng.standard_normal((count, n, xs))).astype(np.complex64)
+    W = rng.uniform(-0.1, 1.0, (count, n, xs)).astype(np.float32)
+    eul = synth.inverse_euler_f32(rng.uniform(-180, 180, count), rng.uniform(0, 180, count), rng.uniform(0, 360, count))
+    device.backproject_posed(0, n, F, W, eul)
+    gre, gim, gw = device.bp_get(0)
+    data = np.zeros(shape, np.complex128); weight = np.zeros(shape, np.float64)
+    for i in range(count):
+        backproject2Dto3D(data, weight, F[i], eul[i].reshape(3, 3).astype(np.float64), W[i], r_max, 2.0)
+    assert np.abs(weight).max() > 0
+    for got, want in ((gre, data.real), (gim, data.imag), (gw, weight)):
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    # the staged (device-resident) entry points do the same
+    device.bp_clear(0)
+    device.bp_posed_stage(n, F, W, eul)
+    device.bp_posed_run(0)
+    gre2, _, gw2 = device.bp_get(0)
+    assert np.abs(gw2 - weight).max() <= 2e-5 * np.abs(weight).max()
+    assert np.abs(gre2 - data.real).max() <= 2e-5 * np.abs(data.real).max()
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

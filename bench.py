@@ -50,6 +50,9 @@ WORKLOADS = {
     # coarse window 54 px: the coarse cross term is the dense contraction that runs on the tensor cores
     "class3d_256_global": (dict(ori_size=256, current_size=128, healpix_order=3, offset_range=5.0, offset_step=2.0, nr_classes=4,
                                 snr=0.05, pixel_size=1.0, n_blobs=200, nr_groups=8), 256),
+    # BASELINE config #1: 2D classification, K = 10, 64-px particles, psi step 6 deg, offset range 5 / step 2
+    "class2d_64": (dict(ori_size=64, nr_classes=10, ref_dim=2, psi_step=6.0, offset_range=5.0, offset_step=2.0, snr=0.1,
+                        pixel_size=3.0, n_blobs=25, nr_groups=8), 2000),
     "tiny": (dict(ori_size=32, healpix_order=1, nr_classes=1, snr=0.3, n_blobs=20), 16),
 }
 
@@ -169,17 +172,24 @@ def run_ours(args):
     kw, dflt = WORKLOADS[args.workload]
     P = args.pool or dflt
     t0 = time.time()
-    # references first (the projector callback needs them on the device)
-    from relion_b200 import synth
-    refs = []
-    for k in range(kw.get("nr_classes", 1)):
-        vol = synth.make_phantom(kw["ori_size"], n_blobs=kw.get("n_blobs", 40), seed=1993 + 17 * k)
-        data, r_max = synth.reference_ft(vol, current_size=kw.get("current_size") or kw["ori_size"], padding_factor=2.0)
-        refs.append(data.astype(np.complex64))
-        dev.set_reference(k, refs[-1], r_max, 2.0)
-    # every rank searches its own shard of the data set: same references, different particles (weak scaling)
-    wl = make_workload(args.workload, n_particles=P, seed=1993 + 1000 * rank, projector=projector,
-                       refs_override=(refs, r_max), **kw)
+    if kw.get("ref_dim", 3) == 2:
+        # 2D references: small enough for the numpy generator
+        wl = make_workload(args.workload, n_particles=P, seed=1993 + 1000 * rank, **kw)
+        wl.model.bp_circle_bound = False                     # backproject2D has no circle bound (BP.h:77)
+        for k, v in enumerate(wl.refs):
+            dev.set_reference(k, v, wl.r_max, 2.0)
+    else:
+        # references first (the projector callback needs them on the device)
+        from relion_b200 import synth
+        refs = []
+        for k in range(kw.get("nr_classes", 1)):
+            vol = synth.make_phantom(kw["ori_size"], n_blobs=kw.get("n_blobs", 40), seed=1993 + 17 * k)
+            data, r_max = synth.reference_ft(vol, current_size=kw.get("current_size") or kw["ori_size"], padding_factor=2.0)
+            refs.append(data.astype(np.complex64))
+            dev.set_reference(k, refs[-1], r_max, 2.0)
+        # every rank searches its own shard of the data set: same references, different particles (weak scaling)
+        wl = make_workload(args.workload, n_particles=P, seed=1993 + 1000 * rank, projector=projector,
+                           refs_override=(refs, r_max), **kw)
     gen_s = time.time() - t0
     dev.set_model(wl.model)
     dev.set_sampling(wl.sampling)
@@ -274,7 +284,8 @@ def run_ours(args):
         if stage_ms[s] > 0:
             stages[s]["algorithmic_GBps"] = round(by[s] / (stage_ms[s] * 1e-3) / 1e9, 1)
             stages[s]["frac_of_hbm_peak"] = round(by[s] / (stage_ms[s] * 1e-3) / 1e9 / peak, 4)
-    tensor_coarse = by["coarse_flops"] > 0 and os.environ.get("RB_COARSE_GEMM", "1") != "0"
+    gemm_env = os.environ.get("RB_COARSE_GEMM", "1")
+    tensor_coarse = by["coarse_flops"] > 0 and gemm_env != "0" and (gemm_env == "2" or wl.sampling.n_dir * wl.sampling.n_psi >= 32)
     if tensor_coarse:
         # useful FLOPs (one fp32-equivalent product per operand pair); the kernel executes 3 TF32 MMAs per product
         d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
@@ -305,7 +316,7 @@ def run_ours(args):
         "config": {"workload": args.workload, "box": wl.model.ori_size, "current_size": wl.model.current_size,
                    "coarse_size": wl.model.coarse_size, "classes": wl.model.nr_classes, "pool_particles_per_gpu": P,
                    "healpix_order": wl.sampling.healpix_order, "coarse_translations": wl.sampling.n_trans,
-                   "oversampling": 1, "search": "local" if wl.pool.dir_off is not None else "global",
+                   "reference_dim": 3 if wl.sampling.is_3d else 2, "oversampling": 1, "search": "local" if wl.pool.dir_off is not None else "global",
                    "mean_coarse_orientations": float(np.mean(np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off))) if wl.pool.dir_off is not None else wl.sampling.n_dir * wl.sampling.n_psi,
                    "mean_fine_orientations": float(pr["n_fine_orient"].mean()), "mean_fine_samples": float(pr["n_fine_samples"].mean()),
                    "l2_policy": "inputs larger than L2 (pool images + 515^3 reference/accumulator >> 126 MB), no flush",

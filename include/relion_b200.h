@@ -17,7 +17,7 @@
  *     the batched rb_estep_pool() replaces the reference's "one particle per OpenMP thread" fan-out
  *     (src/ml_optimiser.cpp:4280), so no concurrent entry is needed.
  *   - there is NO CPU fallback: without a CUDA device rb_ctx_create() fails with RB_ERR_CUDA.
- *   - scope: 3D reference / 2D images, nr_bodies == 1, no helical/tomo, no CC first iteration,
+ *   - scope: 3D or 2D references / 2D images, nr_bodies == 1, no helical/tomo, no CC first iteration,
  *     no SGD/VDAM back-projection (DESIGN.md "out of scope").
  *
  * Index conventions follow the reference:
@@ -79,6 +79,9 @@ int rb_timer_stop(rb_ctx *ctx, double *ms);
  * Reference volumes (AccProjector::setMdlDim + initMdl, acc_projector_impl.h:5-312; fed from
  * MlModel::PPref[k].data, cuda_ml_optimiser.cu:116-127).
  * vol: complex (re,im) pairs, [mdlZ][mdlY][mdlX], x >= 0 half, mdlInitY = mdlInitZ = -(mdlY-1)/2.
+ * mdlZ == 1: a 2D reference (2D classification, project2Dmodel acc_projectorkernel_impl.h:233-300); pass
+ * rot = tilt = 0 in rb_sampling and n_over_rot = 2^oversampling.  rb_bp_init with mdlZ == 1 likewise gives a 2D
+ * accumulator (backproject2D, BP.cuh:22-172) and rb_bp_get then returns [mdlY][mdlX] arrays.
  * ---------------------------------------------------------------------------------------------- */
 int rb_set_reference(rb_ctx *ctx, int iclass, const double *vol_complex,
                      int mdlX, int mdlY, int mdlZ, int mdlInitY, int mdlInitZ,

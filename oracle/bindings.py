@@ -65,6 +65,8 @@ class ok_kernel_table(C.Structure):
                                     C.c_ulong, C.c_float, C.c_float, f32p, C.c_ulong)),
         ("bp_sync_alloc", C.CFUNCTYPE(C.c_void_p, C.c_int, C.c_int)),
         ("bp_sync_free", C.CFUNCTYPE(None, C.c_void_p)),
+        ("backproject2d", C.CFUNCTYPE(None, BP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                                      C.c_ulong, C.c_float, C.c_float, f32p, C.c_ulong)),
     ]
 
 
@@ -128,20 +130,29 @@ class Projector:
     """ok_projector over a complex64 [Z, Y, X] volume."""
 
     def __init__(self, vol: np.ndarray, r_max: int, padding_factor: float = 2.0):
+        vol = np.asarray(vol)
+        self.is_2d = vol.ndim == 2
+        if self.is_2d:
+            # 2D reference: two planes, the second one zero, z origin 0.  With in-plane rotations zp == 0 and the 3D
+            # kernels reduce exactly to project2Dmodel (tests/test_oracle.py pins this against the reference's 2D kernels)
+            vol = np.stack([vol, np.zeros_like(vol)])
         self.vol = np.ascontiguousarray(vol, dtype=np.complex64)
         z, y, x = self.vol.shape
         init = -((y - 1) // 2)
-        self.struct = ok_projector(_fp(self.vol.view(np.float32)), x, y, z, init, init, r_max, padding_factor)
+        self.struct = ok_projector(_fp(self.vol.view(np.float32)), x, y, z, init, 0 if self.is_2d else init, r_max, padding_factor)
 
 
 class Backprojector:
     def __init__(self, shape_zyx, r_max: int, padding_factor: float = 2.0):
-        z, y, x = shape_zyx
+        """shape (Z, Y, X), or (Y, X) for the 2D accumulator of 2D classification (mdlZ == 1 -> backproject2D)."""
+        self.is_2d = len(shape_zyx) == 2
+        z, y, x = ((1,) + tuple(shape_zyx)) if self.is_2d else shape_zyx
         self.real = np.zeros(shape_zyx, np.float32)
         self.imag = np.zeros(shape_zyx, np.float32)
         self.weight = np.zeros(shape_zyx, np.float32)
         init = -((y - 1) // 2)
-        self.struct = ok_backprojector(_fp(self.real), _fp(self.imag), _fp(self.weight), x, y, z, init, init, r_max, padding_factor, None)
+        self.struct = ok_backprojector(_fp(self.real), _fp(self.imag), _fp(self.weight), x, y, z, init, 0 if self.is_2d else init,
+                                       r_max, padding_factor, None)
 
 
 class Oracle:
@@ -272,8 +283,9 @@ class Oracle:
         tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
         re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32)
         w = np.ascontiguousarray(weights, np.float32); c = np.ascontiguousarray(ctfs, np.float32); mi = np.ascontiguousarray(minvsigma2, np.float32)
-        self.K.backproject(C.byref(bp.struct), n // 2 + 1, n, _fp(re), _fp(im), _fp(tx), _fp(ty), _fp(w), _fp(mi), _fp(c),
-                           len(tx), float(sig_w), float(weight_norm), _fp(e), e.shape[0])
+        fn = self.K.backproject2d if bp.is_2d else self.K.backproject
+        fn(C.byref(bp.struct), n // 2 + 1, n, _fp(re), _fp(im), _fp(tx), _fp(ty), _fp(w), _fp(mi), _fp(c),
+           len(tx), float(sig_w), float(weight_norm), _fp(e), e.shape[0])
 
 
 def backproject_posed(shape_zyx, F2D, Fctf, eulers, r_max, padding_factor=2.0, out=None):

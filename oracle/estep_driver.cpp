@@ -524,7 +524,8 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 			        parts.data(), &AA[(size_t) k * S.Npf], &XA[(size_t) k * S.Npf],
 			        Tf, po.sum_weight, po.significant_weight, part_scale);
 			ok_backprojector bpk = S.bps[k];
-			K->backproject(&bpk, S.nf / 2 + 1, S.nf, nr.data(), ni.data(), S.ftx.data(), S.fty.data(),
+			// 2D accumulators (2D classification) go through backproject2D, acc_helper_functions_impl.h:505-577
+			(bpk.mdlZ == 1 ? K->backproject2d : K->backproject)(&bpk, S.nf / 2 + 1, S.nf, nr.data(), ni.data(), S.ftx.data(), S.fty.data(),
 			               sw.data(), minvs2.data(), ctfs.data(), Tf, po.significant_weight, po.sum_weight,
 			               c.eulers.data(), On);
 			for (int j = 0; j < S.Npf; j++)                                                  // :3467-3482

@@ -129,6 +129,16 @@ typedef struct {
 	 * (AccBackprojector::mutexes, src/acc/acc_backprojector_impl.h:61) */
 	void *(*bp_sync_alloc)(int mdlY, int mdlZ);
 	void (*bp_sync_free)(void *sync);
+
+	/* CpuKernels::backproject2D<CTF_PREMULTIPLIED=false> (src/acc/cpu/cpu_kernels/BP.h:11-218): 2D classification,
+	 * accumulators [mdlY][mdlX] (ok_backprojector with mdlZ == 1).  Projection-type kernels need no 2D twin: a 2D
+	 * reference is handed to them as a two-plane volume whose second plane is zero (see oracle/bindings.py Projector). */
+	void (*backproject2d)(const ok_backprojector *bp, int imgX, int imgY,
+	                      const float *img_re, const float *img_im,
+	                      const float *trans_x, const float *trans_y,
+	                      const float *weights, const float *Minvsigma2s, const float *ctfs,
+	                      unsigned long trans_num, float significant_weight, float weight_norm,
+	                      const float *eulers, unsigned long image_count);
 } ok_kernel_table;
 
 #ifdef __cplusplus

@@ -159,6 +159,21 @@ void refk_backproject(const ok_backprojector *bp, int imgX, int imgY,
 		(unsigned) bp->mdlX, (unsigned) bp->mdlY, bp->mdlInitY, bp->mdlInitZ, mutexes);
 }
 
+void refk_backproject2d(const ok_backprojector *bp, int imgX, int imgY,
+		const float *img_re, const float *img_im, const float *trans_x, const float *trans_y,
+		const float *weights, const float *Minvsigma2s, const float *ctfs,
+		unsigned long trans_num, float significant_weight, float weight_norm,
+		const float *eulers, unsigned long image_count)
+{
+	std::vector<tbb::spin_mutex> local;
+	tbb::spin_mutex *mutexes = (tbb::spin_mutex *) bp->sync;
+	if (!mutexes) { local = std::vector<tbb::spin_mutex>((size_t) bp->mdlY); mutexes = local.data(); }
+	CpuKernels::backproject2D<false>(image_count, 128, (XFLOAT *) img_re, (XFLOAT *) img_im, (XFLOAT *) trans_x, (XFLOAT *) trans_y,
+		(XFLOAT *) weights, (XFLOAT *) Minvsigma2s, (XFLOAT *) ctfs, trans_num, significant_weight, weight_norm, (XFLOAT *) eulers,
+		bp->real, bp->imag, bp->weight, bp->maxR, bp->maxR * bp->maxR, bp->padding_factor,
+		(unsigned) imgX, (unsigned) imgY, (unsigned) (imgX * imgY), (unsigned) bp->mdlX, bp->mdlInitY, mutexes);
+}
+
 void *refk_bp_sync_alloc(int mdlY, int mdlZ) { return new tbb::spin_mutex[(size_t) mdlY * mdlZ]; }
 void refk_bp_sync_free(void *s) { delete[] (tbb::spin_mutex *) s; }
 
@@ -176,8 +191,54 @@ const ok_kernel_table table = {
 	refk_backproject,
 	refk_bp_sync_alloc,
 	refk_bp_sync_free,
+	refk_backproject2d,
 };
 
 } // namespace
 
 extern "C" const ok_kernel_table *refk_kernel_table(void) { return &table; }
+
+// ---- the reference's own 2D-reference kernels (2D classification), used only to PIN the two-plane embedding that the
+// oracle driver and the CUDA library use for 2D references (tests/test_oracle.py::test_2d_embedding_matches_reference_2d_kernels)
+extern "C" {
+
+// AccProjectorKernel::project2Dmodel (acc_projectorkernel_impl.h:233-300) over a half image, coarse-pass y wrap
+void refk2d_project(const float *mdl_complex, int mdlX, int mdlY, int mdlInitY, int mdlMaxR, float padding_factor,
+                    int imgX, int imgY, const float *e, float *out_re, float *out_im)
+{
+	int imgMaxR = imgX - 1;
+	int maxR = mdlMaxR >= imgMaxR ? imgMaxR : mdlMaxR;
+	AccProjectorKernel k(mdlX, mdlY, 0, imgX, imgY, 1, mdlInitY, 0, padding_factor, maxR, (std::complex<XFLOAT> *) mdl_complex);
+	for (int iy = 0; iy < imgY; iy++)
+	{
+		int y = iy > k.maxR ? iy - imgY : iy;
+		for (int x = 0; x < imgX; x++)
+			k.project2Dmodel(x, y, e[0], e[1], e[3], e[4], out_re[iy * imgX + x], out_im[iy * imgX + x]);
+	}
+}
+
+// CpuKernels::diff2_coarse<REF3D = false> as runDiff2KernelCoarse dispatches it for 2D references
+void refk2d_diff2_coarse(const float *mdl_complex, int mdlX, int mdlY, int mdlInitY, int mdlMaxR, float padding_factor,
+                         int imgX, int imgY, const float *eulers, unsigned long O,
+                         const float *trans_x, const float *trans_y, unsigned long T,
+                         const float *img_re, const float *img_im, const float *corr, float *diff2s)
+{
+	int imgMaxR = imgX - 1;
+	int maxR = mdlMaxR >= imgMaxR ? imgMaxR : mdlMaxR;
+	AccProjectorKernel k(mdlX, mdlY, 0, imgX, imgY, 1, mdlInitY, 0, padding_factor, maxR, (std::complex<XFLOAT> *) mdl_complex);
+	unsigned long image_size = (unsigned long) imgX * imgY;
+	std::vector<float> tz(T, 0.f);
+	unsigned long rest = O % D2C_BLOCK_SIZE_2D;
+	unsigned long even = O - rest;
+	if (even)
+		CpuKernels::diff2_coarse<false, false, D2C_BLOCK_SIZE_2D, D2C_EULERS_PER_BLOCK_2D, PREFETCH_FRACTION_2D>(
+			even / D2C_EULERS_PER_BLOCK_2D, (XFLOAT *) eulers, (XFLOAT *) trans_x, (XFLOAT *) trans_y, tz.data(),
+			(XFLOAT *) img_re, (XFLOAT *) img_im, k, (XFLOAT *) corr, diff2s, T, image_size);
+	if (rest)
+		CpuKernels::diff2_coarse<false, false, D2C_BLOCK_SIZE_2D, 1, PREFETCH_FRACTION_2D>(
+			rest, (XFLOAT *) &eulers[9 * even], (XFLOAT *) trans_x, (XFLOAT *) trans_y, tz.data(),
+			(XFLOAT *) img_re, (XFLOAT *) img_im, k, (XFLOAT *) corr, &diff2s[T * even], T, image_size);
+}
+
+} // extern "C"
+

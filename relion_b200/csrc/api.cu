@@ -171,12 +171,14 @@ int rb_sync_tables(rb_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 // reference volumes / accumulators
 // ---------------------------------------------------------------------------------------------
-static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int initY, int initZ, int maxR, double pf)
+static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int &mdlZ, int initY, int &initZ, int maxR, double pf)
 {
 	RB_ARG(ctx, "ctx is NULL");
 	RB_ARG(k >= 0 && k < RB_MAX_CLASSES, "class index %d out of range", k);
-	RB_ARG(mdlX > 1 && mdlY > 1 && mdlZ > 1, "rb_set_reference: only 3D references are supported (got %dx%dx%d)", mdlX, mdlY, mdlZ);
+	RB_ARG(mdlX > 1 && mdlY > 1 && mdlZ >= 1, "rb_set_reference: bad dimensions %dx%dx%d", mdlX, mdlY, mdlZ);
 	RB_CUDA(cudaSetDevice(ctx->device));
+	ctx->ref_2d[k] = (mdlZ == 1);
+	if (mdlZ == 1) { mdlZ = 2; initZ = 0; }             // 2D reference (AccProjector with mdlZ == 0 in the reference): plane 1 stays zero
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
 	RB_CHECK(ctx->proj_buf[k].ensure(n * sizeof(float2)));
 	RB_CHECK(ctx->proj8_buf[k].ensure(n * 4 * sizeof(float4)));
@@ -188,17 +190,18 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ
 	p.mdlX = mdlX; p.mdlY = mdlY; p.mdlZ = mdlZ; p.mdlXY = mdlX * mdlY;
 	p.mdlInitY = initY; p.mdlInitZ = initZ; p.mdlMaxR = maxR; p.padding_factor = (float) pf;
 	ctx->has_proj[k] = true;
+	if (ctx->ref_2d[k]) RB_CUDA(cudaMemsetAsync(ctx->proj_buf[k].as<float2>() + (size_t) mdlX * mdlY, 0, (size_t) mdlX * mdlY * sizeof(float2), ctx->stream));
 	return RB_OK;
 }
 
 extern "C" int rb_set_reference(rb_ctx *ctx, int k, const double *vol, int mdlX, int mdlY, int mdlZ,
                                 int initY, int initZ, int maxR, double pf)
 {
+	const size_t nin = (size_t) mdlX * mdlY * mdlZ;
 	RB_CHECK(set_reference_common(ctx, k, mdlX, mdlY, mdlZ, initY, initZ, maxR, pf));
-	size_t n = (size_t) mdlX * mdlY * mdlZ;
-	RB_CHECK(ctx->scratch[2].ensure(n * 2 * sizeof(double)));
-	RB_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, vol, n * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-	RB_CHECK(rbk_convert_volume(ctx, ctx->scratch[2].as<double>(), ctx->proj_buf[k].as<float2>(), n));
+	RB_CHECK(ctx->scratch[2].ensure(nin * 2 * sizeof(double)));
+	RB_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, vol, nin * 2 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CHECK(rbk_convert_volume(ctx, ctx->scratch[2].as<double>(), ctx->proj_buf[k].as<float2>(), nin));
 	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>(), ctx->proj2_buf[k].as<float4>()));
 	RB_CHECK(rb_sync_tables(ctx));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -209,9 +212,9 @@ extern "C" int rb_set_reference(rb_ctx *ctx, int k, const double *vol, int mdlX,
 extern "C" int rb_set_reference_f32(rb_ctx *ctx, int k, const float *vol, int mdlX, int mdlY, int mdlZ,
                                     int initY, int initZ, int maxR, double pf)
 {
+	const size_t nin = (size_t) mdlX * mdlY * mdlZ;
 	RB_CHECK(set_reference_common(ctx, k, mdlX, mdlY, mdlZ, initY, initZ, maxR, pf));
-	size_t n = (size_t) mdlX * mdlY * mdlZ;
-	RB_CUDA(cudaMemcpyAsync(ctx->proj_buf[k].p, vol, n * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(ctx->proj_buf[k].p, vol, nin * sizeof(float2), cudaMemcpyHostToDevice, ctx->stream));
 	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>(), ctx->proj2_buf[k].as<float4>()));
 	RB_CHECK(rb_sync_tables(ctx));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -222,8 +225,10 @@ extern "C" int rb_bp_init(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int 
 {
 	RB_ARG(ctx, "ctx is NULL");
 	RB_ARG(k >= 0 && k < RB_MAX_CLASSES, "class index %d out of range", k);
-	RB_ARG(mdlX > 1 && mdlY > 1 && mdlZ > 1, "rb_bp_init: only 3D accumulators are supported");
+	RB_ARG(mdlX > 1 && mdlY > 1 && mdlZ >= 1, "rb_bp_init: bad dimensions %dx%dx%d", mdlX, mdlY, mdlZ);
 	RB_CUDA(cudaSetDevice(ctx->device));
+	ctx->bp_2d[k] = (mdlZ == 1);
+	if (mdlZ == 1) { mdlZ = 2; initZ = 0; }             // 2D accumulator: plane 1 only ever receives zeros (fz == 0)
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
 	RB_CHECK(ctx->bp_buf[k].ensure(n * sizeof(float4)));
 	RbBackprojector &b = ctx->bp[k];
@@ -252,9 +257,10 @@ extern "C" int rb_bp_get(rb_ctx *ctx, int k, float *real, float *imag, float *we
 	RB_CHECK(ctx->scratch[2].ensure(3 * n * sizeof(float)));
 	float *t = ctx->scratch[2].as<float>();
 	RB_CHECK(rbk_bp_deinterleave(ctx, b.vol, t, t + n, t + 2 * n, n));
-	RB_CUDA(cudaMemcpyAsync(real, t, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-	RB_CUDA(cudaMemcpyAsync(imag, t + n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-	RB_CUDA(cudaMemcpyAsync(weight, t + 2 * n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	const size_t nout = ctx->bp_2d[k] ? (size_t) b.mdlX * b.mdlY : n;   // a 2D accumulator hands back its [Y][X] plane
+	RB_CUDA(cudaMemcpyAsync(real, t, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(imag, t + n, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(weight, t + 2 * n, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->scratch[2].release();
 	return RB_OK;

@@ -195,6 +195,9 @@ struct rb_ctx {
 	RbBackprojector bp[RB_MAX_CLASSES];
 	DevBuf bp_buf[RB_MAX_CLASSES];
 	bool has_proj[RB_MAX_CLASSES] = {false}, has_bp[RB_MAX_CLASSES] = {false};
+	// 2D references / accumulators (2D classification) live in a two-plane volume [2][Y][X] whose second plane is zero:
+	// with in-plane rotations zp == 0, so the trilinear code paths reduce exactly to project2Dmodel / backproject2D
+	bool ref_2d[RB_MAX_CLASSES] = {false}, bp_2d[RB_MAX_CLASSES] = {false};
 
 	bool has_sampling = false, has_model = false;
 	rb_sampling h_samp{};            // scalar fields only (pointers are not kept)

@@ -469,10 +469,12 @@ bool rbk_coarse_gemm_applicable(rb_ctx *ctx, const PoolSlot &s)
 {
 	if (s.has_priors) return false;                       // local searches: per-particle orientation lists, no shared A
 	const char *e = getenv("RB_COARSE_GEMM");
-	const int mode = e ? atoi(e) : 1;                     // 0: never, 1: when the orientation grid is large enough, 2: always
+	const int mode = e ? atoi(e) : 1;                     // 0: never, 1: from 32 orientations, 2: always
 	if (mode == 0) return false;
+	// measured: already at 60 orientations (2D classification, one quarter-filled 128-row tile per class) the contraction
+	// beats the SIMT kernel 7x (4.5 ms vs 33 ms for 2000 particles x 10 classes x 64 px)
 	const long long O = (long long) ctx->d_samp.n_dir * ctx->d_samp.n_psi;
-	return mode == 2 || O >= 256;
+	return mode == 2 || O >= 32;
 }
 
 int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)

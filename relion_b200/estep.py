@@ -249,7 +249,9 @@ class MlDeviceBundle:
 
     # ---- projectors / back-projectors ---------------------------------------------------------
     def set_reference(self, iclass: int, vol: np.ndarray, r_max: int, padding_factor: float = 2.0):
-        """vol: complex [Z, Y, X] padded Fourier volume (MlModel::PPref[k].data layout)."""
+        """vol: complex [Z, Y, X] padded Fourier volume (MlModel::PPref[k].data layout), or [Y, X] for a 2D reference."""
+        if vol.ndim == 2:
+            vol = vol[None]
         z, y, x = vol.shape
         init = -((y - 1) // 2)
         if vol.dtype == np.complex128:
@@ -261,6 +263,9 @@ class MlDeviceBundle:
         capi.check(self.lib, st)
 
     def bp_init(self, iclass: int, shape_zyx, r_max: int, padding_factor: float = 2.0):
+        self._keep[("bp_2d", iclass)] = len(shape_zyx) == 2
+        if len(shape_zyx) == 2:
+            shape_zyx = (1,) + tuple(shape_zyx)
         z, y, x = shape_zyx
         init = -((y - 1) // 2)
         capi.check(self.lib, self.lib.rb_bp_init(self.ctx, iclass, x, y, z, init, init, r_max, padding_factor))
@@ -270,11 +275,13 @@ class MlDeviceBundle:
         capi.check(self.lib, self.lib.rb_bp_clear(self.ctx, iclass))
 
     def bp_get(self, iclass: int):
-        z, y, x = self._keep[("bp_shape", iclass)]
+        z, y, x = self._keep[("bp_shape", iclass)]    # z == 1: 2D accumulator, the library returns its [Y][X] plane
         re = np.empty((z, y, x), np.float32)
         im = np.empty_like(re)
         w = np.empty_like(re)
         capi.check(self.lib, self.lib.rb_bp_get(self.ctx, iclass, _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(w, C.c_float)))
+        if self._keep.get(("bp_2d", iclass)):
+            return re[0], im[0], w[0]
         return re, im, w
 
     def bp_device_tensor(self, iclass: int):

@@ -114,6 +114,7 @@ class Sampling:
     trans_y: np.ndarray = None
     over_trans_x: np.ndarray = None  # [n_trans*n_over_trans]
     over_trans_y: np.ndarray = None
+    is_3d: bool = True           # False: 2D references, psi-only sampling (HealpixSampling with is_3D == false)
 
     @property
     def n_dir(self):
@@ -129,7 +130,8 @@ class Sampling:
 
     @property
     def n_over_rot(self):
-        return 8 ** self.oversampling
+        # oversamplingFactorOrientations (src/healpix_sampling.cpp:1644-1651): 8^order in 3D, 2^order in 2D
+        return (8 if self.is_3d else 2) ** self.oversampling
 
     @property
     def n_over_trans(self):
@@ -190,6 +192,22 @@ def make_sampling(healpix_order: int, offset_range: float, offset_step: float, o
             s.over_rot = np.broadcast_to(crot[:, None, :, None], (npix, nr_psi, nd, nov)).reshape(-1).copy()
             s.over_tilt = np.broadcast_to(ctilt[:, None, :, None], (npix, nr_psi, nd, nov)).reshape(-1).copy()
             s.over_psi = np.broadcast_to(opsi[None, :, None, :], (npix, nr_psi, nd, nov)).reshape(-1).copy()
+    return s
+
+
+def make_sampling_2d(psi_step: float, offset_range: float, offset_step: float, oversampling: int = 1) -> Sampling:
+    """Psi-only sampling of 2D classification (HealpixSampling::setOrientations / getOrientations, 2D branches,
+    src/healpix_sampling.cpp:471-480, 1832-1870): one direction (rot = tilt = 0), n_over_rot = 2^oversampling psi values."""
+    s3 = make_sampling(0, offset_range, offset_step, oversampling, psi_step=psi_step, build_oversampled=False)
+    s = Sampling(-1, s3.psi_step, offset_range, offset_step, oversampling, is_3d=False)
+    s.rot = np.zeros(1); s.tilt = np.zeros(1); s.psi = s3.psi
+    s.trans_x, s.trans_y, s.over_trans_x, s.over_trans_y = s3.trans_x, s3.trans_y, s3.over_trans_x, s3.over_trans_y
+    nov = 2 ** oversampling
+    if oversampling == 0:
+        s.over_psi = s.psi.copy()
+    else:
+        s.over_psi = (s.psi[:, None] - 0.5 * s.psi_step + (0.5 + np.arange(nov))[None, :] * s.psi_step / nov).reshape(-1).copy()
+    s.over_rot = np.zeros_like(s.over_psi); s.over_tilt = np.zeros_like(s.over_psi)
     return s
 
 

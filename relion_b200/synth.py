@@ -112,6 +112,57 @@ def reference_ft(vol: np.ndarray, current_size: int | None = None, padding_facto
     return np.ascontiguousarray(sub), r_max
 
 
+def make_phantom_2d(n: int, n_blobs: int = 25, seed: int = 1993, radius_frac: float = 0.32) -> np.ndarray:
+    """Asymmetric sum of 2D Gaussian blobs; [n, n] float64, origin at n//2 (a 2D class average)."""
+    rng = np.random.default_rng(seed)
+    c = np.arange(n) - n // 2
+    y, x = np.meshgrid(c, c, indexing="ij")
+    img = np.zeros((n, n), np.float64)
+    R = radius_frac * n
+    for _ in range(n_blobs):
+        while True:
+            p = rng.uniform(-R, R, 2)
+            if np.linalg.norm(p) < R:
+                break
+        sg = rng.uniform(0.02, 0.06) * n
+        img += rng.uniform(0.5, 1.5) * np.exp(-((x - p[0]) ** 2 + (y - p[1]) ** 2) / (2 * sg * sg))
+    return img
+
+
+def reference_ft_2d(img: np.ndarray, current_size: int | None = None, padding_factor: float = 2.0):
+    """computeFourierTransformMap for a 2D reference used with 2D images (src/projector.cpp:116-592, ref_dim == 2,
+    data_dim == 2: normfft = pf^2).  Returns (data complex128 [pad, pad//2+1], y origin at (pad-1)//2, r_max)."""
+    ori = img.shape[0]
+    r_max = min((current_size if current_size else ori) // 2, ori // 2)
+    padori = int(math.floor(padding_factor * ori + 0.5))
+    padori += padori % 2
+    pf = padori / ori
+    c = np.arange(ori) - ori // 2
+    y, x = np.meshgrid(c, c, indexing="ij")
+    rval = np.sqrt(x * x + y * y) / (ori * pf)
+    sinc = np.ones_like(rval)
+    nz = rval > 0
+    sinc[nz] = np.sin(np.pi * rval[nz]) / (np.pi * rval[nz])
+    v = img.astype(np.float64) / (sinc * sinc)                              # griddingCorrect, TRILINEAR (:595-628)
+    Mpad = np.zeros((padori, padori), np.float64)
+    o = padori // 2 - ori // 2
+    Mpad[o:o + ori, o:o + ori] = v
+    F = np.fft.rfft2(np.fft.ifftshift(Mpad)) / float(padori) ** 2
+    normfft = pf * pf
+    pad = pad_size_for(r_max, pf)
+    h = (pad - 1) // 2
+    max_r2 = int(math.floor(r_max * pf + 0.5)) ** 2
+    k = np.arange(-h, h + 1)
+    kx = np.arange(0, pad // 2 + 1)
+    kin = (k >= -(padori // 2 - 1)) & (k <= padori // 2)
+    kxin = kx <= padori // 2
+    sub = np.zeros((pad, pad // 2 + 1), np.complex128)
+    sub[np.ix_(kin, kxin)] = F[np.ix_(k[kin] % padori, kx[kxin])] * normfft
+    ky, kxx = np.meshgrid(k, kx, indexing="ij")
+    sub[(ky * ky + kxx * kxx) > max_r2] = 0
+    return np.ascontiguousarray(sub), r_max
+
+
 # --------------------------------------------------------------------------------------------------
 # CTF
 # --------------------------------------------------------------------------------------------------
@@ -165,7 +216,13 @@ class CTF:
 # numpy Fourier-slice projection (float64) for small tests and data generation
 # --------------------------------------------------------------------------------------------------
 def project_numpy(data: np.ndarray, r_max: int, padding_factor: float, A_inv: np.ndarray, n: int) -> np.ndarray:
-    """Central slice [n, n//2+1] complex128 of the padded volume `data` (Projector::project, trilinear)."""
+    """Central slice [n, n//2+1] complex128 of the padded volume `data` (Projector::project, trilinear); a 2D
+    `data` [pad, pad//2+1] is rotated in plane (Projector::rotate2D) through the same code with a zero second plane."""
+    if data.ndim == 2:
+        pad2 = data.shape[0]
+        emb = np.zeros((pad2, pad2, data.shape[1]), data.dtype)
+        emb[(pad2 - 1) // 2] = data                       # the z = 0 plane of a centred volume
+        data = emb
     pad = data.shape[0]
     init = -((pad - 1) // 2)
     xs = n // 2 + 1

@@ -44,7 +44,7 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
                   pixel_size: float = 2.0, particle_diameter: Optional[float] = None,
                   nr_groups: int = 2, adaptive_fraction: float = 0.999, coarse_size: Optional[int] = None,
                   projector: Optional[Callable] = None, n_blobs: int = 40, refs_override=None,
-                  ref_seed: int = 1993) -> Workload:
+                  ref_seed: int = 1993, ref_dim: int = 3, psi_step: float = 6.0) -> Workload:
     """Build a complete, seeded E-step problem.
 
     projector(vol_complex64, r_max, pf, eulers[n,9] float32, n) -> [n_img, n, n//2+1] complex: how noise-free
@@ -60,12 +60,21 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
         refs = []
         r_max = None
         for k in range(nr_classes):
-            vol = synth.make_phantom(ori_size, n_blobs=n_blobs, seed=ref_seed + 17 * k)
-            data, r_max = synth.reference_ft(vol, current_size=current_size, padding_factor=pf)
+            if ref_dim == 2:
+                img = synth.make_phantom_2d(ori_size, n_blobs=n_blobs, seed=ref_seed + 17 * k)
+                data, r_max = synth.reference_ft_2d(img, current_size=current_size, padding_factor=pf)
+            else:
+                vol = synth.make_phantom(ori_size, n_blobs=n_blobs, seed=ref_seed + 17 * k)
+                data, r_max = synth.reference_ft(vol, current_size=current_size, padding_factor=pf)
             refs.append(data.astype(np.complex64))
     # ---- sampling ---------------------------------------------------------------------------
-    s = smp.make_sampling(healpix_order, offset_range, offset_step, oversampling=1)
-    ang_step = smp.angular_sampling(healpix_order)
+    if ref_dim == 2:
+        assert not local_search, "2D classification searches psi globally"
+        s = smp.make_sampling_2d(psi_step, offset_range, offset_step, oversampling=1)
+        ang_step = s.psi_step
+    else:
+        s = smp.make_sampling(healpix_order, offset_range, offset_step, oversampling=1)
+        ang_step = smp.angular_sampling(healpix_order)
     diameter = particle_diameter or 0.7 * ori_size * pixel_size
     if coarse_size is None:
         coarse_size = coarse_size_for(ori_size, pixel_size, ang_step, diameter, current_size)
@@ -128,5 +137,6 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
         pool.dir_idx = np.concatenate(di).astype(np.int32); pool.dir_prior = np.concatenate(dp)
         pool.psi_idx = np.concatenate(pi_).astype(np.int32); pool.psi_prior = np.concatenate(pp)
     pad = refs[0].shape[0]
+    bp_shape = (pad, pad // 2 + 1) if refs[0].ndim == 2 else (pad, pad, pad // 2 + 1)
     truth = dict(cls=cls, rot=rot, tilt=tilt, psi=psi, shifts=shifts, idir=idir, ipsi=ipsi, iover_rot=io, itrans_over=it)
-    return Workload(name, model, s, refs, r_max, pf, pool, truth, (pad, pad, pad // 2 + 1))
+    return Workload(name, model, s, refs, r_max, pf, pool, truth, bp_shape)

@@ -361,6 +361,20 @@ def test_backproject_posed_against_reference_algorithm(device, n, count, r_max):
     assert np.abs(gre2 - data.real).max() <= 2e-5 * np.abs(data.real).max()
 
 
+@pytest.mark.parametrize("coarse", ["gemm", "simt"])
+def test_pool_2d_classification(device, oracle, monkeypatch, coarse):
+    """BASELINE config #1 regime: 2D references (project2Dmodel / backproject2D), K classes, psi-only sampling with
+    2 oversampled psi per coarse one.  The library embeds a 2D reference in a two-plane volume (rb_set_reference with
+    mdlZ == 1); the oracle's 2D back-projection is the reference's backproject2D (no circle bound)."""
+    monkeypatch.setenv("RB_COARSE_GEMM", "2" if coarse == "gemm" else "0")
+    wl = make_workload(ori_size=32, n_particles=24, nr_classes=3, seed=33, snr=0.2, ref_dim=2, psi_step=10.0)
+    wl.model.bp_circle_bound = False
+    res, ores = _compare_pool(device, oracle, wl)
+    assert np.mean(res.particles["best_class"] == wl.truth["cls"]) >= 0.9
+    gre, gim, gw = device.bp_get(0)
+    assert gw.shape == wl.bp_shape
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -238,3 +238,87 @@ def test_backproject_posed_port_matches_numpy_restatement():
     np.testing.assert_allclose(re, data.real, rtol=0, atol=1e-12 * np.abs(data).max())
     np.testing.assert_allclose(im, data.imag, rtol=0, atol=1e-12 * np.abs(data).max())
     np.testing.assert_allclose(w, weight, rtol=0, atol=1e-12 * weight.max())
+
+
+def _inplane_eulers(psi_deg):
+    from relion_b200 import synth
+    psi = np.asarray(psi_deg, np.float64)
+    return synth.inverse_euler_f32(np.zeros_like(psi), np.zeros_like(psi), psi)
+
+
+def test_2d_embedding_matches_reference_2d_kernels():
+    """2D references (2D classification, BASELINE config #1) are handed to the projection-type kernels as a two-plane
+    volume whose second plane is zero.  With in-plane rotations zp == 0, so project3Dmodel must reproduce the reference's
+    own project2Dmodel bit for bit, and diff2_coarse<REF3D> its <REF2D> instantiation to summation-order rounding.
+    The 2D back-projection has its own kernel (no circle bound on x): port vs the reference's backproject2D."""
+    import ctypes as C
+    from oracle.bindings import Oracle, Projector, Backprojector, have_reference, REF_LIB
+    from relion_b200 import synth
+    if not have_reference():
+        pytest.skip("oracle/_ref/librefkernels.so not built")
+    ref = Oracle("reference"); port = Oracle("port")
+    lib = C.CDLL(REF_LIB)
+    f32p = C.POINTER(C.c_float)
+    fp = lambda a: a.ctypes.data_as(f32p)
+    rng = np.random.default_rng(3)
+    n = 24; xs = n // 2 + 1; r_max = n // 2
+    img = synth.make_phantom_2d(n, seed=4)
+    data, _ = synth.reference_ft_2d(img, padding_factor=2.0)
+    data = data.astype(np.complex64)
+    pad, mx = data.shape
+    inity = -((pad - 1) // 2)
+    P = Projector(data, r_max, 2.0)
+    assert P.vol.shape == (2, pad, mx) and not P.vol[1].any()
+    eul = _inplane_eulers(rng.uniform(0, 360, 7))
+    for e in eul:
+        want_re = np.zeros((n, xs), np.float32); want_im = np.zeros((n, xs), np.float32)
+        lib.refk2d_project(fp(np.ascontiguousarray(data).view(np.float32)), mx, pad, inity, r_max, C.c_float(2.0), xs, n, fp(e), fp(want_re), fp(want_im))
+        for orc in (ref, port):
+            got = orc.project(P, n, e)
+            assert np.array_equal(got.real, want_re) and np.array_equal(got.imag, want_im), orc.kind
+    # coarse diff2
+    O, T = 300, 5
+    eul = _inplane_eulers(rng.uniform(0, 360, O))
+    tx = (-2 * np.pi * rng.uniform(-3, 3, T) / n).astype(np.float32); ty = (-2 * np.pi * rng.uniform(-3, 3, T) / n).astype(np.float32)
+    re = rng.standard_normal((n, xs)).astype(np.float32); im = rng.standard_normal((n, xs)).astype(np.float32)
+    corr = rng.uniform(0.5, 2.0, (n, xs)).astype(np.float32)
+    want = np.zeros((O, T), np.float32)
+    lib.refk2d_diff2_coarse(fp(np.ascontiguousarray(data).view(np.float32)), mx, pad, inity, r_max, C.c_float(2.0), xs, n, fp(eul), C.c_ulong(O),
+                            fp(tx), fp(ty), C.c_ulong(T), fp(re), fp(im), fp(corr), fp(want))
+    for orc in (ref, port):
+        np.testing.assert_allclose(orc.diff2_coarse(P, n, eul, tx, ty, re, im, corr), want, rtol=2e-6)
+    # back-projection: restated 2D kernel against the reference's
+    O, T = 9, 4
+    eul = _inplane_eulers(rng.uniform(0, 360, O))
+    weights = rng.random((O, T)).astype(np.float32); weights[rng.random((O, T)) < 0.4] = np.finfo(np.float32).min
+    ctfs = rng.uniform(-1, 1, (n, xs)).astype(np.float32)
+    tx, ty = tx[:T], ty[:T]
+    b_ref = Backprojector((pad, mx), r_max, 2.0); b_port = Backprojector((pad, mx), r_max, 2.0)
+    ref.backproject(b_ref, n, eul, tx, ty, re, im, weights, corr, ctfs, 2.5, 0.3)
+    port.backproject(b_port, n, eul, tx, ty, re, im, weights, corr, ctfs, 2.5, 0.3)
+    assert np.abs(b_ref.weight).max() > 0
+    for a, b in ((b_port.real, b_ref.real), (b_port.imag, b_ref.imag), (b_port.weight, b_ref.weight)):
+        np.testing.assert_allclose(a, b, rtol=0, atol=2e-6 * np.abs(b).max())
+
+
+def test_2d_classification_pool_oracle():
+    """The oracle driver on a 2D-classification pool (K = 3 classes, psi-only sampling): classes and in-plane angles of
+    clean particles are recovered; port and reference-compiled kernels agree."""
+    from relion_b200.workload import make_workload
+    from oracle.bindings import Oracle, Projector, Backprojector, have_reference
+    wl = make_workload(ori_size=32, n_particles=16, nr_classes=3, seed=5, snr=0.5, ref_dim=2, psi_step=12.0)
+    assert wl.sampling.n_dir == 1 and wl.sampling.n_over_rot == 2 and wl.bp_shape == (67, 34)
+    out = {}
+    for kind in ["port"] + (["reference"] if have_reference() else []):
+        refs = [Projector(v, wl.r_max, 2.0) for v in wl.refs]
+        bps = [Backprojector(wl.bp_shape, wl.r_max, 2.0) for _ in wl.refs]
+        st, res, _ = Oracle(kind).estep_pool(wl.model, wl.sampling, refs, bps, wl.pool, num_threads=0)
+        assert st == 0
+        out[kind] = (res.particles, bps)
+        assert np.mean(res.particles["best_class"] == wl.truth["cls"]) == 1.0
+        assert np.mean(res.particles["best_ipsi"] == wl.truth["ipsi"]) >= 0.9
+    if "reference" in out:
+        a, b = out["port"], out["reference"]
+        assert np.array_equal(a[0]["best_ihidden_over"], b[0]["best_ihidden_over"])
+        for k in range(3):
+            np.testing.assert_allclose(a[1][k].weight, b[1][k].weight, rtol=0, atol=1e-4 * np.abs(b[1][k].weight).max())

@@ -57,6 +57,15 @@ WORKLOADS = {
 }
 
 
+def ncu_traffic(workload, pool, kernel):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/traffic_r01.json), or None."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(workload, {})
+        return int(d[kernel]) if d.get("pool") == pool and kernel in d else None
+    except Exception:
+        return None
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -305,6 +314,9 @@ def run_ours(args):
                     "share_of_step": round(stage_ms[dom] / max(stage_ms["total"], 1e-9), 3),
                     "note": "executed = 3 TF32 MMAs per fp32-equivalent product (3xTF32); useful = executed / 3"}
 
+    if dom == "coarse" and not tensor_coarse and wl.pool.dir_off is not None and os.environ.get("RB_COARSE_FUSED", "1") != "0":
+        roofline["kernel"] = "k_coarse_fused"
+    roofline["traffic"] = ncu_traffic(args.workload, P, roofline["kernel"])
     # ---- CPU baseline on a bounded sample (all host cores) ------------------------------------------
     cpu = cpu_baseline(wl, sample=args.cpu_sample)
 
@@ -504,7 +516,7 @@ def run_reconstruct(args):
            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(P * n * xs * 12 + P * 36), "d2h_bytes_per_step": 0},
            "gpu_launches": int(launches), "clocks": clocks,
            "roofline": {"kernel": "k_backproject_posed", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                        "frac": round(ach / peak, 4), "traffic": None, "peak_source": peak_src,
+                        "frac": round(ach / peak, 4), "traffic": ncu_traffic("reconstruct_256", P, "k_backproject_posed"), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": bytes_per_launch},
            "cpu_baseline": cpu}
     print(json.dumps(out))

@@ -235,6 +235,10 @@ def run_ours(args):
         dev.sync_all_backprojects()
         n_w += 1
     res0 = dev.estep_fetch(0)
+    if world > 1:
+        # warm the NCCL communicator / NVLink channels on the accumulator buffers (the first collective sets them up)
+        parallel.all_reduce_backprojectors(dev, wl.model.nr_classes)
+        torch.cuda.synchronize()
     for k in range(wl.model.nr_classes):
         dev.bp_clear(k)
     launches0 = dev.launch_count()
@@ -450,6 +454,9 @@ def run_reconstruct(args):
     t_w = time.perf_counter(); n_w = 0
     while n_w < args.warmup or time.perf_counter() - t_w < 1.0:
         dev.bp_posed_run(0); dev.sync_all_backprojects(); n_w += 1
+    if world > 1:
+        parallel.all_reduce_backprojectors(dev, 1)           # NCCL warm-up
+        torch.cuda.synchronize()
     dev.bp_clear(0)
     launches0 = dev.launch_count()
     barrier()

@@ -284,6 +284,30 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = P * world * args.steps / float(t.item())
 
+    # ---- end to end from RAW particle images: rb_pool_prepare (translate / norm / mask / FFT / CTF on the device) + E-step ----
+    e2e_raw = None
+    if True:
+        from relion_b200.workload import raw_pool_from
+        raw = raw_pool_from(wl, seed=5 + rank)
+        raw.images = torch.from_numpy(raw.images).pin_memory()
+        h2d_raw = raw.images.numel() * 4 + P * 120
+        for wslot in range(2):
+            dev.pool_prepare(wslot, raw, want_power=False)
+            dev.estep_slot(wslot)
+        barrier()
+        t1 = time.perf_counter()
+        dev.pool_prepare(0, raw, want_power=False)
+        for i in range(args.steps):
+            if i + 1 < args.steps:
+                dev.pool_prepare((i + 1) % 2, raw, want_power=False)
+            dev.estep_slot(i % 2)
+        dev.sync_all_backprojects()
+        t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=f"cuda:{local}")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_raw = {"value": round(P * world * args.steps / float(t.item()), 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d_raw),
+                   "d2h_bytes_per_step": int(d2h), "note": "real-space images in, image preparation (getFourierTransformsAndCtfs) on the device"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -338,6 +362,7 @@ def run_ours(args):
                    "l2_policy": "inputs larger than L2 (pool images + 515^3 reference/accumulator >> 126 MB), no flush",
                    "parallelism": f"particles sharded over {world} GPU(s), references replicated"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "e2e_from_raw_images": e2e_raw,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
         "datagen_s": round(gen_s, 1),
     }

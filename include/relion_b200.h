@@ -235,6 +235,37 @@ int rb_estep_slot_nocopy(rb_ctx *ctx, int slot, unsigned flags);
 int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out);
 
 /* ------------------------------------------------------------------------------------------------
+ * Image preparation on the device ("next" row 1): getFourierTransformsAndCtfs
+ * (acc_ml_optimiser_impl.h:11-1010) for a whole pool: integer translation by the rounded old offset and norm
+ * correction, transform of the unmasked image (Fimg_nomask), soft circular zero-mask, transform of the masked
+ * image (Fimg), power spectrum / highres_Xi2 beyond the current size, CTF image from the CTF parameters.
+ * Covered branch: 2D images, one body, --zero_mask, no helix / tomo / beam tilt / MTF, CTF without phase flipping.
+ * The slot is then ready for rb_estep_slot exactly as after rb_pool_upload.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+	int n_particles;
+	int image_size;              /* box size n == rb_model.ori_size                                */
+	const float *images;         /* [P][n][n] real-space particle images (exp_imagedata as XFLOAT)  */
+	const double *norm_factor;   /* [P] avg_norm_correction / normcorr; NULL = 1 (:421)             */
+	const double *old_offset;    /* [P][2] METADATA_XOFF/YOFF, rounded inside like :216             */
+	const double *prior_offset;  /* [P][2]                                                          */
+	const int *group_id, *optics_group;   /* [P]                                                    */
+	/* CTF (CTF::setValuesByGroup + getFftwImage, :822-840): per particle; NULL Bfac/scale/phase = 0/1/0 */
+	const double *ctf_defU, *ctf_defV, *ctf_defAngle, *ctf_Bfac, *ctf_scale, *ctf_phase_shift;
+	const double *og_kV, *og_Cs, *og_Q0;  /* [nr_optics_groups] kV, mm, fraction                    */
+	double mask_radius;          /* particle_diameter / (2 pixel_size) in pixels; < 0: n/2 (:556)   */
+	double width_mask_edge;      /* --mask_edge width in pixels                                     */
+	/* local angular searches, as in rb_particles (all NULL: global search)                         */
+	const int *dir_off, *dir_idx; const double *dir_prior;
+	const int *psi_off, *psi_idx; const double *psi_prior;
+} rb_raw_particles;
+/* power_img: [P][n/2+1] spectrum of the masked full-size transform (op.power_img, used by the host for sigma2_noise
+ * beyond the current size), may be NULL. */
+int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *raw, float *power_img);
+/* read a staged pool back (parity tests of the preparation): [P][cs][cs/2+1] arrays, any pointer may be NULL */
+int rb_pool_download(rb_ctx *ctx, int slot, float *Fimg, float *Fimg_nomask, float *Fctf, double *highres_Xi2);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage-level entry points (kernel-granularity twins of AccUtilities::* / run*Kernel,
  * src/acc/utilities.h:946-1620, acc_helper_functions_impl.h).  Used by the parity tests and usable
  * by an adapter that keeps the reference's per-particle driver.

@@ -67,6 +67,20 @@ class rb_particles(C.Structure):
     ]
 
 
+class rb_raw_particles(C.Structure):
+    _fields_ = [
+        ("n_particles", C.c_int), ("image_size", C.c_int),
+        ("images", c_float_p), ("norm_factor", c_double_p), ("old_offset", c_double_p), ("prior_offset", c_double_p),
+        ("group_id", c_int_p), ("optics_group", c_int_p),
+        ("ctf_defU", c_double_p), ("ctf_defV", c_double_p), ("ctf_defAngle", c_double_p),
+        ("ctf_Bfac", c_double_p), ("ctf_scale", c_double_p), ("ctf_phase_shift", c_double_p),
+        ("og_kV", c_double_p), ("og_Cs", c_double_p), ("og_Q0", c_double_p),
+        ("mask_radius", C.c_double), ("width_mask_edge", C.c_double),
+        ("dir_off", c_int_p), ("dir_idx", c_int_p), ("dir_prior", c_double_p),
+        ("psi_off", c_int_p), ("psi_idx", c_int_p), ("psi_prior", c_double_p),
+    ]
+
+
 class rb_particle_out(C.Structure):
     _fields_ = [
         ("best_ihidden_over", C.c_int64),
@@ -120,6 +134,8 @@ PROTOTYPES = {
     "rb_set_pdf_direction": (C.c_int, [C.c_void_p, c_double_p]),
     "rb_estep_pool": (C.c_int, [C.c_void_p, C.POINTER(rb_particles), C.POINTER(rb_pool_out), C.c_uint]),
     "rb_pool_upload": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_particles)]),
+    "rb_pool_prepare": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_raw_particles), c_float_p]),
+    "rb_pool_download": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p, c_double_p]),
     "rb_estep_slot": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_pool_out), C.c_uint]),
     "rb_estep_slot_nocopy": (C.c_int, [C.c_void_p, C.c_int, C.c_uint]),
     "rb_estep_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_pool_out)]),

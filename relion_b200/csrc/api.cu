@@ -99,6 +99,8 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
 	for (auto &b : ctx->wc_buf) b.release();
+	for (auto &b : ctx->prep_buf) b.release();
+	for (int i = 0; i < RB_NUM_SLOTS; i++) for (auto &b : ctx->prep_raw[i]) b.release();
 	for (int i = 0; i < 2; i++) { for (auto &b : ctx->posed_buf[i]) b.release(); if (ctx->posed_ev[i]) cudaEventDestroy(ctx->posed_ev[i]); }
 	for (int i = 0; i < RB_NUM_SLOTS; i++) release_slot(ctx->slot[i]);
 	for (auto &kv : ctx->stage_ev) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
@@ -489,16 +491,19 @@ static size_t env_size(const char *name, size_t dflt)
 	return (size_t) strtoull(v, nullptr, 10);
 }
 
-extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool)
+// Shared by rb_pool_upload (prepared Fourier images from the host) and rb_pool_prepare (raw images, prepared on the device):
+// per-particle metadata, prior lists, work buffers; copy_images == false leaves Fimg / Fimg_nomask / Fctf to the caller.
+static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy_images)
 {
 	RB_ARG(ctx && pool, "rb_pool_upload: NULL argument");
 	RB_ARG(slot >= 0 && slot < RB_NUM_SLOTS, "rb_pool_upload: slot %d out of range", slot);
 	if (!ctx->has_model || !ctx->has_sampling) { rb_set_error("rb_pool_upload: set model and sampling first"); return RB_ERR_STATE; }
 	const int P = pool->n_particles;
 	RB_ARG(P > 0, "rb_pool_upload: empty pool");
-	RB_ARG(pool->Fimg && pool->Fimg_nomask && pool->group_id && pool->optics_group && pool->highres_Xi2 && pool->old_offset && pool->prior_offset,
+	RB_ARG(pool->group_id && pool->optics_group && pool->highres_Xi2 && pool->old_offset && pool->prior_offset,
 	       "rb_pool_upload: NULL particle array");
-	RB_ARG(!ctx->h_model.do_ctf_correction || pool->Fctf, "rb_pool_upload: Fctf missing with do_ctf_correction");
+	RB_ARG(!copy_images || (pool->Fimg && pool->Fimg_nomask), "rb_pool_upload: NULL image array");
+	RB_ARG(!copy_images || !ctx->h_model.do_ctf_correction || pool->Fctf, "rb_pool_upload: Fctf missing with do_ctf_correction");
 	const bool priors = pool->dir_idx != nullptr;
 	RB_ARG(!priors || (pool->dir_off && pool->dir_prior && pool->psi_off && pool->psi_idx && pool->psi_prior), "rb_pool_upload: incomplete prior lists");
 	RB_ARG(priors || ctx->d_model.pdf_direction, "rb_pool_upload: pdf_direction needed without orientational priors");
@@ -547,12 +552,12 @@ extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool)
 	cudaStream_t cs = ctx->copy_stream;
 	const size_t img_bytes = (size_t) P * M.Npf * sizeof(float2);
 	RB_CHECK(s.Fimg.ensure(img_bytes)); RB_CHECK(s.Fnomask.ensure(img_bytes));
-	RB_CUDA(cudaMemcpyAsync(s.Fimg.p, pool->Fimg, img_bytes, cudaMemcpyHostToDevice, cs));
-	RB_CUDA(cudaMemcpyAsync(s.Fnomask.p, pool->Fimg_nomask, img_bytes, cudaMemcpyHostToDevice, cs));
-	if (ctx->h_model.do_ctf_correction)
+	if (ctx->h_model.do_ctf_correction) RB_CHECK(s.Fctf.ensure(img_bytes / 2));
+	if (copy_images)
 	{
-		RB_CHECK(s.Fctf.ensure(img_bytes / 2));
-		RB_CUDA(cudaMemcpyAsync(s.Fctf.p, pool->Fctf, img_bytes / 2, cudaMemcpyHostToDevice, cs));
+		RB_CUDA(cudaMemcpyAsync(s.Fimg.p, pool->Fimg, img_bytes, cudaMemcpyHostToDevice, cs));
+		RB_CUDA(cudaMemcpyAsync(s.Fnomask.p, pool->Fimg_nomask, img_bytes, cudaMemcpyHostToDevice, cs));
+		if (ctx->h_model.do_ctf_correction) RB_CUDA(cudaMemcpyAsync(s.Fctf.p, pool->Fctf, img_bytes / 2, cudaMemcpyHostToDevice, cs));
 	}
 	RB_CHECK(s.meta.ensure(P * sizeof(RbPartMeta)));
 	RB_CUDA(cudaMemcpyAsync(s.meta.p, s.h_meta.data(), P * sizeof(RbPartMeta), cudaMemcpyHostToDevice, cs));
@@ -592,6 +597,105 @@ extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool)
 		RB_CHECK(s.slices.ensure((size_t) s.slice_capacity * slice_bytes));
 	}
 	RB_CHECK(s.pair_list.ensure((cap_fs / ov + 1) * 4));
+	return RB_OK;
+}
+
+extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool) { return pool_setup(ctx, slot, pool, true); }
+
+// getFourierTransformsAndCtfs for the whole pool on the device (kernels_prep.cu)
+extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *raw, float *power_img)
+{
+	RB_ARG(ctx && raw, "rb_pool_prepare: NULL argument");
+	if (!ctx->has_model || !ctx->has_sampling) { rb_set_error("rb_pool_prepare: set model and sampling first"); return RB_ERR_STATE; }
+	const int P = raw->n_particles, n = raw->image_size;
+	RB_ARG(P > 0 && raw->images && raw->old_offset && raw->prior_offset && raw->group_id && raw->optics_group, "rb_pool_prepare: NULL particle array");
+	RB_ARG(n == ctx->h_model.ori_size, "rb_pool_prepare: image size %d differs from the model's ori_size %d", n, ctx->h_model.ori_size);
+	RB_ARG(n % 2 == 0 && n / 2 + 1 <= 1024, "rb_pool_prepare: image size %d unsupported", n);
+	const bool do_ctf = ctx->h_model.do_ctf_correction != 0;
+	RB_ARG(!do_ctf || (raw->ctf_defU && raw->ctf_defV && raw->ctf_defAngle && raw->og_kV && raw->og_Cs && raw->og_Q0), "rb_pool_prepare: CTF parameters missing");
+	// rounded old offsets (my_old_offset.selfROUND, acc_ml_optimiser_impl.h:216; ROUND of src/macros.h:197)
+	std::vector<double> old_r((size_t) 2 * P), xi2((size_t) P, 0.);
+	std::vector<int> shift((size_t) 2 * P);
+	std::vector<float> norm((size_t) P, 1.f);
+	std::vector<double> ctfpar;
+	for (int i = 0; i < 2 * P; i++)
+	{
+		const double v = raw->old_offset[i];
+		shift[i] = v > 0 ? (int) (v + 0.5) : (int) (v - 0.5);
+		old_r[i] = (double) shift[i];
+	}
+	if (raw->norm_factor) for (int p = 0; p < P; p++) norm[p] = (float) raw->norm_factor[p];
+	if (do_ctf)
+	{
+		ctfpar.resize((size_t) P * 9);
+		for (int p = 0; p < P; p++)
+		{
+			// CTF::initialise (src/ctf.cpp:211-261)
+			const int og = raw->optics_group[p];
+			RB_ARG(og >= 0 && og < ctx->h_model.nr_optics_groups, "rb_pool_prepare: optics group of particle %d out of range", p);
+			const double local_Cs = raw->og_Cs[og] * 1e7, local_kV = raw->og_kV[og] * 1e3, Q0 = raw->og_Q0[og];
+			const double az = raw->ctf_defAngle[p] * 3.14159265358979323846 / 180.0;
+			const double lam = 12.2643247 / sqrt(local_kV * (1.0 + local_kV * 0.978466e-6));
+			double *q = &ctfpar[(size_t) p * 9];
+			q[0] = 3.14159265358979323846 / 2 * 2 * lam;
+			q[1] = 3.14159265358979323846 / 2 * local_Cs * lam * lam * lam;
+			q[2] = atan(Q0 / sqrt(1 - Q0 * Q0));
+			q[3] = -(raw->ctf_Bfac ? raw->ctf_Bfac[p] : 0.) / 4.0;
+			q[4] = (raw->ctf_phase_shift ? raw->ctf_phase_shift[p] : 0.) * 3.14159265358979323846 / 180.0;
+			const double ca = cos(az), sa = sin(az), dU = -raw->ctf_defU[p], dV = -raw->ctf_defV[p];
+			q[5] = ca * ca * dU + sa * sa * dV;            // A = Q^T D Q, Q = [[ca, sa], [-sa, ca]], D = diag(-defU, -defV)
+			q[6] = ca * sa * dU - sa * ca * dV;
+			q[7] = sa * sa * dU + ca * ca * dV;
+			q[8] = raw->ctf_scale ? raw->ctf_scale[p] : 1.0;
+		}
+	}
+	rb_particles pool;
+	memset(&pool, 0, sizeof(pool));
+	pool.n_particles = P; pool.group_id = raw->group_id; pool.optics_group = raw->optics_group;
+	pool.highres_Xi2 = xi2.data(); pool.old_offset = old_r.data(); pool.prior_offset = raw->prior_offset;
+	pool.dir_off = raw->dir_off; pool.dir_idx = raw->dir_idx; pool.dir_prior = raw->dir_prior;
+	pool.psi_off = raw->psi_off; pool.psi_idx = raw->psi_idx; pool.psi_prior = raw->psi_prior;
+	RB_CHECK(pool_setup(ctx, slot, &pool, false));
+	PoolSlot &s = ctx->slot[slot];
+	// raw images + small tables on the copy stream (overlaps the compute of the other slot), kernels on the compute stream
+	DevBuf &bRaw = ctx->prep_raw[slot][0], &bShift = ctx->prep_raw[slot][1], &bNorm = ctx->prep_raw[slot][2], &bCtf = ctx->prep_raw[slot][3];
+	DevBuf &bPow = ctx->prep_buf[3];
+	const size_t raw_bytes = (size_t) P * n * n * 4;
+	RB_CHECK(bRaw.ensure(raw_bytes)); RB_CHECK(bShift.ensure((size_t) P * 8)); RB_CHECK(bNorm.ensure((size_t) P * 4));
+	RB_CHECK(bCtf.ensure(std::max<size_t>(ctfpar.size() * 8, 8))); RB_CHECK(bPow.ensure((size_t) P * (n / 2 + 1) * 4));
+	cudaStream_t cs = ctx->copy_stream;
+	RB_CUDA(cudaMemcpyAsync(bRaw.p, raw->images, raw_bytes, cudaMemcpyHostToDevice, cs));
+	RB_CUDA(cudaMemcpyAsync(bShift.p, shift.data(), (size_t) P * 8, cudaMemcpyHostToDevice, cs));
+	RB_CUDA(cudaMemcpyAsync(bNorm.p, norm.data(), (size_t) P * 4, cudaMemcpyHostToDevice, cs));
+	if (do_ctf) RB_CUDA(cudaMemcpyAsync(bCtf.p, ctfpar.data(), ctfpar.size() * 8, cudaMemcpyHostToDevice, cs));
+	RB_CUDA(cudaEventRecord(s.uploaded, cs));
+	RB_CUDA(cudaStreamSynchronize(cs));            // shift / norm / ctfpar are host temporaries
+	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+	RB_CHECK(rbk_prepare_pool(ctx, s, bRaw.as<float>(), bShift.as<int>(), bNorm.as<float>(), do_ctf ? bCtf.as<double>() : nullptr, n,
+	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>()));
+	if (power_img)
+	{
+		RB_CUDA(cudaMemcpyAsync(power_img, bPow.p, (size_t) P * (n / 2 + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+		RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	}
+	RB_CUDA(cudaEventRecord(s.uploaded, ctx->stream));   // rb_estep_slot waits for the preparation
+	return RB_OK;
+}
+
+// read a staged / prepared pool back (tests): any pointer may be NULL
+extern "C" int rb_pool_download(rb_ctx *ctx, int slot, float *Fimg, float *Fimg_nomask, float *Fctf, double *highres_Xi2)
+{
+	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_pool_download: slot %d not staged", slot);
+	PoolSlot &s = ctx->slot[slot];
+	const size_t img_bytes = (size_t) s.P * ctx->d_model.Npf * sizeof(float2);
+	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+	if (Fimg) RB_CUDA(cudaMemcpyAsync(Fimg, s.Fimg.p, img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	if (Fimg_nomask) RB_CUDA(cudaMemcpyAsync(Fimg_nomask, s.Fnomask.p, img_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	if (Fctf && ctx->h_model.do_ctf_correction) RB_CUDA(cudaMemcpyAsync(Fctf, s.Fctf.p, img_bytes / 2, cudaMemcpyDeviceToHost, ctx->stream));
+	std::vector<RbPartMeta> m(s.P);
+	RB_CUDA(cudaMemcpyAsync(m.data(), s.meta.p, s.P * sizeof(RbPartMeta), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	if (highres_Xi2) for (int p = 0; p < s.P; p++) highres_Xi2[p] = 2.0 * (double) m[p].xi2_half;
 	return RB_OK;
 }
 

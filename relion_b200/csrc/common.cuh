@@ -218,6 +218,8 @@ struct rb_ctx {
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
 	DevBuf scratch[8];
 	DevBuf wc_buf[10];
+	DevBuf prep_buf[4];              // device image preparation (kernels_prep.cu): cuFFT input / output, background values, spectra
+	DevBuf prep_raw[RB_NUM_SLOTS][4];   // per slot: raw images, shifts, norm factors, CTF parameters (filled on the copy stream)
 	DevBuf posed_buf[2][3];          // staged posed images (F2D, Fctf, matrices), two buffers for upload / compute overlap
 	int posed_n = 0, posed_count = 0;   // what rb_bp_posed_stage left in posed_buf[0]
 	cudaEvent_t posed_ev[2] = {nullptr, nullptr};               // partials / compact list of the multi-CTA coarse weight conversion
@@ -259,6 +261,10 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4);
 bool rbk_coarse_fused_applicable(rb_ctx *ctx, const PoolSlot &s);
 int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4);
 int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int M, int N, int K, float *dC);
+
+// kernels_prep.cu: getFourierTransformsAndCtfs on the device, batched over the pool
+int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
+                     int n, float radius, float cosine_width, float *d_power);
 
 // kernels_weights.cu
 int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s);

@@ -1,0 +1,207 @@
+// relion_b200 — image preparation on the device (SURVEY.md §8f "next" row 1): what getFourierTransformsAndCtfs
+// (/root/reference/src/acc/acc_ml_optimiser_impl.h:11-1010) does per particle on one host thread with one cuFFT plan,
+// batched here over the whole pool.  Branch covered: 2D images, one body, zero-masking, no helix / tomo / beam tilt / MTF.
+//
+//   raw image --translate (rounded old offset), x norm factor--> t          TranslateAndNormCorrect, utilities_impl.h:374-436
+//   t        --centre (shift n/2), FFT / n^2, window to current size--> Fimg_nomask      normalizeAndTransformImage :438-486
+//   t        --soft circular mask to the background value of its edge--> m               helper.cpp:117-253
+//   m        --centre, FFT / n^2, window--> Fimg;  full-size |F|^2 per shell --> power_img, highres_Xi2    helper.h:468-540
+//   CTF parameters --> Fctf on the current-size window                                    CTF::getFftwImage, src/ctf.h:184-256
+// The FFTs are cuFFT (library, batched R2C); everything around them is fused into four small kernels.
+#include "device_utils.cuh"
+#include <cufft.h>
+
+struct PrepRaw {
+	const float *raw;            // [P][n][n]
+	const int *shift;            // [P][2] rounded old offsets (dx, dy)
+	const float *norm;           // [P]
+	const float *bg;             // [P] background value of the soft edge (masked pass)
+	int n;
+	float radius, radius_p, cosine_width;
+};
+
+// translated + norm-corrected pixel (y, x) of particle p (cpu_translate2D: targets outside the box are dropped, the rest is zero)
+__device__ __forceinline__ float prep_translated(const PrepRaw &A, int p, int y, int x)
+{
+	const int sx = x - A.shift[2 * p], sy = y - A.shift[2 * p + 1];
+	if (sx < 0 || sy < 0 || sx >= A.n || sy >= A.n) return 0.f;
+	return __ldg(A.raw + ((size_t) p * A.n + sy) * A.n + sx) * A.norm[p];
+}
+
+// soft-edge weight of pixel (y, x): 0 inside radius, 1 beyond radius_p, raised cosine in between
+__device__ __forceinline__ float prep_edge(const PrepRaw &A, int y, int x, bool &inside)
+{
+	const int cx = x - A.n / 2, cy = y - A.n / 2;
+	const float r = sqrtf((float) (cx * cx + cy * cy));
+	inside = r < A.radius;
+	if (inside) return 0.f;
+	if (r > A.radius_p) return 1.f;
+	return 0.5f + 0.5f * cosf((A.radius_p - r) / A.cosine_width * (float) M_PI);
+}
+
+// background value = sum(edge * t) / sum(edge) over r >= radius (softMaskBackgroundValue + getSumOnDevice, :632-652)
+__global__ void __launch_bounds__(256)
+k_prep_mask_bg(PrepRaw A, float *bg)
+{
+	__shared__ double dred[32];
+	const int p = blockIdx.x;
+	double s = 0., sb = 0.;
+	for (int i = threadIdx.x; i < A.n * A.n; i += blockDim.x)
+	{
+		const int y = i / A.n, x = i - y * A.n;
+		bool inside;
+		const float e = prep_edge(A, y, x, inside);
+		if (!inside) { s += (double) e; sb += (double) (e * prep_translated(A, p, y, x)); }
+	}
+	s = block_sum(s, dred);
+	sb = block_sum(sb, dred);
+	if (threadIdx.x == 0) bg[p] = (float) (sb / s);
+}
+
+// cuFFT input: translated (and, in the masked pass, soft-masked) image with the origin moved to pixel (0, 0)
+// (runCenterFFT(forward = false): circular shift by n/2)
+template <bool MASKED>
+__global__ void __launch_bounds__(256)
+k_prep_real(PrepRaw A, float *real)
+{
+	const int p = blockIdx.y, n = A.n;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += gridDim.x * blockDim.x)
+	{
+		const int yc = i / n, xc = i - yc * n;
+		const int y = (yc + n / 2) % n, x = (xc + n / 2) % n;
+		float v = prep_translated(A, p, y, x);
+		if (MASKED)
+		{
+			bool inside;
+			const float e = prep_edge(A, y, x, inside);
+			if (!inside) v = (e == 1.f) ? A.bg[p] : v * (1.f - e) + A.bg[p] * e;        // cosineFilter, helper.cpp:234-247
+		}
+		real[(size_t) p * n * n + i] = v;
+	}
+}
+
+// scale by 1/n^2 and window to the current size (windowFourierTransform2, shrinking branch)
+__global__ void __launch_bounds__(256)
+k_prep_window(const float2 *F, float2 *out, int n, int cs, float scale)
+{
+	const int p = blockIdx.y;
+	const int xf = n / 2 + 1, xo = cs / 2 + 1;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cs * xo; i += gridDim.x * blockDim.x)
+	{
+		const int iy = i / xo, x = i - iy * xo;
+		const int ip = iy < xo ? iy : iy - cs;
+		const float2 v = F[((size_t) p * n + (ip < 0 ? ip + n : ip)) * xf + x];
+		out[(size_t) p * cs * xo + i] = make_float2(v.x * scale, v.y * scale);
+	}
+}
+
+// power spectrum of the full-size transform and the power beyond the current size (powerClass); one CTA per particle
+__global__ void __launch_bounds__(256)
+k_prep_power(const float2 *F, int n, int cs, float scale, float *power, RbPartMeta *metas)
+{
+	__shared__ double s_spec[1024];
+	__shared__ double dred[32];
+	const int p = blockIdx.x;
+	const int xf = n / 2 + 1;
+	for (int i = threadIdx.x; i < xf; i += blockDim.x) s_spec[i] = 0.;
+	__syncthreads();
+	double xi2 = 0.;
+	const int res_limit = cs / 2 + 1;
+	for (int i = threadIdx.x; i < n * xf; i += blockDim.x)
+	{
+		const int iy = i / xf, x = i - iy * xf;
+		const int y = iy < xf ? iy : iy - n;
+		const int ires = (int) (sqrtf((float) (x * x + y * y)) + 0.5f);
+		if (ires < xf && !(x == 0 && y < 0))
+		{
+			const float2 v = F[(size_t) p * n * xf + i];
+			const float vr = v.x * scale, vi = v.y * scale;
+			const double nf = (double) (vr * vr + vi * vi);
+			atomicAdd(&s_spec[ires], nf);
+			if (ires >= res_limit) xi2 += nf;
+		}
+	}
+	xi2 = block_sum(xi2, dred);
+	__syncthreads();
+	if (power) for (int i = threadIdx.x; i < xf; i += blockDim.x) power[(size_t) p * xf + i] = (float) s_spec[i];
+	if (threadIdx.x == 0) metas[p].xi2_half = (float) (xi2 / 2.);
+}
+
+// CTF::getCTF with damping, no flips (src/ctf.h:184-256) evaluated in double like the host code, on the current-size window
+__global__ void __launch_bounds__(256)
+k_prep_ctf(const double *par, float *Fctf, int cs, double xs_angstrom)
+{
+	const int p = blockIdx.y;
+	const double *q = par + (size_t) p * 9;   // K1, K2, K3, K4, K5, Axx, Axy, Ayy, scale
+	const int xo = cs / 2 + 1;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cs * xo; i += gridDim.x * blockDim.x)
+	{
+		const int iy = i / xo, jp = i - iy * xo;
+		const int ip = iy < xo ? iy : iy - cs;
+		const double X = (double) jp / xs_angstrom, Y = (double) ip / xs_angstrom;
+		const double u2 = X * X + Y * Y;
+		const double gamma = q[0] * (q[5] * X * X + 2.0 * q[6] * X * Y + q[7] * Y * Y) + q[1] * u2 * u2 - q[4] - q[2];
+		double r = -sin(gamma) * exp(q[3] * u2) * q[8];
+		if (fabs(r) < 1e-8) r = r < 0 ? -1e-8 : 1e-8;                                    // ctf.h:229-232
+		Fctf[(size_t) p * cs * xo + i] = (float) r;
+	}
+}
+
+struct PrepPlan { int n = 0, batch = 0; cufftHandle plan = 0; bool valid = false; };
+static PrepPlan g_plan;
+
+static int get_plan(rb_ctx *ctx, int n, int batch, cufftHandle *out)
+{
+	if (!g_plan.valid || g_plan.n != n || g_plan.batch != batch)
+	{
+		if (g_plan.valid) cufftDestroy(g_plan.plan);
+		g_plan.valid = false;
+		int dims[2] = {n, n};
+		cufftResult r = cufftPlanMany(&g_plan.plan, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, batch);
+		if (r != CUFFT_SUCCESS) { rb_set_error("cufftPlanMany(%d x %d, batch %d) failed (%d)", n, n, batch, (int) r); return RB_ERR_CUDA; }
+		g_plan.n = n; g_plan.batch = batch; g_plan.valid = true;
+	}
+	cufftResult r = cufftSetStream(g_plan.plan, ctx->stream);
+	if (r != CUFFT_SUCCESS) { rb_set_error("cufftSetStream failed (%d)", (int) r); return RB_ERR_CUDA; }
+	*out = g_plan.plan;
+	return RB_OK;
+}
+
+// d_raw: [P][n][n] device, d_shift [P][2], d_norm [P], d_ctfpar [P][9] (nullptr: Fctf untouched), outputs into the slot buffers
+int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
+                     int n, float radius, float cosine_width, float *d_power)
+{
+	const RbModelDev &M = ctx->d_model;
+	const int P = s.P, cs = M.current_size;
+	const int xf = n / 2 + 1, xo = cs / 2 + 1;
+	DevBuf &bReal = ctx->prep_buf[0], &bF = ctx->prep_buf[1], &bBg = ctx->prep_buf[2];
+	RB_CHECK(bReal.ensure((size_t) P * n * n * 4)); RB_CHECK(bF.ensure((size_t) P * n * xf * 8)); RB_CHECK(bBg.ensure((size_t) P * 4));
+	cufftHandle plan;
+	RB_CHECK(get_plan(ctx, n, P, &plan));
+	PrepRaw A;
+	A.raw = d_raw; A.shift = d_shift; A.norm = d_norm; A.bg = bBg.as<float>(); A.n = n;
+	A.radius = radius < 0.f ? (float) n / 2.f : radius; A.cosine_width = cosine_width; A.radius_p = A.radius + cosine_width;
+	const float scale = 1.f / ((float) n * (float) n);
+	dim3 gr((n * n + 255) / 256 > 64 ? 64 : (n * n + 255) / 256, P), gw((cs * xo + 255) / 256 > 64 ? 64 : (cs * xo + 255) / 256, P);
+	// unmasked image -> Fimg_nomask
+	k_prep_real<false><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
+	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed"); return RB_ERR_CUDA; }
+	ctx->launches++;
+	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fnomask.as<float2>(), n, cs, scale); RB_LAUNCH_CHECK(ctx);
+	// masked image -> Fimg, power spectrum, highres_Xi2
+	k_prep_mask_bg<<<P, 256, 0, ctx->stream>>>(A, bBg.as<float>()); RB_LAUNCH_CHECK(ctx);
+	k_prep_real<true><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
+	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed"); return RB_ERR_CUDA; }
+	ctx->launches++;
+	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fimg.as<float2>(), n, cs, scale); RB_LAUNCH_CHECK(ctx);
+	if (cs < n)
+	{
+		k_prep_power<<<P, 256, 0, ctx->stream>>>(bF.as<float2>(), n, cs, scale, d_power, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
+	}
+	else if (d_power) RB_CUDA(cudaMemsetAsync(d_power, 0, (size_t) P * xf * 4, ctx->stream));
+	if (d_ctfpar)
+	{
+		k_prep_ctf<<<gw, 256, 0, ctx->stream>>>(d_ctfpar, s.Fctf.as<float>(), cs, (double) M.ori_size * M.pixel_size); RB_LAUNCH_CHECK(ctx);
+	}
+	return RB_OK;
+}

@@ -177,6 +177,55 @@ def marshal_model(p: ModelParams):
     return m
 
 
+@dataclasses.dataclass
+class RawParticlePool:
+    """One pool of raw particle images + metadata, what getFourierTransformsAndCtfs starts from (rb_raw_particles)."""
+    images: np.ndarray              # [P, n, n] float32 real space (numpy or pinned torch tensor)
+    old_offset: np.ndarray          # [P, 2]
+    prior_offset: np.ndarray        # [P, 2]
+    group_id: np.ndarray
+    optics_group: np.ndarray
+    ctf_defU: Optional[np.ndarray] = None
+    ctf_defV: Optional[np.ndarray] = None
+    ctf_defAngle: Optional[np.ndarray] = None
+    ctf_Bfac: Optional[np.ndarray] = None
+    ctf_scale: Optional[np.ndarray] = None
+    ctf_phase_shift: Optional[np.ndarray] = None
+    og_kV: Optional[np.ndarray] = None
+    og_Cs: Optional[np.ndarray] = None
+    og_Q0: Optional[np.ndarray] = None
+    norm_factor: Optional[np.ndarray] = None
+    mask_radius: float = -1.0
+    width_mask_edge: float = 5.0
+    dir_off: Optional[np.ndarray] = None
+    dir_idx: Optional[np.ndarray] = None
+    dir_prior: Optional[np.ndarray] = None
+    psi_off: Optional[np.ndarray] = None
+    psi_idx: Optional[np.ndarray] = None
+    psi_prior: Optional[np.ndarray] = None
+
+    @property
+    def n_particles(self):
+        return int(self.group_id.shape[0])
+
+
+def marshal_raw_pool(pool: RawParticlePool):
+    m = _Marshalled()
+    st = capi.rb_raw_particles()
+    st.n_particles = pool.n_particles
+    img = pool.images if hasattr(pool.images, "data_ptr") else np.ascontiguousarray(pool.images, np.float32)
+    st.image_size = int(img.shape[-1])
+    st.images = _ptr(m.hold(img), C.c_float)
+    for name in ("norm_factor", "old_offset", "prior_offset", "ctf_defU", "ctf_defV", "ctf_defAngle", "ctf_Bfac", "ctf_scale",
+                 "ctf_phase_shift", "og_kV", "og_Cs", "og_Q0", "dir_prior", "psi_prior"):
+        setattr(st, name, _ptr(m.hold(_f64(getattr(pool, name))), C.c_double))
+    for name in ("group_id", "optics_group", "dir_off", "dir_idx", "psi_off", "psi_idx"):
+        setattr(st, name, _ptr(m.hold(_i32(getattr(pool, name))), C.c_int))
+    st.mask_radius, st.width_mask_edge = float(pool.mask_radius), float(pool.width_mask_edge)
+    m.struct = st
+    return m
+
+
 def marshal_pool(pool: ParticlePool):
     m = _Marshalled()
     st = capi.rb_particles()
@@ -338,6 +387,25 @@ class MlDeviceBundle:
         self._keep[("pool", slot)] = mp   # host buffers must outlive the asynchronous copy
         capi.check(self.lib, self.lib.rb_pool_upload(self.ctx, slot, C.byref(mp.struct)))
         self._keep[("pool_n", slot)] = pool.n_particles
+
+    def pool_prepare(self, slot: int, raw: RawParticlePool, want_power: bool = True):
+        """rb_pool_prepare: getFourierTransformsAndCtfs on the device; returns power_img [P, n/2+1] (or None)."""
+        mp = marshal_raw_pool(raw)
+        self._keep[("pool", slot)] = mp
+        n = int(mp.struct.image_size)
+        power = np.zeros((raw.n_particles, n // 2 + 1), np.float32) if want_power else None
+        capi.check(self.lib, self.lib.rb_pool_prepare(self.ctx, slot, C.byref(mp.struct), _ptr(power, C.c_float)))
+        self._keep[("pool_n", slot)] = raw.n_particles
+        return power
+
+    def pool_download(self, slot: int, current_size: int):
+        P = self._keep[("pool_n", slot)]
+        xs = current_size // 2 + 1
+        F = np.empty((P, current_size, xs), np.complex64); F0 = np.empty_like(F)
+        Cc = np.ones((P, current_size, xs), np.float32); xi2 = np.zeros(P, np.float64)
+        capi.check(self.lib, self.lib.rb_pool_download(self.ctx, slot, _ptr(F.view(np.float32), C.c_float), _ptr(F0.view(np.float32), C.c_float),
+                                                       _ptr(Cc, C.c_float), _ptr(xi2, C.c_double)))
+        return F, F0, Cc, xi2
 
     def estep_slot(self, slot: int, skip_maximization: bool = False) -> PoolResult:
         out = self._new_out(self._keep[("pool_n", slot)])

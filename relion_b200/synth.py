@@ -286,6 +286,7 @@ class SyntheticParticles:
     shift: np.ndarray         # [P, 2] true shifts in pixels
     sigma2_noise: np.ndarray  # [ori_size//2+1]
     highres_Xi2: np.ndarray   # [P]
+    ctf_params: np.ndarray = None   # [P, 3] defU, defV, defAngle (300 kV, Cs 2.7 mm, Q0 0.1)
 
 
 def phase_shift_image(n: int, ori_size: int, sx: float, sy: float) -> np.ndarray:
@@ -310,9 +311,11 @@ def make_particles(slices: np.ndarray, ori_size: int, angpix: float, snr: float,
     Fctf = np.empty((P, n, xs), np.float32)
     Fn = np.empty((P, n, xs), np.complex64)
     Fn0 = np.empty((P, n, xs), np.complex64)
+    ctf_params = np.zeros((P, 3), np.float64)
     for p in range(P):
         d = rng.uniform(*defocus_range)
-        ctf = CTF(d, d + rng.uniform(-500.0, 500.0), rng.uniform(0.0, 180.0))
+        ctf_params[p] = (d, d + rng.uniform(-500.0, 500.0), rng.uniform(0.0, 180.0))
+        ctf = CTF(*ctf_params[p])
         c = ctf.fftw_image(n, ori_size, angpix)
         Fctf[p] = c
         Fn[p] = slices[p] * c * np.conj(phase_shift_image(n, ori_size, shifts[p, 0], shifts[p, 1]))
@@ -337,10 +340,26 @@ def make_particles(slices: np.ndarray, ori_size: int, angpix: float, snr: float,
         xi2 = rng.uniform(0.9, 1.1, P) * 2.0 * s2 * npix_hi
     return SyntheticParticles(Fn, Fn0, Fctf,
                               np.asarray(rot, np.float64), np.asarray(tilt, np.float64), np.asarray(psi, np.float64),
-                              np.asarray(shifts, np.float64), sigma2, xi2)
+                              np.asarray(shifts, np.float64), sigma2, xi2, ctf_params)
 
 
 def inverse_euler_f32(rot, tilt, psi) -> np.ndarray:
     """[n, 9] float32 inverted (transposed) ZYZ matrices, the layout the kernels take."""
     A = euler_matrix(np.asarray(rot, np.float64), np.asarray(tilt, np.float64), np.asarray(psi, np.float64))
     return np.ascontiguousarray(np.swapaxes(A, -1, -2).reshape(-1, 9).astype(np.float32))
+
+
+def raw_images_from_ft(F: np.ndarray, ori_size: int) -> np.ndarray:
+    """Real-space particle images [P, n, n] float32 whose (unmasked) RELION transform, windowed to F's size, is F
+    (up to the Hermitian symmetrisation of the x = 0 column): the inverse of normalizeAndTransformImage
+    (zero-pad to ori_size, unnormalised inverse FFT, origin back to the box centre)."""
+    P, cs, xs = F.shape
+    n = ori_size
+    out = np.empty((P, n, n), np.float32)
+    iy = np.arange(cs)
+    ip = np.where(iy < xs, iy, iy - cs)
+    for p in range(P):
+        Fp = np.zeros((n, n // 2 + 1), np.complex128)
+        Fp[ip % n, :xs] = F[p]
+        out[p] = np.roll(np.fft.irfft2(Fp, s=(n, n)) * float(n * n), (n // 2, n // 2), axis=(0, 1))
+    return out

@@ -138,5 +138,30 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
         pool.psi_idx = np.concatenate(pi_).astype(np.int32); pool.psi_prior = np.concatenate(pp)
     pad = refs[0].shape[0]
     bp_shape = (pad, pad // 2 + 1) if refs[0].ndim == 2 else (pad, pad, pad // 2 + 1)
-    truth = dict(cls=cls, rot=rot, tilt=tilt, psi=psi, shifts=shifts, idir=idir, ipsi=ipsi, iover_rot=io, itrans_over=it)
+    truth = dict(cls=cls, rot=rot, tilt=tilt, psi=psi, shifts=shifts, idir=idir, ipsi=ipsi, iover_rot=io, itrans_over=it,
+                 ctf_params=parts.ctf_params)
     return Workload(name, model, s, refs, r_max, pf, pool, truth, bp_shape)
+
+
+def raw_pool_from(wl: Workload, seed: int = 0, mask_radius: Optional[float] = None, width_mask_edge: float = 3.0,
+                  max_old_offset: float = 2.4):
+    """A RawParticlePool (real-space images + CTF parameters + metadata) for the image-preparation path: the images are the
+    inverse transforms of the workload's unmasked Fourier particles, the old offsets random non-integers (they get rounded and
+    applied as integer shifts), the norm factors close to 1."""
+    from .estep import RawParticlePool
+    rng = np.random.default_rng(seed)
+    P = wl.pool.n_particles
+    F0 = np.asarray(wl.pool.Fimg_nomask.numpy() if hasattr(wl.pool.Fimg_nomask, "numpy") else wl.pool.Fimg_nomask)
+    F0 = F0.view(np.complex64).reshape(P, wl.model.current_size, wl.model.current_size // 2 + 1)
+    images = synth.raw_images_from_ft(F0, wl.model.ori_size)
+    cp = wl.truth["ctf_params"]
+    raw = RawParticlePool(images=images, old_offset=rng.uniform(-max_old_offset, max_old_offset, (P, 2)), prior_offset=np.zeros((P, 2)),
+                          group_id=wl.pool.group_id, optics_group=wl.pool.optics_group,
+                          ctf_defU=cp[:, 0].copy(), ctf_defV=cp[:, 1].copy(), ctf_defAngle=cp[:, 2].copy(),
+                          og_kV=np.array([300.0]), og_Cs=np.array([2.7]), og_Q0=np.array([0.1]),
+                          norm_factor=rng.uniform(0.9, 1.1, P),
+                          mask_radius=(0.42 * wl.model.ori_size if mask_radius is None else mask_radius), width_mask_edge=width_mask_edge,
+                          dir_off=wl.pool.dir_off, dir_idx=wl.pool.dir_idx, dir_prior=wl.pool.dir_prior,
+                          psi_off=wl.pool.psi_off, psi_idx=wl.pool.psi_idx, psi_prior=wl.pool.psi_prior)
+    return raw
+

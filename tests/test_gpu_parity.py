@@ -375,6 +375,37 @@ def test_pool_2d_classification(device, oracle, monkeypatch, coarse):
     assert gw.shape == wl.bp_shape
 
 
+@pytest.mark.parametrize("ori,cur,local", [(32, 32, False), (40, 28, False), (32, 32, True)])
+def test_pool_prepare_matches_reference_algorithm(device, ori, cur, local):
+    """getFourierTransformsAndCtfs on the device (rb_pool_prepare) against its numpy restatement
+    (oracle/prepare.py): transforms of the unmasked and the zero-masked image, CTF image, highres_Xi2, power spectrum;
+    then the E-step on the device-prepared slot against the E-step on the oracle-prepared pool."""
+    from relion_b200.workload import raw_pool_from
+    from oracle.prepare import prepared_pool as oracle_prepared_pool
+    wl = make_workload(ori_size=ori, current_size=cur, healpix_order=2 if local else 1, n_particles=9, seed=70 + ori + cur, snr=0.3,
+                       local_search=local, nr_groups=1)
+    raw = raw_pool_from(wl, seed=3)
+    _setup(device, wl)
+    power = device.pool_prepare(0, raw)
+    F, F0, Cc, xi2 = device.pool_download(0, cur)
+    pool, opower = oracle_prepared_pool(wl, raw)
+    for got, want in ((F, pool.Fimg), (F0, pool.Fimg_nomask)):
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    assert np.abs(F - F0).max() > 1e-4 * np.abs(F0).max()          # the mask did something
+    np.testing.assert_allclose(Cc, pool.Fctf, rtol=0, atol=2e-6)
+    np.testing.assert_allclose(xi2, pool.highres_Xi2, rtol=1e-4, atol=1e-9 * max(np.abs(pool.highres_Xi2).max(), 1.0))
+    np.testing.assert_allclose(power, opower, rtol=1e-4, atol=1e-6 * max(opower.max(), 1e-30))
+    if cur < ori:
+        assert xi2.min() > 0
+    got = device.estep_slot(0)
+    for k in range(wl.model.nr_classes):
+        device.bp_clear(k)
+    want = device.expectation_some_particles(pool)
+    assert np.array_equal(got.particles["best_ihidden_over"], want.particles["best_ihidden_over"])
+    assert np.mean(got.particles["nr_significant_coarse"] == want.particles["nr_significant_coarse"]) >= 0.8
+    np.testing.assert_allclose(got.particles["dLL_nolog"], want.particles["dLL_nolog"], rtol=1e-4)
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

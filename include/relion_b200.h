@@ -105,6 +105,13 @@ int rb_bp_get(rb_ctx *ctx, int iclass, float *real, float *imag, float *weight);
  * src/ml_optimiser_mpi.cpp:2028-2185).  The pointer stays valid until rb_bp_init/rb_ctx_destroy. */
 int rb_bp_device_buffer(rb_ctx *ctx, int iclass, void **dptr, size_t *n_floats);
 
+/* Reconstruction of a map from accumulator iclass on the device (SURVEY.md 8f "next" row 2): BackProjector::reconstruct,
+ * default skip_gridding branch (src/backprojector.cpp:1379-1575) + windowToOridimRealSpace (:2530-2665) + griddingCorrect
+ * (src/projector.cpp:595-628).  tau2: [n_tau2] spectrum for the MAP term (NULL: plain weighted average, do_map == false);
+ * vol_out: [ori_size]^3 floats, origin at ori_size/2.  The accumulator is left untouched (all-reduce it first on several GPUs). */
+int rb_reconstruct(rb_ctx *ctx, int iclass, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map,
+                   float *vol_out);
+
 /* ------------------------------------------------------------------------------------------------
  * Sampling tables for this iteration (outputs of HealpixSampling, src/healpix_sampling.cpp:
  * getDirection/getPsiAngle :1662-1700, getOrientations :1832, getTranslationsInPixel :1724).

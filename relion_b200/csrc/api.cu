@@ -100,6 +100,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (auto &b : ctx->gemm_buf) b.release();
 	for (auto &b : ctx->wc_buf) b.release();
 	for (auto &b : ctx->prep_buf) b.release();
+	for (auto &b : ctx->recon_buf) b.release();
 	for (int i = 0; i < RB_NUM_SLOTS; i++) for (auto &b : ctx->prep_raw[i]) b.release();
 	for (int i = 0; i < 2; i++) { for (auto &b : ctx->posed_buf[i]) b.release(); if (ctx->posed_ev[i]) cudaEventDestroy(ctx->posed_ev[i]); }
 	for (int i = 0; i < RB_NUM_SLOTS; i++) release_slot(ctx->slot[i]);
@@ -263,6 +264,30 @@ extern "C" int rb_bp_get(rb_ctx *ctx, int k, float *real, float *imag, float *we
 	RB_CUDA(cudaMemcpyAsync(real, t, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaMemcpyAsync(imag, t + n, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaMemcpyAsync(weight, t + 2 * n, nout * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->scratch[2].release();
+	return RB_OK;
+}
+
+// BackProjector::reconstruct (default skip_gridding branch) on the device
+extern "C" int rb_reconstruct(rb_ctx *ctx, int k, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map, float *vol_out)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_reconstruct: accumulator %d not initialised", k);
+	RB_ARG(!ctx->bp_2d[k], "rb_reconstruct: 2D accumulators are not supported yet");
+	RB_ARG(vol_out && ori_size > 0 && ori_size % 2 == 0, "rb_reconstruct: bad arguments");
+	RB_ARG(!tau2 || n_tau2 > 0, "rb_reconstruct: tau2 without a length");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	const size_t n = (size_t) ori_size * ori_size * ori_size;
+	RB_CHECK(ctx->scratch[2].ensure(n * sizeof(float)));
+	double *d_tau2 = nullptr;
+	if (tau2)
+	{
+		RB_CHECK(ctx->scratch[3].ensure((size_t) n_tau2 * 8));
+		RB_CUDA(cudaMemcpyAsync(ctx->scratch[3].p, tau2, (size_t) n_tau2 * 8, cudaMemcpyHostToDevice, ctx->stream));
+		d_tau2 = ctx->scratch[3].as<double>();
+	}
+	RB_CHECK(rbk_reconstruct(ctx, ctx->bp[k], ori_size, d_tau2, n_tau2, tau2_fudge, minres_map, ctx->scratch[2].as<float>()));
+	RB_CUDA(cudaMemcpyAsync(vol_out, ctx->scratch[2].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->scratch[2].release();
 	return RB_OK;

@@ -218,6 +218,7 @@ struct rb_ctx {
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
 	DevBuf scratch[8];
 	DevBuf wc_buf[10];
+	DevBuf recon_buf[3];             // reconstruction on the device (kernels_recon.cu): FFT input / output, radial sums
 	DevBuf prep_buf[4];              // device image preparation (kernels_prep.cu): cuFFT input / output, background values, spectra
 	DevBuf prep_raw[RB_NUM_SLOTS][4];   // per slot: raw images, shifts, norm factors, CTF parameters (filled on the copy stream)
 	DevBuf posed_buf[2][3];          // staged posed images (F2D, Fctf, matrices), two buffers for upload / compute overlap
@@ -265,6 +266,10 @@ int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int M, 
 // kernels_prep.cu: getFourierTransformsAndCtfs on the device, batched over the pool
 int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
                      int n, float radius, float cosine_width, float *d_power);
+
+// kernels_recon.cu: BackProjector::reconstruct (skip_gridding) + windowToOridimRealSpace + griddingCorrect on the device
+int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,
+                    float *d_vol_out);
 
 // kernels_weights.cu
 int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s);

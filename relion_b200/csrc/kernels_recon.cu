@@ -1,0 +1,194 @@
+// relion_b200 — reconstruction of a map from the back-projection accumulators on the device (SURVEY.md §8f "next" row 2).
+//
+// BackProjector::reconstruct, default skip_gridding branch (/root/reference/src/backprojector.cpp:1379-1575: decenter,
+// MAP regularisation of the weights :1463-1507, division by max(weight, radial average / 1000) :1513-1573), followed by
+// windowToOridimRealSpace (:2530-2665: window the transform to pad*ori, CenterFFTbySign, inverse FFT, window to the box,
+// normalise, softMaskOutsideMap src/mask.cpp:43-96) and Projector::griddingCorrect (src/projector.cpp:595-628).
+// The accumulator never leaves the device; the 3D inverse FFT is cuFFT (library), the rest is fused into five kernels.
+#include "device_utils.cuh"
+#include <cufft.h>
+
+struct ReconArgs {
+	const float4 *acc;              // (re, im, weight, 0) [mdlZ][mdlY][mdlX], centred in y and z
+	int mdlX, mdlY, mdlZ, initY, initZ;
+	int pad;                        // pad_size of the accumulator (= mdlY)
+	int r_max; float pf;
+	long long max_r2, round_max_r2;
+	const double *tau2; int n_tau2; double tau2_fudge, oversampling_correction; int minres_map;   // tau2 == nullptr: no MAP term
+	double *radsum; double *radcnt; // [r_max]
+	int padori, ori;
+};
+
+__device__ __forceinline__ int fftw_freq(int k, int n) { return k < n / 2 + 1 ? k : k - n; }
+
+// regularised weight of FFTW-index voxel (kp, ip, jp) of the pad^3 transform (decenter + MAP term)
+__device__ __forceinline__ double recon_weight(const ReconArgs &A, int kp, int ip, int jp, long long r2, float4 *val)
+{
+	float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+	if (r2 <= A.max_r2) v = __ldg(A.acc + ((size_t) (kp - A.initZ) * A.mdlY + (ip - A.initY)) * A.mdlX + jp);   // decenter, projector.h:249-260
+	if (val) *val = v;
+	double w = (double) v.z;
+	if (A.tau2 && r2 < A.max_r2)
+	{
+		const int ires = (int) floor(sqrt((double) r2) / (double) A.pf + 0.5);
+		const double t = A.tau2[ires < A.n_tau2 ? ires : A.n_tau2 - 1];
+		double invtau2;
+		if (t > 0.) invtau2 = 1. / (A.oversampling_correction * A.tau2_fudge * t);
+		else invtau2 = w > 1e-20 ? 1. / (0.001 * w) : 0.;
+		if (ires >= A.minres_map) w += invtau2;
+	}
+	return w;
+}
+
+// radial average of the (regularised) weights over r2 < round(r_max pf r_max pf), shells floor(r / pf)   (:1513-1540)
+__global__ void __launch_bounds__(256)
+k_recon_radavg(ReconArgs A)
+{
+	__shared__ double s_sum[1024], s_cnt[1024];
+	for (int i = threadIdx.x; i < A.r_max; i += blockDim.x) { s_sum[i] = 0.; s_cnt[i] = 0.; }
+	__syncthreads();
+	const int xh = A.pad / 2 + 1;
+	const size_t n = (size_t) A.pad * A.pad * xh;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int jp = (int) (i % xh), ii = (int) ((i / xh) % A.pad), kk = (int) (i / ((size_t) xh * A.pad));
+		const int ip = fftw_freq(ii, A.pad), kp = fftw_freq(kk, A.pad);
+		const long long r2 = (long long) kp * kp + (long long) ip * ip + (long long) jp * jp;
+		if (r2 < A.round_max_r2)
+		{
+			const int ires = (int) floor(sqrt((double) r2) / (double) A.pf);
+			if (ires < A.r_max)
+			{
+				atomicAdd(&s_sum[ires], recon_weight(A, kp, ip, jp, r2, nullptr));
+				atomicAdd(&s_cnt[ires], 1.);
+			}
+		}
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < A.r_max; i += blockDim.x)
+		if (s_cnt[i] > 0.) { atomicAdd(A.radsum + i, s_sum[i]); atomicAdd(A.radcnt + i, s_cnt[i]); }
+}
+
+// Fconv = data / max(weight, radavg / 1000), windowed to the pad*ori transform, sign-centred: the input of the inverse FFT
+__global__ void __launch_bounds__(256)
+k_recon_fin(ReconArgs A, float2 *Fin)
+{
+	const int xo = A.padori / 2 + 1;
+	const size_t n = (size_t) A.padori * A.padori * xo;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int j = (int) (i % xo), ii = (int) ((i / xo) % A.padori), kk = (int) (i / ((size_t) xo * A.padori));
+		const int ip = fftw_freq(ii, A.padori), kp = fftw_freq(kk, A.padori);        // windowFourierTransform: same (kp, ip, jp)
+		float2 out = make_float2(0.f, 0.f);
+		const int half = A.pad / 2;                                                    // frequencies held by the pad^3 transform
+		if (j <= half && ip >= -half && ip <= half && kp >= -half && kp <= half)
+		{
+			const long long r2 = (long long) kp * kp + (long long) ip * ip + (long long) j * j;
+			float4 v;
+			const double w0 = recon_weight(A, kp, ip, j, r2, &v);
+			int ires = (int) floor(sqrt((double) r2) / (double) A.pf);
+			if (ires > A.r_max - 1) ires = A.r_max - 1;
+			const double ra = A.radsum[ires] / (1000. * (A.radcnt[ires] > 0. ? A.radcnt[ires] : 1.));
+			const double w = w0 > ra ? w0 : ra;                                         // :1547
+			double re = (double) v.x, im = (double) v.y;
+			if (w != 0.) { re /= w; im /= w; }
+			if ((kk ^ ii ^ j) & 1) { re = -re; im = -im; }                              // CenterFFTbySign, src/fftw.h:390-403
+			out = make_float2((float) re, (float) im);
+		}
+		Fin[i] = out;
+	}
+}
+
+// window to the box, normalise, and accumulate the background sums of softMaskOutsideMap (radius ori/2, width 3)
+__global__ void __launch_bounds__(256)
+k_recon_window(const float *real, float *vol, int padori, int ori, float inv_normfft, double *bg_sums)
+{
+	__shared__ double dred[32];
+	const size_t n = (size_t) ori * ori * ori;
+	const int o = padori / 2 - ori / 2;
+	const float radius = (float) ori / 2.f, radius_p = radius + 3.f;
+	double s = 0., sb = 0.;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int x = (int) (i % ori), y = (int) ((i / ori) % ori), z = (int) (i / ((size_t) ori * ori));
+		const float v = real[((size_t) (z + o) * padori + (y + o)) * padori + (x + o)] * inv_normfft;
+		vol[i] = v;
+		const int cx = x - ori / 2, cy = y - ori / 2, cz = z - ori / 2;
+		const float r = sqrtf((float) (cx * cx + cy * cy + cz * cz));
+		if (r >= radius)
+		{
+			const float rc = r > radius_p ? 1.f : 0.5f + 0.5f * cosf((float) M_PI * (radius_p - r) / 3.f);
+			s += (double) rc; sb += (double) (rc * v);
+		}
+	}
+	s = block_sum(s, dred);
+	sb = block_sum(sb, dred);
+	if (threadIdx.x == 0) { atomicAdd(bg_sums, s); atomicAdd(bg_sums + 1, sb); }
+}
+
+// soft mask to the background value + gridding correction (divide by sinc^2(r / (ori pf)))
+__global__ void __launch_bounds__(256)
+k_recon_finish(float *vol, int ori, float pf, const double *bg_sums)
+{
+	const size_t n = (size_t) ori * ori * ori;
+	const float radius = (float) ori / 2.f, radius_p = radius + 3.f;
+	const float bg = (float) (bg_sums[1] / bg_sums[0]);
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int x = (int) (i % ori), y = (int) ((i / ori) % ori), z = (int) (i / ((size_t) ori * ori));
+		const int cx = x - ori / 2, cy = y - ori / 2, cz = z - ori / 2;
+		const float r = sqrtf((float) (cx * cx + cy * cy + cz * cz));
+		float v = vol[i];
+		if (r >= radius)
+		{
+			const float rc = r > radius_p ? 1.f : 0.5f + 0.5f * cosf((float) M_PI * (radius_p - r) / 3.f);
+			v = (1.f - rc) * v + rc * bg;
+		}
+		if (r > 0.f)
+		{
+			const float rval = r / ((float) ori * pf);
+			const float sinc = sinf((float) M_PI * rval) / ((float) M_PI * rval);
+			v /= sinc * sinc;
+		}
+		vol[i] = v;
+	}
+}
+
+// d_vol_out: [ori][ori][ori] device floats
+int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,
+                    float *d_vol_out)
+{
+	ReconArgs A;
+	memset(&A, 0, sizeof(A));
+	A.acc = bp.vol; A.mdlX = bp.mdlX; A.mdlY = bp.mdlY; A.mdlZ = bp.mdlZ; A.initY = bp.mdlInitY; A.initZ = bp.mdlInitZ;
+	A.pad = bp.mdlY; A.r_max = bp.maxR; A.pf = bp.padding_factor;
+	const long long rr = (long long) floor((double) bp.maxR * (double) bp.padding_factor + 0.5);
+	A.max_r2 = rr * rr;
+	A.round_max_r2 = (long long) floor((double) bp.maxR * bp.padding_factor * bp.maxR * bp.padding_factor + 0.5);
+	A.tau2 = d_tau2; A.n_tau2 = n_tau2; A.tau2_fudge = tau2_fudge; A.minres_map = minres_map;
+	A.oversampling_correction = (double) bp.padding_factor * bp.padding_factor * bp.padding_factor;
+	int padori = (int) floor((double) bp.padding_factor * ori + 0.5);
+	padori += padori % 2;
+	A.padori = padori; A.ori = ori;
+	if (A.r_max > 1024) { rb_set_error("rb_reconstruct: r_max %d too large", A.r_max); return RB_ERR_ARG; }
+	const size_t nfin = (size_t) padori * padori * (padori / 2 + 1), nreal = (size_t) padori * padori * padori;
+	DevBuf &bFin = ctx->recon_buf[0], &bReal = ctx->recon_buf[1], &bRad = ctx->recon_buf[2];
+	RB_CHECK(bFin.ensure(nfin * 8)); RB_CHECK(bReal.ensure(nreal * 4)); RB_CHECK(bRad.ensure((size_t) (2 * 1024 + 2) * 8));
+	RB_CUDA(cudaMemsetAsync(bRad.p, 0, (size_t) (2 * 1024 + 2) * 8, ctx->stream));
+	A.radsum = bRad.as<double>(); A.radcnt = A.radsum + 1024;
+	double *bg_sums = A.radsum + 2048;
+	k_recon_radavg<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
+	k_recon_fin<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(A, bFin.as<float2>()); RB_LAUNCH_CHECK(ctx);
+	cufftHandle plan;
+	if (cufftPlan3d(&plan, padori, padori, padori, CUFFT_C2R) != CUFFT_SUCCESS) { rb_set_error("cufftPlan3d(%d^3) failed", padori); return RB_ERR_CUDA; }
+	cufftSetStream(plan, ctx->stream);
+	const cufftResult r = cufftExecC2R(plan, bFin.as<cufftComplex>(), bReal.as<float>());
+	ctx->launches++;
+	if (r != CUFFT_SUCCESS) { cufftDestroy(plan); rb_set_error("cufftExecC2R failed (%d)", (int) r); return RB_ERR_CUDA; }
+	const float inv_normfft = 1.f / (bp.padding_factor * bp.padding_factor * bp.padding_factor * (float) ori);   // ref_dim 3, data_dim 2 (:2583-2586)
+	k_recon_window<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(bReal.as<float>(), d_vol_out, padori, ori, inv_normfft, bg_sums); RB_LAUNCH_CHECK(ctx);
+	k_recon_finish<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(d_vol_out, ori, bp.padding_factor, bg_sums); RB_LAUNCH_CHECK(ctx);
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	cufftDestroy(plan);
+	return RB_OK;
+}

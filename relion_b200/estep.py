@@ -333,6 +333,14 @@ class MlDeviceBundle:
             return re[0], im[0], w[0]
         return re, im, w
 
+    def reconstruct(self, iclass: int, ori_size: int, tau2=None, tau2_fudge: float = 1.0, minres_map: int = 0) -> np.ndarray:
+        """rb_reconstruct: BackProjector::reconstruct (skip_gridding) on the device; [ori, ori, ori] float32."""
+        out = np.empty((ori_size,) * 3, np.float32)
+        t = _f64(tau2)
+        capi.check(self.lib, self.lib.rb_reconstruct(self.ctx, iclass, ori_size, _ptr(t, C.c_double), 0 if t is None else len(t),
+                                                     float(tau2_fudge), int(minres_map), _ptr(out, C.c_float)))
+        return out
+
     def bp_device_tensor(self, iclass: int):
         """The interleaved (re, im, weight, 0) accumulator as a torch CUDA tensor sharing the library's memory
         (for torch.distributed.all_reduce over NCCL — replaces MlOptimiserMpi::combineAllWeightedSums)."""

@@ -406,6 +406,27 @@ def test_pool_prepare_matches_reference_algorithm(device, ori, cur, local):
     np.testing.assert_allclose(got.particles["dLL_nolog"], want.particles["dLL_nolog"], rtol=1e-4)
 
 
+@pytest.mark.parametrize("ori,cur,with_tau2", [(32, 32, False), (32, 32, True), (40, 28, True)])
+def test_reconstruct_on_device(device, ori, cur, with_tau2):
+    """SURVEY 8f row 2: rb_reconstruct (BackProjector::reconstruct, skip_gridding, + windowToOridimRealSpace +
+    griddingCorrect on the device) against the numpy restatement applied to the same accumulator."""
+    from oracle import reconstruct as rc
+    wl = make_workload(ori_size=ori, current_size=cur, healpix_order=1, n_particles=60, seed=80 + ori, snr=0.5)
+    _setup(device, wl)
+    device.expectation_some_particles(wl.pool)
+    tau2 = None
+    if with_tau2:
+        tau2 = 1e-3 / (1.0 + np.arange(ori // 2 + 1)) ** 2
+        tau2[-2:] = 0.0                                        # the tau2 <= 0 branch (:1483-1487)
+    got = device.reconstruct(0, ori, tau2=tau2, tau2_fudge=2.0, minres_map=2)
+    gre, gim, gw = device.bp_get(0)
+    want = rc.reconstruct(gre, gim, gw, ori, wl.r_max, wl.padding_factor, tau2=tau2, tau2_fudge=2.0, minres_map=2)
+    assert np.abs(want).max() > 0
+    assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
+    f = rc.fsc(got.astype(np.float64), want)
+    assert f.min() >= 0.9999, f
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -90,6 +90,13 @@ int rb_set_reference_f32(rb_ctx *ctx, int iclass, const float *vol_complex,
                          int mdlX, int mdlY, int mdlZ, int mdlInitY, int mdlInitZ,
                          int mdlMaxR, double padding_factor);
 
+/* Reference of class iclass from a real-space map on the device (SURVEY.md 8f "next" row 3): Projector::
+ * computeFourierTransformMap (src/projector.cpp:116-592) for a 3D reference used with 2D images: gridding correction,
+ * zero-padding, forward FFT, centring, windowing to r_max = current_size / 2, normfft.  map: [ori_size]^3 floats, origin
+ * at ori_size/2; power_spectrum: [ori_size/2+1] radial power of the reference (tau2 input of the M-step), may be NULL. */
+int rb_set_reference_from_map(rb_ctx *ctx, int iclass, const float *map, int ori_size, int current_size, double padding_factor,
+                              double *power_spectrum);
+
 /* ------------------------------------------------------------------------------------------------
  * Back-projection accumulators (AccBackprojector::setMdlDim/initMdl/clear/getMdlData,
  * acc_backprojector_impl.h:13-186).  Device layout is one interleaved float4 (re, im, weight, 0)

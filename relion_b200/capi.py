@@ -125,6 +125,7 @@ PROTOTYPES = {
     "rb_timer_stop": (C.c_int, [C.c_void_p, c_double_p]),
     "rb_set_reference": (C.c_int, [C.c_void_p, C.c_int, c_double_p] + [C.c_int] * 6 + [C.c_double]),
     "rb_set_reference_f32": (C.c_int, [C.c_void_p, C.c_int, c_float_p] + [C.c_int] * 6 + [C.c_double]),
+    "rb_set_reference_from_map": (C.c_int, [C.c_void_p, C.c_int, c_float_p, C.c_int, C.c_int, C.c_double, c_double_p]),
     "rb_bp_init": (C.c_int, [C.c_void_p, C.c_int] + [C.c_int] * 6 + [C.c_double]),
     "rb_bp_clear": (C.c_int, [C.c_void_p, C.c_int]),
     "rb_bp_get": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p]),

@@ -224,6 +224,31 @@ extern "C" int rb_set_reference_f32(rb_ctx *ctx, int k, const float *vol, int md
 	return RB_OK;
 }
 
+// Projector::computeFourierTransformMap on the device: real-space map -> padded Fourier reference of class k
+extern "C" int rb_set_reference_from_map(rb_ctx *ctx, int k, const float *map, int ori_size, int current_size, double padding_factor,
+                                         double *power_spectrum)
+{
+	RB_ARG(ctx && map, "rb_set_reference_from_map: NULL argument");
+	RB_ARG(ori_size > 0 && ori_size % 2 == 0 && ori_size / 2 + 1 <= 1024, "rb_set_reference_from_map: box size %d unsupported", ori_size);
+	if (current_size <= 0 || current_size > ori_size) current_size = ori_size;
+	int padori = (int) floor(padding_factor * ori_size + 0.5);
+	padori += padori % 2;
+	const double pfe = (double) padori / (double) ori_size;
+	const int r_max = std::min(current_size / 2, ori_size / 2);
+	const int pad = 2 * ((int) floor(pfe * r_max + 0.5) + 1) + 1;                      // Projector::initialiseData, src/projector.cpp:70
+	int mdlX = pad / 2 + 1, mdlY = pad, mdlZ = pad, initY = -((pad - 1) / 2), initZ = initY;
+	RB_CHECK(set_reference_common(ctx, k, mdlX, mdlY, mdlZ, initY, initZ, r_max, pfe));
+	const size_t n = (size_t) ori_size * ori_size * ori_size;
+	RB_CHECK(ctx->scratch[2].ensure(n * sizeof(float)));
+	RB_CUDA(cudaMemcpyAsync(ctx->scratch[2].p, map, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CHECK(rbk_ftmap(ctx, ctx->scratch[2].as<float>(), ori_size, r_max, (float) padding_factor, ctx->proj_buf[k].as<float2>(), pad, power_spectrum));
+	RB_CHECK(rbk_expand_volume(ctx, ctx->proj[k], ctx->proj8_buf[k].as<float4>(), ctx->proj2_buf[k].as<float4>()));
+	RB_CHECK(rb_sync_tables(ctx));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->scratch[2].release();
+	return RB_OK;
+}
+
 extern "C" int rb_bp_init(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int initY, int initZ, int maxR, double pf)
 {
 	RB_ARG(ctx, "ctx is NULL");

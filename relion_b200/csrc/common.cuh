@@ -271,6 +271,8 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,
                     float *d_vol_out);
 
+int rbk_ftmap(rb_ctx *ctx, const float *d_vol, int ori, int r_max, float pf, float2 *d_data, int pad, double *h_power);
+
 // kernels_weights.cu
 int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s);
 int rbk_fine_setup_pool(rb_ctx *ctx, PoolSlot &s);

@@ -192,3 +192,101 @@ int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const doubl
 	cufftDestroy(plan);
 	return RB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// The inverse direction (SURVEY.md §8f "next" row 3): Projector::computeFourierTransformMap
+// (/root/reference/src/projector.cpp:116-592) for a 3D reference used with 2D images: gridding correction (divide by
+// sinc^2, :595-628), zero-padding to pad*ori, forward FFT (normalised), CenterFFTbySign, window to the projector's
+// (2 (round(pf r_max) + 1) + 1)^3 half volume with everything beyond round(pf r_max) zeroed, scaled by normfft = pf^3 ori
+// (:147-163), radial power spectrum (:497-545).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_ftmap_pad(const float *vol, float *real, int ori, int padori, float pf)
+{
+	const size_t n = (size_t) padori * padori * padori;
+	const int o = padori / 2 - ori / 2;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int x = (int) (i % padori) - o, y = (int) ((i / padori) % padori) - o, z = (int) (i / ((size_t) padori * padori)) - o;
+		float v = 0.f;
+		if (x >= 0 && x < ori && y >= 0 && y < ori && z >= 0 && z < ori)
+		{
+			v = vol[((size_t) z * ori + y) * ori + x];
+			const int cx = x - ori / 2, cy = y - ori / 2, cz = z - ori / 2;
+			const float r = sqrtf((float) (cx * cx + cy * cy + cz * cz));
+			if (r > 0.f)
+			{
+				const float rval = r / ((float) ori * pf);
+				const float sinc = sinf((float) M_PI * rval) / ((float) M_PI * rval);
+				v /= sinc * sinc;
+			}
+		}
+		real[i] = v;
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_ftmap_window(const float2 *F, float2 *data, int padori, int pad, long long max_r2, float scale, float pf, double *pow_sum, double *pow_cnt, int nshell)
+{
+	__shared__ double s_sum[1024], s_cnt[1024];
+	for (int i = threadIdx.x; i < nshell; i += blockDim.x) { s_sum[i] = 0.; s_cnt[i] = 0.; }
+	__syncthreads();
+	const int xd = pad / 2 + 1, h = (pad - 1) / 2, xf = padori / 2 + 1;
+	const size_t n = (size_t) pad * pad * xd;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int jp = (int) (i % xd), ip = (int) ((i / xd) % pad) - h, kp = (int) (i / ((size_t) xd * pad)) - h;
+		const long long r2 = (long long) kp * kp + (long long) ip * ip + (long long) jp * jp;
+		float2 out = make_float2(0.f, 0.f);
+		const bool in_fft = kp >= -(padori / 2 - 1) && kp <= padori / 2 && ip >= -(padori / 2 - 1) && ip <= padori / 2 && jp <= padori / 2;
+		if (r2 <= max_r2 && in_fft)
+		{
+			const int k = kp < 0 ? kp + padori : kp, ii = ip < 0 ? ip + padori : ip;
+			const float2 v = F[((size_t) k * padori + ii) * xf + jp];
+			const float sg = ((k ^ ii ^ jp) & 1) ? -scale : scale;                       // CenterFFTbySign, 1/N and normfft folded in
+			out = make_float2(v.x * sg, v.y * sg);
+			const int ires = (int) floor(sqrt((double) r2) / (double) pf + 0.5);
+			if (ires < nshell) { atomicAdd(&s_sum[ires], 0.5 * ((double) out.x * out.x + (double) out.y * out.y)); atomicAdd(&s_cnt[ires], 1.); }
+		}
+		data[i] = out;
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < nshell; i += blockDim.x)
+		if (s_cnt[i] > 0.) { atomicAdd(pow_sum + i, s_sum[i]); atomicAdd(pow_cnt + i, s_cnt[i]); }
+}
+
+// d_vol: [ori]^3 device floats; d_data: the projector's compact (re, im) volume [pad][pad][pad/2+1]; h_power: [ori/2+1] host doubles or nullptr
+int rbk_ftmap(rb_ctx *ctx, const float *d_vol, int ori, int r_max, float pf, float2 *d_data, int pad, double *h_power)
+{
+	int padori = (int) floor((double) pf * ori + 0.5);
+	padori += padori % 2;
+	const float pfe = (float) padori / (float) ori;                                   // re-calculated padding factor (:133)
+	const size_t nreal = (size_t) padori * padori * padori, nF = (size_t) padori * padori * (padori / 2 + 1);
+	DevBuf &bF = ctx->recon_buf[0], &bReal = ctx->recon_buf[1], &bRad = ctx->recon_buf[2];
+	RB_CHECK(bF.ensure(nF * 8)); RB_CHECK(bReal.ensure(nreal * 4)); RB_CHECK(bRad.ensure((size_t) (2 * 1024 + 2) * 8));
+	RB_CUDA(cudaMemsetAsync(bRad.p, 0, (size_t) (2 * 1024 + 2) * 8, ctx->stream));
+	k_ftmap_pad<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(d_vol, bReal.as<float>(), ori, padori, pfe); RB_LAUNCH_CHECK(ctx);
+	cufftHandle plan;
+	if (cufftPlan3d(&plan, padori, padori, padori, CUFFT_R2C) != CUFFT_SUCCESS) { rb_set_error("cufftPlan3d(%d^3) failed", padori); return RB_ERR_CUDA; }
+	cufftSetStream(plan, ctx->stream);
+	const cufftResult r = cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>());
+	ctx->launches++;
+	if (r != CUFFT_SUCCESS) { cufftDestroy(plan); rb_set_error("cufftExecR2C failed (%d)", (int) r); return RB_ERR_CUDA; }
+	const long long rr = (long long) floor((double) r_max * pfe + 0.5);
+	const float scale = (pfe * pfe * pfe * (float) ori) / ((float) padori * (float) padori * (float) padori);   // normfft / N
+	const int nshell = ori / 2 + 1;
+	double *pow_sum = bRad.as<double>(), *pow_cnt = pow_sum + 1024;
+	k_ftmap_window<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(bF.as<float2>(), d_data, padori, pad, rr * rr, scale, pfe, pow_sum, pow_cnt, nshell);
+	RB_LAUNCH_CHECK(ctx);
+	if (h_power)
+	{
+		std::vector<double> ps(nshell), pc(nshell);
+		RB_CUDA(cudaMemcpyAsync(ps.data(), pow_sum, nshell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		RB_CUDA(cudaMemcpyAsync(pc.data(), pow_cnt, nshell * 8, cudaMemcpyDeviceToHost, ctx->stream));
+		RB_CUDA(cudaStreamSynchronize(ctx->stream));
+		for (int i = 0; i < nshell; i++) h_power[i] = pc[i] < 1. ? 0. : ps[i] / pc[i];                              // :563-568
+	}
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	cufftDestroy(plan);
+	return RB_OK;
+}

@@ -311,6 +311,15 @@ class MlDeviceBundle:
             st = self.lib.rb_set_reference_f32(self.ctx, iclass, _ptr(v.view(np.float32), C.c_float), x, y, z, init, init, r_max, padding_factor)
         capi.check(self.lib, st)
 
+    def set_reference_from_map(self, iclass: int, vol: np.ndarray, current_size: int = 0, padding_factor: float = 2.0):
+        """rb_set_reference_from_map: computeFourierTransformMap on the device; returns the radial power spectrum [ori/2+1]."""
+        v = np.ascontiguousarray(vol, np.float32)
+        ori = v.shape[0]
+        ps = np.zeros(ori // 2 + 1, np.float64)
+        capi.check(self.lib, self.lib.rb_set_reference_from_map(self.ctx, iclass, _ptr(v, C.c_float), ori, int(current_size), float(padding_factor),
+                                                                _ptr(ps, C.c_double)))
+        return ps
+
     def bp_init(self, iclass: int, shape_zyx, r_max: int, padding_factor: float = 2.0):
         self._keep[("bp_2d", iclass)] = len(shape_zyx) == 2
         if len(shape_zyx) == 2:

@@ -427,6 +427,32 @@ def test_reconstruct_on_device(device, ori, cur, with_tau2):
     assert f.min() >= 0.9999, f
 
 
+@pytest.mark.parametrize("ori,cur", [(32, 32), (40, 28)])
+def test_reference_from_map_on_device(device, oracle, ori, cur):
+    """SURVEY 8f row 3: rb_set_reference_from_map (Projector::computeFourierTransformMap on the device): central slices of the
+    device-made reference against slices of the numpy restatement (synth.reference_ft, float64); power spectrum."""
+    from oracle.bindings import Projector
+    vol = synth.make_phantom(ori, n_blobs=30, seed=9)
+    ps = device.set_reference_from_map(0, vol, current_size=cur)
+    data, r_max = synth.reference_ft(vol, current_size=cur)
+    ref = Projector(data.astype(np.complex64), r_max, 2.0)
+    rng = np.random.default_rng(1)
+    eul = synth.inverse_euler_f32(rng.uniform(-180, 180, 6), rng.uniform(0, 180, 6), rng.uniform(0, 360, 6))
+    got = device.project(0, cur, eul)
+    for i in range(len(eul)):
+        want = oracle.project(ref, cur, eul[i])
+        assert np.abs(got[i] - want).max() <= 2e-5 * np.abs(want).max()
+    # radial power spectrum of the reference (:497-568)
+    pad = data.shape[0]; h = (pad - 1) // 2
+    k = np.arange(-h, h + 1); kx = np.arange(pad // 2 + 1)
+    kz, ky, kxx = np.meshgrid(k, k, kx, indexing="ij")
+    r2 = kz * kz + ky * ky + kxx * kxx
+    inr = r2 <= int(np.floor(r_max * 2.0 + 0.5)) ** 2
+    ires = np.floor(np.sqrt(r2[inr]) / 2.0 + 0.5).astype(int)
+    want_ps = np.bincount(ires, weights=0.5 * np.abs(data[inr]) ** 2, minlength=ori // 2 + 1) / np.maximum(np.bincount(ires, minlength=ori // 2 + 1), 1)
+    np.testing.assert_allclose(ps[:len(want_ps)], want_ps[:len(ps)], rtol=2e-4, atol=1e-9 * want_ps.max())
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

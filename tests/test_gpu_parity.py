@@ -453,6 +453,40 @@ def test_reference_from_map_on_device(device, oracle, ori, cur):
     np.testing.assert_allclose(ps[:len(want_ps)], want_ps[:len(ps)], rtol=2e-4, atol=1e-9 * want_ps.max())
 
 
+def test_refinement_iterations_stay_on_the_device(device):
+    """The three 'next' rows chained around the hot path: map -> reference (rb_set_reference_from_map) -> E-step over a pool
+    of RAW images (rb_pool_prepare + rb_estep_slot) -> map (rb_reconstruct), three times, starting from a blurred phantom.
+    The reconstruction must converge towards the phantom the particles were projected from (FSC at low resolution)."""
+    from oracle import reconstruct as rc
+    from relion_b200.workload import raw_pool_from
+    ori = 32
+    wl = make_workload(ori_size=ori, healpix_order=1, n_particles=300, seed=90, snr=1.0, nr_groups=1)
+    raw = raw_pool_from(wl, seed=4, max_old_offset=0.0, mask_radius=0.45 * ori)
+    raw.norm_factor[:] = 1.0
+    truth = synth.make_phantom(ori, n_blobs=40, seed=1993)
+    # blurred start: keep only the lowest shells
+    F = np.fft.fftn(truth)
+    f = np.fft.fftfreq(ori) * ori
+    kz, ky, kx = np.meshgrid(f, f, f, indexing="ij")
+    start = np.real(np.fft.ifftn(F * np.exp(-(kz ** 2 + ky ** 2 + kx ** 2) / (2 * 2.0 ** 2))))
+    device.set_model(wl.model)
+    device.set_sampling(wl.sampling)
+    device.bp_init(0, wl.bp_shape, wl.r_max, wl.padding_factor)
+    cur = start
+    fscs = []
+    for it in range(3):
+        device.set_reference_from_map(0, cur)
+        device.bp_clear(0)
+        device.pool_prepare(0, raw, want_power=False)
+        res = device.estep_slot(0)
+        cur = device.reconstruct(0, ori).astype(np.float64)
+        fscs.append(rc.fsc(cur, truth))
+    assert fscs[0][1:4].min() > 0.9, fscs[0]
+    assert fscs[-1][1:6].min() > 0.95, fscs[-1]
+    assert fscs[-1][4:8].mean() >= fscs[0][4:8].mean() - 0.02, (fscs[0], fscs[-1])
+    assert np.mean(res.particles["best_idir"] == wl.truth["idir"]) > 0.5      # 30-degree grid: neighbours / pole degeneracy allowed
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

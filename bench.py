@@ -50,6 +50,9 @@ WORKLOADS = {
     # coarse window 54 px: the coarse cross term is the dense contraction that runs on the tensor cores
     "class3d_256_global": (dict(ori_size=256, current_size=128, healpix_order=3, offset_range=5.0, offset_step=2.0, nr_classes=4,
                                 snr=0.05, pixel_size=1.0, n_blobs=200, nr_groups=8), 256),
+    # BASELINE config #5 sizing: 400-px box, 803^3 padded reference / accumulator (16.6 GB expanded reference per class)
+    "refine3d_400_local": (dict(ori_size=400, healpix_order=4, offset_range=3.0, offset_step=1.0, nr_classes=1, snr=0.05,
+                                local_search=True, pixel_size=1.0, n_blobs=200, nr_groups=8), 256),
     # BASELINE config #1: 2D classification, K = 10, 64-px particles, psi step 6 deg, offset range 5 / step 2
     "class2d_64": (dict(ori_size=64, nr_classes=10, ref_dim=2, psi_step=6.0, offset_range=5.0, offset_step=2.0, snr=0.1,
                         pixel_size=3.0, n_blobs=25, nr_groups=8), 2000),

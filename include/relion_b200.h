@@ -112,6 +112,11 @@ int rb_bp_get(rb_ctx *ctx, int iclass, float *real, float *imag, float *weight);
  * src/ml_optimiser_mpi.cpp:2028-2185).  The pointer stays valid until rb_bp_init/rb_ctx_destroy. */
 int rb_bp_device_buffer(rb_ctx *ctx, int iclass, void **dptr, size_t *n_floats);
 
+/* BackProjector::symmetrise (src/backprojector.cpp:2136-2480) on accumulator iclass: enforceHermitianSymmetry of the x = 0
+ * plane, then applyPointGroupSymmetry with the nsym rotation matrices R ([nsym][9] row-major, the R of
+ * SymList::get_matrices; nsym == 0 for C1).  RELION calls this before every reconstruct (src/ml_optimiser.cpp:4930-5044). */
+int rb_bp_symmetrise(rb_ctx *ctx, int iclass, const double *R, int nsym);
+
 /* Reconstruction of a map from accumulator iclass on the device (SURVEY.md 8f "next" row 2): BackProjector::reconstruct,
  * default skip_gridding branch (src/backprojector.cpp:1379-1575) + windowToOridimRealSpace (:2530-2665) + griddingCorrect
  * (src/projector.cpp:595-628).  tau2: [n_tau2] spectrum for the MAP term (NULL: plain weighted average, do_map == false);

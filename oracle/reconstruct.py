@@ -64,6 +64,50 @@ def gridding_correct(vol: np.ndarray, ori_size: int, padding_factor: float) -> n
     return vol / (sinc * sinc)
 
 
+def symmetrise(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, r_max: int, padding_factor: float, rotations=()):
+    """BackProjector::symmetrise (src/backprojector.cpp:2136-2480): enforceHermitianSymmetry + applyPointGroupSymmetry
+    on centred [Z, Y, X] arrays; returns new (real, imag, weight) float64."""
+    data = real.astype(np.float64) + 1j * imag.astype(np.float64)
+    w = weight.astype(np.float64).copy()
+    Z, Y, X = data.shape
+    hz, hy = (Z - 1) // 2, (Y - 1) // 2
+    # enforceHermitianSymmetry (:2148-2165)
+    for iz in range(-hz, Z - hz):
+        for iy in range(0 if iz < 0 else 1, Y - hy):
+            if -iz + hz >= Z or -iy + hy < 0:
+                continue
+            a, b = (iz + hz, iy + hy, 0), (-iz + hz, -iy + hy, 0)
+            fs = data[a] + np.conj(data[b])
+            data[a], data[b] = fs, np.conj(fs)
+            sw = w[a] + w[b]
+            w[a] = w[b] = sw
+    if len(rotations):
+        rr = int(math.floor(r_max * padding_factor + 0.5))
+        kz, ky, kx = np.meshgrid(np.arange(Z) - hz, np.arange(Y) - hy, np.arange(X), indexing="ij")
+        inside = (kx * kx + ky * ky + kz * kz) <= rr * rr
+        sum_d, sum_w = data.copy(), w.copy()
+        x, y, z = kx[inside].astype(np.float64), ky[inside].astype(np.float64), kz[inside].astype(np.float64)
+        for R in np.asarray(rotations, np.float64).reshape(-1, 3, 3):
+            xp = x * R[0, 0] + y * R[0, 1] + z * R[0, 2]
+            yp = x * R[1, 0] + y * R[1, 1] + z * R[1, 2]
+            zp = x * R[2, 0] + y * R[2, 1] + z * R[2, 2]
+            neg = xp < 0
+            xp = np.where(neg, -xp, xp); yp = np.where(neg, -yp, yp); zp = np.where(neg, -zp, zp)
+            x0 = np.floor(xp).astype(int); fx = xp - x0
+            y0 = np.floor(yp).astype(int); fy = yp - y0; y0 += hy
+            z0 = np.floor(zp).astype(int); fz = zp - z0; z0 += hz
+            vd = np.zeros(x.shape, np.complex128); vw = np.zeros(x.shape)
+            for dz, wz in ((0, 1 - fz), (1, fz)):
+                for dy, wy in ((0, 1 - fy), (1, fy)):
+                    for dx, wx in ((0, 1 - fx), (1, fx)):
+                        vd += data[z0 + dz, y0 + dy, x0 + dx] * (wz * wy * wx)
+                        vw += w[z0 + dz, y0 + dy, x0 + dx] * (wz * wy * wx)
+            sum_d[inside] += np.where(neg, np.conj(vd), vd)
+            sum_w[inside] += vw
+        data, w = sum_d, sum_w
+    return data.real, data.imag, w
+
+
 def reconstruct(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, ori_size: int, r_max: int,
                 padding_factor: float = 2.0, tau2: np.ndarray | None = None, tau2_fudge: float = 1.0,
                 minres_map: int = 0) -> np.ndarray:

@@ -294,6 +294,25 @@ extern "C" int rb_bp_get(rb_ctx *ctx, int k, float *real, float *imag, float *we
 	return RB_OK;
 }
 
+// BackProjector::symmetrise on the device accumulator: Hermitian symmetry of the x = 0 plane + point-group symmetry mates
+extern "C" int rb_bp_symmetrise(rb_ctx *ctx, int k, const double *R, int nsym)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_symmetrise: accumulator %d not initialised", k);
+	RB_ARG(!ctx->bp_2d[k], "rb_bp_symmetrise: 2D accumulators are not supported");
+	RB_ARG(nsym >= 0 && (nsym == 0 || R), "rb_bp_symmetrise: bad symmetry list");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	float *d_R = nullptr;
+	if (nsym > 0)
+	{
+		std::vector<float> r((size_t) nsym * 9);
+		for (size_t i = 0; i < r.size(); i++) r[i] = (float) R[i];
+		RB_CHECK(upload(ctx, ctx->scratch[3], r.data(), r.size() * 4));
+		d_R = ctx->scratch[3].as<float>();
+	}
+	RB_CHECK(rbk_bp_symmetrise(ctx, ctx->bp[k], ctx->recon_buf[1], d_R, nsym));
+	return RB_OK;
+}
+
 // BackProjector::reconstruct (default skip_gridding branch) on the device
 extern "C" int rb_reconstruct(rb_ctx *ctx, int k, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map, float *vol_out)
 {

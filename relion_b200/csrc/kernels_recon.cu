@@ -290,3 +290,87 @@ int rbk_ftmap(rb_ctx *ctx, const float *d_vol, int ori, int r_max, float pf, flo
 	cufftDestroy(plan);
 	return RB_OK;
 }
+
+// ---------------------------------------------------------------------------------------------
+// BackProjector::symmetrise (/root/reference/src/backprojector.cpp:2136-2146) on the interleaved accumulator:
+// enforceHermitianSymmetry (:2148-2165) on the x = 0 plane, then applyPointGroupSymmetry (:2324-2480): every voxel inside
+// round(r_max pf) receives the trilinearly interpolated values of its nsym symmetry mates (Hermitian fold for x < 0).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_bp_hermitian(float4 *acc, int mdlX, int mdlY, int mdlZ, int initY, int initZ)
+{
+	const int finY = mdlY - 1 + initY, finZ = mdlZ - 1 + initZ;
+	const int n = mdlZ * mdlY;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+	{
+		const int iz = i / mdlY + initZ, iy = i % mdlY + initY;
+		const int starty = iz < 0 ? 0 : 1;
+		if (iy < starty || iy > finY || -iz < initZ || -iz > finZ || -iy < initY) continue;
+		float4 *a = acc + ((size_t) (iz - initZ) * mdlY + (iy - initY)) * mdlX;
+		float4 *b = acc + ((size_t) (-iz - initZ) * mdlY + (-iy - initY)) * mdlX;
+		const float4 va = *a, vb = *b;
+		const float sr = va.x + vb.x, si = va.y - vb.y, sw = va.z + vb.z;             // fsum = a + conj(b)
+		*a = make_float4(sr, si, sw, 0.f);
+		*b = make_float4(sr, -si, sw, 0.f);
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_bp_pointgroup(const float4 *acc, float4 *out, int mdlX, int mdlY, int mdlZ, int initY, int initZ, long long rmax2, const float *R, int nsym)
+{
+	const size_t n = (size_t) mdlX * mdlY * mdlZ;
+	const size_t sy = mdlX, sz = (size_t) mdlX * mdlY;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int j = (int) (i % mdlX), iy = (int) ((i / mdlX) % mdlY) + initY, iz = (int) (i / sz) + initZ;
+		float4 s = acc[i];
+		const long long r2 = (long long) j * j + (long long) iy * iy + (long long) iz * iz;
+		if (r2 <= rmax2)
+		{
+			const float x = (float) j, y = (float) iy, z = (float) iz;
+			for (int m = 0; m < nsym; m++)
+			{
+				const float *r = R + 9 * m;
+				float xp = x * r[0] + y * r[1] + z * r[2];
+				float yp = x * r[3] + y * r[4] + z * r[5];
+				float zp = x * r[6] + y * r[7] + z * r[8];
+				const bool neg = xp < 0.f;
+				if (neg) { xp = -xp; yp = -yp; zp = -zp; }
+				const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+				const float fx = xp - fx0, fy = yp - fy0, fz = zp - fz0;
+				const int x0 = (int) fx0, y0 = (int) fy0 - initY, z0 = (int) fz0 - initZ;
+				if (x0 < 0 || y0 < 0 || z0 < 0 || x0 + 1 >= mdlX || y0 + 1 >= mdlY || z0 + 1 >= mdlZ) continue;
+				const float4 *b = acc + (size_t) z0 * sz + (size_t) y0 * sy + x0;
+				const float4 d000 = __ldg(b), d001 = __ldg(b + 1), d010 = __ldg(b + sy), d011 = __ldg(b + sy + 1);
+				const float4 d100 = __ldg(b + sz), d101 = __ldg(b + sz + 1), d110 = __ldg(b + sz + sy), d111 = __ldg(b + sz + sy + 1);
+#define RB_LERP3(c) ({ \
+	const float dx00 = d000.c + (d001.c - d000.c) * fx, dx01 = d100.c + (d101.c - d100.c) * fx; \
+	const float dx10 = d010.c + (d011.c - d010.c) * fx, dx11 = d110.c + (d111.c - d110.c) * fx; \
+	const float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy; \
+	dxy0 + (dxy1 - dxy0) * fz; })
+				const float vr = RB_LERP3(x), vi = RB_LERP3(y), vw = RB_LERP3(z);
+#undef RB_LERP3
+				s.x += vr; s.y += neg ? -vi : vi; s.z += vw;
+			}
+		}
+		out[i] = s;
+	}
+}
+
+int rbk_bp_symmetrise(rb_ctx *ctx, const RbBackprojector &bp, DevBuf &tmp, const float *d_R, int nsym)
+{
+	k_bp_hermitian<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(bp.vol, bp.mdlX, bp.mdlY, bp.mdlZ, bp.mdlInitY, bp.mdlInitZ);
+	RB_LAUNCH_CHECK(ctx);
+	if (nsym > 0)
+	{
+		const size_t n = (size_t) bp.mdlX * bp.mdlY * bp.mdlZ;
+		RB_CHECK(tmp.ensure(n * sizeof(float4)));
+		const long long rr = (long long) floor((double) bp.maxR * (double) bp.padding_factor + 0.5);
+		k_bp_pointgroup<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(bp.vol, tmp.as<float4>(), bp.mdlX, bp.mdlY, bp.mdlZ, bp.mdlInitY, bp.mdlInitZ,
+			rr * rr, d_R, nsym);
+		RB_LAUNCH_CHECK(ctx);
+		RB_CUDA(cudaMemcpyAsync(bp.vol, tmp.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+	}
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}

@@ -342,6 +342,11 @@ class MlDeviceBundle:
             return re[0], im[0], w[0]
         return re, im, w
 
+    def bp_symmetrise(self, iclass: int, rotations=None):
+        """rb_bp_symmetrise: Hermitian symmetry of the x = 0 plane + point-group mates; rotations [nsym, 3, 3] (None: C1)."""
+        r = None if rotations is None or len(rotations) == 0 else np.ascontiguousarray(rotations, np.float64).reshape(-1, 9)
+        capi.check(self.lib, self.lib.rb_bp_symmetrise(self.ctx, iclass, _ptr(r, C.c_double), 0 if r is None else r.shape[0]))
+
     def reconstruct(self, iclass: int, ori_size: int, tau2=None, tau2_fudge: float = 1.0, minres_map: int = 0) -> np.ndarray:
         """rb_reconstruct: BackProjector::reconstruct (skip_gridding) on the device; [ori, ori, ori] float32."""
         out = np.empty((ori_size,) * 3, np.float32)

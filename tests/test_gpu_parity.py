@@ -487,6 +487,26 @@ def test_refinement_iterations_stay_on_the_device(device):
     assert np.mean(res.particles["best_idir"] == wl.truth["idir"]) > 0.5      # 30-degree grid: neighbours / pole degeneracy allowed
 
 
+@pytest.mark.parametrize("group", ["C1", "D2", "C3"])
+def test_symmetrise_on_device(device, group):
+    """rb_bp_symmetrise (enforceHermitianSymmetry + applyPointGroupSymmetry on the device accumulator) against the numpy
+    restatement; D2 = three two-fold axes (BASELINE config #5), C3 exercises the interpolation."""
+    from oracle import reconstruct as rc
+    wl = make_workload(ori_size=32, healpix_order=1, n_particles=40, seed=95, snr=0.5)
+    _setup(device, wl)
+    device.expectation_some_particles(wl.pool)
+    gre, gim, gw = device.bp_get(0)
+    rz = lambda a: np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1.0]])
+    rots = {"C1": [], "D2": [np.diag([1.0, -1, -1]), np.diag([-1.0, 1, -1]), np.diag([-1.0, -1, 1])],
+            "C3": [rz(2 * np.pi / 3), rz(4 * np.pi / 3)]}[group]
+    device.bp_symmetrise(0, rots)
+    sre, sim, sw = device.bp_get(0)
+    wre, wim, ww = rc.symmetrise(gre, gim, gw, wl.r_max, wl.padding_factor, rots)
+    for got, want in ((sre, wre), (sim, wim), (sw, ww)):
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    assert np.abs(sw - gw).max() > 0
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -362,7 +362,7 @@ def run_ours(args):
                    "reference_dim": 3 if wl.sampling.is_3d else 2, "oversampling": 1, "search": "local" if wl.pool.dir_off is not None else "global",
                    "mean_coarse_orientations": float(np.mean(np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off))) if wl.pool.dir_off is not None else wl.sampling.n_dir * wl.sampling.n_psi,
                    "mean_fine_orientations": float(pr["n_fine_orient"].mean()), "mean_fine_samples": float(pr["n_fine_samples"].mean()),
-                   "l2_policy": "inputs larger than L2 (pool images + 515^3 reference/accumulator >> 126 MB), no flush",
+                   "l2_policy": "inputs larger than L2 (pool images + padded reference / accumulator >> 126 MB), no flush",
                    "parallelism": f"particles sharded over {world} GPU(s), references replicated"},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "e2e_from_raw_images": e2e_raw,

@@ -484,6 +484,28 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	const int nshell = m->ori_size / 2 + 1, K = m->nr_classes;
 	std::vector<uint32_t> pc, pf;
 	make_pixlist(m->coarse_size, pc); make_pixlist(m->current_size, pf);
+	{
+		// The coarse kernels are order-agnostic over this list, and the fused kernel projects 16 consecutive entries per
+		// warp-row: grouping them as W x H image tiles instead of row segments makes neighbouring lanes land in
+		// neighbouring voxels, i.e. fewer distinct 128-byte lines per divergent load (RB_PIX_TILE=WxH, 16x1 = row order).
+		auto tile_sort = [](std::vector<uint32_t> &v, int tw, int th) {
+			if (th <= 1) return;
+			std::stable_sort(v.begin(), v.end(), [tw, th](uint32_t a, uint32_t b) {
+				const int ya = rb_pix_y(a) + 512, yb = rb_pix_y(b) + 512, xa = rb_pix_x(a), xb = rb_pix_x(b);
+				if (ya / th != yb / th) return ya / th < yb / th;
+				if (xa / tw != xb / tw) return xa / tw < xb / tw;
+				if (ya != yb) return ya < yb;
+				return xa < xb;
+			});
+		};
+		int tw = 4, th = 4;                          // measured (tools/sweep_tiles.sh): 16x1 8.94 ms, 4x4 7.88 ms, 2x4 7.96 ms, 8x2 8.52 ms
+		if (const char *e = getenv("RB_PIX_TILE")) { if (sscanf(e, "%dx%d", &tw, &th) != 2 || tw < 1 || th < 1) { tw = 4; th = 4; } }
+		tile_sort(pc, tw, th);
+		// the store stage walks the fine list with two lanes per pixel: tiles put a warp's reductions into one small 3D patch
+		int fw = 4, fh = 4;                          // store stage: 16x1 5.50 ms, 4x4 5.32 ms, 4x2 5.28 ms
+		if (const char *e = getenv("RB_PIX_TILE_F")) { if (sscanf(e, "%dx%d", &fw, &fh) != 2 || fw < 1 || fh < 1) { fw = 4; fh = 4; } }
+		tile_sort(pf, fw, fh);
+	}
 	RB_CHECK(upload(ctx, ctx->m_pix_c, pc.data(), pc.size() * 4));
 	RB_CHECK(upload(ctx, ctx->m_pix_f, pf.data(), pf.size() * 4));
 	std::vector<RbRow> rc, rf;

@@ -507,6 +507,23 @@ def test_symmetrise_on_device(device, group):
     assert np.abs(sw - gw).max() > 0
 
 
+@pytest.mark.parametrize("local", [True, False])
+def test_pool_128px_against_reference_kernels(device, local):
+    """A mid-size pool (128-px box, several 128-orientation tiles, hundreds of K-blocks in the tensor-core kernels) against
+    RELION's own compiled ALTCPU kernels driven by the restated orchestration (oracle kind 'reference')."""
+    from oracle.bindings import Oracle, have_reference
+    if not have_reference():
+        pytest.skip("oracle/_ref/librefkernels.so not built")
+    if local:
+        wl = make_workload(ori_size=128, healpix_order=3, offset_range=3.0, offset_step=1.0, n_particles=6, seed=101, snr=0.1,
+                           local_search=True, pixel_size=2.0, n_blobs=60)
+    else:
+        wl = make_workload(ori_size=128, current_size=64, healpix_order=2, offset_range=5.0, offset_step=2.0, n_particles=6, seed=102,
+                           snr=0.1, pixel_size=2.0, n_blobs=60)
+    res, ores = _compare_pool(device, Oracle("reference"), wl)
+    assert np.array_equal(res.particles["best_ihidden_over"], ores.particles["best_ihidden_over"])
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

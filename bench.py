@@ -277,9 +277,12 @@ def run_ours(args):
     t1 = time.perf_counter()
     dev.pool_upload(0, pool)
     for i in range(args.steps):
+        dev.estep_slot_nocopy(i % 2)                         # enqueue pool i
+        if i >= 1:
+            res = dev.estep_fetch((i - 1) % 2)               # D2H of pool i-1's results while pool i computes
         if i + 1 < args.steps:
-            dev.pool_upload((i + 1) % 2, pool)
-        res = dev.estep_slot(i % 2)
+            dev.pool_upload((i + 1) % 2, pool)               # H2D of pool i+1 while pool i computes
+    res = dev.estep_fetch((args.steps - 1) % 2)
     dev.sync_all_backprojects()
     e2e_s = time.perf_counter() - t1
     t = torch.tensor([e2e_s], dtype=torch.float64, device=f"cuda:{local}")
@@ -301,9 +304,12 @@ def run_ours(args):
         t1 = time.perf_counter()
         dev.pool_prepare(0, raw, want_power=False)
         for i in range(args.steps):
+            dev.estep_slot_nocopy(i % 2)
+            if i >= 1:
+                dev.estep_fetch((i - 1) % 2)
             if i + 1 < args.steps:
                 dev.pool_prepare((i + 1) % 2, raw, want_power=False)
-            dev.estep_slot(i % 2)
+        dev.estep_fetch((args.steps - 1) % 2)
         dev.sync_all_backprojects()
         t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=f"cuda:{local}")
         if world > 1:

@@ -247,10 +247,11 @@ int rb_estep_pool(rb_ctx *ctx, const rb_particles *pool, rb_pool_out *out, unsig
  * recommended); rb_estep_slot runs the E-step on a staged slot. */
 int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool);
 int rb_estep_slot(rb_ctx *ctx, int slot, rb_pool_out *out, unsigned flags);
-/* Device-resident timing helper for roofline measurement: re-runs the compute of an already
- * uploaded slot without any host<->device copy of particle data or results. */
+/* Asynchronous pair: rb_estep_slot_nocopy only enqueues the E-step of a staged slot (no host<->device copy, returns
+ * immediately); rb_estep_fetch waits for THAT slot's completion event on a separate stream and reads its results, so a
+ * pipelined caller runs   launch(i) ; fetch(i-1) ; upload(i+1)   and keeps the GPU busy across pools.  A slot must be
+ * fetched before it is uploaded again.  (Also the device-resident timing entry of bench.py.) */
 int rb_estep_slot_nocopy(rb_ctx *ctx, int slot, unsigned flags);
-/* fetch results of the last rb_estep_slot_nocopy */
 int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out);
 
 /* ------------------------------------------------------------------------------------------------

@@ -68,7 +68,12 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
 	ctx->num_sms = prop.multiProcessorCount;
 	RB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
 	RB_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
-	for (int i = 0; i < RB_NUM_SLOTS; i++) RB_CUDA(cudaEventCreateWithFlags(&ctx->slot[i].uploaded, cudaEventDisableTiming));
+	for (int i = 0; i < RB_NUM_SLOTS; i++)
+	{
+		RB_CUDA(cudaEventCreateWithFlags(&ctx->slot[i].uploaded, cudaEventDisableTiming));
+		RB_CUDA(cudaEventCreateWithFlags(&ctx->slot[i].done, cudaEventDisableTiming));
+	}
+	RB_CUDA(cudaStreamCreateWithFlags(&ctx->fetch_stream, cudaStreamNonBlocking));
 	memset(ctx->proj, 0, sizeof(ctx->proj));
 	memset(ctx->bp, 0, sizeof(ctx->bp));
 	*out = ctx;
@@ -83,6 +88,7 @@ static void release_slot(PoolSlot &s)
 	                  &s.fimg4, &s.cimg4, &s.slices};
 	for (DevBuf *b : bufs) b->release();
 	if (s.uploaded) cudaEventDestroy(s.uploaded);
+	if (s.done) cudaEventDestroy(s.done);
 }
 
 extern "C" void rb_ctx_destroy(rb_ctx *ctx)
@@ -107,6 +113,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (auto &kv : ctx->stage_ev) { cudaEventDestroy(kv.second.first); cudaEventDestroy(kv.second.second); }
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
+	if (ctx->fetch_stream) cudaStreamDestroy(ctx->fetch_stream);
 	delete ctx;
 }
 
@@ -836,6 +843,7 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	if (!(flags & 1u)) RB_CHECK(rbk_store_pool(ctx, s));
 	RB_CHECK(rb_stage_end(ctx, "store"));
 	RB_CHECK(rb_stage_end(ctx, "total"));
+	RB_CUDA(cudaEventRecord(s.done, ctx->stream));
 	return RB_OK;
 }
 
@@ -848,12 +856,16 @@ static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
 	std::vector<float> shells((size_t) P * M.nshell);
 	std::vector<double> pd((size_t) K * S.n_dir), pcl(K);
 	int counters[16];
-	RB_CUDA(cudaMemcpyAsync(st.data(), s.state.p, P * sizeof(RbPartState), cudaMemcpyDeviceToHost, ctx->stream));
-	RB_CUDA(cudaMemcpyAsync(shells.data(), s.shells.p, shells.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
-	RB_CUDA(cudaMemcpyAsync(pd.data(), s.out_pdf_dir.p, pd.size() * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	RB_CUDA(cudaMemcpyAsync(pcl.data(), s.out_pdf_class.p, K * 8, cudaMemcpyDeviceToHost, ctx->stream));
-	RB_CUDA(cudaMemcpyAsync(counters, s.counters.p, 64, cudaMemcpyDeviceToHost, ctx->stream));
-	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	// results travel on their own stream behind the slot's completion event, so the E-step of the other slot (already
+	// enqueued on the compute stream) keeps running while these are read
+	cudaStream_t fs = ctx->fetch_stream;
+	RB_CUDA(cudaStreamWaitEvent(fs, s.done, 0));
+	RB_CUDA(cudaMemcpyAsync(st.data(), s.state.p, P * sizeof(RbPartState), cudaMemcpyDeviceToHost, fs));
+	RB_CUDA(cudaMemcpyAsync(shells.data(), s.shells.p, shells.size() * 4, cudaMemcpyDeviceToHost, fs));
+	RB_CUDA(cudaMemcpyAsync(pd.data(), s.out_pdf_dir.p, pd.size() * 8, cudaMemcpyDeviceToHost, fs));
+	RB_CUDA(cudaMemcpyAsync(pcl.data(), s.out_pdf_class.p, K * 8, cudaMemcpyDeviceToHost, fs));
+	RB_CUDA(cudaMemcpyAsync(counters, s.counters.p, 64, cudaMemcpyDeviceToHost, fs));
+	RB_CUDA(cudaStreamSynchronize(fs));
 	if (counters[2])
 	{
 		rb_set_error("fine-pass workspace too small: %lld orientations / %lld samples needed, capacity %zu / %zu; split the pool or raise "

@@ -180,12 +180,13 @@ struct PoolSlot {
 	long long slice_capacity = 0;   // number of fine orientations whose slice fits the cache
 	std::vector<RbPartMeta> h_meta;
 	cudaEvent_t uploaded = nullptr;
+	cudaEvent_t done = nullptr;     // recorded when the E-step of this slot has been enqueued completely; rb_estep_fetch waits on it
 };
 
 struct rb_ctx {
 	int device = 0;
 	int num_sms = 0;
-	cudaStream_t stream = nullptr, copy_stream = nullptr;
+	cudaStream_t stream = nullptr, copy_stream = nullptr, fetch_stream = nullptr;
 	long long launches = 0;
 
 	RbProjector proj[RB_MAX_CLASSES];

@@ -524,6 +524,28 @@ def test_pool_128px_against_reference_kernels(device, local):
     assert np.array_equal(res.particles["best_ihidden_over"], ores.particles["best_ihidden_over"])
 
 
+def test_pipelined_slots_equal_sequential_calls(device):
+    """launch(i) ; fetch(i-1) ; upload(i+1) over two device slots (rb_estep_slot_nocopy / rb_estep_fetch / rb_pool_upload)
+    must give exactly the per-particle results of one rb_estep_pool call per pool."""
+    wls = [make_workload(ori_size=32, healpix_order=1, n_particles=7 + i, seed=110 + i, snr=0.3) for i in range(4)]
+    _setup(device, wls[0])
+    seq = [device.expectation_some_particles(w.pool).particles for w in wls]
+    for k in range(wls[0].model.nr_classes):
+        device.bp_clear(k)
+    got = [None] * len(wls)
+    device.pool_upload(0, wls[0].pool)
+    for i in range(len(wls)):
+        device.estep_slot_nocopy(i % 2)
+        if i >= 1:
+            got[i - 1] = device.estep_fetch((i - 1) % 2).particles
+        if i + 1 < len(wls):
+            device.pool_upload((i + 1) % 2, wls[i + 1].pool)
+    got[-1] = device.estep_fetch((len(wls) - 1) % 2).particles
+    for a, b in zip(seq, got):
+        for key in ("best_ihidden_over", "nr_significant_coarse", "n_fine_samples", "min_diff2_coarse", "sum_weight", "dLL_nolog"):
+            assert np.array_equal(a[key], b[key]), key
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -64,6 +64,7 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
 		return RB_ERR_CUDA;
 	}
 	rb_ctx *ctx = new rb_ctx();
+	for (int i = 0; i < RB_MAX_CLASSES; i++) ctx->gemmA_stamp[i] = -1;
 	ctx->device = device;
 	ctx->num_sms = prop.multiProcessorCount;
 	RB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -104,6 +105,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
+	for (int i = 0; i < RB_MAX_CLASSES; i++) for (auto &b : ctx->gemmA[i]) b.release();
 	for (auto &b : ctx->wc_buf) b.release();
 	for (auto &b : ctx->prep_buf) b.release();
 	for (auto &b : ctx->recon_buf) b.release();
@@ -188,6 +190,7 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int &mdl
 	RB_ARG(mdlX > 1 && mdlY > 1 && mdlZ >= 1, "rb_set_reference: bad dimensions %dx%dx%d", mdlX, mdlY, mdlZ);
 	RB_CUDA(cudaSetDevice(ctx->device));
 	ctx->ref_2d[k] = (mdlZ == 1);
+	ctx->ref_version[k]++;
 	if (mdlZ == 1) { mdlZ = 2; initZ = 0; }             // 2D reference (AccProjector with mdlZ == 0 in the reference): plane 1 stays zero
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
 	RB_CHECK(ctx->proj_buf[k].ensure(n * sizeof(float2)));
@@ -363,6 +366,7 @@ extern "C" int rb_set_sampling(rb_ctx *ctx, const rb_sampling *s)
 	RB_ARG(s->rot && s->tilt && s->psi && s->trans_x && s->trans_y, "rb_set_sampling: NULL table");
 	RB_ARG(s->n_over_rot >= 1 && s->n_over_trans >= 1, "rb_set_sampling: oversampling factors must be >= 1");
 	RB_ARG(s->n_over_rot == 1 || (s->over_rot && s->over_tilt && s->over_psi), "rb_set_sampling: oversampled orientations missing");
+	ctx->samp_version++;
 	RB_ARG(s->n_over_trans == 1 || (s->over_trans_x && s->over_trans_y), "rb_set_sampling: oversampled translations missing");
 	RB_ARG(ctx->has_model, "rb_set_sampling: call rb_set_model first (translations are scaled by ori_size)");
 	if ((long long) s->n_trans * s->n_over_trans > 2048)
@@ -488,6 +492,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	RB_ARG(m->sigma2_fudge > 0., "rb_set_model: sigma2_fudge must be > 0");
 	RB_CUDA(cudaSetDevice(ctx->device));
 	ctx->h_model = *m;
+	ctx->model_version++;
 	const int nshell = m->ori_size / 2 + 1, K = m->nr_classes;
 	std::vector<uint32_t> pc, pf;
 	make_pixlist(m->coarse_size, pc); make_pixlist(m->current_size, pf);

@@ -226,6 +226,10 @@ struct rb_ctx {
 	int posed_n = 0, posed_count = 0;   // what rb_bp_posed_stage left in posed_buf[0]
 	cudaEvent_t posed_ev[2] = {nullptr, nullptr};               // partials / compact list of the multi-CTA coarse weight conversion
 	DevBuf gemm_buf[10];             // operands of the tensor-core coarse pass (kernels_gemm.cu)
+	// orientation operands (A, |A|^2; TF32 hi / lo) depend on the reference and the sampling only: cached across pools
+	DevBuf gemmA[RB_MAX_CLASSES][4];
+	long long gemmA_stamp[RB_MAX_CLASSES];
+	long long ref_version[RB_MAX_CLASSES] = {0}, samp_version = 0, model_version = 0;
 };
 
 int rb_stage_begin(rb_ctx *ctx, const char *name);

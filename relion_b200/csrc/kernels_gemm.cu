@@ -495,8 +495,17 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	DevBuf &bAhi = ctx->gemm_buf[0], &bAlo = ctx->gemm_buf[1], &bA2hi = ctx->gemm_buf[2], &bA2lo = ctx->gemm_buf[3];
 	DevBuf &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5], &bB2hi = ctx->gemm_buf[6], &bB2lo = ctx->gemm_buf[7];
 	DevBuf &bBase = ctx->gemm_buf[8], &bX2 = ctx->gemm_buf[9];
-	RB_CHECK(bAhi.ensure(mchunk * kpad * 4)); RB_CHECK(bAlo.ensure(mchunk * kpad * 4));
-	RB_CHECK(bA2hi.ensure(mchunk * k2pad * 4)); RB_CHECK(bA2lo.ensure(mchunk * k2pad * 4));
+	{
+		// shared chunk buffers: only needed when the per-class cache below does not apply
+		const size_t a_all = round_up((size_t) O, GM_BM) * (kpad + k2pad) * 2 * sizeof(float);
+		const char *ce0 = getenv("RB_GEMM_CACHE_BYTES");
+		const size_t budget0 = ce0 ? (size_t) strtoull(ce0, nullptr, 10) : ((size_t) 24 << 30);
+		if (!(mchunk >= round_up((size_t) O, GM_BM) && a_all * (size_t) K <= budget0))
+		{
+			RB_CHECK(bAhi.ensure(mchunk * kpad * 4)); RB_CHECK(bAlo.ensure(mchunk * kpad * 4));
+			RB_CHECK(bA2hi.ensure(mchunk * k2pad * 4)); RB_CHECK(bA2lo.ensure(mchunk * k2pad * 4));
+		}
+	}
 	RB_CHECK(bBhi.ensure(Npad * kpad * 4)); RB_CHECK(bBlo.ensure(Npad * kpad * 4));
 	RB_CHECK(bB2hi.ensure(N2pad * k2pad * 4)); RB_CHECK(bB2lo.ensure(N2pad * k2pad * 4));
 	RB_CHECK(bBase.ensure(mchunk * N2pad * 4)); RB_CHECK(bX2.ensure(N2pad * 4));
@@ -508,20 +517,41 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 		bBhi.as<float>(), bBlo.as<float>(), kpad, bB2hi.as<float>(), bB2lo.as<float>(), k2pad, bX2.as<float>());
 	RB_LAUNCH_CHECK(ctx);
 
+	// The orientation operands only change with the reference, the sampling or the window sizes: when a class' whole grid
+	// fits one chunk and the cache budget, they are built once per iteration and reused by every pool.
+	const size_t a_bytes = round_up((size_t) O, GM_BM) * (kpad + k2pad) * 2 * sizeof(float);
+	const char *ce = getenv("RB_GEMM_CACHE_BYTES");
+	const size_t cache_budget = ce ? (size_t) strtoull(ce, nullptr, 10) : ((size_t) 24 << 30);
+	const bool use_cache = mchunk >= round_up((size_t) O, GM_BM) && a_bytes * (size_t) K <= cache_budget;
 	for (int cls = 0; cls < K; cls++)
 		for (int o0 = 0; o0 < O; o0 += (int) mchunk)
 		{
 			const int rows = std::min<int>((int) mchunk, O - o0);
 			const int rows_pad = (int) round_up((size_t) rows, GM_BM);
-			dim3 ga((unsigned) std::min<size_t>((kpad / 2 + 255) / 256, 64), (unsigned) rows_pad);
-			k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[cls], S.coarse_eulers, M.pix_c, npix, n, o0, rows, rows_pad,
-				bAhi.as<float>(), bAlo.as<float>(), kpad, bA2hi.as<float>(), bA2lo.as<float>(), k2pad);
-			RB_LAUNCH_CHECK(ctx);
+			float *Ahi = bAhi.as<float>(), *Alo = bAlo.as<float>(), *A2hi = bA2hi.as<float>(), *A2lo = bA2lo.as<float>();
+			bool build = true;
+			if (use_cache)
+			{
+				DevBuf *c = ctx->gemmA[cls];
+				RB_CHECK(c[0].ensure((size_t) rows_pad * kpad * 4)); RB_CHECK(c[1].ensure((size_t) rows_pad * kpad * 4));
+				RB_CHECK(c[2].ensure((size_t) rows_pad * k2pad * 4)); RB_CHECK(c[3].ensure((size_t) rows_pad * k2pad * 4));
+				Ahi = c[0].as<float>(); Alo = c[1].as<float>(); A2hi = c[2].as<float>(); A2lo = c[3].as<float>();
+				const long long stamp = (ctx->ref_version[cls] << 40) ^ (ctx->samp_version << 20) ^ ctx->model_version;
+				build = ctx->gemmA_stamp[cls] != stamp;
+				ctx->gemmA_stamp[cls] = stamp;
+			}
+			if (build)
+			{
+				dim3 ga((unsigned) std::min<size_t>((kpad / 2 + 255) / 256, 64), (unsigned) rows_pad);
+				k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[cls], S.coarse_eulers, M.pix_c, npix, n, o0, rows, rows_pad,
+					Ahi, Alo, kpad, A2hi, A2lo, k2pad);
+				RB_LAUNCH_CHECK(ctx);
+			}
 			// norm term base[o][p]
 			GemmEpilogue E0;
 			memset(&E0, 0, sizeof(E0));
 			E0.mode = 0; E0.C = bBase.as<float>(); E0.ldc = (int) N2pad; E0.M = rows; E0.N = P;
-			RB_CHECK(launch_gemm(ctx, bA2hi.as<float>(), bA2lo.as<float>(), rows_pad, bB2hi.as<float>(), bB2lo.as<float>(), N2pad, k2pad, E0));
+			RB_CHECK(launch_gemm(ctx, A2hi, A2lo, rows_pad, bB2hi.as<float>(), bB2lo.as<float>(), N2pad, k2pad, E0));
 			// cross term + diff2 epilogue
 			GemmEpilogue E1;
 			memset(&E1, 0, sizeof(E1));
@@ -529,7 +559,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 			E1.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>(); E1.Mweight = s.Mweight.as<float>();
 			E1.base = bBase.as<float>(); E1.ldbase = (int) N2pad; E1.x2 = bX2.as<float>();
 			E1.T = T; E1.P = P; E1.O = O; E1.cls = cls; E1.o_first = o0; E1.M = rows; E1.N = P * T;
-			RB_CHECK(launch_gemm(ctx, bAhi.as<float>(), bAlo.as<float>(), rows_pad, bBhi.as<float>(), bBlo.as<float>(), Npad, kpad, E1));
+			RB_CHECK(launch_gemm(ctx, Ahi, Alo, rows_pad, bBhi.as<float>(), bBlo.as<float>(), Npad, kpad, E1));
 		}
 	return RB_OK;
 }

@@ -16,6 +16,7 @@
 // everything below the current prefix.  Sums are fixed-tree fp64 reductions, hence deterministic.
 #include "device_utils.cuh"
 #include <cstdlib>
+#include <algorithm>
 
 static const int WT_THREADS = 512;   // 16 fp64 bins + 16 counters per thread: keep 128 registers available
 
@@ -258,9 +259,9 @@ k_weights_coarse(const RbPartMeta *metas, RbPartState *states, float *Mweight,
 // One CTA per particle would stream ~13 passes over megabytes with 512 threads (65 ms for a 256-particle pool at
 // HEALPix order 3, where at low SNR most weights are non-zero).  Here every phase is spread over (chunk, particle) CTAs:
 //   k_wc_max     max of the log-weights                                         (read)
-//   k_wc_exp     weights in place + per-particle histogram over the top 13 bits of the fp32 pattern: (fp64 mass, count)
-//                per bin.  A bin holds values of ONE binary exponent, so its fp64 mass is exact (multiples of 2^(e-23),
-//                < 2^29 of them) whatever the order of the atomics: the result is deterministic.        (read + write)
+//   k_wc_exp     weights in place + per-particle histogram over the top 13 bits of the fp32 pattern: (mass, count) per
+//                bin.  A bin holds values of ONE binary exponent e, so its mass is 2^(e-23) times the INTEGER sum of the
+//                24-bit significands: native 64-bit integer atomics, exact and independent of their order.  (read + write)
 //   k_wc_pick    one CTA per particle: total mass, threshold, the bin in which the cumulative mass crosses it
 //   k_wc_gather  compaction of the elements of that bin (a tiny fraction)                                (read)
 //   k_wc_finish  the radix descent of block_significance on the compact list, seeded with the mass / count below the bin
@@ -284,39 +285,57 @@ struct WcArgs {
 	const float *pdf_offset; const unsigned char *pdf_offset_zero;
 	int T, nchunk, P; long long n;               // n: dense elements per particle (identical for all particles)
 	float *pmax; float *pav; long long *pai;
-	double *hsum; int *hcnt;                     // [P][WC_BINS]
+	unsigned long long *hsum; int *hcnt;         // [P][WC_BINS]: sum of the 24-bit significands of the bin's values (exact), count
 	WcPick *pick;                                // [P]
 	long long *gtot;                             // [P][2] number of gathered elements (picked bin, maxsig bin)
 	float *compact_a, *compact_r;                // [P][cap]
 	long long cap;
 };
 
-// log-weight of dense element (io, it) (cuda_kernel_weights_exponent_coarse, helper.cuh:16-46)
-__device__ __forceinline__ float wc_logw(const WcArgs &A, const RbPartMeta &m, int p, int io, int it, float d, float min_diff2)
+// Both streaming kernels evaluate the log-weight of dense element (io, it) like cuda_kernel_weights_exponent_coarse
+// (helper.cuh:16-46), four consecutive elements per thread (one 16-byte load when the particle block is 16-byte aligned),
+// with the translation priors of the particle in shared memory.
+__device__ __forceinline__ void wc_load4(const float *w, long long i, long long i1, bool vec, float (&v)[4])
 {
-	if (d < min_diff2 || A.pdf_orient_zero[m.prior_off + io] || A.pdf_offset_zero[(size_t) p * A.T + it]) return RB_LOWEST;   // helper.cuh:39-42
-	return A.pdf_orient[m.prior_off + io] + A.pdf_offset[(size_t) p * A.T + it] + min_diff2 - d;
+	if (vec && i + 3 < i1) { const float4 q = *(const float4 *) (w + i); v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+	else
+#pragma unroll
+		for (int j = 0; j < 4; j++) v[j] = (i + j < i1) ? w[i + j] : 0.f;
 }
-
-// walks i = i0 + tid, += WC_THREADS while keeping (io, it) = (i / T, i % T) without a division per element
-struct WcIndex {
-	int io, it, dio, dit, T;
-	__device__ WcIndex(long long i, int T_) : T(T_) { io = (int) (i / T_); it = (int) (i - (long long) io * T_); dio = WC_THREADS / T_; dit = WC_THREADS - dio * T_; }
-	__device__ void next() { io += dio; it += dit; if (it >= T) { it -= T; io++; } }
-};
 
 __global__ void __launch_bounds__(WC_THREADS)
 k_wc_max(WcArgs A)
 {
 	__shared__ float fred[32];
+	__shared__ float s_pt[64];
+	__shared__ unsigned char s_tz[64];
 	const int c = blockIdx.x, p = blockIdx.y;
 	const RbPartMeta m = A.metas[p];
 	const float min_diff2 = __int_as_float(A.states[p].min_diff2_bits);
 	const float *w = A.Mweight + m.coarse_off;
+	const bool vec = (m.coarse_off & 3) == 0;
+	if (threadIdx.x < A.T) { s_pt[threadIdx.x] = A.pdf_offset[(size_t) p * A.T + threadIdx.x]; s_tz[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + threadIdx.x]; }
+	__syncthreads();
 	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
 	float mx = RB_LOWEST;
-	WcIndex ix(i0 + threadIdx.x, A.T);
-	for (long long i = i0 + threadIdx.x; i < i1; i += WC_THREADS, ix.next()) mx = fmaxf(mx, wc_logw(A, m, p, ix.io, ix.it, w[i], min_diff2));
+	for (long long i = i0 + 4 * threadIdx.x; i < i1; i += 4 * WC_THREADS)
+	{
+		float v[4];
+		wc_load4(w, i, i1, vec, v);
+		int io = (int) (i / A.T), it = (int) (i - (long long) io * A.T);
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			if (i + j < i1)
+			{
+				float l = RB_LOWEST;
+				if (!(v[j] < min_diff2 || A.pdf_orient_zero[m.prior_off + io] || s_tz[it]))              // helper.cuh:39-42
+					l = A.pdf_orient[m.prior_off + io] + s_pt[it] + min_diff2 - v[j];
+				mx = fmaxf(mx, l);
+			}
+			if (++it == A.T) { it = 0; io++; }
+		}
+	}
 	mx = block_max(mx, fred);
 	if (threadIdx.x == 0) A.pmax[(size_t) p * A.nchunk + c] = mx;
 }
@@ -325,15 +344,19 @@ __global__ void __launch_bounds__(WC_THREADS)
 k_wc_exp(WcArgs A)
 {
 	extern __shared__ unsigned char wc_smem[];
-	double *h_s = (double *) wc_smem;                 // [WC_BINS]
-	int *h_c = (int *) (h_s + WC_BINS);               // [WC_BINS]
+	unsigned long long *h_s = (unsigned long long *) wc_smem;   // [WC_BINS]
+	int *h_c = (int *) (h_s + WC_BINS);                          // [WC_BINS]
 	__shared__ ArgMaxSmem am;
 	__shared__ float s_wmax;
+	__shared__ float s_pt[64];
+	__shared__ unsigned char s_tz[64];
 	const int c = blockIdx.x, p = blockIdx.y;
 	const RbPartMeta m = A.metas[p];
 	const float min_diff2 = __int_as_float(A.states[p].min_diff2_bits);
 	float *w = A.Mweight + m.coarse_off;
-	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { h_s[i] = 0.; h_c[i] = 0; }
+	const bool vec = (m.coarse_off & 3) == 0;
+	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { h_s[i] = 0ull; h_c[i] = 0; }
+	if (threadIdx.x < A.T) { s_pt[threadIdx.x] = A.pdf_offset[(size_t) p * A.T + threadIdx.x]; s_tz[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + threadIdx.x]; }
 	if (threadIdx.x < 32)
 	{
 		float mx = RB_LOWEST;
@@ -345,18 +368,38 @@ k_wc_exp(WcArgs A)
 	const float add = 50.f - s_wmax;                                               // acc_ml_optimiser_impl.h:2201-2207
 	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
 	float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
-	WcIndex ix(i0 + threadIdx.x, A.T);
-	for (long long i = i0 + threadIdx.x; i < i1; i += WC_THREADS, ix.next())
+	for (long long i = i0 + 4 * threadIdx.x; i < i1; i += 4 * WC_THREADS)
 	{
-		const float a = wc_logw(A, m, p, ix.io, ix.it, w[i], min_diff2) + add;
-		const float e = (a < -88.f) ? 0.f : expf(a);                               // helper.cuh:57-66
-		w[i] = e;
-		if (e > 0.f)
+		float v[4], e[4];
+		wc_load4(w, i, i1, vec, v);
+		int io = (int) (i / A.T), it = (int) (i - (long long) io * A.T);
+#pragma unroll
+		for (int j = 0; j < 4; j++)
 		{
-			const int bin = (int) (__float_as_uint(e) >> WC_SHIFT);
-			atomicAdd(h_s + bin, (double) e); atomicAdd(h_c + bin, 1);
+			e[j] = 0.f;
+			if (i + j < i1)
+			{
+				float l = RB_LOWEST;
+				if (!(v[j] < min_diff2 || A.pdf_orient_zero[m.prior_off + io] || s_tz[it]))
+					l = A.pdf_orient[m.prior_off + io] + s_pt[it] + min_diff2 - v[j];
+				const float a = l + add;
+				e[j] = (a < -88.f) ? 0.f : expf(a);                                // helper.cuh:57-66
+				if (e[j] > 0.f)
+				{
+					const unsigned bits = __float_as_uint(e[j]);
+					const int bin = (int) (bits >> WC_SHIFT);
+					// significand as an integer (normal: implicit one; denormal: exponent field 0)
+					const unsigned long long sig = (bits >> 23) ? ((bits & 0x7fffffu) | 0x800000u) : (bits & 0x7fffffu);
+					atomicAdd(h_s + bin, sig); atomicAdd(h_c + bin, 1);
+				}
+				if (e[j] > bv) { bv = e[j]; bi = i + j; }
+			}
+			if (++it == A.T) { it = 0; io++; }
 		}
-		if (e > bv) { bv = e; bi = i; }
+		if (vec && i + 3 < i1) *(float4 *) (w + i) = make_float4(e[0], e[1], e[2], e[3]);
+		else
+#pragma unroll
+			for (int j = 0; j < 4; j++) if (i + j < i1) w[i + j] = e[j];
 	}
 	float ov; long long oi;
 	block_argmax(bv, bi, am, ov, oi);
@@ -366,6 +409,13 @@ k_wc_exp(WcArgs A)
 		if (h_c[i]) { atomicAdd(A.hsum + (size_t) p * WC_BINS + i, h_s[i]); atomicAdd(A.hcnt + (size_t) p * WC_BINS + i, h_c[i]); }
 }
 
+// exact mass of histogram bin b: integer significand sum times 2^(exponent - 23)  (denormal bins: exponent field 0 -> 2^-149)
+__device__ __forceinline__ double wc_bin_mass(unsigned long long sig_sum, int bin)
+{
+	const int ef = bin >> 4;                          // the 8 exponent bits of the pattern
+	return ldexp((double) sig_sum, (ef ? ef : 1) - 127 - 23);
+}
+
 // one CTA per particle: argmax over chunks, total mass, threshold, bin selection
 __global__ void __launch_bounds__(WC_THREADS)
 k_wc_pick(WcArgs A, RbModelDev M)
@@ -373,10 +423,10 @@ k_wc_pick(WcArgs A, RbModelDev M)
 	__shared__ double dred[32];
 	__shared__ long long lred[32];
 	const int p = blockIdx.x;
-	const double *hs = A.hsum + (size_t) p * WC_BINS;
+	__shared__ double hs[WC_BINS];
 	const int *hc = A.hcnt + (size_t) p * WC_BINS;
 	double t = 0.; long long cnt = 0;
-	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { t += hs[i]; cnt += hc[i]; }
+	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { hs[i] = wc_bin_mass(A.hsum[(size_t) p * WC_BINS + i], i); t += hs[i]; cnt += hc[i]; }
 	t = block_sum(t, dred);
 	cnt = block_sum(cnt, lred);
 	if (threadIdx.x != 0) return;
@@ -601,7 +651,7 @@ static int weights_coarse_large(rb_ctx *ctx, PoolSlot &s, long long n)
 	RB_CHECK(ctx->wc_buf[8].ensure((size_t) P * A.cap * 4));
 	RB_CHECK(ctx->wc_buf[9].ensure(maxsig ? (size_t) P * A.cap * 4 : 16));
 	A.pmax = ctx->wc_buf[0].as<float>(); A.pav = ctx->wc_buf[1].as<float>(); A.pai = ctx->wc_buf[2].as<long long>();
-	A.hsum = ctx->wc_buf[3].as<double>(); A.hcnt = ctx->wc_buf[4].as<int>(); A.pick = ctx->wc_buf[5].as<WcPick>();
+	A.hsum = ctx->wc_buf[3].as<unsigned long long>(); A.hcnt = ctx->wc_buf[4].as<int>(); A.pick = ctx->wc_buf[5].as<WcPick>();
 	A.gtot = ctx->wc_buf[6].as<long long>();
 	A.compact_a = ctx->wc_buf[8].as<float>(); A.compact_r = ctx->wc_buf[9].as<float>();
 	RB_CUDA(cudaMemsetAsync(A.hsum, 0, (size_t) P * WC_BINS * 8, ctx->stream));
@@ -627,7 +677,7 @@ int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 		const long long n = (long long) ctx->d_model.nr_classes * ctx->d_samp.n_dir * ctx->d_samp.n_psi * ctx->d_samp.n_trans;
 		const char *e = getenv("RB_WEIGHTS_LARGE");
 		const long long min_n = e ? atoll(e) : (1 << 17);
-		if (n >= min_n && n > 1) return weights_coarse_large(ctx, s, n);
+		if (n >= min_n && n > 1 && ctx->d_samp.n_trans <= 64) return weights_coarse_large(ctx, s, n);
 	}
 	k_weights_coarse<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
 		s.Mweight.as<float>(), s.pdf_orient.as<float>(), s.pdf_orient_zero.as<unsigned char>(),
@@ -639,18 +689,22 @@ int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 // ---- fine-pass setup -------------------------------------------------------------------------
 static const int FS_THREADS = 256;
 
+// Orientations are handled in chunks of FS_CHUNK so that large dense arrays (global searches: 10^5 orientations per particle)
+// spread over many CTAs: count per (chunk, particle), prefix over the chunks of a particle, ordered fill per chunk.
+static const int FS_CHUNK = 2048;
+
 __global__ void __launch_bounds__(FS_THREADS)
-k_fine_count(const RbPartMeta *metas, RbPartState *states, const float *Mweight, RbModelDev M, int T)
+k_fine_count(const RbPartMeta *metas, const RbPartState *states, const float *Mweight, RbModelDev M, int T, int nchunk, int *part_so, int *part_pair)
 {
 	__shared__ int red[32];
-	const int p = blockIdx.x;
+	const int c = blockIdx.x, p = blockIdx.y;
 	const RbPartMeta m = metas[p];
-	RbPartState *st = states + p;
 	const int ndense = M.nr_classes * m.nd * m.np;
 	const float *w = Mweight + m.coarse_off;
-	const float sig = st->csig_weight;
+	const float sig = states[p].csig_weight;
 	int nso = 0, npair = 0;
-	for (int o = threadIdx.x; o < ndense; o += FS_THREADS)
+	const int o1 = min(ndense, (c + 1) * FS_CHUNK);
+	for (int o = c * FS_CHUNK + threadIdx.x; o < o1; o += FS_THREADS)
 	{
 		int cnt = 0;
 		for (int t = 0; t < T; t++) cnt += (w[(long long) o * T + t] >= sig) ? 1 : 0;   // arrayOverThreshold
@@ -658,7 +712,23 @@ k_fine_count(const RbPartMeta *metas, RbPartState *states, const float *Mweight,
 	}
 	nso = block_sum(nso, red);
 	npair = block_sum(npair, red);
-	if (threadIdx.x == 0) { st->n_so = nso; st->n_pairs = npair; }
+	if (threadIdx.x == 0) { part_so[(size_t) p * nchunk + c] = nso; part_pair[(size_t) p * nchunk + c] = npair; }
+}
+
+// per particle: totals and exclusive prefix over its chunks (in place)
+__global__ void k_fine_chunkscan(RbPartState *states, int nchunk, int *part_so, int *part_pair)
+{
+	const int p = blockIdx.x;
+	if (threadIdx.x != 0) return;
+	int a = 0, b = 0;
+	for (int c = 0; c < nchunk; c++)
+	{
+		const size_t k = (size_t) p * nchunk + c;
+		const int va = part_so[k], vb = part_pair[k];
+		part_so[k] = a; part_pair[k] = b;
+		a += va; b += vb;
+	}
+	states[p].n_so = a; states[p].n_pairs = b;
 }
 
 // exclusive scan over the particles of the pool (single CTA)
@@ -701,25 +771,27 @@ k_fine_scan(RbPartState *states, int P, int NOR, int NOT, long long cap_fo, long
 __global__ void __launch_bounds__(FS_THREADS)
 k_fine_fill(const RbPartMeta *metas, const RbPartState *states, const float *Mweight,
             const int *dir_idx, const int *psi_idx, RbModelDev M, RbSamplingDev S,
-            int *pair_list, RbFineOrient *fo, long long *fs_ihid, const int *counters)
+            int *pair_list, RbFineOrient *fo, long long *fs_ihid, const int *counters, int nchunk, const int *part_so, const int *part_pair)
 {
 	__shared__ int s_scan_f[FS_THREADS], s_scan_c[FS_THREADS];
 	__shared__ int s_run_f, s_run_c;
 	if (counters[2]) return;   // capacity overflow: host reports RB_ERR_CAPACITY
-	const int p = blockIdx.x;
+	const int chunk = blockIdx.x, p = blockIdx.y;
 	const RbPartMeta m = metas[p];
 	const RbPartState st = states[p];
 	const int T = S.n_trans, NOR = S.n_over_rot, NOT = S.n_over_trans;
 	const int no = m.nd * m.np, ndense = M.nr_classes * no;
 	const float *w = Mweight + m.coarse_off;
 	const float sig = st.csig_weight;
-	if (threadIdx.x == 0) { s_run_f = 0; s_run_c = 0; }
+	if (chunk * FS_CHUNK >= ndense) return;
+	if (threadIdx.x == 0) { s_run_f = part_so[(size_t) p * nchunk + chunk]; s_run_c = part_pair[(size_t) p * nchunk + chunk]; }
 	__syncthreads();
-	for (int c0 = 0; c0 < ndense; c0 += FS_THREADS)
+	const int c_end = min(ndense, (chunk + 1) * FS_CHUNK);
+	for (int c0 = chunk * FS_CHUNK; c0 < c_end; c0 += FS_THREADS)
 	{
 		const int o = c0 + threadIdx.x;
 		int cnt = 0;
-		if (o < ndense) for (int t = 0; t < T; t++) cnt += (w[(long long) o * T + t] >= sig) ? 1 : 0;
+		if (o < c_end) for (int t = 0; t < T; t++) cnt += (w[(long long) o * T + t] >= sig) ? 1 : 0;
 		const int flag = cnt > 0;
 		s_scan_f[threadIdx.x] = flag; s_scan_c[threadIdx.x] = cnt;
 		__syncthreads();
@@ -777,15 +849,21 @@ k_fine_fill(const RbPartMeta *metas, const RbPartState *states, const float *Mwe
 int rbk_fine_setup_pool(rb_ctx *ctx, PoolSlot &s)
 {
 	const int T = ctx->d_samp.n_trans;
-	k_fine_count<<<s.P, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
-		s.Mweight.as<float>(), ctx->d_model, T);
+	const int nchunk = std::max(1, (s.max_no * ctx->d_model.nr_classes + FS_CHUNK - 1) / FS_CHUNK);
+	RB_CHECK(ctx->wc_buf[7].ensure((size_t) 2 * s.P * nchunk * 4));
+	int *part_so = ctx->wc_buf[7].as<int>(), *part_pair = part_so + (size_t) s.P * nchunk;
+	dim3 grid(nchunk, s.P);
+	k_fine_count<<<grid, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
+		s.Mweight.as<float>(), ctx->d_model, T, nchunk, part_so, part_pair);
+	RB_LAUNCH_CHECK(ctx);
+	k_fine_chunkscan<<<s.P, 32, 0, ctx->stream>>>(s.state.as<RbPartState>(), nchunk, part_so, part_pair);
 	RB_LAUNCH_CHECK(ctx);
 	k_fine_scan<<<1, 1024, 0, ctx->stream>>>(s.state.as<RbPartState>(), s.P, ctx->d_samp.n_over_rot, ctx->d_samp.n_over_trans,
 		(long long) ctx->fine_orient_capacity, (long long) ctx->fine_sample_capacity, s.counters.as<int>());
 	RB_LAUNCH_CHECK(ctx);
-	k_fine_fill<<<s.P, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
+	k_fine_fill<<<grid, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
 		s.Mweight.as<float>(), s.dir_idx.as<int>(), s.psi_idx.as<int>(), ctx->d_model, ctx->d_samp,
-		s.pair_list.as<int>(), s.fo.as<RbFineOrient>(), s.fs_ihid.as<long long>(), s.counters.as<int>());
+		s.pair_list.as<int>(), s.fo.as<RbFineOrient>(), s.fs_ihid.as<long long>(), s.counters.as<int>(), nchunk, part_so, part_pair);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

@@ -546,6 +546,27 @@ def test_pipelined_slots_equal_sequential_calls(device):
             assert np.array_equal(a[key], b[key]), key
 
 
+@pytest.mark.parametrize("local", [False, True])
+def test_pool_many_translations(device, oracle, local):
+    """81 coarse translations (offset range 5, step 1): more than the 32-translation tiles of the fused kernel (local searches fall
+    back to the SIMT coarse kernel) and more than one 64-entry prior table of the multi-CTA weight conversion."""
+    wl = make_workload(ori_size=32, healpix_order=2 if local else 1, offset_range=5.0, offset_step=1.0, n_particles=5, seed=120,
+                       snr=0.3, local_search=local)
+    assert wl.sampling.n_trans == 81
+    _compare_pool(device, oracle, wl)
+
+
+@pytest.mark.parametrize("local", [False, True])
+def test_pool_class_with_zero_prior_is_skipped(device, oracle, local):
+    """A class whose pdf_class is zero is never evaluated (acc_ml_optimiser_impl.h:1069): its Mweight entries stay at lowest()
+    through every coarse path, no particle may pick it, and its accumulator stays empty."""
+    wl = make_workload(ori_size=32, healpix_order=2 if local else 1, n_particles=8, nr_classes=3, seed=121, snr=0.3, local_search=local)
+    wl.model.pdf_class = np.array([0.5, 0.0, 0.5])
+    res, _ = _compare_pool(device, oracle, wl, pose_frac=0.0)
+    assert not np.any(res.particles["best_class"] == 1)
+    assert np.all(device.bp_get(1)[2] == 0)
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

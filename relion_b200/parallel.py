@@ -100,3 +100,62 @@ def all_reduce_backprojectors(bundle, nr_classes: int):
     for k in range(nr_classes):
         t = bundle.bp_device_tensor(k)
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+
+# --------------------------------------------------------------------------------------------------
+# gold-standard half-sets and dynamic pool hand-out
+# --------------------------------------------------------------------------------------------------
+def half_set_of_rank(rank: int) -> int:
+    """Which random half-set a rank works on: alternating, as MlOptimiserMpi assigns followers
+    (/root/reference/src/ml_optimiser_mpi.cpp:125-160: odd followers half 1, even followers half 2); 0-based here."""
+    return rank % 2
+
+
+def make_half_set_groups(world_size: int):
+    """One process group per half-set (the analogue of splitC, src/mpi.cpp:79): the back-projection accumulators and the
+    weighted sums of a half are summed within its group only.  Every rank must call this (new_group is collective).
+    Returns [group_half0, group_half1]; with world_size == 1 both halves live on the one rank and no group is needed."""
+    import torch.distributed as dist
+    if world_size < 2:
+        return [None, None]
+    return [dist.new_group([r for r in range(world_size) if half_set_of_rank(r) == h]) for h in (0, 1)]
+
+
+def all_reduce_tensor(t, group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_reduce_backprojectors_group(bundle, nr_classes: int, group=None):
+    """all_reduce_backprojectors restricted to a half-set group."""
+    bundle.sync_all_backprojects()
+    for k in range(nr_classes):
+        all_reduce_tensor(bundle.bp_device_tensor(k), group)
+
+
+def all_reduce_wsums_group(sums: Dict[str, np.ndarray], group=None, device=None) -> Dict[str, np.ndarray]:
+    import torch
+    pack = pack_wsums(sums)
+    t = torch.from_numpy(pack.vector.copy())
+    if device is not None:
+        t = t.to(device)
+    all_reduce_tensor(t, group)
+    pack.vector = t.cpu().numpy()
+    return unpack_wsums(pack)
+
+
+class PoolQueue:
+    """Dynamic hand-out of pools to ranks: particles of local searches differ ~10x in cost, so ranks take the next pool from
+    a shared counter instead of owning a fixed range (what RELION's leader does over MPI, src/ml_optimiser_mpi.cpp:1400-1690;
+    here an atomic add on a torch.distributed TCPStore, no data-path collective).  One counter per half-set."""
+
+    def __init__(self, store, n_pools: int, half: int = 0, iteration: int = 0):
+        self.store, self.n_pools = store, int(n_pools)
+        self.key = f"rb_pool_queue_{iteration}_{half}"
+
+    def next(self):
+        """Index of the next pool for the calling rank, or None when the half-set is exhausted."""
+        i = int(self.store.add(self.key, 1)) - 1
+        return i if i < self.n_pools else None

@@ -98,3 +98,52 @@ def test_two_ranks_equal_one_rank():
         np.testing.assert_allclose(sums2[k], sums1[k], rtol=1e-9, atol=1e-12, err_msg=k)
     vol1 = np.stack([bps1[0].real, bps1[0].imag, bps1[0].weight])
     assert np.abs(vol2 - vol1).max() <= 1e-5 * np.abs(vol1).max()
+
+
+def _half_worker(rank, world, port, q):
+    import os
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    import torch
+    import torch.distributed as dist
+    from relion_b200 import parallel
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    groups = parallel.make_half_set_groups(world)
+    half = parallel.half_set_of_rank(rank)
+    # every rank contributes (rank + 1): the sum must stay inside the half-set
+    t = parallel.all_reduce_tensor(torch.full((3,), float(rank + 1), dtype=torch.float64), groups[half])
+    sums = parallel.all_reduce_wsums_group({"LL": np.array(float(rank + 1)), "pdf_class": np.full(2, 10.0 * (rank + 1))}, groups[half])
+    # dynamic pool hand-out: 11 pools per half, every pool taken exactly once
+    store = dist.TCPStore("127.0.0.1", port + 1, world, is_master=(rank == 0), timeout=__import__("datetime").timedelta(seconds=60))
+    queue = parallel.PoolQueue(store, 11, half=half)
+    mine = []
+    while True:
+        i = queue.next()
+        if i is None:
+            break
+        mine.append(i)
+    q.put((rank, half, t.tolist(), float(sums["LL"]), sums["pdf_class"].tolist(), mine))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_half_set_groups_and_pool_queue():
+    """Four gloo ranks, two half-sets: reductions stay inside a half (splitC analogue), the shared counter hands every pool of a
+    half to exactly one of its ranks."""
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_half_worker, args=(r, 4, port, q)) for r in range(4)]
+    for p in procs:
+        p.start()
+    out = sorted(q.get(timeout=180) for _ in range(4))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, half, t, ll, pc, mine in out:
+        want = sum(r + 1 for r in range(4) if r % 2 == half)
+        assert t == [float(want)] * 3 and ll == float(want) and pc == [10.0 * want] * 2
+    for half in (0, 1):
+        taken = sorted(i for rank, h, _, _, _, mine in out if h == half for i in mine)
+        assert taken == list(range(11))

@@ -16,6 +16,7 @@
 // lane k owns 8 of the (up to) 32 translations of the pass, i.e. 16 accumulator registers instead of 64.
 // Rows are dealt q, q+64, q+128, ... so that every quad gets the same number of pixels (+-2 %).
 #include "img_src.cuh"
+#include <cstdlib>
 
 static const int FI_THREADS = 256;
 static const int FI_QUADS = FI_THREADS / 4;
@@ -251,6 +252,196 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Variant with the gathers staged through shared memory by cp.async: a lane keeps FA_DEPTH 16-byte copies of its cell
+// quarter in flight without holding them in registers (the register-prefetch kernel above is bound by latency x bytes in
+// flight: 768 lanes x 16 B per SM).  Per pixel a quad issues: the cell quarter (16 B, lane k -> quarter k), component k of
+// the prepared image value (4 B) and stores component k of (fx, fy, fz, flags); the consumer reads its own quarter and the
+// quad's four components back.  Same arithmetic, same summation order as k_diff2_fine.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
+{
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int FA_DEPTH, int FA_MINB>
+__global__ void __launch_bounds__(FI_THREADS, FA_MINB)
+k_diff2_fine_async(FineArgs A, RbModelDev M)
+{
+	extern __shared__ float4 s_dyn[];
+	float4 *s_px = s_dyn;                                   // [xs][16] phase table
+	const int xs = A.n / 2 + 1;
+	float4 *s_cell = s_px + xs * 16;                        // [FA_DEPTH][FI_THREADS]
+	float *s_frac = (float *) (s_cell + FA_DEPTH * FI_THREADS);   // [FA_DEPTH][FI_THREADS]
+	float *s_img = s_frac + FA_DEPTH * FI_THREADS;          // [FA_DEPTH][FI_THREADS]
+	__shared__ float s_ux[FI_TF], s_uy[FI_TF];
+	__shared__ float s_red[FI_THREADS / 32][FI_TF + 1];
+	__shared__ float s_e[6];
+
+	const int nwork = A.counters[0];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int k = threadIdx.x & 3, qd = threadIdx.x >> 2, qbase = threadIdx.x & ~3;
+	const unsigned qmask = 0xFu << (lane & ~3);
+
+	for (int w = blockIdx.x; w < nwork; w += gridDim.x)
+	{
+		const RbFineOrient F = A.fo[w];
+		const int nsamp = F.n_t * A.NOT, cls = F.iclass, p = F.particle;
+		const long long out_off = F.sample_off;
+		const float xi2_half = A.metas[p].xi2_half;
+		__syncthreads();
+		if (threadIdx.x < 6) s_e[threadIdx.x] = A.fo[w].e[threadIdx.x + threadIdx.x / 2];
+		const float4 *img = A.img4 + (size_t) p * A.n * xs;
+		float2 *slice = (A.slices && w < A.slice_capacity) ? A.slices + (size_t) w * A.n * xs : nullptr;
+		const RbProjK8 pk = rb_make_projk8(A.projs[cls], xs);
+		float bmin = FLT_MAX;
+
+		for (int c0 = 0; c0 < nsamp; c0 += FI_TF)
+		{
+			const int ntr = min(FI_TF, nsamp - c0);
+			const int nj = (ntr + 7) >> 3;
+			__syncthreads();
+			if (threadIdx.x < FI_TF)
+			{
+				float ux = 0.f, uy = 0.f;
+				if (threadIdx.x < ntr)
+				{
+					const int j = c0 + threadIdx.x;
+					const int it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
+					ux = A.tx[it] * 0.15915494309189535f; uy = A.ty[it] * 0.15915494309189535f;
+				}
+				s_ux[threadIdx.x] = ux; s_uy[threadIdx.x] = uy;
+			}
+			__syncthreads();
+			for (int i = threadIdx.x; i < xs * 16; i += FI_THREADS)
+			{
+				const int x = i >> 4, f = i & 15;
+				if (f < nj * 4)
+				{
+					const float2 p0 = rb_phase(x, 0, s_ux[2 * f], 0.f), p1 = rb_phase(x, 0, s_ux[2 * f + 1], 0.f);
+					s_px[i] = make_float4(p0.x, p0.y, p1.x, p1.y);
+				}
+			}
+			__syncthreads();
+			const float e0 = s_e[0], e1 = s_e[1], e3 = s_e[2], e4 = s_e[3], e6 = s_e[4], e7 = s_e[5];
+
+			float tot[8];
+#pragma unroll
+			for (int i = 0; i < 8; i++) tot[i] = 0.f;
+			float base = 0.f;
+
+			for (int r = qd; r < A.nrows; r += FI_QUADS)
+			{
+				const RbRow rd = A.rows[r];
+				const float4 *img_row = img + (size_t) rd.iy * xs;
+				float2 *slice_row = (slice && c0 == 0) ? slice + (size_t) rd.iy * xs : nullptr;
+				float accr[8], acci[8];
+#pragma unroll
+				for (int i = 0; i < 8; i++) { accr[i] = 0.f; acci[i] = 0.f; }
+
+				// issue pixel x into ring slot (x % FA_DEPTH)
+				auto issue = [&](int x)
+				{
+					const int slot = x % FA_DEPTH;
+					float xp = (e0 * x + e1 * rd.y) * pk.pf;
+					float yp = (e3 * x + e4 * rd.y) * pk.pf;
+					float zp = (e6 * x + e7 * rd.y) * pk.pf;
+					const int r2 = (int) (xp * xp + yp * yp + zp * zp);
+					const bool inside = r2 <= pk.maxR2_padded;
+					const bool inv = xp < 0.f;
+					if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+					const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+					const float comp = k == 0 ? xp - fx0 : (k == 1 ? yp - fy0 : (k == 2 ? zp - fz0 : __int_as_float((inside ? 1 : 0) | (inv ? 2 : 0))));
+					s_frac[slot * FI_THREADS + threadIdx.x] = comp;
+					if (inside)
+					{
+						const size_t cell = (size_t) ((int) fz0 - pk.mdlInitZ) * (size_t) pk.mdlXY + (size_t) ((int) fy0 - pk.mdlInitY) * (size_t) pk.mdlX + (size_t) (int) fx0;
+						cp_async16(s_cell + slot * FI_THREADS + threadIdx.x, pk.mdl8 + 4 * cell + k);
+					}
+					else s_cell[slot * FI_THREADS + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+					cp_async4(s_img + slot * FI_THREADS + threadIdx.x, (const float *) (img_row + x) + k);
+					cp_async_commit();
+				};
+#pragma unroll
+				for (int d = 0; d < FA_DEPTH; d++) { if (d <= rd.x_hi) issue(d); else cp_async_commit(); }
+				for (int x = 0; x <= rd.x_hi; x++)
+				{
+					const int slot = x % FA_DEPTH;
+					cp_async_wait<FA_DEPTH - 1>();
+					__syncwarp(qmask);                                  // the quad's four copies of this pixel are visible
+					const float4 q = s_cell[slot * FI_THREADS + threadIdx.x];
+					const float4 fr = *(const float4 *) (s_frac + slot * FI_THREADS + qbase);
+					const float4 im = *(const float4 *) (s_img + slot * FI_THREADS + qbase);
+					__syncwarp(qmask);                                  // everyone has read the slot before it is refilled
+					if (x + FA_DEPTH <= rd.x_hi) issue(x + FA_DEPTH); else cp_async_commit();
+					FineFetch f;
+					f.q = q; f.fx = fr.x; f.fy = fr.y; f.fz = fr.z; f.flags = __float_as_int(fr.w);
+					const float2 ref = fine_finish(f, k, qmask);
+					if (slice_row && k == 0) slice_row[x] = ref;
+					const float hc = im.z;
+					const float zr = hc * (ref.x * im.x + ref.y * im.y);
+					const float zi = hc * (ref.x * im.y - ref.y * im.x);
+					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
+					const float4 *pp = s_px + (x << 4) + k;
+#pragma unroll
+					for (int j = 0; j < 4; j++)
+					{
+						if (j < nj)
+						{
+							const float4 cs = pp[j * 4];
+							accr[2 * j] = fmaf(zr, cs.x, fmaf(-zi, cs.y, accr[2 * j]));
+							acci[2 * j] = fmaf(zr, cs.y, fmaf(zi, cs.x, acci[2 * j]));
+							accr[2 * j + 1] = fmaf(zr, cs.z, fmaf(-zi, cs.w, accr[2 * j + 1]));
+							acci[2 * j + 1] = fmaf(zr, cs.w, fmaf(zi, cs.z, acci[2 * j + 1]));
+						}
+					}
+				}
+				cp_async_wait<0>();
+#pragma unroll
+				for (int j = 0; j < 4; j++)
+#pragma unroll
+					for (int h = 0; h < 2; h++)
+					{
+						const int t = 2 * (j * 4 + k) + h;
+						if (t < ntr)
+						{
+							const float2 py = rb_phase(0, rd.y, 0.f, s_uy[t]);
+							tot[2 * j + h] += accr[2 * j + h] * py.x - acci[2 * j + h] * py.y;
+						}
+					}
+			}
+#pragma unroll
+			for (int i = 0; i < 8; i++)
+			{
+				float v = tot[i];
+				v += __shfl_xor_sync(RB_FULL_MASK, v, 4);
+				v += __shfl_xor_sync(RB_FULL_MASK, v, 8);
+				v += __shfl_xor_sync(RB_FULL_MASK, v, 16);
+				if (lane < 4) s_red[wid][2 * ((i >> 1) * 4 + k) + (i & 1)] = v;
+			}
+			base = warp_sum(base);
+			if (lane == 0) s_red[wid][FI_TF] = base;
+			__syncthreads();
+			if (threadIdx.x < ntr)
+			{
+				float c = 0.f, b = 0.f;
+#pragma unroll
+				for (int ww = 0; ww < FI_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][FI_TF]; }
+				const float v = fmaxf((b - 2.f * c) + xi2_half, 0.f);
+				A.fs_w[out_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v);
+			}
+		}
+		if (threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
+	}
+}
+
 static int launch_fine(rb_ctx *ctx, FineArgs &A, int grid)
 {
 	const int xs = A.n / 2 + 1;
@@ -291,6 +482,33 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	A.projs = ctx->d_proj.as<RbProjector>();
 	A.rows = M.rows_f; A.nrows = M.nrows_f; A.n = n;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
+	// cp.async-staged variant whenever three CTAs per SM still fit next to the phase table (measured at 256 px: 6.44 ms vs
+	// 6.97 ms; with two CTAs per SM it loses: 9.9 vs 9.2 ms at 400 px with a 6-deep ring)
+	static int use_async = -1;
+	if (use_async < 0) { const char *e = getenv("RB_FINE_ASYNC"); use_async = e ? atoi(e) : 1; }
+	if (use_async)
+	{
+		const size_t table = (size_t) xs * 16 * sizeof(float4);
+		const size_t ring1 = (size_t) FI_THREADS * (sizeof(float4) + 2 * sizeof(float));
+		const size_t limit = 74 * 1024;
+		// ring depth 2 (measured: depth 2 / 3 / 4 within 1 % at 256 px, depth 2 best at 400 px where it keeps 3 CTAs per SM);
+		// RB_FINE_ASYNC=4 tries four CTAs per SM (64 registers)
+		const int mode = (use_async > 1) ? use_async : (table + 2 * ring1 <= limit ? 2 : 0);
+		if (mode == 2 || mode == 4)
+		{
+			const size_t sm = table + 2 * ring1;
+			static size_t configured[2] = {0, 0};
+			void (*kern)(FineArgs, RbModelDev) = mode == 2 ? k_diff2_fine_async<2, 3> : k_diff2_fine_async<2, 4>;
+			if (sm > configured[mode == 4])
+			{
+				RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+				configured[mode == 4] = sm;
+			}
+			kern<<<ctx->num_sms * (mode == 4 ? 4 : 3), FI_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
+			RB_LAUNCH_CHECK(ctx);
+			return RB_OK;
+		}
+	}
 	return launch_fine(ctx, A, ctx->num_sms * 3);
 }
 

@@ -25,11 +25,16 @@
 #include <cuda.h>
 #include <cstdlib>
 
-static const int GM_BM = 128, GM_BN = 256, GM_BK = 32, GM_STAGES = 2;
+// K-block 32 (128-byte swizzle, 2 stages of 96 KB) or 16 (64-byte swizzle, 4 stages of 48 KB): same bytes in flight, the
+// finer one hides the TMA latency behind a deeper ring.  Operands are padded in K to GM_BK = 32 either way.
+static const int GM_BM = 128, GM_BN = 256, GM_BK = 32;
 static const int GM_THREADS = 192;
-static const uint32_t GM_A_BYTES = GM_BM * GM_BK * 4, GM_B_BYTES = GM_BN * GM_BK * 4;
-static const uint32_t GM_STAGE_BYTES = 2 * GM_A_BYTES + 2 * GM_B_BYTES;
-static const size_t GM_SMEM = (size_t) GM_STAGES * GM_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+template <int BK> struct GemmCfg {
+	static const int STAGES = BK == 32 ? 2 : 4;
+	static const uint32_t A_BYTES = GM_BM * BK * 4, B_BYTES = GM_BN * BK * 4;
+	static const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+	static const size_t SMEM = (size_t) STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+};
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -99,6 +104,18 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr)
 	return d;
 }
 
+// the same for rows of 64 bytes (CU_TENSOR_MAP_SWIZZLE_64B, layout type 4): 8-row groups 512 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_k_sw64(uint32_t smem_addr)
+{
+	uint64_t d = 0;
+	d |= (uint64_t) ((smem_addr & 0x3FFFF) >> 4);
+	d |= (uint64_t) 1 << 16;
+	d |= (uint64_t) (512 >> 4) << 32;
+	d |= (uint64_t) 1 << 46;
+	d |= (uint64_t) 4 << 61;
+	return d;
+}
+
 // instruction descriptor, kind::tf32: D fp32 (1 @ [4,6)), A/B TF32 (2 @ [7,10), [10,13)), both K-major, N >> 3 @ [17,23),
 // M >> 4 @ [24,29)
 __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
@@ -136,24 +153,27 @@ struct GemmEpilogue {
 	int M, N;                        // valid extent of this launch (rows of the chunk, columns)
 };
 
+template <int BK>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
               int num_kblocks, GemmEpilogue E)
 {
+	constexpr int STAGES = GemmCfg<BK>::STAGES;
+	constexpr uint32_t A_BYTES = GemmCfg<BK>::A_BYTES, B_BYTES = GemmCfg<BK>::B_BYTES, STAGE_BYTES = GemmCfg<BK>::STAGE_BYTES;
 	extern __shared__ uint8_t gm_smem_raw[];
 	const uint32_t raw = smem_u32(gm_smem_raw);
 	const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-byte aligned (128-byte swizzle atom)
-	const uint32_t bars = tiles + GM_STAGES * GM_STAGE_BYTES;            // full[stages], empty[stages], tmem_full, tmem slot
+	const uint32_t bars = tiles + STAGES * STAGE_BYTES;            // full[stages], empty[stages], tmem_full, tmem slot
 	uint8_t *bars_generic = gm_smem_raw + (bars - raw);
-	const uint32_t full0 = bars, empty0 = bars + 8 * GM_STAGES, tmem_full = bars + 16 * GM_STAGES, tmem_slot = tmem_full + 8;
+	const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES, tmem_slot = tmem_full + 8;
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	const int n_tile = blockIdx.x, m_tile = blockIdx.y;
 
 	if (warp == 0 && lane == 0)
 	{
-		for (int s = 0; s < GM_STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+		for (int s = 0; s < STAGES; s++) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
 		mbar_init(tmem_full, 1);
 		asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	}
@@ -165,7 +185,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	__syncthreads();
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-	const uint32_t tmem_base = *(volatile uint32_t *) (bars_generic + 16 * GM_STAGES + 8);
+	const uint32_t tmem_base = *(volatile uint32_t *) (bars_generic + 16 * STAGES + 8);
 
 	if (warp == 0)
 	{
@@ -173,15 +193,15 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 		{
 			for (int kb = 0; kb < num_kblocks; kb++)
 			{
-				const int s = kb % GM_STAGES;
-				const uint32_t ph = (kb / GM_STAGES) & 1;
+				const int s = kb % STAGES;
+				const uint32_t ph = (kb / STAGES) & 1;
 				mbar_wait(empty0 + 8 * s, ph ^ 1);                       // slot free (first round passes immediately)
-				const uint32_t st = tiles + s * GM_STAGE_BYTES;
-				mbar_expect_tx(full0 + 8 * s, GM_STAGE_BYTES);
-				tma_load_2d(st, &tmAhi, full0 + 8 * s, kb * GM_BK, m_tile * GM_BM);
-				tma_load_2d(st + GM_A_BYTES, &tmAlo, full0 + 8 * s, kb * GM_BK, m_tile * GM_BM);
-				tma_load_2d(st + 2 * GM_A_BYTES, &tmBhi, full0 + 8 * s, kb * GM_BK, n_tile * GM_BN);
-				tma_load_2d(st + 2 * GM_A_BYTES + GM_B_BYTES, &tmBlo, full0 + 8 * s, kb * GM_BK, n_tile * GM_BN);
+				const uint32_t st = tiles + s * STAGE_BYTES;
+				mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
+				tma_load_2d(st, &tmAhi, full0 + 8 * s, kb * BK, m_tile * GM_BM);
+				tma_load_2d(st + A_BYTES, &tmAlo, full0 + 8 * s, kb * BK, m_tile * GM_BM);
+				tma_load_2d(st + 2 * A_BYTES, &tmBhi, full0 + 8 * s, kb * BK, n_tile * GM_BN);
+				tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBlo, full0 + 8 * s, kb * BK, n_tile * GM_BN);
 			}
 		}
 	}
@@ -192,15 +212,17 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 			const uint32_t idesc = umma_idesc_tf32(GM_BM, GM_BN);
 			for (int kb = 0; kb < num_kblocks; kb++)
 			{
-				const int s = kb % GM_STAGES;
-				const uint32_t ph = (kb / GM_STAGES) & 1;
+				const int s = kb % STAGES;
+				const uint32_t ph = (kb / STAGES) & 1;
 				mbar_wait(full0 + 8 * s, ph);                            // TMA bytes have landed
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-				const uint32_t st = tiles + s * GM_STAGE_BYTES;
-				const uint64_t ahi = umma_desc_k_sw128(st), alo = umma_desc_k_sw128(st + GM_A_BYTES);
-				const uint64_t bhi = umma_desc_k_sw128(st + 2 * GM_A_BYTES), blo = umma_desc_k_sw128(st + 2 * GM_A_BYTES + GM_B_BYTES);
+				const uint32_t st = tiles + s * STAGE_BYTES;
+				const uint64_t ahi = BK == 32 ? umma_desc_k_sw128(st) : umma_desc_k_sw64(st);
+				const uint64_t alo = BK == 32 ? umma_desc_k_sw128(st + A_BYTES) : umma_desc_k_sw64(st + A_BYTES);
+				const uint64_t bhi = BK == 32 ? umma_desc_k_sw128(st + 2 * A_BYTES) : umma_desc_k_sw64(st + 2 * A_BYTES);
+				const uint64_t blo = BK == 32 ? umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES) : umma_desc_k_sw64(st + 2 * A_BYTES + B_BYTES);
 #pragma unroll
-				for (int ks = 0; ks < GM_BK / 8; ks++)
+				for (int ks = 0; ks < BK / 8; ks++)
 				{
 					const uint64_t adv = (uint64_t) ((ks * 8 * 4) >> 4);  // 32 bytes per K step inside the swizzle atom
 					// the two correction products (2^-11 of the main one) go to their own accumulator: the tensor core truncates
@@ -311,7 +333,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tmap(CUtensorMap *map, const float *base, size_t rows, size_t kpad, int box_rows)
+static int make_tmap(CUtensorMap *map, const float *base, size_t rows, size_t kpad, int box_rows, int bk = 32)
 {
 	static PFN_encodeTiled fn = nullptr;
 	if (!fn)
@@ -324,10 +346,11 @@ static int make_tmap(CUtensorMap *map, const float *base, size_t rows, size_t kp
 	}
 	const cuuint64_t dims[2] = {(cuuint64_t) kpad, (cuuint64_t) rows};
 	const cuuint64_t strides[1] = {(cuuint64_t) kpad * sizeof(float)};
-	const cuuint32_t box[2] = {(cuuint32_t) GM_BK, (cuuint32_t) box_rows};
+	const cuuint32_t box[2] = {(cuuint32_t) bk, (cuuint32_t) box_rows};
 	const cuuint32_t estr[2] = {1, 1};
 	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	                bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+	                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) { rb_set_error("cuTensorMapEncodeTiled failed (%d) rows=%zu kpad=%zu", (int) r, rows, kpad); return RB_ERR_CUDA; }
 	return RB_OK;
 }
@@ -338,17 +361,21 @@ static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; 
 static int launch_gemm(rb_ctx *ctx, const float *Ahi, const float *Alo, size_t Mpad, const float *Bhi, const float *Blo, size_t Npad,
                        size_t Kpad, const GemmEpilogue &E)
 {
+	static int bk = 0;
+	if (!bk) { const char *e = getenv("RB_GEMM_BK"); bk = (e && atoi(e) == 32) ? 32 : 16; }
 	CUtensorMap ta, tal, tb, tbl;
-	RB_CHECK(make_tmap(&ta, Ahi, Mpad, Kpad, GM_BM)); RB_CHECK(make_tmap(&tal, Alo, Mpad, Kpad, GM_BM));
-	RB_CHECK(make_tmap(&tb, Bhi, Npad, Kpad, GM_BN)); RB_CHECK(make_tmap(&tbl, Blo, Npad, Kpad, GM_BN));
+	RB_CHECK(make_tmap(&ta, Ahi, Mpad, Kpad, GM_BM, bk)); RB_CHECK(make_tmap(&tal, Alo, Mpad, Kpad, GM_BM, bk));
+	RB_CHECK(make_tmap(&tb, Bhi, Npad, Kpad, GM_BN, bk)); RB_CHECK(make_tmap(&tbl, Blo, Npad, Kpad, GM_BN, bk));
 	static bool configured = false;
 	if (!configured)
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GM_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<32>::SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<16>::SMEM));
 		configured = true;
 	}
 	dim3 grid((unsigned) (Npad / GM_BN), (unsigned) (Mpad / GM_BM));
-	k_gemm_tf32x3<<<grid, GM_THREADS, GM_SMEM, ctx->stream>>>(ta, tal, tb, tbl, (int) (Kpad / GM_BK), E);
+	if (bk == 32) k_gemm_tf32x3<32><<<grid, GM_THREADS, GemmCfg<32>::SMEM, ctx->stream>>>(ta, tal, tb, tbl, (int) (Kpad / 32), E);
+	else k_gemm_tf32x3<16><<<grid, GM_THREADS, GemmCfg<16>::SMEM, ctx->stream>>>(ta, tal, tb, tbl, (int) (Kpad / 16), E);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

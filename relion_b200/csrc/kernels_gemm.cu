@@ -602,7 +602,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 // issue slots; what is left is the gather.
 // ---------------------------------------------------------------------------------------------
 static const int FU_BM = 128, FU_BN = 32, FU_PIX = 16, FU_STAGES = 2;
-static const int FU_PRODUCERS = 256, FU_THREADS = 64 + FU_PRODUCERS;
+// producer warps per CTA: 8 (two CTAs per SM) or 16 (one CTA per SM, half the shared memory -> more L1 for the gathers)
 static const uint32_t FU_A_BYTES = FU_BM * 128, FU_B_BYTES = FU_BN * 128;
 static const uint32_t FU_STAGE_BYTES = 2 * FU_A_BYTES + 2 * FU_B_BYTES;            // 40 KB
 static const size_t FU_SMEM = (size_t) FU_STAGES * FU_STAGE_BYTES + 1024 + 128;
@@ -624,9 +624,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-__global__ void __launch_bounds__(FU_THREADS, 2)
+template <int NPW>
+__global__ void __launch_bounds__(64 + 32 * NPW, NPW == 8 ? 2 : 1)
 k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, FusedArgs A, RbSamplingDev S)
 {
+	constexpr int FU_PRODUCERS = 32 * NPW, FU_THREADS = 64 + FU_PRODUCERS, NJ = 64 / NPW;   // rows per producer thread
 	extern __shared__ uint8_t fu_smem_raw[];
 	__shared__ float s_e[FU_BM][6];
 	__shared__ unsigned char s_valid[FU_BM];
@@ -734,9 +736,9 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 		const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
 		const float4 *mdl2 = A.projs[cls].mdl2;
 		const float4 *img = A.img4 + (size_t) p * A.n * imgX;
-		float bacc[8];
+		float bacc[NJ];
 #pragma unroll
-		for (int j = 0; j < 8; j++) bacc[j] = 0.f;
+		for (int j = 0; j < NJ; j++) bacc[j] = 0.f;
 		for (int kb = 0; kb < nkb; kb++)
 		{
 			const int s = kb % FU_STAGES;
@@ -750,11 +752,11 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 				x = rb_pix_x(pkx); y = rb_pix_y(pkx);
 				hc = __ldg(img + rb_src_index(x, y, A.n)).z;
 			}
-			float2 ref[8];
+			float2 ref[NJ];
 #pragma unroll
-			for (int j = 0; j < 8; j++)
+			for (int j = 0; j < NJ; j++)
 			{
-				const int r = pw * 16 + 2 * j + rsub;
+				const int r = pw * (2 * NJ) + 2 * j + rsub;
 				ref[j] = make_float2(0.f, 0.f);
 				if (pix_ok && s_valid[r])
 					ref[j] = rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
@@ -763,9 +765,9 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 			mbar_wait(empty0 + 8 * s, ph ^ 1);                       // the MMAs that read this slot have retired
 			uint8_t *st = tiles_generic + (size_t) s * FU_STAGE_BYTES;
 #pragma unroll
-			for (int j = 0; j < 8; j++)
+			for (int j = 0; j < NJ; j++)
 			{
-				const int r = pw * 16 + 2 * j + rsub;
+				const int r = pw * (2 * NJ) + 2 * j + rsub;
 				float2 h, l;
 				tf32_split(ref[j].x, h.x, l.x); tf32_split(ref[j].y, h.y, l.y);
 				const uint32_t off = (uint32_t) r * 128u + ((uint32_t) ((i >> 1) ^ (r & 7)) << 4) + (uint32_t) (i & 1) * 8u;
@@ -777,14 +779,14 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 		}
 		// norm term per row: sum over the 16 lanes that share a row
 #pragma unroll
-		for (int j = 0; j < 8; j++)
+		for (int j = 0; j < NJ; j++)
 		{
 			float v = bacc[j];
 			v += __shfl_xor_sync(RB_FULL_MASK, v, 8); v += __shfl_xor_sync(RB_FULL_MASK, v, 4);
 			v += __shfl_xor_sync(RB_FULL_MASK, v, 2); v += __shfl_xor_sync(RB_FULL_MASK, v, 1);
-			if (i == 0) s_base[pw * 16 + 2 * j + rsub] = v;
+			if (i == 0) s_base[pw * (2 * NJ) + 2 * j + rsub] = v;
 		}
-		asm volatile("bar.sync 1, %0;" ::"n"(FU_PRODUCERS) : "memory");     // producers only
+		asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");     // producers only
 		if (pw < 4)
 		{
 			// ---- epilogue: warps 2..5 <-> TMEM lane quarters (warp % 4) ----
@@ -863,14 +865,20 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	A.img4 = cimg4; A.x2 = bX2.as<float>(); A.projs = ctx->d_proj.as<RbProjector>();
 	A.pix = M.pix_c; A.npix = npix; A.n = n; A.T = T; A.num_kblocks = nkb;
 	A.tiles_per_class = (s.max_no + FU_BM - 1) / FU_BM;
+	static int npw = 0;
+	// measured (256 px, hp4 local): 8 warps x 2 CTAs/SM (166 KB of shared memory, 32 KB of L1 left) 7.98 ms; 16 warps x 1 CTA/SM
+	// (83 KB, 128 KB of L1 for the gathers) 6.69 ms.  Loads that bypass L1 allocation: 18.6 ms - the corner rows do get reused.
+	if (!npw) { const char *e = getenv("RB_FUSED_WARPS"); npw = (e && atoi(e) == 8) ? 8 : 16; }
 	static bool configured = false;
 	if (!configured)
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		configured = true;
 	}
 	dim3 grid((unsigned) (A.tiles_per_class * K), (unsigned) P);
-	k_coarse_fused<<<grid, FU_THREADS, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+	if (npw == 16) k_coarse_fused<16><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+	else k_coarse_fused<8><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

@@ -567,6 +567,18 @@ def test_pool_class_with_zero_prior_is_skipped(device, oracle, local):
     assert np.all(device.bp_get(1)[2] == 0)
 
 
+@pytest.mark.parametrize("cache_slices", [0, 5])
+def test_pool_store_stage_without_slice_cache(device, oracle, monkeypatch, cache_slices):
+    """The store stage re-gathers the reference for fine orientations whose slice did not fit the cache the fine pass fills
+    (k_store<SLICED=false>); with the default 4 GiB budget that path never runs, so force it: no cache at all, and a cache of
+    five slices (both kernels contribute to the same accumulators)."""
+    wl = make_workload(ori_size=32, healpix_order=2, n_particles=8, nr_classes=1, seed=130, snr=0.2, local_search=True)
+    npf = wl.model.current_size * (wl.model.current_size // 2 + 1)
+    monkeypatch.setenv("RB_SLICE_CACHE_BYTES", str(cache_slices * npf * 8))
+    res, _ = _compare_pool(device, oracle, wl)
+    assert res.particles["n_fine_orient"].sum() > cache_slices
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

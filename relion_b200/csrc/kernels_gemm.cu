@@ -23,15 +23,21 @@
 // per K-block of 32.
 #include "img_src.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cstdlib>
 
 // K-block 32 (128-byte swizzle, 2 stages of 96 KB) or 16 (64-byte swizzle, 4 stages of 48 KB): same bytes in flight, the
 // finer one hides the TMA latency behind a deeper ring.  Operands are padded in K to GM_BK = 32 either way.
 static const int GM_BM = 128, GM_BN = 256, GM_BK = 32;
+static const int GM_MPAD = 256;      // operand rows are padded to a CTA pair's 256 (two 128-row tiles)
 static const int GM_THREADS = 192;
-template <int BK> struct GemmCfg {
-	static const int STAGES = BK == 32 ? 2 : 4;
-	static const uint32_t A_BYTES = GM_BM * BK * 4, B_BYTES = GM_BN * BK * 4;
+// TWO: a pair of CTAs on the two SMs of a TPC (cluster 2x1) computes a 256 x 256 tile with tcgen05.mma.cta_group::2 -
+// each CTA stages its own 128 rows of A and only HALF of the B tile, so the L2 -> shared-memory traffic per flop drops by
+// a third (the contraction is bound by that traffic, not by the tensor pipe, once the correction products run in bf16).
+template <int BK, bool TWO = false> struct GemmCfg {
+	static const int B_ROWS = TWO ? GM_BN / 2 : GM_BN;
+	static const int STAGES = (BK == 32 ? 2 : 4) * (TWO ? 3 : 2) / 2;
+	static const uint32_t A_BYTES = GM_BM * BK * 4, B_BYTES = B_ROWS * BK * 4;
 	static const uint32_t STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 	static const size_t SMEM = (size_t) STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
 };
@@ -75,6 +81,59 @@ __device__ __forceinline__ void tcgen05_mma_tf32(uint32_t tmem_d, uint64_t adesc
 		"setp.ne.b32 p, %4, 0;\n\t"
 		"tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
 		::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tcgen05_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	asm volatile(
+		"{\n\t.reg .pred p;\n\t"
+		"setp.ne.b32 p, %4, 0;\n\t"
+		"tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+		::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants ----
+__device__ __forceinline__ uint32_t cluster_ctarank()
+{
+	uint32_t r;
+	asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+	return r;
+}
+__device__ __forceinline__ void cluster_sync_all()
+{
+	asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in the CTA of rank `rank`
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank)
+{
+	uint32_t r;
+	asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+	return r;
+}
+// TMA load into this CTA's shared memory whose bytes are counted on the LEADER CTA's mbarrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t leader_bar, int c0, int c1)
+{
+	asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+	             ::"r"(dst), "l"(map), "r"(leader_bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint32_t bar)    // arrives on `bar` in both CTAs of the pair
+{
+	asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+	             ::"r"(bar), "h"((uint16_t) 3) : "memory");
+}
+template <bool BF16>
+__device__ __forceinline__ void tcgen05_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+	if (BF16)
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"setp.ne.b32 p, %4, 0;\n\t"
+			"tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+			::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+	else
+		asm volatile(
+			"{\n\t.reg .pred p;\n\t"
+			"setp.ne.b32 p, %4, 0;\n\t"
+			"tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+			::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
 {
@@ -123,6 +182,12 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32(int M, int N)
 	return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
 }
 
+// kind::f16 with BF16 operands (1 @ [7,10), [10,13)), fp32 accumulator
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N)
+{
+	return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t) (N >> 3) << 17) | ((uint32_t) (M >> 4) << 24);
+}
+
 __device__ __forceinline__ float tf32_round(float v)
 {
 	uint32_t r;
@@ -133,6 +198,36 @@ __device__ __forceinline__ void tf32_split(float v, float &hi, float &lo)
 {
 	hi = tf32_round(v);
 	lo = tf32_round(v - hi);
+}
+
+// mixed split: the main product stays TF32 x TF32; the two correction products (2^-11 of it) only need ~9 bits, so their
+// operands are stored as bf16 (hi' = bf16(hi), lo' = bf16(v - hi)) and run at twice the TF32 rate.  `lo` is then two
+// bf16 planes of `plane` elements each, [hi' | lo'], in the bytes the fp32 lo array would take.
+__device__ __forceinline__ void store_split2(float *hi, float *lo, size_t plane, size_t idx, float a, float b)
+{
+	float2 h, l;
+	tf32_split(a, h.x, l.x); tf32_split(b, h.y, l.y);
+	*(float2 *) (hi + idx) = h;
+	if (plane == 0) *(float2 *) (lo + idx) = l;
+	else
+	{
+		__nv_bfloat16 *b16 = (__nv_bfloat16 *) lo;
+		*(__nv_bfloat162 *) (b16 + idx) = __floats2bfloat162_rn(h.x, h.y);
+		*(__nv_bfloat162 *) (b16 + plane + idx) = __floats2bfloat162_rn(a - h.x, b - h.y);
+	}
+}
+__device__ __forceinline__ void store_split1(float *hi, float *lo, size_t plane, size_t idx, float a)
+{
+	float h, l;
+	tf32_split(a, h, l);
+	hi[idx] = h;
+	if (plane == 0) lo[idx] = l;
+	else
+	{
+		__nv_bfloat16 *b16 = (__nv_bfloat16 *) lo;
+		b16[idx] = __float2bfloat16_rn(h);
+		b16[plane + idx] = __float2bfloat16_rn(a - h);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -151,16 +246,25 @@ struct GemmEpilogue {
 	int T, P, O, cls, o_first;       // o_first: first orientation of this M chunk
 	// common
 	int M, N;                        // valid extent of this launch (rows of the chunk, columns)
+	int exp;                         // timing experiments only (RB_GEMM_EXP): 1 no bf16 MMAs, 2 no tf32 MMAs, 3 grouped issue, 4 no MMAs
 };
 
-template <int BK>
+// MIXED (BK = 32 only): tmAlo / tmBlo are the bf16 hi' planes, tmAlb / tmBlb the bf16 lo' planes; the stage holds
+// A_hi 16 KB (tf32, 128-byte rows) | A_hi' 8 KB | A_lo' 8 KB (bf16, 64-byte rows) | B_hi | B_hi' | B_lo' likewise.
+// TWO: launched with cluster dims (2, 1, 1) on a grid (2 * n tiles, m pairs); rank 0 of the pair issues the MMAs.
+template <int BK, bool MIXED, bool TWO>
 __global__ void __launch_bounds__(GM_THREADS, 1)
 k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__ CUtensorMap tmAlo,
+              const __grid_constant__ CUtensorMap tmAlb,
               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo,
+              const __grid_constant__ CUtensorMap tmBlb,
               int num_kblocks, GemmEpilogue E)
 {
-	constexpr int STAGES = GemmCfg<BK>::STAGES;
-	constexpr uint32_t A_BYTES = GemmCfg<BK>::A_BYTES, B_BYTES = GemmCfg<BK>::B_BYTES, STAGE_BYTES = GemmCfg<BK>::STAGE_BYTES;
+	static_assert(!MIXED || BK == 32, "mixed split uses K-blocks of 32");
+	typedef GemmCfg<BK, TWO> Cfg;
+	constexpr int STAGES = Cfg::STAGES;
+	constexpr uint32_t A_BYTES = Cfg::A_BYTES, B_BYTES = Cfg::B_BYTES, STAGE_BYTES = Cfg::STAGE_BYTES;
+	constexpr int MMA_M = TWO ? 2 * GM_BM : GM_BM;
 	extern __shared__ uint8_t gm_smem_raw[];
 	const uint32_t raw = smem_u32(gm_smem_raw);
 	const uint32_t tiles = (raw + 1023u) & ~1023u;                       // 1024-byte aligned (128-byte swizzle atom)
@@ -169,7 +273,11 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 	const uint32_t full0 = bars, empty0 = bars + 8 * STAGES, tmem_full = bars + 16 * STAGES, tmem_slot = tmem_full + 8;
 
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	const int n_tile = blockIdx.x, m_tile = blockIdx.y;
+	// pairs: the two CTAs of a cluster must be neighbours in x (the driver refuses cta_group::2 kernels otherwise), so the
+	// grid is (2 * n tiles, m pairs).  Either way x runs over the n tiles first: a wave of CTAs then shares all of B (which
+	// stays in L2 from wave to wave) and streams a few rows of A, instead of streaming half of A per wave.
+	const uint32_t rank = TWO ? cluster_ctarank() : 0;                   // pair: rank 1 stages its halves, rank 0 also issues
+	const int n_tile = TWO ? blockIdx.x >> 1 : blockIdx.x, m_tile = TWO ? 2 * blockIdx.y + (int) rank : blockIdx.y;
 
 	if (warp == 0 && lane == 0)
 	{
@@ -179,11 +287,19 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 	}
 	if (warp == 1)
 	{
-		asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
-		asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		if (TWO)
+		{
+			asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+		}
+		else
+		{
+			asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512) : "memory");
+			asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+		}
 	}
 	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-	__syncthreads();
+	if (TWO) cluster_sync_all(); else __syncthreads();                   // pair: the peer's barriers must exist before remote arrivals
 	asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 	const uint32_t tmem_base = *(volatile uint32_t *) (bars_generic + 16 * STAGES + 8);
 
@@ -191,50 +307,118 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 	{
 		if (lane == 0)
 		{
+			const int b_row = n_tile * GM_BN + (int) rank * Cfg::B_ROWS;
 			for (int kb = 0; kb < num_kblocks; kb++)
 			{
 				const int s = kb % STAGES;
 				const uint32_t ph = (kb / STAGES) & 1;
 				mbar_wait(empty0 + 8 * s, ph ^ 1);                       // slot free (first round passes immediately)
 				const uint32_t st = tiles + s * STAGE_BYTES;
-				mbar_expect_tx(full0 + 8 * s, STAGE_BYTES);
-				tma_load_2d(st, &tmAhi, full0 + 8 * s, kb * BK, m_tile * GM_BM);
-				tma_load_2d(st + A_BYTES, &tmAlo, full0 + 8 * s, kb * BK, m_tile * GM_BM);
-				tma_load_2d(st + 2 * A_BYTES, &tmBhi, full0 + 8 * s, kb * BK, n_tile * GM_BN);
-				tma_load_2d(st + 2 * A_BYTES + B_BYTES, &tmBlo, full0 + 8 * s, kb * BK, n_tile * GM_BN);
+				// pair: all bytes of both CTAs are counted on the leader's barrier, which alone is armed (for both halves)
+				const uint32_t fb = TWO ? mapa_shared(full0 + 8 * s, 0) : full0 + 8 * s;
+				if (!TWO) mbar_expect_tx(fb, STAGE_BYTES);
+				else if (rank == 0) mbar_expect_tx(full0 + 8 * s, 2 * STAGE_BYTES);
+				auto load = [&](uint32_t dst, const CUtensorMap *map, int row)
+				{
+					if (TWO) tma_load_2d_pair(dst, map, fb, kb * BK, row); else tma_load_2d(dst, map, fb, kb * BK, row);
+				};
+				load(st, &tmAhi, m_tile * GM_BM);
+				if (MIXED)
+				{
+					load(st + A_BYTES, &tmAlo, m_tile * GM_BM);
+					load(st + A_BYTES + A_BYTES / 2, &tmAlb, m_tile * GM_BM);
+					load(st + 2 * A_BYTES, &tmBhi, b_row);
+					load(st + 2 * A_BYTES + B_BYTES, &tmBlo, b_row);
+					load(st + 2 * A_BYTES + B_BYTES + B_BYTES / 2, &tmBlb, b_row);
+				}
+				else
+				{
+					load(st + A_BYTES, &tmAlo, m_tile * GM_BM);
+					load(st + 2 * A_BYTES, &tmBhi, b_row);
+					load(st + 2 * A_BYTES + B_BYTES, &tmBlo, b_row);
+				}
 			}
 		}
 	}
 	else if (warp == 1)
 	{
-		if (lane == 0)
+		if (lane == 0 && rank == 0)
 		{
-			const uint32_t idesc = umma_idesc_tf32(GM_BM, GM_BN);
+			const uint32_t idesc = umma_idesc_tf32(MMA_M, GM_BN), idesc16 = umma_idesc_bf16(MMA_M, GM_BN);
+			auto mma32 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc)
+			{
+				if (TWO) tcgen05_mma_pair<false>(d, a, b, idesc, acc); else tcgen05_mma_tf32(d, a, b, idesc, acc);
+			};
+			auto mma16 = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc)
+			{
+				if (TWO) tcgen05_mma_pair<true>(d, a, b, idesc16, acc); else tcgen05_mma_bf16(d, a, b, idesc16, acc);
+			};
 			for (int kb = 0; kb < num_kblocks; kb++)
 			{
 				const int s = kb % STAGES;
 				const uint32_t ph = (kb / STAGES) & 1;
-				mbar_wait(full0 + 8 * s, ph);                            // TMA bytes have landed
+				mbar_wait(full0 + 8 * s, ph);                            // TMA bytes have landed (in both CTAs of a pair)
 				asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 				const uint32_t st = tiles + s * STAGE_BYTES;
-				const uint64_t ahi = BK == 32 ? umma_desc_k_sw128(st) : umma_desc_k_sw64(st);
-				const uint64_t alo = BK == 32 ? umma_desc_k_sw128(st + A_BYTES) : umma_desc_k_sw64(st + A_BYTES);
-				const uint64_t bhi = BK == 32 ? umma_desc_k_sw128(st + 2 * A_BYTES) : umma_desc_k_sw64(st + 2 * A_BYTES);
-				const uint64_t blo = BK == 32 ? umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES) : umma_desc_k_sw64(st + 2 * A_BYTES + B_BYTES);
-#pragma unroll
-				for (int ks = 0; ks < BK / 8; ks++)
+				// the two correction products (2^-11 of the main one) go to their own accumulator: the tensor core truncates
+				// every accumulate to fp32, and three times fewer accumulations into the large sum means three times
+				// less truncation drift; the epilogue adds the two accumulators
+				if (MIXED)
 				{
-					const uint64_t adv = (uint64_t) ((ks * 8 * 4) >> 4);  // 32 bytes per K step inside the swizzle atom
-					// the two correction products (2^-11 of the main one) go to their own accumulator: the tensor core truncates
-					// every accumulate to fp32, and three times fewer accumulations into the large sum means three times
-					// less truncation drift; the epilogue adds the two accumulators
-					tcgen05_mma_tf32(tmem_base + GM_BN, alo + adv, bhi + adv, idesc, (kb | ks) != 0);
-					tcgen05_mma_tf32(tmem_base + GM_BN, ahi + adv, blo + adv, idesc, 1);
-					tcgen05_mma_tf32(tmem_base, ahi + adv, bhi + adv, idesc, (kb | ks) != 0);
+					const uint64_t a32 = umma_desc_k_sw128(st), b32 = umma_desc_k_sw128(st + 2 * A_BYTES);
+					const uint64_t ah = umma_desc_k_sw64(st + A_BYTES), al = umma_desc_k_sw64(st + A_BYTES + A_BYTES / 2);
+					const uint64_t bh = umma_desc_k_sw64(st + 2 * A_BYTES + B_BYTES), bl = umma_desc_k_sw64(st + 2 * A_BYTES + B_BYTES + B_BYTES / 2);
+					if (E.exp == 0)
+					{
+#pragma unroll
+						for (int ks = 0; ks < 2; ks++)                   // 16 K values per step: one bf16 K16 = two tf32 K8
+						{
+							const uint64_t adv16 = (uint64_t) ((ks * 16 * 2) >> 4);
+							mma16(tmem_base + GM_BN, al + adv16, bh + adv16, (kb | ks) != 0);
+							mma16(tmem_base + GM_BN, ah + adv16, bl + adv16, 1);
+							const uint64_t adv0 = (uint64_t) ((ks * 16 * 4) >> 4), adv1 = (uint64_t) (((ks * 16 + 8) * 4) >> 4);
+							mma32(tmem_base, a32 + adv0, b32 + adv0, (kb | ks) != 0);
+							mma32(tmem_base, a32 + adv1, b32 + adv1, 1);
+						}
+					}
+					else
+					{
+						if (E.exp == 2 || E.exp == 3)
+#pragma unroll
+							for (int ks = 0; ks < 2; ks++)
+							{
+								const uint64_t adv16 = (uint64_t) ((ks * 16 * 2) >> 4);
+								mma16(tmem_base + GM_BN, al + adv16, bh + adv16, (kb | ks) != 0);
+								mma16(tmem_base + GM_BN, ah + adv16, bl + adv16, 1);
+							}
+						if (E.exp == 1 || E.exp == 3)
+#pragma unroll
+							for (int ks = 0; ks < 4; ks++)
+							{
+								const uint64_t adv0 = (uint64_t) ((ks * 8 * 4) >> 4);
+								mma32(tmem_base, a32 + adv0, b32 + adv0, (kb | ks) != 0);
+							}
+					}
 				}
-				tcgen05_commit(empty0 + 8 * s);                          // frees the smem slot when these MMAs retire
+				else
+				{
+					const uint64_t ahi = BK == 32 ? umma_desc_k_sw128(st) : umma_desc_k_sw64(st);
+					const uint64_t alo = BK == 32 ? umma_desc_k_sw128(st + A_BYTES) : umma_desc_k_sw64(st + A_BYTES);
+					const uint64_t bhi = BK == 32 ? umma_desc_k_sw128(st + 2 * A_BYTES) : umma_desc_k_sw64(st + 2 * A_BYTES);
+					const uint64_t blo = BK == 32 ? umma_desc_k_sw128(st + 2 * A_BYTES + B_BYTES) : umma_desc_k_sw64(st + 2 * A_BYTES + B_BYTES);
+#pragma unroll
+					for (int ks = 0; ks < BK / 8; ks++)
+					{
+						const uint64_t adv = (uint64_t) ((ks * 8 * 4) >> 4);  // 32 bytes per K step inside the swizzle atom
+						mma32(tmem_base + GM_BN, alo + adv, bhi + adv, (kb | ks) != 0);
+						mma32(tmem_base + GM_BN, ahi + adv, blo + adv, 1);
+						mma32(tmem_base, ahi + adv, bhi + adv, (kb | ks) != 0);
+					}
+				}
+				// frees the smem slot (in both CTAs) when these MMAs retire
+				if (TWO) tcgen05_commit_pair(empty0 + 8 * s); else tcgen05_commit(empty0 + 8 * s);
 			}
-			tcgen05_commit(tmem_full);                                   // accumulator complete
+			if (TWO) tcgen05_commit_pair(tmem_full); else tcgen05_commit(tmem_full);   // accumulators complete
 		}
 	}
 	else
@@ -318,11 +502,12 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 		}
 		asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 	}
-	__syncthreads();
+	if (TWO) cluster_sync_all(); else __syncthreads();                   // pair: neither CTA may leave while the other still reads it
 	if (warp == 1)
 	{
 		asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-		asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+		if (TWO) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+		else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
 	}
 }
 
@@ -333,7 +518,7 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32
                                     const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_tmap(CUtensorMap *map, const float *base, size_t rows, size_t kpad, int box_rows, int bk = 32)
+static int make_tmap(CUtensorMap *map, const void *base, size_t rows, size_t kpad, int box_rows, int bk = 32, bool bf16 = false)
 {
 	static PFN_encodeTiled fn = nullptr;
 	if (!fn)
@@ -344,55 +529,104 @@ static int make_tmap(CUtensorMap *map, const float *base, size_t rows, size_t kp
 		if (!p || qr != cudaDriverEntryPointSuccess) { rb_set_error("cuTensorMapEncodeTiled not available from the driver"); return RB_ERR_CUDA; }
 		fn = (PFN_encodeTiled) p;
 	}
+	const size_t esize = bf16 ? 2 : 4;
 	const cuuint64_t dims[2] = {(cuuint64_t) kpad, (cuuint64_t) rows};
-	const cuuint64_t strides[1] = {(cuuint64_t) kpad * sizeof(float)};
+	const cuuint64_t strides[1] = {(cuuint64_t) kpad * esize};
 	const cuuint32_t box[2] = {(cuuint32_t) bk, (cuuint32_t) box_rows};
 	const cuuint32_t estr[2] = {1, 1};
-	CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-	                bk == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-	                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	CUresult r = fn(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void *) base, dims, strides, box, estr,
+	                CU_TENSOR_MAP_INTERLEAVE_NONE, bk * esize == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+	                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
 	if (r != CUDA_SUCCESS) { rb_set_error("cuTensorMapEncodeTiled failed (%d) rows=%zu kpad=%zu", (int) r, rows, kpad); return RB_ERR_CUDA; }
 	return RB_OK;
 }
 
 static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
-// A_hi/A_lo: [Mpad][Kpad], B_hi/B_lo: [Npad][Kpad] (Mpad % 128 == 0, Npad % 256 == 0, Kpad % 32 == 0, zero padded)
-static int launch_gemm(rb_ctx *ctx, const float *Ahi, const float *Alo, size_t Mpad, const float *Bhi, const float *Blo, size_t Npad,
-                       size_t Kpad, const GemmEpilogue &E)
+// RB_GEMM_MODE: bit 0 = bf16 operands for the two correction products (see store_split2), bit 1 = CTA pairs
+// (cta_group::2, 256 x 256 tiles).  Default 3; 0 is the single-CTA 3xTF32 kernel (K-block from RB_GEMM_BK).
+static int gemm_mode()
 {
-	static int bk = 0;
-	if (!bk) { const char *e = getenv("RB_GEMM_BK"); bk = (e && atoi(e) == 32) ? 32 : 16; }
-	CUtensorMap ta, tal, tb, tbl;
-	RB_CHECK(make_tmap(&ta, Ahi, Mpad, Kpad, GM_BM, bk)); RB_CHECK(make_tmap(&tal, Alo, Mpad, Kpad, GM_BM, bk));
-	RB_CHECK(make_tmap(&tb, Bhi, Npad, Kpad, GM_BN, bk)); RB_CHECK(make_tmap(&tbl, Blo, Npad, Kpad, GM_BN, bk));
+	static int m = -1;
+	if (m < 0) { const char *e = getenv("RB_GEMM_MODE"); m = e ? atoi(e) & 3 : 3; }
+	return m;
+}
+static bool gemm_mixed() { return gemm_mode() & 1; }
+
+template <int BK, bool MIXED, bool TWO>
+static int launch_gemm_variant(rb_ctx *ctx, dim3 grid, const CUtensorMap (&t)[6], int nkb, const GemmEpilogue &E)
+{
+	typedef GemmCfg<BK, TWO> Cfg;
 	static bool configured = false;
 	if (!configured)
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<32>::SMEM));
-		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) GemmCfg<16>::SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<BK, MIXED, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::SMEM));
 		configured = true;
 	}
-	dim3 grid((unsigned) (Npad / GM_BN), (unsigned) (Mpad / GM_BM));
-	if (bk == 32) k_gemm_tf32x3<32><<<grid, GM_THREADS, GemmCfg<32>::SMEM, ctx->stream>>>(ta, tal, tb, tbl, (int) (Kpad / 32), E);
-	else k_gemm_tf32x3<16><<<grid, GM_THREADS, GemmCfg<16>::SMEM, ctx->stream>>>(ta, tal, tb, tbl, (int) (Kpad / 16), E);
+	cudaLaunchConfig_t cfg = {};
+	cfg.gridDim = grid; cfg.blockDim = dim3(GM_THREADS); cfg.dynamicSmemBytes = Cfg::SMEM; cfg.stream = ctx->stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeClusterDimension;
+	attr[0].val.clusterDim.x = TWO ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+	cfg.attrs = attr; cfg.numAttrs = 1;
+	RB_CUDA(cudaLaunchKernelEx(&cfg, k_gemm_tf32x3<BK, MIXED, TWO>, t[0], t[1], t[2], t[3], t[4], t[5], nkb, E));
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
+}
+
+// A_hi/A_lo: [Mpad][Kpad], B_hi/B_lo: [Npad][Kpad] (Mpad % 256 == 0, Npad % 256 == 0, Kpad % 32 == 0, zero padded); with the
+// mixed split the lo arrays hold the two bf16 planes instead
+static int launch_gemm(rb_ctx *ctx, const float *Ahi, const float *Alo, size_t Mpad, const float *Bhi, const float *Blo, size_t Npad,
+                       size_t Kpad, const GemmEpilogue &E_in)
+{
+	static int bk = 0;
+	if (!bk) { const char *e = getenv("RB_GEMM_BK"); bk = (e && atoi(e) == 32) ? 32 : 16; }
+	const int mode = gemm_mode();
+	const bool mixed = mode & 1, two = mode & 2;
+	const int kb = mode ? 32 : bk;
+	const int b_rows = two ? GM_BN / 2 : GM_BN;
+	if (Mpad % GM_MPAD || Npad % GM_BN || Kpad % GM_BK) { rb_set_error("launch_gemm: operands not padded"); return RB_ERR_ARG; }
+	dim3 grid((unsigned) (Npad / GM_BN), (unsigned) (Mpad / GM_BM));
+	if (two) grid = dim3((unsigned) (2 * (Npad / GM_BN)), (unsigned) (Mpad / GM_MPAD));
+	if (grid.y > 65535) { rb_set_error("launch_gemm: too many tiles (%u) for one launch", grid.y); return RB_ERR_ARG; }
+	CUtensorMap t[6];
+	RB_CHECK(make_tmap(&t[0], Ahi, Mpad, Kpad, GM_BM, kb)); RB_CHECK(make_tmap(&t[3], Bhi, Npad, Kpad, b_rows, kb));
+	if (mixed)
+	{
+		const __nv_bfloat16 *Ab = (const __nv_bfloat16 *) Alo, *Bb = (const __nv_bfloat16 *) Blo;
+		RB_CHECK(make_tmap(&t[1], Ab, Mpad, Kpad, GM_BM, 32, true)); RB_CHECK(make_tmap(&t[2], Ab + Mpad * Kpad, Mpad, Kpad, GM_BM, 32, true));
+		RB_CHECK(make_tmap(&t[4], Bb, Npad, Kpad, b_rows, 32, true)); RB_CHECK(make_tmap(&t[5], Bb + Npad * Kpad, Npad, Kpad, b_rows, 32, true));
+	}
+	else
+	{
+		RB_CHECK(make_tmap(&t[1], Alo, Mpad, Kpad, GM_BM, kb)); t[2] = t[1];
+		RB_CHECK(make_tmap(&t[4], Blo, Npad, Kpad, b_rows, kb)); t[5] = t[4];
+	}
+	const int nkb = (int) (Kpad / kb);
+	static int exp = -1;
+	if (exp < 0) { const char *e = getenv("RB_GEMM_EXP"); exp = e ? atoi(e) : 0; }
+	GemmEpilogue E = E_in;
+	E.exp = exp;
+	switch (mode)
+	{
+	case 3: return launch_gemm_variant<32, true, true>(ctx, grid, t, nkb, E);
+	case 2: return launch_gemm_variant<32, false, true>(ctx, grid, t, nkb, E);
+	case 1: return launch_gemm_variant<32, true, false>(ctx, grid, t, nkb, E);
+	default: return kb == 32 ? launch_gemm_variant<32, false, false>(ctx, grid, t, nkb, E) : launch_gemm_variant<16, false, false>(ctx, grid, t, nkb, E);
+	}
 }
 
 // ---------------------------------------------------------------------------------------------
 // operand builders
 // ---------------------------------------------------------------------------------------------
 // generic split of a row-major [rows][cols] fp32 matrix into zero-padded hi/lo [rows_pad][kpad]
-__global__ void k_split_pad(const float *src, int rows, int cols, float *hi, float *lo, size_t rows_pad, size_t kpad)
+__global__ void k_split_pad(const float *src, int rows, int cols, float *hi, float *lo, size_t rows_pad, size_t kpad, size_t plane)
 {
 	const size_t n = rows_pad * kpad;
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
 	{
 		const size_t r = i / kpad, c = i - r * kpad;
-		float h = 0.f, l = 0.f;
-		if (r < (size_t) rows && c < (size_t) cols) tf32_split(src[r * cols + c], h, l);
-		hi[i] = h; lo[i] = l;
+		store_split1(hi, lo, plane, i, (r < (size_t) rows && c < (size_t) cols) ? src[r * cols + c] : 0.f);
 	}
 }
 
@@ -401,9 +635,10 @@ __global__ void k_split_pad(const float *src, int rows, int cols, float *hi, flo
 // their squared moduli for the norm term.
 __global__ void __launch_bounds__(256)
 k_gemm_build_A(RbProjector pj, const float *coarse_eulers, const uint32_t *pix, int npix, int n, int o_first, int rows, int rows_pad,
-               float *Ahi, float *Alo, size_t kpad, float *A2hi, float *A2lo, size_t k2pad)
+               float *Ahi, float *Alo, size_t kpad, float *A2hi, float *A2lo, size_t k2pad, int mixed)
 {
 	const int r = blockIdx.y;
+	const size_t plane = mixed ? (size_t) rows_pad * kpad : 0, plane2 = mixed ? (size_t) rows_pad * k2pad : 0;
 	const int imgX = n / 2 + 1;
 	const RbProjK pk = rb_make_projk(pj, imgX);
 	const bool live = r < rows;
@@ -422,16 +657,8 @@ k_gemm_build_A(RbProjector pj, const float *coarse_eulers, const uint32_t *pix, 
 			const uint32_t pkx = __ldg(pix + i);
 			ref = rb_project3d_xp(pk, pj.mdl2, rb_pix_x(pkx), rb_pix_y(pkx), e0, e1, e3, e4, e6, e7);
 		}
-		float2 h, l;
-		tf32_split(ref.x, h.x, l.x); tf32_split(ref.y, h.y, l.y);
-		*(float2 *) (Ahi + (size_t) r * kpad + 2 * i) = h;
-		*(float2 *) (Alo + (size_t) r * kpad + 2 * i) = l;
-		if ((size_t) i < k2pad)
-		{
-			float h2, l2;
-			tf32_split(ref.x * ref.x + ref.y * ref.y, h2, l2);
-			A2hi[(size_t) r * k2pad + i] = h2; A2lo[(size_t) r * k2pad + i] = l2;
-		}
+		store_split2(Ahi, Alo, plane, (size_t) r * kpad + 2 * i, ref.x, ref.y);
+		if ((size_t) i < k2pad) store_split1(A2hi, A2lo, plane2, (size_t) r * k2pad + i, ref.x * ref.x + ref.y * ref.y);
 	}
 }
 
@@ -441,7 +668,7 @@ k_gemm_build_A(RbProjector pj, const float *coarse_eulers, const uint32_t *pix, 
 // B2 / x2 outputs are optional (nullptr).
 __global__ void __launch_bounds__(256)
 k_gemm_build_B(const float4 *img4, const uint32_t *pix, int npix, int n, const float *tx, const float *ty, int T, int tstride, int P,
-               float *Bhi, float *Blo, size_t kpad, float *B2hi, float *B2lo, size_t k2pad, float *x2)
+               float *Bhi, float *Blo, size_t kpad, float *B2hi, float *B2lo, size_t k2pad, float *x2, size_t plane, size_t plane2)
 {
 	__shared__ float red[32];
 	const int col = blockIdx.x;                  // 0 .. Npad-1
@@ -471,16 +698,8 @@ k_gemm_build_B(const float4 *img4, const uint32_t *pix, int npix, int n, const f
 			y.y = hc * (im.y * cc + im.x * ss);
 			if (t == 0) acc += hc * (im.x * im.x + im.y * im.y);
 		}
-		float2 h, l;
-		tf32_split(y.x, h.x, l.x); tf32_split(y.y, h.y, l.y);
-		*(float2 *) (Bhi + (size_t) col * kpad + 2 * i) = h;
-		*(float2 *) (Blo + (size_t) col * kpad + 2 * i) = l;
-		if (B2hi && t == 0 && live && (size_t) i < k2pad)
-		{
-			float h2, l2;
-			tf32_split(hc, h2, l2);
-			B2hi[(size_t) p * k2pad + i] = h2; B2lo[(size_t) p * k2pad + i] = l2;
-		}
+		store_split2(Bhi, Blo, plane, (size_t) col * kpad + 2 * i, y.x, y.y);
+		if (B2hi && t == 0 && live && (size_t) i < k2pad) store_split1(B2hi, B2lo, plane2, (size_t) p * k2pad + i, hc);
 	}
 	if (t == 0 && live)
 	{
@@ -516,18 +735,18 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	// orientation chunk: bounded operand memory (A and A2, hi + lo)
 	const size_t budget = (size_t) 6 << 30;
 	size_t mchunk = budget / ((kpad + k2pad) * 2 * sizeof(float));
-	mchunk = std::max<size_t>(GM_BM, mchunk / GM_BM * GM_BM);
-	mchunk = std::min<size_t>(mchunk, round_up((size_t) O, GM_BM));
+	mchunk = std::max<size_t>(GM_MPAD, mchunk / GM_MPAD * GM_MPAD);
+	mchunk = std::min<size_t>(mchunk, round_up((size_t) O, GM_MPAD));
 
 	DevBuf &bAhi = ctx->gemm_buf[0], &bAlo = ctx->gemm_buf[1], &bA2hi = ctx->gemm_buf[2], &bA2lo = ctx->gemm_buf[3];
 	DevBuf &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5], &bB2hi = ctx->gemm_buf[6], &bB2lo = ctx->gemm_buf[7];
 	DevBuf &bBase = ctx->gemm_buf[8], &bX2 = ctx->gemm_buf[9];
 	{
 		// shared chunk buffers: only needed when the per-class cache below does not apply
-		const size_t a_all = round_up((size_t) O, GM_BM) * (kpad + k2pad) * 2 * sizeof(float);
+		const size_t a_all = round_up((size_t) O, GM_MPAD) * (kpad + k2pad) * 2 * sizeof(float);
 		const char *ce0 = getenv("RB_GEMM_CACHE_BYTES");
 		const size_t budget0 = ce0 ? (size_t) strtoull(ce0, nullptr, 10) : ((size_t) 24 << 30);
-		if (!(mchunk >= round_up((size_t) O, GM_BM) && a_all * (size_t) K <= budget0))
+		if (!(mchunk >= round_up((size_t) O, GM_MPAD) && a_all * (size_t) K <= budget0))
 		{
 			RB_CHECK(bAhi.ensure(mchunk * kpad * 4)); RB_CHECK(bAlo.ensure(mchunk * kpad * 4));
 			RB_CHECK(bA2hi.ensure(mchunk * k2pad * 4)); RB_CHECK(bA2lo.ensure(mchunk * k2pad * 4));
@@ -541,20 +760,21 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	RB_CUDA(cudaMemsetAsync(bB2hi.p, 0, N2pad * k2pad * 4, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(bB2lo.p, 0, N2pad * k2pad * 4, ctx->stream));
 	k_gemm_build_B<<<(unsigned) Npad, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, T, P,
-		bBhi.as<float>(), bBlo.as<float>(), kpad, bB2hi.as<float>(), bB2lo.as<float>(), k2pad, bX2.as<float>());
+		bBhi.as<float>(), bBlo.as<float>(), kpad, bB2hi.as<float>(), bB2lo.as<float>(), k2pad, bX2.as<float>(),
+		gemm_mixed() ? Npad * kpad : 0, gemm_mixed() ? N2pad * k2pad : 0);
 	RB_LAUNCH_CHECK(ctx);
 
 	// The orientation operands only change with the reference, the sampling or the window sizes: when a class' whole grid
 	// fits one chunk and the cache budget, they are built once per iteration and reused by every pool.
-	const size_t a_bytes = round_up((size_t) O, GM_BM) * (kpad + k2pad) * 2 * sizeof(float);
+	const size_t a_bytes = round_up((size_t) O, GM_MPAD) * (kpad + k2pad) * 2 * sizeof(float);
 	const char *ce = getenv("RB_GEMM_CACHE_BYTES");
 	const size_t cache_budget = ce ? (size_t) strtoull(ce, nullptr, 10) : ((size_t) 24 << 30);
-	const bool use_cache = mchunk >= round_up((size_t) O, GM_BM) && a_bytes * (size_t) K <= cache_budget;
+	const bool use_cache = mchunk >= round_up((size_t) O, GM_MPAD) && a_bytes * (size_t) K <= cache_budget;
 	for (int cls = 0; cls < K; cls++)
 		for (int o0 = 0; o0 < O; o0 += (int) mchunk)
 		{
 			const int rows = std::min<int>((int) mchunk, O - o0);
-			const int rows_pad = (int) round_up((size_t) rows, GM_BM);
+			const int rows_pad = (int) round_up((size_t) rows, GM_MPAD);
 			float *Ahi = bAhi.as<float>(), *Alo = bAlo.as<float>(), *A2hi = bA2hi.as<float>(), *A2lo = bA2lo.as<float>();
 			bool build = true;
 			if (use_cache)
@@ -571,7 +791,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 			{
 				dim3 ga((unsigned) std::min<size_t>((kpad / 2 + 255) / 256, 64), (unsigned) rows_pad);
 				k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[cls], S.coarse_eulers, M.pix_c, npix, n, o0, rows, rows_pad,
-					Ahi, Alo, kpad, A2hi, A2lo, k2pad);
+					Ahi, Alo, kpad, A2hi, A2lo, k2pad, gemm_mixed() ? 1 : 0);
 				RB_LAUNCH_CHECK(ctx);
 			}
 			// norm term base[o][p]
@@ -853,7 +1073,7 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	DevBuf &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5], &bX2 = ctx->gemm_buf[9];
 	RB_CHECK(bBhi.ensure(rows * kpad * 4)); RB_CHECK(bBlo.ensure(rows * kpad * 4)); RB_CHECK(bX2.ensure((size_t) P * 4));
 	k_gemm_build_B<<<(unsigned) rows, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, FU_BN, P,
-		bBhi.as<float>(), bBlo.as<float>(), kpad, nullptr, nullptr, 0, bX2.as<float>());
+		bBhi.as<float>(), bBlo.as<float>(), kpad, nullptr, nullptr, 0, bX2.as<float>(), 0, 0);
 	RB_LAUNCH_CHECK(ctx);
 	CUtensorMap tb, tbl;
 	RB_CHECK(make_tmap(&tb, bBhi.as<float>(), rows, kpad, FU_BN)); RB_CHECK(make_tmap(&tbl, bBlo.as<float>(), rows, kpad, FU_BN));
@@ -886,13 +1106,13 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 // stage entry: C[M][N] = A[M][K] . B[N][K]^T in 3xTF32 (device pointers, row-major)
 int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int Mr, int Nr, int Kr, float *dC)
 {
-	const size_t Mpad = round_up((size_t) Mr, GM_BM), Npad = round_up((size_t) Nr, GM_BN), Kpad = round_up((size_t) Kr, GM_BK);
+	const size_t Mpad = round_up((size_t) Mr, GM_MPAD), Npad = round_up((size_t) Nr, GM_BN), Kpad = round_up((size_t) Kr, GM_BK);
 	DevBuf &bAhi = ctx->gemm_buf[0], &bAlo = ctx->gemm_buf[1], &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5];
 	RB_CHECK(bAhi.ensure(Mpad * Kpad * 4)); RB_CHECK(bAlo.ensure(Mpad * Kpad * 4));
 	RB_CHECK(bBhi.ensure(Npad * Kpad * 4)); RB_CHECK(bBlo.ensure(Npad * Kpad * 4));
-	k_split_pad<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(dA, Mr, Kr, bAhi.as<float>(), bAlo.as<float>(), Mpad, Kpad);
+	k_split_pad<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(dA, Mr, Kr, bAhi.as<float>(), bAlo.as<float>(), Mpad, Kpad, gemm_mixed() ? Mpad * Kpad : 0);
 	RB_LAUNCH_CHECK(ctx);
-	k_split_pad<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(dB, Nr, Kr, bBhi.as<float>(), bBlo.as<float>(), Npad, Kpad);
+	k_split_pad<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(dB, Nr, Kr, bBhi.as<float>(), bBlo.as<float>(), Npad, Kpad, gemm_mixed() ? Npad * Kpad : 0);
 	RB_LAUNCH_CHECK(ctx);
 	GemmEpilogue E;
 	memset(&E, 0, sizeof(E));

@@ -288,6 +288,8 @@ struct WcArgs {
 	unsigned long long *hsum; int *hcnt;         // [P][WC_BINS]: sum of the 24-bit significands of the bin's values (exact), count
 	WcPick *pick;                                // [P]
 	long long *gtot;                             // [P][2] number of gathered elements (picked bin, maxsig bin)
+	long long *ntot;                             // [P][2] number of non-zero weights, number of them below the picked bin
+	int counts;                                  // per-bin counts are kept (maxsig)
 	float *compact_a, *compact_r;                // [P][cap]
 	long long cap;
 };
@@ -303,60 +305,106 @@ __device__ __forceinline__ void wc_load4(const float *w, long long i, long long 
 		for (int j = 0; j < 4; j++) v[j] = (i + j < i1) ? w[i + j] : 0.f;
 }
 
+// Each CTA walks its chunk in steps of WC_STEP = 8 * WC_THREADS elements: two 16-byte loads per thread in flight.  A thread's
+// run of four consecutive elements (io, it), (io, it + 1), ... needs the orientation prior only when `it` wraps, so the
+// cursor carries it: RB_LOWEST stands for "prior is zero" (helper.cuh:39-42), for orientations and translations alike.
+static const int WC_STEP = 8 * WC_THREADS;
+struct WcCursor {
+	int io, it, dio, dit, T;
+	const float *po; const unsigned char *pz;
+	__device__ __forceinline__ WcCursor(long long i, int T_, int stride, const float *po_, const unsigned char *pz_) : T(T_), po(po_), pz(pz_)
+	{
+		io = (int) (i / T_); it = (int) (i - (long long) io * T_);
+		dio = stride / T_; dit = stride - dio * T_;
+	}
+	__device__ __forceinline__ void advance() { io += dio; it += dit; if (it >= T) { it -= T; io++; } }
+	__device__ __forceinline__ float prior(int o) const { return pz[o] ? RB_LOWEST : po[o]; }
+};
+
+// log-weights of the four elements starting at the cursor (elements at or beyond i1 get RB_LOWEST when CHECK)
+template <bool CHECK>
+__device__ __forceinline__ void wc_logw4(const WcCursor &cur, const float *s_pt, float min_diff2, const float (&v)[4], long long i, long long i1,
+                                         float (&l)[4])
+{
+	int io = cur.io, it = cur.it;
+	float po = (!CHECK || i < i1) ? cur.prior(io) : RB_LOWEST;
+#pragma unroll
+	for (int j = 0; j < 4; j++)
+	{
+		const float pt = s_pt[it];
+		const bool bad = v[j] < min_diff2 || po == RB_LOWEST || pt == RB_LOWEST || (CHECK && i + j >= i1);
+		l[j] = bad ? RB_LOWEST : po + pt + min_diff2 - v[j];
+		if (j < 3 && ++it == cur.T) { it = 0; io++; po = (!CHECK || i + j + 1 < i1) ? cur.prior(io) : RB_LOWEST; }
+	}
+}
+
+__device__ __forceinline__ void wc_stage_priors(const WcArgs &A, int p, float *s_pt)
+{
+	if (threadIdx.x < A.T)
+		s_pt[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + threadIdx.x] ? RB_LOWEST : A.pdf_offset[(size_t) p * A.T + threadIdx.x];
+}
+
 __global__ void __launch_bounds__(WC_THREADS)
 k_wc_max(WcArgs A)
 {
 	__shared__ float fred[32];
 	__shared__ float s_pt[64];
-	__shared__ unsigned char s_tz[64];
 	const int c = blockIdx.x, p = blockIdx.y;
 	const RbPartMeta m = A.metas[p];
 	const float min_diff2 = __int_as_float(A.states[p].min_diff2_bits);
 	const float *w = A.Mweight + m.coarse_off;
 	const bool vec = (m.coarse_off & 3) == 0;
-	if (threadIdx.x < A.T) { s_pt[threadIdx.x] = A.pdf_offset[(size_t) p * A.T + threadIdx.x]; s_tz[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + threadIdx.x]; }
+	wc_stage_priors(A, p, s_pt);
 	__syncthreads();
 	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
 	float mx = RB_LOWEST;
-	for (long long i = i0 + 4 * threadIdx.x; i < i1; i += 4 * WC_THREADS)
+	WcCursor cur(i0 + 4 * threadIdx.x, A.T, 4 * WC_THREADS, A.pdf_orient + m.prior_off, A.pdf_orient_zero + m.prior_off);
+	for (long long base = i0; base < i1; base += WC_STEP)
 	{
-		float v[4];
-		wc_load4(w, i, i1, vec, v);
-		int io = (int) (i / A.T), it = (int) (i - (long long) io * A.T);
+		float v[2][4], l[4];
+		const long long ia = base + 4 * threadIdx.x, ib = ia + 4 * WC_THREADS;
+		const bool full = vec && base + WC_STEP <= i1;
+		wc_load4(w, ia, i1, vec, v[0]);
+		wc_load4(w, ib, i1, vec, v[1]);
 #pragma unroll
-		for (int j = 0; j < 4; j++)
+		for (int h = 0; h < 2; h++)
 		{
-			if (i + j < i1)
-			{
-				float l = RB_LOWEST;
-				if (!(v[j] < min_diff2 || A.pdf_orient_zero[m.prior_off + io] || s_tz[it]))              // helper.cuh:39-42
-					l = A.pdf_orient[m.prior_off + io] + s_pt[it] + min_diff2 - v[j];
-				mx = fmaxf(mx, l);
-			}
-			if (++it == A.T) { it = 0; io++; }
+			if (full) wc_logw4<false>(cur, s_pt, min_diff2, v[h], h ? ib : ia, i1, l);
+			else wc_logw4<true>(cur, s_pt, min_diff2, v[h], h ? ib : ia, i1, l);
+			mx = fmaxf(fmaxf(mx, fmaxf(l[0], l[1])), fmaxf(l[2], l[3]));
+			cur.advance();
 		}
 	}
 	mx = block_max(mx, fred);
 	if (threadIdx.x == 0) A.pmax[(size_t) p * A.nchunk + c] = mx;
 }
 
+// Histogram words per bin in shared memory: 32-bit counters only (a 64-bit shared atomic add compiles to a compare-and-swap
+// spin loop).  Lanes of a warp that hit the same bin are combined first (match.any + redux), then one lane adds the low 16
+// bits and the rest of the combined significand sum to two words (each stays below 2^31 for a chunk of 2^15 elements).
+// COUNTS: also the number of elements per bin (only the --maxsig rank search needs it; otherwise the total number of
+// non-zero weights comes from the ballots here and the count below the picked bin from k_wc_gather).
+template <bool COUNTS>
 __global__ void __launch_bounds__(WC_THREADS)
 k_wc_exp(WcArgs A)
 {
 	extern __shared__ unsigned char wc_smem[];
-	unsigned long long *h_s = (unsigned long long *) wc_smem;   // [WC_BINS]
-	int *h_c = (int *) (h_s + WC_BINS);                          // [WC_BINS]
+	unsigned *h_lo = (unsigned *) wc_smem;                       // [WC_BINS] sum of (combined significand sums & 0xffff)
+	unsigned *h_hi = h_lo + WC_BINS;                             // [WC_BINS] sum of (combined significand sums >> 16)
+	unsigned *h_c = h_hi + WC_BINS;                              // [WC_BINS] count (COUNTS)
 	__shared__ ArgMaxSmem am;
 	__shared__ float s_wmax;
 	__shared__ float s_pt[64];
-	__shared__ unsigned char s_tz[64];
+	__shared__ int s_nz;
 	const int c = blockIdx.x, p = blockIdx.y;
+	const int lane = threadIdx.x & 31;
 	const RbPartMeta m = A.metas[p];
 	const float min_diff2 = __int_as_float(A.states[p].min_diff2_bits);
 	float *w = A.Mweight + m.coarse_off;
 	const bool vec = (m.coarse_off & 3) == 0;
-	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { h_s[i] = 0ull; h_c[i] = 0; }
-	if (threadIdx.x < A.T) { s_pt[threadIdx.x] = A.pdf_offset[(size_t) p * A.T + threadIdx.x]; s_tz[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + threadIdx.x]; }
+	for (int i = threadIdx.x; i < (COUNTS ? 3 : 2) * WC_BINS; i += WC_THREADS) h_lo[i] = 0u;
+	wc_stage_priors(A, p, s_pt);
+	if (threadIdx.x == 0) s_nz = 0;
 	if (threadIdx.x < 32)
 	{
 		float mx = RB_LOWEST;
@@ -367,46 +415,64 @@ k_wc_exp(WcArgs A)
 	__syncthreads();
 	const float add = 50.f - s_wmax;                                               // acc_ml_optimiser_impl.h:2201-2207
 	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
-	float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
-	for (long long i = i0 + 4 * threadIdx.x; i < i1; i += 4 * WC_THREADS)
+	float bv = RB_LOWEST; int brel = 0x7fffffff;                                    // maximum and its index relative to i0
+	int nz_count = 0;                                                              // per thread
+	WcCursor cur(i0 + 4 * threadIdx.x, A.T, 4 * WC_THREADS, A.pdf_orient + m.prior_off, A.pdf_orient_zero + m.prior_off);
+	for (long long base = i0; base < i1; base += WC_STEP)                          // warp-uniform trip count
 	{
-		float v[4], e[4];
-		wc_load4(w, i, i1, vec, v);
-		int io = (int) (i / A.T), it = (int) (i - (long long) io * A.T);
+		float v[2][4];
+		const long long ia = base + 4 * threadIdx.x, ib = ia + 4 * WC_THREADS;
+		const bool full = vec && base + WC_STEP <= i1;
+		wc_load4(w, ia, i1, vec, v[0]);
+		wc_load4(w, ib, i1, vec, v[1]);
 #pragma unroll
-		for (int j = 0; j < 4; j++)
+		for (int h = 0; h < 2; h++)
 		{
-			e[j] = 0.f;
-			if (i + j < i1)
-			{
-				float l = RB_LOWEST;
-				if (!(v[j] < min_diff2 || A.pdf_orient_zero[m.prior_off + io] || s_tz[it]))
-					l = A.pdf_orient[m.prior_off + io] + s_pt[it] + min_diff2 - v[j];
-				const float a = l + add;
-				e[j] = (a < -88.f) ? 0.f : expf(a);                                // helper.cuh:57-66
-				if (e[j] > 0.f)
-				{
-					const unsigned bits = __float_as_uint(e[j]);
-					const int bin = (int) (bits >> WC_SHIFT);
-					// significand as an integer (normal: implicit one; denormal: exponent field 0)
-					const unsigned long long sig = (bits >> 23) ? ((bits & 0x7fffffu) | 0x800000u) : (bits & 0x7fffffu);
-					atomicAdd(h_s + bin, sig); atomicAdd(h_c + bin, 1);
-				}
-				if (e[j] > bv) { bv = e[j]; bi = i + j; }
-			}
-			if (++it == A.T) { it = 0; io++; }
-		}
-		if (vec && i + 3 < i1) *(float4 *) (w + i) = make_float4(e[0], e[1], e[2], e[3]);
-		else
+			const long long i = h ? ib : ia;
+			float l[4], e[4];
+			if (full) wc_logw4<false>(cur, s_pt, min_diff2, v[h], i, i1, l);
+			else wc_logw4<true>(cur, s_pt, min_diff2, v[h], i, i1, l);
 #pragma unroll
-			for (int j = 0; j < 4; j++) if (i + j < i1) w[i + j] = e[j];
+			for (int j = 0; j < 4; j++)
+			{
+				const float a = l[j] + add;
+				e[j] = (a < -88.f) ? 0.f : expf(a);                                // helper.cuh:57-66 (elements beyond i1: l = lowest -> 0)
+				const int rel = (int) (i - i0) + j;
+				if (e[j] > bv && (full || i + j < i1)) { bv = e[j]; brel = rel; }
+				// zero weights take part as (bin 0, significand 0): no divergence around the warp-wide match
+				const unsigned bits = __float_as_uint(e[j]);
+				const int bin = (int) (bits >> WC_SHIFT);
+				// significand as an integer (normal: implicit one; denormal: exponent field 0)
+				const unsigned sig = (bits >> 23) ? ((bits & 0x7fffffu) | 0x800000u) : (bits & 0x7fffffu);
+				nz_count += bits != 0u;
+				const unsigned peers = __match_any_sync(0xffffffffu, bin);
+				const unsigned ssum = __reduce_add_sync(peers, sig);               // <= 32 * 2^24
+				if (ssum && lane == __ffs(peers) - 1)
+				{
+					atomicAdd(h_lo + bin, ssum & 0xffffu); atomicAdd(h_hi + bin, ssum >> 16);
+					if (COUNTS) atomicAdd(h_c + bin, (unsigned) __popc(peers));
+				}
+			}
+			if (full || (vec && i + 3 < i1)) *(float4 *) (w + i) = make_float4(e[0], e[1], e[2], e[3]);
+			else
+#pragma unroll
+				for (int j = 0; j < 4; j++) if (i + j < i1) w[i + j] = e[j];
+			cur.advance();
+		}
 	}
 	float ov; long long oi;
-	block_argmax(bv, bi, am, ov, oi);
+	block_argmax(bv, brel == 0x7fffffff ? 0x7fffffffffffffffLL : i0 + brel, am, ov, oi);
 	if (threadIdx.x == 0) { A.pav[(size_t) p * A.nchunk + c] = ov; A.pai[(size_t) p * A.nchunk + c] = oi; }
+	nz_count = (int) __reduce_add_sync(0xffffffffu, (unsigned) nz_count);
+	if (lane == 0 && nz_count) atomicAdd(&s_nz, nz_count);
 	__syncthreads();
+	if (threadIdx.x == 0 && s_nz) atomicAdd((unsigned long long *) (A.ntot + 2 * p), (unsigned long long) s_nz);
 	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS)
-		if (h_c[i]) { atomicAdd(A.hsum + (size_t) p * WC_BINS + i, h_s[i]); atomicAdd(A.hcnt + (size_t) p * WC_BINS + i, h_c[i]); }
+		if (h_lo[i] | h_hi[i])
+		{
+			atomicAdd(A.hsum + (size_t) p * WC_BINS + i, ((unsigned long long) h_hi[i] << 16) + h_lo[i]);
+			if (COUNTS) atomicAdd(A.hcnt + (size_t) p * WC_BINS + i, (int) h_c[i]);
+		}
 }
 
 // exact mass of histogram bin b: integer significand sum times 2^(exponent - 23)  (denormal bins: exponent field 0 -> 2^-149)
@@ -426,10 +492,15 @@ k_wc_pick(WcArgs A, RbModelDev M)
 	__shared__ double hs[WC_BINS];
 	const int *hc = A.hcnt + (size_t) p * WC_BINS;
 	double t = 0.; long long cnt = 0;
-	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS) { hs[i] = wc_bin_mass(A.hsum[(size_t) p * WC_BINS + i], i); t += hs[i]; cnt += hc[i]; }
+	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS)
+	{
+		hs[i] = wc_bin_mass(A.hsum[(size_t) p * WC_BINS + i], i); t += hs[i];      // a non-empty bin has a positive mass
+		if (A.counts) cnt += hc[i];
+	}
 	t = block_sum(t, dred);
 	cnt = block_sum(cnt, lred);
 	if (threadIdx.x != 0) return;
+	if (!A.counts) cnt = A.ntot[2 * p];
 	RbPartState *st = A.states + p;
 	{
 		float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
@@ -450,14 +521,14 @@ k_wc_pick(WcArgs A, RbModelDev M)
 		double cum = 0.; long long cc = 0; int sel = -1;
 		for (int b = 0; b < WC_BINS; b++)
 		{
-			if (hc[b] > 0 && cum + hs[b] > pk.thr) { sel = b; break; }
-			cum += hs[b]; cc += hc[b];
+			if (hs[b] > 0. && cum + hs[b] > pk.thr) { sel = b; break; }
+			cum += hs[b]; if (A.counts) cc += hc[b];
 		}
 		if (sel >= 0) { pk.mode = 0; pk.bin = sel; pk.base = cum; pk.cbelow = cc; }
 		else
 		{
 			// nothing crosses the threshold: the reference's search leaves idx = 0 -> sorted[0], the smallest weight
-			int b = 0; while (hc[b] == 0) b++;
+			int b = 0; while (hs[b] <= 0.) b++;
 			pk.mode = 1; pk.bin = b; pk.base = 0.; pk.cbelow = 0;
 		}
 		if (M.maximum_significants > 0 && cnt > M.maximum_significants)            // :2301-2306 candidate
@@ -487,6 +558,7 @@ k_wc_gather(WcArgs A)
 	const long long i0 = (long long) c * WC_CHUNK, i1 = min(A.n, i0 + WC_CHUNK);
 	const unsigned ba = (unsigned) pk.bin, br = pk.bin_r >= 0 ? (unsigned) pk.bin_r : 0xffffffffu;
 	const int RUN = 8;
+	int kb = 0;                                                   // non-zero weights below the picked bin (when no per-bin counts are kept)
 	for (long long t0 = i0; t0 < i1; t0 += (long long) WC_THREADS * RUN)
 	{
 		float v[RUN]; int ka = 0, kr = 0;
@@ -497,6 +569,7 @@ k_wc_gather(WcArgs A)
 			v[j] = (b + j < i1) ? w[b + j] : 0.f;
 			const unsigned bin = __float_as_uint(v[j]) >> WC_SHIFT;
 			ka += (v[j] > 0.f && bin == ba); kr += (v[j] > 0.f && bin == br);
+			kb += (v[j] > 0.f && bin < ba);
 		}
 		if (!__syncthreads_or(ka | kr)) continue;
 		s_scan[0][threadIdx.x] = ka; s_scan[1][threadIdx.x] = kr;
@@ -523,6 +596,12 @@ k_wc_gather(WcArgs A)
 			if (v[j] > 0.f && bin == br) { if (pr < A.cap) A.compact_r[(size_t) p * A.cap + pr] = v[j]; pr++; }
 		}
 		__syncthreads();
+	}
+	if (!A.counts)
+	{
+		__shared__ int s_red[32];
+		kb = block_sum(kb, s_red);
+		if (threadIdx.x == 0 && kb) atomicAdd((unsigned long long *) (A.ntot + 2 * p + 1), (unsigned long long) kb);
 	}
 }
 
@@ -602,7 +681,8 @@ k_wc_finish(WcArgs A, RbModelDev M)
 		return;
 	}
 	float sig_w; long long thr_idx;
-	radix_descend_seeded(A.compact_a + (size_t) p * A.cap, na, pk.mode == 1, pk.thr, 0, pk.base, pk.cbelow, sm);
+	const long long cbelow = A.counts ? pk.cbelow : (pk.mode == 1 ? 0 : A.ntot[2 * p + 1]);
+	radix_descend_seeded(A.compact_a + (size_t) p * A.cap, na, pk.mode == 1, pk.thr, 0, pk.base, cbelow, sm);
 	__syncthreads();
 	if (pk.mode == 1) { thr_idx = 0; sig_w = __uint_as_float(sm.prefix); }
 	else
@@ -647,22 +727,29 @@ static int weights_coarse_large(rb_ctx *ctx, PoolSlot &s, long long n)
 	RB_CHECK(ctx->wc_buf[0].ensure(np * 4)); RB_CHECK(ctx->wc_buf[1].ensure(np * 4)); RB_CHECK(ctx->wc_buf[2].ensure(np * 8));
 	RB_CHECK(ctx->wc_buf[3].ensure((size_t) P * WC_BINS * 8)); RB_CHECK(ctx->wc_buf[4].ensure((size_t) P * WC_BINS * 4));
 	RB_CHECK(ctx->wc_buf[5].ensure((size_t) P * sizeof(WcPick)));
-	RB_CHECK(ctx->wc_buf[6].ensure((size_t) P * 16));
+	RB_CHECK(ctx->wc_buf[6].ensure((size_t) P * 16)); RB_CHECK(ctx->wc_buf[7].ensure((size_t) P * 16));
 	RB_CHECK(ctx->wc_buf[8].ensure((size_t) P * A.cap * 4));
 	RB_CHECK(ctx->wc_buf[9].ensure(maxsig ? (size_t) P * A.cap * 4 : 16));
 	A.pmax = ctx->wc_buf[0].as<float>(); A.pav = ctx->wc_buf[1].as<float>(); A.pai = ctx->wc_buf[2].as<long long>();
 	A.hsum = ctx->wc_buf[3].as<unsigned long long>(); A.hcnt = ctx->wc_buf[4].as<int>(); A.pick = ctx->wc_buf[5].as<WcPick>();
-	A.gtot = ctx->wc_buf[6].as<long long>();
+	A.gtot = ctx->wc_buf[6].as<long long>(); A.ntot = ctx->wc_buf[7].as<long long>(); A.counts = maxsig ? 1 : 0;
 	A.compact_a = ctx->wc_buf[8].as<float>(); A.compact_r = ctx->wc_buf[9].as<float>();
 	RB_CUDA(cudaMemsetAsync(A.hsum, 0, (size_t) P * WC_BINS * 8, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(A.hcnt, 0, (size_t) P * WC_BINS * 4, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(A.gtot, 0, (size_t) P * 16, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(A.ntot, 0, (size_t) P * 16, ctx->stream));
 	dim3 grid(A.nchunk, P);
-	const size_t hsm = (size_t) WC_BINS * 12;
 	static bool configured = false;
-	if (!configured) { RB_CUDA(cudaFuncSetAttribute(k_wc_exp, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) hsm)); configured = true; }
+	if (!configured)
+	{
+		RB_CUDA(cudaFuncSetAttribute(k_wc_exp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WC_BINS * 12));
+		RB_CUDA(cudaFuncSetAttribute(k_wc_exp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WC_BINS * 8));
+		configured = true;
+	}
 	k_wc_max<<<grid, WC_THREADS, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
-	k_wc_exp<<<grid, WC_THREADS, hsm, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
+	if (maxsig) k_wc_exp<true><<<grid, WC_THREADS, WC_BINS * 12, ctx->stream>>>(A);
+	else k_wc_exp<false><<<grid, WC_THREADS, WC_BINS * 8, ctx->stream>>>(A);
+	RB_LAUNCH_CHECK(ctx);
 	k_wc_pick<<<P, WC_THREADS, 0, ctx->stream>>>(A, ctx->d_model); RB_LAUNCH_CHECK(ctx);
 	k_wc_gather<<<grid, WC_THREADS, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
 	k_wc_finish<<<P, WT_THREADS, 0, ctx->stream>>>(A, ctx->d_model); RB_LAUNCH_CHECK(ctx);

@@ -286,6 +286,35 @@ int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *raw, float *p
 int rb_pool_download(rb_ctx *ctx, int slot, float *Fimg, float *Fimg_nomask, float *Fctf, double *highres_Xi2);
 
 /* ------------------------------------------------------------------------------------------------
+ * Particle image feed: MRC stacks -> page-locked pool buffers, ahead of the GPU.
+ * Replaces the image half of MlOptimiser::getMetaAndImageDataSubset (src/ml_optimiser.cpp:10285-10406)
+ * and Image<T>::readMRC (src/rwMRC.h:140-283).  Host-only code, usable without a context.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rb_mrc rb_mrc;
+/* open an .mrc / .mrcs file: modes 0 (signed 8-bit), 1, 2, 6, 12; byte-swapped files are detected like rwMRC.h:149 */
+int rb_mrc_open(const char *path, rb_mrc **out);
+/* pixel_size = cell / sampling along x (rwMRC.h:238), 0 when the header does not say; any pointer may be NULL */
+int rb_mrc_info(const rb_mrc *m, int *nx, int *ny, int *nz, int *mode, float *pixel_size);
+/* images `indices[i]` (0-BASED; rlnImageName counts from 1) -> dst[i][ny][nx] as float */
+int rb_mrc_read_images(const rb_mrc *m, const long long *indices, int count, float *dst);
+void rb_mrc_close(rb_mrc *m);
+/* float32 (mode 2) stack / volume with the header fields of Image<T>::writeMRC (rwMRC.h:286-530) */
+int rb_mrc_write(const char *path, const float *data, int nx, int ny, int nz, float pixel_size);
+
+typedef struct rb_feed rb_feed;
+/* `depth` staging buffers of max_particles images of image_size^2 floats (page-locked when a CUDA device is present),
+ * `n_threads` reader threads */
+int rb_feed_create(int image_size, int max_particles, int depth, int n_threads, rb_feed **out);
+/* queue one pool: particle i is image index[i] (0-based) of stack paths[i]; fails with RB_ERR_STATE when every
+ * staging buffer is in use */
+int rb_feed_submit(rb_feed *f, const char *const *paths, const long long *index, int n_particles, int *ticket);
+/* block until the pool is read; *images = [n_particles][n][n], valid until rb_feed_release(ticket) - pass it as
+ * rb_raw_particles.images */
+int rb_feed_wait(rb_feed *f, int ticket, const float **images);
+int rb_feed_release(rb_feed *f, int ticket);
+void rb_feed_destroy(rb_feed *f);
+
+/* ------------------------------------------------------------------------------------------------
  * Stage-level entry points (kernel-granularity twins of AccUtilities::* / run*Kernel,
  * src/acc/utilities.h:946-1620, acc_helper_functions_impl.h).  Used by the parity tests and usable
  * by an adapter that keeps the reference's per-particle driver.

@@ -139,6 +139,16 @@ PROTOTYPES = {
     "rb_pool_upload": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_particles)]),
     "rb_pool_prepare": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_raw_particles), c_float_p]),
     "rb_pool_download": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p, c_double_p]),
+    "rb_mrc_open": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "rb_mrc_info": (C.c_int, [C.c_void_p] + [C.POINTER(C.c_int)] * 4 + [c_float_p]),
+    "rb_mrc_read_images": (C.c_int, [C.c_void_p, C.POINTER(C.c_longlong), C.c_int, c_float_p]),
+    "rb_mrc_close": (None, [C.c_void_p]),
+    "rb_mrc_write": (C.c_int, [C.c_char_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_float]),
+    "rb_feed_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "rb_feed_submit": (C.c_int, [C.c_void_p, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong), C.c_int, C.POINTER(C.c_int)]),
+    "rb_feed_wait": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(c_float_p)]),
+    "rb_feed_release": (C.c_int, [C.c_void_p, C.c_int]),
+    "rb_feed_destroy": (None, [C.c_void_p]),
     "rb_estep_slot": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_pool_out), C.c_uint]),
     "rb_estep_slot_nocopy": (C.c_int, [C.c_void_p, C.c_int, C.c_uint]),
     "rb_estep_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_pool_out)]),

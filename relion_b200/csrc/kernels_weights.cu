@@ -380,8 +380,8 @@ k_wc_max(WcArgs A)
 }
 
 // Histogram words per bin in shared memory: 32-bit counters only (a 64-bit shared atomic add compiles to a compare-and-swap
-// spin loop).  Lanes of a warp that hit the same bin are combined first (match.any + redux), then one lane adds the low 16
-// bits and the rest of the combined significand sum to two words (each stays below 2^31 for a chunk of 2^15 elements).
+// spin loop).  Lanes of a warp that hit the same bin are combined first (match.any + redux), then one lane adds the combined
+// significand sum to a 32-bit word and counts its (rare) carries in a second one.
 // COUNTS: also the number of elements per bin (only the --maxsig rank search needs it; otherwise the total number of
 // non-zero weights comes from the ballots here and the count below the picked bin from k_wc_gather).
 template <bool COUNTS>
@@ -389,8 +389,8 @@ __global__ void __launch_bounds__(WC_THREADS)
 k_wc_exp(WcArgs A)
 {
 	extern __shared__ unsigned char wc_smem[];
-	unsigned *h_lo = (unsigned *) wc_smem;                       // [WC_BINS] sum of (combined significand sums & 0xffff)
-	unsigned *h_hi = h_lo + WC_BINS;                             // [WC_BINS] sum of (combined significand sums >> 16)
+	unsigned *h_lo = (unsigned *) wc_smem;                       // [WC_BINS] low word of the significand sum
+	unsigned *h_hi = h_lo + WC_BINS;                             // [WC_BINS] its carries
 	unsigned *h_c = h_hi + WC_BINS;                              // [WC_BINS] count (COUNTS)
 	__shared__ ArgMaxSmem am;
 	__shared__ float s_wmax;
@@ -449,7 +449,8 @@ k_wc_exp(WcArgs A)
 				const unsigned ssum = __reduce_add_sync(peers, sig);               // <= 32 * 2^24
 				if (ssum && lane == __ffs(peers) - 1)
 				{
-					atomicAdd(h_lo + bin, ssum & 0xffffu); atomicAdd(h_hi + bin, ssum >> 16);
+					const unsigned old = atomicAdd(h_lo + bin, ssum);              // wraps at most 2^7 times per chunk
+					if (old + ssum < old) atomicAdd(h_hi + bin, 1u);               // ... and the carries are counted
 					if (COUNTS) atomicAdd(h_c + bin, (unsigned) __popc(peers));
 				}
 			}
@@ -470,7 +471,7 @@ k_wc_exp(WcArgs A)
 	for (int i = threadIdx.x; i < WC_BINS; i += WC_THREADS)
 		if (h_lo[i] | h_hi[i])
 		{
-			atomicAdd(A.hsum + (size_t) p * WC_BINS + i, ((unsigned long long) h_hi[i] << 16) + h_lo[i]);
+			atomicAdd(A.hsum + (size_t) p * WC_BINS + i, ((unsigned long long) h_hi[i] << 32) + h_lo[i]);
 			if (COUNTS) atomicAdd(A.hcnt + (size_t) p * WC_BINS + i, (int) h_c[i]);
 		}
 }

@@ -406,6 +406,64 @@ def test_pool_prepare_matches_reference_algorithm(device, ori, cur, local):
     np.testing.assert_allclose(got.particles["dLL_nolog"], want.particles["dLL_nolog"], rtol=1e-4)
 
 
+def test_estep_from_star_and_mrc_files_equals_in_memory_pool(device, tmp_path):
+    """particles written as two MRC stacks + a RELION 3.1 STAR file, streamed back through the native
+    feed (rb_feed_*) and ParticleSet.pool, must give the same prepared slot and the same E-step result as the in-memory
+    RawParticlePool they were written from - bit for bit, the inputs are identical."""
+    from relion_b200 import particle_io, star
+    from relion_b200.workload import raw_pool_from
+    wl = make_workload(ori_size=32, current_size=24, healpix_order=1, n_particles=10, seed=91, snr=0.3, nr_groups=1)
+    raw = raw_pool_from(wl, seed=5)
+    raw.norm_factor = np.round(raw.norm_factor, 3)                                      # survive the text round trip exactly
+    raw.old_offset = np.round(raw.old_offset, 2)
+    P, n, ps = raw.n_particles, wl.model.ori_size, wl.model.pixel_size
+    images = np.asarray(raw.images, np.float32)
+    half = P // 2
+    particle_io.write_mrc(str(tmp_path / "micA.mrcs"), images[:half], ps)
+    particle_io.write_mrc(str(tmp_path / "micB.mrcs"), images[half:], ps)
+    optics = star.StarTable("optics", {"rlnOpticsGroupName": ["opticsGroup1"], "rlnOpticsGroup": [1], "rlnVoltage": [300.0],
+                                       "rlnSphericalAberration": [2.7], "rlnAmplitudeContrast": [0.1], "rlnImagePixelSize": [float(ps)],
+                                       "rlnImageSize": [n], "rlnImageDimensionality": [2]})
+    avg_norm = 0.97
+    names = ["%06d@%s" % ((i if i < half else i - half) + 1, "micA.mrcs" if i < half else "micB.mrcs") for i in range(P)]
+    parts = star.StarTable("particles", {
+        "rlnImageName": names, "rlnGroupName": ["group1"] * P, "rlnOpticsGroup": [1] * P,
+        "rlnDefocusU": [float(v) for v in raw.ctf_defU], "rlnDefocusV": [float(v) for v in raw.ctf_defV],
+        "rlnDefocusAngle": [float(v) for v in raw.ctf_defAngle],
+        "rlnOriginXAngst": [float(v) * ps for v in raw.old_offset[:, 0]], "rlnOriginYAngst": [float(v) * ps for v in raw.old_offset[:, 1]],
+        "rlnNormCorrection": [avg_norm / float(v) for v in raw.norm_factor]})
+    star.write_star(str(tmp_path / "particles.star"), [optics, parts])
+    pset = particle_io.ParticleSet.read(str(tmp_path / "particles.star"))
+    assert len(pset) == P and pset.image_size() == n
+    _setup(device, wl)
+    device.pool_prepare(0, raw)
+    want_prep = device.pool_download(0, wl.model.current_size)
+    want = device.estep_slot(0)
+    for k in range(wl.model.nr_classes):
+        device.bp_clear(k)
+    feed = particle_io.ParticleFeed(image_size=n, max_particles=P, depth=2, n_threads=2)
+    chunks = list(pset.stream(feed, pool_size=P, avg_norm_correction=avg_norm, mask_radius=raw.mask_radius, width_mask_edge=raw.width_mask_edge))
+    assert len(chunks) == 1
+    # the generator released the buffer when it finished; stream again and use the pool while it is valid
+    for ids, pool in pset.stream(feed, pool_size=P, avg_norm_correction=avg_norm, mask_radius=raw.mask_radius, width_mask_edge=raw.width_mask_edge):
+        np.testing.assert_array_equal(np.asarray(pool.images), images[ids])
+        np.testing.assert_allclose(pool.norm_factor, raw.norm_factor[ids], rtol=1e-5)
+        np.testing.assert_allclose(pool.old_offset, raw.old_offset[ids], atol=1e-5)
+        np.testing.assert_allclose(pool.ctf_defU, raw.ctf_defU[ids], atol=1e-5)
+        # remove the last-digit rounding of the text file: from here on the inputs are identical
+        pool.norm_factor, pool.old_offset = raw.norm_factor[ids], raw.old_offset[ids]
+        pool.ctf_defU, pool.ctf_defV, pool.ctf_defAngle = raw.ctf_defU[ids], raw.ctf_defV[ids], raw.ctf_defAngle[ids]
+        device.pool_prepare(1, pool)
+        got_prep = device.pool_download(1, wl.model.current_size)
+        got = device.estep_slot(1)
+    feed.close()
+    for a, b in zip(got_prep, want_prep):
+        np.testing.assert_array_equal(a, b)
+    assert np.array_equal(got.particles["best_ihidden_over"], want.particles["best_ihidden_over"])
+    np.testing.assert_array_equal(got.particles["dLL_nolog"], want.particles["dLL_nolog"])
+    np.testing.assert_allclose(got.wsum_sigma2_noise, want.wsum_sigma2_noise, rtol=2e-6)     # float atomics: order of the adds
+
+
 @pytest.mark.parametrize("ori,cur,with_tau2", [(32, 32, False), (32, 32, True), (40, 28, True)])
 def test_reconstruct_on_device(device, ori, cur, with_tau2):
     """SURVEY 8f row 2: rb_reconstruct (BackProjector::reconstruct, skip_gridding, + windowToOridimRealSpace +

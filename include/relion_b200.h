@@ -124,6 +124,14 @@ int rb_bp_symmetrise(rb_ctx *ctx, int iclass, const double *R, int nsym);
 int rb_reconstruct(rb_ctx *ctx, int iclass, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map,
                    float *vol_out);
 
+/* BackProjector::updateSSNRarrays (src/backprojector.cpp:1041-1204) on accumulator iclass (2D or 3D): sigma2 = shell
+ * average of the inverse noise power of the reconstruction; tau2 recomputed from `fsc` (gold-standard FSC between the
+ * half-maps) when update_tau2_with_fsc, else kept; data_vs_prior and fourier_coverage for model.star.  All spectra are
+ * [ori_size/2 + 1] doubles; fsc / avgctf2 may be NULL.  Call it on the all-reduced accumulator, before rb_reconstruct. */
+int rb_update_ssnr(rb_ctx *ctx, int iclass, int ori_size, double tau2_fudge, double *tau2_io, double *sigma2_out,
+                   double *data_vs_prior_out, double *fourier_coverage_out, const double *fsc, const double *avgctf2,
+                   int update_tau2_with_fsc, int is_whole_instead_of_half);
+
 /* ------------------------------------------------------------------------------------------------
  * Sampling tables for this iteration (outputs of HealpixSampling, src/healpix_sampling.cpp:
  * getDirection/getPsiAngle :1662-1700, getOrientations :1832, getTranslationsInPixel :1724).

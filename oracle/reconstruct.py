@@ -173,3 +173,59 @@ def fsc(map1: np.ndarray, map2: np.ndarray) -> np.ndarray:
     d1 = np.bincount(idx[ok], weights=(np.abs(F1) ** 2)[ok], minlength=n // 2 + 1)
     d2 = np.bincount(idx[ok], weights=(np.abs(F2) ** 2)[ok], minlength=n // 2 + 1)
     return num / np.sqrt(np.maximum(d1 * d2, 1e-300))
+
+
+def update_ssnr(weight: np.ndarray, ori_size: int, r_max: int, padding_factor: float, tau2_fudge: float, tau2: np.ndarray,
+                fsc: np.ndarray | None = None, avgctf2: np.ndarray | None = None, update_tau2_with_fsc: bool = False,
+                is_whole_instead_of_half: bool = False):
+    """BackProjector::updateSSNRarrays (src/backprojector.cpp:1041-1204) on a centred weight array [Z, Y, X] (3D) or
+    [Y, X] (2D): returns (tau2, sigma2, data_vs_prior, fourier_coverage), each [ori_size/2 + 1] float64."""
+    w = np.asarray(weight, np.float64)
+    ns = ori_size // 2 + 1
+    rr = int(math.floor(r_max * padding_factor + 0.5))
+    max_r2 = rr * rr
+    if w.ndim == 3:
+        Z, Y, X = w.shape
+        kz, ky, kx = np.meshgrid(np.arange(Z) - (Z - 1) // 2, np.arange(Y) - (Y - 1) // 2, np.arange(X), indexing="ij")
+        r2 = kz * kz + ky * ky + kx * kx
+        oc = padding_factor ** 3
+    else:
+        Y, X = w.shape
+        ky, kx = np.meshgrid(np.arange(Y) - (Y - 1) // 2, np.arange(X), indexing="ij")
+        r2 = ky * ky + kx * kx
+        oc = padding_factor ** 2
+    inside = r2 < max_r2
+    ires = np.floor(np.sqrt(r2[inside].astype(np.float64)) / padding_factor + 0.5).astype(np.int64)      # ROUND
+    wi = w[inside]
+    s = np.bincount(ires, weights=oc * wi, minlength=ns)[:ns]
+    counter = np.bincount(ires, minlength=ns)[:ns].astype(np.float64)
+    if np.any((s > 0) & (s <= 1e-20)):
+        raise ValueError("unexpectedly small, yet non-zero sigma2 value")
+    sigma2 = np.where(s > 1e-20, counter / np.where(s > 1e-20, s, 1.0), 0.0)
+    tau2 = np.array(tau2, np.float64, copy=True)
+    dvp = np.zeros(ns)
+    if update_tau2_with_fsc:
+        f = np.maximum(0.001, np.asarray(fsc, np.float64))
+        if is_whole_instead_of_half:
+            f = np.sqrt(2.0 * f / (f + 1.0))
+        f = np.minimum(0.999, f)
+        ssnr = f / (1.0 - f) * tau2_fudge
+        tau2 = ssnr * sigma2
+        dvp = ssnr.copy()
+    if np.any(tau2 < 0):
+        raise ValueError("Negative values encountered for tau2 spectrum")
+    t = tau2[ires]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        invtau2 = np.where(t > 0, 1.0 / (oc * tau2_fudge * np.where(t > 0, t, 1.0)), 1.0 / (0.001 * wi))
+        if avgctf2 is not None:
+            a = np.asarray(avgctf2, np.float64)[ires]
+            invtau2 = np.where((t > 0) & (a > 0), invtau2 / np.where(a > 0, a, 1.0), invtau2)
+        ratio = wi / invtau2
+    ratio = np.where(np.isnan(ratio), 0.0, ratio)              # weight 0 with tau2 0: 0 / inf
+    cov = np.bincount(ires, weights=(ratio >= 1.0).astype(np.float64), minlength=ns)[:ns]
+    if not update_tau2_with_fsc:
+        dsum = np.bincount(ires, weights=ratio, minlength=ns)[:ns]
+        idx = np.arange(ns)
+        dvp = np.where(idx > r_max, 0.0, np.where(counter < 0.001, 999.0, dsum / np.maximum(counter, 1e-300)))
+    cov = np.where(counter > 0, cov / np.maximum(counter, 1.0), cov)
+    return tau2, sigma2, dvp, cov

@@ -347,6 +347,18 @@ extern "C" int rb_reconstruct(rb_ctx *ctx, int k, int ori_size, const double *ta
 	return RB_OK;
 }
 
+// BackProjector::updateSSNRarrays on the device accumulator
+extern "C" int rb_update_ssnr(rb_ctx *ctx, int k, int ori_size, double tau2_fudge, double *tau2_io, double *sigma2_out,
+                              double *data_vs_prior_out, double *fourier_coverage_out, const double *fsc, const double *avgctf2,
+                              int update_tau2_with_fsc, int is_whole_instead_of_half)
+{
+	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_update_ssnr: accumulator %d not initialised", k);
+	RB_ARG(tau2_io && sigma2_out && data_vs_prior_out && fourier_coverage_out && ori_size > 0, "rb_update_ssnr: NULL spectrum");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	return rbk_update_ssnr(ctx, ctx->bp[k], ctx->bp_2d[k], ori_size, tau2_fudge, tau2_io, sigma2_out, data_vs_prior_out, fourier_coverage_out,
+	                       fsc, avgctf2, update_tau2_with_fsc != 0, is_whole_instead_of_half != 0);
+}
+
 extern "C" int rb_bp_device_buffer(rb_ctx *ctx, int k, void **dptr, size_t *n_floats)
 {
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_device_buffer: accumulator %d not initialised", k);

@@ -194,6 +194,119 @@ int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// BackProjector::updateSSNRarrays (/root/reference/src/backprojector.cpp:1041-1204): the spectra the M-step needs next to
+// the map - sigma2 (shell average of the inverse noise power in the reconstruction), tau2 (from the FSC between the
+// half-maps when asked), data_vs_prior and fourier_coverage.  Two passes over the weight plane of the accumulator, shell
+// sums in fp64; the handful of per-shell formulas in between run on the host.
+// ---------------------------------------------------------------------------------------------
+struct SsnrArgs {
+	const float4 *acc; int mdlX, mdlY, mdlZ, initY, initZ;
+	long long max_r2; float pf; int nshell;
+	double oc, tau2_fudge;
+	const double *tau2, *avgctf2;   // pass 2
+	double *sum_a, *sum_b, *cnt;    // pass 1: sum of oc * w, -, count; pass 2: sum of w / invtau2, coverage count, count
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(256)
+k_ssnr_pass(SsnrArgs A)
+{
+	__shared__ double s_a[1024], s_b[1024], s_c[1024];
+	for (int i = threadIdx.x; i < A.nshell; i += blockDim.x) { s_a[i] = 0.; s_b[i] = 0.; s_c[i] = 0.; }
+	__syncthreads();
+	const size_t n = (size_t) A.mdlZ * A.mdlY * A.mdlX;
+	for (size_t idx = blockIdx.x * (size_t) blockDim.x + threadIdx.x; idx < n; idx += (size_t) gridDim.x * blockDim.x)
+	{
+		const int j = (int) (idx % A.mdlX), i = (int) ((idx / A.mdlX) % A.mdlY) + A.initY;
+		const int k = A.mdlZ > 1 ? (int) (idx / ((size_t) A.mdlX * A.mdlY)) + A.initZ : 0;
+		const long long r2 = (long long) k * k + (long long) i * i + (long long) j * j;
+		if (r2 >= A.max_r2) continue;
+		const int ires = (int) floor(sqrt((double) r2) / (double) A.pf + 0.5);
+		if (ires >= A.nshell) continue;
+		const double w = (double) __ldg(A.acc + idx).z;
+		if (PASS == 1) atomicAdd(&s_a[ires], A.oc * w);
+		else
+		{
+			const double t = A.tau2[ires];
+			double invtau2;
+			if (t > 0.)
+			{
+				invtau2 = 1. / (A.oc * A.tau2_fudge * t);
+				if (A.avgctf2 && A.avgctf2[ires] > 0.) invtau2 *= 1. / A.avgctf2[ires];
+			}
+			else invtau2 = 1. / (0.001 * w);                  // tau2 == 0: "use small value instead" (:1153-1157)
+			const double ratio = w / invtau2;                  // w == 0 with tau2 == 0: 0 / inf = 0
+			if (ratio == ratio) atomicAdd(&s_a[ires], ratio);
+			if (ratio >= 1.) atomicAdd(&s_b[ires], 1.);
+		}
+		atomicAdd(&s_c[ires], 1.);
+	}
+	__syncthreads();
+	for (int i = threadIdx.x; i < A.nshell; i += blockDim.x)
+		if (s_c[i] > 0.) { atomicAdd(A.sum_a + i, s_a[i]); atomicAdd(A.sum_b + i, s_b[i]); atomicAdd(A.cnt + i, s_c[i]); }
+}
+
+int rbk_update_ssnr(rb_ctx *ctx, const RbBackprojector &bp, bool is_2d, int ori, double tau2_fudge, double *tau2_io, double *sigma2_out,
+                    double *dvp_out, double *cov_out, const double *fsc, const double *avgctf2, bool update_with_fsc, bool whole)
+{
+	const int ns = ori / 2 + 1;
+	if (ns > 1024) { rb_set_error("rb_update_ssnr: ori_size %d too large", ori); return RB_ERR_ARG; }
+	if (update_with_fsc && !fsc) { rb_set_error("rb_update_ssnr: update_tau2_with_fsc needs an fsc spectrum"); return RB_ERR_ARG; }
+	SsnrArgs A;
+	memset(&A, 0, sizeof(A));
+	A.acc = bp.vol; A.mdlX = bp.mdlX; A.mdlY = bp.mdlY; A.mdlZ = is_2d ? 1 : bp.mdlZ; A.initY = bp.mdlInitY; A.initZ = bp.mdlInitZ;
+	const long long rr = (long long) floor((double) bp.maxR * (double) bp.padding_factor + 0.5);
+	A.max_r2 = rr * rr; A.pf = bp.padding_factor; A.nshell = ns;
+	A.oc = is_2d ? (double) bp.padding_factor * bp.padding_factor : (double) bp.padding_factor * bp.padding_factor * bp.padding_factor;
+	A.tau2_fudge = tau2_fudge;
+	DevBuf &b = ctx->recon_buf[2];
+	RB_CHECK(b.ensure((size_t) 5 * 1024 * 8));
+	double *d = b.as<double>();
+	A.sum_a = d; A.sum_b = d + 1024; A.cnt = d + 2048;
+	double *d_tau2 = d + 3072, *d_ctf2 = d + 4096;
+	std::vector<double> h((size_t) 3 * 1024);
+	RB_CUDA(cudaMemsetAsync(d, 0, (size_t) 3 * 1024 * 8, ctx->stream));
+	k_ssnr_pass<1><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
+	RB_CUDA(cudaMemcpyAsync(h.data(), d, (size_t) 3 * 1024 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	std::vector<double> sigma2(ns), tau2(tau2_io, tau2_io + ns), dvp(ns, 0.), counter(h.begin() + 2048, h.begin() + 2048 + ns);
+	for (int i = 0; i < ns; i++)
+	{
+		const double s = h[i];
+		if (s > 1e-20) sigma2[i] = counter[i] / s;
+		else if (s == 0.) sigma2[i] = 0.;
+		else { rb_set_error("rb_update_ssnr: unexpectedly small, yet non-zero sigma2 value %g in shell %d", s, i); return RB_ERR_ARG; }
+	}
+	if (update_with_fsc)
+		for (int i = 0; i < ns; i++)
+		{
+			double f = std::max(0.001, fsc[i]);
+			if (whole) f = sqrt(2. * f / (f + 1.));
+			f = std::min(0.999, f);
+			const double ssnr = f / (1. - f) * tau2_fudge;
+			tau2[i] = ssnr * sigma2[i];
+			dvp[i] = ssnr;
+		}
+	for (int i = 0; i < ns; i++)
+		if (tau2[i] < 0.) { rb_set_error("rb_update_ssnr: negative value %g in the tau2 spectrum (shell %d)", tau2[i], i); return RB_ERR_ARG; }
+	RB_CUDA(cudaMemcpyAsync(d_tau2, tau2.data(), (size_t) ns * 8, cudaMemcpyHostToDevice, ctx->stream));
+	if (avgctf2) RB_CUDA(cudaMemcpyAsync(d_ctf2, avgctf2, (size_t) ns * 8, cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(d, 0, (size_t) 3 * 1024 * 8, ctx->stream));
+	A.tau2 = d_tau2; A.avgctf2 = avgctf2 ? d_ctf2 : nullptr;
+	k_ssnr_pass<2><<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
+	RB_CUDA(cudaMemcpyAsync(h.data(), d, (size_t) 3 * 1024 * 8, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	for (int i = 0; i < ns; i++)
+	{
+		const double c = h[2048 + i];
+		if (!update_with_fsc) dvp[i] = i > bp.maxR ? 0. : (c < 0.001 ? 999. : h[i] / c);
+		cov_out[i] = c > 0. ? h[1024 + i] / c : h[1024 + i];
+		tau2_io[i] = tau2[i]; sigma2_out[i] = sigma2[i]; dvp_out[i] = dvp[i];
+	}
+	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // The inverse direction (SURVEY.md §8f "next" row 3): Projector::computeFourierTransformMap
 // (/root/reference/src/projector.cpp:116-592) for a 3D reference used with 2D images: gridding correction (divide by
 // sinc^2, :595-628), zero-padding to pad*ori, forward FFT (normalised), CenterFFTbySign, window to the projector's

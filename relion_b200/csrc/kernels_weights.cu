@@ -321,34 +321,55 @@ struct WcCursor {
 	__device__ __forceinline__ float prior(int o) const { return pz[o] ? RB_LOWEST : po[o]; }
 };
 
-// log-weights of the four elements starting at the cursor (elements at or beyond i1 get RB_LOWEST when CHECK)
+// log-weights of the four elements starting at the cursor (elements at or beyond i1 get RB_LOWEST when CHECK).
+// s_pt holds the translation priors twice over (index it + j needs no wrap), RB_LOWEST where the prior is zero: with a
+// lowest orientation or translation prior the sum stays at (or below) RB_LOWEST, so one max() replaces the tests of
+// cuda_kernel_weights_exponent_coarse (helper.cuh:39-42) and valid elements see exactly its arithmetic.
 template <bool CHECK>
 __device__ __forceinline__ void wc_logw4(const WcCursor &cur, const float *s_pt, float min_diff2, const float (&v)[4], long long i, long long i1,
                                          float (&l)[4])
 {
+	if (cur.T >= 4)
+	{
+		// at most one orientation boundary inside the run: elements j < r belong to io, the others to io + 1
+		const int r = cur.T - cur.it;
+		const float po0 = (!CHECK || i < i1) ? cur.prior(cur.io) : RB_LOWEST;
+		const float po1 = (r < 4 && (!CHECK || i + r < i1)) ? cur.prior(cur.io + 1) : RB_LOWEST;
+#pragma unroll
+		for (int j = 0; j < 4; j++)
+		{
+			const float po = j < r ? po0 : po1;
+			const float lw = fmaxf(po + s_pt[cur.it + j] + min_diff2 - v[j], RB_LOWEST);
+			l[j] = (v[j] < min_diff2 || (CHECK && i + j >= i1)) ? RB_LOWEST : lw;
+		}
+		return;
+	}
 	int io = cur.io, it = cur.it;
 	float po = (!CHECK || i < i1) ? cur.prior(io) : RB_LOWEST;
 #pragma unroll
 	for (int j = 0; j < 4; j++)
 	{
-		const float pt = s_pt[it];
-		const bool bad = v[j] < min_diff2 || po == RB_LOWEST || pt == RB_LOWEST || (CHECK && i + j >= i1);
-		l[j] = bad ? RB_LOWEST : po + pt + min_diff2 - v[j];
+		const float lw = fmaxf(po + s_pt[it] + min_diff2 - v[j], RB_LOWEST);
+		l[j] = (v[j] < min_diff2 || (CHECK && i + j >= i1)) ? RB_LOWEST : lw;
 		if (j < 3 && ++it == cur.T) { it = 0; io++; po = (!CHECK || i + j + 1 < i1) ? cur.prior(io) : RB_LOWEST; }
 	}
 }
 
+// translation priors of particle p, twice over: s_pt[k] = prior[k mod T] for k < 2T (T <= 64)
 __device__ __forceinline__ void wc_stage_priors(const WcArgs &A, int p, float *s_pt)
 {
-	if (threadIdx.x < A.T)
-		s_pt[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + threadIdx.x] ? RB_LOWEST : A.pdf_offset[(size_t) p * A.T + threadIdx.x];
+	if (threadIdx.x < 2 * A.T)
+	{
+		const int t = threadIdx.x < A.T ? threadIdx.x : threadIdx.x - A.T;
+		s_pt[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + t] ? RB_LOWEST : A.pdf_offset[(size_t) p * A.T + t];
+	}
 }
 
 __global__ void __launch_bounds__(WC_THREADS)
 k_wc_max(WcArgs A)
 {
 	__shared__ float fred[32];
-	__shared__ float s_pt[64];
+	__shared__ float s_pt[128];
 	const int c = blockIdx.x, p = blockIdx.y;
 	const RbPartMeta m = A.metas[p];
 	const float min_diff2 = __int_as_float(A.states[p].min_diff2_bits);
@@ -394,7 +415,7 @@ k_wc_exp(WcArgs A)
 	unsigned *h_c = h_hi + WC_BINS;                              // [WC_BINS] count (COUNTS)
 	__shared__ ArgMaxSmem am;
 	__shared__ float s_wmax;
-	__shared__ float s_pt[64];
+	__shared__ float s_pt[128];
 	__shared__ int s_nz;
 	const int c = blockIdx.x, p = blockIdx.y;
 	const int lane = threadIdx.x & 31;

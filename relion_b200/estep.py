@@ -355,6 +355,21 @@ class MlDeviceBundle:
                                                      float(tau2_fudge), int(minres_map), _ptr(out, C.c_float)))
         return out
 
+    def update_ssnr(self, iclass: int, ori_size: int, tau2, tau2_fudge: float = 1.0, fsc=None, avgctf2=None,
+                    update_tau2_with_fsc: bool = False, is_whole_instead_of_half: bool = False):
+        """rb_update_ssnr: BackProjector::updateSSNRarrays on the device accumulator.
+        Returns (tau2, sigma2, data_vs_prior, fourier_coverage), each [ori_size/2 + 1] float64."""
+        ns = ori_size // 2 + 1
+        t = np.array(tau2, np.float64, copy=True)
+        if t.shape != (ns,):
+            raise ValueError(f"tau2 must have {ns} shells")
+        sigma2, dvp, cov = np.zeros(ns), np.zeros(ns), np.zeros(ns)
+        f, a = _f64(fsc), _f64(avgctf2)
+        capi.check(self.lib, self.lib.rb_update_ssnr(self.ctx, iclass, ori_size, float(tau2_fudge), _ptr(t, C.c_double), _ptr(sigma2, C.c_double),
+                                                     _ptr(dvp, C.c_double), _ptr(cov, C.c_double), _ptr(f, C.c_double), _ptr(a, C.c_double),
+                                                     1 if update_tau2_with_fsc else 0, 1 if is_whole_instead_of_half else 0))
+        return t, sigma2, dvp, cov
+
     def bp_device_tensor(self, iclass: int):
         """The interleaved (re, im, weight, 0) accumulator as a torch CUDA tensor sharing the library's memory
         (for torch.distributed.all_reduce over NCCL — replaces MlOptimiserMpi::combineAllWeightedSums)."""

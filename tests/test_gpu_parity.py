@@ -464,6 +464,36 @@ def test_estep_from_star_and_mrc_files_equals_in_memory_pool(device, tmp_path):
     np.testing.assert_allclose(got.wsum_sigma2_noise, want.wsum_sigma2_noise, rtol=2e-6)     # float atomics: order of the adds
 
 
+@pytest.mark.parametrize("ref_dim,with_fsc,whole", [(3, False, False), (3, True, False), (3, True, True), (2, False, False)])
+def test_update_ssnr_on_device(device, ref_dim, with_fsc, whole):
+    """SURVEY 8f row 2: rb_update_ssnr (BackProjector::updateSSNRarrays: sigma2, FSC-based tau2, data_vs_prior, Fourier
+    coverage) on the device accumulator against the numpy restatement applied to the downloaded weights."""
+    from oracle import reconstruct as rc
+    ori = 32
+    if ref_dim == 3:
+        wl = make_workload(ori_size=ori, healpix_order=1, n_particles=40, seed=95, snr=0.5)
+    else:
+        wl = make_workload(ori_size=ori, n_particles=40, seed=96, snr=0.5, ref_dim=2, psi_step=30.0, nr_classes=2)
+    _setup(device, wl)
+    device.expectation_some_particles(wl.pool)
+    _, _, w = device.bp_get(0)
+    ns = ori // 2 + 1
+    rng = np.random.default_rng(7)
+    tau2 = 1e-3 / (1.0 + np.arange(ns)) ** 2
+    tau2[5] = 0.0                                                   # the "use small value instead" branch
+    fsc = np.clip(1.0 - np.arange(ns) / ns + 0.05 * rng.standard_normal(ns), -0.1, 1.0) if with_fsc else None
+    avgctf2 = rng.uniform(0.3, 1.0, ns) if with_fsc else None
+    got = device.update_ssnr(0, ori, tau2, tau2_fudge=2.0, fsc=fsc, avgctf2=avgctf2, update_tau2_with_fsc=with_fsc,
+                             is_whole_instead_of_half=whole)
+    want = rc.update_ssnr(w, ori, wl.r_max, wl.padding_factor, 2.0, tau2, fsc=fsc, avgctf2=avgctf2,
+                          update_tau2_with_fsc=with_fsc, is_whole_instead_of_half=whole)
+    for g, x, name in zip(got, want, ("tau2", "sigma2", "data_vs_prior", "fourier_coverage")):
+        np.testing.assert_allclose(g, x, rtol=1e-9, atol=1e-300, err_msg=name)
+    assert got[1].max() > 0 and (got[3] > 0).any()                  # something was measured
+    if with_fsc:
+        assert not np.allclose(got[0], tau2)                        # tau2 was replaced by the FSC-based estimate
+
+
 @pytest.mark.parametrize("ori,cur,with_tau2", [(32, 32, False), (32, 32, True), (40, 28, True)])
 def test_reconstruct_on_device(device, ori, cur, with_tau2):
     """SURVEY 8f row 2: rb_reconstruct (BackProjector::reconstruct, skip_gridding, + windowToOridimRealSpace +

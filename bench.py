@@ -377,7 +377,17 @@ def run_ours(args):
             roofline["note"] = ("algorithmic gather bytes over the kernel time; the 106-px core of the reference stays in L2 (DRAM traffic is "
                                 "~10x smaller, see traffic) and the kernel is bound by L1 line throughput of divergent loads")
     # ---- CPU baseline on a bounded sample (all host cores) ------------------------------------------
-    cpu = cpu_baseline(wl, sample=args.cpu_sample)
+    # a first sample of --cpu-sample particles sizes a second one of about 12 s of CPU work (capped by the pool)
+    # (rank 0 of a single-GPU run only: with N > 1 the other ranks' host threads would share the cores)
+    if world > 1 or rank != 0:
+        cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
+               "sample": "not measured at N > 1 (see the N = 1 line)", "seconds": 0.0}
+    else:
+        cpu = cpu_baseline(wl, sample=args.cpu_sample)
+    if world == 1 and args.cpu_sample > 0 and 0 < cpu["seconds"] < 6.0:
+        n2 = min(P, int(args.cpu_sample * 12.0 / cpu["seconds"]))
+        if n2 > args.cpu_sample:
+            cpu = cpu_baseline(wl, sample=n2)
 
     pr = res0.particles
     out = {

@@ -180,6 +180,11 @@ typedef struct {
 	int ctf_premultiplied;
 	int bp_circle_bound;         /* 1: drop x >= floor(sqrt((n/2)^2-y^2)) like ALTCPU BP.h:565 (default);
 	                                0: CUDA BP.cuh behaviour (no extra bound)                */
+	int do_cc;                   /* (iter == 1 && do_firstiter_cc) || do_always_cc (acc_ml_optimiser_impl.h:1164):
+	                                normalised cross-correlation instead of the Gaussian squared difference in both
+	                                passes (cuda_kernel_diff2_CC_coarse / _fine, diff2.cuh:336-640), weight one for the
+	                                best pose and zero elsewhere (:2012-2071); rb_particle_out.dLL_nolog is then
+	                                -min_diff2, which IS the particle's dLL (:3571-3572, no logsigma2 term)       */
 } rb_model;
 int rb_set_model(rb_ctx *ctx, const rb_model *m);
 /* Call order: rb_set_model, rb_set_sampling, then (without orientational priors) rb_set_pdf_direction:
@@ -338,6 +343,15 @@ int rb_diff2_coarse(rb_ctx *ctx, int iclass, int img_size,
                     const float *img_re, const float *img_im, const float *corr,
                     float *diff2s);
 
+/* The same with the first-iteration cross-correlation criterion (runDiff2KernelCoarse with do_CC,
+ * acc_helper_functions_impl.h:1737-1809 -> cuda_kernel_diff2_CC_coarse, diff2.cuh:336-460):
+ * diff2s[o*T+t] += -sum(corr Re(A_o conj(S_t X))) / sqrt(sum(corr |A_o|^2)) */
+int rb_diff2_cc_coarse(rb_ctx *ctx, int iclass, int img_size,
+                       const float *eulers, int n_orient,
+                       const float *trans_x, const float *trans_y, int n_trans,
+                       const float *img_re, const float *img_im, const float *corr,
+                       float *diff2s);
+
 /* The coarse-pass contraction of GLOBAL searches, exposed for parity tests: C[M][N] = A[M][K] . B[N][K]^T on the
  * tcgen05 tensor cores with 3xTF32 operand splitting (FP32-equivalent accuracy; north_star "tensor cores are used
  * only for the coarse-pass cross term Re<X_t, CTF*A_r>").  Inside rb_estep_pool the same kernel computes
@@ -353,6 +367,15 @@ int rb_diff2_fine(rb_ctx *ctx, int iclass, int img_size,
                   const uint64_t *rot_idx, const uint64_t *trans_idx,
                   const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
                   float *diff2s, int n_weights);
+
+/* runDiff2KernelFine with do_CC (acc_helper_functions_impl.h:1922-1997 -> cuda_kernel_diff2_CC_fine, diff2.cuh:464-640) */
+int rb_diff2_cc_fine(rb_ctx *ctx, int iclass, int img_size,
+                     const float *eulers, int n_orient,
+                     const float *trans_x, const float *trans_y, int n_trans,
+                     const float *img_re, const float *img_im, const float *corr,
+                     const uint64_t *rot_idx, const uint64_t *trans_idx,
+                     const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
+                     float *diff2s, int n_weights);
 
 /* convertAllSquaredDifferencesToWeights, dense form (acc_ml_optimiser_impl.h:2188-2345):
  * in: diff2 [n_orient*n_trans] (Mweight), priors; out: weights in place, significance flags.

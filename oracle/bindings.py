@@ -67,6 +67,9 @@ class ok_kernel_table(C.Structure):
         ("bp_sync_free", C.CFUNCTYPE(None, C.c_void_p)),
         ("backproject2d", C.CFUNCTYPE(None, BP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                       C.c_ulong, C.c_float, C.c_float, f32p, C.c_ulong)),
+        ("diff2_cc_coarse", C.CFUNCTYPE(None, PP, C.c_int, C.c_int, f32p, C.c_ulong, f32p, f32p, C.c_ulong, f32p, f32p, f32p, f32p)),
+        ("diff2_cc_fine", C.CFUNCTYPE(None, PP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p,
+                                      C.c_ulong, C.c_ulong, C.c_ulong, ulp, ulp, ulp, ulp, f32p)),
     ]
 
 
@@ -229,12 +232,24 @@ class Oracle:
         self.K.project(C.byref(ref.struct), xs, n, _fp(e), _fp(re), _fp(im))
         return re + 1j * im
 
-    def diff2_coarse(self, ref: Projector, n, eulers, tx, ty, re, im, corr, init=None):
+    def diff2_coarse(self, ref: Projector, n, eulers, tx, ty, re, im, corr, init=None, cc=False):
         e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
         tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
         re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32); corr = np.ascontiguousarray(corr, np.float32)
         out = np.zeros((e.shape[0], len(tx)), np.float32) if init is None else np.ascontiguousarray(init, np.float32).copy()
-        self.K.diff2_coarse(C.byref(ref.struct), n // 2 + 1, n, _fp(e), e.shape[0], _fp(tx), _fp(ty), len(tx), _fp(re), _fp(im), _fp(corr), _fp(out))
+        (self.K.diff2_cc_coarse if cc else self.K.diff2_coarse)(C.byref(ref.struct), n // 2 + 1, n, _fp(e), e.shape[0], _fp(tx), _fp(ty), len(tx), _fp(re), _fp(im), _fp(corr), _fp(out))
+        return out
+
+    def diff2_cc_fine(self, ref: Projector, n, eulers, tx, ty, re, im, corr, rot_idx, trans_idx, job_idx, job_num):
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32); corr = np.ascontiguousarray(corr, np.float32)
+        ri = np.ascontiguousarray(rot_idx, np.uint64); ti = np.ascontiguousarray(trans_idx, np.uint64)
+        ji = np.ascontiguousarray(job_idx, np.uint64); jn = np.ascontiguousarray(job_num, np.uint64)
+        out = np.zeros(len(ri), np.float32)
+        up = lambda a: a.ctypes.data_as(ulp)
+        self.K.diff2_cc_fine(C.byref(ref.struct), n // 2 + 1, n, _fp(e), _fp(tx), _fp(ty), _fp(re), _fp(im), _fp(corr),
+                             e.shape[0], len(tx), len(ji), up(ri), up(ti), up(ji), up(jn), _fp(out))
         return out
 
     def diff2_fine(self, ref: Projector, n, eulers, tx, ty, re, im, corr, sum_init, rot_idx, trans_idx, job_idx, job_num):

@@ -156,12 +156,21 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 	//      src/ml_optimiser.cpp:6826-6879; pixel correction :1251-1268; buildCorrImage
 	//      acc_helper_functions_impl.h:164-196) ----
 	struct Win { std::vector<float> re, im, corr, ctf, minvs2; };
+	const bool do_cc = m->do_cc != 0;     // (iter == 1 && do_firstiter_cc) || do_always_cc  (:1164)
 	auto prep = [&](int n, const std::vector<int> &Mres, Win &w) {
 		int Np = n * (n / 2 + 1);
 		std::vector<float> F(2 * (size_t) Np), C(Np, 1.f);
 		if (n == S.nf) { memcpy(F.data(), Fimg_full, sizeof(float) * 2 * Np); if (Fctf_full) memcpy(C.data(), Fctf_full, sizeof(float) * Np); }
 		else { window_ft(Fimg_full, S.nf, F.data(), n, 2); if (Fctf_full) window_ft(Fctf_full, S.nf, C.data(), n, 1); }
 		w.re.resize(Np); w.im.resize(Np); w.corr.resize(Np); w.ctf = C; w.minvs2.assign(Np, 0.f);
+		// exp_local_sqrtXi2: power of the windowed (masked) transform, all its pixels (src/ml_optimiser.cpp:6846-6856)
+		double sqrtXi2 = 0.;
+		if (do_cc)
+		{
+			double sumxi2 = 0.;
+			for (int i = 0; i < Np; i++) sumxi2 += (double) F[2 * i] * (double) F[2 * i] + (double) F[2 * i + 1] * (double) F[2 * i + 1];
+			sqrtXi2 = sqrt(sumxi2);
+		}
 		for (int i = 0; i < Np; i++)
 		{
 			int ires = Mres[i];
@@ -174,6 +183,7 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 			w.re[i] = (float) ((double) F[2 * i] * pixel_correction);
 			w.im[i] = (float) ((double) F[2 * i + 1] * pixel_correction);
 			float c = (float) mi;
+			if (do_cc) c = (float) (1. / (sqrtXi2 * sqrtXi2));                                 // buildCorrImage :172-174
 			if (m->do_ctf_correction && m->refs_are_ctf_corrected) c = (float) (c * ((double) C[i] * (double) C[i]));
 			if (m->do_scale_correction) { float ms = (float) m->scale_correction[group]; c *= ms * ms; }
 			w.corr[i] = c;
@@ -202,7 +212,11 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 			if (!O) continue;
 			std::vector<float> allW(O * T, 0.f);
 			const float xi = (float) (highres_Xi2 / 2.);                                    // :1290-1296
-			for (auto &v : allW) v += xi;
+			if (!do_cc) for (auto &v : allW) v += xi;                                       // :1287-1297: no Xi2 term with CC
+			if (do_cc)
+				K->diff2_cc_coarse(&S.refs[k], S.nc / 2 + 1, S.nc, eul.data(), O, S.ctx.data(), S.cty.data(), T,
+				                   wc.re.data(), wc.im.data(), wc.corr.data(), allW.data());
+			else
 			K->diff2_coarse(&S.refs[k], S.nc / 2 + 1, S.nc, eul.data(), O, S.ctx.data(), S.cty.data(), T,
 			                wc.re.data(), wc.im.data(), wc.corr.data(), allW.data());
 			for (size_t o = 0; o < O; o++)                                                   // mapAllWeightsToMweights (helper.cu:782-796)
@@ -249,15 +263,32 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 	// ---- weights, pass 0 (:2180-2350) ----
 	// NB the reference passes ONE pdf_offset block (class 0's) to the coarse kernel for all classes
 	// (kernel indexes itrans only); for 3D references all classes share the same prior, so identical.
+	std::vector<unsigned char> significant(nCoarse, 0);
+	rb_particle_out &po = out->particles[p];
+	memset(&po, 0, sizeof(po));
+	po.min_diff2_coarse = min_diff2;
+	if (do_cc)
+	{
+		// :2012-2071: the smallest diff2 gets weight one, everything else zero; significant_weight = 0.999, NR_SIGN = 1.
+		// (The reference takes the arg-min over the whole Mweight array, lowest()-initialised entries included; the
+		// supported case is the one it is used in, a global search where every entry has been computed.)
+		int64_t amin = -1;
+		for (int64_t i = 0; i < nCoarse; i++)
+			if (Mweight[i] > LOWEST && (amin < 0 || Mweight[i] < Mweight[amin])) amin = i;
+		if (amin < 0) return RB_ERR_NO_SIGNIFICANT;
+		for (int64_t i = 0; i < nCoarse; i++) Mweight[i] = 0.f;
+		Mweight[amin] = 1.f;
+		significant[amin] = 1;
+		po.nr_significant_coarse = 1;
+		po.sum_weight_coarse = 1.f;                                                        // :1986
+		po.significant_weight_coarse = 0.999f;
+	}
+	else {
 	K->weights_exponent_coarse(pdf_orientation.data(), pdf_orientation_zeros.data(), pdf_offset.data(),
 	                           pdf_offset_zeros.data(), Mweight.data(), min_diff2, Kc * nOrient, T, nCoarse);
 	float wmax = LOWEST;
 	for (int64_t i = 0; i < nCoarse; i++) wmax = std::max(wmax, Mweight[i]);
 	K->exponentiate(Mweight.data(), 50.f - wmax, nCoarse);                                   // :2207
-	std::vector<unsigned char> significant(nCoarse, 0);
-	rb_particle_out &po = out->particles[p];
-	memset(&po, 0, sizeof(po));
-	po.min_diff2_coarse = min_diff2;
 	if (nCoarse > 1)
 	{
 		Sig sg = significance(Mweight.data(), nCoarse, m->adaptive_fraction, m->maximum_significants, true, exact);
@@ -270,6 +301,7 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 		for (int64_t i = 0; i < nCoarse; i++) significant[i] = Mweight[i] >= sg.significant_weight;   // arrayOverThreshold
 	}
 	else { significant[0] = 1; po.nr_significant_coarse = 1; }                              // :2347-2350
+	}
 	if (dump && dbg->coarse_weights) memcpy(dbg->coarse_weights, Mweight.data(), sizeof(float) * nCoarse);
 	if (dump && dbg->coarse_significant) memcpy(dbg->coarse_significant, significant.data(), nCoarse);
 
@@ -379,6 +411,13 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 	{
 		ClassFine &c = cf[k];
 		if (!c.weightNum) continue;
+		if (do_cc)
+			K->diff2_cc_fine(&S.refs[k], S.nf / 2 + 1, S.nf, c.eulers.data(), S.ftx.data(), S.fty.data(),
+			                 wf.re.data(), wf.im.data(), wf.corr.data(),
+			                 c.rot.size(), Tf, c.job_idx.size(),
+			                 c.rot_idx.data(), c.trans_idx.data(), c.job_idx.data(), c.job_num.data(),
+			                 fw.data() + c.firstPos);
+		else
 		K->diff2_fine(&S.refs[k], S.nf / 2 + 1, S.nf, c.eulers.data(), S.ftx.data(), S.fty.data(),
 		              wf.re.data(), wf.im.data(), wf.corr.data(), (float) (highres_Xi2 / 2.),
 		              c.rot.size(), Tf, c.job_idx.size(),
@@ -401,6 +440,20 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 
 	// weights, pass 1 (:2354-2535)
 	float wmaxf = LOWEST;
+	double min_diff2_final;
+	Sig sf;
+	if (do_cc)
+	{
+		// :2012-2071 with exp_ipass == 1: weight one for the smallest diff2; sum_weight stays at its initial value of one
+		// (:1986), significant_weight = 0.999; op.min_diff2 keeps the minimum of the CC values (:1881)
+		size_t amin = 0;
+		for (size_t i = 1; i < newDataSize; i++) if (fw[i] < fw[amin]) amin = i;
+		for (size_t i = 0; i < newDataSize; i++) fw[i] = 0.f;
+		fw[amin] = 1.f;
+		min_diff2_final = (double) min_diff2_f;
+		sf.sum_weight = 1.f; sf.significant_weight = 0.999f; sf.thresholdIdx = 0; sf.n_filtered = 1;
+	}
+	else {
 	for (int k = 0; k < Kc; k++)
 	{
 		ClassFine &c = cf[k];
@@ -416,9 +469,10 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 		if ((m->pdf_class[k] > 0.) && cf[k].weightNum)
 			K->exponentiate(fw.data() + cf[k].firstPos, 50.f - wmaxf, cf[k].weightNum);       // :2440
 	// op.min_diff2 is RFLOAT; the float kernel argument was (XFLOAT)op.min_diff2 (:2411, :2444)
-	double min_diff2_final = (double) min_diff2_f + (double) (50.f - wmaxf);
-	Sig sf = significance(fw.data(), (int64_t) newDataSize, m->adaptive_fraction, 0, false, exact);
+	min_diff2_final = (double) min_diff2_f + (double) (50.f - wmaxf);
+	sf = significance(fw.data(), (int64_t) newDataSize, m->adaptive_fraction, 0, false, exact);
 	if (sf.sum_weight == 0.f) return RB_ERR_SUMWEIGHT_ZERO;                                  // :2505
+	}
 	int64_t amax = 0;
 	for (size_t i = 1; i < newDataSize; i++) if (fw[i] > fw[amax]) amax = (int64_t) i;
 	if (dump && dbg->fine_weights && (int64_t) newDataSize <= dbg->fine_capacity)

@@ -3,7 +3,8 @@
  *
  * Restates accDoExpectationOneParticle (/root/reference/src/acc/acc_ml_optimiser_impl.h:3672-3962)
  * for the supported subset (3D reference, 2D images, one image per particle, nr_bodies == 1,
- * adaptive_oversampling > 0, no CC, no helices) on top of a kernel table (oracle_kernels.h), so the
+ * adaptive_oversampling > 0, Gaussian or first-iteration cross-correlation criterion, no helices) on top of a
+ * kernel table (oracle_kernels.h), so the
  * same orchestration runs on the compiled reference kernels ("reference") or on the restated ones
  * ("port").  Inputs/outputs use the product's public structs (include/relion_b200.h) so that a test
  * can hand the identical descriptors to rb_estep_pool() and to oracle_estep_pool().

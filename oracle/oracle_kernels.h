@@ -139,6 +139,25 @@ typedef struct {
 	                      const float *weights, const float *Minvsigma2s, const float *ctfs,
 	                      unsigned long trans_num, float significant_weight, float weight_norm,
 	                      const float *eulers, unsigned long image_count);
+
+	/* CpuKernels::diff2_CC_coarse_2D<REF3D=true> (src/acc/cpu/cpu_kernels/diff2.h:611-742): first-iteration cross-correlation
+	 * (--firstiter_cc / --always_cc).  diff2s[o*T+t] += -sum(corr Re(ref conj(shift_t img))) / sqrt(sum(corr |ref|^2)) */
+	void (*diff2_cc_coarse)(const ok_projector *p, int imgX, int imgY,
+	                        const float *eulers, unsigned long O,
+	                        const float *trans_x, const float *trans_y, unsigned long T,
+	                        const float *img_re, const float *img_im, const float *corr,
+	                        float *diff2s);
+
+	/* CpuKernels::diff2_CC_fine_2D<REF3D=true> (src/acc/cpu/cpu_kernels/diff2.h:904-1050) */
+	void (*diff2_cc_fine)(const ok_projector *p, int imgX, int imgY,
+	                      const float *eulers,
+	                      const float *trans_x, const float *trans_y,
+	                      const float *img_re, const float *img_im, const float *corr,
+	                      unsigned long orientation_num, unsigned long translation_num,
+	                      unsigned long num_jobs,
+	                      const unsigned long *rot_idx, const unsigned long *trans_idx,
+	                      const unsigned long *job_idx, const unsigned long *job_num,
+	                      float *diff2s);
 } ok_kernel_table;
 
 #ifdef __cplusplus

@@ -174,6 +174,32 @@ void refk_backproject2d(const ok_backprojector *bp, int imgX, int imgY,
 		(unsigned) imgX, (unsigned) imgY, (unsigned) (imgX * imgY), (unsigned) bp->mdlX, bp->mdlInitY, mutexes);
 }
 
+// first-iteration cross-correlation kernels, dispatched as runDiff2KernelCoarse / runDiff2KernelFine do for a 3D reference
+// and 2D data (acc_helper_functions_impl.h:1761-1777, :1950-1973 -> AccUtilities::diff2_CC_coarse / diff2_CC_fine)
+void refk_diff2_cc_coarse(const ok_projector *p, int imgX, int imgY,
+		const float *eulers, unsigned long O,
+		const float *trans_x, const float *trans_y, unsigned long T,
+		const float *img_re, const float *img_im, const float *corr, float *diff2s)
+{
+	AccProjectorKernel k = make_kernel(p, imgX, imgY);
+	CpuKernels::diff2_CC_coarse_2D<true>(O, (XFLOAT *) eulers, (XFLOAT *) img_re, (XFLOAT *) img_im,
+		(XFLOAT *) trans_x, (XFLOAT *) trans_y, k, (XFLOAT *) corr, diff2s, T, (unsigned long) imgX * imgY, (XFLOAT) 0);
+}
+
+void refk_diff2_cc_fine(const ok_projector *p, int imgX, int imgY, const float *eulers,
+		const float *trans_x, const float *trans_y,
+		const float *img_re, const float *img_im, const float *corr,
+		unsigned long orientation_num, unsigned long translation_num, unsigned long num_jobs,
+		const unsigned long *rot_idx, const unsigned long *trans_idx,
+		const unsigned long *job_idx, const unsigned long *job_num, float *diff2s)
+{
+	AccProjectorKernel k = make_kernel(p, imgX, imgY);
+	CpuKernels::diff2_CC_fine_2D<true>(num_jobs, (XFLOAT *) eulers, (XFLOAT *) img_re, (XFLOAT *) img_im,
+		(XFLOAT *) trans_x, (XFLOAT *) trans_y, k, (XFLOAT *) corr, diff2s, (unsigned long) imgX * imgY,
+		(XFLOAT) 0 /*sum_init: unused*/, (XFLOAT) 0 /*sqrtXi2: unused*/, orientation_num, translation_num, num_jobs,
+		(unsigned long *) rot_idx, (unsigned long *) trans_idx, (unsigned long *) job_idx, (unsigned long *) job_num);
+}
+
 void *refk_bp_sync_alloc(int mdlY, int mdlZ) { return new tbb::spin_mutex[(size_t) mdlY * mdlZ]; }
 void refk_bp_sync_free(void *s) { delete[] (tbb::spin_mutex *) s; }
 
@@ -192,6 +218,8 @@ const ok_kernel_table table = {
 	refk_bp_sync_alloc,
 	refk_bp_sync_free,
 	refk_backproject2d,
+	refk_diff2_cc_coarse,
+	refk_diff2_cc_fine,
 };
 
 } // namespace

@@ -53,6 +53,7 @@ class rb_model(C.Structure):
         ("adaptive_fraction", C.c_double), ("maximum_significants", C.c_int),
         ("do_ctf_correction", C.c_int), ("refs_are_ctf_corrected", C.c_int), ("do_scale_correction", C.c_int),
         ("do_map", C.c_int), ("ctf_premultiplied", C.c_int), ("bp_circle_bound", C.c_int),
+        ("do_cc", C.c_int),
     ]
 
 
@@ -157,6 +158,11 @@ PROTOTYPES = {
     "rb_project": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p]),
     "rb_diff2_coarse": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                   c_float_p, c_float_p, c_float_p, c_float_p]),
+    "rb_diff2_cc_coarse": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
+                                     c_float_p, c_float_p, c_float_p, c_float_p]),
+    "rb_diff2_cc_fine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
+                                   c_float_p, c_float_p, c_float_p,
+                                   c_u64_p, c_u64_p, c_u64_p, c_u64_p, C.c_int, c_float_p, C.c_int]),
     "rb_gemm_tf32x3": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, c_float_p]),
     "rb_diff2_fine": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                 c_float_p, c_float_p, c_float_p, C.c_float,

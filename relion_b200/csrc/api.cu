@@ -63,6 +63,13 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
 		rb_set_error("rb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
 		return RB_ERR_CUDA;
 	}
+	// The fine pass and the store stage fetch isolated 64-byte cells: the L2's DRAM fetch granularity is a tuning knob
+	// for them (RB_L2_FETCH = 32 / 64 / 128 bytes; unset = driver default).
+	if (const char *g = getenv("RB_L2_FETCH"))
+	{
+		int v = atoi(g);
+		if (v == 32 || v == 64 || v == 128) RB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v));
+	}
 	rb_ctx *ctx = new rb_ctx();
 	for (int i = 0; i < RB_MAX_CLASSES; i++) ctx->gemmA_stamp[i] = -1;
 	ctx->device = device;
@@ -86,7 +93,7 @@ static void release_slot(PoolSlot &s)
 	DevBuf *bufs[] = {&s.Fimg, &s.Fnomask, &s.Fctf, &s.meta, &s.state, &s.dir_idx, &s.dir_prior, &s.psi_idx, &s.psi_prior,
 	                  &s.Mweight, &s.pdf_orient, &s.pdf_orient_zero, &s.pdf_offset, &s.pdf_offset_zero,
 	                  &s.so_list, &s.pair_list, &s.fo, &s.fs_w, &s.fs_ihid, &s.counters, &s.shells, &s.out_pdf_dir, &s.out_pdf_class,
-	                  &s.fimg4, &s.cimg4, &s.slices};
+	                  &s.fimg4, &s.cimg4, &s.slices, &s.cc_corr};
 	for (DevBuf *b : bufs) b->release();
 	if (s.uploaded) cudaEventDestroy(s.uploaded);
 	if (s.done) cudaEventDestroy(s.done);
@@ -572,6 +579,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	d.do_ctf_correction = m->do_ctf_correction; d.refs_are_ctf_corrected = m->refs_are_ctf_corrected;
 	d.do_scale_correction = m->do_scale_correction; d.do_map = m->do_map; d.ctf_premultiplied = m->ctf_premultiplied;
 	d.bp_circle_bound = m->bp_circle_bound;
+	d.do_cc = m->do_cc;
 	// pdf_direction needs n_dir, which belongs to the sampling: keep a host copy until both are known
 	ctx->m_pdf_dir.release();
 	if (m->pdf_direction && ctx->has_sampling)
@@ -1021,9 +1029,9 @@ extern "C" int rb_gemm_tf32x3(rb_ctx *ctx, const float *A, const float *B, int M
 	return RB_OK;
 }
 
-extern "C" int rb_diff2_coarse(rb_ctx *ctx, int k, int n, const float *eulers, int O,
-                               const float *tx, const float *ty, int T,
-                               const float *re, const float *im, const float *corr, float *diff2s)
+static int diff2_coarse_entry(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                              const float *tx, const float *ty, int T,
+                              const float *re, const float *im, const float *corr, float *diff2s, int cc)
 {
 	RB_CHECK(check_proj(ctx, k, n));
 	StageBufs sb(ctx);
@@ -1032,18 +1040,32 @@ extern "C" int rb_diff2_coarse(rb_ctx *ctx, int k, int n, const float *eulers, i
 	RB_CHECK(sb.up(eulers, (size_t) O * 9, &d_e)); RB_CHECK(sb.up(tx, T, &d_tx)); RB_CHECK(sb.up(ty, T, &d_ty));
 	RB_CHECK(sb.up(re, np, &d_re)); RB_CHECK(sb.up(im, np, &d_im)); RB_CHECK(sb.up(corr, np, &d_c));
 	RB_CHECK(sb.up(diff2s, (size_t) O * T, &d_o));
-	RB_CHECK(rbk_diff2_coarse_stage(ctx, ctx->proj[k], n, d_e, O, d_tx, d_ty, T, d_re, d_im, d_c, d_o));
+	RB_CHECK(rbk_diff2_coarse_stage(ctx, ctx->proj[k], n, d_e, O, d_tx, d_ty, T, d_re, d_im, d_c, d_o, cc));
 	RB_CUDA(cudaMemcpyAsync(diff2s, d_o, (size_t) O * T * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return RB_OK;
 }
 
-extern "C" int rb_diff2_fine(rb_ctx *ctx, int k, int n, const float *eulers, int O,
-                             const float *tx, const float *ty, int T,
-                             const float *re, const float *im, const float *corr, float sum_init,
-                             const uint64_t *rot_idx, const uint64_t *trans_idx,
-                             const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
-                             float *diff2s, int n_weights)
+extern "C" int rb_diff2_coarse(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                               const float *tx, const float *ty, int T,
+                               const float *re, const float *im, const float *corr, float *diff2s)
+{
+	return diff2_coarse_entry(ctx, k, n, eulers, O, tx, ty, T, re, im, corr, diff2s, 0);
+}
+
+extern "C" int rb_diff2_cc_coarse(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                                  const float *tx, const float *ty, int T,
+                                  const float *re, const float *im, const float *corr, float *diff2s)
+{
+	return diff2_coarse_entry(ctx, k, n, eulers, O, tx, ty, T, re, im, corr, diff2s, 1);
+}
+
+static int diff2_fine_entry(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                            const float *tx, const float *ty, int T,
+                            const float *re, const float *im, const float *corr, float sum_init,
+                            const uint64_t *rot_idx, const uint64_t *trans_idx,
+                            const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
+                            float *diff2s, int n_weights, int cc)
 {
 	RB_CHECK(check_proj(ctx, k, n));
 	for (int j = 0; j < n_jobs; j++) RB_ARG(job_num[j] <= 16, "rb_diff2_fine: job %d has %llu translations (max 16)", j, (unsigned long long) job_num[j]);
@@ -1058,10 +1080,32 @@ extern "C" int rb_diff2_fine(rb_ctx *ctx, int k, int n, const float *eulers, int
 	RB_CHECK(sb.up((const unsigned long long *) trans_idx, (size_t) n_weights, &d_ti));
 	RB_CHECK(sb.up((const unsigned long long *) job_idx, (size_t) n_jobs, &d_ji));
 	RB_CHECK(sb.up((const unsigned long long *) job_num, (size_t) n_jobs, &d_jn));
-	RB_CHECK(rbk_diff2_fine_stage(ctx, ctx->proj[k], n, d_e, d_tx, d_ty, d_re, d_im, d_c, sum_init, d_ri, d_ti, d_ji, d_jn, n_jobs, d_o));
+	RB_CHECK(rbk_diff2_fine_stage(ctx, ctx->proj[k], n, d_e, d_tx, d_ty, d_re, d_im, d_c, sum_init, d_ri, d_ti, d_ji, d_jn, n_jobs, d_o, cc));
 	RB_CUDA(cudaMemcpyAsync(diff2s, d_o, (size_t) n_weights * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return RB_OK;
+}
+
+extern "C" int rb_diff2_fine(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                             const float *tx, const float *ty, int T,
+                             const float *re, const float *im, const float *corr, float sum_init,
+                             const uint64_t *rot_idx, const uint64_t *trans_idx,
+                             const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
+                             float *diff2s, int n_weights)
+{
+	return diff2_fine_entry(ctx, k, n, eulers, O, tx, ty, T, re, im, corr, sum_init, rot_idx, trans_idx, job_idx, job_num, n_jobs,
+	                        diff2s, n_weights, 0);
+}
+
+extern "C" int rb_diff2_cc_fine(rb_ctx *ctx, int k, int n, const float *eulers, int O,
+                                const float *tx, const float *ty, int T,
+                                const float *re, const float *im, const float *corr,
+                                const uint64_t *rot_idx, const uint64_t *trans_idx,
+                                const uint64_t *job_idx, const uint64_t *job_num, int n_jobs,
+                                float *diff2s, int n_weights)
+{
+	return diff2_fine_entry(ctx, k, n, eulers, O, tx, ty, T, re, im, corr, 0.f, rot_idx, trans_idx, job_idx, job_num, n_jobs,
+	                        diff2s, n_weights, 1);
 }
 
 extern "C" int rb_convert_weights(rb_ctx *ctx, float *weights, int64_t n_orient, int n_trans,

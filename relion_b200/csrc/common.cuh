@@ -154,6 +154,7 @@ struct RbModelDev {
 	double pixel_size, s2off, adaptive_fraction;
 	int maximum_significants;
 	int do_ctf_correction, refs_are_ctf_corrected, do_scale_correction, do_map, ctf_premultiplied, bp_circle_bound;
+	int do_cc;               // first-iteration cross-correlation criterion (acc_ml_optimiser_impl.h:1164)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -176,6 +177,7 @@ struct PoolSlot {
 	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;
 	DevBuf so_list, pair_list, fo, fs_w, fs_ihid, counters, shells, out_pdf_dir, out_pdf_class;
 	DevBuf fimg4, cimg4;            // prepared (corrected) images of the pool at the fine / coarse window
+	DevBuf cc_corr;                 // do_cc: [2][P] 1 / sqrtXi2^2 of the coarse / fine window (buildCorrImage)
 	DevBuf slices;                  // reference slices written by the fine pass, re-read by the store stage
 	long long slice_capacity = 0;   // number of fine orientations whose slice fits the cache
 	std::vector<RbPartMeta> h_meta;
@@ -253,13 +255,14 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s);
 int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s);
 int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int O,
                            const float *d_tx, const float *d_ty, int T, const float *d_re, const float *d_im,
-                           const float *d_corr, float *d_out);
+                           const float *d_corr, float *d_out, int cc = 0);
+int rbk_cc_corr_pool(rb_ctx *ctx, PoolSlot &s);   // do_cc: 1 / sqrtXi2^2 of the coarse and the fine window, per particle
 int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers,
                          const float *d_tx, const float *d_ty, const float *d_re, const float *d_im,
                          const float *d_corr, float sum_init,
                          const unsigned long long *d_rot_idx, const unsigned long long *d_trans_idx,
                          const unsigned long long *d_job_idx, const unsigned long long *d_job_num, int n_jobs,
-                         float *d_out);
+                         float *d_out, int cc = 0);
 
 // kernels_gemm.cu: global-search coarse pass as a 3xTF32 tcgen05 contraction
 bool rbk_coarse_gemm_applicable(rb_ctx *ctx, const PoolSlot &s);

@@ -14,6 +14,8 @@ struct ImgSrc {
 	int do_ctf_refs;               // do_ctf_correction && refs_are_ctf_corrected
 	int do_scale;
 	int n_array;                   // window size the arrays are stored at
+	float cc_corr;                 // > 0: cross-correlation criterion, corr = 1 / sqrtXi2^2 on every pixel, DC included
+	                               // (buildCorrImage, acc_helper_functions_impl.h:172-174)
 };
 
 // by array index + shell index (ires only matters in pool mode)
@@ -29,6 +31,7 @@ __device__ __forceinline__ void img_load_idx(const ImgSrc &s, int idx, int ires,
 		float2 F = __ldg(s.F + idx);
 		float pc = s.inv_scale;
 		float c = ires > 0 ? __ldg(s.minvs2 + ires) : 0.f;       // DC excluded (src/ml_optimiser.cpp:6874-6879)
+		if (s.cc_corr > 0.f) c = s.cc_corr;
 		if (s.do_ctf_refs)
 		{
 			float ctf = __ldg(s.ctf + idx);
@@ -57,6 +60,7 @@ __device__ __forceinline__ void img_src_pool(ImgSrc &src, const RbModelDev &M, c
 	src.do_ctf_refs = M.do_ctf_correction && M.refs_are_ctf_corrected && src.ctf;
 	src.do_scale = M.do_scale_correction;
 	src.n_array = M.current_size;
+	src.cc_corr = 0.f;
 }
 
 // prepared image: corrections applied once per particle instead of once per (orientation, pixel)
@@ -67,6 +71,9 @@ struct PrepArgs {
 	const RbRow *rows; int nrows;  // valid runs
 	int n;
 	float4 *out;
+	// cross-correlation criterion: the prepared weight is corr itself (the CC kernels do not halve it, diff2.h:712-713);
+	// pool mode takes the per-particle 1 / sqrtXi2^2 from cc_corr[p]
+	int cc; const float *cc_corr;
 };
 
 static __global__ void k_prep_img4(PrepArgs A, RbModelDev M)
@@ -74,7 +81,7 @@ static __global__ void k_prep_img4(PrepArgs A, RbModelDev M)
 	const int xs = A.n / 2 + 1;
 	const int p = blockIdx.y;
 	ImgSrc src = A.src;
-	if (!src.re) img_src_pool(src, M, A.metas[p], A.Fimg, A.Fctf, p);
+	if (!src.re) { img_src_pool(src, M, A.metas[p], A.Fimg, A.Fctf, p); if (A.cc) src.cc_corr = A.cc_corr[p]; }
 	float4 *out = A.out + (size_t) p * A.n * xs;
 	// rows without any valid pixel keep zero weight: clear first, then fill the runs
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < A.nrows * xs; i += gridDim.x * blockDim.x)
@@ -88,7 +95,7 @@ static __global__ void k_prep_img4(PrepArgs A, RbModelDev M)
 		{
 			float2 X; float corr;
 			img_load_idx(src, rb_src_index(x, rd.y, src.n_array), ires, X, corr);   // windowFourierTransform (src/fftw.h:850-856)
-			v = make_float4(X.x, X.y, corr * 0.5f, 0.f);
+			v = make_float4(X.x, X.y, A.cc ? corr : corr * 0.5f, 0.f);
 		}
 		out[idx] = v;
 	}

@@ -80,6 +80,9 @@ struct CoarseArgs {
 	const float *tx, *ty; int T;
 	int ny, yoff;                  // extent / offset of the y phase table
 	int tiles_per_class;           // CTAs per class (tiles never straddle classes)
+	int cc;                        // cross-correlation criterion (cuda_kernel_diff2_CC_coarse, diff2.cuh:336-460; ALTCPU
+	                               // cpu_kernels/diff2.h:611-742): value = -sum(corr Re(A conj X_t)) / sqrt(sum(corr |A|^2)),
+	                               // img4.z holds corr (not corr/2), no Xi2 term, no running minimum (values are negative)
 };
 
 template <int CO_EO, int CO_TT, bool XP>
@@ -170,7 +173,7 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 					         : rb_project3d(pk, x, y, s_e[e][0], s_e[e][1], s_e[e][2], s_e[e][3], s_e[e][4], s_e[e][5]);
 				zr[e] = hc * (ref.x * im.x + ref.y * im.y);
 				zi[e] = hc * (ref.x * im.y - ref.y * im.x);
-				base[e] += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
+				base[e] += hc * ((ref.x * ref.x + ref.y * ref.y) + (A.cc ? 0.f : (im.x * im.x + im.y * im.y)));
 			}
 			const float2 *txp = tab_x + x, *typ = tab_y + (y + yoff);
 #pragma unroll
@@ -203,19 +206,19 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 				float cr = 0.f, bs = 0.f;
 #pragma unroll
 				for (int w = 0; w < CO_THREADS / 32; w++) { cr += s_red[w][threadIdx.x]; bs += s_base[w][e]; }
-				float v = fmaxf(bs - 2.f * cr, 0.f);
+				float v = A.cc ? -(cr / sqrtf(bs)) : fmaxf(bs - 2.f * cr, 0.f);   // CC: diff2.h:729-735
 				const int o = o0 + e;
 				if (stage) A.st_out[(size_t) o * A.T + t0 + t] += v;          // += like the reference kernel
 				else
 				{
-					v += m.xi2_half;                                          // :1290-1296
+					if (!A.cc) v += m.xi2_half;                               // :1287-1297 (no Xi2 term with CC)
 					A.Mweight[m.coarse_off + (long long) o * A.T + t0 + t] = v;
 					bmin = fminf(bmin, v);
 				}
 			}
 		}
 	}
-	if (!stage)
+	if (!stage && !A.cc)
 	{
 		bmin = -block_max(-bmin, s_min);
 		if (threadIdx.x == 0 && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].min_diff2_bits, bmin);
@@ -259,6 +262,45 @@ __global__ void k_fill(float *p, float v, size_t n)
 	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) p[i] = v;
 }
 
+// exp_local_sqrtXi2 (src/ml_optimiser.cpp:6846-6856): sqrt of the power of ALL pixels of the masked transform windowed to
+// the pass' size, accumulated in double; buildCorrImage (acc_helper_functions_impl.h:172-174) turns it into the uniform
+// weight 1 / (sqrtXi2 * sqrtXi2).  One CTA per (particle, window): blockIdx.y = 0 coarse window, 1 fine window.
+__global__ void __launch_bounds__(256)
+k_cc_corr(const float2 *Fimg, int n_src, int n_coarse, int P, float *out)
+{
+	__shared__ double red[8];
+	const int p = blockIdx.x, which = blockIdx.y;
+	const int n = which ? n_src : n_coarse, xs = n / 2 + 1;
+	const float2 *F = Fimg + (size_t) p * n_src * (n_src / 2 + 1);
+	double acc = 0.;
+	for (int i = threadIdx.x; i < n * xs; i += blockDim.x)
+	{
+		const int iy = i / xs, x = i - iy * xs;
+		const int y = iy < xs ? iy : iy - n;                      // windowFourierTransform (src/fftw.h:850-856)
+		const float2 v = __ldg(F + rb_src_index(x, y, n_src));
+		acc += (double) v.x * (double) v.x + (double) v.y * (double) v.y;
+	}
+	for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(RB_FULL_MASK, acc, o);
+	if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+	__syncthreads();
+	if (threadIdx.x == 0)
+	{
+		double t = 0.;
+		for (int w = 0; w < 8; w++) t += red[w];
+		const double sq = sqrt(t);
+		out[(size_t) which * P + p] = (float) (1. / (sq * sq));
+	}
+}
+
+int rbk_cc_corr_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	const RbModelDev &M = ctx->d_model;
+	RB_CHECK(s.cc_corr.ensure((size_t) 2 * s.P * sizeof(float)));
+	k_cc_corr<<<dim3(s.P, 2), 256, 0, ctx->stream>>>(s.Fimg.as<float2>(), M.current_size, M.coarse_size, s.P, s.cc_corr.as<float>());
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
 int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 {
 	// Mweight <- lowest() (acc_ml_optimiser_impl.h:3849)
@@ -274,14 +316,21 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 	PA.metas = s.meta.as<RbPartMeta>(); PA.Fimg = s.Fimg.as<float2>();
 	PA.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
 	PA.ires = M.ires_c; PA.rows = M.rows_c; PA.nrows = M.nrows_c; PA.n = nc; PA.out = s.cimg4.as<float4>();
+	if (M.do_cc)
+	{
+		// exp_local_sqrtXi2 of both windows (src/ml_optimiser.cpp:6846-6856) -> 1 / sqrtXi2^2 per particle
+		RB_CHECK(rbk_cc_corr_pool(ctx, s));
+		PA.cc = 1; PA.cc_corr = s.cc_corr.as<float>();
+	}
 	dim3 pg((M.nrows_c * xsc + 255) / 256, s.P);
 	k_prep_img4<<<pg, 256, 0, ctx->stream>>>(PA, M);
 	RB_LAUNCH_CHECK(ctx);
 
+	// The cross-correlation criterion (first iteration only: a coarse grid at a small window) stays on the SIMT kernel.
 	// global searches: the cross term is a dense contraction shared by the whole pool -> tensor cores
-	if (rbk_coarse_gemm_applicable(ctx, s)) return rbk_diff2_coarse_gemm_pool(ctx, s, s.cimg4.as<float4>());
+	if (!M.do_cc && rbk_coarse_gemm_applicable(ctx, s)) return rbk_diff2_coarse_gemm_pool(ctx, s, s.cimg4.as<float4>());
 	// local searches: projection fused with the contraction, per (particle, 128-orientation tile)
-	if (rbk_coarse_fused_applicable(ctx, s)) return rbk_diff2_coarse_fused_pool(ctx, s, s.cimg4.as<float4>());
+	if (!M.do_cc && rbk_coarse_fused_applicable(ctx, s)) return rbk_diff2_coarse_fused_pool(ctx, s, s.cimg4.as<float4>());
 
 	CoarseArgs A;
 	memset(&A, 0, sizeof(A));
@@ -294,12 +343,13 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 	A.pix = ctx->d_model.pix_c; A.npix = ctx->d_model.nvc; A.n = ctx->d_model.coarse_size;
 	A.tx = ctx->d_samp.ctx; A.ty = ctx->d_samp.cty; A.T = ctx->d_samp.n_trans;
 	A.ny = A.n + 1; A.yoff = A.n / 2;
+	A.cc = M.do_cc;
 	return launch_coarse(ctx, A, s.max_no, ctx->d_model.nr_classes, s.P);
 }
 
 int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int O,
                            const float *d_tx, const float *d_ty, int T, const float *d_re, const float *d_im,
-                           const float *d_corr, float *d_out)
+                           const float *d_corr, float *d_out, int cc)
 {
 	// full pixel list with the coarse kernel's y-wrap: y > maxR -> y - imgY (diff2.cuh:89-90, diff2.h:109-110)
 	const int imgX = n / 2 + 1;
@@ -326,6 +376,7 @@ int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const floa
 	memset(&PA, 0, sizeof(PA));
 	PA.src.re = d_re; PA.src.im = d_im; PA.src.corr = d_corr; PA.src.n_array = n;
 	PA.rows = ctx->scratch[7].as<RbRow>(); PA.nrows = (int) rows.size(); PA.n = n; PA.out = ctx->scratch[6].as<float4>();
+	PA.cc = cc;
 	k_prep_img4<<<dim3((n * imgX + 255) / 256, 1), 256, 0, ctx->stream>>>(PA, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
 	CoarseArgs A;
@@ -336,5 +387,6 @@ int rbk_diff2_coarse_stage(rb_ctx *ctx, const RbProjector &pj, int n, const floa
 	A.pix = ctx->scratch[0].as<uint32_t>(); A.npix = (int) pix.size(); A.n = n;
 	A.tx = d_tx; A.ty = d_ty; A.T = T;
 	A.ny = 2 * n + 1; A.yoff = n;   // un-wrapped rows can reach -n when the projector's r_max < n/2
+	A.cc = cc;
 	return launch_coarse(ctx, A, O, 1, 1);
 }

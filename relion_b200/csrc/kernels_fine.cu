@@ -37,6 +37,8 @@ struct FineArgs {
 	const RbProjector *projs;
 	const RbRow *rows; int nrows; int n;
 	const float *tx, *ty; int NOT;
+	int cc;                        // cross-correlation criterion (cuda_kernel_diff2_CC_fine, diff2.cuh:464-640; ALTCPU
+	                               // cpu_kernels/diff2.h:904-1050): img4.z holds corr, value = -cross / sqrt(sum corr |A|^2)
 };
 
 struct FineFetch {
@@ -193,7 +195,7 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 					const float hc = cur.img.z;
 					const float zr = hc * (ref.x * cur.img.x + ref.y * cur.img.y);
 					const float zi = hc * (ref.x * cur.img.y - ref.y * cur.img.x);
-					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (cur.img.x * cur.img.x + cur.img.y * cur.img.y));
+					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (A.cc ? 0.f : (cur.img.x * cur.img.x + cur.img.y * cur.img.y)));
 					const float4 *pp = s_px + (x << 4) + k;
 #pragma unroll
 					for (int j = 0; j < 4; j++)
@@ -243,12 +245,12 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 				float c = 0.f, b = 0.f;
 #pragma unroll
 				for (int ww = 0; ww < FI_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][FI_TF]; }
-				float v = fmaxf((b - 2.f * c) + xi2_half, 0.f);
+				float v = A.cc ? -c / sqrtf(b) : fmaxf((b - 2.f * c) + xi2_half, 0.f);        // CC: diff2.h:1041-1046
 				if (stage) A.st_out[out_off + c0 + threadIdx.x] += v;                         // diff2.h:424-428
 				else { A.fs_w[out_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v); }
 			}
 		}
-		if (!stage && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
+		if (!stage && !A.cc && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
 	}
 }
 
@@ -388,7 +390,7 @@ k_diff2_fine_async(FineArgs A, RbModelDev M)
 					const float hc = im.z;
 					const float zr = hc * (ref.x * im.x + ref.y * im.y);
 					const float zi = hc * (ref.x * im.y - ref.y * im.x);
-					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
+					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (A.cc ? 0.f : (im.x * im.x + im.y * im.y)));
 					const float4 *pp = s_px + (x << 4) + k;
 #pragma unroll
 					for (int j = 0; j < 4; j++)
@@ -434,11 +436,11 @@ k_diff2_fine_async(FineArgs A, RbModelDev M)
 				float c = 0.f, b = 0.f;
 #pragma unroll
 				for (int ww = 0; ww < FI_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][FI_TF]; }
-				const float v = fmaxf((b - 2.f * c) + xi2_half, 0.f);
+				const float v = A.cc ? -c / sqrtf(b) : fmaxf((b - 2.f * c) + xi2_half, 0.f);
 				A.fs_w[out_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v);
 			}
 		}
-		if (threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
+		if (!A.cc && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);   // CC values are negative: the minimum is taken by k_weights_cc_fine
 	}
 }
 
@@ -468,6 +470,7 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	PA.metas = s.meta.as<RbPartMeta>(); PA.Fimg = s.Fimg.as<float2>();
 	PA.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
 	PA.ires = M.ires_f; PA.rows = M.rows_f; PA.nrows = M.nrows_f; PA.n = n; PA.out = s.fimg4.as<float4>();
+	if (M.do_cc) { PA.cc = 1; PA.cc_corr = s.cc_corr.as<float>() + s.P; }   // [1][P]: the fine window's 1 / sqrtXi2^2
 	dim3 pg((M.nrows_f * xs + 255) / 256, s.P);
 	k_prep_img4<<<pg, 256, 0, ctx->stream>>>(PA, M);
 	RB_LAUNCH_CHECK(ctx);
@@ -482,6 +485,7 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	A.projs = ctx->d_proj.as<RbProjector>();
 	A.rows = M.rows_f; A.nrows = M.nrows_f; A.n = n;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
+	A.cc = M.do_cc;
 	// cp.async-staged variant whenever three CTAs per SM still fit next to the phase table (measured at 256 px: 6.44 ms vs
 	// 6.97 ms; with two CTAs per SM it loses: 9.9 vs 9.2 ms at 400 px with a 6-deep ring)
 	static int use_async = -1;
@@ -517,7 +521,7 @@ int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float 
                          const float *d_corr, float sum_init,
                          const unsigned long long *d_rot_idx, const unsigned long long *d_trans_idx,
                          const unsigned long long *d_job_idx, const unsigned long long *d_job_num, int n_jobs,
-                         float *d_out)
+                         float *d_out, int cc)
 {
 	// rows with the fine kernels' rule (diff2.cuh:268-274, diff2.h:344-355): rows in the dead band
 	// maxR < iy < imgY-maxR contribute only the pixel x = maxR (which projects to zero)
@@ -544,6 +548,7 @@ int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float 
 	memset(&PA, 0, sizeof(PA));
 	PA.src.re = d_re; PA.src.im = d_im; PA.src.corr = d_corr; PA.src.n_array = n;
 	PA.rows = ctx->scratch[0].as<RbRow>(); PA.nrows = (int) rows.size(); PA.n = n; PA.out = ctx->scratch[6].as<float4>();
+	PA.cc = cc;
 	k_prep_img4<<<dim3((n * xs + 255) / 256, 1), 256, 0, ctx->stream>>>(PA, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
 	FineArgs A;
@@ -555,6 +560,7 @@ int rbk_diff2_fine_stage(rb_ctx *ctx, const RbProjector &pj, int n, const float 
 	A.projs = ctx->scratch[1].as<RbProjector>();
 	A.rows = ctx->scratch[0].as<RbRow>(); A.nrows = (int) rows.size(); A.n = n;
 	A.tx = d_tx; A.ty = d_ty; A.NOT = 1;
+	A.cc = cc;
 	int grid = n_jobs < ctx->num_sms * 3 ? n_jobs : ctx->num_sms * 3;
 	if (grid < 1) return RB_OK;
 	return launch_fine(ctx, A, grid);

@@ -778,8 +778,80 @@ static int weights_coarse_large(rb_ctx *ctx, PoolSlot &s, long long n)
 	return RB_OK;
 }
 
+// ---- cross-correlation criterion (first iteration, --firstiter_cc / --always_cc) --------------------------------------
+// convertAllSquaredDifferencesToWeights, acc_ml_optimiser_impl.h:2012-2071: no priors, no exponentials.  The pose with the
+// smallest value gets weight one, every other weight is zero; significant_weight = 0.999, NR_SIGN = 1, sum_weight keeps its
+// initial value of one (:1986).  Ties go to the first index (getArgMinOnDevice).  Entries that were never computed
+// (lowest(), orientations without prior) are skipped.
+__global__ void __launch_bounds__(WT_THREADS)
+k_weights_cc_coarse(const RbPartMeta *metas, RbPartState *states, float *Mweight, RbModelDev M, int T)
+{
+	__shared__ ArgMaxSmem am;
+	const int p = blockIdx.x;
+	const RbPartMeta m = metas[p];
+	RbPartState *st = states + p;
+	const long long n = (long long) M.nr_classes * m.nd * m.np * T;
+	float *w = Mweight + m.coarse_off;
+	float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
+	for (long long i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const float d = w[i];
+		if (d > RB_LOWEST && -d > bv) { bv = -d; bi = i; }
+	}
+	float best; long long arg;
+	block_argmax(bv, bi, am, best, arg);
+	const bool none = arg == 0x7fffffffffffffffLL;
+	__syncthreads();
+	for (long long i = threadIdx.x; i < n; i += blockDim.x) w[i] = (i == arg) ? 1.f : 0.f;
+	if (threadIdx.x == 0)
+	{
+		st->min_diff2 = none ? 0.f : -best;
+		st->cmax_weight = 1.f; st->cmax_index = none ? 0 : arg;
+		st->csum_weight = 1.f; st->n_nonzero = none ? 0 : 1;
+		st->csig_weight = 0.999f; st->nr_sig_coarse = none ? 0 : 1;
+		if (none) st->status = RB_ERR_NO_SIGNIFICANT;
+	}
+}
+
+__global__ void __launch_bounds__(WT_THREADS)
+k_weights_cc_fine(RbPartState *states, float *fs_w, int NOR, int NOT, const int *counters)
+{
+	__shared__ ArgMaxSmem am;
+	if (counters[2]) return;
+	const int p = blockIdx.x;
+	RbPartState *st = states + p;
+	const long long n = (long long) st->n_pairs * NOR * NOT;
+	if (n == 0) { if (threadIdx.x == 0 && st->status == 0) st->status = RB_ERR_NO_SIGNIFICANT; return; }
+	float *w = fs_w + st->fs_base;
+	float bv = RB_LOWEST; long long bi = 0x7fffffffffffffffLL;
+	for (long long i = threadIdx.x; i < n; i += blockDim.x)
+	{
+		const float d = w[i];
+		if (-d > bv) { bv = -d; bi = i; }
+	}
+	float best; long long arg;
+	block_argmax(bv, bi, am, best, arg);
+	if (arg == 0x7fffffffffffffffLL) arg = 0;                     // only NaNs: keep the reference's first element
+	__syncthreads();
+	for (long long i = threadIdx.x; i < n; i += blockDim.x) w[i] = (i == arg) ? 1.f : 0.f;
+	if (threadIdx.x == 0)
+	{
+		st->fmin_diff2 = -best;                                                             // :1881
+		st->min_diff2_final = (double) -best;                                               // no "+ 50 - max" (:2444 is the other branch)
+		st->fmax_weight = 1.f; st->fmax_sample = arg;
+		st->fsum_weight = 1.f; st->fsig_weight = 0.999f;
+	}
+}
+
 int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 {
+	if (ctx->d_model.do_cc)
+	{
+		k_weights_cc_coarse<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
+			s.Mweight.as<float>(), ctx->d_model, ctx->d_samp.n_trans);
+		RB_LAUNCH_CHECK(ctx);
+		return RB_OK;
+	}
 	if (!s.has_priors)
 	{
 		// global search: every particle has the same dense size
@@ -1038,6 +1110,13 @@ k_weights_fine(const RbPartMeta *metas, RbPartState *states, float *fs_w, const 
 
 int rbk_weights_fine_pool(rb_ctx *ctx, PoolSlot &s)
 {
+	if (ctx->d_model.do_cc)
+	{
+		k_weights_cc_fine<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.state.as<RbPartState>(), s.fs_w.as<float>(),
+			ctx->d_samp.n_over_rot, ctx->d_samp.n_over_trans, s.counters.as<int>());
+		RB_LAUNCH_CHECK(ctx);
+		return RB_OK;
+	}
 	k_weights_fine<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
 		s.fs_w.as<float>(), s.fs_ihid.as<long long>(), s.pdf_orient.as<float>(), s.pdf_orient_zero.as<unsigned char>(),
 		s.pdf_offset.as<float>(), s.pdf_offset_zero.as<unsigned char>(), ctx->d_model,

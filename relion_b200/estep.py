@@ -72,6 +72,7 @@ class ModelParams:
     do_map: bool = True
     ctf_premultiplied: bool = False
     bp_circle_bound: bool = True
+    do_cc: bool = False                      # (iter == 1 and do_firstiter_cc) or do_always_cc
 
 
 @dataclasses.dataclass
@@ -173,6 +174,7 @@ def marshal_model(p: ModelParams):
     st.do_map = int(p.do_map)
     st.ctf_premultiplied = int(p.ctf_premultiplied)
     st.bp_circle_bound = int(p.bp_circle_bound)
+    st.do_cc = int(p.do_cc)
     m.struct = st
     return m
 
@@ -478,12 +480,14 @@ class MlDeviceBundle:
         capi.check(self.lib, self.lib.rb_project(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0], _ptr(out.view(np.float32), C.c_float)))
         return out
 
-    def diff2_coarse(self, iclass, img_size, eulers, tx, ty, re, im, corr, init=None):
+    def diff2_coarse(self, iclass, img_size, eulers, tx, ty, re, im, corr, init=None, cc=False):
+        """runDiff2KernelCoarse; cc=True: the first-iteration cross-correlation kernel (rb_diff2_cc_coarse)."""
         e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
         tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
         re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32); corr = np.ascontiguousarray(corr, np.float32)
         out = np.zeros((e.shape[0], len(tx)), np.float32) if init is None else np.ascontiguousarray(init, np.float32).copy()
-        capi.check(self.lib, self.lib.rb_diff2_coarse(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0],
+        fn = self.lib.rb_diff2_cc_coarse if cc else self.lib.rb_diff2_coarse
+        capi.check(self.lib, fn(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0],
                                                       _ptr(tx, C.c_float), _ptr(ty, C.c_float), len(tx),
                                                       _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(corr, C.c_float), _ptr(out, C.c_float)))
         return out
@@ -495,6 +499,21 @@ class MlDeviceBundle:
         out = np.empty((A.shape[0], B.shape[0]), np.float32)
         capi.check(self.lib, self.lib.rb_gemm_tf32x3(self.ctx, _ptr(A, C.c_float), _ptr(B, C.c_float), A.shape[0], B.shape[0], A.shape[1],
                                                      _ptr(out, C.c_float)))
+        return out
+
+    def diff2_cc_fine(self, iclass, img_size, eulers, tx, ty, re, im, corr, rot_idx, trans_idx, job_idx, job_num):
+        """runDiff2KernelFine with the first-iteration cross-correlation criterion (rb_diff2_cc_fine)."""
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        tx = np.ascontiguousarray(tx, np.float32); ty = np.ascontiguousarray(ty, np.float32)
+        re = np.ascontiguousarray(re, np.float32); im = np.ascontiguousarray(im, np.float32); corr = np.ascontiguousarray(corr, np.float32)
+        ri = np.ascontiguousarray(rot_idx, np.uint64); ti = np.ascontiguousarray(trans_idx, np.uint64)
+        ji = np.ascontiguousarray(job_idx, np.uint64); jn = np.ascontiguousarray(job_num, np.uint64)
+        out = np.zeros(len(ri), np.float32)
+        capi.check(self.lib, self.lib.rb_diff2_cc_fine(self.ctx, iclass, img_size, _ptr(e, C.c_float), e.shape[0],
+                                                       _ptr(tx, C.c_float), _ptr(ty, C.c_float), len(tx),
+                                                       _ptr(re, C.c_float), _ptr(im, C.c_float), _ptr(corr, C.c_float),
+                                                       _ptr(ri, C.c_uint64), _ptr(ti, C.c_uint64), _ptr(ji, C.c_uint64), _ptr(jn, C.c_uint64),
+                                                       len(ji), _ptr(out, C.c_float), len(ri)))
         return out
 
     def diff2_fine(self, iclass, img_size, eulers, tx, ty, re, im, corr, sum_init, rot_idx, trans_idx, job_idx, job_num):

@@ -44,7 +44,7 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
                   pixel_size: float = 2.0, particle_diameter: Optional[float] = None,
                   nr_groups: int = 2, adaptive_fraction: float = 0.999, coarse_size: Optional[int] = None,
                   projector: Optional[Callable] = None, n_blobs: int = 40, refs_override=None,
-                  ref_seed: int = 1993, ref_dim: int = 3, psi_step: float = 6.0) -> Workload:
+                  ref_seed: int = 1993, ref_dim: int = 3, psi_step: float = 6.0, do_cc: bool = False) -> Workload:
     """Build a complete, seeded E-step problem.
 
     projector(vol_complex64, r_max, pf, eulers[n,9] float32, n) -> [n_img, n, n//2+1] complex: how noise-free
@@ -115,7 +115,8 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
     model = ModelParams(nr_classes=nr_classes, ori_size=ori_size, coarse_size=coarse_size, current_size=current_size,
                         pixel_size=pixel_size, sigma2_noise=sigma2, scale_correction=scale, pdf_class=pdf_class,
                         pdf_direction=None if local_search else pdf_direction, data_vs_prior_class=dvp,
-                        sigma2_offset=(offset_range * pixel_size / 1.5) ** 2, adaptive_fraction=adaptive_fraction)
+                        sigma2_offset=(offset_range * pixel_size / 1.5) ** 2, adaptive_fraction=adaptive_fraction,
+                        do_cc=do_cc)
     # ---- pool ------------------------------------------------------------------------------------
     group = rng.integers(0, nr_groups, P).astype(np.int32)
     pool = ParticlePool(Fimg=parts.Fimg, Fimg_nomask=parts.Fimg_nomask, Fctf=parts.Fctf, group_id=group,

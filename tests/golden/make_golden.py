@@ -23,6 +23,9 @@ CASES = {
     "global_k2": dict(ori_size=24, healpix_order=1, n_particles=4, nr_classes=2, seed=5, snr=0.3),
     "local_k1": dict(ori_size=32, healpix_order=2, n_particles=3, nr_classes=1, seed=6, snr=0.2, local_search=True),
     "window_k1": dict(ori_size=40, current_size=28, healpix_order=1, n_particles=3, nr_classes=1, seed=8, snr=0.3),
+    # first-iteration cross-correlation criterion (--firstiter_cc): the reference's diff2_CC_coarse / diff2_CC_fine kernels
+    "cc_global_k1": dict(ori_size=24, healpix_order=1, n_particles=4, nr_classes=1, seed=9, snr=0.3, do_cc=True),
+    "cc_window_k1": dict(ori_size=40, current_size=28, healpix_order=1, n_particles=3, nr_classes=1, seed=10, snr=0.1, do_cc=True),
 }
 
 
@@ -51,7 +54,10 @@ def run_case(kind, kw):
 if __name__ == "__main__":
     build(ref=True)
     here = os.path.dirname(os.path.abspath(__file__))
+    only = sys.argv[1:]
     for name, kw in CASES.items():
+        if only and name not in only:
+            continue
         d = run_case("reference", kw)
         np.savez_compressed(os.path.join(here, f"estep_reference_{name}.npz"), **d)
         print(name, "written", {k: v.shape for k, v in d.items() if hasattr(v, "shape") and v.ndim}.__len__(), "arrays")

@@ -173,6 +173,51 @@ def test_wavg_and_backproject_stage(device, oracle):
         assert np.abs(g - w).max() <= 1e-4 * np.abs(w).max()
 
 
+@pytest.mark.parametrize("n,O,T,r_max_cut", [(14, 37, 9, False), (32, 5, 21, False), (32, 256 + 3, 30, False), (24, 8, 5, True)])
+def test_diff2_cc_coarse_stage(device, oracle, n, O, T, r_max_cut):
+    """First-iteration cross-correlation criterion, coarse kernel (diff2_CC_coarse, cpu_kernels/diff2.h:611-742)."""
+    from oracle.bindings import Projector
+    wl = make_workload(ori_size=32, n_particles=2, seed=12)
+    r_max = 7 if r_max_cut else wl.r_max
+    device.set_reference(0, wl.refs[0], r_max, wl.padding_factor)
+    ref = Projector(wl.refs[0], r_max, wl.padding_factor)
+    eul, tx, ty, re, im, corr = _stage_inputs(wl, n, 2, O, T)
+    corr[0, 0] = 0.7          # the CC weight does not vanish at the origin
+    init = np.full((O, T), 0.25, np.float32)
+    got = device.diff2_coarse(0, n, eul, tx, ty, re, im, corr, init=init, cc=True)
+    want = oracle.diff2_coarse(ref, n, eul, tx, ty, re, im, corr, init=init, cc=True)
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want - 0.25).max()
+
+
+@pytest.mark.parametrize("n,r_max_cut", [(32, False), (18, False), (32, True)])
+def test_diff2_cc_fine_stage(device, oracle, n, r_max_cut):
+    """First-iteration cross-correlation criterion, fine kernel (diff2_CC_fine, cpu_kernels/diff2.h:904-1050)."""
+    from oracle.bindings import Projector
+    wl = make_workload(ori_size=32, n_particles=2, seed=13)
+    r_max = 9 if r_max_cut else wl.r_max
+    device.set_reference(0, wl.refs[0], r_max, wl.padding_factor)
+    ref = Projector(wl.refs[0], r_max, wl.padding_factor)
+    O, T = 11, 36
+    eul, tx, ty, re, im, corr = _stage_inputs(wl, n, 3, O, T)
+    corr[0, 0] = 1.3
+    rng = np.random.default_rng(5)
+    rot_idx, trans_idx, job_idx, job_num = [], [], [], []
+    for o in range(O):
+        t = 0
+        while t < T:
+            if rng.random() < 0.5:
+                t += 1
+                continue
+            ln = int(min(rng.integers(1, 5), T - t))
+            job_idx.append(len(rot_idx)); job_num.append(ln)
+            for j in range(ln):
+                rot_idx.append(o); trans_idx.append(t + j)
+            t += ln + 1
+    got = device.diff2_cc_fine(0, n, eul, tx, ty, re, im, corr, rot_idx, trans_idx, job_idx, job_num)
+    want = oracle.diff2_cc_fine(ref, n, eul, tx, ty, re, im, corr, rot_idx, trans_idx, job_idx, job_num)
+    assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+
+
 def _compare_pool(device, oracle, wl, pose_frac=0.995):
     from oracle.bindings import Projector, Backprojector
     _setup(device, wl)
@@ -237,6 +282,23 @@ def test_pool_global_search_through_fused_kernel(device, oracle, monkeypatch):
     monkeypatch.setenv("RB_COARSE_FUSED", "2")
     wl = make_workload(ori_size=32, healpix_order=1, n_particles=5, nr_classes=2, seed=29, snr=0.3)
     _compare_pool(device, oracle, wl)
+
+
+@pytest.mark.parametrize("kw", [dict(ori_size=32, healpix_order=1, n_particles=12, nr_classes=1, seed=41, snr=0.3),
+                                dict(ori_size=40, current_size=28, healpix_order=1, n_particles=8, nr_classes=1, seed=42, snr=0.1),
+                                dict(ori_size=32, n_particles=16, nr_classes=1, seed=43, snr=0.5, ref_dim=2, psi_step=12.0)])
+def test_pool_firstiter_cc(device, oracle, kw):
+    """--firstiter_cc / --always_cc: cross-correlation kernels in both passes, weight one for the best pose
+    (acc_ml_optimiser_impl.h:1164, 1287, 2012-2071, 3571)."""
+    wl = make_workload(do_cc=True, **kw)
+    if kw.get("ref_dim") == 2:
+        wl.model.bp_circle_bound = False
+    res, ores = _compare_pool(device, oracle, wl)
+    g = res.particles
+    assert np.all(g["nr_significant_coarse"] == 1)
+    assert np.all(g["n_fine_samples"] == wl.sampling.n_over_rot * wl.sampling.n_over_trans)
+    assert np.all(g["sum_weight"] == 1.0) and np.all(g["pmax"] == 1.0)
+    assert np.all(g["dLL_nolog"] > 0)           # = -min_diff2: the best normalised cross-correlation is positive
 
 
 def test_pool_reduced_current_size(device, oracle):

@@ -52,7 +52,7 @@ def _check_against(d, g, rtol=5e-5):
             np.testing.assert_allclose(d[k], g[k], rtol=1e-4, err_msg=k)
 
 
-@pytest.mark.parametrize("name", ["global_k2", "local_k1", "window_k1"])
+@pytest.mark.parametrize("name", ["global_k2", "local_k1", "window_k1", "cc_global_k1", "cc_window_k1"])
 def test_port_matches_reference_golden(name):
     mod = _cases()
     g = np.load(os.path.join(GOLD, f"estep_reference_{name}.npz"))
@@ -60,7 +60,7 @@ def test_port_matches_reference_golden(name):
     _check_against(d, g)
 
 
-@pytest.mark.parametrize("name", ["global_k2"])
+@pytest.mark.parametrize("name", ["global_k2", "cc_global_k1"])
 def test_compiled_reference_matches_golden(name):
     from oracle.bindings import have_reference
     if not have_reference():

@@ -63,13 +63,6 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
 		rb_set_error("rb_ctx_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major, prop.minor);
 		return RB_ERR_CUDA;
 	}
-	// The fine pass and the store stage fetch isolated 64-byte cells: the L2's DRAM fetch granularity is a tuning knob
-	// for them (RB_L2_FETCH = 32 / 64 / 128 bytes; unset = driver default).
-	if (const char *g = getenv("RB_L2_FETCH"))
-	{
-		int v = atoi(g);
-		if (v == 32 || v == 64 || v == 128) RB_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)v));
-	}
 	rb_ctx *ctx = new rb_ctx();
 	for (int i = 0; i < RB_MAX_CLASSES; i++) ctx->gemmA_stamp[i] = -1;
 	ctx->device = device;
@@ -108,6 +101,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
+	                  &ctx->m_cc[0], &ctx->m_cc[1], &ctx->m_cc[2], &ctx->m_cc[3], &ctx->m_cc[4],
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp};
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
@@ -460,7 +454,9 @@ extern "C" int rb_set_sampling(rb_ctx *ctx, const rb_sampling *s)
 static inline int iround(double x) { return (int) (x > 0 ? floor(x + 0.5) : -floor(-x + 0.5)); }
 
 // pixels with Mresol >= 0 for window n (src/ml_optimiser.cpp:5784-5811), in FFTW order
-static void make_pixlist(int n, std::vector<uint32_t> &out)
+// full_x0: keep the redundant half of the x = 0 column (jp == 0, ip < 0).  Mresol excludes it (Minvsigma2 is zero there),
+// but the cross-correlation kernels weight every pixel with 1 / sqrtXi2^2 (buildCorrImage), so it contributes there.
+static void make_pixlist(int n, std::vector<uint32_t> &out, bool full_x0 = false)
 {
 	const int xs = n / 2 + 1;
 	out.clear();
@@ -470,13 +466,13 @@ static void make_pixlist(int n, std::vector<uint32_t> &out)
 		for (int jp = 0; jp < xs; jp++)
 		{
 			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
-			if (ires < xs && !(jp == 0 && ip < 0)) out.push_back(rb_pack_pix(jp, ip, ires));
+			if (ires < xs && (full_x0 || !(jp == 0 && ip < 0))) out.push_back(rb_pack_pix(jp, ip, ires));
 		}
 	}
 }
 
 // the same pixel set as row runs + a dense shell map
-static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_map)
+static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_map, bool full_x0 = false)
 {
 	const int xs = n / 2 + 1;
 	rows.clear();
@@ -488,7 +484,7 @@ static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_
 		for (int jp = 0; jp < xs; jp++)
 		{
 			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
-			if (ires < xs && !(jp == 0 && ip < 0))
+			if (ires < xs && (full_x0 || !(jp == 0 && ip < 0)))
 			{
 				ires_map[(size_t) iy * xs + jp] = (short) ires;
 				if (lo < 0) lo = jp;
@@ -569,6 +565,27 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	d.nrows_c = (int) rc.size(); d.nrows_f = (int) rf.size();
 	d.rows_c = ctx->m_rows_c.as<RbRow>(); d.rows_f = ctx->m_rows_f.as<RbRow>();
 	d.ires_c = ctx->m_ires_c.as<short>(); d.ires_f = ctx->m_ires_f.as<short>();
+	// pixel sets of the two diff2 passes: the Mresol sets above, or with the cross-correlation criterion every pixel
+	// inside the window's circle
+	d.d2_nvc = d.nvc; d.d2_pix_c = d.pix_c;
+	d.d2_nrows_c = d.nrows_c; d.d2_rows_c = d.rows_c; d.d2_ires_c = d.ires_c;
+	d.d2_nrows_f = d.nrows_f; d.d2_rows_f = d.rows_f; d.d2_ires_f = d.ires_f;
+	if (m->do_cc)
+	{
+		std::vector<uint32_t> pcc;
+		std::vector<RbRow> rcc, rfc;
+		std::vector<short> icc, ifc;
+		make_pixlist(m->coarse_size, pcc, true);
+		make_rows(m->coarse_size, rcc, icc, true); make_rows(m->current_size, rfc, ifc, true);
+		RB_CHECK(upload(ctx, ctx->m_cc[0], pcc.data(), pcc.size() * 4));
+		RB_CHECK(upload(ctx, ctx->m_cc[1], rcc.data(), rcc.size() * sizeof(RbRow)));
+		RB_CHECK(upload(ctx, ctx->m_cc[2], icc.data(), icc.size() * sizeof(short)));
+		RB_CHECK(upload(ctx, ctx->m_cc[3], rfc.data(), rfc.size() * sizeof(RbRow)));
+		RB_CHECK(upload(ctx, ctx->m_cc[4], ifc.data(), ifc.size() * sizeof(short)));
+		d.d2_nvc = (int) pcc.size(); d.d2_pix_c = ctx->m_cc[0].as<uint32_t>();
+		d.d2_nrows_c = (int) rcc.size(); d.d2_rows_c = ctx->m_cc[1].as<RbRow>(); d.d2_ires_c = ctx->m_cc[2].as<short>();
+		d.d2_nrows_f = (int) rfc.size(); d.d2_rows_f = ctx->m_cc[3].as<RbRow>(); d.d2_ires_f = ctx->m_cc[4].as<short>();
+	}
 	d.minvs2 = ctx->m_minvs2.as<float>();
 	d.pdf_class = ctx->m_pdf_class.as<double>();
 	d.pdf_direction = nullptr;

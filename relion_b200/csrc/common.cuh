@@ -147,6 +147,11 @@ struct RbModelDev {
 	int nrows_c, nrows_f;
 	const RbRow *rows_c, *rows_f;
 	const short *ires_c, *ires_f;   // [n][n/2+1], -1 = excluded
+	// pixel sets the SIMT diff2 kernels walk: the sets above, or (do_cc) every pixel inside the window's circle
+	int d2_nvc, d2_nrows_c, d2_nrows_f;
+	const uint32_t *d2_pix_c;
+	const RbRow *d2_rows_c, *d2_rows_f;
+	const short *d2_ires_c, *d2_ires_f;
 	const float *minvs2;     // [nr_optics_groups][nshell] 1/(fudge*sigma2), entry 0 kept (DC restored for store)
 	const double *pdf_direction; // [K][n_dir]
 	const double *pdf_class;
@@ -211,6 +216,7 @@ struct rb_ctx {
 	       s_tx, s_ty, s_otx, s_oty;
 	DevBuf m_pix_c, m_pix_f, m_minvs2, m_pdf_dir, m_pdf_class, m_dvp;
 	DevBuf m_rows_c, m_rows_f, m_ires_c, m_ires_f;
+	DevBuf m_cc[5];                  // do_cc: coarse pixel list, coarse rows / shell map, fine rows / shell map with the full x = 0 column
 	DevBuf d_proj, d_bp;             // device copies of the projector / backprojector tables
 	std::vector<double> h_scale_correction;
 

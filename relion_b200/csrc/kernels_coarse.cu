@@ -315,14 +315,14 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 	memset(&PA, 0, sizeof(PA));
 	PA.metas = s.meta.as<RbPartMeta>(); PA.Fimg = s.Fimg.as<float2>();
 	PA.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
-	PA.ires = M.ires_c; PA.rows = M.rows_c; PA.nrows = M.nrows_c; PA.n = nc; PA.out = s.cimg4.as<float4>();
+	PA.ires = M.d2_ires_c; PA.rows = M.d2_rows_c; PA.nrows = M.d2_nrows_c; PA.n = nc; PA.out = s.cimg4.as<float4>();
 	if (M.do_cc)
 	{
 		// exp_local_sqrtXi2 of both windows (src/ml_optimiser.cpp:6846-6856) -> 1 / sqrtXi2^2 per particle
 		RB_CHECK(rbk_cc_corr_pool(ctx, s));
 		PA.cc = 1; PA.cc_corr = s.cc_corr.as<float>();
 	}
-	dim3 pg((M.nrows_c * xsc + 255) / 256, s.P);
+	dim3 pg((M.d2_nrows_c * xsc + 255) / 256, s.P);
 	k_prep_img4<<<pg, 256, 0, ctx->stream>>>(PA, M);
 	RB_LAUNCH_CHECK(ctx);
 
@@ -340,7 +340,7 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 	A.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>();
 	A.Mweight = s.Mweight.as<float>();
 	A.projs = ctx->d_proj.as<RbProjector>();
-	A.pix = ctx->d_model.pix_c; A.npix = ctx->d_model.nvc; A.n = ctx->d_model.coarse_size;
+	A.pix = ctx->d_model.d2_pix_c; A.npix = ctx->d_model.d2_nvc; A.n = ctx->d_model.coarse_size;
 	A.tx = ctx->d_samp.ctx; A.ty = ctx->d_samp.cty; A.T = ctx->d_samp.n_trans;
 	A.ny = A.n + 1; A.yoff = A.n / 2;
 	A.cc = M.do_cc;

@@ -94,6 +94,7 @@ __device__ __forceinline__ float2 fine_finish(const FineFetch &f, int k, unsigne
 	return r;
 }
 
+template <bool CC>
 __global__ void __launch_bounds__(FI_THREADS, 3)
 k_diff2_fine(FineArgs A, RbModelDev M)
 {
@@ -195,7 +196,7 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 					const float hc = cur.img.z;
 					const float zr = hc * (ref.x * cur.img.x + ref.y * cur.img.y);
 					const float zi = hc * (ref.x * cur.img.y - ref.y * cur.img.x);
-					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (A.cc ? 0.f : (cur.img.x * cur.img.x + cur.img.y * cur.img.y)));
+					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (CC ? 0.f : (cur.img.x * cur.img.x + cur.img.y * cur.img.y)));
 					const float4 *pp = s_px + (x << 4) + k;
 #pragma unroll
 					for (int j = 0; j < 4; j++)
@@ -245,12 +246,12 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 				float c = 0.f, b = 0.f;
 #pragma unroll
 				for (int ww = 0; ww < FI_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][FI_TF]; }
-				float v = A.cc ? -c / sqrtf(b) : fmaxf((b - 2.f * c) + xi2_half, 0.f);        // CC: diff2.h:1041-1046
+				float v = CC ? -c / sqrtf(b) : fmaxf((b - 2.f * c) + xi2_half, 0.f);          // CC: diff2.h:1041-1046
 				if (stage) A.st_out[out_off + c0 + threadIdx.x] += v;                         // diff2.h:424-428
 				else { A.fs_w[out_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v); }
 			}
 		}
-		if (!stage && !A.cc && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
+		if (!stage && !CC && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
 	}
 }
 
@@ -273,7 +274,7 @@ __device__ __forceinline__ void cp_async4(void *smem, const void *gmem)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int FA_DEPTH, int FA_MINB>
+template <int FA_DEPTH, int FA_MINB, bool CC>
 __global__ void __launch_bounds__(FI_THREADS, FA_MINB)
 k_diff2_fine_async(FineArgs A, RbModelDev M)
 {
@@ -390,7 +391,7 @@ k_diff2_fine_async(FineArgs A, RbModelDev M)
 					const float hc = im.z;
 					const float zr = hc * (ref.x * im.x + ref.y * im.y);
 					const float zi = hc * (ref.x * im.y - ref.y * im.x);
-					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (A.cc ? 0.f : (im.x * im.x + im.y * im.y)));
+					if (k == 0) base += hc * ((ref.x * ref.x + ref.y * ref.y) + (CC ? 0.f : (im.x * im.x + im.y * im.y)));
 					const float4 *pp = s_px + (x << 4) + k;
 #pragma unroll
 					for (int j = 0; j < 4; j++)
@@ -436,11 +437,11 @@ k_diff2_fine_async(FineArgs A, RbModelDev M)
 				float c = 0.f, b = 0.f;
 #pragma unroll
 				for (int ww = 0; ww < FI_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][FI_TF]; }
-				const float v = A.cc ? -c / sqrtf(b) : fmaxf((b - 2.f * c) + xi2_half, 0.f);
+				const float v = CC ? -c / sqrtf(b) : fmaxf((b - 2.f * c) + xi2_half, 0.f);
 				A.fs_w[out_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v);
 			}
 		}
-		if (!A.cc && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);   // CC values are negative: the minimum is taken by k_weights_cc_fine
+		if (!CC && threadIdx.x < FI_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);   // CC values are negative: the minimum is taken by k_weights_cc_fine
 	}
 }
 
@@ -448,13 +449,14 @@ static int launch_fine(rb_ctx *ctx, FineArgs &A, int grid)
 {
 	const int xs = A.n / 2 + 1;
 	size_t sm = (size_t) xs * 16 * sizeof(float4);
-	static size_t configured = 0;
-	if (sm > configured)
+	static size_t configured[2] = {0, 0};
+	void (*kern)(FineArgs, RbModelDev) = A.cc ? k_diff2_fine<true> : k_diff2_fine<false>;
+	if (sm > configured[A.cc ? 1 : 0])
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_diff2_fine, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-		configured = sm;
+		RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+		configured[A.cc ? 1 : 0] = sm;
 	}
-	k_diff2_fine<<<grid, FI_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
+	kern<<<grid, FI_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
@@ -469,9 +471,9 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	memset(&PA, 0, sizeof(PA));
 	PA.metas = s.meta.as<RbPartMeta>(); PA.Fimg = s.Fimg.as<float2>();
 	PA.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
-	PA.ires = M.ires_f; PA.rows = M.rows_f; PA.nrows = M.nrows_f; PA.n = n; PA.out = s.fimg4.as<float4>();
+	PA.ires = M.d2_ires_f; PA.rows = M.d2_rows_f; PA.nrows = M.d2_nrows_f; PA.n = n; PA.out = s.fimg4.as<float4>();
 	if (M.do_cc) { PA.cc = 1; PA.cc_corr = s.cc_corr.as<float>() + s.P; }   // [1][P]: the fine window's 1 / sqrtXi2^2
-	dim3 pg((M.nrows_f * xs + 255) / 256, s.P);
+	dim3 pg((M.d2_nrows_f * xs + 255) / 256, s.P);
 	k_prep_img4<<<pg, 256, 0, ctx->stream>>>(PA, M);
 	RB_LAUNCH_CHECK(ctx);
 
@@ -483,7 +485,7 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	A.img4 = s.fimg4.as<float4>();
 	A.slices = s.slices.as<float2>(); A.slice_capacity = s.slice_capacity;
 	A.projs = ctx->d_proj.as<RbProjector>();
-	A.rows = M.rows_f; A.nrows = M.nrows_f; A.n = n;
+	A.rows = M.d2_rows_f; A.nrows = M.d2_nrows_f; A.n = n;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
 	A.cc = M.do_cc;
 	// cp.async-staged variant whenever three CTAs per SM still fit next to the phase table (measured at 256 px: 6.44 ms vs
@@ -501,12 +503,14 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 		if (mode == 2 || mode == 4)
 		{
 			const size_t sm = table + 2 * ring1;
-			static size_t configured[2] = {0, 0};
-			void (*kern)(FineArgs, RbModelDev) = mode == 2 ? k_diff2_fine_async<2, 3> : k_diff2_fine_async<2, 4>;
-			if (sm > configured[mode == 4])
+			static size_t configured[4] = {0, 0, 0, 0};
+			void (*kern)(FineArgs, RbModelDev) = A.cc ? (mode == 2 ? k_diff2_fine_async<2, 3, true> : k_diff2_fine_async<2, 4, true>)
+			                                          : (mode == 2 ? k_diff2_fine_async<2, 3, false> : k_diff2_fine_async<2, 4, false>);
+			const int ci = (mode == 4 ? 1 : 0) + (A.cc ? 2 : 0);
+			if (sm > configured[ci])
 			{
 				RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-				configured[mode == 4] = sm;
+				configured[ci] = sm;
 			}
 			kern<<<ctx->num_sms * (mode == 4 ? 4 : 3), FI_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
 			RB_LAUNCH_CHECK(ctx);

@@ -101,7 +101,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
-	                  &ctx->m_cc[0], &ctx->m_cc[1], &ctx->m_cc[2], &ctx->m_cc[3], &ctx->m_cc[4],
+	                  &ctx->m_cc[0], &ctx->m_cc[1], &ctx->m_cc[2], &ctx->m_cc[3], &ctx->m_cc[4], &ctx->m_cc[5],
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp};
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
@@ -535,6 +535,16 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	}
 	RB_CHECK(upload(ctx, ctx->m_pix_c, pc.data(), pc.size() * 4));
 	RB_CHECK(upload(ctx, ctx->m_pix_f, pf.data(), pf.size() * 4));
+	// --no_map: Minvsigma2 is one on EVERY pixel in the back-projection (acc_ml_optimiser_impl.h:3110-3115), so the redundant
+	// half of the x = 0 column, which Mresol excludes, is back-projected as well: the store stage then walks the full list
+	size_t n_store = pf.size();
+	if (!m->do_map)
+	{
+		std::vector<uint32_t> pfull;
+		make_pixlist(m->current_size, pfull, true);
+		n_store = pfull.size();
+		RB_CHECK(upload(ctx, ctx->m_cc[5], pfull.data(), pfull.size() * 4));
+	}
 	std::vector<RbRow> rc, rf;
 	std::vector<short> ic, iff;
 	make_rows(m->coarse_size, rc, ic); make_rows(m->current_size, rf, iff);
@@ -562,6 +572,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	d.Npc = m->coarse_size * (m->coarse_size / 2 + 1); d.Npf = m->current_size * (m->current_size / 2 + 1);
 	d.nvc = (int) pc.size(); d.nvf = (int) pf.size();
 	d.pix_c = ctx->m_pix_c.as<uint32_t>(); d.pix_f = ctx->m_pix_f.as<uint32_t>();
+	d.pix_store = m->do_map ? d.pix_f : ctx->m_cc[5].as<uint32_t>(); d.nv_store = (int) n_store;
 	d.nrows_c = (int) rc.size(); d.nrows_f = (int) rf.size();
 	d.rows_c = ctx->m_rows_c.as<RbRow>(); d.rows_f = ctx->m_rows_f.as<RbRow>();
 	d.ires_c = ctx->m_ires_c.as<short>(); d.ires_f = ctx->m_ires_f.as<short>();

@@ -143,6 +143,7 @@ struct RbModelDev {
 	int Npc, Npf;            // full half-image sizes n*(n/2+1)
 	int nvc, nvf;            // valid-pixel list lengths
 	const uint32_t *pix_c, *pix_f;
+	const uint32_t *pix_store; int nv_store;   // pixel list of the store stage: pix_f, or with --no_map the full x = 0 column too
 	// the same pixel sets as row runs (one entry per image row holding valid pixels) and dense shell maps
 	int nrows_c, nrows_f;
 	const RbRow *rows_c, *rows_f;
@@ -216,7 +217,8 @@ struct rb_ctx {
 	       s_tx, s_ty, s_otx, s_oty;
 	DevBuf m_pix_c, m_pix_f, m_minvs2, m_pdf_dir, m_pdf_class, m_dvp;
 	DevBuf m_rows_c, m_rows_f, m_ires_c, m_ires_f;
-	DevBuf m_cc[5];                  // do_cc: coarse pixel list, coarse rows / shell map, fine rows / shell map with the full x = 0 column
+	DevBuf m_cc[6];                  // do_cc: coarse pixel list, coarse rows / shell map, fine rows / shell map with the full x = 0 column;
+	                                 // [5]: !do_map: fine pixel list of the store stage with the full x = 0 column
 	DevBuf d_proj, d_bp;             // device copies of the projector / backprojector tables
 	std::vector<double> h_scale_correction;
 

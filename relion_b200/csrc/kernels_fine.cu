@@ -39,6 +39,7 @@ struct FineArgs {
 	const float *tx, *ty; int NOT;
 	int cc;                        // cross-correlation criterion (cuda_kernel_diff2_CC_fine, diff2.cuh:464-640; ALTCPU
 	                               // cpu_kernels/diff2.h:904-1050): img4.z holds corr, value = -cross / sqrt(sum corr |A|^2)
+	int *queue;                    // pool mode: work queue counter (zero at launch), see rb_next_work
 };
 
 struct FineFetch {
@@ -110,7 +111,8 @@ k_diff2_fine(FineArgs A, RbModelDev M)
 	const int k = threadIdx.x & 3, qd = threadIdx.x >> 2;
 	const unsigned qmask = 0xFu << (lane & ~3);
 
-	for (int w = blockIdx.x; w < nwork; w += gridDim.x)
+	__shared__ int s_next;
+	for (int w = rb_next_work(A.queue, &s_next, 0, true); w < nwork; w = rb_next_work(A.queue, &s_next, w, false))
 	{
 		int nsamp, cls = 0, p = 0;
 		long long out_off;
@@ -293,7 +295,8 @@ k_diff2_fine_async(FineArgs A, RbModelDev M)
 	const int k = threadIdx.x & 3, qd = threadIdx.x >> 2, qbase = threadIdx.x & ~3;
 	const unsigned qmask = 0xFu << (lane & ~3);
 
-	for (int w = blockIdx.x; w < nwork; w += gridDim.x)
+	__shared__ int s_next;
+	for (int w = rb_next_work(A.queue, &s_next, 0, true); w < nwork; w = rb_next_work(A.queue, &s_next, w, false))
 	{
 		const RbFineOrient F = A.fo[w];
 		const int nsamp = F.n_t * A.NOT, cls = F.iclass, p = F.particle;
@@ -488,6 +491,7 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 	A.rows = M.d2_rows_f; A.nrows = M.d2_nrows_f; A.n = n;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
 	A.cc = M.do_cc;
+	A.queue = s.counters.as<int>() + 8;
 	// cp.async-staged variant whenever three CTAs per SM still fit next to the phase table (measured at 256 px: 6.44 ms vs
 	// 6.97 ms; with two CTAs per SM it loses: 9.9 vs 9.2 ms at 400 px with a 6-deep ring)
 	static int use_async = -1;

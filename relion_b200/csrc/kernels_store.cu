@@ -143,6 +143,7 @@ struct StoreArgs {
 	const uint32_t *pix; int npix; int n;
 	const float *tx, *ty; int NOT;
 	const float2 *slices; long long slice_capacity;   // slices cached by the fine pass ([fine orientation][n][n/2+1])
+	int *queue;                    // two work queue counters (sliced launch, gather launch), zero at launch: rb_next_work
 };
 
 static const int ST_CHUNK = 256;   // significant samples held in shared memory at a time
@@ -204,8 +205,11 @@ k_store(StoreArgs A, RbModelDev M)
 	const int w_end = SLICED ? (int) (cap < nfo ? cap : nfo) : nfo;
 	const int half = A.n / 2;
 
-	for (int w = w_begin + blockIdx.x; w < w_end; w += gridDim.x)
+	__shared__ int s_next;
+	int *queue = A.queue ? A.queue + (SLICED ? 0 : 1) : nullptr;
+	for (int wi = rb_next_work(queue, &s_next, 0, true); w_begin + wi < w_end; wi = rb_next_work(queue, &s_next, wi, false))
 	{
+		const int w = w_begin + wi;
 		const RbFineOrient F = A.fo[w];
 		const int p = F.particle;
 		const RbPartState *st = A.states + p;
@@ -311,8 +315,10 @@ k_store(StoreArgs A, RbModelDev M)
 						const float xa = (ref.x * cur.X.x + ref.y * cur.X.y) * phr - (ref.x * cur.X.y - ref.y * cur.X.x) * phi;
 						const float aa = W * refn;
 						const float wd = fmaxf(W * (refn + Xn) - 2.f * xa, 0.f);
-						atomicAdd(&s_shell[ires], wd);
-						if (dvp[ires] && M.do_scale_correction) { aXA += (double) xa; aAA += (double) aa; }   // :3473-3479
+						// (x = 0, y < 0) is only in the list with --no_map: Mresol excludes it from the shell sums (:3466-3494)
+						const bool in_mresol = !(x == 0 && y < 0);
+						if (in_mresol) atomicAdd(&s_shell[ires], wd);
+						if (in_mresol && dvp[ires] && M.do_scale_correction) { aXA += (double) xa; aAA += (double) aa; }   // :3473-3479
 						// back-projection
 						const float minvs2 = M.do_map ? __ldg(mtab + ires) : 1.f;                          // :2586, :3110-3115
 						const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                       // BP.cuh:280-289
@@ -392,9 +398,10 @@ int rbk_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.fo = s.fo.as<RbFineOrient>(); A.pair_list = s.pair_list.as<int>(); A.counters = s.counters.as<int>();
 	A.fs_w = s.fs_w.as<float>(); A.shells = s.shells.as<float>();
 	A.projs = ctx->d_proj.as<RbProjector>(); A.bps = ctx->d_bp.as<RbBackprojector>();
-	A.pix = ctx->d_model.pix_f; A.npix = ctx->d_model.nvf; A.n = ctx->d_model.current_size;
+	A.pix = ctx->d_model.pix_store; A.npix = ctx->d_model.nv_store; A.n = ctx->d_model.current_size;
 	A.tx = ctx->d_samp.ftx; A.ty = ctx->d_samp.fty; A.NOT = ctx->d_samp.n_over_trans;
 	A.slices = s.slices.as<float2>(); A.slice_capacity = s.slice_capacity;
+	A.queue = s.counters.as<int>() + 9;
 	// measured on the headline pool (tools/sweep_variants.sh): depth 2 / 2 CTAs per SM 5.66 ms, depth 3 / 3 CTAs 5.93 ms,
 	// depth 4 / 3 CTAs 6.10 ms: the stage is bound by the reductions' L2 round trips, not by load latency
 	if (A.slices && A.slice_capacity > 0)

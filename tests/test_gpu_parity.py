@@ -301,6 +301,16 @@ def test_pool_firstiter_cc(device, oracle, kw):
     assert np.all(g["dLL_nolog"] > 0)           # = -min_diff2: the best normalised cross-correlation is positive
 
 
+@pytest.mark.parametrize("flags", [dict(do_map=False), dict(do_scale_correction=False), dict(do_ctf_correction=False),
+                                   dict(do_map=False, do_scale_correction=False, do_ctf_correction=False)])
+def test_pool_optimiser_flags(device, oracle, flags):
+    """--no_map (all-ones Minvsigma2 in the back-projection, :3110-3115), no --scale, no --ctf."""
+    wl = make_workload(ori_size=32, healpix_order=1, n_particles=8, nr_classes=1, seed=61, snr=0.3)
+    for k, v in flags.items():
+        setattr(wl.model, k, v)
+    _compare_pool(device, oracle, wl)
+
+
 def test_pool_reduced_current_size(device, oracle):
     wl = make_workload(ori_size=40, current_size=28, healpix_order=1, n_particles=6, seed=23, snr=0.3)
     _compare_pool(device, oracle, wl)

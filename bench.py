@@ -154,7 +154,9 @@ def stage_bytes(wl, res):
     fine = (64.0 * ofs * npf + 12.0 * npf + 4.0 * sf).sum()
     # fused wavg + back-projection, SURVEY.md §8d figures: wavg gather 64 B + back-projection 204 B
     # (8 corners x 3 arrays x 4 B, x2 read-modify-write, + 12 B inputs) per pixel of every fine orientation
-    store = ((64.0 + 204.0) * ofs * npf).sum()
+    # that holds at least one significant sample (n_bp_orient: the others are skipped by the reference kernels as well)
+    obp = p["n_bp_orient"].astype(np.float64)
+    store = ((64.0 + 204.0) * obp * npf).sum()
     # global searches: the coarse pass is the contraction [O x 2Np] . [2Np x P T] per class (+ the norm term [O x Np] . [Np x P])
     coarse_flops = (2.0 * (2 * npc) * n_or * T + 2.0 * npc * n_or).sum() if wl.pool.dir_off is None else 0.0
     return {"coarse": coarse, "fine": fine, "store": store, "coarse_flops": coarse_flops}

@@ -235,6 +235,8 @@ typedef struct {
 	float sum_weight;            /* op.sum_weight (fine pass)                                     */
 	float significant_weight;    /* op.significant_weight (fine pass)                             */
 	float pmax;                  /* METADATA_PMAX = max_weight / sum_weight                       */
+	int n_bp_orient;             /* fine orientations holding >= 1 significant sample: the ones wavg / back-projection
+	                                actually process (diagnostics / roofline; 0 with do_skip_maximization)          */
 	double dLL_nolog;            /* log(sum_weight) - min_diff2  (host subtracts logsigma2)       */
 	double wsum_norm_correction; /* sum over shells ires>-1 of wdiff2                              */
 	double wsum_XA, wsum_AA;     /* exp_wsum_scale_correction_XA/AA before the /scale division     */

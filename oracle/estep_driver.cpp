@@ -573,6 +573,12 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 			size_t On = c.rot.size();
 			std::vector<float> sw(On * Tf, LOWEST);                                          // :3247-3252
 			for (size_t i = 0; i < c.weightNum; i++) sw[c.rot_idx[i] * Tf + c.trans_idx[i]] = fw[c.firstPos + i];
+			for (size_t io = 0; io < On; io++)                                               // orientations the kernels below do work for
+			{
+				bool any = false;
+				for (int t = 0; t < Tf; t++) any |= sw[io * Tf + t] >= po.significant_weight;  // wavg.cuh:106, BP.cuh:278
+				po.n_bp_orient += any;
+			}
 			K->wavg(&S.refs[k], S.nf / 2 + 1, S.nf, c.eulers.data(), On, fr.data(), fi.data(),
 			        S.ftx.data(), S.fty.data(), sw.data(), ctfs.data(),
 			        parts.data(), &AA[(size_t) k * S.Npf], &XA[(size_t) k * S.Npf],

@@ -90,7 +90,7 @@ class rb_particle_out(C.Structure):
         ("nr_significant_coarse", C.c_int), ("n_fine_orient", C.c_int), ("n_fine_samples", C.c_int),
         ("min_diff2_coarse", C.c_float), ("sum_weight_coarse", C.c_float), ("significant_weight_coarse", C.c_float),
         ("min_diff2", C.c_float), ("max_weight", C.c_float), ("sum_weight", C.c_float),
-        ("significant_weight", C.c_float), ("pmax", C.c_float),
+        ("significant_weight", C.c_float), ("pmax", C.c_float), ("n_bp_orient", C.c_int),
         ("dLL_nolog", C.c_double), ("wsum_norm_correction", C.c_double),
         ("wsum_XA", C.c_double), ("wsum_AA", C.c_double), ("sumw", C.c_double), ("wsum_sigma2_offset", C.c_double),
     ]

@@ -936,7 +936,7 @@ static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
 			rb_particle_out &o = out->particles[p];
 			memset(&o, 0, sizeof(o));
 			o.nr_significant_coarse = q.nr_sig_coarse;
-			o.n_fine_orient = q.n_so * NOR; o.n_fine_samples = q.n_pairs * NOR * NOT;
+			o.n_fine_orient = q.n_so * NOR; o.n_fine_samples = q.n_pairs * NOR * NOT; o.n_bp_orient = q.n_bp;
 			o.min_diff2_coarse = q.min_diff2; o.sum_weight_coarse = q.csum_weight; o.significant_weight_coarse = q.csig_weight;
 			if (q.status != 0)
 			{

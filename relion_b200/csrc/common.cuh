@@ -111,6 +111,7 @@ struct RbPartState {
 	double min_diff2_final;
 	long long best_ihid;     // ihidden_over of the maximum-weight fine sample
 	int status;
+	int n_bp;                // fine orientations the store stage processed (>= 1 significant sample)
 	// store-stage accumulators
 	double wsum_norm, wsum_XA, wsum_AA, sumw, wsum_s2off;
 };

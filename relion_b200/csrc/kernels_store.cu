@@ -236,6 +236,7 @@ k_store(StoreArgs A, RbModelDev M)
 		__syncthreads();
 		const int nsig = s_nsig;
 		if (nsig == 0) continue;
+		if (threadIdx.x == 0) atomicAdd(&A.states[p].n_bp, 1);
 
 		const RbPartMeta m = A.metas[p];
 		const float2 *X = A.Fimg + (size_t) p * M.Npf, *X0 = A.Fnomask + (size_t) p * M.Npf;

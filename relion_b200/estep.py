@@ -105,7 +105,7 @@ _OUT_DTYPE = np.dtype([
     ("nr_significant_coarse", np.int32), ("n_fine_orient", np.int32), ("n_fine_samples", np.int32),
     ("min_diff2_coarse", np.float32), ("sum_weight_coarse", np.float32), ("significant_weight_coarse", np.float32),
     ("min_diff2", np.float32), ("max_weight", np.float32), ("sum_weight", np.float32),
-    ("significant_weight", np.float32), ("pmax", np.float32),
+    ("significant_weight", np.float32), ("pmax", np.float32), ("n_bp_orient", np.int32),
     ("dLL_nolog", np.float64), ("wsum_norm_correction", np.float64),
     ("wsum_XA", np.float64), ("wsum_AA", np.float64), ("sumw", np.float64), ("wsum_sigma2_offset", np.float64),
 ], align=True)

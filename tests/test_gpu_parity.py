@@ -238,6 +238,7 @@ def _compare_pool(device, oracle, wl, pose_frac=0.995):
     np.testing.assert_allclose(g["pmax"][ok], o["pmax"][ok], rtol=2e-3, atol=1e-6)
     np.testing.assert_allclose(g["sum_weight"][ok], o["sum_weight"][ok], rtol=2e-3)
     np.testing.assert_allclose(g["sumw"][ok], o["sumw"][ok], rtol=1e-4)
+    assert np.mean(g["n_bp_orient"][ok] == o["n_bp_orient"][ok]) >= 0.9, (g["n_bp_orient"], o["n_bp_orient"])
     np.testing.assert_allclose(g["wsum_sigma2_offset"][ok], o["wsum_sigma2_offset"][ok], rtol=2e-3, atol=1e-6)
     np.testing.assert_allclose(g["wsum_norm_correction"][ok], o["wsum_norm_correction"][ok], rtol=2e-3)
     np.testing.assert_allclose(g["wsum_XA"][ok], o["wsum_XA"][ok], rtol=5e-3, atol=1e-3 * np.abs(o["wsum_XA"]).max())

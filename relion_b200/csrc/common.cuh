@@ -174,6 +174,10 @@ struct DevBuf {
 	template <typename T> T *as() const { return (T *) p; }
 };
 
+// cudaFuncSetAttribute applies to the current device only: launchers remember what they configured per device
+// (several MlDeviceBundles, one per GPU, may live in one process)
+static const int RB_MAX_DEVICES = 64;
+
 struct PoolSlot {
 	int P = 0;
 	bool has_priors = false;

@@ -229,11 +229,12 @@ template <int EO, int TT, bool XP>
 static int launch_coarse_cfg(rb_ctx *ctx, CoarseArgs &A, int no_max, int n_classes, int P)
 {
 	size_t sm = (size_t) TT * ((A.n / 2 + 1) + A.ny) * sizeof(float2);
-	static size_t configured = 0;
-	if (sm > configured)
+	static size_t configured[RB_MAX_DEVICES] = {};
+	size_t &cfg = configured[ctx->device % RB_MAX_DEVICES];
+	if (sm > cfg)
 	{
 		RB_CUDA(cudaFuncSetAttribute(k_diff2_coarse<EO, TT, XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-		configured = sm;
+		cfg = sm;
 	}
 	A.tiles_per_class = (no_max + EO - 1) / EO;
 	dim3 grid(A.tiles_per_class * n_classes, P);

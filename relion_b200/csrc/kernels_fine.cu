@@ -452,12 +452,13 @@ static int launch_fine(rb_ctx *ctx, FineArgs &A, int grid)
 {
 	const int xs = A.n / 2 + 1;
 	size_t sm = (size_t) xs * 16 * sizeof(float4);
-	static size_t configured[2] = {0, 0};
+	static size_t configured[RB_MAX_DEVICES][2] = {};
+	size_t &cfg = configured[ctx->device % RB_MAX_DEVICES][A.cc ? 1 : 0];
 	void (*kern)(FineArgs, RbModelDev) = A.cc ? k_diff2_fine<true> : k_diff2_fine<false>;
-	if (sm > configured[A.cc ? 1 : 0])
+	if (sm > cfg)
 	{
 		RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-		configured[A.cc ? 1 : 0] = sm;
+		cfg = sm;
 	}
 	kern<<<grid, FI_THREADS, sm, ctx->stream>>>(A, ctx->d_model);
 	RB_LAUNCH_CHECK(ctx);
@@ -507,7 +508,8 @@ int rbk_diff2_fine_pool(rb_ctx *ctx, PoolSlot &s)
 		if (mode == 2 || mode == 4)
 		{
 			const size_t sm = table + 2 * ring1;
-			static size_t configured[4] = {0, 0, 0, 0};
+			static size_t configured_dev[RB_MAX_DEVICES][4] = {};
+			size_t *configured = configured_dev[ctx->device % RB_MAX_DEVICES];
 			void (*kern)(FineArgs, RbModelDev) = A.cc ? (mode == 2 ? k_diff2_fine_async<2, 3, true> : k_diff2_fine_async<2, 4, true>)
 			                                          : (mode == 2 ? k_diff2_fine_async<2, 3, false> : k_diff2_fine_async<2, 4, false>);
 			const int ci = (mode == 4 ? 1 : 0) + (A.cc ? 2 : 0);

@@ -557,7 +557,8 @@ template <int BK, bool MIXED, bool TWO>
 static int launch_gemm_variant(rb_ctx *ctx, dim3 grid, const CUtensorMap (&t)[6], int nkb, const GemmEpilogue &E)
 {
 	typedef GemmCfg<BK, TWO> Cfg;
-	static bool configured = false;
+	static bool configured_dev[RB_MAX_DEVICES] = {};
+	bool &configured = configured_dev[ctx->device % RB_MAX_DEVICES];
 	if (!configured)
 	{
 		RB_CUDA(cudaFuncSetAttribute(k_gemm_tf32x3<BK, MIXED, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) Cfg::SMEM));
@@ -1091,7 +1092,8 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	// measured (256 px, hp4 local): 8 warps x 2 CTAs/SM (166 KB of shared memory, 32 KB of L1 left) 7.98 ms; 16 warps x 1 CTA/SM
 	// (83 KB, 128 KB of L1 for the gathers) 6.69 ms.  Loads that bypass L1 allocation: 18.6 ms - the corner rows do get reused.
 	if (!npw) { const char *e = getenv("RB_FUSED_WARPS"); npw = (e && atoi(e) == 8) ? 8 : 16; }
-	static bool configured = false;
+	static bool configured_dev[RB_MAX_DEVICES] = {};
+	bool &configured = configured_dev[ctx->device % RB_MAX_DEVICES];
 	if (!configured)
 	{
 		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));

@@ -761,7 +761,8 @@ static int weights_coarse_large(rb_ctx *ctx, PoolSlot &s, long long n)
 	RB_CUDA(cudaMemsetAsync(A.gtot, 0, (size_t) P * 16, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(A.ntot, 0, (size_t) P * 16, ctx->stream));
 	dim3 grid(A.nchunk, P);
-	static bool configured = false;
+	static bool configured_dev[RB_MAX_DEVICES] = {};
+	bool &configured = configured_dev[ctx->device % RB_MAX_DEVICES];
 	if (!configured)
 	{
 		RB_CUDA(cudaFuncSetAttribute(k_wc_exp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WC_BINS * 12));

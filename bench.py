@@ -56,6 +56,10 @@ WORKLOADS = {
     # BASELINE config #1: 2D classification, K = 10, 64-px particles, psi step 6 deg, offset range 5 / step 2
     "class2d_64": (dict(ori_size=64, nr_classes=10, ref_dim=2, psi_step=6.0, offset_range=5.0, offset_step=2.0, snr=0.1,
                         pixel_size=3.0, n_blobs=25, nr_groups=8), 2000),
+    # BASELINE config #3, state (i): first iteration of a 3D auto-refine with --firstiter_cc (cross-correlation criterion):
+    # HEALPix order 2 global search (4 608 orientations), 21 translations, 30 A initial low-pass -> 40-px current size
+    "refine3d_128_firstiter_cc": (dict(ori_size=128, current_size=40, healpix_order=2, offset_range=5.0, offset_step=2.0, nr_classes=1,
+                                       snr=0.05, pixel_size=2.0, n_blobs=100, nr_groups=8, do_cc=True), 256),
     "tiny": (dict(ori_size=32, healpix_order=1, nr_classes=1, snr=0.3, n_blobs=20), 16),
 }
 
@@ -370,8 +374,11 @@ def run_ours(args):
                             "fp32-equivalent product, a tf32 product counted twice) over the coarse stage time (operand builders "
                             "included); useful fp32-equivalent rate = tensor_TFLOPs_useful"}
 
-    if dom == "coarse" and not tensor_coarse and wl.pool.dir_off is not None and os.environ.get("RB_COARSE_FUSED", "1") != "0":
+    if dom == "coarse" and not tensor_coarse and wl.pool.dir_off is not None and os.environ.get("RB_COARSE_FUSED", "1") != "0" and not wl.model.do_cc:
         roofline["kernel"] = "k_coarse_fused"
+    xs_f = wl.model.current_size // 2 + 1
+    if dom == "fine" and os.environ.get("RB_FINE_ASYNC", "1") != "0" and xs_f * 256 + 2 * 256 * 24 <= 74 * 1024:
+        roofline["kernel"] = "k_diff2_fine_async"     # the cp.async-staged variant (kernels_fine.cu: rbk_diff2_fine_pool)
     roofline["traffic"] = ncu_traffic(args.workload, P, roofline["kernel"])
     if roofline["bound"] == "hbm":
         roofline["frac_of_nominal_8000"] = round(roofline["achieved"] / 8000.0, 4)

@@ -244,6 +244,7 @@ struct GemmEpilogue {
 	const float *base; int ldbase;   // [o][p] norm term
 	const float *x2;                 // [p] sum c |X'|^2
 	int T, P, O, cls, o_first;       // o_first: first orientation of this M chunk
+	int cc;                          // cross-correlation criterion: value = -cross / sqrt(norm term) (diff2.cuh:336-460), no minimum
 	// common
 	int M, N;                        // valid extent of this launch (rows of the chunk, columns)
 	int exp;                         // timing experiments only (RB_GEMM_EXP): 1 no bf16 MMAs, 2 no tf32 MMAs, 3 grouped issue, 4 no MMAs
@@ -467,7 +468,8 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 					const RbPartMeta m = E.metas[pp];
 					const long long oc = (long long) E.cls * E.O + o;
 					pvalid = !E.pdf_orient_zero[m.prior_off + oc];
-					bsum = E.base[(size_t) row * E.ldbase + pp] + E.x2[pp];
+					bsum = E.base[(size_t) row * E.ldbase + pp] + (E.cc ? 0.f : E.x2[pp]);
+					if (E.cc) bsum = sqrtf(bsum);                                        // CC: the norm term alone, as its root
 					xi2 = m.xi2_half;
 					woff = m.coarse_off + oc * E.T;
 				}
@@ -475,7 +477,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 			auto flush_min = [&](int pp)
 			{
 				const float wm = -warp_max(-bmin);
-				if (lane == 0 && pp < E.P && wm < FLT_MAX) rb_atomic_min_pos(&E.states[pp].min_diff2_bits, wm);
+				if (lane == 0 && pp < E.P && wm < FLT_MAX && !E.cc) rb_atomic_min_pos(&E.states[pp].min_diff2_bits, wm);   // CC values are negative: k_weights_cc_coarse takes the minimum
 				bmin = FLT_MAX;
 			};
 			load_particle(p);
@@ -486,6 +488,16 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 				tmem_ld32(trow + GM_BN + c * 32, v2);
 #pragma unroll
 				for (int j = 0; j < 32; j++) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(v2[j]));
+				if (E.cc)
+				{
+#pragma unroll
+					for (int j = 0; j < 32; j++)
+					{
+						if (pvalid) E.Mweight[woff + t] = -(__uint_as_float(v[j]) / bsum);         // diff2.h:729-735
+						if (++t == E.T) { t = 0; p++; load_particle(p); }
+					}
+					continue;
+				}
 #pragma unroll
 				for (int j = 0; j < 32; j++)
 				{
@@ -730,7 +742,8 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	const RbSamplingDev &S = ctx->d_samp;
 	const int P = s.P, T = S.n_trans, K = M.nr_classes;
 	const int O = S.n_dir * S.n_psi;
-	const int npix = M.nvc, n = M.coarse_size;
+	const int npix = M.d2_nvc, n = M.coarse_size;        // d2_*: with the CC criterion every pixel of the window's circle
+	const uint32_t *pix = M.d2_pix_c;
 	const size_t kpad = round_up((size_t) 2 * npix, GM_BK), k2pad = round_up((size_t) npix, GM_BK);
 	const size_t Npad = round_up((size_t) P * T, GM_BN), N2pad = round_up((size_t) P, GM_BN);
 	// orientation chunk: bounded operand memory (A and A2, hi + lo)
@@ -760,7 +773,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	// particle operands (independent of the class)
 	RB_CUDA(cudaMemsetAsync(bB2hi.p, 0, N2pad * k2pad * 4, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(bB2lo.p, 0, N2pad * k2pad * 4, ctx->stream));
-	k_gemm_build_B<<<(unsigned) Npad, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, T, P,
+	k_gemm_build_B<<<(unsigned) Npad, 256, 0, ctx->stream>>>(cimg4, pix, npix, n, S.ctx, S.cty, T, T, P,
 		bBhi.as<float>(), bBlo.as<float>(), kpad, bB2hi.as<float>(), bB2lo.as<float>(), k2pad, bX2.as<float>(),
 		gemm_mixed() ? Npad * kpad : 0, gemm_mixed() ? N2pad * k2pad : 0);
 	RB_LAUNCH_CHECK(ctx);
@@ -791,7 +804,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 			if (build)
 			{
 				dim3 ga((unsigned) std::min<size_t>((kpad / 2 + 255) / 256, 64), (unsigned) rows_pad);
-				k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[cls], S.coarse_eulers, M.pix_c, npix, n, o0, rows, rows_pad,
+				k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[cls], S.coarse_eulers, pix, npix, n, o0, rows, rows_pad,
 					Ahi, Alo, kpad, A2hi, A2lo, k2pad, gemm_mixed() ? 1 : 0);
 				RB_LAUNCH_CHECK(ctx);
 			}
@@ -807,6 +820,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 			E1.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>(); E1.Mweight = s.Mweight.as<float>();
 			E1.base = bBase.as<float>(); E1.ldbase = (int) N2pad; E1.x2 = bX2.as<float>();
 			E1.T = T; E1.P = P; E1.O = O; E1.cls = cls; E1.o_first = o0; E1.M = rows; E1.N = P * T;
+			E1.cc = M.do_cc;
 			RB_CHECK(launch_gemm(ctx, Ahi, Alo, rows_pad, bBhi.as<float>(), bBlo.as<float>(), Npad, kpad, E1));
 		}
 	return RB_OK;

@@ -288,9 +288,11 @@ def test_pool_global_search_through_fused_kernel(device, oracle, monkeypatch):
 @pytest.mark.parametrize("kw", [dict(ori_size=32, healpix_order=1, n_particles=12, nr_classes=1, seed=41, snr=0.3),
                                 dict(ori_size=40, current_size=28, healpix_order=1, n_particles=8, nr_classes=1, seed=42, snr=0.1),
                                 dict(ori_size=32, n_particles=16, nr_classes=1, seed=43, snr=0.5, ref_dim=2, psi_step=12.0)])
-def test_pool_firstiter_cc(device, oracle, kw):
+@pytest.mark.parametrize("coarse", ["gemm", "simt"])
+def test_pool_firstiter_cc(device, oracle, monkeypatch, kw, coarse):
     """--firstiter_cc / --always_cc: cross-correlation kernels in both passes, weight one for the best pose
-    (acc_ml_optimiser_impl.h:1164, 1287, 2012-2071, 3571)."""
+    (acc_ml_optimiser_impl.h:1164, 1287, 2012-2071, 3571); coarse pass through the tensor-core contraction and the SIMT kernel."""
+    monkeypatch.setenv("RB_COARSE_GEMM", "2" if coarse == "gemm" else "0")
     wl = make_workload(do_cc=True, **kw)
     if kw.get("ref_dim") == 2:
         wl.model.bp_circle_bound = False

@@ -742,6 +742,33 @@ def test_pool_store_stage_without_slice_cache(device, oracle, monkeypatch, cache
     assert res.particles["n_fine_orient"].sum() > cache_slices
 
 
+def test_two_device_bundles_in_one_process(device):
+    """RELION drives several GPUs from the threads of one process (one MlDeviceBundle per device): contexts on different
+    devices must not share per-device state (kernel attributes, streams, buffers).  Needs a box with >= 2 GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from relion_b200.estep import MlDeviceBundle
+    wl = make_workload(ori_size=64, healpix_order=2, n_particles=12, nr_classes=1, seed=71, snr=0.2, local_search=True)
+    wg = make_workload(ori_size=32, healpix_order=1, n_particles=8, nr_classes=2, seed=72, snr=0.3)
+    second = MlDeviceBundle(1)
+    try:
+        out = {}
+        for name, dev, w in (("local0", device, wl), ("local1", second, wl), ("global1", second, wg), ("global0", device, wg)):
+            _setup(dev, w)
+            out[name] = (dev.expectation_some_particles(w.pool), [dev.bp_get(k) for k in range(w.model.nr_classes)])
+        for a, b in (("local0", "local1"), ("global0", "global1")):
+            ra, rb = out[a][0].particles, out[b][0].particles
+            for f in ("best_ihidden_over", "nr_significant_coarse", "n_fine_samples"):
+                assert np.array_equal(ra[f], rb[f]), (a, b, f)
+            np.testing.assert_allclose(ra["dLL_nolog"], rb["dLL_nolog"], rtol=1e-6)
+            for ka, kb in zip(out[a][1], out[b][1]):
+                for x, y in zip(ka, kb):
+                    assert np.abs(x - y).max() <= 1e-5 * max(np.abs(y).max(), 1e-12)
+    finally:
+        second.close()
+
+
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()

@@ -304,9 +304,13 @@ int rbk_cc_corr_pool(rb_ctx *ctx, PoolSlot &s)
 
 int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 {
-	// Mweight <- lowest() (acc_ml_optimiser_impl.h:3849)
-	k_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(s.Mweight.as<float>(), RB_LOWEST, (size_t) s.total_coarse);
-	RB_LAUNCH_CHECK(ctx);
+	// Mweight <- lowest() (acc_ml_optimiser_impl.h:3849); the contraction's epilogue writes every entry itself
+	const bool gemm_path = rbk_coarse_gemm_applicable(ctx, s);
+	if (!gemm_path)
+	{
+		k_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(s.Mweight.as<float>(), RB_LOWEST, (size_t) s.total_coarse);
+		RB_LAUNCH_CHECK(ctx);
+	}
 	// images at the coarse window with all corrections applied, once per particle
 	const RbModelDev &M = ctx->d_model;
 	const int nc = M.coarse_size, xsc = nc / 2 + 1;
@@ -329,7 +333,7 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 
 	// global searches: the cross term is a dense contraction shared by the whole pool -> tensor cores (also with the
 	// cross-correlation criterion: same cross and norm terms, different epilogue)
-	if (rbk_coarse_gemm_applicable(ctx, s)) return rbk_diff2_coarse_gemm_pool(ctx, s, s.cimg4.as<float4>());
+	if (gemm_path) return rbk_diff2_coarse_gemm_pool(ctx, s, s.cimg4.as<float4>());
 	// local searches: projection fused with the contraction, per (particle, 128-orientation tile); the CC criterion with
 	// local searches (--always_cc late in a refinement) stays on the SIMT kernel
 	if (!M.do_cc && rbk_coarse_fused_applicable(ctx, s)) return rbk_diff2_coarse_fused_pool(ctx, s, s.cimg4.as<float4>());

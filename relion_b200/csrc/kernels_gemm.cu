@@ -459,12 +459,16 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 			const bool row_ok = row < E.M;
 			int p = n0 / E.T, t = n0 - p * E.T;
 			float bmin = FLT_MAX;
-			bool pvalid = false; float bsum = 0.f, xi2 = 0.f; long long woff = 0;
+			// pvalid: the entry is computed; pwrite && !pvalid: orientation without prior (or class with pdf_class == 0), the
+			// entry gets the lowest() that Mweight is initialised with in the reference (:3849) — the epilogue covers every
+			// entry of the pool's Mweight, so no separate fill pass is needed on this path
+			bool pvalid = false, pwrite = false; float bsum = 0.f, xi2 = 0.f; long long woff = 0;
 			auto load_particle = [&](int pp)
 			{
-				pvalid = false;
+				pvalid = false; pwrite = false;
 				if (pp < E.P && row_ok)
 				{
+					pwrite = true;
 					const RbPartMeta m = E.metas[pp];
 					const long long oc = (long long) E.cls * E.O + o;
 					pvalid = !E.pdf_orient_zero[m.prior_off + oc];
@@ -494,6 +498,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 					for (int j = 0; j < 32; j++)
 					{
 						if (pvalid) E.Mweight[woff + t] = -(__uint_as_float(v[j]) / bsum);         // diff2.h:729-735
+						else if (pwrite) E.Mweight[woff + t] = RB_LOWEST;
 						if (++t == E.T) { t = 0; p++; load_particle(p); }
 					}
 					continue;
@@ -507,6 +512,7 @@ k_gemm_tf32x3(const __grid_constant__ CUtensorMap tmAhi, const __grid_constant__
 						E.Mweight[woff + t] = d;
 						bmin = fminf(bmin, d);
 					}
+					else if (pwrite) E.Mweight[woff + t] = RB_LOWEST;
 					if (++t == E.T) { flush_min(p); t = 0; p++; load_particle(p); }
 				}
 			}

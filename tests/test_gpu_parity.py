@@ -314,6 +314,18 @@ def test_pool_optimiser_flags(device, oracle, flags):
     _compare_pool(device, oracle, wl)
 
 
+@pytest.mark.parametrize("coarse", ["gemm", "simt"])
+def test_pool_global_search_with_zero_prior_directions(device, oracle, monkeypatch, coarse):
+    """Directions with pdf_direction == 0 are never computed and stay at lowest() in Mweight (:3849, helper.cuh:39-42)."""
+    monkeypatch.setenv("RB_COARSE_GEMM", "2" if coarse == "gemm" else "0")
+    wl = make_workload(ori_size=32, healpix_order=1, n_particles=8, nr_classes=2, seed=81, snr=0.3)
+    pd = np.array(wl.model.pdf_direction, dtype=np.float64, copy=True)
+    pd[0, 1::3] = 0.0
+    pd[1, ::4] = 0.0
+    wl.model.pdf_direction = pd
+    _compare_pool(device, oracle, wl)
+
+
 def test_pool_reduced_current_size(device, oracle):
     wl = make_workload(ori_size=40, current_size=28, healpix_order=1, n_particles=6, seed=23, snr=0.3)
     _compare_pool(device, oracle, wl)

@@ -107,6 +107,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
 	for (int i = 0; i < RB_MAX_CLASSES; i++) for (auto &b : ctx->gemmA[i]) b.release();
+	for (auto &b : ctx->gemmA_all) b.release();
 	for (auto &b : ctx->wc_buf) b.release();
 	for (auto &b : ctx->prep_buf) b.release();
 	for (auto &b : ctx->recon_buf) b.release();

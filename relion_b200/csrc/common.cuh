@@ -244,6 +244,8 @@ struct rb_ctx {
 	// orientation operands (A, |A|^2; TF32 hi / lo) depend on the reference and the sampling only: cached across pools
 	DevBuf gemmA[RB_MAX_CLASSES][4];
 	long long gemmA_stamp[RB_MAX_CLASSES];
+	DevBuf gemmA_all[4];             // the classes' orientation operands stacked along M (few orientations per class: 2D classification)
+	long long gemmA_all_stamp = -1;
 	long long ref_version[RB_MAX_CLASSES] = {0}, samp_version = 0, model_version = 0;
 };
 

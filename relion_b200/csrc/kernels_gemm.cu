@@ -652,19 +652,23 @@ __global__ void k_split_pad(const float *src, int rows, int cols, float *hi, flo
 // A operands of one class for orientations [o_first, o_first + rows): projections at the coarse window
 // (AccProjectorKernel::project3Dmodel, acc_projectorkernel_impl.h:161-231), interleaved (re, im) per valid pixel, and
 // their squared moduli for the norm term.
+// projs != nullptr: rows of ALL classes stacked, row r = class r / o_per_class, orientation r % o_per_class (pj is ignored).
 __global__ void __launch_bounds__(256)
 k_gemm_build_A(RbProjector pj, const float *coarse_eulers, const uint32_t *pix, int npix, int n, int o_first, int rows, int rows_pad,
-               float *Ahi, float *Alo, size_t kpad, float *A2hi, float *A2lo, size_t k2pad, int mixed)
+               float *Ahi, float *Alo, size_t kpad, float *A2hi, float *A2lo, size_t k2pad, int mixed,
+               const RbProjector *projs, int o_per_class)
 {
 	const int r = blockIdx.y;
 	const size_t plane = mixed ? (size_t) rows_pad * kpad : 0, plane2 = mixed ? (size_t) rows_pad * k2pad : 0;
 	const int imgX = n / 2 + 1;
-	const RbProjK pk = rb_make_projk(pj, imgX);
 	const bool live = r < rows;
+	int o = o_first + r;
+	if (projs && live) { pj = projs[r / o_per_class]; o = r % o_per_class; }
+	const RbProjK pk = rb_make_projk(pj, imgX);
 	float e0 = 0, e1 = 0, e3 = 0, e4 = 0, e6 = 0, e7 = 0;
 	if (live)
 	{
-		const float *eu = coarse_eulers + (size_t) (o_first + r) * 9;
+		const float *eu = coarse_eulers + (size_t) o * 9;
 		e0 = eu[0]; e1 = eu[1]; e3 = eu[3]; e4 = eu[4]; e6 = eu[6]; e7 = eu[7];
 	}
 	const int half = (int) (kpad / 2);
@@ -790,6 +794,44 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	const char *ce = getenv("RB_GEMM_CACHE_BYTES");
 	const size_t cache_budget = ce ? (size_t) strtoull(ce, nullptr, 10) : ((size_t) 24 << 30);
 	const bool use_cache = mchunk >= round_up((size_t) O, GM_MPAD) && a_bytes * (size_t) K <= cache_budget;
+
+	// Few orientations per class (2D classification: 60 in-plane rotations, K = 10 .. 200 classes): a class fills a fraction
+	// of one 256-row tile.  Mweight's orientation index is class-major (iorientclass = class * O + o), so the classes' rows
+	// simply stack along M: one contraction over K * O rows instead of K quarter-filled ones.
+	const size_t stacked_pad = round_up((size_t) K * O, GM_MPAD);
+	const char *se = getenv("RB_GEMM_STACK");                      // 0: one contraction per class (A/B)
+	if ((!se || atoi(se) != 0) && K > 1 && use_cache && stacked_pad < (size_t) K * round_up((size_t) O, GM_MPAD))
+	{
+		const int rows = K * O, rows_pad = (int) stacked_pad;
+		DevBuf *c = ctx->gemmA_all;
+		RB_CHECK(c[0].ensure((size_t) rows_pad * kpad * 4)); RB_CHECK(c[1].ensure((size_t) rows_pad * kpad * 4));
+		RB_CHECK(c[2].ensure((size_t) rows_pad * k2pad * 4)); RB_CHECK(c[3].ensure((size_t) rows_pad * k2pad * 4));
+		RB_CHECK(bBase.ensure((size_t) rows_pad * N2pad * 4));
+		long long stamp = (ctx->samp_version << 20) ^ ctx->model_version;
+		for (int cls = 0; cls < K; cls++) stamp = stamp * 1000003LL + ctx->ref_version[cls];
+		if (ctx->gemmA_all_stamp != stamp)
+		{
+			dim3 ga((unsigned) std::min<size_t>((kpad / 2 + 255) / 256, 64), (unsigned) rows_pad);
+			k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[0], S.coarse_eulers, pix, npix, n, 0, rows, rows_pad,
+				c[0].as<float>(), c[1].as<float>(), kpad, c[2].as<float>(), c[3].as<float>(), k2pad, gemm_mixed() ? 1 : 0,
+				ctx->d_proj.as<RbProjector>(), O);
+			RB_LAUNCH_CHECK(ctx);
+			ctx->gemmA_all_stamp = stamp;
+		}
+		GemmEpilogue E0;
+		memset(&E0, 0, sizeof(E0));
+		E0.mode = 0; E0.C = bBase.as<float>(); E0.ldc = (int) N2pad; E0.M = rows; E0.N = P;
+		RB_CHECK(launch_gemm(ctx, c[2].as<float>(), c[3].as<float>(), rows_pad, bB2hi.as<float>(), bB2lo.as<float>(), N2pad, k2pad, E0));
+		GemmEpilogue E1;
+		memset(&E1, 0, sizeof(E1));
+		E1.mode = 1; E1.metas = s.meta.as<RbPartMeta>(); E1.states = s.state.as<RbPartState>();
+		E1.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>(); E1.Mweight = s.Mweight.as<float>();
+		E1.base = bBase.as<float>(); E1.ldbase = (int) N2pad; E1.x2 = bX2.as<float>();
+		E1.T = T; E1.P = P; E1.O = rows; E1.cls = 0; E1.o_first = 0; E1.M = rows; E1.N = P * T;   // row = iorientclass
+		E1.cc = M.do_cc;
+		RB_CHECK(launch_gemm(ctx, c[0].as<float>(), c[1].as<float>(), rows_pad, bBhi.as<float>(), bBlo.as<float>(), Npad, kpad, E1));
+		return RB_OK;
+	}
 	for (int cls = 0; cls < K; cls++)
 		for (int o0 = 0; o0 < O; o0 += (int) mchunk)
 		{
@@ -811,7 +853,7 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 			{
 				dim3 ga((unsigned) std::min<size_t>((kpad / 2 + 255) / 256, 64), (unsigned) rows_pad);
 				k_gemm_build_A<<<ga, 256, 0, ctx->stream>>>(ctx->proj[cls], S.coarse_eulers, pix, npix, n, o0, rows, rows_pad,
-					Ahi, Alo, kpad, A2hi, A2lo, k2pad, gemm_mixed() ? 1 : 0);
+					Ahi, Alo, kpad, A2hi, A2lo, k2pad, gemm_mixed() ? 1 : 0, nullptr, 0);
 				RB_LAUNCH_CHECK(ctx);
 			}
 			// norm term base[o][p]

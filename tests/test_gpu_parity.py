@@ -255,7 +255,10 @@ def _compare_pool(device, oracle, wl, pose_frac=0.995):
     return res, ores
 
 
-def test_pool_global_search(device, oracle):
+@pytest.mark.parametrize("stack", ["1", "0"])
+def test_pool_global_search(device, oracle, monkeypatch, stack):
+    """Two classes through the tensor-core contraction: class rows stacked along M (default) or one contraction per class."""
+    monkeypatch.setenv("RB_GEMM_STACK", stack)
     wl = make_workload(ori_size=32, healpix_order=1, n_particles=12, nr_classes=2, seed=21, snr=0.3)
     _compare_pool(device, oracle, wl)
 

@@ -858,9 +858,9 @@ int rbk_weights_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 		// global search: every particle has the same dense size
 		const long long n = (long long) ctx->d_model.nr_classes * ctx->d_samp.n_dir * ctx->d_samp.n_psi * ctx->d_samp.n_trans;
 		const char *e = getenv("RB_WEIGHTS_LARGE");
-		// measured at 96 768 elements per particle (HEALPix order 2, 21 translations, 256 particles): 0.85 ms vs 1.12 ms for the
-		// one-CTA-per-particle kernel
-		const long long min_n = e ? atoll(e) : (1 << 16);
+		// measured against the one-CTA-per-particle kernel: 0.85 vs 1.12 ms at 96 768 elements per particle (HEALPix order 2,
+		// 21 translations, 256 particles), 0.89 vs 1.01 ms at 12 600 (2D classification, K = 10, 2000 particles)
+		const long long min_n = e ? atoll(e) : (1 << 13);
 		if (n >= min_n && n > 1 && ctx->d_samp.n_trans <= 64) return weights_coarse_large(ctx, s, n);
 	}
 	k_weights_coarse<<<s.P, WT_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),

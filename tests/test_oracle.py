@@ -71,6 +71,37 @@ def test_compiled_reference_matches_golden(name):
     _check_against(d, g, rtol=1e-6)
 
 
+def test_cc_kernels_port_matches_compiled_reference():
+    """Kernel level: the restated cross-correlation kernels against the reference's own diff2_CC_coarse_2D / diff2_CC_fine_2D
+    (cpu_kernels/diff2.h:611-742, 904-1050) on random inputs, including a projector whose r_max cuts the window."""
+    from oracle.bindings import Oracle, Projector, have_reference
+    if not have_reference():
+        pytest.skip("oracle/_ref/librefkernels.so not built (needs /root/reference)")
+    port, ref = Oracle("port"), Oracle("reference")
+    wl = make_workload(ori_size=32, n_particles=2, seed=12)
+    rng = np.random.default_rng(4)
+    for n, r_max in ((32, wl.r_max), (20, wl.r_max), (32, 9)):
+        pj = Projector(wl.refs[0], r_max, wl.padding_factor)
+        xs = n // 2 + 1
+        O, T = 9, 7
+        eul = synth.inverse_euler_f32(rng.uniform(-180, 180, O), rng.uniform(0, 180, O), rng.uniform(0, 360, O))
+        tx = (-2 * np.pi * rng.uniform(-4, 4, T) / 32).astype(np.float32)
+        ty = (-2 * np.pi * rng.uniform(-4, 4, T) / 32).astype(np.float32)
+        re = rng.standard_normal((n, xs)).astype(np.float32)
+        im = rng.standard_normal((n, xs)).astype(np.float32)
+        corr = rng.uniform(0.5, 2.0, (n, xs)).astype(np.float32)
+        a = port.diff2_coarse(pj, n, eul, tx, ty, re, im, corr, cc=True)
+        b = ref.diff2_coarse(pj, n, eul, tx, ty, re, im, corr, cc=True)
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+        rot_idx = np.repeat(np.arange(O), T); trans_idx = np.tile(np.arange(T), O)
+        job_idx = np.arange(0, O * T, T); job_num = np.full(O, T)
+        a = port.diff2_cc_fine(pj, n, eul, tx, ty, re, im, corr, rot_idx, trans_idx, job_idx, job_num)
+        b = ref.diff2_cc_fine(pj, n, eul, tx, ty, re, im, corr, rot_idx, trans_idx, job_idx, job_num)
+        np.testing.assert_allclose(a, b, rtol=1e-5, atol=1e-6)
+        # the two kernels compute the same quantity (fine = coarse on the same orientation / translation grid)
+        np.testing.assert_allclose(a.reshape(O, T), port.diff2_coarse(pj, n, eul, tx, ty, re, im, corr, cc=True), rtol=2e-5, atol=2e-6)
+
+
 def test_ctf_known_answer():
     # tests/ctf.cpp:5-10: setValues(10000, 12000, 90, 300, 2.7, 0.1, 0, 1, 0); getCTF(10, 10) == Approx(0.59154)
     c = synth.CTF(10000.0, 12000.0, 90.0, 300.0, 2.7, 0.1, 0.0, 1.0, 0.0)

@@ -353,3 +353,22 @@ def test_2d_classification_pool_oracle():
         assert np.array_equal(a[0]["best_ihidden_over"], b[0]["best_ihidden_over"])
         for k in range(3):
             np.testing.assert_allclose(a[1][k].weight, b[1][k].weight, rtol=0, atol=1e-4 * np.abs(b[1][k].weight).max())
+
+
+def test_bench_reference_arm_runs_on_cpu():
+    """bench.py --impl reference times the reference's CPU kernels (oracle/_ref, else the port) and prints the contract's JSON
+    line; under torchrun only rank 0 works."""
+    import json
+    import sys
+    env = dict(os.environ, RANK="0", WORLD_SIZE="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample", "8"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    assert d["impl"] == "reference" and d["value"] > 0 and d["unit"] == "particles/s" and d["higher_is_better"] is True
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    env["RANK"] = "1"; env["WORLD_SIZE"] = "2"
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip() == ""

@@ -51,9 +51,11 @@ def unpack_wsums(pack: WsumPack) -> Dict[str, np.ndarray]:
 
 
 def fold_pool_result(sums: Dict[str, np.ndarray], result, group_id: np.ndarray, optics_group: np.ndarray,
-                     nr_groups: int, nr_optics_groups: int, scale_correction: np.ndarray, logsigma2: np.ndarray):
+                     nr_groups: int, nr_optics_groups: int, scale_correction: np.ndarray, logsigma2: np.ndarray,
+                     do_cc: bool = False):
     """Host bookkeeping of storeWeightedSums after the kernels (acc_ml_optimiser_impl.h:3546-3657), in fp64:
-    folds one pool's per-particle outputs into the running weighted sums of this rank."""
+    folds one pool's per-particle outputs into the running weighted sums of this rank.
+    do_cc (first-iteration cross-correlation criterion): dLL = -min_diff2 without the logsigma2 term (:3571-3572)."""
     p = result.particles
     nshell = result.wsum_sigma2_noise.shape[1]
     z = lambda *s: np.zeros(s, np.float64)
@@ -62,7 +64,7 @@ def fold_pool_result(sums: Dict[str, np.ndarray], result, group_id: np.ndarray, 
                         ("wsum_reference_power", (nr_groups,)), ("pdf_direction", result.wsum_pdf_direction.shape),
                         ("pdf_class", result.wsum_pdf_class.shape)):
         sums.setdefault(name, z(*shape))
-    dll = p["dLL_nolog"] - logsigma2[optics_group]
+    dll = p["dLL_nolog"] if do_cc else p["dLL_nolog"] - logsigma2[optics_group]
     sums["LL"] = sums["LL"] + dll.sum()
     sums["ave_Pmax"] = sums["ave_Pmax"] + p["pmax"].astype(np.float64).sum()
     sums["sigma2_offset"] = sums["sigma2_offset"] + p["wsum_sigma2_offset"].sum()

@@ -147,3 +147,22 @@ def test_half_set_groups_and_pool_queue():
     for half in (0, 1):
         taken = sorted(i for rank, h, _, _, _, mine in out if h == half for i in mine)
         assert taken == list(range(11))
+
+
+def test_fold_pool_result_cc_has_no_logsigma2_term():
+    """With the cross-correlation criterion dLL = -min_diff2 / nr_images (acc_ml_optimiser_impl.h:3571-3572): no logsigma2."""
+    from oracle.bindings import Oracle, Projector, Backprojector
+    from relion_b200.workload import make_workload
+    wl = make_workload(ori_size=24, healpix_order=1, n_particles=4, nr_classes=1, seed=9, snr=0.3, do_cc=True)
+    o = Oracle("port")
+    refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
+    bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
+    st, res, _ = o.estep_pool(wl.model, wl.sampling, refs, bps, wl.pool, num_threads=1)
+    assert st == 0
+    logsigma2 = np.array([123.0])
+    args = (res, wl.pool.group_id, wl.pool.optics_group, len(wl.model.scale_correction), 1, np.asarray(wl.model.scale_correction, np.float64), logsigma2)
+    cc = parallel.fold_pool_result({}, *args, do_cc=True)
+    gauss = parallel.fold_pool_result({}, *args)
+    np.testing.assert_allclose(cc["LL"], -res.particles["min_diff2"].astype(np.float64).sum(), rtol=1e-6)
+    np.testing.assert_allclose(cc["LL"] - gauss["LL"], 123.0 * wl.pool.n_particles, rtol=1e-12)
+    assert cc["ave_Pmax"] == wl.pool.n_particles          # weight one for the best pose

@@ -136,6 +136,51 @@ def build_workload(name, pool, seed, projector=None):
     return make_workload(name, n_particles=P, seed=seed, projector=projector, **kw), P
 
 
+def build_device_workload(dev, name, P, seed=1993):
+    """The named workload with `P` particles, references already on `dev`; noise-free slices of 3D references come from the
+    device projector (rb_project), 2D references are small enough for the numpy generator.  Model / sampling / accumulators
+    are left to the caller (dev.set_model, dev.set_sampling, dev.bp_init)."""
+    from relion_b200.workload import make_workload
+    from relion_b200 import synth
+    kw, _ = WORKLOADS[name]
+    if kw.get("ref_dim", 3) == 2:
+        wl = make_workload(name, n_particles=P, seed=seed, **kw)
+        wl.model.bp_circle_bound = False                     # backproject2D has no circle bound (BP.h:77)
+        for k, v in enumerate(wl.refs):
+            dev.set_reference(k, v, wl.r_max, 2.0)
+        return wl
+    refs = []
+    r_max = None
+    for k in range(kw.get("nr_classes", 1)):
+        vol = synth.make_phantom(kw["ori_size"], n_blobs=kw.get("n_blobs", 40), seed=1993 + 17 * k)
+        data, r_max = synth.reference_ft(vol, current_size=kw.get("current_size") or kw["ori_size"], padding_factor=2.0)
+        refs.append(data.astype(np.complex64))
+        dev.set_reference(k, refs[-1], r_max, 2.0)
+
+    def projector(k, eul, n):
+        return dev.project(k, n, eul)
+
+    return make_workload(name, n_particles=P, seed=seed, projector=projector, refs_override=(refs, r_max), **kw)
+
+
+def workload_config(name, P, world):
+    """The part of `config` that names the workload: identical in the `ours` and `reference` arms (the driver compares them)."""
+    from relion_b200 import sampling as smp
+    if name == "reconstruct_256":
+        return {"workload": name, "box": 256, "padding": 2.0, "particles_per_step_per_gpu": P, "poses": "uniform SO(3)",
+                "l2_policy": "accumulator (1.1 GB) and image batch both larger than L2, no flush",
+                "parallelism": f"particles sharded over {world} GPU(s), one accumulator per GPU"}
+    kw, _ = WORKLOADS[name]
+    return {"workload": name, "box": kw["ori_size"], "current_size": kw.get("current_size") or kw["ori_size"],
+            "classes": kw.get("nr_classes", 1), "pool_particles_per_gpu": P,
+            "healpix_order": kw.get("healpix_order"), "psi_step": kw.get("psi_step") if kw.get("ref_dim", 3) == 2 else None,
+            "offset_range": kw.get("offset_range", 3.0), "offset_step": kw.get("offset_step", 2.0),
+            "reference_dim": kw.get("ref_dim", 3), "oversampling": 1, "search": "local" if kw.get("local_search") else "global",
+            "criterion": "cross-correlation" if kw.get("do_cc") else "gaussian",
+            "l2_policy": "inputs larger than L2 (pool images + padded reference / accumulator >> 126 MB), no flush",
+            "parallelism": f"particles sharded over {world} GPU(s), references replicated"}
+
+
 def valid_pixels(n):
     from relion_b200.synth import mresol
     return int((mresol(n) >= 0).sum())
@@ -181,33 +226,10 @@ def run_ours(args):
     dev = MlDeviceBundle(local)
 
     # data generation (not timed): slices of the 256-px pool come from the device projector
-    ref_holder = {}
-
-    def projector(k, eul, n):
-        return dev.project(k, n, eul)
-
-    from relion_b200.workload import make_workload
-    kw, dflt = WORKLOADS[args.workload]
-    P = args.pool or dflt
+    P = args.pool or WORKLOADS[args.workload][1]
     t0 = time.time()
-    if kw.get("ref_dim", 3) == 2:
-        # 2D references: small enough for the numpy generator
-        wl = make_workload(args.workload, n_particles=P, seed=1993 + 1000 * rank, **kw)
-        wl.model.bp_circle_bound = False                     # backproject2D has no circle bound (BP.h:77)
-        for k, v in enumerate(wl.refs):
-            dev.set_reference(k, v, wl.r_max, 2.0)
-    else:
-        # references first (the projector callback needs them on the device)
-        from relion_b200 import synth
-        refs = []
-        for k in range(kw.get("nr_classes", 1)):
-            vol = synth.make_phantom(kw["ori_size"], n_blobs=kw.get("n_blobs", 40), seed=1993 + 17 * k)
-            data, r_max = synth.reference_ft(vol, current_size=kw.get("current_size") or kw["ori_size"], padding_factor=2.0)
-            refs.append(data.astype(np.complex64))
-            dev.set_reference(k, refs[-1], r_max, 2.0)
-        # every rank searches its own shard of the data set: same references, different particles (weak scaling)
-        wl = make_workload(args.workload, n_particles=P, seed=1993 + 1000 * rank, projector=projector,
-                           refs_override=(refs, r_max), **kw)
+    # every rank searches its own shard of the data set: same references, different particles (weak scaling)
+    wl = build_device_workload(dev, args.workload, P, seed=1993 + 1000 * rank)
     gen_s = time.time() - t0
     dev.set_model(wl.model)
     dev.set_sampling(wl.sampling)
@@ -392,33 +414,46 @@ def run_ours(args):
         cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "reference",
                "sample": "not measured at N > 1 (see the N = 1 line)", "seconds": 0.0}
     else:
-        cpu = cpu_baseline(wl, sample=args.cpu_sample)
-    if world == 1 and args.cpu_sample > 0 and 0 < cpu["seconds"] < 6.0:
-        n2 = min(P, int(args.cpu_sample * 12.0 / cpu["seconds"]))
-        if n2 > args.cpu_sample:
-            cpu = cpu_baseline(wl, sample=n2)
+        cores = os.cpu_count() or 1
+        n1 = args.cpu_sample if args.cpu_sample > 0 else min(P, max(8 * cores, 64))
+        cpu = cpu_baseline(wl, sample=n1)
+        if 0 < cpu["seconds"] < 6.0 and n1 < P:
+            n2 = min(P, int(n1 * 12.0 / cpu["seconds"]))
+            if n2 > n1:
+                cpu = cpu_baseline(wl, sample=n2)
+
+    # ---- parity inside the run: the first particles of the SAME pool through the CPU oracle (RELION's own kernels) -----
+    parity = None
+    if args.parity_sample > 0:
+        from oracle.parity import parity_block
+        from oracle.bindings import have_reference
+        try:
+            parity = parity_block(dev, wl, "reference" if have_reference() else "port", min(P, args.parity_sample))
+            parity["ok"] = bool(parity["pose_agree"] >= 0.995 and parity["ll_rel_max"] <= 1e-4 and parity["nsig_on_gpu_weights"]["mismatch"] == 0)
+        except Exception as e:  # noqa: BLE001
+            parity = {"ok": False, "error": repr(e)[:300]}
 
     pr = res0.particles
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "box": wl.model.ori_size, "current_size": wl.model.current_size,
-                   "coarse_size": wl.model.coarse_size, "classes": wl.model.nr_classes, "pool_particles_per_gpu": P,
-                   "healpix_order": wl.sampling.healpix_order, "coarse_translations": wl.sampling.n_trans,
-                   "reference_dim": 3 if wl.sampling.is_3d else 2, "oversampling": 1, "search": "local" if wl.pool.dir_off is not None else "global",
-                   "mean_coarse_orientations": float(np.mean(np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off))) if wl.pool.dir_off is not None else wl.sampling.n_dir * wl.sampling.n_psi,
-                   "mean_fine_orientations": float(pr["n_fine_orient"].mean()), "mean_fine_samples": float(pr["n_fine_samples"].mean()),
-                   "l2_policy": "inputs larger than L2 (pool images + padded reference / accumulator >> 126 MB), no flush",
-                   "parallelism": f"particles sharded over {world} GPU(s), references replicated"},
+        "config": workload_config(args.workload, P, world),
+        "workload_stats": {"coarse_size": wl.model.coarse_size, "coarse_translations": wl.sampling.n_trans,
+                           "mean_coarse_orientations": float(np.mean(np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off))) if wl.pool.dir_off is not None else wl.sampling.n_dir * wl.sampling.n_psi,
+                           "mean_fine_orientations": float(pr["n_fine_orient"].mean()), "mean_fine_samples": float(pr["n_fine_samples"].mean()),
+                           "mean_bp_orientations": float(pr["n_bp_orient"].mean())},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "e2e_from_raw_images": e2e_raw, "e2e_from_mrc_stacks": e2e_files,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
-        "datagen_s": round(gen_s, 1),
+        "parity": parity, "datagen_s": round(gen_s, 1),
     }
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+    if parity is not None and not parity.get("ok", False):
+        print("bench.py: parity check against the CPU oracle FAILED: " + json.dumps(parity), file=sys.stderr)
+        sys.exit(3)
 
 
 def e2e_from_files(dev, wl, raw, steps, barrier, world, local, d2h):
@@ -532,16 +567,18 @@ def run_reference(args):
         return run_reference_reconstruct(args)
     kw, dflt = WORKLOADS[args.workload]
     from relion_b200.workload import make_workload
-    n = args.cpu_sample
+    P = args.pool or dflt
+    cores = os.cpu_count() or 1
+    # one particle per OpenMP thread and local-search particles differ ~10x in cost: a step of `cores` particles would time
+    # the slowest particle.  >= 8 particles per core (or the whole pool) lets the dynamic schedule even that out.
+    n = args.cpu_sample if args.cpu_sample > 0 else min(P, max(8 * cores, 64))
     wl = make_workload(args.workload, n_particles=n, seed=1993, **kw)   # numpy projector: none of our kernels on this path
     cpu = cpu_baseline(wl, sample=n, steps=args.steps, warmup=min(args.warmup, 1))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     out = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": round(1e3 * n / cpu["value"], 3), "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "box": wl.model.ori_size, "current_size": wl.model.current_size,
-                      "coarse_size": wl.model.coarse_size, "classes": wl.model.nr_classes, "sample_particles_per_step": n,
-                      "healpix_order": wl.sampling.healpix_order, "coarse_translations": wl.sampling.n_trans, "world_size": world},
+           "config": workload_config(args.workload, P, max(world, args.gpus)),
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -643,7 +680,7 @@ def run_reconstruct(args):
     ach = bytes_per_launch * args.steps / (kernel_ms * 1e-3) / 1e9
     # CPU baseline: the compiled restatement of BackProjector::backproject2Dto3D, one thread as relion_reconstruct runs it
     from oracle.bindings import backproject_posed as cpu_bp
-    ns = min(P, max(8, args.cpu_sample * 16))
+    ns = min(P, max(8, (args.cpu_sample or 32) * 16))
     acc = tuple(np.zeros(shape, np.float64) for _ in range(3))
     for a_ in acc:
         a_.fill(0.0)                                         # map the pages before timing
@@ -656,10 +693,8 @@ def run_reconstruct(args):
     out = {"metric": "particles/sec, posed back-projection only (relion_reconstruct path, 256 px, pad 2)", "value": round(value, 1), "unit": UNIT,
            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_max / args.steps, 4),
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "reconstruct_256", "box": n, "padding": pf, "accumulator": list(shape), "particles_per_step_per_gpu": P,
-                      "poses": "uniform SO(3)", "scattered_pixels_per_image": npr,
-                      "l2_policy": "accumulator (1.1 GB) and image batch (0.8 GB) both larger than L2, no flush",
-                      "parallelism": f"particles sharded over {world} GPU(s), one accumulator per GPU"},
+           "config": workload_config("reconstruct_256", P, world),
+           "workload_stats": {"accumulator": list(shape), "scattered_pixels_per_image": npr},
            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(P * n * xs * 12 + P * 36), "d2h_bytes_per_step": 0},
            "gpu_launches": int(launches), "clocks": clocks,
            "roofline": {"kernel": "k_backproject_posed", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
@@ -678,7 +713,7 @@ def run_reference_reconstruct(args):
     from oracle.bindings import backproject_posed as cpu_bp
     n, r_max, pf = 256, 128, 2.0
     xs = n // 2 + 1
-    ns = max(8, args.cpu_sample * 16)
+    ns = max(8, (args.cpu_sample or 32) * 16)
     rng = np.random.default_rng(1)
     c = synth.CTF(20000.0, 20300.0, 30.0).fftw_image(n, n, 1.0).astype(np.float32)
     F = (rng.standard_normal((ns, n, xs)) + 1j * rng.standard_normal((ns, n, xs))).astype(np.complex64) * c
@@ -700,7 +735,7 @@ def run_reference_reconstruct(args):
     print(json.dumps({"impl": "reference", "metric": "particles/sec, posed back-projection only (relion_reconstruct path, 256 px, pad 2)",
                       "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": round(1e3 * ns / v, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-                      "data": "synthetic", "config": {"workload": "reconstruct_256", "box": n, "padding": pf, "sample_images_per_step": ns},
+                      "data": "synthetic", "config": workload_config("reconstruct_256", args.pool or 2048, max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus)),
                       "cpu_baseline": cpu, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
@@ -712,7 +747,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="refine3d_256_local", choices=sorted(WORKLOADS) + ["reconstruct_256"])
     ap.add_argument("--pool", type=int, default=0, help="particles per pool per GPU (default: workload specific)")
-    ap.add_argument("--cpu-sample", type=int, default=32, help="particles in the bounded CPU sample")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the bounded CPU sample (0: 8 per host core, at least 64, at most the pool)")
+    ap.add_argument("--parity-sample", type=int, default=256, help="particles of the same pool checked against the CPU oracle inside the run (0: off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

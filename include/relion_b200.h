@@ -17,8 +17,9 @@
  *     the batched rb_estep_pool() replaces the reference's "one particle per OpenMP thread" fan-out
  *     (src/ml_optimiser.cpp:4280), so no concurrent entry is needed.
  *   - there is NO CPU fallback: without a CUDA device rb_ctx_create() fails with RB_ERR_CUDA.
- *   - scope: 3D or 2D references / 2D images, nr_bodies == 1, no helical/tomo, no CC first iteration,
- *     no SGD/VDAM back-projection (DESIGN.md "out of scope").
+ *   - scope: 3D or 2D references / 2D images, nr_bodies == 1, no helical/tomo; both criteria (Gaussian squared
+ *     difference and the first-iteration / --always_cc cross-correlation, rb_model.do_cc); no SGD/VDAM
+ *     back-projection (DESIGN.md "out of scope").
  *
  * Index conventions follow the reference:
  *   coarse hidden index  ihidden      = ((iclass*n_dir + idir)*n_psi + ipsi)*n_trans + itrans
@@ -268,6 +269,12 @@ int rb_estep_slot(rb_ctx *ctx, int slot, rb_pool_out *out, unsigned flags);
  * fetched before it is uploaded again.  (Also the device-resident timing entry of bench.py.) */
 int rb_estep_slot_nocopy(rb_ctx *ctx, int slot, unsigned flags);
 int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out);
+
+/* Test hook: the coarse-pass posterior weights of one particle of a slot after its E-step (the reference's Mweight block
+ * after convertAllSquaredDifferencesToWeights(0), acc_ml_optimiser_impl.h:2188-2345): n = nr_classes * nd * np * n_trans
+ * floats in coarse hidden-index order.  Parity tests feed them to the reference's own significance rule
+ * (acc_helper_functions.h:226-232).  Valid until the slot is uploaded again; *n_out receives n (out may be NULL to query). */
+int rb_debug_coarse_weights(rb_ctx *ctx, int slot, int particle, float *out, long long capacity, long long *n_out);
 
 /* ------------------------------------------------------------------------------------------------
  * Image preparation on the device ("next" row 1): getFourierTransformsAndCtfs

@@ -989,6 +989,22 @@ extern "C" int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out)
 	return fetch_slot(ctx, ctx->slot[slot], out);
 }
 
+extern "C" int rb_debug_coarse_weights(rb_ctx *ctx, int slot, int particle, float *out, long long capacity, long long *n_out)
+{
+	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_debug_coarse_weights: slot %d not uploaded", slot);
+	PoolSlot &s = ctx->slot[slot];
+	RB_ARG(particle >= 0 && particle < s.P, "rb_debug_coarse_weights: particle %d out of range", particle);
+	const RbPartMeta &m = s.h_meta[particle];
+	const long long n = (long long) ctx->d_model.nr_classes * m.nd * m.np * ctx->d_samp.n_trans;
+	if (n_out) *n_out = n;
+	if (!out) return RB_OK;
+	RB_ARG(capacity >= n, "rb_debug_coarse_weights: buffer of %lld floats, %lld needed", capacity, n);
+	RB_CUDA(cudaSetDevice(ctx->device));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	RB_CUDA(cudaMemcpy(out, s.Mweight.as<float>() + m.coarse_off, (size_t) n * 4, cudaMemcpyDeviceToHost));
+	return RB_OK;
+}
+
 extern "C" int rb_estep_slot(rb_ctx *ctx, int slot, rb_pool_out *out, unsigned flags)
 {
 	RB_CHECK(rb_estep_slot_nocopy(ctx, slot, flags));

@@ -459,6 +459,14 @@ class MlDeviceBundle:
         capi.check(self.lib, self.lib.rb_estep_fetch(self.ctx, slot, C.byref(out.struct)))
         return out.result
 
+    def debug_coarse_weights(self, slot: int, particle: int) -> np.ndarray:
+        """Coarse-pass weights of one particle of a slot after its E-step (rb_debug_coarse_weights, test hook)."""
+        n = C.c_longlong()
+        capi.check(self.lib, self.lib.rb_debug_coarse_weights(self.ctx, slot, particle, None, 0, C.byref(n)))
+        w = np.empty(n.value, np.float32)
+        capi.check(self.lib, self.lib.rb_debug_coarse_weights(self.ctx, slot, particle, _ptr(w, C.c_float), n.value, C.byref(n)))
+        return w
+
     def stage_ms(self, name: str) -> float:
         return float(self.lib.rb_stage_ms(self.ctx, name.encode()))
 

@@ -218,19 +218,28 @@ def test_diff2_cc_fine_stage(device, oracle, n, r_max_cut):
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
 
 
-def _compare_pool(device, oracle, wl, pose_frac=0.995):
+def _compare_pool(device, oracle, wl, pose_frac=0.995, exact_threshold=True, num_threads=0):
     from oracle.bindings import Projector, Backprojector
+    from oracle.parity import classify_significance
     _setup(device, wl)
     res = device.expectation_some_particles(wl.pool)
     refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
     bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
-    st, ores, _ = oracle.estep_pool(wl.model, wl.sampling, refs, bps, wl.pool, num_threads=0, exact_threshold=True)
+    st, ores, _ = oracle.estep_pool(wl.model, wl.sampling, refs, bps, wl.pool, num_threads=num_threads, exact_threshold=exact_threshold)
     assert st == 0
     g, o = res.particles, ores.particles
     agree = np.mean(g["best_ihidden_over"] == o["best_ihidden_over"])
     assert agree >= pose_frac, agree
     np.testing.assert_allclose(g["min_diff2_coarse"], o["min_diff2_coarse"], rtol=2e-5)
-    # counts: identical unless the oracle's own decision sits on a rounding edge (different diff2 rounding)
+    # Significant-pose counts (north_star: "agree exactly whenever the reference's diff2 are identical").  The GPU's own
+    # coarse weights go through the REFERENCE's rule (fp32 sequential scan, acc_helper_functions.h:226-232): the count must
+    # be the same, or the cumulative sum must sit on the threshold within the rounding of an fp32 scan (oracle/parity.py).
+    if not wl.model.do_cc:
+        sig = classify_significance(device, 0, g, oracle, wl.model.adaptive_fraction, wl.model.maximum_significants)
+        assert sig["mismatch"] == 0, sig
+        assert sig["rounding_edge"] <= max(1, 0.1 * len(g)), sig
+    # against the oracle's own run the weights differ in the last bits (expf, summation order), so a count may move by one
+    # where its threshold is such an edge: those particles are masked out of the weighted-sum comparisons below
     same = g["nr_significant_coarse"] == o["nr_significant_coarse"]
     assert same.mean() >= 0.9, (g["nr_significant_coarse"], o["nr_significant_coarse"])
     ok = same & (g["n_fine_samples"] == o["n_fine_samples"]) & (g["best_ihidden_over"] == o["best_ihidden_over"])

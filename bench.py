@@ -294,6 +294,16 @@ def run_ours(args):
     ms_max = float(t.item())
     value = P * world * args.steps / (ms_max / 1e3)
 
+    if args.kernels_only:
+        # profiling runs (ncu): the device-resident timed region only
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                              "ms_per_step": round(ms_max / args.steps, 4), "stages": {k: round(v, 4) for k, v in stage_ms.items()},
+                              "config": workload_config(args.workload, P, world), "note": "--kernels-only (profiling run)"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end-to-end through rb_estep_pool with host buffers ---------------------------------------
     # Every step: H2D of one pool from pinned host memory (rb_pool_upload), the whole E-step, D2H of the per-particle
     # results (rb_estep_slot).  Two device slots: the upload of pool i+1 overlaps the compute of pool i, as a RELION
@@ -748,6 +758,7 @@ def main():
     ap.add_argument("--workload", default="refine3d_256_local", choices=sorted(WORKLOADS) + ["reconstruct_256"])
     ap.add_argument("--pool", type=int, default=0, help="particles per pool per GPU (default: workload specific)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the bounded CPU sample (0: 8 per host core, at least 64, at most the pool)")
+    ap.add_argument("--kernels-only", action="store_true", help="device-resident timed region only (for ncu)")
     ap.add_argument("--parity-sample", type=int, default=256, help="particles of the same pool checked against the CPU oracle inside the run (0: off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -86,7 +86,7 @@ static void release_slot(PoolSlot &s)
 	DevBuf *bufs[] = {&s.Fimg, &s.Fnomask, &s.Fctf, &s.meta, &s.state, &s.dir_idx, &s.dir_prior, &s.psi_idx, &s.psi_prior,
 	                  &s.Mweight, &s.pdf_orient, &s.pdf_orient_zero, &s.pdf_offset, &s.pdf_offset_zero,
 	                  &s.so_list, &s.pair_list, &s.fo, &s.fs_w, &s.fs_ihid, &s.counters, &s.shells, &s.out_pdf_dir, &s.out_pdf_class,
-	                  &s.fimg4, &s.cimg4, &s.slices, &s.cc_corr};
+	                  &s.fimg4, &s.cimg4, &s.slices, &s.cc_corr, &s.simg4, &s.sst, &s.sctf, &s.bp_cnt, &s.bp_item_of, &s.bp_items, &s.bp_samp};
 	for (DevBuf *b : bufs) b->release();
 	if (s.uploaded) cudaEventDestroy(s.uploaded);
 	if (s.done) cudaEventDestroy(s.done);
@@ -102,7 +102,8 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
 	                  &ctx->m_cc[0], &ctx->m_cc[1], &ctx->m_cc[2], &ctx->m_cc[3], &ctx->m_cc[4], &ctx->m_cc[5],
-	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp};
+	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp,
+	                  &ctx->m_pix_rs, &ctx->band_slices};
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
@@ -546,6 +547,32 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 		n_store = pfull.size();
 		RB_CHECK(upload(ctx, ctx->m_cc[5], pfull.data(), pfull.size() * 4));
 	}
+	// band-major kernels: the store-stage pixel set sorted by |r| (ties by angle), the diff2 set first
+	std::vector<uint32_t> prs;
+	{
+		std::vector<uint32_t> all;
+		make_pixlist(m->current_size, all, !m->do_map);
+		auto in_d2 = [](uint32_t v) { return !(rb_pix_x(v) == 0 && rb_pix_y(v) < 0); };
+		auto radial = [](uint32_t a, uint32_t b) {
+			const int xa = rb_pix_x(a), ya = rb_pix_y(a), xb = rb_pix_x(b), yb = rb_pix_y(b);
+			const int ra = xa * xa + ya * ya, rb2 = xb * xb + yb * yb;
+			if (ra != rb2) return ra < rb2;
+			const double ta = atan2((double) ya, (double) xa), tb = atan2((double) yb, (double) xb);
+			if (ta != tb) return ta < tb;
+			return a < b;
+		};
+		std::vector<uint32_t> extra;
+		for (uint32_t v : all) (in_d2(v) ? prs : extra).push_back(v);
+		std::sort(prs.begin(), prs.end(), radial); std::sort(extra.begin(), extra.end(), radial);
+		const int nd2 = (int) prs.size();
+		prs.insert(prs.end(), extra.begin(), extra.end());
+		const int nst = (int) prs.size();
+		const int npad = (nst + 127) / 128 * 128;
+		prs.resize(npad, rb_pack_pix(0, 0, 0));
+		RB_CHECK(upload(ctx, ctx->m_pix_rs, prs.data(), prs.size() * 4));
+		ctx->d_model.pix_rs = ctx->m_pix_rs.as<uint32_t>();
+		ctx->d_model.nv_rs_d2 = nd2; ctx->d_model.nv_rs_st = nst; ctx->d_model.nv_rs_pad = npad;
+	}
 	std::vector<RbRow> rc, rf;
 	std::vector<short> ic, iff;
 	make_rows(m->coarse_size, rc, ic); make_rows(m->current_size, rf, iff);
@@ -737,7 +764,7 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 	const long long ov = (long long) S.n_over_rot * S.n_over_trans;
 	size_t cap_fs = (size_t) std::min<long long>(s.total_coarse * ov, (long long) env_size("RB_FINE_SAMPLE_CAP", (size_t) 1 << 26));
 	size_t cap_fo = (size_t) std::min<long long>(s.total_prior * S.n_over_rot, (long long) env_size("RB_FINE_ORIENT_CAP", (size_t) 1 << 22));
-	ctx->fine_sample_capacity = cap_fs; ctx->fine_orient_capacity = cap_fo;
+	s.cap_fs = cap_fs; s.cap_fo = cap_fo;
 	RB_CHECK(s.fs_w.ensure(cap_fs * 4)); RB_CHECK(s.fs_ihid.ensure(cap_fs * 8));
 	RB_CHECK(s.fo.ensure(cap_fo * sizeof(RbFineOrient)));
 	// slice cache: the fine pass leaves every projected slice here so the store stage streams it instead of
@@ -745,8 +772,26 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 	{
 		const size_t slice_bytes = (size_t) M.Npf * sizeof(float2);
 		const size_t budget = env_size("RB_SLICE_CACHE_BYTES", (size_t) 4 << 30);
-		s.slice_capacity = (long long) std::min<size_t>(cap_fo, budget / slice_bytes);
-		RB_CHECK(s.slices.ensure((size_t) s.slice_capacity * slice_bytes));
+		// band-major path: one buffer of band-ordered slices per context (grows to the largest request, never shrinks)
+		const size_t band_bytes = (size_t) M.nv_rs_pad * sizeof(float2);
+		const long long band_cap = (long long) std::min<size_t>(cap_fo, budget / band_bytes);
+		const bool band = !M.do_cc && band_cap > 0 && env_size("RB_BAND", 1) != 0;
+		if (band)
+		{
+			if (band_cap > ctx->band_slice_capacity || ctx->band_slices.bytes < (size_t) band_cap * band_bytes)
+			{
+				RB_CUDA(cudaStreamSynchronize(ctx->stream));      // the other slot's E-step may still read the old buffer
+				RB_CHECK(ctx->band_slices.ensure((size_t) band_cap * band_bytes));
+			}
+			ctx->band_slice_capacity = band_cap;
+			s.slice_capacity = 0;
+		}
+		else
+		{
+			ctx->band_slice_capacity = 0;
+			s.slice_capacity = (long long) std::min<size_t>(cap_fo, budget / slice_bytes);
+			RB_CHECK(s.slices.ensure((size_t) s.slice_capacity * slice_bytes));
+		}
 	}
 	RB_CHECK(s.pair_list.ensure((cap_fs / ov + 1) * 4));
 	return RB_OK;
@@ -884,8 +929,10 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	RB_CHECK(rbk_fine_setup_pool(ctx, s));
 	RB_CHECK(rb_stage_end(ctx, "fine_setup"));
 
+	const bool band = rbk_band_applicable(ctx);
 	RB_CHECK(rb_stage_begin(ctx, "fine"));
-	RB_CHECK(rbk_diff2_fine_pool(ctx, s));
+	if (band) RB_CHECK(rbk_band_fine_pool(ctx, s));
+	else RB_CHECK(rbk_diff2_fine_pool(ctx, s));
 	RB_CHECK(rb_stage_end(ctx, "fine"));
 
 	RB_CHECK(rb_stage_begin(ctx, "weights_fine"));
@@ -894,7 +941,7 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	RB_CHECK(rb_stage_end(ctx, "weights_fine"));
 
 	RB_CHECK(rb_stage_begin(ctx, "store"));
-	if (!(flags & 1u)) RB_CHECK(rbk_store_pool(ctx, s));
+	if (!(flags & 1u)) RB_CHECK(band ? rbk_band_store_pool(ctx, s) : rbk_store_pool(ctx, s));
 	RB_CHECK(rb_stage_end(ctx, "store"));
 	RB_CHECK(rb_stage_end(ctx, "total"));
 	RB_CUDA(cudaEventRecord(s.done, ctx->stream));
@@ -924,7 +971,13 @@ static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
 	{
 		rb_set_error("fine-pass workspace too small: %lld orientations / %lld samples needed, capacity %zu / %zu; split the pool or raise "
 		             "RB_FINE_ORIENT_CAP / RB_FINE_SAMPLE_CAP", ((long long *) counters)[2], ((long long *) counters)[3],
-		             ctx->fine_orient_capacity, ctx->fine_sample_capacity);
+		             s.cap_fo, s.cap_fs);
+		return RB_ERR_CAPACITY;
+	}
+	if (counters[3])
+	{
+		rb_set_error("store-stage workspace too small: %lld significant fine samples in the pool; split the pool or raise RB_BP_SAMPLE_CAP",
+		             ((long long *) counters)[6]);
 		return RB_ERR_CAPACITY;
 	}
 	int status = RB_OK;

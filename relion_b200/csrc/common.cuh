@@ -145,6 +145,10 @@ struct RbModelDev {
 	int nvc, nvf;            // valid-pixel list lengths
 	const uint32_t *pix_c, *pix_f;
 	const uint32_t *pix_store; int nv_store;   // pixel list of the store stage: pix_f, or with --no_map the full x = 0 column too
+	// band-major kernels (kernels_band.cu): the store-stage pixel set sorted by |r| (ties by angle).  Entries [0, nv_rs_d2) are
+	// the diff2 set (Mresol >= 0), [nv_rs_d2, nv_rs_st) the extra x = 0 half column of --no_map; nv_rs_pad = row stride of the
+	// band-ordered arrays (slices, particle images)
+	const uint32_t *pix_rs; int nv_rs_d2, nv_rs_st, nv_rs_pad;
 	// the same pixel sets as row runs (one entry per image row holding valid pixels) and dense shell maps
 	int nrows_c, nrows_f;
 	const RbRow *rows_c, *rows_f;
@@ -191,6 +195,11 @@ struct PoolSlot {
 	DevBuf cc_corr;                 // do_cc: [2][P] 1 / sqrtXi2^2 of the coarse / fine window (buildCorrImage)
 	DevBuf slices;                  // reference slices written by the fine pass, re-read by the store stage
 	long long slice_capacity = 0;   // number of fine orientations whose slice fits the cache
+	size_t cap_fo = 0, cap_fs = 0;  // capacity of this slot's fine-pass lists (fo / fs_w, fs_ihid)
+	// band-major path (kernels_band.cu)
+	DevBuf simg4, sst, sctf;        // band-ordered particle images: prepared image, (X, X0), ctf * scale
+	DevBuf bp_cnt, bp_item_of, bp_items, bp_samp;   // fine orientations holding significant samples + their (phase, weight) tables
+	int band_rounds = 0;
 	std::vector<RbPartMeta> h_meta;
 	cudaEvent_t uploaded = nullptr;
 	cudaEvent_t done = nullptr;     // recorded when the E-step of this slot has been enqueued completely; rb_estep_fetch waits on it
@@ -228,7 +237,9 @@ struct rb_ctx {
 	std::vector<double> h_scale_correction;
 
 	PoolSlot slot[RB_NUM_SLOTS];
-	size_t fine_orient_capacity = 0, fine_sample_capacity = 0;
+	DevBuf m_pix_rs;
+	DevBuf band_slices;              // band-ordered slices of one round of fine orientations (shared by the slots: E-steps run one after the other)
+	long long band_slice_capacity = 0;
 
 	// stage timing
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
@@ -308,6 +319,11 @@ int rbk_convert_weights_stage(rb_ctx *ctx, float *d_w, long long n_orient, int n
                               const float *d_pdf_t, const unsigned char *d_pdf_tz,
                               double adaptive_fraction, int maxsig, int filter_zero,
                               unsigned char *d_sig, rb_weights_out *d_out);
+
+// kernels_band.cu: band-major (L2-resident) fine pass and store stage
+bool rbk_band_applicable(rb_ctx *ctx);
+int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s);
 
 // kernels_store.cu
 int rbk_collect_pool(rb_ctx *ctx, PoolSlot &s);

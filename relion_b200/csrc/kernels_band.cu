@@ -1,0 +1,792 @@
+// relion_b200 — band-major fine pass and store stage (sm_100a): the volume traffic of the two HBM-bound stages made
+// L2-resident.
+//
+// Replaces, for a whole pool: cuda_kernel_diff2_fine (/root/reference/src/acc/cuda/cuda_kernels/diff2.cuh:193-332),
+// cuda_kernel_wavg (wavg.cuh:13-152) and cuda_kernel_backproject3D (BP.cuh:174-403); ALTCPU twins
+// cpu_kernels/diff2.h:284-430, wavg.h:22-199, BP.h:497-753.
+//
+// Why.  A 512-particle pool at 256 px makes 1.8e8 trilinear samples into a half sphere of 3.5e7 voxels: every 64-byte cell
+// of the expanded reference is needed ~5 times per pool, every accumulator voxel is hit ~10 times.  When a CTA walks one
+// slice (orientation-major order), concurrent CTAs touch unrelated parts of Fourier space, nothing is reused in the 126 MB
+// L2 and every sample costs a random 64-byte DRAM read (3.1 TB/s ceiling, 1.55x the algorithmic bytes) or a DRAM
+// read-modify-write.  Here the work is ordered RADIAL-BAND-MAJOR: the pixel list is sorted by |r|, cut into tiles of
+// BD_TP pixels (a ring 0.3 - 0.6 pixels thick at the edge of a 256-px image), and the work queue runs over
+// (tile, chunk of orientations) with the tile as the slow index.  All resident CTAs therefore work inside one thin
+// spherical shell at a time: ~45 MB of reference cells, ~15 MB of accumulator - the shell is read from HBM once, hit in
+// L2 by every orientation of the pool, and (store stage) written back once.
+//
+//   k_prep_sorted     particle images -> band-ordered arrays (prepared image for diff2; X, X0, ctf for the store stage)
+//   k_project_band    fine orientations x tile -> slices in band order.  One lane owns one sample (address arithmetic once
+//                     per sample), the 64-byte cell is fetched by the lane's QUAD with four 16-byte cp.async (one L1 line
+//                     visit per sample), three stages in flight per warp.
+//   k_diff2_slices    streams slice + prepared image per fine orientation: diff2 of all its fine translations
+//   k_bp_*            compact list of the fine orientations holding >= 1 significant sample, with (phase, weight) tables
+//   k_store_band      (tile, chunk of those orientations): wavg sums + trilinear scatter (red.global.add.v4.f32) into the
+//                     L2-resident shell of the accumulator
+#include "img_src.cuh"
+#include <cstdlib>
+#include <algorithm>
+
+static const int BD_THREADS = 256;
+static const int BD_TP = 128;                    // pixels per tile
+static const int BD_WPT = BD_TP / 32;            // warps per tile row
+static const int BD_NPH = BD_THREADS / BD_TP;    // orientation phases per CTA
+static const int BD_DEPTH = 3;                   // cp.async stages per warp
+static const int BD_MAXCHUNK = 64;
+
+__device__ __forceinline__ void bd_cp_async16(void *smem, const void *gmem)
+{
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void bd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bd_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void bd_red_add_v4(float4 *addr, float a, float b, float c)
+{
+	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
+}
+
+// work items of a (tile, chunk) queue: the tile is the slow index, so the resident CTAs stay inside one radial band.
+// The next item is requested while the current one is processed (the atomic's round trip is hidden).
+struct BandQueue {
+	int *counter; int *s_slot;
+	__device__ __forceinline__ int first() const { return (int) blockIdx.x; }
+	__device__ __forceinline__ void prefetch() const { if (threadIdx.x == 0) *s_slot = (int) gridDim.x + atomicAdd(counter, 1); }
+	__device__ __forceinline__ int next() const { __syncthreads(); const int v = *s_slot; __syncthreads(); return v; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// band-ordered particle images
+// ---------------------------------------------------------------------------------------------
+struct BandPrepArgs {
+	const RbPartMeta *metas; const float2 *Fimg, *Fnomask; const float *Fctf;
+	const uint32_t *pix; int nd2, nst, stride;
+	float4 *simg4;      // [P][stride] (X'.re, X'.im, corr / 2, 0): diff2 passes
+	float4 *sst;        // [P][stride] (X.re, X.im, X0.re, X0.im): store stage
+	float *sctf;        // [P][stride] ctf * part_scale
+};
+
+static __global__ void __launch_bounds__(256)
+k_prep_sorted(BandPrepArgs A, RbModelDev M)
+{
+	const int p = blockIdx.y;
+	const RbPartMeta m = A.metas[p];
+	ImgSrc src;
+	img_src_pool(src, M, m, A.Fimg, A.Fctf, p);
+	const float2 *X = A.Fimg + (size_t) p * M.Npf, *X0 = A.Fnomask + (size_t) p * M.Npf;
+	const float *C = A.Fctf ? A.Fctf + (size_t) p * M.Npf : nullptr;
+	for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < A.stride; ip += gridDim.x * blockDim.x)
+	{
+		float4 d = make_float4(0.f, 0.f, 0.f, 0.f), s = d;
+		float c = 0.f;
+		if (ip < A.nst)
+		{
+			const uint32_t pk = __ldg(A.pix + ip);
+			const int x = rb_pix_x(pk), y = rb_pix_y(pk), ires = rb_pix_ires(pk);
+			const int idx = rb_src_index(x, y, M.current_size);
+			if (ip < A.nd2)
+			{
+				float2 Xc; float corr;
+				img_load_idx(src, idx, ires, Xc, corr);
+				d = make_float4(Xc.x, Xc.y, corr * 0.5f, 0.f);
+			}
+			const float2 a = __ldg(X + idx), b = __ldg(X0 + idx);
+			s = make_float4(a.x, a.y, b.x, b.y);
+			c = C ? __ldg(C + idx) * m.part_scale : m.part_scale;                              // acc_ml_optimiser_impl.h:3087-3096
+		}
+		A.simg4[(size_t) p * A.stride + ip] = d;
+		A.sst[(size_t) p * A.stride + ip] = s;
+		A.sctf[(size_t) p * A.stride + ip] = c;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// projection, band-major
+// ---------------------------------------------------------------------------------------------
+struct BandProjArgs {
+	const RbFineOrient *fo;
+	const int *indir;            // nullptr: orientation j of the round is fo[begin + j]; else fo[indir[begin + j].w] (RbBpItem list)
+	const int *count_ptr;        // number of list entries (device): counters[0] or the BP list length
+	int begin, capacity;         // this round covers list entries [begin, min(count, begin + capacity))
+	const uint32_t *pix; int npix, stride;
+	float2 *slices;              // [capacity][stride]
+	const RbProjector *projs; int imgX; int nr_classes;
+	int *queue;
+	int chunk_min;
+};
+
+struct RbBpItem { int w; int samp_off; int nsig; float W; };
+
+struct BandProjSmem {
+	float4 cell[BD_THREADS / 32][BD_DEPTH][32 * 4];
+	float4 frac[BD_THREADS / 32][BD_DEPTH][32];
+	float e[BD_MAXCHUNK][6];
+	int cls[BD_MAXCHUNK];
+	int next;
+};
+
+static __global__ void __launch_bounds__(BD_THREADS, 3)
+k_project_band(BandProjArgs A)
+{
+	extern __shared__ __align__(16) unsigned char bd_smem_raw[];
+	BandProjSmem &S = *reinterpret_cast<BandProjSmem *>(bd_smem_raw);
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int k = lane & 3, qbase = lane & ~3;
+	const int total = *A.count_ptr;
+	const int n = min(A.capacity, total - A.begin);
+	if (n <= 0) return;
+	const int ntiles = (A.npix + BD_TP - 1) / BD_TP;
+	// chunk: about one tile's worth of items per resident wave, so that the wave stays inside one band
+	int chunk = (n + (int) gridDim.x - 1) / (int) gridDim.x;
+	chunk = max(A.chunk_min, min(BD_MAXCHUNK, chunk));
+	const int nchunks = (n + chunk - 1) / chunk;
+	const long long nitems = (long long) ntiles * nchunks;
+	BandQueue Q{A.queue, &S.next};
+	const RbProjK8 pk0 = rb_make_projk8(A.projs[0], A.imgX);
+
+	for (long long item = Q.first(); item < nitems; item = Q.next())
+	{
+		Q.prefetch();
+		const int tile = (int) (item / nchunks), c = (int) (item - (long long) tile * nchunks);
+		const int o0 = c * chunk, no = min(chunk, n - o0);
+		// orientation matrices of the chunk
+		for (int i = threadIdx.x; i < no * 6; i += BD_THREADS)
+		{
+			const int j = i / 6, q = i - j * 6;
+			const int li = A.begin + o0 + j;
+			const int w = A.indir ? A.indir[4 * li] : li;
+			S.e[j][q] = A.fo[w].e[q + q / 2];                                   // elements 0,1,3,4,6,7
+			if (q == 0) S.cls[j] = A.fo[w].iclass;
+		}
+		__syncthreads();
+		const int ip = tile * BD_TP + (wid % BD_WPT) * 32 + lane;
+		const bool have = ip < A.npix;
+		int x = 0, y = 0;
+		if (have) { const uint32_t pkx = __ldg(A.pix + ip); x = rb_pix_x(pkx); y = rb_pix_y(pkx); }
+		const int ph = wid / BD_WPT;
+		const int nmy = (no - ph + BD_NPH - 1) / BD_NPH;                        // orientations ph, ph + BD_NPH, ...
+		float4 *cells = &S.cell[wid][0][0];
+		float4 *fracs = &S.frac[wid][0][0];
+
+		auto issue = [&](int jj)
+		{
+			const int j = ph + jj * BD_NPH, slot = jj % BD_DEPTH;
+			const float e0 = S.e[j][0], e1 = S.e[j][1], e3 = S.e[j][2], e4 = S.e[j][3], e6 = S.e[j][4], e7 = S.e[j][5];
+			const RbProjK8 pk = A.nr_classes == 1 ? pk0 : rb_make_projk8(A.projs[S.cls[j]], A.imgX);
+			float xp = (e0 * x + e1 * y) * pk.pf;
+			float yp = (e3 * x + e4 * y) * pk.pf;
+			float zp = (e6 * x + e7 * y) * pk.pf;
+			const int r2 = (int) (xp * xp + yp * yp + zp * zp);
+			const bool inside = have && r2 <= pk.maxR2_padded;
+			const bool inv = xp < 0.f;
+			if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+			const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+			fracs[slot * 32 + lane] = make_float4(xp - fx0, yp - fy0, zp - fz0, __int_as_float((inside ? 1 : 0) | (inv ? 2 : 0)));
+			const int cell = inside ? (((int) fz0 - pk.mdlInitZ) * pk.mdlXY + ((int) fy0 - pk.mdlInitY) * pk.mdlX + (int) fx0) : -1;
+			float4 *dst = cells + slot * 128;
+#pragma unroll
+			for (int r = 0; r < 4; r++)
+			{
+				const int s = qbase + r;                                          // sample (lane) whose cell this round fetches
+				const int cs = __shfl_sync(RB_FULL_MASK, cell, s);
+				if (cs >= 0) bd_cp_async16(dst + s * 4 + ((k + (s >> 1)) & 3), pk.mdl8 + 4 * (size_t) cs + k);
+			}
+		};
+
+#pragma unroll
+		for (int d = 0; d < BD_DEPTH - 1; d++) { if (d < nmy) issue(d); bd_cp_commit(); }
+		for (int jj = 0; jj < nmy; jj++)
+		{
+			if (jj + BD_DEPTH - 1 < nmy) issue(jj + BD_DEPTH - 1);
+			bd_cp_commit();
+			bd_cp_wait<BD_DEPTH - 1>();
+			__syncwarp();
+			const int slot = jj % BD_DEPTH;
+			const float4 fr = fracs[slot * 32 + lane];
+			const int flags = __float_as_int(fr.w);
+			float2 ref = make_float2(0.f, 0.f);
+			if (flags & 1)
+			{
+				const float4 *src = cells + slot * 128 + lane * 4;
+				const int rot = lane >> 1;
+				const float4 q0 = src[(0 + rot) & 3], q1 = src[(1 + rot) & 3], q2 = src[(2 + rot) & 3], q3 = src[(3 + rot) & 3];
+				{
+					const float dx00 = q0.x + (q0.z - q0.x) * fr.x, dx10 = q1.x + (q1.z - q1.x) * fr.x;
+					const float dx01 = q2.x + (q2.z - q2.x) * fr.x, dx11 = q3.x + (q3.z - q3.x) * fr.x;
+					const float dxy0 = dx00 + (dx10 - dx00) * fr.y, dxy1 = dx01 + (dx11 - dx01) * fr.y;
+					ref.x = dxy0 + (dxy1 - dxy0) * fr.z;
+				}
+				{
+					const float dx00 = q0.y + (q0.w - q0.y) * fr.x, dx10 = q1.y + (q1.w - q1.y) * fr.x;
+					const float dx01 = q2.y + (q2.w - q2.y) * fr.x, dx11 = q3.y + (q3.w - q3.y) * fr.x;
+					const float dxy0 = dx00 + (dx10 - dx00) * fr.y, dxy1 = dx01 + (dx11 - dx01) * fr.y;
+					ref.y = dxy0 + (dxy1 - dxy0) * fr.z;
+				}
+				if (flags & 2) ref.y = -ref.y;
+			}
+			__syncwarp();                                                          // the slot is free for the next issue
+			if (have)
+			{
+				const int j = ph + jj * BD_NPH;
+				__stcs(A.slices + (size_t) (o0 + j) * A.stride + ip, ref);
+			}
+		}
+		bd_cp_wait<0>();
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// diff2 of every fine sample from the band-ordered slices (streaming)
+// ---------------------------------------------------------------------------------------------
+struct BandDiffArgs {
+	const RbPartMeta *metas; RbPartState *states;
+	const RbFineOrient *fo; const int *pair_list; const int *counters;
+	float *fs_w;
+	const float4 *simg4; const float2 *slices; const uint32_t *pix; int nd2, stride;
+	int begin, capacity;
+	const float *tx, *ty; int NOT;
+	int *queue;
+};
+
+template <int NT>
+__device__ __forceinline__ void band_diff_pass(const float2 *__restrict__ slice, const float4 *__restrict__ img, const uint32_t *__restrict__ pix,
+                                               int nd2, const float *s_ux, const float *s_uy, float (&acc)[NT], float &base)
+{
+#pragma unroll
+	for (int t = 0; t < NT; t++) acc[t] = 0.f;
+	base = 0.f;
+	for (int ip = threadIdx.x; ip < nd2; ip += BD_THREADS)
+	{
+		const uint32_t pk = __ldg(pix + ip);
+		const int x = rb_pix_x(pk), y = rb_pix_y(pk);
+		const float2 ref = __ldcs(slice + ip);
+		const float4 im = __ldg(img + ip);
+		const float hc = im.z;
+		const float zr = hc * (ref.x * im.x + ref.y * im.y);
+		const float zi = hc * (ref.x * im.y - ref.y * im.x);
+		base += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
+		const float fx = (float) x, fy = (float) y;
+#pragma unroll
+		for (int t = 0; t < NT; t++)
+		{
+			float u = fmaf(fx, s_ux[t], fy * s_uy[t]);
+			u -= rintf(u);
+			float s, c;
+			__sincosf(6.283185307179586f * u, &s, &c);
+			acc[t] = fmaf(zr, c, fmaf(-zi, s, acc[t]));
+		}
+	}
+}
+
+static const int BD_TF = 32;   // translations per pass
+
+static __global__ void __launch_bounds__(BD_THREADS, 3)
+k_diff2_slices(BandDiffArgs A)
+{
+	__shared__ float s_ux[BD_TF], s_uy[BD_TF];
+	__shared__ float s_red[BD_THREADS / 32][BD_TF + 1];
+	__shared__ int s_next;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int total = A.counters[0];
+	const int n = min(A.capacity, total - A.begin);
+	for (int wi = rb_next_work(A.queue, &s_next, 0, true); wi < n; wi = rb_next_work(A.queue, &s_next, wi, false))
+	{
+		const int w = A.begin + wi;
+		const RbFineOrient F = A.fo[w];
+		const int nsamp = F.n_t * A.NOT, p = F.particle;
+		const float xi2_half = A.metas[p].xi2_half;
+		const float4 *img = A.simg4 + (size_t) p * A.stride;
+		const float2 *slice = A.slices + (size_t) wi * A.stride;
+		float bmin = FLT_MAX;
+		for (int c0 = 0; c0 < nsamp; c0 += BD_TF)
+		{
+			const int ntr = min(BD_TF, nsamp - c0);
+			__syncthreads();
+			if (threadIdx.x < BD_TF)
+			{
+				float ux = 0.f, uy = 0.f;
+				if (threadIdx.x < ntr)
+				{
+					const int j = c0 + threadIdx.x;
+					const int it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
+					ux = A.tx[it] * 0.15915494309189535f; uy = A.ty[it] * 0.15915494309189535f;   // radians -> turns per pixel
+				}
+				s_ux[threadIdx.x] = ux; s_uy[threadIdx.x] = uy;
+			}
+			__syncthreads();
+			float acc[BD_TF], base;
+			if (ntr <= 4)
+			{
+				float a4[4]; band_diff_pass<4>(slice, img, A.pix, A.nd2, s_ux, s_uy, a4, base);
+#pragma unroll
+				for (int t = 0; t < BD_TF; t++) acc[t] = t < 4 ? a4[t & 3] : 0.f;
+			}
+			else if (ntr <= 8)
+			{
+				float a8[8]; band_diff_pass<8>(slice, img, A.pix, A.nd2, s_ux, s_uy, a8, base);
+#pragma unroll
+				for (int t = 0; t < BD_TF; t++) acc[t] = t < 8 ? a8[t & 7] : 0.f;
+			}
+			else if (ntr <= 16)
+			{
+				float a16[16]; band_diff_pass<16>(slice, img, A.pix, A.nd2, s_ux, s_uy, a16, base);
+#pragma unroll
+				for (int t = 0; t < BD_TF; t++) acc[t] = t < 16 ? a16[t & 15] : 0.f;
+			}
+			else band_diff_pass<BD_TF>(slice, img, A.pix, A.nd2, s_ux, s_uy, acc, base);
+			// fixed-order reduction: lanes, then warps
+#pragma unroll
+			for (int t = 0; t < BD_TF; t++)
+			{
+				if (t < ntr)
+				{
+					const float v = warp_sum(acc[t]);
+					if (lane == 0) s_red[wid][t] = v;
+				}
+			}
+			base = warp_sum(base);
+			if (lane == 0) s_red[wid][BD_TF] = base;
+			__syncthreads();
+			if (threadIdx.x < ntr)
+			{
+				float c = 0.f, b = 0.f;
+#pragma unroll
+				for (int ww = 0; ww < BD_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][BD_TF]; }
+				const float v = fmaxf((b - 2.f * c) + xi2_half, 0.f);
+				A.fs_w[F.sample_off + c0 + threadIdx.x] = v; bmin = fminf(bmin, v);
+			}
+		}
+		if (threadIdx.x < BD_TF && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// list of the fine orientations that hold significant samples (the only ones wavg / back-projection work on)
+// ---------------------------------------------------------------------------------------------
+struct BpListArgs {
+	const RbPartState *states_c; RbPartState *states;
+	const RbFineOrient *fo; const int *pair_list; int *counters;   // counters[0] fine orientations, [10] BP items, [11] BP samples, [2] overflow
+	const float *fs_w;
+	int *cnt;                    // [cap_fo] significant samples per fine orientation, then exclusive prefix
+	int *item_of;                // [cap_fo] BP item index of a fine orientation (or -1)
+	RbBpItem *items; float4 *samp; long long samp_cap;
+	const float *tx, *ty; int NOT;
+};
+
+static __global__ void __launch_bounds__(256)
+k_bp_count(BpListArgs A)
+{
+	if (A.counters[2]) return;
+	const int nfo = A.counters[0];
+	const int lane = threadIdx.x & 31;
+	for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nfo; w += gridDim.x * (blockDim.x >> 5))
+	{
+		const RbFineOrient F = A.fo[w];
+		const RbPartState *st = A.states_c + F.particle;
+		int cnt = 0;
+		if (st->status == 0)
+		{
+			const float sig = st->fsig_weight;
+			const int nsamp = F.n_t * A.NOT;
+			for (int j = lane; j < nsamp; j += 32) cnt += A.fs_w[F.sample_off + j] >= sig ? 1 : 0;   // wavg.cuh:106 / BP.cuh:278
+			cnt = warp_sum(cnt);
+		}
+		if (lane == 0) A.cnt[w] = cnt;
+	}
+}
+
+// single CTA: exclusive prefixes of (has samples, number of samples) over the fine orientations
+static __global__ void __launch_bounds__(1024)
+k_bp_scan(BpListArgs A)
+{
+	__shared__ long long s_a[1024], s_b[1024];
+	if (A.counters[2]) { if (threadIdx.x == 0) { A.counters[10] = 0; A.counters[11] = 0; } return; }
+	const int nfo = A.counters[0];
+	const int per = (nfo + 1023) / 1024;
+	const int i0 = min(nfo, threadIdx.x * per), i1 = min(nfo, i0 + per);
+	long long a = 0, b = 0;
+	for (int i = i0; i < i1; i++) { const int c = A.cnt[i]; a += c > 0; b += c; }
+	s_a[threadIdx.x] = a; s_b[threadIdx.x] = b;
+	__syncthreads();
+	for (int off = 1; off < 1024; off <<= 1)
+	{
+		long long ta = 0, tb = 0;
+		if (threadIdx.x >= off) { ta = s_a[threadIdx.x - off]; tb = s_b[threadIdx.x - off]; }
+		__syncthreads();
+		s_a[threadIdx.x] += ta; s_b[threadIdx.x] += tb;
+		__syncthreads();
+	}
+	long long ea = s_a[threadIdx.x] - a, eb = s_b[threadIdx.x] - b;
+	const bool overflow = s_b[1023] > A.samp_cap;
+	for (int i = i0; i < i1; i++)
+	{
+		const int c = A.cnt[i];
+		A.item_of[i] = (c > 0 && !overflow) ? (int) ea : -1;
+		A.cnt[i] = (int) eb;
+		ea += c > 0; eb += c;
+	}
+	if (threadIdx.x == 1023)
+	{
+		A.counters[10] = overflow ? 0 : (int) s_a[1023];
+		A.counters[11] = overflow ? 0 : (int) s_b[1023];
+		if (overflow) { A.counters[3] = 1; ((long long *) A.counters)[6] = s_b[1023]; }   // counters[12..13]: samples needed
+	}
+}
+
+static __global__ void __launch_bounds__(256)
+k_bp_fill(BpListArgs A)
+{
+	if (A.counters[2] || A.counters[3]) return;
+	const int nfo = A.counters[0];
+	const int lane = threadIdx.x & 31;
+	for (int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < nfo; w += gridDim.x * (blockDim.x >> 5))
+	{
+		const int item = A.item_of[w];
+		if (item < 0) continue;
+		const RbFineOrient F = A.fo[w];
+		const RbPartState *st = A.states_c + F.particle;
+		const float sig = st->fsig_weight, wni = 1.0f / st->fsum_weight;
+		const int nsamp = F.n_t * A.NOT, soff = A.cnt[w];
+		int run = 0;
+		for (int j0 = 0; j0 < nsamp; j0 += 32)
+		{
+			const int j = j0 + lane;
+			const float wv = j < nsamp ? A.fs_w[F.sample_off + j] : -1.f;
+			const bool s = j < nsamp && wv >= sig;
+			const unsigned b = __ballot_sync(RB_FULL_MASK, s);
+			if (s)
+			{
+				const int pos = run + __popc(b & ((1u << lane) - 1));
+				const int it = A.pair_list[F.pair_off + j / A.NOT] * A.NOT + (j % A.NOT);
+				A.samp[soff + pos] = make_float4(A.tx[it] * 0.15915494309189535f, A.ty[it] * 0.15915494309189535f, wv * wni, 0.f);   // weight * weight_norm_inverse (wavg.h:138)
+			}
+			run += __popc(b);
+		}
+		__syncwarp();
+		if (lane == 0)
+		{
+			float W = 0.f;
+			for (int i = 0; i < run; i++) W += A.samp[soff + i].z;
+			RbBpItem it; it.w = w; it.samp_off = soff; it.nsig = run; it.W = W;
+			A.items[item] = it;
+			atomicAdd(&A.states[F.particle].n_bp, 1);
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// wavg + back-projection, band-major
+// ---------------------------------------------------------------------------------------------
+struct BandStoreArgs {
+	const RbPartMeta *metas; RbPartState *states;
+	const RbFineOrient *fo; const RbBpItem *items; const float4 *samp; const int *counters;
+	int begin, capacity;         // this round covers BP items [begin, min(nbp, begin + capacity))
+	int slice_by_item;           // 1: slices are indexed by (item - begin) (re-projected rounds); 0: by fine orientation index
+	const float4 *sst; const float *sctf; const float2 *slices; const uint32_t *pix; int nst, stride;
+	float *shells;               // [P][nshell]
+	const RbBackprojector *bps;
+	int n; int *queue; int chunk_min;
+};
+
+struct BandStoreSmem {
+	RbBpItem item[BD_MAXCHUNK];
+	float e[BD_MAXCHUNK][6];
+	int particle[BD_MAXCHUNK], cls[BD_MAXCHUNK];
+	int next;
+};
+
+static __global__ void __launch_bounds__(BD_THREADS, 2)
+k_store_band(BandStoreArgs A, RbModelDev M)
+{
+	__shared__ BandStoreSmem S;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	if (A.counters[2] || A.counters[3]) return;
+	const int total = A.counters[10];
+	const int n = min(A.capacity, total - A.begin);
+	if (n <= 0) return;
+	const int ntiles = (A.nst + BD_TP - 1) / BD_TP;
+	int chunk = (n + (int) gridDim.x - 1) / (int) gridDim.x;
+	chunk = max(A.chunk_min, min(BD_MAXCHUNK, chunk));
+	const int nchunks = (n + chunk - 1) / chunk;
+	const long long nitems = (long long) ntiles * nchunks;
+	const int half = A.n / 2;
+	BandQueue Q{A.queue, &S.next};
+
+	for (long long item = Q.first(); item < nitems; item = Q.next())
+	{
+		Q.prefetch();
+		const int tile = (int) (item / nchunks), c = (int) (item - (long long) tile * nchunks);
+		const int o0 = c * chunk, no = min(chunk, n - o0);
+		for (int j = threadIdx.x; j < no; j += BD_THREADS)
+		{
+			const RbBpItem it = A.items[A.begin + o0 + j];
+			S.item[j] = it;
+			S.particle[j] = A.fo[it.w].particle; S.cls[j] = A.fo[it.w].iclass;
+		}
+		for (int i = threadIdx.x; i < no * 6; i += BD_THREADS)
+		{
+			const int j = i / 6, q = i - j * 6;
+			S.e[j][q] = A.fo[A.items[A.begin + o0 + j].w].e[q + q / 2];
+		}
+		__syncthreads();
+		const int ip = tile * BD_TP + (wid % BD_WPT) * 32 + lane;
+		const bool have = ip < A.nst;
+		int x = 0, y = 0, ires = 0;
+		if (have) { const uint32_t pkx = __ldg(A.pix + ip); x = rb_pix_x(pkx); y = rb_pix_y(pkx); ires = rb_pix_ires(pkx); }
+		// (x = 0, y < 0) is only in the list with --no_map: Mresol excludes it from the shell sums (:3466-3494)
+		const bool in_mresol = have && !(x == 0 && y < 0);
+		bool circle_ok = true;
+		if (M.bp_circle_bound) { const int xmax = (int) sqrtf((float) (half * half - y * y)); circle_ok = x < xmax; }   // BP.h:565
+		const float fxp = (float) x, fyp = (float) y;
+
+		for (int j = wid / BD_WPT; j < no; j += BD_NPH)
+		{
+			const RbBpItem it = S.item[j];
+			const int p = S.particle[j], cls = S.cls[j];
+			const size_t so = (size_t) (A.slice_by_item ? (o0 + j) : (it.w - 0)) * A.stride + ip;
+			const size_t po = (size_t) p * A.stride + ip;
+			float2 ref = make_float2(0.f, 0.f); float4 XX = make_float4(0.f, 0.f, 0.f, 0.f); float ctf = 0.f;
+			if (have) { ref = __ldcs(A.slices + so); XX = __ldg(A.sst + po); ctf = __ldg(A.sctf + po); }
+			const RbPartMeta *mp = A.metas + p;
+			const float part_scale = __ldg(&mp->part_scale);
+			const int og = __ldg(&mp->og);
+			if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                                  // wavg.cuh:96-104
+			else { ref.x *= part_scale; ref.y *= part_scale; }
+			float phr = 0.f, phi = 0.f;
+			const float4 *sp = A.samp + it.samp_off;
+			for (int t = 0; t < it.nsig; t++)
+			{
+				const float4 sv = __ldg(sp + t);
+				float u = fmaf(fxp, sv.x, fyp * sv.y);
+				u -= rintf(u);
+				float sn, cs;
+				__sincosf(6.283185307179586f * u, &sn, &cs);
+				phr = fmaf(sv.z, cs, phr); phi = fmaf(sv.z, sn, phi);
+			}
+			const float W = it.W;
+			const float refn = ref.x * ref.x + ref.y * ref.y;
+			const float Xn = XX.x * XX.x + XX.y * XX.y;
+			const float xa = (ref.x * XX.x + ref.y * XX.y) * phr - (ref.x * XX.y - ref.y * XX.x) * phi;
+			const float aa = W * refn;
+			float wd = in_mresol ? fmaxf(W * (refn + Xn) - 2.f * xa, 0.f) : 0.f;
+			// shell sums: the 32 pixels of a warp are neighbours in |r|, i.e. they sit in one or two shells
+			{
+				unsigned todo = __ballot_sync(RB_FULL_MASK, in_mresol);
+				while (todo)
+				{
+					const int leader = __ffs(todo) - 1;
+					const int cur = __shfl_sync(RB_FULL_MASK, ires, leader);
+					const bool mine = in_mresol && ires == cur;
+					const float v = warp_sum(mine ? wd : 0.f);
+					if (lane == leader && v != 0.f) atomicAdd(A.shells + (size_t) p * M.nshell + cur, v);
+					todo &= ~__ballot_sync(RB_FULL_MASK, mine);
+				}
+			}
+			if (M.do_scale_correction)                                                                        // :3473-3479
+			{
+				const bool use = in_mresol && M.dvp_gt3[(size_t) cls * M.nshell + ires];
+				const double sxa = warp_sum(use ? (double) xa : 0.), saa = warp_sum(use ? (double) aa : 0.);
+				if (lane == 0 && (sxa != 0. || saa != 0.))
+				{
+					atomicAdd(&A.states[p].wsum_XA, sxa);
+					atomicAdd(&A.states[p].wsum_AA, saa);
+				}
+			}
+			// back-projection
+			const RbBackprojector bp = A.bps[cls];
+			const int max_r2_vol = (int) (bp.maxR * bp.maxR * bp.padding_factor * bp.padding_factor);   // BP.cuh:209
+			int cell = -1;
+			float sfx = 0.f, sfy = 0.f, sfz = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
+			if (have)
+			{
+				const float minvs2 = M.do_map ? __ldg(M.minvs2 + (size_t) og * M.nshell + ires) : 1.f;     // :2586, :3110-3115
+				const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                                // BP.cuh:280-289
+				Fw = W * g * ctf;
+				if (Fw > 0.f && circle_ok)
+				{
+					Fr = (XX.z * phr - XX.w * phi) * g;
+					Fi = (XX.z * phi + XX.w * phr) * g;
+					const float e0 = S.e[j][0], e1 = S.e[j][1], e3 = S.e[j][2], e4 = S.e[j][3], e6 = S.e[j][4], e7 = S.e[j][5];
+					float xp = (e0 * x + e1 * y) * bp.padding_factor;                                          // BP.cuh:301-347
+					float yp = (e3 * x + e4 * y) * bp.padding_factor;
+					float zp = (e6 * x + e7 * y) * bp.padding_factor;
+					if (xp * xp + yp * yp + zp * zp <= (float) max_r2_vol)
+					{
+						if (xp < 0.f) { xp = -xp; yp = -yp; zp = -zp; Fi = -Fi; }
+						const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+						sfx = xp - fx0; sfy = yp - fy0; sfz = zp - fz0;
+						cell = (((int) fz0 - bp.mdlInitZ) * bp.mdlY + ((int) fy0 - bp.mdlInitY)) * bp.mdlX + (int) fx0;
+					}
+				}
+			}
+			// two lanes per pixel, one per x-neighbour: the two 16-byte reductions of a corner pair share a 32-byte sector
+#pragma unroll
+			for (int h = 0; h < 2; h++)
+			{
+				const int src = 16 * h + (lane >> 1);
+				const int cc = __shfl_sync(RB_FULL_MASK, cell, src);
+				const float fx = __shfl_sync(RB_FULL_MASK, sfx, src), fy = __shfl_sync(RB_FULL_MASK, sfy, src), fz = __shfl_sync(RB_FULL_MASK, sfz, src);
+				const float vr = __shfl_sync(RB_FULL_MASK, Fr, src), vi = __shfl_sync(RB_FULL_MASK, Fi, src), vw = __shfl_sync(RB_FULL_MASK, Fw, src);
+				if (cc >= 0)
+				{
+					const int px = lane & 1;
+					const float wx = px ? fx : 1.f - fx;
+					const float mfy = 1.f - fy, mfz = 1.f - fz;
+					float4 *b = bp.vol + (size_t) cc + px;
+					const size_t sy = bp.mdlX, sz = (size_t) bp.mdlX * bp.mdlY;
+					float d2;
+					d2 = mfz * mfy * wx; bd_red_add_v4(b, d2 * vr, d2 * vi, d2 * vw);
+					d2 = mfz * fy * wx;  bd_red_add_v4(b + sy, d2 * vr, d2 * vi, d2 * vw);
+					d2 = fz * mfy * wx;  bd_red_add_v4(b + sz, d2 * vr, d2 * vi, d2 * vw);
+					d2 = fz * fy * wx;   bd_red_add_v4(b + sz + sy, d2 * vr, d2 * vi, d2 * vw);
+				}
+			}
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static int env_int(const char *name, int dflt)
+{
+	const char *v = getenv(name);
+	return (v && *v) ? atoi(v) : dflt;
+}
+
+bool rbk_band_applicable(rb_ctx *ctx)
+{
+	// decided by pool_setup (api.cu): not with the cross-correlation criterion (it stays on k_diff2_fine / k_store), not with
+	// RB_BAND=0 or without room for the band-ordered slices
+	return !ctx->d_model.do_cc && ctx->d_model.pix_rs && ctx->band_slice_capacity > 0;
+}
+
+// per-pool buffers and the band-ordered images (once per E-step of a slot)
+int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	const RbModelDev &M = ctx->d_model;
+	const size_t stride = (size_t) M.nv_rs_pad;
+	RB_CHECK(s.simg4.ensure((size_t) s.P * stride * sizeof(float4)));
+	RB_CHECK(s.sst.ensure((size_t) s.P * stride * sizeof(float4)));
+	RB_CHECK(s.sctf.ensure((size_t) s.P * stride * sizeof(float)));
+	BandPrepArgs A;
+	memset(&A, 0, sizeof(A));
+	A.metas = s.meta.as<RbPartMeta>(); A.Fimg = s.Fimg.as<float2>(); A.Fnomask = s.Fnomask.as<float2>();
+	A.Fctf = ctx->h_model.do_ctf_correction ? s.Fctf.as<float>() : nullptr;
+	A.pix = M.pix_rs; A.nd2 = M.nv_rs_d2; A.nst = M.nv_rs_st; A.stride = (int) stride;
+	A.simg4 = s.simg4.as<float4>(); A.sst = s.sst.as<float4>(); A.sctf = s.sctf.as<float>();
+	dim3 g((unsigned) ((stride + 255) / 256), s.P);
+	k_prep_sorted<<<g, 256, 0, ctx->stream>>>(A, M);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const int *count_ptr, int begin, int capacity, int *queue)
+{
+	const RbModelDev &M = ctx->d_model;
+	BandProjArgs A;
+	memset(&A, 0, sizeof(A));
+	A.fo = s.fo.as<RbFineOrient>(); A.indir = indir; A.count_ptr = count_ptr; A.begin = begin; A.capacity = capacity;
+	A.pix = M.pix_rs; A.npix = M.nv_rs_st; A.stride = M.nv_rs_pad;
+	A.slices = ctx->band_slices.as<float2>();
+	A.projs = ctx->d_proj.as<RbProjector>(); A.imgX = M.current_size / 2 + 1; A.nr_classes = M.nr_classes;
+	A.queue = queue;
+	A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_CHUNK_MIN", 8));
+	static bool configured[RB_MAX_DEVICES] = {};
+	const size_t sm = sizeof(BandProjSmem);
+	if (!configured[ctx->device % RB_MAX_DEVICES])
+	{
+		RB_CUDA(cudaFuncSetAttribute(k_project_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+		configured[ctx->device % RB_MAX_DEVICES] = true;
+	}
+	RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
+	k_project_band<<<ctx->num_sms * env_int("RB_BAND_PROJ_CTAS", 3), BD_THREADS, sm, ctx->stream>>>(A);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// fine pass: projection of every fine orientation (band-major), then the streaming diff2 pass; in rounds when the slices of
+// all fine orientations the pool could produce do not fit the slice buffer (rounds beyond the actual count exit at once)
+int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	const RbModelDev &M = ctx->d_model;
+	RB_CHECK(rbk_band_prepare_pool(ctx, s));
+	const long long cap = ctx->band_slice_capacity;
+	const long long worst = (long long) s.cap_fo;
+	const int rounds = (int) std::min<long long>((worst + cap - 1) / cap, 4096);
+	int *queue = s.counters.as<int>() + 8;
+	for (int r = 0; r < rounds; r++)
+	{
+		const int begin = (int) (r * cap);
+		RB_CHECK(launch_project_band(ctx, s, nullptr, s.counters.as<int>(), begin, (int) cap, queue));
+		BandDiffArgs D;
+		memset(&D, 0, sizeof(D));
+		D.metas = s.meta.as<RbPartMeta>(); D.states = s.state.as<RbPartState>();
+		D.fo = s.fo.as<RbFineOrient>(); D.pair_list = s.pair_list.as<int>(); D.counters = s.counters.as<int>();
+		D.fs_w = s.fs_w.as<float>();
+		D.simg4 = s.simg4.as<float4>(); D.slices = ctx->band_slices.as<float2>(); D.pix = M.pix_rs; D.nd2 = M.nv_rs_d2; D.stride = M.nv_rs_pad;
+		D.begin = begin; D.capacity = (int) cap;
+		D.tx = ctx->d_samp.ftx; D.ty = ctx->d_samp.fty; D.NOT = ctx->d_samp.n_over_trans;
+		D.queue = queue + 1;
+		RB_CUDA(cudaMemsetAsync(queue + 1, 0, 4, ctx->stream));
+		k_diff2_slices<<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D);
+		RB_LAUNCH_CHECK(ctx);
+	}
+	s.band_rounds = rounds;
+	return RB_OK;
+}
+
+int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
+{
+	const RbModelDev &M = ctx->d_model;
+	const long long cap_fo = (long long) s.cap_fo;
+	RB_CHECK(s.bp_cnt.ensure((size_t) cap_fo * 4)); RB_CHECK(s.bp_item_of.ensure((size_t) cap_fo * 4));
+	RB_CHECK(s.bp_items.ensure((size_t) cap_fo * sizeof(RbBpItem)));
+	const long long samp_cap = std::min<long long>((long long) s.cap_fs, (long long) env_int("RB_BP_SAMPLE_CAP", 1 << 22));
+	RB_CHECK(s.bp_samp.ensure((size_t) samp_cap * sizeof(float4)));
+	BpListArgs L;
+	memset(&L, 0, sizeof(L));
+	L.states_c = s.state.as<RbPartState>(); L.states = s.state.as<RbPartState>();
+	L.fo = s.fo.as<RbFineOrient>(); L.pair_list = s.pair_list.as<int>(); L.counters = s.counters.as<int>();
+	L.fs_w = s.fs_w.as<float>(); L.cnt = s.bp_cnt.as<int>(); L.item_of = s.bp_item_of.as<int>();
+	L.items = s.bp_items.as<RbBpItem>(); L.samp = s.bp_samp.as<float4>(); L.samp_cap = samp_cap;
+	L.tx = ctx->d_samp.ftx; L.ty = ctx->d_samp.fty; L.NOT = ctx->d_samp.n_over_trans;
+	k_bp_count<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(L);
+	RB_LAUNCH_CHECK(ctx);
+	k_bp_scan<<<1, 1024, 0, ctx->stream>>>(L);
+	RB_LAUNCH_CHECK(ctx);
+	k_bp_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(L);
+	RB_LAUNCH_CHECK(ctx);
+
+	BandStoreArgs A;
+	memset(&A, 0, sizeof(A));
+	A.metas = s.meta.as<RbPartMeta>(); A.states = s.state.as<RbPartState>();
+	A.fo = s.fo.as<RbFineOrient>(); A.items = s.bp_items.as<RbBpItem>(); A.samp = s.bp_samp.as<float4>(); A.counters = s.counters.as<int>();
+	A.sst = s.sst.as<float4>(); A.sctf = s.sctf.as<float>(); A.slices = ctx->band_slices.as<float2>();
+	A.pix = M.pix_rs; A.nst = M.nv_rs_st; A.stride = M.nv_rs_pad;
+	A.shells = s.shells.as<float>(); A.bps = ctx->d_bp.as<RbBackprojector>();
+	A.n = M.current_size; A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_STORE_CHUNK_MIN", 4));
+	int *queue = s.counters.as<int>() + 14;
+	const int grid = ctx->num_sms * env_int("RB_BAND_STORE_CTAS", 2);
+	if (s.band_rounds <= 1)
+	{
+		// the slices of every fine orientation are still in the buffer, indexed by fine orientation
+		A.begin = 0; A.capacity = 0x7fffffff; A.slice_by_item = 0; A.queue = queue;
+		RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
+		k_store_band<<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
+		RB_LAUNCH_CHECK(ctx);
+		return RB_OK;
+	}
+	// several rounds: the buffer was reused, project the listed orientations again, round by round
+	const long long cap = ctx->band_slice_capacity;
+	for (int r = 0; r < s.band_rounds; r++)
+	{
+		const int begin = (int) (r * cap);
+		RB_CHECK(launch_project_band(ctx, s, (const int *) s.bp_items.p, s.counters.as<int>() + 10, begin, (int) cap, queue + 1));
+		A.begin = begin; A.capacity = (int) cap; A.slice_by_item = 1; A.queue = queue;
+		RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
+		k_store_band<<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
+		RB_LAUNCH_CHECK(ctx);
+	}
+	return RB_OK;
+}

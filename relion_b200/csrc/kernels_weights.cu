@@ -1043,7 +1043,7 @@ int rbk_fine_setup_pool(rb_ctx *ctx, PoolSlot &s)
 	k_fine_chunkscan<<<s.P, 32, 0, ctx->stream>>>(s.state.as<RbPartState>(), nchunk, part_so, part_pair);
 	RB_LAUNCH_CHECK(ctx);
 	k_fine_scan<<<1, 1024, 0, ctx->stream>>>(s.state.as<RbPartState>(), s.P, ctx->d_samp.n_over_rot, ctx->d_samp.n_over_trans,
-		(long long) ctx->fine_orient_capacity, (long long) ctx->fine_sample_capacity, s.counters.as<int>());
+		(long long) s.cap_fo, (long long) s.cap_fs, s.counters.as<int>());
 	RB_LAUNCH_CHECK(ctx);
 	k_fine_fill<<<grid, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
 		s.Mweight.as<float>(), s.dir_idx.as<int>(), s.psi_idx.as<int>(), ctx->d_model, ctx->d_samp,

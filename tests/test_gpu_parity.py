@@ -754,6 +754,34 @@ def test_pool_class_with_zero_prior_is_skipped(device, oracle, local):
     assert np.all(device.bp_get(1)[2] == 0)
 
 
+@pytest.mark.parametrize("kw", [dict(ori_size=32, healpix_order=2, n_particles=10, nr_classes=1, seed=140, snr=0.2, local_search=True),
+                                dict(ori_size=32, healpix_order=1, n_particles=9, nr_classes=2, seed=141, snr=0.3),
+                                dict(ori_size=40, current_size=28, healpix_order=1, n_particles=7, nr_classes=1, seed=142, snr=0.05)])
+@pytest.mark.parametrize("flags", [dict(), dict(do_map=False)])
+def test_band_major_path_equals_orientation_major_path(device, oracle, monkeypatch, kw, flags):
+    """The band-major fine pass / store stage (kernels_band.cu: projection per radial band into band-ordered slices, streaming
+    diff2, store by (band, orientation chunk)) against the orientation-major kernels (RB_BAND=0) on the same pool: same
+    fine-pass lists and poses, sums equal up to the summation order; both against the oracle.  --no_map adds the extra
+    x = 0 half column to the store-stage pixel set."""
+    wl = make_workload(**kw)
+    for k, v in flags.items():
+        setattr(wl.model, k, v)
+    out = {}
+    for band in ("0", "1"):
+        monkeypatch.setenv("RB_BAND", band)
+        res, _ = _compare_pool(device, oracle, wl, pose_frac=0.9 if kw["snr"] < 0.1 else 0.995)
+        out[band] = (res, [device.bp_get(k) for k in range(wl.model.nr_classes)])
+    a, b = out["0"][0].particles, out["1"][0].particles
+    for key in ("nr_significant_coarse", "n_fine_orient", "n_fine_samples", "best_ihidden_over", "n_bp_orient"):
+        assert np.array_equal(a[key], b[key]), key
+    for key in ("min_diff2", "sum_weight", "pmax", "dLL_nolog", "wsum_norm_correction", "wsum_XA", "wsum_AA", "sumw", "wsum_sigma2_offset"):
+        np.testing.assert_allclose(a[key], b[key], rtol=2e-4, atol=1e-6 * max(np.abs(a[key]).max(), 1e-30), err_msg=key)
+    np.testing.assert_allclose(out["0"][0].wsum_sigma2_noise, out["1"][0].wsum_sigma2_noise, rtol=1e-3, atol=1e-5 * np.abs(out["0"][0].wsum_sigma2_noise).max())
+    for ka, kb in zip(out["0"][1], out["1"][1]):
+        for x, y in zip(ka, kb):
+            assert np.abs(x - y).max() <= 1e-4 * max(np.abs(x).max(), 1e-12)
+
+
 @pytest.mark.parametrize("cache_slices", [0, 5])
 def test_pool_store_stage_without_slice_cache(device, oracle, monkeypatch, cache_slices):
     """The store stage re-gathers the reference for fine orientations whose slice did not fit the cache the fine pass fills

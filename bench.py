@@ -274,7 +274,8 @@ def run_ours(args):
         dev.bp_clear(k)
     launches0 = dev.launch_count()
     barrier()
-    stage_names = ["coarse", "weights_coarse", "fine_setup", "fine", "weights_fine", "store", "total"]
+    stage_names = ["coarse", "weights_coarse", "fine_setup", "fine", "weights_fine", "store", "total",
+                   "fine_prep", "fine_project", "fine_diff2", "store_list", "store_band"]
     stage_ms = {s: 0.0 for s in stage_names}
     dev.timer_start()
     for _ in range(args.steps):
@@ -443,6 +444,8 @@ def run_ours(args):
         except Exception as e:  # noqa: BLE001
             parity = {"ok": False, "error": repr(e)[:300]}
 
+    ref_cuda = ref_cuda_block(wl, args.ref_cuda_sample, stage_ms, P) if args.ref_cuda_sample > 0 else None
+
     pr = res0.particles
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -456,7 +459,7 @@ def run_ours(args):
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "e2e_from_raw_images": e2e_raw, "e2e_from_mrc_stacks": e2e_files,
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
-        "parity": parity, "datagen_s": round(gen_s, 1),
+        "parity": parity, "ref_cuda": ref_cuda, "datagen_s": round(gen_s, 1),
     }
     print(json.dumps(out))
     if world > 1:
@@ -529,6 +532,44 @@ def e2e_from_files(dev, wl, raw, steps, barrier, world, local, d2h):
                 "note": "MRC stacks (page cache) -> native feed -> page-locked staging -> rb_pool_prepare -> E-step; STAR metadata via ParticleSet"}
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
+
+
+def ref_cuda_block(wl, n, stage_ms, P):
+    """The reference's OWN CUDA kernels (oracle/_ref/librefcuda.so: diff2.cuh, wavg.cuh, BP.cuh compiled for sm_100 from
+    /root/reference, launched per particle with the reference's grid shapes) on the first n particles of the same pool, on this
+    GPU: summed CUDA-event time per kernel family, next to our stage times per particle.  A reported baseline."""
+    from oracle.bindings import Oracle, Projector, Backprojector, have_refcuda
+    from oracle.parity import pool_slice
+    if not have_refcuda():
+        return {"unavailable": "oracle/_ref/librefcuda.so not built (needs /root/reference in the dev container)"}
+    try:
+        orc = Oracle("refcuda")
+        n = min(n, wl.pool.n_particles)
+        sub = pool_slice(wl.pool, n, wl.model.current_size)
+        refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
+        bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
+        # first pass: texture upload, allocations, module load; second pass timed
+        orc.estep_pool(wl.model, wl.sampling, refs, bps, pool_slice(wl.pool, min(n, 4), wl.model.current_size), num_threads=1)
+        orc.cuda_timers(reset=True)
+        t0 = time.perf_counter()
+        st, _, _ = orc.estep_pool(wl.model, wl.sampling, refs, bps, sub, num_threads=1, exact_threshold=False)
+        wall = time.perf_counter() - t0
+        assert st == 0, st
+        ms, launches = orc.cuda_timers(reset=True)
+        orc.release_cuda()
+        tot = sum(ms.values())
+        ours = {"coarse": stage_ms["coarse"] / P, "fine": stage_ms["fine"] / P, "store": stage_ms["store"] / P, "total": stage_ms["total"] / P}
+        refp = {"coarse": ms["coarse"] / n, "fine": ms["fine"] / n, "store": (ms["wavg"] + ms["backproject"]) / n, "total": tot / n}
+        return {"particles": n, "coarse_ms": round(ms["coarse"], 3), "fine_ms": round(ms["fine"], 3), "wavg_ms": round(ms["wavg"], 3),
+                "bp_ms": round(ms["backproject"], 3), "kernel_launches": launches,
+                "kernel_ms_per_particle": round(tot / n, 4), "particles_per_s": round(n / (tot * 1e-3), 1),
+                "particles_per_s_wall_incl_host_driver": round(n / wall, 1),
+                "ours_ms_per_particle": {k: round(v, 5) for k, v in ours.items()},
+                "speedup_vs_ref_cuda_kernels": {k: round(refp[k] / ours[k], 2) for k in ours if ours[k] > 0},
+                "note": "reference CUDA kernels (texture projector, sm_100) launched one particle at a time as the reference does; "
+                        "particles_per_s = particles / summed kernel time (host orchestration and copies excluded)"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": repr(e)[:300]}
 
 
 def cpu_baseline(wl, sample, kind=None, steps=1, warmup=0):
@@ -759,6 +800,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0, help="particles per pool per GPU (default: workload specific)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the bounded CPU sample (0: 8 per host core, at least 64, at most the pool)")
     ap.add_argument("--kernels-only", action="store_true", help="device-resident timed region only (for ncu)")
+    ap.add_argument("--ref-cuda-sample", type=int, default=64, help="particles run through the reference's own CUDA kernels on this GPU (0: off)")
     ap.add_argument("--parity-sample", type=int, default=256, help="particles of the same pool checked against the CPU oracle inside the run (0: off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

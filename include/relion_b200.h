@@ -113,6 +113,35 @@ int rb_bp_get(rb_ctx *ctx, int iclass, float *real, float *imag, float *weight);
  * src/ml_optimiser_mpi.cpp:2028-2185).  The pointer stays valid until rb_bp_init/rb_ctx_destroy. */
 int rb_bp_device_buffer(rb_ctx *ctx, int iclass, void **dptr, size_t *n_floats);
 
+/* ------------------------------------------------------------------------------------------------
+ * Per-iteration reduction over the GPUs of one box (replaces MlOptimiserMpi::combineAllWeightedSums,
+ * src/ml_optimiser_mpi.cpp:2028-2185, and MlWsumModel::pack / unpack, src/ml_model.cpp:1881-2049): NCCL over NVLink,
+ * loaded at run time (libnccl.so.2, or RB_NCCL_LIB).  One rb_comm per context (rank).
+ *   several processes, one GPU each : rank 0 calls rb_comm_unique_id, ships the 128 bytes to the others by any means,
+ *                                     every rank calls rb_comm_create
+ *   one process, several GPUs       : rb_comm_create_all (what RELION's threads-per-device layout needs); the collective
+ *                                     calls of the ranks then come from different threads, or from one thread between
+ *                                     rb_comm_group_start / rb_comm_group_end
+ * rb_bp_allreduce sums the accumulators of all nr_classes classes in place, on the context's own stream (ordered after
+ * the E-step, waits for completion): the zero pad lane of the float4 voxels does not travel.  rb_wsum_allreduce sums one
+ * fp64 host vector holding every other weighted sum in MlWsumModel::pack order (relion_b200::WsumPack in the C++ adapter).
+ * rb_bp_allreduce_nccl takes a caller-owned ncclComm_t (e.g. a half-set communicator made with ncclCommSplit) and may
+ * return without waiting (wait == 0: later library calls on the context are stream-ordered behind it anyway).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rb_comm rb_comm;
+int rb_comm_unique_id(void *id128);
+int rb_comm_create(rb_ctx *ctx, int nranks, int rank, const void *id128, rb_comm **out);
+int rb_comm_create_all(rb_ctx *const *ctxs, int n, rb_comm **out);
+void rb_comm_destroy(rb_comm *comm);
+int rb_comm_size(const rb_comm *comm);
+int rb_comm_rank(const rb_comm *comm);
+void *rb_comm_handle(rb_comm *comm);            /* the ncclComm_t */
+int rb_comm_group_start(void);
+int rb_comm_group_end(void);
+int rb_bp_allreduce(rb_ctx *ctx, rb_comm *comm);
+int rb_bp_allreduce_nccl(rb_ctx *ctx, void *nccl_comm, int nr_classes, int wait);
+int rb_wsum_allreduce(rb_ctx *ctx, rb_comm *comm, double *wsums, size_t n);
+
 /* BackProjector::symmetrise (src/backprojector.cpp:2136-2480) on accumulator iclass: enforceHermitianSymmetry of the x = 0
  * plane, then applyPointGroupSymmetry with the nsym rotation matrices R ([nsym][9] row-major, the R of
  * SymList::get_matrices; nsym == 0 for C1).  RELION calls this before every reconstruct (src/ml_optimiser.cpp:4930-5044). */

@@ -7,6 +7,9 @@ Two kernel providers share one E-step driver (oracle/estep_driver.cpp):
   kind="reference"  oracle/_ref/librefkernels.so   the reference's own ALTCPU kernels compiled from
                                                    /root/reference by oracle/Makefile (prebuilt .so travels
                                                    to the GPU box; absent => RuntimeError, never a silent swap)
+  kind="refcuda"    oracle/_ref/librefcuda.so      the reference's own CUDA kernels (diff2.cuh, wavg.cuh, BP.cuh, texture
+                                                   projector) compiled for sm_100 (oracle/ref_cuda_kernels.cu): the TIMING
+                                                   baseline "reference --gpu path" of bench.py; needs a GPU, one host thread
 """
 from __future__ import annotations
 
@@ -23,6 +26,7 @@ from relion_b200.estep import (ModelParams, ParticlePool, marshal_model, marshal
 HERE = os.path.dirname(os.path.abspath(__file__))
 PORT_LIB = os.path.join(HERE, "liboracle.so")
 REF_LIB = os.path.join(HERE, "_ref", "librefkernels.so")
+REFCUDA_LIB = os.path.join(HERE, "_ref", "librefcuda.so")
 
 f32p = C.POINTER(C.c_float)
 u8p = C.POINTER(C.c_ubyte)
@@ -94,6 +98,10 @@ def have_reference() -> bool:
     return os.path.exists(REF_LIB)
 
 
+def have_refcuda() -> bool:
+    return os.path.exists(REFCUDA_LIB)
+
+
 def _load(kind: str):
     if kind in _libs:
         return _libs[kind]
@@ -119,6 +127,15 @@ def _load(kind: str):
         ref.refk_kernel_table.restype = C.POINTER(ok_kernel_table)
         table = ref.refk_kernel_table()
         _libs["_ref_handle"] = ref
+    elif kind == "refcuda":
+        if not os.path.exists(REFCUDA_LIB):
+            raise RuntimeError(f"{REFCUDA_LIB} missing: build it in the dev container with `make -C oracle refcuda`")
+        rc = C.CDLL(REFCUDA_LIB)
+        rc.refcuda_kernel_table.restype = C.POINTER(ok_kernel_table)
+        rc.refcuda_timers.argtypes = [C.POINTER(C.c_double), C.POINTER(C.c_long), C.c_int]
+        rc.refcuda_bp_download.argtypes = [BP]
+        table = rc.refcuda_kernel_table()
+        _libs["_refcuda_handle"] = rc
     else:
         raise ValueError(kind)
     _libs[kind] = (port, table)
@@ -204,12 +221,25 @@ class Oracle:
                                         C.byref(dbg) if dbg is not None else None)
         for s in syncs:
             self.K.bp_sync_free(s)
+        if self.kind == "refcuda":
+            for k in range(K):
+                _libs["_refcuda_handle"].refcuda_bp_download(C.byref(barr[k]))
         if dbg is not None:
             n = int(dbg.fine_count)
             dbg_arrays["fine_count"] = n
             for k in ("fine_ihidden_over", "fine_diff2", "fine_weights"):
                 dbg_arrays[k] = dbg_arrays[k][:n]
         return st, out.result, dbg_arrays
+
+    def cuda_timers(self, reset=False):
+        """kind="refcuda": summed device time (ms) and launch counts of the reference's CUDA kernels since the last reset."""
+        ms = (C.c_double * 4)(); n = (C.c_long * 4)()
+        _libs["_refcuda_handle"].refcuda_timers(ms, n, 1 if reset else 0)
+        names = ("coarse", "fine", "wavg", "backproject")
+        return {k: float(ms[i]) for i, k in enumerate(names)}, {k: int(n[i]) for i, k in enumerate(names)}
+
+    def release_cuda(self):
+        _libs["_refcuda_handle"].refcuda_release()
 
     def significance(self, weights, adaptive_fraction=0.999, maxsig=0, filter_zero=True, exact=False):
         w = np.ascontiguousarray(weights, np.float32)

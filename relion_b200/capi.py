@@ -135,6 +135,18 @@ PROTOTYPES = {
     "rb_update_ssnr": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p,
                                  c_double_p, c_double_p, C.c_int, C.c_int]),
     "rb_bp_device_buffer": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
+    "rb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "rb_comm_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "rb_comm_create_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_void_p)]),
+    "rb_comm_destroy": (None, [C.c_void_p]),
+    "rb_comm_size": (C.c_int, [C.c_void_p]),
+    "rb_comm_rank": (C.c_int, [C.c_void_p]),
+    "rb_comm_handle": (C.c_void_p, [C.c_void_p]),
+    "rb_comm_group_start": (C.c_int, []),
+    "rb_comm_group_end": (C.c_int, []),
+    "rb_bp_allreduce": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "rb_bp_allreduce_nccl": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int]),
+    "rb_wsum_allreduce": (C.c_int, [C.c_void_p, C.c_void_p, c_double_p, C.c_size_t]),
     "rb_set_sampling": (C.c_int, [C.c_void_p, C.POINTER(rb_sampling)]),
     "rb_set_model": (C.c_int, [C.c_void_p, C.POINTER(rb_model)]),
     "rb_set_pdf_direction": (C.c_int, [C.c_void_p, c_double_p]),

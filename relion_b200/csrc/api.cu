@@ -103,7 +103,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
 	                  &ctx->m_cc[0], &ctx->m_cc[1], &ctx->m_cc[2], &ctx->m_cc[3], &ctx->m_cc[4], &ctx->m_cc[5],
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp,
-	                  &ctx->m_pix_rs, &ctx->band_slices};
+	                  &ctx->m_pix_rs, &ctx->band_slices, &ctx->band_tabc, &ctx->band_tabo, &ctx->band_tabu, &ctx->comm_buf, &ctx->comm_buf2};
 	for (DevBuf *b : bufs) b->release();
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
@@ -427,6 +427,21 @@ extern "C" int rb_set_sampling(rb_ctx *ctx, const rb_sampling *s)
 		oty[t] = s->over_trans_y ? s->over_trans_y[t] : s->trans_y[t];
 		ftxv[t] = (float) (-2 * M_PI * otx[t] / os);
 		ftyv[t] = (float) (-2 * M_PI * oty[t] / os);
+	}
+	// band-major diff2 pass: do the oversampled translations factorise into coarse translation + fixed offset?
+	{
+		const int NOT = s->n_over_trans;
+		bool sep = true;
+		for (int t = 0; t < T && sep; t++)
+			for (int j = 0; j < NOT; j++)
+			{
+				const double dx = otx[t * NOT + j] - s->trans_x[t], dy = oty[t * NOT + j] - s->trans_y[t];
+				if (fabs(dx - (otx[j] - s->trans_x[0])) > 1e-9 || fabs(dy - (oty[j] - s->trans_y[0])) > 1e-9) { sep = false; break; }
+			}
+		ctx->band_separable = sep;
+		ctx->h_band_u.assign((size_t) 2 * (T + NOT), 0.);
+		for (int t = 0; t < T; t++) { ctx->h_band_u[t] = -s->trans_x[t] / os; ctx->h_band_u[T + t] = -s->trans_y[t] / os; }
+		for (int j = 0; j < NOT; j++) { ctx->h_band_u[2 * T + j] = -(otx[j] - s->trans_x[0]) / os; ctx->h_band_u[2 * T + NOT + j] = -(oty[j] - s->trans_y[0]) / os; }
 	}
 	RB_CHECK(upload(ctx, ctx->s_ctx, ctxv.data(), T * 4)); RB_CHECK(upload(ctx, ctx->s_cty, ctyv.data(), T * 4));
 	RB_CHECK(upload(ctx, ctx->s_ftx, ftxv.data(), Tf * 4)); RB_CHECK(upload(ctx, ctx->s_fty, ftyv.data(), Tf * 4));
@@ -766,13 +781,15 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 	size_t cap_fo = (size_t) std::min<long long>(s.total_prior * S.n_over_rot, (long long) env_size("RB_FINE_ORIENT_CAP", (size_t) 1 << 22));
 	s.cap_fs = cap_fs; s.cap_fo = cap_fo;
 	RB_CHECK(s.fs_w.ensure(cap_fs * 4)); RB_CHECK(s.fs_ihid.ensure(cap_fs * 8));
-	RB_CHECK(s.fo.ensure(cap_fo * sizeof(RbFineOrient)));
 	// slice cache: the fine pass leaves every projected slice here so the store stage streams it instead of
 	// gathering from the reference a second time; orientations beyond the budget fall back to the gather
 	{
 		const size_t slice_bytes = (size_t) M.Npf * sizeof(float2);
-		const size_t budget = env_size("RB_SLICE_CACHE_BYTES", (size_t) 4 << 30);
-		// band-major path: one buffer of band-ordered slices per context (grows to the largest request, never shrinks)
+		const size_t budget = env_size("RB_SLICE_CACHE_BYTES", (size_t) 8 << 30);
+		// band-major path: one buffer of band-ordered slices per context (grows to the largest request, never shrinks).  The
+		// host does not know how many fine orientations the coarse pass will leave, so it launches a fixed number of rounds
+		// (RB_BAND_ROUNDS, default 4; rounds beyond the actual count exit at once) and the fine lists are capped accordingly:
+		// a pool that needs more reports RB_ERR_CAPACITY like any other fine-pass overflow.
 		const size_t band_bytes = (size_t) M.nv_rs_pad * sizeof(float2);
 		const long long band_cap = (long long) std::min<size_t>(cap_fo, budget / band_bytes);
 		const bool band = !M.do_cc && band_cap > 0 && env_size("RB_BAND", 1) != 0;
@@ -785,14 +802,20 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 			}
 			ctx->band_slice_capacity = band_cap;
 			s.slice_capacity = 0;
+			const long long max_rounds = (long long) std::max<size_t>(1, env_size("RB_BAND_ROUNDS", 4));
+			s.band_rounds = (int) std::min<long long>(((long long) cap_fo + band_cap - 1) / band_cap, max_rounds);
+			cap_fo = (size_t) std::min<long long>((long long) cap_fo, s.band_rounds * band_cap);
+			s.cap_fo = cap_fo;
 		}
 		else
 		{
 			ctx->band_slice_capacity = 0;
+			s.band_rounds = 0;
 			s.slice_capacity = (long long) std::min<size_t>(cap_fo, budget / slice_bytes);
 			RB_CHECK(s.slices.ensure((size_t) s.slice_capacity * slice_bytes));
 		}
 	}
+	RB_CHECK(s.fo.ensure(cap_fo * sizeof(RbFineOrient)));
 	RB_CHECK(s.pair_list.ensure((cap_fs / ov + 1) * 4));
 	return RB_OK;
 }
@@ -970,7 +993,7 @@ static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
 	if (counters[2])
 	{
 		rb_set_error("fine-pass workspace too small: %lld orientations / %lld samples needed, capacity %zu / %zu; split the pool or raise "
-		             "RB_FINE_ORIENT_CAP / RB_FINE_SAMPLE_CAP", ((long long *) counters)[2], ((long long *) counters)[3],
+		             "RB_FINE_ORIENT_CAP / RB_FINE_SAMPLE_CAP (band-major path: RB_SLICE_CACHE_BYTES x RB_BAND_ROUNDS)", ((long long *) counters)[2], ((long long *) counters)[3],
 		             s.cap_fo, s.cap_fs);
 		return RB_ERR_CAPACITY;
 	}

@@ -238,8 +238,14 @@ struct rb_ctx {
 
 	PoolSlot slot[RB_NUM_SLOTS];
 	DevBuf m_pix_rs;
+	DevBuf comm_buf, comm_buf2;      // staging of the NCCL reductions (comm.cu): planar accumulator, fp64 weighted sums
 	DevBuf band_slices;              // band-ordered slices of one round of fine orientations (shared by the slots: E-steps run one after the other)
 	long long band_slice_capacity = 0;
+	// phase tables of the band-major diff2 pass (kernels_band.cu): [n_trans][stride] and [n_over_trans][stride] float2
+	DevBuf band_tabc, band_tabo, band_tabu;
+	bool band_separable = false;     // over_trans[t * NOT + j] == trans[t] + d[j] (checked by rb_set_sampling)
+	std::vector<double> h_band_u;    // turns per pixel: coarse x [T], coarse y [T], offsets x [NOT], offsets y [NOT]
+	long long band_tab_model = -1, band_tab_samp = -1;
 
 	// stage timing
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
@@ -324,6 +330,7 @@ int rbk_convert_weights_stage(rb_ctx *ctx, float *d_w, long long n_orient, int n
 bool rbk_band_applicable(rb_ctx *ctx);
 int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s);
 int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_band_phase_tables(rb_ctx *ctx, bool &ok);
 
 // kernels_store.cu
 int rbk_collect_pool(rb_ctx *ctx, PoolSlot &s);

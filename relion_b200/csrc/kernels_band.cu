@@ -46,6 +46,49 @@ __device__ __forceinline__ void bd_red_add_v4(float4 *addr, float a, float b, fl
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
 }
 
+__device__ __forceinline__ void bd_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// Radial range (in pixels^2) of tile `tile` of the band-ordered pixel list
+__device__ __forceinline__ void bd_tile_r2(const uint32_t *pix, int npix, int tile, int &lo, int &hi)
+{
+	const uint32_t a = __ldg(pix + tile * BD_TP), b = __ldg(pix + min((tile + 1) * BD_TP, npix) - 1);
+	const int xa = rb_pix_x(a), ya = rb_pix_y(a), xb = rb_pix_x(b), yb = rb_pix_y(b);
+	lo = xa * xa + ya * ya; hi = xb * xb + yb * yb;
+	if (lo > hi) { const int t = lo; lo = hi; hi = t; }
+}
+
+// Shell prefetch.  The band sweep touches every voxel of a spherical shell exactly when the sweep front reaches it, in an
+// order set by the orientations: first touches are RANDOM 64-byte (reference cell) / 32-byte (accumulator) DRAM reads, which
+// HBM serves at ~20 G requests/s (tools/l2_gather_bench.cu: 1.2-1.4 TB/s for 64-byte gathers, against 9 TB/s once the lines
+// are in L2).  So every work item also walks its share of the (z, y) rows of the shell that the sweep reaches `ahead` tiles
+// later and prefetches the run of voxels the shell cuts out of each row, 128 bytes at a time, IN ADDRESS ORDER: the shell
+// arrives in L2 as a stream and the gathers / reductions that follow hit.
+// Volume geometry: x in [0, X), y in [initY, initY + Y), z likewise; `bytes_per_voxel` 64 (expanded reference) or 16 (accumulator).
+__device__ __forceinline__ void bd_prefetch_shell(const char *base, int X, int Y, int Z, int initY, int initZ, int bytes_per_voxel,
+                                                  float Rlo, float Rhi, int part, int nparts)
+{
+	const int Rh = (int) ceilf(Rhi);
+	const int side = 2 * Rh + 1;
+	const int nrows = side * side;
+	const int per = (nrows + nparts - 1) / nparts;
+	const int r1 = min(nrows, (part + 1) * per);
+	const float Rlo2 = Rlo > 0.f ? Rlo * Rlo : 0.f, Rhi2 = Rhi * Rhi;
+	const int vpl = 128 / bytes_per_voxel;                      // voxels per 128-byte line
+	for (int row = part * per + (int) threadIdx.x; row < r1; row += (int) blockDim.x)
+	{
+		const int zz = row / side - Rh, yy = row - (row / side) * side - Rh;
+		const float rho2 = (float) (zz * zz + yy * yy);
+		if (rho2 > Rhi2) continue;
+		const int yi = yy - initY, zi = zz - initZ;
+		if (yi < 0 || yi >= Y || zi < 0 || zi >= Z) continue;
+		int x_hi = (int) sqrtf(Rhi2 - rho2) + 1;
+		int x_lo = rho2 < Rlo2 ? (int) sqrtf(Rlo2 - rho2) - 1 : 0;
+		x_lo = max(x_lo, 0); x_hi = min(x_hi, X - 1);
+		const char *rowp = base + ((size_t) zi * Y + yi) * (size_t) X * bytes_per_voxel;
+		for (int x = (x_lo / vpl) * vpl; x <= x_hi; x += vpl) bd_prefetch_l2(rowp + (size_t) x * bytes_per_voxel);
+	}
+}
+
 // work items of a (tile, chunk) queue: the tile is the slow index, so the resident CTAs stay inside one radial band.
 // The next item is requested while the current one is processed (the atomic's round trip is hidden).
 struct BandQueue {
@@ -113,40 +156,105 @@ struct BandProjArgs {
 	const RbProjector *projs; int imgX; int nr_classes;
 	int *queue;
 	int chunk_min;
+	int prefetch_ahead;          // tiles the shell prefetch runs ahead of the sweep (0: off)
+	const int *nfo_ptr; int only_if_nfo_above;   // re-projection rounds of the store stage: run only when the fine pass needed several rounds
 };
 
 struct RbBpItem { int w; int samp_off; int nsig; float W; };
 
+static const int BD_STAGE_F4 = 32 * 4 + 16;   // float4 per stage: sample s keeps its four quarters at chunks 4 s + (s >> 1) + c
+                                                // (the s >> 1 padding makes both the quad-wise cp.async writes and the lane-wise
+                                                // 64-byte reads conflict free: four shared-memory wavefronts per 512 bytes)
+
 struct BandProjSmem {
-	float4 cell[BD_THREADS / 32][BD_DEPTH][32 * 4];
-	float4 frac[BD_THREADS / 32][BD_DEPTH][32];
+	float4 cell[BD_THREADS / 32][BD_DEPTH][BD_STAGE_F4];
 	float e[BD_MAXCHUNK][6];
 	int cls[BD_MAXCHUNK];
 	int next;
 };
 
+// what a lane keeps about a sample in flight: trilinear fractions and flags (bit0 inside r_max, bit1 Hermitian mate)
+struct BandFrac { float fx, fy, fz; int flags; };
+
+template <bool MULTI>
+__device__ __forceinline__ void band_issue(const BandProjArgs &A, const BandProjSmem &S, const RbProjK8 &pk0, int j, int x, int y, bool have,
+                                           int lane, float4 *dst, BandFrac &f)
+{
+	const float2 ea = *(const float2 *) &S.e[j][0], eb = *(const float2 *) &S.e[j][2], ec = *(const float2 *) &S.e[j][4];
+	RbProjK8 pk = pk0;
+	if (MULTI) pk = rb_make_projk8(A.projs[S.cls[j]], A.imgX);
+	float xp = (ea.x * x + ea.y * y) * pk.pf;
+	float yp = (eb.x * x + eb.y * y) * pk.pf;
+	float zp = (ec.x * x + ec.y * y) * pk.pf;
+	const int r2 = (int) (xp * xp + yp * yp + zp * zp);
+	const bool inside = have && r2 <= pk.maxR2_padded;
+	const bool inv = xp < 0.f;
+	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+	f.fx = xp - fx0; f.fy = yp - fy0; f.fz = zp - fz0;
+	f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
+	const int cell = inside ? (((int) fz0 - pk.mdlInitZ) * pk.mdlXY + ((int) fy0 - pk.mdlInitY) * pk.mdlX + (int) fx0) : -1;
+	const int k = lane & 3, qbase = lane & ~3;
+#pragma unroll
+	for (int r = 0; r < 4; r++)
+	{
+		const int s = qbase + r;                                              // sample (lane) whose cell this round fetches
+		const int cs = __shfl_sync(RB_FULL_MASK, cell, s);
+		if (cs >= 0) bd_cp_async16(dst + 4 * s + (s >> 1) + k, pk.mdl8 + 4 * (size_t) cs + k);
+	}
+}
+
+__device__ __forceinline__ float2 band_consume(const float4 *src_stage, int lane, const BandFrac &f)
+{
+	float2 ref = make_float2(0.f, 0.f);
+	if (f.flags & 1)
+	{
+		const float4 *src = src_stage + 4 * lane + (lane >> 1);
+		const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+		{
+			const float dx00 = q0.x + (q0.z - q0.x) * f.fx, dx10 = q1.x + (q1.z - q1.x) * f.fx;
+			const float dx01 = q2.x + (q2.z - q2.x) * f.fx, dx11 = q3.x + (q3.z - q3.x) * f.fx;
+			const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+			ref.x = dxy0 + (dxy1 - dxy0) * f.fz;
+		}
+		{
+			const float dx00 = q0.y + (q0.w - q0.y) * f.fx, dx10 = q1.y + (q1.w - q1.y) * f.fx;
+			const float dx01 = q2.y + (q2.w - q2.y) * f.fx, dx11 = q3.y + (q3.w - q3.y) * f.fx;
+			const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+			ref.y = dxy0 + (dxy1 - dxy0) * f.fz;
+		}
+		if (f.flags & 2) ref.y = -ref.y;
+	}
+	return ref;
+}
+
+template <bool MULTI>
 static __global__ void __launch_bounds__(BD_THREADS, 3)
 k_project_band(BandProjArgs A)
 {
 	extern __shared__ __align__(16) unsigned char bd_smem_raw[];
 	BandProjSmem &S = *reinterpret_cast<BandProjSmem *>(bd_smem_raw);
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	const int k = lane & 3, qbase = lane & ~3;
 	const int total = *A.count_ptr;
 	const int n = min(A.capacity, total - A.begin);
 	if (n <= 0) return;
+	if (A.nfo_ptr && *A.nfo_ptr <= A.only_if_nfo_above) return;
 	const int ntiles = (A.npix + BD_TP - 1) / BD_TP;
 	// chunk: about one tile's worth of items per resident wave, so that the wave stays inside one band
 	int chunk = (n + (int) gridDim.x - 1) / (int) gridDim.x;
 	chunk = max(A.chunk_min, min(BD_MAXCHUNK, chunk));
 	const int nchunks = (n + chunk - 1) / chunk;
 	const long long nitems = (long long) ntiles * nchunks;
-	BandQueue Q{A.queue, &S.next};
 	const RbProjK8 pk0 = rb_make_projk8(A.projs[0], A.imgX);
+	const int ph = wid / BD_WPT;
+	float4 *cells = &S.cell[wid][0][0];
+	// samples of the round against voxels of the half sphere: below ~1.5 per voxel a whole-shell prefetch would fetch more than it saves
+	const float pf_rmax = pk0.pf * (float) pk0.maxR + 1.f;
+	const bool do_prefetch = A.prefetch_ahead > 0 && (float) n * (float) A.npix > 1.5f * 2.0944f * pf_rmax * pf_rmax * pf_rmax;
 
-	for (long long item = Q.first(); item < nitems; item = Q.next())
+	long long item = blockIdx.x;
+	while (item < nitems)
 	{
-		Q.prefetch();
 		const int tile = (int) (item / nchunks), c = (int) (item - (long long) tile * nchunks);
 		const int o0 = c * chunk, no = min(chunk, n - o0);
 		// orientation matrices of the chunk
@@ -156,82 +264,70 @@ k_project_band(BandProjArgs A)
 			const int li = A.begin + o0 + j;
 			const int w = A.indir ? A.indir[4 * li] : li;
 			S.e[j][q] = A.fo[w].e[q + q / 2];                                   // elements 0,1,3,4,6,7
-			if (q == 0) S.cls[j] = A.fo[w].iclass;
+			if (MULTI && q == 0) S.cls[j] = A.fo[w].iclass;
+		}
+		// the next item is requested now and looked at after this one is done: the atomic's round trip is hidden
+		int pending = 0;
+		if (threadIdx.x == 0) pending = atomicAdd(A.queue, 1);
+		// this item's share of the shell the sweep reaches `prefetch_ahead` tiles from now (the first items also cover the tiles
+		// in between); only when the orientations of the round cover the sphere densely
+		if (do_prefetch)
+		{
+			const int t0 = tile == 0 ? 0 : tile + A.prefetch_ahead, t1 = tile + A.prefetch_ahead;
+			for (int tp = t0; tp <= t1 && tp < ntiles; tp++)
+			{
+				int lo, hi;
+				bd_tile_r2(A.pix, A.npix, tp, lo, hi);
+				const float Rlo = pk0.pf * sqrtf((float) lo) - 2.f, Rhi = fminf(pk0.pf * sqrtf((float) hi) + 1.f, pf_rmax);
+				for (int k = 0; k < (MULTI ? A.nr_classes : 1); k++)
+				{
+					const RbProjector &pj = A.projs[k];
+					bd_prefetch_shell((const char *) pj.mdl8, pj.mdlX, pj.mdlY, pj.mdlZ, pj.mdlInitY, pj.mdlInitZ, 64, Rlo, Rhi, c, nchunks);
+				}
+			}
 		}
 		__syncthreads();
 		const int ip = tile * BD_TP + (wid % BD_WPT) * 32 + lane;
 		const bool have = ip < A.npix;
 		int x = 0, y = 0;
 		if (have) { const uint32_t pkx = __ldg(A.pix + ip); x = rb_pix_x(pkx); y = rb_pix_y(pkx); }
-		const int ph = wid / BD_WPT;
 		const int nmy = (no - ph + BD_NPH - 1) / BD_NPH;                        // orientations ph, ph + BD_NPH, ...
-		float4 *cells = &S.cell[wid][0][0];
-		float4 *fracs = &S.frac[wid][0][0];
+		float2 *out = A.slices + (size_t) o0 * A.stride + ip;
 
-		auto issue = [&](int jj)
-		{
-			const int j = ph + jj * BD_NPH, slot = jj % BD_DEPTH;
-			const float e0 = S.e[j][0], e1 = S.e[j][1], e3 = S.e[j][2], e4 = S.e[j][3], e6 = S.e[j][4], e7 = S.e[j][5];
-			const RbProjK8 pk = A.nr_classes == 1 ? pk0 : rb_make_projk8(A.projs[S.cls[j]], A.imgX);
-			float xp = (e0 * x + e1 * y) * pk.pf;
-			float yp = (e3 * x + e4 * y) * pk.pf;
-			float zp = (e6 * x + e7 * y) * pk.pf;
-			const int r2 = (int) (xp * xp + yp * yp + zp * zp);
-			const bool inside = have && r2 <= pk.maxR2_padded;
-			const bool inv = xp < 0.f;
-			if (inv) { xp = -xp; yp = -yp; zp = -zp; }
-			const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
-			fracs[slot * 32 + lane] = make_float4(xp - fx0, yp - fy0, zp - fz0, __int_as_float((inside ? 1 : 0) | (inv ? 2 : 0)));
-			const int cell = inside ? (((int) fz0 - pk.mdlInitZ) * pk.mdlXY + ((int) fy0 - pk.mdlInitY) * pk.mdlX + (int) fx0) : -1;
-			float4 *dst = cells + slot * 128;
+		// three stages in flight per warp; the loop is unrolled by the depth so that the stage of a sample is a
+		// compile-time constant and its fractions stay in registers
+		BandFrac f[BD_DEPTH];
 #pragma unroll
-			for (int r = 0; r < 4; r++)
-			{
-				const int s = qbase + r;                                          // sample (lane) whose cell this round fetches
-				const int cs = __shfl_sync(RB_FULL_MASK, cell, s);
-				if (cs >= 0) bd_cp_async16(dst + s * 4 + ((k + (s >> 1)) & 3), pk.mdl8 + 4 * (size_t) cs + k);
-			}
-		};
-
-#pragma unroll
-		for (int d = 0; d < BD_DEPTH - 1; d++) { if (d < nmy) issue(d); bd_cp_commit(); }
-		for (int jj = 0; jj < nmy; jj++)
+		for (int d = 0; d < BD_DEPTH - 1; d++)
 		{
-			if (jj + BD_DEPTH - 1 < nmy) issue(jj + BD_DEPTH - 1);
+			if (d < nmy) band_issue<MULTI>(A, S, pk0, ph + d * BD_NPH, x, y, have, lane, cells + d * BD_STAGE_F4, f[d]);
 			bd_cp_commit();
-			bd_cp_wait<BD_DEPTH - 1>();
-			__syncwarp();
-			const int slot = jj % BD_DEPTH;
-			const float4 fr = fracs[slot * 32 + lane];
-			const int flags = __float_as_int(fr.w);
-			float2 ref = make_float2(0.f, 0.f);
-			if (flags & 1)
+		}
+#pragma unroll 1
+		for (int jj0 = 0; jj0 < nmy; jj0 += BD_DEPTH)
+		{
+#pragma unroll
+			for (int u = 0; u < BD_DEPTH; u++)
 			{
-				const float4 *src = cells + slot * 128 + lane * 4;
-				const int rot = lane >> 1;
-				const float4 q0 = src[(0 + rot) & 3], q1 = src[(1 + rot) & 3], q2 = src[(2 + rot) & 3], q3 = src[(3 + rot) & 3];
+				const int jj = jj0 + u;
+				if (jj < nmy)
 				{
-					const float dx00 = q0.x + (q0.z - q0.x) * fr.x, dx10 = q1.x + (q1.z - q1.x) * fr.x;
-					const float dx01 = q2.x + (q2.z - q2.x) * fr.x, dx11 = q3.x + (q3.z - q3.x) * fr.x;
-					const float dxy0 = dx00 + (dx10 - dx00) * fr.y, dxy1 = dx01 + (dx11 - dx01) * fr.y;
-					ref.x = dxy0 + (dxy1 - dxy0) * fr.z;
+					const int un = (u + BD_DEPTH - 1) % BD_DEPTH;
+					if (jj + BD_DEPTH - 1 < nmy)
+						band_issue<MULTI>(A, S, pk0, ph + (jj + BD_DEPTH - 1) * BD_NPH, x, y, have, lane, cells + un * BD_STAGE_F4, f[un]);
+					bd_cp_commit();
+					bd_cp_wait<BD_DEPTH - 1>();
+					__syncwarp();
+					const float2 ref = band_consume(cells + u * BD_STAGE_F4, lane, f[u]);
+					__syncwarp();                                                  // the stage is free for the next issue
+					if (have) __stcs(out + (size_t) (ph + jj * BD_NPH) * A.stride, ref);
 				}
-				{
-					const float dx00 = q0.y + (q0.w - q0.y) * fr.x, dx10 = q1.y + (q1.w - q1.y) * fr.x;
-					const float dx01 = q2.y + (q2.w - q2.y) * fr.x, dx11 = q3.y + (q3.w - q3.y) * fr.x;
-					const float dxy0 = dx00 + (dx10 - dx00) * fr.y, dxy1 = dx01 + (dx11 - dx01) * fr.y;
-					ref.y = dxy0 + (dxy1 - dxy0) * fr.z;
-				}
-				if (flags & 2) ref.y = -ref.y;
-			}
-			__syncwarp();                                                          // the slot is free for the next issue
-			if (have)
-			{
-				const int j = ph + jj * BD_NPH;
-				__stcs(A.slices + (size_t) (o0 + j) * A.stride + ip, ref);
 			}
 		}
 		bd_cp_wait<0>();
+		if (threadIdx.x == 0) S.next = (int) gridDim.x + pending;
+		__syncthreads();
+		item = S.next;
 	}
 }
 
@@ -275,6 +371,138 @@ __device__ __forceinline__ void band_diff_pass(const float2 *__restrict__ slice,
 			__sincosf(6.283185307179586f * u, &s, &c);
 			acc[t] = fmaf(zr, c, fmaf(-zi, s, acc[t]));
 		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase tables.  RELION's oversampled translations are the coarse ones plus a fixed set of offsets
+// (HealpixSampling::getTranslationsInPixel, src/healpix_sampling.cpp:1724-1790): over[t * NOT + j] = trans[t] + d[j], so the
+// phase of fine translation (t, j) at a pixel factorises: e^{i phi_t} e^{i phi_j}.  Both factors are tabulated once per
+// (model, sampling) in band order, [t][pixel] and [j][pixel] (fp64 sincos): 6 MB + 0.8 MB at 256 px / 29 translations,
+// L2-resident, read coalesced.  The diff2 pass then needs no transcendental at all: per (pixel, coarse translation) one
+// 8-byte load and a complex product, per fine sample two FMAs.  rb_set_sampling checks the factorisation; samplings that do
+// not factorise (or NOT not in {1, 4}) take the generic kernel, which evaluates sincos per (pixel, sample).
+// ---------------------------------------------------------------------------------------------
+static __global__ void __launch_bounds__(256)
+k_band_tables(const uint32_t *pix, int npix, int stride, const double *ucx, const double *ucy, int T, const double *uox, const double *uoy, int NOT,
+              float2 *tabc, float2 *tabo)
+{
+	const int ip = blockIdx.x * blockDim.x + threadIdx.x;
+	if (ip >= stride) return;
+	const int t = blockIdx.y;
+	double x = 0., y = 0.;
+	if (ip < npix) { const uint32_t pk = pix[ip]; x = rb_pix_x(pk); y = rb_pix_y(pk); }
+	double u = (t < T) ? x * ucx[t] + y * ucy[t] : x * uox[t - T] + y * uoy[t - T];   // turns
+	u -= rint(u);
+	double sn, cs;
+	sincospi(2. * u, &sn, &cs);
+	float2 *dst = (t < T) ? tabc + (size_t) t * stride : tabo + (size_t) (t - T) * stride;
+	dst[ip] = make_float2((float) cs, (float) sn);
+}
+
+template <int NC, int NOT>
+__device__ __forceinline__ void band_diff_pass_sep(const float2 *__restrict__ slice, const float4 *__restrict__ img, int nd2, int stride,
+                                                   const float2 *__restrict__ tabc, const float2 *__restrict__ tabo, const int *s_tc,
+                                                   float (&acc)[NC * NOT], float &base)
+{
+#pragma unroll
+	for (int t = 0; t < NC * NOT; t++) acc[t] = 0.f;
+	base = 0.f;
+	for (int ip = threadIdx.x; ip < nd2; ip += BD_THREADS)
+	{
+		const float2 ref = __ldcs(slice + ip);
+		const float4 im = __ldg(img + ip);
+		float2 po[NOT];
+#pragma unroll
+		for (int j = 0; j < NOT; j++) po[j] = NOT > 1 ? __ldg(tabo + (size_t) j * stride + ip) : make_float2(1.f, 0.f);
+		float2 pc[NC];
+#pragma unroll
+		for (int c = 0; c < NC; c++) pc[c] = __ldg(tabc + (size_t) s_tc[c] * stride + ip);
+		const float hc = im.z;
+		const float zr = hc * (ref.x * im.x + ref.y * im.y);
+		const float zi = hc * (ref.x * im.y - ref.y * im.x);
+		base += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
+#pragma unroll
+		for (int c = 0; c < NC; c++)
+		{
+			const float cr = zr * pc[c].x - zi * pc[c].y, ci = zr * pc[c].y + zi * pc[c].x;     // Z e^{i phi_c}
+#pragma unroll
+			for (int j = 0; j < NOT; j++) acc[c * NOT + j] = fmaf(cr, po[j].x, fmaf(-ci, po[j].y, acc[c * NOT + j]));   // Re(Z e^{i phi_c} e^{i phi_j})
+		}
+	}
+}
+
+static const int BD_NCMAX = 8;   // coarse translations per pass of the factorised kernel
+
+template <int NOT>
+static __global__ void __launch_bounds__(BD_THREADS, 3)
+k_diff2_slices_sep(BandDiffArgs A, const float2 *tabc, const float2 *tabo)
+{
+	__shared__ int s_tc[BD_NCMAX];
+	__shared__ float s_red[BD_THREADS / 32][BD_NCMAX * NOT + 1];
+	__shared__ int s_next;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const int total = A.counters[0];
+	const int n = min(A.capacity, total - A.begin);
+	for (int wi = rb_next_work(A.queue, &s_next, 0, true); wi < n; wi = rb_next_work(A.queue, &s_next, wi, false))
+	{
+		const int w = A.begin + wi;
+		const RbFineOrient F = A.fo[w];
+		const int p = F.particle;
+		const float xi2_half = A.metas[p].xi2_half;
+		const float4 *img = A.simg4 + (size_t) p * A.stride;
+		const float2 *slice = A.slices + (size_t) wi * A.stride;
+		float bmin = FLT_MAX;
+		for (int c0 = 0; c0 < F.n_t; c0 += BD_NCMAX)
+		{
+			const int nc = min(BD_NCMAX, F.n_t - c0);
+			__syncthreads();
+			if (threadIdx.x < BD_NCMAX) s_tc[threadIdx.x] = A.pair_list[F.pair_off + c0 + min((int) threadIdx.x, nc - 1)];   // padding repeats the last one
+			__syncthreads();
+			float acc[BD_NCMAX * NOT], base;
+			if (nc == 1)
+			{
+				float a[NOT]; band_diff_pass_sep<1, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
+#pragma unroll
+				for (int t = 0; t < BD_NCMAX * NOT; t++) acc[t] = t < NOT ? a[t % NOT] : 0.f;
+			}
+			else if (nc == 2)
+			{
+				float a[2 * NOT]; band_diff_pass_sep<2, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
+#pragma unroll
+				for (int t = 0; t < BD_NCMAX * NOT; t++) acc[t] = t < 2 * NOT ? a[t % (2 * NOT)] : 0.f;
+			}
+			else if (nc <= 4)
+			{
+				float a[4 * NOT]; band_diff_pass_sep<4, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
+#pragma unroll
+				for (int t = 0; t < BD_NCMAX * NOT; t++) acc[t] = t < 4 * NOT ? a[t % (4 * NOT)] : 0.f;
+			}
+			else band_diff_pass_sep<BD_NCMAX, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, acc, base);
+			const int ntr = nc * NOT;
+			// fixed-order reduction: lanes, then warps
+#pragma unroll
+			for (int t = 0; t < BD_NCMAX * NOT; t++)
+			{
+				if (t < ntr)
+				{
+					const float v = warp_sum(acc[t]);
+					if (lane == 0) s_red[wid][t] = v;
+				}
+			}
+			base = warp_sum(base);
+			if (lane == 0) s_red[wid][BD_NCMAX * NOT] = base;
+			__syncthreads();
+			if (threadIdx.x < ntr)
+			{
+				float c = 0.f, b = 0.f;
+#pragma unroll
+				for (int ww = 0; ww < BD_THREADS / 32; ww++) { c += s_red[ww][threadIdx.x]; b += s_red[ww][BD_NCMAX * NOT]; }
+				const float v = fmaxf((b - 2.f * c) + xi2_half, 0.f);
+				A.fs_w[F.sample_off + (long long) c0 * NOT + threadIdx.x] = v; bmin = fminf(bmin, v);
+			}
+		}
+		if (threadIdx.x < BD_NCMAX * NOT && bmin < FLT_MAX) rb_atomic_min_pos(&A.states[p].fmin_bits, bmin);
 	}
 }
 
@@ -481,26 +709,34 @@ struct BandStoreArgs {
 	const RbPartMeta *metas; RbPartState *states;
 	const RbFineOrient *fo; const RbBpItem *items; const float4 *samp; const int *counters;
 	int begin, capacity;         // this round covers BP items [begin, min(nbp, begin + capacity))
-	int slice_by_item;           // 1: slices are indexed by (item - begin) (re-projected rounds); 0: by fine orientation index
+	int slice_by_item;           // 1: slices are indexed by (item - begin) (re-projected rounds, run only when the fine pass took
+	                             // several rounds: counters[0] > fits); 0: by fine orientation index (only when counters[0] <= fits)
+	int fits;                    // slice buffer capacity in fine orientations
 	const float4 *sst; const float *sctf; const float2 *slices; const uint32_t *pix; int nst, stride;
 	float *shells;               // [P][nshell]
 	const RbBackprojector *bps;
 	int n; int *queue; int chunk_min;
+	int prefetch_ahead; int nr_classes;
 };
 
 struct BandStoreSmem {
 	RbBpItem item[BD_MAXCHUNK];
 	float e[BD_MAXCHUNK][6];
-	int particle[BD_MAXCHUNK], cls[BD_MAXCHUNK];
+	int particle[BD_MAXCHUNK], cls[BD_MAXCHUNK], og[BD_MAXCHUNK];
+	float part_scale[BD_MAXCHUNK];
 	int next;
 };
 
-static __global__ void __launch_bounds__(BD_THREADS, 2)
+struct BandStoreIn { float2 ref; float4 XX; float ctf; };
+
+template <bool MULTI>
+static __global__ void __launch_bounds__(BD_THREADS, 3)
 k_store_band(BandStoreArgs A, RbModelDev M)
 {
 	__shared__ BandStoreSmem S;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	if (A.counters[2] || A.counters[3]) return;
+	if ((A.counters[0] > A.fits) != (A.slice_by_item != 0)) return;
 	const int total = A.counters[10];
 	const int n = min(A.capacity, total - A.begin);
 	if (n <= 0) return;
@@ -510,23 +746,45 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 	const int nchunks = (n + chunk - 1) / chunk;
 	const long long nitems = (long long) ntiles * nchunks;
 	const int half = A.n / 2;
-	BandQueue Q{A.queue, &S.next};
+	const RbBackprojector bp0 = A.bps[0];
+	const int ph = wid / BD_WPT;
+	const float pf_rmax = bp0.padding_factor * (float) bp0.maxR + 1.f;
+	const bool do_prefetch = A.prefetch_ahead > 0 && (float) n * (float) A.nst > 1.5f * 2.0944f * pf_rmax * pf_rmax * pf_rmax;
 
-	for (long long item = Q.first(); item < nitems; item = Q.next())
+	long long item = blockIdx.x;
+	while (item < nitems)
 	{
-		Q.prefetch();
 		const int tile = (int) (item / nchunks), c = (int) (item - (long long) tile * nchunks);
 		const int o0 = c * chunk, no = min(chunk, n - o0);
 		for (int j = threadIdx.x; j < no; j += BD_THREADS)
 		{
 			const RbBpItem it = A.items[A.begin + o0 + j];
+			const int p = A.fo[it.w].particle;
 			S.item[j] = it;
-			S.particle[j] = A.fo[it.w].particle; S.cls[j] = A.fo[it.w].iclass;
+			S.particle[j] = p; S.cls[j] = A.fo[it.w].iclass;
+			S.og[j] = A.metas[p].og; S.part_scale[j] = A.metas[p].part_scale;
 		}
 		for (int i = threadIdx.x; i < no * 6; i += BD_THREADS)
 		{
 			const int j = i / 6, q = i - j * 6;
 			S.e[j][q] = A.fo[A.items[A.begin + o0 + j].w].e[q + q / 2];
+		}
+		int pending = 0;
+		if (threadIdx.x == 0) pending = atomicAdd(A.queue, 1);      // next item, looked at after this one
+		if (do_prefetch)                                             // accumulator shell of the tiles ahead, in address order
+		{
+			const int t0 = tile == 0 ? 0 : tile + A.prefetch_ahead, t1 = tile + A.prefetch_ahead;
+			for (int tp = t0; tp <= t1 && tp < ntiles; tp++)
+			{
+				int lo, hi;
+				bd_tile_r2(A.pix, A.nst, tp, lo, hi);
+				const float Rlo = bp0.padding_factor * sqrtf((float) lo) - 2.f, Rhi = fminf(bp0.padding_factor * sqrtf((float) hi) + 1.f, pf_rmax);
+				for (int k = 0; k < (MULTI ? A.nr_classes : 1); k++)
+				{
+					const RbBackprojector &b = A.bps[k];
+					bd_prefetch_shell((const char *) b.vol, b.mdlX, b.mdlY, b.mdlZ, b.mdlInitY, b.mdlInitZ, 16, Rlo, Rhi, c, nchunks);
+				}
+			}
 		}
 		__syncthreads();
 		const int ip = tile * BD_TP + (wid % BD_WPT) * 32 + lane;
@@ -539,17 +797,26 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 		if (M.bp_circle_bound) { const int xmax = (int) sqrtf((float) (half * half - y * y)); circle_ok = x < xmax; }   // BP.h:565
 		const float fxp = (float) x, fyp = (float) y;
 
-		for (int j = wid / BD_WPT; j < no; j += BD_NPH)
+		// the inputs of the next orientation are requested before the current one is worked on
+		auto fetch = [&](int j, BandStoreIn &in)
 		{
+			in.ref = make_float2(0.f, 0.f); in.XX = make_float4(0.f, 0.f, 0.f, 0.f); in.ctf = 0.f;
+			if (have)
+			{
+				const size_t so = (size_t) (A.slice_by_item ? (o0 + j) : S.item[j].w) * A.stride + ip;
+				const size_t po = (size_t) S.particle[j] * A.stride + ip;
+				in.ref = __ldcs(A.slices + so); in.XX = __ldg(A.sst + po); in.ctf = __ldg(A.sctf + po);
+			}
+		};
+		BandStoreIn cur, nxt;
+		if (ph < no) fetch(ph, cur);
+		for (int j = ph; j < no; j += BD_NPH)
+		{
+			if (j + BD_NPH < no) fetch(j + BD_NPH, nxt);
 			const RbBpItem it = S.item[j];
-			const int p = S.particle[j], cls = S.cls[j];
-			const size_t so = (size_t) (A.slice_by_item ? (o0 + j) : (it.w - 0)) * A.stride + ip;
-			const size_t po = (size_t) p * A.stride + ip;
-			float2 ref = make_float2(0.f, 0.f); float4 XX = make_float4(0.f, 0.f, 0.f, 0.f); float ctf = 0.f;
-			if (have) { ref = __ldcs(A.slices + so); XX = __ldg(A.sst + po); ctf = __ldg(A.sctf + po); }
-			const RbPartMeta *mp = A.metas + p;
-			const float part_scale = __ldg(&mp->part_scale);
-			const int og = __ldg(&mp->og);
+			const int p = S.particle[j], cls = MULTI ? S.cls[j] : 0;
+			float2 ref = cur.ref; const float4 XX = cur.XX; const float ctf = cur.ctf;
+			const float part_scale = S.part_scale[j];
 			if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                                  // wavg.cuh:96-104
 			else { ref.x *= part_scale; ref.y *= part_scale; }
 			float phr = 0.f, phi = 0.f;
@@ -575,10 +842,10 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 				while (todo)
 				{
 					const int leader = __ffs(todo) - 1;
-					const int cur = __shfl_sync(RB_FULL_MASK, ires, leader);
-					const bool mine = in_mresol && ires == cur;
+					const int curs = __shfl_sync(RB_FULL_MASK, ires, leader);
+					const bool mine = in_mresol && ires == curs;
 					const float v = warp_sum(mine ? wd : 0.f);
-					if (lane == leader && v != 0.f) atomicAdd(A.shells + (size_t) p * M.nshell + cur, v);
+					if (lane == leader && v != 0.f) atomicAdd(A.shells + (size_t) p * M.nshell + curs, v);
 					todo &= ~__ballot_sync(RB_FULL_MASK, mine);
 				}
 			}
@@ -593,13 +860,14 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 				}
 			}
 			// back-projection
-			const RbBackprojector bp = A.bps[cls];
+			RbBackprojector bp = bp0;
+			if (MULTI) bp = A.bps[cls];
 			const int max_r2_vol = (int) (bp.maxR * bp.maxR * bp.padding_factor * bp.padding_factor);   // BP.cuh:209
 			int cell = -1;
 			float sfx = 0.f, sfy = 0.f, sfz = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
 			if (have)
 			{
-				const float minvs2 = M.do_map ? __ldg(M.minvs2 + (size_t) og * M.nshell + ires) : 1.f;     // :2586, :3110-3115
+				const float minvs2 = M.do_map ? __ldg(M.minvs2 + (size_t) S.og[j] * M.nshell + ires) : 1.f;   // :2586, :3110-3115
 				const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                                // BP.cuh:280-289
 				Fw = W * g * ctf;
 				if (Fw > 0.f && circle_ok)
@@ -641,7 +909,11 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 					d2 = fz * fy * wx;   bd_red_add_v4(b + sz + sy, d2 * vr, d2 * vi, d2 * vw);
 				}
 			}
+			cur = nxt;
 		}
+		if (threadIdx.x == 0) S.next = (int) gridDim.x + pending;
+		__syncthreads();
+		item = S.next;
 	}
 }
 
@@ -659,6 +931,31 @@ bool rbk_band_applicable(rb_ctx *ctx)
 	// decided by pool_setup (api.cu): not with the cross-correlation criterion (it stays on k_diff2_fine / k_store), not with
 	// RB_BAND=0 or without room for the band-ordered slices
 	return !ctx->d_model.do_cc && ctx->d_model.pix_rs && ctx->band_slice_capacity > 0;
+}
+
+// phase tables of the current (model, sampling), rebuilt when either changed; ok == false: the sampling does not factorise
+int rbk_band_phase_tables(rb_ctx *ctx, bool &ok)
+{
+	ok = false;
+	static int on = -1;
+	if (on < 0) on = env_int("RB_BAND_TABLES", 1);
+	const int NOT = ctx->d_samp.n_over_trans, T = ctx->d_samp.n_trans;
+	if (!on || !ctx->band_separable || !(NOT == 1 || NOT == 4)) return RB_OK;
+	ok = true;
+	if (ctx->band_tab_model == ctx->model_version && ctx->band_tab_samp == ctx->samp_version) return RB_OK;
+	const RbModelDev &M = ctx->d_model;
+	const size_t stride = (size_t) M.nv_rs_pad;
+	RB_CHECK(ctx->band_tabc.ensure((size_t) T * stride * sizeof(float2)));
+	RB_CHECK(ctx->band_tabo.ensure((size_t) NOT * stride * sizeof(float2)));
+	RB_CHECK(ctx->band_tabu.ensure((size_t) 2 * (T + NOT) * sizeof(double)));
+	RB_CUDA(cudaMemcpyAsync(ctx->band_tabu.p, ctx->h_band_u.data(), (size_t) 2 * (T + NOT) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+	const double *u = ctx->band_tabu.as<double>();
+	dim3 g((unsigned) ((stride + 255) / 256), T + NOT);
+	k_band_tables<<<g, 256, 0, ctx->stream>>>(M.pix_rs, M.nv_rs_st, (int) stride, u, u + T, T, u + 2 * T, u + 2 * T + NOT, NOT,
+	                                          ctx->band_tabc.as<float2>(), ctx->band_tabo.as<float2>());
+	RB_LAUNCH_CHECK(ctx);
+	ctx->band_tab_model = ctx->model_version; ctx->band_tab_samp = ctx->samp_version;
+	return RB_OK;
 }
 
 // per-pool buffers and the band-ordered images (once per E-step of a slot)
@@ -681,7 +978,8 @@ int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s)
 	return RB_OK;
 }
 
-static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const int *count_ptr, int begin, int capacity, int *queue)
+static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const int *count_ptr, int begin, int capacity, int *queue,
+                               const int *nfo_ptr = nullptr, int only_if_nfo_above = 0)
 {
 	const RbModelDev &M = ctx->d_model;
 	BandProjArgs A;
@@ -691,16 +989,21 @@ static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const
 	A.slices = ctx->band_slices.as<float2>();
 	A.projs = ctx->d_proj.as<RbProjector>(); A.imgX = M.current_size / 2 + 1; A.nr_classes = M.nr_classes;
 	A.queue = queue;
-	A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_CHUNK_MIN", 8));
+	A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_CHUNK_MIN", 16));
+	A.prefetch_ahead = env_int("RB_BAND_PREFETCH", 2);
+	A.nfo_ptr = nfo_ptr; A.only_if_nfo_above = only_if_nfo_above;
 	static bool configured[RB_MAX_DEVICES] = {};
 	const size_t sm = sizeof(BandProjSmem);
 	if (!configured[ctx->device % RB_MAX_DEVICES])
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_project_band, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+		RB_CUDA(cudaFuncSetAttribute(k_project_band<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
+		RB_CUDA(cudaFuncSetAttribute(k_project_band<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
 		configured[ctx->device % RB_MAX_DEVICES] = true;
 	}
 	RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
-	k_project_band<<<ctx->num_sms * env_int("RB_BAND_PROJ_CTAS", 3), BD_THREADS, sm, ctx->stream>>>(A);
+	const int grid = ctx->num_sms * env_int("RB_BAND_PROJ_CTAS", 3);
+	if (M.nr_classes > 1) k_project_band<true><<<grid, BD_THREADS, sm, ctx->stream>>>(A);
+	else k_project_band<false><<<grid, BD_THREADS, sm, ctx->stream>>>(A);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
@@ -710,15 +1013,20 @@ static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const
 int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s)
 {
 	const RbModelDev &M = ctx->d_model;
+	RB_CHECK(rb_stage_begin(ctx, "fine_prep"));
 	RB_CHECK(rbk_band_prepare_pool(ctx, s));
+	bool tables = false;
+	RB_CHECK(rbk_band_phase_tables(ctx, tables));
+	RB_CHECK(rb_stage_end(ctx, "fine_prep"));
 	const long long cap = ctx->band_slice_capacity;
-	const long long worst = (long long) s.cap_fo;
-	const int rounds = (int) std::min<long long>((worst + cap - 1) / cap, 4096);
+	const int rounds = s.band_rounds;               // pool_setup: ceil(cap_fo / cap), at most RB_BAND_ROUNDS
 	int *queue = s.counters.as<int>() + 8;
 	for (int r = 0; r < rounds; r++)
 	{
 		const int begin = (int) (r * cap);
+		if (r == 0) RB_CHECK(rb_stage_begin(ctx, "fine_project"));
 		RB_CHECK(launch_project_band(ctx, s, nullptr, s.counters.as<int>(), begin, (int) cap, queue));
+		if (r == 0) { RB_CHECK(rb_stage_end(ctx, "fine_project")); RB_CHECK(rb_stage_begin(ctx, "fine_diff2")); }
 		BandDiffArgs D;
 		memset(&D, 0, sizeof(D));
 		D.metas = s.meta.as<RbPartMeta>(); D.states = s.state.as<RbPartState>();
@@ -729,10 +1037,13 @@ int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s)
 		D.tx = ctx->d_samp.ftx; D.ty = ctx->d_samp.fty; D.NOT = ctx->d_samp.n_over_trans;
 		D.queue = queue + 1;
 		RB_CUDA(cudaMemsetAsync(queue + 1, 0, 4, ctx->stream));
-		k_diff2_slices<<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D);
+		const int NOT = ctx->d_samp.n_over_trans;
+		if (tables && NOT == 4) k_diff2_slices_sep<4><<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D, ctx->band_tabc.as<float2>(), ctx->band_tabo.as<float2>());
+		else if (tables && NOT == 1) k_diff2_slices_sep<1><<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D, ctx->band_tabc.as<float2>(), ctx->band_tabo.as<float2>());
+		else k_diff2_slices<<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D);
 		RB_LAUNCH_CHECK(ctx);
+		if (r == 0) RB_CHECK(rb_stage_end(ctx, "fine_diff2"));
 	}
-	s.band_rounds = rounds;
 	return RB_OK;
 }
 
@@ -751,12 +1062,14 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 	L.fs_w = s.fs_w.as<float>(); L.cnt = s.bp_cnt.as<int>(); L.item_of = s.bp_item_of.as<int>();
 	L.items = s.bp_items.as<RbBpItem>(); L.samp = s.bp_samp.as<float4>(); L.samp_cap = samp_cap;
 	L.tx = ctx->d_samp.ftx; L.ty = ctx->d_samp.fty; L.NOT = ctx->d_samp.n_over_trans;
+	RB_CHECK(rb_stage_begin(ctx, "store_list"));
 	k_bp_count<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(L);
 	RB_LAUNCH_CHECK(ctx);
 	k_bp_scan<<<1, 1024, 0, ctx->stream>>>(L);
 	RB_LAUNCH_CHECK(ctx);
 	k_bp_fill<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(L);
 	RB_LAUNCH_CHECK(ctx);
+	RB_CHECK(rb_stage_end(ctx, "store_list"));
 
 	BandStoreArgs A;
 	memset(&A, 0, sizeof(A));
@@ -765,27 +1078,31 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.sst = s.sst.as<float4>(); A.sctf = s.sctf.as<float>(); A.slices = ctx->band_slices.as<float2>();
 	A.pix = M.pix_rs; A.nst = M.nv_rs_st; A.stride = M.nv_rs_pad;
 	A.shells = s.shells.as<float>(); A.bps = ctx->d_bp.as<RbBackprojector>();
-	A.n = M.current_size; A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_STORE_CHUNK_MIN", 4));
+	A.n = M.current_size; A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_STORE_CHUNK_MIN", 16));
+	A.prefetch_ahead = env_int("RB_BAND_STORE_PREFETCH", 2); A.nr_classes = M.nr_classes;
 	int *queue = s.counters.as<int>() + 14;
-	const int grid = ctx->num_sms * env_int("RB_BAND_STORE_CTAS", 2);
-	if (s.band_rounds <= 1)
-	{
-		// the slices of every fine orientation are still in the buffer, indexed by fine orientation
-		A.begin = 0; A.capacity = 0x7fffffff; A.slice_by_item = 0; A.queue = queue;
-		RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
-		k_store_band<<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
-		RB_LAUNCH_CHECK(ctx);
-		return RB_OK;
-	}
-	// several rounds: the buffer was reused, project the listed orientations again, round by round
+	const int grid = ctx->num_sms * env_int("RB_BAND_STORE_CTAS", 3);
+	const bool multi = M.nr_classes > 1;
 	const long long cap = ctx->band_slice_capacity;
-	for (int r = 0; r < s.band_rounds; r++)
+	A.fits = (int) std::min<long long>(cap, 0x7fffffff);
+	// (a) the fine pass fitted one round (decided on the device: counters[0] <= cap): its slices are still in the buffer
+	A.begin = 0; A.capacity = 0x7fffffff; A.slice_by_item = 0; A.queue = queue;
+	RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
+	RB_CHECK(rb_stage_begin(ctx, "store_band"));
+	if (multi) k_store_band<true><<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
+	else k_store_band<false><<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
+	RB_LAUNCH_CHECK(ctx);
+	RB_CHECK(rb_stage_end(ctx, "store_band"));
+	// (b) it took several rounds and the buffer was reused: project the listed orientations again, round by round (these
+	// launches exit at once in case (a))
+	for (int r = 0; r < s.band_rounds && s.band_rounds > 1; r++)
 	{
 		const int begin = (int) (r * cap);
-		RB_CHECK(launch_project_band(ctx, s, (const int *) s.bp_items.p, s.counters.as<int>() + 10, begin, (int) cap, queue + 1));
+		RB_CHECK(launch_project_band(ctx, s, (const int *) s.bp_items.p, s.counters.as<int>() + 10, begin, (int) cap, queue + 1, s.counters.as<int>(), A.fits));
 		A.begin = begin; A.capacity = (int) cap; A.slice_by_item = 1; A.queue = queue;
 		RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
-		k_store_band<<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
+		if (multi) k_store_band<true><<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
+		else k_store_band<false><<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
 		RB_LAUNCH_CHECK(ctx);
 	}
 	return RB_OK;

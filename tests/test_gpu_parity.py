@@ -790,6 +790,7 @@ def test_pool_store_stage_without_slice_cache(device, oracle, monkeypatch, cache
     wl = make_workload(ori_size=32, healpix_order=2, n_particles=8, nr_classes=1, seed=130, snr=0.2, local_search=True)
     npf = wl.model.current_size * (wl.model.current_size // 2 + 1)
     monkeypatch.setenv("RB_SLICE_CACHE_BYTES", str(cache_slices * npf * 8))
+    monkeypatch.setenv("RB_BAND_ROUNDS", "100000")          # band-major path: as many rounds of a few slices as the pool needs
     res, _ = _compare_pool(device, oracle, wl)
     assert res.particles["n_fine_orient"].sum() > cache_slices
 

@@ -17,9 +17,10 @@
 //
 //   k_prep_sorted     particle images -> band-ordered arrays (prepared image for diff2; X, X0, ctf for the store stage)
 //   k_project_band    fine orientations x tile -> slices in band order.  One lane owns one sample (address arithmetic once
-//                     per sample), the 64-byte cell is fetched by the lane's QUAD with four 16-byte cp.async (one L1 line
-//                     visit per sample), three stages in flight per warp.
-//   k_diff2_slices    streams slice + prepared image per fine orientation: diff2 of all its fine translations
+//                     per sample), the 64-byte cell is fetched by the lane's QUAD with four 16-byte loads (one L1 line visit
+//                     per sample) and handed over through a conflict-free shared-memory tile; one sample ahead in flight.
+//   k_diff2_slices*   streams slice + prepared image per fine orientation: diff2 of all its fine translations; phases from
+//                     L2-resident tables when the oversampled translations factorise (no transcendental in the loop)
 //   k_bp_*            compact list of the fine orientations holding >= 1 significant sample, with (phase, weight) tables
 //   k_store_band      (tile, chunk of those orientations): wavg sums + trilinear scatter (red.global.add.v4.f32) into the
 //                     L2-resident shell of the accumulator
@@ -31,72 +32,12 @@ static const int BD_THREADS = 256;
 static const int BD_TP = 128;                    // pixels per tile
 static const int BD_WPT = BD_TP / 32;            // warps per tile row
 static const int BD_NPH = BD_THREADS / BD_TP;    // orientation phases per CTA
-static const int BD_DEPTH = 3;                   // cp.async stages per warp
 static const int BD_MAXCHUNK = 64;
-
-__device__ __forceinline__ void bd_cp_async16(void *smem, const void *gmem)
-{
-	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t) __cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void bd_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void bd_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 __device__ __forceinline__ void bd_red_add_v4(float4 *addr, float a, float b, float c)
 {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
 }
-
-__device__ __forceinline__ void bd_prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
-
-// Radial range (in pixels^2) of tile `tile` of the band-ordered pixel list
-__device__ __forceinline__ void bd_tile_r2(const uint32_t *pix, int npix, int tile, int &lo, int &hi)
-{
-	const uint32_t a = __ldg(pix + tile * BD_TP), b = __ldg(pix + min((tile + 1) * BD_TP, npix) - 1);
-	const int xa = rb_pix_x(a), ya = rb_pix_y(a), xb = rb_pix_x(b), yb = rb_pix_y(b);
-	lo = xa * xa + ya * ya; hi = xb * xb + yb * yb;
-	if (lo > hi) { const int t = lo; lo = hi; hi = t; }
-}
-
-// Shell prefetch.  The band sweep touches every voxel of a spherical shell exactly when the sweep front reaches it, in an
-// order set by the orientations: first touches are RANDOM 64-byte (reference cell) / 32-byte (accumulator) DRAM reads, which
-// HBM serves at ~20 G requests/s (tools/l2_gather_bench.cu: 1.2-1.4 TB/s for 64-byte gathers, against 9 TB/s once the lines
-// are in L2).  So every work item also walks its share of the (z, y) rows of the shell that the sweep reaches `ahead` tiles
-// later and prefetches the run of voxels the shell cuts out of each row, 128 bytes at a time, IN ADDRESS ORDER: the shell
-// arrives in L2 as a stream and the gathers / reductions that follow hit.
-// Volume geometry: x in [0, X), y in [initY, initY + Y), z likewise; `bytes_per_voxel` 64 (expanded reference) or 16 (accumulator).
-__device__ __forceinline__ void bd_prefetch_shell(const char *base, int X, int Y, int Z, int initY, int initZ, int bytes_per_voxel,
-                                                  float Rlo, float Rhi, int part, int nparts)
-{
-	const int Rh = (int) ceilf(Rhi);
-	const int side = 2 * Rh + 1;
-	const int nrows = side * side;
-	const int per = (nrows + nparts - 1) / nparts;
-	const int r1 = min(nrows, (part + 1) * per);
-	const float Rlo2 = Rlo > 0.f ? Rlo * Rlo : 0.f, Rhi2 = Rhi * Rhi;
-	const int vpl = 128 / bytes_per_voxel;                      // voxels per 128-byte line
-	for (int row = part * per + (int) threadIdx.x; row < r1; row += (int) blockDim.x)
-	{
-		const int zz = row / side - Rh, yy = row - (row / side) * side - Rh;
-		const float rho2 = (float) (zz * zz + yy * yy);
-		if (rho2 > Rhi2) continue;
-		const int yi = yy - initY, zi = zz - initZ;
-		if (yi < 0 || yi >= Y || zi < 0 || zi >= Z) continue;
-		int x_hi = (int) sqrtf(Rhi2 - rho2) + 1;
-		int x_lo = rho2 < Rlo2 ? (int) sqrtf(Rlo2 - rho2) - 1 : 0;
-		x_lo = max(x_lo, 0); x_hi = min(x_hi, X - 1);
-		const char *rowp = base + ((size_t) zi * Y + yi) * (size_t) X * bytes_per_voxel;
-		for (int x = (x_lo / vpl) * vpl; x <= x_hi; x += vpl) bd_prefetch_l2(rowp + (size_t) x * bytes_per_voxel);
-	}
-}
-
-// work items of a (tile, chunk) queue: the tile is the slow index, so the resident CTAs stay inside one radial band.
-// The next item is requested while the current one is processed (the atomic's round trip is hidden).
-struct BandQueue {
-	int *counter; int *s_slot;
-	__device__ __forceinline__ int first() const { return (int) blockIdx.x; }
-	__device__ __forceinline__ void prefetch() const { if (threadIdx.x == 0) *s_slot = (int) gridDim.x + atomicAdd(counter, 1); }
-	__device__ __forceinline__ int next() const { __syncthreads(); const int v = *s_slot; __syncthreads(); return v; }
-};
 
 // ---------------------------------------------------------------------------------------------
 // band-ordered particle images
@@ -156,29 +97,33 @@ struct BandProjArgs {
 	const RbProjector *projs; int imgX; int nr_classes;
 	int *queue;
 	int chunk_min;
-	int prefetch_ahead;          // tiles the shell prefetch runs ahead of the sweep (0: off)
 	const int *nfo_ptr; int only_if_nfo_above;   // re-projection rounds of the store stage: run only when the fine pass needed several rounds
 };
 
 struct RbBpItem { int w; int samp_off; int nsig; float W; };
 
-static const int BD_STAGE_F4 = 32 * 4 + 16;   // float4 per stage: sample s keeps its four quarters at chunks 4 s + (s >> 1) + c
-                                                // (the s >> 1 padding makes both the quad-wise cp.async writes and the lane-wise
-                                                // 64-byte reads conflict free: four shared-memory wavefronts per 512 bytes)
+static const int BD_STAGE_F4 = 32 * 4 + 16;   // float4 per warp staging tile: sample s keeps its four quarters at chunks 4 s + (s >> 1) + c
+                                                // (the s >> 1 padding makes both the quad-wise writes and the lane-wise 64-byte
+                                                // reads conflict free: four shared-memory wavefronts per 512 bytes)
 
 struct BandProjSmem {
-	float4 cell[BD_THREADS / 32][BD_DEPTH][BD_STAGE_F4];
+	float4 cell[BD_THREADS / 32][BD_STAGE_F4];
 	float e[BD_MAXCHUNK][6];
 	int cls[BD_MAXCHUNK];
 	int next;
 };
 
-// what a lane keeps about a sample in flight: trilinear fractions and flags (bit0 inside r_max, bit1 Hermitian mate)
+// what a lane keeps about a sample in flight: trilinear fractions and flags (bit0 inside r_max, bit1 Hermitian mate),
+// and the four 16-byte pieces it fetched for its QUAD: piece r is quarter (lane & 3) of the cell of the quad's sample r
 struct BandFrac { float fx, fy, fz; int flags; };
+struct BandLoad { float4 q[4]; BandFrac f; };
 
+// Gathers go through plain 16-byte loads (LDG.128): per instruction the 8 quads of a warp touch 8 cells, one L1 line visit
+// per sample.  (cp.async into shared memory was measured 2.6x slower here: with 8 distinct lines per instruction every line
+// becomes its own shared-memory write transaction, ~40 cycles per instruction against ~16 for the register path.)
 template <bool MULTI>
 __device__ __forceinline__ void band_issue(const BandProjArgs &A, const BandProjSmem &S, const RbProjK8 &pk0, int j, int x, int y, bool have,
-                                           int lane, float4 *dst, BandFrac &f)
+                                           int lane, BandLoad &L)
 {
 	const float2 ea = *(const float2 *) &S.e[j][0], eb = *(const float2 *) &S.e[j][2], ec = *(const float2 *) &S.e[j][4];
 	RbProjK8 pk = pk0;
@@ -191,49 +136,52 @@ __device__ __forceinline__ void band_issue(const BandProjArgs &A, const BandProj
 	const bool inv = xp < 0.f;
 	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
 	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
-	f.fx = xp - fx0; f.fy = yp - fy0; f.fz = zp - fz0;
-	f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
+	L.f.fx = xp - fx0; L.f.fy = yp - fy0; L.f.fz = zp - fz0;
+	L.f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
 	const int cell = inside ? (((int) fz0 - pk.mdlInitZ) * pk.mdlXY + ((int) fy0 - pk.mdlInitY) * pk.mdlX + (int) fx0) : -1;
 	const int k = lane & 3, qbase = lane & ~3;
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 	{
-		const int s = qbase + r;                                              // sample (lane) whose cell this round fetches
-		const int cs = __shfl_sync(RB_FULL_MASK, cell, s);
-		if (cs >= 0) bd_cp_async16(dst + 4 * s + (s >> 1) + k, pk.mdl8 + 4 * (size_t) cs + k);
+		const int cs = __shfl_sync(RB_FULL_MASK, cell, qbase + r);             // cell of the quad's sample r
+		L.q[r] = cs >= 0 ? __ldcg(pk.mdl8 + 4 * (size_t) cs + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 	}
 }
 
-__device__ __forceinline__ float2 band_consume(const float4 *src_stage, int lane, const BandFrac &f)
+// quad-transpose through the warp's staging tile, then the trilinear interpolation of the lane's own sample
+__device__ __forceinline__ float2 band_consume(float4 *tile, int lane, const BandLoad &L)
 {
-	float2 ref = make_float2(0.f, 0.f);
-	if (f.flags & 1)
+	const int k = lane & 3, qbase = lane & ~3;
+#pragma unroll
+	for (int r = 0; r < 4; r++) { const int s = qbase + r; tile[4 * s + (s >> 1) + k] = L.q[r]; }
+	__syncwarp();
+	const float4 *src = tile + 4 * lane + (lane >> 1);
+	const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+	__syncwarp();
+	const BandFrac &f = L.f;
+	float2 ref;
 	{
-		const float4 *src = src_stage + 4 * lane + (lane >> 1);
-		const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
-		{
-			const float dx00 = q0.x + (q0.z - q0.x) * f.fx, dx10 = q1.x + (q1.z - q1.x) * f.fx;
-			const float dx01 = q2.x + (q2.z - q2.x) * f.fx, dx11 = q3.x + (q3.z - q3.x) * f.fx;
-			const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
-			ref.x = dxy0 + (dxy1 - dxy0) * f.fz;
-		}
-		{
-			const float dx00 = q0.y + (q0.w - q0.y) * f.fx, dx10 = q1.y + (q1.w - q1.y) * f.fx;
-			const float dx01 = q2.y + (q2.w - q2.y) * f.fx, dx11 = q3.y + (q3.w - q3.y) * f.fx;
-			const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
-			ref.y = dxy0 + (dxy1 - dxy0) * f.fz;
-		}
-		if (f.flags & 2) ref.y = -ref.y;
+		const float dx00 = q0.x + (q0.z - q0.x) * f.fx, dx10 = q1.x + (q1.z - q1.x) * f.fx;
+		const float dx01 = q2.x + (q2.z - q2.x) * f.fx, dx11 = q3.x + (q3.z - q3.x) * f.fx;
+		const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		ref.x = dxy0 + (dxy1 - dxy0) * f.fz;
 	}
+	{
+		const float dx00 = q0.y + (q0.w - q0.y) * f.fx, dx10 = q1.y + (q1.w - q1.y) * f.fx;
+		const float dx01 = q2.y + (q2.w - q2.y) * f.fx, dx11 = q3.y + (q3.w - q3.y) * f.fx;
+		const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		ref.y = dxy0 + (dxy1 - dxy0) * f.fz;
+	}
+	if (f.flags & 2) ref.y = -ref.y;
+	if (!(f.flags & 1)) ref = make_float2(0.f, 0.f);
 	return ref;
 }
 
-template <bool MULTI>
-static __global__ void __launch_bounds__(BD_THREADS, 3)
+template <bool MULTI, int MINB>
+static __global__ void __launch_bounds__(BD_THREADS, MINB)
 k_project_band(BandProjArgs A)
 {
-	extern __shared__ __align__(16) unsigned char bd_smem_raw[];
-	BandProjSmem &S = *reinterpret_cast<BandProjSmem *>(bd_smem_raw);
+	__shared__ BandProjSmem S;
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 	const int total = *A.count_ptr;
 	const int n = min(A.capacity, total - A.begin);
@@ -247,10 +195,7 @@ k_project_band(BandProjArgs A)
 	const long long nitems = (long long) ntiles * nchunks;
 	const RbProjK8 pk0 = rb_make_projk8(A.projs[0], A.imgX);
 	const int ph = wid / BD_WPT;
-	float4 *cells = &S.cell[wid][0][0];
-	// samples of the round against voxels of the half sphere: below ~1.5 per voxel a whole-shell prefetch would fetch more than it saves
-	const float pf_rmax = pk0.pf * (float) pk0.maxR + 1.f;
-	const bool do_prefetch = A.prefetch_ahead > 0 && (float) n * (float) A.npix > 1.5f * 2.0944f * pf_rmax * pf_rmax * pf_rmax;
+	float4 *tile_buf = &S.cell[wid][0];
 
 	long long item = blockIdx.x;
 	while (item < nitems)
@@ -269,23 +214,6 @@ k_project_band(BandProjArgs A)
 		// the next item is requested now and looked at after this one is done: the atomic's round trip is hidden
 		int pending = 0;
 		if (threadIdx.x == 0) pending = atomicAdd(A.queue, 1);
-		// this item's share of the shell the sweep reaches `prefetch_ahead` tiles from now (the first items also cover the tiles
-		// in between); only when the orientations of the round cover the sphere densely
-		if (do_prefetch)
-		{
-			const int t0 = tile == 0 ? 0 : tile + A.prefetch_ahead, t1 = tile + A.prefetch_ahead;
-			for (int tp = t0; tp <= t1 && tp < ntiles; tp++)
-			{
-				int lo, hi;
-				bd_tile_r2(A.pix, A.npix, tp, lo, hi);
-				const float Rlo = pk0.pf * sqrtf((float) lo) - 2.f, Rhi = fminf(pk0.pf * sqrtf((float) hi) + 1.f, pf_rmax);
-				for (int k = 0; k < (MULTI ? A.nr_classes : 1); k++)
-				{
-					const RbProjector &pj = A.projs[k];
-					bd_prefetch_shell((const char *) pj.mdl8, pj.mdlX, pj.mdlY, pj.mdlZ, pj.mdlInitY, pj.mdlInitZ, 64, Rlo, Rhi, c, nchunks);
-				}
-			}
-		}
 		__syncthreads();
 		const int ip = tile * BD_TP + (wid % BD_WPT) * 32 + lane;
 		const bool have = ip < A.npix;
@@ -294,37 +222,16 @@ k_project_band(BandProjArgs A)
 		const int nmy = (no - ph + BD_NPH - 1) / BD_NPH;                        // orientations ph, ph + BD_NPH, ...
 		float2 *out = A.slices + (size_t) o0 * A.stride + ip;
 
-		// three stages in flight per warp; the loop is unrolled by the depth so that the stage of a sample is a
-		// compile-time constant and its fractions stay in registers
-		BandFrac f[BD_DEPTH];
-#pragma unroll
-		for (int d = 0; d < BD_DEPTH - 1; d++)
+		// one orientation ahead: the loads of the next sample are in flight while the current one is interpolated
+		BandLoad cur, nxt;
+		if (nmy > 0) band_issue<MULTI>(A, S, pk0, ph, x, y, have, lane, cur);
+		for (int jj = 0; jj < nmy; jj++)
 		{
-			if (d < nmy) band_issue<MULTI>(A, S, pk0, ph + d * BD_NPH, x, y, have, lane, cells + d * BD_STAGE_F4, f[d]);
-			bd_cp_commit();
+			if (jj + 1 < nmy) band_issue<MULTI>(A, S, pk0, ph + (jj + 1) * BD_NPH, x, y, have, lane, nxt);
+			const float2 ref = band_consume(tile_buf, lane, cur);
+			if (have) __stcs(out + (size_t) (ph + jj * BD_NPH) * A.stride, ref);
+			cur = nxt;
 		}
-#pragma unroll 1
-		for (int jj0 = 0; jj0 < nmy; jj0 += BD_DEPTH)
-		{
-#pragma unroll
-			for (int u = 0; u < BD_DEPTH; u++)
-			{
-				const int jj = jj0 + u;
-				if (jj < nmy)
-				{
-					const int un = (u + BD_DEPTH - 1) % BD_DEPTH;
-					if (jj + BD_DEPTH - 1 < nmy)
-						band_issue<MULTI>(A, S, pk0, ph + (jj + BD_DEPTH - 1) * BD_NPH, x, y, have, lane, cells + un * BD_STAGE_F4, f[un]);
-					bd_cp_commit();
-					bd_cp_wait<BD_DEPTH - 1>();
-					__syncwarp();
-					const float2 ref = band_consume(cells + u * BD_STAGE_F4, lane, f[u]);
-					__syncwarp();                                                  // the stage is free for the next issue
-					if (have) __stcs(out + (size_t) (ph + jj * BD_NPH) * A.stride, ref);
-				}
-			}
-		}
-		bd_cp_wait<0>();
 		if (threadIdx.x == 0) S.next = (int) gridDim.x + pending;
 		__syncthreads();
 		item = S.next;
@@ -716,7 +623,7 @@ struct BandStoreArgs {
 	float *shells;               // [P][nshell]
 	const RbBackprojector *bps;
 	int n; int *queue; int chunk_min;
-	int prefetch_ahead; int nr_classes;
+	int nr_classes;
 };
 
 struct BandStoreSmem {
@@ -748,8 +655,6 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 	const int half = A.n / 2;
 	const RbBackprojector bp0 = A.bps[0];
 	const int ph = wid / BD_WPT;
-	const float pf_rmax = bp0.padding_factor * (float) bp0.maxR + 1.f;
-	const bool do_prefetch = A.prefetch_ahead > 0 && (float) n * (float) A.nst > 1.5f * 2.0944f * pf_rmax * pf_rmax * pf_rmax;
 
 	long long item = blockIdx.x;
 	while (item < nitems)
@@ -771,21 +676,6 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 		}
 		int pending = 0;
 		if (threadIdx.x == 0) pending = atomicAdd(A.queue, 1);      // next item, looked at after this one
-		if (do_prefetch)                                             // accumulator shell of the tiles ahead, in address order
-		{
-			const int t0 = tile == 0 ? 0 : tile + A.prefetch_ahead, t1 = tile + A.prefetch_ahead;
-			for (int tp = t0; tp <= t1 && tp < ntiles; tp++)
-			{
-				int lo, hi;
-				bd_tile_r2(A.pix, A.nst, tp, lo, hi);
-				const float Rlo = bp0.padding_factor * sqrtf((float) lo) - 2.f, Rhi = fminf(bp0.padding_factor * sqrtf((float) hi) + 1.f, pf_rmax);
-				for (int k = 0; k < (MULTI ? A.nr_classes : 1); k++)
-				{
-					const RbBackprojector &b = A.bps[k];
-					bd_prefetch_shell((const char *) b.vol, b.mdlX, b.mdlY, b.mdlZ, b.mdlInitY, b.mdlInitZ, 16, Rlo, Rhi, c, nchunks);
-				}
-			}
-		}
 		__syncthreads();
 		const int ip = tile * BD_TP + (wid % BD_WPT) * 32 + lane;
 		const bool have = ip < A.nst;
@@ -990,20 +880,12 @@ static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const
 	A.projs = ctx->d_proj.as<RbProjector>(); A.imgX = M.current_size / 2 + 1; A.nr_classes = M.nr_classes;
 	A.queue = queue;
 	A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_CHUNK_MIN", 16));
-	A.prefetch_ahead = env_int("RB_BAND_PREFETCH", 2);
 	A.nfo_ptr = nfo_ptr; A.only_if_nfo_above = only_if_nfo_above;
-	static bool configured[RB_MAX_DEVICES] = {};
-	const size_t sm = sizeof(BandProjSmem);
-	if (!configured[ctx->device % RB_MAX_DEVICES])
-	{
-		RB_CUDA(cudaFuncSetAttribute(k_project_band<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-		RB_CUDA(cudaFuncSetAttribute(k_project_band<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) sm));
-		configured[ctx->device % RB_MAX_DEVICES] = true;
-	}
 	RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
-	const int grid = ctx->num_sms * env_int("RB_BAND_PROJ_CTAS", 3);
-	if (M.nr_classes > 1) k_project_band<true><<<grid, BD_THREADS, sm, ctx->stream>>>(A);
-	else k_project_band<false><<<grid, BD_THREADS, sm, ctx->stream>>>(A);
+	const int ctas = env_int("RB_BAND_PROJ_CTAS", 3);
+	const int grid = ctx->num_sms * ctas;
+	if (M.nr_classes > 1) { if (ctas >= 3) k_project_band<true, 3><<<grid, BD_THREADS, 0, ctx->stream>>>(A); else k_project_band<true, 2><<<grid, BD_THREADS, 0, ctx->stream>>>(A); }
+	else { if (ctas >= 3) k_project_band<false, 3><<<grid, BD_THREADS, 0, ctx->stream>>>(A); else k_project_band<false, 2><<<grid, BD_THREADS, 0, ctx->stream>>>(A); }
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
@@ -1079,7 +961,7 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.pix = M.pix_rs; A.nst = M.nv_rs_st; A.stride = M.nv_rs_pad;
 	A.shells = s.shells.as<float>(); A.bps = ctx->d_bp.as<RbBackprojector>();
 	A.n = M.current_size; A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_STORE_CHUNK_MIN", 16));
-	A.prefetch_ahead = env_int("RB_BAND_STORE_PREFETCH", 2); A.nr_classes = M.nr_classes;
+	A.nr_classes = M.nr_classes;
 	int *queue = s.counters.as<int>() + 14;
 	const int grid = ctx->num_sms * env_int("RB_BAND_STORE_CTAS", 3);
 	const bool multi = M.nr_classes > 1;

@@ -17,7 +17,7 @@ def _built():
     """Make sure the native artefacts exist (no-op when already built in-tree)."""
     lib = os.path.join(ROOT, "relion_b200", "librelion_b200.so")
     orc = os.path.join(ROOT, "oracle", "liboracle.so")
-    shim = os.path.join(ROOT, "tests", "cpp", "libadapter_shim.so")
+    shim = os.path.join(ROOT, "tests", "cpp", "estep_multi_gpu")
     if not (os.path.exists(lib) and os.path.exists(orc) and os.path.exists(shim)):
         import __graft_entry__ as g
         g.build()

@@ -1,99 +1,173 @@
-"""The C++ host adapter (include/relion_b200_adapter.hpp): AccProjector / AccBackprojector / MlDeviceBundle /
-MlOptimiserCuda with the reference's names and call sequence (src/acc/cuda/cuda_ml_optimiser.h:18-144), driven through
-tests/cpp/adapter_shim.cpp the way src/ml_optimiser.cpp:3577-3869 drives the reference's objects."""
-import ctypes as C
+"""The C++ host adapter (include/relion_b200_adapter.hpp): AccProjector / AccBackprojector / MlDeviceBundle(MlOptimiser *) /
+MlOptimiserCuda(MlOptimiser *, MlDeviceBundle *, const char *) with the reference's names, constructor signatures and call
+sequence (src/acc/cuda/cuda_ml_optimiser.h:18-144), the host bookkeeping of storeWeightedSums in C++ and the NCCL twin of
+MlOptimiserMpi::combineAllWeightedSums.
+
+ * compile check against the REAL reference headers (tests/cpp/relion_callsites.cpp, CPU, needs /root/reference);
+ * tests/cpp/estep_multi_gpu (C++, no Python in the loop) on the mock MlOptimiser of tests/cpp/mock_relion: one-GPU E-step
+   against the same particles split over two ranks + combineAllWeightedSums (NCCL when the box has two GPUs, host sum
+   otherwise), then its metadata rows and weighted sums against the Python host mirror.
+"""
 import os
+import struct
+import subprocess
 
 import numpy as np
 import pytest
 
-from relion_b200 import capi
-from relion_b200.estep import marshal_model, marshal_sampling, marshal_pool, make_pool_out
-from relion_b200.workload import make_workload
+from relion_b200.workload import make_workload, raw_pool_from
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-SHIM = os.path.join(ROOT, "tests", "cpp", "libadapter_shim.so")
+EXE = os.path.join(ROOT, "tests", "cpp", "estep_multi_gpu")
+
+# exp_metadata columns (src/ml_optimiser.h:51-80)
+ROT, TILT, PSI, XOFF, YOFF, ZOFF, CLASS, DLL, PMAX, NR_SIGN, NORM = range(11)
+DEFU, DEFV, DEFANG, BFAC, KFAC, PHASE = range(11, 17)
+NCOL = 25
 
 
-def _shim():
-    if not os.path.exists(SHIM):
+def _exe():
+    if not os.path.exists(EXE):
         import __graft_entry__ as g
         g.build()
-    lib = C.CDLL(SHIM)
-    lib.adapter_estep.restype = C.c_int
-    return lib
+    return EXE
 
 
-def _run(wl, device=0, skip_maximization=False, nr_threads=3):
-    lib = _shim()
-    K = wl.model.nr_classes
-    mm, ms, mp = marshal_model(wl.model), marshal_sampling(wl.sampling), marshal_pool(wl.pool)
-    out = make_pool_out(wl.pool.n_particles, wl.model.ori_size // 2 + 1, K, wl.sampling.n_dir)
-    refs = [np.ascontiguousarray(v if v.ndim == 3 else v[None], np.complex128) for v in wl.refs]   # MlModel::PPref is double
-    z, y, x = refs[0].shape
-    init = -((y - 1) // 2)
-    bz, by, bx = wl.bp_shape if len(wl.bp_shape) == 3 else (1,) + tuple(wl.bp_shape)
-    ref_dims = np.array([[x, y, z, init, init if z > 1 else 0, wl.r_max]] * K, np.int32)
-    bp_dims = np.array([[bx, by, bz, -((by - 1) // 2), -((bz - 1) // 2) if bz > 1 else 0, wl.r_max]] * K, np.int32)
-    pp = (C.c_void_p * K)(*[r.ctypes.data for r in refs])
-    bps = [[np.zeros((bz, by, bx), np.float32) for _ in range(K)] for _ in range(3)]
-    ptrs = [(C.c_void_p * K)(*[a.ctypes.data for a in arrs]) for arrs in bps]
-    err = C.create_string_buffer(1024)
-    rc = lib.adapter_estep(device, C.byref(mm.struct), C.byref(ms.struct), K, pp, ref_dims.ctypes.data_as(C.c_void_p),
-                           bp_dims.ctypes.data_as(C.c_void_p), C.c_float(wl.padding_factor), C.byref(mp.struct), C.byref(out.struct),
-                           int(skip_maximization), nr_threads, ptrs[0], ptrs[1], ptrs[2], err, len(err))
-    return rc, err.value.decode(), out.result, bps
+def _dump(path, arrays):
+    """name -> array file read by tests/cpp/estep_multi_gpu.cpp (dtype codes 0 float64, 1 float32, 2 int32)."""
+    with open(path, "wb") as f:
+        for name, a in arrays.items():
+            a = np.ascontiguousarray(a)
+            code = {np.dtype(np.float64): 0, np.dtype(np.float32): 1, np.dtype(np.int32): 2}[a.dtype]
+            nb = name.encode()
+            f.write(struct.pack("<i", len(nb))); f.write(nb)
+            f.write(struct.pack("<ii", code, a.ndim)); f.write(struct.pack("<%dq" % a.ndim, *a.shape))
+            f.write(a.tobytes())
 
 
-def test_adapter_without_gpu_throws_relion_error():
+def _workload_arrays(wl, raw, avg_norm=1.0):
+    s, m = wl.sampling, wl.model
+    N = raw.n_particles
+    sc = lambda v: np.array([float(v)], np.float64)
+    md = np.zeros((N, NCOL), np.float64)
+    md[:, 17:25] = 999.0                                                       # no priors given
+    md[:, ROT], md[:, TILT], md[:, PSI] = wl.truth["rot"], wl.truth["tilt"], wl.truth["psi"]
+    md[:, XOFF:YOFF + 1] = raw.old_offset
+    md[:, NORM] = avg_norm / raw.norm_factor
+    md[:, DEFU], md[:, DEFV], md[:, DEFANG] = raw.ctf_defU, raw.ctf_defV, raw.ctf_defAngle
+    md[:, KFAC] = 1.0
+    ps = float(m.pixel_size)
+    refs = np.stack([np.ascontiguousarray(v, np.complex128) for v in wl.refs])
+    a = {
+        "nr_classes": sc(m.nr_classes), "ori_size": sc(m.ori_size), "pixel_size": sc(ps), "nr_groups": sc(len(m.scale_correction)),
+        "sigma2_offset": sc(m.sigma2_offset), "avg_norm_correction": sc(avg_norm), "local_search": sc(raw.dir_off is not None),
+        "sigma2_ang": sc(4.0), "r_max": sc(wl.r_max), "healpix_order": sc(s.healpix_order), "n_over_rot": sc(s.n_over_rot),
+        "n_over_trans": sc(s.n_over_trans), "coarse_size": sc(m.coarse_size), "current_size": sc(m.current_size),
+        "adaptive_fraction": sc(m.adaptive_fraction), "particle_diameter": sc(2.0 * raw.mask_radius * ps), "width_mask_edge": sc(raw.width_mask_edge),
+        "refs": refs.view(np.float64).reshape(refs.shape + (2,)),
+        "sigma2_noise": np.asarray(m.sigma2_noise, np.float64).reshape(-1), "scale_correction": np.asarray(m.scale_correction, np.float64),
+        "pdf_class": np.asarray(m.pdf_class, np.float64), "data_vs_prior_class": np.asarray(m.data_vs_prior_class, np.float64),
+        "rot": np.asarray(s.rot, np.float64), "tilt": np.asarray(s.tilt, np.float64), "psi": np.asarray(s.psi, np.float64),
+        "over_rot": np.asarray(s.over_rot, np.float64), "over_tilt": np.asarray(s.over_tilt, np.float64), "over_psi": np.asarray(s.over_psi, np.float64),
+        "trans_x": np.asarray(s.trans_x, np.float64) * ps, "trans_y": np.asarray(s.trans_y, np.float64) * ps,
+        "over_trans_x": np.asarray(s.over_trans_x, np.float64) * ps, "over_trans_y": np.asarray(s.over_trans_y, np.float64) * ps,
+        "metadata": md, "images": np.asarray(raw.images, np.float32), "group_id": np.asarray(raw.group_id, np.int32),
+    }
+    if raw.dir_off is not None:
+        a.update(dir_off=np.asarray(raw.dir_off, np.int32), dir_idx=np.asarray(raw.dir_idx, np.int32), dir_prior=np.asarray(raw.dir_prior, np.float64),
+                 psi_off=np.asarray(raw.psi_off, np.int32), psi_idx=np.asarray(raw.psi_idx, np.int32), psi_prior=np.asarray(raw.psi_prior, np.float64))
+    return a, md
+
+
+def test_adapter_compiles_against_the_reference_headers():
+    """RELION's own call sites keep compiling: the adapter + the three accelerator call sites of src/ml_optimiser.cpp against the
+    real src/ml_optimiser.h (declaration-only stubs for fftw3.h / tiffio.h / png.h, nothing linked)."""
+    if not os.path.isdir("/root/reference/src"):
+        pytest.skip("reference tree not present (GPU box)")
+    cpp = os.path.join(ROOT, "tests", "cpp")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-w", "-I" + os.path.join(cpp, "relion_stubs"), "-I/root/reference",
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(cpp, "relion_callsites.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+
+
+def test_adapter_without_gpu_throws_relion_error(tmp_path):
     """No CPU fallback: MlDeviceBundle::setDevice throws (the reference's HANDLE_ERROR -> REPORT_ERROR) when there is no device."""
     import torch
     if torch.cuda.is_available():
         pytest.skip("a GPU is present")
-    wl = make_workload(ori_size=16, healpix_order=1, n_particles=1, seed=3)
-    rc, msg, _, _ = _run(wl)
-    assert rc == -1
-    assert "relion_b200" in msg and "no CUDA device" in msg and "relion_b200_adapter.hpp" in msg, msg
+    wl = make_workload(ori_size=16, healpix_order=1, n_particles=2, seed=3, nr_groups=1)
+    raw = raw_pool_from(wl, seed=1)
+    arrays, _ = _workload_arrays(wl, raw)
+    _dump(str(tmp_path / "w.bin"), arrays)
+    r = subprocess.run([_exe(), str(tmp_path / "w.bin"), str(tmp_path / "o.bin"), "1"], capture_output=True, text=True)
+    assert r.returncode == 1
+    assert "relion_b200" in r.stderr and "no CUDA device" in r.stderr and "relion_b200_adapter.hpp" in r.stderr, r.stderr
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kw", [dict(ori_size=32, healpix_order=1, n_particles=10, nr_classes=2, seed=51, snr=0.3),
-                                dict(ori_size=32, healpix_order=2, n_particles=6, nr_classes=1, seed=52, snr=0.2, local_search=True)])
-def test_adapter_estep_equals_python_host_mirror_and_oracle(device, kw):
-    from oracle.bindings import Oracle, Projector, Backprojector
+@pytest.mark.parametrize("kw", [dict(ori_size=32, healpix_order=1, n_particles=21, nr_classes=2, seed=51, snr=0.3, nr_groups=3),
+                                dict(ori_size=40, current_size=28, healpix_order=2, n_particles=14, nr_classes=1, seed=52, snr=0.2, local_search=True, nr_groups=2)])
+def test_cpp_estep_reduction_and_bookkeeping(device, tmp_path, kw):
+    """tests/cpp/estep_multi_gpu: 1-rank run == 2-rank run + combineAllWeightedSums (inside the program), and its metadata rows /
+    weighted sums == the Python host mirror on the same raw pool (same library underneath, bookkeeping done twice)."""
+    import torch
+    from relion_b200 import parallel
     wl = make_workload(**kw)
-    rc, msg, res, bps = _run(wl)
-    assert rc == 0, msg
-    # same library behind both host sides: identical decisions, sums equal up to the order of the atomics
-    device.set_model(wl.model); device.set_sampling(wl.sampling)
+    raw = raw_pool_from(wl, seed=7)
+    arrays, md0 = _workload_arrays(wl, raw, avg_norm=0.95)
+    _dump(str(tmp_path / "w.bin"), arrays)
+    r = subprocess.run([_exe(), str(tmp_path / "w.bin"), str(tmp_path / "o.bin"), "2", "8"], capture_output=True, text=True)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+    if torch.cuda.device_count() >= 2:
+        assert "NCCL" in r.stdout
+    buf = open(tmp_path / "o.bin", "rb").read()
+    nm = struct.unpack_from("<q", buf, 0)[0]
+    md = np.frombuffer(buf, np.float64, nm, 8).reshape(-1, NCOL)
+    npk = struct.unpack_from("<q", buf, 8 + 8 * nm)[0]
+    pack = np.frombuffer(buf, np.float64, npk, 16 + 8 * nm)
+
+    # the Python host mirror on the same pool
+    m, s = wl.model, wl.sampling
+    device.set_model(m); device.set_sampling(s)
     for k, v in enumerate(wl.refs):
         device.set_reference(k, v.astype(np.complex128), wl.r_max, wl.padding_factor)
         device.bp_init(k, wl.bp_shape, wl.r_max, wl.padding_factor)
-    py = device.expectation_some_particles(wl.pool)
-    for f in ("best_ihidden_over", "nr_significant_coarse", "n_fine_samples"):
-        assert np.array_equal(res.particles[f], py.particles[f]), f
-    np.testing.assert_allclose(res.particles["dLL_nolog"], py.particles["dLL_nolog"], rtol=1e-6)
-    np.testing.assert_allclose(res.wsum_pdf_class, py.wsum_pdf_class, rtol=1e-6)
-    for k in range(wl.model.nr_classes):
-        gre, gim, gw = device.bp_get(k)
-        for a, b in ((bps[0][k], gre), (bps[1][k], gim), (bps[2][k], gw)):
-            assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-12)
-    # and against the oracle
-    o = Oracle("port")
-    refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
-    obp = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
-    st, ores, _ = o.estep_pool(wl.model, wl.sampling, refs, obp, wl.pool, num_threads=0, exact_threshold=True)
-    assert st == 0
-    assert np.mean(res.particles["best_ihidden_over"] == ores.particles["best_ihidden_over"]) >= 0.995
-    np.testing.assert_allclose(res.particles["dLL_nolog"], ores.particles["dLL_nolog"], rtol=1e-4)
-    for k in range(wl.model.nr_classes):
-        assert np.abs(bps[2][k] - obp[k].weight).max() <= 5e-3 * np.abs(obp[k].weight).max()
-
-
-@pytest.mark.gpu
-def test_adapter_error_behaviour_on_the_device():
-    """A bad model is reported like the reference reports CUDA errors: RelionError with the library's message."""
-    wl = make_workload(ori_size=16, healpix_order=1, n_particles=1, seed=3)
-    wl.model.current_size = 18            # > ori_size
-    rc, msg, _, _ = _run(wl)
-    assert rc == -1 and "current_size" in msg, msg
+    power = device.pool_prepare(0, raw)
+    res = device.estep_slot(0)
+    p = res.particles
+    if raw.dir_off is not None:
+        gd = np.array([raw.dir_idx[raw.dir_off[i] + p["best_idir"][i]] for i in range(len(p))])
+        gp = np.array([raw.psi_idx[raw.psi_off[i] + p["best_ipsi"][i]] for i in range(len(p))])
+    else:
+        gd, gp = p["best_idir"], p["best_ipsi"]
+    g = (gd * s.n_psi + gp) * s.n_over_rot + p["best_iover_rot"]
+    np.testing.assert_array_equal(md[:, ROT], np.asarray(s.over_rot)[g])
+    np.testing.assert_array_equal(md[:, TILT], np.asarray(s.over_tilt)[g])
+    np.testing.assert_array_equal(md[:, PSI], np.asarray(s.over_psi)[g])
+    it = p["best_itrans"] * s.n_over_trans + p["best_iover_trans"]
+    ps = float(m.pixel_size)
+    rnd = np.where(raw.old_offset > 0, np.floor(raw.old_offset + 0.5), -np.floor(-raw.old_offset + 0.5))
+    np.testing.assert_allclose(md[:, XOFF], rnd[:, 0] + np.asarray(s.over_trans_x)[it] * ps / ps, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(md[:, YOFF], rnd[:, 1] + np.asarray(s.over_trans_y)[it] * ps / ps, rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(md[:, CLASS], p["best_class"] + 1)
+    np.testing.assert_array_equal(md[:, NR_SIGN], p["nr_significant_coarse"])
+    np.testing.assert_allclose(md[:, PMAX], p["pmax"], rtol=1e-6)
+    # dLL = log(sum_weight) - min_diff2 - logsigma2 (acc_ml_optimiser_impl.h:3556-3574)
+    from relion_b200.synth import mresol
+    ir = mresol(m.current_size)
+    sig = np.asarray(m.sigma2_noise, np.float64).reshape(-1)
+    logsigma2 = np.log(2 * np.pi * sig[ir[ir > 0]]).sum()
+    np.testing.assert_allclose(md[:, DLL], p["dLL_nolog"] - logsigma2, rtol=1e-6)
+    # norm correction (:3505-3538): sqrt(2 * (wsum_norm + power beyond the current size)) times the old value / avg
+    hi = power[:, m.current_size // 2 + 1:].astype(np.float64).sum(axis=1)
+    np.testing.assert_allclose(md[:, NORM], (md0[:, NORM] / 0.95) * np.sqrt(2.0 * (p["wsum_norm_correction"] + hi)), rtol=2e-4)
+    # packed weighted sums: MlWsumModel::pack order, LL first, then ave_Pmax, sigma2_offset, avg_norm_correction
+    np.testing.assert_allclose(pack[0], (p["dLL_nolog"] - logsigma2).sum(), rtol=1e-6)
+    np.testing.assert_allclose(pack[1], p["pmax"].astype(np.float64).sum(), rtol=1e-6)
+    np.testing.assert_allclose(pack[2], p["wsum_sigma2_offset"].sum(), rtol=1e-5)
+    np.testing.assert_allclose(pack[3], md[:, NORM].sum(), rtol=1e-9)
+    nshell = m.ori_size // 2 + 1
+    s2 = res.wsum_sigma2_noise.astype(np.float64).sum(axis=0)
+    s2[m.current_size // 2 + 1:] += power[:, m.current_size // 2 + 1:].astype(np.float64).sum(axis=0)
+    np.testing.assert_allclose(pack[7:7 + nshell], s2, rtol=2e-4, atol=1e-9 * s2.max())

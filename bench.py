@@ -65,10 +65,12 @@ WORKLOADS = {
 
 
 def ncu_traffic(workload, pool, kernel):
-    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/traffic_r01.json), or None."""
+    """DRAM bytes per launch of `kernel` from the committed ncu capture of this workload (profiles/traffic_r02.json, written by
+    tools/sass_hash.py record), or None: the capture only counts while the kernel's SASS is the one that was profiled."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "traffic_r01.json"))).get(workload, {})
-        return int(d[kernel]) if d.get("pool") == pool and kernel in d else None
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_hash
+        return sass_hash.traffic(workload, pool, kernel)
     except Exception:
         return None
 
@@ -136,13 +138,28 @@ def build_workload(name, pool, seed, projector=None):
     return make_workload(name, n_particles=P, seed=seed, projector=projector, **kw), P
 
 
-def build_device_workload(dev, name, P, seed=1993):
+def build_device_workload(dev, name, P, seed=1993, host_refs=True, keep_refs=False):
     """The named workload with `P` particles, references already on `dev`; noise-free slices of 3D references come from the
     device projector (rb_project), 2D references are small enough for the numpy generator.  Model / sampling / accumulators
-    are left to the caller (dev.set_model, dev.set_sampling, dev.bp_init)."""
+    are left to the caller (dev.set_model, dev.set_sampling, dev.bp_init).
+    host_refs=False: the references are made on the device from the phantom maps (rb_set_reference_from_map) and wl.refs only
+    carries their shape: much faster for the 400-px box, but no host copy for the CPU oracle.
+    keep_refs=True (with host_refs=False): the references already on the device stay as they are."""
     from relion_b200.workload import make_workload
     from relion_b200 import synth
     kw, _ = WORKLOADS[name]
+    if not host_refs and kw.get("ref_dim", 3) == 3:
+        cur = kw.get("current_size") or kw["ori_size"]
+        r_max = min(cur // 2, kw["ori_size"] // 2)
+        pad = synth.pad_size_for(r_max, 2.0)
+        for k in range(kw.get("nr_classes", 1)):
+            if keep_refs:
+                break
+            vol = synth.make_phantom(kw["ori_size"], n_blobs=kw.get("n_blobs", 40), seed=1993 + 17 * k)
+            dev.set_reference_from_map(k, vol, current_size=cur)
+        shape_only = [np.broadcast_to(np.zeros(1, np.complex64), (pad, pad, pad // 2 + 1))] * kw.get("nr_classes", 1)
+        return make_workload(name, n_particles=P, seed=seed, projector=lambda k, eul, n: dev.project(k, n, eul),
+                             refs_override=(shape_only, r_max), **kw)
     if kw.get("ref_dim", 3) == 2:
         wl = make_workload(name, n_particles=P, seed=seed, **kw)
         wl.model.bp_circle_bound = False                     # backproject2D has no circle bound (BP.h:77)
@@ -211,6 +228,231 @@ def stage_bytes(wl, res):
     return {"coarse": coarse, "fine": fine, "store": store, "coarse_flops": coarse_flops}
 
 
+def build_rooflines(workload, P, wl, stage_ms, stages, by, peak, peak_src, tensor_coarse):
+    """One roofline entry per hot kernel group; the headline `roofline` is the one the metric names (fine diff2, then the
+    back-projection), the dominant kernel of the step follows in `roofline_kernels` with the bound it really has."""
+    total = max(stage_ms["total"], 1e-9)
+    band = stage_ms.get("fine_project", -1.0) > 0
+    entries = []
+
+    def hbm(kernel, stage, ms, note, traffic_kernels):
+        ach = by[stage] / (ms * 1e-3) / 1e9
+        tr = [ncu_traffic(workload, P, k) for k in traffic_kernels]
+        return {"kernel": kernel, "stage": stage, "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "frac_of_nominal_8000": round(ach / 8000.0, 4),
+                "traffic": (sum(tr) if all(t is not None for t in tr) else None), "peak_source": peak_src,
+                "ms": round(ms, 4), "share_of_step": round(ms / total, 3), "algorithmic_bytes_per_launch": by[stage], "note": note}
+
+    if stage_ms["fine"] > 0:
+        if band:
+            entries.append(hbm("k_project_band + k_diff2_slices_sep", "fine", stage_ms["fine"],
+                               "fine diff2 = band-major projection into slices + streaming diff2; algorithmic bytes 64 O_f Np + 12 Np + 4 S_f "
+                               "(SURVEY 8d) over the whole fine stage; the reference cells are L2 hits after the first touch of a shell "
+                               "(traffic), the projection is bound by outstanding gathers per SM, not by DRAM bytes",
+                               ["k_project_band", "k_diff2_slices_sep"]))
+        else:
+            entries.append(hbm("k_diff2_fine_async", "fine", stage_ms["fine"], "orientation-major fine kernel (cross-correlation criterion / RB_BAND=0)", ["k_diff2_fine_async"]))
+    if stage_ms["store"] > 0:
+        entries.append(hbm("k_store_band" if band else "k_store", "store", stage_ms["store"],
+                           "wavg + back-projection; algorithmic bytes (64 + 204) O_bp Np (SURVEY 8d: gather + read-modify-write of 8 corners x 3 arrays); "
+                           "band-major order keeps the accumulator shell in L2, the red.global.add.v4.f32 stream runs at L2 rate", ["k_store_band" if band else "k_store"]))
+    if stage_ms["coarse"] > 0:
+        if tensor_coarse:
+            entries.append({"kernel": "k_gemm_tf32x3", "stage": "coarse", "bound": "tensor", "achieved": stages["coarse"]["tensor_bf16_equivalent_TFLOPs"],
+                            "peak": stages["coarse"]["bf16_peak_TFLOPs"], "unit": "TFLOP/s", "frac": stages["coarse"]["frac_of_tensor_peak"],
+                            "traffic": ncu_traffic(workload, P, "k_gemm_tf32x3"), "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
+                            "ms": round(stage_ms["coarse"], 4), "share_of_step": round(stage_ms["coarse"] / total, 3),
+                            "note": "achieved = tensor-pipe work in bf16-equivalent FLOPs (" + stages["coarse"]["products"] + " products per "
+                                    "fp32-equivalent product, a tf32 product counted twice) over the coarse stage time (operand builders "
+                                    "included); useful fp32-equivalent rate = tensor_TFLOPs_useful"})
+        else:
+            fused = wl.pool.dir_off is not None and os.environ.get("RB_COARSE_FUSED", "1") != "0" and not wl.model.do_cc and wl.sampling.n_trans <= 32
+            ach = by["coarse"] / (stage_ms["coarse"] * 1e-3) / 1e9
+            entries.append({"kernel": "k_coarse_fused" if fused else "k_diff2_coarse", "stage": "coarse", "bound": "l1tex",
+                            "achieved": round(ach, 1), "unit": "GB/s (algorithmic gather bytes; NOT an HBM figure)", "peak": None, "frac": None,
+                            "traffic": ncu_traffic(workload, P, "k_coarse_fused" if fused else "k_diff2_coarse"),
+                            "ms": round(stage_ms["coarse"], 4), "share_of_step": round(stage_ms["coarse"] / total, 3),
+                            "algorithmic_bytes_per_launch": by["coarse"],
+                            "note": "local-search coarse pass: the coarse window of the reference stays in L2 (DRAM traffic ~10x below the "
+                                    "algorithmic gather bytes), the kernel is bound by the L1's line throughput for divergent 16-byte gathers "
+                                    "(ncu: l1tex throughput 76 %, 25.8 sectors per request, tensor pipe 3.5 %): no HBM or tensor roofline applies"})
+    order = {"fine": 0, "store": 1, "coarse": 2}
+    if tensor_coarse and stage_ms["coarse"] >= max(stage_ms["fine"], stage_ms["store"]):
+        order = {"coarse": 0, "fine": 1, "store": 2}     # global searches: the contraction is the step
+    entries.sort(key=lambda e: order[e["stage"]])
+    head = dict(entries[0]) if entries else None
+    return head, entries
+
+
+def quick_workload(dev, name, P, steps=5, warmup=3, parity_sample=0):
+    """Compact result of another BASELINE.json configuration on the same context (single GPU): device-resident and end-to-end
+    particles/s, stage times, roofline entries, optionally parity against the CPU oracle on a few particles."""
+    import torch
+    kw, dflt = WORKLOADS[name]
+    P = P or dflt
+    t0 = time.time()
+    wl = build_device_workload(dev, name, P, seed=1993, host_refs=parity_sample > 0 or kw.get("ref_dim", 3) == 2)
+    dev.set_model(wl.model)
+    dev.set_sampling(wl.sampling)
+    for k in range(wl.model.nr_classes):
+        dev.bp_init(k, wl.bp_shape, wl.r_max, wl.padding_factor)
+    pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+    pool = wl.pool
+    pool.Fimg, pool.Fimg_nomask, pool.Fctf = pin(pool.Fimg.view(np.float32)), pin(pool.Fimg_nomask.view(np.float32)), pin(pool.Fctf)
+    gen_s = time.time() - t0
+    dev.pool_upload(0, pool)
+    for _ in range(warmup):
+        dev.estep_slot_nocopy(0)
+    dev.sync_all_backprojects()
+    res0 = dev.estep_fetch(0)
+    stage_names = ["coarse", "weights_coarse", "fine_setup", "fine", "weights_fine", "store", "total", "fine_project", "fine_diff2", "store_band"]
+    dev.timer_start()
+    for _ in range(steps):
+        dev.estep_slot_nocopy(0)
+    ms = dev.timer_stop()
+    stage_ms = {s: dev.stage_ms(s) for s in stage_names}
+    # end to end: upload / launch / fetch pipelined over two slots, host buffers pinned
+    for wslot in range(2):
+        dev.pool_upload(wslot, pool)
+        dev.estep_slot(wslot)
+    dev.sync_all_backprojects()
+    t1 = time.perf_counter()
+    dev.pool_upload(0, pool)
+    for i in range(steps):
+        dev.estep_slot_nocopy(i % 2)
+        if i >= 1:
+            dev.estep_fetch((i - 1) % 2)
+        if i + 1 < steps:
+            dev.pool_upload((i + 1) % 2, pool)
+    dev.estep_fetch((steps - 1) % 2)
+    dev.sync_all_backprojects()
+    e2e_s = time.perf_counter() - t1
+    peak, peak_src = peaks()
+    by = stage_bytes(wl, res0)
+    stages = {s: {"ms": round(stage_ms[s], 4)} for s in stage_names}
+    gemm_env = os.environ.get("RB_COARSE_GEMM", "1")
+    tensor_coarse = by["coarse_flops"] > 0 and gemm_env != "0" and (gemm_env == "2" or wl.sampling.n_dir * wl.sampling.n_psi >= 32)
+    if tensor_coarse:
+        d = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+        bf16_peak = float(d.get("bf16_tflops_sustained", 1400.0))
+        mixed = int(os.environ.get("RB_GEMM_MODE", "3")) & 1
+        units = 4 if mixed else 6
+        tfs = by["coarse_flops"] / (stage_ms["coarse"] * 1e-3) / 1e12
+        stages["coarse"].update({"tensor_TFLOPs_useful": round(tfs, 1), "tensor_bf16_equivalent_TFLOPs": round(units * tfs, 1),
+                                 "bf16_peak_TFLOPs": round(bf16_peak, 1), "frac_of_tensor_peak": round(units * tfs / bf16_peak, 4),
+                                 "products": "1 tf32 + 2 bf16" if mixed else "3 tf32"})
+    _, entries = build_rooflines(name, P, wl, stage_ms, stages, by, peak, peak_src, tensor_coarse)
+    out = {"config": workload_config(name, P, 1), "value": round(P * steps / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms / steps, 4),
+           "e2e": round(P * steps / e2e_s, 1), "steps": steps, "stages_ms": {k: round(v, 3) for k, v in stage_ms.items() if v >= 0},
+           "roofline_kernels": [{k: e[k] for k in ("kernel", "bound", "achieved", "unit", "peak", "frac", "ms", "share_of_step")} for e in entries],
+           "datagen_s": round(gen_s, 1)}
+    if parity_sample > 0:
+        from oracle.parity import parity_block
+        from oracle.bindings import have_reference
+        try:
+            out["parity"] = parity_block(dev, wl, "reference" if have_reference() else "port", min(P, parity_sample))
+        except Exception as e:  # noqa: BLE001
+            out["parity"] = {"error": repr(e)[:200]}
+    return out
+
+
+def quick_reconstruct(dev, P=1024, steps=3):
+    """BASELINE config #2 in compact form: posed back-projection of P images at 256 px (device-resident and through rb_backproject_posed)."""
+    import torch
+    from relion_b200 import synth
+    n, r_max, pf = 256, 128, 2.0
+    xs = n // 2 + 1
+    rng = np.random.default_rng(1)
+    ctfs = np.stack([synth.CTF(d, d + 300.0, 30.0).fftw_image(n, n, 1.0) for d in rng.uniform(10000, 30000, 8)]).astype(np.float32)
+    ci = rng.integers(0, 8, P)
+    F = torch.empty((P, n, xs, 2), dtype=torch.float32).pin_memory()
+    W = torch.empty((P, n, xs), dtype=torch.float32).pin_memory()
+    Fn, Wn = F.numpy(), W.numpy()
+    for p0 in range(0, P, 256):
+        p1 = min(P, p0 + 256)
+        c = ctfs[ci[p0:p1]]
+        Fn[p0:p1] = rng.standard_normal((p1 - p0, n, xs, 2), dtype=np.float32) * c[..., None]
+        Wn[p0:p1] = c * c
+    Fn[:, 0, 0, :] = 0.0
+    R = synth.inverse_euler_f32(rng.uniform(-180, 180, P), np.degrees(np.arccos(rng.uniform(-1, 1, P))), rng.uniform(0, 360, P))
+    pad = synth.pad_size_for(r_max, pf)
+    dev.bp_init(0, (pad, pad, pad // 2 + 1), r_max, pf)
+    dev.bp_posed_stage(n, F, W, R)
+    for _ in range(2):
+        dev.bp_posed_run(0)
+    dev.sync_all_backprojects()
+    dev.timer_start()
+    for _ in range(steps):
+        dev.bp_posed_run(0)
+    ms = dev.timer_stop()
+    dev.backproject_posed(0, n, F, W, R)
+    dev.sync_all_backprojects()
+    t1 = time.perf_counter()
+    for _ in range(steps):
+        dev.backproject_posed(0, n, F, W, R)
+    dev.sync_all_backprojects()
+    e2e_s = time.perf_counter() - t1
+    iy = np.arange(n); yy = np.where(iy < xs, iy, iy - n)[:, None]; xx = np.arange(xs)[None, :]
+    inside = (xx * xx + yy * yy <= r_max * r_max) & ~((xx == 0) & (yy < 0))
+    npr = float((inside[None] & (Wn[:64] > 0)).sum(axis=(1, 2)).mean())
+    peak, _ = peaks()
+    ach = 204.0 * npr * P * steps / (ms * 1e-3) / 1e9
+    return {"config": workload_config("reconstruct_256", P, 1), "value": round(P * steps / (ms * 1e-3), 1), "unit": UNIT,
+            "ms_per_step": round(ms / steps, 4), "e2e": round(P * steps / e2e_s, 1), "steps": steps,
+            "roofline_kernels": [{"kernel": "k_backproject_posed", "bound": "hbm", "achieved": round(ach, 1), "unit": "GB/s", "peak": peak,
+                                  "frac": round(ach / peak, 4)}]}
+
+
+def other_workloads_block(dev, args):
+    """BASELINE.json configs #1, #2, #4 (regime) and #5 (sizing) in the same driver-run line: compact, single GPU."""
+    out = {}
+    plan = [("class2d_64", lambda: quick_workload(dev, "class2d_64", 2000, parity_sample=64)),
+            ("class3d_256_global", lambda: quick_workload(dev, "class3d_256_global", 256)),
+            ("refine3d_400_local", lambda: quick_workload(dev, "refine3d_400_local", 256)),
+            ("reconstruct_256", lambda: quick_reconstruct(dev))]
+    for name, fn in plan:
+        try:
+            out[name] = fn()
+        except Exception as e:  # noqa: BLE001
+            out[name] = {"error": repr(e)[:300]}
+    return out
+
+
+def allreduce_parity_check(dev, comm, workload, wl, rank, world, per_rank=16):
+    """Every rank builds the SAME small pool (fixed seed), works on its shard, the accumulators and the weighted sums are
+    all-reduced over NCCL (rb_bp_allreduce / rb_wsum_allreduce); rank 0 then runs the whole pool alone and compares."""
+    from relion_b200 import parallel
+    from oracle.parity import pool_range
+    n = per_rank * world
+    chk = build_device_workload(dev, workload, n, seed=4242, host_refs=False, keep_refs=True) if WORKLOADS[workload][0].get("ref_dim", 3) == 3 else wl
+    K = wl.model.nr_classes
+    a, b = parallel.shard_range(n, rank, world)
+    for k in range(K):
+        dev.bp_clear(k)
+    dev.pool_upload(0, pool_range(chk.pool, a, b, wl.model.current_size))
+    res = dev.estep_slot(0)
+    sums = comm.all_reduce_wsums({"LL": np.array(res.particles["dLL_nolog"].sum()), "pmax": np.array(float(res.particles["pmax"].sum()))})
+    comm.all_reduce_backprojectors()
+    if rank != 0:
+        return None
+    tot = [dev.bp_get(k) for k in range(K)]
+    for k in range(K):
+        dev.bp_clear(k)
+    dev.pool_upload(0, pool_range(chk.pool, 0, n, wl.model.current_size))
+    one = dev.estep_slot(0)
+    single = [dev.bp_get(k) for k in range(K)]
+    rel = 0.0
+    for k in range(K):
+        for x, y in zip(tot[k], single[k]):
+            m = float(np.abs(y).max())
+            if m > 0:
+                rel = max(rel, float(np.abs(x - y).max()) / m)
+    ll1 = float(one.particles["dLL_nolog"].sum())
+    ll_rel = abs(float(sums["LL"]) - ll1) / max(abs(ll1), 1e-30)
+    return {"particles": n, "ranks": world, "bp_rel_max": float("%.3g" % rel), "ll_rel": float("%.3g" % ll_rel),
+            "ok": bool(rel <= 1e-5 and ll_rel <= 1e-9), "note": "all-reduced accumulators / LL of the sharded run vs the same particles on rank 0 alone"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -235,6 +477,9 @@ def run_ours(args):
     dev.set_sampling(wl.sampling)
     for k in range(wl.model.nr_classes):
         dev.bp_init(k, wl.bp_shape, wl.r_max, wl.padding_factor)
+    # the per-iteration reduction runs through the library's own NCCL communicator (rb_comm_*, C / NCCL on the library's
+    # stream); torch.distributed only carries the unique id, the barrier and the max over ranks of the timings
+    comm = parallel.DeviceComm(dev) if world > 1 else None
 
     # pinned host copies of the pool (what the RELION adapter would stage per pool)
     pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
@@ -268,8 +513,7 @@ def run_ours(args):
     res0 = dev.estep_fetch(0)
     if world > 1:
         # warm the NCCL communicator / NVLink channels on the accumulator buffers (the first collective sets them up)
-        parallel.all_reduce_backprojectors(dev, wl.model.nr_classes)
-        torch.cuda.synchronize()
+        parallel.all_reduce_backprojectors(dev, wl.model.nr_classes, comm)
     for k in range(wl.model.nr_classes):
         dev.bp_clear(k)
     launches0 = dev.launch_count()
@@ -280,13 +524,23 @@ def run_ours(args):
     dev.timer_start()
     for _ in range(args.steps):
         dev.estep_slot_nocopy(0)
+    allreduce_ms = None
     if world > 1:
-        parallel.all_reduce_backprojectors(dev, wl.model.nr_classes)
-        torch.cuda.synchronize()
+        dev.sync_all_backprojects()
+        t_ar = time.perf_counter()
+        parallel.all_reduce_backprojectors(dev, wl.model.nr_classes, comm)     # rb_bp_allreduce: same stream, complete on return
+        allreduce_ms = (time.perf_counter() - t_ar) * 1e3
     ms = dev.timer_stop()
     for s in stage_names:   # stage events of the last timed step (all steps do identical work)
         stage_ms[s] = dev.stage_ms(s)
     barrier()
+    # ---- N > 1: the reduced result equals a single-GPU run (same particles sharded over the ranks vs all on rank 0) ----
+    allreduce_parity = None
+    if world > 1:
+        allreduce_parity = allreduce_parity_check(dev, comm, args.workload, wl, rank, world)
+        for k in range(wl.model.nr_classes):
+            dev.bp_clear(k)
+        barrier()
     clocks = sampler.stop()
     launches = dev.launch_count() - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
@@ -393,31 +647,7 @@ def run_ours(args):
                                  "tensor_bf16_equivalent_TFLOPs": round(units * tfs, 1), "bf16_peak_TFLOPs": round(bf16_peak, 1),
                                  "frac_of_tensor_peak": round(units * tfs / bf16_peak, 4),
                                  "products": "1 tf32 + 2 bf16" if mixed else "3 tf32"})
-    ach = by[dom] / (stage_ms[dom] * 1e-3) / 1e9
-    roofline = {"kernel": {"coarse": "k_diff2_coarse", "fine": "k_diff2_fine", "store": "k_store"}[dom],
-                "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-                "traffic": None, "peak_source": peak_src, "share_of_step": round(stage_ms[dom] / max(stage_ms["total"], 1e-9), 3),
-                "algorithmic_bytes_per_launch": by[dom]}
-    if dom == "coarse" and tensor_coarse:
-        roofline = {"kernel": "k_gemm_tf32x3", "bound": "tensor", "achieved": stages["coarse"]["tensor_bf16_equivalent_TFLOPs"],
-                    "peak": stages["coarse"]["bf16_peak_TFLOPs"], "unit": "TFLOP/s", "frac": stages["coarse"]["frac_of_tensor_peak"],
-                    "traffic": None, "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained",
-                    "share_of_step": round(stage_ms[dom] / max(stage_ms["total"], 1e-9), 3),
-                    "note": "achieved = tensor-pipe work in bf16-equivalent FLOPs (" + stages["coarse"]["products"] + " products per "
-                            "fp32-equivalent product, a tf32 product counted twice) over the coarse stage time (operand builders "
-                            "included); useful fp32-equivalent rate = tensor_TFLOPs_useful"}
-
-    if dom == "coarse" and not tensor_coarse and wl.pool.dir_off is not None and os.environ.get("RB_COARSE_FUSED", "1") != "0" and not wl.model.do_cc:
-        roofline["kernel"] = "k_coarse_fused"
-    xs_f = wl.model.current_size // 2 + 1
-    if dom == "fine" and os.environ.get("RB_FINE_ASYNC", "1") != "0" and xs_f * 256 + 2 * 256 * 24 <= 74 * 1024:
-        roofline["kernel"] = "k_diff2_fine_async"     # the cp.async-staged variant (kernels_fine.cu: rbk_diff2_fine_pool)
-    roofline["traffic"] = ncu_traffic(args.workload, P, roofline["kernel"])
-    if roofline["bound"] == "hbm":
-        roofline["frac_of_nominal_8000"] = round(roofline["achieved"] / 8000.0, 4)
-        if roofline["kernel"] in ("k_coarse_fused", "k_diff2_coarse"):
-            roofline["note"] = ("algorithmic gather bytes over the kernel time; the 106-px core of the reference stays in L2 (DRAM traffic is "
-                                "~10x smaller, see traffic) and the kernel is bound by L1 line throughput of divergent loads")
+    roofline, roofline_kernels = build_rooflines(args.workload, P, wl, stage_ms, stages, by, peak, peak_src, tensor_coarse)
     # ---- CPU baseline on a bounded sample (all host cores) ------------------------------------------
     # a first sample of --cpu-sample particles sizes a second one of about 12 s of CPU work (capped by the pool)
     # (rank 0 of a single-GPU run only: with N > 1 the other ranks' host threads would share the cores)
@@ -445,6 +675,8 @@ def run_ours(args):
             parity = {"ok": False, "error": repr(e)[:300]}
 
     ref_cuda = ref_cuda_block(wl, args.ref_cuda_sample, stage_ms, P) if args.ref_cuda_sample > 0 else None
+    # the other BASELINE.json configurations, compact (they replace the model / references of the context: last)
+    other = other_workloads_block(dev, args) if (world == 1 and args.other_workloads and args.workload == "refine3d_256_local") else None
 
     pr = res0.particles
     out = {
@@ -458,8 +690,9 @@ def run_ours(args):
                            "mean_bp_orientations": float(pr["n_bp_orient"].mean())},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "e2e_from_raw_images": e2e_raw, "e2e_from_mrc_stacks": e2e_files,
-        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "stages": stages, "cpu_baseline": cpu,
-        "parity": parity, "ref_cuda": ref_cuda, "datagen_s": round(gen_s, 1),
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_kernels": roofline_kernels, "stages": stages, "cpu_baseline": cpu,
+        "parity": parity, "ref_cuda": ref_cuda, "allreduce_ms": None if allreduce_ms is None else round(allreduce_ms, 3),
+        "allreduce_parity": allreduce_parity, "other_workloads": other, "datagen_s": round(gen_s, 1),
     }
     print(json.dumps(out))
     if world > 1:
@@ -800,6 +1033,7 @@ def main():
     ap.add_argument("--pool", type=int, default=0, help="particles per pool per GPU (default: workload specific)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="particles in the bounded CPU sample (0: 8 per host core, at least 64, at most the pool)")
     ap.add_argument("--kernels-only", action="store_true", help="device-resident timed region only (for ncu)")
+    ap.add_argument("--other-workloads", type=int, default=1, help="also run the other BASELINE.json configurations in compact form (N = 1 only)")
     ap.add_argument("--ref-cuda-sample", type=int, default=64, help="particles run through the reference's own CUDA kernels on this GPU (0: off)")
     ap.add_argument("--parity-sample", type=int, default=256, help="particles of the same pool checked against the CPU oracle inside the run (0: off)")
     args = ap.parse_args()

@@ -58,6 +58,27 @@ def classify_significance(device, slot: int, result_particles, oracle, adaptive_
     return out
 
 
+def pool_range(pool, a: int, b: int, current_size: int):
+    """Particles [a, b) of a ParticlePool (per-particle prior lists cut and re-based accordingly)."""
+    from relion_b200.estep import ParticlePool
+    as_np = lambda x, dt: np.asarray(x.numpy() if hasattr(x, "numpy") else x).view(dt) if x is not None else None
+    P = int(pool.group_id.shape[0])
+    size, xs = current_size, current_size // 2 + 1
+    F = as_np(pool.Fimg, np.complex64).reshape(P, size, xs)
+    F0 = as_np(pool.Fimg_nomask, np.complex64).reshape(P, size, xs)
+    Cc = as_np(pool.Fctf, np.float32)
+    sub = ParticlePool(Fimg=np.ascontiguousarray(F[a:b]), Fimg_nomask=np.ascontiguousarray(F0[a:b]),
+                       Fctf=None if Cc is None else np.ascontiguousarray(Cc.reshape(P, size, xs)[a:b]),
+                       group_id=pool.group_id[a:b], optics_group=pool.optics_group[a:b], highres_Xi2=pool.highres_Xi2[a:b],
+                       old_offset=pool.old_offset[a:b], prior_offset=pool.prior_offset[a:b])
+    if pool.dir_off is not None:
+        d0, d1, p0, p1 = pool.dir_off[a], pool.dir_off[b], pool.psi_off[a], pool.psi_off[b]
+        sub.dir_off = (pool.dir_off[a:b + 1] - d0).astype(np.int32); sub.psi_off = (pool.psi_off[a:b + 1] - p0).astype(np.int32)
+        sub.dir_idx = pool.dir_idx[d0:d1]; sub.dir_prior = pool.dir_prior[d0:d1]
+        sub.psi_idx = pool.psi_idx[p0:p1]; sub.psi_prior = pool.psi_prior[p0:p1]
+    return sub
+
+
 def pool_slice(pool, n: int, current_size: int):
     """The first n particles of a ParticlePool (per-particle prior lists cut accordingly)."""
     from relion_b200.estep import ParticlePool

@@ -111,6 +111,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (auto &b : ctx->gemmA_all) b.release();
 	for (auto &b : ctx->wc_buf) b.release();
 	for (auto &b : ctx->prep_buf) b.release();
+	rbk_prepare_release(ctx);
 	for (auto &b : ctx->recon_buf) b.release();
 	for (int i = 0; i < RB_NUM_SLOTS; i++) for (auto &b : ctx->prep_raw[i]) b.release();
 	for (int i = 0; i < 2; i++) { for (auto &b : ctx->posed_buf[i]) b.release(); if (ctx->posed_ev[i]) cudaEventDestroy(ctx->posed_ev[i]); }

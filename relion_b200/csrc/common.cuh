@@ -253,6 +253,7 @@ struct rb_ctx {
 	DevBuf wc_buf[10];
 	DevBuf recon_buf[3];             // reconstruction on the device (kernels_recon.cu): FFT input / output, radial sums
 	DevBuf prep_buf[4];              // device image preparation (kernels_prep.cu): cuFFT input / output, background values, spectra
+	int prep_plan = 0, prep_plan_n = 0, prep_plan_batch = 0;   // this context's batched 2D R2C cuFFT plan (cufftHandle is an int); 0 batch: none
 	DevBuf prep_raw[RB_NUM_SLOTS][4];   // per slot: raw images, shifts, norm factors, CTF parameters (filled on the copy stream)
 	DevBuf posed_buf[2][3];          // staged posed images (F2D, Fctf, matrices), two buffers for upload / compute overlap
 	int posed_n = 0, posed_count = 0;   // what rb_bp_posed_stage left in posed_buf[0]
@@ -304,6 +305,7 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4);
 int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int M, int N, int K, float *dC);
 
 // kernels_prep.cu: getFourierTransformsAndCtfs on the device, batched over the pool
+void rbk_prepare_release(rb_ctx *ctx);
 int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
                      int n, float radius, float cosine_width, float *d_power);
 

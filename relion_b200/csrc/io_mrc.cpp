@@ -269,28 +269,53 @@ struct rb_feed {
 	std::condition_variable cv_work, cv_done;
 	std::deque<std::shared_ptr<FeedJob>> queue;            // jobs with images left to hand out
 	std::map<int, std::shared_ptr<FeedJob>> jobs;          // all unreleased jobs
-	std::map<std::string, rb_mrc *> stacks;                // "only open new stacks" (src/ml_optimiser.cpp:10370-10377)
+	// open stacks, least recently used first in `lru`: at most `max_open` stay open (the reference keeps ONE stack open and
+	// "only opens new stacks", src/ml_optimiser.cpp:10369-10377; particle sets span thousands of per-micrograph files, an
+	// unbounded cache would run into RLIMIT_NOFILE).  Readers hold a shared_ptr, so an evicted stack closes when its last
+	// reader is done with it.
+	std::map<std::string, std::shared_ptr<rb_mrc>> stacks;
+	std::deque<std::string> lru;
+	size_t max_open = 64;
+	std::mutex stack_mu;
 	std::vector<std::thread> threads;
 	int next_ticket = 1;
 	bool stop = false;
 };
 
-static rb_mrc *feed_stack(rb_feed *f, const std::string &path, std::string &err)
+static std::shared_ptr<rb_mrc> feed_stack(rb_feed *f, const std::string &path, std::string &err)
 {
-	std::lock_guard<std::mutex> lk(f->mu);
-	auto it = f->stacks.find(path);
-	if (it != f->stacks.end()) return it->second;
-	rb_mrc *m = nullptr;
-	if (rb_mrc_open(path.c_str(), &m) != RB_OK) { err = rb_last_error(); return nullptr; }
+	{
+		std::lock_guard<std::mutex> lk(f->stack_mu);
+		auto it = f->stacks.find(path);
+		if (it != f->stacks.end())
+		{
+			// move to the most-recently-used end
+			for (auto q = f->lru.begin(); q != f->lru.end(); ++q) if (*q == path) { f->lru.erase(q); break; }
+			f->lru.push_back(path);
+			return it->second;
+		}
+	}
+	// open / validate outside every lock: submit, wait and the other readers are not held up by the file system
+	rb_mrc *raw = nullptr;
+	if (rb_mrc_open(path.c_str(), &raw) != RB_OK) { err = rb_last_error(); return nullptr; }
+	std::shared_ptr<rb_mrc> m(raw, [](rb_mrc *x) { rb_mrc_close(x); });
 	if (m->h.nx != f->image_size || m->h.ny != f->image_size)
 	{
 		char msg[512];
 		snprintf(msg, sizeof(msg), "incorrect image size: %s holds %d x %d images, the pool expects %d", path.c_str(), m->h.nx, m->h.ny, f->image_size);
 		err = msg;                                                                         // src/ml_optimiser.cpp:10382-10387
-		rb_mrc_close(m);
 		return nullptr;
 	}
+	std::lock_guard<std::mutex> lk(f->stack_mu);
+	auto it = f->stacks.find(path);
+	if (it != f->stacks.end()) return it->second;                                         // another reader opened it meanwhile
 	f->stacks[path] = m;
+	f->lru.push_back(path);
+	while (f->lru.size() > f->max_open)
+	{
+		f->stacks.erase(f->lru.front());                                                   // closes once no reader holds it
+		f->lru.pop_front();
+	}
 	return m;
 }
 
@@ -311,12 +336,12 @@ static void feed_worker(rb_feed *f)
 		}
 		std::string err;
 		int st = RB_OK;
-		rb_mrc *m = feed_stack(f, job->paths[i], err);
+		std::shared_ptr<rb_mrc> m = feed_stack(f, job->paths[i], err);
 		if (!m) st = RB_ERR_ARG;
 		else
 		{
 			const size_t npix = (size_t) f->image_size * f->image_size;
-			st = mrc_read_one(m, job->index[i], f->buffers[job->buffer] + (size_t) i * npix, raw);
+			st = mrc_read_one(m.get(), job->index[i], f->buffers[job->buffer] + (size_t) i * npix, raw);
 			if (st != RB_OK) err = rb_last_error();
 		}
 		{
@@ -336,6 +361,7 @@ extern "C" int rb_feed_create(int image_size, int max_particles, int depth, int 
 	}
 	std::unique_ptr<rb_feed> f(new rb_feed);
 	f->image_size = image_size; f->max_particles = max_particles; f->depth = depth;
+	if (const char *e = getenv("RB_FEED_MAX_OPEN")) { const long v = atol(e); if (v >= 1) f->max_open = (size_t) v; }
 	const size_t bytes = (size_t) max_particles * image_size * image_size * sizeof(float);
 	// page-locked so that the upload of a pool is one asynchronous copy; a machine without a CUDA device (I/O unit tests)
 	// gets ordinary memory - this is I/O staging, the E-step itself has no such fallback
@@ -429,7 +455,7 @@ extern "C" void rb_feed_destroy(rb_feed *f)
 		f->cv_work.notify_all();
 	}
 	for (auto &t : f->threads) t.join();
-	for (auto &kv : f->stacks) rb_mrc_close(kv.second);
+	f->stacks.clear(); f->lru.clear();               // shared_ptr deleters close the files
 	for (float *p : f->buffers) { if (f->pinned) cudaFreeHost(p); else free(p); }
 	delete f;
 }

@@ -147,24 +147,29 @@ k_prep_ctf(const double *par, float *Fctf, int cs, double xs_angstrom)
 	}
 }
 
-struct PrepPlan { int n = 0, batch = 0; cufftHandle plan = 0; bool valid = false; };
-static PrepPlan g_plan;
-
+// One plan per context: a cuFFT plan belongs to the device that was current when it was made, and contexts run on their own host threads.
 static int get_plan(rb_ctx *ctx, int n, int batch, cufftHandle *out)
 {
-	if (!g_plan.valid || g_plan.n != n || g_plan.batch != batch)
+	if (ctx->prep_plan_batch == 0 || ctx->prep_plan_n != n || ctx->prep_plan_batch != batch)
 	{
-		if (g_plan.valid) cufftDestroy(g_plan.plan);
-		g_plan.valid = false;
+		if (ctx->prep_plan_batch) cufftDestroy((cufftHandle) ctx->prep_plan);
+		ctx->prep_plan_batch = 0;
 		int dims[2] = {n, n};
-		cufftResult r = cufftPlanMany(&g_plan.plan, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, batch);
+		cufftHandle h;
+		cufftResult r = cufftPlanMany(&h, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_R2C, batch);
 		if (r != CUFFT_SUCCESS) { rb_set_error("cufftPlanMany(%d x %d, batch %d) failed (%d)", n, n, batch, (int) r); return RB_ERR_CUDA; }
-		g_plan.n = n; g_plan.batch = batch; g_plan.valid = true;
+		ctx->prep_plan = (int) h; ctx->prep_plan_n = n; ctx->prep_plan_batch = batch;
 	}
-	cufftResult r = cufftSetStream(g_plan.plan, ctx->stream);
+	cufftResult r = cufftSetStream((cufftHandle) ctx->prep_plan, ctx->stream);
 	if (r != CUFFT_SUCCESS) { rb_set_error("cufftSetStream failed (%d)", (int) r); return RB_ERR_CUDA; }
-	*out = g_plan.plan;
+	*out = (cufftHandle) ctx->prep_plan;
 	return RB_OK;
+}
+
+void rbk_prepare_release(rb_ctx *ctx)
+{
+	if (ctx->prep_plan_batch) cufftDestroy((cufftHandle) ctx->prep_plan);
+	ctx->prep_plan_batch = 0;
 }
 
 // d_raw: [P][n][n] device, d_shift [P][2], d_norm [P], d_ctfpar [P][9] (nullptr: Fctf untouched), outputs into the slot buffers
@@ -185,13 +190,13 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 	dim3 gr((n * n + 255) / 256 > 64 ? 64 : (n * n + 255) / 256, P), gw((cs * xo + 255) / 256 > 64 ? 64 : (cs * xo + 255) / 256, P);
 	// unmasked image -> Fimg_nomask
 	k_prep_real<false><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
-	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed"); return RB_ERR_CUDA; }
+	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 	ctx->launches++;
 	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fnomask.as<float2>(), n, cs, scale); RB_LAUNCH_CHECK(ctx);
 	// masked image -> Fimg, power spectrum, highres_Xi2
 	k_prep_mask_bg<<<P, 256, 0, ctx->stream>>>(A, bBg.as<float>()); RB_LAUNCH_CHECK(ctx);
 	k_prep_real<true><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
-	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed"); return RB_ERR_CUDA; }
+	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 	ctx->launches++;
 	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fimg.as<float2>(), n, cs, scale); RB_LAUNCH_CHECK(ctx);
 	if (cs < n)

@@ -269,3 +269,34 @@ def test_results_go_back_into_the_particle_table(tmp_path):
     assert t.column("rlnNrOfSignificantSamples", np.int64).tolist() == [0, 12, 345, 0]
     np.testing.assert_allclose(t.column("rlnNormCorrection", np.float64), [1.25, 1.1, 0.9, 1.0])
     assert again.group_id.tolist() == ps.group_id.tolist() and again.image_index.tolist() == ps.image_index.tolist()
+
+
+def test_feed_keeps_a_bounded_number_of_stacks_open(tmp_path, monkeypatch):
+    """Particle sets span thousands of per-micrograph stacks: the feed keeps at most RB_FEED_MAX_OPEN of them open (least
+    recently used closed first; the reference keeps one, src/ml_optimiser.cpp:10369-10377), so the descriptor count stays
+    bounded while every image still arrives."""
+    monkeypatch.setenv("RB_FEED_MAX_OPEN", "3")
+    n, per, nstacks = 8, 4, 20
+    rng = np.random.default_rng(3)
+    stacks = []
+    for s in range(nstacks):
+        imgs = rng.standard_normal((per, n, n)).astype(np.float32)
+        path = str(tmp_path / ("mic%03d.mrcs" % s))
+        particle_io.write_mrc(path, imgs, 1.0)
+        stacks.append((path, imgs))
+    fds0 = len(os.listdir("/proc/self/fd"))
+    feed = particle_io.ParticleFeed(image_size=n, max_particles=per * 2, depth=2, n_threads=3)
+    peak = 0
+    for rep in range(2):                                   # second sweep re-opens evicted stacks
+        for s in range(0, nstacks, 2):
+            paths = [stacks[s][0]] * per + [stacks[s + 1][0]] * per
+            idx = list(range(per)) * 2
+            t = feed.submit(paths, idx)
+            got = feed.wait(t)
+            np.testing.assert_array_equal(got[:per], stacks[s][1])
+            np.testing.assert_array_equal(got[per:], stacks[s + 1][1])
+            feed.release(t)
+            peak = max(peak, len(os.listdir("/proc/self/fd")) - fds0)
+    feed.close()
+    assert peak <= 3 + 3, peak                             # the cache limit plus stacks still held by the reader threads
+    assert len(os.listdir("/proc/self/fd")) <= fds0 + 1

@@ -427,6 +427,10 @@ def allreduce_parity_check(dev, comm, workload, wl, rank, world, per_rank=16):
     chk = build_device_workload(dev, workload, n, seed=4242, host_refs=False, keep_refs=True) if WORKLOADS[workload][0].get("ref_dim", 3) == 3 else wl
     K = wl.model.nr_classes
     a, b = parallel.shard_range(n, rank, world)
+    # the timed workload's model (noise spectra, group scales) is seeded per rank: the check runs under the check pool's own
+    # model, which is the same on every rank, as the replicated model of a real run is
+    dev.set_model(chk.model)
+    dev.set_sampling(chk.sampling)
     for k in range(K):
         dev.bp_clear(k)
     dev.pool_upload(0, pool_range(chk.pool, a, b, wl.model.current_size))
@@ -434,6 +438,7 @@ def allreduce_parity_check(dev, comm, workload, wl, rank, world, per_rank=16):
     sums = comm.all_reduce_wsums({"LL": np.array(res.particles["dLL_nolog"].sum()), "pmax": np.array(float(res.particles["pmax"].sum()))})
     comm.all_reduce_backprojectors()
     if rank != 0:
+        dev.set_model(wl.model); dev.set_sampling(wl.sampling)
         return None
     tot = [dev.bp_get(k) for k in range(K)]
     for k in range(K):
@@ -448,6 +453,7 @@ def allreduce_parity_check(dev, comm, workload, wl, rank, world, per_rank=16):
             if m > 0:
                 rel = max(rel, float(np.abs(x - y).max()) / m)
     ll1 = float(one.particles["dLL_nolog"].sum())
+    dev.set_model(wl.model); dev.set_sampling(wl.sampling)
     ll_rel = abs(float(sums["LL"]) - ll1) / max(abs(ll1), 1e-30)
     return {"particles": n, "ranks": world, "bp_rel_max": float("%.3g" % rel), "ll_rel": float("%.3g" % ll_rel),
             "ok": bool(rel <= 1e-5 and ll_rel <= 1e-9), "note": "all-reduced accumulators / LL of the sharded run vs the same particles on rank 0 alone"}
@@ -552,9 +558,9 @@ def run_ours(args):
     if args.kernels_only:
         # profiling runs (ncu): the device-resident timed region only
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                              "ms_per_step": round(ms_max / args.steps, 4), "stages": {k: round(v, 4) for k, v in stage_ms.items()},
-                              "config": workload_config(args.workload, P, world), "note": "--kernels-only (profiling run)"}))
+            emit({"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                  "ms_per_step": round(ms_max / args.steps, 4), "stages": {k: round(v, 4) for k, v in stage_ms.items()},
+                  "config": workload_config(args.workload, P, world), "note": "--kernels-only (profiling run)"})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -694,7 +700,7 @@ def run_ours(args):
         "parity": parity, "ref_cuda": ref_cuda, "allreduce_ms": None if allreduce_ms is None else round(allreduce_ms, 3),
         "allreduce_parity": allreduce_parity, "other_workloads": other, "datagen_s": round(gen_s, 1),
     }
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
     if parity is not None and not parity.get("ok", False):
@@ -865,7 +871,7 @@ def run_reference(args):
            "config": workload_config(args.workload, P, max(world, args.gpus)),
            "cpu_baseline": cpu,
            "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
 
 
 def run_reconstruct(args):
@@ -985,7 +991,7 @@ def run_reconstruct(args):
                         "frac": round(ach / peak, 4), "traffic": ncu_traffic("reconstruct_256", P, "k_backproject_posed"), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": bytes_per_launch},
            "cpu_baseline": cpu}
-    print(json.dumps(out))
+    emit(out)
     if world > 1:
         dist.destroy_process_group()
 
@@ -1016,7 +1022,7 @@ def run_reference_reconstruct(args):
             times.append(time.perf_counter() - t0)
     v = round(ns * len(times) / sum(times), 2)
     cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": f"{ns} images per step, {len(times)} step(s), one thread, double accumulators"}
-    print(json.dumps({"impl": "reference", "metric": "particles/sec, posed back-projection only (relion_reconstruct path, 256 px, pad 2)",
+    emit(({"impl": "reference", "metric": "particles/sec, posed back-projection only (relion_reconstruct path, 256 px, pad 2)",
                       "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                       "ms_per_step": round(1e3 * ns / v, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                       "data": "synthetic", "config": workload_config("reconstruct_256", args.pool or 2048, max(int(os.environ.get("WORLD_SIZE", "1")), args.gpus)),
@@ -1039,6 +1045,31 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print on file descriptor 1 while the run lasts
+    # (NCCL's version banner, OpenMP notices) goes to stderr; the line itself is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _dispatch(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(json_fd, 1)
+        os.close(json_fd)
+        if _JSON_LINES:
+            sys.stdout.write(_JSON_LINES[-1] + "\n")
+            sys.stdout.flush()
+
+
+_JSON_LINES = []
+
+
+def emit(obj):
+    """The run's result line (the last one emitted is the one printed on stdout)."""
+    _JSON_LINES.append(json.dumps(obj))
+
+
+def _dispatch(args):
     if args.workload == "reconstruct_256" and args.impl == "ours":
         run_reconstruct(args)
     elif args.impl == "reference":

@@ -215,6 +215,13 @@ typedef struct {
 	                                passes (cuda_kernel_diff2_CC_coarse / _fine, diff2.cuh:336-640), weight one for the
 	                                best pose and zero elsewhere (:2012-2071); rb_particle_out.dLL_nolog is then
 	                                -min_diff2, which IS the particle's dLL (:3571-3572, no logsigma2 term)       */
+	const double *prior_offset_class; /* [nr_classes][2] pixels: mymodel.prior_offset_class, the per-class centre of the
+	                                translation prior of 2D references (ref_dim == 2: acc_ml_optimiser_impl.h:2100-2104
+	                                for the fine-pass weights, :2673-2677 for wsum_sigma2_offset).  As in the reference
+	                                the coarse-pass weights use the FIRST class' centre for every class (the coarse kernel
+	                                indexes pdf_offset by translation only, :2187-2196).  Pass it for 2D references
+	                                (zeros at iteration 1); NULL (3D references): rb_particles.prior_offset is the centre
+	                                and rb_pool_out.wsum_prior_offset_class stays untouched                       */
 } rb_model;
 int rb_set_model(rb_ctx *ctx, const rb_model *m);
 /* Call order: rb_set_model, rb_set_sampling, then (without orientational priors) rb_set_pdf_direction:
@@ -279,6 +286,9 @@ typedef struct {
 	float *wsum_sigma2_noise;    /* [P][ori_size/2+1] per-particle thr_wsum_sigma2_noise (may be NULL) */
 	double *wsum_pdf_direction;  /* [nr_classes][n_dir]  += over the pool (may be NULL)           */
 	double *wsum_pdf_class;      /* [nr_classes]         += over the pool (may be NULL)           */
+	double *wsum_prior_offset_class; /* [nr_classes][2] += over the pool, Angstrom: thr_wsum_prior_offsetx/y_class
+	                                (acc_ml_optimiser_impl.h:2847-2851), accumulated when rb_model.prior_offset_class is
+	                                given (2D references); may be NULL                                              */
 } rb_pool_out;
 
 /* Batched E-step over a pool: coarse diff2 -> weights/significance -> fine diff2 -> weights ->

@@ -279,6 +279,12 @@ public:
 		rm.ctf_premultiplied = o.mydata.obsModel.getCtfPremultiplied(0);
 		rm.bp_circle_bound = 1;
 		rm.do_cc = (o.iter == 1 && o.do_firstiter_cc) || o.do_always_cc;                   // :1164
+		h_prior_class.clear();
+		if (m.ref_dim == 2 && m.nr_bodies == 1)                                             // :2100-2104, :2673-2677
+		{
+			for (int k = 0; k < K; k++) { h_prior_class.push_back(XX(m.prior_offset_class[k])); h_prior_class.push_back(YY(m.prior_offset_class[k])); }
+			rm.prior_offset_class = h_prior_class.data();
+		}
 		RB_TRY(rb_set_model(ctx, &rm));
 
 		// ---- sampling tables (HealpixSampling stays RELION's: getOrientations :1832, getTranslationsInPixel :1724) ----
@@ -364,7 +370,7 @@ public:
 
 private:
 	// host copies the C-ABI structs point into (alive until the next setupFixedSizedObjects)
-	std::vector<double> h_sigma2, h_scale, h_pdf_class, h_pdf_dir, h_dvp, s_rot, s_tilt, s_psi, s_orot, s_otilt, s_opsi, s_tx, s_ty, s_otx, s_oty;
+	std::vector<double> h_sigma2, h_scale, h_pdf_class, h_prior_class, h_pdf_dir, h_dvp, s_rot, s_tilt, s_psi, s_orot, s_otilt, s_opsi, s_tx, s_ty, s_otx, s_oty;
 	MlDeviceBundle(const MlDeviceBundle &);
 	MlDeviceBundle &operator=(const MlDeviceBundle &);
 };
@@ -469,8 +475,10 @@ public:
 		std::vector<rb_particle_out> parts(P);
 		std::vector<float> wsum_sigma2((size_t) P * nshell);
 		const int n_dir = (int) o.sampling.NrDirections();
-		std::vector<double> wsum_pdf_dir((size_t) K * n_dir, 0.), wsum_pdf_class(K, 0.);
+		std::vector<double> wsum_pdf_dir((size_t) K * n_dir, 0.), wsum_pdf_class(K, 0.), wsum_prior_class(2 * (size_t) K, 0.);
 		rb_pool_out out;
+		memset(&out, 0, sizeof(out));
+		out.wsum_prior_offset_class = wsum_prior_class.data();
 		out.particles = parts.data(); out.wsum_sigma2_noise = wsum_sigma2.data(); out.wsum_pdf_direction = wsum_pdf_dir.data(); out.wsum_pdf_class = wsum_pdf_class.data();
 		RB_TRY(rb_pool_prepare(bundle->ctx, 0, &raw, power_img.data()));
 		RB_TRY(rb_estep_slot(bundle->ctx, 0, &out, o.do_skip_maximization ? 1u : 0u));
@@ -539,6 +547,11 @@ public:
 			for (int k = 0; k < K; k++)
 			{
 				w.pdf_class[k] += wsum_pdf_class[k];
+				if (o.mymodel.ref_dim == 2)                                                                                     // :3639-3642
+				{
+					XX(w.prior_offset_class[k]) += wsum_prior_class[2 * k];
+					YY(w.prior_offset_class[k]) += wsum_prior_class[2 * k + 1];
+				}
 				if (!(o.do_skip_align || o.do_skip_rotate))
 					for (int d = 0; d < n_dir && d < (int) MULTIDIM_SIZE(w.pdf_direction[k]); d++) DIRECT_MULTIDIM_ELEM(w.pdf_direction[k], d) += wsum_pdf_dir[(size_t) k * n_dir + d];
 			}

@@ -245,6 +245,10 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 	const double oldx = pool->old_offset[2 * p], oldy = pool->old_offset[2 * p + 1];
 	const double prx = pool->prior_offset[2 * p], pry = pool->prior_offset[2 * p + 1];
 	for (int k = 0; k < Kc; k++)
+	{
+		// :2094-2111: 2D references carry their own prior centre (mymodel.prior_offset_class), else op.prior
+		const double prx = m->prior_offset_class ? m->prior_offset_class[2 * k] : pool->prior_offset[2 * p];
+		const double pry = m->prior_offset_class ? m->prior_offset_class[2 * k + 1] : pool->prior_offset[2 * p + 1];
 		for (int t = 0; t < T; t++)
 		{
 			// NB: sampling.translations_x are in Angstrom in RELION >= 3.1 and converted per pixel size; the
@@ -259,10 +263,12 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 			pdf_offset_zeros[(size_t) k * T + t] = z;
 			pdf_offset[(size_t) k * T + t] = (float) pdf;
 		}
+	}
 
 	// ---- weights, pass 0 (:2180-2350) ----
 	// NB the reference passes ONE pdf_offset block (class 0's) to the coarse kernel for all classes
-	// (kernel indexes itrans only); for 3D references all classes share the same prior, so identical.
+	// (kernel indexes itrans only, :2187-2196); for 3D references all classes share the same prior, so identical;
+	// for 2D references with their own prior centres the coarse weights of every class use the first class' centre.
 	std::vector<unsigned char> significant(nCoarse, 0);
 	rb_particle_out &po = out->particles[p];
 	memset(&po, 0, sizeof(po));
@@ -507,13 +513,18 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 		{
 			double xs = oldx + s->over_trans_x[it], ys = oldy + s->over_trans_y[it];         // :2703-2704
 			oox[it] = (float) xs; ooy[it] = (float) ys;
-			double dx = prx - xs, dy = pry - ys;
-			oo2[it] = (float) (dx * dx + dy * dy);                                           // :2736
 		}
 		for (int k = 0; k < Kc; k++)
 		{
 			ClassFine &c = cf[k];
 			if ((m->pdf_class[k] == 0.) || c.rot.empty()) continue;
+			const double cprx = m->prior_offset_class ? m->prior_offset_class[2 * k] : prx;   // :2673-2686
+			const double cpry = m->prior_offset_class ? m->prior_offset_class[2 * k + 1] : pry;
+			for (int it = 0; it < Tf; it++)
+			{
+				double dx = cprx - (oldx + s->over_trans_x[it]), dy = cpry - (oldy + s->over_trans_y[it]);
+				oo2[it] = (float) (dx * dx + dy * dy);                                       // :2736
+			}
 			// makeJobsForCollect (acc_helper_functions_impl.h:104-139): one job per run of equal rot_idx
 			std::vector<unsigned long> jo, je;
 			if (c.weightNum)
@@ -541,6 +552,11 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 				po.sumw += pw[n];
 				acc_pdf_class[k] += pw[n];
 				po.wsum_sigma2_offset += m->pixel_size * m->pixel_size * ps2[n];
+				if (m->prior_offset_class)                                                   // :2847-2851 (ref_dim == 2)
+				{
+					acc_pdf_class[Kc + 2 * k] += m->pixel_size * ppx[n];
+					acc_pdf_class[Kc + 2 * k + 1] += m->pixel_size * ppy[n];
+				}
 			}
 		}
 	}
@@ -730,7 +746,7 @@ int oracle_estep_pool(const ok_kernel_table *K, const rb_model *m, const rb_samp
 	const int Kc = m->nr_classes;
 	int status = 0;
 	int nt = num_threads > 0 ? num_threads : omp_get_max_threads();
-	std::vector<std::vector<double>> tdir(nt, std::vector<double>((size_t) Kc * s->n_dir, 0.)), tcls(nt, std::vector<double>(Kc, 0.));
+	std::vector<std::vector<double>> tdir(nt, std::vector<double>((size_t) Kc * s->n_dir, 0.)), tcls(nt, std::vector<double>((size_t) 3 * Kc, 0.));   // [Kc] pdf_class + [Kc][2] prior-offset sums
 #pragma omp parallel for schedule(dynamic, 1) num_threads(nt)
 	for (int p = 0; p < P; p++)
 	{
@@ -746,6 +762,8 @@ int oracle_estep_pool(const ok_kernel_table *K, const rb_model *m, const rb_samp
 	{
 		if (out->wsum_pdf_direction) for (size_t i = 0; i < tdir[t].size(); i++) out->wsum_pdf_direction[i] += tdir[t][i];
 		if (out->wsum_pdf_class) for (int k = 0; k < Kc; k++) out->wsum_pdf_class[k] += tcls[t][k];
+		if (out->wsum_prior_offset_class && m->prior_offset_class)
+			for (int k = 0; k < 2 * Kc; k++) out->wsum_prior_offset_class[k] += tcls[t][Kc + k];
 	}
 	return status;
 }

@@ -54,6 +54,7 @@ class rb_model(C.Structure):
         ("do_ctf_correction", C.c_int), ("refs_are_ctf_corrected", C.c_int), ("do_scale_correction", C.c_int),
         ("do_map", C.c_int), ("ctf_premultiplied", C.c_int), ("bp_circle_bound", C.c_int),
         ("do_cc", C.c_int),
+        ("prior_offset_class", c_double_p),
     ]
 
 
@@ -102,6 +103,7 @@ class rb_pool_out(C.Structure):
         ("wsum_sigma2_noise", c_float_p),
         ("wsum_pdf_direction", c_double_p),
         ("wsum_pdf_class", c_double_p),
+        ("wsum_prior_offset_class", c_double_p),
     ]
 
 

@@ -125,6 +125,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 
 extern "C" int rb_sync(rb_ctx *ctx)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx, "rb_sync: ctx is NULL");
 	RB_CUDA(cudaStreamSynchronize(ctx->copy_stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -154,6 +155,7 @@ int rb_stage_end(rb_ctx *ctx, const char *name)
 }
 extern "C" double rb_stage_ms(rb_ctx *ctx, const char *stage)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	if (!ctx || !stage) return -1.;
 	auto it = ctx->stage_ev.find(stage);
 	if (it == ctx->stage_ev.end()) return -1.;
@@ -164,12 +166,14 @@ extern "C" double rb_stage_ms(rb_ctx *ctx, const char *stage)
 
 extern "C" int rb_timer_start(rb_ctx *ctx)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx, "rb_timer_start: ctx is NULL");
 	return rb_stage_begin(ctx, "__timer");
 }
 
 extern "C" int rb_timer_stop(rb_ctx *ctx, double *ms)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && ms, "rb_timer_stop: NULL argument");
 	RB_CHECK(rb_stage_end(ctx, "__timer"));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -285,6 +289,7 @@ extern "C" int rb_bp_init(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int 
 
 extern "C" int rb_bp_clear(rb_ctx *ctx, int k)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_clear: accumulator %d not initialised", k);
 	const RbBackprojector &b = ctx->bp[k];
 	RB_CUDA(cudaMemsetAsync(b.vol, 0, (size_t) b.mdlX * b.mdlY * b.mdlZ * sizeof(float4), ctx->stream));
@@ -293,6 +298,7 @@ extern "C" int rb_bp_clear(rb_ctx *ctx, int k)
 
 extern "C" int rb_bp_get(rb_ctx *ctx, int k, float *real, float *imag, float *weight)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_get: accumulator %d not initialised", k);
 	const RbBackprojector &b = ctx->bp[k];
 	size_t n = (size_t) b.mdlX * b.mdlY * b.mdlZ;
@@ -603,7 +609,13 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 		for (int i = 0; i < nshell; i++)
 			mv[(size_t) g * nshell + i] = (float) (1. / (m->sigma2_fudge * m->sigma2_noise[(size_t) g * nshell + i]));
 	RB_CHECK(upload(ctx, ctx->m_minvs2, mv.data(), mv.size() * 4));
-	RB_CHECK(upload(ctx, ctx->m_pdf_class, m->pdf_class, K * sizeof(double)));
+	{
+		// [K] pdf_class, then [K][2] prior_offset_class
+		std::vector<double> pc((size_t) 3 * K, 0.);
+		for (int k = 0; k < K; k++) pc[k] = m->pdf_class[k];
+		if (m->prior_offset_class) for (int k = 0; k < 2 * K; k++) pc[K + k] = m->prior_offset_class[k];
+		RB_CHECK(upload(ctx, ctx->m_pdf_class, pc.data(), pc.size() * sizeof(double)));
+	}
 	std::vector<unsigned char> dvp((size_t) K * nshell, 0);
 	if (m->data_vs_prior_class)
 		for (size_t i = 0; i < dvp.size(); i++) dvp[i] = m->data_vs_prior_class[i] > 3.;
@@ -643,6 +655,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	}
 	d.minvs2 = ctx->m_minvs2.as<float>();
 	d.pdf_class = ctx->m_pdf_class.as<double>();
+	d.prior_offset_class = m->prior_offset_class ? ctx->m_pdf_class.as<double>() + K : nullptr;
 	d.pdf_direction = nullptr;
 	d.dvp_gt3 = ctx->m_dvp.as<unsigned char>();
 	d.pixel_size = m->pixel_size;
@@ -661,7 +674,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	}
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->h_model.sigma2_noise = nullptr; ctx->h_model.scale_correction = nullptr; ctx->h_model.pdf_class = nullptr;
-	ctx->h_model.data_vs_prior_class = nullptr;
+	ctx->h_model.data_vs_prior_class = nullptr; ctx->h_model.prior_offset_class = nullptr;
 	ctx->has_model = true;
 	return RB_OK;
 }
@@ -669,6 +682,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 // pdf_direction depends on both model (values) and sampling (n_dir): dedicated setter so call order is free
 extern "C" int rb_set_pdf_direction(rb_ctx *ctx, const double *pdf_direction)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && pdf_direction && ctx->has_model && ctx->has_sampling, "rb_set_pdf_direction: needs model and sampling");
 	RB_CHECK(upload(ctx, ctx->m_pdf_dir, pdf_direction, (size_t) ctx->d_model.nr_classes * ctx->d_samp.n_dir * sizeof(double)));
 	ctx->d_model.pdf_direction = ctx->m_pdf_dir.as<double>();
@@ -772,10 +786,10 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 	RB_CHECK(s.state.ensure(P * sizeof(RbPartState)));
 	RB_CHECK(s.Mweight.ensure((size_t) s.total_coarse * 4));
 	RB_CHECK(s.pdf_orient.ensure((size_t) s.total_prior * 4)); RB_CHECK(s.pdf_orient_zero.ensure((size_t) s.total_prior));
-	RB_CHECK(s.pdf_offset.ensure((size_t) P * T * 4)); RB_CHECK(s.pdf_offset_zero.ensure((size_t) P * T));
+	RB_CHECK(s.pdf_offset.ensure((size_t) P * M.prior_classes() * T * 4)); RB_CHECK(s.pdf_offset_zero.ensure((size_t) P * M.prior_classes() * T));
 	RB_CHECK(s.counters.ensure(64));
 	RB_CHECK(s.shells.ensure((size_t) P * M.nshell * 4));
-	RB_CHECK(s.out_pdf_dir.ensure((size_t) K * S.n_dir * 8)); RB_CHECK(s.out_pdf_class.ensure((size_t) K * 8));
+	RB_CHECK(s.out_pdf_dir.ensure((size_t) K * S.n_dir * 8)); RB_CHECK(s.out_pdf_class.ensure((size_t) 3 * K * 8));   // [K] + [K][2] prior-offset sums
 	// fine-pass capacity: all coarse samples significant is the worst case; bound it by a budget
 	const long long ov = (long long) S.n_over_rot * S.n_over_trans;
 	size_t cap_fs = (size_t) std::min<long long>(s.total_coarse * ov, (long long) env_size("RB_FINE_SAMPLE_CAP", (size_t) 1 << 26));
@@ -826,6 +840,7 @@ extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool) {
 // getFourierTransformsAndCtfs for the whole pool on the device (kernels_prep.cu)
 extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *raw, float *power_img)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && raw, "rb_pool_prepare: NULL argument");
 	if (!ctx->has_model || !ctx->has_sampling) { rb_set_error("rb_pool_prepare: set model and sampling first"); return RB_ERR_STATE; }
 	const int P = raw->n_particles, n = raw->image_size;
@@ -906,6 +921,7 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 // read a staged / prepared pool back (tests): any pointer may be NULL
 extern "C" int rb_pool_download(rb_ctx *ctx, int slot, float *Fimg, float *Fimg_nomask, float *Fctf, double *highres_Xi2)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_pool_download: slot %d not staged", slot);
 	PoolSlot &s = ctx->slot[slot];
 	const size_t img_bytes = (size_t) s.P * ctx->d_model.Npf * sizeof(float2);
@@ -938,7 +954,7 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	RB_CUDA(cudaMemsetAsync(s.counters.p, 0, 64, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(s.shells.p, 0, (size_t) s.P * M.nshell * 4, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(s.out_pdf_dir.p, 0, (size_t) M.nr_classes * S.n_dir * 8, ctx->stream));
-	RB_CUDA(cudaMemsetAsync(s.out_pdf_class.p, 0, (size_t) M.nr_classes * 8, ctx->stream));
+	RB_CUDA(cudaMemsetAsync(s.out_pdf_class.p, 0, (size_t) 3 * M.nr_classes * 8, ctx->stream));
 
 	RB_CHECK(rb_stage_begin(ctx, "coarse"));
 	RB_CHECK(rbk_prep_priors(ctx, s));
@@ -979,7 +995,7 @@ static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
 	const int P = s.P, K = M.nr_classes, T = S.n_trans, NOR = S.n_over_rot, NOT = S.n_over_trans;
 	std::vector<RbPartState> st(P);
 	std::vector<float> shells((size_t) P * M.nshell);
-	std::vector<double> pd((size_t) K * S.n_dir), pcl(K);
+	std::vector<double> pd((size_t) K * S.n_dir), pcl((size_t) 3 * K);
 	int counters[16];
 	// results travel on their own stream behind the slot's completion event, so the E-step of the other slot (already
 	// enqueued on the compute stream) keeps running while these are read
@@ -988,7 +1004,7 @@ static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
 	RB_CUDA(cudaMemcpyAsync(st.data(), s.state.p, P * sizeof(RbPartState), cudaMemcpyDeviceToHost, fs));
 	RB_CUDA(cudaMemcpyAsync(shells.data(), s.shells.p, shells.size() * 4, cudaMemcpyDeviceToHost, fs));
 	RB_CUDA(cudaMemcpyAsync(pd.data(), s.out_pdf_dir.p, pd.size() * 8, cudaMemcpyDeviceToHost, fs));
-	RB_CUDA(cudaMemcpyAsync(pcl.data(), s.out_pdf_class.p, K * 8, cudaMemcpyDeviceToHost, fs));
+	RB_CUDA(cudaMemcpyAsync(pcl.data(), s.out_pdf_class.p, (size_t) 3 * K * 8, cudaMemcpyDeviceToHost, fs));
 	RB_CUDA(cudaMemcpyAsync(counters, s.counters.p, 64, cudaMemcpyDeviceToHost, fs));
 	RB_CUDA(cudaStreamSynchronize(fs));
 	if (counters[2])
@@ -1051,17 +1067,21 @@ static int fetch_slot(rb_ctx *ctx, PoolSlot &s, rb_pool_out *out)
 	if (out && out->wsum_sigma2_noise) memcpy(out->wsum_sigma2_noise, shells.data(), shells.size() * 4);
 	if (out && out->wsum_pdf_direction) for (size_t i = 0; i < pd.size(); i++) out->wsum_pdf_direction[i] += pd[i];
 	if (out && out->wsum_pdf_class) for (int k = 0; k < K; k++) out->wsum_pdf_class[k] += pcl[k];
+	if (out && out->wsum_prior_offset_class && ctx->d_model.prior_offset_class)
+		for (int k = 0; k < 2 * K; k++) out->wsum_prior_offset_class[k] += pcl[K + k];
 	return status;
 }
 
 extern "C" int rb_estep_slot_nocopy(rb_ctx *ctx, int slot, unsigned flags)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_estep_slot_nocopy: slot %d not uploaded", slot);
 	return run_slot(ctx, ctx->slot[slot], flags);
 }
 
 extern "C" int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_estep_fetch: slot %d not uploaded", slot);
 	return fetch_slot(ctx, ctx->slot[slot], out);
 }
@@ -1084,12 +1104,14 @@ extern "C" int rb_debug_coarse_weights(rb_ctx *ctx, int slot, int particle, floa
 
 extern "C" int rb_estep_slot(rb_ctx *ctx, int slot, rb_pool_out *out, unsigned flags)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_CHECK(rb_estep_slot_nocopy(ctx, slot, flags));
 	return fetch_slot(ctx, ctx->slot[slot], out);
 }
 
 extern "C" int rb_estep_pool(rb_ctx *ctx, const rb_particles *pool, rb_pool_out *out, unsigned flags)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_CHECK(rb_pool_upload(ctx, 0, pool));
 	return rb_estep_slot(ctx, 0, out, flags);
 }
@@ -1124,6 +1146,7 @@ static int check_proj(rb_ctx *ctx, int k, int img_size)
 
 extern "C" int rb_project(rb_ctx *ctx, int k, int n, const float *eulers, int count, float *out_complex)
 {
+	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_CHECK(check_proj(ctx, k, n));
 	StageBufs sb(ctx);
 	float *d_e; float2 *d_o;

@@ -161,11 +161,15 @@ struct RbModelDev {
 	const float *minvs2;     // [nr_optics_groups][nshell] 1/(fudge*sigma2), entry 0 kept (DC restored for store)
 	const double *pdf_direction; // [K][n_dir]
 	const double *pdf_class;
+	const double *prior_offset_class; // [K][2] pixels (2D references) or nullptr: the particle's own prior
 	const unsigned char *dvp_gt3; // [K][nshell] data_vs_prior_class > 3
 	double pixel_size, s2off, adaptive_fraction;
 	int maximum_significants;
 	int do_ctf_correction, refs_are_ctf_corrected, do_scale_correction, do_map, ctf_premultiplied, bp_circle_bound;
 	int do_cc;               // first-iteration cross-correlation criterion (acc_ml_optimiser_impl.h:1164)
+	// blocks of pdf_offset per particle: [Kp][n_trans], Kp = K with per-class prior centres, else 1.  Block 0 serves the
+	// coarse pass for every class, as in the reference
+	__host__ __device__ int prior_classes() const { return prior_offset_class ? nr_classes : 1; }
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -33,16 +33,21 @@ __global__ void k_prep_priors(const RbPartMeta *metas, RbModelDev M, RbSamplingD
 	}
 	if (blockIdx.x == 0)
 	{
-		for (int t = threadIdx.x; t < S.n_trans; t += blockDim.x)
+		// one block per class when the references are 2D and carry their own prior centre (:2100-2104), else one block
+		const int Kp = M.prior_classes();
+		for (int kt = threadIdx.x; kt < Kp * S.n_trans; kt += blockDim.x)
 		{
+			const int k = kt / S.n_trans, t = kt - k * S.n_trans;
+			const double prx = M.prior_offset_class ? M.prior_offset_class[2 * k] : m.prx;
+			const double pry = M.prior_offset_class ? M.prior_offset_class[2 * k + 1] : m.pry;
 			double offx = m.oldx + S.trans_x[t], offy = m.oldy + S.trans_y[t];
-			double tdiff2 = (offx - m.prx) * (offx - m.prx) / (-2. * M.s2off) + (offy - m.pry) * (offy - m.pry) / (-2. * M.s2off);
+			double tdiff2 = (offx - prx) * (offx - prx) / (-2. * M.s2off) + (offy - pry) * (offy - pry) / (-2. * M.s2off);
 			tdiff2 *= M.pixel_size * M.pixel_size;
 			double pdf; bool z;
 			if (M.s2off < 0.0001) { z = tdiff2 > 0.; pdf = z ? 0. : 1.; }
 			else { z = false; pdf = tdiff2; }
-			pdf_offset_zero[(size_t) p * S.n_trans + t] = z;
-			pdf_offset[(size_t) p * S.n_trans + t] = (float) pdf;
+			pdf_offset_zero[(size_t) p * Kp * S.n_trans + kt] = z;
+			pdf_offset[(size_t) p * Kp * S.n_trans + kt] = (float) pdf;
 		}
 		if (threadIdx.x == 0)
 		{

@@ -76,7 +76,7 @@ __device__ __forceinline__ void build_tables_st(float2 *tab_x, float2 *tab_y, in
 __global__ void __launch_bounds__(256)
 k_collect(const RbPartMeta *metas, RbPartState *states, const RbFineOrient *fo, const int *pair_list,
           const float *fs_w, const long long *fs_ihid, const int *dir_idx, RbModelDev M, RbSamplingDev S,
-          double *out_pdf_dir, double *out_pdf_class, const int *counters)
+          double *out_pdf_dir, double *out_pdf_class, double *out_prior_class, const int *counters)
 {
 	__shared__ double dred[32];
 	if (counters[2]) return;
@@ -91,16 +91,20 @@ k_collect(const RbPartMeta *metas, RbPartState *states, const RbFineOrient *fo, 
 	for (int i = threadIdx.x; i < nfo; i += blockDim.x)
 	{
 		const RbFineOrient F = fo[st->fo_base + i];
-		float sw = 0.f, ss2 = 0.f;
+		float sw = 0.f, ss2 = 0.f, spx = 0.f, spy = 0.f;
+		// centre of the translation prior: the class' own for 2D references (:2673-2677), else the particle's
+		const double prx = M.prior_offset_class ? M.prior_offset_class[2 * F.iclass] : m.prx;
+		const double pry = M.prior_offset_class ? M.prior_offset_class[2 * F.iclass + 1] : m.pry;
 		for (int j = 0; j < F.n_t * NOT; j++)
 		{
 			float w = fs_w[F.sample_off + j];
 			w = (w >= sig) ? w / sumw : 0.f;                                          // helper.cuh:118-127
 			const int it = pair_list[F.pair_off + j / NOT] * NOT + (j % NOT);
 			const double xs = m.oldx + S.over_trans_x[it], ys = m.oldy + S.over_trans_y[it];
-			const double dx = m.prx - xs, dy = m.pry - ys;
+			const double dx = prx - xs, dy = pry - ys;
 			const float o2 = (float) (dx * dx + dy * dy);                             // :2728-2736
 			sw += w; ss2 += w * o2;
+			spx += w * (float) xs; spy += w * (float) ys;                             // helper.cuh:129-131
 		}
 		const int idl = F.iorient / m.np;
 		const int mydir = m.dir_off < 0 ? idl : dir_idx[m.dir_off + idl];             // :2833-2837
@@ -108,6 +112,11 @@ k_collect(const RbPartMeta *metas, RbPartState *states, const RbFineOrient *fo, 
 		{
 			atomicAdd(out_pdf_dir + (size_t) F.iclass * S.n_dir + mydir, (double) sw);
 			atomicAdd(out_pdf_class + F.iclass, (double) sw);
+			if (M.prior_offset_class)                                                 // :2847-2851
+			{
+				atomicAdd(out_prior_class + 2 * F.iclass, M.pixel_size * (double) spx);
+				atomicAdd(out_prior_class + 2 * F.iclass + 1, M.pixel_size * (double) spy);
+			}
 		}
 		a_w += (double) sw;
 		a_s2 += M.pixel_size * M.pixel_size * (double) ss2;                           // :2845
@@ -125,7 +134,8 @@ int rbk_collect_pool(rb_ctx *ctx, PoolSlot &s)
 {
 	k_collect<<<s.P, 256, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(), s.fo.as<RbFineOrient>(),
 		s.pair_list.as<int>(), s.fs_w.as<float>(), s.fs_ihid.as<long long>(), s.dir_idx.as<int>(),
-		ctx->d_model, ctx->d_samp, s.out_pdf_dir.as<double>(), s.out_pdf_class.as<double>(), s.counters.as<int>());
+		ctx->d_model, ctx->d_samp, s.out_pdf_dir.as<double>(), s.out_pdf_class.as<double>(),
+		s.out_pdf_class.as<double>() + ctx->d_model.nr_classes, s.counters.as<int>());
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

@@ -238,7 +238,7 @@ k_weights_coarse(const RbPartMeta *metas, RbPartState *states, float *Mweight,
 	float *w = Mweight + m.coarse_off;
 	const float min_diff2 = __int_as_float(st->min_diff2_bits);
 	DenseOut o = dense_convert(w, n, T, pdf_orient + m.prior_off, pdf_orient_zero + m.prior_off,
-	                           pdf_offset + (size_t) p * T, pdf_offset_zero + (size_t) p * T, min_diff2,
+	                           pdf_offset + (size_t) p * M.prior_classes() * T, pdf_offset_zero + (size_t) p * M.prior_classes() * T, min_diff2,
 	                           M.adaptive_fraction, M.maximum_significants, sm, am, fred);
 	if (threadIdx.x == 0)
 	{
@@ -283,7 +283,7 @@ struct WcArgs {
 	const RbPartMeta *metas; RbPartState *states; float *Mweight;
 	const float *pdf_orient; const unsigned char *pdf_orient_zero;
 	const float *pdf_offset; const unsigned char *pdf_offset_zero;
-	int T, nchunk, P; long long n;               // n: dense elements per particle (identical for all particles)
+	int T, Tp, nchunk, P; long long n;           // n: dense elements per particle (identical for all particles); Tp: floats of pdf_offset per particle
 	float *pmax; float *pav; long long *pai;
 	unsigned long long *hsum; int *hcnt;         // [P][WC_BINS]: sum of the 24-bit significands of the bin's values (exact), count
 	WcPick *pick;                                // [P]
@@ -361,7 +361,7 @@ __device__ __forceinline__ void wc_stage_priors(const WcArgs &A, int p, float *s
 	if (threadIdx.x < 2 * A.T)
 	{
 		const int t = threadIdx.x < A.T ? threadIdx.x : threadIdx.x - A.T;
-		s_pt[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.T + t] ? RB_LOWEST : A.pdf_offset[(size_t) p * A.T + t];
+		s_pt[threadIdx.x] = A.pdf_offset_zero[(size_t) p * A.Tp + t] ? RB_LOWEST : A.pdf_offset[(size_t) p * A.Tp + t];   // block 0 (:2187-2196)
 	}
 }
 
@@ -741,7 +741,7 @@ static int weights_coarse_large(rb_ctx *ctx, PoolSlot &s, long long n)
 	A.metas = s.meta.as<RbPartMeta>(); A.states = s.state.as<RbPartState>(); A.Mweight = s.Mweight.as<float>();
 	A.pdf_orient = s.pdf_orient.as<float>(); A.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>();
 	A.pdf_offset = s.pdf_offset.as<float>(); A.pdf_offset_zero = s.pdf_offset_zero.as<unsigned char>();
-	A.T = ctx->d_samp.n_trans; A.n = n; A.nchunk = (int) ((n + WC_CHUNK - 1) / WC_CHUNK); A.P = P;
+	A.T = ctx->d_samp.n_trans; A.Tp = ctx->d_model.prior_classes() * A.T; A.n = n; A.nchunk = (int) ((n + WC_CHUNK - 1) / WC_CHUNK); A.P = P;
 	const size_t np = (size_t) P * A.nchunk;
 	// one 1/16-octave bin of one particle; n / 8 is generous (the weights span ~200 octaves), overflow -> RB_ERR_CAPACITY
 	A.cap = std::max<long long>(1024, n / 8);
@@ -1071,14 +1071,17 @@ k_weights_fine(const RbPartMeta *metas, RbPartState *states, float *fs_w, const 
 	float *w = fs_w + st->fs_base;
 	const long long *ih = fs_ihid + st->fs_base;
 	const float *po = pdf_orient + m.prior_off; const unsigned char *pz = pdf_orient_zero + m.prior_off;
-	const float *pt = pdf_offset + (size_t) p * T; const unsigned char *tz = pdf_offset_zero + (size_t) p * T;
+	// per-class block of translation priors (2D references with their own prior centre, :2399-2400), else one block
+	const int Kp = M.prior_classes(), no = m.nd * m.np;
+	const float *pt = pdf_offset + (size_t) p * Kp * T; const unsigned char *tz = pdf_offset_zero + (size_t) p * Kp * T;
 	const float min_diff2 = __int_as_float(st->fmin_bits);                                  // :1881
 	const long long ov = (long long) NOR * NOT;
 	float mx = RB_LOWEST;
 	for (long long i = threadIdx.x; i < n; i += blockDim.x)
 	{
 		const long long ihidden = ih[i] / ov;
-		const int it = (int) (ihidden % T); const long long io = ihidden / T;
+		const long long io = ihidden / T;
+		const int it = (int) (ihidden % T) + (Kp > 1 ? (int) (io / no) * T : 0);
 		const float d = w[i];
 		float l;
 		if (d < min_diff2 || pz[io] || tz[it]) l = RB_LOWEST;                               // helper.cu:66-74

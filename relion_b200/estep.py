@@ -73,6 +73,7 @@ class ModelParams:
     ctf_premultiplied: bool = False
     bp_circle_bound: bool = True
     do_cc: bool = False                      # (iter == 1 and do_firstiter_cc) or do_always_cc
+    prior_offset_class: Optional[np.ndarray] = None   # [K, 2] pixels: mymodel.prior_offset_class (2D references), None for 3D
 
 
 @dataclasses.dataclass
@@ -118,6 +119,7 @@ class PoolResult:
     wsum_sigma2_noise: np.ndarray   # [P, ori_size/2+1] float32
     wsum_pdf_direction: np.ndarray  # [K, n_dir] float64
     wsum_pdf_class: np.ndarray      # [K] float64
+    wsum_prior_offset_class: Optional[np.ndarray] = None   # [K, 2] float64, Angstrom (2D references with prior_offset_class)
 
 
 class _Marshalled:
@@ -175,6 +177,9 @@ def marshal_model(p: ModelParams):
     st.ctf_premultiplied = int(p.ctf_premultiplied)
     st.bp_circle_bound = int(p.bp_circle_bound)
     st.do_cc = int(p.do_cc)
+    if p.prior_offset_class is not None:
+        poc = m.hold(_f64(np.asarray(p.prior_offset_class).reshape(p.nr_classes, 2)))
+        st.prior_offset_class = _ptr(poc, C.c_double)
     m.struct = st
     return m
 
@@ -269,8 +274,10 @@ def make_pool_out(n_particles: int, nshell: int, nr_classes: int, n_dir: int):
     st.wsum_sigma2_noise = _ptr(shells, C.c_float)
     st.wsum_pdf_direction = _ptr(pdir, C.c_double)
     st.wsum_pdf_class = _ptr(pcls, C.c_double)
+    poff = m.hold(np.zeros((nr_classes, 2), dtype=np.float64))
+    st.wsum_prior_offset_class = _ptr(poff, C.c_double)
     m.struct = st
-    m.result = PoolResult(parts, shells, pdir, pcls)
+    m.result = PoolResult(parts, shells, pdir, pcls, poff)
     return m
 
 

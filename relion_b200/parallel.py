@@ -94,6 +94,8 @@ def fold_pool_result(sums: Dict[str, np.ndarray], result, group_id: np.ndarray, 
     np.add.at(sums["wsum_reference_power"], group_id, p["wsum_AA"] / (sc * sc))
     sums["pdf_direction"] = sums["pdf_direction"] + result.wsum_pdf_direction
     sums["pdf_class"] = sums["pdf_class"] + result.wsum_pdf_class
+    if getattr(result, "wsum_prior_offset_class", None) is not None:                # 2D references (:3639-3642)
+        sums["prior_offset_class"] = sums.get("prior_offset_class", 0.0) + result.wsum_prior_offset_class
     if norm_correction is not None:
         new = (np.asarray(norm_correction, np.float64) / avg_norm_correction) * np.sqrt(2.0 * wsum_norm)      # :3525-3531
         sums["avg_norm_correction"] = sums["avg_norm_correction"] + new.sum()

@@ -254,6 +254,10 @@ def _compare_pool(device, oracle, wl, pose_frac=0.995, exact_threshold=True, num
     np.testing.assert_allclose(g["wsum_AA"][ok], o["wsum_AA"][ok], rtol=5e-3)
     sh = np.abs(ores.wsum_sigma2_noise).max()
     assert np.abs(res.wsum_sigma2_noise[ok] - ores.wsum_sigma2_noise[ok]).max() <= 5e-3 * sh
+    if wl.model.prior_offset_class is not None:
+        # thr_wsum_prior_offsetx/y_class (:2847-2851): sums of weight x offset; the tolerance is relative to the largest sum
+        scale = max(np.abs(ores.wsum_prior_offset_class).max(), wl.model.pixel_size * 1e-3 * len(g))
+        assert np.abs(res.wsum_prior_offset_class - ores.wsum_prior_offset_class).max() <= 2e-3 * scale + (0 if ok.all() else scale)
     if ok.all():
         np.testing.assert_allclose(res.wsum_pdf_class, ores.wsum_pdf_class, rtol=1e-4)
         assert np.abs(res.wsum_pdf_direction - ores.wsum_pdf_direction).max() <= 2e-3
@@ -472,6 +476,25 @@ def test_pool_2d_classification(device, oracle, monkeypatch, coarse):
     assert np.mean(res.particles["best_class"] == wl.truth["cls"]) >= 0.9
     gre, gim, gw = device.bp_get(0)
     assert gw.shape == wl.bp_shape
+
+
+def test_class2d_per_class_prior_offsets(device, oracle):
+    """2D references carry their own centre of the translation prior (mymodel.prior_offset_class,
+    acc_ml_optimiser_impl.h:2100-2104, 2673-2677): per-class pdf_offset in the fine-pass weights, the first class' block in
+    the coarse pass (:2187-2196), per-class wsum_sigma2_offset and the wsum_prior_offset_class sums (:2847-2851).  A tight
+    sigma2_offset makes the prior matter."""
+    wl = make_workload(ori_size=32, n_particles=24, nr_classes=3, seed=35, snr=0.3, ref_dim=2, psi_step=10.0)
+    wl.model.prior_offset_class = np.array([[0.8, -0.6], [-1.3, 0.4], [0.2, 1.7]])
+    wl.model.sigma2_offset = 2.0
+    wl.model.bp_circle_bound = False          # the reference's backproject2D has no circle bound (see test_pool_2d_classification)
+    res, ores = _compare_pool(device, oracle, wl, pose_frac=0.95)
+    assert np.abs(ores.wsum_prior_offset_class).max() > 0
+    # and the prior is really the per-class one: with the particle's own (zero) centre the sums differ
+    wl.model.prior_offset_class = None
+    _setup(device, wl)
+    plain = device.expectation_some_particles(wl.pool)
+    assert np.abs(plain.particles["wsum_sigma2_offset"] - res.particles["wsum_sigma2_offset"]).max() > 1e-3
+    assert not np.abs(plain.wsum_prior_offset_class).any()
 
 
 @pytest.mark.parametrize("ori,cur,local", [(32, 32, False), (40, 28, False), (32, 32, True)])

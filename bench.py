@@ -148,6 +148,8 @@ def build_device_workload(dev, name, P, seed=1993, host_refs=True, keep_refs=Fal
     from relion_b200.workload import make_workload
     from relion_b200 import synth
     kw, _ = WORKLOADS[name]
+    if os.environ.get("RB_BENCH_COARSE_SIZE"):          # experiments only (cache-footprint studies of the coarse pass)
+        kw = dict(kw, coarse_size=int(os.environ["RB_BENCH_COARSE_SIZE"]))
     if not host_refs and kw.get("ref_dim", 3) == 3:
         cur = kw.get("current_size") or kw["ori_size"]
         r_max = min(cur // 2, kw["ori_size"] // 2)

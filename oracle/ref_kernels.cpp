@@ -15,9 +15,13 @@
  * (tbb::spin_mutex comes from oracle/shim/tbb/spin_mutex.h).
  *
  * The two helpers that live in src/acc/cpu/cpu_kernels/helper.cpp (exponentiate_weights_fine,
- * cpu_kernel_make_eulers_3D) cannot be taken from that file: it includes src/acc/utilities.h and
- * acc_helper_functions.h, which pull in MlOptimiser (FFTW, MPI, TIFF).  For those two entries the
- * table points at the restatement in port_kernels.cpp (flagged in `kind_notes`).
+ * cpu_kernel_make_eulers_3D) come from that file itself, compiled as a second translation unit of this
+ * library (oracle/Makefile): it includes src/acc/utilities.h and acc_helper_functions.h, which pull in
+ * MlOptimiser's header, so it is built against declaration-level stand-ins for fftw3.h / tiffio.h / png.h
+ * (tests/cpp/relion_stubs) and mpi.h / tbb (oracle/shim); the only symbol it needs from elsewhere is
+ * rnd_gaus (noise fill), defined below as a call that aborts.  The same file also gives the image-preparation
+ * helpers (cpu_translate2D, softMaskBackgroundValue, cosineFilter; powerClass is a template of helper.h)
+ * that pin oracle/prepare.py (refk_prep_* below).
  */
 #include "src/acc/cpu/device_stubs.h"
 #include "src/acc/acc_ptr.h"
@@ -36,11 +40,8 @@
 
 #include "oracle_kernels.h"
 
-// restated helpers (see header comment) — defined in port_kernels.cpp, compiled into this .so too
-extern "C" void portk_make_eulers_3d(const float *, const float *, const float *, float *, unsigned long);
-extern "C" void portk_exponentiate_weights_fine(const float *, const unsigned char *, const float *,
-		const unsigned char *, float *, float, unsigned long, unsigned long, const unsigned long *,
-		const unsigned long *, const unsigned long *, const unsigned long *, long);
+// needed by helper.cpp's noise-fill helpers only (never reached from here)
+float rnd_gaus(float, float) { abort(); }
 
 namespace {
 
@@ -200,18 +201,38 @@ void refk_diff2_cc_fine(const ok_projector *p, int imgX, int imgY, const float *
 		(unsigned long *) rot_idx, (unsigned long *) trans_idx, (unsigned long *) job_idx, (unsigned long *) job_num);
 }
 
+// cpu_kernel_make_eulers_3D<invert = true, doL = false, doR = false> (helper.cpp:744-875), the instantiation the E-step uses
+void refk_make_eulers_3d(const float *alphas, const float *betas, const float *gammas, float *eulers, unsigned long n)
+{
+	const int bs = 128;                                                           // BLOCK_SIZE of the call site (acc_ml_optimiser_impl.h generateEulerMatrices)
+	CpuKernels::cpu_kernel_make_eulers_3D<true, false, false>((int) ((n + bs - 1) / bs), bs, (XFLOAT *) alphas, (XFLOAT *) betas,
+		(XFLOAT *) gammas, (XFLOAT *) eulers, n, NULL, NULL);
+}
+
+// CpuKernels::exponentiate_weights_fine (helper.cpp:27-61)
+void refk_exponentiate_weights_fine(const float *pdf_orientation, const unsigned char *pdf_orientation_zeros, const float *pdf_offset,
+		const unsigned char *pdf_offset_zeros, float *weights, float min_diff2, unsigned long oversamples_orient,
+		unsigned long oversamples_trans, const unsigned long *rot_id, const unsigned long *trans_idx, const unsigned long *job_idx,
+		const unsigned long *job_num, long n_jobs)
+{
+	static_assert(sizeof(bool) == 1, "bool flags are passed as bytes");
+	CpuKernels::exponentiate_weights_fine((XFLOAT *) pdf_orientation, (bool *) pdf_orientation_zeros, (XFLOAT *) pdf_offset,
+		(bool *) pdf_offset_zeros, weights, min_diff2, oversamples_orient, oversamples_trans, (unsigned long *) rot_id,
+		(unsigned long *) trans_idx, (unsigned long *) job_idx, (unsigned long *) job_num, n_jobs);
+}
+
 void *refk_bp_sync_alloc(int mdlY, int mdlZ) { return new tbb::spin_mutex[(size_t) mdlY * mdlZ]; }
 void refk_bp_sync_free(void *s) { delete[] (tbb::spin_mutex *) s; }
 
 const ok_kernel_table table = {
 	"reference",
-	portk_make_eulers_3d,            // restated: helper.cpp is not buildable standalone
+	refk_make_eulers_3d,
 	refk_project,
 	refk_diff2_coarse,
 	refk_diff2_fine,
 	refk_weights_exponent_coarse,
 	refk_exponentiate,
-	portk_exponentiate_weights_fine, // restated: helper.cpp is not buildable standalone
+	refk_exponentiate_weights_fine,
 	refk_collect2jobs,
 	refk_wavg,
 	refk_backproject,
@@ -270,3 +291,40 @@ void refk2d_diff2_coarse(const float *mdl_complex, int mdlX, int mdlY, int mdlIn
 
 } // extern "C"
 
+// ---- the reference's own image-preparation helpers (getFourierTransformsAndCtfs, acc_ml_optimiser_impl.h:216-772), used only
+// to PIN oracle/prepare.py (tests/test_reference_host.py) ----------------------------------------------------------------
+extern "C" {
+
+// cpu_translate2D (helper.cpp:255-282): out must be zero-filled by the caller, as the call site does (utilities_impl.h:374-436)
+void refk_prep_translate2d(const float *in, float *out, int n, int dx, int dy)
+{
+	CpuKernels::cpu_translate2D<XFLOAT>((XFLOAT *) in, out, (size_t) n * n, n, n, dx, dy);
+}
+
+// softMaskBackgroundValue + cosineFilter with the zero mask (acc_ml_optimiser_impl.h:610-668; launch shape utilities_impl.h:494, 571)
+void refk_prep_soft_mask(float *img, int n, float radius, float cosine_width, float *bg_out)
+{
+	if (radius < 0) radius = (float) n / 2.f;
+	const float radius_p = radius + cosine_width;
+	std::vector<XFLOAT> sum(SOFTMASK_BLOCK_SIZE, 0), sum_bg(SOFTMASK_BLOCK_SIZE, 0);
+	CpuKernels::softMaskBackgroundValue(128, SOFTMASK_BLOCK_SIZE, img, (long) n * n, n, n, 1, n / 2, n / 2, 0, radius, radius_p, cosine_width,
+	                                    sum.data(), sum_bg.data());
+	double s = 0., sb = 0.;
+	for (int i = 0; i < SOFTMASK_BLOCK_SIZE; i++) { s += sum[i]; sb += sum_bg[i]; }
+	const XFLOAT bg = (XFLOAT) (sb / s);
+	CpuKernels::cosineFilter(128, SOFTMASK_BLOCK_SIZE, img, (long) n * n, n, n, 1, n / 2, n / 2, 0, false, img, radius, radius_p, cosine_width, bg);
+	if (bg_out) *bg_out = bg;
+}
+
+// powerClass<false> (helper.h:467-540) on a full-size transform [n][n/2+1] (interleaved complex)
+void refk_prep_power_class(const float *F, int n, int current_size, float *spectrum, float *highres_Xi2)
+{
+	const int xdim = n / 2 + 1;
+	const size_t sz = (size_t) n * xdim;
+	for (int i = 0; i < xdim; i++) spectrum[i] = 0.f;
+	*highres_Xi2 = 0.f;
+	CpuKernels::powerClass<false>((int) ((sz + POWERCLASS_BLOCK_SIZE - 1) / POWERCLASS_BLOCK_SIZE), (ACCCOMPLEX *) F, spectrum, sz, (size_t) xdim,
+	                              xdim, n, 1, current_size / 2 + 1, highres_Xi2);
+}
+
+}  // extern "C"

@@ -907,7 +907,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <int NPW>
+template <int NPW, int G256>
 __global__ void __launch_bounds__(64 + 32 * NPW, NPW == 8 ? 2 : 1)
 k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, FusedArgs A, RbSamplingDev S)
 {
@@ -1019,6 +1019,7 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 		const int i = lane & 15, rsub = lane >> 4;
 		const int imgX = A.n / 2 + 1;
 		const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
+		const RbProjK8 pk8 = rb_make_projk8(A.projs[cls], imgX);
 		const float4 *mdl2 = A.projs[cls].mdl2;
 		const float4 *img = A.img4 + (size_t) p * A.n * imgX;
 		float bacc[NJ];
@@ -1044,7 +1045,8 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 				const int r = pw * (2 * NJ) + 2 * j + rsub;
 				ref[j] = make_float2(0.f, 0.f);
 				if (pix_ok && s_valid[r])
-					ref[j] = rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
+					ref[j] = G256 ? rb_project3d_c256(pk8, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5])
+					              : rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
 				bacc[j] = fmaf(hc, ref[j].x * ref[j].x + ref[j].y * ref[j].y, bacc[j]);
 			}
 			mbar_wait(empty0 + 8 * s, ph ^ 1);                       // the MMAs that read this slot have retired
@@ -1158,13 +1160,26 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	bool &configured = configured_dev[ctx->device % RB_MAX_DEVICES];
 	if (!configured)
 	{
-		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
-		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		configured = true;
 	}
+	// gather: 0 = x-pair copy, four 16-byte loads per sample; 1 = expanded cells, two 32-byte loads per sample
+	static int g256 = -1;
+	if (g256 < 0) { const char *e = getenv("RB_FUSED_G256"); g256 = e ? atoi(e) != 0 : 0; }
 	dim3 grid((unsigned) P, (unsigned) (A.tiles_per_class * K));
-	if (npw == 16) k_coarse_fused<16><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
-	else k_coarse_fused<8><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+	if (npw == 16)
+	{
+		if (g256) k_coarse_fused<16, 1><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+		else k_coarse_fused<16, 0><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+	}
+	else
+	{
+		if (g256) k_coarse_fused<8, 1><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+		else k_coarse_fused<8, 0><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+	}
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

@@ -2,6 +2,7 @@
 // Product code: no reference to oracle/; fails loudly without a CUDA device (no CPU fallback).
 #include "common.cuh"
 #include <cstdarg>
+#include <nvtx3/nvToolsExt.h>
 #include <cstdlib>
 #include <cmath>
 #include <algorithm>
@@ -64,7 +65,7 @@ extern "C" int rb_ctx_create(int device, rb_ctx **out)
 		return RB_ERR_CUDA;
 	}
 	rb_ctx *ctx = new rb_ctx();
-	for (int i = 0; i < RB_MAX_CLASSES; i++) ctx->gemmA_stamp[i] = -1;
+	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->gemmA_stamp[i] = -1; ctx->core_stamp[i] = -1; ctx->core_R[i] = 0; }
 	ctx->device = device;
 	ctx->num_sms = prop.multiProcessorCount;
 	RB_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
@@ -97,7 +98,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->proj2_buf[i].release(); ctx->bp_buf[i].release(); }
+	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->proj2_buf[i].release(); ctx->proj2c_buf[i].release(); ctx->bp_buf[i].release(); }
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
@@ -105,6 +106,8 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp,
 	                  &ctx->m_pix_rs, &ctx->band_slices, &ctx->band_tabc, &ctx->band_tabo, &ctx->band_tabu, &ctx->comm_buf, &ctx->comm_buf2};
 	for (DevBuf *b : bufs) b->release();
+	for (rb_ctx::BlockTable *t : ctx->blk_tables) { t->buf.release(); delete t; }
+	ctx->blk_tables.clear();
 	for (auto &b : ctx->scratch) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
 	for (int i = 0; i < RB_MAX_CLASSES; i++) for (auto &b : ctx->gemmA[i]) b.release();
@@ -134,8 +137,13 @@ extern "C" int rb_sync(rb_ctx *ctx)
 
 extern "C" long long rb_launch_count(rb_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
+// Stage brackets: a cudaEvent pair per stage (rb_stage_ms) and an NVTX range of the same name on the calling thread, so that a
+// timeline tool (nsys / ncu --nvtx) shows the stages the way the reference's CTIC/CTOC timers and its CUDA_PROFILING NVTX
+// ranges do (/root/reference/src/acc/cuda/cuda_settings.h, src/acc/acc_ml_optimiser_impl.h LAUNCH_PRIVATE_ERROR / CTIC blocks).
+// nvtx3 is header-only and a no-op (one predictable branch) when no tool is attached.
 int rb_stage_begin(rb_ctx *ctx, const char *name)
 {
+	if (name[0] != '_') nvtxRangePushA(name);
 	auto it = ctx->stage_ev.find(name);
 	if (it == ctx->stage_ev.end())
 	{
@@ -150,6 +158,7 @@ int rb_stage_end(rb_ctx *ctx, const char *name)
 {
 	auto it = ctx->stage_ev.find(name);
 	if (it == ctx->stage_ev.end()) return RB_OK;
+	if (name[0] != '_') nvtxRangePop();
 	RB_CUDA(cudaEventRecord(it->second.second, ctx->stream));
 	return RB_OK;
 }
@@ -191,6 +200,47 @@ int rb_sync_tables(rb_ctx *ctx)
 // ---------------------------------------------------------------------------------------------
 // reference volumes / accumulators
 // ---------------------------------------------------------------------------------------------
+// Block table of an expanded reference (RbProjector::blk): rank of every 4 x 4 x 4 block when the blocks are ordered by the
+// squared distance of their centre from the origin (counting sort on the integer key, ties in index order: deterministic).
+// RB_BLOCK_SORT=0 keeps the blocks in (z, y, x) order (A/B).
+static int block_table(rb_ctx *ctx, int mdlX, int mdlY, int mdlZ, int initY, int initZ, const uint32_t **table)
+{
+	const int geom[5] = {mdlX, mdlY, mdlZ, initY, initZ};
+	for (rb_ctx::BlockTable *t : ctx->blk_tables)
+		if (!memcmp(t->geom, geom, sizeof(geom))) { *table = t->buf.as<uint32_t>(); return RB_OK; }
+	const int nbx = (mdlX + 3) / 4, nby = (mdlY + 3) / 4, nbz = (mdlZ + 3) / 4;
+	const size_t nb = (size_t) nbx * nby * nbz;
+	std::vector<uint32_t> key(nb), rank(nb);
+	uint32_t kmax = 0;
+	for (int bz = 0; bz < nbz; bz++)
+		for (int by = 0; by < nby; by++)
+			for (int bx = 0; bx < nbx; bx++)
+			{
+				const long long cx = 4 * bx + 2, cy = 4 * by + 2 + initY, cz = 4 * bz + 2 + initZ;
+				const uint32_t kk = (uint32_t) (cx * cx + cy * cy + cz * cz);
+				key[((size_t) bz * nby + by) * nbx + bx] = kk;
+				kmax = std::max(kmax, kk);
+			}
+	const char *e = getenv("RB_BLOCK_SORT");
+	if (e && atoi(e) == 0) { for (size_t i = 0; i < nb; i++) rank[i] = (uint32_t) i; }
+	else
+	{
+		std::vector<uint32_t> start((size_t) kmax + 2, 0);
+		for (size_t i = 0; i < nb; i++) start[key[i] + 1]++;
+		for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
+		for (size_t i = 0; i < nb; i++) rank[i] = start[key[i]]++;
+	}
+	rb_ctx::BlockTable *t = new rb_ctx::BlockTable();
+	memcpy(t->geom, geom, sizeof(geom));
+	int rc = t->buf.ensure(nb * sizeof(uint32_t));
+	if (rc != RB_OK) { delete t; return rc; }
+	RB_CUDA(cudaMemcpyAsync(t->buf.p, rank.data(), nb * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->blk_tables.push_back(t);
+	*table = t->buf.as<uint32_t>();
+	return RB_OK;
+}
+
 static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int &mdlZ, int initY, int &initZ, int maxR, double pf)
 {
 	RB_ARG(ctx, "ctx is NULL");
@@ -201,8 +251,13 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int &mdl
 	ctx->ref_version[k]++;
 	if (mdlZ == 1) { mdlZ = 2; initZ = 0; }             // 2D reference (AccProjector with mdlZ == 0 in the reference): plane 1 stays zero
 	size_t n = (size_t) mdlX * mdlY * mdlZ;
+	const int nbx = (mdlX + 3) / 4, nby = (mdlY + 3) / 4, nbz = (mdlZ + 3) / 4;
+	const size_t ncell = (size_t) nbx * nby * nbz * 64;
+	RB_ARG(ncell < ((size_t) 1 << 31), "rb_set_reference: %dx%dx%d voxels exceed the cell index range", mdlX, mdlY, mdlZ);
+	const uint32_t *blk = nullptr;
+	RB_CHECK(block_table(ctx, mdlX, mdlY, mdlZ, initY, initZ, &blk));
 	RB_CHECK(ctx->proj_buf[k].ensure(n * sizeof(float2)));
-	RB_CHECK(ctx->proj8_buf[k].ensure(n * 4 * sizeof(float4)));
+	RB_CHECK(ctx->proj8_buf[k].ensure(ncell * 4 * sizeof(float4)));
 	RB_CHECK(ctx->proj2_buf[k].ensure(n * sizeof(float4)));
 	RbProjector &p = ctx->proj[k];
 	p.mdl = ctx->proj_buf[k].as<float2>();
@@ -210,8 +265,53 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int &mdl
 	p.mdl2 = ctx->proj2_buf[k].as<float4>();
 	p.mdlX = mdlX; p.mdlY = mdlY; p.mdlZ = mdlZ; p.mdlXY = mdlX * mdlY;
 	p.mdlInitY = initY; p.mdlInitZ = initZ; p.mdlMaxR = maxR; p.padding_factor = (float) pf;
+	p.c2X = mdlX; p.c2XY = p.mdlXY; p.c2InitY = initY; p.c2InitZ = initZ;       // full x-pair copy until a pool asks for the core
+	p.blk = blk; p.nbx = nbx; p.nbxy = nbx * nby;
+	ctx->core_stamp[k] = -1;
 	ctx->has_proj[k] = true;
 	if (ctx->ref_2d[k]) RB_CUDA(cudaMemsetAsync(ctx->proj_buf[k].as<float2>() + (size_t) mdlX * mdlY, 0, (size_t) mdlX * mdlY * sizeof(float2), ctx->stream));
+	return RB_OK;
+}
+
+// projector of class k with the full x-pair copy (stage entry points run at arbitrary image sizes)
+static RbProjector proj_full(rb_ctx *ctx, int k)
+{
+	RbProjector p = ctx->proj[k];
+	p.mdl2 = ctx->proj2_buf[k].as<float4>();
+	p.c2X = p.mdlX; p.c2XY = p.mdlXY; p.c2InitY = p.mdlInitY; p.c2InitZ = p.mdlInitZ;
+	return p;
+}
+
+// Coarse pass of a pool: point mdl2 at a contiguous x-pair copy of the sphere the coarse window can sample (RbProjector::c2*),
+// rebuilt when the reference or the coarse size changed.  RB_COARSE_CORE=0 keeps the full copy (A/B).
+static int ensure_coarse_core(rb_ctx *ctx)
+{
+	static int on = -1;
+	if (on < 0) { const char *e = getenv("RB_COARSE_CORE"); on = e ? atoi(e) : 1; }
+	const RbModelDev &M = ctx->d_model;
+	bool changed = false;
+	for (int k = 0; k < M.nr_classes; k++)
+	{
+		RbProjector &p = ctx->proj[k];
+		const int imgMaxR = M.coarse_size / 2;                                           // imgX - 1 (rb_make_projk)
+		const int maxR = p.mdlMaxR >= imgMaxR ? imgMaxR : p.mdlMaxR;
+		const int R = (int) ceil((double) maxR * p.padding_factor) + 1;                  // |coordinate| <= maxR * pf
+		const int cX = R + 1, cY = 2 * R + 2, cInit = -R;
+		const bool want = on && !ctx->ref_2d[k] && (size_t) cX * cY * cY * 2 < (size_t) p.mdlXY * p.mdlZ;
+		if (!want)
+		{
+			if (ctx->core_stamp[k] >= 0) { p = proj_full(ctx, k); ctx->core_stamp[k] = -1; changed = true; }
+			continue;
+		}
+		if (ctx->core_stamp[k] == ctx->ref_version[k] && ctx->core_R[k] == R) continue;
+		RB_CHECK(ctx->proj2c_buf[k].ensure((size_t) cX * cY * cY * sizeof(float4)));
+		RB_CHECK(rbk_xpair_core(ctx, p, cX, cY, cInit, cInit, ctx->proj2c_buf[k].as<float4>()));
+		p.mdl2 = ctx->proj2c_buf[k].as<float4>();
+		p.c2X = cX; p.c2XY = cX * cY; p.c2InitY = cInit; p.c2InitZ = cInit;
+		ctx->core_stamp[k] = ctx->ref_version[k]; ctx->core_R[k] = R;
+		changed = true;
+	}
+	if (changed) RB_CHECK(rb_sync_tables(ctx));
 	return RB_OK;
 }
 
@@ -949,6 +1049,7 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 		if (!(flags & 1u) && !ctx->has_bp[k]) { rb_set_error("rb_estep: accumulator %d not initialised", k); return RB_ERR_STATE; }
 	}
 	RB_CUDA(cudaSetDevice(ctx->device));
+	RB_CHECK(ensure_coarse_core(ctx));
 	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
 	RB_CHECK(rb_stage_begin(ctx, "total"));
 	RB_CUDA(cudaMemsetAsync(s.counters.p, 0, 64, ctx->stream));
@@ -1185,7 +1286,7 @@ static int diff2_coarse_entry(rb_ctx *ctx, int k, int n, const float *eulers, in
 	RB_CHECK(sb.up(eulers, (size_t) O * 9, &d_e)); RB_CHECK(sb.up(tx, T, &d_tx)); RB_CHECK(sb.up(ty, T, &d_ty));
 	RB_CHECK(sb.up(re, np, &d_re)); RB_CHECK(sb.up(im, np, &d_im)); RB_CHECK(sb.up(corr, np, &d_c));
 	RB_CHECK(sb.up(diff2s, (size_t) O * T, &d_o));
-	RB_CHECK(rbk_diff2_coarse_stage(ctx, ctx->proj[k], n, d_e, O, d_tx, d_ty, T, d_re, d_im, d_c, d_o, cc));
+	RB_CHECK(rbk_diff2_coarse_stage(ctx, proj_full(ctx, k), n, d_e, O, d_tx, d_ty, T, d_re, d_im, d_c, d_o, cc));
 	RB_CUDA(cudaMemcpyAsync(diff2s, d_o, (size_t) O * T * 4, cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return RB_OK;

@@ -56,6 +56,18 @@ struct RbProjector {
 	int mdlInitY, mdlInitZ;
 	int mdlMaxR;
 	float padding_factor;
+	// Geometry of mdl2.  The coarse pass only samples inside the coarse window's sphere; while a pool runs, mdl2 is a
+	// CONTIGUOUS copy of that core (77 MB at 256 px / coarse window 106) instead of a sub-box strewn over every z-plane of the
+	// full volume: it stays in L2 and inside the TLB's reach (128 entries x 2 MB; a core embedded in the 515 x 515 x 258
+	// volume touches > 200 pages and every L1 miss walks the page table).  Stage entry points use the full copy.
+	int c2X, c2XY, c2InitY, c2InitZ;
+	// Addressing of mdl8.  The cells live in 4 x 4 x 4 blocks (4 KB) ordered by the distance of the block centre from the
+	// origin, blk[] = rank of block (bz, by, bx): a thin spherical shell - what the band-major kernels sweep - is then one
+	// contiguous range of memory (<= 125 pages at the edge of a 256-px reference) instead of a slice through all 2190 pages
+	// of the volume.  Measured (tools/shell_prefetch_bench.cu): 64-byte gathers in a shell 35 G/s in [z][y][x] order
+	// (TLB-miss bound, L2-resident or not), 160 - 200 G/s in this order.
+	const uint32_t *blk;
+	int nbx, nbxy;
 };
 
 // AccBackprojector state (acc_backprojector.h:24-60); accumulator is float4 (re, im, weight, 0)
@@ -219,6 +231,12 @@ struct rb_ctx {
 	DevBuf proj_buf[RB_MAX_CLASSES];
 	DevBuf proj8_buf[RB_MAX_CLASSES];
 	DevBuf proj2_buf[RB_MAX_CLASSES];
+	DevBuf proj2c_buf[RB_MAX_CLASSES];               // x-pair copy of the coarse-window core (RbProjector::c2*)
+	long long core_stamp[RB_MAX_CLASSES];            // ref_version the core was built from (-1: none), and its half width
+	int core_R[RB_MAX_CLASSES];
+	// radius-sorted block tables of the expanded references (RbProjector::blk), one per volume geometry
+	struct BlockTable { int geom[5]; DevBuf buf; };
+	std::vector<BlockTable *> blk_tables;
 	RbBackprojector bp[RB_MAX_CLASSES];
 	DevBuf bp_buf[RB_MAX_CLASSES];
 	bool has_proj[RB_MAX_CLASSES] = {false}, has_bp[RB_MAX_CLASSES] = {false};
@@ -282,6 +300,7 @@ int rb_sync_tables(rb_ctx *ctx);   // refresh d_proj / d_bp device tables
 int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt, const float *d_psi, int n_dir, int n_psi, float *d_eulers);
 int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
 int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2);
+int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
 int rbk_backproject_posed(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers);
 int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out);

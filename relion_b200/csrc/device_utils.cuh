@@ -78,6 +78,14 @@ __host__ __device__ inline RbProjK rb_make_projk(const RbProjector &p, int imgX)
 	return k;
 }
 
+// geometry of the x-pair copy (RbProjector::mdl2, the coarse-window core while a pool runs)
+__host__ __device__ inline RbProjK rb_make_projk2(const RbProjector &p, int imgX)
+{
+	RbProjK k = rb_make_projk(p, imgX);
+	k.mdlX = p.c2X; k.mdlXY = p.c2XY; k.mdlInitY = p.c2InitY; k.mdlInitZ = p.c2InitZ;
+	return k;
+}
+
 // AccProjectorKernel::project3Dmodel, 2D-image overload, exact fp32 lerps (PROJECTOR_NO_TEXTURES /
 // CpuKernels::complex3D semantics: acc_projectorkernel_impl.h:161-231, cpu_kernels/cpu_utils.h:159-205).
 // One 8-byte load per tap (re,im interleaved) instead of the reference's two separate textures.
@@ -154,15 +162,24 @@ __device__ __forceinline__ float2 rb_project3d_xp(const RbProjK &k, const float4
 // exactly two 32-byte sectors.  Arithmetic identical to rb_project3d.
 struct RbProjK8 {
 	const float4 *mdl8;
+	const uint32_t *blk; int nbx, nbxy;
 	int mdlX, mdlXY, mdlInitY, mdlInitZ, maxR, maxR2_padded;
 	float pf;
 };
+// index (in 64-byte cells) of the cell whose origin is voxel (x0, yi, zi), yi / zi counted from the array edge: rank of its
+// 4 x 4 x 4 block in the radius-sorted block order, then (z, y, x) inside the block (see RbProjector::blk)
+__device__ __forceinline__ int rb_cell8(const uint32_t *blk, int nbx, int nbxy, int x0, int yi, int zi)
+{
+	const uint32_t rank = __ldg(blk + (zi >> 2) * nbxy + (yi >> 2) * nbx + (x0 >> 2));
+	return (int) ((rank << 6) | (uint32_t) (((zi & 3) << 4) | ((yi & 3) << 2) | (x0 & 3)));
+}
 __host__ __device__ inline RbProjK8 rb_make_projk8(const RbProjector &p, int imgX)
 {
 	RbProjK8 k;
 	int imgMaxR = imgX - 1;
 	k.maxR = p.mdlMaxR >= imgMaxR ? imgMaxR : p.mdlMaxR;
 	k.mdl8 = p.mdl8; k.mdlX = p.mdlX; k.mdlXY = p.mdlXY; k.mdlInitY = p.mdlInitY; k.mdlInitZ = p.mdlInitZ;
+	k.blk = p.blk; k.nbx = p.nbx; k.nbxy = p.nbxy;
 	k.pf = p.padding_factor;
 	k.maxR2_padded = (int) (k.maxR * k.maxR * k.pf * k.pf);
 	return k;
@@ -180,7 +197,7 @@ __device__ __forceinline__ float2 rb_project3d_x8(const RbProjK8 &k, int x, int 
 	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
 	const float fx = xp - fx0, fy = yp - fy0, fz = zp - fz0;
 	const int x0 = (int) fx0, y0 = (int) fy0, z0 = (int) fz0;
-	const float4 *b = k.mdl8 + 4 * ((size_t) (z0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) (y0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) x0);
+	const float4 *b = k.mdl8 + 4 * (size_t) rb_cell8(k.blk, k.nbx, k.nbxy, x0, y0 - k.mdlInitY, z0 - k.mdlInitZ);
 	const float4 q0 = __ldg(b), q1 = __ldg(b + 1), q2 = __ldg(b + 2), q3 = __ldg(b + 3);
 	float2 r;
 	{
@@ -220,7 +237,7 @@ __device__ __forceinline__ float2 rb_project3d_c256(const RbProjK8 &k, int x, in
 	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
 	const float fx = xp - fx0, fy = yp - fy0, fz = zp - fz0;
 	const int x0 = (int) fx0, y0 = (int) fy0, z0 = (int) fz0;
-	const float4 *b = k.mdl8 + 4 * ((size_t) (z0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) (y0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) x0);
+	const float4 *b = k.mdl8 + 4 * (size_t) rb_cell8(k.blk, k.nbx, k.nbxy, x0, y0 - k.mdlInitY, z0 - k.mdlInitZ);
 	float4 q0, q1, q2, q3;
 	rb_ldg256(b, q0, q1);
 	rb_ldg256(b + 2, q2, q3);
@@ -263,7 +280,7 @@ __device__ __forceinline__ void rb_proj_issue(const RbProjK8 &k, int x, int y,
 	f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
 	if (inside)
 	{
-		const float4 *b = k.mdl8 + 4 * ((size_t) ((int) fz0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) ((int) fy0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) (int) fx0);
+		const float4 *b = k.mdl8 + 4 * (size_t) rb_cell8(k.blk, k.nbx, k.nbxy, (int) fx0, (int) fy0 - k.mdlInitY, (int) fz0 - k.mdlInitZ);
 		f.q0 = __ldg(b); f.q1 = __ldg(b + 1); f.q2 = __ldg(b + 2); f.q3 = __ldg(b + 3);
 	}
 	else f.q0 = f.q1 = f.q2 = f.q3 = make_float4(0.f, 0.f, 0.f, 0.f);

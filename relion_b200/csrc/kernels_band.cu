@@ -121,9 +121,12 @@ struct BandLoad { float4 q[4]; BandFrac f; };
 // Gathers go through plain 16-byte loads (LDG.128): per instruction the 8 quads of a warp touch 8 cells, one L1 line visit
 // per sample.  (cp.async into shared memory was measured 2.6x slower here: with 8 distinct lines per instruction every line
 // becomes its own shared-memory write transaction, ~40 cycles per instruction against ~16 for the register path.)
+// Two steps, so that the block-table look-up of sample j + 2 (RbProjector::blk) is in flight while the cell of sample j + 1 is
+// being fetched and sample j is interpolated.
+struct BandAddr { BandFrac f; uint32_t rank; int sub; };
+
 template <bool MULTI>
-__device__ __forceinline__ void band_issue(const BandProjArgs &A, const BandProjSmem &S, const RbProjK8 &pk0, int j, int x, int y, bool have,
-                                           int lane, BandLoad &L)
+__device__ __forceinline__ void band_addr(const BandProjArgs &A, const BandProjSmem &S, const RbProjK8 &pk0, int j, int x, int y, bool have, BandAddr &a)
 {
 	const float2 ea = *(const float2 *) &S.e[j][0], eb = *(const float2 *) &S.e[j][2], ec = *(const float2 *) &S.e[j][4];
 	RbProjK8 pk = pk0;
@@ -136,15 +139,26 @@ __device__ __forceinline__ void band_issue(const BandProjArgs &A, const BandProj
 	const bool inv = xp < 0.f;
 	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
 	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
-	L.f.fx = xp - fx0; L.f.fy = yp - fy0; L.f.fz = zp - fz0;
-	L.f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
-	const int cell = inside ? (((int) fz0 - pk.mdlInitZ) * pk.mdlXY + ((int) fy0 - pk.mdlInitY) * pk.mdlX + (int) fx0) : -1;
+	a.f.fx = xp - fx0; a.f.fy = yp - fy0; a.f.fz = zp - fz0;
+	a.f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
+	const int x0 = (int) fx0, yi = (int) fy0 - pk.mdlInitY, zi = (int) fz0 - pk.mdlInitZ;
+	a.sub = ((zi & 3) << 4) | ((yi & 3) << 2) | (x0 & 3);
+	a.rank = inside ? __ldg(pk.blk + (zi >> 2) * pk.nbxy + (yi >> 2) * pk.nbx + (x0 >> 2)) : 0u;
+}
+
+template <bool MULTI>
+__device__ __forceinline__ void band_fetch(const BandProjArgs &A, const BandProjSmem &S, const RbProjK8 &pk0, int j, const BandAddr &a, int lane, BandLoad &L)
+{
+	const float4 *mdl8 = pk0.mdl8;
+	if (MULTI) mdl8 = A.projs[S.cls[j]].mdl8;
+	L.f = a.f;
+	const int cell = (a.f.flags & 1) ? (int) ((a.rank << 6) | (uint32_t) a.sub) : -1;
 	const int k = lane & 3, qbase = lane & ~3;
 #pragma unroll
 	for (int r = 0; r < 4; r++)
 	{
 		const int cs = __shfl_sync(RB_FULL_MASK, cell, qbase + r);             // cell of the quad's sample r
-		L.q[r] = cs >= 0 ? __ldcg(pk.mdl8 + 4 * (size_t) cs + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+		L.q[r] = cs >= 0 ? __ldcg(mdl8 + 4 * (size_t) cs + k) : make_float4(0.f, 0.f, 0.f, 0.f);
 	}
 }
 
@@ -222,15 +236,18 @@ k_project_band(BandProjArgs A)
 		const int nmy = (no - ph + BD_NPH - 1) / BD_NPH;                        // orientations ph, ph + BD_NPH, ...
 		float2 *out = A.slices + (size_t) o0 * A.stride + ip;
 
-		// one orientation ahead: the loads of the next sample are in flight while the current one is interpolated
+		// two orientations ahead: table look-up of sample jj + 2, cell loads of sample jj + 1, interpolation of sample jj
+		BandAddr a1, a2;
 		BandLoad cur, nxt;
-		if (nmy > 0) band_issue<MULTI>(A, S, pk0, ph, x, y, have, lane, cur);
+		if (nmy > 0) { band_addr<MULTI>(A, S, pk0, ph, x, y, have, a1); band_fetch<MULTI>(A, S, pk0, ph, a1, lane, cur); }
+		if (nmy > 1) band_addr<MULTI>(A, S, pk0, ph + BD_NPH, x, y, have, a1);
 		for (int jj = 0; jj < nmy; jj++)
 		{
-			if (jj + 1 < nmy) band_issue<MULTI>(A, S, pk0, ph + (jj + 1) * BD_NPH, x, y, have, lane, nxt);
+			if (jj + 2 < nmy) band_addr<MULTI>(A, S, pk0, ph + (jj + 2) * BD_NPH, x, y, have, a2);
+			if (jj + 1 < nmy) band_fetch<MULTI>(A, S, pk0, ph + (jj + 1) * BD_NPH, a1, lane, nxt);
 			const float2 ref = band_consume(tile_buf, lane, cur);
 			if (have) __stcs(out + (size_t) (ph + jj * BD_NPH) * A.stride, ref);
-			cur = nxt;
+			cur = nxt; a1 = a2;
 		}
 		if (threadIdx.x == 0) S.next = (int) gridDim.x + pending;
 		__syncthreads();

@@ -139,7 +139,7 @@ k_diff2_coarse(CoarseArgs A, RbModelDev M, RbSamplingDev S)
 	if (!any) return;   // Mweight stays lowest() (acc_ml_optimiser_impl.h:3849)
 
 	const float4 *img = A.img4 + (size_t) p * A.n * imgX;
-	const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
+	const RbProjK pk = XP ? rb_make_projk2(A.projs[cls], imgX) : rb_make_projk(A.projs[cls], imgX);   // XP: geometry of the x-pair copy
 	const float4 *mdl2 = A.projs[cls].mdl2;   // nullptr in stage mode with a caller-supplied projector copy
 
 	float bmin = FLT_MAX;

@@ -65,7 +65,7 @@ __device__ __forceinline__ void fine_issue(const RbProjK8 &pk, const float4 *img
 	f.q = make_float4(0.f, 0.f, 0.f, 0.f);
 	if (inside)
 	{
-		const size_t cell = (size_t) ((int) fz0 - pk.mdlInitZ) * (size_t) pk.mdlXY + (size_t) ((int) fy0 - pk.mdlInitY) * (size_t) pk.mdlX + (size_t) (int) fx0;
+		const size_t cell = (size_t) rb_cell8(pk.blk, pk.nbx, pk.nbxy, (int) fx0, (int) fy0 - pk.mdlInitY, (int) fz0 - pk.mdlInitZ);
 		f.q = __ldg(pk.mdl8 + 4 * cell + k);
 	}
 	f.img = __ldg(img_row + x);
@@ -368,7 +368,7 @@ k_diff2_fine_async(FineArgs A, RbModelDev M)
 					s_frac[slot * FI_THREADS + threadIdx.x] = comp;
 					if (inside)
 					{
-						const size_t cell = (size_t) ((int) fz0 - pk.mdlInitZ) * (size_t) pk.mdlXY + (size_t) ((int) fy0 - pk.mdlInitY) * (size_t) pk.mdlX + (size_t) (int) fx0;
+						const size_t cell = (size_t) rb_cell8(pk.blk, pk.nbx, pk.nbxy, (int) fx0, (int) fy0 - pk.mdlInitY, (int) fz0 - pk.mdlInitZ);
 						cp_async16(s_cell + slot * FI_THREADS + threadIdx.x, pk.mdl8 + 4 * cell + k);
 					}
 					else s_cell[slot * FI_THREADS + threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);

@@ -664,7 +664,7 @@ k_gemm_build_A(RbProjector pj, const float *coarse_eulers, const uint32_t *pix, 
 	const bool live = r < rows;
 	int o = o_first + r;
 	if (projs && live) { pj = projs[r / o_per_class]; o = r % o_per_class; }
-	const RbProjK pk = rb_make_projk(pj, imgX);
+	const RbProjK pk = rb_make_projk2(pj, imgX);
 	float e0 = 0, e1 = 0, e3 = 0, e4 = 0, e6 = 0, e7 = 0;
 	if (live)
 	{
@@ -1018,7 +1018,7 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 		const int pw = pt >> 5;
 		const int i = lane & 15, rsub = lane >> 4;
 		const int imgX = A.n / 2 + 1;
-		const RbProjK pk = rb_make_projk(A.projs[cls], imgX);
+		const RbProjK pk = rb_make_projk2(A.projs[cls], imgX);
 		const RbProjK8 pk8 = rb_make_projk8(A.projs[cls], imgX);
 		const float4 *mdl2 = A.projs[cls].mdl2;
 		const float4 *img = A.img4 + (size_t) p * A.n * imgX;

@@ -61,7 +61,7 @@ __global__ void k_expand_volume(RbProjector pj, float4 *out, float4 *out2)
 		const float2 d010 = hy ? b[pj.mdlX] : zero, d011 = (hy && hx) ? b[pj.mdlX + 1] : zero;
 		const float2 d100 = hz ? b[pj.mdlXY] : zero, d101 = (hz && hx) ? b[pj.mdlXY + 1] : zero;
 		const float2 d110 = (hz && hy) ? b[pj.mdlXY + pj.mdlX] : zero, d111 = (hz && hy && hx) ? b[pj.mdlXY + pj.mdlX + 1] : zero;
-		float4 *o = out + 4 * v;
+		float4 *o = out + 4 * (size_t) rb_cell8(pj.blk, pj.nbx, pj.nbxy, x, y, z);      // radius-sorted 4 x 4 x 4 blocks (RbProjector::blk)
 		o[0] = make_float4(d000.x, d000.y, d001.x, d001.y);
 		o[1] = make_float4(d010.x, d010.y, d011.x, d011.y);
 		o[2] = make_float4(d100.x, d100.y, d101.x, d101.y);
@@ -73,6 +73,34 @@ __global__ void k_expand_volume(RbProjector pj, float4 *out, float4 *out2)
 int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2)
 {
 	k_expand_volume<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(pj, d_out, d_out2);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
+// x-pair copy of the box [0, cX) x [cInitY, cInitY + cY) x [cInitZ, cInitZ + cY) of the reference, contiguous (RbProjector::c2*);
+// voxels outside the stored volume read as zero
+__global__ void k_xpair_core(RbProjector pj, int cX, int cY, int cInitY, int cInitZ, float4 *out)
+{
+	const size_t n = (size_t) cX * cY * cY;
+	for (size_t v = blockIdx.x * (size_t) blockDim.x + threadIdx.x; v < n; v += (size_t) gridDim.x * blockDim.x)
+	{
+		const int x = (int) (v % cX);
+		const int y = (int) ((v / cX) % cY) + cInitY - pj.mdlInitY;
+		const int z = (int) (v / ((size_t) cX * cY)) + cInitZ - pj.mdlInitZ;
+		float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (y >= 0 && y < pj.mdlY && z >= 0 && z < pj.mdlZ && x < pj.mdlX)
+		{
+			const float2 *b = pj.mdl + ((size_t) z * pj.mdlXY + (size_t) y * pj.mdlX + x);
+			const float2 a = b[0], c = x + 1 < pj.mdlX ? b[1] : make_float2(0.f, 0.f);
+			o = make_float4(a.x, a.y, c.x, c.y);
+		}
+		out[v] = o;
+	}
+}
+
+int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out)
+{
+	k_xpair_core<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(pj, cX, cY, cInitY, cInitZ, d_out);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

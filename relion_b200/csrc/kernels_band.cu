@@ -34,6 +34,12 @@ static const int BD_WPT = BD_TP / 32;            // warps per tile row
 static const int BD_NPH = BD_THREADS / BD_TP;    // orientation phases per CTA
 static const int BD_MAXCHUNK = 64;
 
+// Band-major arrays are TILE-major: element (row, pixel ip) of an array with `nrows` rows (fine orientations of the round,
+// particles) sits at ((ip / BD_TP) * nrows + row) * BD_TP + ip % BD_TP.  What the resident CTAs of a band sweep touch at one
+// time - one tile of every row - is then a contiguous range (a few 2 MB pages) instead of one 1 KB piece out of every row of
+// a 1.4 GB array (700 pages: every access a TLB miss that also evicts the pages of the reference shell).
+__device__ __forceinline__ size_t bd_at(int row, int ip, int nrows) { return ((size_t) (ip >> 7) * (size_t) nrows + (size_t) row) * BD_TP + (size_t) (ip & (BD_TP - 1)); }
+
 __device__ __forceinline__ void bd_red_add_v4(float4 *addr, float a, float b, float c)
 {
 	asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(0.f) : "memory");
@@ -46,8 +52,8 @@ struct BandPrepArgs {
 	const RbPartMeta *metas; const float2 *Fimg, *Fnomask; const float *Fctf;
 	const uint32_t *pix; int nd2, nst, stride;
 	float4 *simg4;      // [P][stride] (X'.re, X'.im, corr / 2, 0): diff2 passes
-	float4 *sst;        // [P][stride] (X.re, X.im, X0.re, X0.im): store stage
-	float *sctf;        // [P][stride] ctf * part_scale
+	float4 *sst;        // tile-major [stride / BD_TP][P][BD_TP] (X.re, X.im, X0.re, X0.im): store stage
+	float *sctf;        // tile-major, ctf * part_scale
 };
 
 static __global__ void __launch_bounds__(256)
@@ -79,8 +85,8 @@ k_prep_sorted(BandPrepArgs A, RbModelDev M)
 			c = C ? __ldg(C + idx) * m.part_scale : m.part_scale;                              // acc_ml_optimiser_impl.h:3087-3096
 		}
 		A.simg4[(size_t) p * A.stride + ip] = d;
-		A.sst[(size_t) p * A.stride + ip] = s;
-		A.sctf[(size_t) p * A.stride + ip] = c;
+		A.sst[bd_at(p, ip, (int) gridDim.y)] = s;
+		A.sctf[bd_at(p, ip, (int) gridDim.y)] = c;
 	}
 }
 
@@ -93,7 +99,7 @@ struct BandProjArgs {
 	const int *count_ptr;        // number of list entries (device): counters[0] or the BP list length
 	int begin, capacity;         // this round covers list entries [begin, min(count, begin + capacity))
 	const uint32_t *pix; int npix, stride;
-	float2 *slices;              // [capacity][stride]
+	float2 *slices;              // tile-major [stride / BD_TP][n][BD_TP], n = orientations of the round
 	const RbProjector *projs; int imgX; int nr_classes;
 	int *queue;
 	int chunk_min;
@@ -234,7 +240,6 @@ k_project_band(BandProjArgs A)
 		int x = 0, y = 0;
 		if (have) { const uint32_t pkx = __ldg(A.pix + ip); x = rb_pix_x(pkx); y = rb_pix_y(pkx); }
 		const int nmy = (no - ph + BD_NPH - 1) / BD_NPH;                        // orientations ph, ph + BD_NPH, ...
-		float2 *out = A.slices + (size_t) o0 * A.stride + ip;
 
 		// two orientations ahead: table look-up of sample jj + 2, cell loads of sample jj + 1, interpolation of sample jj
 		BandAddr a1, a2;
@@ -246,7 +251,7 @@ k_project_band(BandProjArgs A)
 			if (jj + 2 < nmy) band_addr<MULTI>(A, S, pk0, ph + (jj + 2) * BD_NPH, x, y, have, a2);
 			if (jj + 1 < nmy) band_fetch<MULTI>(A, S, pk0, ph + (jj + 1) * BD_NPH, a1, lane, nxt);
 			const float2 ref = band_consume(tile_buf, lane, cur);
-			if (have) __stcs(out + (size_t) (ph + jj * BD_NPH) * A.stride, ref);
+			if (have) __stcs(A.slices + bd_at(o0 + ph + jj * BD_NPH, ip, n), ref);
 			cur = nxt; a1 = a2;
 		}
 		if (threadIdx.x == 0) S.next = (int) gridDim.x + pending;
@@ -269,7 +274,7 @@ struct BandDiffArgs {
 };
 
 template <int NT>
-__device__ __forceinline__ void band_diff_pass(const float2 *__restrict__ slice, const float4 *__restrict__ img, const uint32_t *__restrict__ pix,
+__device__ __forceinline__ void band_diff_pass(const float2 *__restrict__ slices, int row, int nrows, const float4 *__restrict__ img, const uint32_t *__restrict__ pix,
                                                int nd2, const float *s_ux, const float *s_uy, float (&acc)[NT], float &base)
 {
 #pragma unroll
@@ -279,7 +284,7 @@ __device__ __forceinline__ void band_diff_pass(const float2 *__restrict__ slice,
 	{
 		const uint32_t pk = __ldg(pix + ip);
 		const int x = rb_pix_x(pk), y = rb_pix_y(pk);
-		const float2 ref = __ldcs(slice + ip);
+		const float2 ref = __ldcs(slices + bd_at(row, ip, nrows));
 		const float4 im = __ldg(img + ip);
 		const float hc = im.z;
 		const float zr = hc * (ref.x * im.x + ref.y * im.y);
@@ -325,7 +330,7 @@ k_band_tables(const uint32_t *pix, int npix, int stride, const double *ucx, cons
 }
 
 template <int NC, int NOT>
-__device__ __forceinline__ void band_diff_pass_sep(const float2 *__restrict__ slice, const float4 *__restrict__ img, int nd2, int stride,
+__device__ __forceinline__ void band_diff_pass_sep(const float2 *__restrict__ slices, int row, int nrows, const float4 *__restrict__ img, int nd2, int stride,
                                                    const float2 *__restrict__ tabc, const float2 *__restrict__ tabo, const int *s_tc,
                                                    float (&acc)[NC * NOT], float &base)
 {
@@ -334,7 +339,7 @@ __device__ __forceinline__ void band_diff_pass_sep(const float2 *__restrict__ sl
 	base = 0.f;
 	for (int ip = threadIdx.x; ip < nd2; ip += BD_THREADS)
 	{
-		const float2 ref = __ldcs(slice + ip);
+		const float2 ref = __ldcs(slices + bd_at(row, ip, nrows));
 		const float4 im = __ldg(img + ip);
 		float2 po[NOT];
 #pragma unroll
@@ -375,7 +380,6 @@ k_diff2_slices_sep(BandDiffArgs A, const float2 *tabc, const float2 *tabo)
 		const int p = F.particle;
 		const float xi2_half = A.metas[p].xi2_half;
 		const float4 *img = A.simg4 + (size_t) p * A.stride;
-		const float2 *slice = A.slices + (size_t) wi * A.stride;
 		float bmin = FLT_MAX;
 		for (int c0 = 0; c0 < F.n_t; c0 += BD_NCMAX)
 		{
@@ -386,23 +390,23 @@ k_diff2_slices_sep(BandDiffArgs A, const float2 *tabc, const float2 *tabo)
 			float acc[BD_NCMAX * NOT], base;
 			if (nc == 1)
 			{
-				float a[NOT]; band_diff_pass_sep<1, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
+				float a[NOT]; band_diff_pass_sep<1, NOT>(A.slices, wi, n, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
 #pragma unroll
 				for (int t = 0; t < BD_NCMAX * NOT; t++) acc[t] = t < NOT ? a[t % NOT] : 0.f;
 			}
 			else if (nc == 2)
 			{
-				float a[2 * NOT]; band_diff_pass_sep<2, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
+				float a[2 * NOT]; band_diff_pass_sep<2, NOT>(A.slices, wi, n, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
 #pragma unroll
 				for (int t = 0; t < BD_NCMAX * NOT; t++) acc[t] = t < 2 * NOT ? a[t % (2 * NOT)] : 0.f;
 			}
 			else if (nc <= 4)
 			{
-				float a[4 * NOT]; band_diff_pass_sep<4, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
+				float a[4 * NOT]; band_diff_pass_sep<4, NOT>(A.slices, wi, n, img, A.nd2, A.stride, tabc, tabo, s_tc, a, base);
 #pragma unroll
 				for (int t = 0; t < BD_NCMAX * NOT; t++) acc[t] = t < 4 * NOT ? a[t % (4 * NOT)] : 0.f;
 			}
-			else band_diff_pass_sep<BD_NCMAX, NOT>(slice, img, A.nd2, A.stride, tabc, tabo, s_tc, acc, base);
+			else band_diff_pass_sep<BD_NCMAX, NOT>(A.slices, wi, n, img, A.nd2, A.stride, tabc, tabo, s_tc, acc, base);
 			const int ntr = nc * NOT;
 			// fixed-order reduction: lanes, then warps
 #pragma unroll
@@ -448,7 +452,6 @@ k_diff2_slices(BandDiffArgs A)
 		const int nsamp = F.n_t * A.NOT, p = F.particle;
 		const float xi2_half = A.metas[p].xi2_half;
 		const float4 *img = A.simg4 + (size_t) p * A.stride;
-		const float2 *slice = A.slices + (size_t) wi * A.stride;
 		float bmin = FLT_MAX;
 		for (int c0 = 0; c0 < nsamp; c0 += BD_TF)
 		{
@@ -469,23 +472,23 @@ k_diff2_slices(BandDiffArgs A)
 			float acc[BD_TF], base;
 			if (ntr <= 4)
 			{
-				float a4[4]; band_diff_pass<4>(slice, img, A.pix, A.nd2, s_ux, s_uy, a4, base);
+				float a4[4]; band_diff_pass<4>(A.slices, wi, n, img, A.pix, A.nd2, s_ux, s_uy, a4, base);
 #pragma unroll
 				for (int t = 0; t < BD_TF; t++) acc[t] = t < 4 ? a4[t & 3] : 0.f;
 			}
 			else if (ntr <= 8)
 			{
-				float a8[8]; band_diff_pass<8>(slice, img, A.pix, A.nd2, s_ux, s_uy, a8, base);
+				float a8[8]; band_diff_pass<8>(A.slices, wi, n, img, A.pix, A.nd2, s_ux, s_uy, a8, base);
 #pragma unroll
 				for (int t = 0; t < BD_TF; t++) acc[t] = t < 8 ? a8[t & 7] : 0.f;
 			}
 			else if (ntr <= 16)
 			{
-				float a16[16]; band_diff_pass<16>(slice, img, A.pix, A.nd2, s_ux, s_uy, a16, base);
+				float a16[16]; band_diff_pass<16>(A.slices, wi, n, img, A.pix, A.nd2, s_ux, s_uy, a16, base);
 #pragma unroll
 				for (int t = 0; t < BD_TF; t++) acc[t] = t < 16 ? a16[t & 15] : 0.f;
 			}
-			else band_diff_pass<BD_TF>(slice, img, A.pix, A.nd2, s_ux, s_uy, acc, base);
+			else band_diff_pass<BD_TF>(A.slices, wi, n, img, A.pix, A.nd2, s_ux, s_uy, acc, base);
 			// fixed-order reduction: lanes, then warps
 #pragma unroll
 			for (int t = 0; t < BD_TF; t++)
@@ -640,7 +643,7 @@ struct BandStoreArgs {
 	float *shells;               // [P][nshell]
 	const RbBackprojector *bps;
 	int n; int *queue; int chunk_min;
-	int nr_classes;
+	int nr_classes; int P;
 };
 
 struct BandStoreSmem {
@@ -664,6 +667,7 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 	const int total = A.counters[10];
 	const int n = min(A.capacity, total - A.begin);
 	if (n <= 0) return;
+	const int nrows = A.slice_by_item ? n : A.counters[0];     // rows of the tile-major slice array: what the producing round projected
 	const int ntiles = (A.nst + BD_TP - 1) / BD_TP;
 	int chunk = (n + (int) gridDim.x - 1) / (int) gridDim.x;
 	chunk = max(A.chunk_min, min(BD_MAXCHUNK, chunk));
@@ -710,8 +714,8 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 			in.ref = make_float2(0.f, 0.f); in.XX = make_float4(0.f, 0.f, 0.f, 0.f); in.ctf = 0.f;
 			if (have)
 			{
-				const size_t so = (size_t) (A.slice_by_item ? (o0 + j) : S.item[j].w) * A.stride + ip;
-				const size_t po = (size_t) S.particle[j] * A.stride + ip;
+				const size_t so = bd_at(A.slice_by_item ? (o0 + j) : S.item[j].w, ip, nrows);
+				const size_t po = bd_at(S.particle[j], ip, A.P);
 				in.ref = __ldcs(A.slices + so); in.XX = __ldg(A.sst + po); in.ctf = __ldg(A.sctf + po);
 			}
 		};
@@ -978,7 +982,7 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.pix = M.pix_rs; A.nst = M.nv_rs_st; A.stride = M.nv_rs_pad;
 	A.shells = s.shells.as<float>(); A.bps = ctx->d_bp.as<RbBackprojector>();
 	A.n = M.current_size; A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_STORE_CHUNK_MIN", 16));
-	A.nr_classes = M.nr_classes;
+	A.nr_classes = M.nr_classes; A.P = s.P;
 	int *queue = s.counters.as<int>() + 14;
 	const int grid = ctx->num_sms * env_int("RB_BAND_STORE_CTAS", 3);
 	const bool multi = M.nr_classes > 1;

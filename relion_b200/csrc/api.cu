@@ -98,13 +98,13 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->proj2_buf[i].release(); ctx->proj2c_buf[i].release(); ctx->bp_buf[i].release(); }
+	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->proj2_buf[i].release(); ctx->proj2c_buf[i].release(); ctx->bp_buf[i].release(); ctx->bp_blk_buf[i].release(); }
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
 	                  &ctx->m_cc[0], &ctx->m_cc[1], &ctx->m_cc[2], &ctx->m_cc[3], &ctx->m_cc[4], &ctx->m_cc[5],
 	                  &ctx->m_pix_c, &ctx->m_pix_f, &ctx->m_minvs2, &ctx->m_pdf_dir, &ctx->m_pdf_class, &ctx->m_dvp, &ctx->d_proj, &ctx->d_bp,
-	                  &ctx->m_pix_rs, &ctx->band_slices, &ctx->band_tabc, &ctx->band_tabo, &ctx->band_tabu, &ctx->comm_buf, &ctx->comm_buf2};
+	                  &ctx->m_pix_rs, &ctx->band_slices, &ctx->band_tabc, &ctx->band_tabo, &ctx->band_tabu, &ctx->comm_buf, &ctx->comm_buf2, &ctx->posed_pix, &ctx->posed_sorted};
 	for (DevBuf *b : bufs) b->release();
 	for (rb_ctx::BlockTable *t : ctx->blk_tables) { t->buf.release(); delete t; }
 	ctx->blk_tables.clear();
@@ -382,6 +382,22 @@ extern "C" int rb_bp_init(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int 
 	b.mdlX = mdlX; b.mdlY = mdlY; b.mdlZ = mdlZ; b.mdlInitY = initY; b.mdlInitZ = initZ; b.maxR = maxR; b.padding_factor = (float) pf;
 	ctx->has_bp[k] = true;
 	RB_CUDA(cudaMemsetAsync(b.vol, 0, n * sizeof(float4), ctx->stream));
+	// padded block accumulator of the band-major kernels (3D accumulators; RB_BP_BLOCKS=0: scatter into vol)
+	b.blkvol = nullptr; b.blk = nullptr; b.nbx = b.nbxy = 0;
+	ctx->bp_blk_dirty[k] = false;
+	{
+		const char *e = getenv("RB_BP_BLOCKS");
+		const int nbx = (mdlX + 3) / 4, nby = (mdlY + 3) / 4, nbz = (mdlZ + 3) / 4;
+		const size_t nvox = (size_t) nbx * nby * nbz * 128;
+		if (!(e && atoi(e) == 0) && !ctx->bp_2d[k] && nvox < ((size_t) 1 << 31))
+		{
+			const uint32_t *blk = nullptr;
+			RB_CHECK(block_table(ctx, mdlX, mdlY, mdlZ, initY, initZ, &blk));
+			RB_CHECK(ctx->bp_blk_buf[k].ensure(nvox * sizeof(float4)));
+			b.blkvol = ctx->bp_blk_buf[k].as<float4>(); b.blk = blk; b.nbx = nbx; b.nbxy = nbx * nby;
+			RB_CUDA(cudaMemsetAsync(b.blkvol, 0, nvox * sizeof(float4), ctx->stream));
+		}
+	}
 	RB_CHECK(rb_sync_tables(ctx));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	return RB_OK;
@@ -393,6 +409,20 @@ extern "C" int rb_bp_clear(rb_ctx *ctx, int k)
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_clear: accumulator %d not initialised", k);
 	const RbBackprojector &b = ctx->bp[k];
 	RB_CUDA(cudaMemsetAsync(b.vol, 0, (size_t) b.mdlX * b.mdlY * b.mdlZ * sizeof(float4), ctx->stream));
+	if (b.blkvol && ctx->bp_blk_dirty[k])
+	{
+		RB_CUDA(cudaMemsetAsync(b.blkvol, 0, ctx->bp_blk_buf[k].bytes, ctx->stream));
+		ctx->bp_blk_dirty[k] = false;
+	}
+	return RB_OK;
+}
+
+// contributions the band-major kernels left in the padded block accumulator -> vol
+int rb_bp_fold(rb_ctx *ctx, int k)
+{
+	if (!ctx->has_bp[k] || !ctx->bp[k].blkvol || !ctx->bp_blk_dirty[k]) return RB_OK;
+	RB_CHECK(rbk_bp_fold(ctx, ctx->bp[k]));
+	ctx->bp_blk_dirty[k] = false;
 	return RB_OK;
 }
 
@@ -400,6 +430,7 @@ extern "C" int rb_bp_get(rb_ctx *ctx, int k, float *real, float *imag, float *we
 {
 	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_get: accumulator %d not initialised", k);
+	RB_CHECK(rb_bp_fold(ctx, k));
 	const RbBackprojector &b = ctx->bp[k];
 	size_t n = (size_t) b.mdlX * b.mdlY * b.mdlZ;
 	RB_CHECK(ctx->scratch[2].ensure(3 * n * sizeof(float)));
@@ -429,6 +460,7 @@ extern "C" int rb_bp_symmetrise(rb_ctx *ctx, int k, const double *R, int nsym)
 		RB_CHECK(upload(ctx, ctx->scratch[3], r.data(), r.size() * 4));
 		d_R = ctx->scratch[3].as<float>();
 	}
+	RB_CHECK(rb_bp_fold(ctx, k));
 	RB_CHECK(rbk_bp_symmetrise(ctx, ctx->bp[k], ctx->recon_buf[1], d_R, nsym));
 	return RB_OK;
 }
@@ -450,6 +482,7 @@ extern "C" int rb_reconstruct(rb_ctx *ctx, int k, int ori_size, const double *ta
 		RB_CUDA(cudaMemcpyAsync(ctx->scratch[3].p, tau2, (size_t) n_tau2 * 8, cudaMemcpyHostToDevice, ctx->stream));
 		d_tau2 = ctx->scratch[3].as<double>();
 	}
+	RB_CHECK(rb_bp_fold(ctx, k));
 	RB_CHECK(rbk_reconstruct(ctx, ctx->bp[k], ori_size, d_tau2, n_tau2, tau2_fudge, minres_map, ctx->scratch[2].as<float>()));
 	RB_CUDA(cudaMemcpyAsync(vol_out, ctx->scratch[2].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -465,6 +498,7 @@ extern "C" int rb_update_ssnr(rb_ctx *ctx, int k, int ori_size, double tau2_fudg
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_update_ssnr: accumulator %d not initialised", k);
 	RB_ARG(tau2_io && sigma2_out && data_vs_prior_out && fourier_coverage_out && ori_size > 0, "rb_update_ssnr: NULL spectrum");
 	RB_CUDA(cudaSetDevice(ctx->device));
+	RB_CHECK(rb_bp_fold(ctx, k));
 	return rbk_update_ssnr(ctx, ctx->bp[k], ctx->bp_2d[k], ori_size, tau2_fudge, tau2_io, sigma2_out, data_vs_prior_out, fourier_coverage_out,
 	                       fsc, avgctf2, update_tau2_with_fsc != 0, is_whole_instead_of_half != 0);
 }
@@ -472,6 +506,9 @@ extern "C" int rb_update_ssnr(rb_ctx *ctx, int k, int ori_size, double tau2_fudg
 extern "C" int rb_bp_device_buffer(rb_ctx *ctx, int k, void **dptr, size_t *n_floats)
 {
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_device_buffer: accumulator %d not initialised", k);
+	RB_CUDA(cudaSetDevice(ctx->device));
+	RB_CHECK(rb_bp_fold(ctx, k));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));      // the caller works on the buffer from its own stream
 	const RbBackprojector &b = ctx->bp[k];
 	if (dptr) *dptr = b.vol;
 	if (n_floats) *n_floats = (size_t) b.mdlX * b.mdlY * b.mdlZ * 4;
@@ -1082,7 +1119,11 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	RB_CHECK(rb_stage_end(ctx, "weights_fine"));
 
 	RB_CHECK(rb_stage_begin(ctx, "store"));
-	if (!(flags & 1u)) RB_CHECK(band ? rbk_band_store_pool(ctx, s) : rbk_store_pool(ctx, s));
+	if (!(flags & 1u))
+	{
+		RB_CHECK(band ? rbk_band_store_pool(ctx, s) : rbk_store_pool(ctx, s));
+		if (band) for (int k = 0; k < M.nr_classes; k++) ctx->bp_blk_dirty[k] = ctx->bp[k].blkvol != nullptr;
+	}
 	RB_CHECK(rb_stage_end(ctx, "store"));
 	RB_CHECK(rb_stage_end(ctx, "total"));
 	RB_CUDA(cudaEventRecord(s.done, ctx->stream));
@@ -1454,6 +1495,7 @@ extern "C" int rb_backproject_posed(rb_ctx *ctx, int k, int n, int count,
 		RB_CUDA(cudaEventRecord(uploaded, ctx->copy_stream));
 		RB_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded, 0));
 		RB_CHECK(rbk_backproject_posed(ctx, ctx->bp[k], n, c, ctx->posed_buf[ib][0].as<float2>(), ctx->posed_buf[ib][1].as<float>(), ctx->posed_buf[ib][2].as<float>()));
+		ctx->bp_blk_dirty[k] = ctx->bp[k].blkvol != nullptr;
 		RB_CUDA(cudaEventRecord(ctx->posed_ev[ib], ctx->stream));
 	}
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1483,6 +1525,7 @@ extern "C" int rb_bp_posed_run(rb_ctx *ctx, int k)
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_posed_run: accumulator %d not initialised", k);
 	if (ctx->posed_count < 1) { rb_set_error("rb_bp_posed_run: nothing staged (rb_bp_posed_stage)"); return RB_ERR_STATE; }
 	RB_CUDA(cudaSetDevice(ctx->device));
+	ctx->bp_blk_dirty[k] = ctx->bp[k].blkvol != nullptr;
 	return rbk_backproject_posed(ctx, ctx->bp[k], ctx->posed_n, ctx->posed_count, ctx->posed_buf[0][0].as<float2>(),
 	                             ctx->posed_buf[0][1].as<float>(), ctx->posed_buf[0][2].as<float>());
 }

@@ -135,6 +135,7 @@ extern "C" int rb_bp_allreduce_nccl(rb_ctx *ctx, void *nccl_comm, int nr_classes
 		for (int k = 0; k < nr_classes; k++)
 		{
 			RB_ARG(ctx->has_bp[k], "rb_bp_allreduce: accumulator %d not initialised", k);
+			RB_CHECK(rb_bp_fold(ctx, k));
 			const RbBackprojector &b = ctx->bp[k];
 			const size_t n = (size_t) b.mdlX * b.mdlY * b.mdlZ;
 			RB_CHECK(ctx->comm_buf.ensure(3 * n * sizeof(float)));

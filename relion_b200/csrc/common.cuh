@@ -77,7 +77,22 @@ struct RbBackprojector {
 	int mdlInitY, mdlInitZ;
 	int maxR;
 	float padding_factor;
+	// Scatter target of the band-major kernels (nullptr: scatter into vol).  The voxels of every 4 x 4 x 4 block are kept
+	// together with their +1 halo (5 x 5 x 5 -> 128 float4 = 2 KB, so the eight corners of any cell that starts in the block
+	// are in it: y stride 5, z stride 25) and the blocks are ordered by radius like the expanded reference's (RbProjector::blk):
+	// a band sweep reduces into one contiguous range instead of a slice through all ~520 pages of vol.  Measured
+	// (tools/shell_prefetch_bench.cu): 8 x red.v4 per sample in a shell 10.7 G samples/s into [z][y][x], 28.8 G into this.
+	// rb_bp_fold adds the blocks into vol (and clears them) before anything reads vol.
+	float4 *blkvol;
+	const uint32_t *blk;
+	int nbx, nbxy;
 };
+// voxel index inside blkvol of the origin of cell (x0, yi, zi); its corners are at +1, +5, +25 (and sums)
+__device__ __forceinline__ size_t rb_bp_blk_cell(const RbBackprojector &b, int x0, int yi, int zi)
+{
+	const uint32_t rank = __ldg(b.blk + (zi >> 2) * b.nbxy + (yi >> 2) * b.nbx + (x0 >> 2));
+	return ((size_t) rank << 7) + (size_t) ((zi & 3) * 25 + (yi & 3) * 5 + (x0 & 3));
+}
 
 // Pixel list entry for one window size: packed (x:10 | (y+512):11 | (ires+1):11).
 // The list holds only pixels with Mresol >= 0 (ires >= 0), i.e. inside the Nyquist circle and not
@@ -239,6 +254,8 @@ struct rb_ctx {
 	std::vector<BlockTable *> blk_tables;
 	RbBackprojector bp[RB_MAX_CLASSES];
 	DevBuf bp_buf[RB_MAX_CLASSES];
+	DevBuf bp_blk_buf[RB_MAX_CLASSES];               // padded block accumulators (RbBackprojector::blkvol)
+	bool bp_blk_dirty[RB_MAX_CLASSES] = {false};     // blkvol holds contributions that are not in vol yet (rb_bp_fold)
 	bool has_proj[RB_MAX_CLASSES] = {false}, has_bp[RB_MAX_CLASSES] = {false};
 	// 2D references / accumulators (2D classification) live in a two-plane volume [2][Y][X] whose second plane is zero:
 	// with in-plane rotations zp == 0, so the trilinear code paths reduce exactly to project2Dmodel / backproject2D
@@ -278,6 +295,8 @@ struct rb_ctx {
 	int prep_plan = 0, prep_plan_n = 0, prep_plan_batch = 0;   // this context's batched 2D R2C cuFFT plan (cufftHandle is an int); 0 batch: none
 	DevBuf prep_raw[RB_NUM_SLOTS][4];   // per slot: raw images, shifts, norm factors, CTF parameters (filled on the copy stream)
 	DevBuf posed_buf[2][3];          // staged posed images (F2D, Fctf, matrices), two buffers for upload / compute overlap
+	DevBuf posed_pix, posed_sorted;  // band-major posed back-projection: pixel list of the image size, band-ordered images of a chunk
+	int posed_pix_n = 0, posed_pix_count = 0;
 	int posed_n = 0, posed_count = 0;   // what rb_bp_posed_stage left in posed_buf[0]
 	cudaEvent_t posed_ev[2] = {nullptr, nullptr};               // partials / compact list of the multi-CTA coarse weight conversion
 	DevBuf gemm_buf[10];             // operands of the tensor-core coarse pass (kernels_gemm.cu)
@@ -292,6 +311,8 @@ struct rb_ctx {
 int rb_stage_begin(rb_ctx *ctx, const char *name);
 int rb_stage_end(rb_ctx *ctx, const char *name);
 int rb_sync_tables(rb_ctx *ctx);   // refresh d_proj / d_bp device tables
+int rb_bp_fold(rb_ctx *ctx, int k);  // blkvol -> vol (no-op when clean); every reader of vol calls it first
+int rbk_bp_fold(rb_ctx *ctx, const RbBackprojector &bp);
 
 // ---------------------------------------------------------------------------------------------
 // kernel launchers (one per .cu)
@@ -303,6 +324,7 @@ int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 
 int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
 int rbk_backproject_posed(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers);
+int rbk_backproject_posed_band(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers);
 int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out);
 
 // kernels_diff2.cu

@@ -794,7 +794,8 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 						if (xp < 0.f) { xp = -xp; yp = -yp; zp = -zp; Fi = -Fi; }
 						const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
 						sfx = xp - fx0; sfy = yp - fy0; sfz = zp - fz0;
-						cell = (((int) fz0 - bp.mdlInitZ) * bp.mdlY + ((int) fy0 - bp.mdlInitY)) * bp.mdlX + (int) fx0;
+						cell = bp.blkvol ? (int) rb_bp_blk_cell(bp, (int) fx0, (int) fy0 - bp.mdlInitY, (int) fz0 - bp.mdlInitZ)
+						                 : (((int) fz0 - bp.mdlInitZ) * bp.mdlY + ((int) fy0 - bp.mdlInitY)) * bp.mdlX + (int) fx0;
 					}
 				}
 			}
@@ -811,13 +812,158 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 					const int px = lane & 1;
 					const float wx = px ? fx : 1.f - fx;
 					const float mfy = 1.f - fy, mfz = 1.f - fz;
-					float4 *b = bp.vol + (size_t) cc + px;
-					const size_t sy = bp.mdlX, sz = (size_t) bp.mdlX * bp.mdlY;
+					float4 *b = (bp.blkvol ? bp.blkvol : bp.vol) + (size_t) cc + px;
+					const size_t sy = bp.blkvol ? 5 : bp.mdlX, sz = bp.blkvol ? 25 : (size_t) bp.mdlX * bp.mdlY;
 					float d2;
 					d2 = mfz * mfy * wx; bd_red_add_v4(b, d2 * vr, d2 * vi, d2 * vw);
 					d2 = mfz * fy * wx;  bd_red_add_v4(b + sy, d2 * vr, d2 * vi, d2 * vw);
 					d2 = fz * mfy * wx;  bd_red_add_v4(b + sz, d2 * vr, d2 * vi, d2 * vw);
 					d2 = fz * fy * wx;   bd_red_add_v4(b + sz + sy, d2 * vr, d2 * vi, d2 * vw);
+				}
+			}
+			cur = nxt;
+		}
+		if (threadIdx.x == 0) S.next = (int) gridDim.x + pending;
+		__syncthreads();
+		item = S.next;
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Posed back-projection (relion_reconstruct, BASELINE config #2), band-major.
+// BackProjector::backproject2Dto3D (/root/reference/src/backprojector.cpp:55-357) for a batch of images: the per-sample
+// arithmetic is k_backproject_posed's (kernels_misc.cu: fp64 positions, the reference's pixel set), the ORDER is the store
+// stage's: the images are first copied into band order (tile-major float4 (re, im, ctf^2, 0)), then work items (tile,
+// chunk of images) sweep Fourier space shell by shell, so the accumulator shell being reduced into stays in L2 instead
+// of every image dragging its own great circle through the 1.1 GB accumulator.
+// ---------------------------------------------------------------------------------------------
+struct PosedBandArgs {
+	RbBackprojector bp; int n, count;
+	const float2 *F2D; const float *Fctf; const float *eulers;
+	const uint32_t *pix; int npix, stride;
+	float4 *sF;                  // tile-major [stride / BD_TP][count][BD_TP]
+	int *queue; int chunk_min;
+};
+
+static __global__ void __launch_bounds__(256)
+k_posed_sort(PosedBandArgs A)
+{
+	const int img = blockIdx.y, xs = A.n / 2 + 1;
+	const float2 *F = A.F2D + (size_t) img * A.n * xs;
+	const float *W = A.Fctf + (size_t) img * A.n * xs;
+	for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < A.stride; ip += gridDim.x * blockDim.x)
+	{
+		float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (ip < A.npix)
+		{
+			const uint32_t pk = __ldg(A.pix + ip);
+			const int x = rb_pix_x(pk), y = rb_pix_y(pk);
+			const int idx = (y < 0 ? y + A.n : y) * xs + x;
+			const float2 v = __ldg(F + idx);
+			o = make_float4(v.x, v.y, __ldg(W + idx), 0.f);
+		}
+		A.sF[bd_at(img, ip, A.count)] = o;
+	}
+}
+
+struct PosedBandSmem { double a[BD_MAXCHUNK][6]; double ata[BD_MAXCHUNK][3]; int next; };
+
+static __global__ void __launch_bounds__(BD_THREADS, 3)
+k_posed_band(PosedBandArgs A)
+{
+	__shared__ PosedBandSmem S;
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	const RbBackprojector bp = A.bp;
+	const double pf = (double) bp.padding_factor;
+	const long long rr = (long long) floor((double) bp.maxR * pf + 0.5);
+	const double max_r2 = (double) (rr * rr);
+	const size_t sy = bp.blkvol ? 5 : bp.mdlX, sz = bp.blkvol ? 25 : (size_t) bp.mdlX * bp.mdlY;
+	const int n = A.count;
+	const int ntiles = (A.npix + BD_TP - 1) / BD_TP;
+	int chunk = (n + (int) gridDim.x - 1) / (int) gridDim.x;
+	chunk = max(A.chunk_min, min(BD_MAXCHUNK, chunk));
+	const int nchunks = (n + chunk - 1) / chunk;
+	const long long nitems = (long long) ntiles * nchunks;
+	const int ph = wid / BD_WPT;
+
+	long long item = blockIdx.x;
+	while (item < nitems)
+	{
+		const int tile = (int) (item / nchunks), c = (int) (item - (long long) tile * nchunks);
+		const int o0 = c * chunk, no = min(chunk, n - o0);
+		for (int j = threadIdx.x; j < no; j += BD_THREADS)
+		{
+			const float *e = A.eulers + (size_t) (o0 + j) * 9;
+			const double a00 = (double) e[0] * pf, a01 = (double) e[1] * pf, a10 = (double) e[3] * pf, a11 = (double) e[4] * pf,
+			             a20 = (double) e[6] * pf, a21 = (double) e[7] * pf;
+			S.a[j][0] = a00; S.a[j][1] = a01; S.a[j][2] = a10; S.a[j][3] = a11; S.a[j][4] = a20; S.a[j][5] = a21;
+			S.ata[j][0] = a00 * a00 + a10 * a10 + a20 * a20; S.ata[j][1] = a00 * a01 + a10 * a11 + a20 * a21;
+			S.ata[j][2] = a01 * a01 + a11 * a11 + a21 * a21;
+		}
+		int pending = 0;
+		if (threadIdx.x == 0) pending = atomicAdd(A.queue, 1);
+		__syncthreads();
+		const int ip = tile * BD_TP + (wid % BD_WPT) * 32 + lane;
+		const bool have = ip < A.npix;
+		int x = 0, y = 0;
+		if (have) { const uint32_t pkx = __ldg(A.pix + ip); x = rb_pix_x(pkx); y = rb_pix_y(pkx); }
+		float4 cur = make_float4(0.f, 0.f, 0.f, 0.f), nxt = cur;
+		if (have && ph < no) cur = __ldcs(A.sF + bd_at(o0 + ph, ip, n));
+		for (int j = ph; j < no; j += BD_NPH)
+		{
+			if (have && j + BD_NPH < no) nxt = __ldcs(A.sF + bd_at(o0 + j + BD_NPH, ip, n));
+			long long cell = -1;
+			float sfx = 0.f, sfy = 0.f, sfz = 0.f, vr = 0.f, vi = 0.f, vw = 0.f;
+			if (have && cur.z > 0.f)
+			{
+				// The reference first solves |A (x, y)|^2 <= max_r2 for the x-range of the row (:118-128, a double sqrt and two
+				// divisions) and then tests the same quadratic form per pixel (:150): the two can only disagree when a pixel sits on
+				// the sphere to rounding, so the row solve is evaluated for those pixels alone.
+				double xp = S.a[j][0] * x + S.a[j][1] * y, yp = S.a[j][2] * x + S.a[j][3] * y, zp = S.a[j][4] * x + S.a[j][5] * y;
+				const double r2 = xp * xp + yp * yp + zp * zp;
+				bool ok = r2 <= max_r2;
+				if (ok && max_r2 - r2 < 1e-9 * max_r2)
+				{
+					const double AtA_xx = S.ata[j][0], AtA_xy = S.ata[j][1], AtA_yy = S.ata[j][2];
+					const double discr = AtA_xy * AtA_xy * y * y - AtA_xx * (AtA_yy * y * y - max_r2);
+					ok = discr >= 0.;
+					if (ok)
+					{
+						const double d = sqrt(discr) / AtA_xx, q = -AtA_xy * y / AtA_xx;
+						ok = x >= (int) ceil(q - d) && x <= (int) floor(q + d);
+					}
+				}
+				if (ok)
+				{
+					float2 v = make_float2(cur.x, cur.y);
+					if (xp < 0.) { xp = -xp; yp = -yp; zp = -zp; v.y = -v.y; }
+					const double fx0 = floor(xp), fy0 = floor(yp), fz0 = floor(zp);
+					const int x0 = (int) fx0, y0 = (int) fy0 - bp.mdlInitY, z0 = (int) fz0 - bp.mdlInitZ;
+					if (x0 >= 0 && x0 + 1 < bp.mdlX && y0 >= 0 && y0 + 1 < bp.mdlY && z0 >= 0 && z0 + 1 < bp.mdlZ)   // :213-218
+					{
+						sfx = (float) (xp - fx0); sfy = (float) (yp - fy0); sfz = (float) (zp - fz0);
+						vr = v.x; vi = v.y; vw = cur.z;
+						cell = bp.blkvol ? (long long) rb_bp_blk_cell(bp, x0, y0, z0) : ((long long) z0 * bp.mdlY + y0) * bp.mdlX + x0;
+					}
+				}
+			}
+#pragma unroll
+			for (int h = 0; h < 2; h++)
+			{
+				const int src = 16 * h + (lane >> 1);
+				const long long cc = __shfl_sync(RB_FULL_MASK, cell, src);
+				const float fx = __shfl_sync(RB_FULL_MASK, sfx, src), fy = __shfl_sync(RB_FULL_MASK, sfy, src), fz = __shfl_sync(RB_FULL_MASK, sfz, src);
+				const float r = __shfl_sync(RB_FULL_MASK, vr, src), im = __shfl_sync(RB_FULL_MASK, vi, src), w = __shfl_sync(RB_FULL_MASK, vw, src);
+				if (cc >= 0)
+				{
+					const int px = lane & 1;
+					const float wx = px ? fx : 1.f - fx, mfy = 1.f - fy, mfz = 1.f - fz;
+					float4 *b = (bp.blkvol ? bp.blkvol : bp.vol) + (size_t) cc + px;
+					float dd;
+					dd = mfz * mfy * wx; bd_red_add_v4(b, dd * r, dd * im, dd * w);
+					dd = mfz * fy * wx;  bd_red_add_v4(b + sy, dd * r, dd * im, dd * w);
+					dd = fz * mfy * wx;  bd_red_add_v4(b + sz, dd * r, dd * im, dd * w);
+					dd = fz * fy * wx;   bd_red_add_v4(b + sz + sy, dd * r, dd * im, dd * w);
 				}
 			}
 			cur = nxt;
@@ -1008,5 +1154,57 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 		else k_store_band<false><<<grid, BD_THREADS, 0, ctx->stream>>>(A, M);
 		RB_LAUNCH_CHECK(ctx);
 	}
+	return RB_OK;
+}
+
+// band-ordered pixel list of an n x (n/2+1) half transform: every pixel backproject2Dto3D can use (x = 0 only for y >= 0)
+static int posed_pixlist(rb_ctx *ctx, int n)
+{
+	if (ctx->posed_pix_n == n) return RB_OK;
+	const int xs = n / 2 + 1;
+	std::vector<uint32_t> v;
+	v.reserve((size_t) n * xs);
+	for (int i = 0; i < n; i++)
+		for (int x = 0; x < xs; x++)
+		{
+			const int y = i < xs ? i : i - n;
+			if (y < 0 && x == 0) continue;                                       // first_allowed_x (backprojector.cpp:107-116)
+			v.push_back(rb_pack_pix(x, y, 0));
+		}
+	std::sort(v.begin(), v.end(), [](uint32_t a, uint32_t b) {
+		const int xa = rb_pix_x(a), ya = rb_pix_y(a), xb = rb_pix_x(b), yb = rb_pix_y(b);
+		const int ra = xa * xa + ya * ya, rb2 = xb * xb + yb * yb;
+		if (ra != rb2) return ra < rb2;
+		const double ta = atan2((double) ya, (double) xa), tb = atan2((double) yb, (double) xb);
+		if (ta != tb) return ta < tb;
+		return a < b;
+	});
+	ctx->posed_pix_count = (int) v.size();
+	v.resize((v.size() + BD_TP - 1) / BD_TP * BD_TP, rb_pack_pix(0, 0, 0));
+	RB_CHECK(ctx->posed_pix.ensure(v.size() * 4));
+	RB_CUDA(cudaMemcpyAsync(ctx->posed_pix.p, v.data(), v.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->posed_pix_n = n;
+	return RB_OK;
+}
+
+int rbk_backproject_posed_band(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers)
+{
+	if (count < 1) return RB_OK;
+	RB_CHECK(posed_pixlist(ctx, n));
+	PosedBandArgs A;
+	memset(&A, 0, sizeof(A));
+	A.bp = bp; A.n = n; A.count = count; A.F2D = d_F; A.Fctf = d_W; A.eulers = d_eulers;
+	A.pix = ctx->posed_pix.as<uint32_t>(); A.npix = ctx->posed_pix_count; A.stride = (A.npix + BD_TP - 1) / BD_TP * BD_TP;
+	RB_CHECK(ctx->posed_sorted.ensure((size_t) count * A.stride * sizeof(float4) + 64));
+	A.sF = ctx->posed_sorted.as<float4>();
+	A.queue = (int *) ((char *) ctx->posed_sorted.p + (size_t) count * A.stride * sizeof(float4));
+	A.chunk_min = std::max(BD_NPH, env_int("RB_POSED_CHUNK_MIN", 8));
+	RB_CUDA(cudaMemsetAsync(A.queue, 0, 4, ctx->stream));
+	dim3 g((unsigned) ((A.stride + 255) / 256), (unsigned) count);
+	k_posed_sort<<<g, 256, 0, ctx->stream>>>(A);
+	RB_LAUNCH_CHECK(ctx);
+	k_posed_band<<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(A);
+	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

@@ -105,6 +105,62 @@ int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInit
 	return RB_OK;
 }
 
+// padded block accumulator -> canonical accumulator: voxel (x, y, z) is local (x & 3, ...) of its own block and, where a
+// coordinate is a multiple of 4, local 4 of the block before it along that axis: up to 8 copies, each read (and cleared)
+// by exactly one voxel, summed in a fixed order
+__global__ void k_bp_fold(RbBackprojector bp)
+{
+	const size_t n = (size_t) bp.mdlX * bp.mdlY * bp.mdlZ;
+	const int nbx = bp.nbx, nby = bp.nbxy / bp.nbx;
+	const int nbz = (bp.mdlZ + 3) >> 2;
+	for (size_t v = blockIdx.x * (size_t) blockDim.x + threadIdx.x; v < n; v += (size_t) gridDim.x * blockDim.x)
+	{
+		const int x = (int) (v % bp.mdlX);
+		const int y = (int) ((v / bp.mdlX) % bp.mdlY);
+		const int z = (int) (v / ((size_t) bp.mdlX * bp.mdlY));
+		float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+		for (int cz = 0; cz < 2; cz++)
+		{
+			int bz = z >> 2, lz = z & 3;
+			if (cz) { if (lz != 0 || bz == 0) continue; bz--; lz = 4; }
+			if (bz >= nbz) continue;
+			for (int cy = 0; cy < 2; cy++)
+			{
+				int by = y >> 2, ly = y & 3;
+				if (cy) { if (ly != 0 || by == 0) continue; by--; ly = 4; }
+				if (by >= nby) continue;
+				for (int cx = 0; cx < 2; cx++)
+				{
+					int bx = x >> 2, lx = x & 3;
+					if (cx) { if (lx != 0 || bx == 0) continue; bx--; lx = 4; }
+					if (bx >= nbx) continue;
+					const uint32_t rank = bp.blk[(bz * nby + by) * nbx + bx];
+					float4 *p = bp.blkvol + ((size_t) rank << 7) + (lz * 25 + ly * 5 + lx);
+					const float4 a = *p;
+					if (a.x != 0.f || a.y != 0.f || a.z != 0.f)
+					{
+						acc.x += a.x; acc.y += a.y; acc.z += a.z;
+						*p = make_float4(0.f, 0.f, 0.f, 0.f);
+					}
+				}
+			}
+		}
+		if (acc.x != 0.f || acc.y != 0.f || acc.z != 0.f)
+		{
+			float4 c = bp.vol[v];
+			c.x += acc.x; c.y += acc.y; c.z += acc.z;
+			bp.vol[v] = c;
+		}
+	}
+}
+
+int rbk_bp_fold(rb_ctx *ctx, const RbBackprojector &bp)
+{
+	k_bp_fold<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(bp);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
 // AccBackprojector::getMdlData (acc_backprojector_impl.h:109-138): interleaved float4 -> three SoA arrays
 __global__ void k_bp_deinterleave(const float4 *vol, float *re, float *im, float *w, size_t n)
 {
@@ -248,6 +304,10 @@ k_backproject_posed(RbBackprojector bp, int n, int count, const float2 *F2D, con
 int rbk_backproject_posed(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers)
 {
 	if (count < 1) return RB_OK;
+	// band-major order (kernels_band.cu) unless RB_POSED_BAND=0 or the batch is too small to fill the GPU shell by shell
+	static int band = -1;
+	if (band < 0) { const char *e = getenv("RB_POSED_BAND"); band = e ? atoi(e) : 1; }
+	if (band && (count >= 64 || band == 2)) return rbk_backproject_posed_band(ctx, bp, n, count, d_F, d_W, d_eulers);
 	const int grid = count < ctx->num_sms * 8 ? count : ctx->num_sms * 8;
 	k_backproject_posed<<<grid, 256, 0, ctx->stream>>>(bp, n, count, d_F, d_W, d_eulers);
 	RB_LAUNCH_CHECK(ctx);

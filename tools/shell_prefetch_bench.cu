@@ -43,6 +43,12 @@ __global__ void __launch_bounds__(256) k_cells(float R, float dR, int n, uint32_
 		const uint32_t rank = table[(((zi >> lb) * nby) + (yi >> lb)) * nbx + (xi >> lb)];
 		c = (rank << (3 * lb)) + ((zi & m) << (2 * lb)) + ((yi & m) << lb) + (xi & m);
 	}
+	if (layout == 5)                                                           // accumulator: radius-sorted 4^3 blocks stored with their +1 halo (5^3 -> 128 voxels)
+	{
+		const int nbx = (X + 3) >> 2, nby = (Y + 3) >> 2;
+		const uint32_t rank = table[(((zi >> 2) * nby) + (yi >> 2)) * nbx + (xi >> 2)];
+		c = (rank << 7) + (zi & 3) * 25 + (yi & 3) * 5 + (xi & 3);
+	}
 	if (layout == 4) c = (hash32(c) % ncompact) << 15;                         // one 64-byte gather per 2 MB page, ncompact pages: TLB reach
 	cells[i] = c;
 }
@@ -61,6 +67,21 @@ __global__ void __launch_bounds__(256) k_gather(const float4 *vol, const uint32_
 		acc += v[0].x + v[1].w + v[2].y + v[3].z;
 	}
 	if (acc == 123.456f) out[0] = acc;
+}
+
+// the store stage's scatter: two lanes per sample, each four red.global.add.v4.f32 (16-byte voxels) at +0, +sy, +sz, +sy+sz
+__global__ void __launch_bounds__(256) k_scatter(float4 *acc, const uint32_t *cells, int n, uint32_t sy, uint32_t sz)
+{
+	const uint32_t px = threadIdx.x & 1;
+	const int np = (gridDim.x * blockDim.x) >> 1;
+	for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 1; i < n; i += np)
+	{
+		float4 *b = acc + (size_t) __ldg(cells + i) + px;
+		asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(b), "f"(1.f) : "memory");
+		asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(b + sy), "f"(1.f) : "memory");
+		asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(b + sz), "f"(1.f) : "memory");
+		asm volatile("red.global.add.v4.f32 [%0], {%1, %1, %1, %1};" ::"l"(b + sy + sz), "f"(1.f) : "memory");
+	}
 }
 
 // MODE 0: prefetch.global.L2 per cell, 1: bulk prefetch per run, 2: loads
@@ -133,7 +154,7 @@ int main()
 		const double ng = (double) n;
 		uint32_t *cells_d; cudaMalloc(&cells_d, (size_t) n * 4);
 		k_cells<<<(n + 255) / 256, 256>>>(R, dR, n, cells_d, 0, 0);
-		for (int lb = 1; lb <= 3; lb++)
+		for (int lb = 2; lb <= 2; lb++)
 		{
 			const int m = (1 << lb) - 1, nbx = (X + m) >> lb, nby = (Y + m) >> lb, nbz = (Z + m) >> lb;
 			const size_t nb = (size_t) nbx * nby * nbz;
@@ -153,6 +174,19 @@ int main()
 			auto g2 = [&] { k_gather<<<grid, 256>>>((const float4 *) vol, c2, n, out); };
 			flush_l2(); const float c = timed(g2); const float w = timed(g2);
 			printf("R=%5.0f dR=%.1f  layout radius-sorted %d^3 blocks: cold %.3f ms (%.1f G/s)  warm %.3f ms (%.1f G/s)\n", R, dR, 1 << lb, c, ng / c * 1e-6, w, ng / w * 1e-6);
+			if (lb == 2)
+			{
+				// scatter: canonical [z][y][x] accumulator against padded radius-sorted blocks
+				uint32_t *c5; cudaMalloc(&c5, (size_t) n * 4);
+				k_cells<<<(n + 255) / 256, 256>>>(R, dR, n, c5, 5, 0, tab_d, 2);
+				auto s0 = [&] { k_scatter<<<grid, 256>>>((float4 *) vol, cells_d, n, X, X * Y); };
+				auto s5 = [&] { k_scatter<<<grid, 256>>>((float4 *) vol, c5, n, 5, 25); };
+				flush_l2(); const float a0 = timed(s0); const float a1 = timed(s0);
+				flush_l2(); const float b0 = timed(s5); const float b1 = timed(s5);
+				printf("R=%5.0f dR=%.1f  scatter (8 x red.v4 per sample): [z][y][x] cold %.3f ms warm %.3f ms (%.1f G samples/s) | padded sorted blocks cold %.3f ms warm %.3f ms (%.1f G samples/s)\n",
+				       R, dR, a0, a1, ng / a1 * 1e-6, b0, b1, ng / b1 * 1e-6);
+				cudaFree(c5);
+			}
 			cudaFree(c2); cudaFree(tab_d);
 		}
 		for (int layout = 1; layout <= 2; layout++)

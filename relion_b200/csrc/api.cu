@@ -210,7 +210,9 @@ static int block_table(rb_ctx *ctx, int mdlX, int mdlY, int mdlZ, int initY, int
 		if (!memcmp(t->geom, geom, sizeof(geom))) { *table = t->buf.as<uint32_t>(); return RB_OK; }
 	const int nbx = (mdlX + 3) / 4, nby = (mdlY + 3) / 4, nbz = (mdlZ + 3) / 4;
 	const size_t nb = (size_t) nbx * nby * nbz;
-	std::vector<uint32_t> key(nb), rank(nb);
+	const int kbx = (nbx + 3) / 4, kby = (nby + 3) / 4, kbz = (nbz + 1) / 2;            // bricks of 4 x 4 x 2 blocks (rb_blk_slot)
+	const size_t nslot = (size_t) kbx * kby * kbz * 32;
+	std::vector<uint32_t> key(nb), rank(nb), slots(nslot, 0u);
 	uint32_t kmax = 0;
 	for (int bz = 0; bz < nbz; bz++)
 		for (int by = 0; by < nby; by++)
@@ -230,11 +232,15 @@ static int block_table(rb_ctx *ctx, int mdlX, int mdlY, int mdlZ, int initY, int
 		for (size_t i = 1; i < start.size(); i++) start[i] += start[i - 1];
 		for (size_t i = 0; i < nb; i++) rank[i] = start[key[i]]++;
 	}
+	for (int bz = 0; bz < nbz; bz++)
+		for (int by = 0; by < nby; by++)
+			for (int bx = 0; bx < nbx; bx++)
+				slots[rb_blk_slot(kbx, kbx * kby, bx, by, bz)] = rank[((size_t) bz * nby + by) * nbx + bx];
 	rb_ctx::BlockTable *t = new rb_ctx::BlockTable();
 	memcpy(t->geom, geom, sizeof(geom));
-	int rc = t->buf.ensure(nb * sizeof(uint32_t));
+	int rc = t->buf.ensure(nslot * sizeof(uint32_t));
 	if (rc != RB_OK) { delete t; return rc; }
-	RB_CUDA(cudaMemcpyAsync(t->buf.p, rank.data(), nb * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaMemcpyAsync(t->buf.p, slots.data(), nslot * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->blk_tables.push_back(t);
 	*table = t->buf.as<uint32_t>();
@@ -266,7 +272,7 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int &mdl
 	p.mdlX = mdlX; p.mdlY = mdlY; p.mdlZ = mdlZ; p.mdlXY = mdlX * mdlY;
 	p.mdlInitY = initY; p.mdlInitZ = initZ; p.mdlMaxR = maxR; p.padding_factor = (float) pf;
 	p.c2X = mdlX; p.c2XY = p.mdlXY; p.c2InitY = initY; p.c2InitZ = initZ;       // full x-pair copy until a pool asks for the core
-	p.blk = blk; p.nbx = nbx; p.nbxy = nbx * nby;
+	p.blk = blk; p.nbx = (nbx + 3) / 4; p.nbxy = p.nbx * ((nby + 3) / 4);       // brick grid of the table (rb_blk_slot)
 	ctx->core_stamp[k] = -1;
 	ctx->has_proj[k] = true;
 	if (ctx->ref_2d[k]) RB_CUDA(cudaMemsetAsync(ctx->proj_buf[k].as<float2>() + (size_t) mdlX * mdlY, 0, (size_t) mdlX * mdlY * sizeof(float2), ctx->stream));
@@ -394,7 +400,7 @@ extern "C" int rb_bp_init(rb_ctx *ctx, int k, int mdlX, int mdlY, int mdlZ, int 
 			const uint32_t *blk = nullptr;
 			RB_CHECK(block_table(ctx, mdlX, mdlY, mdlZ, initY, initZ, &blk));
 			RB_CHECK(ctx->bp_blk_buf[k].ensure(nvox * sizeof(float4)));
-			b.blkvol = ctx->bp_blk_buf[k].as<float4>(); b.blk = blk; b.nbx = nbx; b.nbxy = nbx * nby;
+			b.blkvol = ctx->bp_blk_buf[k].as<float4>(); b.blk = blk; b.nbx = (nbx + 3) / 4; b.nbxy = b.nbx * ((nby + 3) / 4);
 			RB_CUDA(cudaMemsetAsync(b.blkvol, 0, nvox * sizeof(float4), ctx->stream));
 		}
 	}

@@ -42,6 +42,15 @@ static const int RB_NUM_SLOTS = 2;
 // device-side descriptors
 // ---------------------------------------------------------------------------------------------
 
+// Slot of block (bx, by, bz) in a block-rank table (RbProjector::blk, RbBackprojector::blk).  The table itself is stored in
+// BRICKS of 4 x 4 x 2 blocks (32 entries = one 128-byte line per 16 x 16 x 8 voxels): the 32 lanes of a warp look up the
+// blocks along an arc ~64 voxels long, which crosses 4-8 bricks but ~16 rows of a [bz][by][bx] table.
+// nbx / nbxy: bricks along x, bricks per z-layer of bricks.
+__host__ __device__ inline uint32_t rb_blk_slot(int nbx, int nbxy, int bx, int by, int bz)
+{
+	return ((uint32_t) ((bz >> 1) * nbxy + (by >> 2) * nbx + (bx >> 2)) << 5) | (uint32_t) (((bz & 1) << 4) | ((by & 3) << 2) | (bx & 3));
+}
+
 // AccProjectorKernel state (acc_projectorkernel_impl.h:19-69); volume is interleaved (re,im)
 struct RbProjector {
 	const float2 *mdl;
@@ -90,7 +99,7 @@ struct RbBackprojector {
 // voxel index inside blkvol of the origin of cell (x0, yi, zi); its corners are at +1, +5, +25 (and sums)
 __device__ __forceinline__ size_t rb_bp_blk_cell(const RbBackprojector &b, int x0, int yi, int zi)
 {
-	const uint32_t rank = __ldg(b.blk + (zi >> 2) * b.nbxy + (yi >> 2) * b.nbx + (x0 >> 2));
+	const uint32_t rank = __ldg(b.blk + rb_blk_slot(b.nbx, b.nbxy, x0 >> 2, yi >> 2, zi >> 2));
 	return ((size_t) rank << 7) + (size_t) ((zi & 3) * 25 + (yi & 3) * 5 + (x0 & 3));
 }
 

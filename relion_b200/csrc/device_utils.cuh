@@ -170,7 +170,7 @@ struct RbProjK8 {
 // 4 x 4 x 4 block in the radius-sorted block order, then (z, y, x) inside the block (see RbProjector::blk)
 __device__ __forceinline__ int rb_cell8(const uint32_t *blk, int nbx, int nbxy, int x0, int yi, int zi)
 {
-	const uint32_t rank = __ldg(blk + (zi >> 2) * nbxy + (yi >> 2) * nbx + (x0 >> 2));
+	const uint32_t rank = __ldg(blk + rb_blk_slot(nbx, nbxy, x0 >> 2, yi >> 2, zi >> 2));
 	return (int) ((rank << 6) | (uint32_t) (((zi & 3) << 4) | ((yi & 3) << 2) | (x0 & 3)));
 }
 __host__ __device__ inline RbProjK8 rb_make_projk8(const RbProjector &p, int imgX)

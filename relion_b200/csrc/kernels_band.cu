@@ -32,7 +32,7 @@ static const int BD_THREADS = 256;
 static const int BD_TP = 128;                    // pixels per tile
 static const int BD_WPT = BD_TP / 32;            // warps per tile row
 static const int BD_NPH = BD_THREADS / BD_TP;    // orientation phases per CTA
-static const int BD_MAXCHUNK = 64;
+static const int BD_MAXCHUNK = 128;
 
 // Band-major arrays are TILE-major: element (row, pixel ip) of an array with `nrows` rows (fine orientations of the round,
 // particles) sits at ((ip / BD_TP) * nrows + row) * BD_TP + ip % BD_TP.  What the resident CTAs of a band sweep touch at one
@@ -56,6 +56,8 @@ struct BandPrepArgs {
 	float *sctf;        // tile-major, ctf * part_scale
 };
 
+// WHICH: 0 = the diff2 pass' prepared image (fine stage), 1 = the store stage's X, X0, ctf
+template <int WHICH>
 static __global__ void __launch_bounds__(256)
 k_prep_sorted(BandPrepArgs A, RbModelDev M)
 {
@@ -74,19 +76,25 @@ k_prep_sorted(BandPrepArgs A, RbModelDev M)
 			const uint32_t pk = __ldg(A.pix + ip);
 			const int x = rb_pix_x(pk), y = rb_pix_y(pk), ires = rb_pix_ires(pk);
 			const int idx = rb_src_index(x, y, M.current_size);
-			if (ip < A.nd2)
+			if (WHICH == 0 && ip < A.nd2)
 			{
 				float2 Xc; float corr;
 				img_load_idx(src, idx, ires, Xc, corr);
 				d = make_float4(Xc.x, Xc.y, corr * 0.5f, 0.f);
 			}
-			const float2 a = __ldg(X + idx), b = __ldg(X0 + idx);
-			s = make_float4(a.x, a.y, b.x, b.y);
-			c = C ? __ldg(C + idx) * m.part_scale : m.part_scale;                              // acc_ml_optimiser_impl.h:3087-3096
+			if (WHICH == 1)
+			{
+				const float2 a = __ldg(X + idx), b = __ldg(X0 + idx);
+				s = make_float4(a.x, a.y, b.x, b.y);
+				c = C ? __ldg(C + idx) * m.part_scale : m.part_scale;                              // acc_ml_optimiser_impl.h:3087-3096
+			}
 		}
-		A.simg4[(size_t) p * A.stride + ip] = d;
-		A.sst[bd_at(p, ip, (int) gridDim.y)] = s;
-		A.sctf[bd_at(p, ip, (int) gridDim.y)] = c;
+		if (WHICH == 0) A.simg4[(size_t) p * A.stride + ip] = d;
+		else
+		{
+			A.sst[bd_at(p, ip, (int) gridDim.y)] = s;
+			A.sctf[bd_at(p, ip, (int) gridDim.y)] = c;
+		}
 	}
 }
 
@@ -108,12 +116,11 @@ struct BandProjArgs {
 
 struct RbBpItem { int w; int samp_off; int nsig; float W; };
 
-static const int BD_STAGE_F4 = 32 * 4 + 16;   // float4 per warp staging tile: sample s keeps its four quarters at chunks 4 s + (s >> 1) + c
-                                                // (the s >> 1 padding makes both the quad-wise writes and the lane-wise 64-byte
-                                                // reads conflict free: four shared-memory wavefronts per 512 bytes)
+static const int BD_STAGE_ROW = 33;           // float2 per piece row of a warp's exchange tile: piece k of sample s sits at k * 33 + s, which makes
+                                                // both the quad-wise 8-byte writes and the lane-wise 8-byte reads conflict free (2 wavefronts per 256 bytes)
 
 struct BandProjSmem {
-	float4 cell[BD_THREADS / 32][BD_STAGE_F4];
+	float2 cell[BD_THREADS / 32][4 * BD_STAGE_ROW];
 	float e[BD_MAXCHUNK][6];
 	int cls[BD_MAXCHUNK];
 	int next;
@@ -149,7 +156,7 @@ __device__ __forceinline__ void band_addr(const BandProjArgs &A, const BandProjS
 	a.f.flags = (inside ? 1 : 0) | (inv ? 2 : 0);
 	const int x0 = (int) fx0, yi = (int) fy0 - pk.mdlInitY, zi = (int) fz0 - pk.mdlInitZ;
 	a.sub = ((zi & 3) << 4) | ((yi & 3) << 2) | (x0 & 3);
-	a.rank = inside ? __ldg(pk.blk + (zi >> 2) * pk.nbxy + (yi >> 2) * pk.nbx + (x0 >> 2)) : 0u;
+	a.rank = inside ? __ldg(pk.blk + rb_blk_slot(pk.nbx, pk.nbxy, x0 >> 2, yi >> 2, zi >> 2)) : 0u;
 }
 
 template <bool MULTI>
@@ -168,28 +175,31 @@ __device__ __forceinline__ void band_fetch(const BandProjArgs &A, const BandProj
 	}
 }
 
-// quad-transpose through the warp's staging tile, then the trilinear interpolation of the lane's own sample
-__device__ __forceinline__ float2 band_consume(float4 *tile, int lane, const BandLoad &L)
+// The lane holds piece k = (lane & 3) of the cells of its quad's four samples: (z, y) corner pair k, voxels x and x + 1.  It
+// does the x-interpolation of those four pieces itself (the owner's fx comes by shuffle; same arithmetic, so the result is
+// bit-identical to interpolating on the owner), which halves what has to cross the quad: 8-byte (re, im) values go through
+// the warp's exchange tile, and the owner finishes with the y- and z-interpolation of its own sample.
+__device__ __forceinline__ float2 band_consume(float2 *tile, int lane, const BandLoad &L)
 {
 	const int k = lane & 3, qbase = lane & ~3;
 #pragma unroll
-	for (int r = 0; r < 4; r++) { const int s = qbase + r; tile[4 * s + (s >> 1) + k] = L.q[r]; }
+	for (int r = 0; r < 4; r++)
+	{
+		const float fxr = __shfl_sync(RB_FULL_MASK, L.f.fx, qbase + r);
+		const float4 q = L.q[r];
+		tile[k * BD_STAGE_ROW + qbase + r] = make_float2(q.x + (q.z - q.x) * fxr, q.y + (q.w - q.y) * fxr);
+	}
 	__syncwarp();
-	const float4 *src = tile + 4 * lane + (lane >> 1);
-	const float4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
+	const float2 d00 = tile[lane], d10 = tile[BD_STAGE_ROW + lane], d01 = tile[2 * BD_STAGE_ROW + lane], d11 = tile[3 * BD_STAGE_ROW + lane];
 	__syncwarp();
 	const BandFrac &f = L.f;
 	float2 ref;
 	{
-		const float dx00 = q0.x + (q0.z - q0.x) * f.fx, dx10 = q1.x + (q1.z - q1.x) * f.fx;
-		const float dx01 = q2.x + (q2.z - q2.x) * f.fx, dx11 = q3.x + (q3.z - q3.x) * f.fx;
-		const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		const float dxy0 = d00.x + (d10.x - d00.x) * f.fy, dxy1 = d01.x + (d11.x - d01.x) * f.fy;
 		ref.x = dxy0 + (dxy1 - dxy0) * f.fz;
 	}
 	{
-		const float dx00 = q0.y + (q0.w - q0.y) * f.fx, dx10 = q1.y + (q1.w - q1.y) * f.fx;
-		const float dx01 = q2.y + (q2.w - q2.y) * f.fx, dx11 = q3.y + (q3.w - q3.y) * f.fx;
-		const float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		const float dxy0 = d00.y + (d10.y - d00.y) * f.fy, dxy1 = d01.y + (d11.y - d01.y) * f.fy;
 		ref.y = dxy0 + (dxy1 - dxy0) * f.fz;
 	}
 	if (f.flags & 2) ref.y = -ref.y;
@@ -215,7 +225,7 @@ k_project_band(BandProjArgs A)
 	const long long nitems = (long long) ntiles * nchunks;
 	const RbProjK8 pk0 = rb_make_projk8(A.projs[0], A.imgX);
 	const int ph = wid / BD_WPT;
-	float4 *tile_buf = &S.cell[wid][0];
+	float2 *tile_buf = &S.cell[wid][0];
 
 	long long item = blockIdx.x;
 	while (item < nitems)
@@ -1015,14 +1025,13 @@ int rbk_band_phase_tables(rb_ctx *ctx, bool &ok)
 	return RB_OK;
 }
 
-// per-pool buffers and the band-ordered images (once per E-step of a slot)
-int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s)
+// per-pool buffers and the band-ordered images (once per E-step of a slot): which = 0 before the fine pass, 1 before the store stage
+int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s, int which)
 {
 	const RbModelDev &M = ctx->d_model;
 	const size_t stride = (size_t) M.nv_rs_pad;
-	RB_CHECK(s.simg4.ensure((size_t) s.P * stride * sizeof(float4)));
-	RB_CHECK(s.sst.ensure((size_t) s.P * stride * sizeof(float4)));
-	RB_CHECK(s.sctf.ensure((size_t) s.P * stride * sizeof(float)));
+	if (which == 0) RB_CHECK(s.simg4.ensure((size_t) s.P * stride * sizeof(float4)));
+	else { RB_CHECK(s.sst.ensure((size_t) s.P * stride * sizeof(float4))); RB_CHECK(s.sctf.ensure((size_t) s.P * stride * sizeof(float))); }
 	BandPrepArgs A;
 	memset(&A, 0, sizeof(A));
 	A.metas = s.meta.as<RbPartMeta>(); A.Fimg = s.Fimg.as<float2>(); A.Fnomask = s.Fnomask.as<float2>();
@@ -1030,7 +1039,8 @@ int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s)
 	A.pix = M.pix_rs; A.nd2 = M.nv_rs_d2; A.nst = M.nv_rs_st; A.stride = (int) stride;
 	A.simg4 = s.simg4.as<float4>(); A.sst = s.sst.as<float4>(); A.sctf = s.sctf.as<float>();
 	dim3 g((unsigned) ((stride + 255) / 256), s.P);
-	k_prep_sorted<<<g, 256, 0, ctx->stream>>>(A, M);
+	if (which == 0) k_prep_sorted<0><<<g, 256, 0, ctx->stream>>>(A, M);
+	else k_prep_sorted<1><<<g, 256, 0, ctx->stream>>>(A, M);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
@@ -1046,7 +1056,7 @@ static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const
 	A.slices = ctx->band_slices.as<float2>();
 	A.projs = ctx->d_proj.as<RbProjector>(); A.imgX = M.current_size / 2 + 1; A.nr_classes = M.nr_classes;
 	A.queue = queue;
-	A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_CHUNK_MIN", 16));
+	A.chunk_min = std::max(BD_NPH, env_int("RB_BAND_CHUNK_MIN", 48));   // measured (256 px, 6768 fine orientations): 16: 2.54 ms, 32: 2.36, 48: 2.30, 64: 2.31, 96: 2.44, 128: 2.56
 	A.nfo_ptr = nfo_ptr; A.only_if_nfo_above = only_if_nfo_above;
 	RB_CUDA(cudaMemsetAsync(queue, 0, 4, ctx->stream));
 	const int ctas = env_int("RB_BAND_PROJ_CTAS", 3);
@@ -1063,7 +1073,7 @@ int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s)
 {
 	const RbModelDev &M = ctx->d_model;
 	RB_CHECK(rb_stage_begin(ctx, "fine_prep"));
-	RB_CHECK(rbk_band_prepare_pool(ctx, s));
+	RB_CHECK(rbk_band_prepare_pool(ctx, s, 0));
 	bool tables = false;
 	RB_CHECK(rbk_band_phase_tables(ctx, tables));
 	RB_CHECK(rb_stage_end(ctx, "fine_prep"));
@@ -1112,6 +1122,7 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 	L.items = s.bp_items.as<RbBpItem>(); L.samp = s.bp_samp.as<float4>(); L.samp_cap = samp_cap;
 	L.tx = ctx->d_samp.ftx; L.ty = ctx->d_samp.fty; L.NOT = ctx->d_samp.n_over_trans;
 	RB_CHECK(rb_stage_begin(ctx, "store_list"));
+	RB_CHECK(rbk_band_prepare_pool(ctx, s, 1));
 	k_bp_count<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(L);
 	RB_LAUNCH_CHECK(ctx);
 	k_bp_scan<<<1, 1024, 0, ctx->stream>>>(L);

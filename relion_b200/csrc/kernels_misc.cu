@@ -111,8 +111,7 @@ int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInit
 __global__ void k_bp_fold(RbBackprojector bp)
 {
 	const size_t n = (size_t) bp.mdlX * bp.mdlY * bp.mdlZ;
-	const int nbx = bp.nbx, nby = bp.nbxy / bp.nbx;
-	const int nbz = (bp.mdlZ + 3) >> 2;
+	const int nbx = (bp.mdlX + 3) >> 2, nby = (bp.mdlY + 3) >> 2, nbz = (bp.mdlZ + 3) >> 2;
 	for (size_t v = blockIdx.x * (size_t) blockDim.x + threadIdx.x; v < n; v += (size_t) gridDim.x * blockDim.x)
 	{
 		const int x = (int) (v % bp.mdlX);
@@ -134,7 +133,7 @@ __global__ void k_bp_fold(RbBackprojector bp)
 					int bx = x >> 2, lx = x & 3;
 					if (cx) { if (lx != 0 || bx == 0) continue; bx--; lx = 4; }
 					if (bx >= nbx) continue;
-					const uint32_t rank = bp.blk[(bz * nby + by) * nbx + bx];
+					const uint32_t rank = bp.blk[rb_blk_slot(bp.nbx, bp.nbxy, bx, by, bz)];
 					float4 *p = bp.blkvol + ((size_t) rank << 7) + (lz * 25 + ly * 5 + lx);
 					const float4 a = *p;
 					if (a.x != 0.f || a.y != 0.f || a.z != 0.f)

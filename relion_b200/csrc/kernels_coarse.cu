@@ -334,9 +334,9 @@ int rbk_diff2_coarse_pool(rb_ctx *ctx, PoolSlot &s)
 	// global searches: the cross term is a dense contraction shared by the whole pool -> tensor cores (also with the
 	// cross-correlation criterion: same cross and norm terms, different epilogue)
 	if (gemm_path) return rbk_diff2_coarse_gemm_pool(ctx, s, s.cimg4.as<float4>());
-	// local searches: projection fused with the contraction, per (particle, 128-orientation tile); the CC criterion with
-	// local searches (--always_cc late in a refinement) stays on the SIMT kernel
-	if (!M.do_cc && rbk_coarse_fused_applicable(ctx, s)) return rbk_diff2_coarse_fused_pool(ctx, s, s.cimg4.as<float4>());
+	// local searches: projection fused with the contraction, per (particle, 128-orientation tile), for both criteria
+	// (--always_cc late in a refinement: CC epilogue)
+	if (rbk_coarse_fused_applicable(ctx, s)) return rbk_diff2_coarse_fused_pool(ctx, s, s.cimg4.as<float4>());
 
 	CoarseArgs A;
 	memset(&A, 0, sizeof(A));

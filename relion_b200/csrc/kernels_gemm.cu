@@ -900,6 +900,8 @@ struct FusedArgs {
 	const RbProjector *projs;
 	const uint32_t *pix; int npix; int n;
 	int T; int tiles_per_class; int num_kblocks;
+	int Tstride, t0;               // Mweight row length and first translation of this pass (T <= 32 translations per pass)
+	int cc;                        // cross-correlation criterion: value = -cross / sqrt(norm term), no xi2 term, no minimum (diff2.cuh:336-460)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
@@ -1088,13 +1090,14 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 			if (s_valid[r])
 			{
 				const float bs = s_base[r] + A.x2[p];
-				float *out = A.Mweight + m.coarse_off + (long long) (o0 + r) * A.T;
+				float *out = A.Mweight + m.coarse_off + (long long) (o0 + r) * A.Tstride + A.t0;
 #pragma unroll
 				for (int t = 0; t < 32; t++)
 				{
 					if (t < A.T)
 					{
 						const float cr = __uint_as_float(v[t]) + __uint_as_float(v2[t]);
+						if (A.cc) { out[t] = -(cr / sqrtf(s_base[r])); continue; }          // diff2.h:729-735; k_weights_cc_coarse takes the minimum
 						const float d = fmaxf(bs - 2.f * cr, 0.f) + m.xi2_half;           // diff2.cuh:170-186, :1290-1296
 						out[t] = d;
 						bmin = fminf(bmin, d);
@@ -1124,7 +1127,7 @@ bool rbk_coarse_fused_applicable(rb_ctx *ctx, const PoolSlot &s)
 {
 	const char *e = getenv("RB_COARSE_FUSED");
 	const int mode = e ? atoi(e) : 1;
-	if (mode == 0 || ctx->d_samp.n_trans > FU_BN) return false;
+	if (mode == 0 || ctx->d_samp.n_trans > 8 * FU_BN) return false;   // more than 32 translations: several passes of 32 (below)
 	return mode == 2 || s.has_priors;                      // default: the local-search path
 }
 
@@ -1133,15 +1136,13 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	const RbModelDev &M = ctx->d_model;
 	const RbSamplingDev &S = ctx->d_samp;
 	const int P = s.P, T = S.n_trans, K = M.nr_classes;
-	const int npix = M.nvc, n = M.coarse_size;
+	const int npix = M.d2_nvc, n = M.coarse_size;         // d2_*: with the CC criterion every pixel of the window's circle
+	const uint32_t *pixlist = M.d2_pix_c;
 	const int nkb = (npix + FU_PIX - 1) / FU_PIX;
 	const size_t kpad = (size_t) nkb * 32;
 	const size_t rows = (size_t) P * FU_BN;
 	DevBuf &bBhi = ctx->gemm_buf[4], &bBlo = ctx->gemm_buf[5], &bX2 = ctx->gemm_buf[9];
 	RB_CHECK(bBhi.ensure(rows * kpad * 4)); RB_CHECK(bBlo.ensure(rows * kpad * 4)); RB_CHECK(bX2.ensure((size_t) P * 4));
-	k_gemm_build_B<<<(unsigned) rows, 256, 0, ctx->stream>>>(cimg4, M.pix_c, npix, n, S.ctx, S.cty, T, FU_BN, P,
-		bBhi.as<float>(), bBlo.as<float>(), kpad, nullptr, nullptr, 0, bX2.as<float>(), 0, 0);
-	RB_LAUNCH_CHECK(ctx);
 	CUtensorMap tb, tbl;
 	RB_CHECK(make_tmap(&tb, bBhi.as<float>(), rows, kpad, FU_BN)); RB_CHECK(make_tmap(&tbl, bBlo.as<float>(), rows, kpad, FU_BN));
 	FusedArgs A;
@@ -1150,7 +1151,7 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	A.dir_idx = s.dir_idx.as<int>(); A.psi_idx = s.psi_idx.as<int>();
 	A.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>(); A.Mweight = s.Mweight.as<float>();
 	A.img4 = cimg4; A.x2 = bX2.as<float>(); A.projs = ctx->d_proj.as<RbProjector>();
-	A.pix = M.pix_c; A.npix = npix; A.n = n; A.T = T; A.num_kblocks = nkb;
+	A.pix = pixlist; A.npix = npix; A.n = n; A.num_kblocks = nkb; A.cc = M.do_cc;
 	A.tiles_per_class = (s.max_no + FU_BM - 1) / FU_BM;
 	static int npw = 0;
 	// measured (256 px, hp4 local): 8 warps x 2 CTAs/SM (166 KB of shared memory, 32 KB of L1 left) 7.98 ms; 16 warps x 1 CTA/SM
@@ -1170,17 +1171,28 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	static int g256 = -1;
 	if (g256 < 0) { const char *e = getenv("RB_FUSED_G256"); g256 = e ? atoi(e) != 0 : 0; }
 	dim3 grid((unsigned) P, (unsigned) (A.tiles_per_class * K));
-	if (npw == 16)
+	// The tile holds 32 translations (TMEM columns, B operand rows): samplings with more (--offset_range 5 --offset_step 1: 81,
+	// healpix_sampling.cpp:399-440) take ceil(T / 32) passes, each with its own B operand, writing its columns of Mweight.  The
+	// projection is repeated per pass; the SIMT kernel this replaces is 10-40x slower than one pass.
+	for (int t0 = 0; t0 < T; t0 += FU_BN)
 	{
-		if (g256) k_coarse_fused<16, 1><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
-		else k_coarse_fused<16, 0><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+		const int Tc = std::min(FU_BN, T - t0);
+		k_gemm_build_B<<<(unsigned) rows, 256, 0, ctx->stream>>>(cimg4, pixlist, npix, n, S.ctx + t0, S.cty + t0, Tc, FU_BN, P,
+			bBhi.as<float>(), bBlo.as<float>(), kpad, nullptr, nullptr, 0, bX2.as<float>(), 0, 0);
+		RB_LAUNCH_CHECK(ctx);
+		A.T = Tc; A.Tstride = T; A.t0 = t0;
+		if (npw == 16)
+		{
+			if (g256) k_coarse_fused<16, 1><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			else k_coarse_fused<16, 0><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+		}
+		else
+		{
+			if (g256) k_coarse_fused<8, 1><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			else k_coarse_fused<8, 0><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+		}
+		RB_LAUNCH_CHECK(ctx);
 	}
-	else
-	{
-		if (g256) k_coarse_fused<8, 1><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
-		else k_coarse_fused<8, 0><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
-	}
-	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
 

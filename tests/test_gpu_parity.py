@@ -320,6 +320,17 @@ def test_pool_firstiter_cc(device, oracle, monkeypatch, kw, coarse):
     assert np.all(g["dLL_nolog"] > 0)           # = -min_diff2: the best normalised cross-correlation is positive
 
 
+@pytest.mark.parametrize("fused", ["1", "0"])
+def test_pool_always_cc_local_search(device, oracle, monkeypatch, fused):
+    """--always_cc late in a refinement: the cross-correlation criterion with LOCAL searches, through the fused projection +
+    tcgen05 kernel (CC epilogue: -cross / sqrt(norm)) and through the SIMT coarse kernel."""
+    monkeypatch.setenv("RB_COARSE_FUSED", fused)
+    wl = make_workload(do_cc=True, ori_size=32, healpix_order=2, n_particles=10, nr_classes=1, seed=47, snr=0.3, local_search=True)
+    res, _ = _compare_pool(device, oracle, wl)
+    assert np.all(res.particles["nr_significant_coarse"] == 1)
+    assert np.all(res.particles["sum_weight"] == 1.0)
+
+
 @pytest.mark.parametrize("flags", [dict(do_map=False), dict(do_scale_correction=False), dict(do_ctf_correction=False),
                                    dict(do_map=False, do_scale_correction=False, do_ctf_correction=False)])
 def test_pool_optimiser_flags(device, oracle, flags):
@@ -758,8 +769,9 @@ def test_pipelined_slots_equal_sequential_calls(device):
 
 @pytest.mark.parametrize("local", [False, True])
 def test_pool_many_translations(device, oracle, local):
-    """81 coarse translations (offset range 5, step 1): more than the 32-translation tiles of the fused kernel (local searches fall
-    back to the SIMT coarse kernel) and more than one 64-entry prior table of the multi-CTA weight conversion."""
+    """81 coarse translations (offset range 5, step 1): more than the 32-translation tiles of the fused kernel (local searches
+    take three passes of 32 / 32 / 17 translations through it) and more than one 64-entry prior table of the multi-CTA weight
+    conversion."""
     wl = make_workload(ori_size=32, healpix_order=2 if local else 1, offset_range=5.0, offset_step=1.0, n_particles=5, seed=120,
                        snr=0.3, local_search=local)
     assert wl.sampling.n_trans == 81

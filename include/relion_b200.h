@@ -18,8 +18,8 @@
  *     (src/ml_optimiser.cpp:4280), so no concurrent entry is needed.
  *   - there is NO CPU fallback: without a CUDA device rb_ctx_create() fails with RB_ERR_CUDA.
  *   - scope: 3D or 2D references / 2D images, nr_bodies == 1, no helical/tomo; both criteria (Gaussian squared
- *     difference and the first-iteration / --always_cc cross-correlation, rb_model.do_cc); no SGD/VDAM
- *     back-projection (DESIGN.md "out of scope").
+ *     difference and the first-iteration / --always_cc cross-correlation, rb_model.do_cc); weighted-image and
+ *     gradient (SGD / VDAM residual, rb_model.do_grad) back-projection.
  *
  * Index conventions follow the reference:
  *   coarse hidden index  ihidden      = ((iclass*n_dir + idir)*n_psi + ipsi)*n_trans + itrans
@@ -222,6 +222,12 @@ typedef struct {
 	                                indexes pdf_offset by translation only, :2187-2196).  Pass it for 2D references
 	                                (zeros at iteration 1); NULL (3D references): rb_particles.prior_offset is the centre
 	                                and rb_pool_out.wsum_prior_offset_class stays untouched                       */
+	int do_grad;                 /* gradient (SGD / VDAM) refinement, baseMLO->do_grad (acc_ml_optimiser_impl.h:3418): the
+	                                back-projection accumulates the weighted RESIDUAL sum_t w_t (X_t - CTF A) instead of the
+	                                weighted image (cuda_kernel_backproject3D_SGD, BP.cuh:406-656; ALTCPU BP.h:757-1047: every
+	                                pixel, no circle bound); 3D references.  With grad_pseudo_halfsets (= do_grad in
+	                                src/ml_optimiser.cpp:1192) particles go into accumulator iclass + (part_id % 2) * nr_classes
+	                                (:3395-3400): initialise 2 * nr_classes accumulators and pass rb_particles.bp_offset    */
 } rb_model;
 int rb_set_model(rb_ctx *ctx, const rb_model *m);
 /* Call order: rb_set_model, rb_set_sampling, then (without orientational priors) rb_set_pdf_direction:
@@ -254,6 +260,8 @@ typedef struct {
 	const int *psi_off;          /* [P+1]                                                         */
 	const int *psi_idx;          /* pointer_psi_nonzeroprior                                      */
 	const double *psi_prior;     /* psi_prior                                                     */
+	const int *bp_offset;        /* [P] or NULL (0): added to the class index to select the accumulator the particle is
+	                                back-projected into (pseudo half-sets of gradient refinement: (part_id % 2) * nr_classes) */
 } rb_particles;
 
 /* Per-particle results (what storeWeightedSums writes to exp_metadata and folds into wsum_model,
@@ -339,6 +347,7 @@ typedef struct {
 	/* local angular searches, as in rb_particles (all NULL: global search)                         */
 	const int *dir_off, *dir_idx; const double *dir_prior;
 	const int *psi_off, *psi_idx; const double *psi_prior;
+	const int *bp_offset;        /* as in rb_particles                                              */
 } rb_raw_particles;
 /* power_img: [P][n/2+1] spectrum of the masked full-size transform (op.power_img, used by the host for sigma2_noise
  * beyond the current size), may be NULL. */

@@ -29,7 +29,7 @@
  *                                                      summed on the devices (rb_bp_allreduce), everything else as one fp64
  *                                                      vector in MlWsumModel::pack order (WsumPack, src/ml_model.cpp:1881-2049)
  * Scope limits (RB_REPORT_ERROR when violated): nr_bodies == 1, one image per particle, 2D images, every optics group with
- * the model's box and pixel size, no helices / tomo / SGD.
+ * the model's box and pixel size, no helices / tomo; gradient refinement (do_grad, pseudo half-sets) with 3D references.
  * Errors: the reference's HANDLE_ERROR / CRITICAL end in REPORT_ERROR, which throws RelionError (src/error.h,
  * src/acc/cuda/cuda_settings.h:48-68).  RB_REPORT_ERROR throws relion_b200::RelionError; compile with
  * -DRB_REPORT_ERROR=REPORT_ERROR inside RELION to throw its own type.  There is no CPU fallback.
@@ -279,6 +279,7 @@ public:
 		rm.ctf_premultiplied = o.mydata.obsModel.getCtfPremultiplied(0);
 		rm.bp_circle_bound = 1;
 		rm.do_cc = (o.iter == 1 && o.do_firstiter_cc) || o.do_always_cc;                   // :1164
+		rm.do_grad = o.do_grad ? 1 : 0;                                                    // acc_ml_optimiser_impl.h:3418
 		h_prior_class.clear();
 		if (m.ref_dim == 2 && m.nr_bodies == 1)                                             // :2100-2104, :2673-2677
 		{
@@ -320,7 +321,19 @@ public:
 		if (rm.pdf_direction) RB_TRY(rb_set_pdf_direction(ctx, rm.pdf_direction));
 
 		// ---- projectors / back-projectors (cuda_ml_optimiser.cu:98-152) ----
-		projectors.resize(K); backprojectors.resize(K);
+		// gradient refinement with pseudo half-sets: wsum_model.BPref holds 2 K accumulators, particle part_id goes into
+		// iclass + (part_id % 2) * K (acc_ml_optimiser_impl.h:3395-3400, cuda_ml_optimiser.cu:121-141)
+		const int nbp = o.grad_pseudo_halfsets ? 2 * K : K;
+		if ((int) o.wsum_model.BPref.size() < nbp) RB_REPORT_ERROR("MlDeviceBundle::setupFixedSizedObjects: wsum_model.BPref holds fewer accumulators than the pseudo half-sets need");
+		projectors.resize(K); backprojectors.resize(nbp);
+		for (int k = K; k < nbp; k++)
+		{
+			BackProjector &bp = o.wsum_model.BPref[k];
+			backprojectors[k].ctx = ctx; backprojectors[k].iclass = k;
+			backprojectors[k].setMdlDim((int) XSIZE(bp.data), (int) YSIZE(bp.data), (int) ZSIZE(bp.data), (int) STARTINGY(bp.data), (int) STARTINGZ(bp.data),
+			                            bp.r_max, (XFLOAT) bp.padding_factor);
+			backprojectors[k].initMdl();
+		}
 		for (int k = 0; k < K; k++)
 		{
 			Projector &pp = m.PPref[k];
@@ -460,6 +473,13 @@ public:
 		memset(&raw, 0, sizeof(raw));
 		raw.n_particles = P; raw.image_size = n; raw.images = images.data(); raw.norm_factor = norm_factor.data();
 		raw.old_offset = old_offset.data(); raw.prior_offset = prior_offset.data(); raw.group_id = group_id.data(); raw.optics_group = optics_group.data();
+		std::vector<int> bp_offset;
+		if (o.grad_pseudo_halfsets)
+		{
+			bp_offset.resize(P);
+			for (int p = 0; p < P; p++) bp_offset[p] = (int) ((first + p) % 2) * m.nr_classes;       // acc_ml_optimiser_impl.h:3397-3399
+			raw.bp_offset = bp_offset.data();
+		}
 		raw.ctf_defU = defU.data(); raw.ctf_defV = defV.data(); raw.ctf_defAngle = defA.data(); raw.ctf_Bfac = bfac.data(); raw.ctf_scale = kfac.data();
 		raw.ctf_phase_shift = phs.data(); raw.og_kV = og_kV.data(); raw.og_Cs = og_Cs.data(); raw.og_Q0 = og_Q0.data();
 		raw.mask_radius = o.particle_diameter / (2. * m.pixel_size);                                                           // :556

@@ -74,6 +74,8 @@ class ok_kernel_table(C.Structure):
         ("diff2_cc_coarse", C.CFUNCTYPE(None, PP, C.c_int, C.c_int, f32p, C.c_ulong, f32p, f32p, C.c_ulong, f32p, f32p, f32p, f32p)),
         ("diff2_cc_fine", C.CFUNCTYPE(None, PP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p,
                                       C.c_ulong, C.c_ulong, C.c_ulong, ulp, ulp, ulp, ulp, f32p)),
+        ("backproject_sgd", C.CFUNCTYPE(None, BP, PP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                                        C.c_ulong, C.c_float, C.c_float, f32p, C.c_ulong)),
     ]
 
 
@@ -190,10 +192,11 @@ class Oracle:
         out = make_pool_out(pool.n_particles, model.ori_size // 2 + 1, model.nr_classes, sampling.n_dir)
         K = model.nr_classes
         parr = (ok_projector * K)(*[r.struct for r in refs])
-        barr = (ok_backprojector * K)(*[b.struct for b in bps])
+        nb = len(bps)                # K, or 2 K with the pseudo half-sets of gradient refinement (pool.bp_offset)
+        barr = (ok_backprojector * nb)(*[b.struct for b in bps])
         syncs = []
         if num_threads != 1:
-            for k in range(K):
+            for k in range(nb):
                 s = self.K.bp_sync_alloc(barr[k].mdlY, barr[k].mdlZ)
                 barr[k].sync = s
                 syncs.append(s)
@@ -222,7 +225,7 @@ class Oracle:
         for s in syncs:
             self.K.bp_sync_free(s)
         if self.kind == "refcuda":
-            for k in range(K):
+            for k in range(nb):
                 _libs["_refcuda_handle"].refcuda_bp_download(C.byref(barr[k]))
         if dbg is not None:
             n = int(dbg.fine_count)

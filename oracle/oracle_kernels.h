@@ -158,6 +158,17 @@ typedef struct {
 	                      const unsigned long *rot_idx, const unsigned long *trans_idx,
 	                      const unsigned long *job_idx, const unsigned long *job_num,
 	                      float *diff2s);
+
+	/* CpuKernels::backproject3D_SGD<DATA3D=false, CTF_PREMULTIPLIED=false> (src/acc/cpu/cpu_kernels/BP.h:757-1047; CUDA twin
+	 * BP.cuh:406-656): gradient refinement (baseMLO->do_grad).  Per pixel the weighted RESIDUAL
+	 * sum_t w_t (shift_t(img) - ctf * ref) is back-projected instead of the weighted image; every pixel of the half image
+	 * (no circle bound), phases by sincosf per (pixel, translation). */
+	void (*backproject_sgd)(const ok_backprojector *bp, const ok_projector *p, int imgX, int imgY,
+	                        const float *img_re, const float *img_im,
+	                        const float *trans_x, const float *trans_y,
+	                        const float *weights, const float *Minvsigma2s, const float *ctfs,
+	                        unsigned long trans_num, float significant_weight, float weight_norm,
+	                        const float *eulers, unsigned long image_count);
 } ok_kernel_table;
 
 #ifdef __cplusplus

@@ -55,6 +55,7 @@ class rb_model(C.Structure):
         ("do_map", C.c_int), ("ctf_premultiplied", C.c_int), ("bp_circle_bound", C.c_int),
         ("do_cc", C.c_int),
         ("prior_offset_class", c_double_p),
+        ("do_grad", C.c_int),
     ]
 
 
@@ -66,6 +67,7 @@ class rb_particles(C.Structure):
         ("highres_Xi2", c_double_p), ("old_offset", c_double_p), ("prior_offset", c_double_p),
         ("dir_off", c_int_p), ("dir_idx", c_int_p), ("dir_prior", c_double_p),
         ("psi_off", c_int_p), ("psi_idx", c_int_p), ("psi_prior", c_double_p),
+        ("bp_offset", c_int_p),
     ]
 
 
@@ -80,6 +82,7 @@ class rb_raw_particles(C.Structure):
         ("mask_radius", C.c_double), ("width_mask_edge", C.c_double),
         ("dir_off", c_int_p), ("dir_idx", c_int_p), ("dir_prior", c_double_p),
         ("psi_off", c_int_p), ("psi_idx", c_int_p), ("psi_prior", c_double_p),
+        ("bp_offset", c_int_p),
     ]
 
 

@@ -808,6 +808,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	d.do_scale_correction = m->do_scale_correction; d.do_map = m->do_map; d.ctf_premultiplied = m->ctf_premultiplied;
 	d.bp_circle_bound = m->bp_circle_bound;
 	d.do_cc = m->do_cc;
+	d.do_grad = m->do_grad;
 	// pdf_direction needs n_dir, which belongs to the sampling: keep a host copy until both are known
 	ctx->m_pdf_dir.release();
 	if (m->pdf_direction && ctx->has_sampling)
@@ -868,6 +869,7 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 	s.P = P; s.has_priors = priors;
 	s.h_meta.resize(P);
 	long long coff = 0, poff = 0; int max_no = 0;
+	s.max_bp_off = 0;
 	for (int p = 0; p < P; p++)
 	{
 		RbPartMeta &m = s.h_meta[p];
@@ -892,6 +894,9 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 		}
 		m.part_scale = ps;
 		m.xi2_half = (float) (pool->highres_Xi2[p] / 2.);
+		m.bp_off = pool->bp_offset ? pool->bp_offset[p] : 0;
+		RB_ARG(m.bp_off >= 0 && m.bp_off + K <= RB_MAX_CLASSES, "rb_pool_upload: particle %d: accumulator offset %d out of range", p, m.bp_off);
+		s.max_bp_off = std::max(s.max_bp_off, m.bp_off);
 		m.oldx = pool->old_offset[2 * p]; m.oldy = pool->old_offset[2 * p + 1];
 		m.prx = pool->prior_offset[2 * p]; m.pry = pool->prior_offset[2 * p + 1];
 		m.coarse_off = coff; m.prior_off = poff;
@@ -1034,6 +1039,7 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 	pool.highres_Xi2 = xi2.data(); pool.old_offset = old_r.data(); pool.prior_offset = raw->prior_offset;
 	pool.dir_off = raw->dir_off; pool.dir_idx = raw->dir_idx; pool.dir_prior = raw->dir_prior;
 	pool.psi_off = raw->psi_off; pool.psi_idx = raw->psi_idx; pool.psi_prior = raw->psi_prior;
+	pool.bp_offset = raw->bp_offset;
 	RB_CHECK(pool_setup(ctx, slot, &pool, false));
 	PoolSlot &s = ctx->slot[slot];
 	// raw images + small tables on the copy stream (overlaps the compute of the other slot), kernels on the compute stream
@@ -1090,7 +1096,11 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	{
 		if (!ctx->has_proj[k]) { rb_set_error("rb_estep: reference %d not set", k); return RB_ERR_STATE; }
 		if (!(flags & 1u) && !ctx->has_bp[k]) { rb_set_error("rb_estep: accumulator %d not initialised", k); return RB_ERR_STATE; }
+		if (!(flags & 1u) && s.max_bp_off > 0 && !ctx->has_bp[k + s.max_bp_off]) { rb_set_error("rb_estep: accumulator %d (pseudo half-set) not initialised", k + s.max_bp_off); return RB_ERR_STATE; }
 	}
+	if (M.do_grad && !(flags & 1u))
+		for (int k = 0; k < M.nr_classes; k++)
+			if (ctx->ref_2d[k]) { rb_set_error("rb_estep: do_grad with 2D references is not supported"); return RB_ERR_STATE; }
 	RB_CUDA(cudaSetDevice(ctx->device));
 	RB_CHECK(ensure_coarse_core(ctx));
 	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
@@ -1128,7 +1138,7 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	if (!(flags & 1u))
 	{
 		RB_CHECK(band ? rbk_band_store_pool(ctx, s) : rbk_store_pool(ctx, s));
-		if (band) for (int k = 0; k < M.nr_classes; k++) ctx->bp_blk_dirty[k] = ctx->bp[k].blkvol != nullptr;
+		if (band) for (int k = 0; k < RB_MAX_CLASSES; k++) if (ctx->has_bp[k]) ctx->bp_blk_dirty[k] = ctx->bp[k].blkvol != nullptr;
 	}
 	RB_CHECK(rb_stage_end(ctx, "store"));
 	RB_CHECK(rb_stage_end(ctx, "total"));

@@ -126,6 +126,7 @@ struct RbPartMeta {
 	float scale;             // scale_correction[group] (1 if !do_scale_correction)
 	float part_scale;        // clamped scale used by wavg/BP (acc_ml_optimiser_impl.h:3059-3079)
 	float xi2_half;          // (XFLOAT)(highres_Xi2 / 2)
+	int bp_off;              // accumulator = class + bp_off (pseudo half-sets of gradient refinement)
 	double oldx, oldy, prx, pry;
 	long long coarse_off;    // offset of this particle's dense Mweight block
 	long long prior_off;     // offset of its pdf_orientation block (K*nd*np)
@@ -203,6 +204,7 @@ struct RbModelDev {
 	int maximum_significants;
 	int do_ctf_correction, refs_are_ctf_corrected, do_scale_correction, do_map, ctf_premultiplied, bp_circle_bound;
 	int do_cc;               // first-iteration cross-correlation criterion (acc_ml_optimiser_impl.h:1164)
+	int do_grad;             // SGD / VDAM: back-project the weighted residual (BP.cuh:406-656), every pixel (no circle bound)
 	// blocks of pdf_offset per particle: [Kp][n_trans], Kp = K with per-class prior centres, else 1.  Block 0 serves the
 	// coarse pass for every class, as in the reference
 	__host__ __device__ int prior_classes() const { return prior_offset_class ? nr_classes : 1; }
@@ -227,6 +229,7 @@ struct PoolSlot {
 	bool has_priors = false;
 	int max_no = 0;                 // max over particles of nd*np
 	long long total_coarse = 0;     // sum over particles of K*nd*np*T
+	int max_bp_off = 0;             // largest RbPartMeta::bp_off of the pool
 	long long total_prior = 0;
 	DevBuf Fimg, Fnomask, Fctf, meta, state, dir_idx, dir_prior, psi_idx, psi_prior;
 	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;

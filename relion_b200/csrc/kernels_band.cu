@@ -659,7 +659,7 @@ struct BandStoreArgs {
 struct BandStoreSmem {
 	RbBpItem item[BD_MAXCHUNK];
 	float e[BD_MAXCHUNK][6];
-	int particle[BD_MAXCHUNK], cls[BD_MAXCHUNK], og[BD_MAXCHUNK];
+	int particle[BD_MAXCHUNK], cls[BD_MAXCHUNK], og[BD_MAXCHUNK], bpi[BD_MAXCHUNK];
 	float part_scale[BD_MAXCHUNK];
 	int next;
 };
@@ -698,7 +698,7 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 			const int p = A.fo[it.w].particle;
 			S.item[j] = it;
 			S.particle[j] = p; S.cls[j] = A.fo[it.w].iclass;
-			S.og[j] = A.metas[p].og; S.part_scale[j] = A.metas[p].part_scale;
+			S.og[j] = A.metas[p].og; S.part_scale[j] = A.metas[p].part_scale; S.bpi[j] = A.fo[it.w].iclass + A.metas[p].bp_off;
 		}
 		for (int i = threadIdx.x; i < no * 6; i += BD_THREADS)
 		{
@@ -715,7 +715,7 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 		// (x = 0, y < 0) is only in the list with --no_map: Mresol excludes it from the shell sums (:3466-3494)
 		const bool in_mresol = have && !(x == 0 && y < 0);
 		bool circle_ok = true;
-		if (M.bp_circle_bound) { const int xmax = (int) sqrtf((float) (half * half - y * y)); circle_ok = x < xmax; }   // BP.h:565
+		if (M.bp_circle_bound && !M.do_grad) { const int xmax = (int) sqrtf((float) (half * half - y * y)); circle_ok = x < xmax; }   // BP.h:565 (not in the SGD kernel, BP.h:757-1047)
 		const float fxp = (float) x, fyp = (float) y;
 
 		// the inputs of the next orientation are requested before the current one is worked on
@@ -737,6 +737,7 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 			const RbBpItem it = S.item[j];
 			const int p = S.particle[j], cls = MULTI ? S.cls[j] : 0;
 			float2 ref = cur.ref; const float4 XX = cur.XX; const float ctf = cur.ctf;
+			const float2 ref_ctf = make_float2(ref.x * ctf, ref.y * ctf);                                 // BP.cuh:520-521 (SGD)
 			const float part_scale = S.part_scale[j];
 			if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                                  // wavg.cuh:96-104
 			else { ref.x *= part_scale; ref.y *= part_scale; }
@@ -782,7 +783,7 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 			}
 			// back-projection
 			RbBackprojector bp = bp0;
-			if (MULTI) bp = A.bps[cls];
+			if (MULTI) bp = A.bps[S.bpi[j]];
 			const int max_r2_vol = (int) (bp.maxR * bp.maxR * bp.padding_factor * bp.padding_factor);   // BP.cuh:209
 			int cell = -1;
 			float sfx = 0.f, sfy = 0.f, sfz = 0.f, Fr = 0.f, Fi = 0.f, Fw = 0.f;
@@ -795,6 +796,7 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 				{
 					Fr = (XX.z * phr - XX.w * phi) * g;
 					Fi = (XX.z * phi + XX.w * phr) * g;
+					if (M.do_grad) { Fr -= ref_ctf.x * (W * g); Fi -= ref_ctf.y * (W * g); }                  // sum_t w_t (X_t - CTF A), BP.cuh:540-541
 					const float e0 = S.e[j][0], e1 = S.e[j][1], e3 = S.e[j][2], e4 = S.e[j][3], e6 = S.e[j][4], e7 = S.e[j][5];
 					float xp = (e0 * x + e1 * y) * bp.padding_factor;                                          // BP.cuh:301-347
 					float yp = (e3 * x + e4 * y) * bp.padding_factor;
@@ -1142,7 +1144,7 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 	A.nr_classes = M.nr_classes; A.P = s.P;
 	int *queue = s.counters.as<int>() + 14;
 	const int grid = ctx->num_sms * env_int("RB_BAND_STORE_CTAS", 3);
-	const bool multi = M.nr_classes > 1;
+	const bool multi = M.nr_classes > 1 || s.max_bp_off > 0;
 	const long long cap = ctx->band_slice_capacity;
 	A.fits = (int) std::min<long long>(cap, 0x7fffffff);
 	// (a) the fine pass fitted one round (decided on the device: counters[0] <= cap): its slices are still in the buffer

@@ -255,7 +255,7 @@ k_store(StoreArgs A, RbModelDev M)
 		const float *mtab = M.minvs2 + (size_t) m.og * M.nshell;
 		const unsigned char *dvp = M.dvp_gt3 + (size_t) F.iclass * M.nshell;
 		const RbProjK8 pk = rb_make_projk8(A.projs[F.iclass], imgX);
-		const RbBackprojector bp = A.bps[F.iclass];
+		const RbBackprojector bp = A.bps[F.iclass + m.bp_off];
 		const int max_r2_vol = (int) (bp.maxR * bp.maxR * bp.padding_factor * bp.padding_factor);   // BP.cuh:209
 		const float wni = 1.0f / sumw;
 		double aXA = 0., aAA = 0.;
@@ -312,6 +312,7 @@ k_store(StoreArgs A, RbModelDev M)
 						if constexpr (SLICED) ref = cur.ref.r;
 						else ref = (cur.ref.pf.flags & 1) ? rb_proj_finish(cur.ref.pf) : make_float2(0.f, 0.f);
 						const float ctf = cur.ctf;
+						const float2 ref_ctf = make_float2(ref.x * ctf, ref.y * ctf);                      // BP.cuh:520-521 (SGD)
 						if (M.refs_are_ctf_corrected) { ref.x *= ctf; ref.y *= ctf; }                     // wavg.cuh:96-104
 						else { ref.x *= m.part_scale; ref.y *= m.part_scale; }
 						float phr = 0.f, phi = 0.f;
@@ -335,7 +336,7 @@ k_store(StoreArgs A, RbModelDev M)
 						const float g = M.ctf_premultiplied ? minvs2 : ctf * minvs2;                       // BP.cuh:280-289
 						Fw = W * g * ctf;
 						bool do_bp = Fw > 0.f;
-						if (M.bp_circle_bound)
+						if (M.bp_circle_bound && !M.do_grad)                                                 // the SGD kernel walks every pixel (BP.h:757-1047)
 						{
 							const int xmax = (int) sqrtf((float) (half * half - y * y));                  // BP.h:565
 							do_bp = do_bp && (x < xmax);
@@ -344,6 +345,7 @@ k_store(StoreArgs A, RbModelDev M)
 						{
 							Fr = (cur.X0.x * phr - cur.X0.y * phi) * g;
 							Fi = (cur.X0.x * phi + cur.X0.y * phr) * g;
+							if (M.do_grad) { Fr -= ref_ctf.x * (W * g); Fi -= ref_ctf.y * (W * g); }             // sum_t w_t (X_t - CTF A), BP.cuh:540-541
 							// position in the accumulator (BP.cuh:301-347)
 							float xp = (e0 * x + e1 * y) * bp.padding_factor;
 							float yp = (e3 * x + e4 * y) * bp.padding_factor;

@@ -74,6 +74,7 @@ class ModelParams:
     bp_circle_bound: bool = True
     do_cc: bool = False                      # (iter == 1 and do_firstiter_cc) or do_always_cc
     prior_offset_class: Optional[np.ndarray] = None   # [K, 2] pixels: mymodel.prior_offset_class (2D references), None for 3D
+    do_grad: bool = False                    # gradient (SGD / VDAM) refinement: residual back-projection
 
 
 @dataclasses.dataclass
@@ -93,6 +94,7 @@ class ParticlePool:
     psi_off: Optional[np.ndarray] = None
     psi_idx: Optional[np.ndarray] = None
     psi_prior: Optional[np.ndarray] = None
+    bp_offset: Optional[np.ndarray] = None   # [P] int32: accumulator = class + bp_offset (pseudo half-sets of gradient refinement)
 
     @property
     def n_particles(self):
@@ -177,6 +179,7 @@ def marshal_model(p: ModelParams):
     st.ctf_premultiplied = int(p.ctf_premultiplied)
     st.bp_circle_bound = int(p.bp_circle_bound)
     st.do_cc = int(p.do_cc)
+    st.do_grad = int(p.do_grad)
     if p.prior_offset_class is not None:
         poc = m.hold(_f64(np.asarray(p.prior_offset_class).reshape(p.nr_classes, 2)))
         st.prior_offset_class = _ptr(poc, C.c_double)
@@ -210,6 +213,7 @@ class RawParticlePool:
     psi_off: Optional[np.ndarray] = None
     psi_idx: Optional[np.ndarray] = None
     psi_prior: Optional[np.ndarray] = None
+    bp_offset: Optional[np.ndarray] = None
 
     @property
     def n_particles(self):
@@ -226,7 +230,7 @@ def marshal_raw_pool(pool: RawParticlePool):
     for name in ("norm_factor", "old_offset", "prior_offset", "ctf_defU", "ctf_defV", "ctf_defAngle", "ctf_Bfac", "ctf_scale",
                  "ctf_phase_shift", "og_kV", "og_Cs", "og_Q0", "dir_prior", "psi_prior"):
         setattr(st, name, _ptr(m.hold(_f64(getattr(pool, name))), C.c_double))
-    for name in ("group_id", "optics_group", "dir_off", "dir_idx", "psi_off", "psi_idx"):
+    for name in ("group_id", "optics_group", "dir_off", "dir_idx", "psi_off", "psi_idx", "bp_offset"):
         setattr(st, name, _ptr(m.hold(_i32(getattr(pool, name))), C.c_int))
     st.mask_radius, st.width_mask_edge = float(pool.mask_radius), float(pool.width_mask_edge)
     m.struct = st
@@ -259,6 +263,7 @@ def marshal_pool(pool: ParticlePool):
     st.psi_off = _ptr(m.hold(_i32(pool.psi_off)), C.c_int)
     st.psi_idx = _ptr(m.hold(_i32(pool.psi_idx)), C.c_int)
     st.psi_prior = _ptr(m.hold(_f64(pool.psi_prior)), C.c_double)
+    st.bp_offset = _ptr(m.hold(_i32(pool.bp_offset)), C.c_int)
     m.struct = st
     return m
 

@@ -24,11 +24,12 @@ def oracle():
     return Oracle("port")
 
 
-def _setup(device, wl):
+def _setup(device, wl, n_acc=None):
     device.set_model(wl.model)
     device.set_sampling(wl.sampling)
     for k, v in enumerate(wl.refs):
         device.set_reference(k, v, wl.r_max, wl.padding_factor)
+    for k in range(n_acc or len(wl.refs)):
         device.bp_init(k, wl.bp_shape, wl.r_max, wl.padding_factor)
 
 
@@ -218,13 +219,14 @@ def test_diff2_cc_fine_stage(device, oracle, n, r_max_cut):
     assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
 
 
-def _compare_pool(device, oracle, wl, pose_frac=0.995, exact_threshold=True, num_threads=0):
+def _compare_pool(device, oracle, wl, pose_frac=0.995, exact_threshold=True, num_threads=0, n_acc=None):
     from oracle.bindings import Projector, Backprojector
     from oracle.parity import classify_significance
-    _setup(device, wl)
+    n_acc = n_acc or len(wl.refs)
+    _setup(device, wl, n_acc)
     res = device.expectation_some_particles(wl.pool)
     refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
-    bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
+    bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in range(n_acc)]
     st, ores, _ = oracle.estep_pool(wl.model, wl.sampling, refs, bps, wl.pool, num_threads=num_threads, exact_threshold=exact_threshold)
     assert st == 0
     g, o = res.particles, ores.particles
@@ -261,7 +263,7 @@ def _compare_pool(device, oracle, wl, pose_frac=0.995, exact_threshold=True, num
     if ok.all():
         np.testing.assert_allclose(res.wsum_pdf_class, ores.wsum_pdf_class, rtol=1e-4)
         assert np.abs(res.wsum_pdf_direction - ores.wsum_pdf_direction).max() <= 2e-3
-        for k in range(wl.model.nr_classes):
+        for k in range(n_acc):
             gre, gim, gw = device.bp_get(k)
             for a, b in ((gre, bps[k].real), (gim, bps[k].imag), (gw, bps[k].weight)):
                 assert np.abs(a - b).max() <= 5e-3 * max(np.abs(b).max(), 1e-12)
@@ -329,6 +331,23 @@ def test_pool_always_cc_local_search(device, oracle, monkeypatch, fused):
     res, _ = _compare_pool(device, oracle, wl)
     assert np.all(res.particles["nr_significant_coarse"] == 1)
     assert np.all(res.particles["sum_weight"] == 1.0)
+
+
+@pytest.mark.parametrize("band", ["1", "0"])
+@pytest.mark.parametrize("local", [False, True])
+def test_pool_gradient_refinement_backprojection(device, oracle, monkeypatch, band, local):
+    """do_grad (SGD / VDAM): the back-projection accumulates the weighted residual sum_t w_t (X_t - CTF A)
+    (cuda_kernel_backproject3D_SGD, BP.cuh:406-656) and, with the pseudo half-sets that gradient refinement switches on,
+    particle p goes into accumulator class + (p % 2) * K (acc_ml_optimiser_impl.h:3395-3400): 2 K accumulators, through the
+    band-major store kernel and the orientation-major one."""
+    monkeypatch.setenv("RB_BAND", band)
+    wl = make_workload(ori_size=32, healpix_order=2 if local else 1, n_particles=10, nr_classes=2, seed=61, snr=0.3, local_search=local)
+    wl.model.do_grad = True
+    wl.pool.bp_offset = (np.arange(wl.pool.n_particles) % 2 * wl.model.nr_classes).astype(np.int32)
+    res, ores = _compare_pool(device, oracle, wl, n_acc=2 * wl.model.nr_classes)
+    # both halves received something, and the residual accumulators differ from the weighted-image ones
+    for k in range(2 * wl.model.nr_classes):
+        assert np.abs(device.bp_get(k)[2]).max() > 0
 
 
 @pytest.mark.parametrize("flags", [dict(do_map=False), dict(do_scale_correction=False), dict(do_ctf_correction=False),

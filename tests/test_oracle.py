@@ -372,3 +372,38 @@ def test_bench_reference_arm_runs_on_cpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_sgd_backprojection_port_matches_compiled_reference():
+    """Gradient refinement: the restated residual back-projection against the reference's own CpuKernels::backproject3D_SGD
+    (src/acc/cpu/cpu_kernels/BP.h:757-1047, compiled in oracle/_ref) on random weights, a random reference and random poses."""
+    import ctypes as C
+    from oracle.bindings import Oracle, Projector, Backprojector, _fp
+    from relion_b200 import synth
+    try:
+        ref = Oracle("reference")
+    except Exception as exc:                                            # no compiled reference on this machine
+        pytest.skip(str(exc))
+    port = Oracle("port")
+    rng = np.random.default_rng(77)
+    n, r_max, pf, O, T = 24, 10, 2.0, 5, 7
+    xs = n // 2 + 1
+    pad = synth.pad_size_for(r_max, pf)
+    shape = (pad, pad, pad // 2 + 1)
+    vol = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex64)
+    eul = synth.inverse_euler_f32(rng.uniform(-180, 180, O), rng.uniform(0, 180, O), rng.uniform(0, 360, O)).astype(np.float32)
+    img = (rng.standard_normal((n, xs)) + 1j * rng.standard_normal((n, xs))).astype(np.complex64)
+    re, im = np.ascontiguousarray(img.real), np.ascontiguousarray(img.imag)
+    tx = (rng.uniform(-3, 3, T) * 2 * np.pi / n).astype(np.float32); ty = (rng.uniform(-3, 3, T) * 2 * np.pi / n).astype(np.float32)
+    w = rng.uniform(0, 1, (O, T)).astype(np.float32)
+    minvs2 = rng.uniform(0.5, 2, (n, xs)).astype(np.float32); ctfs = rng.uniform(-1, 1, (n, xs)).astype(np.float32)
+    outs = []
+    for orc in (ref, port):
+        proj = Projector(vol, r_max, pf)
+        bp = Backprojector(shape, r_max, pf)
+        orc.K.backproject_sgd(C.byref(bp.struct), C.byref(proj.struct), xs, n, _fp(re), _fp(im), _fp(tx), _fp(ty), _fp(w), _fp(minvs2), _fp(ctfs),
+                              T, 0.3, 2.5, _fp(eul), O)
+        outs.append((bp.real.copy(), bp.imag.copy(), bp.weight.copy()))
+    assert np.abs(outs[0][2]).max() > 0
+    for a, b in zip(outs[0], outs[1]):
+        assert np.abs(a - b).max() <= 2e-5 * np.abs(a).max()

@@ -322,13 +322,16 @@ int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out);
  * floats in coarse hidden-index order.  Parity tests feed them to the reference's own significance rule
  * (acc_helper_functions.h:226-232).  Valid until the slot is uploaded again; *n_out receives n (out may be NULL to query). */
 int rb_debug_coarse_weights(rb_ctx *ctx, int slot, int particle, float *out, long long capacity, long long *n_out);
+/* Test hook: the noise images [n_particles][image_size][image_size] the last rb_pool_prepare with noise_seed blended into
+ * (centred like the particle images).  Tests rebuild the masked image from them exactly. */
+int rb_debug_prep_noise(rb_ctx *ctx, int n_particles, int image_size, float *out);
 
 /* ------------------------------------------------------------------------------------------------
  * Image preparation on the device ("next" row 1): getFourierTransformsAndCtfs
  * (acc_ml_optimiser_impl.h:11-1010) for a whole pool: integer translation by the rounded old offset and norm
  * correction, transform of the unmasked image (Fimg_nomask), soft circular zero-mask, transform of the masked
  * image (Fimg), power spectrum / highres_Xi2 beyond the current size, CTF image from the CTF parameters.
- * Covered branch: 2D images, one body, --zero_mask, no helix / tomo / beam tilt / MTF, CTF without phase flipping.
+ * Covered branch: 2D images, one body, zero- or noise-filled soft mask, no helix / tomo / beam tilt / MTF, CTF without phase flipping.
  * The slot is then ready for rb_estep_slot exactly as after rb_pool_upload.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -348,6 +351,13 @@ typedef struct {
 	const int *dir_off, *dir_idx; const double *dir_prior;
 	const int *psi_off, *psi_idx; const double *psi_prior;
 	const int *bp_offset;        /* as in rb_particles                                              */
+	const int64_t *noise_seed;   /* [P] random_seed + part_id, or NULL.  NULL: --zero_mask (soft mask towards the background
+	                                value of the image's own edge).  Non-NULL: RELION's default, the soft mask blends into a NOISE
+	                                image with the spectrum sqrt(sigma2_fudge * sigma2_noise[optics group]) (makeNoiseImage,
+	                                src/acc/utilities_impl.h:231-371: independent complex normals per Fourier pixel, inverse FFT;
+	                                cosineFilter with the noise as the fill value, acc_ml_optimiser_impl.h:355-400, 660-668).
+	                                The generator is counter-based on (seed, pixel): reproducible, but - like the reference's
+	                                curand and CPU generators among themselves - not the same random numbers as RELION's */
 } rb_raw_particles;
 /* power_img: [P][n/2+1] spectrum of the masked full-size transform (op.power_img, used by the host for sigma2_noise
  * beyond the current size), may be NULL. */

@@ -480,6 +480,13 @@ public:
 			for (int p = 0; p < P; p++) bp_offset[p] = (int) ((first + p) % 2) * m.nr_classes;       // acc_ml_optimiser_impl.h:3397-3399
 			raw.bp_offset = bp_offset.data();
 		}
+		std::vector<int64_t> noise_seed;
+		if (!o.do_zero_mask)                                                                          // noise-filled soft mask, seed as acc_ml_optimiser_impl.h:371
+		{
+			noise_seed.resize(P);
+			for (int p = 0; p < P; p++) noise_seed[p] = (int64_t) o.random_seed + (int64_t) (first + p);
+			raw.noise_seed = noise_seed.data();
+		}
 		raw.ctf_defU = defU.data(); raw.ctf_defV = defV.data(); raw.ctf_defAngle = defA.data(); raw.ctf_Bfac = bfac.data(); raw.ctf_scale = kfac.data();
 		raw.ctf_phase_shift = phs.data(); raw.og_kV = og_kV.data(); raw.og_Cs = og_Cs.data(); raw.og_Q0 = og_Q0.data();
 		raw.mask_radius = o.particle_diameter / (2. * m.pixel_size);                                                           // :556

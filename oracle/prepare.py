@@ -60,6 +60,33 @@ def soft_mask(img: np.ndarray, radius: float, cosine_width: float):
     return np.where(r < radius, img, img * (1.0 - rc) + bg * rc), bg
 
 
+def noise_mask(img: np.ndarray, noise: np.ndarray, radius: float, cosine_width: float):
+    """Noise-filled soft mask (RELION's default, !do_zero_mask): cosineFilter with the noise image as the fill value
+    (/root/reference/src/acc/cpu/cpu_kernels/helper.cpp:228-247, acc_ml_optimiser_impl.h:660-668)."""
+    n = img.shape[0]
+    if radius < 0:
+        radius = n / 2.0
+    radius_p = radius + cosine_width
+    c = np.arange(n) - n // 2
+    y, x = np.meshgrid(c, c, indexing="ij")
+    r = np.sqrt((x * x + y * y).astype(np.float64))
+    rc = np.where(r > radius_p, 1.0, np.where(r < radius, 0.0, 0.5 + 0.5 * np.cos((radius_p - r) / cosine_width * np.pi)))
+    return np.where(r < radius, img, img * (1.0 - rc) + noise * rc)
+
+
+def noise_image_shell_power(n: int, spectrum: np.ndarray):
+    """Expected mean |F|^2 per shell of the 1/N-normalised transform of a noise image made like makeNoiseImage
+    (/root/reference/src/acc/utilities_impl.h:231-371): independent complex normals (variance spectrum[ires]^2 per component) on
+    the half transform, zero beyond the last shell.  Columns 0 < x < n/2 keep their value (2 spectrum^2); the self-conjugate
+    columns x = 0 and x = n/2 are symmetrised by the inverse real transform."""
+    xf = n // 2 + 1
+    iy = np.arange(n); y = np.where(iy >= xf, iy - n, iy)
+    x = np.arange(xf)
+    ires = np.rint(np.sqrt((x[None, :] ** 2 + y[:, None] ** 2).astype(np.float64))).astype(int)
+    scale = np.where(ires < min(xf, spectrum.shape[0]), spectrum[np.minimum(ires, spectrum.shape[0] - 1)], 0.0)
+    return ires, 2.0 * scale ** 2
+
+
 def power_class(F_full: np.ndarray, current_size: int):
     """(spectrum [n/2+1], highres_Xi2): |F|^2 per shell of the full-size transform; Xi2 = power in shells >= current/2+1."""
     n = F_full.shape[0]

@@ -83,6 +83,7 @@ class rb_raw_particles(C.Structure):
         ("dir_off", c_int_p), ("dir_idx", c_int_p), ("dir_prior", c_double_p),
         ("psi_off", c_int_p), ("psi_idx", c_int_p), ("psi_prior", c_double_p),
         ("bp_offset", c_int_p),
+        ("noise_seed", C.POINTER(C.c_int64)),
     ]
 
 
@@ -173,6 +174,7 @@ PROTOTYPES = {
     "rb_estep_slot_nocopy": (C.c_int, [C.c_void_p, C.c_int, C.c_uint]),
     "rb_estep_fetch": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_pool_out)]),
     "rb_debug_coarse_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_longlong, C.POINTER(C.c_longlong)]),
+    "rb_debug_prep_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "rb_project": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p]),
     "rb_diff2_coarse": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                   c_float_p, c_float_p, c_float_p, c_float_p]),

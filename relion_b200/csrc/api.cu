@@ -817,6 +817,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 		d.pdf_direction = ctx->m_pdf_dir.as<double>();
 	}
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	ctx->h_sigma2_noise.assign(m->sigma2_noise, m->sigma2_noise + (size_t) m->nr_optics_groups * nshell);
 	ctx->h_model.sigma2_noise = nullptr; ctx->h_model.scale_correction = nullptr; ctx->h_model.pdf_class = nullptr;
 	ctx->h_model.data_vs_prior_class = nullptr; ctx->h_model.prior_offset_class = nullptr;
 	ctx->has_model = true;
@@ -1056,8 +1057,22 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 	RB_CUDA(cudaEventRecord(s.uploaded, cs));
 	RB_CUDA(cudaStreamSynchronize(cs));            // shift / norm / ctfpar are host temporaries
 	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+	// noise-filled soft mask: per-particle seeds and sqrt(sigma2_fudge * sigma2_noise) per optics group (utilities_impl.h:248-249)
+	const long long *d_seed = nullptr; const float *d_spec = nullptr;
+	if (raw->noise_seed)
+	{
+		const int nshell = ctx->d_model.nshell, nog = ctx->h_model.nr_optics_groups;
+		std::vector<float> spec((size_t) nog * nshell);
+		for (size_t i = 0; i < spec.size(); i++) spec[i] = (float) sqrt(ctx->h_model.sigma2_fudge * ctx->h_sigma2_noise[i]);
+		DevBuf &bSeed = ctx->prep_raw[slot][4], &bSpec = ctx->prep_raw[slot][5];
+		RB_CHECK(bSeed.ensure((size_t) P * 8)); RB_CHECK(bSpec.ensure(spec.size() * 4));
+		RB_CUDA(cudaMemcpyAsync(bSeed.p, raw->noise_seed, (size_t) P * 8, cudaMemcpyHostToDevice, ctx->stream));
+		RB_CUDA(cudaMemcpyAsync(bSpec.p, spec.data(), spec.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+		RB_CUDA(cudaStreamSynchronize(ctx->stream));   // spec is a host temporary
+		d_seed = bSeed.as<long long>(); d_spec = bSpec.as<float>();
+	}
 	RB_CHECK(rbk_prepare_pool(ctx, s, bRaw.as<float>(), bShift.as<int>(), bNorm.as<float>(), do_ctf ? bCtf.as<double>() : nullptr, n,
-	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>()));
+	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>(), d_seed, d_spec));
 	if (power_img)
 	{
 		RB_CUDA(cudaMemcpyAsync(power_img, bPow.p, (size_t) P * (n / 2 + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1242,6 +1257,17 @@ extern "C" int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out)
 	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
 	RB_ARG(ctx && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_estep_fetch: slot %d not uploaded", slot);
 	return fetch_slot(ctx, ctx->slot[slot], out);
+}
+
+extern "C" int rb_debug_prep_noise(rb_ctx *ctx, int n_particles, int image_size, float *out)
+{
+	RB_ARG(ctx && out && n_particles > 0 && image_size > 0, "rb_debug_prep_noise: bad argument");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	const size_t bytes = (size_t) n_particles * image_size * image_size * 4;
+	RB_ARG(ctx->prep_buf[4].bytes >= bytes, "rb_debug_prep_noise: no noise images of that size (rb_pool_prepare with noise_seed first)");
+	RB_CUDA(cudaMemcpyAsync(out, ctx->prep_buf[4].p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
 }
 
 extern "C" int rb_debug_coarse_weights(rb_ctx *ctx, int slot, int particle, float *out, long long capacity, long long *n_out)

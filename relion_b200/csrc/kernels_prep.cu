@@ -16,6 +16,7 @@ struct PrepRaw {
 	const int *shift;            // [P][2] rounded old offsets (dx, dy)
 	const float *norm;           // [P]
 	const float *bg;             // [P] background value of the soft edge (masked pass)
+	const float *noise;          // [P][n][n] noise images (centred like raw) or nullptr: fill value of the soft mask
 	int n;
 	float radius, radius_p, cosine_width;
 };
@@ -74,7 +75,8 @@ k_prep_real(PrepRaw A, float *real)
 		{
 			bool inside;
 			const float e = prep_edge(A, y, x, inside);
-			if (!inside) v = (e == 1.f) ? A.bg[p] : v * (1.f - e) + A.bg[p] * e;        // cosineFilter, helper.cpp:234-247
+			const float fill = A.noise ? __ldg(A.noise + ((size_t) p * n + y) * n + x) : A.bg[p];   // do_noise: defVal = noise[texel] (helper.cpp:231-232)
+			if (!inside) v = (e == 1.f) ? fill : v * (1.f - e) + fill * e;              // cosineFilter, helper.cpp:234-247
 		}
 		real[(size_t) p * n * n + i] = v;
 	}
@@ -147,6 +149,55 @@ k_prep_ctf(const double *par, float *Fctf, int cs, double xs_angstrom)
 	}
 }
 
+// Noise image of the noise-filled mask, Fourier side (makeNoiseImage, utilities_impl.h:231-371 ->
+// RNDnormalDitributionComplexWithPowerModulation2D, cuda_kernels/helper.cu:90-135): every pixel of the half transform an
+// independent complex normal times spectrum[ires] (zero beyond the last shell).  Counter-based generator: splitmix64 of
+// (seed, pixel) -> two uniforms -> Box-Muller, independent of the launch shape.
+__device__ __forceinline__ unsigned long long prep_mix64(unsigned long long z)
+{
+	z += 0x9E3779B97F4A7C15ull;
+	z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+	z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+	return z ^ (z >> 31);
+}
+__global__ void __launch_bounds__(256)
+k_prep_noise_fourier(const long long *seed, const float *spectrum, const RbPartMeta *metas, int nshell, int n, float2 *F)
+{
+	const int p = blockIdx.y, xf = n / 2 + 1;
+	const float *spec = spectrum + (size_t) metas[p].og * nshell;
+	const unsigned long long key = prep_mix64((unsigned long long) seed[p]);
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * xf; i += gridDim.x * blockDim.x)
+	{
+		const int iy = i / xf, x = i - iy * xf;
+		const int y = iy >= xf ? iy - n : iy;
+		const int ires = (int) rintf(sqrtf((float) (x * x + y * y)));
+		float2 v = make_float2(0.f, 0.f);
+		if (ires < xf && ires < nshell)
+		{
+			const unsigned long long h = prep_mix64(key ^ ((unsigned long long) i * 0xD1342543DE82EF95ull));
+			const float u1 = ((float) (unsigned) (h >> 40) + 0.5f) * (1.f / 16777216.f);            // (0, 1)
+			const float u2 = ((float) (unsigned) ((h >> 8) & 0xFFFFFF) + 0.5f) * (1.f / 16777216.f);
+			const float r = sqrtf(-2.f * logf(u1)) * spec[ires];
+			float sn, cs;
+			sincospif(2.f * u2, &sn, &cs);
+			v = make_float2(r * cs, r * sn);
+		}
+		F[(size_t) p * n * xf + i] = v;
+	}
+}
+
+// the inverse transform leaves the origin at pixel (0, 0); the mask works on images centred at (n/2, n/2) like the particle
+__global__ void __launch_bounds__(256)
+k_prep_noise_centre(const float *in, float *out, int n)
+{
+	const int p = blockIdx.y;
+	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n * n; i += gridDim.x * blockDim.x)
+	{
+		const int y = i / n, x = i - y * n;
+		out[(size_t) p * n * n + i] = in[((size_t) p * n + (y + n / 2) % n) * n + (x + n / 2) % n];
+	}
+}
+
 // One plan per context: a cuFFT plan belongs to the device that was current when it was made, and contexts run on their own host threads.
 static int get_plan(rb_ctx *ctx, int n, int batch, cufftHandle *out)
 {
@@ -166,15 +217,36 @@ static int get_plan(rb_ctx *ctx, int n, int batch, cufftHandle *out)
 	return RB_OK;
 }
 
+static int get_plan_inv(rb_ctx *ctx, int n, int batch, cufftHandle *out)
+{
+	if (ctx->prep_plan_inv_batch == 0 || ctx->prep_plan_inv_n != n || ctx->prep_plan_inv_batch != batch)
+	{
+		if (ctx->prep_plan_inv_batch) cufftDestroy((cufftHandle) ctx->prep_plan_inv);
+		ctx->prep_plan_inv_batch = 0;
+		int dims[2] = {n, n};
+		cufftHandle h;
+		cufftResult r = cufftPlanMany(&h, 2, dims, nullptr, 1, 0, nullptr, 1, 0, CUFFT_C2R, batch);
+		if (r != CUFFT_SUCCESS) { rb_set_error("cufftPlanMany(C2R %d x %d, batch %d) failed (%d)", n, n, batch, (int) r); return RB_ERR_CUDA; }
+		ctx->prep_plan_inv = (int) h; ctx->prep_plan_inv_n = n; ctx->prep_plan_inv_batch = batch;
+	}
+	cufftResult r = cufftSetStream((cufftHandle) ctx->prep_plan_inv, ctx->stream);
+	if (r != CUFFT_SUCCESS) { rb_set_error("cufftSetStream failed (%d)", (int) r); return RB_ERR_CUDA; }
+	*out = (cufftHandle) ctx->prep_plan_inv;
+	return RB_OK;
+}
+
 void rbk_prepare_release(rb_ctx *ctx)
 {
 	if (ctx->prep_plan_batch) cufftDestroy((cufftHandle) ctx->prep_plan);
 	ctx->prep_plan_batch = 0;
+	if (ctx->prep_plan_inv_batch) cufftDestroy((cufftHandle) ctx->prep_plan_inv);
+	ctx->prep_plan_inv_batch = 0;
 }
 
 // d_raw: [P][n][n] device, d_shift [P][2], d_norm [P], d_ctfpar [P][9] (nullptr: Fctf untouched), outputs into the slot buffers
+// d_seed / d_spectrum: noise-filled mask (nullptr: zero mask); d_noise_out: optional copy of the noise images (tests)
 int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
-                     int n, float radius, float cosine_width, float *d_power)
+                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed, const float *d_spectrum)
 {
 	const RbModelDev &M = ctx->d_model;
 	const int P = s.P, cs = M.current_size;
@@ -184,7 +256,7 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 	cufftHandle plan;
 	RB_CHECK(get_plan(ctx, n, P, &plan));
 	PrepRaw A;
-	A.raw = d_raw; A.shift = d_shift; A.norm = d_norm; A.bg = bBg.as<float>(); A.n = n;
+	A.raw = d_raw; A.shift = d_shift; A.norm = d_norm; A.bg = bBg.as<float>(); A.n = n; A.noise = nullptr;
 	A.radius = radius < 0.f ? (float) n / 2.f : radius; A.cosine_width = cosine_width; A.radius_p = A.radius + cosine_width;
 	const float scale = 1.f / ((float) n * (float) n);
 	dim3 gr((n * n + 255) / 256 > 64 ? 64 : (n * n + 255) / 256, P), gw((cs * xo + 255) / 256 > 64 ? 64 : (cs * xo + 255) / 256, P);
@@ -194,7 +266,22 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 	ctx->launches++;
 	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fnomask.as<float2>(), n, cs, scale); RB_LAUNCH_CHECK(ctx);
 	// masked image -> Fimg, power spectrum, highres_Xi2
-	k_prep_mask_bg<<<P, 256, 0, ctx->stream>>>(A, bBg.as<float>()); RB_LAUNCH_CHECK(ctx);
+	if (d_seed)
+	{
+		// noise images: Fourier-space normals with the model's noise spectrum -> inverse FFT (unnormalised: the coefficients are in
+		// RELION's 1/N-normalised convention) -> centred, kept in prep_buf[4] until the masked pass has read them
+		DevBuf &bNoise = ctx->prep_buf[4];
+		RB_CHECK(bNoise.ensure((size_t) P * n * n * 4));
+		cufftHandle iplan;
+		RB_CHECK(get_plan_inv(ctx, n, P, &iplan));
+		dim3 gf((n * xf + 255) / 256 > 64 ? 64 : (n * xf + 255) / 256, P);
+		k_prep_noise_fourier<<<gf, 256, 0, ctx->stream>>>(d_seed, d_spectrum, s.meta.as<RbPartMeta>(), M.nshell, n, bF.as<float2>()); RB_LAUNCH_CHECK(ctx);
+		if (cufftExecC2R(iplan, bF.as<cufftComplex>(), bReal.as<float>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecC2R failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
+		ctx->launches++;
+		k_prep_noise_centre<<<gr, 256, 0, ctx->stream>>>(bReal.as<float>(), bNoise.as<float>(), n); RB_LAUNCH_CHECK(ctx);
+		A.noise = bNoise.as<float>();
+	}
+	else k_prep_mask_bg<<<P, 256, 0, ctx->stream>>>(A, bBg.as<float>()); RB_LAUNCH_CHECK(ctx);
 	k_prep_real<true><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
 	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 	ctx->launches++;

@@ -214,6 +214,7 @@ class RawParticlePool:
     psi_idx: Optional[np.ndarray] = None
     psi_prior: Optional[np.ndarray] = None
     bp_offset: Optional[np.ndarray] = None
+    noise_seed: Optional[np.ndarray] = None   # [P] int64 random_seed + part_id: noise-filled soft mask; None: zero mask
 
     @property
     def n_particles(self):
@@ -233,6 +234,8 @@ def marshal_raw_pool(pool: RawParticlePool):
     for name in ("group_id", "optics_group", "dir_off", "dir_idx", "psi_off", "psi_idx", "bp_offset"):
         setattr(st, name, _ptr(m.hold(_i32(getattr(pool, name))), C.c_int))
     st.mask_radius, st.width_mask_edge = float(pool.mask_radius), float(pool.width_mask_edge)
+    if pool.noise_seed is not None:
+        st.noise_seed = m.hold(np.ascontiguousarray(pool.noise_seed, dtype=np.int64)).ctypes.data_as(C.POINTER(C.c_int64))
     m.struct = st
     return m
 
@@ -448,6 +451,12 @@ class MlDeviceBundle:
         capi.check(self.lib, self.lib.rb_pool_prepare(self.ctx, slot, C.byref(mp.struct), _ptr(power, C.c_float)))
         self._keep[("pool_n", slot)] = raw.n_particles
         return power
+
+    def debug_prep_noise(self, n_particles: int, n: int):
+        """Noise images of the last pool_prepare with noise_seed (rb_debug_prep_noise, test hook)."""
+        out = np.empty((n_particles, n, n), np.float32)
+        capi.check(self.lib, self.lib.rb_debug_prep_noise(self.ctx, n_particles, n, _ptr(out, C.c_float)))
+        return out
 
     def pool_download(self, slot: int, current_size: int):
         P = self._keep[("pool_n", slot)]

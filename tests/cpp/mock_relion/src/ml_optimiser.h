@@ -256,14 +256,14 @@ public:
 	long int exp_my_first_part_id, exp_my_last_part_id;
 	std::vector<int> image_coarse_size, image_current_size, image_full_size;
 	std::vector<MultidimArray<int> > Mresol_fine, Mresol_coarse;
-	int iter, adaptive_oversampling, maximum_significants, nr_threads, nr_pool;
+	int iter, adaptive_oversampling, maximum_significants, nr_threads, nr_pool, random_seed;
 	RFLOAT adaptive_fraction, particle_diameter, sigma2_fudge, offset_range_x, offset_range_y, offset_range_z;
 	int width_mask_edge, autosampling_hporder_local_searches;
 	bool do_ctf_correction, refs_are_ctf_corrected, do_scale_correction, do_norm_correction, do_map, do_zero_mask, do_firstiter_cc, do_always_cc,
 	     do_skip_maximization, do_skip_align, do_skip_rotate, do_auto_refine, do_helical_refine, do_gpu, ctf_phase_flipped, only_flip_phases, intact_ctf_first_peak,
 	     do_grad, grad_pseudo_halfsets;                  // src/ml_optimiser.h:357-363
 	std::vector<void *> accDataBundles, gpuOptimisers;      // src/ml_optimiser.h:109
-	MlOptimiser() : exp_my_first_part_id(0), exp_my_last_part_id(-1), iter(2), adaptive_oversampling(1), maximum_significants(-1), nr_threads(1), nr_pool(1),
+	MlOptimiser() : exp_my_first_part_id(0), exp_my_last_part_id(-1), iter(2), adaptive_oversampling(1), maximum_significants(-1), nr_threads(1), nr_pool(1), random_seed(0),
 	                adaptive_fraction(0.999), particle_diameter(-1.), sigma2_fudge(1.), offset_range_x(-1.), offset_range_y(-1.), offset_range_z(-1.),
 	                width_mask_edge(5), autosampling_hporder_local_searches(4),
 	                do_ctf_correction(true), refs_are_ctf_corrected(true), do_scale_correction(true), do_norm_correction(true), do_map(true), do_zero_mask(true),

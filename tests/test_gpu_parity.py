@@ -558,6 +558,57 @@ def test_pool_prepare_matches_reference_algorithm(device, ori, cur, local):
     np.testing.assert_allclose(got.particles["dLL_nolog"], want.particles["dLL_nolog"], rtol=1e-4)
 
 
+def test_pool_prepare_noise_filled_mask(device):
+    """RELION's default soft mask (no --zero_mask): the edge blends into a noise image with the model's noise spectrum
+    (makeNoiseImage + cosineFilter, utilities_impl.h:231-371, acc_ml_optimiser_impl.h:355-400, 660-668).  The random numbers
+    cannot match RELION's (its curand and CPU generators do not match each other either), so: (1) given the device's own noise
+    images, the masked transforms must equal the restated blend exactly; (2) the noise images must have the model's spectrum;
+    (3) same seed -> same image, other seed -> other image."""
+    from relion_b200.workload import raw_pool_from
+    from oracle import prepare as prep
+    ori = 48
+    wl = make_workload(ori_size=ori, healpix_order=1, n_particles=24, seed=91, snr=0.3, nr_groups=1)
+    # a coloured noise spectrum, so that the shape is tested and not just the level
+    nshell = ori // 2 + 1
+    wl.model.sigma2_noise = np.atleast_2d(1e-3 * (1.0 + 3.0 * np.exp(-np.arange(nshell) / 6.0)))
+    wl.model.sigma2_fudge = 1.3
+    raw = raw_pool_from(wl, seed=5)
+    raw.noise_seed = 1234 + np.arange(raw.n_particles, dtype=np.int64)
+    raw.noise_seed[3] = raw.noise_seed[2]                      # two particles with the same seed
+    _setup(device, wl)
+    device.pool_prepare(0, raw)
+    F, F0, _, _ = device.pool_download(0, ori)
+    noise = device.debug_prep_noise(raw.n_particles, ori)
+    # (1) exact blend
+    for p in range(raw.n_particles):
+        dx, dy = (int(np.sign(v) * np.floor(abs(v) + 0.5)) for v in raw.old_offset[p])
+        t = prep.translate_and_norm(np.asarray(raw.images[p], np.float64), dx, dy, 1.0 if raw.norm_factor is None else raw.norm_factor[p])
+        masked = prep.noise_mask(t, noise[p].astype(np.float64), raw.mask_radius, raw.width_mask_edge)
+        want, _ = prep.normalize_and_transform(masked, ori)
+        assert np.abs(F[p] - want).max() <= 2e-5 * np.abs(want).max(), p
+    assert np.abs(F - F0).max() > 1e-4 * np.abs(F0).max()
+    # (3) seeds
+    assert np.array_equal(noise[2], noise[3]) and not np.array_equal(noise[0], noise[1])
+    # (2) spectrum: mean |FT|^2 per shell over the particles against 2 sigma2_fudge sigma2_noise (columns 0 < x < n/2)
+    spec = np.sqrt(wl.model.sigma2_fudge * wl.model.sigma2_noise[0])
+    ires, expect = prep.noise_image_shell_power(ori, spec)
+    P2 = np.zeros(ires.shape)
+    for p in range(raw.n_particles):
+        if p == 3:
+            continue
+        c = np.roll(noise[p].astype(np.float64), (-(ori // 2), -(ori // 2)), axis=(0, 1))
+        P2 += np.abs(np.fft.rfft2(c) / (ori * ori)) ** 2
+    P2 /= raw.n_particles - 1
+    inner = np.zeros(ires.shape, bool); inner[:, 1:ori // 2] = True
+    for shell in range(4, ori // 2 - 1):
+        sel = inner & (ires == shell)
+        assert abs(P2[sel].mean() / expect[sel].mean() - 1.0) < 0.25, (shell, P2[sel].mean(), expect[sel].mean())
+    assert abs(noise.mean()) < 0.05 * noise.std()
+    # and the E-step runs on the noise-masked slot
+    res = device.estep_slot(0)
+    assert np.all(res.particles["sum_weight"] > 0)
+
+
 def test_estep_from_star_and_mrc_files_equals_in_memory_pool(device, tmp_path):
     """particles written as two MRC stacks + a RELION 3.1 STAR file, streamed back through the native
     feed (rb_feed_*) and ParticleSet.pool, must give the same prepared slot and the same E-step result as the in-memory

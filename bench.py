@@ -50,6 +50,9 @@ WORKLOADS = {
     # coarse window 54 px: the coarse cross term is the dense contraction that runs on the tensor cores
     "class3d_256_global": (dict(ori_size=256, current_size=128, healpix_order=3, offset_range=5.0, offset_step=2.0, nr_classes=4,
                                 snr=0.05, pixel_size=1.0, n_blobs=200, nr_groups=8), 256),
+    # BASELINE config #4 itself: K = 8 (the per-iteration reduction then carries eight accumulators)
+    "class3d_256_global_k8": (dict(ori_size=256, current_size=128, healpix_order=3, offset_range=5.0, offset_step=2.0, nr_classes=8,
+                                   snr=0.05, pixel_size=1.0, n_blobs=200, nr_groups=8), 256),
     # BASELINE config #5 sizing: 400-px box, 803^3 padded reference / accumulator (16.6 GB expanded reference per class)
     "refine3d_400_local": (dict(ori_size=400, healpix_order=4, offset_range=3.0, offset_step=1.0, nr_classes=1, snr=0.05,
                                 local_search=True, pixel_size=1.0, n_blobs=200, nr_groups=8), 256),
@@ -530,8 +533,23 @@ def run_ours(args):
                    "fine_prep", "fine_project", "fine_diff2", "store_list", "store_band"]
     stage_ms = {s: 0.0 for s in stage_names}
     dev.timer_start()
-    for _ in range(args.steps):
-        dev.estep_slot_nocopy(0)
+    pools_done = args.steps
+    if args.scaling == "strong":
+        # fixed total work: ranks draw pool indices from one shared counter (what RELION's leader hands out over MPI,
+        # src/ml_optimiser_mpi.cpp:1400-1690) and wait for each pool before asking for the next (dynamic load balance)
+        store = dist.distributed_c10d._get_default_store() if world > 1 else None
+        queue = parallel.PoolQueue(store, args.total_pools, iteration=1) if world > 1 else None
+        pools_done = 0
+        while True:
+            i = queue.next() if queue is not None else (pools_done if pools_done < args.total_pools else None)
+            if i is None:
+                break
+            dev.estep_slot_nocopy(0)
+            dev.sync_all_backprojects()
+            pools_done += 1
+    else:
+        for _ in range(args.steps):
+            dev.estep_slot_nocopy(0)
     allreduce_ms = None
     if world > 1:
         dev.sync_all_backprojects()
@@ -556,13 +574,26 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
     value = P * world * args.steps / (ms_max / 1e3)
+    pools_per_rank = None
+    if args.scaling == "strong":
+        value = P * args.total_pools / (ms_max / 1e3)
+        c = torch.zeros(world, dtype=torch.int64, device=f"cuda:{local}")
+        c[rank] = pools_done
+        if world > 1:
+            dist.all_reduce(c)
+        pools_per_rank = [int(v) for v in c.tolist()]
+        assert sum(pools_per_rank) == args.total_pools, pools_per_rank
 
     if args.kernels_only:
         # profiling runs (ncu): the device-resident timed region only
         if rank == 0:
             emit({"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
                   "ms_per_step": round(ms_max / args.steps, 4), "stages": {k: round(v, 4) for k, v in stage_ms.items()},
-                  "config": workload_config(args.workload, P, world), "note": "--kernels-only (profiling run)"})
+                  "config": workload_config(args.workload, P, world), "scaling": args.scaling,
+                  "strong_scaling": None if args.scaling != "strong" else {"total_pools": args.total_pools, "pools_per_rank": pools_per_rank,
+                                                                            "timed_region_ms": round(ms_max, 3)},
+                  "allreduce_ms": None if allreduce_ms is None else round(allreduce_ms, 3), "allreduce_parity": allreduce_parity,
+                  "note": "--kernels-only (profiling run)"})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -689,9 +720,12 @@ def run_ours(args):
     pr = res0.particles
     out = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_max / args.steps, 4), "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args.workload, P, world),
+        "strong_scaling": None if args.scaling != "strong" else {"total_pools": args.total_pools, "pools_per_rank": pools_per_rank,
+                                                                  "timed_region_ms": round(ms_max, 3),
+                                                                  "note": "fixed total work handed out by a shared queue; one all-reduce closes the region"},
         "workload_stats": {"coarse_size": wl.model.coarse_size, "coarse_translations": wl.sampling.n_trans,
                            "mean_coarse_orientations": float(np.mean(np.diff(wl.pool.dir_off) * np.diff(wl.pool.psi_off))) if wl.pool.dir_off is not None else wl.sampling.n_dir * wl.sampling.n_psi,
                            "mean_fine_orientations": float(pr["n_fine_orient"].mean()), "mean_fine_samples": float(pr["n_fine_samples"].mean()),
@@ -1043,6 +1077,10 @@ def main():
     ap.add_argument("--kernels-only", action="store_true", help="device-resident timed region only (for ncu)")
     ap.add_argument("--other-workloads", type=int, default=1, help="also run the other BASELINE.json configurations in compact form (N = 1 only)")
     ap.add_argument("--ref-cuda-sample", type=int, default=64, help="particles run through the reference's own CUDA kernels on this GPU (0: off)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's contract): every rank runs --steps pools; strong: a FIXED number of pools "
+                         "(--total-pools) is handed out to the ranks from a shared queue (parallel.PoolQueue), fetched results included")
+    ap.add_argument("--total-pools", type=int, default=64, help="--scaling strong: pools of the whole job")
     ap.add_argument("--parity-sample", type=int, default=256, help="particles of the same pool checked against the CPU oracle inside the run (0: off)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -253,14 +253,17 @@ def build_rooflines(workload, P, wl, stage_ms, stages, by, peak, peak_src, tenso
             entries.append(hbm("k_project_band + k_diff2_slices_sep", "fine", stage_ms["fine"],
                                "fine diff2 = band-major projection into slices + streaming diff2; algorithmic bytes 64 O_f Np + 12 Np + 4 S_f "
                                "(SURVEY 8d) over the whole fine stage; the reference cells are L2 hits after the first touch of a shell "
-                               "(traffic), the projection is bound by outstanding gathers per SM, not by DRAM bytes",
+                               "(traffic); the projection is bound by L1 line visits (ncu: l1tex 78 %, issue 48 %), not by DRAM bytes; the "
+                               "band-ordered image copies (0.25 ms) run on a side stream under the coarse pass and are not in this figure",
                                ["k_project_band", "k_diff2_slices_sep"]))
         else:
             entries.append(hbm("k_diff2_fine_async", "fine", stage_ms["fine"], "orientation-major fine kernel (cross-correlation criterion / RB_BAND=0)", ["k_diff2_fine_async"]))
     if stage_ms["store"] > 0:
         entries.append(hbm("k_store_band" if band else "k_store", "store", stage_ms["store"],
                            "wavg + back-projection; algorithmic bytes (64 + 204) O_bp Np (SURVEY 8d: gather + read-modify-write of 8 corners x 3 arrays); "
-                           "band-major order keeps the accumulator shell in L2, the red.global.add.v4.f32 stream runs at L2 rate", ["k_store_band" if band else "k_store"]))
+                           "band-major order keeps the accumulator shell in L2 (padded radius-sorted blocks), the red.global.add.v4.f32 stream runs at "
+                           "the L2's reduction rate: the algorithmic model charges every corner a DRAM round trip that is no longer paid, so frac can "
+                           "exceed 1 (traffic = the DRAM bytes actually moved)", ["k_store_band" if band else "k_store"]))
     if stage_ms["coarse"] > 0:
         if tensor_coarse:
             entries.append({"kernel": "k_gemm_tf32x3", "stage": "coarse", "bound": "tensor", "achieved": stages["coarse"]["tensor_bf16_equivalent_TFLOPs"],

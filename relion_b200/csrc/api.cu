@@ -123,6 +123,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	cudaStreamDestroy(ctx->stream);
 	cudaStreamDestroy(ctx->copy_stream);
 	if (ctx->fetch_stream) cudaStreamDestroy(ctx->fetch_stream);
+	if (ctx->aux_stream) { cudaStreamDestroy(ctx->aux_stream); cudaEventDestroy(ctx->aux_fork); cudaEventDestroy(ctx->aux_join); }
 	delete ctx;
 }
 
@@ -1125,6 +1126,8 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	RB_CUDA(cudaMemsetAsync(s.out_pdf_dir.p, 0, (size_t) M.nr_classes * S.n_dir * 8, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(s.out_pdf_class.p, 0, (size_t) 3 * M.nr_classes * 8, ctx->stream));
 
+	const bool band = rbk_band_applicable(ctx);
+	if (band) RB_CHECK(rbk_band_images_async(ctx, s));
 	RB_CHECK(rb_stage_begin(ctx, "coarse"));
 	RB_CHECK(rbk_prep_priors(ctx, s));
 	RB_CHECK(rbk_diff2_coarse_pool(ctx, s));
@@ -1138,7 +1141,6 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	RB_CHECK(rbk_fine_setup_pool(ctx, s));
 	RB_CHECK(rb_stage_end(ctx, "fine_setup"));
 
-	const bool band = rbk_band_applicable(ctx);
 	RB_CHECK(rb_stage_begin(ctx, "fine"));
 	if (band) RB_CHECK(rbk_band_fine_pool(ctx, s));
 	else RB_CHECK(rbk_diff2_fine_pool(ctx, s));

@@ -252,6 +252,8 @@ struct rb_ctx {
 	int device = 0;
 	int num_sms = 0;
 	cudaStream_t stream = nullptr, copy_stream = nullptr, fetch_stream = nullptr;
+	cudaStream_t aux_stream = nullptr;               // side stream of the band-ordered image copies (rbk_band_images_async)
+	cudaEvent_t aux_fork = nullptr, aux_join = nullptr;
 	long long launches = 0;
 
 	RbProjector proj[RB_MAX_CLASSES];
@@ -390,6 +392,7 @@ int rbk_convert_weights_stage(rb_ctx *ctx, float *d_w, long long n_orient, int n
 // kernels_band.cu: band-major (L2-resident) fine pass and store stage
 bool rbk_band_applicable(rb_ctx *ctx);
 int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s);
+int rbk_band_images_async(rb_ctx *ctx, PoolSlot &s);   // band-ordered particle images on a side stream, joined by rbk_band_fine_pool
 int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s);
 int rbk_band_phase_tables(rb_ctx *ctx, bool &ok);
 

@@ -1028,7 +1028,7 @@ int rbk_band_phase_tables(rb_ctx *ctx, bool &ok)
 }
 
 // per-pool buffers and the band-ordered images (once per E-step of a slot): which = 0 before the fine pass, 1 before the store stage
-int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s, int which)
+int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s, int which, cudaStream_t stream)
 {
 	const RbModelDev &M = ctx->d_model;
 	const size_t stride = (size_t) M.nv_rs_pad;
@@ -1041,8 +1041,8 @@ int rbk_band_prepare_pool(rb_ctx *ctx, PoolSlot &s, int which)
 	A.pix = M.pix_rs; A.nd2 = M.nv_rs_d2; A.nst = M.nv_rs_st; A.stride = (int) stride;
 	A.simg4 = s.simg4.as<float4>(); A.sst = s.sst.as<float4>(); A.sctf = s.sctf.as<float>();
 	dim3 g((unsigned) ((stride + 255) / 256), s.P);
-	if (which == 0) k_prep_sorted<0><<<g, 256, 0, ctx->stream>>>(A, M);
-	else k_prep_sorted<1><<<g, 256, 0, ctx->stream>>>(A, M);
+	if (which == 0) k_prep_sorted<0><<<g, 256, 0, stream>>>(A, M);
+	else k_prep_sorted<1><<<g, 256, 0, stream>>>(A, M);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }
@@ -1071,11 +1071,29 @@ static int launch_project_band(rb_ctx *ctx, PoolSlot &s, const int *indir, const
 
 // fine pass: projection of every fine orientation (band-major), then the streaming diff2 pass; in rounds when the slices of
 // all fine orientations the pool could produce do not fit the slice buffer (rounds beyond the actual count exit at once)
+// The band-ordered copies of the particle images depend on the uploaded pool only: they are made on a side stream while the
+// coarse pass (L1-bound, HBM idle) runs, and joined before the fine pass.
+int rbk_band_images_async(rb_ctx *ctx, PoolSlot &s)
+{
+	if (!ctx->aux_stream)
+	{
+		RB_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+		RB_CUDA(cudaEventCreateWithFlags(&ctx->aux_fork, cudaEventDisableTiming));
+		RB_CUDA(cudaEventCreateWithFlags(&ctx->aux_join, cudaEventDisableTiming));
+	}
+	RB_CUDA(cudaEventRecord(ctx->aux_fork, ctx->stream));              // after the upload and every earlier reader of the buffers
+	RB_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_fork, 0));
+	RB_CHECK(rbk_band_prepare_pool(ctx, s, 0, ctx->aux_stream));
+	RB_CHECK(rbk_band_prepare_pool(ctx, s, 1, ctx->aux_stream));
+	RB_CUDA(cudaEventRecord(ctx->aux_join, ctx->aux_stream));
+	return RB_OK;
+}
+
 int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s)
 {
 	const RbModelDev &M = ctx->d_model;
 	RB_CHECK(rb_stage_begin(ctx, "fine_prep"));
-	RB_CHECK(rbk_band_prepare_pool(ctx, s, 0));
+	RB_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->aux_join, 0));       // band-ordered images (rbk_band_images_async)
 	bool tables = false;
 	RB_CHECK(rbk_band_phase_tables(ctx, tables));
 	RB_CHECK(rb_stage_end(ctx, "fine_prep"));
@@ -1124,7 +1142,6 @@ int rbk_band_store_pool(rb_ctx *ctx, PoolSlot &s)
 	L.items = s.bp_items.as<RbBpItem>(); L.samp = s.bp_samp.as<float4>(); L.samp_cap = samp_cap;
 	L.tx = ctx->d_samp.ftx; L.ty = ctx->d_samp.fty; L.NOT = ctx->d_samp.n_over_trans;
 	RB_CHECK(rb_stage_begin(ctx, "store_list"));
-	RB_CHECK(rbk_band_prepare_pool(ctx, s, 1));
 	k_bp_count<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(L);
 	RB_LAUNCH_CHECK(ctx);
 	k_bp_scan<<<1, 1024, 0, ctx->stream>>>(L);

@@ -347,26 +347,38 @@ __device__ __forceinline__ void band_diff_pass_sep(const float2 *__restrict__ sl
 #pragma unroll
 	for (int t = 0; t < NC * NOT; t++) acc[t] = 0.f;
 	base = 0.f;
-	for (int ip = threadIdx.x; ip < nd2; ip += BD_THREADS)
+	// two neighbouring pixels per thread and step: slice, phase tables and image come as 16-byte loads (the band arrays are
+	// padded to whole tiles and 16-byte aligned at even pixels), half the load instructions of a pixel-per-thread loop
+	for (int ip = 2 * threadIdx.x; ip < nd2; ip += 2 * BD_THREADS)
 	{
-		const float2 ref = __ldcs(slices + bd_at(row, ip, nrows));
-		const float4 im = __ldg(img + ip);
-		float2 po[NOT];
+		const bool two = ip + 1 < nd2;
+		float4 rr = __ldcs((const float4 *) (slices + bd_at(row, ip, nrows)));
+		const float4 ia = __ldg(img + ip);
+		float4 ib = __ldg(img + ip + 1);
+		if (!two) { rr.z = 0.f; rr.w = 0.f; ib = make_float4(0.f, 0.f, 0.f, 0.f); }          // the pad entry of the slice is not written
+		float4 po[NOT];
 #pragma unroll
-		for (int j = 0; j < NOT; j++) po[j] = NOT > 1 ? __ldg(tabo + (size_t) j * stride + ip) : make_float2(1.f, 0.f);
-		float2 pc[NC];
+		for (int j = 0; j < NOT; j++) po[j] = NOT > 1 ? __ldg((const float4 *) (tabo + (size_t) j * stride + ip)) : make_float4(1.f, 0.f, 1.f, 0.f);
+		float4 pc[NC];
 #pragma unroll
-		for (int c = 0; c < NC; c++) pc[c] = __ldg(tabc + (size_t) s_tc[c] * stride + ip);
-		const float hc = im.z;
-		const float zr = hc * (ref.x * im.x + ref.y * im.y);
-		const float zi = hc * (ref.x * im.y - ref.y * im.x);
-		base += hc * ((ref.x * ref.x + ref.y * ref.y) + (im.x * im.x + im.y * im.y));
+		for (int c = 0; c < NC; c++) pc[c] = __ldg((const float4 *) (tabc + (size_t) s_tc[c] * stride + ip));
+		const float zra = ia.z * (rr.x * ia.x + rr.y * ia.y), zia = ia.z * (rr.x * ia.y - rr.y * ia.x);
+		const float zrb = ib.z * (rr.z * ib.x + rr.w * ib.y), zib = ib.z * (rr.z * ib.y - rr.w * ib.x);
+		base += ia.z * ((rr.x * rr.x + rr.y * rr.y) + (ia.x * ia.x + ia.y * ia.y));
+		base += ib.z * ((rr.z * rr.z + rr.w * rr.w) + (ib.x * ib.x + ib.y * ib.y));
 #pragma unroll
 		for (int c = 0; c < NC; c++)
 		{
-			const float cr = zr * pc[c].x - zi * pc[c].y, ci = zr * pc[c].y + zi * pc[c].x;     // Z e^{i phi_c}
+			const float cra = zra * pc[c].x - zia * pc[c].y, cia = zra * pc[c].y + zia * pc[c].x;     // Z e^{i phi_c}
+			const float crb = zrb * pc[c].z - zib * pc[c].w, cib = zrb * pc[c].w + zib * pc[c].z;
 #pragma unroll
-			for (int j = 0; j < NOT; j++) acc[c * NOT + j] = fmaf(cr, po[j].x, fmaf(-ci, po[j].y, acc[c * NOT + j]));   // Re(Z e^{i phi_c} e^{i phi_j})
+			for (int j = 0; j < NOT; j++)
+			{
+				float a = acc[c * NOT + j];
+				a = fmaf(cra, po[j].x, fmaf(-cia, po[j].y, a));                                          // Re(Z e^{i phi_c} e^{i phi_j})
+				a = fmaf(crb, po[j].z, fmaf(-cib, po[j].w, a));
+				acc[c * NOT + j] = a;
+			}
 		}
 	}
 }
@@ -374,7 +386,7 @@ __device__ __forceinline__ void band_diff_pass_sep(const float2 *__restrict__ sl
 static const int BD_NCMAX = 8;   // coarse translations per pass of the factorised kernel
 
 template <int NOT>
-static __global__ void __launch_bounds__(BD_THREADS, 3)
+static __global__ void __launch_bounds__(BD_THREADS, 2)
 k_diff2_slices_sep(BandDiffArgs A, const float2 *tabc, const float2 *tabo)
 {
 	__shared__ int s_tc[BD_NCMAX];
@@ -1117,8 +1129,9 @@ int rbk_band_fine_pool(rb_ctx *ctx, PoolSlot &s)
 		D.queue = queue + 1;
 		RB_CUDA(cudaMemsetAsync(queue + 1, 0, 4, ctx->stream));
 		const int NOT = ctx->d_samp.n_over_trans;
-		if (tables && NOT == 4) k_diff2_slices_sep<4><<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D, ctx->band_tabc.as<float2>(), ctx->band_tabo.as<float2>());
-		else if (tables && NOT == 1) k_diff2_slices_sep<1><<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D, ctx->band_tabc.as<float2>(), ctx->band_tabo.as<float2>());
+		const int dctas = env_int("RB_BAND_DIFF_CTAS", 2);
+	if (tables && NOT == 4) k_diff2_slices_sep<4><<<ctx->num_sms * dctas, BD_THREADS, 0, ctx->stream>>>(D, ctx->band_tabc.as<float2>(), ctx->band_tabo.as<float2>());
+		else if (tables && NOT == 1) k_diff2_slices_sep<1><<<ctx->num_sms * dctas, BD_THREADS, 0, ctx->stream>>>(D, ctx->band_tabc.as<float2>(), ctx->band_tabo.as<float2>());
 		else k_diff2_slices<<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(D);
 		RB_LAUNCH_CHECK(ctx);
 		if (r == 0) RB_CHECK(rb_stage_end(ctx, "fine_diff2"));

@@ -331,7 +331,8 @@ int rb_debug_prep_noise(rb_ctx *ctx, int n_particles, int image_size, float *out
  * (acc_ml_optimiser_impl.h:11-1010) for a whole pool: integer translation by the rounded old offset and norm
  * correction, transform of the unmasked image (Fimg_nomask), soft circular zero-mask, transform of the masked
  * image (Fimg), power spectrum / highres_Xi2 beyond the current size, CTF image from the CTF parameters.
- * Covered branch: 2D images, one body, zero- or noise-filled soft mask, no helix / tomo / beam tilt / MTF, CTF without phase flipping.
+ * Covered branch: 2D images, one body, zero- or noise-filled soft mask, beam tilt / MTF as a per-optics-group factor image, no helix / tomo,
+ * CTF without phase flipping.
  * The slot is then ready for rb_estep_slot exactly as after rb_pool_upload.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -351,6 +352,12 @@ typedef struct {
 	const int *dir_off, *dir_idx; const double *dir_prior;
 	const int *psi_off, *psi_idx; const double *psi_prior;
 	const int *bp_offset;        /* as in rb_particles                                              */
+	const float *og_fourier_factor; /* [nr_optics_groups][current_size][current_size/2+1] complex (re, im) or NULL: per optics group,
+	                                the factor both transforms are multiplied with after windowing: conj(phase correction) of the
+	                                beam tilt / odd Zernike terms (ObservationModel::demodulatePhase,
+	                                src/jaz/single_particle/obs_model.cpp:598-626) times avgMTF / MTF (divideByMtf, :528-584), as
+	                                acc_ml_optimiser_impl.h:535-536 applies them; the host builds the images from the
+	                                observation model once per E-step                                                  */
 	const int64_t *noise_seed;   /* [P] random_seed + part_id, or NULL.  NULL: --zero_mask (soft mask towards the background
 	                                value of the image's own edge).  Non-NULL: RELION's default, the soft mask blends into a NOISE
 	                                image with the spectrum sqrt(sigma2_fudge * sigma2_noise[optics group]) (makeNoiseImage,

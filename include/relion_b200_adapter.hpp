@@ -480,6 +480,33 @@ public:
 			for (int p = 0; p < P; p++) bp_offset[p] = (int) ((first + p) % 2) * m.nr_classes;       // acc_ml_optimiser_impl.h:3397-3399
 			raw.bp_offset = bp_offset.data();
 		}
+		// beam-tilt demodulation and MTF division of both transforms (acc_ml_optimiser_impl.h:535-536 ->
+		// ObservationModel::demodulatePhase / divideByMtf(do_multiply_instead = false, do_correct_average_mtf = true),
+		// src/jaz/single_particle/obs_model.cpp:528-626): one factor image per optics group, applied on the device after windowing
+		std::vector<float> og_factor;
+		{
+			// the reference's own functions applied to an image of ones give the factor exactly as RELION would apply it
+			ObservationModel &obs = o.mydata.obsModel;
+			if (obs.hasOddZernike || obs.hasMultipleMtfs)
+			{
+				const int nog = obs.numberOfOpticsGroups(), xs = cur / 2 + 1;
+				og_factor.assign((size_t) nog * cur * xs * 2, 0.f);
+				for (int g = 0; g < nog; g++)
+				{
+					MultidimArray<Complex> one;
+					one.resize(cur, xs);
+					FOR_ALL_DIRECT_ELEMENTS_IN_MULTIDIMARRAY(one) DIRECT_MULTIDIM_ELEM(one, n) = Complex(1., 0.);
+					obs.demodulatePhase(g, one);
+					obs.divideByMtf(g, one);
+					FOR_ALL_DIRECT_ELEMENTS_IN_MULTIDIMARRAY(one)
+					{
+						og_factor[((size_t) g * cur * xs + n) * 2] = (float) DIRECT_MULTIDIM_ELEM(one, n).real;
+						og_factor[((size_t) g * cur * xs + n) * 2 + 1] = (float) DIRECT_MULTIDIM_ELEM(one, n).imag;
+					}
+				}
+				raw.og_fourier_factor = og_factor.data();
+			}
+		}
 		std::vector<int64_t> noise_seed;
 		if (!o.do_zero_mask)                                                                          // noise-filled soft mask, seed as acc_ml_optimiser_impl.h:371
 		{

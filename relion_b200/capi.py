@@ -83,6 +83,7 @@ class rb_raw_particles(C.Structure):
         ("dir_off", c_int_p), ("dir_idx", c_int_p), ("dir_prior", c_double_p),
         ("psi_off", c_int_p), ("psi_idx", c_int_p), ("psi_prior", c_double_p),
         ("bp_offset", c_int_p),
+        ("og_fourier_factor", c_float_p),
         ("noise_seed", C.POINTER(C.c_int64)),
     ]
 

@@ -1055,25 +1055,36 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 	RB_CUDA(cudaMemcpyAsync(bShift.p, shift.data(), (size_t) P * 8, cudaMemcpyHostToDevice, cs));
 	RB_CUDA(cudaMemcpyAsync(bNorm.p, norm.data(), (size_t) P * 4, cudaMemcpyHostToDevice, cs));
 	if (do_ctf) RB_CUDA(cudaMemcpyAsync(bCtf.p, ctfpar.data(), ctfpar.size() * 8, cudaMemcpyHostToDevice, cs));
-	RB_CUDA(cudaEventRecord(s.uploaded, cs));
-	RB_CUDA(cudaStreamSynchronize(cs));            // shift / norm / ctfpar are host temporaries
-	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
 	// noise-filled soft mask: per-particle seeds and sqrt(sigma2_fudge * sigma2_noise) per optics group (utilities_impl.h:248-249)
 	const long long *d_seed = nullptr; const float *d_spec = nullptr;
+	std::vector<float> spec;
 	if (raw->noise_seed)
 	{
 		const int nshell = ctx->d_model.nshell, nog = ctx->h_model.nr_optics_groups;
-		std::vector<float> spec((size_t) nog * nshell);
+		spec.resize((size_t) nog * nshell);
 		for (size_t i = 0; i < spec.size(); i++) spec[i] = (float) sqrt(ctx->h_model.sigma2_fudge * ctx->h_sigma2_noise[i]);
 		DevBuf &bSeed = ctx->prep_raw[slot][4], &bSpec = ctx->prep_raw[slot][5];
 		RB_CHECK(bSeed.ensure((size_t) P * 8)); RB_CHECK(bSpec.ensure(spec.size() * 4));
-		RB_CUDA(cudaMemcpyAsync(bSeed.p, raw->noise_seed, (size_t) P * 8, cudaMemcpyHostToDevice, ctx->stream));
-		RB_CUDA(cudaMemcpyAsync(bSpec.p, spec.data(), spec.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
-		RB_CUDA(cudaStreamSynchronize(ctx->stream));   // spec is a host temporary
+		RB_CUDA(cudaMemcpyAsync(bSeed.p, raw->noise_seed, (size_t) P * 8, cudaMemcpyHostToDevice, cs));
+		RB_CUDA(cudaMemcpyAsync(bSpec.p, spec.data(), spec.size() * 4, cudaMemcpyHostToDevice, cs));
 		d_seed = bSeed.as<long long>(); d_spec = bSpec.as<float>();
 	}
+	// beam-tilt / MTF factor images of the optics groups
+	const float2 *d_fac = nullptr;
+	if (raw->og_fourier_factor)
+	{
+		const int csz = ctx->h_model.current_size;
+		const size_t fb = (size_t) ctx->h_model.nr_optics_groups * csz * (csz / 2 + 1) * sizeof(float2);
+		DevBuf &bFac = ctx->prep_raw[slot][6];
+		RB_CHECK(bFac.ensure(fb));
+		RB_CUDA(cudaMemcpyAsync(bFac.p, raw->og_fourier_factor, fb, cudaMemcpyHostToDevice, cs));
+		d_fac = bFac.as<float2>();
+	}
+	RB_CUDA(cudaEventRecord(s.uploaded, cs));
+	RB_CUDA(cudaStreamSynchronize(cs));            // shift / norm / ctfpar / spec are host temporaries
+	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
 	RB_CHECK(rbk_prepare_pool(ctx, s, bRaw.as<float>(), bShift.as<int>(), bNorm.as<float>(), do_ctf ? bCtf.as<double>() : nullptr, n,
-	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>(), d_seed, d_spec));
+	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>(), d_seed, d_spec, d_fac));
 	if (power_img)
 	{
 		RB_CUDA(cudaMemcpyAsync(power_img, bPow.p, (size_t) P * (n / 2 + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));

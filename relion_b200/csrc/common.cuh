@@ -309,7 +309,7 @@ struct rb_ctx {
 	int prep_plan_inv = 0, prep_plan_inv_n = 0, prep_plan_inv_batch = 0;   // batched 2D C2R plan of the noise-filled mask
 	std::vector<double> h_sigma2_noise;   // [nr_optics_groups][nshell] (the noise image of the noise-filled mask follows this spectrum)
 	int prep_plan = 0, prep_plan_n = 0, prep_plan_batch = 0;   // this context's batched 2D R2C cuFFT plan (cufftHandle is an int); 0 batch: none
-	DevBuf prep_raw[RB_NUM_SLOTS][6];   // per slot: raw images, shifts, norm factors, CTF parameters (filled on the copy stream)
+	DevBuf prep_raw[RB_NUM_SLOTS][7];   // per slot: raw images, shifts, norm factors, CTF parameters (filled on the copy stream)
 	DevBuf posed_buf[2][3];          // staged posed images (F2D, Fctf, matrices), two buffers for upload / compute overlap
 	DevBuf posed_pix, posed_sorted;  // band-major posed back-projection: pixel list of the image size, band-ordered images of a chunk
 	int posed_pix_n = 0, posed_pix_count = 0;
@@ -368,7 +368,7 @@ int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int M, 
 // kernels_prep.cu: getFourierTransformsAndCtfs on the device, batched over the pool
 void rbk_prepare_release(rb_ctx *ctx);
 int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
-                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed = nullptr, const float *d_spectrum = nullptr);
+                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed = nullptr, const float *d_spectrum = nullptr, const float2 *d_og_factor = nullptr);
 
 // kernels_recon.cu: BackProjector::reconstruct (skip_gridding) + windowToOridimRealSpace + griddingCorrect on the device
 int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,

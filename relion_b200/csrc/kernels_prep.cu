@@ -82,18 +82,22 @@ k_prep_real(PrepRaw A, float *real)
 	}
 }
 
-// scale by 1/n^2 and window to the current size (windowFourierTransform2, shrinking branch)
+// scale by 1/n^2 and window to the current size (windowFourierTransform2, shrinking branch); then the optics group's factor image
+// (beam-tilt demodulation, MTF: obs_model.cpp:528-626 as applied at acc_ml_optimiser_impl.h:535-536) when there is one
 __global__ void __launch_bounds__(256)
-k_prep_window(const float2 *F, float2 *out, int n, int cs, float scale)
+k_prep_window(const float2 *F, float2 *out, int n, int cs, float scale, const float2 *og_factor, const RbPartMeta *metas)
 {
 	const int p = blockIdx.y;
 	const int xf = n / 2 + 1, xo = cs / 2 + 1;
+	const float2 *fac = og_factor ? og_factor + (size_t) metas[p].og * cs * xo : nullptr;
 	for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < cs * xo; i += gridDim.x * blockDim.x)
 	{
 		const int iy = i / xo, x = i - iy * xo;
 		const int ip = iy < xo ? iy : iy - cs;
 		const float2 v = F[((size_t) p * n + (ip < 0 ? ip + n : ip)) * xf + x];
-		out[(size_t) p * cs * xo + i] = make_float2(v.x * scale, v.y * scale);
+		float2 o = make_float2(v.x * scale, v.y * scale);
+		if (fac) { const float2 c = __ldg(fac + i); o = make_float2(o.x * c.x - o.y * c.y, o.x * c.y + o.y * c.x); }
+		out[(size_t) p * cs * xo + i] = o;
 	}
 }
 
@@ -246,7 +250,7 @@ void rbk_prepare_release(rb_ctx *ctx)
 // d_raw: [P][n][n] device, d_shift [P][2], d_norm [P], d_ctfpar [P][9] (nullptr: Fctf untouched), outputs into the slot buffers
 // d_seed / d_spectrum: noise-filled mask (nullptr: zero mask); d_noise_out: optional copy of the noise images (tests)
 int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
-                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed, const float *d_spectrum)
+                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed, const float *d_spectrum, const float2 *d_og_factor)
 {
 	const RbModelDev &M = ctx->d_model;
 	const int P = s.P, cs = M.current_size;
@@ -264,7 +268,7 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 	k_prep_real<false><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
 	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 	ctx->launches++;
-	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fnomask.as<float2>(), n, cs, scale); RB_LAUNCH_CHECK(ctx);
+	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fnomask.as<float2>(), n, cs, scale, d_og_factor, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
 	// masked image -> Fimg, power spectrum, highres_Xi2
 	if (d_seed)
 	{
@@ -285,7 +289,7 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 	k_prep_real<true><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
 	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 	ctx->launches++;
-	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fimg.as<float2>(), n, cs, scale); RB_LAUNCH_CHECK(ctx);
+	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fimg.as<float2>(), n, cs, scale, d_og_factor, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
 	if (cs < n)
 	{
 		k_prep_power<<<P, 256, 0, ctx->stream>>>(bF.as<float2>(), n, cs, scale, d_power, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);

@@ -215,6 +215,7 @@ class RawParticlePool:
     psi_prior: Optional[np.ndarray] = None
     bp_offset: Optional[np.ndarray] = None
     noise_seed: Optional[np.ndarray] = None   # [P] int64 random_seed + part_id: noise-filled soft mask; None: zero mask
+    og_fourier_factor: Optional[np.ndarray] = None   # [nog, cs, cs/2+1] complex64: conj(beam-tilt phase) * avgMTF / MTF per optics group
 
     @property
     def n_particles(self):
@@ -234,6 +235,8 @@ def marshal_raw_pool(pool: RawParticlePool):
     for name in ("group_id", "optics_group", "dir_off", "dir_idx", "psi_off", "psi_idx", "bp_offset"):
         setattr(st, name, _ptr(m.hold(_i32(getattr(pool, name))), C.c_int))
     st.mask_radius, st.width_mask_edge = float(pool.mask_radius), float(pool.width_mask_edge)
+    if pool.og_fourier_factor is not None:
+        st.og_fourier_factor = _ptr(m.hold(np.ascontiguousarray(pool.og_fourier_factor, dtype=np.complex64).view(np.float32)), C.c_float)
     if pool.noise_seed is not None:
         st.noise_seed = m.hold(np.ascontiguousarray(pool.noise_seed, dtype=np.int64)).ctypes.data_as(C.POINTER(C.c_int64))
     m.struct = st

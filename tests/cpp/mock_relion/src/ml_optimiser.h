@@ -126,10 +126,46 @@ public:
 	MultidimArray<RFLOAT> weight;
 };
 
+// src/jaz/image/buffered_image.h: operator()(x, y)
+template <class T> class BufferedImage
+{
+public:
+	int w, h; std::vector<T> data;
+	BufferedImage() : w(0), h(0) {}
+	BufferedImage(int w_, int h_) : w(w_), h(h_), data((size_t) w_ * h_) {}
+	const T &operator()(int x, int y) const { return data[(size_t) y * w + x]; }
+	T &operator()(int x, int y) { return data[(size_t) y * w + x]; }
+};
+
 class ObservationModel
 {
 public:
 	std::vector<RFLOAT> kV, Cs, Q0, pixel_size; std::vector<int> box_size; std::vector<bool> ctf_premultiplied;
+	// beam tilt / odd Zernike phase correction and detector MTF (src/jaz/single_particle/obs_model.h:45-129, obs_model.cpp:528-626)
+	bool hasOddZernike, hasMultipleMtfs;
+	std::vector<BufferedImage<Complex> > phaseCorr; std::vector<BufferedImage<RFLOAT> > mtfImage; BufferedImage<RFLOAT> avgMtfImage;
+	void demodulatePhase(int og, MultidimArray<Complex> &img, bool do_modulate_instead = false)
+	{
+		if (!hasOddZernike || (int) phaseCorr.size() <= og) return;
+		for (int y = 0; y < img.ydim; y++) for (int x = 0; x < img.xdim; x++)
+		{
+			Complex &v = DIRECT_A2D_ELEM(img, y, x); const Complex c = phaseCorr[og](x, y);
+			const RFLOAT ci = do_modulate_instead ? c.imag : -c.imag;
+			v = Complex(v.real * c.real - v.imag * ci, v.real * ci + v.imag * c.real);
+		}
+	}
+	void divideByMtf(int og, MultidimArray<Complex> &img, bool do_multiply_instead = false, bool do_correct_average_mtf = true)
+	{
+		if (do_correct_average_mtf && !hasMultipleMtfs) return;
+		if ((int) mtfImage.size() <= og) return;
+		for (int y = 0; y < img.ydim; y++) for (int x = 0; x < img.xdim; x++)
+		{
+			Complex &v = DIRECT_A2D_ELEM(img, y, x);
+			const RFLOAT f = (do_correct_average_mtf ? avgMtfImage(x, y) : 1.) / mtfImage[og](x, y);
+			v = Complex(v.real * f, v.imag * f);
+		}
+	}
+	ObservationModel() : hasOddZernike(false), hasMultipleMtfs(false) {}
 	bool getCtfPremultiplied(int og) const { return ctf_premultiplied[og]; }
 	RFLOAT getPixelSize(int og) const { return pixel_size[og]; }
 	int getBoxSize(int og) const { return box_size[og]; }

@@ -558,6 +558,30 @@ def test_pool_prepare_matches_reference_algorithm(device, ori, cur, local):
     np.testing.assert_allclose(got.particles["dLL_nolog"], want.particles["dLL_nolog"], rtol=1e-4)
 
 
+def test_pool_prepare_beam_tilt_and_mtf_factor(device):
+    """Beam-tilt demodulation and MTF division (ObservationModel::demodulatePhase / divideByMtf, obs_model.cpp:528-626, applied
+    to both transforms at acc_ml_optimiser_impl.h:535-536) as one complex factor image per optics group, multiplied in after
+    windowing: conj(phase correction) * avgMTF / MTF."""
+    from relion_b200.workload import raw_pool_from
+    from oracle.prepare import prepared_pool as oracle_prepared_pool
+    ori, cur = 40, 28
+    wl = make_workload(ori_size=ori, current_size=cur, healpix_order=1, n_particles=8, seed=97, snr=0.3, nr_groups=1)
+    raw = raw_pool_from(wl, seed=4)
+    rng = np.random.default_rng(5)
+    xs = cur // 2 + 1
+    phase = np.exp(-1j * rng.uniform(-0.6, 0.6, (1, cur, xs)))            # conj of a tilt phase ramp stand-in
+    mtf = rng.uniform(0.4, 1.0, (1, cur, xs)); avg = rng.uniform(0.4, 1.0, (1, cur, xs))
+    factor = (phase * avg / mtf).astype(np.complex64)
+    raw.og_fourier_factor = factor
+    _setup(device, wl)
+    device.pool_prepare(0, raw)
+    F, F0, _, xi2 = device.pool_download(0, cur)
+    pool, _ = oracle_prepared_pool(wl, raw)
+    for got, want in ((F, pool.Fimg * factor[0]), (F0, pool.Fimg_nomask * factor[0])):
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    np.testing.assert_allclose(xi2, pool.highres_Xi2, rtol=1e-4)       # the power beyond the current size is taken before the correction
+
+
 def test_pool_prepare_noise_filled_mask(device):
     """RELION's default soft mask (no --zero_mask): the edge blends into a noise image with the model's noise spectrum
     (makeNoiseImage + cosineFilter, utilities_impl.h:231-371, acc_ml_optimiser_impl.h:355-400, 660-668).  The random numbers
@@ -902,14 +926,13 @@ def test_pool_store_stage_without_slice_cache(device, oracle, monkeypatch, cache
 
 def test_two_device_bundles_in_one_process(device):
     """RELION drives several GPUs from the threads of one process (one MlDeviceBundle per device): contexts on different
-    devices must not share per-device state (kernel attributes, streams, buffers).  Needs a box with >= 2 GPUs."""
+    devices must not share per-device state (kernel attributes, streams, buffers).  On a box with one GPU the second bundle
+    lives on the same device: two independent contexts (own streams, buffers, models) interleaved in one process."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
     from relion_b200.estep import MlDeviceBundle
     wl = make_workload(ori_size=64, healpix_order=2, n_particles=12, nr_classes=1, seed=71, snr=0.2, local_search=True)
     wg = make_workload(ori_size=32, healpix_order=1, n_particles=8, nr_classes=2, seed=72, snr=0.3)
-    second = MlDeviceBundle(1)
+    second = MlDeviceBundle(1 if torch.cuda.device_count() >= 2 else 0)
     try:
         out = {}
         for name, dev, w in (("local0", device, wl), ("local1", second, wl), ("global1", second, wg), ("global0", device, wg)):

@@ -407,7 +407,7 @@ def quick_reconstruct(dev, P=1024, steps=3):
     ach = 204.0 * npr * P * steps / (ms * 1e-3) / 1e9
     return {"config": workload_config("reconstruct_256", P, 1), "value": round(P * steps / (ms * 1e-3), 1), "unit": UNIT,
             "ms_per_step": round(ms / steps, 4), "e2e": round(P * steps / e2e_s, 1), "steps": steps,
-            "roofline_kernels": [{"kernel": "k_backproject_posed", "bound": "hbm", "achieved": round(ach, 1), "unit": "GB/s", "peak": peak,
+            "roofline_kernels": [{"kernel": "k_posed_sort + k_posed_band", "bound": "hbm", "achieved": round(ach, 1), "unit": "GB/s", "peak": peak,
                                   "frac": round(ach / peak, 4)}]}
 
 
@@ -996,6 +996,24 @@ def run_reconstruct(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = P * world * args.steps / float(t.item())
+    # end to end from RAW images: real-space pixels + CTF parameters over PCIe, transform / shift / CTF on the device
+    raw = torch.empty((P, n, n), dtype=torch.float32).pin_memory()
+    rn = raw.numpy()
+    for p0 in range(0, P, 256):
+        rn[p0:min(P, p0 + 256)] = rng.standard_normal((min(P, p0 + 256) - p0, n, n), dtype=np.float32)
+    dfs = rng.uniform(10000, 30000, P)
+    ctfpar = dict(defU=dfs, defV=dfs + 300.0, defAngle=np.full(P, 30.0), kV=[300.0], Cs=[2.7], Q0=[0.1])
+    shifts = rng.uniform(-3, 3, (P, 2))
+    dev.backproject_posed_raw(0, raw, R, shift=shifts, ctf=ctfpar, pixel_size=1.0)
+    barrier()
+    t1 = time.perf_counter()
+    for _ in range(args.steps):
+        dev.backproject_posed_raw(0, raw, R, shift=shifts, ctf=ctfpar, pixel_size=1.0)
+    dev.sync_all_backprojects()
+    t = torch.tensor([time.perf_counter() - t1], dtype=torch.float64, device=f"cuda:{local}")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_raw_value = P * world * args.steps / float(t.item())
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -1025,8 +1043,11 @@ def run_reconstruct(args):
            "config": workload_config("reconstruct_256", P, world),
            "workload_stats": {"accumulator": list(shape), "scattered_pixels_per_image": npr},
            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(P * n * xs * 12 + P * 36), "d2h_bytes_per_step": 0},
+           "e2e_from_raw_images": {"value": round(e2e_raw_value, 1), "unit": UNIT, "h2d_bytes_per_step": int(P * n * n * 4 + P * (36 + 88)),
+                                   "d2h_bytes_per_step": 0, "note": "rb_backproject_posed_raw: real-space images + CTF parameters in; "
+                                   "FourierTransform, CenterFFTbySign, origin shift, CTF, DC removal (reconstructor.cpp:428-745) on the device"},
            "gpu_launches": int(launches), "clocks": clocks,
-           "roofline": {"kernel": "k_backproject_posed", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+           "roofline": {"kernel": "k_posed_sort + k_posed_band", "bound": "hbm", "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
                         "frac": round(ach / peak, 4), "traffic": ncu_traffic("reconstruct_256", P, "k_backproject_posed"), "peak_source": peak_src,
                         "algorithmic_bytes_per_launch": bytes_per_launch},
            "cpu_baseline": cpu}

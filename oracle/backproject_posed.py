@@ -64,3 +64,24 @@ def backproject2Dto3D(data: np.ndarray, weight: np.ndarray, f2d: np.ndarray, A_i
                     dd = wz * wy * wx
                     np.add.at(data, (z0 + dz, y0 + dy, x0 + dx), dd * val)
                     np.add.at(weight, (z0 + dz, y0 + dy, x0 + dx), dd * w)
+
+
+def prepare_particle(img: np.ndarray, shift, ctf_image: np.ndarray | None, ctf_premultiplied: bool = False):
+    """What Reconstructor::backprojectOneParticle does to one 2D particle before backproject2Dto3D
+    (/root/reference/src/reconstructor.cpp:428-745, no Ewald sphere / FOM / subtraction): F2D = FFT(img) / N with
+    CenterFFTbySign (src/fftw.h:390-403), shiftImageInFourierTransform (src/fftw.cpp:874-918: x e^{-2 pi i (x tx + y ty) / n}),
+    F2D *= Fctf unless the data are premultiplied, Fctf = Fctf^2, F2D(0, 0) = 0.  Returns (F2D complex128, Fctf^2 float64)."""
+    n = img.shape[0]
+    xs = n // 2 + 1
+    F = np.fft.rfft2(np.asarray(img, np.float64)) / float(n * n)
+    iy = np.arange(n)[:, None]; x = np.arange(xs)[None, :]
+    F = F * np.where(((iy ^ x) & 1) != 0, -1.0, 1.0)
+    y = np.where(iy < xs, iy, iy - n)
+    tx, ty = (0.0, 0.0) if shift is None else (float(shift[0]), float(shift[1]))
+    if abs(tx / n) >= 1e-6 or abs(ty / n) >= 1e-6:
+        F = F * np.exp(-2j * np.pi * (x * tx + y * ty) / n)
+    c = np.ones((n, xs)) if ctf_image is None else np.asarray(ctf_image, np.float64)
+    if not ctf_premultiplied:
+        F = F * c
+    F[0, 0] = 0.0
+    return F, c * c

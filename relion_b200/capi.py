@@ -88,6 +88,18 @@ class rb_raw_particles(C.Structure):
     ]
 
 
+class rb_posed_raw(C.Structure):
+    _fields_ = [
+        ("n_images", C.c_int), ("image_size", C.c_int),
+        ("images", c_float_p), ("eulers", c_float_p), ("shift", c_double_p),
+        ("ctf_defU", c_double_p), ("ctf_defV", c_double_p), ("ctf_defAngle", c_double_p),
+        ("ctf_Bfac", c_double_p), ("ctf_scale", c_double_p), ("ctf_phase_shift", c_double_p),
+        ("optics_group", c_int_p),
+        ("og_kV", c_double_p), ("og_Cs", c_double_p), ("og_Q0", c_double_p),
+        ("pixel_size", C.c_double), ("ctf_premultiplied", C.c_int),
+    ]
+
+
 class rb_particle_out(C.Structure):
     _fields_ = [
         ("best_ihidden_over", C.c_int64),
@@ -196,6 +208,7 @@ PROTOTYPES = {
     "rb_backproject": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                  c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_float, C.c_float]),
     "rb_backproject_posed": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),
+    "rb_backproject_posed_raw": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(rb_posed_raw)]),
     "rb_bp_posed_stage": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p]),
     "rb_bp_posed_run": (C.c_int, [C.c_void_p, C.c_int]),
 }

@@ -988,6 +988,25 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 extern "C" int rb_pool_upload(rb_ctx *ctx, int slot, const rb_particles *pool) { return pool_setup(ctx, slot, pool, true); }
 
 // getFourierTransformsAndCtfs for the whole pool on the device (kernels_prep.cu)
+// CTF::initialise (src/ctf.cpp:211-261): the nine constants CTF::getCTF evaluates with (K1 .. K5, the astigmatism matrix, scale)
+static void ctf_params(double kV, double Cs, double Q0, double defU, double defV, double defAngle, double Bfac, double phase_shift,
+                       double scale, double *q)
+{
+	const double local_Cs = Cs * 1e7, local_kV = kV * 1e3;
+	const double az = defAngle * 3.14159265358979323846 / 180.0;
+	const double lam = 12.2643247 / sqrt(local_kV * (1.0 + local_kV * 0.978466e-6));
+	q[0] = 3.14159265358979323846 / 2 * 2 * lam;
+	q[1] = 3.14159265358979323846 / 2 * local_Cs * lam * lam * lam;
+	q[2] = atan(Q0 / sqrt(1 - Q0 * Q0));
+	q[3] = -Bfac / 4.0;
+	q[4] = phase_shift * 3.14159265358979323846 / 180.0;
+	const double ca = cos(az), sa = sin(az), dU = -defU, dV = -defV;
+	q[5] = ca * ca * dU + sa * sa * dV;            // A = Q^T D Q, Q = [[ca, sa], [-sa, ca]], D = diag(-defU, -defV)
+	q[6] = ca * sa * dU - sa * ca * dV;
+	q[7] = sa * sa * dU + ca * ca * dV;
+	q[8] = scale;
+}
+
 extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *raw, float *power_img)
 {
 	if (ctx) cudaSetDevice(ctx->device);   // the caller's thread may have another device current
@@ -1016,23 +1035,11 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 		ctfpar.resize((size_t) P * 9);
 		for (int p = 0; p < P; p++)
 		{
-			// CTF::initialise (src/ctf.cpp:211-261)
 			const int og = raw->optics_group[p];
 			RB_ARG(og >= 0 && og < ctx->h_model.nr_optics_groups, "rb_pool_prepare: optics group of particle %d out of range", p);
-			const double local_Cs = raw->og_Cs[og] * 1e7, local_kV = raw->og_kV[og] * 1e3, Q0 = raw->og_Q0[og];
-			const double az = raw->ctf_defAngle[p] * 3.14159265358979323846 / 180.0;
-			const double lam = 12.2643247 / sqrt(local_kV * (1.0 + local_kV * 0.978466e-6));
-			double *q = &ctfpar[(size_t) p * 9];
-			q[0] = 3.14159265358979323846 / 2 * 2 * lam;
-			q[1] = 3.14159265358979323846 / 2 * local_Cs * lam * lam * lam;
-			q[2] = atan(Q0 / sqrt(1 - Q0 * Q0));
-			q[3] = -(raw->ctf_Bfac ? raw->ctf_Bfac[p] : 0.) / 4.0;
-			q[4] = (raw->ctf_phase_shift ? raw->ctf_phase_shift[p] : 0.) * 3.14159265358979323846 / 180.0;
-			const double ca = cos(az), sa = sin(az), dU = -raw->ctf_defU[p], dV = -raw->ctf_defV[p];
-			q[5] = ca * ca * dU + sa * sa * dV;            // A = Q^T D Q, Q = [[ca, sa], [-sa, ca]], D = diag(-defU, -defV)
-			q[6] = ca * sa * dU - sa * ca * dV;
-			q[7] = sa * sa * dU + ca * ca * dV;
-			q[8] = raw->ctf_scale ? raw->ctf_scale[p] : 1.0;
+			ctf_params(raw->og_kV[og], raw->og_Cs[og], raw->og_Q0[og], raw->ctf_defU[p], raw->ctf_defV[p], raw->ctf_defAngle[p],
+			           raw->ctf_Bfac ? raw->ctf_Bfac[p] : 0., raw->ctf_phase_shift ? raw->ctf_phase_shift[p] : 0.,
+			           raw->ctf_scale ? raw->ctf_scale[p] : 1.0, &ctfpar[(size_t) p * 9]);
 		}
 	}
 	rb_particles pool;
@@ -1553,6 +1560,59 @@ extern "C" int rb_backproject_posed(rb_ctx *ctx, int k, int n, int count,
 		ctx->bp_blk_dirty[k] = ctx->bp[k].blkvol != nullptr;
 		RB_CUDA(cudaEventRecord(ctx->posed_ev[ib], ctx->stream));
 	}
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	RB_CUDA(cudaEventDestroy(uploaded));
+	return RB_OK;
+}
+
+// relion_reconstruct from RAW images: FFT, centring, origin shift, CTF and DC removal on the device (rbk_backproject_posed_raw)
+extern "C" int rb_backproject_posed_raw(rb_ctx *ctx, int k, const rb_posed_raw *r)
+{
+	RB_ARG(ctx && r && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_backproject_posed_raw: accumulator %d not initialised", k);
+	const int n = r->image_size, count = r->n_images;
+	RB_ARG(n > 0 && n % 2 == 0 && n <= 1000 && count > 0, "rb_backproject_posed_raw: bad sizes");
+	RB_ARG(r->images && r->eulers, "rb_backproject_posed_raw: NULL argument");
+	const bool do_ctf = r->ctf_defU != nullptr;
+	RB_ARG(!do_ctf || (r->ctf_defV && r->ctf_defAngle && r->og_kV && r->og_Cs && r->og_Q0 && r->pixel_size > 0.), "rb_backproject_posed_raw: CTF parameters missing");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	const size_t npx = (size_t) n * n;
+	// 128 MB chunks: the copy of chunk i + 1 runs under the transform + scatter of chunk i
+	const int chunk = (int) std::max<size_t>(1, std::min<size_t>((size_t) count, ((size_t) 128 << 20) / (npx * 4)));
+	std::vector<double> par((size_t) (do_ctf ? count : 0) * 9);
+	for (int i = 0; i < count && do_ctf; i++)
+	{
+		const int og = r->optics_group ? r->optics_group[i] : 0;
+		ctf_params(r->og_kV[og], r->og_Cs[og], r->og_Q0[og], r->ctf_defU[i], r->ctf_defV[i], r->ctf_defAngle[i], r->ctf_Bfac ? r->ctf_Bfac[i] : 0.,
+		           r->ctf_phase_shift ? r->ctf_phase_shift[i] : 0., r->ctf_scale ? r->ctf_scale[i] : 1.0, &par[(size_t) i * 9]);
+	}
+	// staging: [0] images, [1] ctf parameters + shifts (doubles), [2] matrices; two sets for copy / compute overlap
+	for (int b = 0; b < 2; b++)
+	{
+		RB_CHECK(ctx->posed_buf[b][0].ensure((size_t) chunk * npx * 4)); RB_CHECK(ctx->posed_buf[b][1].ensure((size_t) chunk * 11 * 8));
+		RB_CHECK(ctx->posed_buf[b][2].ensure((size_t) chunk * 36));
+		if (!ctx->posed_ev[b]) RB_CUDA(cudaEventCreateWithFlags(&ctx->posed_ev[b], cudaEventDisableTiming));
+	}
+	ctx->posed_count = 0;
+	cudaEvent_t uploaded;
+	RB_CUDA(cudaEventCreateWithFlags(&uploaded, cudaEventDisableTiming));
+	int ib = 0;
+	for (int i0 = 0; i0 < count; i0 += chunk, ib ^= 1)
+	{
+		const int c = std::min(chunk, count - i0);
+		RB_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->posed_ev[ib], 0));
+		double *d_par = ctx->posed_buf[ib][1].as<double>(), *d_shift = d_par + (size_t) chunk * 9;
+		RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[ib][0].p, r->images + (size_t) i0 * npx, (size_t) c * npx * 4, cudaMemcpyHostToDevice, ctx->copy_stream));
+		if (do_ctf) RB_CUDA(cudaMemcpyAsync(d_par, par.data() + (size_t) i0 * 9, (size_t) c * 72, cudaMemcpyHostToDevice, ctx->copy_stream));
+		if (r->shift) RB_CUDA(cudaMemcpyAsync(d_shift, r->shift + (size_t) i0 * 2, (size_t) c * 16, cudaMemcpyHostToDevice, ctx->copy_stream));
+		RB_CUDA(cudaMemcpyAsync(ctx->posed_buf[ib][2].p, r->eulers + (size_t) i0 * 9, (size_t) c * 36, cudaMemcpyHostToDevice, ctx->copy_stream));
+		RB_CUDA(cudaEventRecord(uploaded, ctx->copy_stream));
+		RB_CUDA(cudaStreamWaitEvent(ctx->stream, uploaded, 0));
+		RB_CHECK(rbk_backproject_posed_raw(ctx, ctx->bp[k], n, c, ctx->posed_buf[ib][0].as<float>(), r->shift ? d_shift : nullptr,
+		                                   do_ctf ? d_par : nullptr, (double) n * r->pixel_size, r->ctf_premultiplied, ctx->posed_buf[ib][2].as<float>()));
+		ctx->bp_blk_dirty[k] = ctx->bp[k].blkvol != nullptr;
+		RB_CUDA(cudaEventRecord(ctx->posed_ev[ib], ctx->stream));
+	}
+	RB_CUDA(cudaStreamSynchronize(ctx->copy_stream));      // par is a host temporary
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	RB_CUDA(cudaEventDestroy(uploaded));
 	return RB_OK;

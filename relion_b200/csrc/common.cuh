@@ -340,6 +340,12 @@ int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 
 int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
 int rbk_backproject_posed(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers);
+struct RbPosedBandLayout { const uint32_t *pix; int npix, stride; float4 *sF; int *queue; };
+int rbk_posed_band_layout(rb_ctx *ctx, int n, int count, RbPosedBandLayout *L);
+int rbk_posed_band_scatter(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float *d_eulers, const RbPosedBandLayout &L);
+// raw images -> FFT, centring sign, shift phase, CTF, DC = 0 -> band-ordered staging buffer -> scatter (kernels_prep.cu)
+int rbk_backproject_posed_raw(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, float *d_images, const double *d_shift,
+                              const double *d_ctfpar, double xs_angstrom, int ctf_premultiplied, const float *d_eulers);
 int rbk_backproject_posed_band(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers);
 int rbk_project(rb_ctx *ctx, const RbProjector &pj, int n, const float *d_eulers, int count, float2 *d_out);
 

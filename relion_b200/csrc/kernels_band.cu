@@ -1231,23 +1231,43 @@ static int posed_pixlist(rb_ctx *ctx, int n)
 	return RB_OK;
 }
 
-int rbk_backproject_posed_band(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers)
+// band-ordered staging of a chunk of images: pixel list of the size, tile-major float4 buffer (re, im, weight, 0)
+int rbk_posed_band_layout(rb_ctx *ctx, int n, int count, RbPosedBandLayout *L)
 {
-	if (count < 1) return RB_OK;
 	RB_CHECK(posed_pixlist(ctx, n));
+	L->pix = ctx->posed_pix.as<uint32_t>(); L->npix = ctx->posed_pix_count; L->stride = (L->npix + BD_TP - 1) / BD_TP * BD_TP;
+	RB_CHECK(ctx->posed_sorted.ensure((size_t) count * L->stride * sizeof(float4) + 64));
+	L->sF = ctx->posed_sorted.as<float4>();
+	L->queue = (int *) ((char *) ctx->posed_sorted.p + (size_t) count * L->stride * sizeof(float4));
+	return RB_OK;
+}
+
+// scatter of a chunk whose band-ordered staging buffer has been filled (k_posed_sort, or the raw-image preparation of
+// kernels_prep.cu, which writes it directly)
+int rbk_posed_band_scatter(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float *d_eulers, const RbPosedBandLayout &L)
+{
 	PosedBandArgs A;
 	memset(&A, 0, sizeof(A));
-	A.bp = bp; A.n = n; A.count = count; A.F2D = d_F; A.Fctf = d_W; A.eulers = d_eulers;
-	A.pix = ctx->posed_pix.as<uint32_t>(); A.npix = ctx->posed_pix_count; A.stride = (A.npix + BD_TP - 1) / BD_TP * BD_TP;
-	RB_CHECK(ctx->posed_sorted.ensure((size_t) count * A.stride * sizeof(float4) + 64));
-	A.sF = ctx->posed_sorted.as<float4>();
-	A.queue = (int *) ((char *) ctx->posed_sorted.p + (size_t) count * A.stride * sizeof(float4));
+	A.bp = bp; A.n = n; A.count = count; A.eulers = d_eulers;
+	A.pix = L.pix; A.npix = L.npix; A.stride = L.stride; A.sF = L.sF; A.queue = L.queue;
 	A.chunk_min = std::max(BD_NPH, env_int("RB_POSED_CHUNK_MIN", 8));
 	RB_CUDA(cudaMemsetAsync(A.queue, 0, 4, ctx->stream));
-	dim3 g((unsigned) ((A.stride + 255) / 256), (unsigned) count);
-	k_posed_sort<<<g, 256, 0, ctx->stream>>>(A);
-	RB_LAUNCH_CHECK(ctx);
 	k_posed_band<<<ctx->num_sms * 3, BD_THREADS, 0, ctx->stream>>>(A);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
+}
+
+int rbk_backproject_posed_band(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers)
+{
+	if (count < 1) return RB_OK;
+	RbPosedBandLayout L;
+	RB_CHECK(rbk_posed_band_layout(ctx, n, count, &L));
+	PosedBandArgs A;
+	memset(&A, 0, sizeof(A));
+	A.bp = bp; A.n = n; A.count = count; A.F2D = d_F; A.Fctf = d_W; A.eulers = d_eulers;
+	A.pix = L.pix; A.npix = L.npix; A.stride = L.stride; A.sF = L.sF; A.queue = L.queue;
+	dim3 g((unsigned) ((A.stride + 255) / 256), (unsigned) count);
+	k_posed_sort<<<g, 256, 0, ctx->stream>>>(A);
+	RB_LAUNCH_CHECK(ctx);
+	return rbk_posed_band_scatter(ctx, bp, n, count, d_eulers, L);
 }

@@ -11,6 +11,9 @@
 #include "device_utils.cuh"
 #include <cufft.h>
 
+// tile-major index of the band-ordered staging buffers (bd_at of kernels_band.cu: 128-pixel tiles)
+__device__ __forceinline__ size_t bd_at_prep(int row, int ip, int nrows) { return ((size_t) (ip >> 7) * (size_t) nrows + (size_t) row) * 128 + (size_t) (ip & 127); }
+
 struct PrepRaw {
 	const float *raw;            // [P][n][n]
 	const int *shift;            // [P][2] rounded old offsets (dx, dy)
@@ -300,4 +303,78 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 		k_prep_ctf<<<gw, 256, 0, ctx->stream>>>(d_ctfpar, s.Fctf.as<float>(), cs, (double) M.ori_size * M.pixel_size); RB_LAUNCH_CHECK(ctx);
 	}
 	return RB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// relion_reconstruct from raw images: what Reconstructor::backprojectOneParticle (/root/reference/src/reconstructor.cpp:428-745)
+// does per particle before backproject2Dto3D, for a chunk of images on the device:
+//   F2D = FFT(img) / n^2, CenterFFTbySign (x (-1)^(i + j), src/fftw.h:390-403), shiftImageInFourierTransform by the particle's
+//   origin offset (x e^{-2 pi i (x tx + y ty) / n}, src/fftw.cpp:874-918, double), Fctf = CTF::getFftwImage (damping, no flips),
+//   F2D *= Fctf (unless the data are CTF-premultiplied), Fctf = Fctf^2, F2D(0, 0) = 0                        (:563-745)
+// written straight into the band-ordered staging buffer of the posed scatter (kernels_band.cu): the images cross PCIe as
+// real-space pixels (4 bytes per pixel instead of 12 per Fourier pixel) and the prepared transforms never exist in [image][pixel] order.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_posed_raw_to_band(const float2 *F, int n, int count, const double *shift, const double *ctfpar, double xs_angstrom, int premultiplied,
+                    const uint32_t *pix, int npix, int stride, float4 *sF)
+{
+	const int img = blockIdx.y, xf = n / 2 + 1;
+	const double *q = ctfpar ? ctfpar + (size_t) img * 9 : nullptr;
+	const double sx = shift ? -shift[2 * img] / (double) n : 0., sy = shift ? -shift[2 * img + 1] / (double) n : 0.;
+	const bool do_shift = fabs(sx) >= 1e-6 || fabs(sy) >= 1e-6;                              // XMIPP_EQUAL_ACCURACY
+	const float scale = 1.f / ((float) n * (float) n);
+	for (int ip = blockIdx.x * blockDim.x + threadIdx.x; ip < stride; ip += gridDim.x * blockDim.x)
+	{
+		float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+		if (ip < npix)
+		{
+			const uint32_t pk = __ldg(pix + ip);
+			const int x = rb_pix_x(pk), y = rb_pix_y(pk);
+			const int iy = y < 0 ? y + n : y;
+			float2 v = __ldg(F + ((size_t) img * n + iy) * xf + x);
+			const float sg = ((iy ^ x) & 1) ? -scale : scale;
+			double re = (double) (v.x * sg), im = (double) (v.y * sg);
+			if (do_shift)
+			{
+				double sn, cs;
+				sincospi(2. * ((double) x * sx + (double) y * sy), &sn, &cs);
+				const double r2 = cs * re - sn * im, i2 = cs * im + sn * re;
+				re = r2; im = i2;
+			}
+			double ctf = 1.;
+			if (q)
+			{
+				const double X = (double) x / xs_angstrom, Y = (double) y / xs_angstrom;
+				const double u2 = X * X + Y * Y;
+				const double gamma = q[0] * (q[5] * X * X + 2.0 * q[6] * X * Y + q[7] * Y * Y) + q[1] * u2 * u2 - q[4] - q[2];
+				ctf = -sin(gamma) * exp(q[3] * u2) * q[8];
+				if (fabs(ctf) < 1e-8) ctf = ctf < 0 ? -1e-8 : 1e-8;                          // ctf.h:229-232
+			}
+			const float cf = (float) ctf;                                                    // Fctf is an RFLOAT image in the reference; fp32 here
+			float fr = (float) re, fi = (float) im;
+			if (!premultiplied) { fr *= cf; fi *= cf; }
+			if (x == 0 && y == 0) { fr = 0.f; fi = 0.f; }                                    // DIRECT_A2D_ELEM(F2D, 0, 0) = 0 (:745)
+			o = make_float4(fr, fi, cf * cf, 0.f);
+		}
+		sF[bd_at_prep(img, ip, count)] = o;
+	}
+}
+
+int rbk_backproject_posed_raw(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, float *d_images, const double *d_shift,
+                              const double *d_ctfpar, double xs_angstrom, int ctf_premultiplied, const float *d_eulers)
+{
+	if (count < 1) return RB_OK;
+	const int xf = n / 2 + 1;
+	DevBuf &bF = ctx->prep_buf[1];
+	RB_CHECK(bF.ensure((size_t) count * n * xf * 8));
+	cufftHandle plan;
+	RB_CHECK(get_plan(ctx, n, count, &plan));
+	if (cufftExecR2C(plan, d_images, bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, count); return RB_ERR_CUDA; }
+	ctx->launches++;
+	RbPosedBandLayout L;
+	RB_CHECK(rbk_posed_band_layout(ctx, n, count, &L));
+	dim3 g((unsigned) ((L.stride + 255) / 256), (unsigned) count);
+	k_posed_raw_to_band<<<g, 256, 0, ctx->stream>>>(bF.as<float2>(), n, count, d_shift, d_ctfpar, xs_angstrom, ctf_premultiplied, L.pix, L.npix, L.stride, L.sF);
+	RB_LAUNCH_CHECK(ctx);
+	return rbk_posed_band_scatter(ctx, bp, n, count, d_eulers, L);
 }

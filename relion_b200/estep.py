@@ -601,6 +601,38 @@ class MlDeviceBundle:
         e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
         capi.check(self.lib, self.lib.rb_backproject_posed(self.ctx, iclass, img_size, e.shape[0], _fptr(F2D), _fptr(Fctf), _ptr(e, C.c_float)))
 
+    def backproject_posed_raw(self, iclass, images, eulers, shift=None, ctf=None, pixel_size=1.0, ctf_premultiplied=False):
+        """rb_backproject_posed_raw: real-space images [n, s, s] float32 (numpy or pinned torch tensor); the transform, centring,
+        origin shift, CTF and DC removal of Reconstructor::backprojectOneParticle run on the device.  ctf: dict with defU, defV,
+        defAngle (per image) and kV, Cs, Q0 (scalars or per optics group), optional Bfac, scale, phase_shift, optics_group."""
+        e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
+        keep = [e]
+        st = capi.rb_posed_raw()
+        st.n_images = e.shape[0]
+        st.image_size = int(images.shape[-1])
+        st.images = _fptr(images)
+        st.eulers = _ptr(e, C.c_float)
+
+        def dbl(a):
+            if a is None:
+                return _ptr(None, C.c_double)
+            a = np.ascontiguousarray(np.atleast_1d(a), np.float64)
+            keep.append(a)
+            return _ptr(a, C.c_double)
+
+        st.shift = dbl(None if shift is None else np.asarray(shift, np.float64).reshape(-1, 2))
+        if ctf is not None:
+            st.ctf_defU, st.ctf_defV, st.ctf_defAngle = dbl(ctf["defU"]), dbl(ctf["defV"]), dbl(ctf["defAngle"])
+            st.ctf_Bfac, st.ctf_scale, st.ctf_phase_shift = dbl(ctf.get("Bfac")), dbl(ctf.get("scale")), dbl(ctf.get("phase_shift"))
+            st.og_kV, st.og_Cs, st.og_Q0 = dbl(ctf["kV"]), dbl(ctf["Cs"]), dbl(ctf["Q0"])
+            if ctf.get("optics_group") is not None:
+                og = np.ascontiguousarray(ctf["optics_group"], np.int32)
+                keep.append(og)
+                st.optics_group = _ptr(og, C.c_int)
+        st.pixel_size = float(pixel_size)
+        st.ctf_premultiplied = int(ctf_premultiplied)
+        capi.check(self.lib, self.lib.rb_backproject_posed_raw(self.ctx, iclass, C.byref(st)))
+
     def bp_posed_stage(self, img_size, F2D, Fctf, eulers):
         e = np.ascontiguousarray(eulers, np.float32).reshape(-1, 9)
         capi.check(self.lib, self.lib.rb_bp_posed_stage(self.ctx, img_size, e.shape[0], _fptr(F2D), _fptr(Fctf), _ptr(e, C.c_float)))

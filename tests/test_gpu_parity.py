@@ -494,6 +494,46 @@ def test_backproject_posed_against_reference_algorithm(device, n, count, r_max):
     assert np.abs(gre2 - data.real).max() <= 2e-5 * np.abs(data.real).max()
 
 
+@pytest.mark.parametrize("n,count,with_ctf", [(32, 80, True), (24, 7, True), (32, 70, False)])
+def test_backproject_posed_from_raw_images(device, n, count, with_ctf):
+    """rb_backproject_posed_raw (transform, CenterFFTbySign, origin shift, CTF, DC removal on the device) against the prepared
+    entry point fed with the restated preparation of Reconstructor::backprojectOneParticle (oracle/backproject_posed.py),
+    and against the restated backproject2Dto3D itself."""
+    from oracle.backproject_posed import backproject2Dto3D, prepare_particle
+    rng = np.random.default_rng(1000 + n + count)
+    xs = n // 2 + 1
+    r_max, angpix = n // 2 - 1, 1.7
+    pad = synth.pad_size_for(r_max, 2.0)
+    shape = (pad, pad, pad // 2 + 1)
+    imgs = rng.standard_normal((count, n, n)).astype(np.float32)
+    shift = rng.uniform(-3.0, 3.0, (count, 2)); shift[0] = 0.0
+    eul = synth.inverse_euler_f32(rng.uniform(-180, 180, count), rng.uniform(0, 180, count), rng.uniform(0, 360, count))
+    ctf = None
+    cimgs = [None] * count
+    if with_ctf:
+        defU = rng.uniform(8000, 22000, count); defV = defU + rng.uniform(-600, 600, count); ang = rng.uniform(0, 180, count)
+        bfac = rng.uniform(0, 80, count)
+        ctf = dict(defU=defU, defV=defV, defAngle=ang, Bfac=bfac, kV=[300.0], Cs=[2.7], Q0=[0.1])
+        cimgs = [synth.CTF(defU[i], defV[i], ang[i], Bfac=bfac[i]).fftw_image(n, n, angpix) for i in range(count)]
+    device.bp_init(0, shape, r_max, 2.0)
+    device.backproject_posed_raw(0, imgs, eul, shift=shift, ctf=ctf, pixel_size=angpix)
+    got = device.bp_get(0)
+    prepared = [prepare_particle(imgs[i], shift[i], cimgs[i]) for i in range(count)]
+    F = np.stack([p[0] for p in prepared]).astype(np.complex64); W = np.stack([p[1] for p in prepared]).astype(np.float32)
+    device.bp_clear(0)
+    device.backproject_posed(0, n, F, W, eul)
+    want = device.bp_get(0)
+    assert np.abs(want[2]).max() > 0
+    for a, b in zip(got, want):
+        assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max()
+    if count <= 10:
+        data = np.zeros(shape, np.complex128); weight = np.zeros(shape, np.float64)
+        for i in range(count):
+            backproject2Dto3D(data, weight, prepared[i][0], eul[i].reshape(3, 3).astype(np.float64), prepared[i][1], r_max, 2.0)
+        for a, b in zip(got, (data.real, data.imag, weight)):
+            assert np.abs(a - b).max() <= 3e-5 * np.abs(b).max()
+
+
 @pytest.mark.parametrize("coarse", ["gemm", "simt"])
 def test_pool_2d_classification(device, oracle, monkeypatch, coarse):
     """BASELINE config #1 regime: 2D references (project2Dmodel / backproject2D), K classes, psi-only sampling with

@@ -151,6 +151,22 @@ def test_image_transform_is_centerfft_fouriertransform_window(n, cs):
 
 
 @needs_ref
+@pytest.mark.parametrize("n,shift", [(32, (0.0, 0.0)), (32, (2.3, -1.7)), (24, (-0.4, 3.1))])
+def test_posed_particle_preparation_is_the_reference_transform_and_shift(n, shift):
+    """oracle.backproject_posed.prepare_particle (the checker of rb_backproject_posed_raw) against the reference's own
+    CenterFFT + FourierTransformer + shiftImageInFourierTransform (src/fftw.cpp:874-918): centring by sign in Fourier space equals
+    the real-space CenterFFT for even boxes, the shift has the reference's sign; only the DC term differs (set to zero)."""
+    from oracle.backproject_posed import prepare_particle
+    rng = np.random.default_rng(n)
+    img = rng.standard_normal((n, n))
+    want = refhost.image_ft(img, n, shift)
+    got, w = prepare_particle(img, shift, None)
+    assert got[0, 0] == 0 and np.all(w == 1.0)
+    want[0, 0] = 0
+    assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()
+
+
+@needs_ref
 def test_image_preparation_helpers_are_the_altcpu_kernels():
     rng = np.random.default_rng(11)
     n, cs = 32, 20

@@ -322,6 +322,9 @@ int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out);
  * floats in coarse hidden-index order.  Parity tests feed them to the reference's own significance rule
  * (acc_helper_functions.h:226-232).  Valid until the slot is uploaded again; *n_out receives n (out may be NULL to query). */
 int rb_debug_coarse_weights(rb_ctx *ctx, int slot, int particle, float *out, long long capacity, long long *n_out);
+/* Test hook: the coarse-pass Euler matrices the device built in rb_set_sampling (cuda_kernel_make_eulers_3D<invert = true>,
+ * src/acc/cuda/cuda_kernels/helper.cuh:713-840; ALTCPU cpu_kernel_make_eulers_3D, cpu_kernels/helper.cpp): [n_dir][n_psi][9] fp32. */
+int rb_debug_coarse_eulers(rb_ctx *ctx, float *out, long long capacity);
 /* Test hook: the noise images [n_particles][image_size][image_size] the last rb_pool_prepare with noise_seed blended into
  * (centred like the particle images).  Tests rebuild the masked image from them exactly. */
 int rb_debug_prep_noise(rb_ctx *ctx, int n_particles, int image_size, float *out);

@@ -1279,6 +1279,17 @@ extern "C" int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out)
 	return fetch_slot(ctx, ctx->slot[slot], out);
 }
 
+extern "C" int rb_debug_coarse_eulers(rb_ctx *ctx, float *out, long long capacity)
+{
+	RB_ARG(ctx && out && ctx->has_sampling, "rb_debug_coarse_eulers: rb_set_sampling first");
+	RB_CUDA(cudaSetDevice(ctx->device));
+	const long long n = (long long) ctx->d_samp.n_dir * ctx->d_samp.n_psi * 9;
+	RB_ARG(capacity >= n, "rb_debug_coarse_eulers: buffer of %lld floats, %lld needed", capacity, n);
+	RB_CUDA(cudaMemcpyAsync(out, ctx->s_coarse_eulers.p, (size_t) n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
 extern "C" int rb_debug_prep_noise(rb_ctx *ctx, int n_particles, int image_size, float *out)
 {
 	RB_ARG(ctx && out && n_particles > 0 && image_size > 0, "rb_debug_prep_noise: bad argument");

@@ -455,6 +455,12 @@ class MlDeviceBundle:
         self._keep[("pool_n", slot)] = raw.n_particles
         return power
 
+    def debug_coarse_eulers(self, n_dir: int, n_psi: int):
+        """Coarse-pass Euler matrices built on the device by set_sampling (rb_debug_coarse_eulers, test hook): [n_dir, n_psi, 9]."""
+        out = np.empty((n_dir, n_psi, 9), np.float32)
+        capi.check(self.lib, self.lib.rb_debug_coarse_eulers(self.ctx, _ptr(out, C.c_float), out.size))
+        return out
+
     def debug_prep_noise(self, n_particles: int, n: int):
         """Noise images of the last pool_prepare with noise_seed (rb_debug_prep_noise, test hook)."""
         out = np.empty((n_particles, n, n), np.float32)

@@ -60,6 +60,25 @@ def test_project(device, oracle, n, r_max_cut):
         assert np.abs(got[i] - want).max() <= 1e-5 * np.abs(want).max()
 
 
+def test_coarse_euler_matrices_stage(device):
+    """the coarse-pass Euler matrices the device builds in rb_set_sampling against the reference's own
+    cpu_kernel_make_eulers_3D<invert = true> (src/acc/cpu/cpu_kernels/helper.cpp, compiled in oracle/_ref; the restated port
+    where the compiled reference is absent): fp32, [n_dir][n_psi][9]."""
+    from oracle.bindings import Oracle
+    try:
+        orc = Oracle("reference")
+    except Exception:
+        orc = Oracle("port")
+    wl = make_workload(ori_size=32, healpix_order=2, n_particles=2, seed=5, snr=0.3)
+    _setup(device, wl)
+    s = wl.sampling
+    got = device.debug_coarse_eulers(s.n_dir, s.n_psi)
+    rot = np.repeat(np.asarray(s.rot, np.float32), s.n_psi); tilt = np.repeat(np.asarray(s.tilt, np.float32), s.n_psi)
+    psi = np.tile(np.asarray(s.psi, np.float32), s.n_dir)
+    want = orc.make_eulers(rot, tilt, psi).reshape(s.n_dir, s.n_psi, 9)
+    assert np.abs(got - want).max() <= 2e-6
+
+
 @pytest.mark.parametrize("n,O,T,r_max_cut", [(14, 37, 9, False), (32, 5, 21, False), (32, 256 + 3, 30, False), (24, 8, 5, True), (16, 1, 1, False)])
 def test_diff2_coarse_stage(device, oracle, n, O, T, r_max_cut):
     from oracle.bindings import Projector

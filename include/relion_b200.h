@@ -325,6 +325,10 @@ int rb_debug_coarse_weights(rb_ctx *ctx, int slot, int particle, float *out, lon
 /* Test hook: the coarse-pass Euler matrices the device built in rb_set_sampling (cuda_kernel_make_eulers_3D<invert = true>,
  * src/acc/cuda/cuda_kernels/helper.cuh:713-840; ALTCPU cpu_kernel_make_eulers_3D, cpu_kernels/helper.cpp): [n_dir][n_psi][9] fp32. */
 int rb_debug_coarse_eulers(rb_ctx *ctx, float *out, long long capacity);
+/* Test hook: the prepared coarse-window image of one particle of a slot after its E-step: [coarse_size][coarse_size/2+1] float4
+ * (X'.re, X'.im, corr / 2, 0) = the pixel_correction / corr_img step (acc_ml_optimiser_impl.h:1251-1268, buildCorrImage
+ * acc_helper_functions_impl.h:164-196, Minvsigma2 src/ml_optimiser.cpp:6868-6879) applied once per particle. */
+int rb_debug_prepared_coarse_image(rb_ctx *ctx, int slot, int particle, float *out);
 /* Test hook: the noise images [n_particles][image_size][image_size] the last rb_pool_prepare with noise_seed blended into
  * (centred like the particle images).  Tests rebuild the masked image from them exactly. */
 int rb_debug_prep_noise(rb_ctx *ctx, int n_particles, int image_size, float *out);

@@ -189,6 +189,7 @@ PROTOTYPES = {
     "rb_debug_coarse_weights": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_longlong, C.POINTER(C.c_longlong)]),
     "rb_debug_prep_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "rb_debug_coarse_eulers": (C.c_int, [C.c_void_p, c_float_p, C.c_longlong]),
+    "rb_debug_prepared_coarse_image": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p]),
     "rb_project": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p]),
     "rb_diff2_coarse": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_int,
                                   c_float_p, c_float_p, c_float_p, c_float_p]),

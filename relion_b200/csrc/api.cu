@@ -1279,6 +1279,20 @@ extern "C" int rb_estep_fetch(rb_ctx *ctx, int slot, rb_pool_out *out)
 	return fetch_slot(ctx, ctx->slot[slot], out);
 }
 
+extern "C" int rb_debug_prepared_coarse_image(rb_ctx *ctx, int slot, int particle, float *out)
+{
+	RB_ARG(ctx && out && slot >= 0 && slot < RB_NUM_SLOTS && ctx->slot[slot].P > 0, "rb_debug_prepared_coarse_image: slot %d not uploaded", slot);
+	PoolSlot &s = ctx->slot[slot];
+	RB_ARG(particle >= 0 && particle < s.P, "rb_debug_prepared_coarse_image: particle %d out of range", particle);
+	RB_CUDA(cudaSetDevice(ctx->device));
+	const int nc = ctx->d_model.coarse_size, xs = nc / 2 + 1;
+	const size_t bytes = (size_t) nc * xs * sizeof(float4);
+	RB_ARG(s.cimg4.bytes >= (size_t) s.P * bytes, "rb_debug_prepared_coarse_image: run the E-step of the slot first");
+	RB_CUDA(cudaMemcpyAsync(out, (const char *) s.cimg4.p + (size_t) particle * bytes, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	return RB_OK;
+}
+
 extern "C" int rb_debug_coarse_eulers(rb_ctx *ctx, float *out, long long capacity)
 {
 	RB_ARG(ctx && out && ctx->has_sampling, "rb_debug_coarse_eulers: rb_set_sampling first");

@@ -455,6 +455,12 @@ class MlDeviceBundle:
         self._keep[("pool_n", slot)] = raw.n_particles
         return power
 
+    def debug_prepared_coarse_image(self, slot: int, particle: int, coarse_size: int):
+        """Prepared coarse-window image of a particle (rb_debug_prepared_coarse_image, test hook): [nc, nc/2+1, 4]."""
+        out = np.empty((coarse_size, coarse_size // 2 + 1, 4), np.float32)
+        capi.check(self.lib, self.lib.rb_debug_prepared_coarse_image(self.ctx, slot, particle, _ptr(out, C.c_float)))
+        return out
+
     def debug_coarse_eulers(self, n_dir: int, n_psi: int):
         """Coarse-pass Euler matrices built on the device by set_sampling (rb_debug_coarse_eulers, test hook): [n_dir, n_psi, 9]."""
         out = np.empty((n_dir, n_psi, 9), np.float32)

@@ -60,6 +60,46 @@ def test_project(device, oracle, n, r_max_cut):
         assert np.abs(got[i] - want).max() <= 1e-5 * np.abs(want).max()
 
 
+@pytest.mark.parametrize("flags", [dict(), dict(do_scale_correction=False), dict(do_ctf_correction=False), dict(refs_are_ctf_corrected=False)])
+def test_image_corrections_stage(device, flags):
+    """pixel_correction and corr_img (acc_ml_optimiser_impl.h:1251-1268, buildCorrImage
+    acc_helper_functions_impl.h:164-196) with Minvsigma2 = 1 / (sigma2_fudge sigma2_noise[ires]) on the Mresol pixels, DC
+    excluded (src/ml_optimiser.cpp:6868-6879), at the coarse window, restated in numpy from those lines."""
+    wl = make_workload(ori_size=40, current_size=32, healpix_order=1, n_particles=6, seed=14, snr=0.3, nr_groups=3)
+    for k, v in flags.items():
+        setattr(wl.model, k, v)
+    wl.model.scale_correction = np.array([0.8, 1.0, 1.3])
+    _setup(device, wl)
+    device.pool_upload(0, wl.pool)
+    device.estep_slot(0)
+    m = wl.model
+    nc, cs = m.coarse_size, m.current_size
+    xs = nc // 2 + 1
+    iy = np.arange(nc); yy = np.where(iy < xs, iy, iy - nc)[:, None]; xx = np.arange(xs)[None, :]
+    ires = np.rint(np.sqrt((xx * xx + yy * yy).astype(np.float64))).astype(int)
+    mresol = (ires < xs) & ~((xx == 0) & (yy < 0))
+    for p in range(wl.pool.n_particles):
+        F = synth.window_ft(np.asarray(wl.pool.Fimg[p]), nc)
+        ctf = synth.window_ft(np.asarray(wl.pool.Fctf[p]), nc).real if m.do_ctf_correction else np.ones((nc, xs))
+        s2 = np.atleast_2d(m.sigma2_noise)[wl.pool.optics_group[p]]
+        minv = np.where(mresol & (ires > 0), 1.0 / (m.sigma2_fudge * s2[np.minimum(ires, len(s2) - 1)]), 0.0)
+        scale = m.scale_correction[wl.pool.group_id[p]] if m.do_scale_correction else 1.0
+        pc = np.full((nc, xs), 1.0 / scale)
+        corr = minv.copy()
+        if m.do_ctf_correction and m.refs_are_ctf_corrected:
+            pc = np.where(np.abs(ctf) > 1e-8, pc / np.where(ctf == 0, 1, ctf), pc)
+            corr = corr * ctf * ctf
+        if m.do_scale_correction:
+            corr = corr * scale * scale
+        got = device.debug_prepared_coarse_image(0, p, nc)
+        sel = mresol
+        want = F * pc
+        assert np.abs(got[..., 0][sel] - want.real[sel]).max() <= 2e-6 * np.abs(want[sel]).max()
+        assert np.abs(got[..., 1][sel] - want.imag[sel]).max() <= 2e-6 * np.abs(want[sel]).max()
+        np.testing.assert_allclose(got[..., 2][sel], 0.5 * corr[sel], rtol=2e-6, atol=1e-30)
+        assert not got[..., 2][~sel].any()
+
+
 def test_coarse_euler_matrices_stage(device):
     """the coarse-pass Euler matrices the device builds in rb_set_sampling against the reference's own
     cpu_kernel_make_eulers_3D<invert = true> (src/acc/cpu/cpu_kernels/helper.cpp, compiled in oracle/_ref; the restated port

@@ -224,8 +224,8 @@ typedef struct {
 	                                and rb_pool_out.wsum_prior_offset_class stays untouched                       */
 	int do_grad;                 /* gradient (SGD / VDAM) refinement, baseMLO->do_grad (acc_ml_optimiser_impl.h:3418): the
 	                                back-projection accumulates the weighted RESIDUAL sum_t w_t (X_t - CTF A) instead of the
-	                                weighted image (cuda_kernel_backproject3D_SGD, BP.cuh:406-656; ALTCPU BP.h:757-1047: every
-	                                pixel, no circle bound); 3D references.  With grad_pseudo_halfsets (= do_grad in
+	                                weighted image (cuda_kernel_backproject3D_SGD / _2D_SGD, BP.cuh:406-826; ALTCPU BP.h:757-1262: every
+	                                pixel, no circle bound); 3D and 2D references.  With grad_pseudo_halfsets (= do_grad in
 	                                src/ml_optimiser.cpp:1192) particles go into accumulator iclass + (part_id % 2) * nr_classes
 	                                (:3395-3400): initialise 2 * nr_classes accumulators and pass rb_particles.bp_offset    */
 } rb_model;

@@ -76,6 +76,8 @@ class ok_kernel_table(C.Structure):
                                       C.c_ulong, C.c_ulong, C.c_ulong, ulp, ulp, ulp, ulp, f32p)),
         ("backproject_sgd", C.CFUNCTYPE(None, BP, PP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
                                         C.c_ulong, C.c_float, C.c_float, f32p, C.c_ulong)),
+        ("backproject2d_sgd", C.CFUNCTYPE(None, BP, PP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, f32p,
+                                          C.c_ulong, C.c_float, C.c_float, f32p, C.c_ulong)),
     ]
 
 

@@ -601,8 +601,8 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 			        Tf, po.sum_weight, po.significant_weight, part_scale);
 			// pseudo half-sets of gradient refinement: iproj_offset = (part_id % 2) * nr_classes (acc_ml_optimiser_impl.h:3395-3400)
 			ok_backprojector bpk = S.bps[k + (pool->bp_offset ? pool->bp_offset[p] : 0)];
-			if (m->do_grad)                                                                  // :3418 -> backproject3D_SGD
-				K->backproject_sgd(&bpk, &S.refs[k], S.nf / 2 + 1, S.nf, nr.data(), ni.data(), S.ftx.data(), S.fty.data(),
+			if (m->do_grad)                                                                  // :3418 -> backproject3D_SGD / backproject2D_SGD
+				(bpk.mdlZ == 1 ? K->backproject2d_sgd : K->backproject_sgd)(&bpk, &S.refs[k], S.nf / 2 + 1, S.nf, nr.data(), ni.data(), S.ftx.data(), S.fty.data(),
 				                   sw.data(), minvs2.data(), ctfs.data(), Tf, po.significant_weight, po.sum_weight, c.eulers.data(), On);
 			else
 			// 2D accumulators (2D classification) go through backproject2D, acc_helper_functions_impl.h:505-577

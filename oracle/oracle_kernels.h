@@ -169,6 +169,15 @@ typedef struct {
 	                        const float *weights, const float *Minvsigma2s, const float *ctfs,
 	                        unsigned long trans_num, float significant_weight, float weight_norm,
 	                        const float *eulers, unsigned long image_count);
+
+	/* CpuKernels::backproject2D_SGD<CTF_PREMULTIPLIED=false> (src/acc/cpu/cpu_kernels/BP.h:1047-1262; CUDA twin BP.cuh:659-826):
+	 * gradient refinement of 2D references (RELION 4's default 2D classification), accumulators [mdlY][mdlX] */
+	void (*backproject2d_sgd)(const ok_backprojector *bp, const ok_projector *p, int imgX, int imgY,
+	                          const float *img_re, const float *img_im,
+	                          const float *trans_x, const float *trans_y,
+	                          const float *weights, const float *Minvsigma2s, const float *ctfs,
+	                          unsigned long trans_num, float significant_weight, float weight_norm,
+	                          const float *eulers, unsigned long image_count);
 } ok_kernel_table;
 
 #ifdef __cplusplus

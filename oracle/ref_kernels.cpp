@@ -194,6 +194,22 @@ void refk_backproject_sgd(const ok_backprojector *bp, const ok_projector *p, int
 		(unsigned) bp->mdlX, (unsigned) bp->mdlY, bp->mdlInitY, bp->mdlInitZ, mutexes);
 }
 
+void refk_backproject2d_sgd(const ok_backprojector *bp, const ok_projector *p, int imgX, int imgY,
+		const float *img_re, const float *img_im, const float *trans_x, const float *trans_y,
+		const float *weights, const float *Minvsigma2s, const float *ctfs,
+		unsigned long trans_num, float significant_weight, float weight_norm,
+		const float *eulers, unsigned long image_count)
+{
+	std::vector<tbb::spin_mutex> local;
+	tbb::spin_mutex *mutexes = (tbb::spin_mutex *) bp->sync;
+	if (!mutexes) { local = std::vector<tbb::spin_mutex>((size_t) bp->mdlY); mutexes = local.data(); }
+	AccProjectorKernel k = make_kernel(p, imgX, imgY);
+	CpuKernels::backproject2D_SGD<false>(image_count, 128, k, (XFLOAT *) img_re, (XFLOAT *) img_im, (XFLOAT *) trans_x, (XFLOAT *) trans_y,
+		(XFLOAT *) weights, (XFLOAT *) Minvsigma2s, (XFLOAT *) ctfs, trans_num, significant_weight, weight_norm, (XFLOAT *) eulers,
+		bp->real, bp->imag, bp->weight, bp->maxR, bp->maxR * bp->maxR, bp->padding_factor,
+		(unsigned) imgX, (unsigned) imgY, (unsigned) (imgX * imgY), (unsigned) bp->mdlX, bp->mdlInitY, mutexes);
+}
+
 // first-iteration cross-correlation kernels, dispatched as runDiff2KernelCoarse / runDiff2KernelFine do for a 3D reference
 // and 2D data (acc_helper_functions_impl.h:1761-1777, :1950-1973 -> AccUtilities::diff2_CC_coarse / diff2_CC_fine)
 void refk_diff2_cc_coarse(const ok_projector *p, int imgX, int imgY,
@@ -261,6 +277,7 @@ const ok_kernel_table table = {
 	refk_diff2_cc_coarse,
 	refk_diff2_cc_fine,
 	refk_backproject_sgd,
+	refk_backproject2d_sgd,
 };
 
 } // namespace

@@ -1132,9 +1132,7 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 		if (!(flags & 1u) && !ctx->has_bp[k]) { rb_set_error("rb_estep: accumulator %d not initialised", k); return RB_ERR_STATE; }
 		if (!(flags & 1u) && s.max_bp_off > 0 && !ctx->has_bp[k + s.max_bp_off]) { rb_set_error("rb_estep: accumulator %d (pseudo half-set) not initialised", k + s.max_bp_off); return RB_ERR_STATE; }
 	}
-	if (M.do_grad && !(flags & 1u))
-		for (int k = 0; k < M.nr_classes; k++)
-			if (ctx->ref_2d[k]) { rb_set_error("rb_estep: do_grad with 2D references is not supported"); return RB_ERR_STATE; }
+
 	RB_CUDA(cudaSetDevice(ctx->device));
 	RB_CHECK(ensure_coarse_core(ctx));
 	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));

@@ -409,6 +409,18 @@ def test_pool_gradient_refinement_backprojection(device, oracle, monkeypatch, ba
         assert np.abs(device.bp_get(k)[2]).max() > 0
 
 
+def test_pool_gradient_refinement_2d_classification(device, oracle):
+    """RELION 4's default 2D classification is a gradient (VDAM) refinement: 2D references, residual back-projection
+    (cuda_kernel_backproject2D_SGD, BP.cuh:659-826), pseudo half-sets -> 2 K 2D accumulators."""
+    wl = make_workload(ori_size=32, n_particles=24, nr_classes=3, seed=63, snr=0.2, ref_dim=2, psi_step=10.0)
+    wl.model.do_grad = True
+    wl.model.bp_circle_bound = False
+    wl.pool.bp_offset = (np.arange(wl.pool.n_particles) % 2 * wl.model.nr_classes).astype(np.int32)
+    _compare_pool(device, oracle, wl, n_acc=2 * wl.model.nr_classes)
+    for k in range(2 * wl.model.nr_classes):
+        assert np.abs(device.bp_get(k)[2]).max() > 0
+
+
 @pytest.mark.parametrize("flags", [dict(do_map=False), dict(do_scale_correction=False), dict(do_ctf_correction=False),
                                    dict(do_map=False, do_scale_correction=False, do_ctf_correction=False)])
 def test_pool_optimiser_flags(device, oracle, flags):

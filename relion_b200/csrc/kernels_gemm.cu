@@ -1020,6 +1020,10 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 		const int pw = pt >> 5;
 		const int i = lane & 15, rsub = lane >> 4;
 		const int imgX = A.n / 2 + 1;
+		// Rows are dealt to the warps in rounds of 2 NPW (round j: rows 2 NPW j + 2 pw + rsub), and only the rounds that hold rows
+		// of this tile are projected: a particle's last tile (177 orientations = 128 + 49) costs its share of the rows, not a full
+		// tile - with rows blocked per warp it took as long as a full one (the busy warps set the pace of every K-block).
+		const int nj = (min(FU_BM, no - oi0) + 2 * NPW - 1) / (2 * NPW);
 		const RbProjK pk = rb_make_projk2(A.projs[cls], imgX);
 		const RbProjK8 pk8 = rb_make_projk8(A.projs[cls], imgX);
 		const float4 *mdl2 = A.projs[cls].mdl2;
@@ -1044,9 +1048,9 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 #pragma unroll
 			for (int j = 0; j < NJ; j++)
 			{
-				const int r = pw * (2 * NJ) + 2 * j + rsub;
+				const int r = 2 * NPW * j + 2 * pw + rsub;
 				ref[j] = make_float2(0.f, 0.f);
-				if (pix_ok && s_valid[r])
+				if (j < nj && pix_ok && s_valid[r])
 					ref[j] = G256 ? rb_project3d_c256(pk8, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5])
 					              : rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
 				bacc[j] = fmaf(hc, ref[j].x * ref[j].x + ref[j].y * ref[j].y, bacc[j]);
@@ -1056,7 +1060,8 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 #pragma unroll
 			for (int j = 0; j < NJ; j++)
 			{
-				const int r = pw * (2 * NJ) + 2 * j + rsub;
+				if (j >= nj) continue;                                 // rows beyond the tile: their accumulator rows are never read
+				const int r = 2 * NPW * j + 2 * pw + rsub;
 				float2 h, l;
 				tf32_split(ref[j].x, h.x, l.x); tf32_split(ref[j].y, h.y, l.y);
 				const uint32_t off = (uint32_t) r * 128u + ((uint32_t) ((i >> 1) ^ (r & 7)) << 4) + (uint32_t) (i & 1) * 8u;
@@ -1073,7 +1078,7 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 			float v = bacc[j];
 			v += __shfl_xor_sync(RB_FULL_MASK, v, 8); v += __shfl_xor_sync(RB_FULL_MASK, v, 4);
 			v += __shfl_xor_sync(RB_FULL_MASK, v, 2); v += __shfl_xor_sync(RB_FULL_MASK, v, 1);
-			if (i == 0) s_base[pw * (2 * NJ) + 2 * j + rsub] = v;
+			if (i == 0) s_base[2 * NPW * j + 2 * pw + rsub] = v;
 		}
 		asm volatile("bar.sync 1, %0;" ::"n"(32 * NPW) : "memory");     // producers only
 		if (pw < 4)

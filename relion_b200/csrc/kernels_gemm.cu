@@ -884,7 +884,10 @@ int rbk_diff2_coarse_gemm_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 // (2 shared-memory loads + 10 FP32 instructions per pixel, translation and 3 orientations) disappears from the SM's
 // issue slots; what is left is the gather.
 // ---------------------------------------------------------------------------------------------
-static const int FU_BM = 128, FU_BN = 32, FU_PIX = 16, FU_STAGES = 2;
+#ifndef RB_FU_STAGES
+#define RB_FU_STAGES 2           // measured (256 px, hp4 local): see DESIGN.md section 7
+#endif
+static const int FU_BM = 128, FU_BN = 32, FU_PIX = 16, FU_STAGES = RB_FU_STAGES;
 // producer warps per CTA: 8 (two CTAs per SM) or 16 (one CTA per SM, half the shared memory -> more L1 for the gathers)
 static const uint32_t FU_A_BYTES = FU_BM * 128, FU_B_BYTES = FU_BN * 128;
 static const uint32_t FU_STAGE_BYTES = 2 * FU_A_BYTES + 2 * FU_B_BYTES;            // 40 KB

@@ -1087,17 +1087,13 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 		RB_CUDA(cudaMemcpyAsync(bFac.p, raw->og_fourier_factor, fb, cudaMemcpyHostToDevice, cs));
 		d_fac = bFac.as<float2>();
 	}
-	RB_CUDA(cudaEventRecord(s.uploaded, cs));
-	RB_CUDA(cudaStreamSynchronize(cs));            // shift / norm / ctfpar / spec are host temporaries
-	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+	// The preparation kernels follow the copies on the COPY stream: they run beside the E-step of the other slot on the compute
+	// stream (which is where a RELION adapter spends its time) instead of in front of this slot's E-step.
 	RB_CHECK(rbk_prepare_pool(ctx, s, bRaw.as<float>(), bShift.as<int>(), bNorm.as<float>(), do_ctf ? bCtf.as<double>() : nullptr, n,
-	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>(), d_seed, d_spec, d_fac));
-	if (power_img)
-	{
-		RB_CUDA(cudaMemcpyAsync(power_img, bPow.p, (size_t) P * (n / 2 + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-		RB_CUDA(cudaStreamSynchronize(ctx->stream));
-	}
-	RB_CUDA(cudaEventRecord(s.uploaded, ctx->stream));   // rb_estep_slot waits for the preparation
+	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>(), d_seed, d_spec, d_fac, cs));
+	if (power_img) RB_CUDA(cudaMemcpyAsync(power_img, bPow.p, (size_t) P * (n / 2 + 1) * 4, cudaMemcpyDeviceToHost, cs));
+	RB_CUDA(cudaEventRecord(s.uploaded, cs));            // rb_estep_slot waits for the preparation
+	RB_CUDA(cudaStreamSynchronize(cs));                  // shift / norm / ctfpar / spec are host temporaries; power_img is the caller's
 	return RB_OK;
 }
 

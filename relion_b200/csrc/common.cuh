@@ -374,7 +374,8 @@ int rbk_gemm_tf32x3_stage(rb_ctx *ctx, const float *dA, const float *dB, int M, 
 // kernels_prep.cu: getFourierTransformsAndCtfs on the device, batched over the pool
 void rbk_prepare_release(rb_ctx *ctx);
 int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
-                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed = nullptr, const float *d_spectrum = nullptr, const float2 *d_og_factor = nullptr);
+                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed = nullptr, const float *d_spectrum = nullptr, const float2 *d_og_factor = nullptr,
+                     cudaStream_t stream = nullptr);
 
 // kernels_recon.cu: BackProjector::reconstruct (skip_gridding) + windowToOridimRealSpace + griddingCorrect on the device
 int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,

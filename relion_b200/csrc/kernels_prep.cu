@@ -206,7 +206,7 @@ k_prep_noise_centre(const float *in, float *out, int n)
 }
 
 // One plan per context: a cuFFT plan belongs to the device that was current when it was made, and contexts run on their own host threads.
-static int get_plan(rb_ctx *ctx, int n, int batch, cufftHandle *out)
+static int get_plan(rb_ctx *ctx, int n, int batch, cufftHandle *out, cudaStream_t stream)
 {
 	if (ctx->prep_plan_batch == 0 || ctx->prep_plan_n != n || ctx->prep_plan_batch != batch)
 	{
@@ -218,13 +218,13 @@ static int get_plan(rb_ctx *ctx, int n, int batch, cufftHandle *out)
 		if (r != CUFFT_SUCCESS) { rb_set_error("cufftPlanMany(%d x %d, batch %d) failed (%d)", n, n, batch, (int) r); return RB_ERR_CUDA; }
 		ctx->prep_plan = (int) h; ctx->prep_plan_n = n; ctx->prep_plan_batch = batch;
 	}
-	cufftResult r = cufftSetStream((cufftHandle) ctx->prep_plan, ctx->stream);
+	cufftResult r = cufftSetStream((cufftHandle) ctx->prep_plan, stream);
 	if (r != CUFFT_SUCCESS) { rb_set_error("cufftSetStream failed (%d)", (int) r); return RB_ERR_CUDA; }
 	*out = (cufftHandle) ctx->prep_plan;
 	return RB_OK;
 }
 
-static int get_plan_inv(rb_ctx *ctx, int n, int batch, cufftHandle *out)
+static int get_plan_inv(rb_ctx *ctx, int n, int batch, cufftHandle *out, cudaStream_t stream)
 {
 	if (ctx->prep_plan_inv_batch == 0 || ctx->prep_plan_inv_n != n || ctx->prep_plan_inv_batch != batch)
 	{
@@ -236,7 +236,7 @@ static int get_plan_inv(rb_ctx *ctx, int n, int batch, cufftHandle *out)
 		if (r != CUFFT_SUCCESS) { rb_set_error("cufftPlanMany(C2R %d x %d, batch %d) failed (%d)", n, n, batch, (int) r); return RB_ERR_CUDA; }
 		ctx->prep_plan_inv = (int) h; ctx->prep_plan_inv_n = n; ctx->prep_plan_inv_batch = batch;
 	}
-	cufftResult r = cufftSetStream((cufftHandle) ctx->prep_plan_inv, ctx->stream);
+	cufftResult r = cufftSetStream((cufftHandle) ctx->prep_plan_inv, stream);
 	if (r != CUFFT_SUCCESS) { rb_set_error("cufftSetStream failed (%d)", (int) r); return RB_ERR_CUDA; }
 	*out = (cufftHandle) ctx->prep_plan_inv;
 	return RB_OK;
@@ -253,25 +253,27 @@ void rbk_prepare_release(rb_ctx *ctx)
 // d_raw: [P][n][n] device, d_shift [P][2], d_norm [P], d_ctfpar [P][9] (nullptr: Fctf untouched), outputs into the slot buffers
 // d_seed / d_spectrum: noise-filled mask (nullptr: zero mask); d_noise_out: optional copy of the noise images (tests)
 int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_shift, const float *d_norm, const double *d_ctfpar,
-                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed, const float *d_spectrum, const float2 *d_og_factor)
+                     int n, float radius, float cosine_width, float *d_power, const long long *d_seed, const float *d_spectrum, const float2 *d_og_factor,
+                     cudaStream_t stream)
 {
+	if (!stream) stream = ctx->stream;
 	const RbModelDev &M = ctx->d_model;
 	const int P = s.P, cs = M.current_size;
 	const int xf = n / 2 + 1, xo = cs / 2 + 1;
 	DevBuf &bReal = ctx->prep_buf[0], &bF = ctx->prep_buf[1], &bBg = ctx->prep_buf[2];
 	RB_CHECK(bReal.ensure((size_t) P * n * n * 4)); RB_CHECK(bF.ensure((size_t) P * n * xf * 8)); RB_CHECK(bBg.ensure((size_t) P * 4));
 	cufftHandle plan;
-	RB_CHECK(get_plan(ctx, n, P, &plan));
+	RB_CHECK(get_plan(ctx, n, P, &plan, stream));
 	PrepRaw A;
 	A.raw = d_raw; A.shift = d_shift; A.norm = d_norm; A.bg = bBg.as<float>(); A.n = n; A.noise = nullptr;
 	A.radius = radius < 0.f ? (float) n / 2.f : radius; A.cosine_width = cosine_width; A.radius_p = A.radius + cosine_width;
 	const float scale = 1.f / ((float) n * (float) n);
 	dim3 gr((n * n + 255) / 256 > 64 ? 64 : (n * n + 255) / 256, P), gw((cs * xo + 255) / 256 > 64 ? 64 : (cs * xo + 255) / 256, P);
 	// unmasked image -> Fimg_nomask
-	k_prep_real<false><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
+	k_prep_real<false><<<gr, 256, 0, stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
 	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 	ctx->launches++;
-	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fnomask.as<float2>(), n, cs, scale, d_og_factor, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
+	k_prep_window<<<gw, 256, 0, stream>>>(bF.as<float2>(), s.Fnomask.as<float2>(), n, cs, scale, d_og_factor, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
 	// masked image -> Fimg, power spectrum, highres_Xi2
 	if (d_seed)
 	{
@@ -280,27 +282,27 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 		DevBuf &bNoise = ctx->prep_buf[4];
 		RB_CHECK(bNoise.ensure((size_t) P * n * n * 4));
 		cufftHandle iplan;
-		RB_CHECK(get_plan_inv(ctx, n, P, &iplan));
+		RB_CHECK(get_plan_inv(ctx, n, P, &iplan, stream));
 		dim3 gf((n * xf + 255) / 256 > 64 ? 64 : (n * xf + 255) / 256, P);
-		k_prep_noise_fourier<<<gf, 256, 0, ctx->stream>>>(d_seed, d_spectrum, s.meta.as<RbPartMeta>(), M.nshell, n, bF.as<float2>()); RB_LAUNCH_CHECK(ctx);
+		k_prep_noise_fourier<<<gf, 256, 0, stream>>>(d_seed, d_spectrum, s.meta.as<RbPartMeta>(), M.nshell, n, bF.as<float2>()); RB_LAUNCH_CHECK(ctx);
 		if (cufftExecC2R(iplan, bF.as<cufftComplex>(), bReal.as<float>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecC2R failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 		ctx->launches++;
-		k_prep_noise_centre<<<gr, 256, 0, ctx->stream>>>(bReal.as<float>(), bNoise.as<float>(), n); RB_LAUNCH_CHECK(ctx);
+		k_prep_noise_centre<<<gr, 256, 0, stream>>>(bReal.as<float>(), bNoise.as<float>(), n); RB_LAUNCH_CHECK(ctx);
 		A.noise = bNoise.as<float>();
 	}
-	else k_prep_mask_bg<<<P, 256, 0, ctx->stream>>>(A, bBg.as<float>()); RB_LAUNCH_CHECK(ctx);
-	k_prep_real<true><<<gr, 256, 0, ctx->stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
+	else k_prep_mask_bg<<<P, 256, 0, stream>>>(A, bBg.as<float>()); RB_LAUNCH_CHECK(ctx);
+	k_prep_real<true><<<gr, 256, 0, stream>>>(A, bReal.as<float>()); RB_LAUNCH_CHECK(ctx);
 	if (cufftExecR2C(plan, bReal.as<float>(), bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, P); return RB_ERR_CUDA; }
 	ctx->launches++;
-	k_prep_window<<<gw, 256, 0, ctx->stream>>>(bF.as<float2>(), s.Fimg.as<float2>(), n, cs, scale, d_og_factor, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
+	k_prep_window<<<gw, 256, 0, stream>>>(bF.as<float2>(), s.Fimg.as<float2>(), n, cs, scale, d_og_factor, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
 	if (cs < n)
 	{
-		k_prep_power<<<P, 256, 0, ctx->stream>>>(bF.as<float2>(), n, cs, scale, d_power, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
+		k_prep_power<<<P, 256, 0, stream>>>(bF.as<float2>(), n, cs, scale, d_power, s.meta.as<RbPartMeta>()); RB_LAUNCH_CHECK(ctx);
 	}
-	else if (d_power) RB_CUDA(cudaMemsetAsync(d_power, 0, (size_t) P * xf * 4, ctx->stream));
+	else if (d_power) RB_CUDA(cudaMemsetAsync(d_power, 0, (size_t) P * xf * 4, stream));
 	if (d_ctfpar)
 	{
-		k_prep_ctf<<<gw, 256, 0, ctx->stream>>>(d_ctfpar, s.Fctf.as<float>(), cs, (double) M.ori_size * M.pixel_size); RB_LAUNCH_CHECK(ctx);
+		k_prep_ctf<<<gw, 256, 0, stream>>>(d_ctfpar, s.Fctf.as<float>(), cs, (double) M.ori_size * M.pixel_size); RB_LAUNCH_CHECK(ctx);
 	}
 	return RB_OK;
 }
@@ -368,7 +370,7 @@ int rbk_backproject_posed_raw(rb_ctx *ctx, const RbBackprojector &bp, int n, int
 	DevBuf &bF = ctx->prep_buf[1];
 	RB_CHECK(bF.ensure((size_t) count * n * xf * 8));
 	cufftHandle plan;
-	RB_CHECK(get_plan(ctx, n, count, &plan));
+	RB_CHECK(get_plan(ctx, n, count, &plan, ctx->stream));
 	if (cufftExecR2C(plan, d_images, bF.as<cufftComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecR2C failed (%d x %d, batch %d)", n, n, count); return RB_ERR_CUDA; }
 	ctx->launches++;
 	RbPosedBandLayout L;

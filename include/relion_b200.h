@@ -153,6 +153,12 @@ int rb_bp_symmetrise(rb_ctx *ctx, int iclass, const double *R, int nsym);
  * vol_out: [ori_size]^3 floats, origin at ori_size/2.  The accumulator is left untouched (all-reduce it first on several GPUs). */
 int rb_reconstruct(rb_ctx *ctx, int iclass, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map,
                    float *vol_out);
+/* The same with the iterative gridding of Pipe & Menon instead of the plain division (--dont_skip_gridding,
+ * src/backprojector.cpp:1577-1700 + convoluteBlobRealSpace :2483-2528): max_iter_preweight iterations (RELION: 10) of
+ * Fnewweight /= |blob-convolution of Fnewweight * Fweight| in double precision, 3D transforms of the padded volume by cuFFT;
+ * normalise as in BackProjector::reconstruct (1 unless the caller rescales the weights). */
+int rb_reconstruct_gridding(rb_ctx *ctx, int iclass, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map,
+                            int max_iter_preweight, double normalise, float *vol_out);
 
 /* BackProjector::updateSSNRarrays (src/backprojector.cpp:1041-1204) on accumulator iclass (2D or 3D): sigma2 = shell
  * average of the inverse noise power of the reconstruction; tau2 recomputed from `fsc` (gold-standard FSC between the

@@ -108,10 +108,32 @@ def symmetrise(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, r_max: in
     return data.real, data.imag, w
 
 
+def ftblob_ratio(rval: np.ndarray, blob_radius: float = 1.9, alpha: float = 15.0, nr_elem: int = 10000) -> np.ndarray:
+    """tab_ftblob(rval) / tab_ftblob(0) of BackProjector (src/backprojector.h:115: TabFtBlob::initialise(blob_radius * 2, alpha,
+    order 0, 10000), src/tabfuncs.cpp:95-121: nearest-below table of kaiser_Fourier_value, zero beyond 0.5;
+    src/funcs.cpp:244-251 with bessi1_5(x) = sqrt(2 / (pi x)) (cosh x - sinh x / x), numerical_recipes.cpp:366-369)."""
+    a = blob_radius * 2.0
+    sampling = 0.5 / nr_elem
+
+    def value(w):
+        arg = 2.0 * np.pi * a * w
+        sigma = np.sqrt(np.abs(alpha * alpha - arg * arg))
+        sigma = np.where(sigma == 0, 1e-300, sigma)
+        i15 = np.sqrt(2.0 / (np.pi * sigma)) * (np.cosh(sigma) - np.sinh(sigma) / sigma)
+        j15 = np.sqrt(2.0 / (np.pi * sigma)) * (np.sin(sigma) / sigma - np.cos(sigma))
+        return np.where(arg > alpha, j15, i15) / sigma ** 1.5
+
+    idx = (np.abs(rval) / sampling).astype(np.int64)
+    tab = value(np.arange(nr_elem) * sampling)
+    return np.where(idx >= nr_elem, 0.0, tab[np.minimum(idx, nr_elem - 1)]) / tab[0]
+
+
 def reconstruct(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, ori_size: int, r_max: int,
                 padding_factor: float = 2.0, tau2: np.ndarray | None = None, tau2_fudge: float = 1.0,
-                minres_map: int = 0) -> np.ndarray:
-    """BackProjector::reconstruct(skip_gridding) for a 3D reference built from 2D images: [ori, ori, ori] float64."""
+                minres_map: int = 0, max_iter_preweight: int = 0) -> np.ndarray:
+    """BackProjector::reconstruct for a 3D reference built from 2D images: [ori, ori, ori] float64.  max_iter_preweight = 0:
+    the default skip_gridding branch; > 0: the iterative gridding of Pipe & Menon (--dont_skip_gridding,
+    /root/reference/src/backprojector.cpp:1577-1700, convoluteBlobRealSpace :2483-2528)."""
     data = real.astype(np.float64) + 1j * imag.astype(np.float64)
     pad = data.shape[0]
     rr = int(math.floor(r_max * padding_factor + 0.5))
@@ -129,15 +151,28 @@ def reconstruct(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, ori_size
                            np.where(Fweight > 1e-20, 1.0 / (0.001 * np.where(Fweight > 1e-20, Fweight, 1.0)), 0.0))
         Fweight = np.where((r2 < max_r2) & (ires >= minres_map), Fweight + invtau2, Fweight)
     Fconv = decenter(data, max_r2)
-    # radial average of the weights / 1000 as the floor of the divisor (:1513-1573)
-    round_max_r2 = int(math.floor(r_max * padding_factor * r_max * padding_factor + 0.5))
-    iresf = np.floor(np.sqrt(r2.astype(np.float64)) / padding_factor).astype(np.int64)
-    inside = r2 < round_max_r2
-    radavg = np.bincount(iresf[inside], weights=Fweight[inside], minlength=r_max)[:r_max]
-    counter = np.bincount(iresf[inside], minlength=r_max)[:r_max].astype(np.float64)
-    radavg = radavg / (1000.0 * np.maximum(counter, 1.0))
-    w = np.maximum(Fweight, radavg[np.minimum(iresf, r_max - 1)])
-    Fconv = np.where(w != 0, Fconv / np.where(w != 0, w, 1.0), Fconv)
+    if max_iter_preweight > 0:
+        # Fnewweight starts as 1 inside the sphere; every iteration divides it by |blob-convolution of (Fnewweight Fweight)|
+        Fnew = (r2 < max_r2).astype(np.float64)
+        kp = np.arange(pad); kp = np.where(kp < pad // 2, kp, kp - pad)          # padhdim = pad_size / 2 (:2487, :2512-2514)
+        kk, ii, jj = np.meshgrid(kp, kp, kp, indexing="ij")
+        blob = ftblob_ratio(np.sqrt((kk * kk + ii * ii + jj * jj).astype(np.float64)) / (ori_size * padding_factor))
+        n3 = float(pad) ** 3
+        for _ in range(max_iter_preweight):
+            M = np.fft.irfftn(Fnew * Fweight, s=(pad,) * 3, axes=(0, 1, 2)) * n3           # unnormalised inverse transform
+            conv = np.fft.rfftn(M * blob, axes=(0, 1, 2)) / n3                              # forward transform divides by N
+            Fnew = np.where(r2 < max_r2, Fnew / np.maximum(1e-6, np.abs(conv)), Fnew)     # Eq. [14] of Pipe & Menon (:1633-1648)
+        Fconv = Fconv * Fnew
+    else:
+        # radial average of the weights / 1000 as the floor of the divisor (:1513-1573)
+        round_max_r2 = int(math.floor(r_max * padding_factor * r_max * padding_factor + 0.5))
+        iresf = np.floor(np.sqrt(r2.astype(np.float64)) / padding_factor).astype(np.int64)
+        inside = r2 < round_max_r2
+        radavg = np.bincount(iresf[inside], weights=Fweight[inside], minlength=r_max)[:r_max]
+        counter = np.bincount(iresf[inside], minlength=r_max)[:r_max].astype(np.float64)
+        radavg = radavg / (1000.0 * np.maximum(counter, 1.0))
+        w = np.maximum(Fweight, radavg[np.minimum(iresf, r_max - 1)])
+        Fconv = np.where(w != 0, Fconv / np.where(w != 0, w, 1.0), Fconv)
 
     # windowToOridimRealSpace
     padoridim = int(math.floor(padding_factor * ori_size + 0.5))

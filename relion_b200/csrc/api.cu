@@ -109,6 +109,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	for (rb_ctx::BlockTable *t : ctx->blk_tables) { t->buf.release(); delete t; }
 	ctx->blk_tables.clear();
 	for (auto &b : ctx->scratch) b.release();
+	for (auto &b : ctx->grid_buf) b.release();
 	for (auto &b : ctx->gemm_buf) b.release();
 	for (int i = 0; i < RB_MAX_CLASSES; i++) for (auto &b : ctx->gemmA[i]) b.release();
 	for (auto &b : ctx->gemmA_all) b.release();
@@ -473,7 +474,8 @@ extern "C" int rb_bp_symmetrise(rb_ctx *ctx, int k, const double *R, int nsym)
 }
 
 // BackProjector::reconstruct (default skip_gridding branch) on the device
-extern "C" int rb_reconstruct(rb_ctx *ctx, int k, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map, float *vol_out)
+static int reconstruct_common(rb_ctx *ctx, int k, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map,
+                              int max_iter_preweight, double normalise, float *vol_out)
 {
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_reconstruct: accumulator %d not initialised", k);
 	RB_ARG(!ctx->bp_2d[k], "rb_reconstruct: 2D accumulators are not supported yet");
@@ -490,11 +492,23 @@ extern "C" int rb_reconstruct(rb_ctx *ctx, int k, int ori_size, const double *ta
 		d_tau2 = ctx->scratch[3].as<double>();
 	}
 	RB_CHECK(rb_bp_fold(ctx, k));
-	RB_CHECK(rbk_reconstruct(ctx, ctx->bp[k], ori_size, d_tau2, n_tau2, tau2_fudge, minres_map, ctx->scratch[2].as<float>()));
+	RB_CHECK(rbk_reconstruct(ctx, ctx->bp[k], ori_size, d_tau2, n_tau2, tau2_fudge, minres_map, ctx->scratch[2].as<float>(), max_iter_preweight, normalise));
 	RB_CUDA(cudaMemcpyAsync(vol_out, ctx->scratch[2].p, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	ctx->scratch[2].release();
 	return RB_OK;
+}
+
+extern "C" int rb_reconstruct(rb_ctx *ctx, int k, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map, float *vol_out)
+{
+	return reconstruct_common(ctx, k, ori_size, tau2, n_tau2, tau2_fudge, minres_map, 0, 1., vol_out);
+}
+
+extern "C" int rb_reconstruct_gridding(rb_ctx *ctx, int k, int ori_size, const double *tau2, int n_tau2, double tau2_fudge, int minres_map,
+                                       int max_iter_preweight, double normalise, float *vol_out)
+{
+	RB_ARG(max_iter_preweight > 0 && max_iter_preweight <= 100, "rb_reconstruct_gridding: max_iter_preweight %d out of range", max_iter_preweight);
+	return reconstruct_common(ctx, k, ori_size, tau2, n_tau2, tau2_fudge, minres_map, max_iter_preweight, normalise, vol_out);
 }
 
 // BackProjector::updateSSNRarrays on the device accumulator

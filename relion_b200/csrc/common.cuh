@@ -304,6 +304,7 @@ struct rb_ctx {
 	std::map<std::string, std::pair<cudaEvent_t, cudaEvent_t>> stage_ev;
 	DevBuf scratch[8];
 	DevBuf wc_buf[10];
+	DevBuf grid_buf[5];              // iterative gridding (kernels_recon.cu): Fweight, Fnewweight, Fconv, real-space volume (double), blob table
 	DevBuf recon_buf[3];             // reconstruction on the device (kernels_recon.cu): FFT input / output, radial sums
 	DevBuf prep_buf[5];              // device image preparation (kernels_prep.cu): cuFFT input / output, background values, spectra
 	int prep_plan_inv = 0, prep_plan_inv_n = 0, prep_plan_inv_batch = 0;   // batched 2D C2R plan of the noise-filled mask
@@ -379,7 +380,7 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 
 // kernels_recon.cu: BackProjector::reconstruct (skip_gridding) + windowToOridimRealSpace + griddingCorrect on the device
 int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,
-                    float *d_vol_out);
+                    float *d_vol_out, int max_iter_preweight = 0, double normalise = 1.);
 
 int rbk_bp_symmetrise(rb_ctx *ctx, const RbBackprojector &bp, DevBuf &tmp, const float *d_R, int nsym);
 int rbk_update_ssnr(rb_ctx *ctx, const RbBackprojector &bp, bool is_2d, int ori, double tau2_fudge, double *tau2_io, double *sigma2_out,

@@ -17,6 +17,8 @@ struct ReconArgs {
 	const double *tau2; int n_tau2; double tau2_fudge, oversampling_correction; int minres_map;   // tau2 == nullptr: no MAP term
 	double *radsum; double *radcnt; // [r_max]
 	int padori, ori;
+	const double *newweight;        // iterative gridding: Fnewweight on the pad^3 half transform (nullptr: skip_gridding branch)
+	double normalise;
 };
 
 __device__ __forceinline__ int fftw_freq(int k, int n) { return k < n / 2 + 1 ? k : k - n; }
@@ -91,7 +93,14 @@ k_recon_fin(ReconArgs A, float2 *Fin)
 			const double ra = A.radsum[ires] / (1000. * (A.radcnt[ires] > 0. ? A.radcnt[ires] : 1.));
 			const double w = w0 > ra ? w0 : ra;                                         // :1547
 			double re = (double) v.x, im = (double) v.y;
-			if (w != 0.) { re /= w; im /= w; }
+			if (A.newweight)
+			{
+				// gridding branch: the data times the iteratively determined weight (:1678-1690)
+				const int kq = kp < 0 ? kp + A.pad : kp, iq = ip < 0 ? ip + A.pad : ip;
+				const double nw = A.newweight[((size_t) kq * A.pad + iq) * (A.pad / 2 + 1) + j] / A.normalise;
+				re *= nw; im *= nw;
+			}
+			else if (w != 0.) { re /= w; im /= w; }
 			if ((kk ^ ii ^ j) & 1) { re = -re; im = -im; }                              // CenterFFTbySign, src/fftw.h:390-403
 			out = make_float2((float) re, (float) im);
 		}
@@ -154,9 +163,120 @@ k_recon_finish(float *vol, int ori, float pf, const double *bg_sums)
 	}
 }
 
+// ---------------------------------------------------------------------------------------------
+// Iterative gridding (--dont_skip_gridding): Eq. [14] of Pipe & Menon (1999) as BackProjector::reconstruct runs it
+// (/root/reference/src/backprojector.cpp:1577-1700): Fnewweight = 1 inside the sphere; max_iter_preweight times
+//   Fconv = Fnewweight * Fweight -> inverse FFT -> x FT of the Kaiser-Bessel blob (convoluteBlobRealSpace, :2483-2528)
+//   -> forward FFT / N -> Fnewweight /= max(1e-6, |Fconv|)  for r2 < max_r2
+// in double like the reference (Fnewweight "can become too large for a float"); the 3D transforms are cuFFT Z2D / D2Z.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_grid_init(ReconArgs A, double *Fw, double *Fnw)
+{
+	const int xh = A.pad / 2 + 1;
+	const size_t n = (size_t) A.pad * A.pad * xh;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int jp = (int) (i % xh), ii = (int) ((i / xh) % A.pad), kk = (int) (i / ((size_t) xh * A.pad));
+		const int ip = fftw_freq(ii, A.pad), kp = fftw_freq(kk, A.pad);
+		const long long r2 = (long long) kp * kp + (long long) ip * ip + (long long) jp * jp;
+		Fw[i] = recon_weight(A, kp, ip, jp, r2, nullptr) / A.normalise;                   // :1583-1587
+		Fnw[i] = r2 < A.max_r2 ? 1. : 0.;                                                // :1596-1606
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_mul(const double *Fw, const double *Fnw, double2 *Fc, size_t n)
+{
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+		Fc[i] = make_double2(Fnw[i] * Fw[i], 0.);
+}
+
+// real space: multiply with tab_ftblob(rval) / tab_ftblob(0), rval = |k| / (ori pf), k wrapped at pad / 2 (:2510-2524)
+__global__ void __launch_bounds__(256)
+k_grid_blob(double *M, int pad, const double *tab, int nr, double sampling, double ori_pf)
+{
+	const size_t n = (size_t) pad * pad * pad;
+	const int h = pad / 2;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int j = (int) (i % pad), ii = (int) ((i / pad) % pad), k = (int) (i / ((size_t) pad * pad));
+		const int jp = j < h ? j : j - pad, ip = ii < h ? ii : ii - pad, kp = k < h ? k : k - pad;
+		const double rval = sqrt((double) ((long long) kp * kp + (long long) ip * ip + (long long) jp * jp)) / ori_pf;
+		const int idx = (int) (rval / sampling);
+		M[i] *= idx >= nr ? 0. : tab[idx];
+	}
+}
+
+__global__ void __launch_bounds__(256)
+k_grid_div(const double2 *Fc, double *Fnw, int pad, long long max_r2, double inv_n)
+{
+	const int xh = pad / 2 + 1;
+	const size_t n = (size_t) pad * pad * xh;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int jp = (int) (i % xh), ii = (int) ((i / xh) % pad), kk = (int) (i / ((size_t) xh * pad));
+		const int ip = fftw_freq(ii, pad), kp = fftw_freq(kk, pad);
+		const long long r2 = (long long) kp * kp + (long long) ip * ip + (long long) jp * jp;
+		if (r2 < max_r2)
+		{
+			const double2 c = Fc[i];
+			const double w = fmax(1e-6, sqrt(c.x * c.x + c.y * c.y) * inv_n);             // :1636-1645
+			Fnw[i] /= w;
+		}
+	}
+}
+
+// Fnewweight of accumulator `A` after max_iter iterations, left in grid_buf[1]
+static int recon_gridding(rb_ctx *ctx, ReconArgs &A, int max_iter, double blob_radius, double blob_alpha)
+{
+	const int pad = A.pad, xh = pad / 2 + 1;
+	const size_t nh = (size_t) pad * pad * xh, nr3 = (size_t) pad * pad * pad;
+	DevBuf &bFw = ctx->grid_buf[0], &bFnw = ctx->grid_buf[1], &bFc = ctx->grid_buf[2], &bM = ctx->grid_buf[3], &bTab = ctx->grid_buf[4];
+	RB_CHECK(bFw.ensure(nh * 8)); RB_CHECK(bFnw.ensure(nh * 8)); RB_CHECK(bFc.ensure(nh * 16)); RB_CHECK(bM.ensure(nr3 * 8));
+	// tab_ftblob (src/tabfuncs.cpp:95-121, src/funcs.cpp:244-251): order 0, radius 2 * blob_radius, 10000 entries over [0, 0.5)
+	const int nr = 10000;
+	const double sampling = 0.5 / nr, a = 2. * blob_radius;
+	std::vector<double> tab(nr);
+	for (int i = 0; i < nr; i++)
+	{
+		const double arg = 2. * M_PI * a * (i * sampling);
+		double sigma = sqrt(fabs(blob_alpha * blob_alpha - arg * arg));
+		if (sigma == 0.) sigma = 1e-300;
+		const double b = arg > blob_alpha ? sqrt(2. / (M_PI * sigma)) * (sin(sigma) / sigma - cos(sigma))
+		                                  : sqrt(2. / (M_PI * sigma)) * (cosh(sigma) - sinh(sigma) / sigma);
+		tab[i] = b / pow(sigma, 1.5);
+	}
+	for (int i = nr - 1; i >= 0; i--) tab[i] /= tab[0];
+	RB_CHECK(bTab.ensure(nr * 8));
+	RB_CUDA(cudaMemcpyAsync(bTab.p, tab.data(), nr * 8, cudaMemcpyHostToDevice, ctx->stream));
+	RB_CUDA(cudaStreamSynchronize(ctx->stream));
+	cufftHandle pinv, pfwd;
+	if (cufftPlan3d(&pinv, pad, pad, pad, CUFFT_Z2D) != CUFFT_SUCCESS) { rb_set_error("cufftPlan3d(Z2D %d^3) failed", pad); return RB_ERR_CUDA; }
+	if (cufftPlan3d(&pfwd, pad, pad, pad, CUFFT_D2Z) != CUFFT_SUCCESS) { cufftDestroy(pinv); rb_set_error("cufftPlan3d(D2Z %d^3) failed", pad); return RB_ERR_CUDA; }
+	cufftSetStream(pinv, ctx->stream); cufftSetStream(pfwd, ctx->stream);
+	const int g = ctx->num_sms * 8;
+	k_grid_init<<<g, 256, 0, ctx->stream>>>(A, bFw.as<double>(), bFnw.as<double>());
+	int rc = RB_OK;
+	for (int it = 0; it < max_iter && rc == RB_OK; it++)
+	{
+		k_grid_mul<<<g, 256, 0, ctx->stream>>>(bFw.as<double>(), bFnw.as<double>(), bFc.as<double2>(), nh);
+		if (cufftExecZ2D(pinv, bFc.as<cufftDoubleComplex>(), bM.as<double>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecZ2D failed"); rc = RB_ERR_CUDA; break; }
+		k_grid_blob<<<g, 256, 0, ctx->stream>>>(bM.as<double>(), pad, bTab.as<double>(), nr, sampling, (double) A.ori * (double) A.pf);
+		if (cufftExecD2Z(pfwd, bM.as<double>(), bFc.as<cufftDoubleComplex>()) != CUFFT_SUCCESS) { rb_set_error("cufftExecD2Z failed"); rc = RB_ERR_CUDA; break; }
+		k_grid_div<<<g, 256, 0, ctx->stream>>>(bFc.as<double2>(), bFnw.as<double>(), pad, A.max_r2, 1. / (double) nr3);
+		ctx->launches += 5;
+	}
+	if (rc == RB_OK && cudaGetLastError() != cudaSuccess) { rb_set_error("gridding kernels failed"); rc = RB_ERR_CUDA; }
+	cudaStreamSynchronize(ctx->stream);
+	cufftDestroy(pinv); cufftDestroy(pfwd);
+	bFw.release(); bFc.release(); bM.release();
+	return rc;
+}
+
 // d_vol_out: [ori][ori][ori] device floats
 int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,
-                    float *d_vol_out)
+                    float *d_vol_out, int max_iter_preweight, double normalise)
 {
 	ReconArgs A;
 	memset(&A, 0, sizeof(A));
@@ -177,6 +297,12 @@ int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const doubl
 	RB_CUDA(cudaMemsetAsync(bRad.p, 0, (size_t) (2 * 1024 + 2) * 8, ctx->stream));
 	A.radsum = bRad.as<double>(); A.radcnt = A.radsum + 1024;
 	double *bg_sums = A.radsum + 2048;
+	A.normalise = normalise > 0. ? normalise : 1.;
+	if (max_iter_preweight > 0)
+	{
+		RB_CHECK(recon_gridding(ctx, A, max_iter_preweight, 1.9, 15.));                 // BackProjector's default blob (src/backprojector.h:84-86)
+		A.newweight = ctx->grid_buf[1].as<double>();
+	}
 	k_recon_radavg<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(A); RB_LAUNCH_CHECK(ctx);
 	k_recon_fin<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(A, bFin.as<float2>()); RB_LAUNCH_CHECK(ctx);
 	cufftHandle plan;
@@ -190,6 +316,7 @@ int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const doubl
 	k_recon_finish<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(d_vol_out, ori, bp.padding_factor, bg_sums); RB_LAUNCH_CHECK(ctx);
 	RB_CUDA(cudaStreamSynchronize(ctx->stream));
 	cufftDestroy(plan);
+	ctx->grid_buf[1].release();
 	return RB_OK;
 }
 

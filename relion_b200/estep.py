@@ -367,10 +367,17 @@ class MlDeviceBundle:
         r = None if rotations is None or len(rotations) == 0 else np.ascontiguousarray(rotations, np.float64).reshape(-1, 9)
         capi.check(self.lib, self.lib.rb_bp_symmetrise(self.ctx, iclass, _ptr(r, C.c_double), 0 if r is None else r.shape[0]))
 
-    def reconstruct(self, iclass: int, ori_size: int, tau2=None, tau2_fudge: float = 1.0, minres_map: int = 0) -> np.ndarray:
-        """rb_reconstruct: BackProjector::reconstruct (skip_gridding) on the device; [ori, ori, ori] float32."""
+    def reconstruct(self, iclass: int, ori_size: int, tau2=None, tau2_fudge: float = 1.0, minres_map: int = 0,
+                    max_iter_preweight: int = 0, normalise: float = 1.0) -> np.ndarray:
+        """rb_reconstruct: BackProjector::reconstruct on the device; [ori, ori, ori] float32.  max_iter_preweight > 0: the iterative
+        gridding branch (rb_reconstruct_gridding), else the default skip_gridding branch."""
         out = np.empty((ori_size,) * 3, np.float32)
         t = _f64(tau2)
+        if max_iter_preweight > 0:
+            capi.check(self.lib, self.lib.rb_reconstruct_gridding(self.ctx, iclass, ori_size, _ptr(t, C.c_double), 0 if t is None else len(t),
+                                                                  float(tau2_fudge), int(minres_map), int(max_iter_preweight), float(normalise),
+                                                                  _ptr(out, C.c_float)))
+            return out
         capi.check(self.lib, self.lib.rb_reconstruct(self.ctx, iclass, ori_size, _ptr(t, C.c_double), 0 if t is None else len(t),
                                                      float(tau2_fudge), int(minres_map), _ptr(out, C.c_float)))
         return out

@@ -853,6 +853,26 @@ def test_reconstruct_on_device(device, ori, cur, with_tau2):
     assert f.min() >= 0.9999, f
 
 
+@pytest.mark.parametrize("ori,cur,with_tau2", [(32, 32, False), (32, 32, True), (40, 28, True)])
+def test_reconstruct_with_iterative_gridding_on_device(device, ori, cur, with_tau2):
+    """--dont_skip_gridding: rb_reconstruct_gridding (ten Pipe & Menon iterations in double, cuFFT Z2D / D2Z of the padded volume)
+    against the numpy restatement that tests/test_reference_host.py pins on BackProjector::reconstruct(skip_gridding = false)."""
+    from oracle import reconstruct as rc
+    wl = make_workload(ori_size=ori, current_size=cur, healpix_order=1, n_particles=60, seed=83 + ori, snr=0.5)
+    _setup(device, wl)
+    device.expectation_some_particles(wl.pool)
+    tau2 = 1e-3 / (1.0 + np.arange(ori // 2 + 1)) ** 2 if with_tau2 else None
+    got = device.reconstruct(0, ori, tau2=tau2, tau2_fudge=2.0, minres_map=2, max_iter_preweight=10)
+    gre, gim, gw = device.bp_get(0)
+    want = rc.reconstruct(gre, gim, gw, ori, wl.r_max, wl.padding_factor, tau2=tau2, tau2_fudge=2.0, minres_map=2, max_iter_preweight=10)
+    assert np.abs(want).max() > 0
+    assert np.abs(got - want).max() <= 2e-4 * np.abs(want).max(), np.abs(got - want).max() / np.abs(want).max()
+    assert rc.fsc(got.astype(np.float64), want).min() >= 0.9999
+    # and it is not the skip_gridding result
+    plain = device.reconstruct(0, ori, tau2=tau2, tau2_fudge=2.0, minres_map=2)
+    assert np.abs(got - plain).max() > 1e-3 * np.abs(want).max()
+
+
 @pytest.mark.parametrize("ori,cur", [(32, 32), (40, 28)])
 def test_reference_from_map_on_device(device, oracle, ori, cur):
     """SURVEY 8f row 3: rb_set_reference_from_map (Projector::computeFourierTransformMap on the device): central slices of the

@@ -151,6 +151,22 @@ def test_image_transform_is_centerfft_fouriertransform_window(n, cs):
 
 
 @needs_ref
+@pytest.mark.parametrize("with_tau2", [False, True])
+def test_reconstruct_with_iterative_gridding_is_backprojector_reconstruct(with_tau2):
+    """--dont_skip_gridding: the restated Pipe & Menon iteration (oracle/reconstruct.py, max_iter_preweight = 10) against the
+    reference's own BackProjector::reconstruct(skip_gridding = false), src/backprojector.cpp:1577-1700."""
+    ori, cur = 24, 24
+    vol, F, W, eul, r_max = _accumulators(ori, cur, n_img=60, seed=9)
+    re, im, w = refhost.backproject(F, _fwd(eul), W, ori, cur, 2.0)
+    tau2 = np.linspace(3.0, 0.05, ori // 2 + 1) if with_tau2 else None
+    want = refhost.reconstruct(re, im, w, ori, cur, 2.0, tau2=tau2, tau2_fudge=1.5, minres_map=1, skip_gridding=False, max_iter_preweight=10)
+    got = rc.reconstruct(re, im, w, ori, r_max, 2.0, tau2=tau2, tau2_fudge=1.5, minres_map=1, max_iter_preweight=10)
+    assert np.abs(got - want).max() <= 1e-9 * np.abs(want).max()
+    skip = rc.reconstruct(re, im, w, ori, r_max, 2.0, tau2=tau2, tau2_fudge=1.5, minres_map=1)
+    assert np.abs(got - skip).max() > 1e-3 * np.abs(want).max()          # the two branches really differ
+
+
+@needs_ref
 @pytest.mark.parametrize("n,shift", [(32, (0.0, 0.0)), (32, (2.3, -1.7)), (24, (-0.4, 3.1))])
 def test_posed_particle_preparation_is_the_reference_transform_and_shift(n, shift):
     """oracle.backproject_posed.prepare_particle (the checker of rb_backproject_posed_raw) against the reference's own

@@ -146,6 +146,13 @@ int rb_wsum_allreduce(rb_ctx *ctx, rb_comm *comm, double *wsums, size_t n);
  * plane, then applyPointGroupSymmetry with the nsym rotation matrices R ([nsym][9] row-major, the R of
  * SymList::get_matrices; nsym == 0 for C1).  RELION calls this before every reconstruct (src/ml_optimiser.cpp:4930-5044). */
 int rb_bp_symmetrise(rb_ctx *ctx, int iclass, const double *R, int nsym);
+/* The same with helical symmetry (BackProjector::symmetrise(nr_helical_asu, helical_twist, helical_rise),
+ * applyHelicalSymmetry src/backprojector.cpp:2167-2322) applied between the Hermitian fold and the point group: the
+ * accumulator also receives its copies rotated about Z by hh * -helical_twist degrees and phase-shifted along z by
+ * hh * helical_rise, hh in [-nr_helical_asu/2, nr_helical_asu/2 + nr_helical_asu%2) without 0.  helical_rise is in pixels (the
+ * caller divides by the pixel size, src/reconstructor.cpp:771), ori_size the unpadded box.  nr_helical_asu < 2: no helical part. */
+int rb_bp_symmetrise_helical(rb_ctx *ctx, int iclass, const double *R, int nsym, int nr_helical_asu, double helical_twist,
+                             double helical_rise, int ori_size);
 
 /* Reconstruction of a map from accumulator iclass on the device (SURVEY.md 8f "next" row 2): BackProjector::reconstruct,
  * default skip_gridding branch (src/backprojector.cpp:1379-1575) + windowToOridimRealSpace (:2530-2665) + griddingCorrect

@@ -64,9 +64,31 @@ def gridding_correct(vol: np.ndarray, ori_size: int, padding_factor: float) -> n
     return vol / (sinc * sinc)
 
 
-def symmetrise(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, r_max: int, padding_factor: float, rotations=()):
-    """BackProjector::symmetrise (src/backprojector.cpp:2136-2480): enforceHermitianSymmetry + applyPointGroupSymmetry
-    on centred [Z, Y, X] arrays; returns new (real, imag, weight) float64."""
+def helical_operators(nr_helical_asu: int, helical_twist: float, helical_rise: float, ori_size: int, padding_factor: float):
+    """The operators of applyHelicalSymmetry (src/backprojector.cpp:2186-2197, :2284-2288): for hh in [-n/2, n/2 + n%2) without 0
+    the rotation about Z by hh * -twist degrees (rotation3DMatrix 'Z', src/transformations.cpp:111-117, entries below 1e-6 zeroed
+    by setSmallValuesToZero) and the phase ramp zshift = hh * rise / (-ori_size * padding_factor) in cycles per voxel of z."""
+    if nr_helical_asu < 2:
+        return np.zeros((0, 3, 3)), np.zeros(0)
+    h_min = -(nr_helical_asu // 2) if nr_helical_asu >= 0 else 0
+    h_max = -h_min + nr_helical_asu % 2
+    Rs, zs = [], []
+    for hh in range(h_min, h_max):
+        if hh == 0:
+            continue
+        a = math.radians(hh * -helical_twist)
+        c, s = math.cos(a), math.sin(a)
+        c = 0.0 if abs(c) < 1e-6 else c
+        s = 0.0 if abs(s) < 1e-6 else s
+        Rs.append([[c, -s, 0.0], [s, c, 0.0], [0.0, 0.0, 1.0]])
+        zs.append(hh * helical_rise / (-ori_size * padding_factor) if abs(helical_rise) > 0 else 0.0)
+    return np.array(Rs, np.float64).reshape(-1, 3, 3), np.array(zs, np.float64)
+
+
+def symmetrise(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, r_max: int, padding_factor: float, rotations=(), helical=None):
+    """BackProjector::symmetrise (src/backprojector.cpp:2136-2480): enforceHermitianSymmetry, applyHelicalSymmetry (when
+    helical = (nr_helical_asu, twist in degrees, rise in pixels, ori_size) is given) and applyPointGroupSymmetry on centred
+    [Z, Y, X] arrays; returns new (real, imag, weight) float64."""
     data = real.astype(np.float64) + 1j * imag.astype(np.float64)
     w = weight.astype(np.float64).copy()
     Z, Y, X = data.shape
@@ -81,13 +103,20 @@ def symmetrise(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, r_max: in
             data[a], data[b] = fs, np.conj(fs)
             sw = w[a] + w[b]
             w[a] = w[b] = sw
-    if len(rotations):
+    passes = []
+    if helical is not None:
+        passes.append(helical_operators(helical[0], helical[1], helical[2], helical[3], padding_factor))
+    rotations = np.asarray(rotations, np.float64).reshape(-1, 3, 3)
+    passes.append((rotations, np.zeros(len(rotations))))
+    for rotations, zshifts in passes:
+        if not len(rotations):
+            continue
         rr = int(math.floor(r_max * padding_factor + 0.5))
         kz, ky, kx = np.meshgrid(np.arange(Z) - hz, np.arange(Y) - hy, np.arange(X), indexing="ij")
         inside = (kx * kx + ky * ky + kz * kz) <= rr * rr
         sum_d, sum_w = data.copy(), w.copy()
         x, y, z = kx[inside].astype(np.float64), ky[inside].astype(np.float64), kz[inside].astype(np.float64)
-        for R in np.asarray(rotations, np.float64).reshape(-1, 3, 3):
+        for R, zshift in zip(rotations, zshifts):
             xp = x * R[0, 0] + y * R[0, 1] + z * R[0, 2]
             yp = x * R[1, 0] + y * R[1, 1] + z * R[1, 2]
             zp = x * R[2, 0] + y * R[2, 1] + z * R[2, 2]
@@ -102,7 +131,10 @@ def symmetrise(real: np.ndarray, imag: np.ndarray, weight: np.ndarray, r_max: in
                     for dx, wx in ((0, 1 - fx), (1, fx)):
                         vd += data[z0 + dz, y0 + dy, x0 + dx] * (wz * wy * wx)
                         vw += w[z0 + dz, y0 + dy, x0 + dx] * (wz * wy * wx)
-            sum_d[inside] += np.where(neg, np.conj(vd), vd)
+            vd = np.where(neg, np.conj(vd), vd)
+            if zshift != 0.0:                                                     # phase ramp of the helical rise (:2284-2296)
+                vd = vd * np.exp(2j * np.pi * z * zshift)
+            sum_d[inside] += vd
             sum_w[inside] += vw
         data, w = sum_d, sum_w
     return data.real, data.imag, w

@@ -136,6 +136,19 @@ int refrec_symmetrise(double *re, double *im, double *w, int ori_size, int ref_d
 	});
 }
 
+// BackProjector::symmetrise with helical symmetry (twist in degrees, rise in pixels) in place
+int refrec_symmetrise_helical(double *re, double *im, double *w, int ori_size, int ref_dim, int current_size, double padding_factor,
+                              const char *sym, int nr_helical_asu, double helical_twist, double helical_rise)
+{
+	return guarded([&] {
+		BackProjector bp(ori_size, ref_dim, sym, TRILINEAR, (float) padding_factor, 10, 0, 1.9, 15, 2, true);
+		bp.initZeros(current_size);
+		load_bp(bp, re, im, w);
+		bp.symmetrise(nr_helical_asu, helical_twist, helical_rise, 1);
+		store_bp(bp, re, im, w);
+	});
+}
+
 // the rotation matrices SymList hands to symmetrise (R of get_matrices, 3x3 row-major each); returns their number or -1
 int refrec_sym_matrices(const char *sym, double *R_out, int capacity)
 {

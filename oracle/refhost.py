@@ -87,6 +87,15 @@ def symmetrise(real, imag, weight, ori_size: int, current_size: int, sym: str, p
     return re, im, w
 
 
+def symmetrise_helical(real, imag, weight, ori_size: int, current_size: int, sym: str, nr_helical_asu: int, helical_twist: float,
+                       helical_rise: float, padding_factor: float = 2.0):
+    """BackProjector::symmetrise(nr_helical_asu, helical_twist [deg], helical_rise [pixels]) of the compiled reference."""
+    re, im, w = (np.array(a, np.float64, copy=True, order="C") for a in (real, imag, weight))
+    _check(_load().refrec_symmetrise_helical(_p(re), _p(im), _p(w), ori_size, re.ndim, current_size, C.c_double(padding_factor),
+                                             sym.encode(), int(nr_helical_asu), C.c_double(helical_twist), C.c_double(helical_rise)))
+    return re, im, w
+
+
 def sym_matrices(sym: str) -> np.ndarray:
     """The R matrices of SymList::get_matrices for point group `sym`: [nsym, 3, 3]."""
     R = np.zeros(9 * 256, np.float64)

@@ -150,6 +150,7 @@ PROTOTYPES = {
     "rb_bp_clear": (C.c_int, [C.c_void_p, C.c_int]),
     "rb_bp_get": (C.c_int, [C.c_void_p, C.c_int, c_float_p, c_float_p, c_float_p]),
     "rb_bp_symmetrise": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int]),
+    "rb_bp_symmetrise_helical": (C.c_int, [C.c_void_p, C.c_int, c_double_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int]),
     "rb_reconstruct": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_double, C.c_int, c_float_p]),
     "rb_reconstruct_gridding": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_double_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_double, c_float_p]),
     "rb_update_ssnr": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, c_double_p, c_double_p, c_double_p, c_double_p,

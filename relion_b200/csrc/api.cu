@@ -454,23 +454,61 @@ extern "C" int rb_bp_get(rb_ctx *ctx, int k, float *real, float *imag, float *we
 }
 
 // BackProjector::symmetrise on the device accumulator: Hermitian symmetry of the x = 0 plane + point-group symmetry mates
-extern "C" int rb_bp_symmetrise(rb_ctx *ctx, int k, const double *R, int nsym)
+static int symmetrise_common(rb_ctx *ctx, int k, const double *R, int nsym, int nr_helical_asu, double helical_twist, double helical_rise,
+                             int ori_size)
 {
 	RB_ARG(ctx && k >= 0 && k < RB_MAX_CLASSES && ctx->has_bp[k], "rb_bp_symmetrise: accumulator %d not initialised", k);
 	RB_ARG(!ctx->bp_2d[k], "rb_bp_symmetrise: 2D accumulators are not supported");
 	RB_ARG(nsym >= 0 && (nsym == 0 || R), "rb_bp_symmetrise: bad symmetry list");
+	RB_ARG(nr_helical_asu < 2 || ori_size > 0, "rb_bp_symmetrise_helical: ori_size must be positive");
 	RB_CUDA(cudaSetDevice(ctx->device));
-	float *d_R = nullptr;
-	if (nsym > 0)
+	// all operators in one upload: [nsym][9] point-group matrices, [nhel][9] helical rotations about Z, [nhel] phase ramps
+	std::vector<float> r((size_t) std::max(nsym, 0) * 9);
+	for (size_t i = 0; i < r.size(); i++) r[i] = (float) R[i];
+	int nhel = 0;
+	std::vector<float> hz;
+	if (nr_helical_asu >= 2)
 	{
-		std::vector<float> r((size_t) nsym * 9);
-		for (size_t i = 0; i < r.size(); i++) r[i] = (float) R[i];
+		// applyHelicalSymmetry (src/backprojector.cpp:2186-2197): hh in [-n/2, n/2 + n%2) without 0, rotation3DMatrix(hh * -twist, 'Z')
+		// (src/transformations.cpp:111-117) with setSmallValuesToZero, zshift = hh * rise / (-ori_size * padding_factor) (:2286-2287)
+		const int h_min = -nr_helical_asu / 2, h_max = -h_min + nr_helical_asu % 2;
+		const double pf = (double) ctx->bp[k].padding_factor;
+		for (int hh = h_min; hh < h_max; hh++)
+		{
+			if (hh == 0) continue;
+			const double ang = (double) hh * (-helical_twist) * M_PI / 180.;
+			double c = cos(ang), s = sin(ang);
+			if (fabs(c) < 1e-6) c = 0.;                                             // XMIPP_EQUAL_ACCURACY (src/macros.h)
+			if (fabs(s) < 1e-6) s = 0.;
+			const float m[9] = { (float) c, (float) -s, 0.f, (float) s, (float) c, 0.f, 0.f, 0.f, 1.f };
+			r.insert(r.end(), m, m + 9);
+			hz.push_back(fabs(helical_rise) > 0. ? (float) ((double) hh * helical_rise / (-(double) ori_size * pf)) : 0.f);
+			nhel++;
+		}
+		r.insert(r.end(), hz.begin(), hz.end());
+	}
+	float *d_R = nullptr, *d_hR = nullptr, *d_hz = nullptr;
+	if (!r.empty())
+	{
 		RB_CHECK(upload(ctx, ctx->scratch[3], r.data(), r.size() * 4));
 		d_R = ctx->scratch[3].as<float>();
+		d_hR = d_R + (size_t) nsym * 9;
+		d_hz = d_hR + (size_t) nhel * 9;
 	}
 	RB_CHECK(rb_bp_fold(ctx, k));
-	RB_CHECK(rbk_bp_symmetrise(ctx, ctx->bp[k], ctx->recon_buf[1], d_R, nsym));
+	RB_CHECK(rbk_bp_symmetrise(ctx, ctx->bp[k], ctx->recon_buf[1], d_R, nsym, d_hR, d_hz, nhel));
 	return RB_OK;
+}
+
+extern "C" int rb_bp_symmetrise(rb_ctx *ctx, int k, const double *R, int nsym)
+{
+	return symmetrise_common(ctx, k, R, nsym, 1, 0., 0., 0);
+}
+
+extern "C" int rb_bp_symmetrise_helical(rb_ctx *ctx, int k, const double *R, int nsym, int nr_helical_asu, double helical_twist,
+                                        double helical_rise, int ori_size)
+{
+	return symmetrise_common(ctx, k, R, nsym, nr_helical_asu, helical_twist, helical_rise, ori_size);
 }
 
 // BackProjector::reconstruct (default skip_gridding branch) on the device

@@ -382,7 +382,8 @@ int rbk_prepare_pool(rb_ctx *ctx, PoolSlot &s, const float *d_raw, const int *d_
 int rbk_reconstruct(rb_ctx *ctx, const RbBackprojector &bp, int ori, const double *d_tau2, int n_tau2, double tau2_fudge, int minres_map,
                     float *d_vol_out, int max_iter_preweight = 0, double normalise = 1.);
 
-int rbk_bp_symmetrise(rb_ctx *ctx, const RbBackprojector &bp, DevBuf &tmp, const float *d_R, int nsym);
+int rbk_bp_symmetrise(rb_ctx *ctx, const RbBackprojector &bp, DevBuf &tmp, const float *d_R, int nsym, const float *d_hR, const float *d_hz,
+                      int nhel);
 int rbk_update_ssnr(rb_ctx *ctx, const RbBackprojector &bp, bool is_2d, int ori, double tau2_fudge, double *tau2_io, double *sigma2_out,
                     double *dvp_out, double *cov_out, const double *fsc, const double *avgctf2, bool update_with_fsc, bool whole);
 int rbk_ftmap(rb_ctx *ctx, const float *d_vol, int ori, int r_max, float pf, float2 *d_data, int pad, double *h_power);

@@ -535,6 +535,8 @@ int rbk_ftmap(rb_ctx *ctx, const float *d_vol, int ori, int r_max, float pf, flo
 // BackProjector::symmetrise (/root/reference/src/backprojector.cpp:2136-2146) on the interleaved accumulator:
 // enforceHermitianSymmetry (:2148-2165) on the x = 0 plane, then applyPointGroupSymmetry (:2324-2480): every voxel inside
 // round(r_max pf) receives the trilinearly interpolated values of its nsym symmetry mates (Hermitian fold for x < 0).
+// applyHelicalSymmetry (:2167-2322) is the same sweep with rotations about Z and, per operator, a phase ramp along z
+// (`zshift[m]`, cycles per voxel of z) applied to the interpolated data term (:2284-2296); it runs between the two.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 k_bp_hermitian(float4 *acc, int mdlX, int mdlY, int mdlZ, int initY, int initZ)
@@ -556,7 +558,7 @@ k_bp_hermitian(float4 *acc, int mdlX, int mdlY, int mdlZ, int initY, int initZ)
 }
 
 __global__ void __launch_bounds__(256)
-k_bp_pointgroup(const float4 *acc, float4 *out, int mdlX, int mdlY, int mdlZ, int initY, int initZ, long long rmax2, const float *R, int nsym)
+k_bp_pointgroup(const float4 *acc, float4 *out, int mdlX, int mdlY, int mdlZ, int initY, int initZ, long long rmax2, const float *R, const float *zshift, int nsym)
 {
 	const size_t n = (size_t) mdlX * mdlY * mdlZ;
 	const size_t sy = mdlX, sz = (size_t) mdlX * mdlY;
@@ -588,26 +590,39 @@ k_bp_pointgroup(const float4 *acc, float4 *out, int mdlX, int mdlY, int mdlZ, in
 	const float dx10 = d010.c + (d011.c - d010.c) * fx, dx11 = d110.c + (d111.c - d110.c) * fx; \
 	const float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy; \
 	dxy0 + (dxy1 - dxy0) * fz; })
-				const float vr = RB_LERP3(x), vi = RB_LERP3(y), vw = RB_LERP3(z);
+				float vr = RB_LERP3(x), vi = RB_LERP3(y);
+				const float vw = RB_LERP3(z);
 #undef RB_LERP3
-				s.x += vr; s.y += neg ? -vi : vi; s.z += vw;
+				if (neg) vi = -vi;
+				if (zshift && zshift[m] != 0.f)
+				{
+					float sn, cs;
+					sincospif(2.f * z * zshift[m], &sn, &cs);
+					const float tr = cs * vr - sn * vi;
+					vi = cs * vi + sn * vr;
+					vr = tr;
+				}
+				s.x += vr; s.y += vi; s.z += vw;
 			}
 		}
 		out[i] = s;
 	}
 }
 
-int rbk_bp_symmetrise(rb_ctx *ctx, const RbBackprojector &bp, DevBuf &tmp, const float *d_R, int nsym)
+int rbk_bp_symmetrise(rb_ctx *ctx, const RbBackprojector &bp, DevBuf &tmp, const float *d_R, int nsym, const float *d_hR, const float *d_hz, int nhel)
 {
 	k_bp_hermitian<<<ctx->num_sms * 2, 256, 0, ctx->stream>>>(bp.vol, bp.mdlX, bp.mdlY, bp.mdlZ, bp.mdlInitY, bp.mdlInitZ);
 	RB_LAUNCH_CHECK(ctx);
-	if (nsym > 0)
+	const size_t n = (size_t) bp.mdlX * bp.mdlY * bp.mdlZ;
+	const long long rr = (long long) floor((double) bp.maxR * (double) bp.padding_factor + 0.5);
+	// the helical operators first: the point group then acts on their sum (:2143-2145)
+	for (int pass = 0; pass < 2; pass++)
 	{
-		const size_t n = (size_t) bp.mdlX * bp.mdlY * bp.mdlZ;
+		const int nops = pass == 0 ? nhel : nsym;
+		if (nops <= 0) continue;
 		RB_CHECK(tmp.ensure(n * sizeof(float4)));
-		const long long rr = (long long) floor((double) bp.maxR * (double) bp.padding_factor + 0.5);
 		k_bp_pointgroup<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(bp.vol, tmp.as<float4>(), bp.mdlX, bp.mdlY, bp.mdlZ, bp.mdlInitY, bp.mdlInitZ,
-			rr * rr, d_R, nsym);
+			rr * rr, pass == 0 ? d_hR : d_R, pass == 0 ? d_hz : nullptr, nops);
 		RB_LAUNCH_CHECK(ctx);
 		RB_CUDA(cudaMemcpyAsync(bp.vol, tmp.p, n * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
 	}

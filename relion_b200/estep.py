@@ -362,10 +362,16 @@ class MlDeviceBundle:
             return re[0], im[0], w[0]
         return re, im, w
 
-    def bp_symmetrise(self, iclass: int, rotations=None):
-        """rb_bp_symmetrise: Hermitian symmetry of the x = 0 plane + point-group mates; rotations [nsym, 3, 3] (None: C1)."""
+    def bp_symmetrise(self, iclass: int, rotations=None, helical=None):
+        """rb_bp_symmetrise: Hermitian symmetry of the x = 0 plane + point-group mates; rotations [nsym, 3, 3] (None: C1).
+        helical = (nr_helical_asu, twist [deg], rise [pixels], ori_size): rb_bp_symmetrise_helical (applyHelicalSymmetry in between)."""
         r = None if rotations is None or len(rotations) == 0 else np.ascontiguousarray(rotations, np.float64).reshape(-1, 9)
-        capi.check(self.lib, self.lib.rb_bp_symmetrise(self.ctx, iclass, _ptr(r, C.c_double), 0 if r is None else r.shape[0]))
+        n = 0 if r is None else r.shape[0]
+        if helical is None:
+            capi.check(self.lib, self.lib.rb_bp_symmetrise(self.ctx, iclass, _ptr(r, C.c_double), n))
+        else:
+            capi.check(self.lib, self.lib.rb_bp_symmetrise_helical(self.ctx, iclass, _ptr(r, C.c_double), n, int(helical[0]),
+                                                                   float(helical[1]), float(helical[2]), int(helical[3])))
 
     def reconstruct(self, iclass: int, ori_size: int, tau2=None, tau2_fudge: float = 1.0, minres_map: int = 0,
                     max_iter_preweight: int = 0, normalise: float = 1.0) -> np.ndarray:

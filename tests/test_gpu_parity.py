@@ -953,6 +953,25 @@ def test_symmetrise_on_device(device, group):
     assert np.abs(sw - gw).max() > 0
 
 
+@pytest.mark.parametrize("nr_asu,twist,rise,with_c2", [(5, 22.03, 1.408, False), (4, -166.7, 0.9, True), (3, 30.0, 0.0, False)])
+def test_symmetrise_with_helical_symmetry_on_device(device, nr_asu, twist, rise, with_c2):
+    """rb_bp_symmetrise_helical (applyHelicalSymmetry between the Hermitian fold and the point group) against the numpy
+    restatement, itself pinned against BackProjector::symmetrise(nr_helical_asu, twist, rise) in tests/test_reference_host.py."""
+    from oracle import reconstruct as rc
+    wl = make_workload(ori_size=32, healpix_order=1, n_particles=40, seed=96, snr=0.5)
+    _setup(device, wl)
+    device.expectation_some_particles(wl.pool)
+    gre, gim, gw = device.bp_get(0)
+    rots = [np.diag([-1.0, -1, 1])] if with_c2 else []
+    device.bp_symmetrise(0, rots, helical=(nr_asu, twist, rise, wl.model.ori_size))
+    sre, sim, sw = device.bp_get(0)
+    wre, wim, ww = rc.symmetrise(gre, gim, gw, wl.r_max, wl.padding_factor, rots, helical=(nr_asu, twist, rise, wl.model.ori_size))
+    for got, want in ((sre, wre), (sim, wim), (sw, ww)):
+        assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max()
+    pre, pim, pw = rc.symmetrise(gre, gim, gw, wl.r_max, wl.padding_factor, rots)
+    assert np.abs(ww - pw).max() > 0.1 * np.abs(pw).max()
+
+
 @pytest.mark.parametrize("local", [True, False])
 def test_pool_128px_against_reference_kernels(device, local):
     """A mid-size pool (128-px box, several 128-orientation tiles, hundreds of K-blocks in the tensor-core kernels) against

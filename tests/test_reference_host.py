@@ -114,6 +114,24 @@ def test_symmetrise_is_backprojector_symmetrise(sym):
 
 
 @needs_ref
+@pytest.mark.parametrize("sym,nr_asu,twist,rise", [("C1", 5, 22.03, 1.408), ("C1", 4, -166.7, 0.9), ("C2", 3, 30.0, 0.0), ("D2", 1, 10.0, 2.0)])
+def test_symmetrise_with_helical_symmetry_is_backprojector_symmetrise(sym, nr_asu, twist, rise):
+    """applyHelicalSymmetry between the Hermitian fold and the point group: odd and even numbers of asymmetrical units,
+    no rise (no phase ramp), nr_asu = 1 (no helical part)."""
+    ori = 20
+    _, F, W, eul, r_max = _accumulators(ori, ori, n_img=25, seed=9)
+    re, im, w = refhost.backproject(F, _fwd(eul), W, ori, ori, 2.0)
+    R = refhost.sym_matrices(sym) if sym != "C1" else np.zeros((0, 3, 3))
+    want = refhost.symmetrise_helical(re, im, w, ori, ori, sym, nr_asu, twist, rise, 2.0)
+    got = rc.symmetrise(re, im, w, r_max, 2.0, R, helical=(nr_asu, twist, rise, ori))
+    for a, b in zip(got, want):
+        assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
+    if nr_asu > 1:
+        plain = rc.symmetrise(re, im, w, r_max, 2.0, R)
+        assert np.abs(got[2] - plain[2]).max() > 0.1 * np.abs(plain[2]).max()
+
+
+@needs_ref
 @pytest.mark.parametrize("with_fsc,whole", [(False, False), (True, False), (True, True)])
 def test_update_ssnr_is_backprojector_update_ssnr_arrays(with_fsc, whole):
     ori = 24

@@ -241,7 +241,20 @@ typedef struct {
 	                                pixel, no circle bound); 3D and 2D references.  With grad_pseudo_halfsets (= do_grad in
 	                                src/ml_optimiser.cpp:1192) particles go into accumulator iclass + (part_id % 2) * nr_classes
 	                                (:3395-3400): initialise 2 * nr_classes accumulators and pass rb_particles.bp_offset    */
+	int ref_max_r;               /* 0, or the references' r_max (rb_set_reference maxR) when it is SMALLER than current_size / 2 —
+	                                an optics group whose box is bigger than the model's (see "Optics groups" below).  The
+	                                reference's fine-pass and wavg kernels then skip the image rows maxR < iy < imgY - maxR
+	                                except their pixel x = maxR (cpu_kernels/diff2.h:347-355, wavg.h:74-82; the coarse kernel keeps
+	                                every pixel, diff2.h:109-110), and so do the pixel sets built here.  rb_estep_* refuses pools
+	                                whose references end inside the window when this is not set                               */
 } rb_model;
+/* Optics groups.  One rb_set_model holds ONE image geometry: ori_size is image_full_size[optics_group], current_size /
+ * coarse_size its image_current_size / image_coarse_size (src/ml_optimiser.cpp:5735-5777), pixel_size its pixel size, sigma2_noise
+ * indexed by the IMAGE's shells.  For an optics group whose box or pixel size differs from the model's
+ * (src/ml_optimiser.cpp:6802-6821, 6840-6875) call rb_set_model + rb_set_sampling again before its pools, with that group's sizes,
+ * sigma2_noise resampled as sigma2[ROUND(remap * ires)] (an infinite sigma2 where the remapped shell leaves the spectrum: Minvsigma2
+ * stays zero there), and pass rb_particles.mat_left = applyScaleDifference(applyAnisoMag(I)) — the references keep their own box
+ * (rb_set_reference) and are read through the scaled matrices.  include/relion_b200_adapter.hpp does exactly this. */
 int rb_set_model(rb_ctx *ctx, const rb_model *m);
 /* Call order: rb_set_model, rb_set_sampling, then (without orientational priors) rb_set_pdf_direction:
  * [nr_classes][n_dir] needs both the model (values) and the sampling (n_dir).  rb_set_model picks
@@ -275,6 +288,14 @@ typedef struct {
 	const double *psi_prior;     /* psi_prior                                                     */
 	const int *bp_offset;        /* [P] or NULL (0): added to the class index to select the accumulator the particle is
 	                                back-projected into (pseudo half-sets of gradient refinement: (part_id % 2) * nr_classes) */
+	const double *mat_left;      /* [9] row-major or NULL: MBL of the pool, every orientation matrix becomes
+	                                inverse(mat_left * A(rot, tilt, psi) * mat_right) in both passes and the store stage
+	                                (cuda_kernel_make_eulers_3D<invert, doL, doR>, helper.cuh:713-840; generateEulerMatrices(...,
+	                                L, R), acc_helper_functions_impl.h:198-262).  The reference passes mag =
+	                                applyScaleDifference(applyAnisoMag(I)) here (acc_ml_optimiser_impl.h:1098-1103): optics groups
+	                                with anisotropic magnification or with a box / pixel size that differs from the model's, and
+	                                Aori * orient_bodies^T * A_rot90 for multi-body refinement.  3D references only. */
+	const double *mat_right;     /* [9] row-major or NULL: MBR (orient_bodies[ibody], :1085) */
 } rb_particles;
 
 /* Per-particle results (what storeWeightedSums writes to exp_metadata and folds into wsum_model,
@@ -385,6 +406,7 @@ typedef struct {
 	                                cosineFilter with the noise as the fill value, acc_ml_optimiser_impl.h:355-400, 660-668).
 	                                The generator is counter-based on (seed, pixel): reproducible, but - like the reference's
 	                                curand and CPU generators among themselves - not the same random numbers as RELION's */
+	const double *mat_left, *mat_right; /* as in rb_particles (NULL: none) */
 } rb_raw_particles;
 /* power_img: [P][n/2+1] spectrum of the masked full-size transform (op.power_img, used by the host for sigma2_noise
  * beyond the current size), may be NULL. */

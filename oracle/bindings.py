@@ -52,7 +52,7 @@ BP = C.POINTER(ok_backprojector)
 class ok_kernel_table(C.Structure):
     _fields_ = [
         ("kind", C.c_char_p),
-        ("make_eulers_3d", C.CFUNCTYPE(None, f32p, f32p, f32p, f32p, C.c_ulong)),
+        ("make_eulers_3d", C.CFUNCTYPE(None, f32p, f32p, f32p, f32p, C.c_ulong, f32p, f32p)),
         ("project", C.CFUNCTYPE(None, PP, C.c_int, C.c_int, f32p, f32p, f32p)),
         ("diff2_coarse", C.CFUNCTYPE(None, PP, C.c_int, C.c_int, f32p, C.c_ulong, f32p, f32p, C.c_ulong, f32p, f32p, f32p, f32p)),
         ("diff2_fine", C.CFUNCTYPE(None, PP, C.c_int, C.c_int, f32p, f32p, f32p, f32p, f32p, f32p, C.c_float,
@@ -254,10 +254,12 @@ class Oracle:
         return dict(threshold_idx=int(idx), sum_weight=float(s.value), significant_weight=float(g.value), n_filtered=int(nf.value))
 
     # ---- kernel-level calls (stage parity) ------------------------------------------------------
-    def make_eulers(self, rot, tilt, psi):
+    def make_eulers(self, rot, tilt, psi, mat_left=None, mat_right=None):
         a = np.ascontiguousarray(rot, np.float32); b = np.ascontiguousarray(tilt, np.float32); g = np.ascontiguousarray(psi, np.float32)
         out = np.zeros((len(a), 9), np.float32)
-        self.K.make_eulers_3d(_fp(a), _fp(b), _fp(g), _fp(out), len(a))
+        L = None if mat_left is None else np.ascontiguousarray(mat_left, np.float32).reshape(9)
+        R = None if mat_right is None else np.ascontiguousarray(mat_right, np.float32).reshape(9)
+        self.K.make_eulers_3d(_fp(a), _fp(b), _fp(g), _fp(out), len(a), None if L is None else _fp(L), None if R is None else _fp(R))
         return out
 
     def project(self, ref: Projector, n, euler9):

@@ -401,7 +401,33 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 			double A[9] = { cg * cc - sg * sa, cg * cs + sg * ca, -cg * sb,
 			               -sg * cc - cg * sa, -sg * cs + cg * ca, sg * sb,
 			                sc, ss, cb };
-			float *e = &c.eulers[9 * i];   // inverse of a rotation = transpose
+			float *e = &c.eulers[9 * i];
+			if (pool->mat_left || pool->mat_right)
+			{   // A = L * A; A = A * R; A = A.inv() (:248-255)
+				double B[9];
+				if (pool->mat_left)
+				{
+					const double *L = pool->mat_left;
+					for (int r = 0; r < 3; r++)
+						for (int q = 0; q < 3; q++) B[r * 3 + q] = L[r * 3] * A[q] + L[r * 3 + 1] * A[3 + q] + L[r * 3 + 2] * A[6 + q];
+					for (int q = 0; q < 9; q++) A[q] = B[q];
+				}
+				if (pool->mat_right)
+				{
+					const double *R = pool->mat_right;
+					for (int r = 0; r < 3; r++)
+						for (int q = 0; q < 3; q++) B[r * 3 + q] = A[r * 3] * R[q] + A[r * 3 + 1] * R[3 + q] + A[r * 3 + 2] * R[6 + q];
+					for (int q = 0; q < 9; q++) A[q] = B[q];
+				}
+				const double det = A[0] * (A[4] * A[8] - A[7] * A[5]) - A[1] * (A[3] * A[8] - A[6] * A[5]) + A[2] * (A[3] * A[7] - A[6] * A[4]);
+				e[0] = (float) ((A[4] * A[8] - A[7] * A[5]) / det); e[1] = (float) ((A[7] * A[2] - A[1] * A[8]) / det);
+				e[2] = (float) ((A[1] * A[5] - A[4] * A[2]) / det); e[3] = (float) ((A[5] * A[6] - A[8] * A[3]) / det);
+				e[4] = (float) ((A[8] * A[0] - A[2] * A[6]) / det); e[5] = (float) ((A[2] * A[3] - A[5] * A[0]) / det);
+				e[6] = (float) ((A[3] * A[7] - A[6] * A[4]) / det); e[7] = (float) ((A[6] * A[1] - A[0] * A[7]) / det);
+				e[8] = (float) ((A[0] * A[4] - A[3] * A[1]) / det);
+				continue;
+			}
+			// inverse of a rotation = transpose
 			e[0] = (float) A[0]; e[1] = (float) A[3]; e[2] = (float) A[6];
 			e[3] = (float) A[1]; e[4] = (float) A[4]; e[5] = (float) A[7];
 			e[6] = (float) A[2]; e[7] = (float) A[5]; e[8] = (float) A[8];
@@ -745,7 +771,9 @@ int oracle_estep_pool(const ok_kernel_table *K, const rb_model *m, const rb_samp
 				g[(size_t) d * s->n_psi + q] = (float) s->psi[q];
 			}
 		S.coarse_eulers.resize(n * 9);
-		K->make_eulers_3d(a.data(), b.data(), g.data(), S.coarse_eulers.data(), n);
+		float Lf[9], Rf[9];                                                          // MBL / MBR as XFLOAT (acc_projector_plan_impl.h:232-245)
+		for (int i = 0; i < 9; i++) { Lf[i] = pool->mat_left ? (float) pool->mat_left[i] : 0.f; Rf[i] = pool->mat_right ? (float) pool->mat_right[i] : 0.f; }
+		K->make_eulers_3d(a.data(), b.data(), g.data(), S.coarse_eulers.data(), n, pool->mat_left ? Lf : NULL, pool->mat_right ? Rf : NULL);
 	}
 	const int P = pool->n_particles;
 	const int Kc = m->nr_classes;

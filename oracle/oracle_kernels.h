@@ -47,9 +47,9 @@ typedef struct {
 typedef struct {
 	const char *kind; /* "reference" | "port" */
 
-	/* cpu_kernel_make_eulers_3D<invert=true,doL=false,doR=false>  (src/acc/cpu/cpu_kernels/helper.cpp, helper.h:725) */
+	/* cpu_kernel_make_eulers_3D<invert=true,doL,doR>  (src/acc/cpu/cpu_kernels/helper.cpp, helper.h:725); L / R: [9] or NULL */
 	void (*make_eulers_3d)(const float *alphas, const float *betas, const float *gammas,
-	                       float *eulers, unsigned long n);
+	                       float *eulers, unsigned long n, const float *L, const float *R);
 
 	/* AccProjectorKernel::project3Dmodel (2D-data overload) over a whole half-image with the fine-pass
 	 * y-wrap (src/acc/acc_projectorkernel_impl.h:161-231, cpu_kernels/diff2.h:344-370) */

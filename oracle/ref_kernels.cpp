@@ -236,12 +236,18 @@ void refk_diff2_cc_fine(const ok_projector *p, int imgX, int imgY, const float *
 		(unsigned long *) rot_idx, (unsigned long *) trans_idx, (unsigned long *) job_idx, (unsigned long *) job_num);
 }
 
-// cpu_kernel_make_eulers_3D<invert = true, doL = false, doR = false> (helper.cpp:744-875), the instantiation the E-step uses
-void refk_make_eulers_3d(const float *alphas, const float *betas, const float *gammas, float *eulers, unsigned long n)
+// cpu_kernel_make_eulers_3D<invert = true, doL, doR> (helper.cpp:744-875), the instantiations the E-step uses
+// (acc_projector_plan_impl.h:246-262 picks them by the shapes of MBL / MBR)
+void refk_make_eulers_3d(const float *alphas, const float *betas, const float *gammas, float *eulers, unsigned long n, const float *L,
+                         const float *R)
 {
 	const int bs = 128;                                                           // BLOCK_SIZE of the call site (acc_ml_optimiser_impl.h generateEulerMatrices)
-	CpuKernels::cpu_kernel_make_eulers_3D<true, false, false>((int) ((n + bs - 1) / bs), bs, (XFLOAT *) alphas, (XFLOAT *) betas,
-		(XFLOAT *) gammas, (XFLOAT *) eulers, n, NULL, NULL);
+	const int grid = (int) ((n + bs - 1) / bs);
+	XFLOAT *a = (XFLOAT *) alphas, *b = (XFLOAT *) betas, *g = (XFLOAT *) gammas, *e = (XFLOAT *) eulers, *l = (XFLOAT *) L, *r = (XFLOAT *) R;
+	if (L && R) CpuKernels::cpu_kernel_make_eulers_3D<true, true, true>(grid, bs, a, b, g, e, n, l, r);
+	else if (L) CpuKernels::cpu_kernel_make_eulers_3D<true, true, false>(grid, bs, a, b, g, e, n, l, NULL);
+	else if (R) CpuKernels::cpu_kernel_make_eulers_3D<true, false, true>(grid, bs, a, b, g, e, n, NULL, r);
+	else CpuKernels::cpu_kernel_make_eulers_3D<true, false, false>(grid, bs, a, b, g, e, n, NULL, NULL);
 }
 
 // CpuKernels::exponentiate_weights_fine (helper.cpp:27-61)

@@ -600,15 +600,10 @@ extern "C" int rb_set_sampling(rb_ctx *ctx, const rb_sampling *s)
 	RB_CHECK(upload(ctx, ctx->s_rot, s->rot, s->n_dir * sizeof(double)));
 	RB_CHECK(upload(ctx, ctx->s_tilt, s->tilt, s->n_dir * sizeof(double)));
 	RB_CHECK(upload(ctx, ctx->s_psi, s->psi, s->n_psi * sizeof(double)));
-	std::vector<float> fr(s->n_dir), ft(s->n_dir), fp(s->n_psi);
-	for (int i = 0; i < s->n_dir; i++) { fr[i] = (float) s->rot[i]; ft[i] = (float) s->tilt[i]; }
-	for (int i = 0; i < s->n_psi; i++) fp[i] = (float) s->psi[i];
-	RB_CHECK(upload(ctx, ctx->scratch[3], fr.data(), fr.size() * 4));
-	RB_CHECK(upload(ctx, ctx->scratch[4], ft.data(), ft.size() * 4));
-	RB_CHECK(upload(ctx, ctx->scratch[5], fp.data(), fp.size() * 4));
 	RB_CHECK(ctx->s_coarse_eulers.ensure(no * 9 * sizeof(float)));
-	RB_CHECK(rbk_make_coarse_eulers(ctx, ctx->scratch[3].as<float>(), ctx->scratch[4].as<float>(), ctx->scratch[5].as<float>(),
-	                                s->n_dir, s->n_psi, ctx->s_coarse_eulers.as<float>()));
+	ctx->coarse_lr = RbLR();
+	RB_CHECK(rbk_make_coarse_eulers(ctx, ctx->s_rot.as<double>(), ctx->s_tilt.as<double>(), ctx->s_psi.as<double>(),
+	                                s->n_dir, s->n_psi, ctx->coarse_lr, ctx->s_coarse_eulers.as<float>()));
 	if (s->n_over_rot > 1 || s->over_rot)
 	{
 		RB_CHECK(upload(ctx, ctx->s_over_rot, s->over_rot, no * s->n_over_rot * sizeof(double)));
@@ -676,7 +671,9 @@ static inline int iround(double x) { return (int) (x > 0 ? floor(x + 0.5) : -flo
 // pixels with Mresol >= 0 for window n (src/ml_optimiser.cpp:5784-5811), in FFTW order
 // full_x0: keep the redundant half of the x = 0 column (jp == 0, ip < 0).  Mresol excludes it (Minvsigma2 is zero there),
 // but the cross-correlation kernels weight every pixel with 1 / sqrtXi2^2 (buildCorrImage), so it contributes there.
-static void make_pixlist(int n, std::vector<uint32_t> &out, bool full_x0 = false)
+// dead > 0: drop the rows the reference's fine / wavg kernels skip when the references end inside the window
+// (maxR = dead < n / 2: rows |ip| > maxR keep only their pixel jp == maxR, cpu_kernels/diff2.h:347-355)
+static void make_pixlist(int n, std::vector<uint32_t> &out, bool full_x0 = false, int dead = 0)
 {
 	const int xs = n / 2 + 1;
 	out.clear();
@@ -686,13 +683,14 @@ static void make_pixlist(int n, std::vector<uint32_t> &out, bool full_x0 = false
 		for (int jp = 0; jp < xs; jp++)
 		{
 			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
+			if (dead > 0 && abs(ip) > dead && jp != dead) continue;
 			if (ires < xs && (full_x0 || !(jp == 0 && ip < 0))) out.push_back(rb_pack_pix(jp, ip, ires));
 		}
 	}
 }
 
 // the same pixel set as row runs + a dense shell map
-static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_map, bool full_x0 = false)
+static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_map, bool full_x0 = false, int dead = 0)
 {
 	const int xs = n / 2 + 1;
 	rows.clear();
@@ -704,6 +702,7 @@ static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_
 		for (int jp = 0; jp < xs; jp++)
 		{
 			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
+			if (dead > 0 && abs(ip) > dead && jp != dead) continue;
 			if (ires < xs && (full_x0 || !(jp == 0 && ip < 0)))
 			{
 				ires_map[(size_t) iy * xs + jp] = (short) ires;
@@ -729,8 +728,11 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	ctx->h_model = *m;
 	ctx->model_version++;
 	const int nshell = m->ori_size / 2 + 1, K = m->nr_classes;
+	RB_ARG(m->ref_max_r >= 0, "rb_set_model: bad ref_max_r %d", m->ref_max_r);
+	const int dead = (m->ref_max_r > 0 && m->ref_max_r < m->current_size / 2) ? m->ref_max_r : 0;
+	ctx->fine_dead_maxR = dead;
 	std::vector<uint32_t> pc, pf;
-	make_pixlist(m->coarse_size, pc); make_pixlist(m->current_size, pf);
+	make_pixlist(m->coarse_size, pc); make_pixlist(m->current_size, pf, false, dead);
 	{
 		// The coarse kernels are order-agnostic over this list, and the fused kernel projects 16 consecutive entries per
 		// warp-row: grouping them as W x H image tiles instead of row segments makes neighbouring lanes land in
@@ -761,7 +763,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	if (!m->do_map)
 	{
 		std::vector<uint32_t> pfull;
-		make_pixlist(m->current_size, pfull, true);
+		make_pixlist(m->current_size, pfull, true, dead);
 		n_store = pfull.size();
 		RB_CHECK(upload(ctx, ctx->m_cc[5], pfull.data(), pfull.size() * 4));
 	}
@@ -769,7 +771,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	std::vector<uint32_t> prs;
 	{
 		std::vector<uint32_t> all;
-		make_pixlist(m->current_size, all, !m->do_map);
+		make_pixlist(m->current_size, all, !m->do_map, dead);
 		auto in_d2 = [](uint32_t v) { return !(rb_pix_x(v) == 0 && rb_pix_y(v) < 0); };
 		auto radial = [](uint32_t a, uint32_t b) {
 			const int xa = rb_pix_x(a), ya = rb_pix_y(a), xb = rb_pix_x(b), yb = rb_pix_y(b);
@@ -793,7 +795,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	}
 	std::vector<RbRow> rc, rf;
 	std::vector<short> ic, iff;
-	make_rows(m->coarse_size, rc, ic); make_rows(m->current_size, rf, iff);
+	make_rows(m->coarse_size, rc, ic); make_rows(m->current_size, rf, iff, false, dead);
 	RB_CHECK(upload(ctx, ctx->m_rows_c, rc.data(), rc.size() * sizeof(RbRow)));
 	RB_CHECK(upload(ctx, ctx->m_rows_f, rf.data(), rf.size() * sizeof(RbRow)));
 	RB_CHECK(upload(ctx, ctx->m_ires_c, ic.data(), ic.size() * sizeof(short)));
@@ -839,7 +841,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 		std::vector<RbRow> rcc, rfc;
 		std::vector<short> icc, ifc;
 		make_pixlist(m->coarse_size, pcc, true);
-		make_rows(m->coarse_size, rcc, icc, true); make_rows(m->current_size, rfc, ifc, true);
+		make_rows(m->coarse_size, rcc, icc, true); make_rows(m->current_size, rfc, ifc, true, dead);
 		RB_CHECK(upload(ctx, ctx->m_cc[0], pcc.data(), pcc.size() * 4));
 		RB_CHECK(upload(ctx, ctx->m_cc[1], rcc.data(), rcc.size() * sizeof(RbRow)));
 		RB_CHECK(upload(ctx, ctx->m_cc[2], icc.data(), icc.size() * sizeof(short)));
@@ -924,6 +926,13 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 	s.h_meta.resize(P);
 	long long coff = 0, poff = 0; int max_no = 0;
 	s.max_bp_off = 0;
+	s.lr = RbLR();
+	if (pool->mat_left || pool->mat_right)
+	{
+		RB_ARG(!ctx->ref_2d[0], "rb_pool_upload: mat_left / mat_right need 3D references (make_eulers_2D takes neither)");
+		if (pool->mat_left) { s.lr.doL = 1; for (int i = 0; i < 9; i++) s.lr.L[i] = pool->mat_left[i]; }
+		if (pool->mat_right) { s.lr.doR = 1; for (int i = 0; i < 9; i++) s.lr.R[i] = pool->mat_right[i]; }
+	}
 	for (int p = 0; p < P; p++)
 	{
 		RbPartMeta &m = s.h_meta[p];
@@ -1101,6 +1110,7 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 	pool.dir_off = raw->dir_off; pool.dir_idx = raw->dir_idx; pool.dir_prior = raw->dir_prior;
 	pool.psi_off = raw->psi_off; pool.psi_idx = raw->psi_idx; pool.psi_prior = raw->psi_prior;
 	pool.bp_offset = raw->bp_offset;
+	pool.mat_left = raw->mat_left; pool.mat_right = raw->mat_right;
 	RB_CHECK(pool_setup(ctx, slot, &pool, false));
 	PoolSlot &s = ctx->slot[slot];
 	// raw images + small tables on the copy stream (overlaps the compute of the other slot), kernels on the compute stream
@@ -1179,11 +1189,25 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 		if (!ctx->has_proj[k]) { rb_set_error("rb_estep: reference %d not set", k); return RB_ERR_STATE; }
 		if (!(flags & 1u) && !ctx->has_bp[k]) { rb_set_error("rb_estep: accumulator %d not initialised", k); return RB_ERR_STATE; }
 		if (!(flags & 1u) && s.max_bp_off > 0 && !ctx->has_bp[k + s.max_bp_off]) { rb_set_error("rb_estep: accumulator %d (pseudo half-set) not initialised", k + s.max_bp_off); return RB_ERR_STATE; }
+		const int half = M.current_size / 2, want = ctx->proj[k].mdlMaxR < half ? ctx->proj[k].mdlMaxR : 0;
+		if (want != ctx->fine_dead_maxR)
+		{
+			rb_set_error("rb_estep: reference %d ends at r_max %d, the image window at %d: rb_model.ref_max_r must be %d (it is %d)", k,
+			             ctx->proj[k].mdlMaxR, half, want, ctx->fine_dead_maxR);
+			return RB_ERR_STATE;
+		}
 	}
 
 	RB_CUDA(cudaSetDevice(ctx->device));
 	RB_CHECK(ensure_coarse_core(ctx));
 	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
+	if (memcmp(&s.lr, &ctx->coarse_lr, sizeof(RbLR)) != 0)
+	{
+		// the coarse matrices are shared by the pools; a pool with other MBL / MBR rebuilds them in stream order
+		ctx->coarse_lr = s.lr;
+		ctx->samp_version++;                                    // invalidates everything derived from the coarse matrices
+		RB_CHECK(rbk_make_coarse_eulers(ctx, S.rot, S.tilt, S.psi, S.n_dir, S.n_psi, ctx->coarse_lr, ctx->s_coarse_eulers.as<float>()));
+	}
 	RB_CHECK(rb_stage_begin(ctx, "total"));
 	RB_CUDA(cudaMemsetAsync(s.counters.p, 0, 64, ctx->stream));
 	RB_CUDA(cudaMemsetAsync(s.shells.p, 0, (size_t) s.P * M.nshell * 4, ctx->stream));

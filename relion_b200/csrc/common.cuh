@@ -165,6 +165,12 @@ struct RbFineOrient {
 	float e[9];
 };
 
+// MBL / MBR of a pool: orientation matrices are inverse(L * A * R) (helper.cuh:713-840)
+struct RbLR {
+	int doL = 0, doR = 0;
+	double L[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+};
+
 struct RbSamplingDev {
 	int n_dir, n_psi, n_over_rot, n_trans, n_over_trans;
 	const float *coarse_eulers;       // [n_dir*n_psi][9]
@@ -230,6 +236,7 @@ struct PoolSlot {
 	int max_no = 0;                 // max over particles of nd*np
 	long long total_coarse = 0;     // sum over particles of K*nd*np*T
 	int max_bp_off = 0;             // largest RbPartMeta::bp_off of the pool
+	RbLR lr;                        // rb_particles.mat_left / mat_right
 	long long total_prior = 0;
 	DevBuf Fimg, Fnomask, Fctf, meta, state, dir_idx, dir_prior, psi_idx, psi_prior;
 	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;
@@ -323,6 +330,8 @@ struct rb_ctx {
 	DevBuf gemmA_all[4];             // the classes' orientation operands stacked along M (few orientations per class: 2D classification)
 	long long gemmA_all_stamp = -1;
 	long long ref_version[RB_MAX_CLASSES] = {0}, samp_version = 0, model_version = 0;
+	RbLR coarse_lr;                 // the MBL / MBR the coarse matrices were last built with
+	int fine_dead_maxR = 0;         // rb_model.ref_max_r when the fine pixel sets were built without the rows beyond it
 };
 
 int rb_stage_begin(rb_ctx *ctx, const char *name);
@@ -335,7 +344,8 @@ int rbk_bp_fold(rb_ctx *ctx, const RbBackprojector &bp);
 // kernel launchers (one per .cu)
 // ---------------------------------------------------------------------------------------------
 // kernels_misc.cu
-int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt, const float *d_psi, int n_dir, int n_psi, float *d_eulers);
+int rbk_make_coarse_eulers(rb_ctx *ctx, const double *d_rot, const double *d_tilt, const double *d_psi, int n_dir, int n_psi, const RbLR &lr,
+                           float *d_eulers);
 int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
 int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2);
 int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);

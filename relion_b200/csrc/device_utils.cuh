@@ -342,14 +342,35 @@ __device__ __forceinline__ int rb_next_work(int *queue, int *s_slot, int prev, b
 __device__ __forceinline__ void rb_atomic_min_pos(int *addr, float v) { atomicMin(addr, __float_as_int(v)); }
 
 // ZYZ Euler matrix, inverted (= transposed), in fp64 then cast: generateEulerMatrices(inverse=true)
-// (acc_helper_functions_impl.h:198-262)
-__device__ inline void rb_euler_fine(double rot, double tilt, double psi, float *e)
+// (acc_helper_functions_impl.h:198-262).  With MBL / MBR: A = L * A; A = A * R; A = A.inv() in fp64 (:248-255).
+__device__ inline void rb_euler_fine(double rot, double tilt, double psi, const RbLR &lr, float *e)
 {
 	const double d2r = 3.14159265358979323846 / 180.0;
 	double sa, ca, sb, cb, sg, cg;
 	sincos(rot * d2r, &sa, &ca); sincos(tilt * d2r, &sb, &cb); sincos(psi * d2r, &sg, &cg);
 	double cc = cb * ca, cs = cb * sa, sc = sb * ca, ss = sb * sa;
-	e[0] = (float) (cg * cc - sg * sa); e[3] = (float) (cg * cs + sg * ca); e[6] = (float) (-cg * sb);
-	e[1] = (float) (-sg * cc - cg * sa); e[4] = (float) (-sg * cs + cg * ca); e[7] = (float) (sg * sb);
-	e[2] = (float) sc; e[5] = (float) ss; e[8] = (float) cb;
+	if (!lr.doL && !lr.doR)
+	{
+		e[0] = (float) (cg * cc - sg * sa); e[3] = (float) (cg * cs + sg * ca); e[6] = (float) (-cg * sb);
+		e[1] = (float) (-sg * cc - cg * sa); e[4] = (float) (-sg * cs + cg * ca); e[7] = (float) (sg * sb);
+		e[2] = (float) sc; e[5] = (float) ss; e[8] = (float) cb;
+		return;
+	}
+	double A[9] = { cg * cc - sg * sa, cg * cs + sg * ca, -cg * sb, -sg * cc - cg * sa, -sg * cs + cg * ca, sg * sb, sc, ss, cb }, B[9];
+	if (lr.doL)
+	{
+		for (int r = 0; r < 3; r++)
+			for (int c = 0; c < 3; c++) B[r * 3 + c] = lr.L[r * 3] * A[c] + lr.L[r * 3 + 1] * A[3 + c] + lr.L[r * 3 + 2] * A[6 + c];
+		for (int k = 0; k < 9; k++) A[k] = B[k];
+	}
+	if (lr.doR)
+	{
+		for (int r = 0; r < 3; r++)
+			for (int c = 0; c < 3; c++) B[r * 3 + c] = A[r * 3] * lr.R[c] + A[r * 3 + 1] * lr.R[3 + c] + A[r * 3 + 2] * lr.R[6 + c];
+		for (int k = 0; k < 9; k++) A[k] = B[k];
+	}
+	const double det = A[0] * (A[4] * A[8] - A[7] * A[5]) - A[1] * (A[3] * A[8] - A[6] * A[5]) + A[2] * (A[3] * A[7] - A[6] * A[4]);
+	e[0] = (float) ((A[4] * A[8] - A[7] * A[5]) / det); e[1] = (float) ((A[7] * A[2] - A[1] * A[8]) / det); e[2] = (float) ((A[1] * A[5] - A[4] * A[2]) / det);
+	e[3] = (float) ((A[5] * A[6] - A[8] * A[3]) / det); e[4] = (float) ((A[8] * A[0] - A[2] * A[6]) / det); e[5] = (float) ((A[2] * A[3] - A[5] * A[0]) / det);
+	e[6] = (float) ((A[3] * A[7] - A[6] * A[4]) / det); e[7] = (float) ((A[6] * A[1] - A[0] * A[7]) / det); e[8] = (float) ((A[0] * A[4] - A[3] * A[1]) / det);
 }

@@ -2,29 +2,70 @@
 // stand-alone projection, posed back-projection.
 #include "device_utils.cuh"
 
-// cuda_kernel_make_eulers_3D<invert=true,doL=false,doR=false> (helper.cuh:713-840): fp32 degrees ->
-// radians -> sincosf -> ZYZ matrix, written transposed (inverse of a rotation).
-__global__ void k_make_coarse_eulers(const float *rot, const float *tilt, const float *psi, int n_dir, int n_psi, float *eulers)
+// cuda_kernel_make_eulers_3D<invert=true,doL,doR> (helper.cuh:713-840): fp32 degrees -> radians -> sincosf -> ZYZ matrix A,
+// B = L (A R) in fp32 when the pool carries MBL / MBR, written inverted: the transpose without L (also with R alone, as the
+// reference does), the adjugate over the determinant with L ("this could have anisotropy, so inverse neq transpose").
+struct CoarseLR { int doL, doR; float L[9], R[9]; };
+
+__global__ void k_make_coarse_eulers(const double *rot, const double *tilt, const double *psi, int n_dir, int n_psi, CoarseLR lr, float *eulers)
 {
 	const int i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n_dir * n_psi) return;
 	const int d = i / n_psi, q = i - d * n_psi;
-	const float a = rot[d] * (float) 3.14159265358979323846 / 180.0f;
-	const float b = tilt[d] * (float) 3.14159265358979323846 / 180.0f;
-	const float g = psi[q] * (float) 3.14159265358979323846 / 180.0f;
+	const float a = (float) rot[d] * (float) 3.14159265358979323846 / 180.0f;     // XFLOAT alphas / betas / gammas of AccProjectorPlan
+	const float b = (float) tilt[d] * (float) 3.14159265358979323846 / 180.0f;
+	const float g = (float) psi[q] * (float) 3.14159265358979323846 / 180.0f;
 	float sa, ca, sb, cb, sg, cg;
 	sincosf(a, &sa, &ca); sincosf(b, &sb, &cb); sincosf(g, &sg, &cg);
 	const float cc = cb * ca, cs = cb * sa, sc = sb * ca, ss = sb * sa;
+	float A[9], B[9];
+	A[0] = cg * cc - sg * sa;  A[1] = cg * cs + sg * ca;  A[2] = -cg * sb;
+	A[3] = -sg * cc - cg * sa; A[4] = -sg * cs + cg * ca; A[5] = sg * sb;
+	A[6] = sc;                 A[7] = ss;                 A[8] = cb;
+	if (lr.doR)
+	{
+		for (int r = 0; r < 3; r++)
+			for (int c = 0; c < 3; c++)
+			{
+				float v = 0.f;
+				for (int k = 0; k < 3; k++) v += A[r * 3 + k] * lr.R[k * 3 + c];
+				B[r * 3 + c] = v;
+			}
+	}
+	else
+		for (int k = 0; k < 9; k++) B[k] = A[k];
 	float *e = eulers + (size_t) i * 9;
-	e[0] = cg * cc - sg * sa;  e[3] = cg * cs + sg * ca;  e[6] = -cg * sb;
-	e[1] = -sg * cc - cg * sa; e[4] = -sg * cs + cg * ca; e[7] = sg * sb;
-	e[2] = sc;                 e[5] = ss;                 e[8] = cb;
+	if (lr.doL)
+	{
+		for (int k = 0; k < 9; k++) A[k] = B[k];
+		for (int r = 0; r < 3; r++)
+			for (int c = 0; c < 3; c++)
+			{
+				float v = 0.f;
+				for (int k = 0; k < 3; k++) v += lr.L[r * 3 + k] * A[k * 3 + c];
+				B[r * 3 + c] = v;
+			}
+		const float det = B[0] * (B[4] * B[8] - B[7] * B[5]) - B[1] * (B[3] * B[8] - B[6] * B[5]) + B[2] * (B[3] * B[7] - B[6] * B[4]);
+		e[0] = (B[4] * B[8] - B[7] * B[5]) / det; e[1] = (B[7] * B[2] - B[1] * B[8]) / det; e[2] = (B[1] * B[5] - B[4] * B[2]) / det;
+		e[3] = (B[5] * B[6] - B[8] * B[3]) / det; e[4] = (B[8] * B[0] - B[2] * B[6]) / det; e[5] = (B[2] * B[3] - B[5] * B[0]) / det;
+		e[6] = (B[3] * B[7] - B[6] * B[4]) / det; e[7] = (B[6] * B[1] - B[0] * B[7]) / det; e[8] = (B[0] * B[4] - B[3] * B[1]) / det;
+	}
+	else
+	{
+		e[0] = B[0]; e[1] = B[3]; e[2] = B[6];
+		e[3] = B[1]; e[4] = B[4]; e[5] = B[7];
+		e[6] = B[2]; e[7] = B[5]; e[8] = B[8];
+	}
 }
 
-int rbk_make_coarse_eulers(rb_ctx *ctx, const float *d_rot, const float *d_tilt, const float *d_psi, int n_dir, int n_psi, float *d_eulers)
+int rbk_make_coarse_eulers(rb_ctx *ctx, const double *d_rot, const double *d_tilt, const double *d_psi, int n_dir, int n_psi, const RbLR &lr,
+                           float *d_eulers)
 {
 	const int n = n_dir * n_psi;
-	k_make_coarse_eulers<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_rot, d_tilt, d_psi, n_dir, n_psi, d_eulers);
+	CoarseLR c;
+	c.doL = lr.doL; c.doR = lr.doR;
+	for (int i = 0; i < 9; i++) { c.L[i] = (float) lr.L[i]; c.R[i] = (float) lr.R[i]; }
+	k_make_coarse_eulers<<<(n + 127) / 128, 128, 0, ctx->stream>>>(d_rot, d_tilt, d_psi, n_dir, n_psi, c, d_eulers);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;
 }

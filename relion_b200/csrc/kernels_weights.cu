@@ -954,7 +954,7 @@ k_fine_scan(RbPartState *states, int P, int NOR, int NOT, long long cap_fo, long
 
 __global__ void __launch_bounds__(FS_THREADS)
 k_fine_fill(const RbPartMeta *metas, const RbPartState *states, const float *Mweight,
-            const int *dir_idx, const int *psi_idx, RbModelDev M, RbSamplingDev S,
+            const int *dir_idx, const int *psi_idx, RbModelDev M, RbSamplingDev S, RbLR lr,
             int *pair_list, RbFineOrient *fo, long long *fs_ihid, const int *counters, int nchunk, const int *part_so, const int *part_pair)
 {
 	__shared__ int s_scan_f[FS_THREADS], s_scan_c[FS_THREADS];
@@ -1010,7 +1010,7 @@ k_fine_fill(const RbPartMeta *metas, const RbPartState *states, const float *Mwe
 					rot = S.over_rot[g]; tilt = S.over_tilt[g]; psi = S.over_psi[g];
 				}
 				else { rot = S.rot[gd]; tilt = S.tilt[gd]; psi = S.psi[gp]; }
-				rb_euler_fine(rot, tilt, psi, F.e);
+				rb_euler_fine(rot, tilt, psi, lr, F.e);
 				fo[st.fo_base + (long long) sidx * NOR + io] = F;
 				// ihidden_over (acc_helper_functions_impl.h:63)
 				j = 0;
@@ -1046,7 +1046,7 @@ int rbk_fine_setup_pool(rb_ctx *ctx, PoolSlot &s)
 		(long long) s.cap_fo, (long long) s.cap_fs, s.counters.as<int>());
 	RB_LAUNCH_CHECK(ctx);
 	k_fine_fill<<<grid, FS_THREADS, 0, ctx->stream>>>(s.meta.as<RbPartMeta>(), s.state.as<RbPartState>(),
-		s.Mweight.as<float>(), s.dir_idx.as<int>(), s.psi_idx.as<int>(), ctx->d_model, ctx->d_samp,
+		s.Mweight.as<float>(), s.dir_idx.as<int>(), s.psi_idx.as<int>(), ctx->d_model, ctx->d_samp, s.lr,
 		s.pair_list.as<int>(), s.fo.as<RbFineOrient>(), s.fs_ihid.as<long long>(), s.counters.as<int>(), nchunk, part_so, part_pair);
 	RB_LAUNCH_CHECK(ctx);
 	return RB_OK;

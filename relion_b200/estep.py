@@ -75,6 +75,7 @@ class ModelParams:
     do_cc: bool = False                      # (iter == 1 and do_firstiter_cc) or do_always_cc
     prior_offset_class: Optional[np.ndarray] = None   # [K, 2] pixels: mymodel.prior_offset_class (2D references), None for 3D
     do_grad: bool = False                    # gradient (SGD / VDAM) refinement: residual back-projection
+    ref_max_r: int = 0                       # the references' r_max when smaller than current_size / 2 (rb_model.ref_max_r)
 
 
 @dataclasses.dataclass
@@ -95,6 +96,8 @@ class ParticlePool:
     psi_idx: Optional[np.ndarray] = None
     psi_prior: Optional[np.ndarray] = None
     bp_offset: Optional[np.ndarray] = None   # [P] int32: accumulator = class + bp_offset (pseudo half-sets of gradient refinement)
+    mat_left: Optional[np.ndarray] = None    # [3, 3] MBL: orientation matrices become inverse(mat_left A mat_right) (magnification / scale
+    mat_right: Optional[np.ndarray] = None   # [3, 3] MBR   difference of the optics group, body matrices)
 
     @property
     def n_particles(self):
@@ -180,6 +183,7 @@ def marshal_model(p: ModelParams):
     st.bp_circle_bound = int(p.bp_circle_bound)
     st.do_cc = int(p.do_cc)
     st.do_grad = int(p.do_grad)
+    st.ref_max_r = int(p.ref_max_r)
     if p.prior_offset_class is not None:
         poc = m.hold(_f64(np.asarray(p.prior_offset_class).reshape(p.nr_classes, 2)))
         st.prior_offset_class = _ptr(poc, C.c_double)
@@ -216,6 +220,8 @@ class RawParticlePool:
     bp_offset: Optional[np.ndarray] = None
     noise_seed: Optional[np.ndarray] = None   # [P] int64 random_seed + part_id: noise-filled soft mask; None: zero mask
     og_fourier_factor: Optional[np.ndarray] = None   # [nog, cs, cs/2+1] complex64: conj(beam-tilt phase) * avgMTF / MTF per optics group
+    mat_left: Optional[np.ndarray] = None
+    mat_right: Optional[np.ndarray] = None
 
     @property
     def n_particles(self):
@@ -239,6 +245,8 @@ def marshal_raw_pool(pool: RawParticlePool):
         st.og_fourier_factor = _ptr(m.hold(np.ascontiguousarray(pool.og_fourier_factor, dtype=np.complex64).view(np.float32)), C.c_float)
     if pool.noise_seed is not None:
         st.noise_seed = m.hold(np.ascontiguousarray(pool.noise_seed, dtype=np.int64)).ctypes.data_as(C.POINTER(C.c_int64))
+    st.mat_left = _ptr(m.hold(_f64(pool.mat_left)), C.c_double)
+    st.mat_right = _ptr(m.hold(_f64(pool.mat_right)), C.c_double)
     m.struct = st
     return m
 
@@ -270,6 +278,8 @@ def marshal_pool(pool: ParticlePool):
     st.psi_idx = _ptr(m.hold(_i32(pool.psi_idx)), C.c_int)
     st.psi_prior = _ptr(m.hold(_f64(pool.psi_prior)), C.c_double)
     st.bp_offset = _ptr(m.hold(_i32(pool.bp_offset)), C.c_int)
+    st.mat_left = _ptr(m.hold(_f64(pool.mat_left)), C.c_double)
+    st.mat_right = _ptr(m.hold(_f64(pool.mat_right)), C.c_double)
     m.struct = st
     return m
 

@@ -235,6 +235,7 @@ def project_numpy(data: np.ndarray, r_max: int, padding_factor: float, A_inv: np
     yp = Ai[1, 0] * x + Ai[1, 1] * y
     zp = Ai[2, 0] * x + Ai[2, 1] * y
     inside = (x * x + y * y) <= my_r_max * my_r_max
+    inside &= (xp * xp + yp * yp + zp * zp) <= (my_r_max * padding_factor) ** 2 * (1 + 1e-6)   # a scaling A_inv can leave the reference
     neg = xp < 0
     xp = np.where(neg, -xp, xp); yp = np.where(neg, -yp, yp); zp = np.where(neg, -zp, zp)
     x0 = np.floor(xp).astype(np.int64); fx = xp - x0

@@ -44,7 +44,8 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
                   pixel_size: float = 2.0, particle_diameter: Optional[float] = None,
                   nr_groups: int = 2, adaptive_fraction: float = 0.999, coarse_size: Optional[int] = None,
                   projector: Optional[Callable] = None, n_blobs: int = 40, refs_override=None,
-                  ref_seed: int = 1993, ref_dim: int = 3, psi_step: float = 6.0, do_cc: bool = False) -> Workload:
+                  ref_seed: int = 1993, ref_dim: int = 3, psi_step: float = 6.0, do_cc: bool = False,
+                  mat_left=None, mat_right=None, ref_box: Optional[int] = None) -> Workload:
     """Build a complete, seeded E-step problem.
 
     projector(vol_complex64, r_max, pf, eulers[n,9] float32, n) -> [n_img, n, n//2+1] complex: how noise-free
@@ -53,6 +54,11 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
     rng = np.random.default_rng(seed)
     current_size = current_size or ori_size
     pf = 2.0
+    # ref_box: the references live in their own box (an optics group whose box differs from the model's, same pixel size):
+    # mat_left then defaults to the scale difference of ObservationModel::applyScaleDifference
+    ref_size = ref_box or ori_size
+    if ref_box is not None and mat_left is None:
+        mat_left = np.eye(3) * (ref_box / ori_size)
     # ---- references -------------------------------------------------------------------------
     if refs_override is not None:
         refs, r_max = refs_override
@@ -64,8 +70,9 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
                 img = synth.make_phantom_2d(ori_size, n_blobs=n_blobs, seed=ref_seed + 17 * k)
                 data, r_max = synth.reference_ft_2d(img, current_size=current_size, padding_factor=pf)
             else:
-                vol = synth.make_phantom(ori_size, n_blobs=n_blobs, seed=ref_seed + 17 * k)
-                data, r_max = synth.reference_ft(vol, current_size=current_size, padding_factor=pf)
+                vol = synth.make_phantom(ref_size, n_blobs=n_blobs, seed=ref_seed + 17 * k)
+                data, r_max = synth.reference_ft(vol, current_size=min(current_size, ref_size) if ref_box is None else ref_size,
+                                                 padding_factor=pf)
             refs.append(data.astype(np.complex64))
     # ---- sampling ---------------------------------------------------------------------------
     if ref_dim == 2:
@@ -90,6 +97,10 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
     it = rng.integers(0, s.n_trans * s.n_over_trans, P)
     shifts = np.stack([s.over_trans_x[it], s.over_trans_y[it]], axis=1)
     eul = synth.inverse_euler_f32(rot, tilt, psi)
+    if mat_left is not None or mat_right is not None:          # inverse(L A R) (generateEulerMatrices, acc_helper_functions_impl.h:248-255)
+        L = np.eye(3) if mat_left is None else np.asarray(mat_left, np.float64).reshape(3, 3)
+        R = np.eye(3) if mat_right is None else np.asarray(mat_right, np.float64).reshape(3, 3)
+        eul = np.stack([np.linalg.inv(L @ e.reshape(3, 3).astype(np.float64).T @ R).reshape(9) for e in eul]).astype(np.float32)
     # ---- noise-free slices ----------------------------------------------------------------------
     n = current_size
     if projector is None:
@@ -116,12 +127,14 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
                         pixel_size=pixel_size, sigma2_noise=sigma2, scale_correction=scale, pdf_class=pdf_class,
                         pdf_direction=None if local_search else pdf_direction, data_vs_prior_class=dvp,
                         sigma2_offset=(offset_range * pixel_size / 1.5) ** 2, adaptive_fraction=adaptive_fraction,
-                        do_cc=do_cc)
+                        do_cc=do_cc, ref_max_r=int(r_max) if r_max < current_size // 2 else 0)
     # ---- pool ------------------------------------------------------------------------------------
     group = rng.integers(0, nr_groups, P).astype(np.int32)
     pool = ParticlePool(Fimg=parts.Fimg, Fimg_nomask=parts.Fimg_nomask, Fctf=parts.Fctf, group_id=group,
                         optics_group=np.zeros(P, np.int32), highres_Xi2=parts.highres_Xi2,
-                        old_offset=np.zeros((P, 2)), prior_offset=np.zeros((P, 2)))
+                        old_offset=np.zeros((P, 2)), prior_offset=np.zeros((P, 2)),
+                        mat_left=None if mat_left is None else np.asarray(mat_left, np.float64).reshape(3, 3),
+                        mat_right=None if mat_right is None else np.asarray(mat_right, np.float64).reshape(3, 3))
     if local_search:
         sig = sigma_ang if sigma_ang is not None else 2.0 * ang_step / 2.0   # 2 x oversampled step (src/ml_optimiser.cpp:2316-2326)
         doff, poff = [0], [0]

@@ -26,6 +26,12 @@ CASES = {
     # first-iteration cross-correlation criterion (--firstiter_cc): the reference's diff2_CC_coarse / diff2_CC_fine kernels
     "cc_global_k1": dict(ori_size=24, healpix_order=1, n_particles=4, nr_classes=1, seed=9, snr=0.3, do_cc=True),
     "cc_window_k1": dict(ori_size=40, current_size=28, healpix_order=1, n_particles=3, nr_classes=1, seed=10, snr=0.1, do_cc=True),
+    # MBL / MBR of the pool (cpu_kernel_make_eulers_3D<true, doL, doR>, generateEulerMatrices(..., L, R)): an anisotropic
+    # magnification matrix with a body rotation, and an optics group whose box differs from the model's (scale difference)
+    "mag_local_k1": dict(ori_size=32, healpix_order=2, n_particles=3, nr_classes=1, seed=21, snr=0.2, local_search=True,
+                         mat_left=[[1.03, 0.012, 0.0], [-0.008, 0.96, 0.0], [0.0, 0.0, 1.0]],
+                         mat_right=[[0.9553364891, -0.2955202067, 0.0], [0.2955202067, 0.9553364891, 0.0], [0.0, 0.0, 1.0]]),
+    "box_global_k1": dict(ori_size=32, ref_box=24, healpix_order=1, n_particles=4, nr_classes=1, seed=22, snr=0.3),
 }
 
 

@@ -972,6 +972,44 @@ def test_symmetrise_with_helical_symmetry_on_device(device, nr_asu, twist, rise,
     assert np.abs(ww - pw).max() > 0.1 * np.abs(pw).max()
 
 
+_MAG_L = [[1.03, 0.012, 0.0], [-0.008, 0.96, 0.0], [0.0, 0.0, 1.0]]
+_BODY_R = [[0.9553364891, -0.2955202067, 0.0], [0.2955202067, 0.9553364891, 0.0], [0.0, 0.0, 1.0]]
+
+
+@pytest.mark.parametrize("case", ["mag_local", "mag_global", "left_only_local", "right_only_global", "other_box_global", "other_box_local"])
+def test_pool_with_left_and_right_matrices(device, oracle, case):
+    """rb_particles.mat_left / mat_right (MBL / MBR: orientation matrices inverse(L A R) in the coarse pass, the fine pass and the
+    store stage; cuda_kernel_make_eulers_3D<invert, doL, doR>, generateEulerMatrices(..., L, R)): anisotropic magnification with a
+    body rotation, each matrix alone, and an optics group whose box differs from the references' (applyScaleDifference: the
+    projection leaves the reference for the outer image shells, which must then read zero)."""
+    kw = dict(ori_size=32, n_particles=12, seed=120, snr=0.2)
+    if case.endswith("local"):
+        kw.update(healpix_order=2, local_search=True)
+    else:
+        kw.update(healpix_order=1)
+    if case.startswith("mag"):
+        kw.update(mat_left=_MAG_L, mat_right=_BODY_R)
+    elif case.startswith("left_only"):
+        kw.update(mat_left=_MAG_L)
+    elif case.startswith("right_only"):
+        kw.update(mat_right=_BODY_R)
+    else:
+        kw.update(ori_size=40, ref_box=32)
+    wl = make_workload(**kw)
+    res, ores = _compare_pool(device, oracle, wl)
+    # the matrices matter: without them the pool has another likelihood
+    plain = make_workload(**kw)
+    plain.pool.mat_left = plain.pool.mat_right = None
+    other = device.expectation_some_particles(plain.pool)
+    assert np.abs(other.particles["dLL_nolog"] - res.particles["dLL_nolog"]).max() > 0.1
+    # ... and a pool with the matrices again gets the coarse matrices rebuilt
+    for k in range(len(wl.refs)):
+        device.bp_clear(k)
+    again = device.expectation_some_particles(wl.pool)
+    assert np.array_equal(again.particles["best_ihidden_over"], res.particles["best_ihidden_over"])
+    np.testing.assert_allclose(again.particles["dLL_nolog"], res.particles["dLL_nolog"], rtol=1e-6)
+
+
 @pytest.mark.parametrize("local", [True, False])
 def test_pool_128px_against_reference_kernels(device, local):
     """A mid-size pool (128-px box, several 128-orientation tiles, hundreds of K-blocks in the tensor-core kernels) against

@@ -52,7 +52,7 @@ def _check_against(d, g, rtol=5e-5):
             np.testing.assert_allclose(d[k], g[k], rtol=1e-4, err_msg=k)
 
 
-@pytest.mark.parametrize("name", ["global_k2", "local_k1", "window_k1", "cc_global_k1", "cc_window_k1"])
+@pytest.mark.parametrize("name", ["global_k2", "local_k1", "window_k1", "cc_global_k1", "cc_window_k1", "mag_local_k1", "box_global_k1"])
 def test_port_matches_reference_golden(name):
     mod = _cases()
     g = np.load(os.path.join(GOLD, f"estep_reference_{name}.npz"))
@@ -60,7 +60,7 @@ def test_port_matches_reference_golden(name):
     _check_against(d, g)
 
 
-@pytest.mark.parametrize("name", ["global_k2", "cc_global_k1"])
+@pytest.mark.parametrize("name", ["global_k2", "cc_global_k1", "mag_local_k1"])
 def test_compiled_reference_matches_golden(name):
     from oracle.bindings import have_reference
     if not have_reference():
@@ -69,6 +69,27 @@ def test_compiled_reference_matches_golden(name):
     g = np.load(os.path.join(GOLD, f"estep_reference_{name}.npz"))
     d = mod.run_case("reference", mod.CASES[name])
     _check_against(d, g, rtol=1e-6)
+
+
+def test_euler_matrices_with_left_and_right_matrices_port_matches_compiled_reference():
+    """cpu_kernel_make_eulers_3D<invert, doL, doR> (cpu_kernels/helper.cpp:744-875) for the four (doL, doR) instantiations:
+    inverse(L A R) as adjugate / determinant with L, the plain transpose without it (R alone included)."""
+    from oracle.bindings import Oracle, have_reference
+    if not have_reference():
+        pytest.skip("oracle/_ref/librefkernels.so not built (needs /root/reference)")
+    port, ref = Oracle("port"), Oracle("reference")
+    rng = np.random.default_rng(31)
+    rot, tilt, psi = rng.uniform(-180, 180, 50), rng.uniform(0, 180, 50), rng.uniform(0, 360, 50)
+    L = np.array([[1.03, 0.012, 0.0], [-0.008, 0.96, 0.0], [0.0, 0.0, 1.0]]) * 0.8
+    c, s = np.cos(0.3), np.sin(0.3)
+    R = np.array([[c, -s, 0], [s, c, 0], [0, 0, 1.0]])
+    for ml, mr in ((None, None), (L, None), (None, R), (L, R)):
+        a, b = port.make_eulers(rot, tilt, psi, ml, mr), ref.make_eulers(rot, tilt, psi, ml, mr)
+        np.testing.assert_allclose(a, b, rtol=0, atol=3e-7)
+        if ml is not None:
+            A = synth.inverse_euler_f32(rot, tilt, psi).reshape(-1, 3, 3).astype(np.float64).transpose(0, 2, 1)
+            want = np.linalg.inv(ml @ A @ (np.eye(3) if mr is None else mr)).reshape(-1, 9)
+            np.testing.assert_allclose(a, want, atol=2e-6)
 
 
 def test_cc_kernels_port_matches_compiled_reference():

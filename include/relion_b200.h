@@ -407,6 +407,9 @@ typedef struct {
 	                                The generator is counter-based on (seed, pixel): reproducible, but - like the reference's
 	                                curand and CPU generators among themselves - not the same random numbers as RELION's */
 	const double *mat_left, *mat_right; /* as in rb_particles (NULL: none) */
+	const double *noise_sigma2;  /* [nr_optics_groups][image_size/2+1] or NULL (rb_model.sigma2_noise): the spectrum the noise of
+	                                the noise-filled mask is drawn from — remapped_sigma2_noise of acc_ml_optimiser_impl.h:374-384, which
+	                                for an optics group with its own box / pixel size is NOT the gather rb_model.sigma2_noise holds */
 } rb_raw_particles;
 /* power_img: [P][n/2+1] spectrum of the masked full-size transform (op.power_img, used by the host for sigma2_noise
  * beyond the current size), may be NULL. */

@@ -39,10 +39,12 @@
 
 #include "relion_b200.h"
 
+#include <algorithm>
 #include <cmath>
 #include <complex>
 #include <cstddef>
 #include <cstring>
+#include <limits>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -208,7 +210,9 @@ public:
 	int device_id;
 	int rank_shared_count;
 
-	MlDeviceBundle(MlOptimiser *baseMLOptimiser) : baseMLO(baseMLOptimiser), ctx(NULL), device_id(-1), rank_shared_count(1) {}
+	int geometry_og;                               // the optics group whose image geometry the library currently holds (-1: none)
+
+	MlDeviceBundle(MlOptimiser *baseMLOptimiser) : baseMLO(baseMLOptimiser), ctx(NULL), device_id(-1), rank_shared_count(1), geometry_og(-1) {}
 
 	/* the reference only records the id and calls cudaSetDevice later; the context is created here so that a missing
 	 * device fails where the reference's first HANDLE_ERROR(cudaSetDevice) would */
@@ -233,23 +237,47 @@ public:
 		return bytes * (size_t) (shares < 1 ? 1 : shares);
 	}
 
-	/* cuda_ml_optimiser.cu:85-152: model + sampling tables, then per class projector and back-projector */
-	void setupFixedSizedObjects()
+	/* Optics groups a and b share one image geometry (box, pixel size, current and coarse window: src/ml_optimiser.cpp:5735-5777) */
+	bool sameGeometry(int a, int b)
 	{
-		if (!ctx) RB_REPORT_ERROR("MlDeviceBundle::setupFixedSizedObjects: setDevice() has not been called");
+		MlOptimiser &o = *baseMLO;
+		return o.image_full_size[a] == o.image_full_size[b] && o.image_current_size[a] == o.image_current_size[b] &&
+		       o.image_coarse_size[a] == o.image_coarse_size[b] &&
+		       std::fabs(o.mydata.getOpticsPixelSize(a) - o.mydata.getOpticsPixelSize(b)) <= 1e-6 * o.mydata.getOpticsPixelSize(b);
+	}
+
+	/* (image box * image pixel) / (model box * model pixel) of optics group og, the factor of applyScaleDifference */
+	RFLOAT remapSizes(int og)
+	{
+		MlOptimiser &o = *baseMLO;
+		return (o.mydata.getOpticsPixelSize(og) * o.mydata.getOpticsImageSize(og)) / (o.mymodel.pixel_size * o.mymodel.ori_size);
+	}
+
+	/* Model and sampling tables in the image geometry of optics group og (include/relion_b200.h "Optics groups"): its box is the
+	 * library's ori_size, its image_current_size / image_coarse_size the windows, its pixel size converts the translations
+	 * (getTranslationsInPixel(..., my_pixel_size), acc_ml_optimiser_impl.h:1203, 1511) and every sigma2_noise spectrum is read at
+	 * ROUND(remap * ires) (src/ml_optimiser.cpp:6840, 6875).  A no-op when the loaded geometry already is that of og. */
+	void setGeometry(int og)
+	{
+		if (!ctx) RB_REPORT_ERROR("MlDeviceBundle::setGeometry: setDevice() has not been called");
+		if (geometry_og >= 0 && sameGeometry(og, geometry_og)) return;
 		MlOptimiser &o = *baseMLO;
 		MlModel &m = o.mymodel;
-		if (m.nr_bodies != 1) RB_REPORT_ERROR("relion_b200: multi-body refinement is not covered");
-		const int K = m.nr_classes, nog = m.nr_optics_groups, nshell = m.ori_size / 2 + 1;
-		for (int g = 0; g < nog; g++)
-			if (o.image_full_size[g] != m.ori_size || o.image_current_size[g] != o.image_current_size[0] || o.image_coarse_size[g] != o.image_coarse_size[0] ||
-			    std::fabs(o.mydata.getOpticsPixelSize(g) - m.pixel_size) > 1e-6 * m.pixel_size)
-				RB_REPORT_ERROR("relion_b200: optics groups with a box or pixel size different from the model's are not covered");
+		const int K = m.nr_classes, nog = m.nr_optics_groups;
+		const int full = o.image_full_size[og], nshell = full / 2 + 1;
+		const RFLOAT my_pixel_size = o.mydata.getOpticsPixelSize(og);
 
 		// ---- model / flags (data contract of SURVEY.md 8b) ----
-		h_sigma2.assign((size_t) nog * nshell, 1.);
+		h_sigma2.assign((size_t) nog * nshell, std::numeric_limits<double>::infinity());      // 1 / inf = 0: Minvsigma2 stays zero (:6877)
 		for (int g = 0; g < nog; g++)
-			for (int i = 0; i < nshell && i < (int) XSIZE(m.sigma2_noise[g]); i++) h_sigma2[(size_t) g * nshell + i] = DIRECT_A1D_ELEM(m.sigma2_noise[g], i);
+		{
+			const RFLOAT remap = 1. / remapSizes(g);                                             // (ori * pixel) / (my_image_size * my_pixel_size), :6840
+			for (int i = 0; i < nshell; i++)
+			{
+				const int ir = ROUND(remap * i);
+				if (ir < (int) XSIZE(m.sigma2_noise[g])) h_sigma2[(size_t) g * nshell + i] = DIRECT_A1D_ELEM(m.sigma2_noise[g], ir);
+			}
+		}
 		h_scale.assign(m.scale_correction.begin(), m.scale_correction.end());
 		if (h_scale.empty()) h_scale.assign(m.nr_groups < 1 ? 1 : m.nr_groups, 1.);
 		h_pdf_class.assign(m.pdf_class.begin(), m.pdf_class.end());
@@ -267,8 +295,14 @@ public:
 		}
 		rb_model rm;
 		memset(&rm, 0, sizeof(rm));
-		rm.nr_classes = K; rm.ori_size = m.ori_size; rm.coarse_size = o.image_coarse_size[0]; rm.current_size = o.image_current_size[0];
-		rm.pixel_size = m.pixel_size;
+		rm.nr_classes = K; rm.ori_size = full; rm.coarse_size = o.image_coarse_size[og]; rm.current_size = o.image_current_size[og];
+		rm.pixel_size = my_pixel_size;
+		// references that end inside this group's window (its box is bigger than the model's): the fine-pass row rule
+		{
+			int ref_r = m.PPref.empty() ? 0 : m.PPref[0].r_max;
+			for (int k = 1; k < K && k < (int) m.PPref.size(); k++) ref_r = std::min(ref_r, (int) m.PPref[k].r_max);
+			rm.ref_max_r = (ref_r > 0 && ref_r < rm.current_size / 2) ? ref_r : 0;
+		}
 		rm.nr_optics_groups = nog; rm.sigma2_noise = h_sigma2.data();
 		rm.nr_groups = (int) h_scale.size(); rm.scale_correction = h_scale.data();
 		rm.pdf_class = h_pdf_class.data(); rm.pdf_direction = h_pdf_dir.empty() ? NULL : h_pdf_dir.data(); rm.data_vs_prior_class = h_dvp.data();
@@ -306,9 +340,9 @@ public:
 		s_tx.assign(n_trans, 0.); s_ty = s_tx; s_otx.assign((size_t) n_trans * not_, 0.); s_oty = s_otx;
 		for (int t = 0; t < n_trans; t++)
 		{
-			o.sampling.getTranslationsInPixel(t, 0, m.pixel_size, a, b, c, false);
+			o.sampling.getTranslationsInPixel(t, 0, my_pixel_size, a, b, c, false);
 			s_tx[t] = a[0]; s_ty[t] = b[0];
-			o.sampling.getTranslationsInPixel(t, ov, m.pixel_size, a, b, c, false);
+			o.sampling.getTranslationsInPixel(t, ov, my_pixel_size, a, b, c, false);
 			for (int i = 0; i < not_; i++) { s_otx[(size_t) t * not_ + i] = a[i]; s_oty[(size_t) t * not_ + i] = b[i]; }
 		}
 		rb_sampling rs;
@@ -319,6 +353,19 @@ public:
 		rs.n_over_trans = not_; rs.over_trans_x = s_otx.data(); rs.over_trans_y = s_oty.data();
 		RB_TRY(rb_set_sampling(ctx, &rs));
 		if (rm.pdf_direction) RB_TRY(rb_set_pdf_direction(ctx, rm.pdf_direction));
+		geometry_og = og;
+	}
+
+	/* cuda_ml_optimiser.cu:85-152: model + sampling tables, then per class projector and back-projector */
+	void setupFixedSizedObjects()
+	{
+		if (!ctx) RB_REPORT_ERROR("MlDeviceBundle::setupFixedSizedObjects: setDevice() has not been called");
+		MlOptimiser &o = *baseMLO;
+		MlModel &m = o.mymodel;
+		if (m.nr_bodies != 1) RB_REPORT_ERROR("relion_b200: multi-body refinement is not covered");
+		const int K = m.nr_classes;
+		geometry_og = -1;
+		setGeometry(0);
 
 		// ---- projectors / back-projectors (cuda_ml_optimiser.cu:98-152) ----
 		// gradient refinement with pseudo half-sets: wsum_model.BPref holds 2 K accumulators, particle part_id goes into
@@ -408,12 +455,36 @@ public:
 	{
 		if (thread_id != 0) return;
 		MlOptimiser &o = *baseMLO;
-		MlModel &m = o.mymodel;
 		const long int first = o.exp_my_first_part_id, last = o.exp_my_last_part_id;
+		// one device call per run of particles that share an image geometry (src/ml_optimiser.cpp:6802-6821: every particle is
+		// processed at its optics group's sizes; exp_imagedata itself holds one common box, :10312-10323)
+		long int run_first = first;
+		while (run_first <= last)
+		{
+			const int og0 = o.mydata.getOpticsGroup(run_first);
+			long int run_last = run_first;
+			while (run_last + 1 <= last && bundle->sameGeometry(o.mydata.getOpticsGroup(run_last + 1), og0)) run_last++;
+			bundle->setGeometry(og0);
+			expectationRun(run_first, run_last);
+			run_first = run_last + 1;
+		}
+	}
+
+private:
+	/* particles run_first .. run_last of the pool (exp_metadata / exp_imagedata rows run_first - exp_my_first_part_id ...), all of
+	 * the image geometry the bundle currently holds */
+	void expectationRun(long int first, long int last)
+	{
+		MlOptimiser &o = *baseMLO;
+		MlModel &m = o.mymodel;
+		const int row0 = (int) (first - o.exp_my_first_part_id);
 		const int P = (int) (last - first + 1);
 		if (P <= 0) return;
-		const int n = m.ori_size, nshell = n / 2 + 1, K = m.nr_classes;
-		const int cur = o.image_current_size[0];
+		const int og0 = o.mydata.getOpticsGroup(first);
+		const int n = o.image_full_size[og0], nshell = n / 2 + 1, K = m.nr_classes;
+		const int cur = o.image_current_size[og0];
+		const RFLOAT my_pixel_size = o.mydata.getOpticsPixelSize(og0);
+		if ((int) YSIZE(o.exp_imagedata) != n) RB_REPORT_ERROR("relion_b200: exp_imagedata does not have the box size of the particles' optics group");
 		const bool use_priors = m.orientational_prior_mode != NOPRIOR && !(o.do_skip_align || o.do_skip_rotate);
 		const bool do_cc = (o.iter == 1 && o.do_firstiter_cc) || o.do_always_cc;
 		const int nog = m.nr_optics_groups;
@@ -431,19 +502,19 @@ public:
 		{
 			const long int part_id = first + p;                       // exp_metadata row p: one image per particle
 			if (o.mydata.numberOfImagesInParticle(part_id) != 1) RB_REPORT_ERROR("relion_b200: particles with several images (tomo) are not covered");
-			for (size_t i = 0; i < (size_t) n * n; i++) images[(size_t) p * n * n + i] = (float) DIRECT_MULTIDIM_ELEM(o.exp_imagedata, (size_t) p * n * n + i);
+			for (size_t i = 0; i < (size_t) n * n; i++) images[(size_t) p * n * n + i] = (float) DIRECT_MULTIDIM_ELEM(o.exp_imagedata, (size_t) (row0 + p) * n * n + i);
 			group_id[p] = (int) o.mydata.getGroupId(part_id); optics_group[p] = o.mydata.getOpticsGroup(part_id);
-			const RFLOAT normcorr = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_NORM);
+			const RFLOAT normcorr = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_NORM);
 			norm_factor[p] = o.do_norm_correction ? m.avg_norm_correction / normcorr : 1.;                                    // :421
-			old_offset[2 * p] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_XOFF); old_offset[2 * p + 1] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_YOFF);
+			old_offset[2 * p] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_XOFF); old_offset[2 * p + 1] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_YOFF);
 			// op.prior (:130-160): the offset prior, 999 = none -> zero
-			RFLOAT px = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_XOFF_PRIOR), py = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_YOFF_PRIOR);
+			RFLOAT px = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_XOFF_PRIOR), py = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_YOFF_PRIOR);
 			if (px > 998.99 && px < 999.01) px = 0.;
 			if (py > 998.99 && py < 999.01) py = 0.;
 			prior_offset[2 * p] = px; prior_offset[2 * p + 1] = py;
-			defU[p] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_CTF_DEFOCUS_U); defV[p] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_CTF_DEFOCUS_V);
-			defA[p] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_CTF_DEFOCUS_ANGLE); bfac[p] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_CTF_BFACTOR);
-			kfac[p] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_CTF_KFACTOR); phs[p] = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_CTF_PHASE_SHIFT);
+			defU[p] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_CTF_DEFOCUS_U); defV[p] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_CTF_DEFOCUS_V);
+			defA[p] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_CTF_DEFOCUS_ANGLE); bfac[p] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_CTF_BFACTOR);
+			kfac[p] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_CTF_KFACTOR); phs[p] = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_CTF_PHASE_SHIFT);
 			if (o.do_ctf_correction)
 			{
 				CTF ctf;                                                                                                         // :822-840
@@ -453,14 +524,14 @@ public:
 			if (use_priors)
 			{
 				// :135-172: prior angles, 999 = none -> the current angles; local searches always centre on the current angles
-				RFLOAT prior_rot = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_ROT_PRIOR), prior_tilt = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_TILT_PRIOR),
-				       prior_psi = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_PSI_PRIOR);
+				RFLOAT prior_rot = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_ROT_PRIOR), prior_tilt = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_TILT_PRIOR),
+				       prior_psi = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_PSI_PRIOR);
 				const bool local_auto = o.do_auto_refine && o.sampling.healpix_order >= o.autosampling_hporder_local_searches;
 				const bool local_class = !o.do_auto_refine && m.orientational_prior_mode == PRIOR_ROTTILT_PSI && m.sigma2_rot > 0. && m.sigma2_tilt > 0. && m.sigma2_psi > 0.;
 				const bool local = local_auto || local_class;
-				if ((prior_rot > 998.99 && prior_rot < 999.01) || local) prior_rot = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_ROT);
-				if ((prior_tilt > 998.99 && prior_tilt < 999.01) || local) prior_tilt = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_TILT);
-				if ((prior_psi > 998.99 && prior_psi < 999.01) || local) prior_psi = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_PSI);
+				if ((prior_rot > 998.99 && prior_rot < 999.01) || local) prior_rot = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_ROT);
+				if ((prior_tilt > 998.99 && prior_tilt < 999.01) || local) prior_tilt = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_TILT);
+				if ((prior_psi > 998.99 && prior_psi < 999.01) || local) prior_psi = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_PSI);
 				o.sampling.selectOrientationsWithNonZeroPriorProbability(prior_rot, prior_tilt, prior_psi, sqrt(m.sigma2_rot), sqrt(m.sigma2_tilt), sqrt(m.sigma2_psi),
 				                                                         ptr_dir[p], pri_dir[p], ptr_psi[p], pri_psi[p]);
 				if (ptr_dir[p].empty() || ptr_psi[p].empty()) RB_REPORT_ERROR("relion_b200: zero orientations fall within the local angular search");   // :176-183
@@ -516,7 +587,36 @@ public:
 		}
 		raw.ctf_defU = defU.data(); raw.ctf_defV = defV.data(); raw.ctf_defAngle = defA.data(); raw.ctf_Bfac = bfac.data(); raw.ctf_scale = kfac.data();
 		raw.ctf_phase_shift = phs.data(); raw.og_kV = og_kV.data(); raw.og_Cs = og_Cs.data(); raw.og_Q0 = og_Q0.data();
-		raw.mask_radius = o.particle_diameter / (2. * m.pixel_size);                                                           // :556
+		raw.mask_radius = o.particle_diameter / (2. * my_pixel_size);                                                          // :550-552
+		// MBL: anisotropic magnification and the scale difference between this optics group and the model (:1098-1103)
+		double mat_left[9];
+		{
+			Matrix2D<RFLOAT> mag;
+			mag.initIdentity(3);
+			mag = o.mydata.obsModel.applyAnisoMag(mag, og0);
+			mag = o.mydata.obsModel.applyScaleDifference(mag, og0, m.ori_size, m.pixel_size);
+			if (!mag.isIdentity())
+			{
+				for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) mat_left[3 * i + j] = mag(i, j);
+				raw.mat_left = mat_left;
+			}
+		}
+		// the spectrum of the noise-filled mask: mymodel.sigma2_noise scattered onto this box (:374-384)
+		std::vector<double> noise_sigma2;
+		if (!o.do_zero_mask)
+		{
+			noise_sigma2.assign((size_t) nog * nshell, 0.);
+			for (int g = 0; g < nog; g++)
+			{
+				const RFLOAT remap = bundle->remapSizes(g);
+				for (int i = 0; i < (int) XSIZE(m.sigma2_noise[g]); i++)
+				{
+					const int ir = ROUND(remap * i);
+					if (ir < nshell) noise_sigma2[(size_t) g * nshell + ir] = DIRECT_A1D_ELEM(m.sigma2_noise[g], i);
+				}
+			}
+			raw.noise_sigma2 = noise_sigma2.data();
+		}
 		raw.width_mask_edge = (double) o.width_mask_edge;
 		if (use_priors)
 		{
@@ -540,11 +640,16 @@ public:
 		// ---- host bookkeeping of storeWeightedSums, in fp64 (acc_ml_optimiser_impl.h:2858-2931, 3466-3656) ----
 		std::vector<double> logsigma2(nog, 0.);
 		for (int g = 0; g < nog; g++)                                                                                          // :3556-3566
+		{
+			if (!bundle->sameGeometry(g, og0)) continue;
+			const RFLOAT remap_g = 1. / bundle->remapSizes(g);                                                                  // :3559
 			FOR_ALL_DIRECT_ELEMENTS_IN_MULTIDIMARRAY(o.Mresol_fine[g])
 			{
 				const int ires = DIRECT_MULTIDIM_ELEM(o.Mresol_fine[g], n);
-				if (ires > 0 && ires < (int) XSIZE(m.sigma2_noise[g])) logsigma2[g] += log(2. * PI * DIRECT_A1D_ELEM(m.sigma2_noise[g], ires));
+				const int ires_remapped = ROUND(remap_g * ires);
+				if (ires > 0 && ires_remapped < (int) XSIZE(m.sigma2_noise[g])) logsigma2[g] += log(2. * PI * DIRECT_A1D_ELEM(m.sigma2_noise[g], ires_remapped));
 			}
+		}
 		std::vector<RFLOAT> rot, tilt, psi, tx, ty, tz;
 		RFLOAT thr_avg_norm_correction = 0., thr_sum_dLL = 0., thr_sum_Pmax = 0., thr_wsum_sigma2_offset = 0.;
 		MlWsumModel &w = o.wsum_model;
@@ -554,16 +659,16 @@ public:
 			const int og = optics_group[p], ig = group_id[p];
 			// metadata row (:2858-2931)
 			o.sampling.getOrientations(r.best_idir, r.best_ipsi, o.adaptive_oversampling, rot, tilt, psi, ptr_dir[p], pri_dir[p], ptr_psi[p], pri_psi[p]);
-			o.sampling.getTranslationsInPixel(r.best_itrans, o.adaptive_oversampling, m.pixel_size, tx, ty, tz, false);
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_ROT) = rot[r.best_iover_rot];
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_TILT) = tilt[r.best_iover_rot];
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_PSI) = psi[r.best_iover_rot];
+			o.sampling.getTranslationsInPixel(r.best_itrans, o.adaptive_oversampling, my_pixel_size, tx, ty, tz, false);                   // :2696
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_ROT) = rot[r.best_iover_rot];
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_TILT) = tilt[r.best_iover_rot];
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_PSI) = psi[r.best_iover_rot];
 			const RFLOAT ox = ROUND(old_offset[2 * p]), oy = ROUND(old_offset[2 * p + 1]);                                      // op.old_offset is the ROUNDED one (:216)
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_XOFF) = ox + tx[r.best_iover_trans];
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_YOFF) = oy + ty[r.best_iover_trans];
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_CLASS) = (RFLOAT) r.best_class + 1;
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_PMAX) = (RFLOAT) r.pmax;
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_NR_SIGN) = (RFLOAT) r.nr_significant_coarse;                            // :2319-2320
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_XOFF) = ox + tx[r.best_iover_trans];
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_YOFF) = oy + ty[r.best_iover_trans];
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_CLASS) = (RFLOAT) r.best_class + 1;
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_PMAX) = (RFLOAT) r.pmax;
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_NR_SIGN) = (RFLOAT) r.nr_significant_coarse;                            // :2319-2320
 			if (o.do_skip_maximization) continue;
 			// sigma2_noise and the norm correction extended beyond the current size with the image's own power spectrum (:3505-3515)
 			RFLOAT exp_wsum_norm_correction = r.wsum_norm_correction;
@@ -572,16 +677,16 @@ public:
 			for (int i = cur / 2 + 1; i < nshell; i++) { thr_sigma2[i] += (RFLOAT) power_img[(size_t) p * nshell + i]; exp_wsum_norm_correction += (RFLOAT) power_img[(size_t) p * nshell + i]; }
 			if (o.do_norm_correction)                                                                                           // :3519-3538
 			{
-				RFLOAT old_norm_correction = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_NORM) / m.avg_norm_correction;
+				RFLOAT old_norm_correction = DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_NORM) / m.avg_norm_correction;
 				const RFLOAT normcorr = old_norm_correction * sqrt(exp_wsum_norm_correction * 2.);
 				thr_avg_norm_correction += normcorr;
-				DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_NORM) = normcorr;
+				DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_NORM) = normcorr;
 			}
 			const RFLOAT dLL = do_cc ? r.dLL_nolog : r.dLL_nolog - logsigma2[og];                                              // :3568-3574
-			DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_DLL) = dLL;
+			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_DLL) = dLL;
 			thr_sum_dLL += dLL; thr_sum_Pmax += (RFLOAT) r.pmax;
 			// the critical section (:3585-3656); this thread is the only writer
-			const RFLOAT remap = (m.ori_size * m.pixel_size) / (o.mydata.getOpticsImageSize(og) * o.mydata.getOpticsPixelSize(og));
+			const RFLOAT remap = 1. / bundle->remapSizes(og);                                                                   // :3617-3618
 			for (int i = 0; i < nshell; i++)
 			{
 				const int i_resam = ROUND(i * remap);

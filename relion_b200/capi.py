@@ -88,6 +88,7 @@ class rb_raw_particles(C.Structure):
         ("og_fourier_factor", c_float_p),
         ("noise_seed", C.POINTER(C.c_int64)),
         ("mat_left", c_double_p), ("mat_right", c_double_p),
+        ("noise_sigma2", c_double_p),
     ]
 
 

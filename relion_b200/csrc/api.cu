@@ -673,7 +673,9 @@ static inline int iround(double x) { return (int) (x > 0 ? floor(x + 0.5) : -flo
 // but the cross-correlation kernels weight every pixel with 1 / sqrtXi2^2 (buildCorrImage), so it contributes there.
 // dead > 0: drop the rows the reference's fine / wavg kernels skip when the references end inside the window
 // (maxR = dead < n / 2: rows |ip| > maxR keep only their pixel jp == maxR, cpu_kernels/diff2.h:347-355)
-static void make_pixlist(int n, std::vector<uint32_t> &out, bool full_x0 = false, int dead = 0)
+// all_pixels: the whole window, corners included (shell index clamped) — the cross-correlation kernels weight EVERY pixel, and a
+// contracting MBL brings corner pixels inside the reference (elsewhere they project to zero and contribute nothing)
+static void make_pixlist(int n, std::vector<uint32_t> &out, bool full_x0 = false, int dead = 0, bool all_pixels = false)
 {
 	const int xs = n / 2 + 1;
 	out.clear();
@@ -684,13 +686,13 @@ static void make_pixlist(int n, std::vector<uint32_t> &out, bool full_x0 = false
 		{
 			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
 			if (dead > 0 && abs(ip) > dead && jp != dead) continue;
-			if (ires < xs && (full_x0 || !(jp == 0 && ip < 0))) out.push_back(rb_pack_pix(jp, ip, ires));
+			if ((ires < xs || all_pixels) && (full_x0 || !(jp == 0 && ip < 0))) out.push_back(rb_pack_pix(jp, ip, std::min(ires, xs - 1)));
 		}
 	}
 }
 
 // the same pixel set as row runs + a dense shell map
-static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_map, bool full_x0 = false, int dead = 0)
+static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_map, bool full_x0 = false, int dead = 0, bool all_pixels = false)
 {
 	const int xs = n / 2 + 1;
 	rows.clear();
@@ -703,9 +705,9 @@ static void make_rows(int n, std::vector<RbRow> &rows, std::vector<short> &ires_
 		{
 			const int ires = iround(sqrt((double) (ip * ip + jp * jp)));
 			if (dead > 0 && abs(ip) > dead && jp != dead) continue;
-			if (ires < xs && (full_x0 || !(jp == 0 && ip < 0)))
+			if ((ires < xs || all_pixels) && (full_x0 || !(jp == 0 && ip < 0)))
 			{
-				ires_map[(size_t) iy * xs + jp] = (short) ires;
+				ires_map[(size_t) iy * xs + jp] = (short) std::min(ires, xs - 1);
 				if (lo < 0) lo = jp;
 				hi = jp;
 			}
@@ -759,11 +761,12 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	RB_CHECK(upload(ctx, ctx->m_pix_f, pf.data(), pf.size() * 4));
 	// --no_map: Minvsigma2 is one on EVERY pixel in the back-projection (acc_ml_optimiser_impl.h:3110-3115), so the redundant
 	// half of the x = 0 column, which Mresol excludes, is back-projected as well: the store stage then walks the full list
+	// ... and the reference's back-projection kernel has no row rule (BP.h:559-565): with dead rows the store list keeps them
 	size_t n_store = pf.size();
-	if (!m->do_map)
+	if (!m->do_map || dead > 0)
 	{
 		std::vector<uint32_t> pfull;
-		make_pixlist(m->current_size, pfull, true, dead);
+		make_pixlist(m->current_size, pfull, !m->do_map, 0);
 		n_store = pfull.size();
 		RB_CHECK(upload(ctx, ctx->m_cc[5], pfull.data(), pfull.size() * 4));
 	}
@@ -771,8 +774,10 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	std::vector<uint32_t> prs;
 	{
 		std::vector<uint32_t> all;
-		make_pixlist(m->current_size, all, !m->do_map, dead);
-		auto in_d2 = [](uint32_t v) { return !(rb_pix_x(v) == 0 && rb_pix_y(v) < 0); };
+		make_pixlist(m->current_size, all, !m->do_map, 0);
+		auto in_d2 = [dead](uint32_t v) {
+			return !(rb_pix_x(v) == 0 && rb_pix_y(v) < 0) && !(dead > 0 && abs(rb_pix_y(v)) > dead && rb_pix_x(v) != dead);
+		};
 		auto radial = [](uint32_t a, uint32_t b) {
 			const int xa = rb_pix_x(a), ya = rb_pix_y(a), xb = rb_pix_x(b), yb = rb_pix_y(b);
 			const int ra = xa * xa + ya * ya, rb2 = xb * xb + yb * yb;
@@ -826,12 +831,13 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	d.Npc = m->coarse_size * (m->coarse_size / 2 + 1); d.Npf = m->current_size * (m->current_size / 2 + 1);
 	d.nvc = (int) pc.size(); d.nvf = (int) pf.size();
 	d.pix_c = ctx->m_pix_c.as<uint32_t>(); d.pix_f = ctx->m_pix_f.as<uint32_t>();
-	d.pix_store = m->do_map ? d.pix_f : ctx->m_cc[5].as<uint32_t>(); d.nv_store = (int) n_store;
+	d.pix_store = (m->do_map && dead == 0) ? d.pix_f : ctx->m_cc[5].as<uint32_t>(); d.nv_store = (int) n_store;
+	d.dead_maxR = dead;
 	d.nrows_c = (int) rc.size(); d.nrows_f = (int) rf.size();
 	d.rows_c = ctx->m_rows_c.as<RbRow>(); d.rows_f = ctx->m_rows_f.as<RbRow>();
 	d.ires_c = ctx->m_ires_c.as<short>(); d.ires_f = ctx->m_ires_f.as<short>();
 	// pixel sets of the two diff2 passes: the Mresol sets above, or with the cross-correlation criterion every pixel
-	// inside the window's circle
+	// of the window (corners included: they project to zero unless a contracting MBL brings them inside the reference)
 	d.d2_nvc = d.nvc; d.d2_pix_c = d.pix_c;
 	d.d2_nrows_c = d.nrows_c; d.d2_rows_c = d.rows_c; d.d2_ires_c = d.ires_c;
 	d.d2_nrows_f = d.nrows_f; d.d2_rows_f = d.rows_f; d.d2_ires_f = d.ires_f;
@@ -840,8 +846,10 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 		std::vector<uint32_t> pcc;
 		std::vector<RbRow> rcc, rfc;
 		std::vector<short> icc, ifc;
-		make_pixlist(m->coarse_size, pcc, true);
-		make_rows(m->coarse_size, rcc, icc, true); make_rows(m->current_size, rfc, ifc, true, dead);
+		// unlike the Gaussian coarse kernel, the cross-correlation coarse kernel has the row rule too (diff2.h:657-666)
+		const int dead_c = (m->ref_max_r > 0 && m->ref_max_r < m->coarse_size / 2) ? m->ref_max_r : 0;
+		make_pixlist(m->coarse_size, pcc, true, dead_c, true);
+		make_rows(m->coarse_size, rcc, icc, true, dead_c, true); make_rows(m->current_size, rfc, ifc, true, dead, true);
 		RB_CHECK(upload(ctx, ctx->m_cc[0], pcc.data(), pcc.size() * 4));
 		RB_CHECK(upload(ctx, ctx->m_cc[1], rcc.data(), rcc.size() * sizeof(RbRow)));
 		RB_CHECK(upload(ctx, ctx->m_cc[2], icc.data(), icc.size() * sizeof(short)));
@@ -1131,7 +1139,8 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 	{
 		const int nshell = ctx->d_model.nshell, nog = ctx->h_model.nr_optics_groups;
 		spec.resize((size_t) nog * nshell);
-		for (size_t i = 0; i < spec.size(); i++) spec[i] = (float) sqrt(ctx->h_model.sigma2_fudge * ctx->h_sigma2_noise[i]);
+		const double *s2 = raw->noise_sigma2 ? raw->noise_sigma2 : ctx->h_sigma2_noise.data();
+		for (size_t i = 0; i < spec.size(); i++) spec[i] = (float) sqrt(ctx->h_model.sigma2_fudge * s2[i]);
 		DevBuf &bSeed = ctx->prep_raw[slot][4], &bSpec = ctx->prep_raw[slot][5];
 		RB_CHECK(bSeed.ensure((size_t) P * 8)); RB_CHECK(bSpec.ensure(spec.size() * 4));
 		RB_CUDA(cudaMemcpyAsync(bSeed.p, raw->noise_seed, (size_t) P * 8, cudaMemcpyHostToDevice, cs));

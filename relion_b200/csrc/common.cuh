@@ -188,6 +188,8 @@ struct RbModelDev {
 	int nvc, nvf;            // valid-pixel list lengths
 	const uint32_t *pix_c, *pix_f;
 	const uint32_t *pix_store; int nv_store;   // pixel list of the store stage: pix_f, or with --no_map the full x = 0 column too
+	int dead_maxR;                             // rb_model.ref_max_r in effect (0: none): rows |y| > dead_maxR keep x == dead_maxR only in
+	                                           // the diff2 / wavg sums; the store list still holds them for the back-projection
 	// band-major kernels (kernels_band.cu): the store-stage pixel set sorted by |r| (ties by angle).  Entries [0, nv_rs_d2) are
 	// the diff2 set (Mresol >= 0), [nv_rs_d2, nv_rs_st) the extra x = 0 half column of --no_map; nv_rs_pad = row stride of the
 	// band-ordered arrays (slices, particle images)

@@ -725,7 +725,9 @@ k_store_band(BandStoreArgs A, RbModelDev M)
 		int x = 0, y = 0, ires = 0;
 		if (have) { const uint32_t pkx = __ldg(A.pix + ip); x = rb_pix_x(pkx); y = rb_pix_y(pkx); ires = rb_pix_ires(pkx); }
 		// (x = 0, y < 0) is only in the list with --no_map: Mresol excludes it from the shell sums (:3466-3494)
-		const bool in_mresol = have && !(x == 0 && y < 0);
+		// ... and so are the rows the reference's wavg kernel skips when the references end inside the window (wavg.h:74-82); its
+		// back-projection kernel still walks them
+		const bool in_mresol = have && !(x == 0 && y < 0) && !(M.dead_maxR > 0 && abs(y) > M.dead_maxR && x != M.dead_maxR);
 		bool circle_ok = true;
 		if (M.bp_circle_bound && !M.do_grad) { const int xmax = (int) sqrtf((float) (half * half - y * y)); circle_ok = x < xmax; }   // BP.h:565 (not in the SGD kernel, BP.h:757-1047)
 		const float fxp = (float) x, fyp = (float) y;

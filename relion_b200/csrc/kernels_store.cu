@@ -328,7 +328,8 @@ k_store(StoreArgs A, RbModelDev M)
 						const float aa = W * refn;
 						const float wd = fmaxf(W * (refn + Xn) - 2.f * xa, 0.f);
 						// (x = 0, y < 0) is only in the list with --no_map: Mresol excludes it from the shell sums (:3466-3494)
-						const bool in_mresol = !(x == 0 && y < 0);
+						// the rows beyond references that end inside the window: skipped by wavg (wavg.h:74-82), walked by the back-projection
+						const bool in_mresol = !(x == 0 && y < 0) && !(M.dead_maxR > 0 && abs(y) > M.dead_maxR && x != M.dead_maxR);
 						if (in_mresol) atomicAdd(&s_shell[ires], wd);
 						if (in_mresol && dvp[ires] && M.do_scale_correction) { aXA += (double) xa; aAA += (double) aa; }   // :3473-3479
 						// back-projection

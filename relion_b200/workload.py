@@ -54,11 +54,12 @@ def make_workload(name: str = "tiny", *, ori_size: int = 32, current_size: Optio
     rng = np.random.default_rng(seed)
     current_size = current_size or ori_size
     pf = 2.0
-    # ref_box: the references live in their own box (an optics group whose box differs from the model's, same pixel size):
-    # mat_left then defaults to the scale difference of ObservationModel::applyScaleDifference
+    # ref_box: the references live in their own box (an optics group whose box `ori_size` differs from the model's `ref_box`, same
+    # pixel size): mat_left then defaults to ObservationModel::applyScaleDifference(I) = (image box * pixel) / (model box * pixel),
+    # so that image pixel i reads the reference at i * ref_box / ori_size
     ref_size = ref_box or ori_size
     if ref_box is not None and mat_left is None:
-        mat_left = np.eye(3) * (ref_box / ori_size)
+        mat_left = np.eye(3) * (ori_size / ref_box)
     # ---- references -------------------------------------------------------------------------
     if refs_override is not None:
         refs, r_max = refs_override
@@ -176,6 +177,7 @@ def raw_pool_from(wl: Workload, seed: int = 0, mask_radius: Optional[float] = No
                           norm_factor=rng.uniform(0.9, 1.1, P),
                           mask_radius=(0.42 * wl.model.ori_size if mask_radius is None else mask_radius), width_mask_edge=width_mask_edge,
                           dir_off=wl.pool.dir_off, dir_idx=wl.pool.dir_idx, dir_prior=wl.pool.dir_prior,
-                          psi_off=wl.pool.psi_off, psi_idx=wl.pool.psi_idx, psi_prior=wl.pool.psi_prior)
+                          psi_off=wl.pool.psi_off, psi_idx=wl.pool.psi_idx, psi_prior=wl.pool.psi_prior,
+                          mat_left=wl.pool.mat_left, mat_right=wl.pool.mat_right)
     return raw
 

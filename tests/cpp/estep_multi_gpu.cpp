@@ -59,7 +59,10 @@ static double scalar(const std::map<std::string, Arr> &d, const char *k) { retur
 static void build_optimiser(MlOptimiser &o, const std::map<std::string, Arr> &d)
 {
 	MlModel &m = o.mymodel;
-	const int K = (int) scalar(d, "nr_classes"), ori = (int) scalar(d, "ori_size"), nshell = ori / 2 + 1;
+	// "ori_size" is the box of the images (one optics group); "model_ori_size", when present, the model's own box: an optics
+	// group whose geometry differs from the model's (src/ml_optimiser.cpp:5735-5777), same pixel size
+	const int K = (int) scalar(d, "nr_classes"), img_size = (int) scalar(d, "ori_size");
+	const int ori = d.count("model_ori_size") ? (int) scalar(d, "model_ori_size") : img_size, nshell = ori / 2 + 1;
 	m.nr_classes = K; m.ori_size = ori; m.pixel_size = scalar(d, "pixel_size"); m.nr_bodies = 1; m.ref_dim = 3; m.data_dim = 2;
 	m.nr_groups = (int) scalar(d, "nr_groups"); m.nr_optics_groups = 1; m.sigma2_offset = scalar(d, "sigma2_offset");
 	m.avg_norm_correction = scalar(d, "avg_norm_correction"); m.padding_factor = 2.;
@@ -109,7 +112,7 @@ static void build_optimiser(MlOptimiser &o, const std::map<std::string, Arr> &d)
 	o.mydata.optics_group_of_particle.assign(N, 0);
 	o.mydata.nr_groups = m.nr_groups;
 	o.mydata.obsModel.kV.assign(1, 300.); o.mydata.obsModel.Cs.assign(1, 2.7); o.mydata.obsModel.Q0.assign(1, 0.1);
-	o.mydata.obsModel.pixel_size.assign(1, m.pixel_size); o.mydata.obsModel.box_size.assign(1, ori); o.mydata.obsModel.ctf_premultiplied.assign(1, false);
+	o.mydata.obsModel.pixel_size.assign(1, m.pixel_size); o.mydata.obsModel.box_size.assign(1, img_size); o.mydata.obsModel.ctf_premultiplied.assign(1, false);
 	// sampling tables
 	HealpixSampling &s = o.sampling;
 	s.healpix_order = (int) scalar(d, "healpix_order"); s.is_3D = true;
@@ -133,7 +136,7 @@ static void build_optimiser(MlOptimiser &o, const std::map<std::string, Arr> &d)
 		}
 	}
 	// optimiser flags / sizes
-	o.image_full_size.assign(1, ori); o.image_current_size.assign(1, (int) scalar(d, "current_size")); o.image_coarse_size.assign(1, (int) scalar(d, "coarse_size"));
+	o.image_full_size.assign(1, img_size); o.image_current_size.assign(1, (int) scalar(d, "current_size")); o.image_coarse_size.assign(1, (int) scalar(d, "coarse_size"));
 	o.iter = 5; o.adaptive_oversampling = 1; o.adaptive_fraction = scalar(d, "adaptive_fraction"); o.maximum_significants = -1;
 	o.particle_diameter = scalar(d, "particle_diameter"); o.width_mask_edge = (int) scalar(d, "width_mask_edge"); o.sigma2_fudge = 1.;
 	o.do_auto_refine = true; o.autosampling_hporder_local_searches = local ? 0 : 99;
@@ -151,7 +154,7 @@ static void build_optimiser(MlOptimiser &o, const std::map<std::string, Arr> &d)
 // one E-step over particles [p0, p1) in pools of `pool` particles (src/ml_optimiser.cpp:3513-3869 around the device calls)
 static void expectation(MlOptimiser &o, const std::map<std::string, Arr> &d, int device, long p0, long p1, int pool, std::vector<double> &metadata_all)
 {
-	const int ori = o.mymodel.ori_size, ncol = (int) d.at("metadata").dims[1];
+	const int ori = o.image_full_size[0], ncol = (int) d.at("metadata").dims[1];   // the images' box
 	const float *img = (const float *) d.at("images").raw.data();              // float32 [N][ori][ori]
 	MlDeviceBundle *b = new MlDeviceBundle(&o);
 	b->setDevice(device);

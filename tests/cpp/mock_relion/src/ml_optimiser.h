@@ -137,10 +137,47 @@ public:
 	T &operator()(int x, int y) { return data[(size_t) y * w + x]; }
 };
 
+// src/matrix2d.h: the few members the adapter touches
+template <class T> class Matrix2D
+{
+public:
+	int mdimx, mdimy; std::vector<T> mdata;
+	Matrix2D() : mdimx(0), mdimy(0) {}
+	Matrix2D(int rows, int cols) : mdimx(cols), mdimy(rows), mdata((size_t) rows * cols, T(0)) {}
+	void initIdentity(int dim) { mdimx = mdimy = dim; mdata.assign((size_t) dim * dim, T(0)); for (int i = 0; i < dim; i++) mdata[(size_t) i * dim + i] = T(1); }
+	T &operator()(int i, int j) { return mdata[(size_t) i * mdimx + j]; }
+	const T &operator()(int i, int j) const { return mdata[(size_t) i * mdimx + j]; }
+	bool isIdentity() const
+	{
+		for (int i = 0; i < mdimy; i++) for (int j = 0; j < mdimx; j++)
+			if (std::fabs((*this)(i, j) - (i == j ? T(1) : T(0))) > 1e-6) return false;          // XMIPP_EQUAL_ACCURACY
+		return true;
+	}
+	Matrix2D &operator*=(T f) { for (size_t i = 0; i < mdata.size(); i++) mdata[i] *= f; return *this; }
+};
+
 class ObservationModel
 {
 public:
 	std::vector<RFLOAT> kV, Cs, Q0, pixel_size; std::vector<int> box_size; std::vector<bool> ctf_premultiplied;
+	// anisotropic magnification and scale differences (src/jaz/single_particle/obs_model.cpp:1306-1340)
+	bool hasMagMatrices; std::vector<Matrix2D<RFLOAT> > magMatrices;
+	Matrix2D<RFLOAT> applyAnisoMag(Matrix2D<RFLOAT> A3D, int og)
+	{
+		if (!hasMagMatrices) return A3D;
+		const Matrix2D<RFLOAT> &M = magMatrices[og];                                                // inverse of the 2x2 block, times A3D
+		const RFLOAT det = M(0, 0) * M(1, 1) - M(0, 1) * M(1, 0);
+		Matrix2D<RFLOAT> inv; inv.initIdentity(3);
+		inv(0, 0) = M(1, 1) / det; inv(0, 1) = -M(0, 1) / det; inv(1, 0) = -M(1, 0) / det; inv(1, 1) = M(0, 0) / det;
+		Matrix2D<RFLOAT> out(3, 3);
+		for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++) out(i, j) += inv(i, k) * A3D(k, j);
+		return out;
+	}
+	Matrix2D<RFLOAT> applyScaleDifference(Matrix2D<RFLOAT> A3D, int og, int s3D, double angpix3D)
+	{
+		A3D *= (box_size[og] * pixel_size[og]) / (s3D * angpix3D);
+		return A3D;
+	}
 	// beam tilt / odd Zernike phase correction and detector MTF (src/jaz/single_particle/obs_model.h:45-129, obs_model.cpp:528-626)
 	bool hasOddZernike, hasMultipleMtfs;
 	std::vector<BufferedImage<Complex> > phaseCorr; std::vector<BufferedImage<RFLOAT> > mtfImage; BufferedImage<RFLOAT> avgMtfImage;
@@ -165,7 +202,7 @@ public:
 			v = Complex(v.real * f, v.imag * f);
 		}
 	}
-	ObservationModel() : hasOddZernike(false), hasMultipleMtfs(false) {}
+	ObservationModel() : hasMagMatrices(false), hasOddZernike(false), hasMultipleMtfs(false) {}
 	bool getCtfPremultiplied(int og) const { return ctf_premultiplied[og]; }
 	RFLOAT getPixelSize(int og) const { return pixel_size[og]; }
 	int getBoxSize(int og) const { return box_size[og]; }

@@ -171,3 +171,75 @@ def test_cpp_estep_reduction_and_bookkeeping(device, tmp_path, kw):
     s2 = res.wsum_sigma2_noise.astype(np.float64).sum(axis=0)
     s2[m.current_size // 2 + 1:] += power[:, m.current_size // 2 + 1:].astype(np.float64).sum(axis=0)
     np.testing.assert_allclose(pack[7:7 + nshell], s2, rtol=2e-4, atol=1e-9 * s2.max())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("img_box,model_box", [(40, 32), (32, 40)])
+def test_cpp_adapter_optics_group_with_its_own_box(device, tmp_path, img_box, model_box):
+    """An optics group whose box differs from the model's (same pixel size) through the C++ adapter: MlDeviceBundle::setGeometry loads
+    the group's image geometry (its box as the library's ori_size, sigma2_noise gathered at ROUND(remap * ires), rb_model.ref_max_r when
+    the references end inside the window), the pool carries mat_left = applyScaleDifference(I), the weighted sigma2 sums are
+    scattered back onto the model's shells (acc_ml_optimiser_impl.h:3615-3625) and logsigma2 reads the remapped shells (:3556-3566).
+    Checked against the Python host mirror, which is given the same image-geometry model directly."""
+    from relion_b200.synth import mresol
+    wl = make_workload(ori_size=img_box, ref_box=model_box, healpix_order=1, n_particles=13, nr_classes=1, seed=61, snr=0.3, nr_groups=2)
+    m, s = wl.model, wl.sampling
+    remap = model_box / img_box                                       # (ori * pixel) / (my_image_size * my_pixel_size)
+    ns_img, ns_mod = img_box // 2 + 1, model_box // 2 + 1
+    rnd = lambda v: np.floor(np.asarray(v, np.float64) + 0.5).astype(np.int64)
+    # the model's own spectrum (on its shells) and what an image of this group sees of it
+    sig_img0 = np.asarray(m.sigma2_noise, np.float64).reshape(-1)
+    sig_mod = np.interp(np.arange(ns_mod) / remap, np.arange(ns_img), sig_img0)
+    gather = rnd(remap * np.arange(ns_img))
+    assert gather.max() < ns_mod
+    m.sigma2_noise = sig_mod[gather][None, :]
+    dvp_mod = np.zeros((1, ns_mod)); dvp_mod[:, : min(ns_mod, ns_img)] = np.asarray(m.data_vs_prior_class)[:, : min(ns_mod, ns_img)]
+    dvp_img = np.zeros((1, ns_img)); dvp_img[:, : min(ns_mod, ns_img)] = dvp_mod[:, : min(ns_mod, ns_img)]
+    m.data_vs_prior_class = dvp_img
+    raw = raw_pool_from(wl, seed=8)
+    assert raw.mat_left is not None and abs(raw.mat_left[0, 0] - img_box / model_box) < 1e-12
+    arrays, md0 = _workload_arrays(wl, raw, avg_norm=0.95)
+    arrays["model_ori_size"] = np.array([float(model_box)])
+    arrays["sigma2_noise"] = sig_mod
+    arrays["data_vs_prior_class"] = dvp_mod
+    _dump(str(tmp_path / "w.bin"), arrays)
+    r = subprocess.run([_exe(), str(tmp_path / "w.bin"), str(tmp_path / "o.bin"), "2", "5"], capture_output=True, text=True)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+    buf = open(tmp_path / "o.bin", "rb").read()
+    nm = struct.unpack_from("<q", buf, 0)[0]
+    md = np.frombuffer(buf, np.float64, nm, 8).reshape(-1, NCOL)
+    npk = struct.unpack_from("<q", buf, 8 + 8 * nm)[0]
+    pack = np.frombuffer(buf, np.float64, npk, 16 + 8 * nm)
+
+    assert m.ref_max_r == (wl.r_max if wl.r_max < img_box // 2 else 0)
+    device.set_model(m); device.set_sampling(s)
+    device.set_reference(0, wl.refs[0].astype(np.complex128), wl.r_max, wl.padding_factor)
+    device.bp_init(0, wl.bp_shape, wl.r_max, wl.padding_factor)
+    power = device.pool_prepare(0, raw)
+    res = device.estep_slot(0)
+    p = res.particles
+    g = (p["best_idir"] * s.n_psi + p["best_ipsi"]) * s.n_over_rot + p["best_iover_rot"]
+    np.testing.assert_array_equal(md[:, ROT], np.asarray(s.over_rot)[g])
+    np.testing.assert_array_equal(md[:, TILT], np.asarray(s.over_tilt)[g])
+    np.testing.assert_array_equal(md[:, PSI], np.asarray(s.over_psi)[g])
+    np.testing.assert_array_equal(md[:, CLASS], p["best_class"] + 1)
+    np.testing.assert_array_equal(md[:, NR_SIGN], p["nr_significant_coarse"])
+    np.testing.assert_allclose(md[:, PMAX], p["pmax"], rtol=1e-6)
+    ir = mresol(m.current_size)
+    logsigma2 = np.log(2 * np.pi * sig_mod[rnd(remap * ir[ir > 0])]).sum()
+    np.testing.assert_allclose(md[:, DLL], p["dLL_nolog"] - logsigma2, rtol=1e-6)
+    np.testing.assert_allclose(pack[0], (p["dLL_nolog"] - logsigma2).sum(), rtol=1e-6)
+    # wsum_model.sigma2_noise lives on the MODEL's shells: image shell i goes to ROUND(i * remap)
+    s2_img = res.wsum_sigma2_noise.astype(np.float64).sum(axis=0)
+    s2_img[m.current_size // 2 + 1:] += power[:, m.current_size // 2 + 1:].astype(np.float64).sum(axis=0)
+    s2_mod = np.zeros(ns_mod)
+    for i in range(ns_img):
+        if gather[i] < ns_mod:
+            s2_mod[gather[i]] += s2_img[i]
+    np.testing.assert_allclose(pack[7:7 + ns_mod], s2_mod, rtol=2e-4, atol=1e-9 * s2_mod.max())
+    # the scale matters: the same pool without it lands somewhere else
+    raw.mat_left = None
+    device.pool_prepare(0, raw)
+    other = device.estep_slot(0)
+    assert np.abs(other.particles["dLL_nolog"] - p["dLL_nolog"]).max() > 0.1

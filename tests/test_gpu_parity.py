@@ -976,13 +976,20 @@ _MAG_L = [[1.03, 0.012, 0.0], [-0.008, 0.96, 0.0], [0.0, 0.0, 1.0]]
 _BODY_R = [[0.9553364891, -0.2955202067, 0.0], [0.2955202067, 0.9553364891, 0.0], [0.0, 0.0, 1.0]]
 
 
-@pytest.mark.parametrize("case", ["mag_local", "mag_global", "left_only_local", "right_only_global", "other_box_global", "other_box_local"])
-def test_pool_with_left_and_right_matrices(device, oracle, case):
+@pytest.mark.parametrize("case", ["mag_local", "mag_global", "left_only_local", "right_only_global", "bigger_box_global", "bigger_box_local",
+                                  "smaller_box_global", "wrong_scale_global", "bigger_box_local_orientation_major", "bigger_box_cc_global"])
+def test_pool_with_left_and_right_matrices(device, oracle, monkeypatch, case):
     """rb_particles.mat_left / mat_right (MBL / MBR: orientation matrices inverse(L A R) in the coarse pass, the fine pass and the
     store stage; cuda_kernel_make_eulers_3D<invert, doL, doR>, generateEulerMatrices(..., L, R)): anisotropic magnification with a
-    body rotation, each matrix alone, and an optics group whose box differs from the references' (applyScaleDifference: the
-    projection leaves the reference for the outer image shells, which must then read zero)."""
+    body rotation, each matrix alone, and optics groups whose box differs from the references' (applyScaleDifference).  A bigger
+    image box: the references end inside the image window and the fine pass skips the rows beyond (rb_model.ref_max_r); a
+    deliberately wrong scale: the projection leaves the reference for the outer image shells, which must then read zero."""
     kw = dict(ori_size=32, n_particles=12, seed=120, snr=0.2)
+    if case.endswith("orientation_major"):
+        monkeypatch.setenv("RB_BAND", "0")                      # k_diff2_fine / k_store instead of the band-major kernels
+        case = case[:-len("_orientation_major")]
+    if "_cc_" in case:
+        kw.update(do_cc=True)                                   # the cross-correlation kernels have the same row rule (diff2.h:657-666)
     if case.endswith("local"):
         kw.update(healpix_order=2, local_search=True)
     else:
@@ -993,15 +1000,19 @@ def test_pool_with_left_and_right_matrices(device, oracle, case):
         kw.update(mat_left=_MAG_L)
     elif case.startswith("right_only"):
         kw.update(mat_right=_BODY_R)
-    else:
+    elif case.startswith("bigger_box"):
         kw.update(ori_size=40, ref_box=32)
+    elif case.startswith("smaller_box"):
+        kw.update(ori_size=32, ref_box=40)
+    else:
+        kw.update(ori_size=40, ref_box=32, mat_left=np.eye(3) * 0.8)
     wl = make_workload(**kw)
     res, ores = _compare_pool(device, oracle, wl)
     # the matrices matter: without them the pool has another likelihood
     plain = make_workload(**kw)
     plain.pool.mat_left = plain.pool.mat_right = None
     other = device.expectation_some_particles(plain.pool)
-    assert np.abs(other.particles["dLL_nolog"] - res.particles["dLL_nolog"]).max() > 0.1
+    assert np.abs(other.particles["dLL_nolog"] - res.particles["dLL_nolog"]).max() > (0.01 if wl.model.do_cc else 0.1)
     # ... and a pool with the matrices again gets the coarse matrices rebuilt
     for k in range(len(wl.refs)):
         device.bp_clear(k)

@@ -98,7 +98,7 @@ extern "C" void rb_ctx_destroy(rb_ctx *ctx)
 	if (!ctx) return;
 	cudaSetDevice(ctx->device);
 	cudaDeviceSynchronize();
-	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->proj2_buf[i].release(); ctx->proj2c_buf[i].release(); ctx->bp_buf[i].release(); ctx->bp_blk_buf[i].release(); }
+	for (int i = 0; i < RB_MAX_CLASSES; i++) { ctx->proj_buf[i].release(); ctx->proj8_buf[i].release(); ctx->proj2_buf[i].release(); ctx->proj2c_buf[i].release(); ctx->proj4c_buf[i].release(); ctx->bp_buf[i].release(); ctx->bp_blk_buf[i].release(); }
 	DevBuf *bufs[] = {&ctx->s_coarse_eulers, &ctx->s_over_rot, &ctx->s_over_tilt, &ctx->s_over_psi, &ctx->s_rot, &ctx->s_tilt,
 	                  &ctx->s_psi, &ctx->s_ctx, &ctx->s_cty, &ctx->s_ftx, &ctx->s_fty, &ctx->s_tx, &ctx->s_ty, &ctx->s_otx, &ctx->s_oty,
 	                  &ctx->m_rows_c, &ctx->m_rows_f, &ctx->m_ires_c, &ctx->m_ires_f,
@@ -274,6 +274,7 @@ static int set_reference_common(rb_ctx *ctx, int k, int mdlX, int mdlY, int &mdl
 	p.mdlX = mdlX; p.mdlY = mdlY; p.mdlZ = mdlZ; p.mdlXY = mdlX * mdlY;
 	p.mdlInitY = initY; p.mdlInitZ = initZ; p.mdlMaxR = maxR; p.padding_factor = (float) pf;
 	p.c2X = mdlX; p.c2XY = p.mdlXY; p.c2InitY = initY; p.c2InitZ = initZ;       // full x-pair copy until a pool asks for the core
+	p.quad = nullptr;
 	p.blk = blk; p.nbx = (nbx + 3) / 4; p.nbxy = p.nbx * ((nby + 3) / 4);       // brick grid of the table (rb_blk_slot)
 	ctx->core_stamp[k] = -1;
 	ctx->has_proj[k] = true;
@@ -287,6 +288,7 @@ static RbProjector proj_full(rb_ctx *ctx, int k)
 	RbProjector p = ctx->proj[k];
 	p.mdl2 = ctx->proj2_buf[k].as<float4>();
 	p.c2X = p.mdlX; p.c2XY = p.mdlXY; p.c2InitY = p.mdlInitY; p.c2InitZ = p.mdlInitZ;
+	p.quad = nullptr;
 	return p;
 }
 
@@ -294,8 +296,9 @@ static RbProjector proj_full(rb_ctx *ctx, int k)
 // rebuilt when the reference or the coarse size changed.  RB_COARSE_CORE=0 keeps the full copy (A/B).
 static int ensure_coarse_core(rb_ctx *ctx)
 {
-	static int on = -1;
+	static int on = -1, quad_on = -1;
 	if (on < 0) { const char *e = getenv("RB_COARSE_CORE"); on = e ? atoi(e) : 1; }
+	if (quad_on < 0) { const char *e = getenv("RB_COARSE_QUAD"); quad_on = e ? atoi(e) : 1; }
 	const RbModelDev &M = ctx->d_model;
 	bool changed = false;
 	for (int k = 0; k < M.nr_classes; k++)
@@ -316,6 +319,14 @@ static int ensure_coarse_core(rb_ctx *ctx)
 		RB_CHECK(rbk_xpair_core(ctx, p, cX, cY, cInit, cInit, ctx->proj2c_buf[k].as<float4>()));
 		p.mdl2 = ctx->proj2c_buf[k].as<float4>();
 		p.c2X = cX; p.c2XY = cX * cY; p.c2InitY = cInit; p.c2InitZ = cInit;
+		p.quad = nullptr;
+		if (quad_on)
+		{
+			// the xy-quad copy of the same core for the fused local kernel: two 32-byte loads per sample
+			RB_CHECK(ctx->proj4c_buf[k].ensure((size_t) cX * cY * cY * 2 * sizeof(float4)));
+			RB_CHECK(rbk_xyquad_core(ctx, proj_full(ctx, k), cX, cY, cInit, cInit, ctx->proj4c_buf[k].as<float4>()));
+			p.quad = ctx->proj4c_buf[k].as<float4>();
+		}
 		ctx->core_stamp[k] = ctx->ref_version[k]; ctx->core_R[k] = R;
 		changed = true;
 	}
@@ -989,6 +1000,17 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 	}
 	RB_CHECK(s.meta.ensure(P * sizeof(RbPartMeta)));
 	RB_CUDA(cudaMemcpyAsync(s.meta.p, s.h_meta.data(), P * sizeof(RbPartMeta), cudaMemcpyHostToDevice, cs));
+	s.has_order = false;
+	if (priors && env_size("RB_COARSE_ORDER", 1) != 0)
+	{
+		s.h_order.resize(P);
+		for (int p = 0; p < P; p++) s.h_order[p] = p;
+		const int *doff = pool->dir_off, *didx = pool->dir_idx;
+		std::stable_sort(s.h_order.begin(), s.h_order.end(), [doff, didx](int a, int b) { return didx[doff[a]] < didx[doff[b]]; });
+		RB_CHECK(s.order.ensure((size_t) P * sizeof(int)));
+		RB_CUDA(cudaMemcpyAsync(s.order.p, s.h_order.data(), (size_t) P * sizeof(int), cudaMemcpyHostToDevice, cs));
+		s.has_order = true;
+	}
 	if (priors)
 	{
 		const size_t nd = pool->dir_off[P], np = pool->psi_off[P];

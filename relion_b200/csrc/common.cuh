@@ -70,6 +70,9 @@ struct RbProjector {
 	// full volume: it stays in L2 and inside the TLB's reach (128 entries x 2 MB; a core embedded in the 515 x 515 x 258
 	// volume touches > 200 pages and every L1 miss walks the page table).  Stage entry points use the full copy.
 	int c2X, c2XY, c2InitY, c2InitZ;
+	// xy-quad copy of the same core (nullptr when not built): per voxel (v[y][x], v[y][x+1], v[y+1][x], v[y+1][x+1]) as one aligned
+	// 32-byte word, c2 geometry — a trilinear sample is TWO 32-byte loads (LDG.E.256), each exactly one sector
+	const float4 *quad;
 	// Addressing of mdl8.  The cells live in 4 x 4 x 4 blocks (4 KB) ordered by the distance of the block centre from the
 	// origin, blk[] = rank of block (bz, by, bx): a thin spherical shell - what the band-major kernels sweep - is then one
 	// contiguous range of memory (<= 125 pages at the edge of a 256-px reference) instead of a slice through all 2190 pages
@@ -239,6 +242,10 @@ struct PoolSlot {
 	long long total_coarse = 0;     // sum over particles of K*nd*np*T
 	int max_bp_off = 0;             // largest RbPartMeta::bp_off of the pool
 	RbLR lr;                        // rb_particles.mat_left / mat_right
+	// local searches: the particles sorted by the first direction of their prior list.  The fused coarse kernel hands CTA column i
+	// particle order[i], so that CTAs in flight together sample neighbouring central planes and share their part of the coarse core
+	// in L2 (a pool in acquisition order scatters the planes over the whole core)
+	DevBuf order; bool has_order = false;
 	long long total_prior = 0;
 	DevBuf Fimg, Fnomask, Fctf, meta, state, dir_idx, dir_prior, psi_idx, psi_prior;
 	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;
@@ -253,6 +260,7 @@ struct PoolSlot {
 	DevBuf bp_cnt, bp_item_of, bp_items, bp_samp;   // fine orientations holding significant samples + their (phase, weight) tables
 	int band_rounds = 0;
 	std::vector<RbPartMeta> h_meta;
+	std::vector<int> h_order;
 	cudaEvent_t uploaded = nullptr;
 	cudaEvent_t done = nullptr;     // recorded when the E-step of this slot has been enqueued completely; rb_estep_fetch waits on it
 };
@@ -269,6 +277,7 @@ struct rb_ctx {
 	DevBuf proj_buf[RB_MAX_CLASSES];
 	DevBuf proj8_buf[RB_MAX_CLASSES];
 	DevBuf proj2_buf[RB_MAX_CLASSES];
+	DevBuf proj4c_buf[RB_MAX_CLASSES];               // xy-quad copy of the coarse-window core (RbProjector::quad)
 	DevBuf proj2c_buf[RB_MAX_CLASSES];               // x-pair copy of the coarse-window core (RbProjector::c2*)
 	long long core_stamp[RB_MAX_CLASSES];            // ref_version the core was built from (-1: none), and its half width
 	int core_R[RB_MAX_CLASSES];
@@ -350,6 +359,7 @@ int rbk_make_coarse_eulers(rb_ctx *ctx, const double *d_rot, const double *d_til
                            float *d_eulers);
 int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
 int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2);
+int rbk_xyquad_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);
 int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);
 int rbk_backproject_posed(rb_ctx *ctx, const RbBackprojector &bp, int n, int count, const float2 *d_F, const float *d_W, const float *d_eulers);

@@ -258,6 +258,42 @@ __device__ __forceinline__ float2 rb_project3d_c256(const RbProjK8 &k, int x, in
 	return r;
 }
 
+// Same sample from the xy-quad copy of the coarse core (RbProjector::quad, geometry of k = rb_make_projk2): the rows y0 / y0 + 1 of
+// plane z0 in one 32-byte load, those of plane z0 + 1 in another.  Arithmetic identical to rb_project3d_xp.
+__device__ __forceinline__ float2 rb_project3d_q256(const RbProjK &k, const float4 *quad, int x, int y,
+                                                    float e0, float e1, float e3, float e4, float e6, float e7)
+{
+	float xp = (e0 * x + e1 * y) * k.pf;
+	float yp = (e3 * x + e4 * y) * k.pf;
+	float zp = (e6 * x + e7 * y) * k.pf;
+	int r2 = (int) (xp * xp + yp * yp + zp * zp);
+	if (r2 > k.maxR2_padded) return make_float2(0.f, 0.f);
+	const bool inv = xp < 0.f;
+	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+	const float fx = xp - fx0, fy = yp - fy0, fz = zp - fz0;
+	const int x0 = (int) fx0, y0 = (int) fy0, z0 = (int) fz0;
+	const float4 *b = quad + 2 * ((size_t) (z0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) (y0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) x0);
+	float4 q0, q1, q2, q3;
+	rb_ldg256(b, q0, q1);
+	rb_ldg256(b + 2 * (size_t) k.mdlXY, q2, q3);
+	float2 r;
+	{
+		float dx00 = q0.x + (q0.z - q0.x) * fx, dx10 = q1.x + (q1.z - q1.x) * fx;
+		float dx01 = q2.x + (q2.z - q2.x) * fx, dx11 = q3.x + (q3.z - q3.x) * fx;
+		float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy;
+		r.x = dxy0 + (dxy1 - dxy0) * fz;
+	}
+	{
+		float dx00 = q0.y + (q0.w - q0.y) * fx, dx10 = q1.y + (q1.w - q1.y) * fx;
+		float dx01 = q2.y + (q2.w - q2.y) * fx, dx11 = q3.y + (q3.w - q3.y) * fx;
+		float dxy0 = dx00 + (dx10 - dx00) * fy, dxy1 = dx01 + (dx11 - dx01) * fy;
+		r.y = dxy0 + (dxy1 - dxy0) * fz;
+	}
+	if (inv) r.y = -r.y;
+	return r;
+}
+
 // Split form of rb_project3d_x8 for software pipelining: rb_proj_issue computes the sample position and
 // issues the four 16-byte loads; rb_proj_finish does the lerps once the data is needed.
 struct RbProjFetch {

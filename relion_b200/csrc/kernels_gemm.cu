@@ -905,6 +905,7 @@ struct FusedArgs {
 	int T; int tiles_per_class; int num_kblocks;
 	int Tstride, t0;               // Mweight row length and first translation of this pass (T <= 32 translations per pass)
 	int cc;                        // cross-correlation criterion: value = -cross / sqrt(norm term), no xi2 term, no minimum (diff2.cuh:336-460)
+	const int *order;              // [P] or nullptr: particle handled by CTA column blockIdx.x (PoolSlot::order)
 };
 
 __device__ __forceinline__ void mbar_arrive(uint32_t bar)
@@ -932,7 +933,7 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	// particle index fastest: the first tiles of all particles (always full) are dispatched before the partial last tiles,
 	// which then fill the tail of the launch (tile-major order left ~10 % of the SM time idle at the end)
-	const int p = blockIdx.x;
+	const int p = A.order ? __ldg(A.order + blockIdx.x) : (int) blockIdx.x;
 	const int cls = blockIdx.y / A.tiles_per_class;
 	const int oi0 = (blockIdx.y - cls * A.tiles_per_class) * FU_BM;
 	const RbPartMeta m = A.metas[p];
@@ -1030,6 +1031,7 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 		const RbProjK pk = rb_make_projk2(A.projs[cls], imgX);
 		const RbProjK8 pk8 = rb_make_projk8(A.projs[cls], imgX);
 		const float4 *mdl2 = A.projs[cls].mdl2;
+		const float4 *quad = A.projs[cls].quad;
 		const float4 *img = A.img4 + (size_t) p * A.n * imgX;
 		float bacc[NJ];
 #pragma unroll
@@ -1054,8 +1056,11 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 				const int r = 2 * NPW * j + 2 * pw + rsub;
 				ref[j] = make_float2(0.f, 0.f);
 				if (j < nj && pix_ok && s_valid[r])
-					ref[j] = G256 ? rb_project3d_c256(pk8, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5])
-					              : rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
+				{
+					if constexpr (G256 == 2) ref[j] = rb_project3d_q256(pk, quad, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
+					else if constexpr (G256 == 1) ref[j] = rb_project3d_c256(pk8, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
+					else ref[j] = rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
+				}
 				bacc[j] = fmaf(hc, ref[j].x * ref[j].x + ref[j].y * ref[j].y, bacc[j]);
 			}
 			mbar_wait(empty0 + 8 * s, ph ^ 1);                       // the MMAs that read this slot have retired
@@ -1159,6 +1164,7 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	A.dir_idx = s.dir_idx.as<int>(); A.psi_idx = s.psi_idx.as<int>();
 	A.pdf_orient_zero = s.pdf_orient_zero.as<unsigned char>(); A.Mweight = s.Mweight.as<float>();
 	A.img4 = cimg4; A.x2 = bX2.as<float>(); A.projs = ctx->d_proj.as<RbProjector>();
+	A.order = s.has_order ? s.order.as<int>() : nullptr;
 	A.pix = pixlist; A.npix = npix; A.n = n; A.num_kblocks = nkb; A.cc = M.do_cc;
 	A.tiles_per_class = (s.max_no + FU_BM - 1) / FU_BM;
 	static int npw = 0;
@@ -1173,11 +1179,18 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		configured = true;
 	}
-	// gather: 0 = x-pair copy, four 16-byte loads per sample; 1 = expanded cells, two 32-byte loads per sample
-	static int g256 = -1;
-	if (g256 < 0) { const char *e = getenv("RB_FUSED_G256"); g256 = e ? atoi(e) != 0 : 0; }
+	// gather: 0 = x-pair copy, four 16-byte loads per sample; 1 = expanded cells, two 32-byte loads per sample; 2 = xy-quad copy of
+	// the coarse core (when ensure_coarse_core built one), two 32-byte loads per sample
+	static int g256_env = -1;
+	if (g256_env < 0) { const char *e = getenv("RB_FUSED_G256"); g256_env = e ? atoi(e) : 0; }
+	int g256 = g256_env;
+	bool have_quad = true;
+	for (int k = 0; k < K; k++) have_quad = have_quad && ctx->proj[k].quad != nullptr;
+	if (have_quad) g256 = 2; else if (g256 == 2) g256 = 0;
 	dim3 grid((unsigned) P, (unsigned) (A.tiles_per_class * K));
 	// The tile holds 32 translations (TMEM columns, B operand rows): samplings with more (--offset_range 5 --offset_step 1: 81,
 	// healpix_sampling.cpp:399-440) take ceil(T / 32) passes, each with its own B operand, writing its columns of Mweight.  The
@@ -1191,12 +1204,14 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 		A.T = Tc; A.Tstride = T; A.t0 = t0;
 		if (npw == 16)
 		{
-			if (g256) k_coarse_fused<16, 1><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			if (g256 == 2) k_coarse_fused<16, 2><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			else if (g256) k_coarse_fused<16, 1><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 			else k_coarse_fused<16, 0><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 		}
 		else
 		{
-			if (g256) k_coarse_fused<8, 1><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			if (g256 == 2) k_coarse_fused<8, 2><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			else if (g256) k_coarse_fused<8, 1><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 			else k_coarse_fused<8, 0><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 		}
 		RB_LAUNCH_CHECK(ctx);

@@ -139,6 +139,38 @@ __global__ void k_xpair_core(RbProjector pj, int cX, int cY, int cInitY, int cIn
 	}
 }
 
+// xy-quad copy of the same box: entry v holds the x-pairs of rows y and y + 1 (two float4)
+__global__ void k_xyquad_core(RbProjector pj, int cX, int cY, int cInitY, int cInitZ, float4 *out)
+{
+	const size_t n = (size_t) cX * cY * cY;
+	for (size_t v = blockIdx.x * (size_t) blockDim.x + threadIdx.x; v < n; v += (size_t) gridDim.x * blockDim.x)
+	{
+		const int x = (int) (v % cX);
+		const int y = (int) ((v / cX) % cY) + cInitY - pj.mdlInitY;
+		const int z = (int) (v / ((size_t) cX * cY)) + cInitZ - pj.mdlInitZ;
+		float4 o[2];
+		for (int dy = 0; dy < 2; dy++)
+		{
+			o[dy] = make_float4(0.f, 0.f, 0.f, 0.f);
+			const int yy = y + dy;
+			if (yy >= 0 && yy < pj.mdlY && z >= 0 && z < pj.mdlZ && x < pj.mdlX)
+			{
+				const float2 *b = pj.mdl + ((size_t) z * pj.mdlXY + (size_t) yy * pj.mdlX + x);
+				const float2 a = b[0], c = x + 1 < pj.mdlX ? b[1] : make_float2(0.f, 0.f);
+				o[dy] = make_float4(a.x, a.y, c.x, c.y);
+			}
+		}
+		out[2 * v] = o[0]; out[2 * v + 1] = o[1];
+	}
+}
+
+int rbk_xyquad_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out)
+{
+	k_xyquad_core<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(pj, cX, cY, cInitY, cInitZ, d_out);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}
+
 int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out)
 {
 	k_xpair_core<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(pj, cX, cY, cInitY, cInitZ, d_out);

@@ -294,6 +294,52 @@ __device__ __forceinline__ float2 rb_project3d_q256(const RbProjK &k, const floa
 	return r;
 }
 
+// Split, branch-free form of rb_project3d_q256: rb_quad_issue computes the position and issues the two loads unconditionally (a sample
+// outside r_max, or one the caller masks out, reads the first word of the copy and is zeroed in rb_quad_finish), so that a thread can
+// have the loads of SEVERAL samples in flight — inside an `if (inside)` region the compiler must finish one sample before it may
+// issue the next one's loads.
+struct RbQuadFetch {
+	float4 q0, q1, q2, q3;
+	float fx, fy, fz;
+	int flags;   // bit0: sample is live (inside r_max and not masked), bit1: Hermitian mate (conjugate)
+};
+__device__ __forceinline__ void rb_quad_issue(const RbProjK &k, const float4 *quad, bool live, int x, int y,
+                                              float e0, float e1, float e3, float e4, float e6, float e7, RbQuadFetch &f)
+{
+	float xp = (e0 * x + e1 * y) * k.pf;
+	float yp = (e3 * x + e4 * y) * k.pf;
+	float zp = (e6 * x + e7 * y) * k.pf;
+	const int r2 = (int) (xp * xp + yp * yp + zp * zp);
+	live = live && r2 <= k.maxR2_padded;
+	const bool inv = xp < 0.f;
+	if (inv) { xp = -xp; yp = -yp; zp = -zp; }
+	const float fx0 = floorf(xp), fy0 = floorf(yp), fz0 = floorf(zp);
+	f.fx = xp - fx0; f.fy = yp - fy0; f.fz = zp - fz0;
+	f.flags = (live ? 1 : 0) | (inv ? 2 : 0);
+	const size_t off = live ? 2 * ((size_t) ((int) fz0 - k.mdlInitZ) * (size_t) k.mdlXY + (size_t) ((int) fy0 - k.mdlInitY) * (size_t) k.mdlX + (size_t) (int) fx0) : 0;
+	rb_ldg256(quad + off, f.q0, f.q1);
+	rb_ldg256(quad + off + (live ? 2 * (size_t) k.mdlXY : 0), f.q2, f.q3);
+}
+__device__ __forceinline__ float2 rb_quad_finish(const RbQuadFetch &f)
+{
+	float2 r;
+	{
+		float dx00 = f.q0.x + (f.q0.z - f.q0.x) * f.fx, dx10 = f.q1.x + (f.q1.z - f.q1.x) * f.fx;
+		float dx01 = f.q2.x + (f.q2.z - f.q2.x) * f.fx, dx11 = f.q3.x + (f.q3.z - f.q3.x) * f.fx;
+		float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		r.x = dxy0 + (dxy1 - dxy0) * f.fz;
+	}
+	{
+		float dx00 = f.q0.y + (f.q0.w - f.q0.y) * f.fx, dx10 = f.q1.y + (f.q1.w - f.q1.y) * f.fx;
+		float dx01 = f.q2.y + (f.q2.w - f.q2.y) * f.fx, dx11 = f.q3.y + (f.q3.w - f.q3.y) * f.fx;
+		float dxy0 = dx00 + (dx10 - dx00) * f.fy, dxy1 = dx01 + (dx11 - dx01) * f.fy;
+		r.y = dxy0 + (dxy1 - dxy0) * f.fz;
+	}
+	if (f.flags & 2) r.y = -r.y;
+	if (!(f.flags & 1)) r = make_float2(0.f, 0.f);
+	return r;
+}
+
 // Split form of rb_project3d_x8 for software pipelining: rb_proj_issue computes the sample position and
 // issues the four 16-byte loads; rb_proj_finish does the lerps once the data is needed.
 struct RbProjFetch {

@@ -1050,6 +1050,31 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 				hc = __ldg(img + rb_src_index(x, y, A.n)).z;
 			}
 			float2 ref[NJ];
+			// G256: 2 / 3 = xy-quad gather with the loads of 4 / 2 rows in flight, 4 = one row at a time
+			constexpr int FU_QUAD_MLP = G256 == 2 ? 4 : G256 == 3 ? 2 : 1;
+			if constexpr (G256 == 2 || G256 == 3)
+			{
+				// the loads of FU_QUAD_MLP rows in flight at once (branch-free issue, then the lerps)
+#pragma unroll
+				for (int j0 = 0; j0 < NJ; j0 += FU_QUAD_MLP)
+				{
+					RbQuadFetch qf[FU_QUAD_MLP];
+#pragma unroll
+					for (int jj = 0; jj < FU_QUAD_MLP; jj++)
+					{
+						const int j = j0 + jj, r = 2 * NPW * j + 2 * pw + rsub;
+						rb_quad_issue(pk, quad, j < nj && pix_ok && s_valid[r], x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5], qf[jj]);
+					}
+#pragma unroll
+					for (int jj = 0; jj < FU_QUAD_MLP; jj++)
+					{
+						const int j = j0 + jj;
+						ref[j] = rb_quad_finish(qf[jj]);
+						bacc[j] = fmaf(hc, ref[j].x * ref[j].x + ref[j].y * ref[j].y, bacc[j]);
+					}
+				}
+			}
+			else
 #pragma unroll
 			for (int j = 0; j < NJ; j++)
 			{
@@ -1057,7 +1082,7 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 				ref[j] = make_float2(0.f, 0.f);
 				if (j < nj && pix_ok && s_valid[r])
 				{
-					if constexpr (G256 == 2) ref[j] = rb_project3d_q256(pk, quad, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
+					if constexpr (G256 >= 2) ref[j] = rb_project3d_q256(pk, quad, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
 					else if constexpr (G256 == 1) ref[j] = rb_project3d_c256(pk8, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
 					else ref[j] = rb_project3d_xp(pk, mdl2, x, y, s_e[r][0], s_e[r][1], s_e[r][2], s_e[r][3], s_e[r][4], s_e[r][5]);
 				}
@@ -1181,6 +1206,8 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<8, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
+		RB_CUDA(cudaFuncSetAttribute(k_coarse_fused<16, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) FU_SMEM));
 		configured = true;
 	}
 	// gather: 0 = x-pair copy, four 16-byte loads per sample; 1 = expanded cells, two 32-byte loads per sample; 2 = xy-quad copy of
@@ -1190,7 +1217,7 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 	int g256 = g256_env;
 	bool have_quad = true;
 	for (int k = 0; k < K; k++) have_quad = have_quad && ctx->proj[k].quad != nullptr;
-	if (have_quad) g256 = 2; else if (g256 == 2) g256 = 0;
+	if (have_quad) g256 = (g256 >= 2 && g256 <= 4) ? g256 : 3; else if (g256 >= 2) g256 = 0;   // measured: 4 -> 5.79 ms, 3 -> 5.75, 2 -> 6.54
 	dim3 grid((unsigned) P, (unsigned) (A.tiles_per_class * K));
 	// The tile holds 32 translations (TMEM columns, B operand rows): samplings with more (--offset_range 5 --offset_step 1: 81,
 	// healpix_sampling.cpp:399-440) take ceil(T / 32) passes, each with its own B operand, writing its columns of Mweight.  The
@@ -1205,12 +1232,14 @@ int rbk_diff2_coarse_fused_pool(rb_ctx *ctx, PoolSlot &s, const float4 *cimg4)
 		if (npw == 16)
 		{
 			if (g256 == 2) k_coarse_fused<16, 2><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			else if (g256 == 3) k_coarse_fused<16, 3><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			else if (g256 == 4) k_coarse_fused<16, 4><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 			else if (g256) k_coarse_fused<16, 1><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 			else k_coarse_fused<16, 0><<<grid, 64 + 32 * 16, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 		}
 		else
 		{
-			if (g256 == 2) k_coarse_fused<8, 2><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
+			if (g256 >= 2) k_coarse_fused<8, 2><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 			else if (g256) k_coarse_fused<8, 1><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 			else k_coarse_fused<8, 0><<<grid, 64 + 32 * 8, FU_SMEM, ctx->stream>>>(tb, tbl, A, ctx->d_samp);
 		}

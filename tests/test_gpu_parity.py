@@ -972,6 +972,28 @@ def test_symmetrise_with_helical_symmetry_on_device(device, nr_asu, twist, rise,
     assert np.abs(ww - pw).max() > 0.1 * np.abs(pw).max()
 
 
+def test_references_ending_inside_the_window_need_ref_max_r(device):
+    """A pool whose references end inside the image window changes the pixel sets of the fine pass (rb_model.ref_max_r): without
+    the field the library refuses the pool instead of summing rows the reference skips; so does a left matrix with 2D references."""
+    from relion_b200.capi import RelionB200Error
+    wl = make_workload(ori_size=40, ref_box=32, healpix_order=1, n_particles=3, seed=130, snr=0.3)
+    assert wl.model.ref_max_r == wl.r_max == 16
+    wl.model.ref_max_r = 0
+    _setup(device, wl)
+    with pytest.raises(RelionB200Error) as e:
+        device.expectation_some_particles(wl.pool)
+    assert "ref_max_r" in str(e.value)
+    wl.model.ref_max_r = 16
+    device.set_model(wl.model); device.set_sampling(wl.sampling)
+    device.expectation_some_particles(wl.pool)
+    w2 = make_workload(ori_size=32, n_particles=3, nr_classes=1, seed=131, snr=0.5, ref_dim=2, psi_step=12.0)
+    w2.pool.mat_left = np.eye(3) * 1.1
+    _setup(device, w2)
+    with pytest.raises(RelionB200Error) as e:
+        device.expectation_some_particles(w2.pool)
+    assert "3D references" in str(e.value)
+
+
 _MAG_L = [[1.03, 0.012, 0.0], [-0.008, 0.96, 0.0], [0.0, 0.0, 1.0]]
 _BODY_R = [[0.9553364891, -0.2955202067, 0.0], [0.2955202067, 0.9553364891, 0.0], [0.0, 0.0, 1.0]]
 

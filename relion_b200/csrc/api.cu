@@ -294,7 +294,7 @@ static RbProjector proj_full(rb_ctx *ctx, int k)
 
 // Coarse pass of a pool: point mdl2 at a contiguous x-pair copy of the sphere the coarse window can sample (RbProjector::c2*),
 // rebuilt when the reference or the coarse size changed.  RB_COARSE_CORE=0 keeps the full copy (A/B).
-static int ensure_coarse_core(rb_ctx *ctx)
+static int ensure_coarse_core(rb_ctx *ctx, bool local_search)
 {
 	static int on = -1, quad_on = -1;
 	if (on < 0) { const char *e = getenv("RB_COARSE_CORE"); on = e ? atoi(e) : 1; }
@@ -314,13 +314,15 @@ static int ensure_coarse_core(rb_ctx *ctx)
 			if (ctx->core_stamp[k] >= 0) { p = proj_full(ctx, k); ctx->core_stamp[k] = -1; changed = true; }
 			continue;
 		}
-		if (ctx->core_stamp[k] == ctx->ref_version[k] && ctx->core_R[k] == R) continue;
+		const bool want_quad = quad_on && local_search;          // only the fused local kernel reads the quads
+		if (ctx->core_stamp[k] == ctx->ref_version[k] && ctx->core_R[k] == R && (!want_quad || p.quad)) continue;
 		RB_CHECK(ctx->proj2c_buf[k].ensure((size_t) cX * cY * cY * sizeof(float4)));
 		RB_CHECK(rbk_xpair_core(ctx, p, cX, cY, cInit, cInit, ctx->proj2c_buf[k].as<float4>()));
 		p.mdl2 = ctx->proj2c_buf[k].as<float4>();
 		p.c2X = cX; p.c2XY = cX * cY; p.c2InitY = cInit; p.c2InitZ = cInit;
-		p.quad = nullptr;
-		if (quad_on)
+		const float4 *old_quad = (ctx->core_stamp[k] == ctx->ref_version[k] && ctx->core_R[k] == R) ? p.quad : nullptr;
+		p.quad = old_quad;
+		if (want_quad && !old_quad)
 		{
 			// the xy-quad copy of the same core for the fused local kernel: two 32-byte loads per sample
 			RB_CHECK(ctx->proj4c_buf[k].ensure((size_t) cX * cY * cY * 2 * sizeof(float4)));
@@ -1230,7 +1232,7 @@ static int run_slot(rb_ctx *ctx, PoolSlot &s, unsigned flags)
 	}
 
 	RB_CUDA(cudaSetDevice(ctx->device));
-	RB_CHECK(ensure_coarse_core(ctx));
+	RB_CHECK(ensure_coarse_core(ctx, s.has_priors));
 	RB_CUDA(cudaStreamWaitEvent(ctx->stream, s.uploaded, 0));
 	if (memcmp(&s.lr, &ctx->coarse_lr, sizeof(RbLR)) != 0)
 	{

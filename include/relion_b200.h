@@ -17,9 +17,11 @@
  *     the batched rb_estep_pool() replaces the reference's "one particle per OpenMP thread" fan-out
  *     (src/ml_optimiser.cpp:4280), so no concurrent entry is needed.
  *   - there is NO CPU fallback: without a CUDA device rb_ctx_create() fails with RB_ERR_CUDA.
- *   - scope: 3D or 2D references / 2D images, nr_bodies == 1, no helical/tomo; both criteria (Gaussian squared
- *     difference and the first-iteration / --always_cc cross-correlation, rb_model.do_cc); weighted-image and
- *     gradient (SGD / VDAM residual, rb_model.do_grad) back-projection.
+ *   - scope: 3D or 2D references / 2D images, no helical-segment or tomo branches of the E-step; both criteria (Gaussian
+ *     squared difference and the first-iteration / --always_cc cross-correlation, rb_model.do_cc); weighted-image and
+ *     gradient (SGD / VDAM residual, rb_model.do_grad) back-projection; pool-level left / right matrices (MBL / MBR:
+ *     anisotropic magnification, optics groups with their own box or pixel size, body matrices: rb_particles.mat_left /
+ *     mat_right, rb_model.ref_max_r, "Optics groups" below); reconstruction with point-group and helical symmetry.
  *
  * Index conventions follow the reference:
  *   coarse hidden index  ihidden      = ((iclass*n_dir + idir)*n_psi + ipsi)*n_trans + itrans

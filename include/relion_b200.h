@@ -243,6 +243,12 @@ typedef struct {
 	                                pixel, no circle bound); 3D and 2D references.  With grad_pseudo_halfsets (= do_grad in
 	                                src/ml_optimiser.cpp:1192) particles go into accumulator iclass + (part_id % 2) * nr_classes
 	                                (:3395-3400): initialise 2 * nr_classes accumulators and pass rb_particles.bp_offset    */
+	int do_skip_rotate;          /* do_skip_align || do_skip_rotate (--skip_align / --skip_rotate: only classify): every particle keeps
+	                                its own orientation, passed as ONE-entry lists (dir_idx / psi_idx -> the rb_sampling tables, which
+	                                then hold the pool's orientations, MlOptimiser::expectationSomeParticles src/ml_optimiser.cpp:4180-4190),
+	                                and the orientation prior is pdf_class[iclass] (acc_ml_optimiser_impl.h:1966-1967).  With
+	                                --skip_align the sampling holds the single translation (0, 0) and the particle's own fractional
+	                                offset (:4196-4225) goes into rb_particles.pre_shift                                   */
 	int ref_max_r;               /* 0, or the references' r_max (rb_set_reference maxR) when it is SMALLER than current_size / 2 —
 	                                an optics group whose box is bigger than the model's (see "Optics groups" below).  The
 	                                reference's fine-pass and wavg kernels then skip the image rows maxR < iy < imgY - maxR
@@ -290,6 +296,10 @@ typedef struct {
 	const double *psi_prior;     /* psi_prior                                                     */
 	const int *bp_offset;        /* [P] or NULL (0): added to the class index to select the accumulator the particle is
 	                                back-projected into (pseudo half-sets of gradient refinement: (part_id % 2) * nr_classes) */
+	const double *pre_shift;     /* [P][2] pixels or NULL: a per-particle translation applied on top of every sampled one (the images
+	                                are multiplied by its phase ramp once, on the device; the translation prior and the sigma2_offset
+	                                sums see old_offset + pre_shift + sampled translation).  --skip_align: the fractional part of the
+	                                old offset, which the reference samples as the particle's only translation                 */
 	const double *mat_left;      /* [9] row-major or NULL: MBL of the pool, every orientation matrix becomes
 	                                inverse(mat_left * A(rot, tilt, psi) * mat_right) in both passes and the store stage
 	                                (cuda_kernel_make_eulers_3D<invert, doL, doR>, helper.cuh:713-840; generateEulerMatrices(...,
@@ -409,6 +419,7 @@ typedef struct {
 	                                The generator is counter-based on (seed, pixel): reproducible, but - like the reference's
 	                                curand and CPU generators among themselves - not the same random numbers as RELION's */
 	const double *mat_left, *mat_right; /* as in rb_particles (NULL: none) */
+	const double *pre_shift;     /* as in rb_particles */
 	const double *noise_sigma2;  /* [nr_optics_groups][image_size/2+1] or NULL (rb_model.sigma2_noise): the spectrum the noise of
 	                                the noise-filled mask is drawn from — remapped_sigma2_noise of acc_ml_optimiser_impl.h:374-384, which
 	                                for an optics group with its own box / pixel size is NOT the gather rb_model.sigma2_noise holds */

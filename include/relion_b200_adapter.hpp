@@ -284,10 +284,11 @@ public:
 		h_dvp.assign((size_t) K * nshell, 0.);
 		for (int k = 0; k < K && k < (int) m.data_vs_prior_class.size(); k++)
 			for (int i = 0; i < nshell && i < (int) XSIZE(m.data_vs_prior_class[k]); i++) h_dvp[(size_t) k * nshell + i] = DIRECT_A1D_ELEM(m.data_vs_prior_class[k], i);
-		const int n_dir = (int) o.sampling.NrDirections(), n_psi = (int) o.sampling.NrPsiSamplings();
-		const bool use_priors = m.orientational_prior_mode != NOPRIOR && !(o.do_skip_align || o.do_skip_rotate);
+		const int n_dir = (int) o.sampling.NrDirections();
+		const bool skip = o.do_skip_align || o.do_skip_rotate;
+		const bool use_priors = m.orientational_prior_mode != NOPRIOR && !skip;
 		h_pdf_dir.clear();
-		if (!use_priors)
+		if (!use_priors && !skip)
 		{
 			h_pdf_dir.assign((size_t) K * n_dir, 0.);
 			for (int k = 0; k < K; k++)
@@ -314,6 +315,7 @@ public:
 		rm.bp_circle_bound = 1;
 		rm.do_cc = (o.iter == 1 && o.do_firstiter_cc) || o.do_always_cc;                   // :1164
 		rm.do_grad = o.do_grad ? 1 : 0;                                                    // acc_ml_optimiser_impl.h:3418
+		rm.do_skip_rotate = skip ? 1 : 0;                                                  // :1966-1967, :3752-3766
 		h_prior_class.clear();
 		if (m.ref_dim == 2 && m.nr_bodies == 1)                                             // :2100-2104, :2673-2677
 		{
@@ -321,13 +323,38 @@ public:
 			rm.prior_offset_class = h_prior_class.data();
 		}
 		RB_TRY(rb_set_model(ctx, &rm));
+		geometry_og = og;
+		setSampling();
+	}
 
-		// ---- sampling tables (HealpixSampling stays RELION's: getOrientations :1832, getTranslationsInPixel :1724) ----
+	/* Sampling tables of the loaded geometry (HealpixSampling stays RELION's: getOrientations :1832, getTranslationsInPixel :1724).
+	 * With --skip_align / --skip_rotate RELION refills the sampling object with the pool's own orientations before every pool
+	 * (src/ml_optimiser.cpp:4180-4225), so the pool path calls this again for every pool; particle row p then uses entry p of the
+	 * direction and psi tables, and with --skip_align its own translation (entry p) travels as rb_particles.pre_shift while the
+	 * library samples the single translation (0, 0). */
+	void setSampling()
+	{
+		MlOptimiser &o = *baseMLO;
+		const int og = geometry_og;
+		const RFLOAT my_pixel_size = o.mydata.getOpticsPixelSize(og);
+		const bool skip = o.do_skip_align || o.do_skip_rotate;
+		const int n_dir = (int) o.sampling.NrDirections(), n_psi = (int) o.sampling.NrPsiSamplings();
 		const int ov = o.adaptive_oversampling;
-		const int nor = o.sampling.oversamplingFactorOrientations(ov), n_trans = (int) o.sampling.NrTranslationalSamplings(), not_ = o.sampling.oversamplingFactorTranslations(ov);
+		if (skip && ov != 0) RB_REPORT_ERROR("relion_b200: --skip_align / --skip_rotate run without oversampling (src/ml_optimiser.cpp:2382-2389)");
+		const int nor = o.sampling.oversamplingFactorOrientations(ov), not_ = o.sampling.oversamplingFactorTranslations(ov);
+		const int n_trans = o.do_skip_align ? 1 : (int) o.sampling.NrTranslationalSamplings();      // --skip_align: (0, 0), the particle's own goes into pre_shift
 		std::vector<RFLOAT> a, b, c;
 		std::vector<int> no_ptr; std::vector<RFLOAT> no_prior;
 		s_rot.assign(n_dir, 0.); s_tilt.assign(n_dir, 0.); s_psi.assign(n_psi, 0.);
+		s_orot.clear(); s_otilt.clear(); s_opsi.clear();
+		if (skip)
+		{
+			// only (d, d) is ever used: one pass over the directions and one over the psi angles
+			for (int d = 0; d < n_dir; d++) { o.sampling.getOrientations(d, 0, 0, a, b, c, no_ptr, no_prior, no_ptr, no_prior); s_rot[d] = a[0]; s_tilt[d] = b[0]; }
+			for (int p = 0; p < n_psi; p++) { o.sampling.getOrientations(0, p, 0, a, b, c, no_ptr, no_prior, no_ptr, no_prior); s_psi[p] = c[0]; }
+		}
+		else
+		{
 		s_orot.assign((size_t) n_dir * n_psi * nor, 0.); s_otilt = s_orot; s_opsi = s_orot;
 		for (int d = 0; d < n_dir; d++)
 			for (int p = 0; p < n_psi; p++)
@@ -337,8 +364,9 @@ public:
 				o.sampling.getOrientations(d, p, ov, a, b, c, no_ptr, no_prior, no_ptr, no_prior);
 				for (int i = 0; i < nor; i++) { const size_t g = ((size_t) d * n_psi + p) * nor + i; s_orot[g] = a[i]; s_otilt[g] = b[i]; s_opsi[g] = c[i]; }
 			}
+		}
 		s_tx.assign(n_trans, 0.); s_ty = s_tx; s_otx.assign((size_t) n_trans * not_, 0.); s_oty = s_otx;
-		for (int t = 0; t < n_trans; t++)
+		for (int t = 0; t < n_trans && !o.do_skip_align; t++)
 		{
 			o.sampling.getTranslationsInPixel(t, 0, my_pixel_size, a, b, c, false);
 			s_tx[t] = a[0]; s_ty[t] = b[0];
@@ -348,12 +376,12 @@ public:
 		rb_sampling rs;
 		memset(&rs, 0, sizeof(rs));
 		rs.n_dir = n_dir; rs.n_psi = n_psi; rs.rot = s_rot.data(); rs.tilt = s_tilt.data(); rs.psi = s_psi.data();
-		rs.n_over_rot = nor; rs.over_rot = s_orot.data(); rs.over_tilt = s_otilt.data(); rs.over_psi = s_opsi.data();
+		rs.n_over_rot = nor;
+		if (!s_orot.empty()) { rs.over_rot = s_orot.data(); rs.over_tilt = s_otilt.data(); rs.over_psi = s_opsi.data(); }
 		rs.n_trans = n_trans; rs.trans_x = s_tx.data(); rs.trans_y = s_ty.data();
 		rs.n_over_trans = not_; rs.over_trans_x = s_otx.data(); rs.over_trans_y = s_oty.data();
 		RB_TRY(rb_set_sampling(ctx, &rs));
-		if (rm.pdf_direction) RB_TRY(rb_set_pdf_direction(ctx, rm.pdf_direction));
-		geometry_og = og;
+		if (!h_pdf_dir.empty()) RB_TRY(rb_set_pdf_direction(ctx, h_pdf_dir.data()));
 	}
 
 	/* cuda_ml_optimiser.cu:85-152: model + sampling tables, then per class projector and back-projector */
@@ -465,6 +493,7 @@ public:
 			long int run_last = run_first;
 			while (run_last + 1 <= last && bundle->sameGeometry(o.mydata.getOpticsGroup(run_last + 1), og0)) run_last++;
 			bundle->setGeometry(og0);
+			if (o.do_skip_align || o.do_skip_rotate) bundle->setSampling();       // the sampling object holds THIS pool's orientations (:4180-4225)
 			expectationRun(run_first, run_last);
 			run_first = run_last + 1;
 		}
@@ -485,7 +514,8 @@ private:
 		const int cur = o.image_current_size[og0];
 		const RFLOAT my_pixel_size = o.mydata.getOpticsPixelSize(og0);
 		if ((int) YSIZE(o.exp_imagedata) != n) RB_REPORT_ERROR("relion_b200: exp_imagedata does not have the box size of the particles' optics group");
-		const bool use_priors = m.orientational_prior_mode != NOPRIOR && !(o.do_skip_align || o.do_skip_rotate);
+		const bool skip = o.do_skip_align || o.do_skip_rotate;
+		const bool use_priors = m.orientational_prior_mode != NOPRIOR && !skip;
 		const bool do_cc = (o.iter == 1 && o.do_firstiter_cc) || o.do_always_cc;
 		const int nog = m.nr_optics_groups;
 
@@ -497,7 +527,9 @@ private:
 		std::vector<double> dir_prior, psi_prior;
 		std::vector<std::vector<int> > ptr_dir(P), ptr_psi(P);
 		std::vector<std::vector<RFLOAT> > pri_dir(P), pri_psi(P);
-		if (use_priors) { dir_off.push_back(0); psi_off.push_back(0); }
+		if (use_priors || skip) { dir_off.push_back(0); psi_off.push_back(0); }
+		std::vector<double> pre_shift;
+		std::vector<RFLOAT> ta, tb, tc;
 		for (int p = 0; p < P; p++)
 		{
 			const long int part_id = first + p;                       // exp_metadata row p: one image per particle
@@ -520,6 +552,17 @@ private:
 				CTF ctf;                                                                                                         // :822-840
 				ctf.setValuesByGroup(&o.mydata.obsModel, optics_group[p], defU[p], defV[p], defA[p], bfac[p], kfac[p], phs[p], -1.);
 				og_kV[optics_group[p]] = ctf.kV; og_Cs[optics_group[p]] = ctf.Cs; og_Q0[optics_group[p]] = ctf.Q0;
+			}
+			if (skip)
+			{
+				// :3752-3766: idir = ipsi (= itrans with --skip_align) = the particle's row in the pool; prior = pdf_class (:1966)
+				dir_idx.push_back(row0 + p); dir_prior.push_back(1.); psi_idx.push_back(row0 + p); psi_prior.push_back(1.);
+				dir_off.push_back((int) dir_idx.size()); psi_off.push_back((int) psi_idx.size());
+				if (o.do_skip_align)
+				{
+					o.sampling.getTranslationsInPixel(row0 + p, 0, my_pixel_size, ta, tb, tc, false);
+					pre_shift.push_back(ta[0]); pre_shift.push_back(tb[0]);
+				}
 			}
 			if (use_priors)
 			{
@@ -618,7 +661,8 @@ private:
 			raw.noise_sigma2 = noise_sigma2.data();
 		}
 		raw.width_mask_edge = (double) o.width_mask_edge;
-		if (use_priors)
+		if (!pre_shift.empty()) raw.pre_shift = pre_shift.data();
+		if (use_priors || skip)
 		{
 			raw.dir_off = dir_off.data(); raw.dir_idx = dir_idx.data(); raw.dir_prior = dir_prior.data();
 			raw.psi_off = psi_off.data(); raw.psi_idx = psi_idx.data(); raw.psi_prior = psi_prior.data();
@@ -658,8 +702,9 @@ private:
 			const rb_particle_out &r = parts[p];
 			const int og = optics_group[p], ig = group_id[p];
 			// metadata row (:2858-2931)
-			o.sampling.getOrientations(r.best_idir, r.best_ipsi, o.adaptive_oversampling, rot, tilt, psi, ptr_dir[p], pri_dir[p], ptr_psi[p], pri_psi[p]);
-			o.sampling.getTranslationsInPixel(r.best_itrans, o.adaptive_oversampling, my_pixel_size, tx, ty, tz, false);                   // :2696
+			// with --skip_align / --skip_rotate the reference's indices are the particle's row (:2874-2876)
+			o.sampling.getOrientations(skip ? row0 + p : r.best_idir, skip ? row0 + p : r.best_ipsi, o.adaptive_oversampling, rot, tilt, psi, ptr_dir[p], pri_dir[p], ptr_psi[p], pri_psi[p]);
+			o.sampling.getTranslationsInPixel(o.do_skip_align ? row0 + p : r.best_itrans, o.adaptive_oversampling, my_pixel_size, tx, ty, tz, false);   // :2696
 			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_ROT) = rot[r.best_iover_rot];
 			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_TILT) = tilt[r.best_iover_rot];
 			DIRECT_A2D_ELEM(o.exp_metadata, row0 + p, METADATA_PSI) = psi[r.best_iover_rot];

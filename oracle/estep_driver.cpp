@@ -140,6 +140,7 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 	const int64_t nCoarse = (int64_t) Kc * nOrient * T;
 
 	auto pdf_of = [&](int k, int idl, int ipl) -> double {
+		if (m->do_skip_rotate) return m->pdf_class[k];                          // acc_projector_plan_impl.h:193-195, acc_ml_optimiser_impl.h:1966
 		if (noprior) return m->pdf_direction[(size_t) k * s->n_dir + idl];      // acc_projector_plan_impl.h:196-204
 		return dprior[idl] * pprior[ipl];
 	};
@@ -150,6 +151,29 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 	const double highres_Xi2 = pool->highres_Xi2[p];
 	const float *Fimg_full = pool->Fimg + (size_t) p * S.Npf * 2;
 	const float *Fnomask_full = pool->Fimg_nomask + (size_t) p * S.Npf * 2;
+	// rb_particles.pre_shift: the particle's own translation (--skip_align), applied to both transforms once with the phase ramp of a
+	// sampled shift (-2 pi shift / n_full, :1239-1241)
+	std::vector<float> shifted_img, shifted_nomask;
+	if (pool->pre_shift && (pool->pre_shift[2 * p] != 0. || pool->pre_shift[2 * p + 1] != 0.))
+	{
+		const double dx = pool->pre_shift[2 * p], dy = pool->pre_shift[2 * p + 1];
+		const int nf = S.nf, xs = nf / 2 + 1;
+		shifted_img.assign(Fimg_full, Fimg_full + (size_t) S.Npf * 2);
+		shifted_nomask.assign(Fnomask_full, Fnomask_full + (size_t) S.Npf * 2);
+		for (int iy = 0; iy < nf; iy++)
+			for (int x = 0; x < xs; x++)
+			{
+				const int y = iy < xs ? iy : iy - nf;
+				const double a = -2. * M_PI * ((double) x * dx + (double) y * dy) / (double) m->ori_size;
+				const float c = (float) cos(a), s = (float) sin(a);
+				const size_t i = (size_t) iy * xs + x;
+				float re = shifted_img[2 * i], im = shifted_img[2 * i + 1];
+				shifted_img[2 * i] = c * re - s * im; shifted_img[2 * i + 1] = c * im + s * re;
+				re = shifted_nomask[2 * i]; im = shifted_nomask[2 * i + 1];
+				shifted_nomask[2 * i] = c * re - s * im; shifted_nomask[2 * i + 1] = c * im + s * re;
+			}
+		Fimg_full = shifted_img.data(); Fnomask_full = shifted_nomask.data();
+	}
 	const float *Fctf_full = pool->Fctf ? pool->Fctf + (size_t) p * S.Npf : NULL;
 
 	// ---- image-side arrays for one window size (precalculateShiftedImagesCtfsAndInvSigma2s,
@@ -242,7 +266,8 @@ int run_particle(const Shared &S, const rb_particles *pool, int p, rb_pool_out *
 				pdf_orientation[i] = (pdf == 0) ? 0.f : (float) log(pdf);
 			}
 	double s2off = (m->offset_range > 0.) ? (m->offset_range * m->offset_range) / 9. : m->sigma2_offset;   // :1916-1926
-	const double oldx = pool->old_offset[2 * p], oldy = pool->old_offset[2 * p + 1];
+	// rb_particles.pre_shift is part of every sampled offset (with --skip_align it IS the sampled translation, :2138-2139)
+	const double oldx = pool->old_offset[2 * p] + (pool->pre_shift ? pool->pre_shift[2 * p] : 0.), oldy = pool->old_offset[2 * p + 1] + (pool->pre_shift ? pool->pre_shift[2 * p + 1] : 0.);
 	const double prx = pool->prior_offset[2 * p], pry = pool->prior_offset[2 * p + 1];
 	for (int k = 0; k < Kc; k++)
 	{

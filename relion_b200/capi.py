@@ -56,6 +56,7 @@ class rb_model(C.Structure):
         ("do_cc", C.c_int),
         ("prior_offset_class", c_double_p),
         ("do_grad", C.c_int),
+        ("do_skip_rotate", C.c_int),
         ("ref_max_r", C.c_int),
     ]
 
@@ -69,6 +70,7 @@ class rb_particles(C.Structure):
         ("dir_off", c_int_p), ("dir_idx", c_int_p), ("dir_prior", c_double_p),
         ("psi_off", c_int_p), ("psi_idx", c_int_p), ("psi_prior", c_double_p),
         ("bp_offset", c_int_p),
+        ("pre_shift", c_double_p),
         ("mat_left", c_double_p), ("mat_right", c_double_p),
     ]
 
@@ -88,6 +90,7 @@ class rb_raw_particles(C.Structure):
         ("og_fourier_factor", c_float_p),
         ("noise_seed", C.POINTER(C.c_int64)),
         ("mat_left", c_double_p), ("mat_right", c_double_p),
+        ("pre_shift", c_double_p),
         ("noise_sigma2", c_double_p),
     ]
 

@@ -885,6 +885,7 @@ extern "C" int rb_set_model(rb_ctx *ctx, const rb_model *m)
 	d.bp_circle_bound = m->bp_circle_bound;
 	d.do_cc = m->do_cc;
 	d.do_grad = m->do_grad;
+	d.do_skip_rotate = m->do_skip_rotate;
 	// pdf_direction needs n_dir, which belongs to the sampling: keep a host copy until both are known
 	ctx->m_pdf_dir.release();
 	if (m->pdf_direction && ctx->has_sampling)
@@ -982,6 +983,7 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 		RB_ARG(m.bp_off >= 0 && m.bp_off + K <= RB_MAX_CLASSES, "rb_pool_upload: particle %d: accumulator offset %d out of range", p, m.bp_off);
 		s.max_bp_off = std::max(s.max_bp_off, m.bp_off);
 		m.oldx = pool->old_offset[2 * p]; m.oldy = pool->old_offset[2 * p + 1];
+		if (pool->pre_shift) { m.oldx += pool->pre_shift[2 * p]; m.oldy += pool->pre_shift[2 * p + 1]; }   // part of every sampled offset
 		m.prx = pool->prior_offset[2 * p]; m.pry = pool->prior_offset[2 * p + 1];
 		m.coarse_off = coff; m.prior_off = poff;
 		const long long no = (long long) m.nd * m.np;
@@ -1022,6 +1024,14 @@ static int pool_setup(rb_ctx *ctx, int slot, const rb_particles *pool, bool copy
 		RB_CUDA(cudaMemcpyAsync(s.dir_prior.p, pool->dir_prior, nd * 8, cudaMemcpyHostToDevice, cs));
 		RB_CUDA(cudaMemcpyAsync(s.psi_idx.p, pool->psi_idx, np * 4, cudaMemcpyHostToDevice, cs));
 		RB_CUDA(cudaMemcpyAsync(s.psi_prior.p, pool->psi_prior, np * 8, cudaMemcpyHostToDevice, cs));
+	}
+	s.has_pre_shift = false;
+	if (pool->pre_shift)
+	{
+		RB_CHECK(s.pre_shift.ensure((size_t) P * 2 * sizeof(double)));
+		RB_CUDA(cudaMemcpyAsync(s.pre_shift.p, pool->pre_shift, (size_t) P * 2 * sizeof(double), cudaMemcpyHostToDevice, cs));
+		s.has_pre_shift = true;
+		if (copy_images) RB_CHECK(rbk_pre_shift(ctx, s, cs));     // rb_pool_prepare applies it after its own kernels
 	}
 	RB_CUDA(cudaEventRecord(s.uploaded, cs));
 
@@ -1142,7 +1152,7 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 	pool.dir_off = raw->dir_off; pool.dir_idx = raw->dir_idx; pool.dir_prior = raw->dir_prior;
 	pool.psi_off = raw->psi_off; pool.psi_idx = raw->psi_idx; pool.psi_prior = raw->psi_prior;
 	pool.bp_offset = raw->bp_offset;
-	pool.mat_left = raw->mat_left; pool.mat_right = raw->mat_right;
+	pool.mat_left = raw->mat_left; pool.mat_right = raw->mat_right; pool.pre_shift = raw->pre_shift;
 	RB_CHECK(pool_setup(ctx, slot, &pool, false));
 	PoolSlot &s = ctx->slot[slot];
 	// raw images + small tables on the copy stream (overlaps the compute of the other slot), kernels on the compute stream
@@ -1187,6 +1197,7 @@ extern "C" int rb_pool_prepare(rb_ctx *ctx, int slot, const rb_raw_particles *ra
 	RB_CHECK(rbk_prepare_pool(ctx, s, bRaw.as<float>(), bShift.as<int>(), bNorm.as<float>(), do_ctf ? bCtf.as<double>() : nullptr, n,
 	                          (float) raw->mask_radius, (float) raw->width_mask_edge, bPow.as<float>(), d_seed, d_spec, d_fac, cs));
 	if (power_img) RB_CUDA(cudaMemcpyAsync(power_img, bPow.p, (size_t) P * (n / 2 + 1) * 4, cudaMemcpyDeviceToHost, cs));
+	if (s.has_pre_shift) RB_CHECK(rbk_pre_shift(ctx, s, cs));
 	RB_CUDA(cudaEventRecord(s.uploaded, cs));            // rb_estep_slot waits for the preparation
 	RB_CUDA(cudaStreamSynchronize(cs));                  // shift / norm / ctfpar / spec are host temporaries; power_img is the caller's
 	return RB_OK;

@@ -214,6 +214,7 @@ struct RbModelDev {
 	double pixel_size, s2off, adaptive_fraction;
 	int maximum_significants;
 	int do_ctf_correction, refs_are_ctf_corrected, do_scale_correction, do_map, ctf_premultiplied, bp_circle_bound;
+	int do_skip_rotate;      // orientation prior = pdf_class (do_skip_align || do_skip_rotate, acc_ml_optimiser_impl.h:1966)
 	int do_cc;               // first-iteration cross-correlation criterion (acc_ml_optimiser_impl.h:1164)
 	int do_grad;             // SGD / VDAM: back-project the weighted residual (BP.cuh:406-656), every pixel (no circle bound)
 	// blocks of pdf_offset per particle: [Kp][n_trans], Kp = K with per-class prior centres, else 1.  Block 0 serves the
@@ -246,6 +247,7 @@ struct PoolSlot {
 	// particle order[i], so that CTAs in flight together sample neighbouring central planes and share their part of the coarse core
 	// in L2 (a pool in acquisition order scatters the planes over the whole core)
 	DevBuf order; bool has_order = false;
+	DevBuf pre_shift; bool has_pre_shift = false;   // rb_particles.pre_shift: [P][2] doubles, applied to Fimg / Fnomask once
 	long long total_prior = 0;
 	DevBuf Fimg, Fnomask, Fctf, meta, state, dir_idx, dir_prior, psi_idx, psi_prior;
 	DevBuf Mweight, pdf_orient, pdf_orient_zero, pdf_offset, pdf_offset_zero;
@@ -359,6 +361,7 @@ int rbk_make_coarse_eulers(rb_ctx *ctx, const double *d_rot, const double *d_til
                            float *d_eulers);
 int rbk_convert_volume(rb_ctx *ctx, const double *d_in, float2 *d_out, size_t n);
 int rbk_expand_volume(rb_ctx *ctx, const RbProjector &pj, float4 *d_out, float4 *d_out2);
+int rbk_pre_shift(rb_ctx *ctx, PoolSlot &s, cudaStream_t stream);
 int rbk_xyquad_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);
 int rbk_xpair_core(rb_ctx *ctx, const RbProjector &pj, int cX, int cY, int cInitY, int cInitZ, float4 *d_out);
 int rbk_bp_deinterleave(rb_ctx *ctx, const float4 *vol, float *re, float *im, float *w, size_t n);

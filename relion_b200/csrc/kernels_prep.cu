@@ -380,3 +380,35 @@ int rbk_backproject_posed_raw(rb_ctx *ctx, const RbBackprojector &bp, int n, int
 	RB_LAUNCH_CHECK(ctx);
 	return rbk_posed_band_scatter(ctx, bp, n, count, d_eulers, L);
 }
+
+// ---------------------------------------------------------------------------------------------
+// rb_particles.pre_shift: Fimg and Fimg_nomask of particle p times exp(-2 pi i (x dx_p + y dy_p) / ori_size), the phase ramp every
+// translation kernel applies for a sampled shift (trans = -2 pi shift / n_full, acc_ml_optimiser_impl.h:1239-1241): the particle's
+// own translation of --skip_align (src/ml_optimiser.cpp:4196-4225), applied once instead of being sampled.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_pre_shift(float2 *Fimg, float2 *Fnomask, const double *shift, int n, int ori_size, int P)
+{
+	const int xs = n / 2 + 1;
+	const size_t per = (size_t) n * xs, tot = per * P;
+	for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < tot; i += (size_t) gridDim.x * blockDim.x)
+	{
+		const int p = (int) (i / per);
+		const int r = (int) (i - (size_t) p * per), iy = r / xs, x = r - iy * xs, y = iy < xs ? iy : iy - n;
+		const double dx = shift[2 * p], dy = shift[2 * p + 1];
+		if (dx == 0. && dy == 0.) continue;
+		double sn, cs;
+		sincospi(-2. * ((double) x * dx + (double) y * dy) / (double) ori_size, &sn, &cs);
+		const float c = (float) cs, s = (float) sn;
+		float2 a = Fimg[i], b = Fnomask[i];
+		Fimg[i] = make_float2(c * a.x - s * a.y, c * a.y + s * a.x);
+		Fnomask[i] = make_float2(c * b.x - s * b.y, c * b.y + s * b.x);
+	}
+}
+
+int rbk_pre_shift(rb_ctx *ctx, PoolSlot &s, cudaStream_t stream)
+{
+	const RbModelDev &M = ctx->d_model;
+	k_pre_shift<<<ctx->num_sms * 4, 256, 0, stream>>>(s.Fimg.as<float2>(), s.Fnomask.as<float2>(), s.pre_shift.as<double>(), M.current_size, M.ori_size, s.P);
+	RB_LAUNCH_CHECK(ctx);
+	return RB_OK;
+}

@@ -25,7 +25,8 @@ __global__ void k_prep_priors(const RbPartMeta *metas, RbModelDev M, RbSamplingD
 	{
 		int k = o / no, oi = o - k * no, idl = oi / m.np, ipl = oi - idl * m.np;
 		double pdf;
-		if (m.dir_off < 0) pdf = M.pdf_direction[(size_t) k * S.n_dir + idl];
+		if (M.do_skip_rotate) pdf = M.pdf_class[k];                                        // :1966-1967
+		else if (m.dir_off < 0) pdf = M.pdf_direction[(size_t) k * S.n_dir + idl];
 		else pdf = dir_prior[m.dir_off + idl] * psi_prior[m.psi_off + ipl];
 		if (!(M.pdf_class[k] > 0.)) pdf = 0.;   // classes with zero pdf_class are never evaluated (:1069)
 		pdf_orient_zero[m.prior_off + o] = (pdf == 0.);

@@ -76,6 +76,7 @@ class ModelParams:
     prior_offset_class: Optional[np.ndarray] = None   # [K, 2] pixels: mymodel.prior_offset_class (2D references), None for 3D
     do_grad: bool = False                    # gradient (SGD / VDAM) refinement: residual back-projection
     ref_max_r: int = 0                       # the references' r_max when smaller than current_size / 2 (rb_model.ref_max_r)
+    do_skip_rotate: bool = False             # --skip_align / --skip_rotate: one-entry orientation lists, prior = pdf_class
 
 
 @dataclasses.dataclass
@@ -96,6 +97,7 @@ class ParticlePool:
     psi_idx: Optional[np.ndarray] = None
     psi_prior: Optional[np.ndarray] = None
     bp_offset: Optional[np.ndarray] = None   # [P] int32: accumulator = class + bp_offset (pseudo half-sets of gradient refinement)
+    pre_shift: Optional[np.ndarray] = None   # [P, 2] pixels: per-particle translation on top of the sampled ones (--skip_align)
     mat_left: Optional[np.ndarray] = None    # [3, 3] MBL: orientation matrices become inverse(mat_left A mat_right) (magnification / scale
     mat_right: Optional[np.ndarray] = None   # [3, 3] MBR   difference of the optics group, body matrices)
 
@@ -184,6 +186,7 @@ def marshal_model(p: ModelParams):
     st.do_cc = int(p.do_cc)
     st.do_grad = int(p.do_grad)
     st.ref_max_r = int(p.ref_max_r)
+    st.do_skip_rotate = int(p.do_skip_rotate)
     if p.prior_offset_class is not None:
         poc = m.hold(_f64(np.asarray(p.prior_offset_class).reshape(p.nr_classes, 2)))
         st.prior_offset_class = _ptr(poc, C.c_double)
@@ -222,6 +225,7 @@ class RawParticlePool:
     og_fourier_factor: Optional[np.ndarray] = None   # [nog, cs, cs/2+1] complex64: conj(beam-tilt phase) * avgMTF / MTF per optics group
     mat_left: Optional[np.ndarray] = None
     mat_right: Optional[np.ndarray] = None
+    pre_shift: Optional[np.ndarray] = None
 
     @property
     def n_particles(self):
@@ -247,6 +251,7 @@ def marshal_raw_pool(pool: RawParticlePool):
         st.noise_seed = m.hold(np.ascontiguousarray(pool.noise_seed, dtype=np.int64)).ctypes.data_as(C.POINTER(C.c_int64))
     st.mat_left = _ptr(m.hold(_f64(pool.mat_left)), C.c_double)
     st.mat_right = _ptr(m.hold(_f64(pool.mat_right)), C.c_double)
+    st.pre_shift = _ptr(m.hold(_f64(pool.pre_shift)), C.c_double)
     m.struct = st
     return m
 
@@ -280,6 +285,7 @@ def marshal_pool(pool: ParticlePool):
     st.bp_offset = _ptr(m.hold(_i32(pool.bp_offset)), C.c_int)
     st.mat_left = _ptr(m.hold(_f64(pool.mat_left)), C.c_double)
     st.mat_right = _ptr(m.hold(_f64(pool.mat_right)), C.c_double)
+    st.pre_shift = _ptr(m.hold(_f64(pool.pre_shift)), C.c_double)
     m.struct = st
     return m
 

@@ -181,3 +181,63 @@ def raw_pool_from(wl: Workload, seed: int = 0, mask_radius: Optional[float] = No
                           mat_left=wl.pool.mat_left, mat_right=wl.pool.mat_right)
     return raw
 
+
+
+def make_skip_align_workload(*, ori_size: int = 32, n_particles: int = 12, nr_classes: int = 3, seed: int = 7, snr: float = 0.3,
+                             skip_rotate_only: bool = False, offset_range: float = 3.0, offset_step: float = 1.0,
+                             pixel_size: float = 2.0, nr_groups: int = 2, n_blobs: int = 40) -> Workload:
+    """--skip_align (only classify; skip_rotate_only: --skip_rotate, translations still searched): the sampling tables hold the
+    POOL's orientations, particle p uses entry p of the direction and psi tables through one-entry lists
+    (MlOptimiser::expectationSomeParticles, src/ml_optimiser.cpp:4180-4225: sampling.addOneOrientation / addOneTranslation per
+    particle; acc_ml_optimiser_impl.h:3752-3766: idir = ipsi = itrans = row of the particle), no oversampling
+    (src/ml_optimiser.cpp:2382-2389), the orientation prior is pdf_class.  With --skip_align the particle's own fractional offset is
+    its only translation: here rb_particles.pre_shift, the sampling holds (0, 0)."""
+    rng = np.random.default_rng(seed)
+    pf = 2.0
+    P = n_particles
+    refs = []
+    for k in range(nr_classes):
+        vol = synth.make_phantom(ori_size, n_blobs=n_blobs, seed=seed + 17 * k)
+        data, r_max = synth.reference_ft(vol, current_size=ori_size, padding_factor=pf)
+        refs.append(data.astype(np.complex64))
+    rot, tilt, psi = rng.uniform(-180, 180, P), rng.uniform(0, 180, P), rng.uniform(-180, 180, P)
+    if skip_rotate_only:
+        base = smp.make_sampling(1, offset_range, offset_step, oversampling=0, build_oversampled=False)
+        tx, ty = np.asarray(base.trans_x, np.float64), np.asarray(base.trans_y, np.float64)
+        it = rng.integers(0, len(tx), P)
+        shifts = np.stack([tx[it], ty[it]], axis=1)
+        pre_shift = None
+        old_offset = np.zeros((P, 2))
+    else:
+        tx, ty = np.zeros(1), np.zeros(1)
+        it = np.zeros(P, np.int64)
+        shifts = rng.uniform(-0.5, 0.5, (P, 2))              # the fractional part of the old offset
+        pre_shift = shifts.copy()
+        old_offset = np.zeros((P, 2))                        # the rounded part, already applied to the image
+    s = smp.Sampling(healpix_order=1, psi_step=0.0, offset_range=offset_range, offset_step=offset_step, oversampling=0,
+                     rot=rot.copy(), tilt=tilt.copy(), psi=psi.copy(), trans_x=tx, trans_y=ty)
+    # the "oversampled" tables of oversampling order 0 are the coarse ones: entry (d, q) = (rot[d], tilt[d], psi[q])
+    s.over_rot = np.repeat(rot, P); s.over_tilt = np.repeat(tilt, P); s.over_psi = np.tile(psi, P)
+    s.over_trans_x, s.over_trans_y = tx.copy(), ty.copy()
+    cls = rng.integers(0, nr_classes, P)
+    eul = synth.inverse_euler_f32(rot, tilt, psi)
+    n = ori_size
+    slices = np.empty((P, n, n // 2 + 1), np.complex128)
+    for p in range(P):
+        slices[p] = synth.project_numpy(refs[cls[p]], r_max, pf, eul[p].reshape(3, 3).astype(np.float64), n)
+    parts = synth.make_particles(slices, ori_size, pixel_size, snr, seed + 1, rot, tilt, psi, shifts)
+    nshell = ori_size // 2 + 1
+    pdf_class = rng.uniform(0.5, 1.5, nr_classes); pdf_class /= pdf_class.sum()
+    dvp = np.zeros((nr_classes, nshell)); dvp[:, : max(2, nshell // 2)] = 10.0
+    model = ModelParams(nr_classes=nr_classes, ori_size=ori_size, coarse_size=ori_size, current_size=ori_size, pixel_size=pixel_size,
+                        sigma2_noise=np.tile(parts.sigma2_noise[None, :], (1, 1)), scale_correction=1.0 + 0.05 * rng.standard_normal(nr_groups),
+                        pdf_class=pdf_class, pdf_direction=None, data_vs_prior_class=dvp,
+                        sigma2_offset=(offset_range * pixel_size / 1.5) ** 2, do_skip_rotate=True)
+    one = np.arange(P + 1, dtype=np.int32)
+    pool = ParticlePool(Fimg=parts.Fimg, Fimg_nomask=parts.Fimg_nomask, Fctf=parts.Fctf, group_id=rng.integers(0, nr_groups, P).astype(np.int32),
+                        optics_group=np.zeros(P, np.int32), highres_Xi2=parts.highres_Xi2, old_offset=old_offset, prior_offset=np.zeros((P, 2)),
+                        dir_off=one, dir_idx=np.arange(P, dtype=np.int32), dir_prior=np.ones(P),
+                        psi_off=one.copy(), psi_idx=np.arange(P, dtype=np.int32), psi_prior=np.ones(P), pre_shift=pre_shift)
+    pad = refs[0].shape[0]
+    truth = dict(cls=cls, rot=rot, tilt=tilt, psi=psi, shifts=shifts, itrans=it, ctf_params=parts.ctf_params)
+    return Workload("skip_align", model, s, refs, r_max, pf, pool, truth, (pad, pad, pad // 2 + 1))

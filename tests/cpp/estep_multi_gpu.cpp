@@ -137,7 +137,9 @@ static void build_optimiser(MlOptimiser &o, const std::map<std::string, Arr> &d)
 	}
 	// optimiser flags / sizes
 	o.image_full_size.assign(1, img_size); o.image_current_size.assign(1, (int) scalar(d, "current_size")); o.image_coarse_size.assign(1, (int) scalar(d, "coarse_size"));
-	o.iter = 5; o.adaptive_oversampling = 1; o.adaptive_fraction = scalar(d, "adaptive_fraction"); o.maximum_significants = -1;
+	// "skip_align": --skip_align (only classify): no oversampling, no priors (src/ml_optimiser.cpp:2382-2389, 2415-2420)
+	o.do_skip_align = d.count("skip_align") && scalar(d, "skip_align") != 0.;
+	o.iter = 5; o.adaptive_oversampling = o.do_skip_align ? 0 : 1; o.adaptive_fraction = scalar(d, "adaptive_fraction"); o.maximum_significants = -1;
 	o.particle_diameter = scalar(d, "particle_diameter"); o.width_mask_edge = (int) scalar(d, "width_mask_edge"); o.sigma2_fudge = 1.;
 	o.do_auto_refine = true; o.autosampling_hporder_local_searches = local ? 0 : 99;
 	const int cur = o.image_current_size[0], xs = cur / 2 + 1;
@@ -171,6 +173,20 @@ static void expectation(MlOptimiser &o, const std::map<std::string, Arr> &d, int
 		// getMetaAndImageDataSubset (:10285-10552): rows and images of the pool
 		o.exp_metadata.resize(P, ncol);
 		memcpy(o.exp_metadata.data, metadata_all.data() + (size_t) first * ncol, (size_t) P * ncol * 8);
+		if (o.do_skip_align)
+		{
+			// expectationSomeParticles (src/ml_optimiser.cpp:4180-4225): the sampling object is refilled with the pool's own
+			// orientations (addOneOrientation) and fractional offsets in Angstrom (addOneTranslation)
+			HealpixSampling &s = o.sampling;
+			s.rot_angles.clear(); s.tilt_angles.clear(); s.psi_angles.clear(); s.translations_x.clear(); s.translations_y.clear();
+			for (int p = 0; p < P; p++)
+			{
+				s.rot_angles.push_back(DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_ROT)); s.tilt_angles.push_back(DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_TILT));
+				s.psi_angles.push_back(DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_PSI));
+				const RFLOAT ox = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_XOFF), oy = DIRECT_A2D_ELEM(o.exp_metadata, p, METADATA_YOFF);
+				s.translations_x.push_back((ox - ROUND(ox)) * o.mymodel.pixel_size); s.translations_y.push_back((oy - ROUND(oy)) * o.mymodel.pixel_size);
+			}
+		}
 		o.exp_imagedata.resize(P, ori, ori);
 		for (size_t i = 0; i < (size_t) P * ori * ori; i++) o.exp_imagedata.data[i] = (RFLOAT) img[(size_t) first * ori * ori + i];
 		// the OpenMP fan-out (:4280-4282), here one after the other: every thread calls in, thread 0 carries the pool

@@ -243,3 +243,53 @@ def test_cpp_adapter_optics_group_with_its_own_box(device, tmp_path, img_box, mo
     device.pool_prepare(0, raw)
     other = device.estep_slot(0)
     assert np.abs(other.particles["dLL_nolog"] - p["dLL_nolog"]).max() > 0.1
+
+
+@pytest.mark.gpu
+def test_cpp_adapter_skip_align(device, tmp_path):
+    """--skip_align through the C++ adapter: RELION refills the sampling object with the pool's own orientations and fractional
+    offsets before every pool (src/ml_optimiser.cpp:4180-4225); the adapter reloads the sampling tables per pool, hands every particle
+    the one-entry lists of its row, passes its translation as rb_particles.pre_shift and looks the metadata row up by the row index
+    (acc_ml_optimiser_impl.h:3752-3766, 2874-2876).  Pools of 5 particles so that rows restart; checked against the Python mirror."""
+    from relion_b200.workload import make_skip_align_workload
+    from relion_b200.synth import mresol
+    wl = make_skip_align_workload(n_particles=13, nr_classes=3, seed=71, snr=0.3, nr_groups=2)
+    m, s = wl.model, wl.sampling
+    raw = raw_pool_from(wl, seed=9)
+    rnd = np.where(raw.old_offset > 0, np.floor(raw.old_offset + 0.5), -np.floor(-raw.old_offset + 0.5))
+    raw.pre_shift = raw.old_offset - rnd
+    arrays, md0 = _workload_arrays(wl, raw, avg_norm=0.95)
+    arrays["skip_align"] = np.array([1.0]); arrays["local_search"] = np.array([0.0])
+    for k in ("dir_off", "dir_idx", "dir_prior", "psi_off", "psi_idx", "psi_prior"):
+        arrays.pop(k, None)
+    _dump(str(tmp_path / "w.bin"), arrays)
+    r = subprocess.run([_exe(), str(tmp_path / "w.bin"), str(tmp_path / "o.bin"), "2", "5"], capture_output=True, text=True)
+    print(r.stdout, r.stderr)
+    assert r.returncode == 0 and "PASS" in r.stdout, r.stdout + r.stderr
+    buf = open(tmp_path / "o.bin", "rb").read()
+    nm = struct.unpack_from("<q", buf, 0)[0]
+    md = np.frombuffer(buf, np.float64, nm, 8).reshape(-1, NCOL)
+    npk = struct.unpack_from("<q", buf, 8 + 8 * nm)[0]
+    pack = np.frombuffer(buf, np.float64, npk, 16 + 8 * nm)
+
+    device.set_model(m); device.set_sampling(s)
+    for k, v in enumerate(wl.refs):
+        device.set_reference(k, v.astype(np.complex128), wl.r_max, wl.padding_factor)
+        device.bp_init(k, wl.bp_shape, wl.r_max, wl.padding_factor)
+    device.pool_prepare(0, raw)
+    res = device.estep_slot(0)
+    p = res.particles
+    # the poses are the particles' own; the class is what the E-step decides
+    np.testing.assert_array_equal(md[:, ROT], wl.truth["rot"])
+    np.testing.assert_array_equal(md[:, PSI], wl.truth["psi"])
+    np.testing.assert_allclose(md[:, XOFF], raw.old_offset[:, 0], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(md[:, YOFF], raw.old_offset[:, 1], rtol=0, atol=1e-12)
+    np.testing.assert_array_equal(md[:, CLASS], p["best_class"] + 1)
+    assert np.mean(p["best_class"] == wl.truth["cls"]) >= 0.8
+    np.testing.assert_allclose(md[:, PMAX], p["pmax"], rtol=1e-6)
+    ir = mresol(m.current_size)
+    sig = np.asarray(m.sigma2_noise, np.float64).reshape(-1)
+    logsigma2 = np.log(2 * np.pi * sig[ir[ir > 0]]).sum()
+    np.testing.assert_allclose(md[:, DLL], p["dLL_nolog"] - logsigma2, rtol=1e-6)
+    np.testing.assert_allclose(pack[0], (p["dLL_nolog"] - logsigma2).sum(), rtol=1e-6)
+    np.testing.assert_allclose(pack[2], p["wsum_sigma2_offset"].sum(), rtol=1e-5)

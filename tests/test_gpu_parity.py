@@ -972,6 +972,25 @@ def test_symmetrise_with_helical_symmetry_on_device(device, nr_asu, twist, rise,
     assert np.abs(ww - pw).max() > 0.1 * np.abs(pw).max()
 
 
+@pytest.mark.parametrize("mode", ["skip_align", "skip_rotate"])
+def test_pool_only_classify(device, oracle, mode):
+    """--skip_align / --skip_rotate (rb_model.do_skip_rotate): every particle keeps its own orientation (one-entry lists into sampling
+    tables that hold the pool's orientations), the orientation prior is pdf_class, and with --skip_align the particle's fractional
+    offset is applied once as rb_particles.pre_shift instead of being its only sampled translation."""
+    from relion_b200.workload import make_skip_align_workload
+    wl = make_skip_align_workload(skip_rotate_only=(mode == "skip_rotate"), n_particles=14, nr_classes=3, seed=140, snr=0.3)
+    res, ores = _compare_pool(device, oracle, wl)
+    assert np.mean(res.particles["best_class"] == wl.truth["cls"]) >= 0.9
+    assert np.array_equal(res.particles["best_itrans"], wl.truth["itrans"])
+    # the prior is pdf_class: other class weights move the class sums
+    np.testing.assert_allclose(res.wsum_pdf_class, ores.wsum_pdf_class, rtol=1e-4)
+    if mode == "skip_align":
+        plain = make_skip_align_workload(n_particles=14, nr_classes=3, seed=140, snr=0.3)
+        plain.pool.pre_shift = None
+        other = device.expectation_some_particles(plain.pool)
+        assert np.abs(other.particles["dLL_nolog"] - res.particles["dLL_nolog"]).max() > 0.1
+
+
 def test_references_ending_inside_the_window_need_ref_max_r(device):
     """A pool whose references end inside the image window changes the pixel sets of the fine pass (rb_model.ref_max_r): without
     the field the library refuses the pool instead of summing rows the reference skips; so does a left matrix with 2D references."""

@@ -1,6 +1,6 @@
 # final round-2 measurement set: memcheck of the newest kernels, stage timing, ncu launch list + full capture of the headline kernels, full bench line
 mkdir -p gpurun_out
-compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -k "left_and_right or pool_local" 2>&1 | tail -5 > gpurun_out/memcheck_fin.txt
+compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -q -x -k "only_classify or left_and_right" 2>&1 | tail -5 > gpurun_out/memcheck_fin.txt
 cat gpurun_out/memcheck_fin.txt
 python bench.py --kernels-only --steps 5 --warmup 3 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['stages'])" | tee gpurun_out/stages_fin.txt
 export RB_BAND_ROUNDS=1

@@ -28,8 +28,10 @@
  *   combineAllWeightedSums()                           src/ml_optimiser_mpi.cpp:2028-2185 over NCCL instead of MPI: accumulators
  *                                                      summed on the devices (rb_bp_allreduce), everything else as one fp64
  *                                                      vector in MlWsumModel::pack order (WsumPack, src/ml_model.cpp:1881-2049)
- * Scope limits (RB_REPORT_ERROR when violated): nr_bodies == 1, one image per particle, 2D images, every optics group with
- * the model's box and pixel size, no helices / tomo; gradient refinement (do_grad, pseudo half-sets) with 3D references.
+ * Scope limits (RB_REPORT_ERROR when violated): nr_bodies == 1, one image per particle, 2D images, no helical refinement
+ * (--helix: translations in helical coordinates are per-particle tables), no tomo, no --only_sample_tilt.  Covered beyond the plain
+ * case: optics groups with their own box / pixel size and anisotropic magnification (setGeometry, mat_left), --skip_align /
+ * --skip_rotate (setSampling per pool, pre_shift), gradient refinement (do_grad, pseudo half-sets), both criteria.
  * Errors: the reference's HANDLE_ERROR / CRITICAL end in REPORT_ERROR, which throws RelionError (src/error.h,
  * src/acc/cuda/cuda_settings.h:48-68).  RB_REPORT_ERROR throws relion_b200::RelionError; compile with
  * -DRB_REPORT_ERROR=REPORT_ERROR inside RELION to throw its own type.  There is no CPU fallback.
@@ -391,6 +393,8 @@ public:
 		MlOptimiser &o = *baseMLO;
 		MlModel &m = o.mymodel;
 		if (m.nr_bodies != 1) RB_REPORT_ERROR("relion_b200: multi-body refinement is not covered");
+		if (o.do_helical_refine) RB_REPORT_ERROR("relion_b200: helical refinement (translations in helical coordinates) is not covered");
+		if (m.data_dim != 2) RB_REPORT_ERROR("relion_b200: 3D data (subtomograms) are not covered");
 		const int K = m.nr_classes;
 		geometry_og = -1;
 		setGeometry(0);

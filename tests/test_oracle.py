@@ -464,3 +464,46 @@ def test_sgd_backprojection_2d_port_matches_compiled_reference():
     assert np.abs(outs[0][2]).max() > 0
     for a, b in zip(outs[0], outs[1]):
         assert np.abs(a - b).max() <= 2e-5 * np.abs(a).max()
+
+
+def test_pre_shift_is_the_sampled_translation_of_skip_align():
+    """rb_particles.pre_shift (the particle's own fractional offset applied to the transforms once) against the reference's way of
+    doing --skip_align: that offset as the particle's ONE sampled translation (src/ml_optimiser.cpp:4196-4225,
+    acc_ml_optimiser_impl.h:3752-3756), through the compiled reference kernels where they are built.  One particle per pool, since the
+    sampled translation is per particle."""
+    import copy
+    from oracle.bindings import Oracle, Projector, Backprojector, have_reference
+    from relion_b200.workload import make_skip_align_workload
+    from relion_b200.estep import ParticlePool
+    o = Oracle("reference" if have_reference() else "port")
+    wl = make_skip_align_workload(n_particles=4, nr_classes=2, seed=81, snr=0.5, ori_size=24)
+    refs = [Projector(v, wl.r_max, wl.padding_factor) for v in wl.refs]
+    P = wl.pool.n_particles
+    for p in range(P):
+        sl = slice(p, p + 1)
+        base = dict(Fimg=wl.pool.Fimg[sl], Fimg_nomask=wl.pool.Fimg_nomask[sl], Fctf=wl.pool.Fctf[sl], group_id=wl.pool.group_id[sl],
+                    optics_group=wl.pool.optics_group[sl], highres_Xi2=wl.pool.highres_Xi2[sl], old_offset=np.zeros((1, 2)),
+                    prior_offset=np.zeros((1, 2)), dir_off=np.array([0, 1], np.int32), dir_idx=np.array([p], np.int32), dir_prior=np.ones(1),
+                    psi_off=np.array([0, 1], np.int32), psi_idx=np.array([p], np.int32), psi_prior=np.ones(1))
+        got = []
+        for mode in ("pre_shift", "sampled"):
+            s = copy.copy(wl.sampling)
+            pool = ParticlePool(**base)
+            if mode == "pre_shift":
+                pool.pre_shift = wl.pool.pre_shift[sl]
+            else:
+                s.trans_x = wl.pool.pre_shift[sl, 0].copy(); s.trans_y = wl.pool.pre_shift[sl, 1].copy()
+                s.over_trans_x, s.over_trans_y = s.trans_x.copy(), s.trans_y.copy()
+            bps = [Backprojector(wl.bp_shape, wl.r_max, wl.padding_factor) for _ in wl.refs]
+            st, out, _ = o.estep_pool(wl.model, s, refs, bps, pool, num_threads=1)
+            assert st == 0
+            got.append((out, bps))
+        (a, ba), (b, bb) = got
+        assert a.particles["best_class"][0] == b.particles["best_class"][0]
+        for f in ("dLL_nolog", "min_diff2", "sum_weight", "wsum_sigma2_offset", "wsum_norm_correction", "wsum_XA", "wsum_AA"):
+            np.testing.assert_allclose(a.particles[f], b.particles[f], rtol=2e-5, atol=1e-6, err_msg=f)
+        np.testing.assert_allclose(a.wsum_sigma2_noise, b.wsum_sigma2_noise, rtol=1e-3, atol=1e-5 * np.abs(b.wsum_sigma2_noise).max())
+        for x, y in zip(ba, bb):
+            for nm in ("real", "imag", "weight"):
+                u, v = getattr(x, nm), getattr(y, nm)
+                assert np.abs(u - v).max() <= 2e-5 * max(np.abs(v).max(), 1e-30), nm

@@ -507,3 +507,41 @@ def test_pre_shift_is_the_sampled_translation_of_skip_align():
             for nm in ("real", "imag", "weight"):
                 u, v = getattr(x, nm), getattr(y, nm)
                 assert np.abs(u - v).max() <= 2e-5 * max(np.abs(v).max(), 1e-30), nm
+
+
+def test_ctypes_mirrors_have_the_layout_of_the_header(tmp_path):
+    """Every struct of include/relion_b200.h that relion_b200/capi.py mirrors: same size, same field names in the same order at the
+    same offsets (a C program compiled against the header prints them).  A field added on one side only would otherwise shift every
+    pointer behind it silently."""
+    import ctypes as C
+    import subprocess
+    from relion_b200 import capi
+    names = ["rb_sampling", "rb_model", "rb_particles", "rb_raw_particles", "rb_posed_raw", "rb_particle_out", "rb_pool_out", "rb_weights_out"]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "relion_b200.h"', 'int main(void) {']
+    for n in names:
+        st = getattr(capi, n)
+        src.append(f'printf("{n} size %zu\\n", sizeof({n}));')
+        for f in st._fields_:
+            src.append(f'printf("{n} {f[0]} %zu\\n", offsetof({n}, {f[0]}));')
+    src += ['return 0; }']
+    c = tmp_path / "layout.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-std=c11", "-I" + os.path.join(ROOT, "include"), str(c), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split("\n")
+    want = {}
+    for line in out:
+        if line.strip():
+            s, f, v = line.split()
+            want[(s, f)] = int(v)
+    hdr = open(os.path.join(ROOT, "include", "relion_b200.h")).read()
+    for n in names:
+        st = getattr(capi, n)
+        assert C.sizeof(st) == want[(n, "size")], n
+        for f in st._fields_:
+            assert getattr(st, f[0]).offset == want[(n, f[0])], (n, f[0])
+        # no member of the C struct is missing from the mirror: the sizes match and the last mirrored field ends the struct
+        last = st._fields_[-1]
+        assert getattr(st, last[0]).offset + C.sizeof(last[1]) + 8 > C.sizeof(st), n
+        assert f"}} {n};" in hdr

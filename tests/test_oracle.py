@@ -545,3 +545,15 @@ def test_ctypes_mirrors_have_the_layout_of_the_header(tmp_path):
         last = st._fields_[-1]
         assert getattr(st, last[0]).offset + C.sizeof(last[1]) + 8 > C.sizeof(st), n
         assert f"}} {n};" in hdr
+
+
+def test_every_environment_switch_is_documented():
+    """INTEGRATION.md section 5 lists every RB_* variable the library or its Python host reads."""
+    import glob
+    import re
+    seen = set()
+    for f in glob.glob(os.path.join(ROOT, "relion_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(ROOT, "relion_b200", "*.py")):
+        seen |= set(re.findall(r'"(RB_[A-Z0-9_]+)"', open(f).read()))
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = sorted(v for v in seen if v not in doc)
+    assert not missing, missing

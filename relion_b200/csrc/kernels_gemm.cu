@@ -1058,6 +1058,12 @@ k_coarse_fused(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant_
 #pragma unroll
 				for (int j0 = 0; j0 < NJ; j0 += FU_QUAD_MLP)
 				{
+					if (j0 >= nj)                                      // CTA-uniform: the rounds beyond a partly filled tile issue no loads at all
+					{
+#pragma unroll
+						for (int jj = 0; jj < FU_QUAD_MLP; jj++) ref[j0 + jj] = make_float2(0.f, 0.f);
+						continue;
+					}
 					RbQuadFetch qf[FU_QUAD_MLP];
 #pragma unroll
 					for (int jj = 0; jj < FU_QUAD_MLP; jj++)
